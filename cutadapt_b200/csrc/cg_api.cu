@@ -1,0 +1,588 @@
+// cg_api.cu -- the C ABI (include/cutadapt_b200.h): contexts, adapter sets, batch dispatch.
+//
+// Host batches are processed as a 2-lane software pipeline: each lane owns a stream, device
+// buffers and pinned bounce buffers; consecutive sub-batches alternate lanes so that the H2D
+// copy of chunk i+1, the fused kernel of chunk i and the D2H copy of chunk i-1 overlap.
+// Caller buffers that are already pinned are copied from/to directly.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/cutadapt_b200.h"
+#include "cg_kernels.cuh"
+#include "cg_setbuild.h"
+
+static_assert(sizeof(cg_match) == 32 && sizeof(cg_match_rec) == 32, "cg_match must be 32 bytes");
+static_assert(sizeof(CgAdapter) == 80 && sizeof(CgEntry) == 32 && sizeof(CgGroup) == 32 &&
+                  sizeof(CgSetHeader) == 64, "table layout");
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+    g_err = buf;
+    return e == cudaErrorMemoryAllocation ? CG_ENOMEM : CG_ECUDA;
+}
+#define CU(x)                                                  \
+    do {                                                       \
+        cudaError_t _e = (x);                                  \
+        if (_e != cudaSuccess) return cuda_fail(_e, #x);       \
+    } while (0)
+
+extern "C" int cg_version(void) { return CG_ABI_VERSION; }
+extern "C" const char *cg_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return CG_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        cap = want;
+        return CG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return CG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMallocHost((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        cap = want;
+        return CG_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf<uint8_t> d_seq, d_qual;
+    DevBuf<int64_t> d_offs;
+    DevBuf<cg_match_rec> d_out;
+    DevBuf<int32_t> d_qtrim;
+    PinBuf<uint8_t> h_seq, h_qual;
+    PinBuf<int64_t> h_offs;
+    PinBuf<cg_match_rec> h_out;
+    PinBuf<int32_t> h_qtrim;
+    // pending result copy-back (bounce -> caller memory) of the chunk in flight
+    bool busy = false;
+    cg_match_rec *dst_out = nullptr; size_t n_out = 0; bool out_bounced = false;
+    int32_t *dst_qtrim = nullptr; size_t n_qtrim = 0; bool qtrim_bounced = false;
+};
+
+struct cg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    Lane lanes[2];
+    int *d_err = nullptr;       // [0] non-ASCII flag, [1] max_len scratch
+    uint8_t *d_enc = nullptr;   // 768 bytes
+    DevBuf<uint32_t> scratch_p;
+    DevBuf<int> scratch_w;
+    long long launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // fused-kernel event pairs
+    std::vector<cudaEvent_t> event_pool;
+    double timed_ms = 0.0;
+    long long timed_n = 0;
+};
+
+struct cg_adapterset {
+    cg_ctx *ctx = nullptr;
+    CgBuiltSet host;
+    uint8_t *d_blob = nullptr;
+    uint64_t *d_masks = nullptr;
+    CgEntry *d_entries = nullptr;   // device pointer into d_blob
+};
+
+// ------------------------------------------------------------------------------------------
+extern "C" int cg_ctx_create(int device, void *stream, cg_ctx **out)
+{
+    if (!out) return fail(CG_EINVAL, "cg_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CG_ECUDA, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                  "); cutadapt_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(CG_EINVAL, "cg_ctx_create: device ordinal out of range");
+    CU(cudaSetDevice(device));
+    cg_ctx *c = new cg_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void **)&c->d_err, 16 * sizeof(int)));
+    CU(cudaMemset(c->d_err, 0, 16 * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_enc, 768));
+    uint8_t enc[768];
+    cg_build_enc_tables(enc);
+    CU(cudaMemcpy(c->d_enc, enc, 768, cudaMemcpyHostToDevice));
+    *out = c;
+    return CG_OK;
+}
+
+static void resolve_timing(cg_ctx *c)
+{
+    for (auto &pr : c->timing) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            c->timed_ms += ms; c->timed_n += 1;
+        }
+        c->event_pool.push_back(pr.first);
+        c->event_pool.push_back(pr.second);
+    }
+    c->timing.clear();
+}
+
+extern "C" int cg_ctx_destroy(cg_ctx *c)
+{
+    if (!c) return CG_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    resolve_timing(c);
+    for (auto ev : c->event_pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        Lane &l = c->lanes[i];
+        l.d_seq.release(); l.d_qual.release(); l.d_offs.release(); l.d_out.release(); l.d_qtrim.release();
+        l.h_seq.release(); l.h_qual.release(); l.h_offs.release(); l.h_out.release(); l.h_qtrim.release();
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
+    c->scratch_p.release(); c->scratch_w.release();
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->d_enc) cudaFree(c->d_enc);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CG_OK;
+}
+
+extern "C" int cg_ctx_synchronize(cg_ctx *c)
+{
+    if (!c) return fail(CG_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(c->lanes[i].stream));
+    return CG_OK;
+}
+
+extern "C" int64_t cg_ctx_launch_count(cg_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int cg_ctx_kernel_time(cg_ctx *c, double *total_ms, int64_t *launches, int reset)
+{
+    if (!c) return fail(CG_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    resolve_timing(c);
+    if (total_ms) *total_ms = c->timed_ms;
+    if (launches) *launches = c->timed_n;
+    if (reset) { c->timed_ms = 0.0; c->timed_n = 0; }
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int cg_adapterset_create(cg_ctx *c, const cg_adapter_desc *adapters, int32_t n_adapters,
+                                    const cg_group_desc *groups, int32_t n_groups, cg_adapterset **out)
+{
+    if (!c || !out) return fail(CG_EINVAL, "cg_adapterset_create: NULL argument");
+    cg_adapterset *s = new cg_adapterset();
+    s->ctx = c;
+    std::string err;
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, s->host, err);
+    if (rc != CG_OK) { delete s; return fail(rc, err); }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_blob, s->host.blob.size());
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_blob, s->host.blob.data(), s->host.blob.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_masks, s->host.masks64.size() * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_masks, s->host.masks64.data(), s->host.masks64.size() * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (s->d_blob) cudaFree(s->d_blob);
+        if (s->d_masks) cudaFree(s->d_masks);
+        delete s;
+        return cuda_fail(e, "adapter set upload");
+    }
+    *out = s;
+    return CG_OK;
+}
+
+extern "C" int cg_adapterset_destroy(cg_adapterset *s)
+{
+    if (!s) return CG_OK;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    if (s->d_blob) cudaFree(s->d_blob);
+    if (s->d_masks) cudaFree(s->d_masks);
+    delete s;
+    return CG_OK;
+}
+
+extern "C" int cg_adapterset_slots(const cg_adapterset *s) { return s ? s->host.slots : 0; }
+
+extern "C" int cg_adapterset_effective_length(const cg_adapterset *s, int32_t adapter, int32_t *out)
+{
+    if (!s || !out || adapter < 0 || adapter >= s->host.n_adapters) return fail(CG_EINVAL, "bad adapter index");
+    *out = s->host.effective_length[adapter];
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Launch of the trimming pass on device-resident data
+// ------------------------------------------------------------------------------------------
+static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
+                       const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
+                       cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed)
+{
+    if (n_reads <= 0) return CG_OK;
+    const int times = p->times < 1 ? 1 : p->times;
+    const bool want_q = p->quality_trim != 0;
+    if (want_q && !d_qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
+    CgKernelArgs a;
+    memset(&a, 0, sizeof a);
+    a.blob = s->d_blob; a.blob_bytes = (uint32_t)s->host.blob.size();
+    a.masks64 = s->d_masks; a.enc = c->d_enc;
+    a.seq = d_seq; a.qual = want_q ? d_qual : nullptr; a.offsets = d_offsets; a.n_reads = n_reads;
+    a.quality_trim = want_q ? 1 : 0; a.cutoff_front = p->cutoff_front; a.cutoff_back = p->cutoff_back;
+    a.qbase = p->quality_base; a.times = times; a.slots = s->host.slots;
+    a.out = d_out; a.qtrim = d_qtrim; a.err_flag = c->d_err;
+    a.col_rows = s->host.max_m + 1;
+
+    const long long tile_cap_ll = ((long long)CG_NT * max_read_len + 32 + 15) / 16 * 16;
+    bool fast = !s->host.any_wide && max_read_len <= CG_PACKED_MAX_N && tile_cap_ll < (1 << 24);
+    size_t smem = 0;
+    int occ = 0;
+    if (fast) {
+        a.tile_cap = (int)tile_cap_ll;
+        smem = cg_fast_smem_bytes(a.blob_bytes, a.tile_cap, a.col_rows, want_q);
+        if (smem > c->smem_optin) fast = false;
+    }
+    if (fast) {
+        CU(cg_fast_occupancy(want_q, smem, &occ));
+        if (occ < 1) fast = false;
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (timed && c->timing.size() < 8192) {
+        for (cudaEvent_t *ev : {&ev0, &ev1}) {
+            if (!c->event_pool.empty()) { *ev = c->event_pool.back(); c->event_pool.pop_back(); }
+            else CU(cudaEventCreate(ev));
+        }
+        CU(cudaEventRecord(ev0, st));
+    }
+    if (fast) {
+        const long long n_tiles = (n_reads + CG_NT - 1) / CG_NT;
+        long long grid = (long long)occ * c->sm_count;
+        if (grid > n_tiles) grid = n_tiles;
+        CU(cg_launch_fast(a, want_q, (int)grid, smem, st));
+    } else {
+        // generic path: thread per read, columns in HBM scratch (16 bytes per cell)
+        const int block = 128;
+        long long threads = (long long)c->sm_count * 8 * block;
+        const long long per_thread = (long long)a.col_rows * 16;
+        while (threads > 32 * block && threads * per_thread > (1LL << 30)) threads /= 2;
+        if (threads > ((n_reads + block - 1) / block) * block) threads = ((n_reads + block - 1) / block) * block;
+        int rc = c->scratch_p.ensure((size_t)threads * a.col_rows);
+        if (rc != CG_OK) return rc;
+        rc = c->scratch_w.ensure((size_t)threads * a.col_rows * 3);
+        if (rc != CG_OK) return rc;
+        a.scratch_p = c->scratch_p.p; a.scratch_w = c->scratch_w.p; a.scratch_stride = threads;
+        CU(cg_launch_generic(a, (int)(threads / block), block, st));
+    }
+    c->launches += 1;
+    if (ev0) {
+        CU(cudaEventRecord(ev1, st));
+        c->timing.emplace_back(ev0, ev1);
+    }
+    return CG_OK;
+}
+
+static int check_err_flag(cg_ctx *c)
+{
+    int flags[2] = {0, 0};
+    CU(cudaMemcpy(flags, c->d_err, sizeof flags, cudaMemcpyDeviceToHost));
+    if (flags[0]) {
+        cudaMemset(c->d_err, 0, sizeof(int));
+        return fail(CG_ENONASCII, "String must contain only ASCII characters");
+    }
+    return CG_OK;
+}
+
+extern "C" int cg_process_batch_device(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq,
+                                       const uint8_t *d_qual, const int64_t *d_offsets, int64_t n_reads,
+                                       int32_t max_read_len, const cg_params *p, cg_match *d_matches,
+                                       int32_t *d_qtrim)
+{
+    if (!c || !s || !p || !d_seq || !d_offsets || !d_matches) return fail(CG_EINVAL, "cg_process_batch_device: NULL argument");
+    if (s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
+    if (((uintptr_t)d_seq & 15) || (d_qual && ((uintptr_t)d_qual & 15)))
+        return fail(CG_EINVAL, "device sequence/quality buffers must be 16-byte aligned");
+    if (n_reads < 0) return fail(CG_EINVAL, "n_reads < 0");
+    CU(cudaSetDevice(c->device));
+    if (max_read_len <= 0) {
+        CU(cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream));
+        CU(cg_launch_max_len(d_offsets, n_reads, c->d_err + 1, c->stream));
+        c->launches += 1;
+        CU(cudaMemcpyAsync(&max_read_len, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return launch_trim(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, (cg_match_rec *)d_matches,
+                       d_qtrim, c->stream, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// Host batches: 2-lane pipeline
+// ------------------------------------------------------------------------------------------
+static bool is_pinned(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int lane_finish(cg_ctx *c, Lane &l)
+{
+    if (!l.busy) return CG_OK;
+    CU(cudaStreamSynchronize(l.stream));
+    if (l.out_bounced && l.n_out) memcpy(l.dst_out, l.h_out.p, l.n_out * sizeof(cg_match_rec));
+    if (l.qtrim_bounced && l.n_qtrim) memcpy(l.dst_qtrim, l.h_qtrim.p, l.n_qtrim * sizeof(int32_t));
+    l.busy = false;
+    return CG_OK;
+}
+
+extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
+                                const int64_t *offsets, int64_t n_reads, const cg_params *p,
+                                cg_match *matches, int32_t *qtrim)
+{
+    if (!c || !s || !p || !offsets || !matches) return fail(CG_EINVAL, "cg_process_batch: NULL argument");
+    if (s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
+    if (n_reads < 0) return fail(CG_EINVAL, "n_reads < 0");
+    if (n_reads == 0) return CG_OK;
+    if (!seq) return fail(CG_EINVAL, "cg_process_batch: seq is NULL");
+    const bool want_q = p->quality_trim != 0;
+    if (want_q && !qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
+    CU(cudaSetDevice(c->device));
+    const int times = p->times < 1 ? 1 : p->times;
+    const size_t rec_per_read = (size_t)times * s->host.slots;
+    const bool seq_pinned = is_pinned(seq), qual_pinned = want_q && is_pinned(qual);
+    const bool offs_pinned = is_pinned(offsets), out_pinned = is_pinned(matches);
+    const bool qt_pinned = qtrim && is_pinned(qtrim);
+
+    const int64_t CHUNK_READS = 1 << 18;
+    const int64_t CHUNK_BYTES = 48LL << 20;
+    int64_t r0 = 0;
+    int lane_idx = 0;
+    int rc = CG_OK;
+    while (r0 < n_reads && rc == CG_OK) {
+        // chunk [r0, r1): bounded by reads and bytes; also compute the longest read
+        int64_t r1 = r0;
+        int max_len = 0;
+        const int64_t byte0 = offsets[r0];
+        while (r1 < n_reads && r1 - r0 < CHUNK_READS) {
+            const int64_t len = offsets[r1 + 1] - offsets[r1];
+            if (len < 0 || len > 2000000000LL) return fail(CG_EINVAL, "offsets must be non-decreasing");
+            if (r1 > r0 && offsets[r1 + 1] - byte0 > CHUNK_BYTES) break;
+            if (len > max_len) max_len = (int)len;
+            ++r1;
+        }
+        const int64_t nr = r1 - r0;
+        const int64_t nbytes = offsets[r1] - byte0;
+        const int pad = (int)(byte0 & 15);
+        Lane &l = c->lanes[lane_idx];
+        lane_idx ^= 1;
+        if ((rc = lane_finish(c, l)) != CG_OK) break;
+        if ((rc = l.d_seq.ensure((size_t)nbytes + 64)) != CG_OK) break;
+        if (want_q && (rc = l.d_qual.ensure((size_t)nbytes + 64)) != CG_OK) break;
+        if ((rc = l.d_offs.ensure((size_t)nr + 1)) != CG_OK) break;
+        if ((rc = l.d_out.ensure((size_t)nr * rec_per_read)) != CG_OK) break;
+        if (qtrim && (rc = l.d_qtrim.ensure((size_t)nr * 2)) != CG_OK) break;
+        // H2D (bounce through pinned memory unless the caller's buffer already is)
+        const uint8_t *src_seq = seq + byte0;
+        if (!seq_pinned) {
+            if ((rc = l.h_seq.ensure((size_t)nbytes + 16)) != CG_OK) break;
+            memcpy(l.h_seq.p, src_seq, (size_t)nbytes);
+            src_seq = l.h_seq.p;
+        }
+        if (nbytes) CU(cudaMemcpyAsync(l.d_seq.p + pad, src_seq, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
+        if (want_q) {
+            const uint8_t *src_q = qual + byte0;
+            if (!qual_pinned) {
+                if ((rc = l.h_qual.ensure((size_t)nbytes + 16)) != CG_OK) break;
+                memcpy(l.h_qual.p, src_q, (size_t)nbytes);
+                src_q = l.h_qual.p;
+            }
+            if (nbytes) CU(cudaMemcpyAsync(l.d_qual.p + pad, src_q, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
+        }
+        const int64_t *src_offs = offsets + r0;
+        if (!offs_pinned) {
+            if ((rc = l.h_offs.ensure((size_t)nr + 1)) != CG_OK) break;
+            memcpy(l.h_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t));
+            src_offs = l.h_offs.p;
+        }
+        CU(cudaMemcpyAsync(l.d_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, l.stream));
+        // offsets stay absolute: hand the kernel a virtual base so that base + offsets[r] lands
+        // in this chunk's buffer with the same 16-byte phase as in the caller's array
+        const uint8_t *vseq = l.d_seq.p + pad - byte0;
+        const uint8_t *vqual = want_q ? l.d_qual.p + pad - byte0 : nullptr;
+        rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, qtrim ? l.d_qtrim.p : nullptr,
+                         l.stream, true);
+        if (rc != CG_OK) break;
+        // D2H
+        cg_match_rec *dst = (cg_match_rec *)matches + (size_t)r0 * rec_per_read;
+        l.n_out = (size_t)nr * rec_per_read; l.dst_out = dst; l.out_bounced = !out_pinned;
+        if (out_pinned) CU(cudaMemcpyAsync(dst, l.d_out.p, l.n_out * sizeof(cg_match_rec), cudaMemcpyDeviceToHost, l.stream));
+        else {
+            if ((rc = l.h_out.ensure(l.n_out)) != CG_OK) break;
+            CU(cudaMemcpyAsync(l.h_out.p, l.d_out.p, l.n_out * sizeof(cg_match_rec), cudaMemcpyDeviceToHost, l.stream));
+        }
+        l.n_qtrim = 0; l.qtrim_bounced = false;
+        if (qtrim) {
+            int32_t *qdst = qtrim + 2 * r0;
+            l.n_qtrim = (size_t)nr * 2; l.dst_qtrim = qdst; l.qtrim_bounced = !qt_pinned;
+            if (qt_pinned) CU(cudaMemcpyAsync(qdst, l.d_qtrim.p, l.n_qtrim * 4, cudaMemcpyDeviceToHost, l.stream));
+            else {
+                if ((rc = l.h_qtrim.ensure(l.n_qtrim)) != CG_OK) break;
+                CU(cudaMemcpyAsync(l.h_qtrim.p, l.d_qtrim.p, l.n_qtrim * 4, cudaMemcpyDeviceToHost, l.stream));
+            }
+        }
+        l.busy = true;
+        r0 = r1;
+    }
+    for (int i = 0; i < 2; ++i) {
+        int rc2 = lane_finish(c, c->lanes[i]);
+        if (rc == CG_OK) rc = rc2;
+    }
+    if (rc != CG_OK) return rc;
+    return check_err_flag(c);
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone batched natives (host pointers; lane 0)
+// ------------------------------------------------------------------------------------------
+static int upload_reads(cg_ctx *c, Lane &l, const uint8_t *bytes, const int64_t *offsets, int64_t n_reads,
+                        bool as_qual)
+{
+    const int64_t total = offsets[n_reads];
+    DevBuf<uint8_t> &d = as_qual ? l.d_qual : l.d_seq;
+    int rc = d.ensure((size_t)total + 64);
+    if (rc != CG_OK) return rc;
+    if ((rc = l.d_offs.ensure((size_t)n_reads + 1)) != CG_OK) return rc;
+    if (total) CU(cudaMemcpyAsync(d.p, bytes, (size_t)total, cudaMemcpyHostToDevice, l.stream));
+    CU(cudaMemcpyAsync(l.d_offs.p, offsets, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, l.stream));
+    return CG_OK;
+}
+
+extern "C" int cg_kmers_present_batch(cg_ctx *c, const cg_kmer_entry *entries, const uint64_t *masks,
+                                      int32_t n_entries, const uint8_t *seq, const int64_t *offsets,
+                                      int64_t n_reads, uint8_t *out)
+{
+    if (!c || !offsets || !out || n_reads < 0 || n_entries < 0) return fail(CG_EINVAL, "cg_kmers_present_batch: bad argument");
+    if (n_reads == 0) return CG_OK;
+    if (offsets[0] != 0) return fail(CG_EINVAL, "offsets[0] must be 0");
+    CU(cudaSetDevice(c->device));
+    Lane &l = c->lanes[0];
+    int rc = lane_finish(c, l);
+    if (rc != CG_OK) return rc;
+    std::vector<CgEntry> ents((size_t)std::max(n_entries, 1));
+    memset(ents.data(), 0, ents.size() * sizeof(CgEntry));
+    for (int e = 0; e < n_entries; ++e) {
+        if (entries[e].search_start > 2000000000LL || entries[e].search_start < -2000000000LL ||
+            entries[e].search_stop > 2000000000LL || entries[e].search_stop < -2000000000LL)
+            return fail(CG_EINVAL, "k-mer window out of range");
+        ents[e].start = (int32_t)entries[e].search_start; ents[e].stop = (int32_t)entries[e].search_stop;
+        ents[e].mask_index = (uint32_t)e;
+        ents[e].init_mask = entries[e].init_mask; ents[e].found_mask = entries[e].found_mask;
+    }
+    CgEntry *d_ents = nullptr;
+    uint64_t *d_masks = nullptr;
+    uint8_t *d_out = nullptr;
+    const size_t mask_words = (size_t)std::max(n_entries, 1) * 128;
+    cudaError_t e = cudaMalloc((void **)&d_ents, ents.size() * sizeof(CgEntry));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_masks, mask_words * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, (size_t)n_reads);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ents, ents.data(), ents.size() * sizeof(CgEntry), cudaMemcpyHostToDevice, l.stream);
+    if (e == cudaSuccess && n_entries > 0) e = cudaMemcpyAsync(d_masks, masks, (size_t)n_entries * 128 * 8, cudaMemcpyHostToDevice, l.stream);
+    if (e == cudaSuccess) {
+        rc = upload_reads(c, l, seq, offsets, n_reads, false);
+        if (rc == CG_OK) {
+            e = cg_launch_kmers_present(d_ents, n_entries, d_masks, l.d_seq.p, l.d_offs.p, n_reads, d_out, c->d_err, l.stream);
+            c->launches += 1;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n_reads, cudaMemcpyDeviceToHost, l.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(l.stream);
+        }
+    }
+    if (d_ents) cudaFree(d_ents);
+    if (d_masks) cudaFree(d_masks);
+    if (d_out) cudaFree(d_out);
+    if (rc != CG_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "cg_kmers_present_batch");
+    return check_err_flag(c);
+}
+
+extern "C" int cg_quality_trim_batch(cg_ctx *c, const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                                     int32_t cutoff_front, int32_t cutoff_back, int32_t base, int32_t *out)
+{
+    if (!c || !offsets || !out || n_reads < 0) return fail(CG_EINVAL, "cg_quality_trim_batch: bad argument");
+    if (n_reads == 0) return CG_OK;
+    if (!qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
+    if (offsets[0] != 0) return fail(CG_EINVAL, "offsets[0] must be 0");
+    CU(cudaSetDevice(c->device));
+    Lane &l = c->lanes[0];
+    int rc = lane_finish(c, l);
+    if (rc != CG_OK) return rc;
+    if ((rc = upload_reads(c, l, qual, offsets, n_reads, true)) != CG_OK) return rc;
+    if ((rc = l.d_qtrim.ensure((size_t)n_reads * 2)) != CG_OK) return rc;
+    CU(cg_launch_quality_trim(l.d_qual.p, l.d_offs.p, n_reads, cutoff_front, cutoff_back, base, l.d_qtrim.p, l.stream));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(out, l.d_qtrim.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaStreamSynchronize(l.stream));
+    return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Statistics
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t cg_stats_size(int32_t n_adapters, int32_t max_len, int32_t kmax)
+{
+    if (n_adapters < 0 || max_len < 0 || kmax < 0) return -1;
+    return 8 + (int64_t)n_adapters * (max_len + 1) * (kmax + 1);
+}
+
+extern "C" int cg_stats_accumulate_device(cg_ctx *c, const cg_adapterset *s, const int64_t *d_offsets,
+                                          int64_t n_reads, const cg_params *p, const cg_match *d_matches,
+                                          const int32_t *d_qtrim, int32_t max_len, int32_t kmax,
+                                          int64_t *d_stats)
+{
+    if (!c || !s || !p || !d_offsets || !d_matches || !d_stats || max_len < 0 || kmax < 0)
+        return fail(CG_EINVAL, "cg_stats_accumulate_device: bad argument");
+    if (n_reads <= 0) return CG_OK;
+    CU(cudaSetDevice(c->device));
+    const int times = p->times < 1 ? 1 : p->times;
+    CU(cg_launch_stats(d_offsets, n_reads, p->quality_trim && d_qtrim, times, s->host.slots,
+                       (const cg_match_rec *)d_matches, d_qtrim, s->host.n_adapters, max_len, kmax,
+                       (unsigned long long *)d_stats, c->stream));
+    c->launches += 1;
+    return CG_OK;
+}

@@ -1,0 +1,490 @@
+// cg_core.cuh -- per-read device functions of the adapter-trimming hot path.
+//
+// Everything here is `__host__ __device__`: the kernels in cg_kernels.cu call it with one
+// lane per read; tests/hostsim compiles the very same functions for the host so that the
+// selection logic can be fuzzed against the oracle on a machine without a GPU.  (The host
+// build exists only under tests/; the shipped library never runs it.)
+//
+// Reference semantics restated here (file:line relative to the reference checkout):
+//   kmers_present_core   _kmer_finder.pyx:170-213, 241-257
+//   locate_core          _align.pyx:298-587       (column-major DP with Ukkonen cut-off,
+//                                                  cost/score/origin triples, cutadapt's
+//                                                  "best overlap" selection, incl. the stale
+//                                                  `origin` at line 565)
+//   compare_core         _align.pyx:651-714       (Prefix/SuffixComparer)
+//   quality_trim_core    qualtrim.pyx:22-73
+//   match_single/linked/multiple   adapters.py:707-724, 758-786, 815-832, 862-890, 915-935,
+//                                  1215-1227, 1265-1286
+//   process_read         modifiers.py:853-858 (QualityTrimmer) + 225-231 (AdapterCutter rounds)
+#pragma once
+#include "cg_types.h"
+
+#define CGK_KIND_ALIGNER 0
+#define CGK_KIND_PREFIX 1
+#define CGK_KIND_SUFFIX 2
+#define CGK_REMOVE_BEFORE 0
+#define CGK_REMOVE_AFTER 1
+#define CGK_REMOVE_AUTO 2
+#define CGK_GROUP_SINGLE 0
+#define CGK_GROUP_LINKED 1
+
+template <class X> CG_HD X cg_min(X a, X b) { return a < b ? a : b; }
+template <class X> CG_HD X cg_max(X a, X b) { return a > b ? a : b; }
+
+// A (sub)sequence of a read, optionally seen back to front (Rightmost* adapters search the
+// reversed read, adapters.py:766,870).
+struct ReadView {
+    const uint8_t *p;
+    int n;
+    int rev;
+    CG_HD uint8_t at(int j) const { return rev ? p[n - 1 - j] : p[j]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// DP cells.
+//
+// Packed32 keeps (cost, score, origin) of _align.pyx:23-26 in ONE 32-bit word so that the
+// three-way tie-broken minimum of _align.pyx:462-476 is a plain unsigned min:
+//
+//   [31..26] cost, saturating at CAP=31     [25..24] priority tag (0 diag, 1 del, 2 ins)
+//   [23..15] score + 64                     [14..0]  origin + 512
+//
+// Candidates get distinct tags, so min() over the words orders by (cost, tag) exactly like
+// "mismatch if <= both, else deletion if <= insertion, else insertion".  Any cell whose cost
+// reaches CAP collapses to the constant INF: such cells can never be part of a reported
+// alignment (reported cost <= k <= 29) and never win a tie-break against a cell that can.
+// Valid for indel_cost == 1, k <= 29, m <= 447, n <= 32255 (the host checks; everything else
+// takes WideCell).  Invariant that keeps the score field from borrowing: score >= -2*cost.
+// ---------------------------------------------------------------------------------------
+struct Packed32 {
+    typedef uint32_t T;
+    static constexpr uint32_t CS = 26, PS = 24, SS = 15, SB = 64, OB = 512, CAP = 31;
+    static constexpr uint32_t INF = CAP << CS;
+    CG_HD static T make(long long cost, int score, int origin)
+    {
+        if (cost >= (long long)CAP) return INF;
+        return ((uint32_t)cost << CS) | ((uint32_t)(score + (int)SB) << SS) | (uint32_t)(origin + (int)OB);
+    }
+    CG_HD static int cost(T w) { return (int)(w >> CS); }
+    CG_HD static int score(T w) { return (int)((w >> SS) & 511u) - (int)SB; }
+    CG_HD static int origin(T w) { return (int)(w & 32767u) - (int)OB; }
+    CG_HD static bool cost_le(T w, int k) { return w < ((uint32_t)(k + 1) << CS); }
+    CG_HD static T clamp(T x) { return x < INF ? x : INF; }
+    CG_HD static T row0_free(T w) { return w + 1u; }                                  // origin += 1
+    CG_HD static T row0_ins(T w, int) { return clamp(w + (1u << CS) - (2u << SS)); }  // cost+1, score-2
+    CG_HD static T match(T d) { return clamp(d + (1u << SS)); }                       // score+1
+    CG_HD static T mismatch(T d, T up, T left, int)
+    {
+        T cd = d + ((1u << CS) - (1u << SS));
+        T cu = up + ((1u << CS) + (1u << PS) - (2u << SS));
+        T cl = left + ((1u << CS) + (2u << PS) - (2u << SS));
+        T b = cg_min(cd, cg_min(cu, cl));
+        b &= ~(3u << PS);
+        return clamp(b);
+    }
+};
+
+// Exact int32 triples for everything Packed32 cannot hold (--no-indels' indel_cost=100000,
+// very long reads/adapters, k > 29).
+struct WideCell {
+    struct T { int cost, score, origin; };
+    CG_HD static T make(long long cost, int score, int origin)
+    {
+        T t;
+        t.cost = (int)(cost > 1000000000LL ? 1000000000LL : cost);
+        t.score = score; t.origin = origin;
+        return t;
+    }
+    CG_HD static int cost(const T &w) { return w.cost; }
+    CG_HD static int score(const T &w) { return w.score; }
+    CG_HD static int origin(const T &w) { return w.origin; }
+    CG_HD static bool cost_le(const T &w, int k) { return w.cost <= k; }
+    CG_HD static T row0_free(T w) { w.origin += 1; return w; }
+    CG_HD static T row0_ins(T w, int ic) { w.cost = w.cost > 1000000000 ? w.cost : w.cost + ic; w.score -= 2; return w; }
+    CG_HD static T match(T d) { d.score += 1; return d; }
+    CG_HD static T mismatch(const T &d, const T &up, const T &left, int ic)
+    {
+        int cd = d.cost + 1, cdel = up.cost > 1000000000 ? up.cost : up.cost + ic;
+        int cins = left.cost > 1000000000 ? left.cost : left.cost + ic;
+        T r;
+        if (cd <= cdel && cd <= cins) { r.cost = cd; r.origin = d.origin; r.score = d.score - 1; }
+        else if (cdel <= cins) { r.cost = cdel; r.origin = up.origin; r.score = up.score - 2; }
+        else { r.cost = cins; r.origin = left.origin; r.score = left.score - 2; }
+        return r;
+    }
+};
+
+// Column stores: element i of this lane's DP column.
+struct PackedCol {                // shared memory, lane-interleaved: conflict-free
+    uint32_t *base; int stride;
+    CG_HD uint32_t get(int i) const { return base[(size_t)i * stride]; }
+    CG_HD void set(int i, uint32_t v) { base[(size_t)i * stride] = v; }
+};
+struct WideCol {                  // global scratch, lane-interleaved: coalesced
+    int *base; long long stride;
+    CG_HD WideCell::T get(int i) const
+    {
+        WideCell::T t;
+        const int *q = base + (long long)(3 * i) * stride;
+        t.cost = q[0]; t.score = q[stride]; t.origin = q[2 * stride];
+        return t;
+    }
+    CG_HD void set(int i, const WideCell::T &t)
+    {
+        int *q = base + (long long)(3 * i) * stride;
+        q[0] = t.cost; q[stride] = t.score; q[2 * stride] = t.origin;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// KmerFinder.kmers_present  (_kmer_finder.pyx:170-213) -- reference-form entries
+// ---------------------------------------------------------------------------------------
+CG_HD bool kmers_present_core(const CgEntry *ents, int count, const uint64_t *masks64,
+                              const ReadView &rv)
+{
+    const long long n = rv.n;
+    for (int e = 0; e < count; ++e) {
+        long long start = ents[e].start, stop = ents[e].stop;
+        if (start < 0) { start += n; if (start < 0) start = 0; }
+        else if (start > n) continue;
+        if (stop < 0) { stop += n; if (stop <= 0) continue; }
+        else if (stop == 0) stop = n;
+        if (stop > n) stop = n;   // the reference would read past the string here (UB); clamp
+        if (stop - start <= 0) continue;
+        const uint64_t *mk = masks64 + 128u * (size_t)ents[e].mask_index;
+        const uint64_t init = ents[e].init_mask, found = ents[e].found_mask;
+        uint64_t R = 0;
+        for (long long i = start; i < stop; ++i) {       // _kmer_finder.pyx:251-257
+            R = ((R << 1) | init) & mk[rv.at((int)i) & 127];
+            if (R & found) return true;
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// Aligner.locate  (_align.pyx:298-587)
+// out6 = (ref_start, ref_stop, query_start, query_stop, score, errors)
+// ---------------------------------------------------------------------------------------
+template <class Cell, class Col>
+CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *ncnt,
+                       const int32_t *maxcost, const uint8_t *enc, const ReadView &rv, Col &col,
+                       int *out6)
+{
+    typedef typename Cell::T T;
+    const int m = A.m, n = rv.n, k = A.k, ic = A.indel_cost;
+    const bool sir = (A.flags & 1) != 0, siq = (A.flags & 2) != 0;
+    const bool eir = (A.flags & 4) != 0, eiq = (A.flags & 8) != 0;
+    const bool ascii = A.compare_ascii != 0;
+
+    int max_n = n, min_n = 0;                                   // _align.pyx:346-352
+    if (!siq) max_n = cg_min(n, m + k);
+    if (!eiq) min_n = cg_max(0, n - m - k);
+
+    for (int i = 0; i <= m; ++i) {                              // _align.pyx:364-383
+        long long c; int s, o;
+        if (!sir && !siq) { s = -2 * i; c = (long long)cg_max(i, min_n) * ic; o = 0; }
+        else if (sir && !siq) { s = 0; c = (long long)min_n * ic; o = cg_min(0, min_n - i); }
+        else if (!sir && siq) { s = -2 * i; c = (long long)i * ic; o = cg_max(0, min_n - i); }
+        else { s = 0; c = (long long)cg_min(i, min_n) * ic; o = min_n - i; }
+        col.set(i, Cell::make(c, s, o));
+    }
+
+    bool have = false;                                          // _align.pyx:391-396
+    int b_origin = 0, b_cost = 0, b_score = 0, b_ref_stop = m, b_q_stop = n;
+    int last = sir ? m : cg_min(m, k + 1);                      // _align.pyx:399-401
+    int last_filled = 0;
+    T stale = Cell::make(0, 0, 0);      // the C variable `origin` of _align.pyx:407 (see :565)
+
+    for (int j = min_n + 1; j <= max_n; ++j) {                  // _align.pyx:433
+        const uint8_t qc = enc[rv.at(j - 1)];
+        T diag = col.get(0);
+        T w0 = siq ? Cell::row0_free(diag) : Cell::row0_ins(diag, ic);   // _align.pyx:438-440
+        col.set(0, w0);
+        T up = w0;
+        int lastok = Cell::cost_le(w0, k) ? 0 : -1;
+        for (int i = 1; i <= last; ++i) {                       // _align.pyx:441-483
+            const T left = col.get(i);
+            const uint8_t rc = ref[i - 1];
+            const bool eq = ascii ? (rc == qc) : ((rc & qc) != 0);
+            const T nw = eq ? Cell::match(diag) : Cell::mismatch(diag, up, left, ic);
+            col.set(i, nw);
+            if (Cell::cost_le(nw, k)) lastok = i;
+            diag = left;
+            up = nw;
+        }
+        if (last >= 1) stale = up;
+        last_filled = last;                                     // _align.pyx:484
+        // `while last >= 0 and column[last].cost > k: last -= 1` == lastok   (_align.pyx:490-491)
+        if (lastok < m) {
+            last = lastok + 1;                                  // _align.pyx:494-495
+        } else if (eiq) {                                       // _align.pyx:496-533
+            stale = up;
+            const int cost = Cell::cost(up), score = Cell::score(up), origin = Cell::origin(up);
+            const int length = m + cg_min(origin, 0);
+            int eff = length;
+            if (A.wildcard_ref) eff = (length < m) ? length - (ncnt[m] - ncnt[m - length]) : A.effective_length;
+            const bool ok = length >= A.min_overlap && cost <= maxcost[eff];
+            const int best_len = m + cg_min(b_origin, 0);
+            if (ok && (!have || (origin <= b_origin + m / 2 && score > b_score) ||
+                       (length > best_len && score > b_score))) {
+                have = true;
+                b_score = score; b_cost = cost; b_origin = origin; b_ref_stop = m; b_q_stop = j;
+                if (cost == 0 && origin >= 0) break;            // _align.pyx:531-533
+            }
+        }
+    }
+
+    if (max_n == n) {                                           // _align.pyx:536-572
+        const int first_i = eir ? 0 : m;
+        const int origin_var = Cell::origin(stale);
+        for (int i = last_filled; i >= first_i; --i) {
+            const T w = col.get(i);
+            if (!Cell::cost_le(w, k)) continue;   // cost > k can never satisfy cost <= floor(eff*rate) <= k
+            const int o = Cell::origin(w), cost = Cell::cost(w), score = Cell::score(w);
+            const int length = i + cg_min(o, 0);
+            int eff = length;
+            if (A.wildcard_ref) {
+                if (length < m) eff = length - (ncnt[i] - ncnt[-cg_min(o, 0)]);
+                else eff = A.effective_length;
+            }
+            const bool ok = length >= A.min_overlap && cost <= maxcost[eff];
+            const int best_len = b_ref_stop + cg_min(b_origin, 0);
+            if (ok && (!have || (origin_var <= b_origin + m / 2 && score > b_score) ||
+                       (length > best_len && score > b_score))) {
+                have = true;
+                b_score = score; b_cost = cost; b_origin = o; b_ref_stop = i; b_q_stop = n;
+            }
+        }
+    }
+    if (!have) return false;                                    // _align.pyx:573-577
+    out6[0] = b_origin >= 0 ? 0 : -b_origin;                    // _align.pyx:579-587
+    out6[1] = b_ref_stop;
+    out6[2] = b_origin >= 0 ? b_origin : 0;
+    out6[3] = b_q_stop;
+    out6[4] = b_score;
+    out6[5] = b_cost;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// PrefixComparer.locate / SuffixComparer.locate  (_align.pyx:651-714)
+// `ref` holds the encoded adapter in its natural orientation for both.
+// ---------------------------------------------------------------------------------------
+CG_HD bool compare_core(const CgAdapter &A, const uint8_t *ref, const uint8_t *enc,
+                        const ReadView &rv, int *out6)
+{
+    const int m = A.m, n = rv.n;
+    const int length = cg_min(m, n);                            // _align.pyx:667
+    const bool ascii = A.compare_ascii != 0, suffix = A.kind == CGK_KIND_SUFFIX;
+    int errors = 0;
+    for (int i = 0; i < length; ++i) {                          // _align.pyx:681-688
+        const uint8_t rc = suffix ? ref[m - 1 - i] : ref[i];
+        const uint8_t qc = enc[suffix ? rv.at(n - 1 - i) : rv.at(i)];
+        errors += ascii ? (rc != qc) : ((rc & qc) == 0);
+    }
+    if (errors > A.max_k_cmp || length < A.min_overlap) return false;   // _align.pyx:690-691
+    const int score = (length - errors) - errors;               // _align.pyx:692
+    if (suffix) { out6[0] = m - length; out6[1] = m; out6[2] = n - length; out6[3] = n; }  // :714
+    else { out6[0] = 0; out6[1] = length; out6[2] = 0; out6[3] = length; }                  // :693
+    out6[4] = score; out6[5] = errors;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// quality_trim_index  (qualtrim.pyx:22-73)
+// ---------------------------------------------------------------------------------------
+CG_HD void quality_trim_core(const uint8_t *q, int n, int cutoff_front, int cutoff_back, int base,
+                             int *start_out, int *stop_out)
+{
+    int s = 0, best = 0, start = 0, stop = n;
+    for (int i = 0; i < n; ++i) {                               // qualtrim.pyx:51-59
+        s += cutoff_front - ((int)(signed char)q[i] - base);
+        if (s < 0) break;
+        if (s > best) { best = s; start = i + 1; }
+    }
+    best = 0; s = 0;
+    for (int i = n - 1; i >= 0; --i) {                          // qualtrim.pyx:62-70
+        s += cutoff_back - ((int)(signed char)q[i] - base);
+        if (s < 0) break;
+        if (s > best) { best = s; stop = i; }
+    }
+    if (start >= stop) { start = 0; stop = 0; }                 // qualtrim.pyx:71-72
+    *start_out = start; *stop_out = stop;
+}
+
+// ---------------------------------------------------------------------------------------
+// Adapter composition
+// ---------------------------------------------------------------------------------------
+struct SetView {
+    const CgSetHeader *h;
+    const CgAdapter *ad;
+    const CgGroup *gr;
+    const CgEntry *en;
+    const uint8_t *pool;
+    const uint64_t *masks64;   // HBM
+    const uint8_t *enc;        // 3 x 256 bytes: upper, acgt, iupac
+};
+
+CG_HD SetView make_set_view(const uint8_t *blob, const uint64_t *masks64, const uint8_t *enc)
+{
+    SetView S;
+    S.h = (const CgSetHeader *)blob;
+    S.ad = (const CgAdapter *)(blob + S.h->adapters_off);
+    S.gr = (const CgGroup *)(blob + S.h->groups_off);
+    S.en = (const CgEntry *)(blob + S.h->entries_off);
+    S.pool = blob + S.h->pool_off;
+    S.masks64 = masks64;
+    S.enc = enc;
+    return S;
+}
+
+// <SingleAdapter>.match_to: prefilter, locate, wrap (adapters.py:707-724, 758-786, 815-832,
+// 862-890, 915-935, 963-975, 1000-1012).
+template <bool ALLOW_WIDE>
+CG_HD bool match_single(const SetView &S, int ai, const uint8_t *p, int n, PackedCol &colp,
+                        WideCol &colw, CgHit &hit)
+{
+    const CgAdapter &A = S.ad[ai];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    if (A.pf_count > 0 && !kmers_present_core(S.en + A.pf_first, A.pf_count, S.masks64, rv)) return false;
+    const uint8_t *ref = S.pool + A.ref_off;
+    const uint8_t *enc = S.enc + 256 * A.query_enc;
+    int o[6];
+    bool found;
+    if (A.kind == CGK_KIND_ALIGNER) {
+        const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+        const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+        if (ALLOW_WIDE && (A.cell_mode == CG_CELL_WIDE || n > CG_PACKED_MAX_N))
+            found = locate_core<WideCell, WideCol>(A, ref, ncnt, maxcost, enc, rv, colw, o);
+        else
+            found = locate_core<Packed32, PackedCol>(A, ref, ncnt, maxcost, enc, rv, colp, o);
+    } else {
+        found = compare_core(A, ref, enc, rv, o);
+    }
+    if (!found) return false;
+    hit.adapter = ai;
+    if (A.reverse) {                                            // adapters.py:777-785, 881-889
+        hit.astart = A.m - o[1]; hit.astop = A.m - o[0];
+        hit.rstart = n - o[3]; hit.rstop = n - o[2];
+    } else {
+        hit.astart = o[0]; hit.astop = o[1]; hit.rstart = o[2]; hit.rstop = o[3];
+    }
+    hit.score = o[4]; hit.errors = o[5];
+    hit.remove = A.remove == CGK_REMOVE_AUTO ? (hit.rstart == 0 ? CGK_REMOVE_BEFORE : CGK_REMOVE_AFTER)
+                                            : A.remove;        // adapters.py:930-935
+    return true;
+}
+
+// Apply Match.trimmed() to the window [s, e)   (adapters.py:453-454, 486-487)
+CG_HD void apply_trim(const CgHit &h, int &s, int &e)
+{
+    if (h.remove == CGK_REMOVE_BEFORE) s += h.rstop;
+    else e = s + h.rstart;
+}
+
+struct GroupHit {
+    CgHit h0, h1;     // SINGLE: h0.  LINKED: h0 = front (adapter -1 if absent), h1 = back.
+    int score, errors;
+};
+
+// One Matchable.match_to on the window [p, p+n)
+template <bool ALLOW_WIDE>
+CG_HD bool match_group(const SetView &S, const CgGroup &G, const uint8_t *p, int n,
+                       PackedCol &colp, WideCol &colw, GroupHit &gh)
+{
+    gh.h0.adapter = -1; gh.h1.adapter = -1;
+    if (G.type == CGK_GROUP_SINGLE) {
+        if (!match_single<ALLOW_WIDE>(S, G.a0, p, n, colp, colw, gh.h0)) return false;
+        gh.score = gh.h0.score; gh.errors = gh.h0.errors;
+        return true;
+    }
+    // LinkedAdapter.match_to  (adapters.py:1215-1227)
+    const bool front = match_single<ALLOW_WIDE>(S, G.a0, p, n, colp, colw, gh.h0);
+    if (!front) gh.h0.adapter = -1;
+    if (G.front_required && !front) return false;
+    int s = 0, e = n;
+    if (front) apply_trim(gh.h0, s, e);                         // sequence[front_match.trim_slice()]
+    const bool back = match_single<ALLOW_WIDE>(S, G.a1, p + s, e - s, colp, colw, gh.h1);
+    if (!back) gh.h1.adapter = -1;
+    if (!back && (G.back_required || !front)) return false;
+    gh.score = (front ? gh.h0.score : 0) + (back ? gh.h1.score : 0);   // adapters.py:1113-1130
+    gh.errors = (front ? gh.h0.errors : 0) + (back ? gh.h1.errors : 0);
+    return true;
+}
+
+#ifndef CG_MATCH_STRUCT_DEFINED
+#define CG_MATCH_STRUCT_DEFINED
+struct cg_match_rec { int32_t adapter, astart, astop, rstart, rstop, score, errors, info; };
+#endif
+
+CG_HD void store_hit(cg_match_rec *dst, const CgHit &h, int group, int searched_len)
+{
+    cg_match_rec r;
+    r.adapter = h.adapter;
+    if (h.adapter < 0) { r.astart = r.astop = r.rstart = r.rstop = r.score = r.errors = 0; r.info = 0; }
+    else {
+        r.astart = h.astart; r.astop = h.astop; r.rstart = h.rstart; r.rstop = h.rstop;
+        r.score = h.score; r.errors = h.errors;
+        r.info = (group & 255) | (h.remove == CGK_REMOVE_AFTER ? 256 : 0) | ((searched_len & 0xFFFF) << 16);
+    }
+#if defined(__CUDA_ARCH__)
+    // two 16-byte stores
+    ((int4 *)dst)[0] = make_int4(r.adapter, r.astart, r.astop, r.rstart);
+    ((int4 *)dst)[1] = make_int4(r.rstop, r.score, r.errors, r.info);
+#else
+    *dst = r;
+#endif
+}
+
+// The whole per-read pass: optional quality trimming, then `times` rounds of
+// MultipleAdapters.match_to + trim  (modifiers.py:853-858, 225-231; adapters.py:1265-1286).
+//   seq/qual : this read's bytes (qual may be null when quality_trim == 0)
+//   out      : times * slots records
+template <bool ALLOW_WIDE>
+CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
+                        int quality_trim, int cutoff_front, int cutoff_back, int qbase, int times,
+                        PackedCol &colp, WideCol &colw, cg_match_rec *out, int32_t *qtrim_out)
+{
+    const int slots = S.h->slots;
+    int s = 0, e = n;
+    if (quality_trim) {
+        quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
+    }
+    if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
+    CgHit none; none.adapter = -1; none.remove = 0;
+    none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
+    bool alive = true;
+    for (int r = 0; r < times; ++r) {
+        cg_match_rec *dst = out + (size_t)r * slots;
+        bool have = false;
+        int best_group = -1;
+        GroupHit best;
+        best.h0 = none; best.h1 = none; best.score = 0; best.errors = 0;
+        if (alive) {
+            for (int g = 0; g < S.h->n_groups; ++g) {           // adapters.py:1271-1286
+                GroupHit gh;
+                if (!match_group<ALLOW_WIDE>(S, S.gr[g], seq + s, e - s, colp, colw, gh)) continue;
+                if (!have || gh.score > best.score || (gh.score == best.score && gh.errors < best.errors)) {
+                    have = true; best = gh; best_group = g;
+                }
+            }
+        }
+        if (!have) {
+            alive = false;                                      // modifiers.py:227-229
+            store_hit(dst, none, 0, 0);
+            if (slots > 1) store_hit(dst + 1, none, 0, 0);
+            continue;
+        }
+        const int searched = e - s;
+        store_hit(dst, best.h0, best_group, searched);
+        if (slots > 1) {
+            int s2 = 0, e2 = searched;
+            if (best.h0.adapter >= 0) apply_trim(best.h0, s2, e2);
+            store_hit(dst + 1, best.h1, best_group, e2 - s2);
+        }
+        // trimmed_read = match.trimmed(trimmed_read)           (modifiers.py:231; adapters.py:1132-1137)
+        if (best.h0.adapter >= 0) apply_trim(best.h0, s, e);
+        if (best.h1.adapter >= 0) apply_trim(best.h1, s, e);
+    }
+}

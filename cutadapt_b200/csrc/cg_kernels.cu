@@ -1,0 +1,390 @@
+// cg_kernels.cu -- sm_100a kernels of the adapter-trimming hot path.
+//
+// cg_trim_fast_kernel   the fused pass: quality trim -> k-mer prefilter -> banded DP ->
+//                       best-adapter selection, one lane per read, persistent CTAs.
+//                       Read bytes are staged HBM -> shared memory as one contiguous 16-byte
+//                       aligned range per 128-read tile with TMA 1-D bulk copies
+//                       (cp.async.bulk + mbarrier complete_tx), double buffered so the copy of
+//                       tile t+1 overlaps the compute of tile t.  The adapter tables (a few
+//                       hundred bytes) and each lane's DP column live in shared memory.
+//                       No tensor cores: this is small-integer DP, not a contraction.
+// cg_trim_generic_kernel  same per-read code (cg_core.cuh) for configurations the fused kernel
+//                       does not cover (wide cells for --no-indels / very long reads):
+//                       reads straight from HBM, DP columns in an HBM scratch.
+// plus the stand-alone batched KmerFinder / quality_trim_index kernels and the statistics
+// reduction.
+#include "cg_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+__host__ __device__ inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// shared-memory carve-up of the fused kernel
+struct FastSmem {
+    size_t bar_off, blob_off, enc_off, seq_off, qual_off, col_off, total;
+};
+__host__ __device__ inline FastSmem fast_smem_layout(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual)
+{
+    FastSmem L;
+    size_t o = 0;
+    L.bar_off = o; o += 16;
+    o = cg_align_up(o, 128);
+    L.blob_off = o; o += cg_align_up(blob_bytes, 16);
+    L.enc_off = o; o += 768;
+    o = cg_align_up(o, 128);
+    L.seq_off = o; o += 2 * (size_t)tile_cap;
+    L.qual_off = o; if (has_qual) o += 2 * (size_t)tile_cap;
+    o = cg_align_up(o, 128);
+    L.col_off = o; o += (size_t)col_rows * CG_NT * sizeof(uint32_t);
+    L.total = cg_align_up(o, 128);
+    return L;
+}
+
+size_t cg_fast_smem_bytes(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual)
+{
+    return fast_smem_layout(blob_bytes, tile_cap, col_rows, has_qual).total;
+}
+
+// ------------------------------------------------------------------------------------------
+// The fused kernel
+// ------------------------------------------------------------------------------------------
+template <bool HAS_QUAL>
+__global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const FastSmem L = fast_smem_layout(a.blob_bytes, a.tile_cap, a.col_rows, HAS_QUAL);
+    uint64_t *bars = (uint64_t *)(smem + L.bar_off);
+    uint8_t *s_blob = smem + L.blob_off;
+    uint8_t *s_enc = smem + L.enc_off;
+    uint8_t *s_seq = smem + L.seq_off;
+    uint8_t *s_qual = smem + L.qual_off;
+    uint32_t *s_col = (uint32_t *)(smem + L.col_off);
+    const int tid = threadIdx.x;
+
+    // adapter tables HBM -> smem (16-byte vectors), encoding tables
+    for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT)
+        ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
+    for (uint32_t i = tid; i < 768 / 16; i += CG_NT)
+        ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+
+    const long long n_reads = a.n_reads;
+    const long long n_tiles = (n_reads + CG_NT - 1) / CG_NT;
+    const uintptr_t seq_base = (uintptr_t)a.seq, qual_base = (uintptr_t)a.qual;
+
+    // producer: one elected lane issues the bulk copies of a tile into stage `st`
+    auto issue = [&](long long tile, int st) {
+        const long long r0 = tile * CG_NT;
+        const long long r1 = (r0 + CG_NT < n_reads) ? r0 + CG_NT : n_reads;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        if (b1 <= b0) return;
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        const uintptr_t sa1 = (seq_base + b1 + 15) & ~(uintptr_t)15;
+        uint32_t bytes = (uint32_t)(sa1 - sa0);
+        uint32_t qbytes = 0;
+        uintptr_t qa0 = 0;
+        if (HAS_QUAL) {
+            qa0 = (qual_base + b0) & ~(uintptr_t)15;
+            qbytes = (uint32_t)(((qual_base + b1 + 15) & ~(uintptr_t)15) - qa0);
+        }
+        mbar_expect_tx(&bars[st], bytes + qbytes);
+        tma_load_1d(s_seq + (size_t)st * a.tile_cap, (const void *)sa0, bytes, &bars[st]);
+        if (HAS_QUAL) tma_load_1d(s_qual + (size_t)st * a.tile_cap, (const void *)qa0, qbytes, &bars[st]);
+    };
+
+    if (tid == 0) {
+        if ((long long)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+        if ((long long)blockIdx.x + gridDim.x < n_tiles) issue((long long)blockIdx.x + gridDim.x, 1);
+    }
+
+    PackedCol colp; colp.base = s_col + tid; colp.stride = CG_NT;
+    WideCol colw; colw.base = nullptr; colw.stride = 0;
+    uint32_t phase0 = 0, phase1 = 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        const long long r0 = tile * CG_NT;
+        const long long r1 = (r0 + CG_NT < n_reads) ? r0 + CG_NT : n_reads;
+        const long long r = r0 + tid;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        long long o0 = 0, o1 = 0;
+        if (r < n_reads) { o0 = a.offsets[r]; o1 = a.offsets[r + 1]; }
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        const uint8_t *tile_seq = s_seq + (size_t)st * a.tile_cap;
+        const uint8_t *tile_qual = s_qual + (size_t)st * a.tile_cap;
+        if (b1 > b0) {
+            if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+            // ASCII check of the staged bases (the reference raises ValueError, _align.pyx:44-45)
+            const uint32_t head = (uint32_t)((seq_base + b0) - sa0);
+            const uint32_t body = (uint32_t)(b1 - b0);
+            const uint32_t nchunks = (head + body + 15) / 16;
+            uint32_t bad = 0;
+            for (uint32_t c = tid; c < nchunks; c += CG_NT) {
+                const uint4 v = ((const uint4 *)tile_seq)[c];
+                if (c == 0 || c == nchunks - 1) {
+                    const uint8_t *pb = tile_seq + 16 * c;
+                    for (uint32_t b = 0; b < 16; ++b) {
+                        const uint32_t idx = 16 * c + b;
+                        if (idx >= head && idx < head + body) bad |= pb[b];
+                    }
+                } else bad |= v.x | v.y | v.z | v.w;
+            }
+            if (bad & 0x80808080u) atomicOr(a.err_flag, 1);
+        }
+        if (r < n_reads) {
+            const int n = (int)(o1 - o0);
+            const uint8_t *p = tile_seq + (size_t)((seq_base + o0) - sa0);
+            const uint8_t *q = nullptr;
+            if (HAS_QUAL) {
+                const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+                q = tile_qual + (size_t)((qual_base + o0) - qa0);
+            }
+            process_read<false>(S, p, q, n, HAS_QUAL ? a.quality_trim : 0, a.cutoff_front, a.cutoff_back,
+                                a.qbase, a.times, colp, colw,
+                                a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr);
+        }
+        __syncthreads();   // every lane is done with stage `st`
+        if (tid == 0) {
+            const long long next = tile + 2LL * gridDim.x;
+            if (next < n_tiles) issue(next, st);
+        }
+    }
+}
+
+cudaError_t cg_fast_occupancy(bool has_qual, size_t smem, int *blocks_per_sm)
+{
+    cudaError_t e;
+    if (has_qual) {
+        e = cudaFuncSetAttribute(cg_trim_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cg_trim_fast_kernel<true>, CG_NT, smem);
+    }
+    e = cudaFuncSetAttribute(cg_trim_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cg_trim_fast_kernel<false>, CG_NT, smem);
+}
+
+cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st)
+{
+    if (has_qual) cg_trim_fast_kernel<true><<<grid, CG_NT, smem, st>>>(a);
+    else cg_trim_fast_kernel<false><<<grid, CG_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic kernel (wide cells / long reads): no staging, columns in HBM scratch
+// ------------------------------------------------------------------------------------------
+__global__ void cg_trim_generic_kernel(const CgKernelArgs a)
+{
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const SetView S = make_set_view(a.blob, a.masks64, a.enc);
+    PackedCol colp; colp.base = a.scratch_p + gtid; colp.stride = (int)a.scratch_stride;
+    WideCol colw; colw.base = a.scratch_w + gtid; colw.stride = a.scratch_stride;
+    for (long long r = gtid; r < a.n_reads; r += nthreads) {
+        const long long o0 = a.offsets[r], o1 = a.offsets[r + 1];
+        const int n = (int)(o1 - o0);
+        const uint8_t *p = a.seq + o0;
+        uint32_t bad = 0;
+        for (int i = 0; i < n; ++i) bad |= p[i];
+        if (bad & 0x80) atomicOr(a.err_flag, 1);
+        process_read<true>(S, p, a.qual ? a.qual + o0 : nullptr, n, a.qual ? a.quality_trim : 0,
+                           a.cutoff_front, a.cutoff_back, a.qbase, a.times, colp, colw,
+                           a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr);
+    }
+}
+
+cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st)
+{
+    cg_trim_generic_kernel<<<grid, block, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone batched KmerFinder.kmers_present (_kmer_finder.pyx:170-213)
+// ------------------------------------------------------------------------------------------
+__global__ void cg_kmers_present_kernel(const CgEntry *ents, int n_entries, const uint64_t *masks,
+                                        const uint8_t *seq, const int64_t *offsets, long long n_reads,
+                                        uint8_t *out, int *err)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        ReadView rv; rv.p = seq + offsets[r]; rv.n = (int)(offsets[r + 1] - offsets[r]); rv.rev = 0;
+        uint32_t bad = 0;
+        for (int i = 0; i < rv.n; ++i) bad |= rv.p[i];
+        if (bad & 0x80) atomicOr(err, 1);
+        out[r] = kmers_present_core(ents, n_entries, masks, rv) ? 1 : 0;
+    }
+}
+
+cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
+                                    const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,
+                                    uint8_t *d_out, int *d_err, cudaStream_t st)
+{
+    const int block = 128;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    cg_kmers_present_kernel<<<(int)grid, block, 0, st>>>(d_entries, n_entries, d_masks, d_seq, d_offsets,
+                                                         n_reads, d_out, d_err);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone batched quality_trim_index (qualtrim.pyx:22-73)
+// ------------------------------------------------------------------------------------------
+__global__ void cg_quality_trim_kernel(const uint8_t *qual, const int64_t *offsets, long long n_reads,
+                                       int cutoff_front, int cutoff_back, int base, int32_t *out)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        int s, e;
+        quality_trim_core(qual + offsets[r], (int)(offsets[r + 1] - offsets[r]), cutoff_front, cutoff_back,
+                          base, &s, &e);
+        out[2 * r] = s; out[2 * r + 1] = e;
+    }
+}
+
+cudaError_t cg_launch_quality_trim(const uint8_t *d_qual, const int64_t *d_offsets, long long n_reads,
+                                   int cutoff_front, int cutoff_back, int base, int32_t *d_out,
+                                   cudaStream_t st)
+{
+    const int block = 128;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    cg_quality_trim_kernel<<<(int)grid, block, 0, st>>>(d_qual, d_offsets, n_reads, cutoff_front,
+                                                        cutoff_back, base, d_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Longest read of a batch (device offsets)
+// ------------------------------------------------------------------------------------------
+__global__ void cg_max_len_kernel(const int64_t *offsets, long long n_reads, int *out)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    int best = 0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        const long long d = offsets[r + 1] - offsets[r];
+        const int v = d > 2147483647LL ? 2147483647 : (int)d;
+        best = v > best ? v : best;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(out, best);
+}
+
+cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *d_out, cudaStream_t st)
+{
+    const int block = 256;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    cg_max_len_kernel<<<(int)grid, block, 0, st>>>(d_offsets, n_reads, d_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Trim statistics: the fixed-layout int64 vector that is all-reduced across GPUs
+// (Statistics.__iadd__ report.py:81-126; EndStatistics.errors adapters.py:96-111,193-199)
+// ------------------------------------------------------------------------------------------
+__global__ void cg_stats_kernel(const int64_t *offsets, long long n_reads, int quality_trim, int times,
+                                int slots, const cg_match_rec *matches, const int32_t *qtrim,
+                                int n_adapters, int max_len, int kmax, unsigned long long *stats)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    unsigned long long n = 0, bp = 0, with_ad = 0, qbp = 0, abp = 0;
+    unsigned long long *hist = stats + 8;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        const long long len = offsets[r + 1] - offsets[r];
+        n += 1; bp += (unsigned long long)len;
+        long long cur = len;
+        if (quality_trim && qtrim) { cur = qtrim[2 * r + 1] - qtrim[2 * r]; qbp += (unsigned long long)(len - cur); }
+        bool any = false;
+        for (int t = 0; t < times; ++t) {
+            for (int s = 0; s < slots; ++s) {
+                const cg_match_rec m = matches[((size_t)r * times + t) * slots + s];
+                if (m.adapter < 0) continue;
+                any = true;
+                const int searched = (m.info >> 16) & 0xFFFF;
+                const int removed = (m.info & 256) ? searched - m.rstart : m.rstop;
+                abp += (unsigned long long)removed;
+                if (m.adapter < n_adapters) {
+                    const int L = removed < 0 ? 0 : (removed > max_len ? max_len : removed);
+                    const int E = m.errors < 0 ? 0 : (m.errors > kmax ? kmax : m.errors);
+                    atomicAdd(&hist[((size_t)m.adapter * (max_len + 1) + L) * (kmax + 1) + E], 1ULL);
+                }
+            }
+        }
+        with_ad += any ? 1 : 0;
+    }
+    // warp-reduce the scalar counters, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        bp += __shfl_xor_sync(0xffffffffu, bp, o);
+        with_ad += __shfl_xor_sync(0xffffffffu, with_ad, o);
+        qbp += __shfl_xor_sync(0xffffffffu, qbp, o);
+        abp += __shfl_xor_sync(0xffffffffu, abp, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[0], n); atomicAdd(&stats[1], bp); atomicAdd(&stats[2], with_ad);
+        atomicAdd(&stats[3], qbp); atomicAdd(&stats[4], abp);
+    }
+}
+
+cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
+                            int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
+                            int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
+                            cudaStream_t st)
+{
+    const int block = 256;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    cg_stats_kernel<<<(int)grid, block, 0, st>>>(d_offsets, n_reads, quality_trim, times, slots, d_matches,
+                                                 d_qtrim, n_adapters, max_len, kmax, d_stats);
+    return cudaGetLastError();
+}

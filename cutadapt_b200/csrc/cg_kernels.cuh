@@ -1,0 +1,50 @@
+// cg_kernels.cuh -- launch-side declarations shared by cg_kernels.cu and cg_api.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cg_core.cuh"
+
+#define CG_NT 128  // lanes (= reads) per CTA tile in the fused kernel
+
+struct CgKernelArgs {
+    // adapter tables (HBM)
+    const uint8_t *blob;
+    uint32_t blob_bytes;
+    const uint64_t *masks64;
+    const uint8_t *enc;  // 768 bytes
+    // batch (HBM)
+    const uint8_t *seq;
+    const uint8_t *qual;
+    const int64_t *offsets;
+    long long n_reads;
+    // parameters
+    int quality_trim, cutoff_front, cutoff_back, qbase, times, slots;
+    // outputs (HBM)
+    cg_match_rec *out;
+    int32_t *qtrim;
+    int *err_flag;
+    // fused-kernel geometry
+    int tile_cap;  // bytes per staged tile (multiple of 16)
+    int col_rows;  // max_m + 1
+    // generic-kernel scratch
+    uint32_t *scratch_p;
+    int *scratch_w;
+    long long scratch_stride;
+};
+
+size_t cg_fast_smem_bytes(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual);
+cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
+cudaError_t cg_fast_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
+cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
+                                    const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,
+                                    uint8_t *d_out, int *d_err, cudaStream_t st);
+cudaError_t cg_launch_quality_trim(const uint8_t *d_qual, const int64_t *d_offsets, long long n_reads,
+                                   int cutoff_front, int cutoff_back, int base, int32_t *d_out,
+                                   cudaStream_t st);
+cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *d_out, cudaStream_t st);
+cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
+                            int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
+                            int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
+                            cudaStream_t st);

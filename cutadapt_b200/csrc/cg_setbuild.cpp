@@ -1,0 +1,208 @@
+// cg_setbuild.cpp -- see cg_setbuild.h.
+//
+// This is the batched equivalent of Aligner.__cinit__/_set_reference (_align.pyx:195-277),
+// PrefixComparer.__init__ (_align.pyx:615-642) and the table part of KmerFinder.__cinit__
+// (_kmer_finder.pyx:106-165): it runs once per adapter set on the host; nothing here is on
+// the per-read path.
+#include "cg_setbuild.h"
+
+#include <math.h>
+#include <string.h>
+
+static void put2(uint8_t *t, char c, uint8_t v)
+{
+    t[(uint8_t)c] = v;
+    t[(uint8_t)(c | 0x20)] = v;
+}
+
+void cg_build_enc_tables(uint8_t *out)
+{
+    uint8_t *up = out, *acgt = out + 256, *iupac = out + 512;
+    for (int c = 0; c < 256; ++c) up[c] = (uint8_t)((c >= 'a' && c <= 'z') ? c - 32 : c);
+    memset(acgt, 0x80, 256);
+    put2(acgt, 'A', 1); put2(acgt, 'C', 2); put2(acgt, 'G', 4); put2(acgt, 'T', 8); put2(acgt, 'U', 8);
+    memset(iupac, 0, 256);
+    const uint8_t A = 1, C = 2, G = 4, T = 8;
+    put2(iupac, 'X', 0); put2(iupac, 'A', A); put2(iupac, 'C', C); put2(iupac, 'G', G);
+    put2(iupac, 'T', T); put2(iupac, 'U', T); put2(iupac, 'R', A | G); put2(iupac, 'Y', C | T);
+    put2(iupac, 'S', G | C); put2(iupac, 'W', A | T); put2(iupac, 'K', G | T); put2(iupac, 'M', A | C);
+    put2(iupac, 'B', C | G | T); put2(iupac, 'D', A | G | T); put2(iupac, 'H', A | C | T);
+    put2(iupac, 'V', A | C | G); put2(iupac, 'N', 0x8F);
+}
+
+static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+static int32_t floor_to_i32(double x)
+{
+    if (!(x == x)) return -1;  // NaN: nothing is acceptable
+    double f = floor(x);
+    if (f > 2000000000.0) return 2000000000;
+    if (f < -1.0) return -1;
+    return (int32_t)f;
+}
+
+int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc *groups, int n_groups,
+                 CgBuiltSet &out, std::string &err)
+{
+    if (n_adapters <= 0 || !ads) { err = "adapter set is empty"; return CG_EINVAL; }
+    if (n_groups <= 0 || !groups) { err = "adapter set has no groups"; return CG_EINVAL; }
+    uint8_t enc[768];
+    cg_build_enc_tables(enc);
+
+    std::vector<CgAdapter> A(n_adapters);
+    std::vector<CgEntry> E;
+    std::vector<uint8_t> pool;
+    out.masks64.clear();
+    out.effective_length.assign(n_adapters, 0);
+    out.max_m = 0; out.any_wide = 0;
+
+    for (int a = 0; a < n_adapters; ++a) {
+        const cg_adapter_desc &d = ads[a];
+        CgAdapter &x = A[a];
+        memset(&x, 0, sizeof x);
+        const int m = d.length;
+        if (m < 0 || (m > 0 && !d.sequence)) { err = "adapter has no sequence"; return CG_EINVAL; }
+        if (m > 65535) { err = "adapter longer than 65535 characters"; return CG_EUNSUPPORTED; }
+        for (int i = 0; i < m; ++i)
+            if (d.sequence[i] & 0x80) { err = "String must contain only ASCII characters"; return CG_ENONASCII; }
+        if (d.kind != CG_KIND_ALIGNER && d.kind != CG_KIND_PREFIX_COMPARER && d.kind != CG_KIND_SUFFIX_COMPARER) {
+            err = "unknown adapter kind"; return CG_EINVAL;
+        }
+        if (d.remove < 0 || d.remove > 2) { err = "unknown remove mode"; return CG_EINVAL; }
+        const bool wr = d.wildcard_ref != 0, wq = d.wildcard_query != 0;
+        x.m = m;
+        x.flags = d.flags & 15;
+        x.min_overlap = d.min_overlap;
+        x.kind = d.kind;
+        x.reverse = d.reverse_read ? 1 : 0;
+        x.remove = d.remove;
+        x.compare_ascii = (!wr && !wq) ? 1 : 0;
+        x.query_enc = wq ? 2 : (wr ? 1 : 0);                  // _align.pyx:322-328, 672-678
+        x.wildcard_ref = wr ? 1 : 0;
+        x.indel_cost = d.indel_cost;
+
+        // encoded adapter bytes
+        x.ref_off = (uint32_t)pool.size();
+        int n_upper = 0, n_lower = 0;
+        for (int i = 0; i < m; ++i) { n_upper += d.sequence[i] == 'N'; n_lower += d.sequence[i] == 'n'; }
+        if (d.kind == CG_KIND_ALIGNER) {
+            if (d.indel_cost < 1) { err = "indel_cost must be at least 1"; return CG_EINVAL; }   // _align.pyx:217-218
+            x.effective_length = m;
+            if (wr) {                                          // _align.pyx:268-272
+                x.effective_length = m - (n_upper + n_lower);
+                if (x.effective_length == 0) { err = "Cannot have only N wildcards in the sequence"; return CG_EINVAL; }
+            }
+            for (int i = 0; i < m; ++i) {
+                const uint8_t c = d.sequence[i];
+                pool.push_back(wr ? enc[512 + c] : wq ? enc[256 + c] : c);   // _align.pyx:272-276
+            }
+            const double km = d.max_error_rate * (double)m;    // _align.pyx:343
+            if (!(km == km) || km > 1.0e9 || km < -1.0e9) { err = "max_error_rate out of range"; return CG_EINVAL; }
+            x.k = (int32_t)km;
+            x.cell_mode = (d.indel_cost != 1 || x.k > CG_PACKED_MAX_K || x.k < 0 || m > CG_PACKED_MAX_M)
+                              ? CG_CELL_WIDE : CG_CELL_PACKED32;
+            if (x.cell_mode == CG_CELL_WIDE) out.any_wide = 1;
+            // n_counts (int32, 4-aligned)                      _align.pyx:260-266
+            while (pool.size() % 4) pool.push_back(0);
+            x.ncount_off = (uint32_t)pool.size();
+            {
+                int32_t c = 0;
+                for (int i = 0; i <= m; ++i) {
+                    pool.insert(pool.end(), (uint8_t *)&c, (uint8_t *)&c + 4);
+                    if (i < m && (d.sequence[i] == 'N' || d.sequence[i] == 'n')) ++c;
+                }
+            }
+            // maxcost[L] = floor(L * rate): "cost <= L * rate" in IEEE double (_align.pyx:513,559)
+            x.maxcost_off = (uint32_t)pool.size();
+            for (int L = 0; L <= m; ++L) {
+                int32_t v = floor_to_i32((double)L * d.max_error_rate);
+                pool.insert(pool.end(), (uint8_t *)&v, (uint8_t *)&v + 4);
+            }
+        } else {
+            x.effective_length = m;
+            if (wr) {                                          // _align.pyx:627-630 (sic: N minus n)
+                x.effective_length -= n_upper - n_lower;
+                if (x.effective_length == 0) { err = "Cannot have only N wildcards in the sequence"; return CG_EINVAL; }
+            }
+            if (!(d.max_error_rate >= 0.0 && d.max_error_rate <= 1.0)) {
+                err = "max_error_rate must be between 0 and 1"; return CG_EINVAL;   // _align.pyx:631-632
+            }
+            x.max_k_cmp = (int32_t)(d.max_error_rate * (double)x.effective_length);  // _align.pyx:633
+            if (d.min_overlap < 1) { err = "min_overlap must be at least 1"; return CG_EINVAL; }  // _align.pyx:634-635
+            for (int i = 0; i < m; ++i) {
+                const uint8_t c = d.sequence[i];
+                pool.push_back(wr ? enc[512 + c] : wq ? enc[256 + c] : enc[c]);      // _align.pyx:637-642
+            }
+            x.cell_mode = CG_CELL_PACKED32;
+        }
+        out.effective_length[a] = x.effective_length;
+        if (m > out.max_m) out.max_m = m;
+
+        // prefilter entries (reference form)
+        x.pf_first = (int32_t)E.size();
+        x.pf_count = 0;
+        if (d.n_kmer_entries > 0) {
+            if (!d.kmer_entries || !d.kmer_masks) { err = "k-mer tables missing"; return CG_EINVAL; }
+            for (int e = 0; e < d.n_kmer_entries; ++e) {
+                const cg_kmer_entry &k = d.kmer_entries[e];
+                if (k.search_start > 2000000000LL || k.search_start < -2000000000LL ||
+                    k.search_stop > 2000000000LL || k.search_stop < -2000000000LL) {
+                    err = "k-mer window out of range"; return CG_EINVAL;
+                }
+                CgEntry ce;
+                memset(&ce, 0, sizeof ce);
+                ce.start = (int32_t)k.search_start; ce.stop = (int32_t)k.search_stop;
+                ce.mask_index = (uint32_t)(out.masks64.size() / 128);
+                ce.init_mask = k.init_mask; ce.found_mask = k.found_mask;
+                E.push_back(ce);
+                out.masks64.insert(out.masks64.end(), d.kmer_masks + 128 * (size_t)e,
+                                   d.kmer_masks + 128 * (size_t)(e + 1));
+            }
+            x.pf_count = d.n_kmer_entries;
+        }
+    }
+
+    std::vector<CgGroup> G(n_groups);
+    out.slots = 1;
+    for (int g = 0; g < n_groups; ++g) {
+        const cg_group_desc &d = groups[g];
+        CgGroup &x = G[g];
+        memset(&x, 0, sizeof x);
+        x.type = d.type; x.a0 = d.a0; x.a1 = d.a1;
+        x.front_required = d.front_required ? 1 : 0; x.back_required = d.back_required ? 1 : 0;
+        if (d.type == CG_GROUP_SINGLE) {
+            if (d.a0 < 0 || d.a0 >= n_adapters) { err = "group refers to an unknown adapter"; return CG_EINVAL; }
+            x.a1 = -1;
+        } else if (d.type == CG_GROUP_LINKED) {
+            if (d.a0 < 0 || d.a0 >= n_adapters || d.a1 < 0 || d.a1 >= n_adapters) {
+                err = "linked group refers to an unknown adapter"; return CG_EINVAL;
+            }
+            if (ads[d.a0].remove == CG_REMOVE_AUTO || ads[d.a1].remove == CG_REMOVE_AUTO) {
+                err = "anywhere adapters cannot be linked"; return CG_EINVAL;
+            }
+            out.slots = 2;
+        } else { err = "unknown group type"; return CG_EINVAL; }
+    }
+    if (n_groups > 256) { err = "more than 256 adapter groups"; return CG_EUNSUPPORTED; }
+
+    // assemble
+    CgSetHeader H;
+    memset(&H, 0, sizeof H);
+    H.n_adapters = n_adapters; H.n_groups = n_groups; H.n_entries = (int32_t)E.size();
+    H.slots = out.slots; H.max_m = out.max_m; H.any_wide = out.any_wide;
+    uint32_t off = (uint32_t)sizeof(CgSetHeader);
+    H.adapters_off = off; off += (uint32_t)(A.size() * sizeof(CgAdapter)); off = align_up(off, 16);
+    H.groups_off = off; off += (uint32_t)(G.size() * sizeof(CgGroup)); off = align_up(off, 16);
+    H.entries_off = off; off += (uint32_t)(E.size() * sizeof(CgEntry)); off = align_up(off, 16);
+    H.pool_off = off; off += (uint32_t)pool.size(); off = align_up(off, 16);
+    H.total_bytes = off;
+    out.blob.assign(off, 0);
+    memcpy(out.blob.data(), &H, sizeof H);
+    memcpy(out.blob.data() + H.adapters_off, A.data(), A.size() * sizeof(CgAdapter));
+    memcpy(out.blob.data() + H.groups_off, G.data(), G.size() * sizeof(CgGroup));
+    if (!E.empty()) memcpy(out.blob.data() + H.entries_off, E.data(), E.size() * sizeof(CgEntry));
+    if (!pool.empty()) memcpy(out.blob.data() + H.pool_off, pool.data(), pool.size());
+    out.n_adapters = n_adapters; out.n_groups = n_groups;
+    if (out.masks64.empty()) out.masks64.assign(128, 0);   // never hand the kernel a null table
+    return CG_OK;
+}

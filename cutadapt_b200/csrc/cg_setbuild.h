@@ -1,0 +1,24 @@
+// cg_setbuild.h -- host-side compiler: cg_adapter_desc[] / cg_group_desc[] -> device blob.
+// Pure C++ (no CUDA) so that tests/hostsim can link it as well.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cutadapt_b200.h"
+#include "cg_types.h"
+
+struct CgBuiltSet {
+    std::vector<uint8_t> blob;       // CgSetHeader | adapters | groups | entries | pool
+    std::vector<uint64_t> masks64;   // 128 words per prefilter entry
+    std::vector<int32_t> effective_length;  // per adapter
+    int slots = 1;
+    int n_adapters = 0, n_groups = 0, max_m = 0, any_wide = 0;
+};
+
+// 3 x 256 bytes: upper, acgt, iupac  (src/cutadapt/_match_tables.py:4-66)
+void cg_build_enc_tables(uint8_t *out768);
+
+// Returns CG_OK or a negative code and fills `err`.
+int cg_build_set(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups,
+                 int n_groups, CgBuiltSet &out, std::string &err);

@@ -1,0 +1,80 @@
+// cg_types.h -- plain-old-data tables shared by the host-side adapter-set compiler and the kernels.
+//
+// An adapter set is compiled once on the host (cg_api.cu: cg_adapterset_create) into one
+// contiguous, position-independent blob:
+//
+//   CgSetHeader | CgAdapter[n_adapters] | CgGroup[n_groups] | CgEntry[n_entries] | pool bytes
+//
+// The blob is copied to HBM once and, at the start of every fused kernel, from HBM into the
+// CTA's shared memory (it is a few hundred bytes to a few KB: adapters are <= a few hundred
+// bases).  The 128 x uint64 needle masks of the k-mer prefilter live in a second HBM array
+// (L1/L2 resident; 1 KiB per search word).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CG_HD __host__ __device__ __forceinline__
+#define CG_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CG_HD inline
+#define CG_HD_NOINLINE
+#endif
+
+enum { CG_CELL_PACKED32 = 0, CG_CELL_WIDE = 1 };
+
+struct CgAdapter {          // 80 bytes
+    int32_t m;              // adapter length
+    int32_t k;              // (int)(max_error_rate * m)                  _align.pyx:343
+    int32_t flags;          // EndSkip bits                               align.py:24-34
+    int32_t min_overlap;
+    int32_t indel_cost;
+    int32_t kind;           // CG_KIND_*
+    int32_t reverse;        // scan the read back to front                adapters.py:766,870
+    int32_t remove;         // CG_REMOVE_*
+    int32_t compare_ascii;  // 1: upper-cased ASCII equality, 0: (a & b) != 0   _align.pyx:442-445
+    int32_t query_enc;      // read encoding table: 0 upper, 1 acgt, 2 iupac     _align.pyx:322-328
+    int32_t wildcard_ref;
+    int32_t effective_length;
+    int32_t max_k_cmp;      // comparers: int(rate * effective_length)    _align.pyx:633
+    int32_t cell_mode;      // CG_CELL_*
+    int32_t pf_first;       // first prefilter entry
+    int32_t pf_count;       // number of prefilter entries; 0 = always pass (MockKmerFinder)
+    uint32_t ref_off;       // pool offset: encoded adapter bytes [m]
+    uint32_t ncount_off;    // pool offset (4-aligned): int32 n_counts[m+1]  _align.pyx:260-266
+    uint32_t maxcost_off;   // pool offset (4-aligned): int32 maxcost[m+1] = floor(L * rate)
+    uint32_t reserved;
+};
+
+struct CgEntry {            // 32 bytes; the reference's KmerSearchEntry  _kmer_finder.pyx:58-63
+    int32_t start;
+    int32_t stop;
+    uint32_t mask_index;    // masks64[128 * mask_index + c]
+    uint32_t pad;
+    uint64_t init_mask;
+    uint64_t found_mask;
+};
+
+struct CgGroup {            // 32 bytes
+    int32_t type, a0, a1, front_required, back_required, pad[3];
+};
+
+struct CgSetHeader {        // 64 bytes
+    int32_t n_adapters, n_groups, n_entries, slots;
+    int32_t max_m;          // longest adapter (DP column height - 1)
+    int32_t any_wide;       // some adapter needs the wide-cell path
+    uint32_t adapters_off, groups_off, entries_off, pool_off;
+    uint32_t total_bytes;   // size of the blob, multiple of 16
+    int32_t pad[5];
+};
+
+// One result of locating a single adapter in a (sub)sequence; coordinates as SingleMatch.
+struct CgHit {
+    int32_t adapter;        // -1 = none
+    int32_t astart, astop, rstart, rstop, score, errors;
+    int32_t remove;         // resolved CG_REMOVE_BEFORE / CG_REMOVE_AFTER
+};
+
+// Packed-cell limits (see cg_core.cuh, struct Packed32)
+#define CG_PACKED_MAX_K 29
+#define CG_PACKED_MAX_M 447
+#define CG_PACKED_MAX_N 32255

@@ -1,0 +1,55 @@
+"""
+Mirror of the hot-path part of ``cutadapt.qualtrim`` (src/cutadapt/qualtrim.pyx:18-73):
+``quality_trim_index`` with the reference's signature, executed on the GPU, plus a batched
+variant.  (In the fused trimming pass the same device function runs as the first stage of the
+kernel; see cutadapt_b200.pipeline.)
+"""
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+class HasNoQualities(Exception):
+    pass
+
+
+def quality_trim_index_batch(
+    qualities: Sequence[str], cutoff_front: int, cutoff_back: int, base: int = 33
+) -> np.ndarray:
+    """(n, 2) int32 array of (start, stop) for every quality string."""
+    if any(q is None for q in qualities):
+        raise HasNoQualities("Cannot do quality trimming when no qualities are available")
+    try:
+        joined = "".join(qualities).encode("latin-1")
+    except UnicodeEncodeError:
+        raise ValueError("Quality data is not ASCII") from None
+    n = len(qualities)
+    out = np.zeros((n, 2), dtype=np.int32)
+    if n == 0:
+        return out
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in qualities], out=offsets[1:])
+    data = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(1, dtype=np.uint8)
+    ctx = _lib.default_context()
+    _lib.check(
+        _lib.lib().cg_quality_trim_batch(
+            ctx.handle, data.ctypes.data, offsets.ctypes.data, n, int(cutoff_front), int(cutoff_back),
+            int(base), out.ctypes.data,
+        )
+    )
+    return out
+
+
+def quality_trim_index(
+    qualities: Optional[str], cutoff_front: int, cutoff_back: int, base: int = 33
+) -> Tuple[int, int]:
+    """
+    Positions (start, stop) of the good-quality segment, BWA style (qualtrim.pyx:22-73).
+    """
+    if qualities is None:
+        raise HasNoQualities("Cannot do quality trimming when no qualities are available")
+    start, stop = quality_trim_index_batch([qualities], cutoff_front, cutoff_back, base)[0]
+    return int(start), int(stop)

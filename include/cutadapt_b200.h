@@ -1,0 +1,224 @@
+/*
+ * cutadapt_b200.h -- C ABI of the B200-native adapter-trimming core.
+ *
+ * Drop-in boundary for ONE hot path of marcelm/cutadapt:
+ *     Adapter.match_to -> KmerFinder.kmers_present -> Aligner.locate   (+ quality_trim_index)
+ * batched per chunk of reads.  Every entry point below states which reference interface it
+ * replaces (file:line relative to the reference checkout).  Plain C types only: no torch,
+ * no C++ types, no Python objects cross this boundary.  The Python host layer
+ * (cutadapt_b200/*.py) binds it with ctypes; INTEGRATION.md shows the stub a cutadapt
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns CG_OK (0) or a negative CG_E* code; the message for the last
+ *     failing call on the calling thread is returned by cg_last_error().
+ *   - "no match" is never an error: it is reported as adapter == -1 in cg_match.
+ *   - the caller owns all host buffers; the library owns device memory inside a cg_ctx.
+ *   - a cg_ctx is bound to one CUDA device and one stream and is NOT thread-safe
+ *     (mirrors "one Aligner per process", _align.pyx:172: the DP column is per-instance).
+ *   - there is no CPU fallback: without a usable CUDA device cg_ctx_create fails.
+ */
+#ifndef CUTADAPT_B200_H
+#define CUTADAPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_ABI_VERSION 1
+
+/* ---- status codes --------------------------------------------------------------------- */
+#define CG_OK 0
+#define CG_EINVAL (-1)    /* bad argument: the reference raises ValueError/TypeError            */
+#define CG_ENONASCII (-2) /* non-ASCII byte in a read/adapter (_align.pyx:44-45, _kmer_finder.pyx:182-183) */
+#define CG_ECUDA (-3)     /* CUDA runtime error                                                  */
+#define CG_ENOMEM (-4)    /* host or device allocation failed (_align.pyx:252-256 MemoryError)   */
+#define CG_EUNSUPPORTED (-5) /* configuration outside what the kernels implement (message says which) */
+#define CG_ENOQUAL (-6)   /* quality trimming requested without qualities (qualtrim.pyx:35-36 HasNoQualities) */
+
+/* ---- Aligner flags: EndSkip (src/cutadapt/align.py:24-34) ------------------------------ */
+#define CG_START_IN_REFERENCE 1
+#define CG_START_IN_QUERY 2
+#define CG_STOP_IN_REFERENCE 4
+#define CG_STOP_IN_QUERY 8
+
+/* ---- what locates the adapter (adapters.py:601-614 vs 1031-1041,1068-1078) ------------- */
+#define CG_KIND_ALIGNER 0        /* Aligner.locate            (_align.pyx:298-587) */
+#define CG_KIND_PREFIX_COMPARER 1 /* PrefixComparer.locate     (_align.pyx:651-693) */
+#define CG_KIND_SUFFIX_COMPARER 2 /* SuffixComparer.locate     (_align.pyx:708-714) */
+
+/* ---- which Match class wraps the alignment (adapters.py:427-493, 925-935) -------------- */
+#define CG_REMOVE_BEFORE 0   /* RemoveBeforeMatch: 5' adapters, keep read[rstop:]      */
+#define CG_REMOVE_AFTER 1    /* RemoveAfterMatch:  3' adapters, keep read[:rstart]     */
+#define CG_REMOVE_AUTO 2     /* AnywhereAdapter: BEFORE iff rstart == 0 else AFTER      */
+
+/* ---- composition of adapters (adapters.py:1181-1286) ----------------------------------- */
+#define CG_GROUP_SINGLE 0   /* one SingleAdapter                                            */
+#define CG_GROUP_LINKED 1   /* LinkedAdapter(front=a0, back=a1)   adapters.py:1215-1227      */
+
+typedef struct cg_ctx cg_ctx;               /* device, stream, staging buffers            */
+typedef struct cg_adapterset cg_adapterset; /* immutable compiled adapter tables on device */
+
+/* One search word of a KmerFinder, exactly the reference's KmerSearchEntry
+ * (_kmer_finder.pyx:58-63) minus mask_offset: the 128 x uint64 needle-mask table of entry e
+ * is masks[128*e .. 128*e+127] (_kmer_finder.pyx:153-154, 226-238). */
+typedef struct cg_kmer_entry {
+    int64_t search_start; /* negative = relative to the end of the read                     */
+    int64_t search_stop;  /* 0 = up to the end; negative = relative to the end               */
+    uint64_t init_mask;   /* one bit at the first character of every packed k-mer           */
+    uint64_t found_mask;  /* one bit at the last character of every packed k-mer            */
+} cg_kmer_entry;
+
+/* One SingleAdapter = the arguments of Aligner.__cinit__ (_align.pyx:195-204) or
+ * PrefixComparer.__init__ (_align.pyx:615-622) plus its KmerFinder tables and the few
+ * attributes adapters.py needs to build the Match (adapters.py:564-599, 684-1089). */
+typedef struct cg_adapter_desc {
+    const uint8_t *sequence;  /* adapter as given to the aligner (ASCII; already reversed
+                                 for Rightmost* adapters, adapters.py:746-750,849-854)      */
+    int32_t length;           /* m                                                          */
+    double max_error_rate;
+    int32_t flags;            /* CG_START_IN_* / CG_STOP_IN_* bits (aligner only)           */
+    int32_t wildcard_ref;     /* IUPAC characters in the adapter are wildcards              */
+    int32_t wildcard_query;   /* IUPAC characters in the read are wildcards                 */
+    int32_t indel_cost;       /* 1, or 100000 for --no-indels (adapters.py:605)             */
+    int32_t min_overlap;
+    int32_t kind;             /* CG_KIND_*                                                  */
+    int32_t reverse_read;     /* 1: match against the reversed read and mirror the
+                                 coordinates back (adapters.py:766-786, 870-890)            */
+    int32_t remove;           /* CG_REMOVE_*                                                */
+    const cg_kmer_entry *kmer_entries; /* NULL / 0 entries = MockKmerFinder (adapters.py:29-31) */
+    const uint64_t *kmer_masks;        /* 128 * n_kmer_entries words                        */
+    int32_t n_kmer_entries;
+    int32_t reserved;
+} cg_adapter_desc;
+
+/* One Matchable in MultipleAdapters order (adapters.py:1265-1286). */
+typedef struct cg_group_desc {
+    int32_t type;            /* CG_GROUP_*                                                  */
+    int32_t a0;              /* adapter index (SINGLE) / front adapter (LINKED)             */
+    int32_t a1;              /* back adapter (LINKED), else -1                              */
+    int32_t front_required;  /* LINKED only                                                 */
+    int32_t back_required;   /* LINKED only                                                 */
+    int32_t reserved[3];
+} cg_group_desc;
+
+/* Per-batch parameters of the fused pass (modifiers.py:840-858 then 200-261). */
+typedef struct cg_params {
+    int32_t quality_trim;    /* 0 = off; 1 = run quality_trim_index first and search read[start:stop] */
+    int32_t cutoff_front;
+    int32_t cutoff_back;
+    int32_t quality_base;    /* 33 or 64                                                     */
+    int32_t times;           /* AdapterCutter(times=...) rounds, >= 1 (modifiers.py:225-231) */
+    int32_t reserved[3];
+} cg_params;
+
+/* One match record (32 bytes).  For round r of read i the records are at
+ *     out[(i * times + r) * slots + s],  slots = cg_adapterset_slots(set)
+ * s = 0 for single adapters; LINKED groups use s = 0 (front) and s = 1 (back), either of
+ * which may be absent (adapter == -1) while the other is present.
+ * Coordinates are those of SingleMatch (adapters.py:334-356): relative to the sequence
+ * that was searched in that round (after quality trimming and earlier rounds). */
+typedef struct cg_match {
+    int32_t adapter; /* index into the adapter array, -1 = no match                         */
+    int32_t astart, astop;
+    int32_t rstart, rstop;
+    int32_t score, errors;
+    int32_t info;    /* bits 0..7: group index; bit 8: RemoveBefore(0)/RemoveAfter(1);
+                        bits 16..31: length of the sequence that was searched (mod 65536)   */
+} cg_match;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int cg_version(void);
+const char *cg_last_error(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to run on (e.g. torch's current stream),
+ * or NULL to let the context create its own. */
+int cg_ctx_create(int device, void *stream, cg_ctx **out);
+int cg_ctx_destroy(cg_ctx *ctx);
+int cg_ctx_synchronize(cg_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t cg_ctx_launch_count(cg_ctx *ctx);
+/* Average device time in ms of the fused trimming kernel since the last reset, measured with
+ * CUDA events on the launching stream; launches = number of samples. */
+int cg_ctx_kernel_time(cg_ctx *ctx, double *total_ms, int64_t *launches, int reset);
+
+/* ---- adapter set (replaces Aligner.__cinit__/_set_reference _align.pyx:195-277 and
+ *      KmerFinder.__cinit__ _kmer_finder.pyx:106-165 for every adapter at once) ----------- */
+int cg_adapterset_create(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n_adapters,
+                         const cg_group_desc *groups, int32_t n_groups, cg_adapterset **out);
+int cg_adapterset_destroy(cg_adapterset *set);
+int cg_adapterset_slots(const cg_adapterset *set); /* 1, or 2 if any group is LINKED */
+/* Aligner.effective_length / PrefixComparer.effective_length (_align.pyx:188,268-271,626-630) */
+int cg_adapterset_effective_length(const cg_adapterset *set, int32_t adapter, int32_t *out);
+
+/* ---- the batched hot path ---------------------------------------------------------------
+ * Replaces, for a whole chunk of reads, the per-read loop
+ *     QualityTrimmer.__call__ (modifiers.py:853-858) -> quality_trim_index (qualtrim.pyx:22-73)
+ *     AdapterCutter.match_and_trim (modifiers.py:225-231)
+ *       -> MultipleAdapters.match_to (adapters.py:1265-1286)
+ *         -> <Adapter>.match_to (adapters.py:707-724, 815-832, ...)
+ *           -> KmerFinder.kmers_present (_kmer_finder.pyx:170-213)
+ *           -> Aligner.locate (_align.pyx:298-587)
+ *
+ * Layout: read i occupies seq[offsets[i] .. offsets[i+1]) (and the same range of qual).
+ *   matches : n_reads * times * slots records
+ *   qtrim   : 2 * n_reads int32 (start, stop) of quality_trim_index; may be NULL
+ *
+ * cg_process_batch: HOST pointers; the library stages through pinned memory and overlaps
+ *   H2D / kernel / D2H in sub-batches on its streams.
+ * cg_process_batch_device: DEVICE pointers (16-byte aligned seq/qual, readable up to the next
+ *   16-byte boundary past offsets[n_reads]); runs asynchronously on the context stream.
+ *   max_read_len must be >= the longest read in the batch (pass 0 to let the library
+ *   compute it with a reduction kernel).
+ */
+int cg_process_batch(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *seq,
+                     const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                     const cg_params *params, cg_match *matches, int32_t *qtrim);
+int cg_process_batch_device(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *d_seq,
+                            const uint8_t *d_qual, const int64_t *d_offsets, int64_t n_reads,
+                            int32_t max_read_len, const cg_params *params, cg_match *d_matches,
+                            int32_t *d_qtrim);
+
+/* ---- stand-alone batched versions of the three native functions -------------------------
+ * KmerFinder.kmers_present (_kmer_finder.pyx:170-213): out[i] = 1/0.  Host pointers. */
+int cg_kmers_present_batch(cg_ctx *ctx, const cg_kmer_entry *entries, const uint64_t *masks,
+                           int32_t n_entries, const uint8_t *seq, const int64_t *offsets,
+                           int64_t n_reads, uint8_t *out);
+/* quality_trim_index (qualtrim.pyx:22-73): out[2i], out[2i+1] = start, stop.  Host pointers. */
+int cg_quality_trim_batch(cg_ctx *ctx, const uint8_t *qual, const int64_t *offsets,
+                          int64_t n_reads, int32_t cutoff_front, int32_t cutoff_back,
+                          int32_t base, int32_t *out);
+
+/* ---- trim statistics (the payload of the end-of-run all-reduce, report.py:81-126) --------
+ * Device-side reduction of a batch's match records into a fixed-layout int64 vector:
+ *   [0] n_reads  [1] total_bp  [2] reads_with_adapters  [3] quality_trimmed_bp
+ *   [4] bp_removed_by_adapters  [5..7] reserved
+ *   then per adapter a: errors histogram  hist[a][removed_len (0..max_len)][errors (0..kmax)]
+ * cg_stats_size() returns the vector length for given (n_adapters, max_len, kmax). */
+int64_t cg_stats_size(int32_t n_adapters, int32_t max_len, int32_t kmax);
+int cg_stats_accumulate_device(cg_ctx *ctx, const cg_adapterset *set, const int64_t *d_offsets,
+                               int64_t n_reads, const cg_params *params,
+                               const cg_match *d_matches, const int32_t *d_qtrim,
+                               int32_t max_len, int32_t kmax, int64_t *d_stats);
+
+/* ---- host-side index helpers (adapters.py:1416-1442 use these to build AdapterIndex) ----
+ * edit_environment (_align.pyx:785-882) / hamming_sphere-based environment
+ * (align.py hamming_environment): enumerate into a caller buffer.
+ * Each record: length byte-string of `stride` bytes (NUL padded), then errors, matches.
+ * Returns the number of records (>= 0) or a negative code; if it exceeds `capacity` only the
+ * first `capacity` are written and the full count is still returned. */
+int64_t cg_edit_environment(const uint8_t *s, int32_t n, int32_t k, int32_t stride,
+                            uint8_t *strings, int32_t *lengths, int32_t *errors,
+                            int32_t *matches, int64_t capacity);
+int64_t cg_hamming_environment(const uint8_t *s, int32_t n, int32_t k, int32_t stride,
+                               uint8_t *strings, int32_t *errors, int32_t *matches,
+                               int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTADAPT_B200_H */

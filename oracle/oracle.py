@@ -1,0 +1,285 @@
+"""
+oracle/oracle.py -- Python face of the CPU oracle.
+
+TEST INFRASTRUCTURE (see the header of cutadapt_oracle.c).  Loads ``liboracle.so`` (the plain-C
+restatement of Aligner.locate / comparers / KmerFinder / quality_trim_index), compiling it with
+gcc on first use, and restates in Python the *composition* the reference does above those
+native functions:
+
+    <Adapter>.match_to          src/cutadapt/adapters.py:707-724, 758-786, 815-832, 862-890,
+                                915-935, 963-975, 1000-1012
+    LinkedAdapter.match_to      adapters.py:1215-1227   (score/errors: 1113-1130)
+    MultipleAdapters.match_to   adapters.py:1265-1286
+    QualityTrimmer + AdapterCutter rounds   modifiers.py:853-858, 225-231
+
+``oracle_process`` consumes the same plain-dict adapter descriptions as the product's
+``cutadapt_b200._lib.AdapterSetSpec`` and produces records in the cg_match layout, so the
+parity tests compare arrays element by element.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "cutadapt_oracle.c")
+SO = os.path.join(HERE, "liboracle.so")
+
+KIND_ALIGNER, KIND_PREFIX, KIND_SUFFIX = 0, 1, 2
+REMOVE_BEFORE, REMOVE_AFTER, REMOVE_AUTO = 0, 1, 2
+GROUP_SINGLE, GROUP_LINKED = 0, 1
+
+MATCH_DTYPE = np.dtype(
+    [("adapter", "<i4"), ("astart", "<i4"), ("astop", "<i4"), ("rstart", "<i4"), ("rstop", "<i4"),
+     ("score", "<i4"), ("errors", "<i4"), ("info", "<i4")]
+)
+
+
+class KmerEntry(C.Structure):
+    _fields_ = [("search_start", C.c_int64), ("search_stop", C.c_int64),
+                ("init_mask", C.c_uint64), ("found_mask", C.c_uint64)]
+
+
+def build(force=False):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-shared", "-fPIC", "-o", SO, SRC])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        handle = C.CDLL(build())
+        u8p, ip = C.c_char_p, C.POINTER(C.c_int)
+        handle.oracle_locate.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_double, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_int, ip]
+        handle.oracle_prefix_compare.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_double, C.c_int,
+                                                 C.c_int, C.c_int, ip]
+        handle.oracle_suffix_compare.argtypes = handle.oracle_prefix_compare.argtypes
+        handle.oracle_effective_length.argtypes = [u8p, C.c_int, C.c_int]
+        handle.oracle_kmer_pack.argtypes = [C.c_int64, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(KmerEntry), C.c_void_p]
+        handle.oracle_kmers_present.argtypes = [C.POINTER(KmerEntry), C.c_void_p, C.c_int, u8p, C.c_int64]
+        handle.oracle_quality_trim_index.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+        handle.oracle_locate_batch.argtypes = [u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(KmerEntry), C.c_void_p, C.c_int, C.c_void_p]
+        _lib = handle
+    return _lib
+
+
+def _b(s):
+    return s if isinstance(s, bytes) else s.encode("latin-1")
+
+
+def _raise(rc):
+    if rc == -2:
+        raise ValueError("String must contain only ASCII characters")
+    if rc == -4:
+        raise MemoryError()
+    raise ValueError(f"oracle: invalid argument (rc={rc})")
+
+
+def locate(reference, query, max_error_rate, flags=15, wildcard_ref=False, wildcard_query=False,
+           indel_cost=1, min_overlap=1):
+    """Aligner(reference, ...).locate(query)   (_align.pyx:298-587)"""
+    out = (C.c_int * 6)()
+    r, q = _b(reference), _b(query)
+    rc = lib().oracle_locate(r, len(r), q, len(q), max_error_rate, flags, int(wildcard_ref),
+                             int(wildcard_query), indel_cost, min_overlap, out)
+    if rc < 0:
+        _raise(rc)
+    return tuple(out) if rc == 1 else None
+
+
+def prefix_compare(reference, query, max_error_rate, wildcard_ref=False, wildcard_query=False, min_overlap=1):
+    out = (C.c_int * 6)()
+    r, q = _b(reference), _b(query)
+    rc = lib().oracle_prefix_compare(r, len(r), q, len(q), max_error_rate, int(wildcard_ref),
+                                     int(wildcard_query), min_overlap, out)
+    if rc < 0:
+        _raise(rc)
+    return tuple(out) if rc == 1 else None
+
+
+def suffix_compare(reference, query, max_error_rate, wildcard_ref=False, wildcard_query=False, min_overlap=1):
+    out = (C.c_int * 6)()
+    r, q = _b(reference), _b(query)
+    rc = lib().oracle_suffix_compare(r, len(r), q, len(q), max_error_rate, int(wildcard_ref),
+                                     int(wildcard_query), min_overlap, out)
+    if rc < 0:
+        _raise(rc)
+    return tuple(out) if rc == 1 else None
+
+
+def quality_trim_index(qualities, cutoff_front, cutoff_back, base=33):
+    q = _b(qualities)
+    a, b = C.c_int(), C.c_int()
+    lib().oracle_quality_trim_index(q, len(q), cutoff_front, cutoff_back, base, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+class KmerTables:
+    """KmerFinder(positions_and_kmers, ref_wildcards, query_wildcards) tables (_kmer_finder.pyx:106-165)"""
+
+    def __init__(self, positions_and_kmers, ref_wildcards=False, query_wildcards=False):
+        total = sum(len(k) for _, _, k in positions_and_kmers)
+        self.entries = (KmerEntry * max(total, 1))()
+        self.masks = np.zeros(128 * max(total, 1), dtype=np.uint64)
+        n = 0
+        for start, stop, kmers in positions_and_kmers:
+            blob = b"".join(_b(k) + b"\0" for k in kmers)
+            got = lib().oracle_kmer_pack(
+                start, 0 if stop is None else stop, blob, len(kmers), int(ref_wildcards), int(query_wildcards),
+                C.cast(C.byref(self.entries, n * C.sizeof(KmerEntry)), C.POINTER(KmerEntry)),
+                self.masks.ctypes.data + 128 * 8 * n,
+            )
+            if got < 0:
+                raise ValueError("k-mer longer than 64 or not ASCII")
+            n += got
+        self.n = n
+
+    def present(self, sequence):
+        s = _b(sequence)
+        rc = lib().oracle_kmers_present(self.entries, self.masks.ctypes.data, self.n, s, len(s))
+        if rc < 0:
+            _raise(rc)
+        return bool(rc)
+
+    def as_lists(self):
+        """(entries as [(start, stop, init, found)], masks uint64[128*n]) -- the C-ABI form."""
+        ents = [(e.search_start, e.search_stop, e.init_mask, e.found_mask) for e in self.entries[: self.n]]
+        return ents, self.masks[: 128 * self.n].copy()
+
+
+# ---- composition ----------------------------------------------------------------------------
+
+
+def _kmer_tables_of(adapter):
+    """Accept either reference-form lists (kmer_entries/kmer_masks) or positions_and_kmers."""
+    if adapter.get("_oracle_kt") is not None:
+        return adapter["_oracle_kt"]
+    kt = None
+    entries = adapter.get("kmer_entries")
+    if entries is not None and len(entries):
+        kt = KmerTables([], False, False)
+        kt.entries = (KmerEntry * len(entries))()
+        for j, (start, stop, init, found) in enumerate(entries):
+            kt.entries[j].search_start, kt.entries[j].search_stop = start, stop
+            kt.entries[j].init_mask, kt.entries[j].found_mask = init, found
+        kt.masks = np.ascontiguousarray(adapter["kmer_masks"], dtype=np.uint64).reshape(-1)
+        kt.n = len(entries)
+    adapter["_oracle_kt"] = kt
+    return kt
+
+
+def match_single(adapter, sequence):
+    """One SingleAdapter.match_to: returns dict(astart, astop, rstart, rstop, score, errors, remove) or None."""
+    seq = sequence[::-1] if adapter.get("reverse_read") else sequence
+    kt = _kmer_tables_of(adapter)
+    if kt is not None and not kt.present(seq):
+        return None
+    kind = adapter.get("kind", KIND_ALIGNER)
+    args = dict(wildcard_ref=adapter.get("wildcard_ref", False), wildcard_query=adapter.get("wildcard_query", False),
+                min_overlap=adapter.get("min_overlap", 1))
+    if kind == KIND_ALIGNER:
+        res = locate(adapter["sequence"], seq, adapter["max_error_rate"], adapter.get("flags", 15),
+                     indel_cost=adapter.get("indel_cost", 1), **args)
+    elif kind == KIND_PREFIX:
+        res = prefix_compare(adapter["sequence"], seq, adapter["max_error_rate"], **args)
+    else:
+        res = suffix_compare(adapter["sequence"], seq, adapter["max_error_rate"], **args)
+    if res is None:
+        return None
+    astart, astop, rstart, rstop, score, errors = res
+    if adapter.get("reverse_read"):                      # adapters.py:777-785, 881-889
+        m, n = len(adapter["sequence"]), len(sequence)
+        astart, astop, rstart, rstop = m - astop, m - astart, n - rstop, n - rstart
+    remove = adapter.get("remove", REMOVE_AFTER)
+    if remove == REMOVE_AUTO:                            # adapters.py:930-935
+        remove = REMOVE_BEFORE if rstart == 0 else REMOVE_AFTER
+    return dict(astart=astart, astop=astop, rstart=rstart, rstop=rstop, score=score, errors=errors, remove=remove)
+
+
+def _trim(hit, s, e):
+    if hit["remove"] == REMOVE_BEFORE:
+        return s + hit["rstop"], e
+    return s, s + hit["rstart"]
+
+
+def match_group(adapters, group, sequence):
+    """Returns (score, errors, front_hit_or_None, back_hit_or_None) or None."""
+    typ, a0, a1, front_required, back_required = group
+    if typ == GROUP_SINGLE:
+        h = match_single(adapters[a0], sequence)
+        if h is None:
+            return None
+        h["adapter"] = a0
+        return h["score"], h["errors"], h, None
+    front = match_single(adapters[a0], sequence)         # adapters.py:1219-1227
+    if front_required and front is None:
+        return None
+    rest = sequence
+    if front is not None:
+        front["adapter"] = a0
+        s, e = _trim(front, 0, len(sequence))
+        rest = sequence[s:e]
+    back = match_single(adapters[a1], rest)
+    if back is None and (back_required or front is None):
+        return None
+    if back is not None:
+        back["adapter"] = a1
+    score = (front["score"] if front else 0) + (back["score"] if back else 0)
+    errors = (front["errors"] if front else 0) + (back["errors"] if back else 0)
+    return score, errors, front, back
+
+
+def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=False, cutoff_front=0,
+                   cutoff_back=0, quality_base=33, times=1):
+    """Whole per-read pass; returns (matches[n, times, slots], qtrim[n, 2])."""
+    if groups is None:
+        groups = [(GROUP_SINGLE, i, -1, 0, 0) for i in range(len(adapters))]
+    slots = 2 if any(g[0] == GROUP_LINKED for g in groups) else 1
+    n = len(sequences)
+    out = np.zeros((n, times, slots), dtype=MATCH_DTYPE)
+    out["adapter"] = -1
+    qtrim = np.zeros((n, 2), dtype=np.int32)
+
+    def put(rec, hit, gi, searched):
+        rec["adapter"] = hit["adapter"]
+        for f in ("astart", "astop", "rstart", "rstop", "score", "errors"):
+            rec[f] = hit[f]
+        rec["info"] = (gi & 255) | (256 if hit["remove"] == REMOVE_AFTER else 0) | ((searched & 0xFFFF) << 16)
+
+    for i, seq in enumerate(sequences):
+        s, e = 0, len(seq)
+        if quality_trim:
+            s, e = quality_trim_index(qualities[i], cutoff_front, cutoff_back, quality_base)
+        qtrim[i] = (s, e)
+        for r in range(times):
+            cur = seq[s:e]
+            best = None
+            for gi, g in enumerate(groups):                  # adapters.py:1271-1286
+                m = match_group(adapters, g, cur)
+                if m is None:
+                    continue
+                if best is None or m[0] > best[1][0] or (m[0] == best[1][0] and m[1] < best[1][1]):
+                    best = (gi, m)
+            if best is None:
+                break                                        # modifiers.py:227-229
+            gi, (_, _, h0, h1) = best
+            searched = e - s
+            if h0 is not None:
+                put(out[i, r, 0], h0, gi, searched)
+            if h1 is not None:
+                s2, e2 = (0, searched) if h0 is None else _trim(h0, 0, searched)
+                put(out[i, r, 1], h1, gi, e2 - s2)
+            if h0 is not None:
+                s, e = _trim(h0, s, e)
+            if h1 is not None:
+                s, e = _trim(h1, s, e)
+    return out, qtrim

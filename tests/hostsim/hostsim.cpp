@@ -1,0 +1,52 @@
+// tests/hostsim/hostsim.cpp -- TEST-ONLY host build of the per-read device functions.
+//
+// Compiles cutadapt_b200/csrc/cg_core.cuh (the exact code the CUDA kernels run, one lane per
+// read) with g++ so that the selection logic, the packed-cell DP and the adapter composition
+// can be fuzzed against the oracle on a box without a GPU.  Nothing in cutadapt_b200/ loads
+// this library; it is not a fallback.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../cutadapt_b200/csrc/cg_core.cuh"
+#include "../../cutadapt_b200/csrc/cg_setbuild.h"
+
+static thread_local std::string g_err;
+
+extern "C" const char *hs_last_error(void) { return g_err.c_str(); }
+
+extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
+                                const cg_group_desc *groups, int n_groups, const uint8_t *seq,
+                                const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                                const cg_params *params, cg_match *matches, int32_t *qtrim,
+                                int force_wide)
+{
+    CgBuiltSet set;
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err);
+    if (rc != CG_OK) return rc;
+    if (force_wide) {
+        CgSetHeader *h = (CgSetHeader *)set.blob.data();
+        CgAdapter *ad = (CgAdapter *)(set.blob.data() + h->adapters_off);
+        for (int a = 0; a < n_adapters; ++a) ad[a].cell_mode = CG_CELL_WIDE;
+    }
+    uint8_t enc[768];
+    cg_build_enc_tables(enc);
+    SetView S = make_set_view(set.blob.data(), set.masks64.data(), enc);
+    std::vector<uint32_t> colp((size_t)set.max_m + 2);
+    std::vector<int> colw(3 * ((size_t)set.max_m + 2));
+    PackedCol pc; pc.base = colp.data(); pc.stride = 1;
+    WideCol wc; wc.base = colw.data(); wc.stride = 1;
+    const int times = params->times < 1 ? 1 : params->times;
+    if (params->quality_trim && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int n = (int)(offsets[r + 1] - offsets[r]);
+        const uint8_t *s = seq + offsets[r];
+        for (int i = 0; i < n; ++i) if (s[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
+        process_read<true>(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
+                           params->cutoff_front, params->cutoff_back, params->quality_base, times, pc,
+                           wc, (cg_match_rec *)(matches + (size_t)r * times * set.slots),
+                           qtrim ? qtrim + 2 * r : nullptr);
+    }
+    return CG_OK;
+}
