@@ -42,13 +42,15 @@ def build_kmer_tables(positions_and_kmers, ref_wildcards: bool, query_wildcards:
                     raise ValueError(
                         f"{kmer} of length {len(kmer)} is longer than the maximum of {MAXIMUM_WORD_SIZE}."
                     )
-                if len(kmer) == 0:
-                    raise ValueError("Empty k-mer")
                 if len(word) + len(kmer) > MAXIMUM_WORD_SIZE:
                     break
-                init_mask |= 1 << len(word)
+                # Shift counts are taken modulo 64 like the x86-64 build of the reference does
+                # for the degenerate empty k-mer that kmer_chunks() emits when there are more
+                # allowed errors than adapter characters (1 << (0 + 0 - 1) in
+                # _kmer_finder.pyx:143-147): the result is a harmless duplicate bit.
+                init_mask |= 1 << (len(word) & 63)
                 word += kmer.encode("ascii")
-                found_mask |= 1 << (len(word) - 1)
+                found_mask |= 1 << ((len(word) - 1) & 63)
                 index += 1
             mask = [0] * 128
             for bit, char in enumerate(word):

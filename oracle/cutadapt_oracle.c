@@ -385,9 +385,11 @@ int oracle_kmer_pack(int64_t start, int64_t stop_or_zero, const char *kmers, int
             for (i = 0; i < len; i++) if (p[i] & 0x80) return -1;
             if (len > 64) return -1;
             if (offset + len > 64) break;
-            init |= 1ULL << offset;
+            /* shift counts modulo 64: what the x86-64 build of the reference does for the
+               degenerate empty k-mer (1ULL << (0 + 0 - 1), _kmer_finder.pyx:143-147) */
+            init |= 1ULL << (offset & 63);
             memcpy(word + offset, p, len);
-            found |= 1ULL << (offset + len - 1);
+            found |= 1ULL << ((offset + len - 1) & 63);
             offset += len;
             p += len + 1;
             index++;
