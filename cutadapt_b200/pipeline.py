@@ -1,0 +1,242 @@
+"""
+Batched per-chunk dispatch: what replaces the per-read loop of the reference's worker.
+
+In the reference every chunk of ~4 MB FASTQ is processed read by read
+(``WorkerProcess.run -> Pipeline.process_reads``, runners.py:174-214, pipeline.py:47-73) and for
+each read ``QualityTrimmer.__call__`` (modifiers.py:853-858) and
+``AdapterCutter.match_and_trim`` (modifiers.py:225-231) call into the native code.  Here one
+chunk is one fused kernel launch:
+
+``BatchTrimmer``   host-side chunks (lists of str or packed uint8 arrays): pack -> C ABI
+                   (H2D, fused kernel, D2H pipelined in the library) -> kept intervals, match
+                   records, optional reference-style Match objects and AdapterStatistics.
+``DeviceBatch``    the same on torch CUDA tensors that are already resident in HBM (this is what
+                   bench.py times for the roofline number and what multi-GPU runs use).
+``allreduce_statistics``  the end-of-run merge of the trim statistics across GPUs: the fixed-layout
+                   int64 vector is summed with one all-reduce (NCCL over NVLink for CUDA tensors,
+                   gloo in the CPU tests).  It stands where the reference merges per-worker
+                   ``Statistics`` objects in the parent (runners.py:372-373, report.py:81-126).
+
+Reads shard across ranks by contiguous ranges (``shard_range``); no read ever needs another rank.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .adapters import Matchable, MultipleAdapters
+
+
+# ---- statistics vector layout (include/cutadapt_b200.h: cg_stats_accumulate_device) ----------
+
+STAT_N_READS, STAT_TOTAL_BP, STAT_WITH_ADAPTERS, STAT_QUALITY_TRIMMED_BP, STAT_ADAPTER_BP = 0, 1, 2, 3, 4
+
+
+def stats_layout(n_adapters: int, max_len: int, kmax: int) -> dict:
+    return {
+        "size": 8 + n_adapters * (max_len + 1) * (kmax + 1),
+        "hist": 8,
+        "shape": (n_adapters, max_len + 1, kmax + 1),
+    }
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, near-equal split of ``n_items`` reads over ``world_size`` ranks."""
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def allreduce_statistics(stats, group=None):
+    """
+    Sum the statistics vector over all ranks in place (torch tensor on any device).
+    One small all-reduce per run: latency-bound, nothing to fuse it with.
+    """
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def kept_intervals(matches: np.ndarray, qtrim: Optional[np.ndarray], lengths: np.ndarray) -> np.ndarray:
+    """
+    (n, 2) array of the part of every read that survives quality trimming and all rounds of
+    adapter removal, relative to the original read -- i.e. the composition of
+    ``read[start:stop]`` (modifiers.py:858) and ``match.trimmed(read)`` (adapters.py:453-454,
+    486-487, 1132-1137) for each round.
+    """
+    n = matches.shape[0]
+    if qtrim is not None:
+        start = qtrim[:, 0].astype(np.int64)
+        stop = qtrim[:, 1].astype(np.int64)
+    else:
+        start = np.zeros(n, dtype=np.int64)
+        stop = lengths.astype(np.int64).copy()
+    for r in range(matches.shape[1]):
+        for s in range(matches.shape[2]):
+            rec = matches[:, r, s]
+            present = rec["adapter"] >= 0
+            after = ((rec["info"] >> 8) & 1).astype(bool)
+            new_stop = start + rec["rstart"]
+            new_start = start + rec["rstop"]
+            stop = np.where(present & after, new_stop, stop)
+            start = np.where(present & ~after, new_start, start)
+    return np.stack([start, stop], axis=1)
+
+
+class TrimResult:
+    """Outcome of one chunk: raw records plus the derived kept interval of every read."""
+
+    def __init__(self, matches, qtrim, intervals):
+        self.matches = matches      # structured array [n, times, slots], dtype MATCH_DTYPE
+        self.qtrim = qtrim          # [n, 2] int32 or None
+        self.intervals = intervals  # [n, 2] int64: read[start:stop] is what remains
+
+    @property
+    def with_adapters(self) -> int:
+        return int((self.matches["adapter"] >= 0).any(axis=(1, 2)).sum())
+
+
+class BatchTrimmer:
+    """
+    Quality trimming + adapter removal for whole chunks of reads.
+
+    adapters          a Matchable (e.g. MultipleAdapters) or a list of adapters
+    times             as AdapterCutter(times=...)          (modifiers.py:98-119)
+    quality_cutoff    None or (cutoff_front, cutoff_back)  as QualityTrimmer (modifiers.py:840-851)
+    """
+
+    def __init__(self, adapters, times: int = 1, quality_cutoff: Optional[Tuple[int, int]] = None,
+                 quality_base: int = 33, ctx: Optional[_lib.Context] = None):
+        self.adapters: Matchable = adapters if isinstance(adapters, Matchable) else MultipleAdapters(list(adapters))
+        self.times = int(times)
+        self.quality_cutoff = quality_cutoff
+        self.quality_base = quality_base
+        self._ctx = ctx
+        self.params = _lib.make_params(
+            quality_trim=quality_cutoff is not None,
+            cutoff_front=quality_cutoff[0] if quality_cutoff else 0,
+            cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
+            quality_base=quality_base,
+            times=times,
+        )
+
+    @property
+    def adapter_set(self) -> _lib.AdapterSet:
+        return self.adapters.adapter_set()
+
+    def process_packed(self, seq: np.ndarray, offsets: np.ndarray, qual: Optional[np.ndarray] = None) -> TrimResult:
+        matches, qtrim = self.adapter_set.process(seq, offsets, qual, self.params)
+        lengths = np.diff(offsets)
+        return TrimResult(matches, qtrim, kept_intervals(matches, qtrim, lengths))
+
+    def process(self, sequences: Sequence[str], qualities: Optional[Sequence[str]] = None) -> TrimResult:
+        seq, offsets = _lib.pack_strings(sequences)
+        qual = None
+        if self.quality_cutoff is not None:
+            if qualities is None or any(q is None for q in qualities):
+                from .qualtrim import HasNoQualities
+
+                raise HasNoQualities("Cannot do quality trimming when no qualities are available")
+            qual, _ = _lib.pack_strings(qualities, "Quality data")
+        return self.process_packed(seq, offsets, qual)
+
+    def match_objects(self, result: TrimResult, sequences: Sequence[str]) -> List[List]:
+        """Per read, the list of reference-style Match objects of its rounds (info.matches)."""
+        self.adapter_set  # make sure the bookkeeping for matches_from_records exists
+        out = []
+        qt = result.qtrim
+        for i, seq in enumerate(sequences):
+            cur = seq if qt is None else seq[qt[i, 0]:qt[i, 1]]
+            found = []
+            for r in range(result.matches.shape[1]):
+                m = self.adapters.matches_from_records(result.matches[i, r], cur)
+                if m is None:
+                    break
+                found.append(m)
+                cur = m.trimmed(cur)
+            out.append(found)
+        return out
+
+    def adapter_statistics(self, result: TrimResult, sequences: Sequence[str]):
+        """AdapterStatistics per adapter, filled like AdapterCutter.__call__ does (modifiers.py:200-207)."""
+        _, _, owners = self.adapters._device_set if self.adapters._device_set else (None, None, None)
+        self.adapter_set
+        _, _, owners = self.adapters._device_set
+        stats = {id(o): o.create_statistics() for o in owners}
+        for matches in self.match_objects(result, sequences):
+            for m in matches:
+                stats[id(m.adapter)].add_match(m)
+        return [stats[id(o)] for o in owners]
+
+
+class DeviceResult:
+    def __init__(self, matches, qtrim, n_reads, offsets):
+        self.matches = matches    # torch int32 [n * times * slots, 8]
+        self.qtrim = qtrim        # torch int32 [n, 2] or None
+        self.n_reads = n_reads
+        self.offsets = offsets
+
+
+class DeviceBatch:
+    """The fused pass on torch CUDA tensors already resident in HBM (cg_process_batch_device)."""
+
+    def __init__(self, adapters, times: int = 1, quality_cutoff: Optional[Tuple[int, int]] = None,
+                 quality_base: int = 33, device: Optional[int] = None):
+        import torch
+
+        self.adapters: Matchable = adapters if isinstance(adapters, Matchable) else MultipleAdapters(list(adapters))
+        self.device = torch.cuda.current_device() if device is None else device
+        # torch's default stream is the legacy stream (handle 0); cudaStreamLegacy (0x1) names it
+        # explicitly so that the library launches on it instead of creating its own stream
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        self.ctx = _lib.Context(self.device, stream)
+        singles, groups, owners = self.adapters._flatten()
+        self.spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups)
+        self.adapter_set = _lib.AdapterSet(self.spec, self.ctx)
+        self.n_adapters = len(singles)
+        self.times = int(times)
+        self.params = _lib.make_params(
+            quality_trim=quality_cutoff is not None,
+            cutoff_front=quality_cutoff[0] if quality_cutoff else 0,
+            cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
+            quality_base=quality_base,
+            times=times,
+        )
+
+    def run(self, seq, offsets, qual=None, max_read_len: int = 0, out=None, qtrim_out=None) -> DeviceResult:
+        import torch
+
+        n = int(offsets.numel() - 1)
+        slots = self.adapter_set.slots
+        if out is None:
+            out = torch.empty((n * self.times * slots, 8), dtype=torch.int32, device=seq.device)
+        want_q = bool(self.params.quality_trim)
+        if want_q and qtrim_out is None:
+            qtrim_out = torch.empty((n, 2), dtype=torch.int32, device=seq.device)
+        _lib.check(
+            _lib.lib().cg_process_batch_device(
+                self.ctx.handle, self.adapter_set.handle, seq.data_ptr(),
+                qual.data_ptr() if (qual is not None and want_q) else None, offsets.data_ptr(), n,
+                int(max_read_len), C.byref(self.params), out.data_ptr(),
+                qtrim_out.data_ptr() if qtrim_out is not None else None,
+            )
+        )
+        return DeviceResult(out, qtrim_out, n, offsets)
+
+    def statistics(self, result: DeviceResult, max_len: int = 150, kmax: int = 3, into=None):
+        """Device-side reduction of a batch into the fixed-layout int64 statistics vector."""
+        import torch
+
+        size = int(_lib.lib().cg_stats_size(self.n_adapters, max_len, kmax))
+        stats = into if into is not None else torch.zeros(size, dtype=torch.int64, device=result.matches.device)
+        _lib.check(
+            _lib.lib().cg_stats_accumulate_device(
+                self.ctx.handle, self.adapter_set.handle, result.offsets.data_ptr(), result.n_reads,
+                C.byref(self.params), result.matches.data_ptr(),
+                result.qtrim.data_ptr() if result.qtrim is not None else None, max_len, kmax, stats.data_ptr(),
+            )
+        )
+        return stats

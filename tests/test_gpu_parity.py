@@ -1,0 +1,374 @@
+"""
+GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle, the
+committed golden vectors and -- at benchmark-like sizes -- size-independent properties.
+Integer/byte/index work: the bar is bit-exact equality.
+"""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from cutadapt_b200 import _lib as L  # noqa: E402
+from oracle import oracle  # noqa: E402
+from util import golden, build_adapters, match_desc, random_reads, reference_or_none  # noqa: E402
+
+FIELDS = ("astart", "astop", "rstart", "rstop", "score", "errors")
+
+
+def rec_tuple(r):
+    return None if r["adapter"] < 0 else [int(r[f]) for f in FIELDS]
+
+
+def run_set(adapters, groups, reads, quals=None, **kw):
+    spec = L.AdapterSetSpec(adapters, groups)
+    aset = L.AdapterSet(spec)
+    data, offsets = L.pack_strings(reads)
+    qd = L.pack_strings(quals)[0] if quals is not None else None
+    return aset.process(data, offsets, qd, L.make_params(**kw))
+
+
+# ---- the three native functions through their reference-shaped Python API --------------------
+
+
+def test_aligner_locate_golden():
+    from cutadapt_b200._align import Aligner
+
+    cases = golden("locate_kat.json.gz")
+    # group by aligner parameters so that each adapter set is uploaded once
+    by_params = {}
+    for ref, q, rate, flags, wr, wq, ic, mo, expected in cases:
+        by_params.setdefault((ref, rate, flags, wr, wq, ic, mo), []).append((q, expected))
+    for (ref, rate, flags, wr, wq, ic, mo), items in by_params.items():
+        al = Aligner(ref, rate, flags, wr, wq, ic, mo)
+        got = al.locate_batch([q for q, _ in items])
+        for (q, expected), g in zip(items, got):
+            assert (list(g) if g is not None else None) == expected, (ref, q, rate, flags, wr, wq, ic, mo)
+
+
+def test_reference_known_answer_tests():
+    """tests/test_align.py:69-146 of the reference, verbatim expectations."""
+    from cutadapt_b200._align import Aligner
+    from cutadapt_b200.adapters import Where
+
+    assert Aligner("", 0, flags=0, min_overlap=0).locate("") == (0, 0, 0, 0, 0, 0)
+    assert Aligner("CCAGTCCTCT", 0.3, flags=Where.PREFIX).locate("CCAGTCCTTTCCTGAGAGT") == (0, 10, 0, 10, 8, 1)
+    assert Aligner("TCGATC", 1.5 / 6, flags=Where.PREFIX).locate("TCGATGC") == (0, 6, 0, 6, 4, 1)
+    assert Aligner("GCCGAACTTCTTAGACTGCCTTAAGGACGT", 0.1, flags=Where.BACK).locate(
+        "CAAATCACCAGAAGGCGCCTAACTTCTTAGACTGCC") == (0, 20, 16, 36, 18, 1)
+    assert Aligner("TTTT", 0.25, flags=Where.BACK).locate("CCTTTT") == (0, 4, 2, 6, 4, 0)
+    assert Aligner("TTTTTT", 0.25, flags=Where.BACK).locate("CCTTTT") == (0, 4, 2, 6, 4, 0)
+    assert Aligner("TTT", 1 / 3, flags=Where.BACK).locate("CCTTTT")[:4] == (0, 3, 2, 5)
+    assert Aligner("CTGAATT", 0.1, flags=Where.BACK).locate("AAAAAAA") is None
+    with pytest.raises(ValueError):
+        Aligner("ACGT", 0.1).locate("AC\xe4GT")
+
+
+def test_comparers_golden():
+    from cutadapt_b200._align import PrefixComparer, SuffixComparer
+
+    for ref, q, rate, wr, wq, mo, p, s in golden("comparer_kat.json.gz")[:400]:
+        got = PrefixComparer(ref, rate, wr, wq, mo).locate(q)
+        assert (list(got) if got else None) == p, ("prefix", ref, q)
+        got = SuffixComparer(ref, rate, wr, wq, mo).locate(q)
+        assert (list(got) if got else None) == s, ("suffix", ref, q)
+
+
+def test_kmer_finder_golden():
+    from cutadapt_b200._kmer_finder import KmerFinder
+
+    for sets, rw, qw, reads in golden("kmer_kat.json.gz")["present"]:
+        kf = KmerFinder([(s, e, k) for s, e, k in sets], rw, qw)
+        got = kf.kmers_present_batch([r for r, _ in reads])
+        assert list(map(bool, got)) == [e for _, e in reads], (sets, rw, qw)
+    kf = KmerFinder([(0, None, ["ACGT"])])
+    assert kf.kmers_present("ttacgttt") is True and kf.kmers_present("ttacttt") is False
+    with pytest.raises(ValueError):
+        kf.kmers_present("AC\xe4GT")
+
+
+def test_quality_trim_golden():
+    from cutadapt_b200.qualtrim import quality_trim_index, quality_trim_index_batch, HasNoQualities
+
+    cases = golden("qualtrim_kat.json.gz")
+    by = {}
+    for q, cf, cb, base, expected in cases:
+        by.setdefault((cf, cb, base), []).append((q, expected))
+    for (cf, cb, base), items in by.items():
+        got = quality_trim_index_batch([q for q, _ in items], cf, cb, base)
+        assert got.tolist() == [e for _, e in items]
+    assert quality_trim_index("IIII####", 0, 20) == (0, 4)
+    with pytest.raises(HasNoQualities):
+        quality_trim_index(None, 0, 20)
+
+
+# ---- adapter classes ------------------------------------------------------------------------
+
+
+def test_adapter_classes_golden():
+    """Every adapter type, linked and multiple adapters: reference match_to() results."""
+    import cutadapt_b200.adapters as PA
+
+    for case in golden("adapters_kat.json.gz"):
+        multi = build_adapters(PA, case["adapters"])
+        reads = [r for r, _ in case["reads"]]
+        got = multi.match_to_batch(reads)
+        for (read, expected), m in zip(case["reads"], got):
+            assert match_desc(m) == expected, (case["adapters"], read)
+
+
+def test_match_objects_behave_like_the_reference():
+    """tests/test_adapters.py:38-76 (leftmost rule) and Match.trimmed / statistics plumbing."""
+    import cutadapt_b200.adapters as PA
+
+    adapter = PA.BackAdapter("ACGT", max_errors=0.0, min_overlap=3, name="a")
+    m = adapter.match_to("TTTACGTCCCACGT")      # two exact occurrences: the leftmost wins
+    assert (m.rstart, m.rstop, m.errors) == (3, 7, 0)
+    assert m.trimmed("TTTACGTCCCACGT") == "TTT" and m.adjacent_base() == "T"
+    assert m.removed_sequence_length() == 11
+    stats = adapter.create_statistics()
+    stats.add_match(m)
+    assert stats.end.errors[11][0] == 1 and stats.end.adjacent_bases["T"] == 1
+    front = PA.FrontAdapter("AAAA", max_errors=0.25, name="f")
+    m = front.match_to("AAATCCCC")
+    assert isinstance(m, PA.RemoveBeforeMatch) and m.trimmed("AAATCCCC") == "CCCC"
+    assert PA.BackAdapter("GGGGGGGG", name="n").match_to("ACACACAC") is None
+    linked = PA.LinkedAdapter(PA.PrefixAdapter("AAAA", name="p"), PA.BackAdapter("TTTT", name="b"), True, False, "lnk")
+    lm = linked.match_to("AAAACCCCTTTTGG")
+    assert lm.front_match.rstop == 4 and lm.back_match.rstart == 4 and lm.trimmed("AAAACCCCTTTTGG") == "CCCC"
+    assert linked.match_to("CCCCAAAATTTT") is None            # required front adapter missing
+
+
+def test_info_file_coordinates_of_the_reference():
+    """Per-read errors/rstart/rstop of tests/cut/illumina.info.txt and illumina5.info.txt."""
+    import cutadapt_b200.adapters as PA
+
+    data = golden("info_file_kat.json.gz")
+    il = data["illumina"]
+    adapter = PA.BackAdapter(il["adapter"], max_errors=0.1, min_overlap=3, name="adapt")
+    got = adapter.match_to_batch([s for s, _ in il["rows"]])
+    for (seq, expected), m in zip(il["rows"], got):
+        assert (None if m is None else [m.errors, m.rstart, m.rstop]) == expected, seq
+    il5 = data["illumina5"]
+    multi = PA.MultipleAdapters([PA.BackAdapter(s, max_errors=0.1, min_overlap=3, name=n) for n, s in il5["adapters"]])
+    aset = multi.adapter_set()
+    seqs = [s for s, _ in il5["rows"]]
+    d, o = L.pack_strings(seqs)
+    recs, _ = aset.process(d, o, None, L.make_params(times=2))
+    for i, (seq, expected) in enumerate(il5["rows"]):
+        rows = []
+        cur = seq
+        for r in range(2):
+            m = multi.matches_from_records(recs[i, r], cur)
+            if m is None:
+                break
+            rows.append([m.errors, m.rstart, m.rstop, m.adapter.name])
+            cur = m.trimmed(cur)
+        assert rows == expected, seq
+
+
+# ---- the fused batch path against the oracle ---------------------------------------------------
+
+
+def test_config1_10k_single_adapter_bit_exact():
+    """BASELINE config 1/2 shape: 150 bp, one 3' adapter AGATCGGAAGAGC, e=0.1."""
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_reads
+
+    reads, _ = make_reads(10000, config=1)
+    adapter = PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a")
+    d = adapter.descriptor()
+    got, _ = run_set([d], None, reads)
+    exp, _ = oracle.oracle_process([d], None, reads)
+    assert (got == exp).all()
+    assert 4500 < int((got["adapter"] >= 0).sum()) < 5500
+    ref = reference_or_none()
+    if ref is not None:                      # and the reference itself, when it travels along
+        import cutadapt.adapters as RA
+
+        ra = RA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a")
+        for read, rec in zip(reads[:3000], got[:3000, 0, 0]):
+            m = ra.match_to(read)
+            assert (None if m is None else [m.astart, m.astop, m.rstart, m.rstop, m.score, m.errors]) == rec_tuple(rec)
+
+
+def test_config3_five_adapters_iupac_linked():
+    """BASELINE config 3 shape: 5 adapters incl. IUPAC wildcards, an N-run and a linked adapter, e=0.15."""
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(3)
+    seqs = ["AGATCGGAAGAGC", "CTGTCTCTTATACACATCT", "VCCGAMCYUCKHRKDCUBBCNUWNSGHCGU",
+            "AGATCGGAAGAGCNNNNNNNNATCTCGTATGCC"]
+    objs = [PA.BackAdapter(s, max_errors=0.15, name=f"a{i}") for i, s in enumerate(seqs)]
+    objs.append(PA.LinkedAdapter(PA.PrefixAdapter("GTTCAGAGTTCTACAGTCCGACGATC", max_errors=0.15, name="f"),
+                                 PA.BackAdapter("TGGAATTCTCGGGTGCCAAGG", max_errors=0.15, name="b"),
+                                 True, False, "linked"))
+    multi = PA.MultipleAdapters(objs)
+    reads = random_reads(rng, seqs + ["GTTCAGAGTTCTACAGTCCGACGATC", "TGGAATTCTCGGGTGCCAAGG"], 6000, "ACGT", 150)
+    reads += random_reads(rng, seqs, 500, "ACGTN", 150)
+    singles, groups, _ = multi._flatten()
+    descs = [s.descriptor() for s in singles]
+    got, _ = run_set(descs, groups, reads)
+    exp, _ = oracle.oracle_process(descs, groups, reads)
+    assert (got == exp).all()
+    assert int((got["adapter"][:, 0, :] >= 0).any(axis=1).sum()) > 1000
+
+
+def test_config4_quality_trim_then_adapter():
+    """BASELINE config 4 shape: -q 20 fused in front of a 33-mer 3' adapter; qualities staged too."""
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_reads
+
+    ad = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+    reads, quals = make_reads(8000, config=4, with_qualities=True, adapter=ad)
+    d = PA.BackAdapter(ad, max_errors=0.1, name="a").descriptor()
+    got, qt = run_set([d], None, reads, quals, quality_trim=True, cutoff_front=0, cutoff_back=20)
+    exp, eqt = oracle.oracle_process([d], None, reads, quals, quality_trim=True, cutoff_back=20)
+    assert (qt == eqt).all() and (got == exp).all()
+    assert int((qt[:, 1] < 150).sum()) > 500
+
+
+def test_random_adapter_sets_against_oracle():
+    """All adapter types, wildcards, --no-indels (wide cells), rounds, quality trimming."""
+    import cutadapt_b200.adapters as PA
+    from util import spec_of
+
+    rng = random.Random(11)
+    types = ["FrontAdapter", "RightmostFrontAdapter", "BackAdapter", "RightmostBackAdapter", "AnywhereAdapter",
+             "NonInternalFrontAdapter", "NonInternalBackAdapter", "PrefixAdapter", "SuffixAdapter"]
+    for trial in range(40):
+        ads, objs = [], []
+        for _ in range(rng.choice([1, 2, 3])):
+            seq = "".join(rng.choice("ACGT" if rng.random() < 0.7 else "ACGTNRY") for _ in range(rng.randint(4, 30)))
+            if set(seq) <= {"N"}:
+                seq = "A" + seq
+            kw = dict(max_errors=rng.choice([0, 0.1, 0.15, 0.2, 0.3]), min_overlap=rng.randint(1, 5),
+                      read_wildcards=rng.random() < 0.2, indels=rng.random() < 0.8)
+            objs.append(getattr(PA, rng.choice(types))(seq, name="x", **kw))
+            ads.append(seq)
+        multi = PA.MultipleAdapters(objs)
+        spec = spec_of(multi)
+        reads = random_reads(rng, ads, 300, rng.choice(["ACGT", "ACGTN", "ACGTacgtn"]), 120)
+        quals = ["".join(chr(33 + rng.choice([2, 2, 15, 30, 38])) for _ in r) for r in reads]
+        times = rng.choice([1, 2])
+        qtrim = rng.random() < 0.5
+        got, qt = run_set(spec.adapters, spec.groups, reads, quals if qtrim else None, quality_trim=qtrim,
+                          cutoff_front=5, cutoff_back=20, times=times)
+        exp, eqt = oracle.oracle_process(spec.adapters, spec.groups, reads, quals, qtrim, 5, 20, 33, times)
+        assert (got == exp).all(), [repr(o) for o in objs]
+        if qtrim:
+            assert (qt == eqt).all()
+
+
+def test_edge_cases_empty_ragged_long():
+    import cutadapt_b200.adapters as PA
+
+    d = PA.BackAdapter("AGATCGGAAGAGC", name="a").descriptor()
+    reads = ["", "A", "AGA", "AGATCGGAAGAGC", "", "T" * 300 + "AGATCGGAAGAGC", "ACGT" * 50, "", "AGAT"]
+    got, _ = run_set([d], None, reads)
+    exp, _ = oracle.oracle_process([d], None, reads)
+    assert (got == exp).all()
+    # only empty reads: nothing to stage at all
+    got, _ = run_set([d], None, ["", "", ""])
+    assert (got["adapter"] == -1).all()
+    # a single read / exactly one tile / one more than a tile
+    for n in (1, 128, 129, 257):
+        reads = ["ACGTACGTAGATCGGAAGAGCAAAA"] * n
+        got, _ = run_set([d], None, reads)
+        assert (got["rstart"][:, 0, 0] == 8).all() and (got["errors"] == 0).all()
+    # very long reads take the generic (wide-cell, unstaged) kernel; 40 kb > packed-cell origin range
+    rng = random.Random(2)
+    long_reads = ["".join(rng.choice("ACGT") for _ in range(40000)) + "AGATCGGAAGAGC" + "ACGT" * 10,
+                  "".join(rng.choice("ACGT") for _ in range(5000))]
+    got, _ = run_set([d], None, long_reads)
+    exp, _ = oracle.oracle_process([d], None, long_reads)
+    assert (got == exp).all() and got["rstart"][0, 0, 0] == 40000
+
+
+def test_non_ascii_reads_raise_like_the_reference():
+    import cutadapt_b200.adapters as PA
+
+    d = PA.BackAdapter("AGATCGGAAGAGC", name="a").descriptor()
+    spec = L.AdapterSetSpec([d])
+    aset = L.AdapterSet(spec)
+    data = np.frombuffer(b"ACGT\xe4CGTAGATCGGAAGAGC", dtype=np.uint8)
+    offsets = np.array([0, data.size], dtype=np.int64)
+    with pytest.raises(ValueError):
+        aset.process(data, offsets)
+    # and the context is usable afterwards
+    got, _ = run_set([d], None, ["ACGTAGATCGGAAGAGC"])
+    assert got["rstart"][0, 0, 0] == 4
+
+
+def test_large_batch_properties():
+    """
+    2 M reads (several pipeline chunks and both lanes): properties that do not need the oracle --
+    idempotence (trimmed reads no longer contain a full adapter), determinism across batch
+    splits, and agreement with the oracle on a strided sample.
+    """
+    import torch
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_read_tensor
+
+    n = 2_000_000
+    seq, _ = make_read_tensor(n, config=2, device="cuda")
+    host = seq.cpu().numpy().reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.int64) * 150
+    d = PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a").descriptor()
+    aset = L.AdapterSet(L.AdapterSetSpec([d]))
+    full, _ = aset.process(host, offsets)
+    # the same reads in two halves give the same records
+    half = n // 2 + 77
+    a, _ = aset.process(host[: half * 150], offsets[: half + 1])
+    b, _ = aset.process(host[half * 150:], offsets[half:] - half * 150)
+    assert (np.concatenate([a, b]) == full).all()
+    # oracle on a strided sample
+    idx = np.arange(0, n, 997)
+    sample = [host[i * 150:(i + 1) * 150].tobytes().decode() for i in idx]
+    exp, _ = oracle.oracle_process([d], None, sample)
+    assert (full[idx] == exp).all()
+    # idempotence: after trimming, an exact full-length adapter can no longer be found
+    hit = full["adapter"][:, 0, 0] >= 0
+    assert 0.45 < hit.mean() < 0.56
+    rstart = np.where(hit, full["rstart"][:, 0, 0], 150)
+    keep = np.arange(150)[None, :] < rstart[:200000, None]
+    trimmed = np.where(keep, host[: 200000 * 150].reshape(-1, 150), ord("X")).reshape(-1)
+    again, _ = aset.process(np.ascontiguousarray(trimmed), offsets[:200001])
+    exact = (again["adapter"][:, 0, 0] >= 0) & (again["errors"][:, 0, 0] == 0) & (again["astop"][:, 0, 0] == 13)
+    assert not exact.any()
+
+
+def test_device_resident_api_and_statistics():
+    """cg_process_batch_device on torch tensors + the statistics vector against a numpy recount."""
+    import ctypes as C
+    import torch
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_read_tensor
+    from cutadapt_b200.pipeline import DeviceBatch, stats_layout
+
+    n = 300_000
+    seq, qual = make_read_tensor(n, config=4, device="cuda", with_qualities=True)
+    multi = PA.MultipleAdapters([PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a")])
+    batch = DeviceBatch(multi, quality_cutoff=(0, 20))
+    res = batch.run(seq.reshape(-1), torch.arange(n + 1, device="cuda", dtype=torch.int64) * 150, qual.reshape(-1),
+                    max_read_len=150)
+    recs = res.matches.cpu().numpy().view(L.MATCH_DTYPE).reshape(n, 1, 1)
+    qt = res.qtrim.cpu().numpy().reshape(n, 2)
+    host = seq.cpu().numpy().reshape(-1)
+    hq = qual.cpu().numpy().reshape(-1)
+    offsets = np.arange(n + 1, dtype=np.int64) * 150
+    exp, eqt = batch.adapter_set.process(host, offsets, hq, batch.params)
+    assert (recs == exp).all() and (qt == eqt).all()
+    stats = batch.statistics(res).cpu().numpy()
+    lay = stats_layout(1, 150, 3)
+    assert stats[0] == n and stats[1] == n * 150
+    hit = recs["adapter"][:, 0, 0] >= 0
+    assert stats[2] == hit.sum()
+    assert stats[3] == (150 - (qt[:, 1] - qt[:, 0])).sum()
+    removed = (qt[:, 1] - qt[:, 0]) - recs["rstart"][:, 0, 0]
+    assert stats[4] == removed[hit].sum()
+    hist = stats[lay["hist"]:].reshape(1, 151, 4)
+    assert hist.sum() == hit.sum()
+    L_, E_ = 20, 0
+    assert hist[0, L_, E_] == ((removed == L_) & (recs["errors"][:, 0, 0] == E_) & hit).sum()

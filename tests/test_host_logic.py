@@ -1,0 +1,167 @@
+"""Host-side logic that needs no GPU: tables, heuristic, table packing, ABI surface, API errors."""
+import base64
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from util import golden, ROOT
+
+
+def test_match_tables_golden():
+    from cutadapt_b200 import _match_tables as T
+
+    g = golden("tables.json.gz")
+    dec = base64.b64decode
+    assert T._acgt_table() == dec(g["acgt"])
+    assert T._iupac_table() == dec(g["iupac"])
+    assert T._upper_table() == dec(g["upper"])
+    for rw in (0, 1):
+        for qw in (0, 1):
+            assert T.matches_lookup(bool(rw), bool(qw)) == [dec(x) for x in g[f"lookup_{rw}{qw}"]]
+
+
+def test_kmer_heuristic_golden():
+    from cutadapt_b200.kmer_heuristic import create_positions_and_kmers
+
+    for ad, mo, er, b, f, i, expected in golden("kmer_kat.json.gz")["heuristic"]:
+        try:
+            res = create_positions_and_kmers(ad, mo, er, bool(b), bool(f), bool(i))
+        except NotImplementedError:
+            assert expected == "NotImplementedError"
+            continue
+        res = sorted(([s, e, sorted(k)] for s, e, k in res),
+                     key=lambda x: (x[0], -(10**9) if x[1] is None else x[1], x[2]))
+        assert res == expected, (ad, mo, er, b, f, i)
+
+
+def test_reference_heuristic_examples():
+    # tests/test_kmer_heuristic.py in the reference: the Illumina adapter at e=0.1, O=3
+    from cutadapt_b200.kmer_heuristic import create_positions_and_kmers, kmer_chunks
+
+    assert kmer_chunks("AABCABCABC", 3) == ["AABC", "ABC"]
+    got = create_positions_and_kmers("AGATCGGAAGAGC", 3, 0.1, True, False)
+    assert got == [(-3, None, ["AGA"]), (-4, None, ["AGAT"]), (-13, None, ["AGATC", "GGAAG"]),
+                   (0, None, ["AGATCGG", "AAGAGC"])]
+
+
+def test_kmer_table_packing_matches_oracle():
+    from cutadapt_b200._kmer_finder import build_kmer_tables
+    from oracle import oracle
+
+    for sets, rw, qw, _ in golden("kmer_kat.json.gz")["present"]:
+        pk = [(s, e, k) for s, e, k in sets]
+        entries, masks = build_kmer_tables(pk, rw, qw)
+        oe, om = oracle.KmerTables(pk, rw, qw).as_lists()
+        assert entries == oe
+        assert (masks == om).all()
+
+
+def test_kmer_finder_errors_and_pickle():
+    from cutadapt_b200._kmer_finder import KmerFinder, MAXIMUM_WORD_SIZE
+
+    assert MAXIMUM_WORD_SIZE == 64
+    with pytest.raises(ValueError):
+        KmerFinder([(0, None, ["A" * 65])])
+    with pytest.raises(TypeError):
+        KmerFinder([(0, None, [b"ACGT"])])
+    kf = KmerFinder([(0, None, ["ACGT", "TTT"]), (-5, None, ["GG"])], True, False)
+    kf2 = pickle.loads(pickle.dumps(kf))
+    assert kf2.positions_and_kmers == kf.positions_and_kmers and kf2.ref_wildcards and not kf2.query_wildcards
+    # more than 64 characters spill into a second word (tests/test_kmer_finder.py:83-89)
+    kf3 = KmerFinder([(0, None, ["A" * 40, "C" * 40])])
+    assert len(kf3.tables[0]) == 2
+
+
+def test_aligner_api_surface():
+    from cutadapt_b200._align import Aligner, PrefixComparer, SuffixComparer
+
+    a = Aligner("ACGTNN", 0.1, flags=14, wildcard_ref=True, min_overlap=3)
+    assert a.effective_length == 4
+    assert repr(a) == ("Aligner(reference='ACGTNN', max_error_rate=0.1, flags=14, wildcard_ref=True, "
+                       "wildcard_query=False, indel_cost=1, min_overlap=3)")
+    b = pickle.loads(pickle.dumps(a))
+    assert repr(b) == repr(a)
+    with pytest.raises(ValueError, match="only N wildcards"):
+        Aligner("NNNNN", 0.1, wildcard_ref=True)
+    with pytest.raises(ValueError, match="indel_cost"):
+        Aligner("ACGT", 0.1, indel_cost=0)
+    with pytest.raises(ValueError):
+        PrefixComparer("ACGT", 1.5)
+    with pytest.raises(ValueError):
+        SuffixComparer("ACGT", 0.1, min_overlap=0)
+    assert PrefixComparer("ACNN", 0.5, wildcard_ref=True).effective_length == 2
+
+
+def test_adapter_classes_construct_like_the_reference():
+    import cutadapt_b200.adapters as PA
+
+    a = PA.BackAdapter("agaucggaagagc", max_errors=2, min_overlap=50, name="x")
+    assert a.sequence == "AGATCGGAAGAGC" and a.min_overlap == 13
+    assert abs(a.max_error_rate - 2 / 13) < 1e-12
+    assert a.adapter_wildcards is False          # only ACGT -> plain comparison (adapters.py:592-595)
+    with pytest.raises(PA.InvalidCharacter):
+        PA.BackAdapter("ACGZ")
+    with pytest.raises(ValueError):
+        PA.BackAdapter("")
+    p = PA.PrefixAdapter("ACGTAC", indels=False)
+    assert isinstance(p.kmer_finder, PA.MockKmerFinder) and p.min_overlap == 6
+    d = p.descriptor()
+    assert d["kind"] == 1 and "kmer_entries" not in d
+    r = PA.RightmostBackAdapter("ACGTT")
+    assert r.descriptor()["reverse_read"] and r.descriptor()["sequence"] == "TTGCA"
+    assert PA.Where.BACK == 14 and PA.Where.FRONT == 11 and PA.Where.ANYWHERE == 15
+    assert PA.Where.PREFIX == 8 and PA.Where.SUFFIX == 2
+    assert PA.Where.FRONT_NOT_INTERNAL == 9 and PA.Where.BACK_NOT_INTERNAL == 6
+    multi = PA.MultipleAdapters([a, PA.LinkedAdapter(PA.PrefixAdapter("ACGT"), PA.BackAdapter("TTTT"), True, False, "l")])
+    singles, groups, owners = multi._flatten()
+    assert len(singles) == 3 and groups == [(0, 0, -1, 0, 0), (1, 1, 2, 1, 0)]
+    pickle.loads(pickle.dumps(multi))
+
+
+def test_environment_generators_golden():
+    from cutadapt_b200._align import edit_environment, hamming_environment, hamming_sphere
+
+    for t, k, ee, he in golden("environment_kat.json.gz"):
+        assert sorted(map(list, edit_environment(t, k))) == ee
+        assert sorted(map(list, hamming_environment(t, k))) == he
+    assert sorted(hamming_sphere("AC", 1)) == sorted(["CC", "GC", "TC", "AA", "AG", "AT"])
+
+
+def test_shared_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no GPU needed) and exports every function include/*.h declares."""
+    from cutadapt_b200 import _lib
+
+    lib = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "cutadapt_b200.h")).read()
+    names = set(re.findall(r"\b(cg_[a-z_]+)\s*\(", header))
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert lib.cg_version() == 1
+    assert lib.cg_stats_size(2, 150, 3) == 8 + 2 * 151 * 4
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device the product refuses to run instead of falling back."""
+    import torch
+    from cutadapt_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.CutadaptB200Error, match="no CPU fallback|CUDA"):
+        _lib.Context(0)
+
+
+def test_product_does_not_import_the_oracle():
+    """Nothing under cutadapt_b200/ may reference oracle/ or the host simulation."""
+    pkg = os.path.join(ROOT, "cutadapt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "liboracle" not in text and "libhostsim" not in text, f

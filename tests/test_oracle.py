@@ -1,0 +1,116 @@
+"""
+The oracle against the reference: every function of oracle/cutadapt_oracle.c is pinned to the
+golden vectors generated from the reference's own compiled code (tests/golden/make_golden.py)
+and, where oracle/_ref travels along, to the reference itself on fresh random inputs.
+"""
+import random
+
+import pytest
+
+from oracle import oracle
+from util import golden, reference_or_none, match_desc, build_adapters
+
+
+def test_locate_golden():
+    cases = golden("locate_kat.json.gz")
+    assert len(cases) > 3000
+    for ref, q, rate, flags, wr, wq, ic, mo, expected in cases:
+        got = oracle.locate(ref, q, rate, flags, wr, wq, ic, mo)
+        assert (list(got) if got is not None else None) == expected, (ref, q, rate, flags, wr, wq, ic, mo)
+
+
+def test_reference_known_answers():
+    # tests/test_align.py:74-107 in the reference
+    assert oracle.locate("CCAGTCCTCT", "CCAGTCCTTTCCTGAGAGT", 0.3, 8) == (0, 10, 0, 10, 8, 1)
+    assert oracle.locate("TCGATC", "TCGATGC", 1.5 / 6, 8) == (0, 6, 0, 6, 4, 1)
+    assert oracle.locate("GCCGAACTTCTTAGACTGCCTTAAGGACGT", "CAAATCACCAGAAGGCGCCTAACTTCTTAGACTGCC", 0.1, 14) == (
+        0, 20, 16, 36, 18, 1)
+    assert oracle.locate("", "", 0, 0, min_overlap=0) == (0, 0, 0, 0, 0, 0)
+    assert oracle.locate("TTTT", "CCTTTT", 0.25, 14) == (0, 4, 2, 6, 4, 0)
+
+
+def test_comparers_golden():
+    for ref, q, rate, wr, wq, mo, p, s in golden("comparer_kat.json.gz"):
+        got = oracle.prefix_compare(ref, q, rate, wr, wq, mo)
+        assert (list(got) if got else None) == p, ("prefix", ref, q)
+        got = oracle.suffix_compare(ref, q, rate, wr, wq, mo)
+        assert (list(got) if got else None) == s, ("suffix", ref, q)
+
+
+def test_kmers_present_golden():
+    for sets, rw, qw, reads in golden("kmer_kat.json.gz")["present"]:
+        tables = oracle.KmerTables([(s, e, k) for s, e, k in sets], rw, qw)
+        for read, expected in reads:
+            assert tables.present(read) == expected, (sets, rw, qw, read)
+
+
+def test_quality_trim_golden():
+    for q, cf, cb, base, expected in golden("qualtrim_kat.json.gz"):
+        assert list(oracle.quality_trim_index(q, cf, cb, base)) == expected, (q, cf, cb, base)
+
+
+def test_non_ascii_is_an_error():
+    with pytest.raises(ValueError):
+        oracle.locate("ACGT", "AC\xe4GT", 0.1)
+
+
+def test_info_file_coordinates():
+    """Per-read coordinates of the reference's golden file tests/cut/illumina.info.txt."""
+    from cutadapt_b200.kmer_heuristic import create_positions_and_kmers
+
+    data = golden("info_file_kat.json.gz")["illumina"]
+    adapter = data["adapter"]
+    tables = oracle.KmerTables(create_positions_and_kmers(adapter, 3, 0.1, True, False), False, False)
+    n_hits = 0
+    for seq, expected in data["rows"]:
+        res = oracle.locate(adapter, seq, 0.1, 14, min_overlap=3) if tables.present(seq) else None
+        if expected is None:
+            assert res is None, seq
+        else:
+            n_hits += 1
+            assert [res[5], res[2], res[3]] == expected, seq
+    assert n_hits > 30
+
+
+@pytest.mark.skipif(reference_or_none() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_against_reference_random():
+    import cutadapt._align as ra
+    from cutadapt.qualtrim import quality_trim_index
+
+    rng = random.Random(77)
+    for _ in range(3000):
+        alpha = rng.choice(["ACGT", "AC", "ACGTN", "ACGTacgtNn", "ACGTRYKMN"])
+        m = rng.randint(1, 20)
+        ref = "".join(rng.choice(alpha) for _ in range(m))
+        wr, wq = rng.random() < 0.3, rng.random() < 0.2
+        if wr and set(ref.upper()) <= {"N"}:
+            continue
+        rate = rng.choice([0, 0.1, 0.2, 0.34, 0.5])
+        flags, ic, mo = rng.randint(0, 15), rng.choice([1, 1, 100000, 3]), rng.randint(1, 4)
+        al = ra.Aligner(ref, rate, flags, wr, wq, ic, mo)
+        for _ in range(4):
+            q = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 40)))
+            if rng.random() < 0.5:
+                pos = rng.randint(0, len(q))
+                q = q[:pos] + ref[rng.randint(0, m // 2):] + q[pos:]
+            assert al.locate(q) == oracle.locate(ref, q, rate, flags, wr, wq, ic, mo), (ref, q, rate, flags)
+        qs = "".join(chr(33 + rng.choice([0, 2, 10, 20, 30, 40])) for _ in range(rng.randint(0, 50)))
+        assert quality_trim_index(qs, 5, 20) == oracle.quality_trim_index(qs, 5, 20)
+
+
+def test_oracle_composition_matches_golden_adapters():
+    """oracle_process (prefilter + locate + best-of / linked) against reference match_to results."""
+    import cutadapt_b200.adapters as PA
+    from util import spec_of
+    import numpy as np
+
+    for case in golden("adapters_kat.json.gz"):
+        multi = build_adapters(PA, case["adapters"])
+        spec = spec_of(multi)
+        reads = [r for r, _ in case["reads"]]
+        recs, _ = oracle.oracle_process(spec.adapters, spec.groups, reads)
+        if recs.shape[2] == 1 and spec.slots == 2:
+            pass
+        for i, (read, expected) in enumerate(case["reads"]):
+            got = match_desc(multi.matches_from_records(recs[i, 0], read))
+            assert got == expected, (case["adapters"], read)

@@ -1,0 +1,133 @@
+"""Shared helpers of the test-suite (test infrastructure only)."""
+import ctypes as C
+import gzip
+import json
+import os
+import random
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def golden(name):
+    with gzip.open(os.path.join(HERE, "golden", name), "rt") as f:
+        return json.load(f)
+
+
+def reference_or_none():
+    """The reference's compiled hot path (oracle/_ref), if it has been built and travels along."""
+    import sys
+
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "cutadapt")):
+        return None
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    try:
+        import cutadapt.adapters  # noqa: F401
+        import cutadapt
+
+        return cutadapt
+    except Exception:
+        return None
+
+
+# ---- hostsim: the device functions compiled for the host (tests only) ------------------------
+
+_hs = None
+
+
+def hostsim_lib():
+    global _hs
+    if _hs is None:
+        from cutadapt_b200 import _lib as L
+
+        lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+        lib.hs_last_error.restype = C.c_char_p
+        lib.hs_process_batch.argtypes = [
+            C.POINTER(L.cg_adapter_desc), C.c_int, C.POINTER(L.cg_group_desc), C.c_int, C.c_void_p,
+            C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(L.cg_params), C.c_void_p, C.c_void_p, C.c_int,
+        ]
+        _hs = lib
+    return _hs
+
+
+def hostsim_process(spec, seqs, quals=None, params=None, force_wide=0):
+    from cutadapt_b200 import _lib as L
+
+    params = params or L.make_params()
+    arr, n, garr, ng = spec.to_ctypes()
+    data, offs = L.pack_strings(seqs)
+    qd = L.pack_strings(quals)[0] if quals is not None else None
+    times = max(1, params.times)
+    out = np.zeros((len(seqs), times, spec.slots), dtype=L.MATCH_DTYPE)
+    qt = np.zeros((len(seqs), 2), dtype=np.int32)
+    rc = hostsim_lib().hs_process_batch(
+        arr, n, garr, ng, data.ctypes.data, qd.ctypes.data if qd is not None else None, offs.ctypes.data,
+        len(seqs), C.byref(params), out.ctypes.data, qt.ctypes.data, force_wide,
+    )
+    if rc:
+        raise RuntimeError((rc, hostsim_lib().hs_last_error()))
+    return out, qt
+
+
+# ---- building adapters from the golden "adapters_kat" specs ----------------------------------
+
+
+def build_adapters(module, specs):
+    """Instantiate [type, seq, kwargs] / ["Linked", front, back, freq, breq] specs with `module`'s classes."""
+    objs = []
+    for spec in specs:
+        if spec[0] == "Linked":
+            _, (t1, s1, k1), (t2, s2, k2), fq, bq = spec
+            front = getattr(module, t1)(s1, name="f", **k1)
+            back = getattr(module, t2)(s2, name="b", **k2)
+            objs.append(module.LinkedAdapter(front, back, fq, bq, "lnk"))
+        else:
+            t, s, k = spec
+            objs.append(getattr(module, t)(s, name="x", **k))
+    return module.MultipleAdapters(objs)
+
+
+def match_desc(m):
+    if m is None:
+        return None
+    if hasattr(m, "front_match"):
+        return ["Linked", match_desc(m.front_match), match_desc(m.back_match)]
+    return [type(m).__name__, m.astart, m.astop, m.rstart, m.rstop, m.score, m.errors]
+
+
+def spec_of(multi):
+    """AdapterSetSpec + bookkeeping for a cutadapt_b200 MultipleAdapters / adapter."""
+    from cutadapt_b200 import _lib as L
+
+    singles, groups, owners = multi._flatten()
+    spec = L.AdapterSetSpec([s.descriptor() for s in singles], groups)
+    multi._device_set = (None, singles, owners)
+    return spec
+
+
+def random_reads(rng, adapters, n_reads, alpha="ACGT", max_len=80):
+    reads = []
+    for _ in range(n_reads):
+        q = "".join(rng.choice(alpha) for _ in range(rng.randint(0, max_len)))
+        for _ in range(rng.choice([0, 1, 1, 2])):
+            ad = rng.choice(adapters)
+            piece = ad if rng.random() < 0.6 else ad[rng.randint(0, len(ad) // 2): rng.randint(len(ad) // 2, len(ad))]
+            piece = list(c if c in "ACGT" else rng.choice("ACGT") for c in piece)
+            for _ in range(rng.choice([0, 0, 1, 2])):
+                if piece:
+                    p = rng.randrange(len(piece))
+                    r = rng.random()
+                    if r < 0.4:
+                        piece[p] = rng.choice(alpha)
+                    elif r < 0.7:
+                        del piece[p]
+                    else:
+                        piece.insert(p, rng.choice(alpha))
+            pos = rng.choice([0, len(q), rng.randint(0, len(q))])
+            q = q[:pos] + "".join(piece) + q[pos:]
+        reads.append(q)
+    return reads
