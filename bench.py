@@ -42,38 +42,56 @@ HOST_WINDOW_READS = 20_000_000           # pinned host window streamed repeatedl
 # CPU arm: the reference (oracle/_ref) or, if it did not travel, the C oracle port
 # ------------------------------------------------------------------------------------------------
 
-def _cpu_worker(args):
-    """Runs in a spawned process: time match_to + trimmed over `reads` `repeat` times."""
-    kind, reads, repeat = args
-    import time as _t
+_WORKER = {}
 
+
+def _cpu_init(kind, path, index, n_workers):
+    """Pool initializer: every worker loads its slice of the sample once and builds the adapter."""
+    with open(path) as f:
+        reads = f.read().split("\n")
+    reads = [r for r in reads if r]
+    per = max(1, len(reads) // n_workers)
+    with index.get_lock():
+        me = index.value
+        index.value += 1
+    _WORKER["reads"] = reads[me * per:(me + 1) * per] or reads[:per]
     if kind == "reference":
         sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
         from cutadapt.adapters import BackAdapter
 
-        adapter = BackAdapter(ADAPTER, max_errors=ERROR_RATE, min_overlap=3)
-        t0 = _t.perf_counter()
-        kept = 0
+        _WORKER["adapter"] = BackAdapter(ADAPTER, max_errors=ERROR_RATE, min_overlap=3)
+    else:
+        from oracle import oracle as O
+        from cutadapt_b200.kmer_heuristic import create_positions_and_kmers
+
+        _WORKER["oracle"] = O
+        _WORKER["tables"] = O.KmerTables(create_positions_and_kmers(ADAPTER, 3, ERROR_RATE, True, False))
+    _WORKER["kind"] = kind
+
+
+def _cpu_worker(repeat):
+    """The reference hot path per read: Adapter.match_to (prefilter + locate) and Match.trimmed."""
+    import time as _t
+
+    reads = _WORKER["reads"]
+    kept = 0
+    t0 = _t.perf_counter()
+    if _WORKER["kind"] == "reference":
+        adapter = _WORKER["adapter"]
         for _ in range(repeat):
             for read in reads:
                 m = adapter.match_to(read)
                 if m is not None:
                     kept += len(m.trimmed(read))
-        return _t.perf_counter() - t0, len(reads) * repeat, kept
     else:
-        from oracle import oracle as O
-        from cutadapt_b200.kmer_heuristic import create_positions_and_kmers
-
-        kt = O.KmerTables(create_positions_and_kmers(ADAPTER, 3, ERROR_RATE, True, False))
-        t0 = _t.perf_counter()
-        kept = 0
+        O, kt = _WORKER["oracle"], _WORKER["tables"]
         for _ in range(repeat):
             for read in reads:
                 if kt.present(read):
                     r = O.locate(ADAPTER, read, ERROR_RATE, 14, min_overlap=3)
                     if r is not None:
                         kept += r[2]
-        return _t.perf_counter() - t0, len(reads) * repeat, kept
+    return _t.perf_counter() - t0, len(reads) * repeat, kept
 
 
 def reference_kind():
@@ -83,29 +101,43 @@ def reference_kind():
     return "port"
 
 
-def cpu_throughput(sample_reads, seconds_target=10.0, cores=None):
-    """reads/s of the CPU implementation over all host cores (spawned workers, pre-parsed reads)."""
-    import multiprocessing as mp
+class CpuArm:
+    """All host cores running the reference hot path on pre-parsed reads (spawned workers)."""
 
-    kind = reference_kind()
-    cores = cores or len(os.sched_getaffinity(0))
-    per = max(1, len(sample_reads) // cores)
-    shares = [sample_reads[i * per:(i + 1) * per] for i in range(cores)]
-    shares = [s for s in shares if s]
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(len(shares)) as pool:
-        # calibration pass (also warms the workers up: imports, adapter construction)
+    def __init__(self, sample_reads, cores=None):
+        import multiprocessing as mp
+        import tempfile
+
+        self.kind = reference_kind()
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.cores = max(1, min(self.cores, len(sample_reads)))
+        fd, self.path = tempfile.mkstemp(suffix=".reads")
+        with os.fdopen(fd, "w") as f:
+            f.write("\n".join(sample_reads))
+        ctx = mp.get_context("spawn")
+        index = ctx.Value("i", 0)
+        self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(self.kind, self.path, index, self.cores))
+        # warm up + calibrate: one pass over each worker's slice
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(kind, s[: max(1, len(s) // 8)], 1) for s in shares])
-        calib = time.perf_counter() - t0
-        rate_guess = sum(max(1, len(s) // 8) for s in shares) / max(calib, 1e-3)
-        total = sum(len(s) for s in shares)
-        repeat = max(1, int(seconds_target * rate_guess / total))
+        res = self.pool.map(_cpu_worker, [1] * self.cores, chunksize=1)
+        self.pass_reads = sum(r[1] for r in res)
+        self.pass_seconds = max(r[0] for r in res)
+
+    def run(self, seconds_target):
+        repeat = max(1, int(round(seconds_target / max(self.pass_seconds, 1e-3))))
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(kind, s, repeat) for s in shares])
+        res = self.pool.map(_cpu_worker, [repeat] * self.cores, chunksize=1)
         wall = time.perf_counter() - t0
-    n = sum(r[1] for r in res)
-    return n / wall, kind, len(shares), n, wall
+        n = sum(r[1] for r in res)
+        return n / wall, n, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
 
 
 # ------------------------------------------------------------------------------------------------
@@ -183,11 +215,14 @@ def main():
         from cutadapt_b200.synth import make_reads
 
         sample, _ = make_reads(400_000, config=2)
+        arm = CpuArm(sample)
+        kind, cores = arm.kind, arm.cores
         vals = []
         for i in range(args.warmup + args.steps):
-            v, kind, cores, n, wall = cpu_throughput(sample, seconds_target=6.0)
+            v, n, wall = arm.run(5.0)
             if i >= args.warmup:
                 vals.append((v, n, wall))
+        arm.close()
         value = sum(n for _, n, _ in vals) / sum(w for _, _, w in vals)
         line = {
             "impl": "reference", "metric": "reads/sec (150bp SE, 1 adapter, e=0.1)", "value": value, "unit": "reads/s",
@@ -229,9 +264,11 @@ def main():
         sample_t, _ = make_read_tensor(400_000, config=2, shard=0, device="cpu")
         raw = sample_t.numpy().tobytes()
         sample = [raw[i * READ_LEN:(i + 1) * READ_LEN].decode() for i in range(sample_t.shape[0])]
-        v, kind, cores, nproc, wall = cpu_throughput(sample, seconds_target=12.0)
-        cpu = {"value": v, "unit": "reads/s", "cores": cores, "kind": kind,
-               "sample": f"{nproc} pre-parsed reads in {wall:.1f}s: Adapter.match_to + Match.trimmed over {cores} processes"}
+        arm = CpuArm(sample)
+        v, nproc, wall = arm.run(12.0)
+        arm.close()
+        cpu = {"value": v, "unit": "reads/s", "cores": arm.cores, "kind": arm.kind,
+               "sample": f"{nproc} pre-parsed reads in {wall:.1f}s: Adapter.match_to + Match.trimmed over {arm.cores} processes"}
 
     seq, _ = make_read_tensor(n, config=2, shard=rank, device=str(dev))
     seq = seq.reshape(-1)

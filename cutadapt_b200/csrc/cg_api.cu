@@ -6,6 +6,7 @@
 // Caller buffers that are already pinned are copied from/to directly.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -279,8 +280,13 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         smem = cg_fast_smem_bytes(a.blob_bytes, a.tile_cap, a.col_rows, want_q);
         if (smem > c->smem_optin) fast = false;
     }
+    // two-phase schedule when the set is one aligner adapter and a single round is asked for;
+    // CUTADAPT_B200_KERNEL=general forces the one-phase kernel (used by the parity tests)
+    const char *kernel_env = getenv("CUTADAPT_B200_KERNEL");
+    const bool force_general = kernel_env && strcmp(kernel_env, "general") == 0;
+    const bool simple = fast && s->host.simple_ok && times == 1 && !force_general;
     if (fast) {
-        CU(cg_fast_occupancy(want_q, smem, &occ));
+        CU(cg_fast_occupancy(want_q, simple, smem, &occ));
         if (occ < 1) fast = false;
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -295,7 +301,7 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         const long long n_tiles = (n_reads + CG_NT - 1) / CG_NT;
         long long grid = (long long)occ * c->sm_count;
         if (grid > n_tiles) grid = n_tiles;
-        CU(cg_launch_fast(a, want_q, (int)grid, smem, st));
+        CU(cg_launch_fast(a, want_q, simple, (int)grid, smem, st));
     } else {
         // generic path: thread per read, columns in HBM scratch (16 bytes per cell)
         const int block = 128;

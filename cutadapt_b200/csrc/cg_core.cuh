@@ -166,10 +166,21 @@ CG_HD bool kmers_present_core(const CgEntry *ents, int count, const uint64_t *ma
 // Aligner.locate  (_align.pyx:298-587)
 // out6 = (ref_start, ref_stop, query_start, query_stop, score, errors)
 // ---------------------------------------------------------------------------------------
+//
+// Windowed mode (cover != 0xFFFFFFFF; only for START_IN_QUERY|STOP_IN_QUERY adapters): the read
+// is cut into 32 groups of (1 << gs) characters and only the groups whose bit is set in `cover`
+// are run through the DP.  A maximal run of set groups starting at character j0 > 0 restarts the
+// DP as if the read began there (column j0: cost i, score -2i, origin j0 -- the path that
+// deletes i adapter characters at column j0).  Every cell of the true matrix with cost <= k whose
+// optimal paths start at or after j0 comes out identical (restarted costs are >= the true ones
+// and equal along those paths, so all tie-breaks agree); the caller guarantees via the locator
+// k-mers (pigeonhole: an alignment with <= k errors contains one of the k+1 adapter chunks
+// exactly) that every bottom-row cell with cost <= k, and the cells the last-column scan can
+// accept, lie at least m + k columns to the right of their run's start.
 template <class Cell, class Col>
 CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *ncnt,
                        const int32_t *maxcost, const uint8_t *enc, const ReadView &rv, Col &col,
-                       int *out6)
+                       int *out6, uint32_t cover = 0xFFFFFFFFu, int gs = 0)
 {
     typedef typename Cell::T T;
     const int m = A.m, n = rv.n, k = A.k, ic = A.indel_cost;
@@ -181,22 +192,48 @@ CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *nc
     if (!siq) max_n = cg_min(n, m + k);
     if (!eiq) min_n = cg_max(0, n - m - k);
 
-    for (int i = 0; i <= m; ++i) {                              // _align.pyx:364-383
-        long long c; int s, o;
-        if (!sir && !siq) { s = -2 * i; c = (long long)cg_max(i, min_n) * ic; o = 0; }
-        else if (sir && !siq) { s = 0; c = (long long)min_n * ic; o = cg_min(0, min_n - i); }
-        else if (!sir && siq) { s = -2 * i; c = (long long)i * ic; o = cg_max(0, min_n - i); }
-        else { s = 0; c = (long long)cg_min(i, min_n) * ic; o = min_n - i; }
-        col.set(i, Cell::make(c, s, o));
-    }
-
     bool have = false;                                          // _align.pyx:391-396
     int b_origin = 0, b_cost = 0, b_score = 0, b_ref_stop = m, b_q_stop = n;
-    int last = sir ? m : cg_min(m, k + 1);                      // _align.pyx:399-401
-    int last_filled = 0;
+    int last = 0, last_filled = 0;
     T stale = Cell::make(0, 0, 0);      // the C variable `origin` of _align.pyx:407 (see :565)
+    const bool windowed = cover != 0xFFFFFFFFu;
+    bool stopped = false;               // early exit (_align.pyx:531-533)
+    int run_lo = min_n, run_hi = max_n; // columns run_lo+1 .. run_hi are computed
+    uint32_t todo = cover;
+    bool reached_end = !windowed;
 
-    for (int j = min_n + 1; j <= max_n; ++j) {                  // _align.pyx:433
+    while (true) {
+      if (windowed) {
+        if (todo == 0) break;
+        // next maximal run of set groups
+        int ga = 0;
+        while (!((todo >> ga) & 1u)) ++ga;
+        int gb = ga;
+        while (gb < 31 && ((todo >> (gb + 1)) & 1u)) ++gb;
+        todo &= ~(((gb == 31 ? 0u : (1u << (gb + 1))) - 1u) & ~((1u << ga) - 1u));
+        run_lo = ga << gs;
+        if (run_lo > 0 && run_lo >= n) break;
+        const long long hi_ll = ((long long)(gb + 1)) << gs;
+        run_hi = hi_ll > n ? n : (int)hi_ll;
+        reached_end = run_hi == n;
+      }
+      if (run_lo == min_n) {
+        for (int i = 0; i <= m; ++i) {                          // _align.pyx:364-383
+            long long c; int s, o;
+            if (!sir && !siq) { s = -2 * i; c = (long long)cg_max(i, min_n) * ic; o = 0; }
+            else if (sir && !siq) { s = 0; c = (long long)min_n * ic; o = cg_min(0, min_n - i); }
+            else if (!sir && siq) { s = -2 * i; c = (long long)i * ic; o = cg_max(0, min_n - i); }
+            else { s = 0; c = (long long)cg_min(i, min_n) * ic; o = min_n - i; }
+            col.set(i, Cell::make(c, s, o));
+        }
+        last = sir ? m : cg_min(m, k + 1);                      // _align.pyx:399-401
+      } else {
+        // restart inside the read: column run_lo of a read that begins at character run_lo
+        for (int i = 0; i <= m; ++i) col.set(i, Cell::make((long long)i * ic, -2 * i, run_lo));
+        last = cg_min(m, k + 1);
+      }
+
+    for (int j = run_lo + 1; j <= run_hi; ++j) {                // _align.pyx:433
         const uint8_t qc = enc[rv.at(j - 1)];
         T diag = col.get(0);
         T w0 = siq ? Cell::row0_free(diag) : Cell::row0_ins(diag, ic);   // _align.pyx:438-440
@@ -230,12 +267,14 @@ CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *nc
                        (length > best_len && score > b_score))) {
                 have = true;
                 b_score = score; b_cost = cost; b_origin = origin; b_ref_stop = m; b_q_stop = j;
-                if (cost == 0 && origin >= 0) break;            // _align.pyx:531-533
+                if (cost == 0 && origin >= 0) { stopped = true; break; }   // _align.pyx:531-533
             }
         }
     }
+      if (stopped || !windowed) break;
+    }
 
-    if (max_n == n) {                                           // _align.pyx:536-572
+    if (max_n == n && (reached_end || stopped)) {               // _align.pyx:536-572
         const int first_i = eir ? 0 : m;
         const int origin_var = Cell::origin(stale);
         for (int i = last_filled; i >= first_i; --i) {
@@ -314,6 +353,104 @@ CG_HD void quality_trim_core(const uint8_t *q, int n, int cutoff_front, int cuto
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused scan stage of the two-phase kernel.
+//
+// The host re-packs the KmerFinder entries of the adapter into 32-bit shift-and words by window
+// type (whole read / suffix / prefix) and adds the "locator" chunks (the k+1 pieces of the whole
+// adapter).  One pass per word answers both questions at once:
+//   * KmerFinder.kmers_present (bit-for-bit the reference's verdict, _kmer_finder.pyx:170-213):
+//     any k-mer of any entry found inside that entry's window;
+//   * where locator chunks end, at a granularity of (1 << gs) characters, as a 32-bit group mask.
+// ---------------------------------------------------------------------------------------
+struct ScanOut {
+    bool pass;
+    uint32_t hits;   // bit g: a locator chunk ends in characters [g << gs, (g+1) << gs)
+};
+
+CG_HD int scan_group_shift(int n)
+{
+    int gs = 4;
+    while ((n >> gs) >= 32) ++gs;
+    return gs;
+}
+
+CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *pool, const ReadView &rv,
+                        int gs, bool always_pass)
+{
+    ScanOut out; out.pass = always_pass; out.hits = 0;
+    const int n = rv.n;
+    for (int w = 0; w < n_words; ++w) {
+        const CgScanWord &W = words[w];
+        const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
+        if (W.type == CG_SCAN_WHOLE) {
+            const uint32_t init = W.init, locf = W.loc_found;
+            uint32_t R = 0, seen = 0;
+            if (locf) {
+                const int G = 1 << gs;
+                for (int p0 = 0; p0 < n; p0 += G) {
+                    const int p1 = cg_min(n, p0 + G);
+                    uint32_t g = 0;
+                    for (int p = p0; p < p1; ++p) {
+                        R = ((R << 1) | init) & mask[rv.at(p) & 127];
+                        g |= R;
+                    }
+                    seen |= g;
+                    if (g & locf) out.hits |= 1u << (p0 >> gs);
+                }
+            } else {
+                for (int p = 0; p < n; ++p) {
+                    R = ((R << 1) | init) & mask[rv.at(p) & 127];
+                    seen |= R;
+                }
+            }
+            if (seen & W.pass_found) out.pass = true;
+        } else if (W.type == CG_SCAN_SUFFIX) {
+            const uint32_t *tab = (const uint32_t *)(pool + W.pos_off);   // {init, found}[span + 1]
+            uint32_t R = 0, seen = 0;
+            for (int p = cg_max(0, n - (int)W.span); p < n; ++p) {
+                const int d = n - p;
+                R = ((R << 1) | tab[2 * d]) & mask[rv.at(p) & 127];
+                seen |= R & tab[2 * d + 1];
+            }
+            if (seen & W.pass_found) out.pass = true;
+        } else {
+            const uint32_t *tab = (const uint32_t *)(pool + W.pos_off);   // {init, found}[span]
+            uint32_t R = 0, seen = 0;
+            const int stop = cg_min(n, (int)W.span);
+            for (int p = 0; p < stop; ++p) {
+                R = ((R << 1) | tab[2 * p]) & mask[rv.at(p) & 127];
+                seen |= R & tab[2 * p + 1];
+            }
+            if (seen & W.pass_found) out.pass = true;
+        }
+    }
+    return out;
+}
+
+// Groups of characters the DP must visit, given the locator hits (see locate_core).
+CG_HD uint32_t window_cover(const CgAdapter &A, int n, int gs, uint32_t hits)
+{
+    if (n <= 0) return 0xFFFFFFFFu;
+    const int reach = A.m + A.k;                 // a hit at p needs characters p+1-reach .. p+reach
+    const int r = (reach + (1 << gs) - 1) >> gs; // in groups
+    uint32_t cover = hits;
+    for (int s = 1; s <= r && s < 32; ++s) cover |= (hits << s) | (hits >> s);
+    const int g_last = (n - 1) >> gs;
+    if (A.flags & 1) {                           // START_IN_REFERENCE: adapter may hang over the read start
+        const int g = cg_min(g_last, (reach - 1 > 0 ? reach - 1 : 0) >> gs);
+        cover |= (g >= 31) ? 0xFFFFFFFFu : ((1u << (g + 1)) - 1u);
+    }
+    if (A.flags & 4) {                           // STOP_IN_REFERENCE: last-column scan (partial adapter at the end)
+        const int g0 = cg_max(0, n - 1 - reach) >> gs;
+        cover |= ~((1u << g0) - 1u);
+    }
+    const uint32_t valid = (g_last >= 31) ? 0xFFFFFFFFu : ((1u << (g_last + 1)) - 1u);
+    cover &= valid;
+    if (cover == valid) return 0xFFFFFFFFu;      // everything: plain DP
+    return cover;
+}
+
+// ---------------------------------------------------------------------------------------
 // Adapter composition
 // ---------------------------------------------------------------------------------------
 struct SetView {
@@ -324,6 +461,7 @@ struct SetView {
     const uint8_t *pool;
     const uint64_t *masks64;   // HBM
     const uint8_t *enc;        // 3 x 256 bytes: upper, acgt, iupac
+    const CgScanWord *scan;    // two-phase program (h->scan_count words), if h->simple_ok
 };
 
 CG_HD SetView make_set_view(const uint8_t *blob, const uint64_t *masks64, const uint8_t *enc)
@@ -336,6 +474,7 @@ CG_HD SetView make_set_view(const uint8_t *blob, const uint64_t *masks64, const 
     S.pool = blob + S.h->pool_off;
     S.masks64 = masks64;
     S.enc = enc;
+    S.scan = (const CgScanWord *)(blob + S.h->scan_off);
     return S;
 }
 
@@ -487,4 +626,63 @@ CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qua
         if (best.h0.adapter >= 0) apply_trim(best.h0, s, e);
         if (best.h1.adapter >= 0) apply_trim(best.h1, s, e);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-phase ("simple") path: one SINGLE aligner adapter, packed cells, one round.
+//   phase A  simple_scan    prefilter verdict + locator hits        (all reads)
+//   phase B  simple_locate  windowed DP + Match wrapping            (reads that passed)
+// The kernel compacts the reads that pass phase A before phase B; tests/hostsim runs both
+// back to back per read.  Results are identical to process_read<>() by construction of the
+// windows (see locate_core) -- tests/test_hostsim.py fuzzes exactly that.
+// ---------------------------------------------------------------------------------------
+CG_HD ScanOut simple_scan(const SetView &S, const uint8_t *p, int n, int *gs_out)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    const int gs = scan_group_shift(n);
+    *gs_out = gs;
+    return scan_core(S.scan, S.h->scan_count, S.pool, rv, gs, A.pf_count == 0);
+}
+
+CG_HD bool simple_locate(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
+                         PackedCol &colp, CgHit &hit)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    const uint8_t *ref = S.pool + A.ref_off;
+    const uint8_t *enc = S.enc + 256 * A.query_enc;
+    const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+    const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+    const uint32_t cover = S.h->windowed ? window_cover(A, n, gs, hits) : 0xFFFFFFFFu;
+    int o[6];
+    if (!locate_core<Packed32, PackedCol>(A, ref, ncnt, maxcost, enc, rv, colp, o, cover, gs)) return false;
+    hit.adapter = 0;
+    if (A.reverse) {
+        hit.astart = A.m - o[1]; hit.astop = A.m - o[0];
+        hit.rstart = n - o[3]; hit.rstop = n - o[2];
+    } else {
+        hit.astart = o[0]; hit.astop = o[1]; hit.rstart = o[2]; hit.rstop = o[3];
+    }
+    hit.score = o[4]; hit.errors = o[5];
+    hit.remove = A.remove == CGK_REMOVE_AUTO ? (hit.rstart == 0 ? CGK_REMOVE_BEFORE : CGK_REMOVE_AFTER)
+                                            : A.remove;
+    return true;
+}
+
+CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
+                               int quality_trim, int cutoff_front, int cutoff_back, int qbase,
+                               PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out)
+{
+    int s = 0, e = n;
+    if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
+    if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
+    CgHit hit; hit.adapter = -1; hit.remove = 0;
+    hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+    int gs;
+    const ScanOut sc = simple_scan(S, seq + s, e - s, &gs);
+    if (sc.pass) {
+        if (!simple_locate(S, seq + s, e - s, sc.hits, gs, colp, hit)) hit.adapter = -1;
+    }
+    store_hit(out, hit, 0, e - s);
 }

@@ -54,14 +54,16 @@ __host__ __device__ inline size_t cg_align_up(size_t x, size_t a) { return (x + 
 
 // shared-memory carve-up of the fused kernel
 struct FastSmem {
-    size_t bar_off, blob_off, enc_off, seq_off, qual_off, col_off, total;
+    size_t bar_off, cnt_off, task_off, blob_off, enc_off, seq_off, qual_off, col_off, total;
 };
 __host__ __device__ inline FastSmem fast_smem_layout(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual)
 {
     FastSmem L;
     size_t o = 0;
     L.bar_off = o; o += 16;
+    L.cnt_off = o; o += 16;                       // two task counters (two-phase kernel)
     o = cg_align_up(o, 128);
+    L.task_off = o; o += CG_NT * 16;              // compacted DP tasks (two-phase kernel)
     L.blob_off = o; o += cg_align_up(blob_bytes, 16);
     L.enc_off = o; o += 768;
     o = cg_align_up(o, 128);
@@ -81,7 +83,11 @@ size_t cg_fast_smem_bytes(uint32_t blob_bytes, int tile_cap, int col_rows, bool 
 // ------------------------------------------------------------------------------------------
 // The fused kernel
 // ------------------------------------------------------------------------------------------
-template <bool HAS_QUAL>
+// SIMPLE = false: every lane runs the complete per-read pass (any adapter set, rounds, linked).
+// SIMPLE = true : two-phase schedule for one aligner adapter: phase A (scan: prefilter verdict +
+//                 locator hits) on all reads of the tile, warp-ballot compaction of the reads that
+//                 pass into a shared-memory task list, phase B (windowed DP) on dense lanes.
+template <bool HAS_QUAL, bool SIMPLE>
 __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -92,6 +98,8 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
     uint8_t *s_seq = smem + L.seq_off;
     uint8_t *s_qual = smem + L.qual_off;
     uint32_t *s_col = (uint32_t *)(smem + L.col_off);
+    uint32_t *s_cnt = (uint32_t *)(smem + L.cnt_off);
+    uint4 *s_task = (uint4 *)(smem + L.task_off);
     const int tid = threadIdx.x;
 
     // adapter tables HBM -> smem (16-byte vectors), encoding tables
@@ -103,6 +111,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         fence_barrier_init();
+        s_cnt[0] = 0; s_cnt[1] = 0;
     }
     __syncthreads();
     const SetView S = make_set_view(s_blob, a.masks64, s_enc);
@@ -171,17 +180,68 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             }
             if (bad & 0x80808080u) atomicOr(a.err_flag, 1);
         }
-        if (r < n_reads) {
-            const int n = (int)(o1 - o0);
-            const uint8_t *p = tile_seq + (size_t)((seq_base + o0) - sa0);
-            const uint8_t *q = nullptr;
-            if (HAS_QUAL) {
-                const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
-                q = tile_qual + (size_t)((qual_base + o0) - qa0);
+        if (!SIMPLE) {
+            if (r < n_reads) {
+                const int n = (int)(o1 - o0);
+                const uint8_t *p = tile_seq + (size_t)((seq_base + o0) - sa0);
+                const uint8_t *q = nullptr;
+                if (HAS_QUAL) {
+                    const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+                    q = tile_qual + (size_t)((qual_base + o0) - qa0);
+                }
+                process_read<false>(S, p, q, n, HAS_QUAL ? a.quality_trim : 0, a.cutoff_front, a.cutoff_back,
+                                    a.qbase, a.times, colp, colw,
+                                    a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr);
             }
-            process_read<false>(S, p, q, n, HAS_QUAL ? a.quality_trim : 0, a.cutoff_front, a.cutoff_back,
-                                a.qbase, a.times, colp, colw,
-                                a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr);
+        } else {
+            // ---- phase A: quality trim + fused scan on every read of the tile ----------------
+            bool pass = false;
+            uint32_t hits = 0, t_off = 0, t_len = 0;
+            int gs = 4;
+            if (r < n_reads) {
+                const int n = (int)(o1 - o0);
+                const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
+                int ts = 0, te = n;
+                if (HAS_QUAL) {
+                    const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+                    const uint8_t *q = tile_qual + (size_t)((qual_base + o0) - qa0);
+                    if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+                }
+                if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+                t_off = off + (uint32_t)ts; t_len = (uint32_t)(te - ts);
+                const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
+                pass = sc.pass; hits = sc.hits;
+                if (!pass) {
+                    CgHit none; none.adapter = -1; none.remove = 0;
+                    none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
+                    store_hit(a.out + (size_t)r * a.slots, none, 0, 0);
+                }
+            }
+            // ---- compaction: reads that passed become dense DP tasks -------------------------
+            uint32_t *cnt = &s_cnt[it & 1];
+            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+            const uint32_t lane = tid & 31;
+            uint32_t base = 0;
+            if (lane == 0 && ballot) base = atomicAdd(cnt, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                const uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
+                s_task[slot] = make_uint4(t_off, t_len, hits, (uint32_t)tid | ((uint32_t)gs << 16));
+            }
+            __syncthreads();
+            const uint32_t n_tasks = *cnt;
+            if (tid == 0) s_cnt[(it + 1) & 1] = 0;
+            // ---- phase B: windowed DP on the compacted tasks ---------------------------------
+            if ((uint32_t)tid < n_tasks) {
+                const uint4 t = s_task[tid];
+                const long long rr = r0 + (long long)(t.w & 0xFFFFu);
+                CgHit hit;
+                if (!simple_locate(S, tile_seq + t.x, (int)t.y, t.z, (int)(t.w >> 16), colp, hit)) {
+                    hit.adapter = -1; hit.remove = 0;
+                    hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+                }
+                store_hit(a.out + (size_t)rr * a.slots, hit, 0, (int)t.y);
+            }
         }
         __syncthreads();   // every lane is done with stage `st`
         if (tid == 0) {
@@ -191,23 +251,24 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
     }
 }
 
-cudaError_t cg_fast_occupancy(bool has_qual, size_t smem, int *blocks_per_sm)
+typedef void (*fast_kernel_t)(const CgKernelArgs);
+static fast_kernel_t pick_fast(bool has_qual, bool simple)
 {
-    cudaError_t e;
-    if (has_qual) {
-        e = cudaFuncSetAttribute(cg_trim_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cg_trim_fast_kernel<true>, CG_NT, smem);
-    }
-    e = cudaFuncSetAttribute(cg_trim_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cg_trim_fast_kernel<false>, CG_NT, smem);
+    if (simple) return has_qual ? cg_trim_fast_kernel<true, true> : cg_trim_fast_kernel<false, true>;
+    return has_qual ? cg_trim_fast_kernel<true, false> : cg_trim_fast_kernel<false, false>;
 }
 
-cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st)
+cudaError_t cg_fast_occupancy(bool has_qual, bool simple, size_t smem, int *blocks_per_sm)
 {
-    if (has_qual) cg_trim_fast_kernel<true><<<grid, CG_NT, smem, st>>>(a);
-    else cg_trim_fast_kernel<false><<<grid, CG_NT, smem, st>>>(a);
+    fast_kernel_t k = pick_fast(has_qual, simple);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, CG_NT, smem);
+}
+
+cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, bool simple, int grid, size_t smem, cudaStream_t st)
+{
+    pick_fast(has_qual, simple)<<<grid, CG_NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -34,8 +34,8 @@ struct CgKernelArgs {
 };
 
 size_t cg_fast_smem_bytes(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual);
-cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
-cudaError_t cg_fast_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, bool simple, int grid, size_t smem, cudaStream_t st);
+cudaError_t cg_fast_occupancy(bool has_qual, bool simple, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
 cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
                                     const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,

@@ -9,6 +9,9 @@
 #include <math.h>
 #include <string.h>
 
+#include <array>
+#include <utility>
+
 static void put2(uint8_t *t, char c, uint8_t v)
 {
     t[(uint8_t)c] = v;
@@ -31,6 +34,179 @@ void cg_build_enc_tables(uint8_t *out)
 }
 
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// Two-phase program: re-pack the KmerFinder entries of ONE adapter into 32-bit scan words and
+// add the locator chunks.  Returns false if the adapter does not fit the scheme (the general
+// fused kernel is used instead); nothing here affects results, only which kernel runs.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct ScanKmer {
+    int len = 0;
+    int window = 0;                       // SUFFIX: characters from the end; PREFIX: from the start
+    bool pass = false, loc = false;
+    std::vector<std::array<uint64_t, 2>> cols;   // per character: set of matching ASCII codes
+    bool same_pattern(const ScanKmer &o) const { return len == o.len && cols == o.cols; }
+};
+
+void put_u32(std::vector<uint8_t> &pool, uint32_t v) { pool.insert(pool.end(), (uint8_t *)&v, (uint8_t *)&v + 4); }
+
+// Split one reference-form entry into its k-mers (init bit .. found bit, _kmer_finder.pyx:143-147)
+bool split_entry(const cg_kmer_entry &e, const uint64_t *mask128, std::vector<ScanKmer> &out, int window)
+{
+    int bit = 0;
+    uint64_t init = e.init_mask, found = e.found_mask;
+    while (init) {
+        while (!((init >> bit) & 1ULL)) ++bit;
+        int end = bit;
+        while (end < 64 && !((found >> end) & 1ULL)) {
+            if (end > bit && ((init >> end) & 1ULL)) return false;   // a second start before the end
+            ++end;
+        }
+        if (end >= 64) return false;
+        ScanKmer k;
+        k.len = end - bit + 1;
+        k.window = window;
+        k.pass = true;
+        if (k.len > 32) return false;
+        k.cols.resize(k.len);
+        for (int t = 0; t < k.len; ++t) {
+            std::array<uint64_t, 2> set = {0, 0};
+            for (int c = 0; c < 128; ++c)
+                if ((mask128[c] >> (bit + t)) & 1ULL) set[c >> 6] |= 1ULL << (c & 63);
+            k.cols[t] = set;
+        }
+        out.push_back(k);
+        init &= ~(1ULL << bit);
+        found &= ~(1ULL << end);
+        bit = end + 1;
+        if (bit >= 64 && init) return false;
+    }
+    return found == 0;
+}
+
+// Pack k-mers of one window type into words.  `gap` leaves one dead bit between k-mers so that the
+// last bit of one cannot seed the first bit of the next while that one is not active.
+void pack_words(const std::vector<ScanKmer> &kmers, uint32_t type, bool gap, std::vector<uint8_t> &pool,
+                std::vector<CgScanWord> &words)
+{
+    size_t i = 0;
+    while (i < kmers.size()) {
+        CgScanWord W;
+        memset(&W, 0, sizeof W);
+        W.type = type;
+        std::vector<uint32_t> mask(128, 0);
+        std::vector<std::pair<int, int>> placed;   // (kmer index, offset)
+        int used = 0;
+        while (i < kmers.size()) {
+            const ScanKmer &k = kmers[i];
+            const int need = k.len + ((gap && used > 0) ? 1 : 0);
+            if (used + need > 32) break;
+            const int off = used + ((gap && used > 0) ? 1 : 0);
+            for (int t = 0; t < k.len; ++t)
+                for (int c = 0; c < 128; ++c)
+                    if ((k.cols[t][c >> 6] >> (c & 63)) & 1ULL) mask[c] |= 1u << (off + t);
+            W.init |= 1u << off;
+            const uint32_t fbit = 1u << (off + k.len - 1);
+            if (k.pass) W.pass_found |= fbit;
+            if (k.loc) W.loc_found |= fbit;
+            if ((uint32_t)k.window > W.span) W.span = (uint32_t)k.window;
+            placed.emplace_back((int)i, off);
+            used = off + k.len;
+            ++i;
+        }
+        while (pool.size() % 4) pool.push_back(0);
+        W.mask_off = (uint32_t)pool.size();
+        for (uint32_t v : mask) put_u32(pool, v);
+        if (type != CG_SCAN_WHOLE) {
+            W.pos_off = (uint32_t)pool.size();
+            const int rows = (type == CG_SCAN_SUFFIX) ? (int)W.span + 1 : (int)W.span;
+            for (int x = 0; x < rows; ++x) {
+                uint32_t init = 0, found = 0;
+                for (auto &pl : placed) {
+                    const ScanKmer &k = kmers[pl.first];
+                    // SUFFIX: x = distance from the end, active while x <= window
+                    // PREFIX: x = position, active while x < window
+                    const bool active = (type == CG_SCAN_SUFFIX) ? (x >= 1 && x <= k.window) : (x < k.window);
+                    if (active) { init |= 1u << pl.second; found |= 1u << (pl.second + k.len - 1); }
+                }
+                put_u32(pool, init);
+                put_u32(pool, found);
+            }
+        }
+        words.push_back(W);
+    }
+}
+
+bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc768,
+                        const uint8_t *enc_ref, std::vector<uint8_t> &pool, std::vector<CgScanWord> &words,
+                        int &windowed)
+{
+    std::vector<ScanKmer> whole, suffix, prefix;
+    for (int e = 0; e < d.n_kmer_entries; ++e) {
+        const cg_kmer_entry &k = d.kmer_entries[e];
+        const uint64_t *mk = d.kmer_masks + 128 * (size_t)e;
+        if (k.search_start == 0 && k.search_stop == 0) {
+            if (!split_entry(k, mk, whole, 0)) return false;
+        } else if (k.search_start < 0 && k.search_stop == 0) {
+            if (-k.search_start > 100000) return false;
+            if (!split_entry(k, mk, suffix, (int)-k.search_start)) return false;
+        } else if (k.search_start == 0 && k.search_stop > 0) {
+            if (k.search_stop > 100000) return false;
+            if (!split_entry(k, mk, prefix, (int)k.search_stop)) return false;
+        } else {
+            return false;
+        }
+    }
+    // locator chunks: the k+1 nearly equal pieces of the whole adapter (pigeonhole principle);
+    // only for adapters whose DP spans the whole read
+    windowed = 0;
+    const bool full_range = (A.flags & 2) && (A.flags & 8);
+    const int m = A.m, pieces = A.k + 1;
+    if (full_range && A.k >= 0 && pieces <= m) {
+        const int base = m / pieces, extra = m % pieces;
+        std::vector<ScanKmer> chunks;
+        bool ok = true;
+        int pos = 0;
+        for (int c = 0; c < pieces && ok; ++c) {
+            const int len = base + (c < extra ? 1 : 0);
+            if (len > 32) { ok = false; break; }
+            ScanKmer k;
+            k.len = len; k.loc = true;
+            k.cols.resize(len);
+            const uint8_t *qenc = enc768 + 256 * A.query_enc;
+            for (int t = 0; t < len; ++t) {
+                std::array<uint64_t, 2> set = {0, 0};
+                const uint8_t rc = enc_ref[pos + t];
+                for (int code = 0; code < 128; ++code) {
+                    const bool eq = A.compare_ascii ? (rc == qenc[code]) : ((rc & qenc[code]) != 0);
+                    if (eq) set[code >> 6] |= 1ULL << (code & 63);
+                }
+                k.cols[t] = set;
+            }
+            pos += len;
+            bool dup = false;
+            for (auto &o : chunks) dup = dup || o.same_pattern(k);
+            if (!dup) chunks.push_back(k);
+        }
+        if (ok) {
+            for (auto &c : chunks) {
+                bool merged = false;
+                for (auto &w : whole)
+                    if (w.same_pattern(c)) { w.loc = true; merged = true; break; }
+                if (!merged) whole.push_back(c);
+            }
+            windowed = 1;
+        }
+    }
+    pack_words(whole, CG_SCAN_WHOLE, false, pool, words);
+    pack_words(suffix, CG_SCAN_SUFFIX, true, pool, words);
+    pack_words(prefix, CG_SCAN_PREFIX, true, pool, words);
+    return words.size() <= 64;
+}
+
+}  // namespace
 
 static int32_t floor_to_i32(double x)
 {
@@ -185,6 +361,22 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     }
     if (n_groups > 256) { err = "more than 256 adapter groups"; return CG_EUNSUPPORTED; }
 
+    // two-phase program for the common case: one SINGLE aligner adapter with packed cells
+    std::vector<CgScanWord> scan_words;
+    int simple_ok = 0, windowed = 0;
+    if (n_adapters == 1 && n_groups == 1 && G[0].type == CG_GROUP_SINGLE && A[0].kind == CG_KIND_ALIGNER &&
+        A[0].cell_mode == CG_CELL_PACKED32) {
+        std::vector<uint8_t> pool2 = pool;
+        std::vector<CgScanWord> words;
+        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed)) {
+            pool.swap(pool2);
+            scan_words.swap(words);
+            simple_ok = 1;
+        } else {
+            windowed = 0;
+        }
+    }
+
     // assemble
     CgSetHeader H;
     memset(&H, 0, sizeof H);
@@ -194,6 +386,8 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     H.adapters_off = off; off += (uint32_t)(A.size() * sizeof(CgAdapter)); off = align_up(off, 16);
     H.groups_off = off; off += (uint32_t)(G.size() * sizeof(CgGroup)); off = align_up(off, 16);
     H.entries_off = off; off += (uint32_t)(E.size() * sizeof(CgEntry)); off = align_up(off, 16);
+    H.scan_off = off; off += (uint32_t)(scan_words.size() * sizeof(CgScanWord)); off = align_up(off, 16);
+    H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed;
     H.pool_off = off; off += (uint32_t)pool.size(); off = align_up(off, 16);
     H.total_bytes = off;
     out.blob.assign(off, 0);
@@ -201,8 +395,10 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     memcpy(out.blob.data() + H.adapters_off, A.data(), A.size() * sizeof(CgAdapter));
     memcpy(out.blob.data() + H.groups_off, G.data(), G.size() * sizeof(CgGroup));
     if (!E.empty()) memcpy(out.blob.data() + H.entries_off, E.data(), E.size() * sizeof(CgEntry));
+    if (!scan_words.empty())
+        memcpy(out.blob.data() + H.scan_off, scan_words.data(), scan_words.size() * sizeof(CgScanWord));
     if (!pool.empty()) memcpy(out.blob.data() + H.pool_off, pool.data(), pool.size());
-    out.n_adapters = n_adapters; out.n_groups = n_groups;
+    out.n_adapters = n_adapters; out.n_groups = n_groups; out.simple_ok = simple_ok;
     if (out.masks64.empty()) out.masks64.assign(128, 0);   // never hand the kernel a null table
     return CG_OK;
 }

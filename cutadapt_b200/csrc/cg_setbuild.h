@@ -13,7 +13,7 @@ struct CgBuiltSet {
     std::vector<uint64_t> masks64;   // 128 words per prefilter entry
     std::vector<int32_t> effective_length;  // per adapter
     int slots = 1;
-    int n_adapters = 0, n_groups = 0, max_m = 0, any_wide = 0;
+    int n_adapters = 0, n_groups = 0, max_m = 0, any_wide = 0, simple_ok = 0;
 };
 
 // 3 x 256 bytes: upper, acgt, iupac  (src/cutadapt/_match_tables.py:4-66)

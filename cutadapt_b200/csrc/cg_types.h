@@ -58,13 +58,34 @@ struct CgGroup {            // 32 bytes
     int32_t type, a0, a1, front_required, back_required, pad[3];
 };
 
+// One 32-bit shift-and word of the fused scan stage (two-phase kernel).  The host re-packs the
+// reference-form k-mer entries of an adapter, plus the "locator" chunks that drive the windowed
+// DP, into 32-bit words grouped by window type (cg_setbuild.cpp: build_scan_program).
+enum { CG_SCAN_WHOLE = 0, CG_SCAN_SUFFIX = 1, CG_SCAN_PREFIX = 2 };
+struct CgScanWord {         // 32 bytes
+    uint32_t type;          // CG_SCAN_*
+    uint32_t span;          // SUFFIX/PREFIX: window length in characters
+    uint32_t init;          // WHOLE: init mask (one bit at the first character of every k-mer)
+    uint32_t pass_found;    // found bits of k-mers that belong to the KmerFinder (prefilter verdict)
+    uint32_t loc_found;     // found bits of locator chunks (they place the DP windows)
+    uint32_t mask_off;      // pool offset (4-aligned): uint32 mask[128] by ASCII code
+    uint32_t pos_off;       // pool offset (4-aligned): SUFFIX: {init, found}[span + 1] by distance
+                            //   from the end; PREFIX: {init, found}[span] by position
+    uint32_t pad;
+};
+
 struct CgSetHeader {        // 64 bytes
     int32_t n_adapters, n_groups, n_entries, slots;
     int32_t max_m;          // longest adapter (DP column height - 1)
     int32_t any_wide;       // some adapter needs the wide-cell path
     uint32_t adapters_off, groups_off, entries_off, pool_off;
     uint32_t total_bytes;   // size of the blob, multiple of 16
-    int32_t pad[5];
+    // two-phase ("simple") program: one SINGLE aligner adapter with packed cells
+    int32_t simple_ok;      // 1: the two-phase kernel may be used (times == 1)
+    int32_t scan_count;     // number of CgScanWord
+    uint32_t scan_off;      // blob offset of CgScanWord[scan_count]
+    int32_t windowed;       // 1: DP may be restricted to windows around locator hits
+    int32_t pad[1];
 };
 
 // One result of locating a single adapter in a (sub)sequence; coordinates as SingleMatch.

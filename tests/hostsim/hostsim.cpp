@@ -25,7 +25,8 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
     CgBuiltSet set;
     int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err);
     if (rc != CG_OK) return rc;
-    if (force_wide) {
+    if (force_wide & 4) return set.simple_ok ? 1 : 0;   // query only: is the two-phase program available?
+    if (force_wide & 1) {
         CgSetHeader *h = (CgSetHeader *)set.blob.data();
         CgAdapter *ad = (CgAdapter *)(set.blob.data() + h->adapters_off);
         for (int a = 0; a < n_adapters; ++a) ad[a].cell_mode = CG_CELL_WIDE;
@@ -43,6 +44,11 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
         const int n = (int)(offsets[r + 1] - offsets[r]);
         const uint8_t *s = seq + offsets[r];
         for (int i = 0; i < n; ++i) if (s[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
+        if ((force_wide & 2) && S.h->simple_ok && times == 1)
+            process_read_simple(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
+                                params->cutoff_front, params->cutoff_back, params->quality_base, pc,
+                                (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);
+        else
         process_read<true>(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                            params->cutoff_front, params->cutoff_back, params->quality_base, times, pc,
                            wc, (cg_match_rec *)(matches + (size_t)r * times * set.slots),

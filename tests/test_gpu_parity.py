@@ -131,8 +131,9 @@ def test_match_objects_behave_like_the_reference():
     stats.add_match(m)
     assert stats.end.errors[11][0] == 1 and stats.end.adjacent_bases["T"] == 1
     front = PA.FrontAdapter("AAAA", max_errors=0.25, name="f")
-    m = front.match_to("AAATCCCC")
-    assert isinstance(m, PA.RemoveBeforeMatch) and m.trimmed("AAATCCCC") == "CCCC"
+    m = front.match_to("CCAAAATCCCC")
+    assert isinstance(m, PA.RemoveBeforeMatch) and m.trimmed("CCAAAATCCCC") == "TCCCC"
+    assert m.removed_sequence_length() == 6
     assert PA.BackAdapter("GGGGGGGG", name="n").match_to("ACACACAC") is None
     linked = PA.LinkedAdapter(PA.PrefixAdapter("AAAA", name="p"), PA.BackAdapter("TTTT", name="b"), True, False, "lnk")
     lm = linked.match_to("AAAACCCCTTTTGG")
@@ -372,3 +373,29 @@ def test_device_resident_api_and_statistics():
     assert hist.sum() == hit.sum()
     L_, E_ = 20, 0
     assert hist[0, L_, E_] == ((removed == L_) & (recs["errors"][:, 0, 0] == E_) & hit).sum()
+
+
+def test_both_kernel_schedules_agree():
+    """The two-phase kernel (default for one adapter) and the one-phase kernel give identical records."""
+    import os
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_reads
+
+    rng = random.Random(8)
+    cases = [(PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a"), make_reads(20000, config=2)[0]),
+             (PA.FrontAdapter("GTTCAGAGTTCTACAGTCCGACGATC", max_errors=0.15, name="f"), None),
+             (PA.AnywhereAdapter("CTGTCTCTTATACACATCT", max_errors=0.2, name="w"), None),
+             (PA.BackAdapter("AGATCGGAAGAGCNNNNNNNNATCTCGTATGCC", max_errors=0.1, name="n"), None),
+             (PA.RightmostFrontAdapter("ACGTTGCATT", max_errors=0.1, name="r"), None)]
+    for adapter, reads in cases:
+        if reads is None:
+            reads = random_reads(rng, [adapter.sequence], 5000, "ACGT", rng.choice([100, 150, 400]))
+        d = adapter.descriptor()
+        got, _ = run_set([d], None, reads)
+        os.environ["CUTADAPT_B200_KERNEL"] = "general"
+        try:
+            ref, _ = run_set([d], None, reads)
+        finally:
+            del os.environ["CUTADAPT_B200_KERNEL"]
+        exp, _ = oracle.oracle_process([d], None, reads)
+        assert (got == exp).all() and (ref == exp).all(), repr(adapter)

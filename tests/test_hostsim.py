@@ -80,3 +80,54 @@ def test_empty_and_ragged_reads():
     exp, _ = oracle.oracle_process(spec.adapters, spec.groups, reads)
     assert (got == exp).all()
     assert got["adapter"][3, 0, 0] == 0 and got["rstart"][3, 0, 0] == 0
+
+
+def test_two_phase_path_equals_general_path():
+    """
+    The scan + windowed-DP schedule of the two-phase kernel (process_read_simple: fused 32-bit scan
+    words, locator hits, restarted DP windows) must reproduce the one-phase path bit for bit --
+    every adapter type, wildcards, short and long reads (both group sizes), several adapter copies
+    per read, partial occurrences at both ends, with and without quality trimming.
+    """
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(2024)
+    types = ["FrontAdapter", "RightmostFrontAdapter", "BackAdapter", "RightmostBackAdapter", "AnywhereAdapter",
+             "NonInternalFrontAdapter", "NonInternalBackAdapter", "PrefixAdapter", "SuffixAdapter", "BackAdapter"]
+    n_windowed = 0
+    for trial in range(250):
+        alpha = rng.choice(["ACGT", "ACGT", "ACGTN", "AC", "ACGTacgtn"])
+        m = rng.choice([rng.randint(3, 12), rng.randint(10, 34), 13, rng.randint(30, 70)])
+        seq = "".join(rng.choice(rng.choice(["ACGT", "ACGT", "ACGTN", "ACGTRYN"])) for _ in range(m))
+        if set(seq) <= {"N"}:
+            seq = "A" + seq
+        kw = dict(max_errors=rng.choice([0, 0.05, 0.1, 0.1, 0.15, 0.2, 0.3]), min_overlap=rng.randint(1, 6),
+                  read_wildcards=rng.random() < 0.15, adapter_wildcards=rng.random() < 0.7)
+        ad = getattr(PA, rng.choice(types))(seq, name="x", **kw)
+        spec = spec_of(ad)
+        reads = random_reads(rng, [seq], 50, alpha, rng.choice([60, 150, 150, 300, 700]))
+        quals = ["".join(chr(33 + rng.choice([2, 2, 20, 30, 38])) for _ in r) for r in reads]
+        qt = rng.random() < 0.3
+        params = L.make_params(quality_trim=qt, cutoff_front=5, cutoff_back=20)
+        a, qa = hostsim_process(spec, reads, quals if qt else None, params, 0)
+        b, qb = hostsim_process(spec, reads, quals if qt else None, params, 2)
+        assert (a == b).all() and (qa == qb).all(), repr(ad)
+        n_windowed += 1
+    assert n_windowed == 250
+
+
+def test_two_phase_on_golden_single_adapters():
+    import cutadapt_b200.adapters as PA
+
+    n = 0
+    for case in golden("adapters_kat.json.gz"):
+        if len(case["adapters"]) != 1 or case["adapters"][0][0] == "Linked":
+            continue
+        multi = build_adapters(PA, case["adapters"])
+        spec = spec_of(multi)
+        reads = [r for r, _ in case["reads"]]
+        recs, _ = hostsim_process(spec, reads, force_wide=2)
+        for i, (read, expected) in enumerate(case["reads"]):
+            assert match_desc(multi.matches_from_records(recs[i, 0], read)) == expected, (case["adapters"], read)
+        n += 1
+    assert n > 40
