@@ -28,6 +28,14 @@
 #define CGK_GROUP_SINGLE 0
 #define CGK_GROUP_LINKED 1
 
+CG_HD int cg_ctz(uint32_t x)   // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 template <class X> CG_HD X cg_min(X a, X b) { return a < b ? a : b; }
 template <class X> CG_HD X cg_max(X a, X b) { return a > b ? a : b; }
 
@@ -670,9 +678,12 @@ CG_HD bool simple_locate(const SetView &S, const uint8_t *p, int n, uint32_t hit
     return true;
 }
 
+CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
+                              bool has_task, CgHit &hit);
+
 CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
                                int quality_trim, int cutoff_front, int cutoff_back, int qbase,
-                               PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out)
+                               PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out, bool use_regs = false)
 {
     int s = 0, e = n;
     if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
@@ -682,7 +693,288 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
     int gs;
     const ScanOut sc = simple_scan(S, seq + s, e - s, &gs);
     if (sc.pass) {
-        if (!simple_locate(S, seq + s, e - s, sc.hits, gs, colp, hit)) hit.adapter = -1;
+        const bool found = (use_regs && S.ad[0].m <= 32)
+                               ? simple_locate_regs(S, seq + s, e - s, sc.hits, gs, true, hit)
+                               : simple_locate(S, seq + s, e - s, sc.hits, gs, colp, hit);
+        if (!found) hit.adapter = -1;
     }
     store_hit(out, hit, 0, e - s);
+}
+
+// ---------------------------------------------------------------------------------------
+// Phase B, register-column variant (adapters with m <= 32).
+//
+//  * refine_runs(): the coarse locator hits of phase A (one bit per 16-character group) are
+//    re-scanned to exact end positions p; a chunk that ends at adapter offset b puts the adapter
+//    start at p + 1 - b, and every alignment with <= k errors through that chunk lies inside
+//    columns [start - k, start + m + k] (the path consumes b adapter characters and at most
+//    b + k read characters before the chunk ends; m - b adapter characters and at most
+//    m - b + k read characters after it).  Runs are merged into at most three disjoint intervals.
+//  * locate_regs<MR>(): the same DP as locate_core, but the packed column lives in registers and
+//    the row loop is unrolled with a warp-uniform bound (max band over the warp's lanes), so there
+//    is no shared-memory traffic and no per-lane trip-count divergence.  Lanes of a warp start
+//    their runs k columns before their own adapter start, so their bands grow in step.
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define CG_WARP_MAX(x) __reduce_max_sync(0xffffffffu, (x))
+#define CG_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+#define CG_WARP_MAX(x) (x)
+#define CG_WARP_ANY(p) (p)
+#endif
+
+struct RunList {
+    int n;
+    int lo0, hi0, lo1, hi1, lo2, hi2;   // sorted, disjoint; run r restarts at column lo_r and
+                                        // computes columns lo_r + 1 .. hi_r
+};
+
+CG_HD void runs_add(RunList &R, int lo, int hi, int n_read)
+{
+    if (lo < 0) lo = 0;
+    if (hi > n_read) hi = n_read;
+    if (hi <= lo) return;
+    if (R.n == 0) { R.lo0 = lo; R.hi0 = hi; R.n = 1; return; }
+    if (R.n == 1) {
+        if (lo <= R.hi0) { R.lo0 = cg_min(R.lo0, lo); R.hi0 = cg_max(R.hi0, hi); }
+        else { R.lo1 = lo; R.hi1 = hi; R.n = 2; }
+        return;
+    }
+    if (R.n == 2) {
+        if (lo <= R.hi1) {
+            R.lo1 = cg_min(R.lo1, lo); R.hi1 = cg_max(R.hi1, hi);
+            if (R.lo1 <= R.hi0) { R.lo0 = cg_min(R.lo0, R.lo1); R.hi0 = cg_max(R.hi0, R.hi1); R.n = 1; }
+        } else { R.lo2 = lo; R.hi2 = hi; R.n = 3; }
+        return;
+    }
+    // three runs already: merge into the last one (a superset is always valid)
+    R.lo2 = cg_min(R.lo2, lo); R.hi2 = cg_max(R.hi2, hi);
+    if (R.lo2 <= R.hi1) {
+        R.lo1 = cg_min(R.lo1, R.lo2); R.hi1 = cg_max(R.hi1, R.hi2); R.n = 2;
+        if (R.lo1 <= R.hi0) { R.lo0 = cg_min(R.lo0, R.lo1); R.hi0 = cg_max(R.hi0, R.hi1); R.n = 1; }
+    }
+}
+
+// Exact positions of the locator hits -> DP runs (windowed adapters only).
+CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
+                       const ReadView &rv, uint32_t hits, int gs, RunList &R)
+{
+    const int n = rv.n, m = A.m, k = A.k;
+    R.n = 0;
+    R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    if (A.flags & 1) runs_add(R, 0, cg_min(n, m + k), n);              // START_IN_REFERENCE
+    if (hits) {
+        for (int w = 0; w < n_words; ++w) {
+            const CgScanWord &W = words[w];
+            if (W.type != CG_SCAN_WHOLE || !W.loc_found) continue;
+            const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
+            const uint8_t *ltab = pool + W.loc_off;
+            const uint32_t init = W.init, locf = W.loc_found;
+            uint32_t todo = hits;
+            while (todo) {
+                // next run of consecutive hit groups
+                const int ga = cg_ctz(todo);
+                const uint32_t rest = ~(todo >> ga);                  // first 0 above ga ends the run
+                const int gb = ga + (rest ? cg_ctz(rest) : 32 - ga) - 1;
+                todo &= ~(((gb >= 31 ? 0u : (1u << (gb + 1))) - 1u) & ~((1u << ga) - 1u));
+                const int p_first = ga << gs;
+                const long long p_end_ll = ((long long)(gb + 1)) << gs;
+                const int p_end = p_end_ll > n ? n : (int)p_end_ll;
+                uint32_t Rr = 0;
+                for (int p = cg_max(0, p_first - 31); p < p_end; ++p) {
+                    Rr = ((Rr << 1) | init) & mask[rv.at(p) & 127];
+                    uint32_t f = Rr & locf;
+                    if (f && p >= p_first) {
+                        while (f) {
+                            const int b = cg_ctz(f);
+                            f &= f - 1;
+                            const int bmin = ltab[2 * b], bmax = ltab[2 * b + 1];
+                            runs_add(R, p + 1 - bmax - k, p + 1 - bmin + m + k, n);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (A.flags & 4) runs_add(R, cg_max(0, n - 1 - m - k), n, n);      // STOP_IN_REFERENCE
+}
+
+template <int MR>
+CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
+                       const uint32_t *peq, const ReadView &rv, const RunList &R, bool has_task, int *out6)
+{
+    typedef Packed32 C;
+    uint32_t c[MR + 1];
+    const int m = A.m, n = rv.n, k = A.k;
+    const bool sir = (A.flags & 1) != 0, siq = (A.flags & 2) != 0;
+    const bool eir = (A.flags & 4) != 0, eiq = (A.flags & 8) != 0;
+    int max_n = n, min_n = 0;
+    if (!siq) max_n = cg_min(n, m + k);
+    if (!eiq) min_n = cg_max(0, n - m - k);
+
+    bool have = false;
+    int b_origin = 0, b_cost = 0, b_score = 0, b_ref_stop = m, b_q_stop = n;
+    int last = 0, last_filled = 0;
+    uint32_t stale = C::make(0, 0, 0);
+    bool stopped = false, reached_end = false;
+    int run = 0, j = R.lo0, jhi = R.hi0;
+    bool active = has_task && R.n > 0, need_init = true;
+#pragma unroll
+    for (int i = 0; i <= MR; ++i) c[i] = C::INF;
+
+    while (CG_WARP_ANY(active)) {
+        if (active && need_init) {
+            need_init = false;
+            if (j == min_n) {
+#pragma unroll
+                for (int i = 0; i <= MR; ++i) {
+                    long long cc; int s, o;
+                    if (!sir && !siq) { s = -2 * i; cc = cg_max(i, min_n); o = 0; }
+                    else if (sir && !siq) { s = 0; cc = min_n; o = cg_min(0, min_n - i); }
+                    else if (!sir && siq) { s = -2 * i; cc = i; o = cg_max(0, min_n - i); }
+                    else { s = 0; cc = cg_min(i, min_n); o = min_n - i; }
+                    c[i] = (i <= m) ? C::make(cc, s, o) : C::INF;
+                }
+                last = sir ? m : cg_min(m, k + 1);
+            } else {
+#pragma unroll
+                for (int i = 0; i <= MR; ++i) c[i] = (i <= m) ? C::make(i, -2 * i, j) : C::INF;
+                last = cg_min(m, k + 1);
+            }
+        }
+        const bool act = active && j < jhi;
+        const int my_last = act ? last : 0;
+        uint32_t pq_lo = 0, pq_hi = 0, diag = 0, up = 0;
+        int lastok = -1;
+        if (act) {
+            const int ch = rv.at(j) & 127;
+            pq_lo = peq[ch];
+            if (MR > 32) pq_hi = peq[128 + ch];
+            diag = c[0];
+            const uint32_t w0 = siq ? C::row0_free(diag) : C::row0_ins(diag, 1);
+            c[0] = w0;
+            up = w0;
+            lastok = C::cost_le(w0, k) ? 0 : -1;
+        }
+        const int wmax = CG_WARP_MAX(my_last);
+#pragma unroll
+        for (int i = 1; i <= MR; ++i) {
+            if (i > wmax) break;
+            const uint32_t left = c[i];
+            const bool eq = (i <= 32) ? (((pq_lo >> ((i - 1) & 31)) & 1u) != 0) : (((pq_hi >> ((i - 33) & 31)) & 1u) != 0);
+            if (i <= my_last) {
+                const uint32_t nw = eq ? C::match(diag) : C::mismatch(diag, up, left, 1);
+                c[i] = nw;
+                if (C::cost_le(nw, k)) lastok = i;
+                up = nw;
+            }
+            diag = left;
+        }
+        if (act) {
+            ++j;
+            if (my_last >= 1) stale = up;
+            last_filled = my_last;
+            if (lastok < m) {
+                last = lastok + 1;
+            } else if (eiq) {
+                stale = up;
+                const int cost = C::cost(up), score = C::score(up), origin = C::origin(up);
+                const int length = m + cg_min(origin, 0);
+                int eff = length;
+                if (A.wildcard_ref) eff = (length < m) ? length - (ncnt[m] - ncnt[m - length]) : A.effective_length;
+                const bool ok = length >= A.min_overlap && cost <= maxcost[eff];
+                const int best_len = m + cg_min(b_origin, 0);
+                if (ok && (!have || (origin <= b_origin + m / 2 && score > b_score) ||
+                           (length > best_len && score > b_score))) {
+                    have = true;
+                    b_score = score; b_cost = cost; b_origin = origin; b_ref_stop = m; b_q_stop = j;
+                    if (cost == 0 && origin >= 0) { stopped = true; active = false; }
+                }
+            }
+        }
+        if (active && j >= jhi) {        // run finished (or empty: the plain run when min_n == max_n)
+            reached_end = (jhi == max_n);
+            ++run;
+            if (run < R.n) {
+                j = run == 1 ? R.lo1 : R.lo2;
+                jhi = run == 1 ? R.hi1 : R.hi2;
+                need_init = true;
+            } else active = false;
+        }
+    }
+
+    if (has_task && max_n == n && reached_end && !stopped) {
+        const int first_i = eir ? 0 : m;
+        const int origin_var = C::origin(stale);
+#pragma unroll
+        for (int i = MR; i >= 0; --i) {
+            if (i > last_filled || i < first_i) continue;
+            const uint32_t w = c[i];
+            if (!C::cost_le(w, k)) continue;
+            const int o = C::origin(w), cost = C::cost(w), score = C::score(w);
+            const int length = i + cg_min(o, 0);
+            int eff = length;
+            if (A.wildcard_ref) {
+                if (length < m) eff = length - (ncnt[i] - ncnt[-cg_min(o, 0)]);
+                else eff = A.effective_length;
+            }
+            const bool ok = length >= A.min_overlap && cost <= maxcost[eff];
+            const int best_len = b_ref_stop + cg_min(b_origin, 0);
+            if (ok && (!have || (origin_var <= b_origin + m / 2 && score > b_score) ||
+                       (length > best_len && score > b_score))) {
+                have = true;
+                b_score = score; b_cost = cost; b_origin = o; b_ref_stop = i; b_q_stop = n;
+            }
+        }
+    }
+    if (!have) return false;
+    out6[0] = b_origin >= 0 ? 0 : -b_origin;
+    out6[1] = b_ref_stop;
+    out6[2] = b_origin >= 0 ? b_origin : 0;
+    out6[3] = b_q_stop;
+    out6[4] = b_score;
+    out6[5] = b_cost;
+    return true;
+}
+
+// Phase B entry for the register path.  ALL lanes of a warp must call it (warp collectives
+// inside); lanes without a task pass has_task = false.
+CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
+                              bool has_task, CgHit &hit)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+    const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+    const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+    RunList R;
+    R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    if (has_task) {
+        const bool full_range = (A.flags & 2) && (A.flags & 8);
+        if (S.h->windowed && full_range && n > 0) {
+            refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, R);
+        } else {
+            // plain: one run over the reference's column range (_align.pyx:346-352)
+            int max_n = n, min_n = 0;
+            if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
+            if (!(A.flags & 8)) min_n = cg_max(0, n - A.m - A.k);
+            R.n = 1; R.lo0 = min_n; R.hi0 = max_n;
+        }
+    }
+    int o[6];
+    bool found;
+    if (A.m <= 16) found = locate_regs<16>(A, ncnt, maxcost, peq, rv, R, has_task, o);
+    else found = locate_regs<32>(A, ncnt, maxcost, peq, rv, R, has_task, o);
+    if (!has_task || !found) return false;
+    hit.adapter = 0;
+    if (A.reverse) {
+        hit.astart = A.m - o[1]; hit.astop = A.m - o[0];
+        hit.rstart = n - o[3]; hit.rstop = n - o[2];
+    } else {
+        hit.astart = o[0]; hit.astop = o[1]; hit.rstart = o[2]; hit.rstop = o[3];
+    }
+    hit.score = o[4]; hit.errors = o[5];
+    hit.remove = A.remove == CGK_REMOVE_AUTO ? (hit.rstart == 0 ? CGK_REMOVE_BEFORE : CGK_REMOVE_AFTER)
+                                            : A.remove;
+    return true;
 }

@@ -231,8 +231,27 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             __syncthreads();
             const uint32_t n_tasks = *cnt;
             if (tid == 0) s_cnt[(it + 1) & 1] = 0;
-            // ---- phase B: windowed DP on the compacted tasks ---------------------------------
-            if ((uint32_t)tid < n_tasks) {
+            // ---- phase B: DP on the compacted tasks -------------------------------------------
+            // m <= 32: column in registers, runs refined to exact hit positions (warp collectives:
+            // every lane of a warp that holds at least one task takes part); longer adapters keep
+            // the shared-memory column.
+            const bool has_task = (uint32_t)tid < n_tasks;
+            const bool warp_has_task = (uint32_t)(tid & ~31) < n_tasks;
+            if (S.ad[0].m <= 32) {
+                if (warp_has_task) {
+                    uint4 t = make_uint4(0, 0, 0, 4u << 16);
+                    if (has_task) t = s_task[tid];
+                    CgHit hit;
+                    const bool found = simple_locate_regs(S, tile_seq + t.x, (int)t.y, t.z, (int)(t.w >> 16), has_task, hit);
+                    if (has_task) {
+                        if (!found) {
+                            hit.adapter = -1; hit.remove = 0;
+                            hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+                        }
+                        store_hit(a.out + (size_t)(r0 + (long long)(t.w & 0xFFFFu)) * a.slots, hit, 0, (int)t.y);
+                    }
+                }
+            } else if (has_task) {
                 const uint4 t = s_task[tid];
                 const long long rr = r0 + (long long)(t.w & 0xFFFFu);
                 CgHit hit;

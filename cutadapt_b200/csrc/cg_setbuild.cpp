@@ -9,6 +9,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <array>
 #include <utility>
 
@@ -46,6 +47,7 @@ struct ScanKmer {
     int len = 0;
     int window = 0;                       // SUFFIX: characters from the end; PREFIX: from the start
     bool pass = false, loc = false;
+    int bmin = 255, bmax = 0;             // locator: adapter offsets (exclusive end) of this chunk
     std::vector<std::array<uint64_t, 2>> cols;   // per character: set of matching ASCII codes
     bool same_pattern(const ScanKmer &o) const { return len == o.len && cols == o.cols; }
 };
@@ -119,6 +121,17 @@ void pack_words(const std::vector<ScanKmer> &kmers, uint32_t type, bool gap, std
         while (pool.size() % 4) pool.push_back(0);
         W.mask_off = (uint32_t)pool.size();
         for (uint32_t v : mask) put_u32(pool, v);
+        if (W.loc_found) {
+            W.loc_off = (uint32_t)pool.size();
+            std::vector<uint8_t> tab(64, 0);
+            for (auto &pl : placed) {
+                const ScanKmer &k = kmers[pl.first];
+                if (!k.loc) continue;
+                const int fb = pl.second + k.len - 1;
+                tab[2 * fb] = (uint8_t)k.bmin; tab[2 * fb + 1] = (uint8_t)k.bmax;
+            }
+            pool.insert(pool.end(), tab.begin(), tab.end());
+        }
         if (type != CG_SCAN_WHOLE) {
             W.pos_off = (uint32_t)pool.size();
             const int rows = (type == CG_SCAN_SUFFIX) ? (int)W.span + 1 : (int)W.span;
@@ -186,15 +199,17 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
                 k.cols[t] = set;
             }
             pos += len;
+            k.bmin = k.bmax = pos;
             bool dup = false;
-            for (auto &o : chunks) dup = dup || o.same_pattern(k);
+            for (auto &o : chunks)
+                if (o.same_pattern(k)) { dup = true; o.bmin = std::min(o.bmin, pos); o.bmax = std::max(o.bmax, pos); }
             if (!dup) chunks.push_back(k);
         }
-        if (ok) {
+        if (ok && m <= 250) {
             for (auto &c : chunks) {
                 bool merged = false;
                 for (auto &w : whole)
-                    if (w.same_pattern(c)) { w.loc = true; merged = true; break; }
+                    if (w.same_pattern(c)) { w.loc = true; w.bmin = c.bmin; w.bmax = c.bmax; merged = true; break; }
                 if (!merged) whole.push_back(c);
             }
             windowed = 1;
@@ -293,6 +308,20 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
             for (int L = 0; L <= m; ++L) {
                 int32_t v = floor_to_i32((double)L * d.max_error_rate);
                 pool.insert(pool.end(), (uint8_t *)&v, (uint8_t *)&v + 4);
+            }
+            // peq[c]: which adapter rows match read character c (same test as _align.pyx:442-445)
+            x.peq_off = (uint32_t)pool.size();
+            {
+                const uint8_t *qenc = enc + 256 * x.query_enc;
+                const uint8_t *eref = pool.data() + x.ref_off;
+                std::vector<uint32_t> lo(128, 0), hi(128, 0);
+                for (int r = 0; r < m && r < 64; ++r)
+                    for (int c = 0; c < 128; ++c) {
+                        const bool eq = x.compare_ascii ? (eref[r] == qenc[c]) : ((eref[r] & qenc[c]) != 0);
+                        if (eq) (r < 32 ? lo[c] : hi[c]) |= 1u << (r & 31);
+                    }
+                for (uint32_t v : lo) pool.insert(pool.end(), (uint8_t *)&v, (uint8_t *)&v + 4);
+                for (uint32_t v : hi) pool.insert(pool.end(), (uint8_t *)&v, (uint8_t *)&v + 4);
             }
         } else {
             x.effective_length = m;

@@ -42,7 +42,8 @@ struct CgAdapter {          // 80 bytes
     uint32_t ref_off;       // pool offset: encoded adapter bytes [m]
     uint32_t ncount_off;    // pool offset (4-aligned): int32 n_counts[m+1]  _align.pyx:260-266
     uint32_t maxcost_off;   // pool offset (4-aligned): int32 maxcost[m+1] = floor(L * rate)
-    uint32_t reserved;
+    uint32_t peq_off;       // pool offset (4-aligned): uint32 peq_lo[128], peq_hi[128]: bit r of
+                            //   peq[c] = adapter row r matches read character c (m <= 64), else 0
 };
 
 struct CgEntry {            // 32 bytes; the reference's KmerSearchEntry  _kmer_finder.pyx:58-63
@@ -71,7 +72,8 @@ struct CgScanWord {         // 32 bytes
     uint32_t mask_off;      // pool offset (4-aligned): uint32 mask[128] by ASCII code
     uint32_t pos_off;       // pool offset (4-aligned): SUFFIX: {init, found}[span + 1] by distance
                             //   from the end; PREFIX: {init, found}[span] by position
-    uint32_t pad;
+    uint32_t loc_off;       // pool offset: uint8 {bmin, bmax}[32] per bit: adapter offsets at which the
+                            //   locator chunk ending in that bit may end (WHOLE words with loc_found)
 };
 
 struct CgSetHeader {        // 64 bytes

@@ -253,7 +253,8 @@ def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=Fal
         rec["adapter"] = hit["adapter"]
         for f in ("astart", "astop", "rstart", "rstop", "score", "errors"):
             rec[f] = hit[f]
-        rec["info"] = (gi & 255) | (256 if hit["remove"] == REMOVE_AFTER else 0) | ((searched & 0xFFFF) << 16)
+        info = (gi & 255) | (256 if hit["remove"] == REMOVE_AFTER else 0) | ((searched & 0xFFFF) << 16)
+        rec["info"] = info - (1 << 32) if info >= (1 << 31) else info   # stored as int32
 
     for i, seq in enumerate(sequences):
         s, e = 0, len(seq)

@@ -47,7 +47,8 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
         if ((force_wide & 2) && S.h->simple_ok && times == 1)
             process_read_simple(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                                 params->cutoff_front, params->cutoff_back, params->quality_base, pc,
-                                (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);
+                                (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr,
+                                (force_wide & 8) != 0);
         else
         process_read<true>(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                            params->cutoff_front, params->cutoff_back, params->quality_base, times, pc,
