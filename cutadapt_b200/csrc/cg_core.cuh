@@ -811,21 +811,28 @@ CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
     int max_n = n, min_n = 0;
     if (!siq) max_n = cg_min(n, m + k);
     if (!eiq) min_n = cg_max(0, n - m - k);
+    const uint32_t kthr = (uint32_t)(k + 1) << C::CS;      // cost <= k  <=>  word < kthr
+    // character access without a per-character branch: p[base + stride * j]
+    const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
+    const int cstride = rv.rev ? -1 : 1;
 
     bool have = false;
     int b_origin = 0, b_cost = 0, b_score = 0, b_ref_stop = m, b_q_stop = n;
     int last = 0, last_filled = 0;
     uint32_t stale = C::make(0, 0, 0);
     bool stopped = false, reached_end = false;
-    int run = 0, j = R.lo0, jhi = R.hi0;
-    bool active = has_task && R.n > 0, need_init = true;
+    const int n_runs = has_task ? R.n : 0;
+    const int max_runs = CG_WARP_MAX(n_runs);
 #pragma unroll
     for (int i = 0; i <= MR; ++i) c[i] = C::INF;
 
-    while (CG_WARP_ANY(active)) {
-        if (active && need_init) {
-            need_init = false;
-            if (j == min_n) {
+    for (int run = 0; run < max_runs; ++run) {
+        const bool mine = run < n_runs && !stopped;
+        const int lo = run == 0 ? R.lo0 : (run == 1 ? R.lo1 : R.lo2);
+        const int hi = run == 0 ? R.hi0 : (run == 1 ? R.hi1 : R.hi2);
+        // ---- column `lo` of this run -----------------------------------------------------------
+        if (mine) {
+            if (lo == min_n) {                                  // _align.pyx:364-383
 #pragma unroll
                 for (int i = 0; i <= MR; ++i) {
                     long long cc; int s, o;
@@ -835,82 +842,87 @@ CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
                     else { s = 0; cc = cg_min(i, min_n); o = min_n - i; }
                     c[i] = (i <= m) ? C::make(cc, s, o) : C::INF;
                 }
-                last = sir ? m : cg_min(m, k + 1);
-            } else {
+                last = sir ? m : cg_min(m, k + 1);              // _align.pyx:399-401
+            } else {                                            // restart inside the read
 #pragma unroll
-                for (int i = 0; i <= MR; ++i) c[i] = (i <= m) ? C::make(i, -2 * i, j) : C::INF;
+                for (int i = 0; i <= MR; ++i) c[i] = (i <= m) ? C::make(i, -2 * i, lo) : C::INF;
                 last = cg_min(m, k + 1);
             }
+            reached_end = (hi == max_n);
         }
-        const bool act = active && j < jhi;
-        const int my_last = act ? last : 0;
-        uint32_t pq_lo = 0, pq_hi = 0, diag = 0, up = 0;
-        int lastok = -1;
-        if (act) {
-            const int ch = rv.at(j) & 127;
-            pq_lo = peq[ch];
+        const int my_len = mine ? hi - lo : 0;
+        const int len = CG_WARP_MAX(my_len);
+        for (int t = 0; t < len; ++t) {
+            const bool act = mine && !stopped && t < my_len;
+            if (!CG_WARP_ANY(act)) break;
+            const int my_last = act ? last : 0;
+            const int jj = act ? lo + t : 0;
+            const int ch = act ? (cp[cstride * jj] & 127) : 0;
+            const uint32_t pq_lo = peq[ch];
+            uint32_t pq_hi = 0;
             if (MR > 32) pq_hi = peq[128 + ch];
-            diag = c[0];
-            const uint32_t w0 = siq ? C::row0_free(diag) : C::row0_ins(diag, 1);
+            uint32_t diag = c[0];
+            uint32_t w0 = siq ? C::row0_free(diag) : C::row0_ins(diag, 1);
+            w0 = act ? w0 : diag;
             c[0] = w0;
-            up = w0;
-            lastok = C::cost_le(w0, k) ? 0 : -1;
-        }
-        const int wmax = CG_WARP_MAX(my_last);
+            uint32_t up = w0;
+            int lastok = (act && w0 < kthr) ? 0 : -1;
+            const int wmax = CG_WARP_MAX(my_last);
 #pragma unroll
-        for (int i = 1; i <= MR; ++i) {
-            if (i > wmax) break;
-            const uint32_t left = c[i];
-            const bool eq = (i <= 32) ? (((pq_lo >> ((i - 1) & 31)) & 1u) != 0) : (((pq_hi >> ((i - 33) & 31)) & 1u) != 0);
-            if (i <= my_last) {
-                const uint32_t nw = eq ? C::match(diag) : C::mismatch(diag, up, left, 1);
-                c[i] = nw;
-                if (C::cost_le(nw, k)) lastok = i;
-                up = nw;
+            for (int i0 = 1; i0 <= MR; i0 += 4) {
+                if (i0 <= wmax) {                               // warp-uniform
+#pragma unroll
+                    for (int i = i0; i < i0 + 4; ++i) {
+                        if (i <= MR) {
+                            const uint32_t left = c[i];
+                            const bool eq = (i <= 32) ? (((pq_lo >> ((i - 1) & 31)) & 1u) != 0)
+                                                      : (((pq_hi >> ((i - 33) & 31)) & 1u) != 0);
+                            const uint32_t mt = C::match(diag);
+                            const uint32_t mm = C::mismatch(diag, up, left, 1);
+                            uint32_t nw = eq ? mt : mm;
+                            const bool in = i <= my_last;
+                            nw = in ? nw : left;
+                            up = in ? nw : up;
+                            lastok = (in && nw < kthr) ? i : lastok;
+                            c[i] = nw;
+                            diag = left;
+                        }
+                    }
+                }
             }
-            diag = left;
-        }
-        if (act) {
-            ++j;
-            if (my_last >= 1) stale = up;
-            last_filled = my_last;
-            if (lastok < m) {
-                last = lastok + 1;
-            } else if (eiq) {
-                stale = up;
-                const int cost = C::cost(up), score = C::score(up), origin = C::origin(up);
-                const int length = m + cg_min(origin, 0);
-                int eff = length;
-                if (A.wildcard_ref) eff = (length < m) ? length - (ncnt[m] - ncnt[m - length]) : A.effective_length;
-                const bool ok = length >= A.min_overlap && cost <= maxcost[eff];
-                const int best_len = m + cg_min(b_origin, 0);
-                if (ok && (!have || (origin <= b_origin + m / 2 && score > b_score) ||
-                           (length > best_len && score > b_score))) {
-                    have = true;
-                    b_score = score; b_cost = cost; b_origin = origin; b_ref_stop = m; b_q_stop = j;
-                    if (cost == 0 && origin >= 0) { stopped = true; active = false; }
+            if (act) {
+                const int j = lo + t + 1;                       // the column just computed
+                if (my_last >= 1) stale = up;
+                last_filled = my_last;
+                if (lastok < m) {
+                    last = lastok + 1;                          // _align.pyx:490-495
+                } else if (eiq) {                               // _align.pyx:496-533
+                    stale = up;
+                    const int cost = C::cost(up), score = C::score(up), origin = C::origin(up);
+                    const int length = m + cg_min(origin, 0);
+                    int eff = length;
+                    if (A.wildcard_ref) eff = (length < m) ? length - (ncnt[m] - ncnt[m - length]) : A.effective_length;
+                    const bool ok = length >= A.min_overlap && cost <= maxcost[eff];
+                    const int best_len = m + cg_min(b_origin, 0);
+                    if (ok && (!have || (origin <= b_origin + m / 2 && score > b_score) ||
+                               (length > best_len && score > b_score))) {
+                        have = true;
+                        b_score = score; b_cost = cost; b_origin = origin; b_ref_stop = m; b_q_stop = j;
+                        if (cost == 0 && origin >= 0) stopped = true;   // _align.pyx:531-533
+                    }
                 }
             }
         }
-        if (active && j >= jhi) {        // run finished (or empty: the plain run when min_n == max_n)
-            reached_end = (jhi == max_n);
-            ++run;
-            if (run < R.n) {
-                j = run == 1 ? R.lo1 : R.lo2;
-                jhi = run == 1 ? R.hi1 : R.hi2;
-                need_init = true;
-            } else active = false;
-        }
     }
 
-    if (has_task && max_n == n && reached_end && !stopped) {
+    if (has_task && n_runs > 0 && max_n == n && reached_end && !stopped) {   // _align.pyx:536-572
         const int first_i = eir ? 0 : m;
         const int origin_var = C::origin(stale);
 #pragma unroll
         for (int i = MR; i >= 0; --i) {
             if (i > last_filled || i < first_i) continue;
             const uint32_t w = c[i];
-            if (!C::cost_le(w, k)) continue;
+            if (!(w < kthr)) continue;
             const int o = C::origin(w), cost = C::cost(w), score = C::score(w);
             const int length = i + cg_min(o, 0);
             int eff = length;
