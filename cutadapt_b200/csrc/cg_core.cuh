@@ -678,29 +678,6 @@ CG_HD bool simple_locate(const SetView &S, const uint8_t *p, int n, uint32_t hit
     return true;
 }
 
-CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
-                              bool has_task, CgHit &hit);
-
-CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
-                               int quality_trim, int cutoff_front, int cutoff_back, int qbase,
-                               PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out, bool use_regs = false)
-{
-    int s = 0, e = n;
-    if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
-    if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
-    CgHit hit; hit.adapter = -1; hit.remove = 0;
-    hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
-    int gs;
-    const ScanOut sc = simple_scan(S, seq + s, e - s, &gs);
-    if (sc.pass) {
-        const bool found = (use_regs && S.ad[0].m <= 32)
-                               ? simple_locate_regs(S, seq + s, e - s, sc.hits, gs, true, hit)
-                               : simple_locate(S, seq + s, e - s, sc.hits, gs, colp, hit);
-        if (!found) hit.adapter = -1;
-    }
-    store_hit(out, hit, 0, e - s);
-}
-
 // ---------------------------------------------------------------------------------------
 // Phase B, register-column variant (adapters with m <= 32).
 //
@@ -797,6 +774,68 @@ CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool
         }
     }
     if (A.flags & 4) runs_add(R, cg_max(0, n - 1 - m - k), n, n);      // STOP_IN_REFERENCE
+}
+
+// Phase A for the register path: the fused scan with the locator hits turned into DP runs on
+// the spot (exact end position p of a chunk -> run [p+1-b-k, p+1-b+m+k]); no second pass.
+CG_HD void scan_runs_core(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
+                          const ReadView &rv, bool always_pass, bool windowed, bool &pass_out, RunList &R)
+{
+    const int n = rv.n, m = A.m, k = A.k;
+    bool pass = always_pass;
+    R.n = 0;
+    R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    if (windowed && (A.flags & 1)) runs_add(R, 0, cg_min(n, m + k), n);       // START_IN_REFERENCE
+    const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
+    const int cstride = rv.rev ? -1 : 1;
+    for (int w = 0; w < n_words; ++w) {
+        const CgScanWord &W = words[w];
+        const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
+        if (W.type == CG_SCAN_WHOLE) {
+            const uint32_t init = W.init;
+            const uint32_t locf = windowed ? W.loc_found : 0u;
+            uint32_t Rr = 0, seen = 0;
+            if (locf) {
+                const uint8_t *ltab = pool + W.loc_off;
+                for (int p = 0; p < n; ++p) {
+                    Rr = ((Rr << 1) | init) & mask[cp[cstride * p] & 127];
+                    seen |= Rr;
+                    uint32_t f = Rr & locf;
+                    while (f) {                                   // rare: a locator chunk ends at p
+                        const int b = cg_ctz(f);
+                        f &= f - 1;
+                        runs_add(R, p + 1 - (int)ltab[2 * b + 1] - k, p + 1 - (int)ltab[2 * b] + m + k, n);
+                    }
+                }
+            } else {
+                for (int p = 0; p < n; ++p) {
+                    Rr = ((Rr << 1) | init) & mask[cp[cstride * p] & 127];
+                    seen |= Rr;
+                }
+            }
+            if (seen & W.pass_found) pass = true;
+        } else if (W.type == CG_SCAN_SUFFIX) {
+            const uint32_t *tab = (const uint32_t *)(pool + W.pos_off);
+            uint32_t Rr = 0, seen = 0;
+            for (int p = cg_max(0, n - (int)W.span); p < n; ++p) {
+                const int d = n - p;
+                Rr = ((Rr << 1) | tab[2 * d]) & mask[cp[cstride * p] & 127];
+                seen |= Rr & tab[2 * d + 1];
+            }
+            if (seen & W.pass_found) pass = true;
+        } else {
+            const uint32_t *tab = (const uint32_t *)(pool + W.pos_off);
+            uint32_t Rr = 0, seen = 0;
+            const int stop = cg_min(n, (int)W.span);
+            for (int p = 0; p < stop; ++p) {
+                Rr = ((Rr << 1) | tab[2 * p]) & mask[cp[cstride * p] & 127];
+                seen |= Rr & tab[2 * p + 1];
+            }
+            if (seen & W.pass_found) pass = true;
+        }
+    }
+    if (windowed && (A.flags & 4)) runs_add(R, cg_max(0, n - 1 - m - k), n, n);   // STOP_IN_REFERENCE
+    pass_out = pass;
 }
 
 template <int MR>
@@ -949,30 +988,41 @@ CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
     return true;
 }
 
-// Phase B entry for the register path.  ALL lanes of a warp must call it (warp collectives
-// inside); lanes without a task pass has_task = false.
-CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
-                              bool has_task, CgHit &hit)
+// Register path entry points.
+//   simple_scan_runs    phase A: prefilter verdict + DP runs of one read
+//   simple_locate_runs  phase B: ALL lanes of a warp must call it (warp collectives inside);
+//                       lanes without a task pass has_task = false.
+CG_HD bool simple_windowed(const SetView &S, int n)
+{
+    const CgAdapter &A = S.ad[0];
+    return S.h->windowed && (A.flags & 2) && (A.flags & 8) && n > 0;
+}
+
+CG_HD bool simple_scan_runs(const SetView &S, const uint8_t *p, int n, RunList &R)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    bool pass;
+    const bool windowed = simple_windowed(S, n);
+    scan_runs_core(S.scan, S.h->scan_count, S.pool, A, rv, A.pf_count == 0, windowed, pass, R);
+    if (!windowed) {
+        // plain: one run over the reference's column range (_align.pyx:346-352)
+        int max_n = n, min_n = 0;
+        if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
+        if (!(A.flags & 8)) min_n = cg_max(0, n - A.m - A.k);
+        R.n = 1; R.lo0 = min_n; R.hi0 = max_n;
+    }
+    return pass;
+}
+
+CG_HD bool simple_locate_runs(const SetView &S, const uint8_t *p, int n, const RunList &R, bool has_task,
+                              CgHit &hit)
 {
     const CgAdapter &A = S.ad[0];
     ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
     const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
     const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
     const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
-    RunList R;
-    R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
-    if (has_task) {
-        const bool full_range = (A.flags & 2) && (A.flags & 8);
-        if (S.h->windowed && full_range && n > 0) {
-            refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, R);
-        } else {
-            // plain: one run over the reference's column range (_align.pyx:346-352)
-            int max_n = n, min_n = 0;
-            if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
-            if (!(A.flags & 8)) min_n = cg_max(0, n - A.m - A.k);
-            R.n = 1; R.lo0 = min_n; R.hi0 = max_n;
-        }
-    }
     int o[6];
     bool found;
     if (A.m <= 16) found = locate_regs<16>(A, ncnt, maxcost, peq, rv, R, has_task, o);
@@ -990,3 +1040,52 @@ CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_
                                             : A.remove;
     return true;
 }
+
+// (host-sim helper) coarse hits -> runs -> register DP, kept to exercise refine_runs()
+CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
+                              bool has_task, CgHit &hit)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    RunList R;
+    R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    if (has_task) {
+        if (simple_windowed(S, n)) refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, R);
+        else {
+            int max_n = n, min_n = 0;
+            if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
+            if (!(A.flags & 8)) min_n = cg_max(0, n - A.m - A.k);
+            R.n = 1; R.lo0 = min_n; R.hi0 = max_n;
+        }
+    }
+    return simple_locate_runs(S, p, n, R, has_task, hit);
+}
+
+CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
+                               int quality_trim, int cutoff_front, int cutoff_back, int qbase,
+                               PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out, int use_regs = 0)
+{
+    int s = 0, e = n;
+    if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
+    if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
+    CgHit hit; hit.adapter = -1; hit.remove = 0;
+    hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+    if (use_regs == 2 && S.ad[0].m <= 32) {
+        RunList R;
+        if (simple_scan_runs(S, seq + s, e - s, R)) {
+            if (!simple_locate_runs(S, seq + s, e - s, R, true, hit)) hit.adapter = -1;
+        }
+        store_hit(out, hit, 0, e - s);
+        return;
+    }
+    int gs;
+    const ScanOut sc = simple_scan(S, seq + s, e - s, &gs);
+    if (sc.pass) {
+        const bool found = (use_regs && S.ad[0].m <= 32)
+                               ? simple_locate_regs(S, seq + s, e - s, sc.hits, gs, true, hit)
+                               : simple_locate(S, seq + s, e - s, sc.hits, gs, colp, hit);
+        if (!found) hit.adapter = -1;
+    }
+    store_hit(out, hit, 0, e - s);
+}
+

@@ -63,7 +63,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(uint32_t blob_bytes, int ti
     L.bar_off = o; o += 16;
     L.cnt_off = o; o += 16;                       // two task counters (two-phase kernel)
     o = cg_align_up(o, 128);
-    L.task_off = o; o += CG_NT * 16;              // compacted DP tasks (two-phase kernel)
+    L.task_off = o; o += CG_NT * 48;              // compacted DP tasks (two-phase kernel): 3 x uint4
     L.blob_off = o; o += cg_align_up(blob_bytes, 16);
     L.enc_off = o; o += 768;
     o = cg_align_up(o, 128);
@@ -195,9 +195,15 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             }
         } else {
             // ---- phase A: quality trim + fused scan on every read of the tile ----------------
+            // m <= 32 ("regs"): the scan turns locator hits into exact DP runs on the spot and phase
+            // B keeps the DP column in registers; longer adapters get coarse hit groups and the
+            // shared-memory column.
+            const bool regs = S.ad[0].m <= 32;
             bool pass = false;
             uint32_t hits = 0, t_off = 0, t_len = 0;
             int gs = 4;
+            RunList runs;
+            runs.n = 0; runs.lo0 = runs.hi0 = runs.lo1 = runs.hi1 = runs.lo2 = runs.hi2 = 0;
             if (r < n_reads) {
                 const int n = (int)(o1 - o0);
                 const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
@@ -209,8 +215,12 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                 }
                 if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
                 t_off = off + (uint32_t)ts; t_len = (uint32_t)(te - ts);
-                const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
-                pass = sc.pass; hits = sc.hits;
+                if (regs) {
+                    pass = simple_scan_runs(S, tile_seq + t_off, (int)t_len, runs);
+                } else {
+                    const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
+                    pass = sc.pass; hits = sc.hits;
+                }
                 if (!pass) {
                     CgHit none; none.adapter = -1; none.remove = 0;
                     none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
@@ -226,23 +236,25 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             base = __shfl_sync(0xffffffffu, base, 0);
             if (pass) {
                 const uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
-                s_task[slot] = make_uint4(t_off, t_len, hits, (uint32_t)tid | ((uint32_t)gs << 16));
+                s_task[3 * slot] = make_uint4(t_off, t_len, hits, (uint32_t)tid | ((uint32_t)gs << 16));
+                s_task[3 * slot + 1] = make_uint4((uint32_t)runs.n, (uint32_t)runs.lo0, (uint32_t)runs.hi0, (uint32_t)runs.lo1);
+                s_task[3 * slot + 2] = make_uint4((uint32_t)runs.hi1, (uint32_t)runs.lo2, (uint32_t)runs.hi2, 0u);
             }
             __syncthreads();
             const uint32_t n_tasks = *cnt;
             if (tid == 0) s_cnt[(it + 1) & 1] = 0;
             // ---- phase B: DP on the compacted tasks -------------------------------------------
-            // m <= 32: column in registers, runs refined to exact hit positions (warp collectives:
-            // every lane of a warp that holds at least one task takes part); longer adapters keep
-            // the shared-memory column.
             const bool has_task = (uint32_t)tid < n_tasks;
             const bool warp_has_task = (uint32_t)(tid & ~31) < n_tasks;
-            if (S.ad[0].m <= 32) {
-                if (warp_has_task) {
-                    uint4 t = make_uint4(0, 0, 0, 4u << 16);
-                    if (has_task) t = s_task[tid];
+            if (regs) {
+                if (warp_has_task) {     // warp collectives inside: whole warps only
+                    uint4 t = make_uint4(0, 0, 0, 0), u = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
+                    if (has_task) { t = s_task[3 * tid]; u = s_task[3 * tid + 1]; v = s_task[3 * tid + 2]; }
+                    RunList R;
+                    R.n = (int)u.x; R.lo0 = (int)u.y; R.hi0 = (int)u.z; R.lo1 = (int)u.w;
+                    R.hi1 = (int)v.x; R.lo2 = (int)v.y; R.hi2 = (int)v.z;
                     CgHit hit;
-                    const bool found = simple_locate_regs(S, tile_seq + t.x, (int)t.y, t.z, (int)(t.w >> 16), has_task, hit);
+                    const bool found = simple_locate_runs(S, tile_seq + t.x, (int)t.y, R, has_task, hit);
                     if (has_task) {
                         if (!found) {
                             hit.adapter = -1; hit.remove = 0;
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                     }
                 }
             } else if (has_task) {
-                const uint4 t = s_task[tid];
+                const uint4 t = s_task[3 * tid];
                 const long long rr = r0 + (long long)(t.w & 0xFFFFu);
                 CgHit hit;
                 if (!simple_locate(S, tile_seq + t.x, (int)t.y, t.z, (int)(t.w >> 16), colp, hit)) {
