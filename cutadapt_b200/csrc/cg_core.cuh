@@ -373,6 +373,8 @@ CG_HD void quality_trim_core(const uint8_t *q, int n, int cutoff_front, int cuto
 struct ScanOut {
     bool pass;
     uint32_t hits;   // bit g: a locator chunk ends in characters [g << gs, (g+1) << gs)
+    uint32_t rs0, rs1;   // shift-and state of the first locator word at the start of the first two
+                         // hit groups: phase B resumes the scan there to get exact end positions
 };
 
 CG_HD int scan_group_shift(int n)
@@ -385,8 +387,13 @@ CG_HD int scan_group_shift(int n)
 CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *pool, const ReadView &rv,
                         int gs, bool always_pass)
 {
-    ScanOut out; out.pass = always_pass; out.hits = 0;
+    ScanOut out; out.pass = always_pass; out.hits = 0; out.rs0 = 0; out.rs1 = 0;
     const int n = rv.n;
+    const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
+    const int cstride = rv.rev ? -1 : 1;
+    // the saved states are only meaningful when a single word carries all locator chunks
+    int n_loc = 0;
+    for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
     for (int w = 0; w < n_words; ++w) {
         const CgScanWord &W = words[w];
         const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
@@ -395,15 +402,22 @@ CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *poo
             uint32_t R = 0, seen = 0;
             if (locf) {
                 const int G = 1 << gs;
+                const bool stash = n_loc == 1;
+                int nh = 0;
                 for (int p0 = 0; p0 < n; p0 += G) {
                     const int p1 = cg_min(n, p0 + G);
+                    const uint32_t r_start = R;
                     uint32_t g = 0;
                     for (int p = p0; p < p1; ++p) {
-                        R = ((R << 1) | init) & mask[rv.at(p) & 127];
+                        R = ((R << 1) | init) & mask[cp[cstride * p] & 127];
                         g |= R;
                     }
                     seen |= g;
-                    if (g & locf) out.hits |= 1u << (p0 >> gs);
+                    const bool hg = (g & locf) != 0;
+                    out.hits |= hg ? (1u << (p0 >> gs)) : 0u;
+                    out.rs0 = (hg && stash && nh == 0) ? r_start : out.rs0;
+                    out.rs1 = (hg && stash && nh == 1) ? r_start : out.rs1;
+                    nh += hg ? 1 : 0;
                 }
             } else {
                 for (int p = 0; p < n; ++p) {
@@ -732,44 +746,57 @@ CG_HD void runs_add(RunList &R, int lo, int hi, int n_read)
     }
 }
 
-// Exact positions of the locator hits -> DP runs (windowed adapters only).
+// Exact positions of the locator hits -> DP runs (windowed adapters only).  For the first locator
+// word the scan resumes at the start of each hit group from the state phase A saved (rs0, rs1) or
+// carries over from the previous group; otherwise it backs up 31 characters (k-mers are <= 32 long).
 CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
-                       const ReadView &rv, uint32_t hits, int gs, RunList &R)
+                       const ReadView &rv, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1, RunList &R)
 {
     const int n = rv.n, m = A.m, k = A.k;
     R.n = 0;
     R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     if (A.flags & 1) runs_add(R, 0, cg_min(n, m + k), n);              // START_IN_REFERENCE
+    const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
+    const int cstride = rv.rev ? -1 : 1;
     if (hits) {
+        int n_loc = 0;
+        for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
         for (int w = 0; w < n_words; ++w) {
             const CgScanWord &W = words[w];
             if (W.type != CG_SCAN_WHOLE || !W.loc_found) continue;
             const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
             const uint8_t *ltab = pool + W.loc_off;
             const uint32_t init = W.init, locf = W.loc_found;
-            uint32_t todo = hits;
+            const bool stash = n_loc == 1;
+            uint32_t todo = hits, Rr = 0;
+            int cur_p = -1, nh = 0;
             while (todo) {
-                // next run of consecutive hit groups
-                const int ga = cg_ctz(todo);
-                const uint32_t rest = ~(todo >> ga);                  // first 0 above ga ends the run
-                const int gb = ga + (rest ? cg_ctz(rest) : 32 - ga) - 1;
-                todo &= ~(((gb >= 31 ? 0u : (1u << (gb + 1))) - 1u) & ~((1u << ga) - 1u));
-                const int p_first = ga << gs;
-                const long long p_end_ll = ((long long)(gb + 1)) << gs;
+                const int g = cg_ctz(todo);
+                todo &= todo - 1;
+                const int p_first = g << gs;
+                const long long p_end_ll = ((long long)(g + 1)) << gs;
                 const int p_end = p_end_ll > n ? n : (int)p_end_ll;
-                uint32_t Rr = 0;
-                for (int p = cg_max(0, p_first - 31); p < p_end; ++p) {
-                    Rr = ((Rr << 1) | init) & mask[rv.at(p) & 127];
+                int p = p_first;
+                if (cur_p == p_first) {
+                    // continues the previous group: Rr is already the state at p_first
+                } else if (stash && nh < 2) {
+                    Rr = nh == 0 ? rs0 : rs1;
+                } else {
+                    Rr = 0;
+                    for (int q = cg_max(0, p_first - 31); q < p_first; ++q)
+                        Rr = ((Rr << 1) | init) & mask[cp[cstride * q] & 127];
+                }
+                ++nh;
+                for (; p < p_end; ++p) {
+                    Rr = ((Rr << 1) | init) & mask[cp[cstride * p] & 127];
                     uint32_t f = Rr & locf;
-                    if (f && p >= p_first) {
-                        while (f) {
-                            const int b = cg_ctz(f);
-                            f &= f - 1;
-                            const int bmin = ltab[2 * b], bmax = ltab[2 * b + 1];
-                            runs_add(R, p + 1 - bmax - k, p + 1 - bmin + m + k, n);
-                        }
+                    while (f) {
+                        const int b = cg_ctz(f);
+                        f &= f - 1;
+                        runs_add(R, p + 1 - (int)ltab[2 * b + 1] - k, p + 1 - (int)ltab[2 * b] + m + k, n);
                     }
                 }
+                cur_p = p_end;
             }
         }
     }
@@ -1041,16 +1068,17 @@ CG_HD bool simple_locate_runs(const SetView &S, const uint8_t *p, int n, const R
     return true;
 }
 
-// (host-sim helper) coarse hits -> runs -> register DP, kept to exercise refine_runs()
+// Phase B entry of the kernel for m <= 32: coarse hits (+ saved scan states) -> exact runs ->
+// register DP.  ALL lanes of a warp must call it.
 CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs,
-                              bool has_task, CgHit &hit)
+                              uint32_t rs0, uint32_t rs1, bool has_task, CgHit &hit)
 {
     const CgAdapter &A = S.ad[0];
     ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
     RunList R;
     R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     if (has_task) {
-        if (simple_windowed(S, n)) refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, R);
+        if (simple_windowed(S, n)) refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, rs0, rs1, R);
         else {
             int max_n = n, min_n = 0;
             if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
@@ -1082,7 +1110,7 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
     const ScanOut sc = simple_scan(S, seq + s, e - s, &gs);
     if (sc.pass) {
         const bool found = (use_regs && S.ad[0].m <= 32)
-                               ? simple_locate_regs(S, seq + s, e - s, sc.hits, gs, true, hit)
+                               ? simple_locate_regs(S, seq + s, e - s, sc.hits, gs, sc.rs0, sc.rs1, true, hit)
                                : simple_locate(S, seq + s, e - s, sc.hits, gs, colp, hit);
         if (!found) hit.adapter = -1;
     }

@@ -63,7 +63,7 @@ __host__ __device__ inline FastSmem fast_smem_layout(uint32_t blob_bytes, int ti
     L.bar_off = o; o += 16;
     L.cnt_off = o; o += 16;                       // two task counters (two-phase kernel)
     o = cg_align_up(o, 128);
-    L.task_off = o; o += CG_NT * 48;              // compacted DP tasks (two-phase kernel): 3 x uint4
+    L.task_off = o; o += CG_NT * 32;              // compacted DP tasks (two-phase kernel): 2 x uint4
     L.blob_off = o; o += cg_align_up(blob_bytes, 16);
     L.enc_off = o; o += 768;
     o = cg_align_up(o, 128);
@@ -195,15 +195,15 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             }
         } else {
             // ---- phase A: quality trim + fused scan on every read of the tile ----------------
-            // m <= 32 ("regs"): the scan turns locator hits into exact DP runs on the spot and phase
-            // B keeps the DP column in registers; longer adapters get coarse hit groups and the
-            // shared-memory column.
+            // The scan reports locator hits per 16-character group plus the scan state at the start of
+            // the first two hit groups.  Phase B (m <= 32, "regs"): resumes the scan there to get exact
+            // end positions -> exact DP runs, DP column in registers.  Longer adapters: group-granular
+            // windows and the shared-memory column.
             const bool regs = S.ad[0].m <= 32;
             bool pass = false;
             uint32_t hits = 0, t_off = 0, t_len = 0;
             int gs = 4;
-            RunList runs;
-            runs.n = 0; runs.lo0 = runs.hi0 = runs.lo1 = runs.hi1 = runs.lo2 = runs.hi2 = 0;
+            uint32_t rs0 = 0, rs1 = 0;
             if (r < n_reads) {
                 const int n = (int)(o1 - o0);
                 const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
@@ -215,12 +215,8 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                 }
                 if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
                 t_off = off + (uint32_t)ts; t_len = (uint32_t)(te - ts);
-                if (regs) {
-                    pass = simple_scan_runs(S, tile_seq + t_off, (int)t_len, runs);
-                } else {
-                    const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
-                    pass = sc.pass; hits = sc.hits;
-                }
+                const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
+                pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
                 if (!pass) {
                     CgHit none; none.adapter = -1; none.remove = 0;
                     none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
@@ -236,9 +232,8 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             base = __shfl_sync(0xffffffffu, base, 0);
             if (pass) {
                 const uint32_t slot = base + __popc(ballot & ((1u << lane) - 1u));
-                s_task[3 * slot] = make_uint4(t_off, t_len, hits, (uint32_t)tid | ((uint32_t)gs << 16));
-                s_task[3 * slot + 1] = make_uint4((uint32_t)runs.n, (uint32_t)runs.lo0, (uint32_t)runs.hi0, (uint32_t)runs.lo1);
-                s_task[3 * slot + 2] = make_uint4((uint32_t)runs.hi1, (uint32_t)runs.lo2, (uint32_t)runs.hi2, 0u);
+                s_task[2 * slot] = make_uint4(t_off, t_len, hits, (uint32_t)tid | ((uint32_t)gs << 16));
+                s_task[2 * slot + 1] = make_uint4(rs0, rs1, 0u, 0u);
             }
             __syncthreads();
             const uint32_t n_tasks = *cnt;
@@ -248,13 +243,11 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             const bool warp_has_task = (uint32_t)(tid & ~31) < n_tasks;
             if (regs) {
                 if (warp_has_task) {     // warp collectives inside: whole warps only
-                    uint4 t = make_uint4(0, 0, 0, 0), u = make_uint4(0, 0, 0, 0), v = make_uint4(0, 0, 0, 0);
-                    if (has_task) { t = s_task[3 * tid]; u = s_task[3 * tid + 1]; v = s_task[3 * tid + 2]; }
-                    RunList R;
-                    R.n = (int)u.x; R.lo0 = (int)u.y; R.hi0 = (int)u.z; R.lo1 = (int)u.w;
-                    R.hi1 = (int)v.x; R.lo2 = (int)v.y; R.hi2 = (int)v.z;
+                    uint4 t = make_uint4(0, 0, 0, 4u << 16), u = make_uint4(0, 0, 0, 0);
+                    if (has_task) { t = s_task[2 * tid]; u = s_task[2 * tid + 1]; }
                     CgHit hit;
-                    const bool found = simple_locate_runs(S, tile_seq + t.x, (int)t.y, R, has_task, hit);
+                    const bool found = simple_locate_regs(S, tile_seq + t.x, (int)t.y, t.z, (int)(t.w >> 16),
+                                                          u.x, u.y, has_task, hit);
                     if (has_task) {
                         if (!found) {
                             hit.adapter = -1; hit.remove = 0;
@@ -264,7 +257,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                     }
                 }
             } else if (has_task) {
-                const uint4 t = s_task[3 * tid];
+                const uint4 t = s_task[2 * tid];
                 const long long rr = r0 + (long long)(t.w & 0xFFFFu);
                 CgHit hit;
                 if (!simple_locate(S, tile_seq + t.x, (int)t.y, t.z, (int)(t.w >> 16), colp, hit)) {
