@@ -289,6 +289,23 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         CU(cg_fast_occupancy(want_q, simple, smem, &occ));
         if (occ < 1) fast = false;
     }
+    // warp-autonomous kernel: one aligner adapter with m <= 32 on the two-phase schedule
+    bool warpk = false;
+    size_t wsmem = 0;
+    int wocc = 0;
+    const bool force_block = kernel_env && strcmp(kernel_env, "block") == 0;
+    if (simple && s->host.max_m <= 32 && !force_block) {
+        const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
+        const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
+        if (mini < (1 << 20)) {
+            a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
+            wsmem = cg_warp_smem_bytes(a.blob_bytes, a.mini_cap, a.carry_slot, want_q);
+            if (wsmem <= c->smem_optin) {
+                CU(cg_warp_occupancy(want_q, wsmem, &wocc));
+                warpk = wocc >= 1;
+            }
+        }
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (timed && c->timing.size() < 8192) {
         for (cudaEvent_t *ev : {&ev0, &ev1}) {
@@ -297,7 +314,14 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         }
         CU(cudaEventRecord(ev0, st));
     }
-    if (fast) {
+    if (warpk) {
+        const long long n_mt = (n_reads + 31) / 32;
+        long long grid = (long long)wocc * c->sm_count;
+        const long long need = (n_mt + 3) / 4;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        CU(cg_launch_warp(a, want_q, (int)grid, wsmem, st));
+    } else if (fast) {
         const long long n_tiles = (n_reads + CG_NT - 1) / CG_NT;
         long long grid = (long long)occ * c->sm_count;
         if (grid > n_tiles) grid = n_tiles;

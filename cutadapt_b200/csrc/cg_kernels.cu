@@ -297,6 +297,251 @@ cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, bool simple, in
 }
 
 // ------------------------------------------------------------------------------------------
+// The warp-autonomous kernel (one aligner adapter with m <= 32, one round).
+//
+// Every warp is its own pipeline -- there is no block-level barrier after set-up:
+//   * it stages its own mini-tiles of 32 reads (one per lane) with TMA 1-D bulk copies into a
+//     private 2-stage ring (lane 0 issues, all lanes wait on the warp's mbarrier);
+//   * phase A on the mini-tile: quality trim + fused scan; failing reads write "no match";
+//   * passing reads become tasks.  The DP (phase B) only ever runs on FULL groups of 32 tasks:
+//     tasks left over (< 32) are copied -- read bytes and scan results -- into a 31-slot carry
+//     buffer and complete the next group, so every DP pass has all lanes busy and the lanes' bands
+//     grow in step;
+//   * a final flush pass handles what is left in the carry buffer.
+// ------------------------------------------------------------------------------------------
+struct WarpSmem {
+    size_t blob_off, enc_off, warp_off, warp_stride;                   // per CTA
+    size_t bar_rel, meta_new_rel, meta_carry_rel, seq_rel, qual_rel, carry_rel;   // inside a warp region
+    size_t total;
+};
+__host__ __device__ inline WarpSmem warp_smem_layout(uint32_t blob_bytes, int mini_cap, int carry_slot, bool has_qual)
+{
+    WarpSmem L;
+    size_t o = 0;
+    L.blob_off = o; o += cg_align_up(blob_bytes, 16);
+    L.enc_off = o; o += 768;
+    o = cg_align_up(o, 128);
+    L.warp_off = o;
+    size_t w = 0;
+    L.bar_rel = w; w += 16;
+    L.meta_new_rel = w; w += 32 * 32;
+    L.meta_carry_rel = w; w += 32 * 32;
+    w = cg_align_up(w, 128);
+    L.seq_rel = w; w += 2 * (size_t)mini_cap;
+    L.qual_rel = w; if (has_qual) w += 2 * (size_t)mini_cap;
+    L.carry_rel = w; w += 31 * (size_t)carry_slot;
+    L.warp_stride = cg_align_up(w, 128);
+    L.total = L.warp_off + 4 * L.warp_stride;
+    return L;
+}
+
+size_t cg_warp_smem_bytes(uint32_t blob_bytes, int mini_cap, int carry_slot, bool has_qual)
+{
+    return warp_smem_layout(blob_bytes, mini_cap, carry_slot, has_qual).total;
+}
+
+// One DP pass of a warp: a single call site keeps the (large) register-DP code out of the loop body.
+__device__ __noinline__ void warp_dp_pass(const SetView &S, const uint8_t *smem_base, const uint4 ma, const uint4 mb,
+                                          bool has_task, cg_match_rec *out, int slots)
+{
+    CgHit hit;
+    const bool found = simple_locate_regs(S, smem_base + ma.x, (int)ma.y, ma.z, (int)ma.w, mb.x, mb.y, has_task, hit);
+    if (has_task) {
+        if (!found) {
+            hit.adapter = -1; hit.remove = 0;
+            hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+        }
+        const long long r = (long long)(((unsigned long long)mb.w << 32) | mb.z);
+        store_hit(out + (size_t)r * slots, hit, 0, (int)ma.y);
+    }
+}
+
+template <bool HAS_QUAL>
+__global__ void __launch_bounds__(CG_NT) cg_trim_warp_kernel(const CgKernelArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const WarpSmem L = warp_smem_layout(a.blob_bytes, a.mini_cap, a.carry_slot, HAS_QUAL);
+    uint8_t *s_blob = smem + L.blob_off;
+    uint8_t *s_enc = smem + L.enc_off;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    uint8_t *wbase = smem + L.warp_off + (size_t)wib * L.warp_stride;
+    uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
+    uint4 *meta_new = (uint4 *)(wbase + L.meta_new_rel);
+    uint4 *meta_carry = (uint4 *)(wbase + L.meta_carry_rel);
+    uint8_t *s_seq = wbase + L.seq_rel;
+    uint8_t *s_qual = wbase + L.qual_rel;
+    uint8_t *s_carry = wbase + L.carry_rel;
+
+    for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
+    for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();          // the only block-wide barrier
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+
+    const long long n_reads = a.n_reads;
+    const long long n_mt = (n_reads + 31) / 32;
+    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
+    const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
+    const uintptr_t seq_base = (uintptr_t)a.seq, qual_base = (uintptr_t)a.qual;
+
+    auto issue = [&](long long mt, int st) {
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        if (b1 <= b0) return;
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        const uint32_t bytes = (uint32_t)(((seq_base + b1 + 15) & ~(uintptr_t)15) - sa0);
+        uint32_t qbytes = 0;
+        uintptr_t qa0 = 0;
+        if (HAS_QUAL) {
+            qa0 = (qual_base + b0) & ~(uintptr_t)15;
+            qbytes = (uint32_t)(((qual_base + b1 + 15) & ~(uintptr_t)15) - qa0);
+        }
+        mbar_expect_tx(&bars[st], bytes + qbytes);
+        tma_load_1d(s_seq + (size_t)st * a.mini_cap, (const void *)sa0, bytes, &bars[st]);
+        if (HAS_QUAL) tma_load_1d(s_qual + (size_t)st * a.mini_cap, (const void *)qa0, qbytes, &bars[st]);
+    };
+    if (lane == 0) {
+        if (wg < n_mt) issue(wg, 0);
+        if (wg + warps_total < n_mt) issue(wg + warps_total, 1);
+    }
+
+    uint32_t phase0 = 0, phase1 = 0;
+    int c_old = 0;                 // tasks waiting in the carry buffer (warp-uniform)
+    int it = 0;
+    long long mt = wg;
+    while (true) {
+        const bool have_tile = mt < n_mt;
+        if (!have_tile && c_old == 0) break;
+        const int st = it & 1;
+        int c_new = 0;
+        const uint8_t *tile_seq = s_seq + (size_t)st * a.mini_cap;
+        if (have_tile) {
+            const long long r0 = mt * 32;
+            const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+            const long long r = r0 + lane;
+            const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+            long long o0 = 0, o1 = 0;
+            if (r < n_reads) { o0 = a.offsets[r]; o1 = a.offsets[r + 1]; }
+            const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+            const uint8_t *tile_qual = s_qual + (size_t)st * a.mini_cap;
+            if (b1 > b0) {
+                if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+                else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+                const uint32_t head = (uint32_t)((seq_base + b0) - sa0);
+                const uint32_t body = (uint32_t)(b1 - b0);
+                const uint32_t nchunks = (head + body + 15) / 16;
+                uint32_t bad = 0;
+                for (uint32_t c = lane; c < nchunks; c += 32) {
+                    const uint4 v = ((const uint4 *)tile_seq)[c];
+                    if (c == 0 || c == nchunks - 1) {
+                        const uint8_t *pb = tile_seq + 16 * c;
+                        for (uint32_t b = 0; b < 16; ++b) {
+                            const uint32_t idx = 16 * c + b;
+                            if (idx >= head && idx < head + body) bad |= pb[b];
+                        }
+                    } else bad |= v.x | v.y | v.z | v.w;
+                }
+                if (bad & 0x80808080u) atomicOr(a.err_flag, 1);
+            }
+            // ---- phase A ------------------------------------------------------------------------
+            bool pass = false;
+            uint32_t hits = 0, rs0 = 0, rs1 = 0, t_off = 0, t_len = 0;
+            int gs = 4;
+            if (r < n_reads) {
+                const int n = (int)(o1 - o0);
+                const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
+                int ts = 0, te = n;
+                if (HAS_QUAL) {
+                    const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+                    const uint8_t *q = tile_qual + (size_t)((qual_base + o0) - qa0);
+                    if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+                }
+                if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+                t_off = off + (uint32_t)ts; t_len = (uint32_t)(te - ts);
+                const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
+                pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
+                if (!pass) {
+                    CgHit none; none.adapter = -1; none.remove = 0;
+                    none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
+                    store_hit(a.out + (size_t)r * a.slots, none, 0, 0);
+                }
+            }
+            const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+            c_new = __popc(ballot);
+            if (pass) {
+                const uint32_t idx = __popc(ballot & ((1u << lane) - 1u));
+                meta_new[2 * idx] = make_uint4((uint32_t)(tile_seq - smem) + t_off, t_len, hits, (uint32_t)gs);
+                meta_new[2 * idx + 1] = make_uint4(rs0, rs1, (uint32_t)((unsigned long long)r & 0xffffffffu),
+                                                   (uint32_t)((unsigned long long)r >> 32));
+            }
+            __syncwarp();
+        }
+        // ---- phase B: only full groups of 32 tasks (or the final flush) --------------------------
+        const int total = c_old + c_new;
+        const bool flush = !have_tile;
+        int first_left = 0, n_left = c_new;      // which new tasks go to the carry buffer afterwards
+        int carry_at = c_old;                    // ... and from which carry slot on
+        if (total >= 32 || flush) {
+            const bool has_task = lane < total;  // total < 32 only when flushing
+            uint4 ma = make_uint4(0, 0, 0, 4), mb = make_uint4(0, 0, 0, 0);
+            if (has_task) {
+                if (lane < c_old) { ma = meta_carry[2 * lane]; mb = meta_carry[2 * lane + 1]; }
+                else { ma = meta_new[2 * (lane - c_old)]; mb = meta_new[2 * (lane - c_old) + 1]; }
+            }
+            warp_dp_pass(S, smem, ma, mb, has_task, a.out, a.slots);
+            __syncwarp();
+            first_left = 32 - c_old;             // new tasks [first_left, c_new) were not processed
+            n_left = total >= 32 ? total - 32 : 0;
+            carry_at = 0;
+            c_old = 0;
+        }
+        // ---- carry the unprocessed new tasks (read bytes + scan results) -------------------------
+        for (int j = 0; j < n_left; ++j) {
+            const uint4 ma = meta_new[2 * (first_left + j)];
+            const uint4 mb = meta_new[2 * (first_left + j) + 1];
+            const uint32_t src = ma.x & ~15u;
+            const uint32_t nch = ((ma.x & 15u) + ma.y + 15u) >> 4;
+            uint8_t *dst = s_carry + (size_t)(carry_at + j) * a.carry_slot;
+            if ((uint32_t)lane < nch) ((uint4 *)dst)[lane] = ((const uint4 *)(smem + src))[lane];
+            if (lane == 0) {
+                meta_carry[2 * (carry_at + j)] = make_uint4((uint32_t)(dst - smem) + (ma.x & 15u), ma.y, ma.z, ma.w);
+                meta_carry[2 * (carry_at + j) + 1] = mb;
+            }
+        }
+        c_old = carry_at + n_left;
+        __syncwarp();
+        if (have_tile) {
+            if (lane == 0) {
+                const long long next = mt + 2 * warps_total;
+                if (next < n_mt) issue(next, st);
+            }
+            mt += warps_total;
+            ++it;
+        }
+    }
+}
+
+cudaError_t cg_warp_occupancy(bool has_qual, size_t smem, int *blocks_per_sm)
+{
+    void (*k)(const CgKernelArgs) = has_qual ? cg_trim_warp_kernel<true> : cg_trim_warp_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, CG_NT, smem);
+}
+
+cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st)
+{
+    if (has_qual) cg_trim_warp_kernel<true><<<grid, CG_NT, smem, st>>>(a);
+    else cg_trim_warp_kernel<false><<<grid, CG_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic kernel (wide cells / long reads): no staging, columns in HBM scratch
 // ------------------------------------------------------------------------------------------
 __global__ void cg_trim_generic_kernel(const CgKernelArgs a)

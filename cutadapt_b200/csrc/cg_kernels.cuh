@@ -27,6 +27,9 @@ struct CgKernelArgs {
     // fused-kernel geometry
     int tile_cap;  // bytes per staged tile (multiple of 16)
     int col_rows;  // max_m + 1
+    // warp-autonomous kernel geometry
+    int mini_cap;    // bytes per staged 32-read mini-tile (multiple of 16)
+    int carry_slot;  // bytes per carried task (multiple of 16)
     // generic-kernel scratch
     uint32_t *scratch_p;
     int *scratch_w;
@@ -36,6 +39,9 @@ struct CgKernelArgs {
 size_t cg_fast_smem_bytes(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual);
 cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, bool simple, int grid, size_t smem, cudaStream_t st);
 cudaError_t cg_fast_occupancy(bool has_qual, bool simple, size_t smem, int *blocks_per_sm);
+size_t cg_warp_smem_bytes(uint32_t blob_bytes, int mini_cap, int carry_slot, bool has_qual);
+cudaError_t cg_warp_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
 cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
                                     const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,
