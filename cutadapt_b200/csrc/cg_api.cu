@@ -105,6 +105,8 @@ struct cg_ctx {
     uint8_t *d_enc = nullptr;   // 768 bytes
     DevBuf<uint32_t> scratch_p;
     DevBuf<int> scratch_w;
+    DevBuf<uint4> tasks;                 // split pipeline: 2 x uint4 per read of a sub-batch
+    unsigned long long *d_task_count = nullptr;
     long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // fused-kernel event pairs
     std::vector<cudaEvent_t> event_pool;
@@ -142,6 +144,8 @@ extern "C" int cg_ctx_create(int device, void *stream, cg_ctx **out)
     for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&c->d_err, 16 * sizeof(int)));
     CU(cudaMemset(c->d_err, 0, 16 * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_task_count, 64));
+    CU(cudaMemset(c->d_task_count, 0, 64));
     CU(cudaMalloc((void **)&c->d_enc, 768));
     uint8_t enc[768];
     cg_build_enc_tables(enc);
@@ -176,7 +180,8 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
         l.h_seq.release(); l.h_qual.release(); l.h_offs.release(); l.h_out.release(); l.h_qtrim.release();
         if (l.stream) cudaStreamDestroy(l.stream);
     }
-    c->scratch_p.release(); c->scratch_w.release();
+    c->scratch_p.release(); c->scratch_w.release(); c->tasks.release();
+    if (c->d_task_count) cudaFree(c->d_task_count);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_enc) cudaFree(c->d_enc);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -289,12 +294,31 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         CU(cg_fast_occupancy(want_q, simple, smem, &occ));
         if (occ < 1) fast = false;
     }
-    // warp-autonomous kernel: one aligner adapter with m <= 32 on the two-phase schedule
+    // split pipeline (default for one aligner adapter with m <= 32): scan kernel -> task list -> DP kernel
+    const bool force_block = kernel_env && strcmp(kernel_env, "block") == 0;
+    const bool force_warp = kernel_env && strcmp(kernel_env, "warp") == 0;
+    bool split = false;
+    size_t scan_smem = 0, dp_smem = 0;
+    int scan_occ = 0, dp_occ = 0;
+    if (simple && s->host.max_m <= 32 && !force_block && !force_warp) {
+        const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
+        const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
+        if (mini < (1 << 20)) {
+            a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
+            scan_smem = cg_scan_smem_bytes(a.blob_bytes, a.mini_cap, want_q);
+            dp_smem = cg_dp_smem_bytes(a.blob_bytes, a.carry_slot);
+            if (scan_smem <= c->smem_optin && dp_smem <= c->smem_optin) {
+                CU(cg_scan_occupancy(want_q, scan_smem, &scan_occ));
+                CU(cg_dp_occupancy(dp_smem, &dp_occ));
+                split = scan_occ >= 1 && dp_occ >= 1;
+            }
+        }
+    }
+    // warp-autonomous fused kernel (kept selectable: CUTADAPT_B200_KERNEL=warp)
     bool warpk = false;
     size_t wsmem = 0;
     int wocc = 0;
-    const bool force_block = kernel_env && strcmp(kernel_env, "block") == 0;
-    if (simple && s->host.max_m <= 32 && !force_block) {
+    if (simple && s->host.max_m <= 32 && force_warp) {
         const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
         const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
         if (mini < (1 << 20)) {
@@ -314,7 +338,31 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         }
         CU(cudaEventRecord(ev0, st));
     }
-    if (warpk) {
+    if (split) {
+        const long long SUB = 8LL << 20;      // reads per sub-batch: bounds the task list to 256 MiB
+        int rc = c->tasks.ensure((size_t)std::min<long long>(n_reads, SUB) * 2);
+        if (rc != CG_OK) return rc;
+        a.tasks = c->tasks.p; a.task_count = c->d_task_count;
+        for (long long r0 = 0; r0 < n_reads; r0 += SUB) {
+            const long long cnt = std::min<long long>(SUB, n_reads - r0);
+            CgKernelArgs b = a;
+            b.offsets = a.offsets + r0;
+            b.n_reads = cnt;
+            b.out = a.out + (size_t)r0 * a.times * a.slots;
+            b.qtrim = a.qtrim ? a.qtrim + 2 * r0 : nullptr;
+            b.task_cap = cnt;
+            CU(cudaMemsetAsync(c->d_task_count, 0, sizeof(unsigned long long), st));
+            const long long n_mt = (cnt + 31) / 32;
+            long long grid = (long long)scan_occ * c->sm_count;
+            grid = std::max<long long>(1, std::min<long long>(grid, (n_mt + 3) / 4));
+            CU(cg_launch_scan(b, want_q, (int)grid, scan_smem, st));
+            long long dgrid = (long long)dp_occ * c->sm_count;
+            dgrid = std::max<long long>(1, std::min<long long>(dgrid, (n_mt + 3) / 4));
+            CU(cg_launch_dp(b, (int)dgrid, dp_smem, st));
+            c->launches += 2;
+        }
+        c->launches -= 1;    // the common tail below adds one
+    } else if (warpk) {
         const long long n_mt = (n_reads + 31) / 32;
         long long grid = (long long)wocc * c->sm_count;
         const long long need = (n_mt + 3) / 4;

@@ -542,6 +542,304 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 }
 
 // ------------------------------------------------------------------------------------------
+// Split pipeline for one aligner adapter (m <= 32), one round:
+//
+//   cg_scan_kernel   phase A on every read at high occupancy (few registers): per-warp TMA-staged
+//                    mini-tiles of 32 reads, quality trim + fused scan; failing reads get their
+//                    "no match" record, passing reads append a 32-byte task (read index, trimmed
+//                    window, locator hit groups, saved scan states) to a list in HBM with one
+//                    warp-aggregated atomic per mini-tile.
+//   cg_dp_kernel     phase B on dense groups of 32 tasks: every lane fetches its task's read window
+//                    into shared memory with its own TMA bulk copy (32 copies, one mbarrier),
+//                    double buffered against the DP of the previous group; then exact runs +
+//                    register-column DP with all 32 lanes busy.
+//
+// The two phases have opposite resource profiles (the scan needs ~40 registers and wants many warps
+// to hide its dependent shift-and chain; the DP wants ~128 registers); fused in one kernel the DP's
+// registers cap the scan's occupancy.  The task list costs ~35 bytes of extra HBM traffic per read,
+// which is noise for a kernel that is instruction-issue bound.
+// ------------------------------------------------------------------------------------------
+struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_rel, qual_rel, total; };
+__host__ __device__ inline ScanSmem scan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
+{
+    ScanSmem L;
+    size_t o = 0;
+    L.blob_off = o; o += cg_align_up(blob_bytes, 16);
+    L.enc_off = o; o += 768;
+    o = cg_align_up(o, 128);
+    L.warp_off = o;
+    size_t w = 0;
+    L.bar_rel = w; w += 16;
+    w = cg_align_up(w, 128);
+    L.seq_rel = w; w += 2 * (size_t)mini_cap;
+    L.qual_rel = w; if (has_qual) w += 2 * (size_t)mini_cap;
+    L.warp_stride = cg_align_up(w, 128);
+    L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
+    return L;
+}
+size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual)
+{
+    return scan_smem_layout(blob_bytes, mini_cap, has_qual).total;
+}
+
+template <bool HAS_QUAL>
+__global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const ScanSmem L = scan_smem_layout(a.blob_bytes, a.mini_cap, HAS_QUAL);
+    uint8_t *s_blob = smem + L.blob_off;
+    uint8_t *s_enc = smem + L.enc_off;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    uint8_t *wbase = smem + L.warp_off + (size_t)wib * L.warp_stride;
+    uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
+    uint8_t *s_seq = wbase + L.seq_rel;
+    uint8_t *s_qual = wbase + L.qual_rel;
+
+    for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
+    for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+
+    const long long n_reads = a.n_reads;
+    const long long n_mt = (n_reads + 31) / 32;
+    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
+    const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
+    const uintptr_t seq_base = (uintptr_t)a.seq, qual_base = (uintptr_t)a.qual;
+
+    auto issue = [&](long long mt, int st) {
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        if (b1 <= b0) return;
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        const uint32_t bytes = (uint32_t)(((seq_base + b1 + 15) & ~(uintptr_t)15) - sa0);
+        uint32_t qbytes = 0;
+        uintptr_t qa0 = 0;
+        if (HAS_QUAL) {
+            qa0 = (qual_base + b0) & ~(uintptr_t)15;
+            qbytes = (uint32_t)(((qual_base + b1 + 15) & ~(uintptr_t)15) - qa0);
+        }
+        mbar_expect_tx(&bars[st], bytes + qbytes);
+        tma_load_1d(s_seq + (size_t)st * a.mini_cap, (const void *)sa0, bytes, &bars[st]);
+        if (HAS_QUAL) tma_load_1d(s_qual + (size_t)st * a.mini_cap, (const void *)qa0, qbytes, &bars[st]);
+    };
+    if (lane == 0) {
+        if (wg < n_mt) issue(wg, 0);
+        if (wg + warps_total < n_mt) issue(wg + warps_total, 1);
+    }
+    uint32_t phase0 = 0, phase1 = 0;
+    int it = 0;
+    for (long long mt = wg; mt < n_mt; mt += warps_total, ++it) {
+        const int st = it & 1;
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long r = r0 + lane;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        long long o0 = 0, o1 = 0;
+        if (r < n_reads) { o0 = a.offsets[r]; o1 = a.offsets[r + 1]; }
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        const uint8_t *tile_seq = s_seq + (size_t)st * a.mini_cap;
+        const uint8_t *tile_qual = s_qual + (size_t)st * a.mini_cap;
+        if (b1 > b0) {
+            if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+            const uint32_t head = (uint32_t)((seq_base + b0) - sa0);
+            const uint32_t body = (uint32_t)(b1 - b0);
+            const uint32_t nchunks = (head + body + 15) / 16;
+            uint32_t bad = 0;
+            for (uint32_t c = lane; c < nchunks; c += 32) {
+                const uint4 v = ((const uint4 *)tile_seq)[c];
+                if (c == 0 || c == nchunks - 1) {
+                    const uint8_t *pb = tile_seq + 16 * c;
+                    for (uint32_t b = 0; b < 16; ++b) {
+                        const uint32_t idx = 16 * c + b;
+                        if (idx >= head && idx < head + body) bad |= pb[b];
+                    }
+                } else bad |= v.x | v.y | v.z | v.w;
+            }
+            if (bad & 0x80808080u) atomicOr(a.err_flag, 1);
+        }
+        bool pass = false;
+        uint32_t hits = 0, rs0 = 0, rs1 = 0;
+        int gs = 4, ts = 0, te = 0;
+        if (r < n_reads) {
+            const int n = (int)(o1 - o0);
+            const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
+            ts = 0; te = n;
+            if (HAS_QUAL) {
+                const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+                const uint8_t *q = tile_qual + (size_t)((qual_base + o0) - qa0);
+                if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+            }
+            if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+            const ScanOut sc = simple_scan(S, tile_seq + off + ts, te - ts, &gs);
+            pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
+            if (!pass) {
+                CgHit none; none.adapter = -1; none.remove = 0;
+                none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
+                store_hit(a.out + (size_t)r * a.slots, none, 0, 0);
+            }
+        }
+        // warp-aggregated append to the task list
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        if (ballot) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.task_count, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                a.tasks[2 * slot] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
+                                               (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
+                a.tasks[2 * slot + 1] = make_uint4(hits, (uint32_t)gs, rs0, rs1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const long long next = mt + 2 * warps_total;
+            if (next < n_mt) issue(next, st);
+        }
+    }
+}
+
+cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm)
+{
+    void (*k)(const CgKernelArgs) = has_qual ? cg_scan_kernel<true> : cg_scan_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, CG_NT, smem);
+}
+cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st)
+{
+    if (has_qual) cg_scan_kernel<true><<<grid, CG_NT, smem, st>>>(a);
+    else cg_scan_kernel<false><<<grid, CG_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+struct DpSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, slot_rel, total; };
+__host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int carry_slot)
+{
+    DpSmem L;
+    size_t o = 0;
+    L.blob_off = o; o += cg_align_up(blob_bytes, 16);
+    L.enc_off = o; o += 768;
+    o = cg_align_up(o, 128);
+    L.warp_off = o;
+    size_t w = 0;
+    L.bar_rel = w; w += 16;
+    w = cg_align_up(w, 128);
+    L.slot_rel = w; w += 2 * 32 * (size_t)carry_slot;
+    L.warp_stride = cg_align_up(w, 128);
+    L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
+    return L;
+}
+size_t cg_dp_smem_bytes(uint32_t blob_bytes, int carry_slot) { return dp_smem_layout(blob_bytes, carry_slot).total; }
+
+__global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const DpSmem L = dp_smem_layout(a.blob_bytes, a.carry_slot);
+    uint8_t *s_blob = smem + L.blob_off;
+    uint8_t *s_enc = smem + L.enc_off;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    uint8_t *wbase = smem + L.warp_off + (size_t)wib * L.warp_stride;
+    uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
+    uint8_t *s_slot = wbase + L.slot_rel;
+
+    for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
+    for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+
+    unsigned long long n_tasks = *a.task_count;
+    if (n_tasks > (unsigned long long)a.task_cap) n_tasks = (unsigned long long)a.task_cap;
+    const long long n_groups = (long long)((n_tasks + 31) / 32);
+    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
+    const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
+    const uintptr_t seq_base = (uintptr_t)a.seq;
+
+    // Fetch: every lane copies its own task's (trimmed) read into its slot of stage `st`.
+    auto fetch = [&](long long g, int st, uint4 &ta, uint4 &tb, uint32_t &soff) {
+        const unsigned long long t = (unsigned long long)g * 32 + lane;
+        const bool has = t < n_tasks;
+        uint32_t bytes = 0;
+        uintptr_t src = 0;
+        ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0);
+        if (has) {
+            ta = a.tasks[2 * t]; tb = a.tasks[2 * t + 1];
+            const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
+            const uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + ta.z;
+            src = addr & ~(uintptr_t)15;
+            bytes = ta.w ? (uint32_t)(((addr + ta.w + 15) & ~(uintptr_t)15) - src) : 0u;
+            soff = (uint32_t)(addr - src);
+        }
+        uint32_t total = bytes;
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        if (total) {
+            if (lane == 0) mbar_expect_tx(&bars[st], total);
+            __syncwarp();
+            if (bytes) tma_load_1d(s_slot + ((size_t)st * 32 + lane) * a.carry_slot, (const void *)src, bytes, &bars[st]);
+        }
+        return total != 0;
+    };
+
+    uint32_t phase0 = 0, phase1 = 0;
+    uint4 ta_n = make_uint4(0, 0, 0, 0), tb_n = make_uint4(0, 4, 0, 0);
+    uint32_t soff_n = 0;
+    bool loaded_n = false;
+    if (wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, soff_n);
+    int it = 0;
+    for (long long g = wg; g < n_groups; g += warps_total, ++it) {
+        const int st = it & 1;
+        const uint4 ta = ta_n, tb = tb_n;
+        const uint32_t soff = soff_n;
+        const bool loaded = loaded_n;
+        // prefetch the next group into the other stage (its previous DP pass has finished)
+        const long long gn = g + warps_total;
+        loaded_n = false;
+        if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, soff_n);
+        if (loaded) {
+            if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+        }
+        const bool has_task = (unsigned long long)g * 32 + lane < n_tasks;
+        const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * a.carry_slot + soff;
+        CgHit hit;
+        const bool found = simple_locate_regs(S, p, (int)ta.w, tb.x, (int)tb.y, tb.z, tb.w, has_task, hit);
+        if (has_task) {
+            if (!found) {
+                hit.adapter = -1; hit.remove = 0;
+                hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+            }
+            const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
+            store_hit(a.out + (size_t)r * a.slots, hit, 0, (int)ta.w);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t cg_dp_occupancy(size_t smem, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(cg_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cg_dp_kernel, CG_NT, smem);
+}
+cudaError_t cg_launch_dp(const CgKernelArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    cg_dp_kernel<<<grid, CG_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic kernel (wide cells / long reads): no staging, columns in HBM scratch
 // ------------------------------------------------------------------------------------------
 __global__ void cg_trim_generic_kernel(const CgKernelArgs a)

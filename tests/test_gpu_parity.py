@@ -391,11 +391,13 @@ def test_both_kernel_schedules_agree():
         if reads is None:
             reads = random_reads(rng, [adapter.sequence], 5000, "ACGT", rng.choice([100, 150, 400]))
         d = adapter.descriptor()
-        got, _ = run_set([d], None, reads)
-        os.environ["CUTADAPT_B200_KERNEL"] = "general"
-        try:
-            ref, _ = run_set([d], None, reads)
-        finally:
-            del os.environ["CUTADAPT_B200_KERNEL"]
         exp, _ = oracle.oracle_process([d], None, reads)
-        assert (got == exp).all() and (ref == exp).all(), repr(adapter)
+        got, _ = run_set([d], None, reads)                       # default: split scan/DP pipeline
+        assert (got == exp).all(), ("default", repr(adapter))
+        for variant in ("general", "block", "warp"):             # the fused kernels
+            os.environ["CUTADAPT_B200_KERNEL"] = variant
+            try:
+                other, _ = run_set([d], None, reads)
+            finally:
+                del os.environ["CUTADAPT_B200_KERNEL"]
+            assert (other == exp).all(), (variant, repr(adapter))
