@@ -384,13 +384,14 @@ CG_HD int scan_group_shift(int n)
     return gs;
 }
 
-CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *pool, const ReadView &rv,
-                        int gs, bool always_pass)
+// REV selects the scan direction at compile time so that character addresses are base + immediate.
+// The mask tables have 256 entries (the upper half is zero), so the loaded byte indexes them directly.
+template <bool REV>
+CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t *pool, const uint8_t *first,
+                            int n, int gs, bool always_pass)
 {
+    // `first` is the first character in scan order; character i is first[REV ? -i : i]
     ScanOut out; out.pass = always_pass; out.hits = 0; out.rs0 = 0; out.rs1 = 0;
-    const int n = rv.n;
-    const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
-    const int cstride = rv.rev ? -1 : 1;
     // the saved states are only meaningful when a single word carries all locator chunks
     int n_loc = 0;
     for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
@@ -400,18 +401,38 @@ CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *poo
         if (W.type == CG_SCAN_WHOLE) {
             const uint32_t init = W.init, locf = W.loc_found;
             uint32_t R = 0, seen = 0;
+            const uint8_t *q = first;
             if (locf) {
-                const int G = 1 << gs;
                 const bool stash = n_loc == 1;
-                int nh = 0;
-                for (int p0 = 0; p0 < n; p0 += G) {
-                    const int p1 = cg_min(n, p0 + G);
+                int nh = 0, p0 = 0;
+                if (gs == 4) {                                   // reads up to 511 characters
+                    for (; p0 + 16 <= n; p0 += 16) {
+                        const uint32_t r_start = R;
+                        uint32_t g = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            R = ((R << 1) | init) & mask[q[REV ? -i : i]];
+                            g |= R;
+                        }
+                        q += REV ? -16 : 16;
+                        seen |= g;
+                        const bool hg = (g & locf) != 0;
+                        out.hits |= hg ? (1u << (p0 >> 4)) : 0u;
+                        out.rs0 = (hg && stash && nh == 0) ? r_start : out.rs0;
+                        out.rs1 = (hg && stash && nh == 1) ? r_start : out.rs1;
+                        nh += hg ? 1 : 0;
+                    }
+                }
+                const int G = 1 << gs;
+                for (; p0 < n; p0 += G) {
+                    const int cnt = cg_min(n - p0, G);
                     const uint32_t r_start = R;
                     uint32_t g = 0;
-                    for (int p = p0; p < p1; ++p) {
-                        R = ((R << 1) | init) & mask[cp[cstride * p] & 127];
+                    for (int i = 0; i < cnt; ++i) {
+                        R = ((R << 1) | init) & mask[q[REV ? -i : i]];
                         g |= R;
                     }
+                    q += REV ? -cnt : cnt;
                     seen |= g;
                     const bool hg = (g & locf) != 0;
                     out.hits |= hg ? (1u << (p0 >> gs)) : 0u;
@@ -420,33 +441,54 @@ CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *poo
                     nh += hg ? 1 : 0;
                 }
             } else {
-                for (int p = 0; p < n; ++p) {
-                    R = ((R << 1) | init) & mask[rv.at(p) & 127];
+                int p = 0;
+                for (; p + 8 <= n; p += 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        R = ((R << 1) | init) & mask[q[REV ? -i : i]];
+                        seen |= R;
+                    }
+                    q += REV ? -8 : 8;
+                }
+                for (; p < n; ++p) {
+                    R = ((R << 1) | init) & mask[*q];
                     seen |= R;
+                    q += REV ? -1 : 1;
                 }
             }
             if (seen & W.pass_found) out.pass = true;
         } else if (W.type == CG_SCAN_SUFFIX) {
             const uint32_t *tab = (const uint32_t *)(pool + W.pos_off);   // {init, found}[span + 1]
             uint32_t R = 0, seen = 0;
-            for (int p = cg_max(0, n - (int)W.span); p < n; ++p) {
-                const int d = n - p;
-                R = ((R << 1) | tab[2 * d]) & mask[rv.at(p) & 127];
+            const int p_lo = cg_max(0, n - (int)W.span);
+            const uint8_t *q = first + (REV ? -p_lo : p_lo);
+            for (int d = n - p_lo; d >= 1; --d) {
+                R = ((R << 1) | tab[2 * d]) & mask[*q];
                 seen |= R & tab[2 * d + 1];
+                q += REV ? -1 : 1;
             }
             if (seen & W.pass_found) out.pass = true;
         } else {
             const uint32_t *tab = (const uint32_t *)(pool + W.pos_off);   // {init, found}[span]
             uint32_t R = 0, seen = 0;
             const int stop = cg_min(n, (int)W.span);
+            const uint8_t *q = first;
             for (int p = 0; p < stop; ++p) {
-                R = ((R << 1) | tab[2 * p]) & mask[rv.at(p) & 127];
+                R = ((R << 1) | tab[2 * p]) & mask[*q];
                 seen |= R & tab[2 * p + 1];
+                q += REV ? -1 : 1;
             }
             if (seen & W.pass_found) out.pass = true;
         }
     }
     return out;
+}
+
+CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *pool, const ReadView &rv,
+                        int gs, bool always_pass)
+{
+    if (rv.rev) return scan_core_dir<true>(words, n_words, pool, rv.p + (rv.n - 1), rv.n, gs, always_pass);
+    return scan_core_dir<false>(words, n_words, pool, rv.p, rv.n, gs, always_pass);
 }
 
 // Groups of characters the DP must visit, given the locator hits (see locate_core).

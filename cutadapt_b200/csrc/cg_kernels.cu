@@ -168,9 +168,12 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
             const uint32_t body = (uint32_t)(b1 - b0);
             const uint32_t nchunks = (head + body + 15) / 16;
             uint32_t bad = 0;
+            // the slack bytes of interior tiles belong to neighbouring reads of the same batch, so only
+            // the very first and very last chunk of the batch need byte-exact masking
+            const bool edge_first = tile == 0, edge_last = tile == n_tiles - 1;
             for (uint32_t c = tid; c < nchunks; c += CG_NT) {
                 const uint4 v = ((const uint4 *)tile_seq)[c];
-                if (c == 0 || c == nchunks - 1) {
+                if ((c == 0 && edge_first) || (c == nchunks - 1 && edge_last)) {
                     const uint8_t *pb = tile_seq + 16 * c;
                     for (uint32_t b = 0; b < 16; ++b) {
                         const uint32_t idx = 16 * c + b;
@@ -436,9 +439,10 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_warp_kernel(const CgKernelArgs 
                 const uint32_t body = (uint32_t)(b1 - b0);
                 const uint32_t nchunks = (head + body + 15) / 16;
                 uint32_t bad = 0;
+                const bool edge_first = mt == 0, edge_last = mt == n_mt - 1;
                 for (uint32_t c = lane; c < nchunks; c += 32) {
                     const uint4 v = ((const uint4 *)tile_seq)[c];
-                    if (c == 0 || c == nchunks - 1) {
+                    if ((c == 0 && edge_first) || (c == nchunks - 1 && edge_last)) {
                         const uint8_t *pb = tile_seq + 16 * c;
                         for (uint32_t b = 0; b < 16; ++b) {
                             const uint32_t idx = 16 * c + b;
@@ -652,9 +656,10 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
             const uint32_t body = (uint32_t)(b1 - b0);
             const uint32_t nchunks = (head + body + 15) / 16;
             uint32_t bad = 0;
+            const bool edge_first = mt == 0, edge_last = mt == n_mt - 1;
             for (uint32_t c = lane; c < nchunks; c += 32) {
                 const uint4 v = ((const uint4 *)tile_seq)[c];
-                if (c == 0 || c == nchunks - 1) {
+                if ((c == 0 && edge_first) || (c == nchunks - 1 && edge_last)) {
                     const uint8_t *pb = tile_seq + 16 * c;
                     for (uint32_t b = 0; b < 16; ++b) {
                         const uint32_t idx = 16 * c + b;

@@ -98,7 +98,7 @@ void pack_words(const std::vector<ScanKmer> &kmers, uint32_t type, bool gap, std
         CgScanWord W;
         memset(&W, 0, sizeof W);
         W.type = type;
-        std::vector<uint32_t> mask(128, 0);
+        std::vector<uint32_t> mask(256, 0);    // 256 entries: any byte indexes it, bytes >= 128 match nothing
         std::vector<std::pair<int, int>> placed;   // (kmer index, offset)
         int used = 0;
         while (i < kmers.size()) {
