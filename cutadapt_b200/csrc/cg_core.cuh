@@ -907,9 +907,36 @@ CG_HD void scan_runs_core(const CgScanWord *words, int n_words, const uint8_t *p
     pass_out = pass;
 }
 
+// Selection state of _align.pyx:391-396 (the `best` match so far); carried from the main DP pass of
+// a read to its end-window pass when the two are scheduled separately.
+struct LocState {
+    int have, b_origin, b_cost, b_score, b_ref_stop, b_q_stop, stopped;
+};
+CG_HD LocState loc_state_init(int m, int n)
+{
+    LocState st;
+    st.have = 0; st.b_origin = 0; st.b_cost = 0; st.b_score = 0; st.b_ref_stop = m; st.b_q_stop = n; st.stopped = 0;
+    return st;
+}
+CG_HD bool loc_state_result(const LocState &st, int *out6)
+{
+    if (!st.have) return false;                                  // _align.pyx:573-587
+    out6[0] = st.b_origin >= 0 ? 0 : -st.b_origin;
+    out6[1] = st.b_ref_stop;
+    out6[2] = st.b_origin >= 0 ? st.b_origin : 0;
+    out6[3] = st.b_q_stop;
+    out6[4] = st.b_score;
+    out6[5] = st.b_cost;
+    return true;
+}
+
+// Processes runs [0, n_use) of R starting from the selection state `st` and leaves the updated state
+// in `st`; the last-column scan (_align.pyx:536-572) is done only when final_scan is set (i.e. when
+// this call covers the read's last run).
 template <int MR>
-CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
-                       const uint32_t *peq, const ReadView &rv, const RunList &R, bool has_task, int *out6)
+CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
+                       const uint32_t *peq, const ReadView &rv, const RunList &R, int n_use, bool has_task,
+                       bool final_scan, LocState &st)
 {
     typedef Packed32 C;
     uint32_t c[MR + 1];
@@ -924,12 +951,12 @@ CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
     const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
     const int cstride = rv.rev ? -1 : 1;
 
-    bool have = false;
-    int b_origin = 0, b_cost = 0, b_score = 0, b_ref_stop = m, b_q_stop = n;
+    bool have = st.have != 0;
+    int b_origin = st.b_origin, b_cost = st.b_cost, b_score = st.b_score, b_ref_stop = st.b_ref_stop, b_q_stop = st.b_q_stop;
     int last = 0, last_filled = 0;
     uint32_t stale = C::make(0, 0, 0);
-    bool stopped = false, reached_end = false;
-    const int n_runs = has_task ? R.n : 0;
+    bool stopped = st.stopped != 0, reached_end = false;
+    const int n_runs = has_task ? n_use : 0;
     const int max_runs = CG_WARP_MAX(n_runs);
 #pragma unroll
     for (int i = 0; i <= MR; ++i) c[i] = C::INF;
@@ -1023,7 +1050,7 @@ CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
         }
     }
 
-    if (has_task && n_runs > 0 && max_n == n && reached_end && !stopped) {   // _align.pyx:536-572
+    if (has_task && final_scan && n_runs > 0 && max_n == n && reached_end && !stopped) {   // _align.pyx:536-572
         const int first_i = eir ? 0 : m;
         const int origin_var = C::origin(stale);
 #pragma unroll
@@ -1047,14 +1074,8 @@ CG_HD bool locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
             }
         }
     }
-    if (!have) return false;
-    out6[0] = b_origin >= 0 ? 0 : -b_origin;
-    out6[1] = b_ref_stop;
-    out6[2] = b_origin >= 0 ? b_origin : 0;
-    out6[3] = b_q_stop;
-    out6[4] = b_score;
-    out6[5] = b_cost;
-    return true;
+    st.have = have ? 1 : 0; st.b_origin = b_origin; st.b_cost = b_cost; st.b_score = b_score;
+    st.b_ref_stop = b_ref_stop; st.b_q_stop = b_q_stop; st.stopped = stopped ? 1 : 0;
 }
 
 // Register path entry points.
@@ -1092,11 +1113,11 @@ CG_HD bool simple_locate_runs(const SetView &S, const uint8_t *p, int n, const R
     const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
     const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
     const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+    LocState st = loc_state_init(A.m, n);
+    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, true, st);
+    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, true, st);
     int o[6];
-    bool found;
-    if (A.m <= 16) found = locate_regs<16>(A, ncnt, maxcost, peq, rv, R, has_task, o);
-    else found = locate_regs<32>(A, ncnt, maxcost, peq, rv, R, has_task, o);
-    if (!has_task || !found) return false;
+    if (!has_task || !loc_state_result(st, o)) return false;
     hit.adapter = 0;
     if (A.reverse) {
         hit.astart = A.m - o[1]; hit.astop = A.m - o[0];
@@ -1131,6 +1152,89 @@ CG_HD bool simple_locate_regs(const SetView &S, const uint8_t *p, int n, uint32_
     return simple_locate_runs(S, p, n, R, has_task, hit);
 }
 
+// ---------------------------------------------------------------------------------------
+// Split scheduling of one read's DP (split pipeline, cg_dp_kernel<false/true>):
+//   main pass : every run except a trailing, separate end window; reads that stop early
+//               (_align.pyx:531-533) or have no separate end window are finished here;
+//   end pass  : the end window (restart + last-column scan) from the carried LocState.
+// ---------------------------------------------------------------------------------------
+CG_HD void hit_from_state(const CgAdapter &A, int n, const LocState &st, CgHit &hit)
+{
+    int o[6];
+    hit.adapter = -1; hit.remove = 0;
+    hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+    if (!loc_state_result(st, o)) return;
+    hit.adapter = 0;
+    if (A.reverse) {
+        hit.astart = A.m - o[1]; hit.astop = A.m - o[0];
+        hit.rstart = n - o[3]; hit.rstop = n - o[2];
+    } else {
+        hit.astart = o[0]; hit.astop = o[1]; hit.rstart = o[2]; hit.rstop = o[3];
+    }
+    hit.score = o[4]; hit.errors = o[5];
+    hit.remove = A.remove == CGK_REMOVE_AUTO ? (hit.rstart == 0 ? CGK_REMOVE_BEFORE : CGK_REMOVE_AFTER)
+                                            : A.remove;
+}
+
+// Main pass.  Returns true when the read is finished (hit is valid); false when its end window is
+// still to be done (st carries the selection state).  ALL lanes of a warp must call it.
+CG_HD bool split_main_pass(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs, uint32_t rs0,
+                           uint32_t rs1, bool has_task, CgHit &hit, LocState &st)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = p; rv.n = n; rv.rev = A.reverse;
+    const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+    const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+    const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+    RunList R;
+    R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    bool split = false;
+    if (has_task) {
+        if (simple_windowed(S, n)) {
+            refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, rs0, rs1, R);
+            // a trailing run that is exactly the end window and not merged with anything
+            if ((A.flags & 4) && R.n >= 2) {
+                const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+                const int lo_last = R.n == 2 ? R.lo1 : R.lo2;
+                const int hi_last = R.n == 2 ? R.hi1 : R.hi2;
+                split = lo_last == lo_end && hi_last == n;
+            }
+        } else {
+            int max_n = n, min_n = 0;
+            if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
+            if (!(A.flags & 8)) min_n = cg_max(0, n - A.m - A.k);
+            R.n = 1; R.lo0 = min_n; R.hi0 = max_n;
+        }
+    }
+    st = loc_state_init(A.m, n);
+    const int n_use = split ? R.n - 1 : R.n;
+    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, n_use, has_task, !split, st);
+    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, n_use, has_task, !split, st);
+    if (!has_task) return true;
+    if (split && !st.stopped) return false;
+    hit_from_state(A, n, st, hit);
+    return true;
+}
+
+// End pass: `tail` points at the first byte that was fetched for the end window (read orientation:
+// forward reads: byte lo_end of the trimmed read; reversed reads: byte 0).
+CG_HD void split_end_pass(const SetView &S, const uint8_t *tail, int n, bool has_task, LocState &st, CgHit &hit)
+{
+    const CgAdapter &A = S.ad[0];
+    const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+    ReadView rv;
+    rv.n = n; rv.rev = A.reverse;
+    rv.p = A.reverse ? tail : tail - lo_end;       // rv.at(j) for j in [lo_end, n) stays inside the fetched bytes
+    const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+    const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+    const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+    RunList R;
+    R.n = 1; R.lo0 = lo_end; R.hi0 = n; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st);
+    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st);
+    if (has_task) hit_from_state(A, n, st, hit);
+}
+
 CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
                                int quality_trim, int cutoff_front, int cutoff_back, int qbase,
                                PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out, int use_regs = 0)
@@ -1140,6 +1244,20 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
     if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
     CgHit hit; hit.adapter = -1; hit.remove = 0;
     hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+    if (use_regs == 3 && S.ad[0].m <= 32) {       // split scheduling: main pass, then the end pass if needed
+        int gs3;
+        const ScanOut sc3 = simple_scan(S, seq + s, e - s, &gs3);
+        if (sc3.pass) {
+            LocState st;
+            if (!split_main_pass(S, seq + s, e - s, sc3.hits, gs3, sc3.rs0, sc3.rs1, true, hit, st)) {
+                const CgAdapter &A = S.ad[0];
+                const int nn = e - s, lo_end = cg_max(0, nn - 1 - A.m - A.k);
+                split_end_pass(S, A.reverse ? seq + s : seq + s + lo_end, nn, true, st, hit);
+            }
+        }
+        store_hit(out, hit, 0, e - s);
+        return;
+    }
     if (use_regs == 2 && S.ad[0].m <= 32) {
         RunList R;
         if (simple_scan_runs(S, seq + s, e - s, R)) {
@@ -1158,4 +1276,6 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
     }
     store_hit(out, hit, 0, e - s);
 }
+
+
 

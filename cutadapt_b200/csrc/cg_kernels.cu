@@ -726,7 +726,7 @@ cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_
 }
 
 struct DpSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, slot_rel, total; };
-__host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int carry_slot)
+__host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int slot_bytes)
 {
     DpSmem L;
     size_t o = 0;
@@ -737,17 +737,25 @@ __host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int carry_
     size_t w = 0;
     L.bar_rel = w; w += 16;
     w = cg_align_up(w, 128);
-    L.slot_rel = w; w += 2 * 32 * (size_t)carry_slot;
+    L.slot_rel = w; w += 2 * 32 * (size_t)slot_bytes;
     L.warp_stride = cg_align_up(w, 128);
     L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
     return L;
 }
-size_t cg_dp_smem_bytes(uint32_t blob_bytes, int carry_slot) { return dp_smem_layout(blob_bytes, carry_slot).total; }
+size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_layout(blob_bytes, slot_bytes).total; }
 
+// END = false: main pass over the scan kernel's task list (2 x uint4 per task:
+//              {r_lo, r_hi, trim_start, length}, {hits, gs, rs0, rs1}); reads whose end window is a
+//              separate run and that did not stop early append a continuation
+//              ({r_lo, r_hi, trim_start, length}, {have, origin, cost, score}, {ref_stop, q_stop, 0, 0}).
+// END = true : end-window pass over the continuation list; only the last m+k+1 characters of the
+//              read are fetched.
+template <bool END>
 __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const DpSmem L = dp_smem_layout(a.blob_bytes, a.carry_slot);
+    const int slot_bytes = END ? a.end_slot : a.carry_slot;
+    const DpSmem L = dp_smem_layout(a.blob_bytes, slot_bytes);
     uint8_t *s_blob = smem + L.blob_off;
     uint8_t *s_enc = smem + L.enc_off;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -764,27 +772,39 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
     }
     __syncthreads();
     const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+    const CgAdapter &A = S.ad[0];
 
-    unsigned long long n_tasks = *a.task_count;
+    unsigned long long n_tasks = END ? *a.task2_count : *a.task_count;
     if (n_tasks > (unsigned long long)a.task_cap) n_tasks = (unsigned long long)a.task_cap;
+    const uint4 *list = END ? a.tasks2 : a.tasks;
+    const int rec = END ? 3 : 2;
     const long long n_groups = (long long)((n_tasks + 31) / 32);
     const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
     const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
     const uintptr_t seq_base = (uintptr_t)a.seq;
 
-    // Fetch: every lane copies its own task's (trimmed) read into its slot of stage `st`.
-    auto fetch = [&](long long g, int st, uint4 &ta, uint4 &tb, uint32_t &soff) {
+    // Fetch: every lane copies the bytes its task needs into its slot of stage `st` with its own
+    // TMA bulk copy; one mbarrier per stage collects all 32 copies.
+    auto fetch = [&](long long g, int st, uint4 &ta, uint4 &tb, uint4 &tc, uint32_t &soff) {
         const unsigned long long t = (unsigned long long)g * 32 + lane;
         const bool has = t < n_tasks;
         uint32_t bytes = 0;
         uintptr_t src = 0;
-        ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0);
+        ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0); tc = make_uint4(0, 0, 0, 0);
         if (has) {
-            ta = a.tasks[2 * t]; tb = a.tasks[2 * t + 1];
+            ta = list[rec * t]; tb = list[rec * t + 1];
+            if (END) tc = list[rec * t + 2];
             const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
-            const uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + ta.z;
+            uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + ta.z;
+            uint32_t len = ta.w;
+            if (END) {
+                const int n = (int)ta.w;
+                const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+                len = (uint32_t)(n - lo_end);
+                if (!A.reverse) addr += (uintptr_t)lo_end;
+            }
             src = addr & ~(uintptr_t)15;
-            bytes = ta.w ? (uint32_t)(((addr + ta.w + 15) & ~(uintptr_t)15) - src) : 0u;
+            bytes = len ? (uint32_t)(((addr + len + 15) & ~(uintptr_t)15) - src) : 0u;
             soff = (uint32_t)(addr - src);
         }
         uint32_t total = bytes;
@@ -792,55 +812,78 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
         if (total) {
             if (lane == 0) mbar_expect_tx(&bars[st], total);
             __syncwarp();
-            if (bytes) tma_load_1d(s_slot + ((size_t)st * 32 + lane) * a.carry_slot, (const void *)src, bytes, &bars[st]);
+            if (bytes) tma_load_1d(s_slot + ((size_t)st * 32 + lane) * slot_bytes, (const void *)src, bytes, &bars[st]);
         }
         return total != 0;
     };
 
     uint32_t phase0 = 0, phase1 = 0;
-    uint4 ta_n = make_uint4(0, 0, 0, 0), tb_n = make_uint4(0, 4, 0, 0);
+    uint4 ta_n = make_uint4(0, 0, 0, 0), tb_n = make_uint4(0, 4, 0, 0), tc_n = make_uint4(0, 0, 0, 0);
     uint32_t soff_n = 0;
     bool loaded_n = false;
-    if (wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, soff_n);
+    if (wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, tc_n, soff_n);
     int it = 0;
     for (long long g = wg; g < n_groups; g += warps_total, ++it) {
         const int st = it & 1;
-        const uint4 ta = ta_n, tb = tb_n;
+        const uint4 ta = ta_n, tb = tb_n, tc = tc_n;
         const uint32_t soff = soff_n;
         const bool loaded = loaded_n;
-        // prefetch the next group into the other stage (its previous DP pass has finished)
-        const long long gn = g + warps_total;
+        const long long gn = g + warps_total;          // prefetch the next group into the other stage
         loaded_n = false;
-        if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, soff_n);
+        if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, tc_n, soff_n);
         if (loaded) {
             if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
             else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
         }
         const bool has_task = (unsigned long long)g * 32 + lane < n_tasks;
-        const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * a.carry_slot + soff;
+        const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * slot_bytes + soff;
+        const int n = (int)ta.w;
         CgHit hit;
-        const bool found = simple_locate_regs(S, p, (int)ta.w, tb.x, (int)tb.y, tb.z, tb.w, has_task, hit);
-        if (has_task) {
-            if (!found) {
-                hit.adapter = -1; hit.remove = 0;
-                hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
-            }
+        hit.adapter = -1; hit.remove = 0;
+        hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+        bool done = true;
+        LocState ls;
+        if (END) {
+            ls.have = (int)tb.x; ls.b_origin = (int)tb.y; ls.b_cost = (int)tb.z; ls.b_score = (int)tb.w;
+            ls.b_ref_stop = (int)tc.x; ls.b_q_stop = (int)tc.y; ls.stopped = 0;
+            split_end_pass(S, p, n, has_task, ls, hit);
+        } else {
+            done = split_main_pass(S, p, n, tb.x, (int)tb.y, tb.z, tb.w, has_task, hit, ls);
+        }
+        if (has_task && done) {
             const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
-            store_hit(a.out + (size_t)r * a.slots, hit, 0, (int)ta.w);
+            store_hit(a.out + (size_t)r * a.slots, hit, 0, n);
+        }
+        if (!END) {
+            const bool cont = has_task && !done;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
+            if (ballot) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.task2_count, (unsigned long long)__popc(ballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cont) {
+                    const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                    a.tasks2[3 * slot] = ta;
+                    a.tasks2[3 * slot + 1] = make_uint4((uint32_t)ls.have, (uint32_t)ls.b_origin, (uint32_t)ls.b_cost, (uint32_t)ls.b_score);
+                    a.tasks2[3 * slot + 2] = make_uint4((uint32_t)ls.b_ref_stop, (uint32_t)ls.b_q_stop, 0u, 0u);
+                }
+            }
         }
         __syncwarp();
     }
 }
 
-cudaError_t cg_dp_occupancy(size_t smem, int *blocks_per_sm)
+cudaError_t cg_dp_occupancy(bool end_pass, size_t smem, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(cg_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*k)(const CgKernelArgs) = end_pass ? cg_dp_kernel<true> : cg_dp_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, cg_dp_kernel, CG_NT, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, CG_NT, smem);
 }
-cudaError_t cg_launch_dp(const CgKernelArgs &a, int grid, size_t smem, cudaStream_t st)
+cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int grid, size_t smem, cudaStream_t st)
 {
-    cg_dp_kernel<<<grid, CG_NT, smem, st>>>(a);
+    if (end_pass) cg_dp_kernel<true><<<grid, CG_NT, smem, st>>>(a);
+    else cg_dp_kernel<false><<<grid, CG_NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,9 @@ struct CgKernelArgs {
     uint4 *tasks;                     // 2 x uint4 per task
     unsigned long long *task_count;   // number of tasks appended by the scan kernel
     long long task_cap;
+    uint4 *tasks2;                    // continuation list (end windows): 3 x uint4 per task
+    unsigned long long *task2_count;
+    int end_slot;                     // bytes per staged end window (multiple of 16)
     // generic-kernel scratch
     uint32_t *scratch_p;
     int *scratch_w;
@@ -49,9 +52,9 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
 cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
-size_t cg_dp_smem_bytes(uint32_t blob_bytes, int carry_slot);
-cudaError_t cg_dp_occupancy(size_t smem, int *blocks_per_sm);
-cudaError_t cg_launch_dp(const CgKernelArgs &a, int grid, size_t smem, cudaStream_t st);
+size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes);
+cudaError_t cg_dp_occupancy(bool end_pass, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int grid, size_t smem, cudaStream_t st);
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
 cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
                                     const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,

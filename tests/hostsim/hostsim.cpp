@@ -48,7 +48,7 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
             process_read_simple(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                                 params->cutoff_front, params->cutoff_back, params->quality_base, pc,
                                 (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr,
-                                (force_wide & 16) ? 2 : ((force_wide & 8) ? 1 : 0));
+                                (force_wide & 32) ? 3 : ((force_wide & 16) ? 2 : ((force_wide & 8) ? 1 : 0)));
         else
         process_read<true>(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                            params->cutoff_front, params->cutoff_back, params->quality_base, times, pc,
