@@ -792,7 +792,8 @@ CG_HD void runs_add(RunList &R, int lo, int hi, int n_read)
 // word the scan resumes at the start of each hit group from the state phase A saved (rs0, rs1) or
 // carries over from the previous group; otherwise it backs up 31 characters (k-mers are <= 32 long).
 CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
-                       const ReadView &rv, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1, RunList &R)
+                       const ReadView &rv, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1, RunList &R,
+                       bool add_end = true)
 {
     const int n = rv.n, m = A.m, k = A.k;
     R.n = 0;
@@ -842,7 +843,7 @@ CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool
             }
         }
     }
-    if (A.flags & 4) runs_add(R, cg_max(0, n - 1 - m - k), n, n);      // STOP_IN_REFERENCE
+    if (add_end && (A.flags & 4)) runs_add(R, cg_max(0, n - 1 - m - k), n, n);      // STOP_IN_REFERENCE
 }
 
 // Phase A for the register path: the fused scan with the locator hits turned into DP runs on
@@ -936,7 +937,7 @@ CG_HD bool loc_state_result(const LocState &st, int *out6)
 template <int MR>
 CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
                        const uint32_t *peq, const ReadView &rv, const RunList &R, int n_use, bool has_task,
-                       bool final_scan, LocState &st)
+                       bool final_scan, LocState &st, bool eval_bottom = true)
 {
     typedef Packed32 C;
     uint32_t c[MR + 1];
@@ -1031,7 +1032,7 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
                 last_filled = my_last;
                 if (lastok < m) {
                     last = lastok + 1;                          // _align.pyx:490-495
-                } else if (eiq) {                               // _align.pyx:496-533
+                } else if (eiq && eval_bottom) {                // _align.pyx:496-533
                     stale = up;
                     const int cost = C::cost(up), score = C::score(up), origin = C::origin(up);
                     const int length = m + cg_min(origin, 0);
@@ -1191,13 +1192,19 @@ CG_HD bool split_main_pass(const SetView &S, const uint8_t *p, int n, uint32_t h
     bool split = false;
     if (has_task) {
         if (simple_windowed(S, n)) {
-            refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, rs0, rs1, R);
-            // a trailing run that is exactly the end window and not merged with anything
-            if ((A.flags & 4) && R.n >= 2) {
+            // runs around the locator hits only; the end window (needed by the last-column scan of
+            // 3' adapters) is a separate pass unless a hit run already covers it.  Every bottom-row
+            // cell with cost <= k lies inside a hit run, so the end pass has none to evaluate.
+            refine_runs(S.scan, S.h->scan_count, S.pool, A, rv, hits, gs, rs0, rs1, R, false);
+            if (A.flags & 4) {
                 const int lo_end = cg_max(0, n - 1 - A.m - A.k);
-                const int lo_last = R.n == 2 ? R.lo1 : R.lo2;
-                const int hi_last = R.n == 2 ? R.hi1 : R.hi2;
-                split = lo_last == lo_end && hi_last == n;
+                if (R.n == 0) {
+                    R.n = 1; R.lo0 = lo_end; R.hi0 = n;                  // nothing but the end window
+                } else {
+                    const int lo_last = R.n == 1 ? R.lo0 : (R.n == 2 ? R.lo1 : R.lo2);
+                    const int hi_last = R.n == 1 ? R.hi0 : (R.n == 2 ? R.hi1 : R.hi2);
+                    split = !(lo_last <= lo_end && hi_last == n);
+                }
             }
         } else {
             int max_n = n, min_n = 0;
@@ -1207,9 +1214,8 @@ CG_HD bool split_main_pass(const SetView &S, const uint8_t *p, int n, uint32_t h
         }
     }
     st = loc_state_init(A.m, n);
-    const int n_use = split ? R.n - 1 : R.n;
-    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, n_use, has_task, !split, st);
-    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, n_use, has_task, !split, st);
+    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, !split, st);
+    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, !split, st);
     if (!has_task) return true;
     if (split && !st.stopped) return false;
     hit_from_state(A, n, st, hit);
@@ -1230,8 +1236,8 @@ CG_HD void split_end_pass(const SetView &S, const uint8_t *tail, int n, bool has
     const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
     RunList R;
     R.n = 1; R.lo0 = lo_end; R.hi0 = n; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
-    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st);
-    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st);
+    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st, false);
+    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st, false);
     if (has_task) hit_from_state(A, n, st, hit);
 }
 
