@@ -312,8 +312,8 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
             end_smem = cg_dp_smem_bytes(a.blob_bytes, a.end_slot);
             if (scan_smem <= c->smem_optin && dp_smem <= c->smem_optin && end_smem <= c->smem_optin) {
                 CU(cg_scan_occupancy(want_q, scan_smem, &scan_occ));
-                CU(cg_dp_occupancy(false, dp_smem, &dp_occ));
-                CU(cg_dp_occupancy(true, end_smem, &end_occ));
+                CU(cg_dp_occupancy(false, s->host.max_m, dp_smem, &dp_occ));
+                CU(cg_dp_occupancy(true, s->host.max_m, end_smem, &end_occ));
                 split = scan_occ >= 1 && dp_occ >= 1 && end_occ >= 1;
             }
         }
@@ -365,10 +365,10 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
             CU(cg_launch_scan(b, want_q, (int)grid, scan_smem, st));
             long long dgrid = (long long)dp_occ * c->sm_count;
             dgrid = std::max<long long>(1, std::min<long long>(dgrid, (n_mt + 3) / 4));
-            CU(cg_launch_dp(b, false, (int)dgrid, dp_smem, st));
+            CU(cg_launch_dp(b, false, s->host.max_m, (int)dgrid, dp_smem, st));
             long long egrid = (long long)end_occ * c->sm_count;
             egrid = std::max<long long>(1, std::min<long long>(egrid, (n_mt + 3) / 4));
-            CU(cg_launch_dp(b, true, (int)egrid, end_smem, st));
+            CU(cg_launch_dp(b, true, s->host.max_m, (int)egrid, end_smem, st));
             c->launches += 3;
         }
         c->launches -= 1;    // the common tail below adds one

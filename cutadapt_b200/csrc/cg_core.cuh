@@ -791,16 +791,17 @@ CG_HD void runs_add(RunList &R, int lo, int hi, int n_read)
 // Exact positions of the locator hits -> DP runs (windowed adapters only).  For the first locator
 // word the scan resumes at the start of each hit group from the state phase A saved (rs0, rs1) or
 // carries over from the previous group; otherwise it backs up 31 characters (k-mers are <= 32 long).
-CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
-                       const ReadView &rv, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1, RunList &R,
-                       bool add_end = true)
+// Hits of one stretch of consecutive hit groups are united into one run (their windows overlap or
+// nearly so; a superset of the exact windows is always valid).
+template <bool REV>
+CG_HD void refine_runs_dir(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
+                           const uint8_t *first, int n, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1,
+                           RunList &R, bool add_end)
 {
-    const int n = rv.n, m = A.m, k = A.k;
+    const int m = A.m, k = A.k;
     R.n = 0;
     R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     if (A.flags & 1) runs_add(R, 0, cg_min(n, m + k), n);              // START_IN_REFERENCE
-    const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
-    const int cstride = rv.rev ? -1 : 1;
     if (hits) {
         int n_loc = 0;
         for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
@@ -813,37 +814,54 @@ CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool
             const bool stash = n_loc == 1;
             uint32_t todo = hits, Rr = 0;
             int cur_p = -1, nh = 0;
+            int wlo = 0x3fffffff, whi = -1;                      // window of the current stretch
             while (todo) {
                 const int g = cg_ctz(todo);
                 todo &= todo - 1;
                 const int p_first = g << gs;
                 const long long p_end_ll = ((long long)(g + 1)) << gs;
                 const int p_end = p_end_ll > n ? n : (int)p_end_ll;
-                int p = p_first;
-                if (cur_p == p_first) {
-                    // continues the previous group: Rr is already the state at p_first
-                } else if (stash && nh < 2) {
-                    Rr = nh == 0 ? rs0 : rs1;
-                } else {
-                    Rr = 0;
-                    for (int q = cg_max(0, p_first - 31); q < p_first; ++q)
-                        Rr = ((Rr << 1) | init) & mask[cp[cstride * q] & 127];
+                if (cur_p != p_first) {
+                    if (whi >= 0) { runs_add(R, wlo, whi, n); wlo = 0x3fffffff; whi = -1; }
+                    if (stash && nh < 2) {
+                        Rr = nh == 0 ? rs0 : rs1;
+                    } else {
+                        Rr = 0;
+                        const int q0 = cg_max(0, p_first - 31);
+                        const uint8_t *q = first + (REV ? -q0 : q0);
+                        for (int i = q0; i < p_first; ++i) {
+                            Rr = ((Rr << 1) | init) & mask[*q];
+                            q += REV ? -1 : 1;
+                        }
+                    }
                 }
                 ++nh;
-                for (; p < p_end; ++p) {
-                    Rr = ((Rr << 1) | init) & mask[cp[cstride * p] & 127];
+                const uint8_t *q = first + (REV ? -p_first : p_first);
+                for (int p = p_first; p < p_end; ++p) {
+                    Rr = ((Rr << 1) | init) & mask[*q];
+                    q += REV ? -1 : 1;
                     uint32_t f = Rr & locf;
                     while (f) {
                         const int b = cg_ctz(f);
                         f &= f - 1;
-                        runs_add(R, p + 1 - (int)ltab[2 * b + 1] - k, p + 1 - (int)ltab[2 * b] + m + k, n);
+                        wlo = cg_min(wlo, p + 1 - (int)ltab[2 * b + 1] - k);
+                        whi = cg_max(whi, p + 1 - (int)ltab[2 * b] + m + k);
                     }
                 }
                 cur_p = p_end;
             }
+            if (whi >= 0) runs_add(R, wlo, whi, n);
         }
     }
     if (add_end && (A.flags & 4)) runs_add(R, cg_max(0, n - 1 - m - k), n, n);      // STOP_IN_REFERENCE
+}
+
+CG_HD void refine_runs(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
+                       const ReadView &rv, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1, RunList &R,
+                       bool add_end = true)
+{
+    if (rv.rev) refine_runs_dir<true>(words, n_words, pool, A, rv.p + (rv.n - 1), rv.n, hits, gs, rs0, rs1, R, add_end);
+    else refine_runs_dir<false>(words, n_words, pool, A, rv.p, rv.n, hits, gs, rs0, rs1, R, add_end);
 }
 
 // Phase A for the register path: the fused scan with the locator hits turned into DP runs on
@@ -1179,6 +1197,7 @@ CG_HD void hit_from_state(const CgAdapter &A, int n, const LocState &st, CgHit &
 
 // Main pass.  Returns true when the read is finished (hit is valid); false when its end window is
 // still to be done (st carries the selection state).  ALL lanes of a warp must call it.
+template <int MR>
 CG_HD bool split_main_pass(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs, uint32_t rs0,
                            uint32_t rs1, bool has_task, CgHit &hit, LocState &st)
 {
@@ -1214,8 +1233,7 @@ CG_HD bool split_main_pass(const SetView &S, const uint8_t *p, int n, uint32_t h
         }
     }
     st = loc_state_init(A.m, n);
-    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, !split, st);
-    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, !split, st);
+    locate_regs<MR>(A, ncnt, maxcost, peq, rv, R, R.n, has_task, !split, st);
     if (!has_task) return true;
     if (split && !st.stopped) return false;
     hit_from_state(A, n, st, hit);
@@ -1224,6 +1242,7 @@ CG_HD bool split_main_pass(const SetView &S, const uint8_t *p, int n, uint32_t h
 
 // End pass: `tail` points at the first byte that was fetched for the end window (read orientation:
 // forward reads: byte lo_end of the trimmed read; reversed reads: byte 0).
+template <int MR>
 CG_HD void split_end_pass(const SetView &S, const uint8_t *tail, int n, bool has_task, LocState &st, CgHit &hit)
 {
     const CgAdapter &A = S.ad[0];
@@ -1236,8 +1255,7 @@ CG_HD void split_end_pass(const SetView &S, const uint8_t *tail, int n, bool has
     const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
     RunList R;
     R.n = 1; R.lo0 = lo_end; R.hi0 = n; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
-    if (A.m <= 16) locate_regs<16>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st, false);
-    else locate_regs<32>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st, false);
+    locate_regs<MR>(A, ncnt, maxcost, peq, rv, R, 1, has_task, true, st, false);
     if (has_task) hit_from_state(A, n, st, hit);
 }
 
@@ -1255,10 +1273,15 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
         const ScanOut sc3 = simple_scan(S, seq + s, e - s, &gs3);
         if (sc3.pass) {
             LocState st;
-            if (!split_main_pass(S, seq + s, e - s, sc3.hits, gs3, sc3.rs0, sc3.rs1, true, hit, st)) {
-                const CgAdapter &A = S.ad[0];
-                const int nn = e - s, lo_end = cg_max(0, nn - 1 - A.m - A.k);
-                split_end_pass(S, A.reverse ? seq + s : seq + s + lo_end, nn, true, st, hit);
+            const CgAdapter &A = S.ad[0];
+            const int nn = e - s, lo_end = cg_max(0, nn - 1 - A.m - A.k);
+            const uint8_t *tail = A.reverse ? seq + s : seq + s + lo_end;
+            if (A.m <= 16) {
+                if (!split_main_pass<16>(S, seq + s, nn, sc3.hits, gs3, sc3.rs0, sc3.rs1, true, hit, st))
+                    split_end_pass<16>(S, tail, nn, true, st, hit);
+            } else {
+                if (!split_main_pass<32>(S, seq + s, nn, sc3.hits, gs3, sc3.rs0, sc3.rs1, true, hit, st))
+                    split_end_pass<32>(S, tail, nn, true, st, hit);
             }
         }
         store_hit(out, hit, 0, e - s);

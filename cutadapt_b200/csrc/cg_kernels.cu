@@ -750,7 +750,7 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 //              ({r_lo, r_hi, trim_start, length}, {have, origin, cost, score}, {ref_stop, q_stop, 0, 0}).
 // END = true : end-window pass over the continuation list; only the last m+k+1 characters of the
 //              read are fetched.
-template <bool END>
+template <bool END, int MR>
 __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -846,9 +846,9 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
         if (END) {
             ls.have = (int)tb.x; ls.b_origin = (int)tb.y; ls.b_cost = (int)tb.z; ls.b_score = (int)tb.w;
             ls.b_ref_stop = (int)tc.x; ls.b_q_stop = (int)tc.y; ls.stopped = 0;
-            split_end_pass(S, p, n, has_task, ls, hit);
+            split_end_pass<MR>(S, p, n, has_task, ls, hit);
         } else {
-            done = split_main_pass(S, p, n, tb.x, (int)tb.y, tb.z, tb.w, has_task, hit, ls);
+            done = split_main_pass<MR>(S, p, n, tb.x, (int)tb.y, tb.z, tb.w, has_task, hit, ls);
         }
         if (has_task && done) {
             const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
@@ -873,17 +873,22 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
     }
 }
 
-cudaError_t cg_dp_occupancy(bool end_pass, size_t smem, int *blocks_per_sm)
+typedef void (*dp_kernel_t)(const CgKernelArgs);
+static dp_kernel_t pick_dp(bool end_pass, int mr)
 {
-    void (*k)(const CgKernelArgs) = end_pass ? cg_dp_kernel<true> : cg_dp_kernel<false>;
+    if (mr <= 16) return end_pass ? cg_dp_kernel<true, 16> : cg_dp_kernel<false, 16>;
+    return end_pass ? cg_dp_kernel<true, 32> : cg_dp_kernel<false, 32>;
+}
+cudaError_t cg_dp_occupancy(bool end_pass, int mr, size_t smem, int *blocks_per_sm)
+{
+    dp_kernel_t k = pick_dp(end_pass, mr);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, CG_NT, smem);
 }
-cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int grid, size_t smem, cudaStream_t st)
+cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int mr, int grid, size_t smem, cudaStream_t st)
 {
-    if (end_pass) cg_dp_kernel<true><<<grid, CG_NT, smem, st>>>(a);
-    else cg_dp_kernel<false><<<grid, CG_NT, smem, st>>>(a);
+    pick_dp(end_pass, mr)<<<grid, CG_NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -53,8 +53,8 @@ size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
 cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
 size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes);
-cudaError_t cg_dp_occupancy(bool end_pass, size_t smem, int *blocks_per_sm);
-cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int grid, size_t smem, cudaStream_t st);
+cudaError_t cg_dp_occupancy(bool end_pass, int mr, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int mr, int grid, size_t smem, cudaStream_t st);
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
 cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
                                     const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,
