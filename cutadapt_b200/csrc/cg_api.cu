@@ -106,7 +106,7 @@ struct cg_ctx {
     DevBuf<uint32_t> scratch_p;
     DevBuf<int> scratch_w;
     DevBuf<uint4> tasks;                 // split pipeline: 2 x uint4 per read of a sub-batch
-    DevBuf<uint4> tasks2;                // continuation list: 3 x uint4 per read of a sub-batch
+    DevBuf<uint4> tasks2, tasks3;        // run-record lists (ping-pong): 4 x uint4 per read of a sub-batch
     unsigned long long *d_task_count = nullptr;
     long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // fused-kernel event pairs
@@ -181,7 +181,7 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
         l.h_seq.release(); l.h_qual.release(); l.h_offs.release(); l.h_out.release(); l.h_qtrim.release();
         if (l.stream) cudaStreamDestroy(l.stream);
     }
-    c->scratch_p.release(); c->scratch_w.release(); c->tasks.release(); c->tasks2.release();
+    c->scratch_p.release(); c->scratch_w.release(); c->tasks.release(); c->tasks2.release(); c->tasks3.release();
     if (c->d_task_count) cudaFree(c->d_task_count);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_enc) cudaFree(c->d_enc);
@@ -299,22 +299,20 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
     const bool force_block = kernel_env && strcmp(kernel_env, "block") == 0;
     const bool force_warp = kernel_env && strcmp(kernel_env, "warp") == 0;
     bool split = false;
-    size_t scan_smem = 0, dp_smem = 0, end_smem = 0;
-    int scan_occ = 0, dp_occ = 0, end_occ = 0;
+    size_t scan_smem = 0, list_smem = 0;
+    int scan_occ = 0, plan_occ = 0, run_occ = 0;
     if (simple && s->host.max_m <= 32 && !force_block && !force_warp) {
         const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
         const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
         if (mini < (1 << 20)) {
             a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
             scan_smem = cg_scan_smem_bytes(a.blob_bytes, a.mini_cap, want_q);
-            a.end_slot = (s->host.max_m + CG_PACKED_MAX_K + 1 + 15) / 16 * 16 + 16;
-            dp_smem = cg_dp_smem_bytes(a.blob_bytes, a.carry_slot);
-            end_smem = cg_dp_smem_bytes(a.blob_bytes, a.end_slot);
-            if (scan_smem <= c->smem_optin && dp_smem <= c->smem_optin && end_smem <= c->smem_optin) {
+            list_smem = cg_dp_smem_bytes(a.blob_bytes, a.carry_slot);
+            if (scan_smem <= c->smem_optin && list_smem <= c->smem_optin) {
                 CU(cg_scan_occupancy(want_q, scan_smem, &scan_occ));
-                CU(cg_dp_occupancy(false, s->host.max_m, dp_smem, &dp_occ));
-                CU(cg_dp_occupancy(true, s->host.max_m, end_smem, &end_occ));
-                split = scan_occ >= 1 && dp_occ >= 1 && end_occ >= 1;
+                CU(cg_list_occupancy(true, s->host.max_m, list_smem, &plan_occ));
+                CU(cg_list_occupancy(false, s->host.max_m, list_smem, &run_occ));
+                split = scan_occ >= 1 && plan_occ >= 1 && run_occ >= 1;
             }
         }
     }
@@ -343,33 +341,40 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         CU(cudaEventRecord(ev0, st));
     }
     if (split) {
-        const long long SUB = 8LL << 20;      // reads per sub-batch: bounds the task list to 256 MiB
-        int rc = c->tasks.ensure((size_t)std::min<long long>(n_reads, SUB) * 2);
+        // scan -> plan -> up to four DP rounds (one run of every unfinished read per round)
+        const long long SUB = 4LL << 20;      // reads per sub-batch: bounds the lists to 128 + 2 x 256 MiB
+        const long long cap = std::min<long long>(n_reads, SUB);
+        int rc = c->tasks.ensure((size_t)cap * 2);
+        if (rc == CG_OK) rc = c->tasks2.ensure((size_t)cap * 4);
+        if (rc == CG_OK) rc = c->tasks3.ensure((size_t)cap * 4);
         if (rc != CG_OK) return rc;
-        rc = c->tasks2.ensure((size_t)std::min<long long>(n_reads, SUB) * 3);
-        if (rc != CG_OK) return rc;
-        a.tasks = c->tasks.p; a.task_count = c->d_task_count;
-        a.tasks2 = c->tasks2.p; a.task2_count = c->d_task_count + 1;
+        unsigned long long *cnt = c->d_task_count;
         for (long long r0 = 0; r0 < n_reads; r0 += SUB) {
-            const long long cnt = std::min<long long>(SUB, n_reads - r0);
+            const long long n_sub = std::min<long long>(SUB, n_reads - r0);
             CgKernelArgs b = a;
             b.offsets = a.offsets + r0;
-            b.n_reads = cnt;
+            b.n_reads = n_sub;
             b.out = a.out + (size_t)r0 * a.times * a.slots;
             b.qtrim = a.qtrim ? a.qtrim + 2 * r0 : nullptr;
-            b.task_cap = cnt;
-            CU(cudaMemsetAsync(c->d_task_count, 0, 2 * sizeof(unsigned long long), st));
-            const long long n_mt = (cnt + 31) / 32;
-            long long grid = (long long)scan_occ * c->sm_count;
-            grid = std::max<long long>(1, std::min<long long>(grid, (n_mt + 3) / 4));
-            CU(cg_launch_scan(b, want_q, (int)grid, scan_smem, st));
-            long long dgrid = (long long)dp_occ * c->sm_count;
-            dgrid = std::max<long long>(1, std::min<long long>(dgrid, (n_mt + 3) / 4));
-            CU(cg_launch_dp(b, false, s->host.max_m, (int)dgrid, dp_smem, st));
-            long long egrid = (long long)end_occ * c->sm_count;
-            egrid = std::max<long long>(1, std::min<long long>(egrid, (n_mt + 3) / 4));
-            CU(cg_launch_dp(b, true, s->host.max_m, (int)egrid, end_smem, st));
-            c->launches += 3;
+            b.task_cap = n_sub;
+            CU(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), st));
+            const long long n_mt = (n_sub + 31) / 32;
+            const long long need = (n_mt + 3) / 4;
+            auto grid_for = [&](int occ) { return (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, need)); };
+            b.tasks = c->tasks.p; b.task_count = cnt;
+            CU(cg_launch_scan(b, want_q, grid_for(scan_occ), scan_smem, st));
+            b.tasks2 = c->tasks2.p; b.task2_count = cnt + 1;
+            CU(cg_launch_list(b, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
+            c->launches += 2;
+            uint4 *lists[2] = {c->tasks2.p, c->tasks3.p};
+            for (int round = 0; round < 4; ++round) {
+                const int in = round & 1, outl = in ^ 1;
+                if (round > 0) CU(cudaMemsetAsync(cnt + 1 + outl, 0, sizeof(unsigned long long), st));
+                b.tasks = lists[in]; b.task_count = cnt + 1 + in;
+                b.tasks2 = lists[outl]; b.task2_count = cnt + 1 + outl;
+                CU(cg_launch_list(b, false, s->host.max_m, grid_for(run_occ), list_smem, st));
+                c->launches += 1;
+            }
         }
         c->launches -= 1;    // the common tail below adds one
     } else if (warpk) {

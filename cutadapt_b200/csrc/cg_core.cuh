@@ -1308,3 +1308,200 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
 
 
 
+
+// ---------------------------------------------------------------------------------------
+// Planned scheduling (split pipeline v2): scan -> plan (refine + classify) -> one DP run per round.
+//
+//  plan_runs()   exact end positions of the locator hits -> up to three hit runs (+ the end window
+//                of 3' adapters as a separate last run unless a hit run covers it).
+//                Exact-occurrence shortcut: if in the leftmost hit stretch every chunk of the adapter
+//                ends at the position implied by one common start s0, and s0 is the smallest start
+//                any hit of that stretch implies, the read contains the adapter exactly at s0 and the
+//                reference would stop there with (0, m, s0, s0+m, m, 0): every earlier bottom-row
+//                candidate contains a hit of this stretch, so it starts at >= s0 - k >= s0 - m/2 and
+//                scores < m, hence is replaced at column s0+m and the exact match ends the search
+//                (_align.pyx:521-533).  No DP is needed for such reads.
+//  run_pass<MR>  one run of one read with the selection state carried in LocState.
+// ---------------------------------------------------------------------------------------
+struct RunPlan {
+    int n_runs;                    // 0..4
+    int lo0, hi0, lo1, hi1, lo2, hi2, lo3, hi3;
+    int end_idx;                   // index of the pure end-window run (no bottom-row candidates), or -1
+    int exact;                     // 1: finished by the exact-occurrence shortcut at start s0
+    int s0;
+};
+
+template <bool REV>
+CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
+                             const uint8_t *first, int n, uint32_t hits, int gs, uint32_t rs0, uint32_t rs1,
+                             bool want_exact, RunList &R, int &exact, int &s0_out)
+{
+    const int m = A.m, k = A.k;
+    R.n = 0;
+    R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    exact = 0; s0_out = 0;
+    if (A.flags & 1) runs_add(R, 0, cg_min(n, m + k), n);              // START_IN_REFERENCE
+    if (!hits) return;
+    int n_loc = 0;
+    for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
+    for (int w = 0; w < n_words; ++w) {
+        const CgScanWord &W = words[w];
+        if (W.type != CG_SCAN_WHOLE || !W.loc_found) continue;
+        const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
+        const uint8_t *ltab = pool + W.loc_off;
+        const uint32_t init = W.init, locf = W.loc_found;
+        const bool stash = n_loc == 1;
+        uint32_t todo = hits, Rr = 0;
+        int cur_p = -1, nh = 0, stretch = 0;
+        int wlo = 0x3fffffff, whi = -1;
+        int s0 = 0x3fffffff;           // smallest implied start in the first stretch ...
+        uint32_t fm = 0;               // ... and the chunks (found bits) that imply exactly s0
+        while (todo) {
+            const int g = cg_ctz(todo);
+            todo &= todo - 1;
+            const int p_first = g << gs;
+            const long long p_end_ll = ((long long)(g + 1)) << gs;
+            const int p_end = p_end_ll > n ? n : (int)p_end_ll;
+            if (cur_p != p_first) {
+                if (whi >= 0) { runs_add(R, wlo, whi, n); wlo = 0x3fffffff; whi = -1; ++stretch; }
+                if (stash && nh < 2) {
+                    Rr = nh == 0 ? rs0 : rs1;
+                } else {
+                    Rr = 0;
+                    const int q0 = cg_max(0, p_first - 31);
+                    const uint8_t *q = first + (REV ? -q0 : q0);
+                    for (int i = q0; i < p_first; ++i) {
+                        Rr = ((Rr << 1) | init) & mask[*q];
+                        q += REV ? -1 : 1;
+                    }
+                }
+            }
+            ++nh;
+            const uint8_t *q = first + (REV ? -p_first : p_first);
+            for (int p = p_first; p < p_end; ++p) {
+                Rr = ((Rr << 1) | init) & mask[*q];
+                q += REV ? -1 : 1;
+                uint32_t f = Rr & locf;
+                while (f) {
+                    const int b = cg_ctz(f);
+                    f &= f - 1;
+                    const int bmin = ltab[2 * b], bmax = ltab[2 * b + 1];
+                    wlo = cg_min(wlo, p + 1 - bmax - k);
+                    whi = cg_max(whi, p + 1 - bmin + m + k);
+                    if (stretch == 0) {
+                        const int s = p + 1 - bmin;
+                        if (s < s0) { s0 = s; fm = 1u << b; }
+                        else if (s == s0) fm |= 1u << b;
+                    }
+                }
+            }
+            cur_p = p_end;
+        }
+        if (whi >= 0) runs_add(R, wlo, whi, n);
+        if (want_exact && fm == locf && s0 >= 0 && s0 + m <= n) { exact = 1; s0_out = s0; }
+    }
+}
+
+CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs, uint32_t rs0,
+                     uint32_t rs1, RunPlan &P)
+{
+    const CgAdapter &A = S.ad[0];
+    P.n_runs = 0; P.lo0 = P.hi0 = P.lo1 = P.hi1 = P.lo2 = P.hi2 = P.lo3 = P.hi3 = 0;
+    P.end_idx = -1; P.exact = 0; P.s0 = 0;
+    if (!simple_windowed(S, n)) {
+        // plain: one run over the reference's column range (_align.pyx:346-352)
+        int max_n = n, min_n = 0;
+        if (!(A.flags & 2)) max_n = cg_min(n, A.m + A.k);
+        if (!(A.flags & 8)) min_n = cg_max(0, n - A.m - A.k);
+        P.n_runs = 1; P.lo0 = min_n; P.hi0 = max_n;
+        return;
+    }
+    RunList R;
+    const bool want_exact = S.h->exact_ok != 0;
+    if (A.reverse) plan_hit_runs_dir<true>(S.scan, S.h->scan_count, S.pool, A, p + (n - 1), n, hits, gs, rs0, rs1, want_exact, R, P.exact, P.s0);
+    else plan_hit_runs_dir<false>(S.scan, S.h->scan_count, S.pool, A, p, n, hits, gs, rs0, rs1, want_exact, R, P.exact, P.s0);
+    if (P.exact) return;
+    P.n_runs = R.n; P.lo0 = R.lo0; P.hi0 = R.hi0; P.lo1 = R.lo1; P.hi1 = R.hi1; P.lo2 = R.lo2; P.hi2 = R.hi2;
+    if (A.flags & 4) {                                           // STOP_IN_REFERENCE: last-column scan
+        const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+        bool covered = false;
+        if (R.n > 0) {
+            const int lo_last = R.n == 1 ? R.lo0 : (R.n == 2 ? R.lo1 : R.lo2);
+            const int hi_last = R.n == 1 ? R.hi0 : (R.n == 2 ? R.hi1 : R.hi2);
+            covered = lo_last <= lo_end && hi_last == n;
+        }
+        if (!covered) {
+            // every bottom-row cell with cost <= k lies inside a hit run, so the separate end window
+            // has none to evaluate
+            P.end_idx = R.n;
+            if (R.n == 0) { P.lo0 = lo_end; P.hi0 = n; }
+            else if (R.n == 1) { P.lo1 = lo_end; P.hi1 = n; }
+            else if (R.n == 2) { P.lo2 = lo_end; P.hi2 = n; }
+            else { P.lo3 = lo_end; P.hi3 = n; }
+            P.n_runs = R.n + 1;
+        }
+    }
+}
+
+CG_HD void hit_exact(const CgAdapter &A, int n, int s0, CgHit &hit)
+{
+    // (0, m, s0, s0 + m, m, 0), mirrored for reversed reads like adapters.py:777-785
+    hit.adapter = 0;
+    if (A.reverse) { hit.astart = 0; hit.astop = A.m; hit.rstart = n - (s0 + A.m); hit.rstop = n - s0; }
+    else { hit.astart = 0; hit.astop = A.m; hit.rstart = s0; hit.rstop = s0 + A.m; }
+    hit.score = A.m; hit.errors = 0;
+    hit.remove = A.remove == CGK_REMOVE_AUTO ? (hit.rstart == 0 ? CGK_REMOVE_BEFORE : CGK_REMOVE_AFTER)
+                                            : A.remove;
+}
+
+// One run [lo, hi] of one read.  `bytes` points at the first fetched byte: read-orientation bytes
+// [lo, hi) for forward reads, [n - hi, n - lo) for reversed reads.  ALL lanes of a warp must call it.
+template <int MR>
+CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int hi, bool eval_bottom,
+                    bool final_scan, bool has_task, LocState &st)
+{
+    const CgAdapter &A = S.ad[0];
+    ReadView rv;
+    rv.n = n; rv.rev = A.reverse;
+    rv.p = A.reverse ? bytes - (n - hi) : bytes - lo;
+    const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+    const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+    const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+    RunList R;
+    R.n = 1; R.lo0 = lo; R.hi0 = hi; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    locate_regs<MR>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
+}
+
+// Host-sim driver of the planned scheduling for one read (tests/hostsim, mode 64).
+CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
+                                int quality_trim, int cutoff_front, int cutoff_back, int qbase,
+                                cg_match_rec *out, int32_t *qtrim_out)
+{
+    int s = 0, e = n;
+    if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
+    if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
+    CgHit hit; hit.adapter = -1; hit.remove = 0;
+    hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+    const CgAdapter &A = S.ad[0];
+    const int nn = e - s;
+    int gs;
+    const ScanOut sc = simple_scan(S, seq + s, nn, &gs);
+    if (sc.pass) {
+        RunPlan P;
+        plan_runs(S, seq + s, nn, sc.hits, gs, sc.rs0, sc.rs1, P);
+        if (P.exact) hit_exact(A, nn, P.s0, hit);
+        else {
+            LocState st = loc_state_init(A.m, nn);
+            for (int r = 0; r < P.n_runs && !st.stopped; ++r) {
+                const int lo = r == 0 ? P.lo0 : (r == 1 ? P.lo1 : (r == 2 ? P.lo2 : P.lo3));
+                const int hi = r == 0 ? P.hi0 : (r == 1 ? P.hi1 : (r == 2 ? P.hi2 : P.hi3));
+                const uint8_t *bytes = A.reverse ? seq + s + (nn - hi) : seq + s + lo;
+                const bool last = r == P.n_runs - 1;
+                if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+                else run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+            }
+            hit_from_state(A, nn, st, hit);
+        }
+    }
+    store_hit(out, hit, 0, nn);
+}

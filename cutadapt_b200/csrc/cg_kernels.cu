@@ -744,17 +744,24 @@ __host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int slot_b
 }
 size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_layout(blob_bytes, slot_bytes).total; }
 
-// END = false: main pass over the scan kernel's task list (2 x uint4 per task:
-//              {r_lo, r_hi, trim_start, length}, {hits, gs, rs0, rs1}); reads whose end window is a
-//              separate run and that did not stop early append a continuation
-//              ({r_lo, r_hi, trim_start, length}, {have, origin, cost, score}, {ref_stop, q_stop, 0, 0}).
-// END = true : end-window pass over the continuation list; only the last m+k+1 characters of the
-//              read are fetched.
-template <bool END, int MR>
-__global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
+// Common frame of the list-driven kernels: a warp walks groups of 32 list records; every lane
+// fetches the bytes its record needs into its own shared-memory slot with its own TMA bulk copy
+// (SASS: one UBLKCP per lane, one mbarrier per stage), double buffered against the work on the
+// previous group.
+//
+//  PLAN = true  (cg_plan_kernel): input = the scan kernel's list (2 x uint4).  Exact end positions of
+//               the locator hits -> runs; reads finished by the exact-occurrence shortcut get their
+//               record, the others append a run record (4 x uint4) for the DP rounds:
+//               {r_lo, r_hi, trim_start, len}, {have, origin, cost, score},
+//               {ref_stop, q_stop, run_idx, n_runs | end_idx << 8}, {lo|hi<<16 of up to 4 runs}
+//  PLAN = false (cg_run_kernel<MR>): one DP run of every record of the input list; reads that are
+//               finished (early exit or last run) get their record, the others move to the output
+//               list with the updated selection state.
+template <bool PLAN, int MR>
+__global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : 3)) cg_list_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int slot_bytes = END ? a.end_slot : a.carry_slot;
+    const int slot_bytes = a.carry_slot;
     const DpSmem L = dp_smem_layout(a.blob_bytes, slot_bytes);
     uint8_t *s_blob = smem + L.blob_off;
     uint8_t *s_enc = smem + L.enc_off;
@@ -774,34 +781,33 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
     const SetView S = make_set_view(s_blob, a.masks64, s_enc);
     const CgAdapter &A = S.ad[0];
 
-    unsigned long long n_tasks = END ? *a.task2_count : *a.task_count;
+    unsigned long long n_tasks = *a.task_count;
     if (n_tasks > (unsigned long long)a.task_cap) n_tasks = (unsigned long long)a.task_cap;
-    const uint4 *list = END ? a.tasks2 : a.tasks;
-    const int rec = END ? 3 : 2;
+    const uint4 *list = a.tasks;
+    const int rec = PLAN ? 2 : 4;
     const long long n_groups = (long long)((n_tasks + 31) / 32);
     const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
     const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
     const uintptr_t seq_base = (uintptr_t)a.seq;
 
-    // Fetch: every lane copies the bytes its task needs into its slot of stage `st` with its own
-    // TMA bulk copy; one mbarrier per stage collects all 32 copies.
-    auto fetch = [&](long long g, int st, uint4 &ta, uint4 &tb, uint4 &tc, uint32_t &soff) {
+    auto fetch = [&](long long g, int st, uint4 &ta, uint4 &tb, uint4 &tc, uint4 &td, uint32_t &soff) {
         const unsigned long long t = (unsigned long long)g * 32 + lane;
         const bool has = t < n_tasks;
         uint32_t bytes = 0;
         uintptr_t src = 0;
-        ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0); tc = make_uint4(0, 0, 0, 0);
+        ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0); tc = make_uint4(0, 0, 0, 0); td = make_uint4(0, 0, 0, 0);
         if (has) {
             ta = list[rec * t]; tb = list[rec * t + 1];
-            if (END) tc = list[rec * t + 2];
+            if (!PLAN) { tc = list[rec * t + 2]; td = list[rec * t + 3]; }
             const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
             uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + ta.z;
             uint32_t len = ta.w;
-            if (END) {
-                const int n = (int)ta.w;
-                const int lo_end = cg_max(0, n - 1 - A.m - A.k);
-                len = (uint32_t)(n - lo_end);
-                if (!A.reverse) addr += (uintptr_t)lo_end;
+            if (!PLAN) {
+                const int n = (int)ta.w, ri = (int)tc.z;
+                const uint32_t pk = ri == 0 ? td.x : (ri == 1 ? td.y : (ri == 2 ? td.z : td.w));
+                const int lo = (int)(pk & 0xffffu), hi = (int)(pk >> 16);
+                len = (uint32_t)(hi - lo);
+                addr += (uintptr_t)(A.reverse ? n - hi : lo);
             }
             src = addr & ~(uintptr_t)15;
             bytes = len ? (uint32_t)(((addr + len + 15) & ~(uintptr_t)15) - src) : 0u;
@@ -818,19 +824,19 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
     };
 
     uint32_t phase0 = 0, phase1 = 0;
-    uint4 ta_n = make_uint4(0, 0, 0, 0), tb_n = make_uint4(0, 4, 0, 0), tc_n = make_uint4(0, 0, 0, 0);
+    uint4 ta_n, tb_n, tc_n, td_n;
     uint32_t soff_n = 0;
     bool loaded_n = false;
-    if (wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, tc_n, soff_n);
+    if (wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, tc_n, td_n, soff_n);
     int it = 0;
     for (long long g = wg; g < n_groups; g += warps_total, ++it) {
         const int st = it & 1;
-        const uint4 ta = ta_n, tb = tb_n, tc = tc_n;
+        const uint4 ta = ta_n, tb = tb_n, tc = tc_n, td = td_n;
         const uint32_t soff = soff_n;
         const bool loaded = loaded_n;
-        const long long gn = g + warps_total;          // prefetch the next group into the other stage
+        const long long gn = g + warps_total;
         loaded_n = false;
-        if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, tc_n, soff_n);
+        if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, tc_n, td_n, soff_n);
         if (loaded) {
             if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
             else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
@@ -838,57 +844,79 @@ __global__ void __launch_bounds__(CG_NT, 4) cg_dp_kernel(const CgKernelArgs a)
         const bool has_task = (unsigned long long)g * 32 + lane < n_tasks;
         const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * slot_bytes + soff;
         const int n = (int)ta.w;
+        const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
         CgHit hit;
         hit.adapter = -1; hit.remove = 0;
         hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
-        bool done = true;
-        LocState ls;
-        if (END) {
+        bool cont = false;
+        uint4 ob = make_uint4(0, 0, 0, 0), oc = make_uint4(0, 0, 0, 0), od = make_uint4(0, 0, 0, 0);
+        if (PLAN) {
+            if (has_task) {
+                RunPlan P;
+                plan_runs(S, p, n, tb.x, (int)tb.y, tb.z, tb.w, P);
+                if (P.exact) hit_exact(A, n, P.s0, hit);
+                else if (P.n_runs > 0) {
+                    cont = true;
+                    oc = make_uint4((uint32_t)A.m, (uint32_t)n, 0u, (uint32_t)P.n_runs | ((uint32_t)(P.end_idx & 15) << 8));
+                    od = make_uint4((uint32_t)P.lo0 | ((uint32_t)P.hi0 << 16), (uint32_t)P.lo1 | ((uint32_t)P.hi1 << 16),
+                                    (uint32_t)P.lo2 | ((uint32_t)P.hi2 << 16), (uint32_t)P.lo3 | ((uint32_t)P.hi3 << 16));
+                }
+            }
+        } else {
+            const int ri = (int)tc.z, n_runs = (int)(tc.w & 255u);
+            int end_idx = (int)((tc.w >> 8) & 15u);
+            if (end_idx == 15) end_idx = -1;
+            const uint32_t pk = ri == 0 ? td.x : (ri == 1 ? td.y : (ri == 2 ? td.z : td.w));
+            const int lo = (int)(pk & 0xffffu), hi = (int)(pk >> 16);
+            LocState ls;
             ls.have = (int)tb.x; ls.b_origin = (int)tb.y; ls.b_cost = (int)tb.z; ls.b_score = (int)tb.w;
             ls.b_ref_stop = (int)tc.x; ls.b_q_stop = (int)tc.y; ls.stopped = 0;
-            split_end_pass<MR>(S, p, n, has_task, ls, hit);
-        } else {
-            done = split_main_pass<MR>(S, p, n, tb.x, (int)tb.y, tb.z, tb.w, has_task, hit, ls);
-        }
-        if (has_task && done) {
-            const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
-            store_hit(a.out + (size_t)r * a.slots, hit, 0, n);
-        }
-        if (!END) {
-            const bool cont = has_task && !done;
-            const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
-            if (ballot) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.task2_count, (unsigned long long)__popc(ballot));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (cont) {
-                    const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-                    a.tasks2[3 * slot] = ta;
-                    a.tasks2[3 * slot + 1] = make_uint4((uint32_t)ls.have, (uint32_t)ls.b_origin, (uint32_t)ls.b_cost, (uint32_t)ls.b_score);
-                    a.tasks2[3 * slot + 2] = make_uint4((uint32_t)ls.b_ref_stop, (uint32_t)ls.b_q_stop, 0u, 0u);
+            const bool last = ri == n_runs - 1;
+            run_pass<MR>(S, p, n, lo, hi, ri != end_idx, last, has_task, ls);
+            if (has_task) {
+                if (ls.stopped || last) hit_from_state(A, n, ls, hit);
+                else {
+                    cont = true;
+                    ob = make_uint4((uint32_t)ls.have, (uint32_t)ls.b_origin, (uint32_t)ls.b_cost, (uint32_t)ls.b_score);
+                    oc = make_uint4((uint32_t)ls.b_ref_stop, (uint32_t)ls.b_q_stop, (uint32_t)(ri + 1), tc.w);
+                    od = td;
                 }
+            }
+        }
+        if (has_task && !cont) store_hit(a.out + (size_t)r * a.slots, hit, 0, n);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
+        if (ballot) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.task2_count, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (cont) {
+                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                a.tasks2[4 * slot] = ta;
+                a.tasks2[4 * slot + 1] = ob;
+                a.tasks2[4 * slot + 2] = oc;
+                a.tasks2[4 * slot + 3] = od;
             }
         }
         __syncwarp();
     }
 }
 
-typedef void (*dp_kernel_t)(const CgKernelArgs);
-static dp_kernel_t pick_dp(bool end_pass, int mr)
+typedef void (*list_kernel_t)(const CgKernelArgs);
+static list_kernel_t pick_list(bool plan, int mr)
 {
-    if (mr <= 16) return end_pass ? cg_dp_kernel<true, 16> : cg_dp_kernel<false, 16>;
-    return end_pass ? cg_dp_kernel<true, 32> : cg_dp_kernel<false, 32>;
+    if (plan) return cg_list_kernel<true, 16>;
+    return mr <= 16 ? cg_list_kernel<false, 16> : cg_list_kernel<false, 32>;
 }
-cudaError_t cg_dp_occupancy(bool end_pass, int mr, size_t smem, int *blocks_per_sm)
+cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm)
 {
-    dp_kernel_t k = pick_dp(end_pass, mr);
+    list_kernel_t k = pick_list(plan, mr);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, CG_NT, smem);
 }
-cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int mr, int grid, size_t smem, cudaStream_t st)
+cudaError_t cg_launch_list(const CgKernelArgs &a, bool plan, int mr, int grid, size_t smem, cudaStream_t st)
 {
-    pick_dp(end_pass, mr)<<<grid, CG_NT, smem, st>>>(a);
+    pick_list(plan, mr)<<<grid, CG_NT, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -34,9 +34,8 @@ struct CgKernelArgs {
     uint4 *tasks;                     // 2 x uint4 per task
     unsigned long long *task_count;   // number of tasks appended by the scan kernel
     long long task_cap;
-    uint4 *tasks2;                    // continuation list (end windows): 3 x uint4 per task
+    uint4 *tasks2;                    // output list of the plan / run kernels: 4 x uint4 per record
     unsigned long long *task2_count;
-    int end_slot;                     // bytes per staged end window (multiple of 16)
     // generic-kernel scratch
     uint32_t *scratch_p;
     int *scratch_w;
@@ -53,8 +52,8 @@ size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
 cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
 size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes);
-cudaError_t cg_dp_occupancy(bool end_pass, int mr, size_t smem, int *blocks_per_sm);
-cudaError_t cg_launch_dp(const CgKernelArgs &a, bool end_pass, int mr, int grid, size_t smem, cudaStream_t st);
+cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_list(const CgKernelArgs &a, bool plan, int mr, int grid, size_t smem, cudaStream_t st);
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
 cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
                                     const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,

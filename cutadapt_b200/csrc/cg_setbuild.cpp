@@ -154,7 +154,7 @@ void pack_words(const std::vector<ScanKmer> &kmers, uint32_t type, bool gap, std
 
 bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc768,
                         const uint8_t *enc_ref, std::vector<uint8_t> &pool, std::vector<CgScanWord> &words,
-                        int &windowed)
+                        int &windowed, int &exact_ok)
 {
     std::vector<ScanKmer> whole, suffix, prefix;
     for (int e = 0; e < d.n_kmer_entries; ++e) {
@@ -214,6 +214,19 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
             }
             windowed = 1;
         }
+    }
+    // Exact-occurrence shortcut (see plan_runs in cg_core.cuh): needs an unambiguous chunk -> offset
+    // map, all chunks in one word, no free adapter start, and k <= m/2.
+    exact_ok = 0;
+    if (windowed && !(A.flags & 1) && A.k <= A.m / 2) {
+        int loc_bits = 0;
+        bool unambiguous = true;
+        for (auto &w : whole)
+            if (w.loc) { loc_bits += w.len; unambiguous = unambiguous && w.bmin == w.bmax; }
+        int all_bits = 0;
+        for (auto &w : whole) all_bits += w.len;
+        // chunk patterns must be pairwise distinct (else bmin != bmax) and everything must share one word
+        if (unambiguous && all_bits <= 32) exact_ok = 1;
     }
     pack_words(whole, CG_SCAN_WHOLE, false, pool, words);
     pack_words(suffix, CG_SCAN_SUFFIX, true, pool, words);
@@ -392,17 +405,17 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
 
     // two-phase program for the common case: one SINGLE aligner adapter with packed cells
     std::vector<CgScanWord> scan_words;
-    int simple_ok = 0, windowed = 0;
+    int simple_ok = 0, windowed = 0, exact_ok = 0;
     if (n_adapters == 1 && n_groups == 1 && G[0].type == CG_GROUP_SINGLE && A[0].kind == CG_KIND_ALIGNER &&
         A[0].cell_mode == CG_CELL_PACKED32) {
         std::vector<uint8_t> pool2 = pool;
         std::vector<CgScanWord> words;
-        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed)) {
+        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed, exact_ok)) {
             pool.swap(pool2);
             scan_words.swap(words);
             simple_ok = 1;
         } else {
-            windowed = 0;
+            windowed = 0; exact_ok = 0;
         }
     }
 
@@ -416,7 +429,7 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     H.groups_off = off; off += (uint32_t)(G.size() * sizeof(CgGroup)); off = align_up(off, 16);
     H.entries_off = off; off += (uint32_t)(E.size() * sizeof(CgEntry)); off = align_up(off, 16);
     H.scan_off = off; off += (uint32_t)(scan_words.size() * sizeof(CgScanWord)); off = align_up(off, 16);
-    H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed;
+    H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed; H.exact_ok = exact_ok;
     H.pool_off = off; off += (uint32_t)pool.size(); off = align_up(off, 16);
     H.total_bytes = off;
     out.blob.assign(off, 0);

@@ -87,7 +87,7 @@ struct CgSetHeader {        // 64 bytes
     int32_t scan_count;     // number of CgScanWord
     uint32_t scan_off;      // blob offset of CgScanWord[scan_count]
     int32_t windowed;       // 1: DP may be restricted to windows around locator hits
-    int32_t pad[1];
+    int32_t exact_ok;       // 1: an exact, leftmost occurrence found by the locator needs no DP at all
 };
 
 // One result of locating a single adapter in a (sub)sequence; coordinates as SingleMatch.

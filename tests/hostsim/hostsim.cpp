@@ -44,7 +44,11 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
         const int n = (int)(offsets[r + 1] - offsets[r]);
         const uint8_t *s = seq + offsets[r];
         for (int i = 0; i < n; ++i) if (s[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
-        if ((force_wide & 2) && S.h->simple_ok && times == 1)
+        if ((force_wide & 64) && S.h->simple_ok && times == 1 && S.ad[0].m <= 32)
+            process_read_planned(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
+                                 params->cutoff_front, params->cutoff_back, params->quality_base,
+                                 (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);
+        else if ((force_wide & 2) && S.h->simple_ok && times == 1)
             process_read_simple(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                                 params->cutoff_front, params->cutoff_back, params->quality_base, pc,
                                 (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr,

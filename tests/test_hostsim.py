@@ -20,7 +20,7 @@ def _single(ref, rate, flags, wr, wq, ic, mo, kind=0):
                                   wildcard_query=wq, indel_cost=ic, min_overlap=mo, kind=kind)])
 
 
-@pytest.mark.parametrize("force_wide", [0, 1, 2, 10, 18, 34])   # packed, wide, two-phase: smem column / registers+refine / registers+inline runs / split main+end passes
+@pytest.mark.parametrize("force_wide", [0, 1, 2, 10, 18, 34, 64])   # packed, wide, two-phase: smem column / registers+refine / registers+inline runs / split main+end passes / planned runs + exact shortcut
 def test_locate_golden(force_wide):
     cases = golden("locate_kat.json.gz")
     for ref, q, rate, flags, wr, wq, ic, mo, expected in cases:
@@ -110,7 +110,7 @@ def test_two_phase_path_equals_general_path():
         qt = rng.random() < 0.3
         params = L.make_params(quality_trim=qt, cutoff_front=5, cutoff_back=20)
         a, qa = hostsim_process(spec, reads, quals if qt else None, params, 0)
-        for mode in (2, 10, 18, 34):
+        for mode in (2, 10, 18, 34, 64):
             b, qb = hostsim_process(spec, reads, quals if qt else None, params, mode)
             assert (a == b).all() and (qa == qb).all(), (mode, repr(ad))
         n_windowed += 1
@@ -127,7 +127,7 @@ def test_two_phase_on_golden_single_adapters():
         multi = build_adapters(PA, case["adapters"])
         spec = spec_of(multi)
         reads = [r for r, _ in case["reads"]]
-        for mode in (2, 10, 18, 34):
+        for mode in (2, 10, 18, 34, 64):
             recs, _ = hostsim_process(spec, reads, force_wide=mode)
             for i, (read, expected) in enumerate(case["reads"]):
                 assert match_desc(multi.matches_from_records(recs[i, 0], read)) == expected, (mode, case["adapters"], read)
