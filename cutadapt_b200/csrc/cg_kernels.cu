@@ -806,8 +806,9 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : 3)) cg_list_
                 const int n = (int)ta.w, ri = (int)tc.z;
                 const uint32_t pk = ri == 0 ? td.x : (ri == 1 ? td.y : (ri == 2 ? td.z : td.w));
                 const int lo = (int)(pk & 0xffffu), hi = (int)(pk >> 16);
-                len = (uint32_t)(hi - lo);
-                addr += (uintptr_t)(A.reverse ? n - hi : lo);
+                // (flag sets without both query ends free can have an empty column range: lo > hi)
+                len = hi > lo ? (uint32_t)(hi - lo) : 0u;
+                if (len) addr += (uintptr_t)(A.reverse ? n - hi : lo);
             }
             src = addr & ~(uintptr_t)15;
             bytes = len ? (uint32_t)(((addr + len + 15) & ~(uintptr_t)15) - src) : 0u;

@@ -218,7 +218,9 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
     // Exact-occurrence shortcut (see plan_runs in cg_core.cuh): needs an unambiguous chunk -> offset
     // map, all chunks in one word, no free adapter start, and k <= m/2.
     exact_ok = 0;
-    if (windowed && !(A.flags & 1) && A.k <= A.m / 2) {
+    // ... and the full-length exact match must itself be acceptable (_align.pyx:511-514)
+    const bool full_ok = A.m >= A.min_overlap && floor((double)A.effective_length * d.max_error_rate) >= 0.0;
+    if (windowed && full_ok && !(A.flags & 1) && A.k <= A.m / 2) {
         int loc_bits = 0;
         bool unambiguous = true;
         for (auto &w : whole)
