@@ -564,6 +564,9 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 // which is noise for a kernel that is instruction-issue bound.
 // ------------------------------------------------------------------------------------------
 struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_rel, qual_rel, total; };
+#ifndef CG_SCAN_STAGES
+#define CG_SCAN_STAGES 1     // per-warp staging depth of the scan kernel (1: more resident warps hide the TMA latency)
+#endif
 __host__ __device__ inline ScanSmem scan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
 {
     ScanSmem L;
@@ -575,8 +578,8 @@ __host__ __device__ inline ScanSmem scan_smem_layout(uint32_t blob_bytes, int mi
     size_t w = 0;
     L.bar_rel = w; w += 16;
     w = cg_align_up(w, 128);
-    L.seq_rel = w; w += 2 * (size_t)mini_cap;
-    L.qual_rel = w; if (has_qual) w += 2 * (size_t)mini_cap;
+    L.seq_rel = w; w += CG_SCAN_STAGES * (size_t)mini_cap;
+    L.qual_rel = w; if (has_qual) w += CG_SCAN_STAGES * (size_t)mini_cap;
     L.warp_stride = cg_align_up(w, 128);
     L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
     return L;
@@ -634,12 +637,12 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
     };
     if (lane == 0) {
         if (wg < n_mt) issue(wg, 0);
-        if (wg + warps_total < n_mt) issue(wg + warps_total, 1);
+        if (CG_SCAN_STAGES > 1 && wg + warps_total < n_mt) issue(wg + warps_total, 1);
     }
     uint32_t phase0 = 0, phase1 = 0;
     int it = 0;
     for (long long mt = wg; mt < n_mt; mt += warps_total, ++it) {
-        const int st = it & 1;
+        const int st = CG_SCAN_STAGES > 1 ? (it & 1) : 0;
         const long long r0 = mt * 32;
         const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
         const long long r = r0 + lane;
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
         }
         __syncwarp();
         if (lane == 0) {
-            const long long next = mt + 2 * warps_total;
+            const long long next = mt + (long long)CG_SCAN_STAGES * warps_total;
             if (next < n_mt) issue(next, st);
         }
     }
