@@ -36,6 +36,14 @@ CG_HD int cg_ctz(uint32_t x)   // x != 0
     return __builtin_ctz(x);
 #endif
 }
+CG_HD uint32_t cg_funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits)   // (hi:lo) >> shift_bits, shift in {0,8,16,24}
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift_bits);
+#else
+    return shift_bits ? (lo >> shift_bits) | (hi << (32 - shift_bits)) : lo;
+#endif
+}
 template <class X> CG_HD X cg_min(X a, X b) { return a < b ? a : b; }
 template <class X> CG_HD X cg_max(X a, X b) { return a > b ? a : b; }
 
@@ -406,12 +414,33 @@ CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t 
                 const bool stash = n_loc == 1;
                 int nh = 0, p0 = 0;
                 if (gs == 4) {                                   // reads up to 511 characters
+                    // 16 characters per step, fetched as aligned 32-bit words (4x fewer shared-memory
+                    // wavefronts than byte loads; the shared-memory pipe is what limits this loop).
+                    // Forward: the unaligned word at q; reverse: the unaligned word at q - 3.
+                    const uintptr_t ua = (uintptr_t)(REV ? q - 3 : q);
+                    const uint32_t sh = (uint32_t)(ua & 3u) * 8u;
+                    const uint32_t *wp = (const uint32_t *)(ua & ~(uintptr_t)3);
+                    uint32_t carry = (p0 + 16 <= n) ? (REV ? wp[1] : wp[0]) : 0u;
                     for (; p0 + 16 <= n; p0 += 16) {
                         const uint32_t r_start = R;
                         uint32_t g = 0;
+                        uint32_t x[4];
+                        if (!REV) {
+                            const uint32_t w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                            x[0] = cg_funnel_r(carry, w1, sh); x[1] = cg_funnel_r(w1, w2, sh);
+                            x[2] = cg_funnel_r(w2, w3, sh); x[3] = cg_funnel_r(w3, w4, sh);
+                            carry = w4; wp += 4;
+                        } else {
+                            const uint32_t w0 = wp[0], m1 = wp[-1], m2 = wp[-2], m3 = wp[-3];
+                            x[0] = cg_funnel_r(w0, carry, sh); x[1] = cg_funnel_r(m1, w0, sh);
+                            x[2] = cg_funnel_r(m2, m1, sh); x[3] = cg_funnel_r(m3, m2, sh);
+                            carry = m3; wp -= 4;
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            R = ((R << 1) | init) & mask[q[REV ? -i : i]];
+                            const uint32_t word = x[i >> 2];
+                            const uint32_t c = REV ? ((word >> (8 * (3 - (i & 3)))) & 255u) : ((word >> (8 * (i & 3))) & 255u);
+                            R = ((R << 1) | init) & mask[c];
                             g |= R;
                         }
                         q += REV ? -16 : 16;

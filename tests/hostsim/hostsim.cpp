@@ -38,6 +38,10 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
     std::vector<int> colw(3 * ((size_t)set.max_m + 2));
     PackedCol pc; pc.base = colp.data(); pc.stride = 1;
     WideCol wc; wc.base = colw.data(); wc.stride = 1;
+    // word-granular character loads may touch up to 7 bytes before/after a read: work on a padded copy
+    std::vector<uint8_t> padded((size_t)offsets[n_reads] + 64, 0);
+    if (offsets[n_reads]) memcpy(padded.data() + 32, seq, (size_t)offsets[n_reads]);
+    seq = padded.data() + 32;
     const int times = params->times < 1 ? 1 : params->times;
     if (params->quality_trim && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
     for (int64_t r = 0; r < n_reads; ++r) {
