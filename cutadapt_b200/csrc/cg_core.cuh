@@ -417,9 +417,12 @@ CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t 
                     // 16 characters per step, fetched as aligned 32-bit words (4x fewer shared-memory
                     // wavefronts than byte loads; the shared-memory pipe is what limits this loop).
                     // Forward: the unaligned word at q; reverse: the unaligned word at q - 3.
-                    const uintptr_t ua = (uintptr_t)(REV ? q - 3 : q);
-                    const uint32_t sh = (uint32_t)(ua & 3u) * 8u;
-                    const uint32_t *wp = (const uint32_t *)(ua & ~(uintptr_t)3);
+                    // (pointer arithmetic on q itself, not on an integer copy, keeps the shared-memory
+                    // address space visible to the compiler: LDS, not generic loads)
+                    const uint8_t *uq = REV ? q - 3 : q;
+                    const uint32_t mis = (uint32_t)((uintptr_t)uq & 3u);
+                    const uint32_t sh = mis * 8u;
+                    const uint32_t *wp = (const uint32_t *)(uq - mis);
                     uint32_t carry = (p0 + 16 <= n) ? (REV ? wp[1] : wp[0]) : 0u;
                     for (; p0 + 16 <= n; p0 += 16) {
                         const uint32_t r_start = R;
