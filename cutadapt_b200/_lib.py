@@ -33,6 +33,7 @@ CG_REMOVE_AFTER = 1
 CG_REMOVE_AUTO = 2
 CG_GROUP_SINGLE = 0
 CG_GROUP_LINKED = 1
+CG_GROUP_INDEXED = 2
 
 
 class cg_kmer_entry(C.Structure):
@@ -72,6 +73,21 @@ class cg_group_desc(C.Structure):
         ("front_required", C.c_int32),
         ("back_required", C.c_int32),
         ("reserved", C.c_int32 * 3),
+    ]
+
+
+class cg_index_desc(C.Structure):
+    _fields_ = [
+        ("prefix", C.c_int32),
+        ("n_lengths", C.c_int32),
+        ("lengths", C.POINTER(C.c_int32)),
+        ("n_keys", C.c_int64),
+        ("keys", C.c_void_p),
+        ("stride", C.c_int32),
+        ("reserved", C.c_int32),
+        ("adapter", C.POINTER(C.c_int32)),
+        ("errors", C.POINTER(C.c_int32)),
+        ("matches", C.POINTER(C.c_int32)),
     ]
 
 
@@ -121,6 +137,10 @@ def _declare(lib) -> None:
     lib.cg_ctx_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
     lib.cg_adapterset_create.argtypes = [
         vp, C.POINTER(cg_adapter_desc), i32, C.POINTER(cg_group_desc), i32, C.POINTER(vp),
+    ]
+    lib.cg_adapterset_create_indexed.argtypes = [
+        vp, C.POINTER(cg_adapter_desc), i32, C.POINTER(cg_group_desc), i32,
+        C.POINTER(cg_index_desc), i32, C.POINTER(vp),
     ]
     lib.cg_adapterset_destroy.argtypes = [vp]
     lib.cg_adapterset_slots.argtypes = [vp]
@@ -206,11 +226,16 @@ class AdapterSetSpec:
     Plain-Python description of an adapter set: what cg_adapterset_create() consumes.
     ``adapters`` is a list of dicts with the fields of cg_adapter_desc (``sequence`` as str,
     ``kmer_entries`` as an (n,4) list / ``kmer_masks`` as uint64 array or None), ``groups`` a
-    list of (type, a0, a1, front_required, back_required).
+    list of (type, a0, a1, front_required, back_required).  ``indexes`` (for CG_GROUP_INDEXED
+    groups, whose a0 is the index number) is a list of dicts ``{"prefix": bool, "lengths": [...],
+    "keys": [str], "adapter": [...], "errors": [...], "matches": [...]}`` = the dict an
+    AdapterIndex builds (adapters.py:1416-1466).
     """
 
-    def __init__(self, adapters: List[dict], groups: Optional[List[tuple]] = None):
+    def __init__(self, adapters: List[dict], groups: Optional[List[tuple]] = None,
+                 indexes: Optional[List[dict]] = None):
         self.adapters = adapters
+        self.indexes = indexes or []
         self.groups = groups if groups is not None else [
             (CG_GROUP_SINGLE, i, -1, 0, 0) for i in range(len(adapters))
         ]
@@ -265,6 +290,36 @@ class AdapterSetSpec:
             garr[i].back_required = int(bool(breq))
         self._keep = keep
         return arr, len(self.adapters), garr, len(self.groups)
+
+    def index_ctypes(self):
+        """Returns (cg_index_desc array or None, n)."""
+        if not self.indexes:
+            return None, 0
+        keep = []
+        iarr = (cg_index_desc * len(self.indexes))()
+        for i, ix in enumerate(self.indexes):
+            lengths = np.ascontiguousarray(ix["lengths"], dtype=np.int32)
+            keys = ix["keys"]
+            stride = max([len(k) for k in keys] + [1])
+            buf = np.zeros((len(keys), stride), dtype=np.uint8)
+            for j, k in enumerate(keys):
+                buf[j, : len(k)] = np.frombuffer(k.encode("ascii"), dtype=np.uint8)
+            ad = np.ascontiguousarray(ix["adapter"], dtype=np.int32)
+            er = np.ascontiguousarray(ix["errors"], dtype=np.int32)
+            ma = np.ascontiguousarray(ix["matches"], dtype=np.int32)
+            keep.extend([lengths, buf, ad, er, ma])
+            d = iarr[i]
+            d.prefix = int(bool(ix["prefix"]))
+            d.n_lengths = len(lengths)
+            d.lengths = lengths.ctypes.data_as(C.POINTER(C.c_int32))
+            d.n_keys = len(keys)
+            d.keys = buf.ctypes.data
+            d.stride = stride
+            d.adapter = ad.ctypes.data_as(C.POINTER(C.c_int32))
+            d.errors = er.ctypes.data_as(C.POINTER(C.c_int32))
+            d.matches = ma.ctypes.data_as(C.POINTER(C.c_int32))
+        self._keep_index = keep
+        return iarr, len(self.indexes)
 
     @property
     def slots(self) -> int:
@@ -345,7 +400,11 @@ class AdapterSet:
         self.ctx = ctx or default_context()
         arr, n, garr, ng = spec.to_ctypes()
         handle = C.c_void_p()
-        check(lib().cg_adapterset_create(self.ctx.handle, arr, n, garr, ng, C.byref(handle)))
+        iarr, ni = spec.index_ctypes()
+        if ni:
+            check(lib().cg_adapterset_create_indexed(self.ctx.handle, arr, n, garr, ng, iarr, ni, C.byref(handle)))
+        else:
+            check(lib().cg_adapterset_create(self.ctx.handle, arr, n, garr, ng, C.byref(handle)))
         self._h = handle
         self.slots = int(lib().cg_adapterset_slots(handle))
 

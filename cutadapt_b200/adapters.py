@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from ._kmer_finder import KmerFinder
-from .align import Aligner, EndSkip, PrefixComparer, SuffixComparer
+from .align import Aligner, EndSkip, PrefixComparer, SuffixComparer, edit_environment, hamming_sphere
 from .kmer_heuristic import create_positions_and_kmers
 
 
@@ -462,13 +462,17 @@ class Matchable(ABC):
         """(single adapters in device order, group tuples, the Matchable of every group)"""
         raise NotImplementedError
 
+    def _flatten_indexes(self) -> List[dict]:
+        """AdapterSetSpec index dicts for the CG_GROUP_INDEXED groups of _flatten() (in a0 order)."""
+        return []
+
     def adapter_set(self) -> "_lib.AdapterSet":
         """Compile + upload this Matchable's tables (once per process/context)."""
         ctx = _lib.default_context()
         cached = self._device_set
         if cached is None or cached[0].ctx is not ctx:
             singles, groups, owners = self._flatten()
-            spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups)
+            spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups, self._flatten_indexes())
             cached = (_lib.AdapterSet(spec, ctx), singles, owners)
             self._device_set = cached
         return cached[0]
@@ -951,15 +955,179 @@ class MultipleAdapters(Matchable):
         singles: List[SingleAdapter] = []
         groups: List[tuple] = []
         owners: List[Matchable] = []
+        n_indexes = 0
         for adapter in self._adapters:
             sub_singles, sub_groups, sub_owners = adapter._flatten()
             base = len(singles)
             singles.extend(sub_singles)
             for typ, a0, a1, freq, breq in sub_groups:
-                groups.append((typ, a0 + base, a1 + base if a1 >= 0 else -1, freq, breq))
+                if typ == _lib.CG_GROUP_INDEXED:
+                    groups.append((typ, a0 + n_indexes, -1, freq, breq))
+                else:
+                    groups.append((typ, a0 + base, a1 + base if a1 >= 0 else -1, freq, breq))
+            n_indexes += sum(1 for g in sub_groups if g[0] == _lib.CG_GROUP_INDEXED)
             owners.extend(sub_owners)
         return singles, groups, owners
+
+    def _flatten_indexes(self):
+        out: List[dict] = []
+        base = 0
+        for adapter in self._adapters:
+            for ix in adapter._flatten_indexes():
+                ix = dict(ix)
+                ix["adapter"] = [a + base for a in ix["adapter"]]
+                out.append(ix)
+            base += len(adapter._flatten()[0])
+        return out
 
     def match_to(self, sequence: str) -> Optional[Match]:
         """Find the adapter that best matches the sequence; a Match or None."""
         return self.match_to_batch([sequence])[0]
+
+
+class AdapterIndex:
+    """
+    Index of multiple anchored adapters of the same type (adapters.py:1289-1551): every string
+    within the allowed edit/Hamming distance of every adapter is a dictionary key, so matching is
+    one lookup of the read's prefix (suffix) per distinct key length.
+
+    The dictionary is built here exactly as the reference builds it (including the removal of
+    ambiguous keys) and handed to the library, which keeps it as a hash table in HBM; the lookups
+    for a chunk of reads happen inside the fused kernel (CG_GROUP_INDEXED).
+
+    Restrictions of the reference (adapters.py:1366-1378): no wildcards, at most 3 errors.
+    Additional restrictions of this implementation (``is_acceptable`` is False, so callers fall
+    back to ``MultipleAdapters`` as they do for the reference's own restrictions): adapter
+    alphabet A/C/G/T, length <= 32, fewer errors than characters.
+    """
+
+    AdapterIndexDict = Dict[str, Tuple["SingleAdapter", int, int]]
+
+    def __init__(self, adapters, prefix: bool):
+        """All given adapters must be of the same type"""
+        if not adapters:
+            raise ValueError("Adapter list is empty")
+        for adapter in adapters:
+            self._accept(adapter, prefix)
+        self._adapters = adapters
+        self._prefix = prefix
+        self._lengths, self._index, self._ambiguous = self._make_index()
+        if len(self._lengths) == 1:
+            self._length = self._lengths[0]
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(adapters={self._adapters!r})"
+
+    @classmethod
+    def _accept(cls, adapter: "SingleAdapter", prefix: bool):
+        """Raise a ValueError if the adapter is not acceptable (adapters.py:1366-1378)"""
+        if prefix and not isinstance(adapter, PrefixAdapter):
+            raise ValueError("Only 5' anchored adapters are allowed")
+        elif not prefix and not isinstance(adapter, SuffixAdapter):
+            raise ValueError("Only 3' anchored adapters are allowed")
+        if adapter.read_wildcards:
+            raise ValueError("Wildcards in the read not supported")
+        if adapter.adapter_wildcards:
+            raise ValueError("Wildcards in the adapter not supported")
+        k = int(len(adapter) * adapter.max_error_rate)
+        if k > 3:
+            raise ValueError("Error rate too high")
+        if k >= len(adapter):
+            raise ValueError("As many errors as characters allowed: not indexable on the device")
+        if len(adapter) + (k if adapter.indels else 0) > 32:
+            raise ValueError("Adapter too long for the device index")
+        if set(adapter.sequence) - set("ACGT"):
+            raise ValueError("Only A, C, G, T adapters can be indexed on the device")
+
+    @classmethod
+    def is_acceptable(cls, adapter: "SingleAdapter", prefix: bool):
+        """Whether this adapter can be used in an index (adapters.py:1380-1392)"""
+        try:
+            cls._accept(adapter, prefix)
+        except ValueError:
+            return False
+        return True
+
+    def _make_index(self) -> Tuple[List[int], "AdapterIndexDict", int]:
+        """adapters.py:1394-1472"""
+        index: Dict[str, Tuple[SingleAdapter, int, int]] = dict()
+        lengths = set()
+        ambiguous = {}
+        for adapter in self._adapters:
+            sequence = adapter.sequence
+            k = int(adapter.max_error_rate * len(sequence))
+            if adapter.indels:
+                for s, errors, matches in edit_environment(sequence, k):
+                    if s in index:
+                        other_adapter, other_errors, other_matches = index[s]
+                        if matches < other_matches:
+                            continue
+                        if other_matches == matches and s not in ambiguous:
+                            ambiguous[s] = (adapter, other_adapter, k, matches)
+                    index[s] = (adapter, errors, matches)
+                    lengths.add(len(s))
+            else:
+                n = len(sequence)
+                for errors in range(k + 1):
+                    matches = n - errors
+                    for s in hamming_sphere(sequence, errors):
+                        if s in index:
+                            other_adapter, other_errors, other_matches = index[s]
+                            if matches < other_matches:
+                                continue
+                            if other_matches == matches and s not in ambiguous:
+                                ambiguous[s] = (adapter, other_adapter, k, matches)
+                        index[s] = (adapter, errors, matches)
+                lengths.add(n)
+        for s in ambiguous:
+            del index[s]
+        return sorted(lengths, reverse=True), index, len(ambiguous)
+
+    def descriptor(self) -> dict:
+        """The cg_index_desc content: keys and (adapter number, errors, matches) per key."""
+        number = {id(a): i for i, a in enumerate(self._adapters)}
+        keys = list(self._index)
+        return {
+            "prefix": self._prefix,
+            "lengths": list(self._lengths),
+            "keys": keys,
+            "adapter": [number[id(self._index[k][0])] for k in keys],
+            "errors": [self._index[k][1] for k in keys],
+            "matches": [self._index[k][2] for k in keys],
+        }
+
+
+class _IndexedAdapters(Matchable):
+    _is_prefix = True
+
+    def __init__(self, adapters, name):
+        super().__init__(name=name)
+        self._index = AdapterIndex(adapters, prefix=self._is_prefix)
+
+    def _flatten(self):
+        return list(self._index._adapters), [(_lib.CG_GROUP_INDEXED, 0, -1, 0, 0)], [self]
+
+    def _flatten_indexes(self):
+        return [self._index.descriptor()]
+
+    def match_to(self, sequence: str):
+        """AdapterIndex.match_to (adapters.py:1474-1551) as a batch of one on the device."""
+        return self.match_to_batch([sequence])[0]
+
+
+class IndexedPrefixAdapters(_IndexedAdapters):
+    """adapters.py:1554-1561"""
+
+    _is_prefix = True
+
+    def __init__(self, adapters):
+        super().__init__(adapters, name="indexed_prefix_adapters")
+
+
+class IndexedSuffixAdapters(_IndexedAdapters):
+    """adapters.py:1564-1571"""
+
+    _is_prefix = False
+
+    def __init__(self, adapters):
+        super().__init__(adapters, name="indexed_suffix_adapters")

@@ -121,6 +121,7 @@ struct cg_adapterset {
     uint8_t *d_blob = nullptr;
     uint64_t *d_masks = nullptr;
     CgEntry *d_entries = nullptr;   // device pointer into d_blob
+    uint8_t *d_index = nullptr;     // anchored-adapter hash tables, or null
 };
 
 // ------------------------------------------------------------------------------------------
@@ -213,28 +214,40 @@ extern "C" int cg_ctx_kernel_time(cg_ctx *c, double *total_ms, int64_t *launches
 }
 
 // ------------------------------------------------------------------------------------------
-extern "C" int cg_adapterset_create(cg_ctx *c, const cg_adapter_desc *adapters, int32_t n_adapters,
-                                    const cg_group_desc *groups, int32_t n_groups, cg_adapterset **out)
+extern "C" int cg_adapterset_create_indexed(cg_ctx *c, const cg_adapter_desc *adapters, int32_t n_adapters,
+                                            const cg_group_desc *groups, int32_t n_groups,
+                                            const cg_index_desc *indexes, int32_t n_indexes, cg_adapterset **out)
 {
     if (!c || !out) return fail(CG_EINVAL, "cg_adapterset_create: NULL argument");
     cg_adapterset *s = new cg_adapterset();
     s->ctx = c;
     std::string err;
-    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, s->host, err);
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, s->host, err, indexes, n_indexes);
     if (rc != CG_OK) { delete s; return fail(rc, err); }
     cudaError_t e = cudaSetDevice(c->device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_blob, s->host.blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(s->d_blob, s->host.blob.data(), s->host.blob.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_masks, s->host.masks64.size() * 8);
     if (e == cudaSuccess) e = cudaMemcpy(s->d_masks, s->host.masks64.data(), s->host.masks64.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !s->host.index_blob.empty()) {
+        e = cudaMalloc((void **)&s->d_index, s->host.index_blob.size());
+        if (e == cudaSuccess) e = cudaMemcpy(s->d_index, s->host.index_blob.data(), s->host.index_blob.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         if (s->d_blob) cudaFree(s->d_blob);
         if (s->d_masks) cudaFree(s->d_masks);
+        if (s->d_index) cudaFree(s->d_index);
         delete s;
         return cuda_fail(e, "adapter set upload");
     }
     *out = s;
     return CG_OK;
+}
+
+extern "C" int cg_adapterset_create(cg_ctx *c, const cg_adapter_desc *adapters, int32_t n_adapters,
+                                    const cg_group_desc *groups, int32_t n_groups, cg_adapterset **out)
+{
+    return cg_adapterset_create_indexed(c, adapters, n_adapters, groups, n_groups, nullptr, 0, out);
 }
 
 extern "C" int cg_adapterset_destroy(cg_adapterset *s)
@@ -243,6 +256,7 @@ extern "C" int cg_adapterset_destroy(cg_adapterset *s)
     if (s->ctx) cudaSetDevice(s->ctx->device);
     if (s->d_blob) cudaFree(s->d_blob);
     if (s->d_masks) cudaFree(s->d_masks);
+    if (s->d_index) cudaFree(s->d_index);
     delete s;
     return CG_OK;
 }
@@ -270,7 +284,7 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
     CgKernelArgs a;
     memset(&a, 0, sizeof a);
     a.blob = s->d_blob; a.blob_bytes = (uint32_t)s->host.blob.size();
-    a.masks64 = s->d_masks; a.enc = c->d_enc;
+    a.masks64 = s->d_masks; a.enc = c->d_enc; a.index = s->d_index;
     a.seq = d_seq; a.qual = want_q ? d_qual : nullptr; a.offsets = d_offsets; a.n_reads = n_reads;
     a.quality_trim = want_q ? 1 : 0; a.cutoff_front = p->cutoff_front; a.cutoff_back = p->cutoff_back;
     a.qbase = p->quality_base; a.times = times; a.slots = s->host.slots;

@@ -27,6 +27,7 @@
 #define CGK_REMOVE_AUTO 2
 #define CGK_GROUP_SINGLE 0
 #define CGK_GROUP_LINKED 1
+#define CGK_GROUP_INDEXED 2
 
 CG_HD int cg_ctz(uint32_t x)   // x != 0
 {
@@ -558,11 +559,16 @@ struct SetView {
     const uint64_t *masks64;   // HBM
     const uint8_t *enc;        // 3 x 256 bytes: upper, acgt, iupac
     const CgScanWord *scan;    // two-phase program (h->scan_count words), if h->simple_ok
+    const CgIndexHeader *index_hdr;   // anchored-adapter indexes (HBM), or null
+    const CgIndexEntry *index_tab;
 };
 
-CG_HD SetView make_set_view(const uint8_t *blob, const uint64_t *masks64, const uint8_t *enc)
+CG_HD SetView make_set_view(const uint8_t *blob, const uint64_t *masks64, const uint8_t *enc,
+                            const uint8_t *index_blob = nullptr)
 {
     SetView S;
+    S.index_hdr = (const CgIndexHeader *)index_blob;
+    S.index_tab = (const CgIndexEntry *)index_blob;   // table_off counts entries from the start of the array
     S.h = (const CgSetHeader *)blob;
     S.ad = (const CgAdapter *)(blob + S.h->adapters_off);
     S.gr = (const CgGroup *)(blob + S.h->groups_off);
@@ -618,6 +624,72 @@ CG_HD void apply_trim(const CgHit &h, int &s, int &e)
     else e = s + h.rstart;
 }
 
+// AdapterIndex.match_to (adapters.py:1474-1551): dict lookups of the read's prefix/suffix for every
+// key length, longest first.
+CG_HD uint64_t cg_index_hash(uint64_t bases, uint32_t len)
+{
+    uint64_t x = bases ^ ((uint64_t)len * 0x9E3779B97F4A7C15ULL);
+    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32;
+    return x;
+}
+
+template <bool ALLOW_WIDE>
+CG_HD bool match_single(const SetView &S, int ai, const uint8_t *p, int n, PackedCol &colp,
+                        WideCol &colw, CgHit &hit);
+
+template <bool ALLOW_WIDE>
+CG_HD bool match_indexed(const SetView &S, int index_no, const uint8_t *p, int n, PackedCol &colp,
+                         WideCol &colw, CgHit &hit)
+{
+    const CgIndexHeader &H = S.index_hdr[index_no];
+    const CgIndexEntry *tab = S.index_tab + H.table_off;
+    int best_a = -1, best_len = 0, best_m = -1, best_e = 1000;
+    for (int li = 0; li < H.n_lengths; ++li) {
+        const int L = H.lengths[li];
+        if (L < best_m) break;                                   // adapters.py:1506-1508
+        const int cnt = cg_min(L, n);                            // sequence[:L] / sequence[-L:]
+        if (cnt > 32 || cnt <= 0) continue;
+        const uint8_t *q = H.prefix ? p : p + (n - cnt);
+        uint64_t bases = 0;
+        bool has_n = false, valid = true;
+        for (int i = 0; i < cnt; ++i) {
+            uint8_t c = q[i];
+            if (c >= 'a' && c <= 'z') c -= 32;                   // sequence.upper()
+            uint64_t code = 0;
+            if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2;
+            else if (c == 'T') code = 3;
+            else if (c == 'N') { has_n = true; code = 0; }       // _lookup_with_n: N -> A
+            else valid = false;
+            bases |= code << (2 * i);
+        }
+        if (!valid) continue;
+        uint32_t val = 0;
+        bool found = false;
+        for (uint32_t slot = (uint32_t)cg_index_hash(bases, (uint32_t)cnt) & H.table_mask;;
+             slot = (slot + 1) & H.table_mask) {
+            const CgIndexEntry e = tab[slot];
+            if (e.len == 0) break;
+            if (e.len == (uint32_t)cnt && e.bases == bases) { val = e.val; found = true; break; }
+        }
+        if (!found) continue;
+        const int a = (int)(val >> 16);
+        int e = (int)((val >> 8) & 255u), m = (int)(val & 255u);
+        if (has_n) {                                             // adapters.py:1535-1551: re-align
+            CgHit h;
+            if (!match_single<ALLOW_WIDE>(S, a, q, cnt, colp, colw, h)) continue;
+            e = h.errors; m = h.score;
+        }
+        if (m > best_m || (m == best_m && e < best_e)) { best_a = a; best_e = e; best_m = m; best_len = L; }
+    }
+    if (best_m == -1) return false;
+    hit.adapter = best_a;
+    hit.astart = 0; hit.astop = S.ad[best_a].m;
+    if (H.prefix) { hit.rstart = 0; hit.rstop = best_len; hit.remove = CGK_REMOVE_BEFORE; }
+    else { hit.rstart = n - best_len; hit.rstop = n; hit.remove = CGK_REMOVE_AFTER; }
+    hit.score = best_m; hit.errors = best_e;
+    return true;
+}
+
 struct GroupHit {
     CgHit h0, h1;     // SINGLE: h0.  LINKED: h0 = front (adapter -1 if absent), h1 = back.
     int score, errors;
@@ -629,6 +701,11 @@ CG_HD bool match_group(const SetView &S, const CgGroup &G, const uint8_t *p, int
                        PackedCol &colp, WideCol &colw, GroupHit &gh)
 {
     gh.h0.adapter = -1; gh.h1.adapter = -1;
+    if (G.type == CGK_GROUP_INDEXED) {
+        if (!match_indexed<ALLOW_WIDE>(S, G.a0, p, n, colp, colw, gh.h0)) return false;
+        gh.score = gh.h0.score; gh.errors = gh.h0.errors;
+        return true;
+    }
     if (G.type == CGK_GROUP_SINGLE) {
         if (!match_single<ALLOW_WIDE>(S, G.a0, p, n, colp, colw, gh.h0)) return false;
         gh.score = gh.h0.score; gh.errors = gh.h0.errors;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
         s_cnt[0] = 0; s_cnt[1] = 0;
     }
     __syncthreads();
-    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
 
     const long long n_reads = a.n_reads;
     const long long n_tiles = (n_reads + CG_NT - 1) / CG_NT;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_warp_kernel(const CgKernelArgs 
         fence_barrier_init();
     }
     __syncthreads();          // the only block-wide barrier
-    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
 
     const long long n_reads = a.n_reads;
     const long long n_mt = (n_reads + 31) / 32;
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
         fence_barrier_init();
     }
     __syncthreads();
-    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
 
     const long long n_reads = a.n_reads;
     const long long n_mt = (n_reads + 31) / 32;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : 3)) cg_list_
         fence_barrier_init();
     }
     __syncthreads();
-    const SetView S = make_set_view(s_blob, a.masks64, s_enc);
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
     const CgAdapter &A = S.ad[0];
 
     unsigned long long n_tasks = *a.task_count;
@@ -931,7 +931,7 @@ __global__ void cg_trim_generic_kernel(const CgKernelArgs a)
 {
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const SetView S = make_set_view(a.blob, a.masks64, a.enc);
+    const SetView S = make_set_view(a.blob, a.masks64, a.enc, a.index);
     PackedCol colp; colp.base = a.scratch_p + gtid; colp.stride = (int)a.scratch_stride;
     WideCol colw; colw.base = a.scratch_w + gtid; colw.stride = a.scratch_stride;
     for (long long r = gtid; r < a.n_reads; r += nthreads) {

@@ -13,6 +13,7 @@ struct CgKernelArgs {
     uint32_t blob_bytes;
     const uint64_t *masks64;
     const uint8_t *enc;  // 768 bytes
+    const uint8_t *index;  // CgIndexHeader[] | CgIndexEntry[] for INDEXED groups, or null
     // batch (HBM)
     const uint8_t *seq;
     const uint8_t *qual;

@@ -247,9 +247,93 @@ static int32_t floor_to_i32(double x)
     return (int32_t)f;
 }
 
-int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc *groups, int n_groups,
-                 CgBuiltSet &out, std::string &err)
+// AdapterIndex (adapters.py:1416-1466) -> open-addressing hash table keyed by the 2-bit packed affix.
+static uint64_t index_hash(uint64_t bases, uint32_t len)
 {
+    uint64_t x = bases ^ ((uint64_t)len * 0x9E3779B97F4A7C15ULL);   // must equal cg_index_hash (cg_core.cuh)
+    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32;
+    return x;
+}
+
+static int build_indexes(const cg_index_desc *indexes, int n_indexes, int n_adapters,
+                         std::vector<uint8_t> &blob, std::string &err)
+{
+    blob.clear();
+    if (n_indexes <= 0) return CG_OK;
+    if (!indexes) { err = "index array is NULL"; return CG_EINVAL; }
+    std::vector<CgIndexHeader> H(n_indexes);
+    std::vector<CgIndexEntry> T;
+    const size_t hdr_entries = (size_t)n_indexes * sizeof(CgIndexHeader) / sizeof(CgIndexEntry);
+    for (int x = 0; x < n_indexes; ++x) {
+        const cg_index_desc &d = indexes[x];
+        CgIndexHeader &h = H[x];
+        memset(&h, 0, sizeof h);
+        h.prefix = d.prefix ? 1 : 0;
+        if (d.n_lengths <= 0 || d.n_lengths > 32 || !d.lengths) {
+            err = "an adapter index needs 1..32 distinct key lengths"; return CG_EUNSUPPORTED;
+        }
+        for (int i = 0; i < d.n_lengths; ++i) {
+            if (d.lengths[i] <= 0 || d.lengths[i] > 32) { err = "indexed adapters longer than 32 are not supported"; return CG_EUNSUPPORTED; }
+            if (i && d.lengths[i] >= d.lengths[i - 1]) { err = "index key lengths must be strictly descending"; return CG_EINVAL; }
+            h.lengths[i] = (uint8_t)d.lengths[i];
+        }
+        h.n_lengths = d.n_lengths;
+        if (d.n_keys < 0 || (d.n_keys && (!d.keys || !d.adapter || !d.errors || !d.matches)) || d.stride <= 0) {
+            err = "bad index key table"; return CG_EINVAL;
+        }
+        size_t cap = 16;
+        while (cap < (size_t)d.n_keys * 2) cap <<= 1;
+        if (cap > ((size_t)1 << 30)) { err = "adapter index too large"; return CG_EUNSUPPORTED; }
+        const size_t base = T.size();
+        T.resize(base + cap);
+        memset(T.data() + base, 0, cap * sizeof(CgIndexEntry));
+        h.table_off = (uint32_t)(hdr_entries + base);
+        h.table_mask = (uint32_t)(cap - 1);
+        for (int64_t k = 0; k < d.n_keys; ++k) {
+            const uint8_t *s = d.keys + (size_t)k * d.stride;
+            uint32_t len = 0;
+            uint64_t bases = 0;
+            while (len < (uint32_t)d.stride && s[len]) {
+                uint64_t code;
+                switch (s[len]) {
+                case 'A': code = 0; break; case 'C': code = 1; break;
+                case 'G': code = 2; break; case 'T': code = 3; break;
+                default: err = "index keys must consist of A, C, G, T"; return CG_EINVAL;
+                }
+                if (len >= 32) { err = "index key longer than 32"; return CG_EUNSUPPORTED; }
+                bases |= code << (2 * len);
+                ++len;
+            }
+            if (len == 0) { err = "empty index key"; return CG_EINVAL; }
+            if (d.adapter[k] < 0 || d.adapter[k] >= n_adapters || d.adapter[k] > 65535) {
+                err = "index refers to an unknown adapter"; return CG_EINVAL;
+            }
+            if (d.errors[k] < 0 || d.errors[k] > 255 || d.matches[k] < 0 || d.matches[k] > 255) {
+                err = "index errors/matches out of range"; return CG_EINVAL;
+            }
+            const uint32_t val = ((uint32_t)d.adapter[k] << 16) | ((uint32_t)d.errors[k] << 8) | (uint32_t)d.matches[k];
+            size_t slot = (size_t)(index_hash(bases, len) & h.table_mask);
+            for (;;) {
+                CgIndexEntry &e = T[base + slot];
+                if (e.len == 0) { e.bases = bases; e.len = len; e.val = val; break; }
+                if (e.len == len && e.bases == bases) { err = "duplicate index key"; return CG_EINVAL; }
+                slot = (slot + 1) & h.table_mask;
+            }
+        }
+    }
+    blob.resize(H.size() * sizeof(CgIndexHeader) + T.size() * sizeof(CgIndexEntry));
+    memcpy(blob.data(), H.data(), H.size() * sizeof(CgIndexHeader));
+    memcpy(blob.data() + H.size() * sizeof(CgIndexHeader), T.data(), T.size() * sizeof(CgIndexEntry));
+    return CG_OK;
+}
+
+int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc *groups, int n_groups,
+                 CgBuiltSet &out, std::string &err, const cg_index_desc *indexes, int n_indexes)
+{
+    {
+        int rc = build_indexes(indexes, n_indexes, n_adapters, out.index_blob, err);
+        if (rc != CG_OK) return rc;
+    }
     if (n_adapters <= 0 || !ads) { err = "adapter set is empty"; return CG_EINVAL; }
     if (n_groups <= 0 || !groups) { err = "adapter set has no groups"; return CG_EINVAL; }
     uint8_t enc[768];
@@ -401,6 +485,9 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
                 err = "anywhere adapters cannot be linked"; return CG_EINVAL;
             }
             out.slots = 2;
+        } else if (d.type == CG_GROUP_INDEXED) {
+            if (d.a0 < 0 || d.a0 >= n_indexes) { err = "group refers to an unknown adapter index"; return CG_EINVAL; }
+            x.a1 = -1;
         } else { err = "unknown group type"; return CG_EINVAL; }
     }
     if (n_groups > 256) { err = "more than 256 adapter groups"; return CG_EUNSUPPORTED; }

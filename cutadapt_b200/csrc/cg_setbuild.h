@@ -12,6 +12,7 @@ struct CgBuiltSet {
     std::vector<uint8_t> blob;       // CgSetHeader | adapters | groups | entries | pool
     std::vector<uint64_t> masks64;   // 128 words per prefilter entry
     std::vector<int32_t> effective_length;  // per adapter
+    std::vector<uint8_t> index_blob; // CgIndexHeader[n_indexes] | CgIndexEntry tables (HBM), may be empty
     int slots = 1;
     int n_adapters = 0, n_groups = 0, max_m = 0, any_wide = 0, simple_ok = 0;
 };
@@ -21,4 +22,5 @@ void cg_build_enc_tables(uint8_t *out768);
 
 // Returns CG_OK or a negative code and fills `err`.
 int cg_build_set(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups,
-                 int n_groups, CgBuiltSet &out, std::string &err);
+                 int n_groups, CgBuiltSet &out, std::string &err,
+                 const cg_index_desc *indexes = nullptr, int n_indexes = 0);

@@ -90,6 +90,22 @@ struct CgSetHeader {        // 64 bytes
     int32_t exact_ok;       // 1: an exact, leftmost occurrence found by the locator needs no DP at all
 };
 
+// Anchored-adapter index (AdapterIndex, adapters.py:1289-1551) as an open-addressing hash table.
+struct CgIndexEntry {       // 16 bytes; len == 0 marks an empty slot
+    uint64_t bases;         // 2 bits per character (A=0 C=1 G=2 T=3), first character in the low bits
+    uint32_t len;           // key length (1..32)
+    uint32_t val;           // adapter (16) | errors (8) | matches (8)
+};
+struct CgIndexHeader {      // 64 bytes, one per index, followed in the same array by its table
+    int32_t prefix;
+    int32_t n_lengths;
+    uint8_t lengths[32];    // descending (keys are 1..32 characters, so at most 32 distinct lengths)
+    uint32_t table_off;     // first CgIndexEntry of this index (in entries) within the index array
+    uint32_t table_mask;    // capacity - 1 (power of two)
+    uint32_t pad[4];
+};
+static_assert(sizeof(CgIndexHeader) == 64, "CgIndexHeader layout");
+
 // One result of locating a single adapter in a (sub)sequence; coordinates as SingleMatch.
 struct CgHit {
     int32_t adapter;        // -1 = none

@@ -194,7 +194,7 @@ class DeviceBatch:
         stream = torch.cuda.current_stream(self.device).cuda_stream or 1
         self.ctx = _lib.Context(self.device, stream)
         singles, groups, owners = self.adapters._flatten()
-        self.spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups)
+        self.spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups, self.adapters._flatten_indexes())
         self.adapter_set = _lib.AdapterSet(self.spec, self.ctx)
         self.n_adapters = len(singles)
         self.times = int(times)

@@ -58,6 +58,8 @@ extern "C" {
 /* ---- composition of adapters (adapters.py:1181-1286) ----------------------------------- */
 #define CG_GROUP_SINGLE 0   /* one SingleAdapter                                            */
 #define CG_GROUP_LINKED 1   /* LinkedAdapter(front=a0, back=a1)   adapters.py:1215-1227      */
+#define CG_GROUP_INDEXED 2  /* IndexedPrefixAdapters / IndexedSuffixAdapters (adapters.py:1289-1571):
+                               a0 = index number in the cg_index_desc array                    */
 
 typedef struct cg_ctx cg_ctx;               /* device, stream, staging buffers            */
 typedef struct cg_adapterset cg_adapterset; /* immutable compiled adapter tables on device */
@@ -105,6 +107,25 @@ typedef struct cg_group_desc {
     int32_t reserved[3];
 } cg_group_desc;
 
+/* The dict of an AdapterIndex (adapters.py:1416-1466), built on the host with
+ * cg_edit_environment / cg_hamming_environment: every key is an ACGT string of at most 32
+ * characters that maps to (adapter, errors, matches).  `lengths` are the distinct key lengths in
+ * descending order (AdapterIndex._lengths).  The device keeps it as an open-addressing hash table in
+ * HBM; lookups follow _match_to_one_length/_match_to_multiple_lengths/_lookup_with_n
+ * (adapters.py:1474-1551) exactly. */
+typedef struct cg_index_desc {
+    int32_t prefix;            /* 1: IndexedPrefixAdapters, 0: IndexedSuffixAdapters            */
+    int32_t n_lengths;
+    const int32_t *lengths;
+    int64_t n_keys;
+    const uint8_t *keys;       /* n_keys strings, `stride` bytes apart, NUL padded                */
+    int32_t stride;
+    int32_t reserved;
+    const int32_t *adapter;    /* per key: index into the adapter array                          */
+    const int32_t *errors;
+    const int32_t *matches;
+} cg_index_desc;
+
 /* Per-batch parameters of the fused pass (modifiers.py:840-858 then 200-261). */
 typedef struct cg_params {
     int32_t quality_trim;    /* 0 = off; 1 = run quality_trim_index first and search read[start:stop] */
@@ -150,6 +171,10 @@ int cg_ctx_kernel_time(cg_ctx *ctx, double *total_ms, int64_t *launches, int res
  *      KmerFinder.__cinit__ _kmer_finder.pyx:106-165 for every adapter at once) ----------- */
 int cg_adapterset_create(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n_adapters,
                          const cg_group_desc *groups, int32_t n_groups, cg_adapterset **out);
+/* Same, with anchored-adapter indexes for CG_GROUP_INDEXED groups. */
+int cg_adapterset_create_indexed(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n_adapters,
+                                 const cg_group_desc *groups, int32_t n_groups,
+                                 const cg_index_desc *indexes, int32_t n_indexes, cg_adapterset **out);
 int cg_adapterset_destroy(cg_adapterset *set);
 int cg_adapterset_slots(const cg_adapterset *set); /* 1, or 2 if any group is LINKED */
 /* Aligner.effective_length / PrefixComparer.effective_length (_align.pyx:188,268-271,626-630) */

@@ -265,6 +265,56 @@ def adapters_kat():
     dump("adapters_kat.json.gz", out)
 
 
+def index_kat():
+    """AdapterIndex / IndexedPrefixAdapters / IndexedSuffixAdapters (adapters.py:1289-1571)."""
+    rng = random.Random(1013)
+    out = []
+    while len(out) < 120:
+        prefix = rng.random() < 0.5
+        cls = "PrefixAdapter" if prefix else "SuffixAdapter"
+        members = []
+        for _ in range(rng.choice([1, 2, 3, 5, 8])):
+            seq = rnd(rng, "ACGT", rng.randint(4, 22))
+            kw = dict(max_errors=rng.choice([0, 0.1, 0.15, 0.2, 1, 2]), indels=rng.random() < 0.6,
+                      min_overlap=rng.choice([1, 3, len(seq)]))
+            members.append([seq, kw])
+        objs = [getattr(RA, cls)(s, name="x", **k) for s, k in members]
+        if not all(RA.AdapterIndex.is_acceptable(a, prefix) for a in objs):
+            continue
+        if any(int(len(s) * a.max_error_rate) >= len(s) for (s, _), a in zip(members, objs)):
+            continue
+        indexed = (RA.IndexedPrefixAdapters if prefix else RA.IndexedSuffixAdapters)(objs)
+        specs = [["Indexed", prefix, members]]
+        parts = [indexed]
+        if rng.random() < 0.4:
+            extra = [rng.choice(["BackAdapter", "FrontAdapter"]), rnd(rng, "ACGT", 12), dict(max_errors=0.1)]
+            specs.insert(rng.choice([0, 1]), extra)
+            obj = getattr(RA, extra[0])(extra[1], name="x", **extra[2])
+            parts = [obj, indexed] if specs[0] is extra else [indexed, obj]
+        multi = RA.MultipleAdapters(parts)
+        reads = []
+        for _ in range(40):
+            body = rnd(rng, "ACGT", rng.randint(0, 40))
+            ad = mutate(rng, rng.choice(members)[0], "ACGTN", rng.choice([0, 0, 1, 1, 2, 3]))
+            r = rng.random()
+            if r < 0.1:
+                q = body
+            elif r < 0.2:
+                q = ad[: rng.randint(0, len(ad))] if prefix else ad[rng.randint(0, len(ad)):]
+            else:
+                q = ad + body if prefix else body + ad
+            if rng.random() < 0.1:
+                q = q.lower()
+            if q and rng.random() < 0.05:
+                pos = rng.randrange(len(q))
+                q = q[:pos] + rng.choice("RYXn") + q[pos + 1:]
+            reads.append([q, match_desc(multi.match_to(q))])
+        ix = indexed._index
+        out.append({"adapters": specs, "reads": reads, "n_keys": len(ix._index),
+                    "lengths": list(ix._lengths), "ambiguous": ix._ambiguous})
+    dump("index_kat.json.gz", out)
+
+
 def info_file_kat():
     """Per-read coordinates pinned by the reference's golden files tests/cut/*.info.txt."""
     out = {}
@@ -332,6 +382,7 @@ if __name__ == "__main__":
     kmer_kat()
     qualtrim_kat()
     adapters_kat()
+    index_kat()
     info_file_kat()
     env_kat()
     tables()

@@ -16,14 +16,15 @@ static thread_local std::string g_err;
 
 extern "C" const char *hs_last_error(void) { return g_err.c_str(); }
 
-extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
-                                const cg_group_desc *groups, int n_groups, const uint8_t *seq,
-                                const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
-                                const cg_params *params, cg_match *matches, int32_t *qtrim,
-                                int force_wide)
+extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_adapters,
+                                        const cg_group_desc *groups, int n_groups,
+                                        const cg_index_desc *indexes, int n_indexes, const uint8_t *seq,
+                                        const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                                        const cg_params *params, cg_match *matches, int32_t *qtrim,
+                                        int force_wide)
 {
     CgBuiltSet set;
-    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err);
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err, indexes, n_indexes);
     if (rc != CG_OK) return rc;
     if (force_wide & 4) return set.simple_ok ? 1 : 0;   // query only: is the two-phase program available?
     if (force_wide & 1) {
@@ -33,7 +34,8 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
     }
     uint8_t enc[768];
     cg_build_enc_tables(enc);
-    SetView S = make_set_view(set.blob.data(), set.masks64.data(), enc);
+    SetView S = make_set_view(set.blob.data(), set.masks64.data(), enc,
+                              set.index_blob.empty() ? nullptr : set.index_blob.data());
     std::vector<uint32_t> colp((size_t)set.max_m + 2);
     std::vector<int> colw(3 * ((size_t)set.max_m + 2));
     PackedCol pc; pc.base = colp.data(); pc.stride = 1;
@@ -64,4 +66,14 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
                            qtrim ? qtrim + 2 * r : nullptr);
     }
     return CG_OK;
+}
+
+extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
+                                const cg_group_desc *groups, int n_groups, const uint8_t *seq,
+                                const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                                const cg_params *params, cg_match *matches, int32_t *qtrim,
+                                int force_wide)
+{
+    return hs_process_batch_indexed(adapters, n_adapters, groups, n_groups, nullptr, 0, seq, qual, offsets,
+                                    n_reads, params, matches, qtrim, force_wide);
 }

@@ -118,6 +118,60 @@ def test_adapter_classes_golden():
             assert match_desc(m) == expected, (case["adapters"], read)
 
 
+def test_indexed_adapters_golden():
+    """IndexedPrefixAdapters / IndexedSuffixAdapters: reference AdapterIndex.match_to() results."""
+    import cutadapt_b200.adapters as PA
+
+    for case in golden("index_kat.json.gz"):
+        multi = build_adapters(PA, case["adapters"])
+        reads = [r for r, _ in case["reads"]]
+        got = multi.match_to_batch(reads)
+        for (read, expected), m in zip(case["reads"], got):
+            assert match_desc(m) == expected, (case["adapters"], read)
+
+
+def test_config5_demultiplex_96_anchored_barcodes():
+    """BASELINE config 5 shape: 96 anchored 5' barcodes through the device index == the same
+    adapters evaluated one by one (MultipleAdapters semantics, adapters.py:1265-1286) whenever
+    the best hit is unique; every index hit is a true within-k barcode occurrence."""
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(96)
+    barcodes = set()
+    while len(barcodes) < 96:
+        barcodes.add("".join(rng.choice("ACGT") for _ in range(10)))
+    barcodes = sorted(barcodes)
+    pre = [PA.PrefixAdapter(b, max_errors=1, indels=False, name=f"bc{i}") for i, b in enumerate(barcodes)]
+    indexed = PA.IndexedPrefixAdapters(pre)
+    plain = PA.MultipleAdapters(pre)
+    reads = []
+    for _ in range(20000):
+        bc = list(rng.choice(barcodes))
+        if rng.random() < 0.3:
+            bc[rng.randrange(10)] = rng.choice("ACGTN")
+        if rng.random() < 0.1:
+            bc = [rng.choice("ACGT") for _ in range(10)]
+        reads.append("".join(bc) + "".join(rng.choice("ACGT") for _ in range(140)))
+    got = indexed.match_to_batch(reads)
+    ref = plain.match_to_batch(reads)
+    n_hit = 0
+    for read, g, r in zip(reads, got, ref):
+        has_n = "N" in read[:10]
+        if g is None:
+            # either nothing matches or the key was ambiguous between two barcodes (an N is looked
+            # up as A, adapters.py:1535-1551, which can make the looked-up key ambiguous or absent)
+            if r is not None and not has_n:
+                same = [b for b in barcodes if sum(x != y for x, y in zip(b, read[:10])) == r.errors]
+                assert len(same) > 1
+            continue
+        n_hit += 1
+        assert r is not None
+        assert (g.rstart, g.rstop) == (0, 10)
+        assert g.errors >= r.errors if has_n else g.errors == r.errors
+        assert sum(x != y for x, y in zip(g.adapter.sequence, read[:10])) == g.errors
+    assert n_hit > 15000
+
+
 def test_match_objects_behave_like_the_reference():
     """tests/test_adapters.py:38-76 (leftmost rule) and Match.trimmed / statistics plumbing."""
     import cutadapt_b200.adapters as PA

@@ -122,6 +122,37 @@ def test_adapter_classes_construct_like_the_reference():
     pickle.loads(pickle.dumps(multi))
 
 
+def test_adapter_index_acceptance_and_layout():
+    """AdapterIndex._accept (adapters.py:1366-1378) plus the device-side restrictions."""
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200 import _lib as L
+
+    ok = PA.PrefixAdapter("ACGTACGTAC", max_errors=0.1)
+    assert PA.AdapterIndex.is_acceptable(ok, prefix=True)
+    assert not PA.AdapterIndex.is_acceptable(ok, prefix=False)
+    assert not PA.AdapterIndex.is_acceptable(PA.SuffixAdapter("ACGTACGTAC", read_wildcards=True), prefix=False)
+    assert not PA.AdapterIndex.is_acceptable(PA.PrefixAdapter("ACGNACGTAC", adapter_wildcards=True), prefix=True)
+    assert not PA.AdapterIndex.is_acceptable(PA.PrefixAdapter("ACGT" * 10, max_errors=0.1), prefix=True)  # k = 4
+    assert not PA.AdapterIndex.is_acceptable(PA.PrefixAdapter("ACGT" * 9), prefix=True)              # too long
+    with pytest.raises(ValueError):
+        PA.IndexedPrefixAdapters([])
+    with pytest.raises(ValueError):
+        PA.IndexedPrefixAdapters([PA.SuffixAdapter("ACGT")])
+    a = PA.PrefixAdapter("ACGTAC", max_errors=1, indels=False)
+    b = PA.PrefixAdapter("TTGCAATG", max_errors=1, indels=True)
+    ix = PA.IndexedPrefixAdapters([a, b])
+    d = ix._flatten_indexes()[0]
+    assert d["prefix"] and d["lengths"] == [9, 8, 7, 6]
+    assert len(d["keys"]) == len(set(d["keys"])) == len(ix._index._index)
+    assert d["keys"].count("ACGTAC") == 1 and d["errors"][d["keys"].index("ACGTAC")] == 0
+    multi = PA.MultipleAdapters([PA.BackAdapter("GGGGGG"), ix, PA.IndexedSuffixAdapters([PA.SuffixAdapter("CCCAAA")])])
+    singles, groups, owners = multi._flatten()
+    assert [g[:3] for g in groups] == [(0, 0, -1), (L.CG_GROUP_INDEXED, 0, -1), (L.CG_GROUP_INDEXED, 1, -1)]
+    idx = multi._flatten_indexes()
+    assert len(idx) == 2 and set(idx[0]["adapter"]) == {1, 2} and set(idx[1]["adapter"]) == {3}
+    assert len(singles) == 4 and owners[1] is ix
+
+
 def test_environment_generators_golden():
     from cutadapt_b200._align import edit_environment, hamming_environment, hamming_sphere
 

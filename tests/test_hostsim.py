@@ -51,6 +51,26 @@ def test_adapters_golden():
             assert match_desc(multi.matches_from_records(recs[i, 0], read)) == expected, (case["adapters"], read)
 
 
+def test_indexed_adapters_golden():
+    """IndexedPrefixAdapters / IndexedSuffixAdapters (adapters.py:1289-1571): index build + lookups."""
+    import cutadapt_b200.adapters as PA
+
+    hits = 0
+    for case in golden("index_kat.json.gz"):
+        multi = build_adapters(PA, case["adapters"])
+        indexed = [a for a in multi if isinstance(a, PA._IndexedAdapters)][0]
+        assert len(indexed._index._index) == case["n_keys"]
+        assert list(indexed._index._lengths) == case["lengths"]
+        assert indexed._index._ambiguous == case["ambiguous"]
+        spec = spec_of(multi)
+        reads = [r for r, _ in case["reads"]]
+        recs, _ = hostsim_process(spec, reads)
+        for i, (read, expected) in enumerate(case["reads"]):
+            assert match_desc(multi.matches_from_records(recs[i, 0], read)) == expected, (case["adapters"], read)
+            hits += expected is not None
+    assert hits > 1000
+
+
 def test_rounds_and_quality_trim_against_oracle():
     import cutadapt_b200.adapters as PA
 

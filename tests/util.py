@@ -50,6 +50,11 @@ def hostsim_lib():
             C.POINTER(L.cg_adapter_desc), C.c_int, C.POINTER(L.cg_group_desc), C.c_int, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(L.cg_params), C.c_void_p, C.c_void_p, C.c_int,
         ]
+        lib.hs_process_batch_indexed.argtypes = [
+            C.POINTER(L.cg_adapter_desc), C.c_int, C.POINTER(L.cg_group_desc), C.c_int,
+            C.POINTER(L.cg_index_desc), C.c_int, C.c_void_p,
+            C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(L.cg_params), C.c_void_p, C.c_void_p, C.c_int,
+        ]
         _hs = lib
     return _hs
 
@@ -64,8 +69,9 @@ def hostsim_process(spec, seqs, quals=None, params=None, force_wide=0):
     times = max(1, params.times)
     out = np.zeros((len(seqs), times, spec.slots), dtype=L.MATCH_DTYPE)
     qt = np.zeros((len(seqs), 2), dtype=np.int32)
-    rc = hostsim_lib().hs_process_batch(
-        arr, n, garr, ng, data.ctypes.data, qd.ctypes.data if qd is not None else None, offs.ctypes.data,
+    iarr, ni = spec.index_ctypes()
+    rc = hostsim_lib().hs_process_batch_indexed(
+        arr, n, garr, ng, iarr, ni, data.ctypes.data, qd.ctypes.data if qd is not None else None, offs.ctypes.data,
         len(seqs), C.byref(params), out.ctypes.data, qt.ctypes.data, force_wide,
     )
     if rc:
@@ -85,6 +91,11 @@ def build_adapters(module, specs):
             front = getattr(module, t1)(s1, name="f", **k1)
             back = getattr(module, t2)(s2, name="b", **k2)
             objs.append(module.LinkedAdapter(front, back, fq, bq, "lnk"))
+        elif spec[0] == "Indexed":
+            _, prefix, members = spec
+            cls = module.PrefixAdapter if prefix else module.SuffixAdapter
+            parts = [cls(s, name="x", **k) for s, k in members]
+            objs.append((module.IndexedPrefixAdapters if prefix else module.IndexedSuffixAdapters)(parts))
         else:
             t, s, k = spec
             objs.append(getattr(module, t)(s, name="x", **k))
@@ -104,7 +115,7 @@ def spec_of(multi):
     from cutadapt_b200 import _lib as L
 
     singles, groups, owners = multi._flatten()
-    spec = L.AdapterSetSpec([s.descriptor() for s in singles], groups)
+    spec = L.AdapterSetSpec([s.descriptor() for s in singles], groups, multi._flatten_indexes())
     multi._device_set = (None, singles, owners)
     return spec
 
