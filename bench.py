@@ -125,14 +125,17 @@ class CpuArm:
         self.pass_seconds = max(r[0] for r in res)
 
     def run(self, seconds_target):
-        # re-calibrate on a warm pass (the first one includes cold caches / frequency ramp)
-        res = self.pool.map(_cpu_worker, [1] * self.cores, chunksize=1)
-        self.pass_seconds = max(r[0] for r in res)
-        repeat = max(1, int(round(seconds_target / max(self.pass_seconds, 1e-3))))
+        # calibrate on a warm, multi-pass run (a single pass is dominated by stragglers / dispatch)
+        if not getattr(self, "rate", None):
+            t0 = time.perf_counter()
+            res = self.pool.map(_cpu_worker, [4] * self.cores, chunksize=1)
+            self.rate = sum(r[1] for r in res) / (time.perf_counter() - t0)
+        repeat = max(1, int(round(seconds_target * self.rate / max(self.pass_reads, 1))))
         t0 = time.perf_counter()
         res = self.pool.map(_cpu_worker, [repeat] * self.cores, chunksize=1)
         wall = time.perf_counter() - t0
         n = sum(r[1] for r in res)
+        self.rate = n / wall
         return n / wall, n, wall
 
     def close(self):

@@ -108,6 +108,8 @@ struct cg_ctx {
     DevBuf<uint4> tasks;                 // split pipeline: 2 x uint4 per read of a sub-batch
     DevBuf<uint4> tasks2, tasks3;        // run-record lists (ping-pong): 4 x uint4 per read of a sub-batch
     unsigned long long *d_task_count = nullptr;
+    DevBuf<cg_match_rec> pass_tmp;       // multi-pass schedule: records of every pass for one sub-batch
+    DevBuf<int32_t> view_base, view_back;
     long long launches = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // fused-kernel event pairs
     std::vector<cudaEvent_t> event_pool;
@@ -122,6 +124,17 @@ struct cg_adapterset {
     uint64_t *d_masks = nullptr;
     CgEntry *d_entries = nullptr;   // device pointer into d_blob
     uint8_t *d_index = nullptr;     // anchored-adapter hash tables, or null
+    // multi-pass schedule (several groups, times == 1): one sub-set per component adapter
+    struct Pass {
+        cg_adapterset *sub = nullptr;
+        int group = 0, role = 0;    // role 1: back adapter of a LINKED group
+        int front_pass = -1;        // role 1: the pass of the front adapter
+        int map_off = 0;            // first entry in pass_map (local -> global adapter numbers)
+    };
+    std::vector<Pass> passes;
+    std::vector<int32_t> pass_map;
+    int32_t *d_pass_map = nullptr;
+    CgSelectTables select_tables;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -183,6 +196,7 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
         if (l.stream) cudaStreamDestroy(l.stream);
     }
     c->scratch_p.release(); c->scratch_w.release(); c->tasks.release(); c->tasks2.release(); c->tasks3.release();
+    c->pass_tmp.release(); c->view_base.release(); c->view_back.release();
     if (c->d_task_count) cudaFree(c->d_task_count);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_enc) cudaFree(c->d_enc);
@@ -214,16 +228,18 @@ extern "C" int cg_ctx_kernel_time(cg_ctx *c, double *total_ms, int64_t *launches
 }
 
 // ------------------------------------------------------------------------------------------
-extern "C" int cg_adapterset_create_indexed(cg_ctx *c, const cg_adapter_desc *adapters, int32_t n_adapters,
-                                            const cg_group_desc *groups, int32_t n_groups,
-                                            const cg_index_desc *indexes, int32_t n_indexes, cg_adapterset **out)
+static void destroy_passes(cg_adapterset *s)
 {
-    if (!c || !out) return fail(CG_EINVAL, "cg_adapterset_create: NULL argument");
-    cg_adapterset *s = new cg_adapterset();
+    for (auto &p : s->passes) cg_adapterset_destroy(p.sub);
+    s->passes.clear();
+    s->pass_map.clear();
+    if (s->d_pass_map) { cudaFree(s->d_pass_map); s->d_pass_map = nullptr; }
+}
+
+// Copies the compiled tables of s->host to the device.
+static int upload_set(cg_ctx *c, cg_adapterset *s)
+{
     s->ctx = c;
-    std::string err;
-    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, s->host, err, indexes, n_indexes);
-    if (rc != CG_OK) { delete s; return fail(rc, err); }
     cudaError_t e = cudaSetDevice(c->device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_blob, s->host.blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(s->d_blob, s->host.blob.data(), s->host.blob.size(), cudaMemcpyHostToDevice);
@@ -237,8 +253,47 @@ extern "C" int cg_adapterset_create_indexed(cg_ctx *c, const cg_adapter_desc *ad
         if (s->d_blob) cudaFree(s->d_blob);
         if (s->d_masks) cudaFree(s->d_masks);
         if (s->d_index) cudaFree(s->d_index);
-        delete s;
+        s->d_blob = nullptr; s->d_masks = nullptr; s->d_index = nullptr;
         return cuda_fail(e, "adapter set upload");
+    }
+    return CG_OK;
+}
+
+extern "C" int cg_adapterset_create_indexed(cg_ctx *c, const cg_adapter_desc *adapters, int32_t n_adapters,
+                                            const cg_group_desc *groups, int32_t n_groups,
+                                            const cg_index_desc *indexes, int32_t n_indexes, cg_adapterset **out)
+{
+    if (!c || !out) return fail(CG_EINVAL, "cg_adapterset_create: NULL argument");
+    cg_adapterset *s = new cg_adapterset();
+    std::string err;
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, s->host, err, indexes, n_indexes);
+    if (rc != CG_OK) { delete s; return fail(rc, err); }
+    rc = upload_set(c, s);
+    if (rc != CG_OK) { delete s; return rc; }
+    // multi-pass schedule (cg_setbuild.cpp: cg_plan_passes); an empty plan keeps the one-kernel schedule
+    CgMultiPlan plan;
+    if (cg_plan_passes(adapters, n_adapters, groups, n_groups, indexes, n_indexes, plan, err) == CG_OK &&
+        !plan.passes.empty()) {
+        bool ok = true;
+        for (auto &pp : plan.passes) {
+            cg_adapterset::Pass P;
+            P.group = pp.group; P.role = pp.role; P.front_pass = pp.front_pass; P.map_off = pp.map_off;
+            P.sub = new cg_adapterset();
+            P.sub->host = std::move(pp.set);
+            if (upload_set(c, P.sub) != CG_OK) { delete P.sub; ok = false; break; }
+            s->passes.push_back(P);
+        }
+        if (ok) {
+            const CgSetHeader *H = (const CgSetHeader *)s->host.blob.data();
+            cg_fill_select_tables((const CgGroup *)(s->host.blob.data() + H->groups_off), s->host.n_groups,
+                                  s->host.slots, plan.passes, s->select_tables);
+            s->pass_map = plan.pass_map;
+            cudaError_t e = cudaMalloc((void **)&s->d_pass_map, s->pass_map.size() * sizeof(int32_t));
+            if (e == cudaSuccess)
+                e = cudaMemcpy(s->d_pass_map, s->pass_map.data(), s->pass_map.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cudaGetLastError(); ok = false; }
+        }
+        if (!ok) destroy_passes(s);
     }
     *out = s;
     return CG_OK;
@@ -257,6 +312,7 @@ extern "C" int cg_adapterset_destroy(cg_adapterset *s)
     if (s->d_blob) cudaFree(s->d_blob);
     if (s->d_masks) cudaFree(s->d_masks);
     if (s->d_index) cudaFree(s->d_index);
+    destroy_passes(s);
     delete s;
     return CG_OK;
 }
@@ -273,9 +329,10 @@ extern "C" int cg_adapterset_effective_length(const cg_adapterset *s, int32_t ad
 // ------------------------------------------------------------------------------------------
 // Launch of the trimming pass on device-resident data
 // ------------------------------------------------------------------------------------------
-static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
-                       const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
-                       cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed)
+static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
+                              const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
+                              cg_match_rec *d_out, int32_t *d_qtrim, const int32_t *d_view, cudaStream_t st,
+                              bool timed)
 {
     if (n_reads <= 0) return CG_OK;
     const int times = p->times < 1 ? 1 : p->times;
@@ -288,7 +345,7 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
     a.seq = d_seq; a.qual = want_q ? d_qual : nullptr; a.offsets = d_offsets; a.n_reads = n_reads;
     a.quality_trim = want_q ? 1 : 0; a.cutoff_front = p->cutoff_front; a.cutoff_back = p->cutoff_back;
     a.qbase = p->quality_base; a.times = times; a.slots = s->host.slots;
-    a.out = d_out; a.qtrim = d_qtrim; a.err_flag = c->d_err;
+    a.out = d_out; a.qtrim = d_qtrim; a.view = d_view; a.err_flag = c->d_err;
     a.col_rows = s->host.max_m + 1;
 
     const long long tile_cap_ll = ((long long)CG_NT * max_read_len + 32 + 15) / 16 * 16;
@@ -309,13 +366,13 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         CU(cg_fast_occupancy(want_q, simple, smem, &occ));
         if (occ < 1) fast = false;
     }
-    // split pipeline (default for one aligner adapter with m <= 32): scan kernel -> task list -> DP kernel
+    // split pipeline (default for one aligner adapter with m <= 64): scan kernel -> task list -> DP kernel
     const bool force_block = kernel_env && strcmp(kernel_env, "block") == 0;
     const bool force_warp = kernel_env && strcmp(kernel_env, "warp") == 0;
     bool split = false;
     size_t scan_smem = 0, list_smem = 0;
     int scan_occ = 0, plan_occ = 0, run_occ = 0;
-    if (simple && s->host.max_m <= 32 && !force_block && !force_warp) {
+    if (simple && s->host.max_m <= 64 && !force_block && !force_warp) {
         const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
         const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
         if (mini < (1 << 20)) {
@@ -370,6 +427,7 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
             b.n_reads = n_sub;
             b.out = a.out + (size_t)r0 * a.times * a.slots;
             b.qtrim = a.qtrim ? a.qtrim + 2 * r0 : nullptr;
+            b.view = a.view ? a.view + 2 * r0 : nullptr;
             b.task_cap = n_sub;
             CU(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), st));
             const long long n_mt = (n_sub + 31) / 32;
@@ -418,6 +476,81 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         CU(cg_launch_generic(a, (int)(threads / block), block, st));
     }
     c->launches += 1;
+    if (ev0) {
+        CU(cudaEventRecord(ev1, st));
+        c->timing.emplace_back(ev0, ev1);
+    }
+    return CG_OK;
+}
+
+// Several groups, one round: per-adapter passes + selection (see plan_passes_for).
+static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
+                       const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
+                       cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed)
+{
+    if (n_reads <= 0) return CG_OK;
+    const int times = p->times < 1 ? 1 : p->times;
+    const char *kernel_env = getenv("CUTADAPT_B200_KERNEL");
+    const bool force_general = kernel_env && strcmp(kernel_env, "general") == 0;
+    if (s->passes.empty() || times != 1 || force_general)
+        return launch_trim_single(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, d_out, d_qtrim, nullptr,
+                                  st, timed);
+    const bool want_q = p->quality_trim != 0;
+    if (want_q && !d_qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
+    const int np = (int)s->passes.size();
+    const long long SUB = 4LL << 20;
+    const long long cap = std::min<long long>(n_reads, SUB);
+    int rc = c->pass_tmp.ensure((size_t)cap * np);
+    if (rc != CG_OK) return rc;
+    bool any_linked = false;
+    for (auto &P : s->passes) any_linked = any_linked || P.role == 1;
+    if (any_linked) { rc = c->view_back.ensure((size_t)cap * 2); if (rc != CG_OK) return rc; }
+    if (want_q && !d_qtrim) { rc = c->view_base.ensure((size_t)cap * 2); if (rc != CG_OK) return rc; }
+
+    CgSelectArgs sel;
+    memset(&sel, 0, sizeof sel);
+    sel.tmp = c->pass_tmp.p; sel.stride = cap; sel.pass_map = s->d_pass_map;
+    sel.t = s->select_tables;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (timed && c->timing.size() < 8192) {
+        for (cudaEvent_t *ev : {&ev0, &ev1}) {
+            if (!c->event_pool.empty()) { *ev = c->event_pool.back(); c->event_pool.pop_back(); }
+            else CU(cudaEventCreate(ev));
+        }
+        CU(cudaEventRecord(ev0, st));
+    }
+    for (long long r0 = 0; r0 < n_reads; r0 += SUB) {
+        const long long n_sub = std::min<long long>(SUB, n_reads - r0);
+        const int64_t *offs = d_offsets + r0;
+        int32_t *qt = want_q ? (d_qtrim ? d_qtrim + 2 * r0 : c->view_base.p) : nullptr;
+        const int32_t *base_view = nullptr;
+        for (int pi = 0; pi < np; ++pi) {
+            const auto &P = s->passes[pi];
+            cg_match_rec *tmp = c->pass_tmp.p + (size_t)pi * cap;
+            cg_params pp = *p;
+            pp.times = 1;
+            const int32_t *view = base_view;
+            if (P.role == 1) {
+                CU(cg_launch_linked_view(c->pass_tmp.p + (size_t)P.front_pass * cap, base_view, offs, n_sub,
+                                         c->view_back.p, st));
+                c->launches += 1;
+                view = c->view_back.p;
+            }
+            if (want_q && pi == 0) {        // the first pass does the quality trimming (fused) for all
+                rc = launch_trim_single(c, P.sub, d_seq, d_qual, offs, n_sub, max_read_len, &pp, tmp, qt, nullptr, st, false);
+                base_view = qt;
+            } else {
+                pp.quality_trim = 0;
+                rc = launch_trim_single(c, P.sub, d_seq, nullptr, offs, n_sub, max_read_len, &pp, tmp, nullptr, view, st, false);
+            }
+            if (rc != CG_OK) return rc;
+        }
+        sel.n_reads = n_sub;
+        sel.out = d_out + (size_t)r0 * s->host.slots;
+        CU(cg_launch_select(sel, st));
+        c->launches += 1;
+    }
     if (ev0) {
         CU(cudaEventRecord(ev1, st));
         c->timing.emplace_back(ev0, ev1);

@@ -756,7 +756,8 @@ CG_HD void store_hit(cg_match_rec *dst, const CgHit &h, int group, int searched_
 template <bool ALLOW_WIDE>
 CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
                         int quality_trim, int cutoff_front, int cutoff_back, int qbase, int times,
-                        PackedCol &colp, WideCol &colw, cg_match_rec *out, int32_t *qtrim_out)
+                        PackedCol &colp, WideCol &colw, cg_match_rec *out, int32_t *qtrim_out,
+                        const int32_t *view = nullptr)
 {
     const int slots = S.h->slots;
     int s = 0, e = n;
@@ -764,6 +765,7 @@ CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qua
         quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
     }
     if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
+    if (view) { s = view[0]; e = view[1]; }                    // per-adapter pass: search read[s:e]
     CgHit none; none.adapter = -1; none.remove = 0;
     none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
     bool alive = true;
@@ -798,6 +800,57 @@ CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qua
         // trimmed_read = match.trimmed(trimmed_read)           (modifiers.py:231; adapters.py:1132-1137)
         if (best.h0.adapter >= 0) apply_trim(best.h0, s, e);
         if (best.h1.adapter >= 0) apply_trim(best.h1, s, e);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Multi-pass schedule: every component adapter of a set is located on its own (one pass each, into
+// a scratch array of records), then these two functions apply the composition rules.
+// ---------------------------------------------------------------------------------------
+// View of a LinkedAdapter's back adapter: sequence[front_match.trim_slice()]  (adapters.py:1220-1222)
+CG_HD void linked_view(const cg_match_rec &front, int &s, int &e)
+{
+    if (front.adapter < 0) return;
+    if (front.info & 256) e = s + front.rstart;          // RemoveAfterMatch
+    else s += front.rstop;                               // RemoveBeforeMatch
+}
+
+// MultipleAdapters.match_to (adapters.py:1271-1286) over the per-pass records: highest score, then
+// fewest errors, then the group listed first; LinkedAdapter.match_to (adapters.py:1215-1227) for
+// LINKED groups.  `load(pass)` returns this read's record of a pass.
+template <class Load>
+CG_HD void select_best(const CgSelectTables &T, const int32_t *pass_map, Load load, cg_match_rec &b0,
+                       cg_match_rec &b1)
+{
+    cg_match_rec none;
+    none.adapter = -1; none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = none.info = 0;
+    b0 = none; b1 = none;
+    bool have = false;
+    int best_score = 0, best_errors = 0;
+    for (int g = 0; g < T.n_groups; ++g) {
+        cg_match_rec h0 = load((int)T.pass0[g]), h1 = none;
+        int score, errors;
+        if (T.gtype[g] != CGK_GROUP_LINKED) {
+            if (h0.adapter < 0) continue;
+            h0.adapter = pass_map[T.map_off[T.pass0[g]] + h0.adapter];
+            score = h0.score; errors = h0.errors;
+        } else {
+            const bool front = h0.adapter >= 0;
+            if (T.front_required[g] && !front) continue;
+            h1 = load((int)T.pass1[g]);
+            const bool back = h1.adapter >= 0;
+            if (!back && (T.back_required[g] || !front)) continue;
+            if (front) h0.adapter = pass_map[T.map_off[T.pass0[g]] + h0.adapter]; else h0 = none;
+            if (back) h1.adapter = pass_map[T.map_off[T.pass1[g]] + h1.adapter]; else h1 = none;
+            score = (front ? h0.score : 0) + (back ? h1.score : 0);
+            errors = (front ? h0.errors : 0) + (back ? h1.errors : 0);
+        }
+        if (!have || score > best_score || (score == best_score && errors < best_errors)) {
+            have = true; best_score = score; best_errors = errors;
+            if (h0.adapter >= 0) h0.info = (h0.info & ~255) | g;
+            if (h1.adapter >= 0) h1.info = (h1.info & ~255) | g;
+            b0 = h0; b1 = h1;
+        }
     }
 }
 
@@ -1607,7 +1660,8 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
                 const uint8_t *bytes = A.reverse ? seq + s + (nn - hi) : seq + s + lo;
                 const bool last = r == P.n_runs - 1;
                 if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-                else run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+                else if (A.m <= 32) run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+                else run_pass<64>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
             }
             hit_from_state(A, nn, st, hit);
         }

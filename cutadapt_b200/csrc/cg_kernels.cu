@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                 }
                 process_read<false>(S, p, q, n, HAS_QUAL ? a.quality_trim : 0, a.cutoff_front, a.cutoff_back,
                                     a.qbase, a.times, colp, colw,
-                                    a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr);
+                                    a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr,
+                                    a.view ? a.view + 2 * r : nullptr);
             }
         } else {
             // ---- phase A: quality trim + fused scan on every read of the tile ----------------
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                     if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
                 }
                 if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+                if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
                 t_off = off + (uint32_t)ts; t_len = (uint32_t)(te - ts);
                 const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
                 pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
@@ -466,6 +468,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_warp_kernel(const CgKernelArgs 
                     if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
                 }
                 if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+                if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
                 t_off = off + (uint32_t)ts; t_len = (uint32_t)(te - ts);
                 const ScanOut sc = simple_scan(S, tile_seq + t_off, (int)t_len, &gs);
                 pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
@@ -546,7 +549,7 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 }
 
 // ------------------------------------------------------------------------------------------
-// Split pipeline for one aligner adapter (m <= 32), one round:
+// Split pipeline for one aligner adapter (m <= 64), one round:
 //
 //   cg_scan_kernel   phase A on every read at high occupancy (few registers): per-warp TMA-staged
 //                    mini-tiles of 32 reads, quality trim + fused scan; failing reads get their
@@ -685,6 +688,7 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
                 if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
             }
             if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+            if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
             const ScanOut sc = simple_scan(S, tile_seq + off + ts, te - ts, &gs);
             pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
             if (!pass) {
@@ -761,7 +765,7 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 //               finished (early exit or last run) get their record, the others move to the output
 //               list with the updated selection state.
 template <bool PLAN, int MR>
-__global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : 3)) cg_list_kernel(const CgKernelArgs a)
+__global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : (MR <= 32 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int slot_bytes = a.carry_slot;
@@ -909,7 +913,7 @@ typedef void (*list_kernel_t)(const CgKernelArgs);
 static list_kernel_t pick_list(bool plan, int mr)
 {
     if (plan) return cg_list_kernel<true, 16>;
-    return mr <= 16 ? cg_list_kernel<false, 16> : cg_list_kernel<false, 32>;
+    return mr <= 16 ? cg_list_kernel<false, 16> : (mr <= 32 ? cg_list_kernel<false, 32> : cg_list_kernel<false, 64>);
 }
 cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm)
 {
@@ -921,6 +925,60 @@ cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm
 cudaError_t cg_launch_list(const CgKernelArgs &a, bool plan, int mr, int grid, size_t smem, cudaStream_t st)
 {
     pick_list(plan, mr)<<<grid, CG_NT, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-pass schedule: view of a linked adapter's back pass, and the final selection
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ cg_match_rec load_rec(const cg_match_rec *p)
+{
+    const int4 a = __ldg((const int4 *)p), b = __ldg((const int4 *)p + 1);
+    cg_match_rec r;
+    r.adapter = a.x; r.astart = a.y; r.astop = a.z; r.rstart = a.w;
+    r.rstop = b.x; r.score = b.y; r.errors = b.z; r.info = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_rec(cg_match_rec *p, const cg_match_rec &r)
+{
+    ((int4 *)p)[0] = make_int4(r.adapter, r.astart, r.astop, r.rstart);
+    ((int4 *)p)[1] = make_int4(r.rstop, r.score, r.errors, r.info);
+}
+
+__global__ void cg_linked_view_kernel(const cg_match_rec *front, const int32_t *base_view, const int64_t *offsets,
+                                      long long n_reads, int32_t *out_view)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    int s = 0, e;
+    if (base_view) { s = base_view[2 * r]; e = base_view[2 * r + 1]; }
+    else e = (int)(offsets[r + 1] - offsets[r]);
+    linked_view(load_rec(front + r), s, e);
+    *(int2 *)(out_view + 2 * r) = make_int2(s, e);
+}
+cudaError_t cg_launch_linked_view(const cg_match_rec *front, const int32_t *base_view, const int64_t *offsets,
+                                  long long n_reads, int32_t *out_view, cudaStream_t st)
+{
+    const int block = 256;
+    cg_linked_view_kernel<<<(unsigned)((n_reads + block - 1) / block), block, 0, st>>>(front, base_view, offsets,
+                                                                                     n_reads, out_view);
+    return cudaGetLastError();
+}
+
+__global__ void cg_select_kernel(const CgSelectArgs a)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_reads) return;
+    cg_match_rec b0, b1;
+    select_best(a.t, a.pass_map, [&](int pass) { return load_rec(a.tmp + (size_t)pass * a.stride + r); }, b0, b1);
+    cg_match_rec *dst = a.out + (size_t)r * a.t.slots;
+    store_rec(dst, b0);
+    if (a.t.slots > 1) store_rec(dst + 1, b1);
+}
+cudaError_t cg_launch_select(const CgSelectArgs &a, cudaStream_t st)
+{
+    const int block = 256;
+    cg_select_kernel<<<(unsigned)((a.n_reads + block - 1) / block), block, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -943,7 +1001,8 @@ __global__ void cg_trim_generic_kernel(const CgKernelArgs a)
         if (bad & 0x80) atomicOr(a.err_flag, 1);
         process_read<true>(S, p, a.qual ? a.qual + o0 : nullptr, n, a.qual ? a.quality_trim : 0,
                            a.cutoff_front, a.cutoff_back, a.qbase, a.times, colp, colw,
-                           a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr);
+                           a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr,
+                                    a.view ? a.view + 2 * r : nullptr);
     }
 }
 

@@ -24,6 +24,8 @@ struct CgKernelArgs {
     // outputs (HBM)
     cg_match_rec *out;
     int32_t *qtrim;
+    const int32_t *view;  // optional per-read (start, stop): search read[start:stop] instead of the
+                          // quality-trimmed read (per-adapter passes of the multi-pass schedule)
     int *err_flag;
     // fused-kernel geometry
     int tile_cap;  // bytes per staged tile (multiple of 16)
@@ -42,6 +44,22 @@ struct CgKernelArgs {
     int *scratch_w;
     long long scratch_stride;
 };
+
+// Multi-pass schedule (several adapters, one round): every component adapter runs as its own pass into a
+// scratch array of records; cg_select_kernel then applies MultipleAdapters.match_to / LinkedAdapter.match_to
+// to the per-adapter results.
+struct CgSelectArgs {
+    const cg_match_rec *tmp;      // [n_passes][stride] records of the passes
+    long long stride;
+    long long n_reads;
+    cg_match_rec *out;            // n_reads * slots
+    const int32_t *pass_map;      // local -> global adapter numbers of all passes, concatenated
+    CgSelectTables t;
+};
+cudaError_t cg_launch_select(const CgSelectArgs &a, cudaStream_t st);
+// view of the back adapter of a LinkedAdapter: the base view with the front match trimmed off
+cudaError_t cg_launch_linked_view(const cg_match_rec *front, const int32_t *base_view, const int64_t *offsets,
+                                  long long n_reads, int32_t *out_view, cudaStream_t st);
 
 size_t cg_fast_smem_bytes(uint32_t blob_bytes, int tile_cap, int col_rows, bool has_qual);
 cudaError_t cg_launch_fast(const CgKernelArgs &a, bool has_qual, bool simple, int grid, size_t smem, cudaStream_t st);

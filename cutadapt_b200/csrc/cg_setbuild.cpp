@@ -533,3 +533,81 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     if (out.masks64.empty()) out.masks64.assign(128, 0);   // never hand the kernel a null table
     return CG_OK;
 }
+
+
+// ---- multi-pass schedule -------------------------------------------------------------------------
+int cg_plan_passes(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
+                   const cg_index_desc *indexes, int n_indexes, CgMultiPlan &plan, std::string &err)
+{
+    plan.passes.clear();
+    plan.pass_map.clear();
+    if (n_groups > CG_MAX_PASSES) return CG_OK;
+    if (n_groups == 1 && groups[0].type != CG_GROUP_LINKED) return CG_OK;
+    int total = 0;
+    for (int g = 0; g < n_groups; ++g) total += groups[g].type == CG_GROUP_LINKED ? 2 : 1;
+    if (total > CG_MAX_PASSES) return CG_OK;
+    bool ok = true;
+    for (int g = 0; g < n_groups && ok; ++g) {
+        const cg_group_desc &G = groups[g];
+        const int comps = G.type == CG_GROUP_LINKED ? 2 : 1;
+        int front_pass = -1;
+        for (int role = 0; role < comps && ok; ++role) {
+            plan.passes.emplace_back();
+            CgPassPlan &P = plan.passes.back();
+            P.group = g; P.role = role; P.front_pass = role ? front_pass : -1;
+            P.map_off = (int)plan.pass_map.size();
+            if (role == 0) front_pass = (int)plan.passes.size() - 1;
+            cg_group_desc G2;
+            memset(&G2, 0, sizeof G2);
+            G2.a1 = -1;
+            if (G.type == CG_GROUP_INDEXED) {
+                if (G.a0 < 0 || G.a0 >= n_indexes) { ok = false; break; }
+                const cg_index_desc &X = indexes[G.a0];
+                std::vector<int> local(n_adapters, -1);
+                std::vector<cg_adapter_desc> sub_ads;
+                std::vector<int32_t> remap((size_t)(X.n_keys > 0 ? X.n_keys : 0));
+                for (int64_t k = 0; k < X.n_keys; ++k) {
+                    const int ga = X.adapter[k];
+                    if (ga < 0 || ga >= n_adapters) { ok = false; break; }
+                    if (local[ga] < 0) {
+                        local[ga] = (int)sub_ads.size();
+                        sub_ads.push_back(adapters[ga]);
+                        plan.pass_map.push_back(ga);
+                    }
+                    remap[(size_t)k] = local[ga];
+                }
+                if (!ok || sub_ads.empty()) { ok = false; break; }
+                cg_index_desc X2 = X;
+                X2.adapter = remap.data();
+                G2.type = CG_GROUP_INDEXED;
+                if (cg_build_set(sub_ads.data(), (int)sub_ads.size(), &G2, 1, P.set, err, &X2, 1) != CG_OK) ok = false;
+            } else {
+                const int ga = role ? G.a1 : G.a0;
+                if (ga < 0 || ga >= n_adapters) { ok = false; break; }
+                plan.pass_map.push_back(ga);
+                G2.type = CG_GROUP_SINGLE;
+                if (cg_build_set(adapters + ga, 1, &G2, 1, P.set, err) != CG_OK) ok = false;
+                else if (adapters[ga].kind == CG_KIND_ALIGNER && !(P.set.simple_ok && P.set.max_m <= 64)) ok = false;
+            }
+        }
+    }
+    if (!ok) { plan.passes.clear(); plan.pass_map.clear(); }
+    return CG_OK;
+}
+
+void cg_fill_select_tables(const CgGroup *groups, int n_groups, int slots, const std::vector<CgPassPlan> &passes,
+                           CgSelectTables &t)
+{
+    memset(&t, 0, sizeof t);
+    t.n_groups = n_groups; t.slots = slots;
+    for (int g = 0; g < n_groups && g < CG_MAX_PASSES; ++g) {
+        t.gtype[g] = (int8_t)groups[g].type;
+        t.front_required[g] = (int8_t)groups[g].front_required;
+        t.back_required[g] = (int8_t)groups[g].back_required;
+    }
+    for (size_t pi = 0; pi < passes.size() && pi < CG_MAX_PASSES; ++pi) {
+        t.map_off[pi] = passes[pi].map_off;
+        if (passes[pi].role == 0) t.pass0[passes[pi].group] = (int8_t)pi;
+        else t.pass1[passes[pi].group] = (int8_t)pi;
+    }
+}

@@ -24,3 +24,23 @@ void cg_build_enc_tables(uint8_t *out768);
 int cg_build_set(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups,
                  int n_groups, CgBuiltSet &out, std::string &err,
                  const cg_index_desc *indexes = nullptr, int n_indexes = 0);
+
+// ---- multi-pass schedule (several groups, one round) ------------------------------------------
+// One single-adapter (or single-index) sub-set per component of every group, so that every aligner
+// adapter runs through the split pipeline (scan -> plan -> DP rounds) on its own; select_best()
+// (cg_core.cuh) then combines the per-adapter records.  Only planned when every aligner component
+// qualifies for that pipeline and there are at most CG_MAX_PASSES components.
+struct CgPassPlan {
+    CgBuiltSet set;
+    int group = 0, role = 0;      // role 1: back adapter of a LINKED group
+    int front_pass = -1;          // role 1: the pass of the front adapter
+    int map_off = 0;              // first entry in pass_map (local -> global adapter numbers)
+};
+struct CgMultiPlan {
+    std::vector<CgPassPlan> passes;   // empty: keep the one-kernel schedule
+    std::vector<int32_t> pass_map;
+};
+int cg_plan_passes(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
+                   const cg_index_desc *indexes, int n_indexes, CgMultiPlan &plan, std::string &err);
+void cg_fill_select_tables(const CgGroup *groups, int n_groups, int slots, const std::vector<CgPassPlan> &passes,
+                           CgSelectTables &t);

@@ -106,6 +106,15 @@ struct CgIndexHeader {      // 64 bytes, one per index, followed in the same arr
 };
 static_assert(sizeof(CgIndexHeader) == 64, "CgIndexHeader layout");
 
+// Multi-pass schedule: which pass holds which component of which group (see cg_setbuild.h).
+#define CG_MAX_PASSES 16
+struct CgSelectTables {
+    int32_t n_groups, slots;
+    int32_t map_off[CG_MAX_PASSES];                 // per pass: first entry in pass_map
+    int8_t gtype[CG_MAX_PASSES], pass0[CG_MAX_PASSES], pass1[CG_MAX_PASSES];      // per group
+    int8_t front_required[CG_MAX_PASSES], back_required[CG_MAX_PASSES];
+};
+
 // One result of locating a single adapter in a (sub)sequence; coordinates as SingleMatch.
 struct CgHit {
     int32_t adapter;        // -1 = none

@@ -34,6 +34,60 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     }
     uint8_t enc[768];
     cg_build_enc_tables(enc);
+    if (force_wide & 128) {
+        // the multi-pass schedule of cg_api.cu (launch_trim): per-component passes + select_best
+        CgMultiPlan plan;
+        rc = cg_plan_passes(adapters, n_adapters, groups, n_groups, indexes, n_indexes, plan, g_err);
+        if (rc != CG_OK) return rc;
+        if (plan.passes.empty() || params->times > 1) return 100;     // schedule not applicable
+        const CgSetHeader *H = (const CgSetHeader *)set.blob.data();
+        CgSelectTables T;
+        cg_fill_select_tables((const CgGroup *)(set.blob.data() + H->groups_off), n_groups, set.slots, plan.passes, T);
+        const int np = (int)plan.passes.size();
+        std::vector<SetView> views(np);
+        int max_m = 0;
+        for (int pi = 0; pi < np; ++pi) {
+            CgBuiltSet &b = plan.passes[pi].set;
+            views[pi] = make_set_view(b.blob.data(), b.masks64.data(), enc, b.index_blob.empty() ? nullptr : b.index_blob.data());
+            if (b.max_m > max_m) max_m = b.max_m;
+        }
+        std::vector<uint32_t> colp((size_t)max_m + 2);
+        std::vector<int> colw(3 * ((size_t)max_m + 2));
+        PackedCol pc; pc.base = colp.data(); pc.stride = 1;
+        WideCol wc; wc.base = colw.data(); wc.stride = 1;
+        std::vector<uint8_t> padded((size_t)offsets[n_reads] + 64, 0);
+        if (offsets[n_reads]) memcpy(padded.data() + 32, seq, (size_t)offsets[n_reads]);
+        const uint8_t *pseq = padded.data() + 32;
+        if (params->quality_trim && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
+        std::vector<cg_match_rec> recs(np);
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const int n = (int)(offsets[r + 1] - offsets[r]);
+            const uint8_t *sq = pseq + offsets[r];
+            for (int i = 0; i < n; ++i) if (sq[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
+            int bs = 0, be = n;
+            if (params->quality_trim)
+                quality_trim_core(qual + offsets[r], n, params->cutoff_front, params->cutoff_back, params->quality_base, &bs, &be);
+            if (qtrim) { qtrim[2 * r] = bs; qtrim[2 * r + 1] = be; }
+            for (int pi = 0; pi < np; ++pi) {
+                const CgPassPlan &P = plan.passes[pi];
+                int vs = bs, ve = be;
+                if (P.role == 1) linked_view(recs[P.front_pass], vs, ve);
+                const SetView &V = views[pi];
+                if (V.h->simple_ok && V.ad[0].m <= 64)
+                    process_read_planned(V, sq + vs, nullptr, ve - vs, 0, 0, 0, 33, &recs[pi], nullptr);
+                else {
+                    const int32_t view[2] = {vs, ve};
+                    process_read<true>(V, sq, nullptr, n, 0, 0, 0, 33, 1, pc, wc, &recs[pi], nullptr, view);
+                }
+            }
+            cg_match_rec b0, b1;
+            select_best(T, plan.pass_map.data(), [&](int pass) { return recs[pass]; }, b0, b1);
+            cg_match_rec *dst = (cg_match_rec *)(matches + (size_t)r * set.slots);
+            dst[0] = b0;
+            if (set.slots > 1) dst[1] = b1;
+        }
+        return CG_OK;
+    }
     SetView S = make_set_view(set.blob.data(), set.masks64.data(), enc,
                               set.index_blob.empty() ? nullptr : set.index_blob.data());
     std::vector<uint32_t> colp((size_t)set.max_m + 2);
@@ -50,7 +104,7 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
         const int n = (int)(offsets[r + 1] - offsets[r]);
         const uint8_t *s = seq + offsets[r];
         for (int i = 0; i < n; ++i) if (s[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
-        if ((force_wide & 64) && S.h->simple_ok && times == 1 && S.ad[0].m <= 32)
+        if ((force_wide & 64) && S.h->simple_ok && times == 1 && S.ad[0].m <= 64)
             process_read_planned(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
                                  params->cutoff_front, params->cutoff_back, params->quality_base,
                                  (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);

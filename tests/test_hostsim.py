@@ -153,3 +153,58 @@ def test_two_phase_on_golden_single_adapters():
                 assert match_desc(multi.matches_from_records(recs[i, 0], read)) == expected, (mode, case["adapters"], read)
         n += 1
     assert n > 40
+
+
+def _multipass(spec, reads, quals=None, params=None):
+    """Mode 128 = the multi-pass schedule (per-component passes + select_best); None if not planned."""
+    try:
+        return hostsim_process(spec, reads, quals, params, force_wide=128)
+    except RuntimeError as e:
+        if e.args[0][0] == 100:
+            return None
+        raise
+
+
+def test_multipass_schedule_golden():
+    """Per-adapter passes + selection == MultipleAdapters / LinkedAdapter / AdapterIndex of the reference."""
+    import cutadapt_b200.adapters as PA
+
+    planned = 0
+    for name in ("adapters_kat.json.gz", "index_kat.json.gz"):
+        for case in golden(name):
+            multi = build_adapters(PA, case["adapters"])
+            spec = spec_of(multi)
+            reads = [r for r, _ in case["reads"]]
+            res = _multipass(spec, reads)
+            if res is None:
+                continue
+            planned += 1
+            for i, (read, expected) in enumerate(case["reads"]):
+                assert match_desc(multi.matches_from_records(res[0][i, 0], read)) == expected, (case["adapters"], read)
+    assert planned > 100
+
+
+def test_multipass_schedule_with_quality_trim_against_oracle():
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(77)
+    planned = 0
+    for _ in range(60):
+        ads = ["".join(rng.choice("ACGT") for _ in range(rng.randint(5, 45))) for _ in range(rng.randint(2, 4))]
+        objs = [rng.choice([PA.BackAdapter, PA.FrontAdapter, PA.AnywhereAdapter, PA.SuffixAdapter])(a, max_errors=0.15, name="a")
+                for a in ads]
+        if rng.random() < 0.5:
+            objs.append(PA.LinkedAdapter(PA.PrefixAdapter(ads[0][:12], max_errors=0.2), PA.BackAdapter(ads[1], max_errors=0.1),
+                                         rng.random() < 0.5, rng.random() < 0.5, "l"))
+        multi = PA.MultipleAdapters(objs)
+        spec = spec_of(multi)
+        reads = random_reads(rng, ads, 40, max_len=120)
+        quals = ["".join(chr(33 + rng.choice([2, 2, 15, 30, 38])) for _ in r) for r in reads]
+        params = L.make_params(quality_trim=True, cutoff_front=rng.choice([0, 10]), cutoff_back=20)
+        res = _multipass(spec, reads, quals, params)
+        assert res is not None
+        planned += 1
+        exp, eqt = oracle.oracle_process(spec.adapters, spec.groups, reads, quals, True, params.cutoff_front, 20, 33, 1)
+        assert (res[1] == eqt).all()
+        assert (res[0] == exp).all()
+    assert planned == 60
