@@ -19,7 +19,7 @@
 
 static_assert(sizeof(cg_match) == 32 && sizeof(cg_match_rec) == 32, "cg_match must be 32 bytes");
 static_assert(sizeof(CgAdapter) == 80 && sizeof(CgEntry) == 32 && sizeof(CgGroup) == 32 &&
-                  sizeof(CgSetHeader) == 64, "table layout");
+                  sizeof(CgSetHeader) == 80, "table layout");
 
 static thread_local std::string g_err;
 

@@ -1564,12 +1564,97 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
     }
 }
 
+// Runs from a bit-vector pass (Myers 1999, semi-global: free start in the read) over the whole
+// searched sequence: D[m][j], the cost of the best alignment of the full adapter ending at column j,
+// is tracked for every j; the reference evaluates a bottom-row candidate only where that cost is
+// <= k (_align.pyx:496-533 with cost <= maxcost[eff] <= k), and such an alignment starts at a column
+// >= j - m - k.  So the DP runs are the unions of [j - m - k, j] over the columns with D[m][j] <= k.
+// The vertical deltas of the last column give cost(i, n) for every adapter prefix i, i.e. whether the
+// last-column scan (_align.pyx:536-572) can accept anything; if not, no end run is needed.
+template <class T>
+CG_HD void plan_runs_myers_t(const CgAdapter &A, const uint32_t *peq, const int32_t *ncnt,
+                             const int32_t *maxcost, const uint8_t *p, int n, RunList &R, bool &need_end)
+{
+    const int m = A.m, k = A.k;
+    const bool sir = (A.flags & 1) != 0, eir = (A.flags & 4) != 0;
+    const T mmask = m >= (int)(8 * sizeof(T)) ? (T) ~(T)0 : (T)(((T)1 << m) - 1);
+    const T top = (T)1 << (m - 1);
+    T Pv = sir ? (T)0 : mmask, Mv = 0;                     // column 0: cost i, or 0 (START_IN_REFERENCE)
+    int score = sir ? 0 : m;
+    const uint8_t *cp = A.reverse ? p + (n - 1) : p;
+    const int cstride = A.reverse ? -1 : 1;
+    int wlo = 0, whi = -1;
+    for (int j = 1; j <= n; ++j) {
+        const int ch = cp[cstride * (j - 1)] & 127;
+        T Eq = (T)peq[ch];
+        if (sizeof(T) > 4) Eq |= (T)((unsigned long long)peq[128 + ch] << 32);
+        const T Xv = Eq | Mv;
+        const T Xh = (T)((((Eq & Pv) + Pv) ^ Pv) | Eq);
+        T Ph = (T)(Mv | ~(Xh | Pv));
+        T Mh = Pv & Xh;
+        score += (Ph & top) ? 1 : 0;
+        score -= (Mh & top) ? 1 : 0;
+        Ph = (T)(Ph << 1); Mh = (T)(Mh << 1);               // row 0 stays 0: START_IN_QUERY
+        Pv = (T)(Mh | ~(Xv | Ph));
+        Mv = Ph & Xv;
+        if (score <= k) {
+            const int lo = cg_max(0, j - m - k);
+            if (whi < 0) wlo = lo;
+            else if (lo > whi) { runs_add(R, wlo, whi, n); wlo = lo; }
+            whi = j;
+        }
+    }
+    if (whi >= 0) runs_add(R, wlo, whi, n);
+    need_end = false;
+    if (eir) {
+        if (sir) need_end = true;                           // prefix length unknown (origin < 0 possible)
+        else {
+            int c = 0;
+            for (int i = 1; i <= m; ++i) {
+                c += (int)((Pv >> (i - 1)) & 1) - (int)((Mv >> (i - 1)) & 1);
+                int eff = i;
+                if (A.wildcard_ref) eff = (i < m) ? i - ncnt[i] : A.effective_length;
+                if (i >= A.min_overlap && c <= maxcost[eff]) { need_end = true; break; }
+            }
+        }
+    }
+}
+
 CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs, uint32_t rs0,
                      uint32_t rs1, RunPlan &P)
 {
     const CgAdapter &A = S.ad[0];
     P.n_runs = 0; P.lo0 = P.hi0 = P.lo1 = P.hi1 = P.lo2 = P.hi2 = P.lo3 = P.hi3 = 0;
     P.end_idx = -1; P.exact = 0; P.s0 = 0;
+    if (S.h->myers && (A.flags & 2) && (A.flags & 8) && n > 0) {
+        const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+        const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+        const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+        RunList R;
+        R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+        bool need_end;
+        if (A.m <= 32) plan_runs_myers_t<uint32_t>(A, peq, ncnt, maxcost, p, n, R, need_end);
+        else plan_runs_myers_t<unsigned long long>(A, peq, ncnt, maxcost, p, n, R, need_end);
+        P.n_runs = R.n; P.lo0 = R.lo0; P.hi0 = R.hi0; P.lo1 = R.lo1; P.hi1 = R.hi1; P.lo2 = R.lo2; P.hi2 = R.hi2;
+        if (need_end) {
+            const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+            bool covered = false;
+            if (R.n > 0) {
+                const int lo_last = R.n == 1 ? R.lo0 : (R.n == 2 ? R.lo1 : R.lo2);
+                const int hi_last = R.n == 1 ? R.hi0 : (R.n == 2 ? R.hi1 : R.hi2);
+                covered = lo_last <= lo_end && hi_last == n;
+            }
+            if (!covered) {
+                P.end_idx = R.n;
+                if (R.n == 0) { P.lo0 = lo_end; P.hi0 = n; }
+                else if (R.n == 1) { P.lo1 = lo_end; P.hi1 = n; }
+                else if (R.n == 2) { P.lo2 = lo_end; P.hi2 = n; }
+                else { P.lo3 = lo_end; P.hi3 = n; }
+                P.n_runs = R.n + 1;
+            }
+        }
+        return;
+    }
     if (!simple_windowed(S, n)) {
         // plain: one run over the reference's column range (_align.pyx:346-352)
         int max_n = n, min_n = 0;

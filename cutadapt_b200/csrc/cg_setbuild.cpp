@@ -154,8 +154,9 @@ void pack_words(const std::vector<ScanKmer> &kmers, uint32_t type, bool gap, std
 
 bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc768,
                         const uint8_t *enc_ref, std::vector<uint8_t> &pool, std::vector<CgScanWord> &words,
-                        int &windowed, int &exact_ok)
+                        int &windowed, int &exact_ok, int &myers)
 {
+    myers = 0;
     std::vector<ScanKmer> whole, suffix, prefix;
     for (int e = 0; e < d.n_kmer_entries; ++e) {
         const cg_kmer_entry &k = d.kmer_entries[e];
@@ -177,6 +178,7 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
     windowed = 0;
     const bool full_range = (A.flags & 2) && (A.flags & 8);
     const int m = A.m, pieces = A.k + 1;
+    if (full_range && A.k >= 0 && pieces > m && m <= 64) myers = 1;
     if (full_range && A.k >= 0 && pieces <= m) {
         const int base = m / pieces, extra = m % pieces;
         std::vector<ScanKmer> chunks;
@@ -205,7 +207,27 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
                 if (o.same_pattern(k)) { dup = true; o.bmin = std::min(o.bmin, pos); o.bmax = std::max(o.bmax, pos); }
             if (!dup) chunks.push_back(k);
         }
-        if (ok && m <= 250) {
+        // How often do the chunks hit by chance?  p_hit = expected hits per read position for uniform
+        // A/C/G/T reads.  A false hit costs a DP window of ~ (m + 2k) x m cells (~7 instructions each);
+        // the bit-vector pass of plan_runs_myers costs ~17 (m <= 32) or ~34 instructions per position and
+        // finds the runs exactly, so it wins once p_hit * 7 m (m + 2k) exceeds that -- adapters with
+        // many wildcards, N runs, or high error rates.
+        double p_hit = 0.0;
+        if (ok) {
+            for (auto &c : chunks) {
+                double p = 1.0;
+                for (auto &set : c.cols) {
+                    int cnt = 0;
+                    for (const char *b = "ACGT"; *b; ++b) cnt += (int)((set[(*b) >> 6] >> ((*b) & 63)) & 1ULL);
+                    p *= cnt / 4.0;
+                }
+                p_hit += p;
+            }
+        }
+        const double myers_cost = m <= 32 ? 17.0 : 34.0;
+        if (m <= 64 && (!ok || p_hit * 7.0 * m * (m + 2.0 * A.k) > myers_cost)) {
+            myers = 1;
+        } else if (ok && m <= 250) {
             for (auto &c : chunks) {
                 bool merged = false;
                 for (auto &w : whole)
@@ -494,17 +516,17 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
 
     // two-phase program for the common case: one SINGLE aligner adapter with packed cells
     std::vector<CgScanWord> scan_words;
-    int simple_ok = 0, windowed = 0, exact_ok = 0;
+    int simple_ok = 0, windowed = 0, exact_ok = 0, myers = 0;
     if (n_adapters == 1 && n_groups == 1 && G[0].type == CG_GROUP_SINGLE && A[0].kind == CG_KIND_ALIGNER &&
         A[0].cell_mode == CG_CELL_PACKED32) {
         std::vector<uint8_t> pool2 = pool;
         std::vector<CgScanWord> words;
-        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed, exact_ok)) {
+        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed, exact_ok, myers)) {
             pool.swap(pool2);
             scan_words.swap(words);
             simple_ok = 1;
         } else {
-            windowed = 0; exact_ok = 0;
+            windowed = 0; exact_ok = 0; myers = 0;
         }
     }
 
@@ -518,7 +540,7 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     H.groups_off = off; off += (uint32_t)(G.size() * sizeof(CgGroup)); off = align_up(off, 16);
     H.entries_off = off; off += (uint32_t)(E.size() * sizeof(CgEntry)); off = align_up(off, 16);
     H.scan_off = off; off += (uint32_t)(scan_words.size() * sizeof(CgScanWord)); off = align_up(off, 16);
-    H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed; H.exact_ok = exact_ok;
+    H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed; H.exact_ok = exact_ok; H.myers = myers;
     H.pool_off = off; off += (uint32_t)pool.size(); off = align_up(off, 16);
     H.total_bytes = off;
     out.blob.assign(off, 0);

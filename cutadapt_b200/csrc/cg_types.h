@@ -76,7 +76,7 @@ struct CgScanWord {         // 32 bytes
                             //   locator chunk ending in that bit may end (WHOLE words with loc_found)
 };
 
-struct CgSetHeader {        // 64 bytes
+struct CgSetHeader {        // 80 bytes
     int32_t n_adapters, n_groups, n_entries, slots;
     int32_t max_m;          // longest adapter (DP column height - 1)
     int32_t any_wide;       // some adapter needs the wide-cell path
@@ -88,6 +88,9 @@ struct CgSetHeader {        // 64 bytes
     uint32_t scan_off;      // blob offset of CgScanWord[scan_count]
     int32_t windowed;       // 1: DP may be restricted to windows around locator hits
     int32_t exact_ok;       // 1: an exact, leftmost occurrence found by the locator needs no DP at all
+    int32_t myers;          // 1: the plan stage finds the DP runs with a bit-vector edit-distance pass over the
+                            //    read instead of locator chunks (adapters whose chunks would hit everywhere)
+    int32_t pad[3];
 };
 
 // Anchored-adapter index (AdapterIndex, adapters.py:1289-1551) as an open-addressing hash table.

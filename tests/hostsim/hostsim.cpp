@@ -26,7 +26,10 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     CgBuiltSet set;
     int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err, indexes, n_indexes);
     if (rc != CG_OK) return rc;
-    if (force_wide & 4) return set.simple_ok ? 1 : 0;   // query only: is the two-phase program available?
+    if (force_wide & 4) {   // query only: bit 0 two-phase program available, 1 windowed, 2 exact shortcut, 3 myers
+        const CgSetHeader *h = (const CgSetHeader *)set.blob.data();
+        return (set.simple_ok ? 1 : 0) | (h->windowed ? 2 : 0) | (h->exact_ok ? 4 : 0) | (h->myers ? 8 : 0);
+    }
     if (force_wide & 1) {
         CgSetHeader *h = (CgSetHeader *)set.blob.data();
         CgAdapter *ad = (CgAdapter *)(set.blob.data() + h->adapters_off);

@@ -1,6 +1,6 @@
 """Resident-throughput of the other BASELINE configurations (not bench lines).
 
-  python tools/measure_configs.py [n_reads]
+  python tools/measure_configs.py [n_reads] [case-name prefix]
 
 Prints one JSON line per configuration: reads/s of DeviceBatch.run on reads resident in HBM,
 CUDA-event timed, plus the fraction of reads with a match.
@@ -21,7 +21,7 @@ def timed(batch, seq, offsets, qual, reps=3):
     n = offsets.numel() - 1
     out = torch.empty((n * batch.times * batch.adapter_set.slots, 8), dtype=torch.int32, device=seq.device)
     qt = torch.empty((n, 2), dtype=torch.int32, device=seq.device)
-    for _ in range(2):
+    for _ in range(1 if reps == 1 else 2):
         batch.run(seq, offsets, qual, max_read_len=150, out=out, qtrim_out=qt)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -73,11 +73,14 @@ def main():
     cases["config5: 96 anchored 5' barcodes, device index"] = (PA.IndexedPrefixAdapters(pre), None, None, dflat)
     cases["config5 without index: 96 PrefixAdapters one by one"] = (PA.MultipleAdapters(pre), None, None, dflat)
 
+    only = sys.argv[2] if len(sys.argv) > 2 else None
     for name, c in cases.items():
+        if only and not name.startswith(only):
+            continue
         ad, qc, q = c[0], c[1], c[2]
         data = c[3] if len(c) > 3 else flat
         batch = DeviceBatch(ad, quality_cutoff=qc)
-        rps, hit = timed(batch, data, offsets, q)
+        rps, hit = timed(batch, data, offsets, q, reps=1 if only else 3)
         line = {"case": name, "reads": n, "reads_per_s": rps, "matched_frac": round(hit, 4)}
         print(json.dumps(line), flush=True)
         results.append(line)
