@@ -1746,6 +1746,7 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
                 const bool last = r == P.n_runs - 1;
                 if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
                 else if (A.m <= 32) run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+                else if (A.m <= 48) run_pass<48>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
                 else run_pass<64>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
             }
             hit_from_state(A, nn, st, hit);

@@ -765,7 +765,7 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 //               finished (early exit or last run) get their record, the others move to the output
 //               list with the updated selection state.
 template <bool PLAN, int MR>
-__global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : (MR <= 32 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
+__global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : (MR <= 48 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int slot_bytes = a.carry_slot;
@@ -913,7 +913,9 @@ typedef void (*list_kernel_t)(const CgKernelArgs);
 static list_kernel_t pick_list(bool plan, int mr)
 {
     if (plan) return cg_list_kernel<true, 16>;
-    return mr <= 16 ? cg_list_kernel<false, 16> : (mr <= 32 ? cg_list_kernel<false, 32> : cg_list_kernel<false, 64>);
+    if (mr <= 16) return cg_list_kernel<false, 16>;
+    if (mr <= 32) return cg_list_kernel<false, 32>;
+    return mr <= 48 ? cg_list_kernel<false, 48> : cg_list_kernel<false, 64>;
 }
 cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm)
 {

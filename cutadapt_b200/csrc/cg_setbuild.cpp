@@ -208,10 +208,10 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
             if (!dup) chunks.push_back(k);
         }
         // How often do the chunks hit by chance?  p_hit = expected hits per read position for uniform
-        // A/C/G/T reads.  A false hit costs a DP window of ~ (m + 2k) x m cells (~7 instructions each);
-        // the bit-vector pass of plan_runs_myers costs ~17 (m <= 32) or ~34 instructions per position and
-        // finds the runs exactly, so it wins once p_hit * 7 m (m + 2k) exceeds that -- adapters with
-        // many wildcards, N runs, or high error rates.
+        // A/C/G/T reads.  A false hit costs a DP window of ~ (m + 2k) x m cells (measured: one cell costs
+        // about 12 instruction slots in the run kernels); the bit-vector pass of plan_runs_myers costs ~17
+        // (m <= 32) or ~34 slots per position and finds the runs exactly, so it wins once
+        // p_hit * 12 m (m + 2k) exceeds that -- adapters with many wildcards, N runs, or high error rates.
         double p_hit = 0.0;
         if (ok) {
             for (auto &c : chunks) {
@@ -225,7 +225,7 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
             }
         }
         const double myers_cost = m <= 32 ? 17.0 : 34.0;
-        if (m <= 64 && (!ok || p_hit * 7.0 * m * (m + 2.0 * A.k) > myers_cost)) {
+        if (m <= 64 && (!ok || p_hit * 12.0 * m * (m + 2.0 * A.k) > myers_cost)) {
             myers = 1;
         } else if (ok && m <= 250) {
             for (auto &c : chunks) {
