@@ -1506,6 +1506,10 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
     if (!hits) return;
     int n_loc = 0;
     for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
+    // exact-occurrence shortcut over all locator words: every word's chunks must imply the same start
+    // within the first stretch of hit groups
+    bool ex_ok = want_exact;
+    int ex_s0 = -1;
     for (int w = 0; w < n_words; ++w) {
         const CgScanWord &W = words[w];
         if (W.type != CG_SCAN_WHOLE || !W.loc_found) continue;
@@ -1525,7 +1529,8 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
             const long long p_end_ll = ((long long)(g + 1)) << gs;
             const int p_end = p_end_ll > n ? n : (int)p_end_ll;
             if (cur_p != p_first) {
-                if (whi >= 0) { runs_add(R, wlo, whi, n); wlo = 0x3fffffff; whi = -1; ++stretch; }
+                if (cur_p >= 0) ++stretch;                       // a gap between hit groups
+                if (whi >= 0) { runs_add(R, wlo, whi, n); wlo = 0x3fffffff; whi = -1; }
                 if (stash && nh < 2) {
                     Rr = nh == 0 ? rs0 : rs1;
                 } else {
@@ -1560,8 +1565,10 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
             cur_p = p_end;
         }
         if (whi >= 0) runs_add(R, wlo, whi, n);
-        if (want_exact && fm == locf && s0 >= 0 && s0 + m <= n) { exact = 1; s0_out = s0; }
+        if (fm == locf && s0 >= 0 && s0 + m <= n && (ex_s0 < 0 || ex_s0 == s0)) ex_s0 = s0;
+        else ex_ok = false;
     }
+    if (ex_ok && ex_s0 >= 0) { exact = 1; s0_out = ex_s0; }
 }
 
 // Runs from a bit-vector pass (Myers 1999, semi-global: free start in the read) over the whole

@@ -238,7 +238,7 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
         }
     }
     // Exact-occurrence shortcut (see plan_runs in cg_core.cuh): needs an unambiguous chunk -> offset
-    // map, all chunks in one word, no free adapter start, and k <= m/2.
+    // map, no free adapter start, and k <= m/2.
     exact_ok = 0;
     // ... and the full-length exact match must itself be acceptable (_align.pyx:511-514)
     const bool full_ok = A.m >= A.min_overlap && floor((double)A.effective_length * d.max_error_rate) >= 0.0;
@@ -247,10 +247,9 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
         bool unambiguous = true;
         for (auto &w : whole)
             if (w.loc) { loc_bits += w.len; unambiguous = unambiguous && w.bmin == w.bmax; }
-        int all_bits = 0;
-        for (auto &w : whole) all_bits += w.len;
-        // chunk patterns must be pairwise distinct (else bmin != bmax) and everything must share one word
-        if (unambiguous && all_bits <= 32) exact_ok = 1;
+        // chunk patterns must be pairwise distinct (else bmin != bmax); the chunks may be spread over
+        // several scan words (plan_hit_runs_dir combines them)
+        if (unambiguous && loc_bits > 0) exact_ok = 1;
     }
     pack_words(whole, CG_SCAN_WHOLE, false, pool, words);
     pack_words(suffix, CG_SCAN_SUFFIX, true, pool, words);
