@@ -168,12 +168,13 @@ def lib():
     if _lib is None:
         with _lib_lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
+                path = os.environ.get("CUTADAPT_B200_LIB", LIB_PATH)
+                if not os.path.exists(path):
                     raise CutadaptB200Error(
-                        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                        f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "
                         "g.build()'` (there is no CPU fallback)"
                     )
-                handle = C.CDLL(LIB_PATH)
+                handle = C.CDLL(path)
                 _declare(handle)
                 _lib = handle
     return _lib

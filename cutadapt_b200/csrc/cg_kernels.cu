@@ -50,6 +50,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     } while (!ok);
 }
 
+// Per-lane asynchronous copies (SASS LDGSTS): every lane moves its own bytes in 16-byte pieces into its
+// own shared-memory slot and waits for its own copy groups (no cross-lane synchronisation needed).
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __host__ __device__ inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // shared-memory carve-up of the fused kernel
@@ -732,6 +741,11 @@ cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_
     return cudaGetLastError();
 }
 
+// Staging depth of the list kernels: 1 = fetch, wait, work (half the shared memory, twice the resident
+// warps to hide the copy latency); 2 = prefetch the next group's bytes while working on this one.
+#ifndef CG_LIST_STAGES
+#define CG_LIST_STAGES 1
+#endif
 struct DpSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, slot_rel, total; };
 __host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int slot_bytes)
 {
@@ -744,7 +758,7 @@ __host__ __device__ inline DpSmem dp_smem_layout(uint32_t blob_bytes, int slot_b
     size_t w = 0;
     L.bar_rel = w; w += 16;
     w = cg_align_up(w, 128);
-    L.slot_rel = w; w += 2 * 32 * (size_t)slot_bytes;
+    L.slot_rel = w; w += CG_LIST_STAGES * 32 * (size_t)slot_bytes;
     L.warp_stride = cg_align_up(w, 128);
     L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
     return L;
@@ -764,8 +778,14 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 //  PLAN = false (cg_run_kernel<MR>): one DP run of every record of the input list; reads that are
 //               finished (early exit or last run) get their record, the others move to the output
 //               list with the updated selection state.
+#ifndef CG_PLAN_BLOCKS
+#define CG_PLAN_BLOCKS 6      // resident CTAs per SM the plan kernel is compiled for (80 registers)
+#endif
+#ifndef CG_RUN16_BLOCKS
+#define CG_RUN16_BLOCKS 5     // same for the run kernel with a 16-row column (95 registers)
+#endif
 template <bool PLAN, int MR>
-__global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : (MR <= 48 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
+__global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_RUN16_BLOCKS : (MR <= 48 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int slot_bytes = a.carry_slot;
@@ -774,16 +794,10 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : (MR <= 48 ? 
     uint8_t *s_enc = smem + L.enc_off;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     uint8_t *wbase = smem + L.warp_off + (size_t)wib * L.warp_stride;
-    uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
     uint8_t *s_slot = wbase + L.slot_rel;
 
     for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
     for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
-    if (lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_barrier_init();
-    }
     __syncthreads();
     const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
     const CgAdapter &A = S.ad[0];
@@ -821,33 +835,34 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? 5 : (MR <= 16 ? 4 : (MR <= 48 ? 
             bytes = len ? (uint32_t)(((addr + len + 15) & ~(uintptr_t)15) - src) : 0u;
             soff = (uint32_t)(addr - src);
         }
-        uint32_t total = bytes;
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        if (total) {
-            if (lane == 0) mbar_expect_tx(&bars[st], total);
-            __syncwarp();
-            if (bytes) tma_load_1d(s_slot + ((size_t)st * 32 + lane) * slot_bytes, (const void *)src, bytes, &bars[st]);
-        }
-        return total != 0;
+        uint8_t *dst = s_slot + ((size_t)st * 32 + lane) * slot_bytes;
+        for (uint32_t o = 0; o < bytes; o += 16) cp_async16(dst + o, (const void *)(src + o));
+        cp_async_commit();
+        return true;
     };
 
-    uint32_t phase0 = 0, phase1 = 0;
     uint4 ta_n, tb_n, tc_n, td_n;
     uint32_t soff_n = 0;
     bool loaded_n = false;
-    if (wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, tc_n, td_n, soff_n);
+    if (CG_LIST_STAGES > 1 && wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, tc_n, td_n, soff_n);
     int it = 0;
     for (long long g = wg; g < n_groups; g += warps_total, ++it) {
-        const int st = it & 1;
+        const int st = CG_LIST_STAGES > 1 ? (it & 1) : 0;
+        if (CG_LIST_STAGES == 1) {
+            fetch(g, 0, ta_n, tb_n, tc_n, td_n, soff_n);
+            cp_async_wait<0>();
+        }
         const uint4 ta = ta_n, tb = tb_n, tc = tc_n, td = td_n;
         const uint32_t soff = soff_n;
-        const bool loaded = loaded_n;
-        const long long gn = g + warps_total;
-        loaded_n = false;
-        if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, tc_n, td_n, soff_n);
-        if (loaded) {
-            if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
-            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+        if (CG_LIST_STAGES > 1) {
+            const bool loaded = loaded_n;
+            const long long gn = g + warps_total;
+            loaded_n = false;
+            if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, tc_n, td_n, soff_n);
+            if (loaded) {
+                if (loaded_n) cp_async_wait<1>();       // the copies of the next group may stay in flight
+                else cp_async_wait<0>();
+            }
         }
         const bool has_task = (unsigned long long)g * 32 + lane < n_tasks;
         const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * slot_bytes + soff;
@@ -1105,10 +1120,19 @@ cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *
 // Trim statistics: the fixed-layout int64 vector that is all-reduced across GPUs
 // (Statistics.__iadd__ report.py:81-126; EndStatistics.errors adapters.py:96-111,193-199)
 // ------------------------------------------------------------------------------------------
+template <bool SMEM_HIST>
 __global__ void cg_stats_kernel(const int64_t *offsets, long long n_reads, int quality_trim, int times,
                                 int slots, const cg_match_rec *matches, const int32_t *qtrim,
                                 int n_adapters, int max_len, int kmax, unsigned long long *stats)
 {
+    // per-CTA histogram in shared memory (32-bit counts, flushed once); the global histogram would
+    // otherwise take one contended atomic per match
+    extern __shared__ unsigned int s_hist[];
+    const int nbins = n_adapters * (max_len + 1) * (kmax + 1);
+    if (SMEM_HIST) {
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+    }
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     unsigned long long n = 0, bp = 0, with_ad = 0, qbp = 0, abp = 0;
     unsigned long long *hist = stats + 8;
@@ -1120,7 +1144,7 @@ __global__ void cg_stats_kernel(const int64_t *offsets, long long n_reads, int q
         bool any = false;
         for (int t = 0; t < times; ++t) {
             for (int s = 0; s < slots; ++s) {
-                const cg_match_rec m = matches[((size_t)r * times + t) * slots + s];
+                const cg_match_rec m = load_rec(matches + ((size_t)r * times + t) * slots + s);
                 if (m.adapter < 0) continue;
                 any = true;
                 const int searched = (m.info >> 16) & 0xFFFF;
@@ -1129,7 +1153,9 @@ __global__ void cg_stats_kernel(const int64_t *offsets, long long n_reads, int q
                 if (m.adapter < n_adapters) {
                     const int L = removed < 0 ? 0 : (removed > max_len ? max_len : removed);
                     const int E = m.errors < 0 ? 0 : (m.errors > kmax ? kmax : m.errors);
-                    atomicAdd(&hist[((size_t)m.adapter * (max_len + 1) + L) * (kmax + 1) + E], 1ULL);
+                    const size_t bin = ((size_t)m.adapter * (max_len + 1) + L) * (kmax + 1) + E;
+                    if (SMEM_HIST) atomicAdd(&s_hist[bin], 1u);
+                    else atomicAdd(&hist[bin], 1ULL);
                 }
             }
         }
@@ -1147,6 +1173,13 @@ __global__ void cg_stats_kernel(const int64_t *offsets, long long n_reads, int q
         atomicAdd(&stats[0], n); atomicAdd(&stats[1], bp); atomicAdd(&stats[2], with_ad);
         atomicAdd(&stats[3], qbp); atomicAdd(&stats[4], abp);
     }
+    if (SMEM_HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+            const unsigned int v = s_hist[i];
+            if (v) atomicAdd(&hist[i], (unsigned long long)v);
+        }
+    }
 }
 
 cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
@@ -1158,7 +1191,13 @@ cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int qua
     long long grid = (n_reads + block - 1) / block;
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    cg_stats_kernel<<<(int)grid, block, 0, st>>>(d_offsets, n_reads, quality_trim, times, slots, d_matches,
-                                                 d_qtrim, n_adapters, max_len, kmax, d_stats);
+    const size_t hist_bytes = (size_t)n_adapters * (max_len + 1) * (kmax + 1) * sizeof(unsigned int);
+    // a CTA handles n_reads / grid reads, so 32-bit per-CTA counts cannot overflow below 2^32 reads per CTA
+    if (hist_bytes <= 48 * 1024 && n_reads / grid < (1LL << 31))
+        cg_stats_kernel<true><<<(int)grid, block, hist_bytes, st>>>(d_offsets, n_reads, quality_trim, times, slots,
+                                                                     d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats);
+    else
+        cg_stats_kernel<false><<<(int)grid, block, 0, st>>>(d_offsets, n_reads, quality_trim, times, slots, d_matches,
+                                                             d_qtrim, n_adapters, max_len, kmax, d_stats);
     return cudaGetLastError();
 }
