@@ -384,7 +384,15 @@ struct ScanOut {
     uint32_t hits;   // bit g: a locator chunk ends in characters [g << gs, (g+1) << gs)
     uint32_t rs0, rs1;   // shift-and state of the first locator word at the start of the first two
                          // hit groups: phase B resumes the scan there to get exact end positions
+    uint32_t bad;        // OR of the characters the first whole-read word consumed (bit 7 of any byte set
+                         // = non-ASCII input); only meaningful if scan_checks_ascii(words, n_words)
 };
+
+// true if scan_core's first word walks the entire searched sequence, so that ScanOut::bad covers it
+CG_HD bool scan_checks_ascii(const CgScanWord *words, int n_words)
+{
+    return n_words > 0 && words[0].type == CG_SCAN_WHOLE;
+}
 
 CG_HD int scan_group_shift(int n)
 {
@@ -395,12 +403,23 @@ CG_HD int scan_group_shift(int n)
 
 // REV selects the scan direction at compile time so that character addresses are base + immediate.
 // The mask tables have 256 entries (the upper half is zero), so the loaded byte indexes them directly.
+// byte `i` (0 = least significant) of a word, zero-extended (SASS PRMT: one instruction, and the table
+// address is then one LEA instead of shift + mask + add)
+CG_HD uint32_t cg_byte(uint32_t word, int i)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(word, 0u, 0x4440u | (uint32_t)i);
+#else
+    return (word >> (8 * i)) & 255u;
+#endif
+}
+
 template <bool REV>
 CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t *pool, const uint8_t *first,
                             int n, int gs, bool always_pass)
 {
     // `first` is the first character in scan order; character i is first[REV ? -i : i]
-    ScanOut out; out.pass = always_pass; out.hits = 0; out.rs0 = 0; out.rs1 = 0;
+    ScanOut out; out.pass = always_pass; out.hits = 0; out.rs0 = 0; out.rs1 = 0; out.bad = 0;
     // the saved states are only meaningful when a single word carries all locator chunks
     int n_loc = 0;
     for (int w = 0; w < n_words; ++w) n_loc += (words[w].type == CG_SCAN_WHOLE && words[w].loc_found) ? 1 : 0;
@@ -440,10 +459,11 @@ CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t 
                             x[2] = cg_funnel_r(m2, m1, sh); x[3] = cg_funnel_r(m3, m2, sh);
                             carry = m3; wp -= 4;
                         }
+                        if (w == 0) out.bad |= x[0] | x[1] | x[2] | x[3];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const uint32_t word = x[i >> 2];
-                            const uint32_t c = REV ? ((word >> (8 * (3 - (i & 3)))) & 255u) : ((word >> (8 * (i & 3))) & 255u);
+                            const uint32_t c = cg_byte(word, REV ? 3 - (i & 3) : (i & 3));
                             R = ((R << 1) | init) & mask[c];
                             g |= R;
                         }
@@ -462,7 +482,9 @@ CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t 
                     const uint32_t r_start = R;
                     uint32_t g = 0;
                     for (int i = 0; i < cnt; ++i) {
-                        R = ((R << 1) | init) & mask[q[REV ? -i : i]];
+                        const uint32_t c = q[REV ? -i : i];
+                        if (w == 0) out.bad |= c;
+                        R = ((R << 1) | init) & mask[c];
                         g |= R;
                     }
                     q += REV ? -cnt : cnt;
@@ -478,13 +500,17 @@ CG_HD ScanOut scan_core_dir(const CgScanWord *words, int n_words, const uint8_t 
                 for (; p + 8 <= n; p += 8) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        R = ((R << 1) | init) & mask[q[REV ? -i : i]];
+                        const uint32_t c = q[REV ? -i : i];
+                        if (w == 0) out.bad |= c;
+                        R = ((R << 1) | init) & mask[c];
                         seen |= R;
                     }
                     q += REV ? -8 : 8;
                 }
                 for (; p < n; ++p) {
-                    R = ((R << 1) | init) & mask[*q];
+                    const uint32_t c = *q;
+                    if (w == 0) out.bad |= c;
+                    R = ((R << 1) | init) & mask[c];
                     seen |= R;
                     q += REV ? -1 : 1;
                 }

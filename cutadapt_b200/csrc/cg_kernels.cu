@@ -624,6 +624,10 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
     __syncthreads();
     const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
 
+    // non-ASCII input (the reference raises ValueError): when the scan program's first word walks the
+    // whole searched sequence the check rides along in the scan (the characters are in registers anyway);
+    // otherwise a cooperative pass over the staged tile does it
+    const bool fold_ascii = scan_checks_ascii(S.scan, S.h->scan_count);
     const long long n_reads = a.n_reads;
     const long long n_mt = (n_reads + 31) / 32;
     const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
@@ -667,6 +671,8 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
         if (b1 > b0) {
             if (st == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
             else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+        }
+        if (b1 > b0 && !fold_ascii) {
             const uint32_t head = (uint32_t)((seq_base + b0) - sa0);
             const uint32_t body = (uint32_t)(b1 - b0);
             const uint32_t nchunks = (head + body + 15) / 16;
@@ -700,6 +706,7 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
             if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
             const ScanOut sc = simple_scan(S, tile_seq + off + ts, te - ts, &gs);
             pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
+            if (fold_ascii && (sc.bad & 0x80808080u)) atomicOr(a.err_flag, 1);
             if (!pass) {
                 CgHit none; none.adapter = -1; none.remove = 0;
                 none.astart = none.astop = none.rstart = none.rstop = none.score = none.errors = 0;
@@ -779,10 +786,10 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 //               finished (early exit or last run) get their record, the others move to the output
 //               list with the updated selection state.
 #ifndef CG_PLAN_BLOCKS
-#define CG_PLAN_BLOCKS 6      // resident CTAs per SM the plan kernel is compiled for (80 registers)
+#define CG_PLAN_BLOCKS 7      // resident CTAs per SM the plan kernel is compiled for (72 registers, no spills)
 #endif
 #ifndef CG_RUN16_BLOCKS
-#define CG_RUN16_BLOCKS 5     // same for the run kernel with a 16-row column (95 registers)
+#define CG_RUN16_BLOCKS 4     // same for the run kernel with a 16-row column (measured: 4 beats 5)
 #endif
 template <bool PLAN, int MR>
 __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_RUN16_BLOCKS : (MR <= 48 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
