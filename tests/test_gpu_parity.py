@@ -455,3 +455,48 @@ def test_both_kernel_schedules_agree():
             finally:
                 del os.environ["CUTADAPT_B200_KERNEL"]
             assert (other == exp).all(), (variant, repr(adapter))
+
+
+def test_multipass_schedule_agrees_with_one_phase_and_oracle():
+    """Adapter sets on the multi-pass schedule (per-adapter pipelines + cg_select_kernel) == the one-phase
+    kernel == the oracle, incl. linked adapters, long/wildcard adapters (bit-vector plan) and quality trimming."""
+    import os
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_reads
+
+    rng = random.Random(88)
+    reads0, quals0 = make_reads(6000, config=3, with_qualities=True)
+    five = [PA.BackAdapter(s, max_errors=0.15, name=f"a{i}") for i, s in enumerate(
+        ["AGATCGGAAGAGC", "CTGTCTCTTATACACATCT", "VCCGAMCYUCKHRKDCUBBCNUWNSGHCGU", "AGATCGGAAGAGCNNNNNNNNATCTCGTATGCC"])]
+    five.append(PA.LinkedAdapter(PA.PrefixAdapter("GTTCAGAGTTCTACAGTCCGACGATC", max_errors=0.15, name="f"),
+                                 PA.BackAdapter("TGGAATTCTCGGGTGCCAAGG", max_errors=0.15, name="b"), True, False, "l"))
+    sets = [PA.MultipleAdapters(five)]
+    for _ in range(6):
+        ads = ["".join(rng.choice("ACGT") for _ in range(rng.randint(8, 60))) for _ in range(rng.randint(2, 4))]
+        objs = [rng.choice([PA.BackAdapter, PA.FrontAdapter, PA.AnywhereAdapter, PA.SuffixAdapter, PA.NonInternalBackAdapter])(
+            a, max_errors=rng.choice([0.05, 0.1, 0.2]), name="x") for a in ads]
+        if rng.random() < 0.6:
+            objs.append(PA.LinkedAdapter(PA.FrontAdapter(ads[0][:14], max_errors=0.1), PA.BackAdapter(ads[1], max_errors=0.1),
+                                         rng.random() < 0.5, rng.random() < 0.5, "l"))
+        sets.append(PA.MultipleAdapters(objs))
+    for k, multi in enumerate(sets):
+        singles, groups, _ = multi._flatten()
+        descs = [s.descriptor() for s in singles]
+        if k == 0:
+            reads, quals = reads0, quals0
+        else:
+            reads = random_reads(rng, [s.sequence for s in singles], 3000, "ACGT", 150)
+            quals = ["".join(chr(33 + rng.choice([2, 2, 15, 30, 38])) for _ in r) for r in reads]
+        for qt in (False, True):
+            kw = dict(quality_trim=True, cutoff_front=5, cutoff_back=20) if qt else {}
+            exp, eqt = oracle.oracle_process(descs, groups, reads, quals if qt else None, qt, 5 if qt else 0, 20 if qt else 0)
+            got, gqt = run_set(descs, groups, reads, quals if qt else None, **kw)
+            assert (got == exp).all(), ("multipass", k, qt)
+            if qt:
+                assert (gqt == eqt).all()
+            os.environ["CUTADAPT_B200_KERNEL"] = "general"
+            try:
+                other, _ = run_set(descs, groups, reads, quals if qt else None, **kw)
+            finally:
+                del os.environ["CUTADAPT_B200_KERNEL"]
+            assert (other == exp).all(), ("general", k, qt)
