@@ -99,6 +99,17 @@ struct Packed32 {
         b &= ~(3u << PS);
         return clamp(b);
     }
+    // Without saturation: only valid where costs cannot reach CAP -- free start in the read keeps
+    // cost(i, j) <= i, so any adapter with m < CAP qualifies (locate_regs<MR <= 16, true>).
+    CG_HD static T match_nc(T d) { return d + (1u << SS); }
+    CG_HD static T mismatch_nc(T d, T up, T left)
+    {
+        T cd = d + ((1u << CS) - (1u << SS));
+        T cu = up + ((1u << CS) + (1u << PS) - (2u << SS));
+        T cl = left + ((1u << CS) + (2u << PS) - (2u << SS));
+        T b = cg_min(cd, cg_min(cu, cl));
+        return b & ~(3u << PS);
+    }
 };
 
 // Exact int32 triples for everything Packed32 cannot hold (--no-indels' indel_cost=100000,
@@ -1140,7 +1151,7 @@ CG_HD bool loc_state_result(const LocState &st, int *out6)
 // Processes runs [0, n_use) of R starting from the selection state `st` and leaves the updated state
 // in `st`; the last-column scan (_align.pyx:536-572) is done only when final_scan is set (i.e. when
 // this call covers the read's last run).
-template <int MR>
+template <int MR, bool NC = false>
 CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
                        const uint32_t *peq, const ReadView &rv, const RunList &R, int n_use, bool has_task,
                        bool final_scan, LocState &st, bool eval_bottom = true)
@@ -1219,8 +1230,8 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
                             const uint32_t left = c[i];
                             const bool eq = (i <= 32) ? (((pq_lo >> ((i - 1) & 31)) & 1u) != 0)
                                                       : (((pq_hi >> ((i - 33) & 31)) & 1u) != 0);
-                            const uint32_t mt = C::match(diag);
-                            const uint32_t mm = C::mismatch(diag, up, left, 1);
+                            const uint32_t mt = NC ? C::match_nc(diag) : C::match(diag);
+                            const uint32_t mm = NC ? C::mismatch_nc(diag, up, left) : C::mismatch(diag, up, left, 1);
                             uint32_t nw = eq ? mt : mm;
                             const bool in = i <= my_last;
                             nw = in ? nw : left;
@@ -1749,7 +1760,9 @@ CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int h
     const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
     RunList R;
     R.n = 1; R.lo0 = lo; R.hi0 = hi; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
-    locate_regs<MR>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
+    // free start in the read bounds every cost by the row number, so short adapters never saturate
+    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
+    else locate_regs<MR, false>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
 }
 
 // Host-sim driver of the planned scheduling for one read (tests/hostsim, mode 64).
