@@ -1581,11 +1581,12 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
                 }
             }
             ++nh;
-            const uint8_t *q = first + (REV ? -p_first : p_first);
-            for (int p = p_first; p < p_end; ++p) {
-                Rr = ((Rr << 1) | init) & mask[*q];
-                q += REV ? -1 : 1;
-                uint32_t f = Rr & locf;
+            // Chunk hits are queued (position, found bits) while the shift-and advances and handled after
+            // the group, lane by lane: handled inside the character loop, the whole warp would execute the
+            // handler at nearly every character because some lane always has a hit there.
+            uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0, qpa = 0, qpb = 0;
+            int qn = 0;
+            auto handle = [&](int p, uint32_t f) {
                 while (f) {
                     const int b = cg_ctz(f);
                     f &= f - 1;
@@ -1598,7 +1599,29 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
                         else if (s == s0) fm |= 1u << b;
                     }
                 }
+            };
+            auto flush = [&]() {
+                for (int e = qn - 1; e >= 0; --e) {            // oldest first
+                    const uint32_t f = e == 3 ? q3 : (e == 2 ? q2 : (e == 1 ? q1 : q0));
+                    const uint32_t pw = e >= 2 ? qpb : qpa;
+                    handle((int)((e & 1) ? (pw >> 16) : (pw & 0xffffu)), f);
+                }
+                qn = 0;
+            };
+            const uint8_t *q = first + (REV ? -p_first : p_first);
+            for (int p = p_first; p < p_end; ++p) {
+                Rr = ((Rr << 1) | init) & mask[*q];
+                q += REV ? -1 : 1;
+                const uint32_t f = Rr & locf;
+                if (f) {
+                    if (qn == 4) flush();
+                    q3 = q2; q2 = q1; q1 = q0; q0 = f;
+                    qpb = (qpb << 16) | (qpa >> 16);
+                    qpa = (qpa << 16) | (uint32_t)p;           // p <= 32255
+                    ++qn;
+                }
             }
+            flush();
             cur_p = p_end;
         }
         if (whi >= 0) runs_add(R, wlo, whi, n);
