@@ -374,7 +374,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     int scan_occ = 0, plan_occ = 0, run_occ = 0;
     if (simple && s->host.max_m <= 64 && !force_block && !force_warp) {
         const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
-        const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
+        const long long cslot = ((long long)max_read_len + 4 + 15) / 16 * 16 + 16;   // + 4: word-granular reads past the last group
         if (mini < (1 << 20)) {
             a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
             scan_smem = cg_scan_smem_bytes(a.blob_bytes, a.mini_cap, want_q);
@@ -393,7 +393,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     int wocc = 0;
     if (simple && s->host.max_m <= 32 && force_warp) {
         const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
-        const long long cslot = ((long long)max_read_len + 15) / 16 * 16 + 16;
+        const long long cslot = ((long long)max_read_len + 4 + 15) / 16 * 16 + 16;   // + 4: word-granular reads past the last group
         if (mini < (1 << 20)) {
             a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
             wsmem = cg_warp_smem_bytes(a.blob_bytes, a.mini_cap, a.carry_slot, want_q);

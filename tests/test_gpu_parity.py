@@ -339,6 +339,21 @@ def test_edge_cases_empty_ragged_long():
     got, _ = run_set([d], None, long_reads)
     exp, _ = oracle.oracle_process([d], None, long_reads)
     assert (got == exp).all() and got["rstart"][0, 0, 0] == 40000
+    # the same ragged batches through the multi-pass schedule (two adapters + a linked adapter), plus
+    # reads longer than 511 (wider scan groups) and long enough for the generic fallback of every pass
+    multi = PA.MultipleAdapters([
+        PA.BackAdapter("AGATCGGAAGAGC", name="a"), PA.FrontAdapter("TTGACCGATTAC", name="b"),
+        PA.LinkedAdapter(PA.PrefixAdapter("ACGTACGT", name="f"), PA.BackAdapter("GGCATTCAGG", name="g"), True, False, "l")])
+    singles, groups, _ = multi._flatten()
+    descs = [s.descriptor() for s in singles]
+    reads = ["", "A", "AGA", "AGATCGGAAGAGC", "", "T" * 300 + "AGATCGGAAGAGC", "ACGT" * 50, "", "AGAT",
+             "ACGTACGT" + "C" * 700 + "GGCATTCAGG" + "A" * 30, "TTGACCGATTAC" + "G" * 1500, "N" * 40,
+             "acgtacgt" + "t" * 20 + "ggcattcagg"] + long_reads
+    got, _ = run_set(descs, groups, reads)
+    exp, _ = oracle.oracle_process(descs, groups, reads)
+    assert (got == exp).all()
+    got, _ = run_set(descs, groups, ["", ""])
+    assert (got["adapter"] == -1).all()
 
 
 def test_non_ascii_reads_raise_like_the_reference():
@@ -354,6 +369,17 @@ def test_non_ascii_reads_raise_like_the_reference():
     # and the context is usable afterwards
     got, _ = run_set([d], None, ["ACGTAGATCGGAAGAGC"])
     assert got["rstart"][0, 0, 0] == 4
+    # every schedule reports it: one-phase kernels, a comparer-only set (cooperative tile check), multi-pass
+    import os
+    d2 = PA.PrefixAdapter("ACGT", indels=False, name="p").descriptor()
+    for descs, env in (([d], "general"), ([d], "block"), ([d2], None), ([d, d2], None)):
+        if env:
+            os.environ["CUTADAPT_B200_KERNEL"] = env
+        try:
+            with pytest.raises(ValueError):
+                L.AdapterSet(L.AdapterSetSpec(descs)).process(data, offsets)
+        finally:
+            os.environ.pop("CUTADAPT_B200_KERNEL", None)
 
 
 def test_large_batch_properties():
