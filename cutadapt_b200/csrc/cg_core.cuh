@@ -1615,37 +1615,14 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
                 qpa = (qpa << 16) | (uint32_t)p;               // p <= 32255
                 ++qn;
             };
+            // (fetching the group as aligned words like the scan kernel does was measured 7 % slower here:
+            // the unrolled body with its predicated queue pushes outweighs the saved byte loads)
             const uint8_t *q = first + (REV ? -p_first : p_first);
-            if (p_end - p_first == 16) {
-                // a full group: the 16 characters as aligned words (see scan_core_dir)
-                const uint8_t *uq = REV ? q - 3 : q;
-                const uint32_t mis = (uint32_t)((uintptr_t)uq & 3u);
-                const uint32_t sh = mis * 8u;
-                const uint32_t *wp = (const uint32_t *)(uq - mis);
-                uint32_t x[4];
-                if (!REV) {
-                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                    x[0] = cg_funnel_r(w0, w1, sh); x[1] = cg_funnel_r(w1, w2, sh);
-                    x[2] = cg_funnel_r(w2, w3, sh); x[3] = cg_funnel_r(w3, w4, sh);
-                } else {
-                    const uint32_t w1 = wp[1], w0 = wp[0], m1 = wp[-1], m2 = wp[-2], m3 = wp[-3];
-                    x[0] = cg_funnel_r(w0, w1, sh); x[1] = cg_funnel_r(m1, w0, sh);
-                    x[2] = cg_funnel_r(m2, m1, sh); x[3] = cg_funnel_r(m3, m2, sh);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t c = cg_byte(x[i >> 2], REV ? 3 - (i & 3) : (i & 3));
-                    Rr = ((Rr << 1) | init) & mask[c];
-                    const uint32_t f = Rr & locf;
-                    if (f) push(p_first + i, f);
-                }
-            } else {
-                for (int p = p_first; p < p_end; ++p) {
-                    Rr = ((Rr << 1) | init) & mask[*q];
-                    q += REV ? -1 : 1;
-                    const uint32_t f = Rr & locf;
-                    if (f) push(p, f);
-                }
+            for (int p = p_first; p < p_end; ++p) {
+                Rr = ((Rr << 1) | init) & mask[*q];
+                q += REV ? -1 : 1;
+                const uint32_t f = Rr & locf;
+                if (f) push(p, f);
             }
             flush();
             cur_p = p_end;
