@@ -35,6 +35,7 @@ ADAPTER = "AGATCGGAAGAGC"
 ERROR_RATE = 0.1
 READ_LEN = 150
 ALGO_BYTES_PER_READ = READ_LEN + 8 + 32
+NCU_DRAM_BYTES_PER_READ = 391    # measured once per round with ncu (profiles/README.md), not in the timed run
 DEFAULT_READS = 100_000_000
 HOST_WINDOW_READS = 20_000_000           # pinned host window streamed repeatedly in the e2e leg
 
@@ -378,7 +379,13 @@ def main():
                        "step": "trim pipeline (scan, plan, DP rounds) + statistics reduction + int64 all-reduce of the statistics",
                        "with_adapters": with_adapters, "reads_counted": total_reads_stat},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the pipeline's kernels at
+                         # 4 M reads (scan 749 MB, plan 617 MB, run rounds ~200 MB; profiles/README.md), scaled to
+                         # the reads of one pass: bytes per launch.  The plan and run kernels re-read the windows
+                         # of the reads that pass the prefilter, hence ~2x the algorithmic bytes.
+                         "traffic": NCU_DRAM_BYTES_PER_READ * n,
+                         "traffic_unit": "bytes per pass (ncu DRAM bytes per read x reads)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "kernel": "trim pipeline: cg_scan_kernel -> cg_list_kernel<plan> -> 4x cg_list_kernel<run> "
                                    "(all kernels of one pass; per-kernel shares in profiles/)",
