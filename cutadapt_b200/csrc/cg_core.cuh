@@ -45,6 +45,34 @@ CG_HD uint32_t cg_funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits)   // (
     return shift_bits ? (lo >> shift_bits) | (hi << (32 - shift_bits)) : lo;
 #endif
 }
+// Byte load through a 32-bit shared-memory address computed once (device only).  Loads through a generic
+// pointer into shared memory make the compiler re-derive the shared window (S2R SR_CgaCtaId + LEA) at
+// every use inside the DP column loop, on the critical path of character -> match mask -> cells.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t cg_lds_u8(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+// character cursor of the plan stage (its read window is always in shared memory on the device)
+#define CG_CHARPTR(name, expr) uint32_t name = (uint32_t)__cvta_generic_to_shared(expr)
+#define CG_CHAR(cursor) cg_lds_u8((uint32_t)(cursor))
+// 32-bit table in shared memory (scan masks, peq): base converted once, entries by index
+__device__ __forceinline__ uint32_t cg_lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+#define CG_TABPTR(name, expr) const uint32_t name = (uint32_t)__cvta_generic_to_shared(expr)
+#define CG_TAB32(tab, i) cg_lds_u32((tab) + 4u * (uint32_t)(i))
+#else
+#define CG_CHARPTR(name, expr) const uint8_t *name = (expr)
+#define CG_CHAR(cursor) ((uint32_t) * (cursor))
+#define CG_TABPTR(name, expr) const uint32_t *name = (expr)
+#define CG_TAB32(tab, i) ((tab)[i])
+#endif
 template <class X> CG_HD X cg_min(X a, X b) { return a < b ? a : b; }
 template <class X> CG_HD X cg_max(X a, X b) { return a > b ? a : b; }
 
@@ -1151,7 +1179,7 @@ CG_HD bool loc_state_result(const LocState &st, int *out6)
 // Processes runs [0, n_use) of R starting from the selection state `st` and leaves the updated state
 // in `st`; the last-column scan (_align.pyx:536-572) is done only when final_scan is set (i.e. when
 // this call covers the read's last run).
-template <int MR, bool NC = false>
+template <int MR, bool NC = false, bool SMEM = false>
 CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
                        const uint32_t *peq, const ReadView &rv, const RunList &R, int n_use, bool has_task,
                        bool final_scan, LocState &st, bool eval_bottom = true)
@@ -1167,6 +1195,9 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
     const uint32_t kthr = (uint32_t)(k + 1) << C::CS;      // cost <= k  <=>  word < kthr
     // character access without a per-character branch: p[base + stride * j]
     const uint8_t *cp = rv.rev ? rv.p + (n - 1) : rv.p;
+#if defined(__CUDA_ARCH__)
+    const uint32_t cp_s = SMEM ? (uint32_t)__cvta_generic_to_shared(cp) : 0u;   // SMEM: the read bytes are in shared memory
+#endif
     const int cstride = rv.rev ? -1 : 1;
 
     bool have = st.have != 0;
@@ -1210,7 +1241,13 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
             if (!CG_WARP_ANY(act)) break;
             const int my_last = act ? last : 0;
             const int jj = act ? lo + t : 0;
+#if defined(__CUDA_ARCH__)
+            int ch = 0;
+            if (SMEM) { if (act) ch = (int)(cg_lds_u8(cp_s + (uint32_t)(cstride * jj)) & 127u); }
+            else ch = act ? (cp[cstride * jj] & 127) : 0;
+#else
             const int ch = act ? (cp[cstride * jj] & 127) : 0;
+#endif
             const uint32_t pq_lo = peq[ch];
             uint32_t pq_hi = 0;
             if (MR > 32) pq_hi = peq[128 + ch];
@@ -1550,8 +1587,8 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
     for (int w = 0; w < n_words; ++w) {
         const CgScanWord &W = words[w];
         if (W.type != CG_SCAN_WHOLE || !W.loc_found) continue;
-        const uint32_t *mask = (const uint32_t *)(pool + W.mask_off);
-        const uint8_t *ltab = pool + W.loc_off;
+        CG_TABPTR(mask, (const uint32_t *)(pool + W.mask_off));
+        CG_CHARPTR(ltab, pool + W.loc_off);
         const uint32_t init = W.init, locf = W.loc_found;
         const bool stash = n_loc == 1;
         uint32_t todo = hits, Rr = 0;
@@ -1573,10 +1610,10 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
                 } else {
                     Rr = 0;
                     const int q0 = cg_max(0, p_first - 31);
-                    const uint8_t *q = first + (REV ? -q0 : q0);
+                    CG_CHARPTR(q, first + (REV ? -q0 : q0));
                     for (int i = q0; i < p_first; ++i) {
-                        Rr = ((Rr << 1) | init) & mask[*q];
-                        q += REV ? -1 : 1;
+                        Rr = ((Rr << 1) | init) & CG_TAB32(mask, CG_CHAR(q));
+                        q = REV ? q - 1 : q + 1;
                     }
                 }
             }
@@ -1590,7 +1627,7 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
                 while (f) {
                     const int b = cg_ctz(f);
                     f &= f - 1;
-                    const int bmin = ltab[2 * b], bmax = ltab[2 * b + 1];
+                    const int bmin = (int)CG_CHAR(ltab + 2 * b), bmax = (int)CG_CHAR(ltab + 2 * b + 1);
                     wlo = cg_min(wlo, p + 1 - bmax - k);
                     whi = cg_max(whi, p + 1 - bmin + m + k);
                     if (stretch == 0) {
@@ -1617,10 +1654,10 @@ CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t
             };
             // (fetching the group as aligned words like the scan kernel does was measured 7 % slower here:
             // the unrolled body with its predicated queue pushes outweighs the saved byte loads)
-            const uint8_t *q = first + (REV ? -p_first : p_first);
+            CG_CHARPTR(q, first + (REV ? -p_first : p_first));
             for (int p = p_first; p < p_end; ++p) {
-                Rr = ((Rr << 1) | init) & mask[*q];
-                q += REV ? -1 : 1;
+                Rr = ((Rr << 1) | init) & CG_TAB32(mask, CG_CHAR(q));
+                q = REV ? q - 1 : q + 1;
                 const uint32_t f = Rr & locf;
                 if (f) push(p, f);
             }
@@ -1651,13 +1688,14 @@ CG_HD void plan_runs_myers_t(const CgAdapter &A, const uint32_t *peq, const int3
     const T top = (T)1 << (m - 1);
     T Pv = sir ? (T)0 : mmask, Mv = 0;                     // column 0: cost i, or 0 (START_IN_REFERENCE)
     int score = sir ? 0 : m;
-    const uint8_t *cp = A.reverse ? p + (n - 1) : p;
+    CG_CHARPTR(cp, A.reverse ? p + (n - 1) : p);
+    CG_TABPTR(peq_t, peq);
     const int cstride = A.reverse ? -1 : 1;
     int wlo = 0, whi = -1;
     for (int j = 1; j <= n; ++j) {
-        const int ch = cp[cstride * (j - 1)] & 127;
-        T Eq = (T)peq[ch];
-        if (sizeof(T) > 4) Eq |= (T)((unsigned long long)peq[128 + ch] << 32);
+        const int ch = (int)(CG_CHAR(cp + cstride * (j - 1)) & 127u);
+        T Eq = (T)CG_TAB32(peq_t, ch);
+        if (sizeof(T) > 4) Eq |= (T)((unsigned long long)CG_TAB32(peq_t, 128 + ch) << 32);
         const T Xv = Eq | Mv;
         const T Xh = (T)((((Eq & Pv) + Pv) ^ Pv) | Eq);
         T Ph = (T)(Mv | ~(Xh | Pv));
@@ -1787,8 +1825,9 @@ CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int h
     RunList R;
     R.n = 1; R.lo0 = lo; R.hi0 = hi; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     // free start in the read bounds every cost by the row number, so short adapters never saturate
-    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
-    else locate_regs<MR, false>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
+    // (run_pass is only called with the run's bytes staged in shared memory on the device)
+    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
+    else locate_regs<MR, false, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
 }
 
 // Host-sim driver of the planned scheduling for one read (tests/hostsim, mode 64).
