@@ -1238,7 +1238,8 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
         const int len = CG_WARP_MAX(my_len);
         for (int t = 0; t < len; ++t) {
             const bool act = mine && !stopped && t < my_len;
-            if (!CG_WARP_ANY(act)) break;
+            // (all lanes stopped early: rare, so the vote is only taken every 8th column)
+            if ((t & 7) == 0 && !CG_WARP_ANY(act)) break;
             const int my_last = act ? last : 0;
             const int jj = act ? lo + t : 0;
 #if defined(__CUDA_ARCH__)
@@ -1252,7 +1253,7 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
             uint32_t pq_hi = 0;
             if (MR > 32) pq_hi = peq[128 + ch];
             uint32_t diag = c[0];
-            uint32_t w0 = siq ? C::row0_free(diag) : C::row0_ins(diag, 1);
+            uint32_t w0 = (NC || siq) ? C::row0_free(diag) : C::row0_ins(diag, 1);   // NC implies a free read start
             w0 = act ? w0 : diag;
             c[0] = w0;
             uint32_t up = w0;
