@@ -1564,7 +1564,8 @@ struct RunPlan {
     int n_runs;                    // 0..4
     int lo0, hi0, lo1, hi1, lo2, hi2, lo3, hi3;
     int end_idx;                   // index of the pure end-window run (no bottom-row candidates), or -1
-    int exact;                     // 1: finished by the exact-occurrence shortcut at start s0
+    int exact;                     // 1: finished by the exact-occurrence shortcut at start s0;
+                                   // 2: by the end-overlap shortcut, s0 = overlap length
     int s0;
 };
 
@@ -1729,6 +1730,49 @@ CG_HD void plan_runs_myers_t(const CgAdapter &A, const uint32_t *peq, const int3
     }
 }
 
+// End-of-read shortcut for reads without any locator hit (no full-adapter alignment with <= k errors
+// exists, so only the last-column scan, _align.pyx:536-572, can produce a result).  A bit-vector pass
+// over the end window [lo_end, n] (same restart as the end run) gives cost(i, n) for every adapter
+// prefix i.  The scan walks i downwards with no best match yet, so the first acceptable i wins and a
+// later (shorter) one replaces it only with a higher score; if every acceptable cell has cost 0 (an
+// exact overlap: score = i) that never happens and the result is the longest exact overlap
+// (0, i, n - i, n, i, 0).  Returns -1: some acceptable cell has errors (run the DP), 0: nothing is
+// acceptable, i > 0: the result is the exact overlap of length i.
+template <class T>
+CG_HD int end_overlap_myers_t(const CgAdapter &A, const uint32_t *peq, const int32_t *ncnt,
+                              const int32_t *maxcost, const uint8_t *p, int n, int lo_end)
+{
+    const int m = A.m;
+    const T mmask = m >= (int)(8 * sizeof(T)) ? (T) ~(T)0 : (T)(((T)1 << m) - 1);
+    T Pv = mmask, Mv = 0;                                   // restart column: cost i
+    CG_CHARPTR(cp, A.reverse ? p + (n - 1) : p);
+    CG_TABPTR(peq_t, peq);
+    const int cstride = A.reverse ? -1 : 1;
+    for (int j = lo_end + 1; j <= n; ++j) {
+        const int ch = (int)(CG_CHAR(cp + cstride * (j - 1)) & 127u);
+        T Eq = (T)CG_TAB32(peq_t, ch);
+        if (sizeof(T) > 4) Eq |= (T)((unsigned long long)CG_TAB32(peq_t, 128 + ch) << 32);
+        const T Xv = Eq | Mv;
+        const T Xh = (T)((((Eq & Pv) + Pv) ^ Pv) | Eq);
+        T Ph = (T)(Mv | ~(Xh | Pv));
+        T Mh = Pv & Xh;
+        Ph = (T)(Ph << 1); Mh = (T)(Mh << 1);               // row 0 stays 0: START_IN_QUERY
+        Pv = (T)(Mh | ~(Xv | Ph));
+        Mv = Ph & Xv;
+    }
+    int c = 0, best = 0;
+    bool inexact = false;
+    for (int i = 1; i <= m; ++i) {
+        c += (int)((Pv >> (i - 1)) & 1) - (int)((Mv >> (i - 1)) & 1);
+        int eff = i;
+        if (A.wildcard_ref) eff = (i < m) ? i - ncnt[i] : A.effective_length;
+        if (i >= A.min_overlap && c <= maxcost[eff]) {
+            if (c == 0) best = i; else inexact = true;
+        }
+    }
+    return inexact ? -1 : best;
+}
+
 CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs, uint32_t rs0,
                      uint32_t rs1, RunPlan &P)
 {
@@ -1780,6 +1824,15 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
     P.n_runs = R.n; P.lo0 = R.lo0; P.hi0 = R.hi0; P.lo1 = R.lo1; P.hi1 = R.hi1; P.lo2 = R.lo2; P.hi2 = R.hi2;
     if (A.flags & 4) {                                           // STOP_IN_REFERENCE: last-column scan
         const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+        if (R.n == 0 && !(A.flags & 1) && A.m <= 64) {           // no hit anywhere: see end_overlap_myers_t
+            const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+            const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+            const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+            const int r = A.m <= 32 ? end_overlap_myers_t<uint32_t>(A, peq, ncnt, maxcost, p, n, lo_end)
+                                    : end_overlap_myers_t<unsigned long long>(A, peq, ncnt, maxcost, p, n, lo_end);
+            if (r == 0) return;                                  // P.n_runs == 0: no match
+            if (r > 0) { P.exact = 2; P.s0 = r; return; }
+        }
         bool covered = false;
         if (R.n > 0) {
             const int lo_last = R.n == 1 ? R.lo0 : (R.n == 2 ? R.lo1 : R.lo2);
@@ -1797,6 +1850,14 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
             P.n_runs = R.n + 1;
         }
     }
+}
+
+// P.exact == 2: the exact overlap of the adapter's first `len` characters with the end of the read
+CG_HD void hit_end_overlap(const CgAdapter &A, int n, int len, CgHit &hit)
+{
+    LocState st = loc_state_init(A.m, n);
+    st.have = 1; st.b_origin = n - len; st.b_cost = 0; st.b_score = len; st.b_ref_stop = len; st.b_q_stop = n;
+    hit_from_state(A, n, st, hit);
 }
 
 CG_HD void hit_exact(const CgAdapter &A, int n, int s0, CgHit &hit)
@@ -1848,7 +1909,8 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
     if (sc.pass) {
         RunPlan P;
         plan_runs(S, seq + s, nn, sc.hits, gs, sc.rs0, sc.rs1, P);
-        if (P.exact) hit_exact(A, nn, P.s0, hit);
+        if (P.exact == 2) hit_end_overlap(A, nn, P.s0, hit);
+        else if (P.exact) hit_exact(A, nn, P.s0, hit);
         else {
             LocState st = loc_state_init(A.m, nn);
             for (int r = 0; r < P.n_runs && !st.stopped; ++r) {

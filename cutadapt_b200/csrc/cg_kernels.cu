@@ -884,7 +884,8 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
             if (has_task) {
                 RunPlan P;
                 plan_runs(S, p, n, tb.x, (int)tb.y, tb.z, tb.w, P);
-                if (P.exact) hit_exact(A, n, P.s0, hit);
+                if (P.exact == 2) hit_end_overlap(A, n, P.s0, hit);
+                else if (P.exact) hit_exact(A, n, P.s0, hit);
                 else if (P.n_runs > 0) {
                     cont = true;
                     oc = make_uint4((uint32_t)A.m, (uint32_t)n, 0u, (uint32_t)P.n_runs | ((uint32_t)(P.end_idx & 15) << 8));
