@@ -151,6 +151,8 @@ def _declare(lib) -> None:
     ]
     lib.cg_kmers_present_batch.argtypes = [vp, C.POINTER(cg_kmer_entry), vp, i32, vp, vp, i64, vp]
     lib.cg_quality_trim_batch.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.cg_nextseq_trim_batch.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.cg_poly_a_trim_batch.argtypes = [vp, vp, vp, i64, i32, vp]
     lib.cg_stats_size.argtypes = [i32, i32, i32]
     lib.cg_stats_size.restype = i64
     lib.cg_stats_accumulate_device.argtypes = [

@@ -806,6 +806,48 @@ extern "C" int cg_quality_trim_batch(cg_ctx *c, const uint8_t *qual, const int64
     return CG_OK;
 }
 
+extern "C" int cg_nextseq_trim_batch(cg_ctx *c, const uint8_t *seq, const uint8_t *qual, const int64_t *offsets,
+                                     int64_t n_reads, int32_t cutoff, int32_t base, int32_t *out)
+{
+    if (!c || !offsets || !out || n_reads < 0) return fail(CG_EINVAL, "cg_nextseq_trim_batch: bad argument");
+    if (n_reads == 0) return CG_OK;
+    if (!qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
+    if (!seq) return fail(CG_EINVAL, "cg_nextseq_trim_batch: seq is NULL");
+    if (offsets[0] != 0) return fail(CG_EINVAL, "offsets[0] must be 0");
+    CU(cudaSetDevice(c->device));
+    Lane &l = c->lanes[0];
+    int rc = lane_finish(c, l);
+    if (rc != CG_OK) return rc;
+    if ((rc = upload_reads(c, l, seq, offsets, n_reads, false)) != CG_OK) return rc;
+    if ((rc = upload_reads(c, l, qual, offsets, n_reads, true)) != CG_OK) return rc;
+    if ((rc = l.d_qtrim.ensure((size_t)n_reads * 2)) != CG_OK) return rc;
+    CU(cg_launch_nextseq_trim(l.d_seq.p, l.d_qual.p, l.d_offs.p, n_reads, cutoff, base, l.d_qtrim.p, l.stream));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(out, l.d_qtrim.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaStreamSynchronize(l.stream));
+    return CG_OK;
+}
+
+extern "C" int cg_poly_a_trim_batch(cg_ctx *c, const uint8_t *seq, const int64_t *offsets, int64_t n_reads,
+                                    int32_t revcomp, int32_t *out)
+{
+    if (!c || !offsets || !out || n_reads < 0) return fail(CG_EINVAL, "cg_poly_a_trim_batch: bad argument");
+    if (n_reads == 0) return CG_OK;
+    if (!seq) return fail(CG_EINVAL, "cg_poly_a_trim_batch: seq is NULL");
+    if (offsets[0] != 0) return fail(CG_EINVAL, "offsets[0] must be 0");
+    CU(cudaSetDevice(c->device));
+    Lane &l = c->lanes[0];
+    int rc = lane_finish(c, l);
+    if (rc != CG_OK) return rc;
+    if ((rc = upload_reads(c, l, seq, offsets, n_reads, false)) != CG_OK) return rc;
+    if ((rc = l.d_qtrim.ensure((size_t)n_reads * 2)) != CG_OK) return rc;
+    CU(cg_launch_poly_a_trim(l.d_seq.p, l.d_offs.p, n_reads, revcomp ? 1 : 0, l.d_qtrim.p, l.stream));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(out, l.d_qtrim.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaStreamSynchronize(l.stream));
+    return CG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Statistics
 // ------------------------------------------------------------------------------------------

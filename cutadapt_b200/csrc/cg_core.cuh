@@ -408,6 +408,42 @@ CG_HD void quality_trim_core(const uint8_t *q, int n, int cutoff_front, int cuto
     *start_out = start; *stop_out = stop;
 }
 
+// nextseq_trim_index (qualtrim.pyx:76-117): the 3' pass with every 'G' counted as quality cutoff - 1
+CG_HD int nextseq_trim_core(const uint8_t *seq, const uint8_t *q, int n, int cutoff, int base)
+{
+    int s = 0, max_qual = 0, max_i = n;
+    for (int i = n - 1; i >= 0; --i) {
+        int v = (int)(signed char)q[i] - base;
+        if (seq[i] == 'G') v = cutoff - 1;
+        s += cutoff - v;
+        if (s < 0) break;
+        if (s > max_qual) { max_qual = s; max_i = i; }
+    }
+    return max_i;
+}
+
+// poly_a_trim_index (qualtrim.pyx:120-169)
+CG_HD int poly_a_trim_core(const uint8_t *seq, int n, int revcomp)
+{
+    int best_score = 0, score = 0, errors = 0, best_index;
+    if (revcomp) {
+        best_index = 0;
+        for (int i = 0; i < n; ++i) {
+            if (seq[i] == 'T') score += 1; else { score -= 2; errors += 1; }
+            if (score > best_score && errors * 5 <= i + 1) { best_score = score; best_index = i + 1; }
+        }
+        if (best_index < 3) best_index = 0;
+    } else {
+        best_index = n;
+        for (int i = n - 1; i >= 0; --i) {
+            if (seq[i] == 'A') score += 1; else { score -= 2; errors += 1; }
+            if (score > best_score && errors * 5 <= n - i) { best_score = score; best_index = i; }
+        }
+        if (best_index > n - 3) best_index = n;
+    }
+    return best_index;
+}
+
 // ---------------------------------------------------------------------------------------
 // Fused scan stage of the two-phase kernel.
 //

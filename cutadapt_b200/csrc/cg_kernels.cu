@@ -1096,6 +1096,53 @@ cudaError_t cg_launch_quality_trim(const uint8_t *d_qual, const int64_t *d_offse
 }
 
 // ------------------------------------------------------------------------------------------
+// Stand-alone batched nextseq_trim_index / poly_a_trim_index (qualtrim.pyx:76-169): the other two
+// per-read scans of the modifier chain (NextseqQualityTrimmer, PolyATrimmer; modifiers.py:825-837,
+// 861-918).  One lane per read; the scans run from the 3' end and stop early, so most reads touch
+// only their last sectors.
+// ------------------------------------------------------------------------------------------
+__global__ void cg_nextseq_trim_kernel(const uint8_t *seq, const uint8_t *qual, const int64_t *offsets,
+                                       long long n_reads, int cutoff, int base, int32_t *out)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        const long long o = offsets[r];
+        out[r] = nextseq_trim_core(seq + o, qual + o, (int)(offsets[r + 1] - o), cutoff, base);
+    }
+}
+__global__ void cg_poly_a_trim_kernel(const uint8_t *seq, const int64_t *offsets, long long n_reads, int revcomp,
+                                      int32_t *out, int *err_flag)
+{
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        const long long o = offsets[r];
+        const int n = (int)(offsets[r + 1] - o);
+        out[r] = poly_a_trim_core(seq + o, n, revcomp);
+    }
+    (void)err_flag;
+}
+cudaError_t cg_launch_nextseq_trim(const uint8_t *d_seq, const uint8_t *d_qual, const int64_t *d_offsets,
+                                   long long n_reads, int cutoff, int base, int32_t *d_out, cudaStream_t st)
+{
+    const int block = 128;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    cg_nextseq_trim_kernel<<<(int)grid, block, 0, st>>>(d_seq, d_qual, d_offsets, n_reads, cutoff, base, d_out);
+    return cudaGetLastError();
+}
+cudaError_t cg_launch_poly_a_trim(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int revcomp,
+                                  int32_t *d_out, cudaStream_t st)
+{
+    const int block = 128;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    cg_poly_a_trim_kernel<<<(int)grid, block, 0, st>>>(d_seq, d_offsets, n_reads, revcomp, d_out, nullptr);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Longest read of a batch (device offsets)
 // ------------------------------------------------------------------------------------------
 __global__ void cg_max_len_kernel(const int64_t *offsets, long long n_reads, int *out)

@@ -85,3 +85,7 @@ cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int qua
                             int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
                             int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
                             cudaStream_t st);
+cudaError_t cg_launch_nextseq_trim(const uint8_t *d_seq, const uint8_t *d_qual, const int64_t *d_offsets,
+                                   long long n_reads, int cutoff, int base, int32_t *d_out, cudaStream_t st);
+cudaError_t cg_launch_poly_a_trim(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int revcomp,
+                                  int32_t *d_out, cudaStream_t st);

@@ -208,7 +208,7 @@ int cg_process_batch_device(cg_ctx *ctx, const cg_adapterset *set, const uint8_t
                             int32_t max_read_len, const cg_params *params, cg_match *d_matches,
                             int32_t *d_qtrim);
 
-/* ---- stand-alone batched versions of the three native functions -------------------------
+/* ---- stand-alone batched versions of the native functions -------------------------
  * KmerFinder.kmers_present (_kmer_finder.pyx:170-213): out[i] = 1/0.  Host pointers. */
 int cg_kmers_present_batch(cg_ctx *ctx, const cg_kmer_entry *entries, const uint64_t *masks,
                            int32_t n_entries, const uint8_t *seq, const int64_t *offsets,
@@ -217,6 +217,14 @@ int cg_kmers_present_batch(cg_ctx *ctx, const cg_kmer_entry *entries, const uint
 int cg_quality_trim_batch(cg_ctx *ctx, const uint8_t *qual, const int64_t *offsets,
                           int64_t n_reads, int32_t cutoff_front, int32_t cutoff_back,
                           int32_t base, int32_t *out);
+/* nextseq_trim_index (qualtrim.pyx:76-117; NextseqQualityTrimmer, modifiers.py:825-837): out[i] = the
+ * index at which read i is cut at its 3' end ('G' counted as quality cutoff - 1).  Host pointers. */
+int cg_nextseq_trim_batch(cg_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int64_t *offsets,
+                          int64_t n_reads, int32_t cutoff, int32_t base, int32_t *out);
+/* poly_a_trim_index (qualtrim.pyx:120-169; PolyATrimmer, modifiers.py:861-918): out[i] = start of the
+ * poly-A tail of read i, or with revcomp != 0 the end of its poly-T head.  Host pointers. */
+int cg_poly_a_trim_batch(cg_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int64_t n_reads,
+                         int32_t revcomp, int32_t *out);
 
 /* ---- trim statistics (the payload of the end-of-run all-reduce, report.py:81-126) --------
  * Device-side reduction of a batch's match records into a fixed-layout int64 vector:

@@ -459,6 +459,45 @@ void oracle_quality_trim_index(const unsigned char *qual, int n, int cutoff_fron
     *start_out = start; *stop_out = stop;
 }
 
+/* nextseq_trim_index (qualtrim.pyx:76-117): like the 3' pass above, but a 'G' counts as quality
+   cutoff - 1.  Returns the index at which the read is cut. */
+int oracle_nextseq_trim_index(const unsigned char *seq, const unsigned char *qual, int n, int cutoff,
+                              int base)
+{
+    int s = 0, max_qual = 0, max_i = n, i;
+    for (i = n - 1; i >= 0; i--) {                                /* qualtrim.pyx:106-116 */
+        int q = (signed char)qual[i] - base;
+        if (seq[i] == 'G') q = cutoff - 1;
+        s += cutoff - q;
+        if (s < 0) break;
+        if (s > max_qual) { max_qual = s; max_i = i; }
+    }
+    return max_i;
+}
+
+/* poly_a_trim_index (qualtrim.pyx:120-169): start of the poly-A tail, or with revcomp the end of
+   the poly-T head; +1 per A (T), -2 otherwise, at most 20 % errors, tails shorter than 3 ignored. */
+int oracle_poly_a_trim_index(const unsigned char *seq, int n, int revcomp)
+{
+    int best_score = 0, score = 0, errors = 0, best_index, i;
+    if (revcomp) {
+        best_index = 0;
+        for (i = 0; i < n; i++) {                                 /* qualtrim.pyx:141-153 */
+            if (seq[i] == 'T') score += 1; else { score -= 2; errors += 1; }
+            if (score > best_score && errors * 5 <= i + 1) { best_score = score; best_index = i + 1; }
+        }
+        if (best_index < 3) best_index = 0;
+    } else {
+        best_index = n;
+        for (i = n - 1; i >= 0; i--) {                            /* qualtrim.pyx:155-167 */
+            if (seq[i] == 'A') score += 1; else { score -= 2; errors += 1; }
+            if (score > best_score && errors * 5 <= n - i) { best_score = score; best_index = i; }
+        }
+        if (best_index > n - 3) best_index = n;
+    }
+    return best_index;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* Batch drivers used by bench.py's "port" CPU baseline and by the tests                 */
 /* ------------------------------------------------------------------------------------ */

@@ -65,6 +65,8 @@ def lib():
                                             C.POINTER(KmerEntry), C.c_void_p]
         handle.oracle_kmers_present.argtypes = [C.POINTER(KmerEntry), C.c_void_p, C.c_int, u8p, C.c_int64]
         handle.oracle_quality_trim_index.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+        handle.oracle_nextseq_trim_index.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
+        handle.oracle_poly_a_trim_index.argtypes = [u8p, C.c_int, C.c_int]
         handle.oracle_locate_batch.argtypes = [u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                                C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.POINTER(KmerEntry), C.c_void_p, C.c_int, C.c_void_p]
@@ -121,6 +123,18 @@ def quality_trim_index(qualities, cutoff_front, cutoff_back, base=33):
     a, b = C.c_int(), C.c_int()
     lib().oracle_quality_trim_index(q, len(q), cutoff_front, cutoff_back, base, C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+def nextseq_trim_index(sequence, qualities, cutoff, base=33):
+    """qualtrim.pyx:76-117"""
+    b, q = _b(sequence), _b(qualities)
+    return int(lib().oracle_nextseq_trim_index(b, q, len(q), cutoff, base))
+
+
+def poly_a_trim_index(sequence, revcomp=False):
+    """qualtrim.pyx:120-169"""
+    b = _b(sequence)
+    return int(lib().oracle_poly_a_trim_index(b, len(b), int(bool(revcomp))))
 
 
 class KmerTables:

@@ -28,7 +28,7 @@ from cutadapt._align import Aligner, PrefixComparer, SuffixComparer, edit_enviro
 from cutadapt.align import hamming_environment  # noqa: E402
 from cutadapt._kmer_finder import KmerFinder  # noqa: E402
 from cutadapt.kmer_heuristic import create_positions_and_kmers  # noqa: E402
-from cutadapt.qualtrim import quality_trim_index  # noqa: E402
+from cutadapt.qualtrim import quality_trim_index, nextseq_trim_index, poly_a_trim_index  # noqa: E402
 from cutadapt import adapters as RA  # noqa: E402
 from cutadapt import _match_tables as RT  # noqa: E402
 
@@ -200,6 +200,61 @@ def qualtrim_kat():
 
 TYPES = ["FrontAdapter", "RightmostFrontAdapter", "BackAdapter", "RightmostBackAdapter", "AnywhereAdapter",
          "NonInternalFrontAdapter", "NonInternalBackAdapter", "PrefixAdapter", "SuffixAdapter"]
+
+
+def trim_scans_kat():
+    """nextseq_trim_index and poly_a_trim_index (qualtrim.pyx:76-169) incl. the reference's own test cases."""
+    from types import SimpleNamespace
+
+    rng = random.Random(1021)
+    nextseq, polya = [], []
+    # the reference's own known-answer test (tests/test_qualtrim.py:7-15): expected 0 and 33
+    for seq, qual, cutoff in [("", "", 22),
+                              ("TCTCGTATGCCGTCTTATGCTTGAAAAAAAAAAGGGGGGGGGGGGGGGGGNNNNNNNNNNNGGNGG",
+                               "AA//EAEE//A6///E//A//EA/EEEEEEAEA//EEEEEEEEEEEEEEE###########EE#EA", 22)]:
+        nextseq.append([seq, qual, cutoff, 33, nextseq_trim_index(SimpleNamespace(sequence=seq, qualities=qual), cutoff, 33)])
+    assert [x[4] for x in nextseq] == [0, 33]
+    for _ in range(1500):
+        n = rng.randint(0, 160)
+        seq = rnd(rng, rng.choice(["ACGT", "ACGTN", "GGGA", "acgtG"]), n)
+        if rng.random() < 0.4 and n:
+            t = rng.randint(1, n)
+            seq = seq[: n - t] + "G" * t
+        qual = "".join(chr(33 + rng.choice([2, 2, 10, 15, 20, 25, 30, 37, 41])) for _ in range(n))
+        cutoff = rng.choice([0, 5, 10, 20, 25, 30])
+        base = rng.choice([33, 33, 64])
+        nextseq.append([seq, qual, cutoff, base, nextseq_trim_index(SimpleNamespace(sequence=seq, qualities=qual), cutoff, base)])
+    # the reference's own known-answer tests (tests/test_qualtrim.py:18-62)
+    tails = [("", ""), ("GGGGGGGGAAAGAAGAAGAAGAAGAAGAAG", ""), ("TTTAGA", ""), ("TTTAGAA", ""), ("TTTAG", "AAA"),
+             ("TCAAGAAGTCCTTTACCAGCTTTC", "AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"),
+             ("TCAAGAAGTCCTTTACCAGCTTTC", "AAATAAAAAAAAAAAAAAAAAAAAAAAAAAAAA"),
+             ("GCAGATCACCTT", "AAAAAAAAAAAAAAAAAAAAAAAAAAAATAAA"), ("GCAGATCACCTT", "AAAAAAAAAAAAAAAAAAAAAAAAAAAAT"),
+             ("GCAGATCACCTT", "AAAAAAAAAAAAAAAAAAAAAAAAAAAATCG"), ("GCAGATCACCTAT", "AAAACAAAAAAACAAAAAAAACAAAAAA"),
+             ("TTTT", "AAATAAAA"), ("GGGGGGGGAAAGAAGAAGAAGAAGAAGAAG", "AAA")]
+    for seq, tail in tails:
+        assert poly_a_trim_index(seq + tail) == len(seq)
+        polya.append([seq + tail, False, len(seq)])
+    heads = [("", ""), ("", "GGGGGGGGAAAGAAGAAGAAGAAGAAGAAG"), ("", "TGTCCC"), ("", "TTGTCCC"), ("TTT", "GTCCC"),
+             ("TTTTTTTTTTTTTTTTTTTTT", "CAAGAAGTCCCCAGCTTTC"),
+             ("TTTATTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "CAAGAAGTCCTTTACCAGCTTTC"),
+             ("TTTTTATTTTTTTTTTTTTTTTTTTTTTTTTT", "GCAGATCACCTT"), ("ATTTTTTTTTTTTTTTTTTTTTTTTTTTT", "GCAGATCACCTT"),
+             ("AGCTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "GCAGATCACCTT"), ("TTTTGTTTTTTTGTTTTTTTTGTTTTTT", "GCAGATCACCTAT"),
+             ("TTTATTTT", "AAAA"), ("TTT", "GGGGGGGGAAAGAAGAAGAAGAAGAAGAAG")]
+    for head, seq in heads:
+        assert poly_a_trim_index(head + seq, revcomp=True) == len(head)
+        polya.append([head + seq, True, len(head)])
+    for _ in range(1500):
+        n = rng.randint(0, 160)
+        seq = rnd(rng, rng.choice(["ACGT", "ACGTN", "AAAC", "TTTG", "acgtA"]), n)
+        if rng.random() < 0.5:
+            tail = mutate(rng, "A" * rng.randint(0, 60), "ACGT", rng.choice([0, 0, 1, 2, 4]))
+            seq = seq + tail
+        if rng.random() < 0.5:
+            head = mutate(rng, "T" * rng.randint(0, 60), "ACGT", rng.choice([0, 0, 1, 2, 4]))
+            seq = head + seq
+        for rc in (False, True):
+            polya.append([seq, rc, poly_a_trim_index(seq, rc)])
+    dump("trim_scans_kat.json.gz", {"nextseq": nextseq, "polya": polya})
 
 
 def match_desc(m):
@@ -381,6 +436,7 @@ if __name__ == "__main__":
     comparer_kat()
     kmer_kat()
     qualtrim_kat()
+    trim_scans_kat()
     adapters_kat()
     index_kat()
     info_file_kat()

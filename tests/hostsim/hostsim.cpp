@@ -134,3 +134,10 @@ extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
     return hs_process_batch_indexed(adapters, n_adapters, groups, n_groups, nullptr, 0, seq, qual, offsets,
                                     n_reads, params, matches, qtrim, force_wide);
 }
+
+// the two stand-alone 3'-end scans (qualtrim.pyx:76-169) as the kernels run them
+extern "C" int hs_nextseq_trim(const uint8_t *seq, const uint8_t *qual, int n, int cutoff, int base)
+{
+    return nextseq_trim_core(seq, qual, n, cutoff, base);
+}
+extern "C" int hs_poly_a_trim(const uint8_t *seq, int n, int revcomp) { return poly_a_trim_core(seq, n, revcomp); }

@@ -103,6 +103,30 @@ def test_quality_trim_golden():
         quality_trim_index(None, 0, 20)
 
 
+def test_trim_scans_golden():
+    """nextseq_trim_index / poly_a_trim_index on the device == the reference (incl. its own KATs)."""
+    from types import SimpleNamespace
+    from cutadapt_b200 import qualtrim as Q
+
+    g = golden("trim_scans_kat.json.gz")
+    by_param = {}
+    for seq, qual, cutoff, base, expected in g["nextseq"]:
+        by_param.setdefault((cutoff, base), []).append((seq, qual, expected))
+    for (cutoff, base), rows in by_param.items():
+        got = Q.nextseq_trim_index_batch([r[0] for r in rows], [r[1] for r in rows], cutoff, base)
+        assert got.tolist() == [r[2] for r in rows]
+    s = SimpleNamespace(sequence="TCTCGTATGCCGTCTTATGCTTGAAAAAAAAAAGGGGGGGGGGGGGGGGGNNNNNNNNNNNGGNGG",
+                        qualities="AA//EAEE//A6///E//A//EA/EEEEEEAEA//EEEEEEEEEEEEEEE###########EE#EA")
+    assert Q.nextseq_trim_index(s, cutoff=22) == 33          # tests/test_qualtrim.py:10-15
+    with pytest.raises(Q.HasNoQualities):
+        Q.nextseq_trim_index(SimpleNamespace(sequence="ACGT", qualities=None), 20)
+    for rc in (False, True):
+        rows = [(seq, e) for seq, r, e in g["polya"] if bool(r) == rc]
+        got = Q.poly_a_trim_index_batch([r[0] for r in rows], rc)
+        assert got.tolist() == [r[1] for r in rows]
+    assert Q.poly_a_trim_index("TTTAG" + "AAA") == 5 and Q.poly_a_trim_index("TTT" + "GTCCC", revcomp=True) == 3
+
+
 # ---- adapter classes ------------------------------------------------------------------------
 
 

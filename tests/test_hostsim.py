@@ -208,3 +208,16 @@ def test_multipass_schedule_with_quality_trim_against_oracle():
         assert (res[1] == eqt).all()
         assert (res[0] == exp).all()
     assert planned == 60
+
+
+def test_trim_scan_device_functions_golden():
+    """The device functions behind cg_nextseq_trim_batch / cg_poly_a_trim_batch, compiled for the host."""
+    import ctypes as C
+    from util import hostsim_lib
+
+    lib = hostsim_lib()
+    g = golden("trim_scans_kat.json.gz")
+    for seq, qual, cutoff, base, expected in g["nextseq"]:
+        assert lib.hs_nextseq_trim(seq.encode(), qual.encode(), len(qual), cutoff, base) == expected
+    for seq, revcomp, expected in g["polya"]:
+        assert lib.hs_poly_a_trim(seq.encode(), len(seq), int(revcomp)) == expected

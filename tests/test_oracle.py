@@ -114,3 +114,12 @@ def test_oracle_composition_matches_golden_adapters():
         for i, (read, expected) in enumerate(case["reads"]):
             got = match_desc(multi.matches_from_records(recs[i, 0], read))
             assert got == expected, (case["adapters"], read)
+
+
+def test_trim_scans_golden():
+    """nextseq_trim_index / poly_a_trim_index of the oracle == the reference (incl. its own KATs)."""
+    g = golden("trim_scans_kat.json.gz")
+    for seq, qual, cutoff, base, expected in g["nextseq"]:
+        assert oracle.nextseq_trim_index(seq, qual, cutoff, base) == expected, (seq, qual, cutoff, base)
+    for seq, revcomp, expected in g["polya"]:
+        assert oracle.poly_a_trim_index(seq, revcomp) == expected, (seq, revcomp)
