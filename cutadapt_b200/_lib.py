@@ -153,6 +153,7 @@ def _declare(lib) -> None:
     lib.cg_quality_trim_batch.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.cg_nextseq_trim_batch.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.cg_poly_a_trim_batch.argtypes = [vp, vp, vp, i64, i32, vp]
+    lib.cg_expected_errors_batch.argtypes = [vp, vp, vp, i64, i32, vp]
     lib.cg_stats_size.argtypes = [i32, i32, i32]
     lib.cg_stats_size.restype = i64
     lib.cg_stats_accumulate_device.argtypes = [

@@ -103,6 +103,7 @@ struct cg_ctx {
     Lane lanes[2];
     int *d_err = nullptr;       // [0] non-ASCII flag, [1] max_len scratch
     uint8_t *d_enc = nullptr;   // 768 bytes
+    double *d_phred = nullptr;  // 256 doubles: 10^(-q/10)
     DevBuf<uint32_t> scratch_p;
     DevBuf<int> scratch_w;
     DevBuf<uint4> tasks;                 // split pipeline: 2 x uint4 per read of a sub-batch
@@ -165,6 +166,12 @@ extern "C" int cg_ctx_create(int device, void *stream, cg_ctx **out)
     uint8_t enc[768];
     cg_build_enc_tables(enc);
     CU(cudaMemcpy(c->d_enc, enc, 768, cudaMemcpyHostToDevice));
+    {
+        double phred[256];
+        cg_build_phred_table(phred);
+        CU(cudaMalloc((void **)&c->d_phred, sizeof phred));
+        CU(cudaMemcpy(c->d_phred, phred, sizeof phred, cudaMemcpyHostToDevice));
+    }
     *out = c;
     return CG_OK;
 }
@@ -200,6 +207,7 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
     if (c->d_task_count) cudaFree(c->d_task_count);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_enc) cudaFree(c->d_enc);
+    if (c->d_phred) cudaFree(c->d_phred);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CG_OK;
@@ -824,6 +832,27 @@ extern "C" int cg_nextseq_trim_batch(cg_ctx *c, const uint8_t *seq, const uint8_
     CU(cg_launch_nextseq_trim(l.d_seq.p, l.d_qual.p, l.d_offs.p, n_reads, cutoff, base, l.d_qtrim.p, l.stream));
     c->launches += 1;
     CU(cudaMemcpyAsync(out, l.d_qtrim.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, l.stream));
+    CU(cudaStreamSynchronize(l.stream));
+    return CG_OK;
+}
+
+extern "C" int cg_expected_errors_batch(cg_ctx *c, const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                                        int32_t base, double *out)
+{
+    if (!c || !offsets || !out || n_reads < 0 || base < 0 || base > 126)
+        return fail(CG_EINVAL, "cg_expected_errors_batch: bad argument");
+    if (n_reads == 0) return CG_OK;
+    if (!qual) return fail(CG_ENOQUAL, "no qualities available");
+    if (offsets[0] != 0) return fail(CG_EINVAL, "offsets[0] must be 0");
+    CU(cudaSetDevice(c->device));
+    Lane &l = c->lanes[0];
+    int rc = lane_finish(c, l);
+    if (rc != CG_OK) return rc;
+    if ((rc = upload_reads(c, l, qual, offsets, n_reads, true)) != CG_OK) return rc;
+    if ((rc = l.d_qtrim.ensure((size_t)n_reads * 2)) != CG_OK) return rc;       // n doubles
+    CU(cg_launch_expected_errors(l.d_qual.p, l.d_offs.p, n_reads, base, c->d_phred, (double *)l.d_qtrim.p, l.stream));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(out, l.d_qtrim.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, l.stream));
     CU(cudaStreamSynchronize(l.stream));
     return CG_OK;
 }

@@ -1121,6 +1121,28 @@ __global__ void cg_poly_a_trim_kernel(const uint8_t *seq, const int64_t *offsets
     }
     (void)err_flag;
 }
+__global__ void cg_expected_errors_kernel(const uint8_t *qual, const int64_t *offsets, long long n_reads, int base,
+                                          const double *table, double *out)
+{
+    __shared__ double s_table[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_table[i] = table[i];
+    __syncthreads();
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+        const long long o = offsets[r];
+        out[r] = expected_errors_core(qual + o, (int)(offsets[r + 1] - o), base, s_table);
+    }
+}
+cudaError_t cg_launch_expected_errors(const uint8_t *d_qual, const int64_t *d_offsets, long long n_reads, int base,
+                                      const double *d_table, double *d_out, cudaStream_t st)
+{
+    const int block = 128;
+    long long grid = (n_reads + block - 1) / block;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    cg_expected_errors_kernel<<<(int)grid, block, 0, st>>>(d_qual, d_offsets, n_reads, base, d_table, d_out);
+    return cudaGetLastError();
+}
 cudaError_t cg_launch_nextseq_trim(const uint8_t *d_seq, const uint8_t *d_qual, const int64_t *d_offsets,
                                    long long n_reads, int cutoff, int base, int32_t *d_out, cudaStream_t st)
 {

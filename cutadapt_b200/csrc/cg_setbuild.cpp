@@ -556,6 +556,11 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
 }
 
 
+void cg_build_phred_table(double *out256)
+{
+    for (int q = 0; q < 256; ++q) out256[q] = pow(10.0, -(double)q / 10.0);
+}
+
 // ---- multi-pass schedule -------------------------------------------------------------------------
 int cg_plan_passes(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
                    const cg_index_desc *indexes, int n_indexes, CgMultiPlan &plan, std::string &err)

@@ -20,6 +20,10 @@ struct CgBuiltSet {
 // 3 x 256 bytes: upper, acgt, iupac  (src/cutadapt/_match_tables.py:4-66)
 void cg_build_enc_tables(uint8_t *out768);
 
+// table[q] = 10^(-q/10) as double, q = 0..255 (the first 94 entries equal SCORE_TO_ERROR_RATE of
+// expected_errors.h bit for bit; tests/golden pins that)
+void cg_build_phred_table(double *out256);
+
 // Returns CG_OK or a negative code and fills `err`.
 int cg_build_set(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups,
                  int n_groups, CgBuiltSet &out, std::string &err,

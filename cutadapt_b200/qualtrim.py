@@ -113,3 +113,31 @@ def poly_a_trim_index_batch(sequences: Sequence[str], revcomp: bool = False) -> 
 def poly_a_trim_index(s: str, revcomp: bool = False) -> int:
     """Start index of the poly-A tail; with revcomp the end of the poly-T head (qualtrim.pyx:120-169)."""
     return int(poly_a_trim_index_batch([s], revcomp)[0])
+
+
+def expected_errors_batch(qualities: Sequence[str], base: int = 33) -> np.ndarray:
+    """float64 array: expected number of errors of every quality string (Edgar & Flyvbjerg 2015)."""
+    n = len(qualities)
+    out = np.zeros(n, dtype=np.float64)
+    if n == 0:
+        return out
+    for q in qualities:
+        if not q.isascii():
+            raise ValueError(f"Quality string contains non-ASCII values: {q}")
+    joined = "".join(qualities).encode("ascii")
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in qualities], out=offsets[1:])
+    data = np.frombuffer(joined, dtype=np.uint8) if joined else np.zeros(1, dtype=np.uint8)
+    ctx = _lib.default_context()
+    _lib.check(_lib.lib().cg_expected_errors_batch(ctx.handle, data.ctypes.data, offsets.ctypes.data, n, int(base),
+                                                   out.ctypes.data))
+    for i in np.nonzero(out < 0.0)[0]:
+        for ch in qualities[int(i)]:
+            if ord(ch) < base or ord(ch) > 126:
+                raise ValueError(f"Not a valid phred value {ord(ch)} for character {ch}")
+    return out
+
+
+def expected_errors(qualities: str, base: int = 33) -> float:
+    """Number of expected errors of a read from its qualities (qualtrim.pyx:172-197), bit-identical double."""
+    return float(expected_errors_batch([qualities], base)[0])

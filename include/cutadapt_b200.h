@@ -221,6 +221,11 @@ int cg_quality_trim_batch(cg_ctx *ctx, const uint8_t *qual, const int64_t *offse
  * index at which read i is cut at its 3' end ('G' counted as quality cutoff - 1).  Host pointers. */
 int cg_nextseq_trim_batch(cg_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int64_t *offsets,
                           int64_t n_reads, int32_t cutoff, int32_t base, int32_t *out);
+/* expected_errors (qualtrim.pyx:172-197; expected_errors.h:95-140): out[i] = the FP64 sum of 10^(-q/10)
+ * over read i's qualities, accumulated in the reference's order (bit-identical doubles); -1.0 marks a
+ * quality character outside [base, 126] (the reference raises ValueError).  Host pointers. */
+int cg_expected_errors_batch(cg_ctx *ctx, const uint8_t *qual, const int64_t *offsets, int64_t n_reads,
+                             int32_t base, double *out);
 /* poly_a_trim_index (qualtrim.pyx:120-169; PolyATrimmer, modifiers.py:861-918): out[i] = start of the
  * poly-A tail of read i, or with revcomp != 0 the end of its poly-T head.  Host pointers. */
 int cg_poly_a_trim_batch(cg_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int64_t n_reads,

@@ -14,6 +14,7 @@
  * All file:line citations are relative to the reference checkout (marcelm/cutadapt).
  * Plain C99, no dependencies:  gcc -O2 -shared -fPIC -o liboracle.so cutadapt_oracle.c
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -496,6 +497,39 @@ int oracle_poly_a_trim_index(const unsigned char *seq, int n, int revcomp)
         if (best_index > n - 3) best_index = n;
     }
     return best_index;
+}
+
+/* expected_errors (qualtrim.pyx:172-197; expected_errors.h:95-140): sum of 10^(-q/10) over the
+   qualities, in four independent accumulators over groups of four characters plus a tail that goes
+   into the first, added up as ((e0 + e1) + e2) + e3.  The order is part of the result (FP64).
+   Returns -1.0 for a character outside [base, 126].  The reference's 94-entry table holds the
+   doubles nearest to 10^(-q/10); pow() reproduces all of them (checked by the golden test). */
+double oracle_expected_errors(const unsigned char *qual, size_t n, unsigned char base)
+{
+    static double table[256];
+    static int ready = 0;
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    unsigned char max_phred = (unsigned char)(126 - base);
+    size_t i = 0;
+    if (!ready) {
+        int q;
+        for (q = 0; q < 256; q++) table[q] = pow(10.0, -(double)q / 10.0);
+        ready = 1;
+    }
+    while (i + 3 < n) {
+        unsigned char p0 = (unsigned char)(qual[i] - base), p1 = (unsigned char)(qual[i + 1] - base);
+        unsigned char p2 = (unsigned char)(qual[i + 2] - base), p3 = (unsigned char)(qual[i + 3] - base);
+        if (p0 > max_phred || p1 > max_phred || p2 > max_phred || p3 > max_phred) return -1.0;
+        e0 += table[p0]; e1 += table[p1]; e2 += table[p2]; e3 += table[p3];
+        i += 4;
+    }
+    while (i < n) {
+        unsigned char ph = (unsigned char)(qual[i] - base);
+        if (ph > max_phred) return -1.0;
+        e0 += table[ph];
+        i += 1;
+    }
+    return e0 + e1 + e2 + e3;
 }
 
 /* ------------------------------------------------------------------------------------ */

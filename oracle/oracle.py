@@ -43,7 +43,7 @@ class KmerEntry(C.Structure):
 
 def build(force=False):
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
-        subprocess.check_call(["gcc", "-O2", "-std=c99", "-shared", "-fPIC", "-o", SO, SRC])
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-shared", "-fPIC", "-o", SO, SRC, "-lm"])
     return SO
 
 
@@ -67,6 +67,8 @@ def lib():
         handle.oracle_quality_trim_index.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
         handle.oracle_nextseq_trim_index.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
         handle.oracle_poly_a_trim_index.argtypes = [u8p, C.c_int, C.c_int]
+        handle.oracle_expected_errors.argtypes = [u8p, C.c_size_t, C.c_ubyte]
+        handle.oracle_expected_errors.restype = C.c_double
         handle.oracle_locate_batch.argtypes = [u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                                C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.POINTER(KmerEntry), C.c_void_p, C.c_int, C.c_void_p]
@@ -135,6 +137,12 @@ def poly_a_trim_index(sequence, revcomp=False):
     """qualtrim.pyx:120-169"""
     b = _b(sequence)
     return int(lib().oracle_poly_a_trim_index(b, len(b), int(bool(revcomp))))
+
+
+def expected_errors(qualities, base=33):
+    """qualtrim.pyx:172-197 (a negative result = invalid quality character)"""
+    q = _b(qualities)
+    return float(lib().oracle_expected_errors(q, len(q), base))
 
 
 class KmerTables:

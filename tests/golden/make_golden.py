@@ -28,7 +28,7 @@ from cutadapt._align import Aligner, PrefixComparer, SuffixComparer, edit_enviro
 from cutadapt.align import hamming_environment  # noqa: E402
 from cutadapt._kmer_finder import KmerFinder  # noqa: E402
 from cutadapt.kmer_heuristic import create_positions_and_kmers  # noqa: E402
-from cutadapt.qualtrim import quality_trim_index, nextseq_trim_index, poly_a_trim_index  # noqa: E402
+from cutadapt.qualtrim import quality_trim_index, nextseq_trim_index, poly_a_trim_index, expected_errors  # noqa: E402
 from cutadapt import adapters as RA  # noqa: E402
 from cutadapt import _match_tables as RT  # noqa: E402
 
@@ -254,7 +254,20 @@ def trim_scans_kat():
             seq = head + seq
         for rc in (False, True):
             polya.append([seq, rc, poly_a_trim_index(seq, rc)])
-    dump("trim_scans_kat.json.gz", {"nextseq": nextseq, "polya": polya})
+    # expected_errors: FP64, results stored as float.hex() so that the comparison is bit-exact.
+    # Single-character strings expose the reference's table SCORE_TO_ERROR_RATE itself.
+    ee = []
+    enc = lambda quals: "".join(chr(q + 33) for q in quals)  # noqa: E731
+    for quals in [[], [10], [20], [30], [10, 10], [10, 20], [20, 10], [10, 10, 10], [10, 20, 30], [10, 10, 20, 30, 40]]:
+        ee.append([enc(quals), 33, expected_errors(enc(quals)).hex()])          # tests/test_qualtrim.py:65-82
+    for q in range(94):
+        ee.append([chr(33 + q), 33, expected_errors(chr(33 + q)).hex()])
+    for _ in range(1500):
+        n = rng.randint(0, 200)
+        base = rng.choice([33, 33, 64])
+        qual = "".join(chr(base + rng.choice([2, 2, 10, 15, 20, 25, 30, 37, 41, rng.randint(0, 126 - base)])) for _ in range(n))
+        ee.append([qual, base, expected_errors(qual, base).hex()])
+    dump("trim_scans_kat.json.gz", {"nextseq": nextseq, "polya": polya, "expected_errors": ee})
 
 
 def match_desc(m):

@@ -141,3 +141,9 @@ extern "C" int hs_nextseq_trim(const uint8_t *seq, const uint8_t *qual, int n, i
     return nextseq_trim_core(seq, qual, n, cutoff, base);
 }
 extern "C" int hs_poly_a_trim(const uint8_t *seq, int n, int revcomp) { return poly_a_trim_core(seq, n, revcomp); }
+extern "C" double hs_expected_errors(const uint8_t *qual, int n, int base)
+{
+    double table[256];
+    cg_build_phred_table(table);
+    return expected_errors_core(qual, n, base, table);
+}

@@ -125,6 +125,14 @@ def test_trim_scans_golden():
         got = Q.poly_a_trim_index_batch([r[0] for r in rows], rc)
         assert got.tolist() == [r[1] for r in rows]
     assert Q.poly_a_trim_index("TTTAG" + "AAA") == 5 and Q.poly_a_trim_index("TTT" + "GTCCC", revcomp=True) == 3
+    # expected_errors: FP64 with the reference's summation order -> bit-identical doubles
+    for base in (33, 64):
+        rows = [(q, e) for q, b, e in g["expected_errors"] if b == base]
+        got = Q.expected_errors_batch([r[0] for r in rows], base)
+        assert [float(x).hex() for x in got] == [r[1] for r in rows]
+    assert Q.expected_errors("5") == pytest.approx(0.01)        # tests/test_qualtrim.py:72
+    with pytest.raises(ValueError):
+        Q.expected_errors("II I")                               # ' ' is below base 33
 
 
 # ---- adapter classes ------------------------------------------------------------------------

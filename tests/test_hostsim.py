@@ -221,3 +221,6 @@ def test_trim_scan_device_functions_golden():
         assert lib.hs_nextseq_trim(seq.encode(), qual.encode(), len(qual), cutoff, base) == expected
     for seq, revcomp, expected in g["polya"]:
         assert lib.hs_poly_a_trim(seq.encode(), len(seq), int(revcomp)) == expected
+    lib.hs_expected_errors.restype = C.c_double
+    for qual, base, expected in g["expected_errors"]:
+        assert float(lib.hs_expected_errors(qual.encode(), len(qual), base)).hex() == expected

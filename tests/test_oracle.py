@@ -123,3 +123,6 @@ def test_trim_scans_golden():
         assert oracle.nextseq_trim_index(seq, qual, cutoff, base) == expected, (seq, qual, cutoff, base)
     for seq, revcomp, expected in g["polya"]:
         assert oracle.poly_a_trim_index(seq, revcomp) == expected, (seq, revcomp)
+    for qual, base, expected in g["expected_errors"]:           # bit-exact doubles
+        assert oracle.expected_errors(qual, base).hex() == expected, (qual, base)
+    assert oracle.expected_errors("II!I ", 33) < 0             # a character below the base
