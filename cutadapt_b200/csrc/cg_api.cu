@@ -653,11 +653,14 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         int64_t r1 = r0;
         int max_len = 0;
         const int64_t byte0 = offsets[r0];
+        const int64_t len0 = offsets[r0 + 1] - offsets[r0];
+        bool uniform = true;                 // all reads of the chunk equally long (typical for raw Illumina data)
         while (r1 < n_reads && r1 - r0 < CHUNK_READS) {
             const int64_t len = offsets[r1 + 1] - offsets[r1];
             if (len < 0 || len > 2000000000LL) return fail(CG_EINVAL, "offsets must be non-decreasing");
             if (r1 > r0 && offsets[r1 + 1] - byte0 > CHUNK_BYTES) break;
             if (len > max_len) max_len = (int)len;
+            uniform = uniform && len == len0;
             ++r1;
         }
         const int64_t nr = r1 - r0;
@@ -688,13 +691,19 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
             }
             if (nbytes) CU(cudaMemcpyAsync(l.d_qual.p + pad, src_q, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
         }
-        const int64_t *src_offs = offsets + r0;
-        if (!offs_pinned) {
-            if ((rc = l.h_offs.ensure((size_t)nr + 1)) != CG_OK) break;
-            memcpy(l.h_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t));
-            src_offs = l.h_offs.p;
+        if (uniform) {
+            // offsets[r0 + i] = byte0 + i * len0: generated on the device, 8 bytes per read less over PCIe
+            CU(cg_launch_fill_offsets(l.d_offs.p, byte0, len0, nr + 1, l.stream));
+            c->launches += 1;
+        } else {
+            const int64_t *src_offs = offsets + r0;
+            if (!offs_pinned) {
+                if ((rc = l.h_offs.ensure((size_t)nr + 1)) != CG_OK) break;
+                memcpy(l.h_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t));
+                src_offs = l.h_offs.p;
+            }
+            CU(cudaMemcpyAsync(l.d_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, l.stream));
         }
-        CU(cudaMemcpyAsync(l.d_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, l.stream));
         // offsets stay absolute: hand the kernel a virtual base so that base + offsets[r] lands
         // in this chunk's buffer with the same 16-byte phase as in the caller's array
         const uint8_t *vseq = l.d_seq.p + pad - byte0;

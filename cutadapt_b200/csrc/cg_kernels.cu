@@ -1164,6 +1164,19 @@ cudaError_t cg_launch_poly_a_trim(const uint8_t *d_seq, const int64_t *d_offsets
     return cudaGetLastError();
 }
 
+// offsets of a chunk of equally long reads: out[i] = base + i * len
+__global__ void cg_fill_offsets_kernel(int64_t *out, long long base, long long len, long long count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = base + i * len;
+}
+cudaError_t cg_launch_fill_offsets(int64_t *d_out, long long base, long long len, long long count, cudaStream_t st)
+{
+    const int block = 256;
+    cg_fill_offsets_kernel<<<(unsigned)((count + block - 1) / block), block, 0, st>>>(d_out, base, len, count);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // Longest read of a batch (device offsets)
 // ------------------------------------------------------------------------------------------

@@ -91,3 +91,4 @@ cudaError_t cg_launch_poly_a_trim(const uint8_t *d_seq, const int64_t *d_offsets
                                   int32_t *d_out, cudaStream_t st);
 cudaError_t cg_launch_expected_errors(const uint8_t *d_qual, const int64_t *d_offsets, long long n_reads, int base,
                                       const double *d_table, double *d_out, cudaStream_t st);
+cudaError_t cg_launch_fill_offsets(int64_t *d_out, long long base, long long len, long long count, cudaStream_t st);
