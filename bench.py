@@ -35,7 +35,7 @@ ADAPTER = "AGATCGGAAGAGC"
 ERROR_RATE = 0.1
 READ_LEN = 150
 ALGO_BYTES_PER_READ = READ_LEN + 8 + 32
-NCU_DRAM_BYTES_PER_READ = 391    # measured once per round with ncu (profiles/README.md), not in the timed run
+NCU_DRAM_BYTES_PER_READ = 380    # measured once per round with ncu (profiles/README.md), not in the timed run
 DEFAULT_READS = 100_000_000
 HOST_WINDOW_READS = 20_000_000           # pinned host window streamed repeatedly in the e2e leg
 
@@ -131,13 +131,19 @@ class CpuArm:
             t0 = time.perf_counter()
             res = self.pool.map(_cpu_worker, [4] * self.cores, chunksize=1)
             self.rate = sum(r[1] for r in res) / (time.perf_counter() - t0)
-        repeat = max(1, int(round(seconds_target * self.rate / max(self.pass_reads, 1))))
-        t0 = time.perf_counter()
-        res = self.pool.map(_cpu_worker, [repeat] * self.cores, chunksize=1)
-        wall = time.perf_counter() - t0
-        n = sum(r[1] for r in res)
-        self.rate = n / wall
-        return n / wall, n, wall
+        # timed rounds until the sample is long enough (the rate estimate improves with every round)
+        total_n, total_wall = 0, 0.0
+        while total_wall < 0.8 * seconds_target:
+            remaining = seconds_target - total_wall
+            repeat = max(1, int(round(remaining * self.rate / max(self.pass_reads, 1))))
+            t0 = time.perf_counter()
+            res = self.pool.map(_cpu_worker, [repeat] * self.cores, chunksize=1)
+            wall = time.perf_counter() - t0
+            n = sum(r[1] for r in res)
+            self.rate = n / wall
+            total_n += n
+            total_wall += wall
+        return total_n / total_wall, total_n, total_wall
 
     def close(self):
         self.pool.close()
@@ -384,7 +390,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the pipeline's kernels at
-                         # 4 M reads (scan 749 MB, plan 617 MB, run rounds ~200 MB; profiles/README.md), scaled to
+                         # 4 M reads (scan 749 MB, plan 615 MB, run rounds ~155 MB; profiles/README.md), scaled to
                          # the reads of one pass: bytes per launch.  The plan and run kernels re-read the windows
                          # of the reads that pass the prefilter, hence ~2x the algorithmic bytes.
                          "traffic": NCU_DRAM_BYTES_PER_READ * n,
