@@ -98,7 +98,9 @@ class cg_params(C.Structure):
         ("cutoff_back", C.c_int32),
         ("quality_base", C.c_int32),
         ("times", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("nextseq_trim", C.c_int32),
+        ("nextseq_cutoff", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -330,8 +332,11 @@ class AdapterSetSpec:
         return 2 if any(g[0] == CG_GROUP_LINKED for g in self.groups) else 1
 
 
-def make_params(quality_trim=False, cutoff_front=0, cutoff_back=0, quality_base=33, times=1) -> cg_params:
+def make_params(quality_trim=False, cutoff_front=0, cutoff_back=0, quality_base=33, times=1,
+                nextseq_cutoff=None) -> cg_params:
     p = cg_params()
+    p.nextseq_trim = int(nextseq_cutoff is not None)
+    p.nextseq_cutoff = int(nextseq_cutoff or 0)
     p.quality_trim = int(bool(quality_trim))
     p.cutoff_front = int(cutoff_front)
     p.cutoff_back = int(cutoff_back)
@@ -434,7 +439,7 @@ class AdapterSet:
         n = int(offsets.size - 1)
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
-        if params.quality_trim and qual is None:
+        if (params.quality_trim or params.nextseq_trim) and qual is None:
             from .qualtrim import HasNoQualities
 
             raise HasNoQualities("Cannot do quality trimming when no qualities are available")
@@ -442,7 +447,7 @@ class AdapterSet:
             qual = np.ascontiguousarray(qual, dtype=np.uint8)
         times = max(1, params.times)
         matches = np.empty((n, times, self.slots), dtype=MATCH_DTYPE)
-        qtrim = np.empty((n, 2), dtype=np.int32) if (want_qtrim or params.quality_trim) else None
+        qtrim = np.empty((n, 2), dtype=np.int32) if (want_qtrim or params.quality_trim or params.nextseq_trim) else None
         if n:
             check(
                 lib().cg_process_batch(

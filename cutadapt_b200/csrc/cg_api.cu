@@ -344,15 +344,17 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
 {
     if (n_reads <= 0) return CG_OK;
     const int times = p->times < 1 ? 1 : p->times;
-    const bool want_q = p->quality_trim != 0;
+    const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
     if (want_q && !d_qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
     CgKernelArgs a;
     memset(&a, 0, sizeof a);
     a.blob = s->d_blob; a.blob_bytes = (uint32_t)s->host.blob.size();
     a.masks64 = s->d_masks; a.enc = c->d_enc; a.index = s->d_index;
     a.seq = d_seq; a.qual = want_q ? d_qual : nullptr; a.offsets = d_offsets; a.n_reads = n_reads;
-    a.quality_trim = want_q ? 1 : 0; a.cutoff_front = p->cutoff_front; a.cutoff_back = p->cutoff_back;
-    a.qbase = p->quality_base; a.times = times; a.slots = s->host.slots;
+    // flags and packed base/cutoff as pre_trim_core expects them
+    a.quality_trim = (p->quality_trim ? 1 : 0) | (p->nextseq_trim ? 2 : 0);
+    a.cutoff_front = p->cutoff_front; a.cutoff_back = p->cutoff_back;
+    a.qbase = (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8); a.times = times; a.slots = s->host.slots;
     a.out = d_out; a.qtrim = d_qtrim; a.view = d_view; a.err_flag = c->d_err;
     a.col_rows = s->host.max_m + 1;
 
@@ -507,7 +509,7 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
     if (s->passes.empty() || times != 1 || force_general)
         return launch_trim_single(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, d_out, d_qtrim, nullptr,
                                   st, timed);
-    const bool want_q = p->quality_trim != 0;
+    const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
     if (want_q && !d_qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
     const int np = (int)s->passes.size();
     long long SUB = 32LL << 20;
@@ -554,7 +556,7 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
                 rc = launch_trim_single(c, P.sub, d_seq, d_qual, offs, n_sub, max_read_len, &pp, tmp, qt, nullptr, st, false);
                 base_view = qt;
             } else {
-                pp.quality_trim = 0;
+                pp.quality_trim = 0; pp.nextseq_trim = 0;
                 rc = launch_trim_single(c, P.sub, d_seq, nullptr, offs, n_sub, max_read_len, &pp, tmp, nullptr, view, st, false);
             }
             if (rc != CG_OK) return rc;
@@ -634,7 +636,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     if (n_reads < 0) return fail(CG_EINVAL, "n_reads < 0");
     if (n_reads == 0) return CG_OK;
     if (!seq) return fail(CG_EINVAL, "cg_process_batch: seq is NULL");
-    const bool want_q = p->quality_trim != 0;
+    const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
     if (want_q && !qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
     CU(cudaSetDevice(c->device));
     const int times = p->times < 1 ? 1 : p->times;
@@ -905,7 +907,7 @@ extern "C" int cg_stats_accumulate_device(cg_ctx *c, const cg_adapterset *s, con
     if (n_reads <= 0) return CG_OK;
     CU(cudaSetDevice(c->device));
     const int times = p->times < 1 ? 1 : p->times;
-    CU(cg_launch_stats(d_offsets, n_reads, p->quality_trim && d_qtrim, times, s->host.slots,
+    CU(cg_launch_stats(d_offsets, n_reads, (p->quality_trim || p->nextseq_trim) && d_qtrim, times, s->host.slots,
                        (const cg_match_rec *)d_matches, d_qtrim, s->host.n_adapters, max_len, kmax,
                        (unsigned long long *)d_stats, c->stream));
     c->launches += 1;

@@ -467,6 +467,23 @@ CG_HD double expected_errors_core(const uint8_t *q, int n, int base, const doubl
     return e0 + e1 + e2 + e3;
 }
 
+// The quality-driven modifiers in front of the adapter search, fused: NextseqQualityTrimmer
+// (modifiers.py:825-837) cuts the 3' end first, then QualityTrimmer (modifiers.py:840-858) works on
+// what is left -- the order cutadapt builds its modifier list in (cli.py:940-953).
+//   flags  bit 0: quality_trim_index, bit 1: nextseq_trim_index
+//   qbase  quality base in bits 0..7, NextSeq cutoff (signed) in bits 8..31
+// Result: the searched interval [*s, *e) of the read.
+CG_HD void pre_trim_core(const uint8_t *seq, const uint8_t *qual, int n, int flags, int cutoff_front,
+                         int cutoff_back, int qbase, int *s, int *e)
+{
+    const int base = qbase & 255;
+    int stop = n;
+    *s = 0;
+    if (flags & 2) stop = nextseq_trim_core(seq, qual, n, qbase >> 8, base);
+    *e = stop;
+    if (flags & 1) quality_trim_core(qual, stop, cutoff_front, cutoff_back, base, s, e);
+}
+
 // ---------------------------------------------------------------------------------------
 // Fused scan stage of the two-phase kernel.
 //
@@ -885,9 +902,7 @@ CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qua
 {
     const int slots = S.h->slots;
     int s = 0, e = n;
-    if (quality_trim) {
-        quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
-    }
+    if (quality_trim) pre_trim_core(seq, qual, n, quality_trim, cutoff_front, cutoff_back, qbase, &s, &e);
     if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
     if (view) { s = view[0]; e = view[1]; }                    // per-adapter pass: search read[s:e]
     CgHit none; none.adapter = -1; none.remove = 0;
@@ -1560,7 +1575,7 @@ CG_HD void process_read_simple(const SetView &S, const uint8_t *seq, const uint8
                                PackedCol &colp, cg_match_rec *out, int32_t *qtrim_out, int use_regs = 0)
 {
     int s = 0, e = n;
-    if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
+    if (quality_trim) pre_trim_core(seq, qual, n, quality_trim, cutoff_front, cutoff_back, qbase, &s, &e);
     if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
     CgHit hit; hit.adapter = -1; hit.remove = 0;
     hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
@@ -1957,7 +1972,7 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
                                 cg_match_rec *out, int32_t *qtrim_out)
 {
     int s = 0, e = n;
-    if (quality_trim) quality_trim_core(qual, n, cutoff_front, cutoff_back, qbase, &s, &e);
+    if (quality_trim) pre_trim_core(seq, qual, n, quality_trim, cutoff_front, cutoff_back, qbase, &s, &e);
     if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
     CgHit hit; hit.adapter = -1; hit.remove = 0;
     hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;

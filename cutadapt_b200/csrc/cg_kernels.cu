@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_fast_kernel(const CgKernelArgs 
                 if (HAS_QUAL) {
                     const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
                     const uint8_t *q = tile_qual + (size_t)((qual_base + o0) - qa0);
-                    if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+                    if (a.quality_trim) pre_trim_core(tile_seq + off, q, n, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
                 }
                 if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
                 if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(CG_NT) cg_trim_warp_kernel(const CgKernelArgs 
                 if (HAS_QUAL) {
                     const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
                     const uint8_t *q = tile_qual + (size_t)((qual_base + o0) - qa0);
-                    if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+                    if (a.quality_trim) pre_trim_core(tile_seq + off, q, n, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
                 }
                 if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
                 if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
@@ -700,7 +700,7 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
             if (HAS_QUAL) {
                 const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
                 const uint8_t *q = tile_qual + (size_t)((qual_base + o0) - qa0);
-                if (a.quality_trim) quality_trim_core(q, n, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+                if (a.quality_trim) pre_trim_core(tile_seq + off, q, n, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
             }
             if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
             if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }

@@ -106,13 +106,15 @@ class BatchTrimmer:
     adapters          a Matchable (e.g. MultipleAdapters) or a list of adapters
     times             as AdapterCutter(times=...)          (modifiers.py:98-119)
     quality_cutoff    None or (cutoff_front, cutoff_back)  as QualityTrimmer (modifiers.py:840-851)
+    nextseq_cutoff    None or the cutoff of NextseqQualityTrimmer (modifiers.py:825-837), applied first
     """
 
     def __init__(self, adapters, times: int = 1, quality_cutoff: Optional[Tuple[int, int]] = None,
-                 quality_base: int = 33, ctx: Optional[_lib.Context] = None):
+                 quality_base: int = 33, ctx: Optional[_lib.Context] = None, nextseq_cutoff: Optional[int] = None):
         self.adapters: Matchable = adapters if isinstance(adapters, Matchable) else MultipleAdapters(list(adapters))
         self.times = int(times)
         self.quality_cutoff = quality_cutoff
+        self.nextseq_cutoff = nextseq_cutoff
         self.quality_base = quality_base
         self._ctx = ctx
         self.params = _lib.make_params(
@@ -121,6 +123,7 @@ class BatchTrimmer:
             cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
             quality_base=quality_base,
             times=times,
+            nextseq_cutoff=nextseq_cutoff,
         )
 
     @property
@@ -135,7 +138,7 @@ class BatchTrimmer:
     def process(self, sequences: Sequence[str], qualities: Optional[Sequence[str]] = None) -> TrimResult:
         seq, offsets = _lib.pack_strings(sequences)
         qual = None
-        if self.quality_cutoff is not None:
+        if self.quality_cutoff is not None or self.nextseq_cutoff is not None:
             if qualities is None or any(q is None for q in qualities):
                 from .qualtrim import HasNoQualities
 
@@ -184,7 +187,7 @@ class DeviceBatch:
     """The fused pass on torch CUDA tensors already resident in HBM (cg_process_batch_device)."""
 
     def __init__(self, adapters, times: int = 1, quality_cutoff: Optional[Tuple[int, int]] = None,
-                 quality_base: int = 33, device: Optional[int] = None):
+                 quality_base: int = 33, device: Optional[int] = None, nextseq_cutoff: Optional[int] = None):
         import torch
 
         self.adapters: Matchable = adapters if isinstance(adapters, Matchable) else MultipleAdapters(list(adapters))
@@ -204,6 +207,7 @@ class DeviceBatch:
             cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
             quality_base=quality_base,
             times=times,
+            nextseq_cutoff=nextseq_cutoff,
         )
 
     def run(self, seq, offsets, qual=None, max_read_len: int = 0, out=None, qtrim_out=None) -> DeviceResult:
@@ -213,7 +217,7 @@ class DeviceBatch:
         slots = self.adapter_set.slots
         if out is None:
             out = torch.empty((n * self.times * slots, 8), dtype=torch.int32, device=seq.device)
-        want_q = bool(self.params.quality_trim)
+        want_q = bool(self.params.quality_trim or self.params.nextseq_trim)
         if want_q and qtrim_out is None:
             qtrim_out = torch.empty((n, 2), dtype=torch.int32, device=seq.device)
         _lib.check(

@@ -126,14 +126,18 @@ typedef struct cg_index_desc {
     const int32_t *matches;
 } cg_index_desc;
 
-/* Per-batch parameters of the fused pass (modifiers.py:840-858 then 200-261). */
+/* Per-batch parameters of the fused pass (modifiers.py:825-858 then 200-261). */
 typedef struct cg_params {
     int32_t quality_trim;    /* 0 = off; 1 = run quality_trim_index first and search read[start:stop] */
     int32_t cutoff_front;
     int32_t cutoff_back;
     int32_t quality_base;    /* 33 or 64                                                     */
     int32_t times;           /* AdapterCutter(times=...) rounds, >= 1 (modifiers.py:225-231) */
-    int32_t reserved[3];
+    int32_t nextseq_trim;    /* 1 = NextseqQualityTrimmer first (modifiers.py:825-837, cli.py:940-945):
+                                the read is cut at nextseq_trim_index(read, nextseq_cutoff, quality_base)
+                                before quality_trim_index (if enabled) runs on what is left               */
+    int32_t nextseq_cutoff;
+    int32_t reserved;
 } cg_params;
 
 /* One match record (32 bytes).  For round r of read i the records are at

@@ -261,8 +261,9 @@ def match_group(adapters, group, sequence):
 
 
 def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=False, cutoff_front=0,
-                   cutoff_back=0, quality_base=33, times=1):
-    """Whole per-read pass; returns (matches[n, times, slots], qtrim[n, 2])."""
+                   cutoff_back=0, quality_base=33, times=1, nextseq_cutoff=None):
+    """Whole per-read pass; returns (matches[n, times, slots], qtrim[n, 2]).
+    Modifier order as cutadapt builds it (cli.py:940-953): NextseqQualityTrimmer, QualityTrimmer, AdapterCutter."""
     if groups is None:
         groups = [(GROUP_SINGLE, i, -1, 0, 0) for i in range(len(adapters))]
     slots = 2 if any(g[0] == GROUP_LINKED for g in groups) else 1
@@ -280,8 +281,10 @@ def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=Fal
 
     for i, seq in enumerate(sequences):
         s, e = 0, len(seq)
-        if quality_trim:
-            s, e = quality_trim_index(qualities[i], cutoff_front, cutoff_back, quality_base)
+        if nextseq_cutoff is not None:                       # modifiers.py:834-837: read[:stop]
+            e = nextseq_trim_index(seq, qualities[i], nextseq_cutoff, quality_base)
+        if quality_trim:                                     # modifiers.py:854-858 on what is left
+            s, e = quality_trim_index(qualities[i][:e], cutoff_front, cutoff_back, quality_base)
         qtrim[i] = (s, e)
         for r in range(times):
             cur = seq[s:e]

@@ -37,6 +37,9 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     }
     uint8_t enc[768];
     cg_build_enc_tables(enc);
+    // flags and packed base/cutoff as pre_trim_core expects them (cg_api.cu: launch_trim_single)
+    const int tflags = (params->quality_trim ? 1 : 0) | (params->nextseq_trim ? 2 : 0);
+    const int tbase = (params->quality_base & 255) | (int)((unsigned)params->nextseq_cutoff << 8);
     if (force_wide & 128) {
         // the multi-pass schedule of cg_api.cu (launch_trim): per-component passes + select_best
         CgMultiPlan plan;
@@ -61,15 +64,15 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
         std::vector<uint8_t> padded((size_t)offsets[n_reads] + 64, 0);
         if (offsets[n_reads]) memcpy(padded.data() + 32, seq, (size_t)offsets[n_reads]);
         const uint8_t *pseq = padded.data() + 32;
-        if (params->quality_trim && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
+        if (tflags && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
         std::vector<cg_match_rec> recs(np);
         for (int64_t r = 0; r < n_reads; ++r) {
             const int n = (int)(offsets[r + 1] - offsets[r]);
             const uint8_t *sq = pseq + offsets[r];
             for (int i = 0; i < n; ++i) if (sq[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
             int bs = 0, be = n;
-            if (params->quality_trim)
-                quality_trim_core(qual + offsets[r], n, params->cutoff_front, params->cutoff_back, params->quality_base, &bs, &be);
+            if (tflags)
+                pre_trim_core(sq, qual + offsets[r], n, tflags, params->cutoff_front, params->cutoff_back, tbase, &bs, &be);
             if (qtrim) { qtrim[2 * r] = bs; qtrim[2 * r + 1] = be; }
             for (int pi = 0; pi < np; ++pi) {
                 const CgPassPlan &P = plan.passes[pi];
@@ -102,23 +105,23 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     if (offsets[n_reads]) memcpy(padded.data() + 32, seq, (size_t)offsets[n_reads]);
     seq = padded.data() + 32;
     const int times = params->times < 1 ? 1 : params->times;
-    if (params->quality_trim && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
+    if (tflags && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
     for (int64_t r = 0; r < n_reads; ++r) {
         const int n = (int)(offsets[r + 1] - offsets[r]);
         const uint8_t *s = seq + offsets[r];
         for (int i = 0; i < n; ++i) if (s[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
         if ((force_wide & 64) && S.h->simple_ok && times == 1 && S.ad[0].m <= 64)
-            process_read_planned(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
-                                 params->cutoff_front, params->cutoff_back, params->quality_base,
+            process_read_planned(S, s, qual ? qual + offsets[r] : nullptr, n, tflags,
+                                 params->cutoff_front, params->cutoff_back, tbase,
                                  (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);
         else if ((force_wide & 2) && S.h->simple_ok && times == 1)
-            process_read_simple(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
-                                params->cutoff_front, params->cutoff_back, params->quality_base, pc,
+            process_read_simple(S, s, qual ? qual + offsets[r] : nullptr, n, tflags,
+                                params->cutoff_front, params->cutoff_back, tbase, pc,
                                 (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr,
                                 (force_wide & 32) ? 3 : ((force_wide & 16) ? 2 : ((force_wide & 8) ? 1 : 0)));
         else
-        process_read<true>(S, s, qual ? qual + offsets[r] : nullptr, n, params->quality_trim,
-                           params->cutoff_front, params->cutoff_back, params->quality_base, times, pc,
+        process_read<true>(S, s, qual ? qual + offsets[r] : nullptr, n, tflags,
+                           params->cutoff_front, params->cutoff_back, tbase, times, pc,
                            wc, (cg_match_rec *)(matches + (size_t)r * times * set.slots),
                            qtrim ? qtrim + 2 * r : nullptr);
     }

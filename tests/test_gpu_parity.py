@@ -316,6 +316,25 @@ def test_config4_quality_trim_then_adapter():
     assert int((qt[:, 1] < 150).sum()) > 500
 
 
+def test_fused_nextseq_trim_then_quality_trim_then_adapter():
+    """--nextseq-trim fused in front of -q and the adapter search (cli.py:940-953 order)."""
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_reads
+
+    ad = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+    reads, quals = make_reads(6000, config=4, with_qualities=True, adapter=ad)
+    rng = random.Random(4)
+    reads = [r[:-t] + "G" * t if (t := rng.choice([0, 0, 5, 20])) else r for r in reads]   # dark cycles
+    for descs, groups in (([PA.BackAdapter(ad, max_errors=0.1, name="a").descriptor()], None),
+                          ([PA.BackAdapter(ad, max_errors=0.1, name="a").descriptor(),
+                            PA.BackAdapter("CTGTCTCTTATACACATCT", max_errors=0.1, name="b").descriptor()], None)):
+        for qt in (False, True):
+            got, gqt = run_set(descs, groups, reads, quals, quality_trim=qt, cutoff_front=0, cutoff_back=20, nextseq_cutoff=20)
+            exp, eqt = oracle.oracle_process(descs, groups, reads, quals, quality_trim=qt, cutoff_back=20, nextseq_cutoff=20)
+            assert (gqt == eqt).all() and (got == exp).all(), (len(descs), qt)
+            assert int((gqt[:, 1] < 150).sum()) > 1500
+
+
 def test_random_adapter_sets_against_oracle():
     """All adapter types, wildcards, --no-indels (wide cells), rounds, quality trimming."""
     import cutadapt_b200.adapters as PA

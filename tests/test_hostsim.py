@@ -224,3 +224,32 @@ def test_trim_scan_device_functions_golden():
     lib.hs_expected_errors.restype = C.c_double
     for qual, base, expected in g["expected_errors"]:
         assert float(lib.hs_expected_errors(qual.encode(), len(qual), base)).hex() == expected
+
+
+def test_fused_nextseq_and_quality_trim_against_oracle():
+    """NextseqQualityTrimmer -> QualityTrimmer -> AdapterCutter fused in one pass, all schedules."""
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(91)
+    for trial in range(40):
+        ads = ["".join(rng.choice("ACGT") for _ in range(rng.randint(6, 30))) for _ in range(rng.randint(1, 3))]
+        objs = [rng.choice([PA.BackAdapter, PA.FrontAdapter])(a, max_errors=0.1, name="a") for a in ads]
+        multi = PA.MultipleAdapters(objs)
+        spec = spec_of(multi)
+        reads = [r + "G" * rng.choice([0, 0, 3, 10]) for r in random_reads(rng, ads, 40, max_len=100)]
+        quals = ["".join(chr(33 + rng.choice([2, 2, 15, 30, 38])) for _ in r) for r in reads]
+        qt = rng.random() < 0.6
+        params = L.make_params(quality_trim=qt, cutoff_front=rng.choice([0, 10]), cutoff_back=20,
+                               nextseq_cutoff=rng.choice([10, 20, 30]))
+        exp, eqt = oracle.oracle_process(spec.adapters, spec.groups, reads, quals, qt, params.cutoff_front, 20, 33, 1,
+                                         nextseq_cutoff=params.nextseq_cutoff)
+        modes = [0, 128] if len(ads) > 1 else [0, 2, 10, 34, 64]
+        for mode in modes:
+            try:
+                got, gqt = hostsim_process(spec, reads, quals, params, force_wide=mode)
+            except RuntimeError as e:
+                if e.args[0][0] == 100:
+                    continue
+                raise
+            assert (gqt == eqt).all(), mode
+            assert (got == exp).all(), mode
