@@ -334,6 +334,10 @@ def main():
         h_off = torch.empty(hw + 1, dtype=torch.int64, pin_memory=True)
         h_off.copy_(offsets[: hw + 1])
         h_out = torch.empty((hw, 8), dtype=torch.int32, pin_memory=True)
+        # worker threads of the library's host side (packing for the compressed transfer): this rank's
+        # share of the host cores
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
+        os.environ.setdefault("CUTADAPT_B200_HOST_THREADS", str(max(2, min(64, cores // max(world, 1)))))
         host_ctx = _lib.Context(local_rank)
         host_set = _lib.AdapterSet(batch.spec, host_ctx)
         params = batch.params
@@ -349,7 +353,18 @@ def main():
                 done += cnt
 
         e2e_step()
+        # for the record: one step with the raw (uncompressed) transfer
+        os.environ["CUTADAPT_B200_H2D_PACK"] = "0"
+        e2e_step()
         barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        barrier()
+        raw_wall = time.perf_counter() - t0
+        os.environ["CUTADAPT_B200_H2D_PACK"] = "1"
+        e2e_step()
+        barrier()
+        host_ctx.transfer_bytes(reset=True)
         l0 = host_ctx.launch_count()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
@@ -361,12 +376,19 @@ def main():
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         wall = float(tw.item())
+        h2d_bytes, d2h_bytes = host_ctx.transfer_bytes()
         e2e = {"value": n * world * e2e_steps / wall, "unit": "reads/s",
-               # the library copies the sequence bytes; the offsets of equally long reads are regenerated
-               # on the device from (first offset, length), so the 8 B/read offset array stays on the host
-               "h2d_bytes_per_step": n * READ_LEN, "d2h_bytes_per_step": n * 32,
+               # counted by the library from the copies it issues (cg_ctx_transfer_bytes): the reads travel as a
+               # base-6 stream, three characters per byte, packed by the library's host threads inside the timed
+               # region and expanded to the caller's bytes on the device; the offsets of equally long reads are
+               # regenerated on the device from (first offset, length)
+               "h2d_bytes_per_step": h2d_bytes // e2e_steps, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                "steps": e2e_steps, "launches": host_ctx.launch_count() - l0,
-               "how": f"cg_process_batch on pinned host buffers (sequences + int64 offsets in, 32-byte records out); "
+               "host_threads": int(os.environ["CUTADAPT_B200_HOST_THREADS"]),
+               "raw_transfer_value": n * world / raw_wall,
+               "how": f"cg_process_batch on pinned host buffers (sequences + int64 offsets in, 32-byte records out), "
+                      f"compressed host-to-device transfer (raw_transfer_value: the same with "
+                      f"CUTADAPT_B200_H2D_PACK=0, {n * READ_LEN} B in per step); "
                       f"the {n}-read step streams a {hw}-read pinned window {passes}x"}
     sampler.stop()
 

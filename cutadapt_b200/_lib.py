@@ -137,6 +137,9 @@ def _declare(lib) -> None:
     lib.cg_ctx_launch_count.argtypes = [vp]
     lib.cg_ctx_launch_count.restype = i64
     lib.cg_ctx_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
+    lib.cg_ctx_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.c_int]
+    lib.cg_pack3_host.argtypes = [vp, i64, i64, i64, i64, vp, vp, i64, i32]
+    lib.cg_pack3_host.restype = i64
     lib.cg_adapterset_create.argtypes = [
         vp, C.POINTER(cg_adapter_desc), i32, C.POINTER(cg_group_desc), i32, C.POINTER(vp),
     ]
@@ -375,6 +378,12 @@ class Context:
         launches = C.c_int64()
         check(lib().cg_ctx_kernel_time(self._h, C.byref(total), C.byref(launches), int(reset)))
         return total.value, launches.value
+
+    def transfer_bytes(self, reset: bool = False) -> Tuple[int, int]:
+        """Bytes cg_process_batch moved host->device and device->host on this context."""
+        h2d, d2h = C.c_int64(), C.c_int64()
+        check(lib().cg_ctx_transfer_bytes(self._h, C.byref(h2d), C.byref(d2h), int(reset)))
+        return h2d.value, d2h.value
 
     def close(self) -> None:
         if self._h:

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/cutadapt_b200.h"
+#include "cg_hostpack.h"
 #include "cg_kernels.cuh"
 #include "cg_setbuild.h"
 
@@ -78,9 +79,13 @@ template <class T> struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+#define CG_N_LANES 3
 struct Lane {
     cudaStream_t stream = nullptr;
-    DevBuf<uint8_t> d_seq, d_qual;
+    DevBuf<uint8_t> d_seq, d_qual, d_pack;
+    DevBuf<uint64_t> d_exc;
+    PinBuf<uint8_t> h_pack;
+    PinBuf<uint64_t> h_exc;
     DevBuf<int64_t> d_offs;
     DevBuf<cg_match_rec> d_out;
     DevBuf<int32_t> d_qtrim;
@@ -100,7 +105,7 @@ struct cg_ctx {
     bool own_stream = false;
     int sm_count = 148;
     size_t smem_optin = 0;
-    Lane lanes[2];
+    Lane lanes[CG_N_LANES];
     int *d_err = nullptr;       // [0] non-ASCII flag, [1] max_len scratch
     uint8_t *d_enc = nullptr;   // 768 bytes
     double *d_phred = nullptr;  // 256 doubles: 10^(-q/10)
@@ -116,6 +121,10 @@ struct cg_ctx {
     std::vector<cudaEvent_t> event_pool;
     double timed_ms = 0.0;
     long long timed_n = 0;
+    // host side of cg_process_batch
+    CgHostPool *pool = nullptr;
+    std::vector<std::vector<uint64_t>> exc_scratch;
+    long long h2d_bytes = 0, d2h_bytes = 0;
 };
 
 struct cg_adapterset {
@@ -157,7 +166,7 @@ extern "C" int cg_ctx_create(int device, void *stream, cg_ctx **out)
     c->smem_optin = prop.sharedMemPerBlockOptin;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
+    for (int i = 0; i < CG_N_LANES; ++i) CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&c->d_err, 16 * sizeof(int)));
     CU(cudaMemset(c->d_err, 0, 16 * sizeof(int)));
     CU(cudaMalloc((void **)&c->d_task_count, 64));
@@ -196,8 +205,11 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
     cudaDeviceSynchronize();
     resolve_timing(c);
     for (auto ev : c->event_pool) cudaEventDestroy(ev);
-    for (int i = 0; i < 2; ++i) {
+    delete c->pool;
+    c->pool = nullptr;
+    for (int i = 0; i < CG_N_LANES; ++i) {
         Lane &l = c->lanes[i];
+        l.d_pack.release(); l.d_exc.release(); l.h_pack.release(); l.h_exc.release();
         l.d_seq.release(); l.d_qual.release(); l.d_offs.release(); l.d_out.release(); l.d_qtrim.release();
         l.h_seq.release(); l.h_qual.release(); l.h_offs.release(); l.h_out.release(); l.h_qtrim.release();
         if (l.stream) cudaStreamDestroy(l.stream);
@@ -218,7 +230,7 @@ extern "C" int cg_ctx_synchronize(cg_ctx *c)
     if (!c) return fail(CG_EINVAL, "ctx is NULL");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(c->lanes[i].stream));
+    for (int i = 0; i < CG_N_LANES; ++i) CU(cudaStreamSynchronize(c->lanes[i].stream));
     return CG_OK;
 }
 
@@ -627,6 +639,49 @@ static int lane_finish(cg_ctx *c, Lane &l)
     return CG_OK;
 }
 
+// Longest read / equal lengths / validity of offsets[r0 .. r1], on the worker pool for large chunks.
+struct OffsetScan { int64_t max_len = 0; bool uniform = true, valid = true; };
+static OffsetScan scan_offsets(cg_ctx *c, const int64_t *offsets, int64_t r0, int64_t r1)
+{
+    const int64_t len0 = offsets[r0 + 1] - offsets[r0];
+    auto part = [&](int64_t a, int64_t b) {
+        OffsetScan o;
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t len = offsets[r + 1] - offsets[r];
+            if (len < 0 || len > 2000000000LL) o.valid = false;
+            if (len > o.max_len) o.max_len = len;
+            o.uniform = o.uniform && len == len0;
+        }
+        return o;
+    };
+    const int64_t nr = r1 - r0;
+    if (!c->pool || nr < (1 << 16)) return part(r0, r1);
+    const int64_t JOB = 1 << 15;
+    const int64_t n_jobs = (nr + JOB - 1) / JOB;
+    std::vector<OffsetScan> parts((size_t)c->pool->size());
+    c->pool->run(n_jobs, [&](int64_t j, int w) {
+        const int64_t a = r0 + j * JOB, b = std::min(r1, a + JOB);
+        const OffsetScan o = part(a, b);
+        OffsetScan &t = parts[(size_t)w];
+        t.max_len = std::max(t.max_len, o.max_len);
+        t.uniform = t.uniform && o.uniform;
+        t.valid = t.valid && o.valid;
+    });
+    OffsetScan t;
+    for (const OffsetScan &o : parts) {
+        t.max_len = std::max(t.max_len, o.max_len);
+        t.uniform = t.uniform && o.uniform;
+        t.valid = t.valid && o.valid;
+    }
+    return t;
+}
+
+static bool h2d_pack_enabled()
+{
+    const char *e = getenv("CUTADAPT_B200_H2D_PACK");
+    return !(e && e[0] == '0');
+}
+
 extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
                                 const int64_t *offsets, int64_t n_reads, const cg_params *p,
                                 cg_match *matches, int32_t *qtrim)
@@ -645,45 +700,94 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     const bool offs_pinned = is_pinned(offsets), out_pinned = is_pinned(matches);
     const bool qt_pinned = qtrim && is_pinned(qtrim);
 
-    const int64_t CHUNK_READS = 1 << 18;
-    const int64_t CHUNK_BYTES = 48LL << 20;
+    // Large batches travel compressed (three characters per byte, cg_hostpack.h): PCIe, not the
+    // kernels, bounds this entry point.  Small ones are not worth waking the worker pool for.
+    const bool pack = h2d_pack_enabled() && n_reads >= (1 << 16);
+    if (pack && !c->pool) {
+        c->pool = new CgHostPool(cg_host_threads_default());
+        c->exc_scratch.resize((size_t)c->pool->size());
+    }
+    const int n_lanes = pack ? CG_N_LANES : 2;
+    const int64_t CHUNK_READS = pack ? (1 << 20) : (1 << 18);
+    const int64_t CHUNK_BYTES = pack ? (192LL << 20) : (48LL << 20);
     int64_t r0 = 0;
     int lane_idx = 0;
     int rc = CG_OK;
     while (r0 < n_reads && rc == CG_OK) {
-        // chunk [r0, r1): bounded by reads and bytes; also compute the longest read
-        int64_t r1 = r0;
-        int max_len = 0;
+        // chunk [r0, r1): bounded by reads and bytes; also find the longest read
+        int64_t r1 = std::min(n_reads, r0 + CHUNK_READS);
+        OffsetScan sc = scan_offsets(c, offsets, r0, r1);
+        if (!sc.valid) return fail(CG_EINVAL, "offsets must be non-decreasing");
         const int64_t byte0 = offsets[r0];
-        const int64_t len0 = offsets[r0 + 1] - offsets[r0];
-        bool uniform = true;                 // all reads of the chunk equally long (typical for raw Illumina data)
-        while (r1 < n_reads && r1 - r0 < CHUNK_READS) {
-            const int64_t len = offsets[r1 + 1] - offsets[r1];
-            if (len < 0 || len > 2000000000LL) return fail(CG_EINVAL, "offsets must be non-decreasing");
-            if (r1 > r0 && offsets[r1 + 1] - byte0 > CHUNK_BYTES) break;
-            if (len > max_len) max_len = (int)len;
-            uniform = uniform && len == len0;
-            ++r1;
+        if (offsets[r1] - byte0 > CHUNK_BYTES && r1 - r0 > 1) {
+            // offsets[r0 .. r1] is non-decreasing: the last read that still fits
+            const int64_t *it = std::upper_bound(offsets + r0 + 1, offsets + r1 + 1, byte0 + CHUNK_BYTES);
+            r1 = std::max<int64_t>(r0 + 1, (it - offsets) - 1);
+            sc = scan_offsets(c, offsets, r0, r1);
         }
+        const int64_t len0 = offsets[r0 + 1] - offsets[r0];
+        const bool uniform = sc.uniform;      // all reads of the chunk equally long (typical for raw Illumina data)
+        const int max_len = (int)sc.max_len;
         const int64_t nr = r1 - r0;
         const int64_t nbytes = offsets[r1] - byte0;
         const int pad = (int)(byte0 & 15);
+        const int64_t a0 = byte0 - pad;       // the chunk's device buffer starts at this absolute position
         Lane &l = c->lanes[lane_idx];
-        lane_idx ^= 1;
+        lane_idx = (lane_idx + 1) % n_lanes;
         if ((rc = lane_finish(c, l)) != CG_OK) break;
-        if ((rc = l.d_seq.ensure((size_t)nbytes + 64)) != CG_OK) break;
         if (want_q && (rc = l.d_qual.ensure((size_t)nbytes + 64)) != CG_OK) break;
         if ((rc = l.d_offs.ensure((size_t)nr + 1)) != CG_OK) break;
         if ((rc = l.d_out.ensure((size_t)nr * rec_per_read)) != CG_OK) break;
         if (qtrim && (rc = l.d_qtrim.ensure((size_t)nr * 2)) != CG_OK) break;
-        // H2D (bounce through pinned memory unless the caller's buffer already is)
-        const uint8_t *src_seq = seq + byte0;
-        if (!seq_pinned) {
-            if ((rc = l.h_seq.ensure((size_t)nbytes + 16)) != CG_OK) break;
-            memcpy(l.h_seq.p, src_seq, (size_t)nbytes);
-            src_seq = l.h_seq.p;
+        // ---- H2D of the sequences ----
+        bool packed_ok = false;
+        if (pack && nbytes > 0) {
+            const int64_t span = offsets[r1] - a0;
+            const int64_t n_stream = ((span + 2) / 3 + 15) / 16 * 16;
+            if ((rc = l.h_pack.ensure((size_t)n_stream)) != CG_OK) break;
+            const int64_t lo = std::max(a0, offsets[0]), hi = offsets[r1];
+            for (auto &v : c->exc_scratch) v.clear();
+            const int64_t JOB = 1 << 16;
+            uint8_t *h_pack = l.h_pack.p;
+            c->pool->run((n_stream + JOB - 1) / JOB, [&](int64_t j, int w) {
+                cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), h_pack,
+                               c->exc_scratch[(size_t)w]);
+            });
+            size_t n_exc = 0;
+            for (auto &v : c->exc_scratch) n_exc += v.size();
+            if ((int64_t)n_exc * 16 <= span) {   // mostly A/C/G/T/N: send the stream, else the raw bytes
+                if ((rc = l.d_pack.ensure((size_t)n_stream)) != CG_OK) break;
+                if ((rc = l.d_seq.ensure((size_t)n_stream * 3 + 64)) != CG_OK) break;
+                if (n_exc) {
+                    if ((rc = l.h_exc.ensure(n_exc)) != CG_OK) break;
+                    if ((rc = l.d_exc.ensure(n_exc)) != CG_OK) break;
+                    size_t k = 0;
+                    for (auto &v : c->exc_scratch) {
+                        if (!v.empty()) memcpy(l.h_exc.p + k, v.data(), v.size() * sizeof(uint64_t));
+                        k += v.size();
+                    }
+                    CU(cudaMemcpyAsync(l.d_exc.p, l.h_exc.p, n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+                }
+                CU(cudaMemcpyAsync(l.d_pack.p, l.h_pack.p, (size_t)n_stream, cudaMemcpyHostToDevice, l.stream));
+                CU(cg_launch_unpack3(l.d_pack.p, n_stream, l.d_seq.p, (const unsigned long long *)l.d_exc.p,
+                                     (long long)n_exc, l.stream));
+                c->launches += n_exc ? 2 : 1;
+                c->h2d_bytes += n_stream + (long long)(n_exc * sizeof(uint64_t));
+                packed_ok = true;
+            }
         }
-        if (nbytes) CU(cudaMemcpyAsync(l.d_seq.p + pad, src_seq, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
+        if (!packed_ok) {
+            // raw bytes (bounced through pinned memory unless the caller's buffer already is)
+            if ((rc = l.d_seq.ensure((size_t)nbytes + 64)) != CG_OK) break;
+            const uint8_t *src_seq = seq + byte0;
+            if (!seq_pinned) {
+                if ((rc = l.h_seq.ensure((size_t)nbytes + 16)) != CG_OK) break;
+                memcpy(l.h_seq.p, src_seq, (size_t)nbytes);
+                src_seq = l.h_seq.p;
+            }
+            if (nbytes) CU(cudaMemcpyAsync(l.d_seq.p + pad, src_seq, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
+            c->h2d_bytes += nbytes;
+        }
         if (want_q) {
             const uint8_t *src_q = qual + byte0;
             if (!qual_pinned) {
@@ -692,6 +796,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
                 src_q = l.h_qual.p;
             }
             if (nbytes) CU(cudaMemcpyAsync(l.d_qual.p + pad, src_q, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
+            c->h2d_bytes += nbytes;
         }
         if (uniform) {
             // offsets[r0 + i] = byte0 + i * len0: generated on the device, 8 bytes per read less over PCIe
@@ -705,11 +810,12 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
                 src_offs = l.h_offs.p;
             }
             CU(cudaMemcpyAsync(l.d_offs.p, src_offs, (size_t)(nr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, l.stream));
+            c->h2d_bytes += (nr + 1) * (long long)sizeof(int64_t);
         }
         // offsets stay absolute: hand the kernel a virtual base so that base + offsets[r] lands
         // in this chunk's buffer with the same 16-byte phase as in the caller's array
-        const uint8_t *vseq = l.d_seq.p + pad - byte0;
-        const uint8_t *vqual = want_q ? l.d_qual.p + pad - byte0 : nullptr;
+        const uint8_t *vseq = l.d_seq.p - a0;
+        const uint8_t *vqual = want_q ? l.d_qual.p - a0 : nullptr;
         rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, qtrim ? l.d_qtrim.p : nullptr,
                          l.stream, true);
         if (rc != CG_OK) break;
@@ -721,6 +827,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
             if ((rc = l.h_out.ensure(l.n_out)) != CG_OK) break;
             CU(cudaMemcpyAsync(l.h_out.p, l.d_out.p, l.n_out * sizeof(cg_match_rec), cudaMemcpyDeviceToHost, l.stream));
         }
+        c->d2h_bytes += (long long)(l.n_out * sizeof(cg_match_rec));
         l.n_qtrim = 0; l.qtrim_bounced = false;
         if (qtrim) {
             int32_t *qdst = qtrim + 2 * r0;
@@ -730,16 +837,46 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
                 if ((rc = l.h_qtrim.ensure(l.n_qtrim)) != CG_OK) break;
                 CU(cudaMemcpyAsync(l.h_qtrim.p, l.d_qtrim.p, l.n_qtrim * 4, cudaMemcpyDeviceToHost, l.stream));
             }
+            c->d2h_bytes += (long long)(l.n_qtrim * 4);
         }
         l.busy = true;
         r0 = r1;
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < CG_N_LANES; ++i) {
         int rc2 = lane_finish(c, c->lanes[i]);
         if (rc == CG_OK) rc = rc2;
     }
     if (rc != CG_OK) return rc;
     return check_err_flag(c);
+}
+
+extern "C" int cg_ctx_transfer_bytes(cg_ctx *c, int64_t *h2d, int64_t *d2h, int reset)
+{
+    if (!c) return fail(CG_EINVAL, "ctx is NULL");
+    if (h2d) *h2d = c->h2d_bytes;
+    if (d2h) *d2h = c->d2h_bytes;
+    if (reset) { c->h2d_bytes = 0; c->d2h_bytes = 0; }
+    return CG_OK;
+}
+
+/* Host-side packer of the compressed transfer, exposed for the CPU tests (no device needed). */
+extern "C" int64_t cg_pack3_host(const uint8_t *seq, int64_t a0, int64_t lo, int64_t hi, int64_t n_stream,
+                                 uint8_t *packed, uint64_t *exceptions, int64_t capacity, int32_t n_threads)
+{
+    if (!seq || !packed || n_stream < 0 || n_threads < 1) return fail(CG_EINVAL, "cg_pack3_host: bad argument");
+    CgHostPool pool(n_threads);
+    std::vector<std::vector<uint64_t>> exc((size_t)pool.size());
+    const int64_t JOB = 4096;
+    pool.run((n_stream + JOB - 1) / JOB, [&](int64_t j, int w) {
+        cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), packed, exc[(size_t)w]);
+    });
+    int64_t n = 0;
+    for (auto &v : exc)
+        for (uint64_t e : v) {
+            if (exceptions && n < capacity) exceptions[n] = e;
+            ++n;
+        }
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,237 @@
+// cg_hostpack.cpp -- host worker pool and the base-6 read packer (see cg_hostpack.h)
+#include "cg_hostpack.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define CG_CPU_RELAX() _mm_pause()
+#else
+#define CG_CPU_RELAX() ((void)0)
+#endif
+
+int cg_host_threads_default()
+{
+    if (const char *e = getenv("CUTADAPT_B200_HOST_THREADS")) {
+        int v = atoi(e);
+        if (v >= 1) return v > 256 ? 256 : v;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    // leave the machine usable: at most half of the hardware threads, 48 at most
+    unsigned n = hw / 2;
+    if (n < 1) n = 1;
+    if (n > 48) n = 48;
+    return (int)n;
+}
+
+CgHostPool::CgHostPool(int n_threads)
+{
+    for (int i = 1; i < n_threads; ++i) workers_.emplace_back([this, i] { worker_main(i); });
+}
+
+CgHostPool::~CgHostPool()
+{
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+        ++generation_;
+    }
+    cv_start_.notify_all();
+    for (auto &t : workers_) t.join();
+}
+
+void CgHostPool::worker_main(int id)
+{
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int64_t, int)> *fn;
+        int64_t n_jobs;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_start_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            if (stop_) return;
+            fn = fn_;
+            n_jobs = n_jobs_;
+        }
+        for (;;) {
+            const int64_t j = next_.fetch_add(1, std::memory_order_relaxed);
+            if (j >= n_jobs) break;
+            (*fn)(j, id);
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--active_ == 0) cv_done_.notify_one();
+        }
+    }
+}
+
+void CgHostPool::run(int64_t n_jobs, const std::function<void(int64_t, int)> &fn)
+{
+    if (n_jobs <= 0) return;
+    if (workers_.empty() || n_jobs == 1) {
+        for (int64_t j = 0; j < n_jobs; ++j) fn(j, 0);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        fn_ = &fn;
+        n_jobs_ = n_jobs;
+        next_.store(0, std::memory_order_relaxed);
+        active_ = (int)workers_.size();
+        ++generation_;
+    }
+    cv_start_.notify_all();
+    for (;;) {
+        const int64_t j = next_.fetch_add(1, std::memory_order_relaxed);
+        if (j >= n_jobs) break;
+        fn(j, 0);
+    }
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return active_ == 0; });
+    fn_ = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// base-6 packer
+// ------------------------------------------------------------------------------------------
+namespace {
+struct PackTables {
+    uint16_t t0[256], t1[256], t2[256];   // code * 36 / * 6 / * 1, bit 8.. = escape marker
+    uint8_t cls[256];
+    PackTables()
+    {
+        for (int c = 0; c < 256; ++c) {
+            int v = CG_PACK_ESCAPE;
+            switch (c) {
+            case 'A': v = 0; break;
+            case 'C': v = 1; break;
+            case 'G': v = 2; break;
+            case 'T': v = 3; break;
+            case 'N': v = 4; break;
+            default: break;
+            }
+            cls[c] = (uint8_t)v;
+            const uint16_t esc = v == CG_PACK_ESCAPE ? 0x100 : 0;
+            t0[c] = (uint16_t)(v * 36) | esc;
+            t1[c] = (uint16_t)(v * 6) | esc;
+            t2[c] = (uint16_t)v | esc;
+        }
+    }
+};
+const PackTables g_pack;
+}  // namespace
+
+#if defined(__x86_64__)
+// AVX2 body of the packer: 24 characters -> 8 stream bytes per step.  The class of a character is
+// looked up by its low nibble (A=1, C=3, G=7, T=4, N=E are distinct) and confirmed by comparing
+// with the expected character; everything else becomes the escape code.  Returns the number of
+// stream bytes written (a multiple of 8); *any_escape is set if an escape code was produced.
+__attribute__((target("avx2"))) static int64_t pack3_avx2(const uint8_t *s, int64_t n_out, uint8_t *dst,
+                                                           bool *any_escape)
+{
+    const __m256i nib = _mm256_set1_epi8(0x0F);
+    const __m256i lut_code = _mm256_setr_epi8(5, 0, 5, 1, 3, 5, 5, 2, 5, 5, 5, 5, 5, 5, 4, 5,
+                                              5, 0, 5, 1, 3, 5, 5, 2, 5, 5, 5, 5, 5, 5, 4, 5);
+    const __m256i lut_char = _mm256_setr_epi8(-1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, 'N', -1,
+                                              -1, 'A', -1, 'C', 'T', -1, -1, 'G', -1, -1, -1, -1, -1, -1, 'N', -1);
+    const __m256i five = _mm256_set1_epi8(CG_PACK_ESCAPE);
+    const __m256i spread = _mm256_setr_epi8(0, 1, 2, -128, 3, 4, 5, -128, 6, 7, 8, -128, 9, 10, 11, -128,
+                                            0, 1, 2, -128, 3, 4, 5, -128, 6, 7, 8, -128, 9, 10, 11, -128);
+    const __m256i weights = _mm256_setr_epi8(36, 6, 1, 0, 36, 6, 1, 0, 36, 6, 1, 0, 36, 6, 1, 0,
+                                             36, 6, 1, 0, 36, 6, 1, 0, 36, 6, 1, 0, 36, 6, 1, 0);
+    const __m256i ones = _mm256_set1_epi16(1);
+    __m256i esc = _mm256_setzero_si256();
+    int64_t k = 0;
+    for (; k + 8 <= n_out; k += 8, s += 24) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)s);
+        const __m128i b = _mm_loadu_si128((const __m128i *)(s + 12));
+        const __m256i x = _mm256_inserti128_si256(_mm256_castsi128_si256(a), b, 1);
+        const __m256i lo = _mm256_and_si256(x, nib);
+        const __m256i cand = _mm256_shuffle_epi8(lut_code, lo);
+        const __m256i expect = _mm256_shuffle_epi8(lut_char, lo);
+        const __m256i ok = _mm256_cmpeq_epi8(x, expect);
+        const __m256i code = _mm256_blendv_epi8(five, cand, ok);
+        const __m256i t = _mm256_shuffle_epi8(code, spread);          // c0 c1 c2 0 | c3 c4 c5 0 | ...
+        esc = _mm256_or_si256(esc, _mm256_cmpeq_epi8(t, five));
+        const __m256i m1 = _mm256_maddubs_epi16(t, weights);           // 36 c0 + 6 c1, c2
+        const __m256i m2 = _mm256_madd_epi16(m1, ones);                // 32-bit: stream byte value
+        const __m256i p16 = _mm256_packus_epi32(m2, m2);
+        const __m256i p8 = _mm256_packus_epi16(p16, p16);
+        const uint32_t w0 = (uint32_t)_mm256_cvtsi256_si32(p8);
+        const uint32_t w1 = (uint32_t)_mm256_extract_epi32(p8, 4);
+        memcpy(dst + k, &w0, 4);
+        memcpy(dst + k + 4, &w1, 4);
+    }
+    *any_escape = !_mm256_testz_si256(esc, esc);
+    return k;
+}
+static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+#else
+static const bool g_have_avx2 = false;
+static int64_t pack3_avx2(const uint8_t *, int64_t, uint8_t *, bool *) { return 0; }
+#endif
+
+void cg_pack3_range(const uint8_t *seq, int64_t a0, int64_t lo, int64_t hi, int64_t i0, int64_t i1,
+                    uint8_t *packed, std::vector<uint64_t> &exc)
+{
+    const PackTables &T = g_pack;
+    int64_t i = i0;
+    // triples that touch positions outside [lo, hi): byte-wise with bounds checks
+    auto slow = [&](int64_t k) {
+        unsigned v = 0;
+        static const int mul[3] = {36, 6, 1};
+        for (int b = 0; b < 3; ++b) {
+            const int64_t pos = a0 + 3 * k + b;
+            if (pos < lo || pos >= hi) continue;   // filler 'A' = 0
+            const uint8_t c = seq[pos];
+            const unsigned code = T.cls[c];
+            v += code * mul[b];
+            if (code == CG_PACK_ESCAPE) exc.push_back(((uint64_t)(pos - a0) << 8) | c);
+        }
+        packed[k] = (uint8_t)v;
+    };
+    // first triple fully inside: a0 + 3k >= lo  ->  k >= ceil((lo - a0) / 3)
+    int64_t k_in0 = lo <= a0 ? 0 : (lo - a0 + 2) / 3;
+    // triples fully inside end before: a0 + 3k + 2 < hi  ->  k < floor((hi - a0) / 3)
+    int64_t k_in1 = hi - a0 >= 3 ? (hi - a0) / 3 : 0;
+    if (k_in0 < i0) k_in0 = i0;
+    if (k_in0 > i1) k_in0 = i1;
+    if (k_in1 > i1) k_in1 = i1;
+    if (k_in1 < k_in0) k_in1 = k_in0;
+    for (; i < k_in0; ++i) slow(i);
+    // fast part in blocks: escapes are detected per block and resolved by a second look
+    const int64_t BLOCK = 256;
+    while (i < k_in1) {
+        const int64_t e = i + BLOCK < k_in1 ? i + BLOCK : k_in1;
+        const uint8_t *s = seq + a0 + 3 * i;
+        unsigned any = 0;
+        int64_t k = i;
+        if (g_have_avx2) {
+            // the vector body reads 28 bytes per step: keep it 4 bytes away from `hi`
+            const int64_t k_safe = (hi - a0 - 4) / 3;
+            const int64_t e_v = e < k_safe ? e : k_safe;
+            if (e_v - i >= 8) {
+                bool escaped = false;
+                const int64_t done = pack3_avx2(s, e_v - i, packed + i, &escaped);
+                if (escaped) any |= 0x100;
+                k += done;
+                s += 3 * done;
+            }
+        }
+        for (; k < e; ++k, s += 3) {
+            const unsigned v = (unsigned)T.t0[s[0]] + T.t1[s[1]] + T.t2[s[2]];
+            packed[k] = (uint8_t)v;
+            any |= v;
+        }
+        if (any >> 8) {
+            const uint8_t *b = seq + a0 + 3 * i, *be = seq + a0 + 3 * e;
+            for (; b < be; ++b)
+                if (T.cls[*b] == CG_PACK_ESCAPE) exc.push_back(((uint64_t)(b - (seq + a0)) << 8) | *b);
+        }
+        i = e;
+    }
+    for (; i < i1; ++i) slow(i);
+}

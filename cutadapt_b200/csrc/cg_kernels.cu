@@ -1178,6 +1178,70 @@ cudaError_t cg_launch_fill_offsets(int64_t *d_out, long long base, long long len
 }
 
 // ------------------------------------------------------------------------------------------
+// Expansion of the compressed host-to-device stream of cg_process_batch (cg_hostpack.h): every
+// stream byte holds three characters of the alphabet {A, C, G, T, N, escape} in base 6; escaped
+// positions are overwritten from the exception list afterwards, which restores the caller's
+// bytes exactly.  One thread expands 16 stream bytes (one 16-byte load) into 48 characters
+// (three 16-byte stores).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cg_unpack3_kernel(const uint4 *__restrict__ packed, uint4 *__restrict__ out,
+                                                          long long n_vec)
+{
+    __shared__ uint32_t lut[256];
+    {
+        const uint32_t ch = 0x41u | (0x43u << 8) | (0x47u << 16) | (0x54u << 24);   // "ACGT"
+        const int i = threadIdx.x;
+        const int v0 = i / 36, v1 = (i / 6) % 6, v2 = i % 6;
+        auto chr = [&](int v) -> uint32_t { return v < 4 ? (ch >> (8 * v)) & 0xFFu : (v == 4 ? 0x4Eu : 0x41u); };
+        lut[i] = chr(v0) | (chr(v1) << 8) | (chr(v2) << 16);
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const uint4 p = __ldg(packed + i);
+        const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+        uint32_t o[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t0 = lut[w[k] & 0xFFu], t1 = lut[(w[k] >> 8) & 0xFFu];
+            const uint32_t t2 = lut[(w[k] >> 16) & 0xFFu], t3 = lut[w[k] >> 24];
+            o[3 * k + 0] = t0 | (t1 << 24);
+            o[3 * k + 1] = (t1 >> 8) | (t2 << 16);
+            o[3 * k + 2] = (t2 >> 16) | (t3 << 8);
+        }
+        out[3 * i + 0] = make_uint4(o[0], o[1], o[2], o[3]);
+        out[3 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        out[3 * i + 2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+}
+__global__ void cg_unpack_fix_kernel(const unsigned long long *__restrict__ exc, long long n_exc, uint8_t *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_exc) {
+        const unsigned long long e = exc[i];
+        out[e >> 8] = (uint8_t)(e & 0xFFu);
+    }
+}
+cudaError_t cg_launch_unpack3(const uint8_t *d_packed, long long packed_bytes, uint8_t *d_out,
+                              const unsigned long long *d_exc, long long n_exc, cudaStream_t st)
+{
+    const long long n_vec = packed_bytes / 16;
+    if (n_vec > 0) {
+        const int block = 256;
+        long long grid = (n_vec + block - 1) / block;
+        if (grid > 148 * 8) grid = 148 * 8;
+        cg_unpack3_kernel<<<(int)grid, block, 0, st>>>((const uint4 *)d_packed, (uint4 *)d_out, n_vec);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (n_exc > 0) {
+        const int block = 256;
+        cg_unpack_fix_kernel<<<(unsigned)((n_exc + block - 1) / block), block, 0, st>>>(d_exc, n_exc, d_out);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Longest read of a batch (device offsets)
 // ------------------------------------------------------------------------------------------
 __global__ void cg_max_len_kernel(const int64_t *offsets, long long n_reads, int *out)

@@ -92,3 +92,7 @@ cudaError_t cg_launch_poly_a_trim(const uint8_t *d_seq, const int64_t *d_offsets
 cudaError_t cg_launch_expected_errors(const uint8_t *d_qual, const int64_t *d_offsets, long long n_reads, int base,
                                       const double *d_table, double *d_out, cudaStream_t st);
 cudaError_t cg_launch_fill_offsets(int64_t *d_out, long long base, long long len, long long count, cudaStream_t st);
+// expansion of the compressed host-to-device stream (cg_hostpack.h): packed_bytes is a multiple of 16,
+// d_out receives 3 * packed_bytes characters, then the n_exc exceptions (position << 8 | byte)
+cudaError_t cg_launch_unpack3(const uint8_t *d_packed, long long packed_bytes, uint8_t *d_out,
+                              const unsigned long long *d_exc, long long n_exc, cudaStream_t st);

@@ -171,6 +171,10 @@ int64_t cg_ctx_launch_count(cg_ctx *ctx);
  * CUDA events on the launching stream; launches = number of samples. */
 int cg_ctx_kernel_time(cg_ctx *ctx, double *total_ms, int64_t *launches, int reset);
 
+/* Bytes cg_process_batch has copied host->device / device->host on this context so far (what actually
+ * crossed PCIe: the compressed read stream + exceptions, qualities, irregular offsets; the records back). */
+int cg_ctx_transfer_bytes(cg_ctx *ctx, int64_t *h2d, int64_t *d2h, int reset);
+
 /* ---- adapter set (replaces Aligner.__cinit__/_set_reference _align.pyx:195-277 and
  *      KmerFinder.__cinit__ _kmer_finder.pyx:106-165 for every adapter at once) ----------- */
 int cg_adapterset_create(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n_adapters,
@@ -197,8 +201,12 @@ int cg_adapterset_effective_length(const cg_adapterset *set, int32_t adapter, in
  *   matches : n_reads * times * slots records
  *   qtrim   : 2 * n_reads int32 (start, stop) of quality_trim_index; may be NULL
  *
- * cg_process_batch: HOST pointers; the library stages through pinned memory and overlaps
- *   H2D / kernel / D2H in sub-batches on its streams.
+ * cg_process_batch: HOST pointers (pageable or pinned); the library overlaps H2D / kernels / D2H in
+ *   sub-batches on its streams.  Batches of >= 65536 reads travel compressed: worker threads of the
+ *   library (CUTADAPT_B200_HOST_THREADS, default half of the hardware threads, at most 48) pack the reads
+ *   three characters per byte (A C G T N; every other byte goes verbatim into an exception list) and a
+ *   device kernel restores the caller's bytes exactly, so results do not depend on it
+ *   (CUTADAPT_B200_H2D_PACK=0 sends the raw bytes).
  * cg_process_batch_device: DEVICE pointers (16-byte aligned seq/qual, readable up to the next
  *   16-byte boundary past offsets[n_reads]); runs asynchronously on the context stream.
  *   max_read_len must be >= the longest read in the batch (pass 0 to let the library
@@ -211,6 +219,13 @@ int cg_process_batch_device(cg_ctx *ctx, const cg_adapterset *set, const uint8_t
                             const uint8_t *d_qual, const int64_t *d_offsets, int64_t n_reads,
                             int32_t max_read_len, const cg_params *params, cg_match *d_matches,
                             int32_t *d_qtrim);
+
+/* The host half of that compressed transfer, callable without a device (tests): packs the characters
+ * at absolute positions a0 .. a0 + 3 * n_stream of `seq` (positions outside [lo, hi) are not read and
+ * count as 'A') into n_stream bytes, base 6, first character most significant; writes up to `capacity`
+ * exceptions (position - a0) << 8 | byte and returns how many there are. */
+int64_t cg_pack3_host(const uint8_t *seq, int64_t a0, int64_t lo, int64_t hi, int64_t n_stream,
+                      uint8_t *packed, uint64_t *exceptions, int64_t capacity, int32_t n_threads);
 
 /* ---- stand-alone batched versions of the native functions -------------------------
  * KmerFinder.kmers_present (_kmer_finder.pyx:170-213): out[i] = 1/0.  Host pointers. */

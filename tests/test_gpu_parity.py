@@ -471,6 +471,64 @@ def test_large_batch_properties():
     assert not exact.any()
 
 
+def test_compressed_transfer_is_lossless(monkeypatch):
+    """
+    cg_process_batch sends large batches as a base-6 stream + exception list (cg_hostpack.h).  Records must
+    equal those of the raw transfer and the oracle's, for ragged reads with lower case, IUPAC, 'N' and
+    arbitrary ASCII bytes, with and without qualities; the stream must be about a third of the bytes.
+    """
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(11)
+    n = 150_000
+    reads, quals = [], []
+    for i in range(n):
+        ln = rng.choice((0, 1, 2, 3, 17, 75, 150, 150, 150, 151, 301))
+        kind = i % 50
+        alphabet = "ACGT" if kind < 30 else ("ACGTN" if kind < 49 else "ACGTNacgtnRYKMSWX.*-z")
+        r = "".join(rng.choice(alphabet) for _ in range(ln))
+        if ln > 40 and rng.random() < 0.5:
+            cut = rng.randrange(10, ln - 5)
+            ad = "AGATCGGAAGAGCACACGTC"
+            if rng.random() < 0.02:
+                ad = ad.lower()
+            r = (r[:cut] + ad + r)[:ln]
+        reads.append(r)
+        quals.append("".join(chr(33 + rng.randrange(2, 41)) for _ in range(ln)))
+    descs = [PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a").descriptor(),
+             PA.FrontAdapter("NACGTTGCA", max_errors=0.2, name="b").descriptor()]
+    for dset, kw, use_q in (([descs[0]], {}, False), (descs, {"times": 2}, False),
+                            ([descs[0]], {"quality_trim": True, "cutoff_back": 20}, True)):
+        aset = L.AdapterSet(L.AdapterSetSpec(dset))
+        data, offsets = L.pack_strings(reads)
+        qd = L.pack_strings(quals)[0] if use_q else None
+        aset.ctx.transfer_bytes(reset=True)
+        monkeypatch.setenv("CUTADAPT_B200_H2D_PACK", "1")
+        packed, qt_p = aset.process(data, offsets, qd, L.make_params(**kw))
+        h2d_packed, d2h = aset.ctx.transfer_bytes(reset=True)
+        monkeypatch.setenv("CUTADAPT_B200_H2D_PACK", "0")
+        raw, qt_r = aset.process(data, offsets, qd, L.make_params(**kw))
+        h2d_raw, _ = aset.ctx.transfer_bytes(reset=True)
+        assert (packed == raw).all()
+        if use_q:
+            assert (qt_p == qt_r).all()
+        assert d2h >= packed.nbytes
+        if not use_q:
+            assert h2d_packed < 0.6 * h2d_raw, (h2d_packed, h2d_raw)
+        idx = list(range(0, n, 41))
+        exp, eqt = oracle.oracle_process(dset, None, [reads[i] for i in idx],
+                                         [quals[i] for i in idx] if use_q else None, **kw)
+        assert (packed[idx] == exp).all()
+    monkeypatch.delenv("CUTADAPT_B200_H2D_PACK")
+    # an offset array that does not start at 0, with an unaligned first read
+    aset = L.AdapterSet(L.AdapterSetSpec([descs[0]]))
+    data, offsets = L.pack_strings(reads)
+    skip = 1234
+    a, _ = aset.process(data, offsets[skip:])
+    b, _ = aset.process(data, offsets)
+    assert (a == b[skip:]).all()
+
+
 def test_device_resident_api_and_statistics():
     """cg_process_batch_device on torch tensors + the statistics vector against a numpy recount."""
     import ctypes as C

@@ -168,12 +168,67 @@ def test_shared_library_exports_every_declared_symbol():
 
     lib = _lib.lib()
     header = open(os.path.join(ROOT, "include", "cutadapt_b200.h")).read()
-    names = set(re.findall(r"\b(cg_[a-z_]+)\s*\(", header))
+    names = set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", header))
     assert len(names) >= 18
     for name in names:
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     assert lib.cg_version() == 1
     assert lib.cg_stats_size(2, 150, 3) == 8 + 2 * 151 * 4
+
+
+def _unpack3(packed, exceptions):
+    """numpy restatement of cg_unpack3_kernel + cg_unpack_fix_kernel"""
+    alphabet = np.frombuffer(b"ACGTNA", dtype=np.uint8)
+    p = packed.astype(np.int64)
+    out = np.empty(p.size * 3, dtype=np.uint8)
+    out[0::3] = alphabet[p // 36]
+    out[1::3] = alphabet[(p // 6) % 6]
+    out[2::3] = alphabet[p % 6]
+    for e in exceptions:
+        out[int(e) >> 8] = int(e) & 0xFF
+    return out
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_compressed_transfer_round_trip(threads):
+    """cg_process_batch's host packer (three characters per byte + exceptions) is lossless."""
+    from cutadapt_b200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n = int(rng.integers(0, 40000)) if trial else 0
+        kind = trial % 4
+        if kind == 0:
+            data = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), n)
+        elif kind == 1:
+            data = rng.choice(np.frombuffer(b"ACGTNacgtnRYU*", dtype=np.uint8), n)
+        elif kind == 2:
+            data = rng.integers(0, 256, n, dtype=np.uint8)
+        else:
+            data = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), n, p=[0.3, 0.2, 0.2, 0.299, 0.001])
+            if n:
+                data[rng.integers(0, n, 3)] = ord("a")
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        buf = np.concatenate([data, np.zeros(8, np.uint8)])     # the packer must not read past `hi`
+        buf[n:] = 0xEE
+        lo = int(rng.integers(0, min(n, 40) + 1))
+        hi = n - int(rng.integers(0, min(n - lo, 5) + 1))
+        a0 = lo - int(rng.integers(0, min(lo, 15) + 1))
+        span = hi - a0
+        n_stream = ((span + 2) // 3 + 15) // 16 * 16
+        packed = np.full(n_stream + 1, 0xCC, dtype=np.uint8)
+        exc = np.zeros(max(n, 1), dtype=np.uint64)
+        cnt = lib.cg_pack3_host(buf.ctypes.data, a0, lo, hi, n_stream, packed.ctypes.data, exc.ctypes.data,
+                                exc.size, threads)
+        assert 0 <= cnt <= exc.size
+        assert packed[n_stream] == 0xCC and (packed[:n_stream] < 216).all()
+        got = _unpack3(packed[:n_stream], exc[:cnt])
+        # positions [lo, hi) come back exactly; everything else is filler 'A'
+        assert (got[lo - a0:hi - a0] == data[lo:hi]).all()
+        assert (got[:lo - a0] == ord("A")).all() and (got[hi - a0:] == ord("A")).all()
+        expected_exc = int((~np.isin(data[lo:hi], np.frombuffer(b"ACGTN", dtype=np.uint8))).sum())
+        assert cnt == expected_exc
 
 
 def test_no_cpu_fallback_without_a_device():
