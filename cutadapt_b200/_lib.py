@@ -104,6 +104,28 @@ class cg_params(C.Structure):
     ]
 
 
+class cg_fastq_params(C.Structure):
+    _fields_ = [
+        ("trim", cg_params),
+        ("minimum_length", C.c_int32),
+        ("maximum_length", C.c_int32),
+        ("discard_trimmed", C.c_int32),
+        ("discard_untrimmed", C.c_int32),
+        ("max_n", C.c_double),
+        ("max_expected_errors", C.c_double),
+        ("reserved", C.c_int32 * 4),
+    ]
+
+
+class cg_fastq_result(C.Structure):
+    _fields_ = [(name, C.c_int64) for name in (
+        "n_records", "n_written", "bp_in", "bp_out", "out_bytes", "with_adapters", "quality_trimmed_bp",
+        "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded")] + [("reserved", C.c_int64 * 4)]
+
+    def as_dict(self) -> dict:
+        return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
+
+
 MATCH_DTYPE = np.dtype(
     [
         ("adapter", "<i4"),
@@ -140,6 +162,10 @@ def _declare(lib) -> None:
     lib.cg_ctx_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.c_int]
     lib.cg_pack3_host.argtypes = [vp, i64, i64, i64, i64, vp, vp, i64, i32]
     lib.cg_pack3_host.restype = i64
+    lib.cg_fastq_trim_chunk.argtypes = [vp, vp, vp, i64, C.POINTER(cg_fastq_params), vp, i64,
+                                        C.POINTER(cg_fastq_result)]
+    lib.cg_fastq_submit.argtypes = [vp, vp, i64, C.POINTER(i32)]
+    lib.cg_fastq_collect.argtypes = [vp, i32, vp, C.POINTER(cg_fastq_params), vp, i64, C.POINTER(cg_fastq_result)]
     lib.cg_adapterset_create.argtypes = [
         vp, C.POINTER(cg_adapter_desc), i32, C.POINTER(cg_group_desc), i32, C.POINTER(vp),
     ]

@@ -99,6 +99,25 @@ struct Lane {
     int32_t *dst_qtrim = nullptr; size_t n_qtrim = 0; bool qtrim_bounced = false;
 };
 
+// One FASTQ chunk in flight (cg_fastq_submit ... cg_fastq_collect)
+#define CG_FQ_SLOTS 2
+struct FastqSlot {
+    cudaStream_t stream = nullptr;
+    bool busy = false;
+    int64_t n_bytes = 0;
+    DevBuf<uint8_t> d_in, d_out, d_seq, d_qual;
+    DevBuf<uint32_t> d_tiles, d_nl;
+    DevBuf<CgFastqRecord> d_rec;
+    DevBuf<int32_t> d_len, d_interval, d_outlen, d_qtrim;
+    DevBuf<int64_t> d_offs, d_outoff;
+    DevBuf<unsigned long long> d_scan;
+    DevBuf<cg_match_rec> d_matches;
+    unsigned long long *d_counters = nullptr;   // [0] newline total, [1..] CG_FQ_COUNTERS
+    int *d_err = nullptr;                       // [0] code, [1] record
+    PinBuf<uint8_t> h_in, h_out;
+    PinBuf<unsigned long long> h_counters;
+};
+
 struct cg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -125,6 +144,12 @@ struct cg_ctx {
     CgHostPool *pool = nullptr;
     std::vector<std::vector<uint64_t>> exc_scratch;
     long long h2d_bytes = 0, d2h_bytes = 0;
+    // ordering of the trimming passes of different lanes over the shared scratch
+    cudaEvent_t scratch_ev = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_busy = false;
+    FastqSlot fq[CG_FQ_SLOTS];
+    int fq_next = 0;
 };
 
 struct cg_adapterset {
@@ -167,6 +192,7 @@ extern "C" int cg_ctx_create(int device, void *stream, cg_ctx **out)
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     for (int i = 0; i < CG_N_LANES; ++i) CU(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming));
     CU(cudaMalloc((void **)&c->d_err, 16 * sizeof(int)));
     CU(cudaMemset(c->d_err, 0, 16 * sizeof(int)));
     CU(cudaMalloc((void **)&c->d_task_count, 64));
@@ -216,6 +242,16 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
     }
     c->scratch_p.release(); c->scratch_w.release(); c->tasks.release(); c->tasks2.release(); c->tasks3.release();
     c->pass_tmp.release(); c->view_base.release(); c->view_back.release();
+    for (FastqSlot &f : c->fq) {
+        f.d_in.release(); f.d_out.release(); f.d_seq.release(); f.d_qual.release(); f.d_tiles.release(); f.d_nl.release();
+        f.d_rec.release(); f.d_len.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
+        f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release();
+        f.h_in.release(); f.h_out.release(); f.h_counters.release();
+        if (f.d_counters) cudaFree(f.d_counters);
+        if (f.d_err) cudaFree(f.d_err);
+        if (f.stream) cudaStreamDestroy(f.stream);
+    }
+    if (c->scratch_ev) cudaEventDestroy(c->scratch_ev);
     if (c->d_task_count) cudaFree(c->d_task_count);
     if (c->d_err) cudaFree(c->d_err);
     if (c->d_enc) cudaFree(c->d_enc);
@@ -510,9 +546,9 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
 }
 
 // Several groups, one round: per-adapter passes + selection (see plan_passes_for).
-static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
-                       const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
-                       cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed)
+static int launch_trim_inner(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
+                             const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
+                             cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed)
 {
     if (n_reads <= 0) return CG_OK;
     const int times = p->times < 1 ? 1 : p->times;
@@ -583,6 +619,22 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
         c->timing.emplace_back(ev0, ev1);
     }
     return CG_OK;
+}
+
+// The work lists, counters and per-pass scratch of a context are shared by all of its streams: the
+// kernels of one trimming pass are ordered after those of the previous pass, whichever lane issued it.
+// (They fill the GPU on their own; what overlaps across lanes are the copies.)
+static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
+                       const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
+                       cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed)
+{
+    if (n_reads <= 0) return CG_OK;
+    if (c->scratch_busy && c->scratch_stream != st) CU(cudaStreamWaitEvent(st, c->scratch_ev, 0));
+    const int rc = launch_trim_inner(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, d_out, d_qtrim, st, timed);
+    CU(cudaEventRecord(c->scratch_ev, st));
+    c->scratch_busy = true;
+    c->scratch_stream = st;
+    return rc;
 }
 
 static int check_err_flag(cg_ctx *c)
@@ -1049,4 +1101,199 @@ extern "C" int cg_stats_accumulate_device(cg_ctx *c, const cg_adapterset *s, con
                        (unsigned long long *)d_stats, c->stream));
     c->launches += 1;
     return CG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FASTQ chunks in, trimmed FASTQ out: the per-chunk worker of the reference
+// (WorkerProcess.run, runners.py:174-214: parse the chunk, run the modifiers and filters per read, format
+// the surviving records) as a handful of kernels around the trimming pass.
+// ------------------------------------------------------------------------------------------
+static void parallel_copy(cg_ctx *c, void *dst, const void *src, size_t n)
+{
+    if (!c->pool || n < (8u << 20)) { memcpy(dst, src, n); return; }
+    const size_t JOB = 4u << 20;
+    c->pool->run((int64_t)((n + JOB - 1) / JOB), [&](int64_t j, int) {
+        const size_t o = (size_t)j * JOB;
+        memcpy((uint8_t *)dst + o, (const uint8_t *)src + o, std::min(JOB, n - o));
+    });
+}
+
+static int fastq_format_error(const int err[2])
+{
+    static const char *what[] = {"", "a record does not start with '@'", "the third line of a record does not start with '+'",
+                                 "sequence and qualities differ in length", "invalid quality value"};
+    return fail(CG_EINVAL, std::string("FASTQ format error in record ") + std::to_string(err[1]) + ": " + what[err[0] & 7]);
+}
+
+extern "C" int cg_fastq_submit(cg_ctx *c, const uint8_t *fastq, int64_t n_bytes, int32_t *slot_out)
+{
+    if (!c || !slot_out || n_bytes < 0 || (n_bytes && !fastq)) return fail(CG_EINVAL, "cg_fastq_submit: bad argument");
+    if (n_bytes >= (1LL << 31)) return fail(CG_EINVAL, "cg_fastq_submit: a chunk must be smaller than 2 GiB");
+    CU(cudaSetDevice(c->device));
+    const int si = c->fq_next;
+    FastqSlot &f = c->fq[si];
+    if (f.busy) return fail(CG_EINVAL, "cg_fastq_submit: all slots are in flight, collect one first");
+    c->fq_next = (si + 1) % CG_FQ_SLOTS;
+    if (!f.stream) CU(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+    if (!f.d_counters) CU(cudaMalloc((void **)&f.d_counters, (1 + CG_FQ_COUNTERS) * sizeof(unsigned long long)));
+    if (!f.d_err) CU(cudaMalloc((void **)&f.d_err, 2 * sizeof(int)));
+    if (!c->pool) {
+        c->pool = new CgHostPool(cg_host_threads_default());
+        c->exc_scratch.resize((size_t)c->pool->size());
+    }
+    int rc;
+    if ((rc = f.d_in.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
+    if ((rc = f.d_tiles.ensure((size_t)cg_fastq_tiles(n_bytes) + 1)) != CG_OK) return rc;
+    if ((rc = f.h_counters.ensure(1 + CG_FQ_COUNTERS)) != CG_OK) return rc;
+    f.n_bytes = n_bytes;
+    CU(cudaMemsetAsync(f.d_counters, 0, (1 + CG_FQ_COUNTERS) * sizeof(unsigned long long), f.stream));
+    const int err_init[2] = {0, 0x7FFFFFFF};
+    CU(cudaMemcpyAsync(f.d_err, err_init, sizeof err_init, cudaMemcpyHostToDevice, f.stream));
+    if (n_bytes) {
+        const uint8_t *src = fastq;
+        if (!is_pinned(fastq)) {
+            if ((rc = f.h_in.ensure((size_t)n_bytes)) != CG_OK) return rc;
+            parallel_copy(c, f.h_in.p, fastq, (size_t)n_bytes);
+            src = f.h_in.p;
+        }
+        CU(cudaMemcpyAsync(f.d_in.p, src, (size_t)n_bytes, cudaMemcpyHostToDevice, f.stream));
+        c->h2d_bytes += n_bytes;
+        CU(cg_launch_fastq_index(f.d_in.p, n_bytes, f.d_tiles.p, f.d_counters, nullptr, 0, f.stream));
+        c->launches += 2;
+    }
+    CU(cudaMemcpyAsync(f.h_counters.p, f.d_counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, f.stream));
+    f.busy = true;
+    *slot_out = si;
+    return CG_OK;
+}
+
+extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                                uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
+{
+    if (!c || !fp || !res || slot < 0 || slot >= CG_FQ_SLOTS) return fail(CG_EINVAL, "cg_fastq_collect: bad argument");
+    if (s && s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
+    FastqSlot &f = c->fq[slot];
+    if (!f.busy) return fail(CG_EINVAL, "cg_fastq_collect: nothing was submitted to this slot");
+    CU(cudaSetDevice(c->device));
+    f.busy = false;
+    memset(res, 0, sizeof *res);
+    cudaStream_t st = f.stream;
+    CU(cudaStreamSynchronize(st));
+    const int64_t n_bytes = f.n_bytes;
+    const long long n_nl = (long long)f.h_counters.p[0];
+    // the last line may come without its newline
+    long long n_lines = n_nl;
+    if (n_bytes > 0) {
+        uint8_t last = 0;
+        CU(cudaMemcpyAsync(&last, f.d_in.p + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (last != '\n') n_lines += 1;
+    }
+    if (n_lines % 4 != 0)
+        return fail(CG_EINVAL, "FASTQ chunk does not consist of complete 4-line records (" + std::to_string(n_lines) +
+                                   " lines)");
+    const long long n = n_lines / 4;
+    res->n_records = n;
+    if (n == 0) return CG_OK;
+    const cg_params *p = &fp->trim;
+    const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
+    const int times = p->times < 1 ? 1 : p->times;
+    const int slots = s ? s->host.slots : 1;
+    int rc;
+    if ((rc = f.d_nl.ensure((size_t)n_nl + 1)) != CG_OK) return rc;
+    if ((rc = f.d_rec.ensure((size_t)n)) != CG_OK) return rc;
+    if ((rc = f.d_len.ensure((size_t)n)) != CG_OK) return rc;
+    if ((rc = f.d_interval.ensure((size_t)n * 2)) != CG_OK) return rc;
+    if ((rc = f.d_outlen.ensure((size_t)n)) != CG_OK) return rc;
+    if ((rc = f.d_outoff.ensure((size_t)n + 1)) != CG_OK) return rc;
+    if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(n) + 1)) != CG_OK) return rc;
+    if (want_q && (rc = f.d_qtrim.ensure((size_t)n * 2)) != CG_OK) return rc;
+    CU(cg_launch_fastq_index(f.d_in.p, n_bytes, f.d_tiles.p, nullptr, f.d_nl.p, 1, st));
+    CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, n_nl, n, f.d_rec.p, f.d_len.p, f.d_err, st));
+    c->launches += 2;
+    int32_t *d_qtrim = want_q ? f.d_qtrim.p : nullptr;
+    const cg_match_rec *d_matches = nullptr;
+    if (s) {
+        // packed reads for the trimming kernels
+        if ((rc = f.d_offs.ensure((size_t)n + 1)) != CG_OK) return rc;
+        if ((rc = f.d_seq.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
+        if (want_q && (rc = f.d_qual.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
+        if ((rc = f.d_matches.ensure((size_t)n * times * slots)) != CG_OK) return rc;
+        CU(cg_launch_scan_i32(f.d_len.p, n, f.d_scan.p, f.d_offs.p, st));
+        CU(cg_launch_fastq_gather(f.d_in.p, f.d_rec.p, f.d_offs.p, n, f.d_seq.p, want_q ? f.d_qual.p : nullptr, st));
+        c->launches += 4;
+        CU(cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), st));
+        CU(cg_launch_max_len(f.d_offs.p, n, c->d_err + 1, st));
+        c->launches += 1;
+        int max_len = 0;
+        int fq_err[2];
+        CU(cudaMemcpyAsync(&max_len, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (fq_err[0]) return fastq_format_error(fq_err);
+        rc = launch_trim(c, s, f.d_seq.p, want_q ? f.d_qual.p : nullptr, f.d_offs.p, n, max_len, p, f.d_matches.p,
+                         d_qtrim, st, true);
+        if (rc != CG_OK) return rc;
+        d_matches = f.d_matches.p;
+    } else if (want_q) {
+        CU(cg_launch_fastq_pretrim(f.d_in.p, f.d_rec.p, f.d_len.p, n, (p->quality_trim ? 1 : 0) | (p->nextseq_trim ? 2 : 0),
+                                   p->cutoff_front, p->cutoff_back,
+                                   (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8), d_qtrim, st));
+        c->launches += 1;
+    }
+    {
+        CgFastqFilter flt;
+        flt.minimum_length = fp->minimum_length;
+        flt.maximum_length = fp->maximum_length;
+        flt.discard_trimmed = fp->discard_trimmed;
+        flt.discard_untrimmed = fp->discard_untrimmed;
+        flt.max_n = fp->max_n;
+        flt.max_ee = fp->max_expected_errors;
+        CU(cg_launch_fastq_outlen(f.d_in.p, f.d_rec.p, f.d_len.p, n, d_matches, times, slots, d_qtrim, flt, c->d_phred,
+                                  f.d_interval.p, f.d_outlen.p, f.d_counters + 1, f.d_err, st));
+        CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
+        c->launches += 4;
+        long long total = 0;
+        int fq_err[2];
+        CU(cudaMemcpyAsync(&total, f.d_outoff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(f.h_counters.p, f.d_counters, (1 + CG_FQ_COUNTERS) * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (fq_err[0]) return fastq_format_error(fq_err);
+        const unsigned long long *k = f.h_counters.p + 1;
+        res->n_written = (int64_t)k[0]; res->bp_in = (int64_t)k[1]; res->bp_out = (int64_t)k[2];
+        res->with_adapters = (int64_t)k[3]; res->too_short = (int64_t)k[4]; res->too_long = (int64_t)k[5];
+        res->quality_trimmed_bp = (int64_t)k[6]; res->discarded = (int64_t)k[7]; res->too_many_n = (int64_t)k[8];
+        res->too_many_expected_errors = (int64_t)k[9];
+        res->out_bytes = total;
+        if (total > out_capacity)
+            return fail(CG_EINVAL, "cg_fastq_collect: output buffer too small (" + std::to_string(total) + " bytes needed)");
+        if (total > 0) {
+            if (!out) return fail(CG_EINVAL, "cg_fastq_collect: out is NULL");
+            if ((rc = f.d_out.ensure((size_t)total + 64)) != CG_OK) return rc;
+            CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, n, f.d_out.p, st));
+            c->launches += 1;
+            if (is_pinned(out)) {
+                CU(cudaMemcpyAsync(out, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+            } else {
+                if ((rc = f.h_out.ensure((size_t)total)) != CG_OK) return rc;
+                CU(cudaMemcpyAsync(f.h_out.p, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                parallel_copy(c, out, f.h_out.p, (size_t)total);
+            }
+            c->d2h_bytes += total;
+        }
+    }
+    return check_err_flag(c);
+}
+
+extern "C" int cg_fastq_trim_chunk(cg_ctx *c, const cg_adapterset *s, const uint8_t *fastq, int64_t n_bytes,
+                                   const cg_fastq_params *fp, uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
+{
+    int32_t slot = -1;
+    int rc = cg_fastq_submit(c, fastq, n_bytes, &slot);
+    if (rc != CG_OK) return rc;
+    return cg_fastq_collect(c, slot, s, fp, out, out_capacity, res);
 }

@@ -1,0 +1,472 @@
+// cg_fastq.cu -- the steps either side of the hot path, on the device:
+//
+//   raw FASTQ chunk  ->  record index  ->  packed reads (what the trimming kernels consume)
+//   match records    ->  kept intervals + filters  ->  trimmed FASTQ bytes
+//
+// In the reference these are dnaio's chunk parser and record writer around the per-read loop
+// (runners.py:116-126 read_chunks, pipeline.py:47-73 process_reads, steps.py:299-319 SingleEndSink,
+// files.py:164-188 ProxyRecordWriter) plus the length / trimmed filters (predicates.py:29-66, 127-160).
+// Everything here is HBM-bound byte shuffling; the chunk crosses PCIe once in each direction.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cg_kernels.cuh"
+
+namespace {
+
+constexpr int FQ_TILE = 8192;        // bytes per CTA in the newline passes
+constexpr int FQ_THREADS = 256;      // 32 bytes per thread
+
+__device__ __forceinline__ uint32_t newline_mask16(uint4 v)
+{
+    // bit i set iff byte i of the 16-byte vector is '\n'
+    uint32_t m = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = w[k] ^ 0x0A0A0A0Au;                        // zero byte where '\n'
+        const uint32_t z = __vcmpeq4(x, 0u);                          // 0xFF per matching byte
+        m |= ((z & 1u) | ((z >> 7) & 2u) | ((z >> 14) & 4u) | ((z >> 21) & 8u)) << (4 * k);
+    }
+    return m;
+}
+
+// bytes [n, padded end) of the last vector are masked off
+__device__ __forceinline__ uint32_t load_mask(const uint8_t *buf, long long n, long long pos)
+{
+    if (pos >= n) return 0;
+    const uint4 v = __ldg((const uint4 *)(buf + pos));
+    uint32_t m = newline_mask16(v);
+    if (pos + 16 > n) m &= (1u << (int)(n - pos)) - 1u;
+    return m;
+}
+
+// pass 1: newlines per tile
+__global__ void __launch_bounds__(FQ_THREADS) fq_count_kernel(const uint8_t *buf, long long n, uint32_t *tile_counts)
+{
+    const long long base = (long long)blockIdx.x * FQ_TILE + threadIdx.x * 32;
+    int c = __popc(load_mask(buf, n, base)) + __popc(load_mask(buf, n, base + 16));
+    __shared__ int warp_sums[FQ_THREADS / 32];
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < FQ_THREADS / 32; ++i) t += warp_sums[i];
+        tile_counts[blockIdx.x] = (uint32_t)t;
+    }
+}
+
+// exclusive scan of up to a few hundred thousand uint32 values by ONE CTA (in place); total -> *total
+__global__ void __launch_bounds__(1024) scan_u32_single_cta_kernel(uint32_t *vals, long long n, unsigned long long *total)
+{
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long v = i < n ? vals[i] : 0;
+        unsigned long long x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += y;
+            }
+            warp_tot[lane] = w;   // inclusive
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        const unsigned long long before = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
+        if (i < n) vals[i] = (uint32_t)before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+// pass 2: positions of all newlines, in order
+__global__ void __launch_bounds__(FQ_THREADS) fq_index_kernel(const uint8_t *buf, long long n, const uint32_t *tile_offsets,
+                                                               uint32_t *nl_pos)
+{
+    const long long base = (long long)blockIdx.x * FQ_TILE + threadIdx.x * 32;
+    const uint32_t m = load_mask(buf, n, base) | (load_mask(buf, n, base + 16) << 16);
+    const int c = __popc(m);
+    __shared__ int warp_sums[FQ_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    int before = x - c;
+    for (int w = 0; w < warp; ++w) before += warp_sums[w];
+    uint32_t out = tile_offsets[blockIdx.x] + (uint32_t)before;
+    uint32_t mm = m;
+    while (mm) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        nl_pos[out++] = (uint32_t)(base + b);
+    }
+}
+
+// line k of the chunk: [start, end) without the line terminator ("\n" or "\r\n")
+__device__ __forceinline__ void line_span(const uint8_t *buf, const uint32_t *nl_pos, long long n_nl, long long n,
+                                          long long k, uint32_t *start, uint32_t *end)
+{
+    const uint32_t s = k == 0 ? 0u : nl_pos[k - 1] + 1u;
+    uint32_t e = k < n_nl ? nl_pos[k] : (uint32_t)n;     // the last line may lack its newline
+    if (e > s && buf[e - 1] == '\r') --e;
+    *start = s; *end = e;
+}
+
+// record r = lines 4r .. 4r+3.  Checks what dnaio's parser checks (first characters, equal lengths).
+__global__ void fq_records_kernel(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl,
+                                  long long n_records, CgFastqRecord *rec, int32_t *seq_len, int *err)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records) return;
+    uint32_t hs, he, ss, se, ps, pe, qs, qe;
+    line_span(buf, nl_pos, n_nl, n, 4 * r, &hs, &he);
+    line_span(buf, nl_pos, n_nl, n, 4 * r + 1, &ss, &se);
+    line_span(buf, nl_pos, n_nl, n, 4 * r + 2, &ps, &pe);
+    line_span(buf, nl_pos, n_nl, n, 4 * r + 3, &qs, &qe);
+    int bad = 0;
+    if (he == hs || buf[hs] != '@') bad = 1;
+    else if (pe == ps || buf[ps] != '+') bad = 2;
+    else if (se - ss != qe - qs) bad = 3;
+    if (bad) {
+        // report the first bad record: err[0] = code, err[1] = record number (smallest; initialised to INT_MAX)
+        atomicMin((unsigned int *)&err[1], (unsigned int)r);
+        atomicMax(&err[0], bad);
+    }
+    CgFastqRecord o;
+    o.hdr_start = hs + 1;                       // without the '@'
+    o.hdr_len = (int32_t)(he - hs) - 1;
+    o.seq_start = ss;
+    o.qual_start = qs;
+    rec[r] = o;
+    seq_len[r] = bad ? 0 : (int32_t)(se - ss);
+}
+
+// ---- exclusive scan int32 -> int64 (n+1 outputs), any n: tile sums, one-CTA scan of the sums, apply ----
+constexpr int SC_TILE = 2048;     // elements per CTA (256 threads x 8)
+
+__global__ void __launch_bounds__(256) scan_tile_sums_kernel(const int32_t *in, long long n, unsigned long long *tile_sums)
+{
+    const long long base = (long long)blockIdx.x * SC_TILE;
+    long long s = 0;
+    for (int k = 0; k < 8; ++k) {
+        const long long i = base + k * 256 + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    __shared__ long long ws[8];
+    for (int d = 16; d; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < 8; ++i) t += ws[i];
+        tile_sums[blockIdx.x] = (unsigned long long)t;
+    }
+}
+__global__ void __launch_bounds__(1024) scan_u64_single_cta_kernel(unsigned long long *vals, long long n)
+{
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < n; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long v = i < n ? vals[i] : 0;
+        unsigned long long x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_tot[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                if (lane >= d) w += y;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long carry = carry_s;
+        if (i < n) vals[i] = carry + (warp ? warp_tot[warp - 1] : 0) + (x - v);
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int32_t *in, long long n, const unsigned long long *tile_offsets,
+                                                          int64_t *out)
+{
+    // thread t owns 8 consecutive elements of the tile
+    const long long base = (long long)blockIdx.x * SC_TILE + threadIdx.x * 8;
+    int32_t v[8];
+    long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        s += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long x = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    __shared__ long long ws[8];
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    long long before = (long long)tile_offsets[blockIdx.x] + (x - s);
+    for (int w = 0; w < warp; ++w) before += ws[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < n) out[base + k] = before;
+        before += v[k];
+        if (base + k == n - 1) out[n] = before;
+    }
+}
+
+// packed reads for the trimming kernels: read r at offsets[r] in seq_out / qual_out
+__global__ void __launch_bounds__(256) fq_gather_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int64_t *offsets,
+                                                         long long n_records, uint8_t *seq_out, uint8_t *qual_out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_records; r += warps) {
+        const CgFastqRecord m = rec[r];
+        const long long o = offsets[r];
+        const int len = (int)(offsets[r + 1] - o);
+        for (int j = lane; j < len; j += 32) seq_out[o + j] = buf[m.seq_start + j];
+        if (qual_out)
+            for (int j = lane; j < len; j += 32) qual_out[o + j] = buf[m.qual_start + j];
+    }
+}
+
+// quality-driven trimming only (no adapter set): NextseqQualityTrimmer + QualityTrimmer straight on the chunk
+__global__ void fq_pretrim_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
+                                  int flags, int cutoff_front, int cutoff_back, int qbase, int32_t *qtrim)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records) return;
+    const CgFastqRecord m = rec[r];
+    int s = 0, e = seq_len[r];
+    if (flags) pre_trim_core(buf + m.seq_start, buf + m.qual_start, e, flags, cutoff_front, cutoff_back, qbase, &s, &e);
+    qtrim[2 * r] = s;
+    qtrim[2 * r + 1] = e;
+}
+
+// What is left of every read (modifiers.py:858 then adapters.py:453-454, 486-487 per round), the filters
+// (TooShort / TooLong, predicates.py:29-66; DiscardTrimmed / DiscardUntrimmed, predicates.py:127-160; in the
+// order cli.py builds them: length filters first) and the size of the output record.
+__global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
+                                 const cg_match_rec *matches, int times, int slots, const int32_t *qtrim,
+                                 CgFastqFilter f, const double *phred, int32_t *interval, int32_t *out_len,
+                                 unsigned long long *counters, int *err)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c_written = 0, c_bp_out = 0, c_short = 0, c_long = 0, c_adapt = 0, c_bp_in = 0, c_qbp = 0,
+                       c_dis = 0, c_n = 0, c_ee = 0;
+    if (r < n_records) {
+        const int n = seq_len[r];
+        int start = 0, stop = n;
+        if (qtrim) { start = qtrim[2 * r]; stop = qtrim[2 * r + 1]; }
+        c_qbp = (unsigned long long)(n - (stop - start));
+        bool matched = false;
+        if (matches) {
+            for (int t = 0; t < times; ++t)
+                for (int s = 0; s < slots; ++s) {
+                    const cg_match_rec m = matches[((size_t)r * times + t) * slots + s];
+                    if (m.adapter < 0) continue;
+                    matched = true;
+                    if ((m.info >> 8) & 1) stop = start + m.rstart;    // RemoveAfterMatch
+                    else start = start + m.rstop;                      // RemoveBeforeMatch
+                }
+        }
+        const int left = stop - start;
+        int keep = 1;
+        if (f.minimum_length > 0 && left < f.minimum_length) { keep = 0; c_short = 1; }
+        else if (f.maximum_length >= 0 && left > f.maximum_length) { keep = 0; c_long = 1; }
+        if (keep && f.max_n >= 0.0) {
+            // TooManyN (predicates.py:96-122): count of 'N'/'n', absolute or as a proportion of the length
+            const uint8_t *sq = buf + rec[r].seq_start + start;
+            int n_count = 0;
+            for (int j = 0; j < left; ++j) n_count += (sq[j] | 0x20) == 'n';
+            const bool too_many = f.max_n < 1.0 ? (left > 0 && (double)n_count / (double)left > f.max_n)
+                                                : (double)n_count > f.max_n;
+            if (too_many) { keep = 0; c_n = 1; }
+        }
+        if (keep && f.max_ee >= 0.0) {
+            // TooManyExpectedErrors (predicates.py:56-71): expected_errors(qualities) with its default base 33
+            const double ee = expected_errors_core(buf + rec[r].qual_start + start, left, 33, phred);
+            if (ee < 0.0) { atomicMin((unsigned int *)&err[1], (unsigned int)r); atomicMax(&err[0], 4); }
+            else if (ee > f.max_ee) { keep = 0; c_ee = 1; }
+        }
+        else if (f.discard_trimmed && matched) { keep = 0; c_dis = 1; }
+        else if (f.discard_untrimmed && !matched) { keep = 0; c_dis = 1; }
+        interval[2 * r] = start;
+        interval[2 * r + 1] = stop;
+        // "@" header "\n" sequence "\n+\n" qualities "\n"
+        out_len[r] = keep ? rec[r].hdr_len + 2 * left + 6 : 0;
+        c_written = keep; c_bp_out = keep ? left : 0; c_adapt = matched; c_bp_in = n;
+    }
+    // one atomic per warp and counter
+    c_written = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_written);
+    c_short = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_short);
+    c_long = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_long);
+    c_adapt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_adapt);
+    c_dis = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_dis);
+    c_n = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_n);
+    c_ee = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_ee);
+    for (int d = 16; d; d >>= 1) {
+        c_bp_out += __shfl_down_sync(0xFFFFFFFFu, c_bp_out, d);
+        c_bp_in += __shfl_down_sync(0xFFFFFFFFu, c_bp_in, d);
+        c_qbp += __shfl_down_sync(0xFFFFFFFFu, c_qbp, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c_written) atomicAdd(&counters[0], c_written);
+        if (c_bp_in) atomicAdd(&counters[1], c_bp_in);
+        if (c_bp_out) atomicAdd(&counters[2], c_bp_out);
+        if (c_adapt) atomicAdd(&counters[3], c_adapt);
+        if (c_short) atomicAdd(&counters[4], c_short);
+        if (c_long) atomicAdd(&counters[5], c_long);
+        if (c_qbp) atomicAdd(&counters[6], c_qbp);
+        if (c_dis) atomicAdd(&counters[7], c_dis);
+        if (c_n) atomicAdd(&counters[8], c_n);
+        if (c_ee) atomicAdd(&counters[9], c_ee);
+    }
+}
+
+// the trimmed records, one warp per record
+__global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *interval,
+                                                        const int64_t *out_off, long long n_records, uint8_t *out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_records; r += warps) {
+        const long long o = out_off[r];
+        if (out_off[r + 1] == o) continue;     // filtered
+        const CgFastqRecord m = rec[r];
+        const int start = interval[2 * r], left = interval[2 * r + 1] - start;
+        uint8_t *p = out + o;
+        if (lane == 0) p[0] = '@';
+        for (int j = lane; j < m.hdr_len; j += 32) p[1 + j] = buf[m.hdr_start + j];
+        p += 1 + m.hdr_len;
+        if (lane == 0) p[0] = '\n';
+        for (int j = lane; j < left; j += 32) p[1 + j] = buf[m.seq_start + start + j];
+        p += 1 + left;
+        if (lane < 3) p[lane] = lane == 1 ? '+' : '\n';
+        for (int j = lane; j < left; j += 32) p[3 + j] = buf[m.qual_start + start + j];
+        if (lane == 0) p[3 + left] = '\n';
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+long long cg_fastq_tiles(long long n_bytes) { return (n_bytes + FQ_TILE - 1) / FQ_TILE; }
+
+cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint32_t *d_tile_counts,
+                                  unsigned long long *d_total, uint32_t *d_nl_pos, int phase, cudaStream_t st)
+{
+    const long long tiles = cg_fastq_tiles(n_bytes);
+    if (tiles <= 0) return cudaSuccess;
+    if (phase == 0) {
+        fq_count_kernel<<<(unsigned)tiles, FQ_THREADS, 0, st>>>(d_buf, n_bytes, d_tile_counts);
+        scan_u32_single_cta_kernel<<<1, 1024, 0, st>>>(d_tile_counts, tiles, d_total);
+    } else {
+        fq_index_kernel<<<(unsigned)tiles, FQ_THREADS, 0, st>>>(d_buf, n_bytes, d_tile_counts, d_nl_pos);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
+                                    long long n_records, CgFastqRecord *d_rec, int32_t *d_seq_len, int *d_err,
+                                    cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_records_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, n_bytes, d_nl_pos, n_newlines, n_records,
+                                                                          d_rec, d_seq_len, d_err);
+    return cudaGetLastError();
+}
+
+long long cg_scan_tiles(long long n) { return (n + SC_TILE - 1) / SC_TILE; }
+
+cudaError_t cg_launch_scan_i32(const int32_t *d_in, long long n, unsigned long long *d_tile_scratch, int64_t *d_out,
+                               cudaStream_t st)
+{
+    if (n <= 0) return cudaMemsetAsync(d_out, 0, sizeof(int64_t), st);
+    const long long tiles = cg_scan_tiles(n);
+    scan_tile_sums_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_in, n, d_tile_scratch);
+    scan_u64_single_cta_kernel<<<1, 1024, 0, st>>>(d_tile_scratch, tiles);
+    scan_apply_kernel<<<(unsigned)tiles, 256, 0, st>>>(d_in, n, d_tile_scratch, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int64_t *d_offsets,
+                                   long long n_records, uint8_t *d_seq, uint8_t *d_qual, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    long long grid = (n_records + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    fq_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_offsets, n_records, d_seq, d_qual);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                    long long n_records, int flags, int cutoff_front, int cutoff_back, int qbase,
+                                    int32_t *d_qtrim, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_pretrim_kernel<<<(unsigned)((n_records + 127) / 128), 128, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, flags,
+                                                                          cutoff_front, cutoff_back, qbase, d_qtrim);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_outlen(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                   long long n_records, const cg_match_rec *d_matches, int times, int slots,
+                                   const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
+                                   int32_t *d_out_len, unsigned long long *d_counters, int *d_err, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_outlen_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches,
+                                                                         times, slots, d_qtrim, f, d_phred, d_interval,
+                                                                         d_out_len, d_counters, d_err);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
+                                  const int64_t *d_out_off, long long n_records, uint8_t *d_out, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    long long grid = (n_records + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    fq_write_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_interval, d_out_off, n_records, d_out);
+    return cudaGetLastError();
+}

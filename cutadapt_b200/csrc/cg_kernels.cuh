@@ -96,3 +96,42 @@ cudaError_t cg_launch_fill_offsets(int64_t *d_out, long long base, long long len
 // d_out receives 3 * packed_bytes characters, then the n_exc exceptions (position << 8 | byte)
 cudaError_t cg_launch_unpack3(const uint8_t *d_packed, long long packed_bytes, uint8_t *d_out,
                               const unsigned long long *d_exc, long long n_exc, cudaStream_t st);
+
+// ---- FASTQ chunk parse / trimmed-record formatting (cg_fastq.cu) ---------------------------------------
+struct CgFastqRecord {       // one 4-line record of the chunk
+    uint32_t hdr_start;      // first character of the name (after '@')
+    int32_t hdr_len;
+    uint32_t seq_start;
+    uint32_t qual_start;
+};
+struct CgFastqFilter {
+    int minimum_length;      // 0 = off
+    int maximum_length;      // < 0 = off
+    int discard_trimmed, discard_untrimmed;
+    double max_n;            // < 0 = off; < 1: proportion of the length
+    double max_ee;           // < 0 = off
+};
+#define CG_FQ_COUNTERS 16    // written, bp_in, bp_out, with_adapters, too_short, too_long, quality_trimmed_bp,
+                             // discarded (trimmed/untrimmed), too_many_n, too_many_expected_errors
+long long cg_fastq_tiles(long long n_bytes);
+long long cg_scan_tiles(long long n);
+// phase 0: newline count per tile + exclusive scan (total -> *d_total); phase 1: positions of the newlines
+cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint32_t *d_tile_counts,
+                                  unsigned long long *d_total, uint32_t *d_nl_pos, int phase, cudaStream_t st);
+cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
+                                    long long n_records, CgFastqRecord *d_rec, int32_t *d_seq_len, int *d_err,
+                                    cudaStream_t st);
+// exclusive scan int32 -> int64, n + 1 outputs; d_tile_scratch: cg_scan_tiles(n) words
+cudaError_t cg_launch_scan_i32(const int32_t *d_in, long long n, unsigned long long *d_tile_scratch, int64_t *d_out,
+                               cudaStream_t st);
+cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int64_t *d_offsets,
+                                   long long n_records, uint8_t *d_seq, uint8_t *d_qual, cudaStream_t st);
+cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                    long long n_records, int flags, int cutoff_front, int cutoff_back, int qbase,
+                                    int32_t *d_qtrim, cudaStream_t st);
+cudaError_t cg_launch_fastq_outlen(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                   long long n_records, const cg_match_rec *d_matches, int times, int slots,
+                                   const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
+                                   int32_t *d_out_len, unsigned long long *d_counters, int *d_err, cudaStream_t st);
+cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
+                                  const int64_t *d_out_off, long long n_records, uint8_t *d_out, cudaStream_t st);

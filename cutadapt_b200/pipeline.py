@@ -175,6 +175,89 @@ class BatchTrimmer:
         return [stats[id(o)] for o in owners]
 
 
+class FastqTrimmer:
+    """
+    FASTQ chunks in, trimmed FASTQ chunks out -- the per-chunk worker of the reference
+    (``WorkerProcess.run``, runners.py:174-214: parse, modifiers, filters, format) as one library call
+    per chunk (``cg_fastq_submit`` / ``cg_fastq_collect``): the chunk is indexed, trimmed, filtered and
+    formatted on the device.
+
+    adapters            a Matchable / list of adapters, or None / [] for quality trimming and filters only
+    quality_cutoff      None or (cutoff_front, cutoff_back)        -q        (modifiers.py:840-858)
+    nextseq_cutoff      None or the --nextseq-trim cutoff                    (modifiers.py:825-837)
+    times               -n                                                   (modifiers.py:225-231)
+    minimum_length, maximum_length   -m / -M                                 (predicates.py:29-53)
+    max_n, max_expected_errors       --max-n / --max-ee                      (predicates.py:56-122)
+    discard_trimmed, discard_untrimmed                                       (predicates.py:127-160)
+
+    ``process_chunk(bytes) -> bytes``; ``process_chunks(iterable)`` keeps one chunk in flight so that the
+    upload of chunk i+1 overlaps the download of chunk i.  ``statistics`` accumulates the counters of
+    ``cg_fastq_result`` over all chunks.  Chunks must consist of complete records (what
+    ``dnaio.read_chunks`` yields).
+    """
+
+    def __init__(self, adapters=None, times: int = 1, quality_cutoff: Optional[Tuple[int, int]] = None,
+                 quality_base: int = 33, nextseq_cutoff: Optional[int] = None, minimum_length: int = 0,
+                 maximum_length: Optional[int] = None, max_n: Optional[float] = None,
+                 max_expected_errors: Optional[float] = None, discard_trimmed: bool = False,
+                 discard_untrimmed: bool = False, ctx: Optional[_lib.Context] = None):
+        if adapters is not None and not isinstance(adapters, Matchable):
+            adapters = MultipleAdapters(list(adapters)) if len(adapters) else None
+        self.adapters = adapters
+        self.ctx = ctx or _lib.default_context()
+        self._set = None
+        if adapters is not None:
+            singles, groups, _ = adapters._flatten()
+            spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups, adapters._flatten_indexes())
+            self._set = _lib.AdapterSet(spec, self.ctx)
+        fp = _lib.cg_fastq_params()
+        fp.trim = _lib.make_params(
+            quality_trim=quality_cutoff is not None,
+            cutoff_front=quality_cutoff[0] if quality_cutoff else 0,
+            cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
+            quality_base=quality_base, times=times, nextseq_cutoff=nextseq_cutoff)
+        fp.minimum_length = int(minimum_length or 0)
+        fp.maximum_length = -1 if maximum_length is None else int(maximum_length)
+        fp.max_n = -1.0 if max_n is None else float(max_n)
+        fp.max_expected_errors = -1.0 if max_expected_errors is None else float(max_expected_errors)
+        fp.discard_trimmed = int(bool(discard_trimmed))
+        fp.discard_untrimmed = int(bool(discard_untrimmed))
+        self.params = fp
+        self.statistics = {}
+
+    def _submit(self, chunk) -> Tuple[int, int, object]:
+        buf = np.frombuffer(chunk, dtype=np.uint8) if not isinstance(chunk, np.ndarray) else chunk
+        slot = C.c_int32(-1)
+        _lib.check(_lib.lib().cg_fastq_submit(self.ctx.handle, buf.ctypes.data if buf.size else None, buf.size,
+                                              C.byref(slot)))
+        return slot.value, buf.size, buf    # buf is kept alive until collect
+
+    def _collect(self, ticket) -> bytes:
+        slot, n_bytes, _ = ticket
+        # trimming only ever shortens a record ("\r\n" -> "\n" and "+name" -> "+" too)
+        out = np.empty(max(n_bytes, 1), dtype=np.uint8)
+        res = _lib.cg_fastq_result()
+        _lib.check(_lib.lib().cg_fastq_collect(
+            self.ctx.handle, slot, self._set.handle if self._set is not None else None, C.byref(self.params),
+            out.ctypes.data, out.size, C.byref(res)))
+        for k, v in res.as_dict().items():
+            self.statistics[k] = self.statistics.get(k, 0) + v
+        return out[: res.out_bytes].tobytes()
+
+    def process_chunk(self, chunk) -> bytes:
+        return self._collect(self._submit(chunk))
+
+    def process_chunks(self, chunks):
+        pending = None
+        for chunk in chunks:
+            ticket = self._submit(chunk)
+            if pending is not None:
+                yield self._collect(pending)
+            pending = ticket
+        if pending is not None:
+            yield self._collect(pending)
+
+
 class DeviceResult:
     def __init__(self, matches, qtrim, n_reads, offsets):
         self.matches = matches    # torch int32 [n * times * slots, 8]

@@ -250,6 +250,44 @@ int cg_expected_errors_batch(cg_ctx *ctx, const uint8_t *qual, const int64_t *of
 int cg_poly_a_trim_batch(cg_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int64_t n_reads,
                          int32_t revcomp, int32_t *out);
 
+/* ---- FASTQ chunks in, trimmed FASTQ out ---------------------------------
+ * The per-chunk worker of the reference as one call: WorkerProcess.run (runners.py:174-214) parses a chunk of
+ * complete 4-line records (dnaio.read_chunks, runners.py:116-126), runs the modifiers per read
+ * (pipeline.py:47-73: NextseqQualityTrimmer, QualityTrimmer, AdapterCutter with action "trim"), the filters
+ * (TooShort, TooLong, TooManyN, TooManyExpectedErrors, then DiscardTrimmed / DiscardUntrimmed:
+ * predicates.py:29-160 in the order of cli.py:700-830) and formats the surviving records
+ * ("@name\nsequence\n+\nqualities\n", SingleEndSink steps.py:299-319).  Here the chunk is indexed, packed,
+ * trimmed, filtered and formatted on the device; it crosses PCIe once in each direction.
+ * "\r\n" line ends are accepted (and written back as "\n", like dnaio). */
+typedef struct cg_fastq_params {
+    cg_params trim;
+    int32_t minimum_length;      /* -m; 0 = off                                                       */
+    int32_t maximum_length;      /* -M; negative = off                                                */
+    int32_t discard_trimmed;     /* --discard-trimmed                                                 */
+    int32_t discard_untrimmed;   /* --discard-untrimmed                                               */
+    double max_n;                /* --max-n; negative = off; below 1: proportion of the read length   */
+    double max_expected_errors;  /* --max-ee; negative = off                                          */
+    int32_t reserved[4];
+} cg_fastq_params;
+typedef struct cg_fastq_result {
+    int64_t n_records, n_written;
+    int64_t bp_in, bp_out;       /* bases read / bases written                                        */
+    int64_t out_bytes;           /* size of the formatted output                                      */
+    int64_t with_adapters, quality_trimmed_bp;
+    int64_t too_short, too_long, too_many_n, too_many_expected_errors, discarded;
+    int64_t reserved[4];
+} cg_fastq_result;
+/* set may be NULL: quality trimming and filters only.  fastq / out: HOST pointers (pinned or pageable).
+ * Errors: CG_EINVAL for malformed FASTQ (message names the record), a too small output buffer (out_bytes in
+ * *res says what is needed), CG_ENONASCII like cg_process_batch. */
+int cg_fastq_trim_chunk(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *fastq, int64_t n_bytes,
+                        const cg_fastq_params *params, uint8_t *out, int64_t out_capacity, cg_fastq_result *res);
+/* The same in two halves so that the upload of the next chunk overlaps the download of this one (two slots):
+ * submit starts the upload and the line index; collect does the rest and returns the output. */
+int cg_fastq_submit(cg_ctx *ctx, const uint8_t *fastq, int64_t n_bytes, int32_t *slot);
+int cg_fastq_collect(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, const cg_fastq_params *params,
+                     uint8_t *out, int64_t out_capacity, cg_fastq_result *res);
+
 /* ---- trim statistics (the payload of the end-of-run all-reduce, report.py:81-126) --------
  * Device-side reduction of a batch's match records into a fixed-layout int64 vector:
  *   [0] n_reads  [1] total_bp  [2] reads_with_adapters  [3] quality_trimmed_bp

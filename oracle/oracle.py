@@ -309,3 +309,103 @@ def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=Fal
             if h1 is not None:
                 s, e = _trim(h1, s, e)
     return out, qtrim
+
+
+# ---------------------------------------------------------------------------------------------
+# FASTQ chunk in -> trimmed FASTQ out: restatement of what one worker of the reference does with a
+# chunk (runners.py:174-214 -> pipeline.py:47-73 -> steps.py:299-319), for the product's
+# cg_fastq_trim_chunk.  dnaio (absent here) only parses and formats; its on-disk conventions are the
+# FASTQ format itself: 4 lines per record, "\r\n" tolerated on input, "@name\nseq\n+\nqual\n" on output.
+# ---------------------------------------------------------------------------------------------
+class FastqFormatError(ValueError):
+    pass
+
+
+def parse_fastq(data: bytes):
+    """[(name, sequence, qualities)] as str; raises FastqFormatError like dnaio's parser does."""
+    if not data:
+        return []
+    lines = data.split(b"\n")
+    if lines[-1] == b"":
+        lines.pop()
+    if len(lines) % 4:
+        raise FastqFormatError(f"FASTQ chunk does not consist of complete 4-line records ({len(lines)} lines)")
+    lines = [ln[:-1] if ln.endswith(b"\r") else ln for ln in lines]
+    records = []
+    for r in range(len(lines) // 4):
+        h, s, p, q = lines[4 * r:4 * r + 4]
+        if not h.startswith(b"@"):
+            raise FastqFormatError(f"record {r}: a record does not start with '@'")
+        if not p.startswith(b"+"):
+            raise FastqFormatError(f"record {r}: the third line of a record does not start with '+'")
+        if len(s) != len(q):
+            raise FastqFormatError(f"record {r}: sequence and qualities differ in length")
+        records.append((h[1:].decode("latin-1"), s.decode("latin-1"), q.decode("latin-1")))
+    return records
+
+
+def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=False, cutoff_front=0, cutoff_back=0,
+                      quality_base=33, times=1, nextseq_cutoff=None, minimum_length=0, maximum_length=-1,
+                      discard_trimmed=False, discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0):
+    """(output bytes, counters dict).  Modifiers as oracle_process; then the filters in the order cli.py:700-830
+    appends them: TooShort, TooLong, TooManyN, TooManyExpectedErrors (predicates.py:29-122), and finally
+    DiscardTrimmed / DiscardUntrimmed (predicates.py:127-160)."""
+    records = parse_fastq(data)
+    seqs = [r[1] for r in records]
+    quals = [r[2] for r in records]
+    n = len(records)
+    if adapters:
+        matches, qtrim = oracle_process(adapters, groups, seqs, quals, quality_trim, cutoff_front, cutoff_back,
+                                        quality_base, times, nextseq_cutoff)
+    else:
+        matches = None
+        qtrim = np.zeros((n, 2), dtype=np.int32)
+        for i, (seq, q) in enumerate(zip(seqs, quals)):
+            s, e = 0, len(seq)
+            if nextseq_cutoff is not None:
+                e = nextseq_trim_index(seq, q, nextseq_cutoff, quality_base)
+            if quality_trim:
+                s, e = quality_trim_index(q[:e], cutoff_front, cutoff_back, quality_base)
+            qtrim[i] = (s, e)
+    out = []
+    c = dict(n_records=n, n_written=0, bp_in=0, bp_out=0, with_adapters=0, quality_trimmed_bp=0, too_short=0,
+             too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0)
+    for i, (name, seq, q) in enumerate(records):
+        s, e = int(qtrim[i, 0]), int(qtrim[i, 1])
+        c["bp_in"] += len(seq)
+        c["quality_trimmed_bp"] += len(seq) - (e - s)
+        matched = False
+        if matches is not None:
+            for r in range(matches.shape[1]):
+                for slot in range(matches.shape[2]):
+                    m = matches[i, r, slot]
+                    if m["adapter"] < 0:
+                        continue
+                    matched = True
+                    if (int(m["info"]) >> 8) & 1:      # RemoveAfterMatch: read[:rstart]      adapters.py:486-487
+                        e = s + int(m["rstart"])
+                    else:                               # RemoveBeforeMatch: read[rstop:]      adapters.py:453-454
+                        s = s + int(m["rstop"])
+        c["with_adapters"] += matched
+        ts, tq = seq[s:e], q[s:e]
+        if minimum_length > 0 and len(ts) < minimum_length:
+            c["too_short"] += 1
+            continue
+        if maximum_length >= 0 and len(ts) > maximum_length:
+            c["too_long"] += 1
+            continue
+        if max_n >= 0:
+            n_count = ts.lower().count("n")
+            if (max_n < 1.0 and len(ts) > 0 and n_count / len(ts) > max_n) or (max_n >= 1.0 and n_count > max_n):
+                c["too_many_n"] += 1
+                continue
+        if max_expected_errors >= 0 and expected_errors(tq) > max_expected_errors:
+            c["too_many_expected_errors"] += 1
+            continue
+        if (discard_trimmed and matched) or (discard_untrimmed and not matched):
+            c["discarded"] += 1
+            continue
+        c["n_written"] += 1
+        c["bp_out"] += len(ts)
+        out.append(f"@{name}\n{ts}\n+\n{tq}\n".encode("latin-1"))
+    return b"".join(out), c

@@ -1,0 +1,151 @@
+"""
+GPU tests (-m gpu) of the FASTQ entry point: FASTQ chunk in, trimmed FASTQ
+out, against the expected output files of the reference's command-line tests and against the oracle.
+Byte work: the bar is byte-identical output.
+"""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from cutadapt_b200.pipeline import FastqTrimmer  # noqa: E402
+from oracle import oracle  # noqa: E402
+from util import fastq_cases, fastq_case_adapters, fastq_case_kwargs, spec_of  # noqa: E402
+
+
+def trimmer_for(options, **extra):
+    kw = fastq_case_kwargs(options)
+    kw.update(extra)
+    if kw.pop("quality_trim", False):
+        kw["quality_cutoff"] = (kw.pop("cutoff_front"), kw.pop("cutoff_back"))
+    return FastqTrimmer(fastq_case_adapters(options), **kw)
+
+
+def oracle_for(options, data, **extra):
+    import cutadapt_b200.adapters as PA
+
+    ads = fastq_case_adapters(options)
+    descs = groups = None
+    if ads:
+        spec = spec_of(PA.MultipleAdapters(ads))
+        descs, groups = spec.adapters, spec.groups
+    kw = fastq_case_kwargs(options)
+    kw.update(extra)
+    return oracle.oracle_fastq_trim(data, descs, groups, **kw)
+
+
+def test_reference_command_line_goldens():
+    """Every FASTQ known-answer case of the reference's test_commandline.py, byte for byte."""
+    for c in fastq_cases():
+        t = trimmer_for(c["options"])
+        got = t.process_chunk(c["input_bytes"])
+        assert got == c["expected_bytes"], c["name"]
+        _, counters = oracle_for(c["options"], c["input_bytes"])
+        for k, v in counters.items():
+            assert t.statistics[k] == v, (c["name"], k)
+        assert t.statistics["out_bytes"] == len(got)
+
+
+def synthetic_fastq(n, seed, crlf=False, final_newline=True):
+    rng = random.Random(seed)
+    adapter = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+    out = []
+    for i in range(n):
+        ln = rng.choice((0, 1, 5, 30, 75, 100, 150, 150, 150, 151, 250))
+        seq = "".join(rng.choice("ACGT") for _ in range(ln))
+        if ln > 30 and rng.random() < 0.6:
+            cut = rng.randrange(5, ln)
+            seq = (seq[:cut] + adapter + seq)[:ln]
+        if rng.random() < 0.05 and ln:
+            seq = "".join(c if rng.random() > 0.2 else "N" for c in seq)
+        if rng.random() < 0.02:
+            seq = seq.lower()
+        qual = "".join(chr(33 + min(41, max(2, int(rng.gauss(32 - 25 * (j / max(ln, 1)) ** 2, 6))))) for j in range(ln))
+        name = f"read{i}" + ("" if rng.random() < 0.5 else f" 1:{rng.choice('NY')}:0:{'ACGT' * rng.randrange(0, 9)}")
+        plus = "+" if rng.random() < 0.9 else "+" + name
+        out.append(f"@{name}\n{seq}\n{plus}\n{qual}\n")
+    data = "".join(out)
+    if crlf:
+        data = data.replace("\n", "\r\n")
+    if not final_newline:
+        data = data[:-2] if crlf else data[:-1]
+    return data.encode()
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "filters", "quality_only", "times2"])
+def test_random_chunks_against_oracle(variant):
+    options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20])
+    extra = {}
+    data = synthetic_fastq(6000, seed=hash(variant) % 1000, crlf=variant == "crlf",
+                           final_newline=variant != "no_final_newline")
+    if variant == "filters":
+        extra = dict(minimum_length=20, maximum_length=140, max_n=0.1, max_expected_errors=2.5, discard_untrimmed=True)
+    elif variant == "quality_only":
+        options = dict(adapters=[], quality_cutoff=[0, 25], nextseq_cutoff=20)
+        extra = dict(minimum_length=1, max_n=3)
+    elif variant == "times2":
+        extra = dict(times=2, discard_trimmed=False)
+    t = trimmer_for(options, **extra)
+    got = t.process_chunk(data)
+    exp, counters = oracle_for(options, data, **extra)
+    assert got == exp
+    for k, v in counters.items():
+        assert t.statistics[k] == v, k
+
+
+def test_many_chunks_in_flight_and_format_errors():
+    """process_chunks (two slots, one chunk in flight) gives the concatenation of the per-chunk results."""
+    options = dict(adapters=[["back", "AGATCGGAAGAGC"]])
+    chunks = [synthetic_fastq(n, seed=50 + i) for i, n in enumerate((1, 3000, 0, 17, 40000, 5, 2500))]
+    t = trimmer_for(options, minimum_length=10)
+    got = list(t.process_chunks(chunks))
+    exp = [oracle_for(options, c, minimum_length=10)[0] for c in chunks]
+    assert got == exp
+    assert t.statistics["n_records"] == sum((1, 3000, 0, 17, 40000, 5, 2500))
+    for bad in (b"@r\nACGT\n+\nIII\n", b"@r\nACGT\n+\n", b"r\nACGT\n+\nIIII\n", b"@r\nACGT\n-\nIIII\n"):
+        with pytest.raises(ValueError):
+            t.process_chunk(bad)
+    # the context stays usable after an error
+    assert t.process_chunk(chunks[3]) == exp[3]
+
+
+def test_large_chunk_properties():
+    """150 MB of FASTQ (1 M records x 150 bp): size-independent properties + the oracle on a sample of records."""
+    n, L = 400_000, 150
+    rng = np.random.default_rng(3)
+    seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), (n, L))
+    ad = np.frombuffer(b"AGATCGGAAGAGCACACGTCTGAACTCCAGTCAC", dtype=np.uint8)
+    starts = rng.integers(20, L, n)
+    has = rng.random(n) < 0.5
+    for j in range(ad.size):
+        pos = starts + j
+        ok = has & (pos < L)
+        seq[np.nonzero(ok)[0], pos[ok]] = ad[j]
+    qual = (33 + np.clip(rng.normal(34, 5, (n, L)), 2, 41)).astype(np.uint8)
+    recs = []
+    for i in range(n):
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, seq[i].tobytes(), qual[i].tobytes()))
+    data = b"".join(recs)
+    options = dict(adapters=[["back", "AGATCGGAAGAGC"]], quality_cutoff=[0, 20])
+    t = trimmer_for(options, minimum_length=25)
+    got = t.process_chunk(data)
+    st = t.statistics
+    assert st["n_records"] == n and st["bp_in"] == n * L
+    assert st["n_written"] + st["too_short"] == n
+    lines = got.split(b"\n")
+    assert lines[-1] == b"" and len(lines) - 1 == 4 * st["n_written"]
+    assert sum(len(x) for x in lines[1::4]) == st["bp_out"]
+    assert all(len(a) == len(b) >= 25 for a, b in zip(lines[1::4][:5000], lines[3::4][:5000]))
+    # output order = input order; a strided sample goes through the oracle record by record
+    idx = list(range(0, n, 1009))
+    sample = b"".join(recs[i] for i in idx)
+    exp, _ = oracle_for(options, sample, minimum_length=25)
+    by_name = {lines[k]: (lines[k + 1], lines[k + 3]) for k in range(0, len(lines) - 1, 4)}
+    exp_lines = exp.split(b"\n")
+    for k in range(0, len(exp_lines) - 1, 4):
+        assert by_name[exp_lines[k]] == (exp_lines[k + 1], exp_lines[k + 3])
+    kept_names = {exp_lines[k] for k in range(0, len(exp_lines) - 1, 4)}
+    for i in idx:
+        assert ((b"@r%d" % i) in by_name) == ((b"@r%d" % i) in kept_names)

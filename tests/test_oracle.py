@@ -126,3 +126,28 @@ def test_trim_scans_golden():
     for qual, base, expected in g["expected_errors"]:           # bit-exact doubles
         assert oracle.expected_errors(qual, base).hex() == expected, (qual, base)
     assert oracle.expected_errors("II!I ", 33) < 0             # a character below the base
+
+
+def test_fastq_oracle_reproduces_the_reference_command_line_goldens():
+    """
+    oracle.oracle_fastq_trim (parse -> modifiers -> filters -> format) against the expected output files of
+    the reference's own command-line tests (tests/golden/fastq/cases.json names test and command line).
+    """
+    from util import fastq_cases, fastq_case_adapters, fastq_case_kwargs, spec_of
+    import cutadapt_b200.adapters as PA
+
+    cases = fastq_cases()
+    assert len(cases) >= 17
+    for c in cases:
+        ads = fastq_case_adapters(c["options"])
+        descs = groups = None
+        if ads:
+            spec = spec_of(PA.MultipleAdapters(ads))
+            descs, groups = spec.adapters, spec.groups
+        got, counters = oracle.oracle_fastq_trim(c["input_bytes"], descs, groups, **fastq_case_kwargs(c["options"]))
+        assert got == c["expected_bytes"], c["name"]
+        assert counters["n_records"] >= counters["n_written"]
+    with pytest.raises(oracle.FastqFormatError):
+        oracle.parse_fastq(b"@r\nACGT\n+\nII\n")
+    with pytest.raises(oracle.FastqFormatError):
+        oracle.parse_fastq(b"@r\nACGT\n+\n")

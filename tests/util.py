@@ -142,3 +142,36 @@ def random_reads(rng, adapters, n_reads, alpha="ACGT", max_len=80):
             q = q[:pos] + "".join(piece) + q[pos:]
         reads.append(q)
     return reads
+
+
+# ---- FASTQ known-answer cases of the reference's command-line tests (tests/golden/fastq) -----------------
+
+def fastq_cases():
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastq")
+    cases = json.load(open(os.path.join(here, "cases.json")))
+    for c in cases:
+        c["input_bytes"] = open(os.path.join(here, c["name"] + ".in.fastq"), "rb").read()
+        c["expected_bytes"] = open(os.path.join(here, c["name"] + ".out.fastq"), "rb").read()
+    return cases
+
+
+def fastq_case_adapters(options):
+    """The adapters of a case as the command line would build them (-e, default -O 3): cutadapt_b200 objects."""
+    import cutadapt_b200.adapters as PA
+
+    kinds = {"back": PA.BackAdapter, "front": PA.FrontAdapter, "anywhere": PA.AnywhereAdapter}
+    e = options.get("error_rate", 0.1)
+    return [kinds[k](seq, max_errors=e, min_overlap=3, name=f"a{i}") for i, (k, seq) in enumerate(options["adapters"])]
+
+
+def fastq_case_kwargs(options):
+    """Keyword arguments shared by oracle.oracle_fastq_trim and (renamed) pipeline.FastqTrimmer."""
+    kw = {}
+    if "quality_cutoff" in options:
+        kw.update(quality_trim=True, cutoff_front=options["quality_cutoff"][0], cutoff_back=options["quality_cutoff"][1])
+    for k in ("quality_base", "nextseq_cutoff", "max_expected_errors", "discard_trimmed", "discard_untrimmed",
+              "minimum_length", "maximum_length", "max_n", "times"):
+        if k in options:
+            kw[k] = options[k]
+    return kw
