@@ -365,6 +365,7 @@ def main():
         e2e_step()
         barrier()
         host_ctx.transfer_bytes(reset=True)
+        host_ctx.host_profile(reset=True)
         l0 = host_ctx.launch_count()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
@@ -385,6 +386,8 @@ def main():
                "h2d_bytes_per_step": h2d_bytes // e2e_steps, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                "steps": e2e_steps, "launches": host_ctx.launch_count() - l0,
                "host_threads": int(os.environ["CUTADAPT_B200_HOST_THREADS"]),
+               "host_profile": {k: (round(v, 4) if isinstance(v, float) else v)
+                                for k, v in host_ctx.host_profile().items()},
                "raw_transfer_value": n * world / raw_wall,
                "how": f"cg_process_batch on pinned host buffers (sequences + int64 offsets in, 32-byte records out), "
                       f"compressed host-to-device transfer (raw_transfer_value: the same with "

@@ -113,14 +113,22 @@ class cg_fastq_params(C.Structure):
         ("discard_untrimmed", C.c_int32),
         ("max_n", C.c_double),
         ("max_expected_errors", C.c_double),
-        ("reserved", C.c_int32 * 4),
+        ("cut_front", C.c_int32),
+        ("cut_back", C.c_int32),
+        ("poly_a", C.c_int32),
+        ("shorten", C.c_int32),
+        ("shorten_length", C.c_int32),
+        ("trim_n", C.c_int32),
+        ("discard_casava", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 
 class cg_fastq_result(C.Structure):
     _fields_ = [(name, C.c_int64) for name in (
         "n_records", "n_written", "bp_in", "bp_out", "out_bytes", "with_adapters", "quality_trimmed_bp",
-        "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded")] + [("reserved", C.c_int64 * 4)]
+        "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded", "casava_filtered")] + [
+        ("reserved", C.c_int64 * 3)]
 
     def as_dict(self) -> dict:
         return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}
@@ -159,6 +167,7 @@ def _declare(lib) -> None:
     lib.cg_ctx_launch_count.argtypes = [vp]
     lib.cg_ctx_launch_count.restype = i64
     lib.cg_ctx_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
+    lib.cg_ctx_host_profile.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     lib.cg_ctx_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.c_int]
     lib.cg_pack3_host.argtypes = [vp, i64, i64, i64, i64, vp, vp, i64, i32]
     lib.cg_pack3_host.restype = i64
@@ -404,6 +413,13 @@ class Context:
         launches = C.c_int64()
         check(lib().cg_ctx_kernel_time(self._h, C.byref(total), C.byref(launches), int(reset)))
         return total.value, launches.value
+
+    def host_profile(self, reset: bool = False) -> dict:
+        """Seconds the host side of cg_process_batch spent per phase (cg_ctx_host_profile)."""
+        out = (C.c_double * 8)()
+        check(lib().cg_ctx_host_profile(self._h, out, int(reset)))
+        return {"total_s": out[0], "offset_scan_s": out[1], "pack_s": out[2], "lane_wait_s": out[3],
+                "drain_s": out[4], "chunks": int(out[5])}
 
     def transfer_bytes(self, reset: bool = False) -> Tuple[int, int]:
         """Bytes cg_process_batch moved host->device and device->host on this context."""

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -144,6 +145,7 @@ struct cg_ctx {
     CgHostPool *pool = nullptr;
     std::vector<std::vector<uint64_t>> exc_scratch;
     long long h2d_bytes = 0, d2h_bytes = 0;
+    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cg_ctx_host_profile
     // ordering of the trimming passes of different lanes over the shared scratch
     cudaEvent_t scratch_ev = nullptr;
     cudaStream_t scratch_stream = nullptr;
@@ -765,10 +767,16 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     int64_t r0 = 0;
     int lane_idx = 0;
     int rc = CG_OK;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const clk::time_point t_begin = clk::now();
     while (r0 < n_reads && rc == CG_OK) {
         // chunk [r0, r1): bounded by reads and bytes; also find the longest read
         int64_t r1 = std::min(n_reads, r0 + CHUNK_READS);
+        const clk::time_point t_scan0 = clk::now();
         OffsetScan sc = scan_offsets(c, offsets, r0, r1);
+        c->prof[1] += secs(t_scan0, clk::now());
+        c->prof[5] += 1;
         if (!sc.valid) return fail(CG_EINVAL, "offsets must be non-decreasing");
         const int64_t byte0 = offsets[r0];
         if (offsets[r1] - byte0 > CHUNK_BYTES && r1 - r0 > 1) {
@@ -786,7 +794,12 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         const int64_t a0 = byte0 - pad;       // the chunk's device buffer starts at this absolute position
         Lane &l = c->lanes[lane_idx];
         lane_idx = (lane_idx + 1) % n_lanes;
-        if ((rc = lane_finish(c, l)) != CG_OK) break;
+        {
+            const clk::time_point t0 = clk::now();
+            rc = lane_finish(c, l);
+            c->prof[3] += secs(t0, clk::now());
+            if (rc != CG_OK) break;
+        }
         if (want_q && (rc = l.d_qual.ensure((size_t)nbytes + 64)) != CG_OK) break;
         if ((rc = l.d_offs.ensure((size_t)nr + 1)) != CG_OK) break;
         if ((rc = l.d_out.ensure((size_t)nr * rec_per_read)) != CG_OK) break;
@@ -801,10 +814,12 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
             for (auto &v : c->exc_scratch) v.clear();
             const int64_t JOB = 1 << 16;
             uint8_t *h_pack = l.h_pack.p;
+            const clk::time_point t_pack0 = clk::now();
             c->pool->run((n_stream + JOB - 1) / JOB, [&](int64_t j, int w) {
                 cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), h_pack,
                                c->exc_scratch[(size_t)w]);
             });
+            c->prof[2] += secs(t_pack0, clk::now());
             size_t n_exc = 0;
             for (auto &v : c->exc_scratch) n_exc += v.size();
             if ((int64_t)n_exc * 16 <= span) {   // mostly A/C/G/T/N: send the stream, else the raw bytes
@@ -894,12 +909,23 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         l.busy = true;
         r0 = r1;
     }
+    const clk::time_point t_drain0 = clk::now();
     for (int i = 0; i < CG_N_LANES; ++i) {
         int rc2 = lane_finish(c, c->lanes[i]);
         if (rc == CG_OK) rc = rc2;
     }
+    c->prof[4] += secs(t_drain0, clk::now());
+    c->prof[0] += secs(t_begin, clk::now());
     if (rc != CG_OK) return rc;
     return check_err_flag(c);
+}
+
+extern "C" int cg_ctx_host_profile(cg_ctx *c, double *out, int reset)
+{
+    if (!c || !out) return fail(CG_EINVAL, "cg_ctx_host_profile: NULL argument");
+    for (int i = 0; i < 8; ++i) out[i] = c->prof[i];
+    if (reset) for (int i = 0; i < 8; ++i) c->prof[i] = 0.0;
+    return CG_OK;
 }
 
 extern "C" int cg_ctx_transfer_bytes(cg_ctx *c, int64_t *h2d, int64_t *d2h, int reset)
@@ -1209,7 +1235,9 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
     if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(n) + 1)) != CG_OK) return rc;
     if (want_q && (rc = f.d_qtrim.ensure((size_t)n * 2)) != CG_OK) return rc;
     CU(cg_launch_fastq_index(f.d_in.p, n_bytes, f.d_tiles.p, nullptr, f.d_nl.p, 1, st));
-    CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, n_nl, n, f.d_rec.p, f.d_len.p, f.d_err, st));
+    if (fp->cut_front < 0 || fp->cut_back < 0) return fail(CG_EINVAL, "cg_fastq_collect: cut_front / cut_back must be >= 0");
+    CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, n_nl, n, fp->cut_front, fp->cut_back, f.d_rec.p, f.d_len.p,
+                               f.d_err, st));
     c->launches += 2;
     int32_t *d_qtrim = want_q ? f.d_qtrim.p : nullptr;
     const cg_match_rec *d_matches = nullptr;
@@ -1249,6 +1277,10 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
         flt.discard_untrimmed = fp->discard_untrimmed;
         flt.max_n = fp->max_n;
         flt.max_ee = fp->max_expected_errors;
+        flt.poly_a = fp->poly_a;
+        flt.shorten = !fp->shorten ? 0 : (fp->shorten_length >= 0 ? fp->shorten_length + 1 : fp->shorten_length);
+        flt.trim_n = fp->trim_n;
+        flt.discard_casava = fp->discard_casava;
         CU(cg_launch_fastq_outlen(f.d_in.p, f.d_rec.p, f.d_len.p, n, d_matches, times, slots, d_qtrim, flt, c->d_phred,
                                   f.d_interval.p, f.d_outlen.p, f.d_counters + 1, f.d_err, st));
         CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
@@ -1266,6 +1298,7 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
         res->with_adapters = (int64_t)k[3]; res->too_short = (int64_t)k[4]; res->too_long = (int64_t)k[5];
         res->quality_trimmed_bp = (int64_t)k[6]; res->discarded = (int64_t)k[7]; res->too_many_n = (int64_t)k[8];
         res->too_many_expected_errors = (int64_t)k[9];
+        res->casava_filtered = (int64_t)k[10];
         res->out_bytes = total;
         if (total > out_capacity)
             return fail(CG_EINVAL, "cg_fastq_collect: output buffer too small (" + std::to_string(total) + " bytes needed)");

@@ -135,8 +135,11 @@ __device__ __forceinline__ void line_span(const uint8_t *buf, const uint32_t *nl
 }
 
 // record r = lines 4r .. 4r+3.  Checks what dnaio's parser checks (first characters, equal lengths).
+// cut_front / cut_back: UnconditionalCutter (-u, modifiers.py:66-95), the first modifier of the chain: the
+// record table simply describes the read without those bases.
 __global__ void fq_records_kernel(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl,
-                                  long long n_records, CgFastqRecord *rec, int32_t *seq_len, int *err)
+                                  long long n_records, int cut_front, int cut_back, CgFastqRecord *rec,
+                                  int32_t *seq_len, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_records) return;
@@ -154,13 +157,17 @@ __global__ void fq_records_kernel(const uint8_t *buf, long long n, const uint32_
         atomicMin((unsigned int *)&err[1], (unsigned int)r);
         atomicMax(&err[0], bad);
     }
+    int len = bad ? 0 : (int32_t)(se - ss);
+    const int cf = cut_front < len ? cut_front : len;      // read[cut_front:]
+    len -= cf;
+    len = cut_back < len ? len - cut_back : 0;             // read[:-cut_back]
     CgFastqRecord o;
     o.hdr_start = hs + 1;                       // without the '@'
     o.hdr_len = (int32_t)(he - hs) - 1;
-    o.seq_start = ss;
-    o.qual_start = qs;
+    o.seq_start = ss + (uint32_t)cf;
+    o.qual_start = qs + (uint32_t)cf;
     rec[r] = o;
-    seq_len[r] = bad ? 0 : (int32_t)(se - ss);
+    seq_len[r] = len;
 }
 
 // ---- exclusive scan int32 -> int64 (n+1 outputs), any n: tile sums, one-CTA scan of the sums, apply ----
@@ -290,7 +297,7 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long c_written = 0, c_bp_out = 0, c_short = 0, c_long = 0, c_adapt = 0, c_bp_in = 0, c_qbp = 0,
-                       c_dis = 0, c_n = 0, c_ee = 0;
+                       c_dis = 0, c_n = 0, c_ee = 0, c_cas = 0;
     if (r < n_records) {
         const int n = seq_len[r];
         int start = 0, stop = n;
@@ -306,6 +313,20 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
                     if ((m.info >> 8) & 1) stop = start + m.rstart;    // RemoveAfterMatch
                     else start = start + m.rstop;                      // RemoveBeforeMatch
                 }
+        }
+        const uint8_t *sq0 = buf + rec[r].seq_start;
+        if (f.poly_a)                                      // PolyATrimmer (modifiers.py:861-879): read[:index]
+            stop = start + poly_a_trim_core(sq0 + start, stop - start, 0);
+        if (f.shorten > 0) {                               // Shortener (modifiers.py:882-899): read[:length]
+            if (stop - start > f.shorten - 1) stop = start + (f.shorten - 1);
+        } else if (f.shorten < 0) {                        //                                   read[length:]
+            if (stop - start > -f.shorten) start = stop + f.shorten;
+        }
+        if (f.trim_n) {                                    // NEndTrimmer (modifiers.py:902-918): upper-case N only
+            int a = start, b = stop;
+            while (a < stop && sq0[a] == 'N') ++a;
+            while (b > start && sq0[b - 1] == 'N') --b;
+            start = a; stop = b < a ? a : b;
         }
         const int left = stop - start;
         int keep = 1;
@@ -326,8 +347,16 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
             if (ee < 0.0) { atomicMin((unsigned int *)&err[1], (unsigned int)r); atomicMax(&err[0], 4); }
             else if (ee > f.max_ee) { keep = 0; c_ee = 1; }
         }
-        else if (f.discard_trimmed && matched) { keep = 0; c_dis = 1; }
-        else if (f.discard_untrimmed && !matched) { keep = 0; c_dis = 1; }
+        if (keep && f.discard_casava) {
+            // CasavaFiltered (predicates.py:125-139): name.partition(" ")[2][1:4] == ":Y:"
+            const uint8_t *h = buf + rec[r].hdr_start;
+            const int hl = rec[r].hdr_len;
+            int sp = 0;
+            while (sp < hl && h[sp] != ' ') ++sp;
+            if (sp + 4 < hl && h[sp + 2] == ':' && h[sp + 3] == 'Y' && h[sp + 4] == ':') { keep = 0; c_cas = 1; }
+        }
+        // the final sink: DiscardTrimmed / DiscardUntrimmed (predicates.py:142-175)
+        if (keep && ((f.discard_trimmed && matched) || (f.discard_untrimmed && !matched))) { keep = 0; c_dis = 1; }
         interval[2 * r] = start;
         interval[2 * r + 1] = stop;
         // "@" header "\n" sequence "\n+\n" qualities "\n"
@@ -342,6 +371,7 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
     c_dis = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_dis);
     c_n = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_n);
     c_ee = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_ee);
+    c_cas = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_cas);
     for (int d = 16; d; d >>= 1) {
         c_bp_out += __shfl_down_sync(0xFFFFFFFFu, c_bp_out, d);
         c_bp_in += __shfl_down_sync(0xFFFFFFFFu, c_bp_in, d);
@@ -358,6 +388,7 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
         if (c_dis) atomicAdd(&counters[7], c_dis);
         if (c_n) atomicAdd(&counters[8], c_n);
         if (c_ee) atomicAdd(&counters[9], c_ee);
+        if (c_cas) atomicAdd(&counters[10], c_cas);
     }
 }
 
@@ -407,12 +438,12 @@ cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint3
 }
 
 cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
-                                    long long n_records, CgFastqRecord *d_rec, int32_t *d_seq_len, int *d_err,
-                                    cudaStream_t st)
+                                    long long n_records, int cut_front, int cut_back, CgFastqRecord *d_rec,
+                                    int32_t *d_seq_len, int *d_err, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_records_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, n_bytes, d_nl_pos, n_newlines, n_records,
-                                                                          d_rec, d_seq_len, d_err);
+                                                                          cut_front, cut_back, d_rec, d_seq_len, d_err);
     return cudaGetLastError();
 }
 

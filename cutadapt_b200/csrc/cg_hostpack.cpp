@@ -35,8 +35,8 @@ CgHostPool::~CgHostPool()
 {
     {
         std::lock_guard<std::mutex> lk(mu_);
-        stop_ = true;
-        ++generation_;
+        stop_.store(true, std::memory_order_release);
+        generation_.fetch_add(1, std::memory_order_release);
     }
     cv_start_.notify_all();
     for (auto &t : workers_) t.join();
@@ -46,25 +46,25 @@ void CgHostPool::worker_main(int id)
 {
     uint64_t seen = 0;
     for (;;) {
-        const std::function<void(int64_t, int)> *fn;
-        int64_t n_jobs;
-        {
+        // wait for the next job set: spin first (about a millisecond), then sleep
+        int spins = 0;
+        while (generation_.load(std::memory_order_acquire) == seen) {
+            if (++spins < 20000) { CG_CPU_RELAX(); continue; }
             std::unique_lock<std::mutex> lk(mu_);
-            cv_start_.wait(lk, [&] { return generation_ != seen; });
-            seen = generation_;
-            if (stop_) return;
-            fn = fn_;
-            n_jobs = n_jobs_;
+            sleepers_.fetch_add(1);   // seq_cst: pairs with run()'s generation_++ / sleepers_ read
+            cv_start_.wait(lk, [&] { return generation_.load() != seen; });
+            sleepers_.fetch_sub(1, std::memory_order_acq_rel);
         }
+        seen = generation_.load(std::memory_order_acquire);
+        if (stop_.load(std::memory_order_acquire)) return;
+        const std::function<void(int64_t, int)> *fn = fn_;
+        const int64_t n_jobs = n_jobs_.load(std::memory_order_acquire);
         for (;;) {
             const int64_t j = next_.fetch_add(1, std::memory_order_relaxed);
             if (j >= n_jobs) break;
             (*fn)(j, id);
         }
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            if (--active_ == 0) cv_done_.notify_one();
-        }
+        pending_.fetch_sub(1, std::memory_order_acq_rel);
     }
 }
 
@@ -75,22 +75,26 @@ void CgHostPool::run(int64_t n_jobs, const std::function<void(int64_t, int)> &fn
         for (int64_t j = 0; j < n_jobs; ++j) fn(j, 0);
         return;
     }
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        fn_ = &fn;
-        n_jobs_ = n_jobs;
-        next_.store(0, std::memory_order_relaxed);
-        active_ = (int)workers_.size();
-        ++generation_;
+    fn_ = &fn;
+    n_jobs_.store(n_jobs, std::memory_order_relaxed);
+    next_.store(0, std::memory_order_relaxed);
+    pending_.store((int)workers_.size(), std::memory_order_relaxed);
+    generation_.fetch_add(1);                                  // publishes the job set (seq_cst)
+    if (sleepers_.load() > 0) {
+        { std::lock_guard<std::mutex> lk(mu_); }
+        cv_start_.notify_all();
     }
-    cv_start_.notify_all();
     for (;;) {
         const int64_t j = next_.fetch_add(1, std::memory_order_relaxed);
         if (j >= n_jobs) break;
         fn(j, 0);
     }
-    std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return active_ == 0; });
+    // every worker checks in (it may still be inside its last job)
+    int spins = 0;
+    while (pending_.load(std::memory_order_acquire) != 0) {
+        if (++spins < 4000) CG_CPU_RELAX();
+        else std::this_thread::yield();
+    }
     fn_ = nullptr;
 }
 

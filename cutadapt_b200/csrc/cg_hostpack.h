@@ -27,16 +27,20 @@ public:
     void run(int64_t n_jobs, const std::function<void(int64_t job, int worker)> &fn);
 
 private:
+    // Workers spin on `generation_` for a while after a job set (the calls of one cg_process_batch come
+    // back to back) and only then go to sleep on the condition variable: waking 60 sleeping threads
+    // through a mutex costs more than packing a chunk.
     void worker_main(int id);
     std::vector<std::thread> workers_;
     std::mutex mu_;
-    std::condition_variable cv_start_, cv_done_;
+    std::condition_variable cv_start_;
     const std::function<void(int64_t, int)> *fn_ = nullptr;
     std::atomic<int64_t> next_{0};
-    int64_t n_jobs_ = 0;
-    uint64_t generation_ = 0;
-    int active_ = 0;
-    bool stop_ = false;
+    std::atomic<int64_t> n_jobs_{0};
+    std::atomic<uint64_t> generation_{0};
+    std::atomic<int> pending_{0};
+    std::atomic<int> sleepers_{0};
+    std::atomic<bool> stop_{false};
 };
 
 int cg_host_threads_default();

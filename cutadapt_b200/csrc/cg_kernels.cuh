@@ -110,17 +110,21 @@ struct CgFastqFilter {
     int discard_trimmed, discard_untrimmed;
     double max_n;            // < 0 = off; < 1: proportion of the length
     double max_ee;           // < 0 = off
+    int poly_a;              // PolyATrimmer after the adapter rounds
+    int shorten;             // Shortener: 0 = off, L + 1 for --length L >= 0, L for --length L < 0
+    int trim_n;              // NEndTrimmer
+    int discard_casava;      // CasavaFiltered
 };
 #define CG_FQ_COUNTERS 16    // written, bp_in, bp_out, with_adapters, too_short, too_long, quality_trimmed_bp,
-                             // discarded (trimmed/untrimmed), too_many_n, too_many_expected_errors
+                             // discarded (trimmed/untrimmed), too_many_n, too_many_expected_errors, casava_filtered
 long long cg_fastq_tiles(long long n_bytes);
 long long cg_scan_tiles(long long n);
 // phase 0: newline count per tile + exclusive scan (total -> *d_total); phase 1: positions of the newlines
 cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint32_t *d_tile_counts,
                                   unsigned long long *d_total, uint32_t *d_nl_pos, int phase, cudaStream_t st);
 cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
-                                    long long n_records, CgFastqRecord *d_rec, int32_t *d_seq_len, int *d_err,
-                                    cudaStream_t st);
+                                    long long n_records, int cut_front, int cut_back, CgFastqRecord *d_rec,
+                                    int32_t *d_seq_len, int *d_err, cudaStream_t st);
 // exclusive scan int32 -> int64, n + 1 outputs; d_tile_scratch: cg_scan_tiles(n) words
 cudaError_t cg_launch_scan_i32(const int32_t *d_in, long long n, unsigned long long *d_tile_scratch, int64_t *d_out,
                                cudaStream_t st);

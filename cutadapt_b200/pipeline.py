@@ -189,6 +189,9 @@ class FastqTrimmer:
     minimum_length, maximum_length   -m / -M                                 (predicates.py:29-53)
     max_n, max_expected_errors       --max-n / --max-ee                      (predicates.py:56-122)
     discard_trimmed, discard_untrimmed                                       (predicates.py:127-160)
+    cut                 -u values (UnconditionalCutter, modifiers.py:66-95), applied first
+    poly_a, length, trim_n           --poly-a / --length / --trim-n, after the adapters (modifiers.py:861-918)
+    discard_casava      --discard-casava                                     (predicates.py:125-139)
 
     ``process_chunk(bytes) -> bytes``; ``process_chunks(iterable)`` keeps one chunk in flight so that the
     upload of chunk i+1 overlaps the download of chunk i.  ``statistics`` accumulates the counters of
@@ -200,7 +203,9 @@ class FastqTrimmer:
                  quality_base: int = 33, nextseq_cutoff: Optional[int] = None, minimum_length: int = 0,
                  maximum_length: Optional[int] = None, max_n: Optional[float] = None,
                  max_expected_errors: Optional[float] = None, discard_trimmed: bool = False,
-                 discard_untrimmed: bool = False, ctx: Optional[_lib.Context] = None):
+                 discard_untrimmed: bool = False, cut: Sequence[int] = (), poly_a: bool = False,
+                 length: Optional[int] = None, trim_n: bool = False, discard_casava: bool = False,
+                 ctx: Optional[_lib.Context] = None):
         if adapters is not None and not isinstance(adapters, Matchable):
             adapters = MultipleAdapters(list(adapters)) if len(adapters) else None
         self.adapters = adapters
@@ -222,6 +227,14 @@ class FastqTrimmer:
         fp.max_expected_errors = -1.0 if max_expected_errors is None else float(max_expected_errors)
         fp.discard_trimmed = int(bool(discard_trimmed))
         fp.discard_untrimmed = int(bool(discard_untrimmed))
+        # -u N removes N bases from the 5' end, -u -N from the 3' end; several values add up per end
+        fp.cut_front = sum(int(c) for c in cut if c > 0)
+        fp.cut_back = sum(-int(c) for c in cut if c < 0)
+        fp.poly_a = int(bool(poly_a))
+        fp.shorten = int(length is not None)
+        fp.shorten_length = int(length or 0)
+        fp.trim_n = int(bool(trim_n))
+        fp.discard_casava = int(bool(discard_casava))
         self.params = fp
         self.statistics = {}
 

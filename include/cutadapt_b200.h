@@ -175,6 +175,12 @@ int cg_ctx_kernel_time(cg_ctx *ctx, double *total_ms, int64_t *launches, int res
  * crossed PCIe: the compressed read stream + exceptions, qualities, irregular offsets; the records back). */
 int cg_ctx_transfer_bytes(cg_ctx *ctx, int64_t *h2d, int64_t *d2h, int reset);
 
+/* Where the host side of cg_process_batch spent its time, in seconds, accumulated over calls:
+ * out[0] total, [1] scanning the offsets, [2] packing reads for the compressed transfer, [3] waiting for a
+ * free lane (= the device or PCIe is the bottleneck), [4] draining the lanes at the end, [5] chunks;
+ * out must hold 8 doubles. */
+int cg_ctx_host_profile(cg_ctx *ctx, double *out, int reset);
+
 /* ---- adapter set (replaces Aligner.__cinit__/_set_reference _align.pyx:195-277 and
  *      KmerFinder.__cinit__ _kmer_finder.pyx:106-165 for every adapter at once) ----------- */
 int cg_adapterset_create(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n_adapters,
@@ -253,9 +259,10 @@ int cg_poly_a_trim_batch(cg_ctx *ctx, const uint8_t *seq, const int64_t *offsets
 /* ---- FASTQ chunks in, trimmed FASTQ out ---------------------------------
  * The per-chunk worker of the reference as one call: WorkerProcess.run (runners.py:174-214) parses a chunk of
  * complete 4-line records (dnaio.read_chunks, runners.py:116-126), runs the modifiers per read
- * (pipeline.py:47-73: NextseqQualityTrimmer, QualityTrimmer, AdapterCutter with action "trim"), the filters
- * (TooShort, TooLong, TooManyN, TooManyExpectedErrors, then DiscardTrimmed / DiscardUntrimmed:
- * predicates.py:29-160 in the order of cli.py:700-830) and formats the surviving records
+ * (pipeline.py:47-73, in the order cli.py:937-975 builds them: UnconditionalCutter, NextseqQualityTrimmer,
+ * QualityTrimmer, AdapterCutter with action "trim", PolyATrimmer, Shortener, NEndTrimmer), the filters
+ * (TooShort, TooLong, TooManyN, TooManyExpectedErrors, CasavaFiltered, then DiscardTrimmed /
+ * DiscardUntrimmed: predicates.py:29-160 in the order of cli.py:700-830) and formats the surviving records
  * ("@name\nsequence\n+\nqualities\n", SingleEndSink steps.py:299-319).  Here the chunk is indexed, packed,
  * trimmed, filtered and formatted on the device; it crosses PCIe once in each direction.
  * "\r\n" line ends are accepted (and written back as "\n", like dnaio). */
@@ -267,15 +274,22 @@ typedef struct cg_fastq_params {
     int32_t discard_untrimmed;   /* --discard-untrimmed                                               */
     double max_n;                /* --max-n; negative = off; below 1: proportion of the read length   */
     double max_expected_errors;  /* --max-ee; negative = off                                          */
-    int32_t reserved[4];
+    int32_t cut_front, cut_back; /* -u N / -u -N (UnconditionalCutter, modifiers.py:66-95): bases removed from
+                                    the 5' / 3' end before anything else; both >= 0                    */
+    int32_t poly_a;              /* --poly-a (PolyATrimmer, modifiers.py:861-879), after the adapters */
+    int32_t shorten;             /* 1 = --length given (Shortener, modifiers.py:882-899) ...          */
+    int32_t shorten_length;      /* ... its value: >= 0 keeps read[:L], < 0 keeps read[L:]            */
+    int32_t trim_n;              /* --trim-n (NEndTrimmer, modifiers.py:902-918)                      */
+    int32_t discard_casava;      /* --discard-casava (CasavaFiltered, predicates.py:125-139)          */
+    int32_t reserved[5];
 } cg_fastq_params;
 typedef struct cg_fastq_result {
     int64_t n_records, n_written;
     int64_t bp_in, bp_out;       /* bases read / bases written                                        */
     int64_t out_bytes;           /* size of the formatted output                                      */
     int64_t with_adapters, quality_trimmed_bp;
-    int64_t too_short, too_long, too_many_n, too_many_expected_errors, discarded;
-    int64_t reserved[4];
+    int64_t too_short, too_long, too_many_n, too_many_expected_errors, discarded, casava_filtered;
+    int64_t reserved[3];
 } cg_fastq_result;
 /* set may be NULL: quality trimming and filters only.  fastq / out: HOST pointers (pinned or pageable).
  * Errors: CG_EINVAL for malformed FASTQ (message names the record), a too small output buffer (out_bytes in

@@ -346,11 +346,14 @@ def parse_fastq(data: bytes):
 
 def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=False, cutoff_front=0, cutoff_back=0,
                       quality_base=33, times=1, nextseq_cutoff=None, minimum_length=0, maximum_length=-1,
-                      discard_trimmed=False, discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0):
+                      discard_trimmed=False, discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0,
+                      cut=(), poly_a=False, length=None, trim_n=False, discard_casava=False):
     """(output bytes, counters dict).  Modifiers as oracle_process; then the filters in the order cli.py:700-830
     appends them: TooShort, TooLong, TooManyN, TooManyExpectedErrors (predicates.py:29-122), and finally
     DiscardTrimmed / DiscardUntrimmed (predicates.py:127-160)."""
     records = parse_fastq(data)
+    for c_len in cut:                                   # UnconditionalCutter, first in the chain (modifiers.py:66-95)
+        records = [(nm, sq[c_len:], q[c_len:]) if c_len > 0 else (nm, sq[:c_len], q[:c_len]) for nm, sq, q in records]
     seqs = [r[1] for r in records]
     quals = [r[2] for r in records]
     n = len(records)
@@ -369,7 +372,7 @@ def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=Fals
             qtrim[i] = (s, e)
     out = []
     c = dict(n_records=n, n_written=0, bp_in=0, bp_out=0, with_adapters=0, quality_trimmed_bp=0, too_short=0,
-             too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0)
+             too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0, casava_filtered=0)
     for i, (name, seq, q) in enumerate(records):
         s, e = int(qtrim[i, 0]), int(qtrim[i, 1])
         c["bp_in"] += len(seq)
@@ -388,6 +391,15 @@ def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=Fals
                         s = s + int(m["rstop"])
         c["with_adapters"] += matched
         ts, tq = seq[s:e], q[s:e]
+        if poly_a:                                      # PolyATrimmer (modifiers.py:861-879)
+            idx = poly_a_trim_index(ts)
+            ts, tq = ts[:idx], tq[:idx]
+        if length is not None:                          # Shortener (modifiers.py:882-899)
+            ts, tq = (ts[:length], tq[:length]) if length >= 0 else (ts[length:], tq[length:])
+        if trim_n:                                      # NEndTrimmer (modifiers.py:902-918): upper-case N only
+            a = len(ts) - len(ts.lstrip("N"))
+            b = len(ts.rstrip("N"))
+            ts, tq = ts[a:b], tq[a:b]
         if minimum_length > 0 and len(ts) < minimum_length:
             c["too_short"] += 1
             continue
@@ -401,6 +413,9 @@ def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=Fals
                 continue
         if max_expected_errors >= 0 and expected_errors(tq) > max_expected_errors:
             c["too_many_expected_errors"] += 1
+            continue
+        if discard_casava and name.partition(" ")[2][1:4] == ":Y:":     # predicates.py:125-139
+            c["casava_filtered"] += 1
             continue
         if (discard_trimmed and matched) or (discard_untrimmed and not matched):
             c["discarded"] += 1

@@ -50,6 +50,14 @@ CASES = [
      dict(adapters=[["back", "CAGTGGAGTA"]])),
     ("front_empty", 790, "-g CWC", "empty.fastq", "empty.fastq",
      dict(adapters=[["front", "CWC"]])),
+    ("unconditional_front", 502, "-u 5", "small.fastq", "unconditional-front.fastq", dict(adapters=[], cut=[5])),
+    ("unconditional_back", 506, "-u -5", "small.fastq", "unconditional-back.fastq", dict(adapters=[], cut=[-5])),
+    ("unconditional_both", 510, "-u -5 -u 5", "small.fastq", "unconditional-both.fastq",
+     dict(adapters=[], cut=[-5, 5])),
+    ("shortened", 738, "--length 5", "small.fastq", "shortened.fastq", dict(adapters=[], length=5)),
+    ("shortened_negative", 742, "--length -5", "small.fastq", "shortened-negative.fastq",
+     dict(adapters=[], length=-5)),
+    ("casava", 770, "--discard-casava", "casava.fastq", "casava.fastq", dict(adapters=[], discard_casava=True)),
     ("maxee", 838, "--max-ee=0.9", "maxee.fastq", "maxee.fastq",
      dict(adapters=[], max_expected_errors=0.9)),
 ]

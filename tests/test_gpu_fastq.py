@@ -60,6 +60,12 @@ def synthetic_fastq(n, seed, crlf=False, final_newline=True):
             seq = (seq[:cut] + adapter + seq)[:ln]
         if rng.random() < 0.05 and ln:
             seq = "".join(c if rng.random() > 0.2 else "N" for c in seq)
+        if rng.random() < 0.1 and ln > 20:
+            tail = rng.randrange(3, 20)
+            seq = seq[:ln - tail] + "".join("A" if rng.random() < 0.93 else "C" for _ in range(tail))
+        if rng.random() < 0.1 and ln > 10:
+            a, b = rng.randrange(0, 4), rng.randrange(0, 4)
+            seq = ("N" * a + seq[a:ln - b] + "N" * b)[:ln]
         if rng.random() < 0.02:
             seq = seq.lower()
         qual = "".join(chr(33 + min(41, max(2, int(rng.gauss(32 - 25 * (j / max(ln, 1)) ** 2, 6))))) for j in range(ln))
@@ -74,7 +80,8 @@ def synthetic_fastq(n, seed, crlf=False, final_newline=True):
     return data.encode()
 
 
-@pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "filters", "quality_only", "times2"])
+@pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "filters", "quality_only", "times2",
+                                     "modifiers", "modifiers2"])
 def test_random_chunks_against_oracle(variant):
     options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20])
     extra = {}
@@ -87,6 +94,11 @@ def test_random_chunks_against_oracle(variant):
         extra = dict(minimum_length=1, max_n=3)
     elif variant == "times2":
         extra = dict(times=2, discard_trimmed=False)
+    elif variant == "modifiers":
+        extra = dict(cut=[3, -2], poly_a=True, length=-90, trim_n=True, discard_casava=True, minimum_length=1)
+    elif variant == "modifiers2":
+        options = dict(adapters=[["anywhere", "AGATCGGAAGAGC"]])
+        extra = dict(cut=[-4, -3, 2], poly_a=True, length=60, trim_n=True, max_n=0, discard_trimmed=True)
     t = trimmer_for(options, **extra)
     got = t.process_chunk(data)
     exp, counters = oracle_for(options, data, **extra)

@@ -171,7 +171,8 @@ def fastq_case_kwargs(options):
     if "quality_cutoff" in options:
         kw.update(quality_trim=True, cutoff_front=options["quality_cutoff"][0], cutoff_back=options["quality_cutoff"][1])
     for k in ("quality_base", "nextseq_cutoff", "max_expected_errors", "discard_trimmed", "discard_untrimmed",
-              "minimum_length", "maximum_length", "max_n", "times"):
+              "minimum_length", "maximum_length", "max_n", "times", "cut", "poly_a", "length", "trim_n",
+              "discard_casava"):
         if k in options:
             kw[k] = options[k]
     return kw
