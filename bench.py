@@ -336,8 +336,10 @@ def main():
         h_out = torch.empty((hw, 8), dtype=torch.int32, pin_memory=True)
         # worker threads of the library's host side (packing for the compressed transfer): this rank's
         # share of the host cores
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
-        os.environ.setdefault("CUTADAPT_B200_HOST_THREADS", str(max(2, min(64, cores // max(world, 1)))))
+        if world > 1:
+            os.environ.setdefault("CUTADAPT_B200_HOST_THREADS",
+                                  str(max(2, min(32, _lib.lib().cg_host_cpus_available() // world))))
+        host_threads = int(_lib.lib().cg_host_threads())
         host_ctx = _lib.Context(local_rank)
         host_set = _lib.AdapterSet(batch.spec, host_ctx)
         params = batch.params
@@ -362,6 +364,7 @@ def main():
         barrier()
         raw_wall = time.perf_counter() - t0
         os.environ["CUTADAPT_B200_H2D_PACK"] = "1"
+        e2e_step()             # lets the compressed share of the transfer settle
         e2e_step()
         barrier()
         host_ctx.transfer_bytes(reset=True)
@@ -385,7 +388,7 @@ def main():
                # regenerated on the device from (first offset, length)
                "h2d_bytes_per_step": h2d_bytes // e2e_steps, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                "steps": e2e_steps, "launches": host_ctx.launch_count() - l0,
-               "host_threads": int(os.environ["CUTADAPT_B200_HOST_THREADS"]),
+               "host_threads": host_threads, "host_cpus_available": int(_lib.lib().cg_host_cpus_available()),
                "host_profile": {k: (round(v, 4) if isinstance(v, float) else v)
                                 for k, v in host_ctx.host_profile().items()},
                "raw_transfer_value": n * world / raw_wall,

@@ -419,7 +419,8 @@ class Context:
         out = (C.c_double * 8)()
         check(lib().cg_ctx_host_profile(self._h, out, int(reset)))
         return {"total_s": out[0], "offset_scan_s": out[1], "pack_s": out[2], "lane_wait_s": out[3],
-                "drain_s": out[4], "chunks": int(out[5])}
+                "drain_s": out[4], "chunks": int(out[5]), "packed_characters": int(out[6]),
+                "pack_fraction": out[7]}
 
     def transfer_bytes(self, reset: bool = False) -> Tuple[int, int]:
         """Bytes cg_process_batch moved host->device and device->host on this context."""

@@ -146,6 +146,7 @@ struct cg_ctx {
     std::vector<std::vector<uint64_t>> exc_scratch;
     long long h2d_bytes = 0, d2h_bytes = 0;
     double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cg_ctx_host_profile
+    double pack_fraction = 0.6;                  // share of a chunk that travels compressed (adapted)
     // ordering of the trimming passes of different lanes over the shared scratch
     cudaEvent_t scratch_ev = nullptr;
     cudaStream_t scratch_stream = nullptr;
@@ -675,6 +676,8 @@ extern "C" int cg_process_batch_device(cg_ctx *c, const cg_adapterset *s, const 
 // ------------------------------------------------------------------------------------------
 // Host batches: 2-lane pipeline
 // ------------------------------------------------------------------------------------------
+static void parallel_copy(cg_ctx *c, void *dst, const void *src, size_t n);
+
 static bool is_pinned(const void *p)
 {
     if (!p) return false;
@@ -730,10 +733,13 @@ static OffsetScan scan_offsets(cg_ctx *c, const int64_t *offsets, int64_t r0, in
     return t;
 }
 
-static bool h2d_pack_enabled()
+// CUTADAPT_B200_H2D_PACK: "0" = raw bytes only, "all" = everything compressed, otherwise adaptive
+static int h2d_pack_mode()
 {
     const char *e = getenv("CUTADAPT_B200_H2D_PACK");
-    return !(e && e[0] == '0');
+    if (e && e[0] == '0') return 0;
+    if (e && strcmp(e, "all") == 0) return 2;
+    return 1;
 }
 
 extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
@@ -756,7 +762,8 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
 
     // Large batches travel compressed (three characters per byte, cg_hostpack.h): PCIe, not the
     // kernels, bounds this entry point.  Small ones are not worth waking the worker pool for.
-    const bool pack = h2d_pack_enabled() && n_reads >= (1 << 16);
+    const int pack_mode = h2d_pack_mode();
+    const bool pack = pack_mode != 0 && n_reads >= (1 << 16);
     if (pack && !c->pool) {
         c->pool = new CgHostPool(cg_host_threads_default());
         c->exc_scratch.resize((size_t)c->pool->size());
@@ -765,7 +772,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     const int64_t CHUNK_READS = pack ? (1 << 20) : (1 << 18);
     const int64_t CHUNK_BYTES = pack ? (192LL << 20) : (48LL << 20);
     int64_t r0 = 0;
-    int lane_idx = 0;
+    int lane_idx = 0, n_chunk = 0;
     int rc = CG_OK;
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -794,10 +801,12 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         const int64_t a0 = byte0 - pad;       // the chunk's device buffer starts at this absolute position
         Lane &l = c->lanes[lane_idx];
         lane_idx = (lane_idx + 1) % n_lanes;
+        double lane_wait_s = 0.0;
         {
             const clk::time_point t0 = clk::now();
             rc = lane_finish(c, l);
-            c->prof[3] += secs(t0, clk::now());
+            lane_wait_s = secs(t0, clk::now());
+            c->prof[3] += lane_wait_s;
             if (rc != CG_OK) break;
         }
         if (want_q && (rc = l.d_qual.ensure((size_t)nbytes + 64)) != CG_OK) break;
@@ -805,56 +814,76 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         if ((rc = l.d_out.ensure((size_t)nr * rec_per_read)) != CG_OK) break;
         if (qtrim && (rc = l.d_qtrim.ensure((size_t)nr * 2)) != CG_OK) break;
         // ---- H2D of the sequences ----
-        bool packed_ok = false;
+        // The first `packed_bytes` of the chunk's buffer travel as the compressed stream, the rest raw: packing
+        // costs host time, raw bytes cost PCIe time, and the split (c->pack_fraction) follows whichever of the
+        // two was the bottleneck for the previous chunks (see the feedback rule below).
+        int64_t packed_bytes = 0;       // characters [a0, a0 + packed_bytes) arrive through the stream
+        double pack_s = 0.0;
         if (pack && nbytes > 0) {
             const int64_t span = offsets[r1] - a0;
-            const int64_t n_stream = ((span + 2) / 3 + 15) / 16 * 16;
-            if ((rc = l.h_pack.ensure((size_t)n_stream)) != CG_OK) break;
-            const int64_t lo = std::max(a0, offsets[0]), hi = offsets[r1];
-            for (auto &v : c->exc_scratch) v.clear();
-            const int64_t JOB = 1 << 16;
-            uint8_t *h_pack = l.h_pack.p;
-            const clk::time_point t_pack0 = clk::now();
-            c->pool->run((n_stream + JOB - 1) / JOB, [&](int64_t j, int w) {
-                cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), h_pack,
-                               c->exc_scratch[(size_t)w]);
-            });
-            c->prof[2] += secs(t_pack0, clk::now());
-            size_t n_exc = 0;
-            for (auto &v : c->exc_scratch) n_exc += v.size();
-            if ((int64_t)n_exc * 16 <= span) {   // mostly A/C/G/T/N: send the stream, else the raw bytes
-                if ((rc = l.d_pack.ensure((size_t)n_stream)) != CG_OK) break;
-                if ((rc = l.d_seq.ensure((size_t)n_stream * 3 + 64)) != CG_OK) break;
-                if (n_exc) {
-                    if ((rc = l.h_exc.ensure(n_exc)) != CG_OK) break;
-                    if ((rc = l.d_exc.ensure(n_exc)) != CG_OK) break;
-                    size_t k = 0;
-                    for (auto &v : c->exc_scratch) {
-                        if (!v.empty()) memcpy(l.h_exc.p + k, v.data(), v.size() * sizeof(uint64_t));
-                        k += v.size();
+            const bool all = pack_mode == 2 || c->pack_fraction >= 0.999 || span < (1 << 20);
+            int64_t n_stream = all ? ((span + 2) / 3 + 15) / 16 * 16
+                                   : (int64_t)(c->pack_fraction * (double)span / 48.0) * 16;
+            if (n_stream > 0) {
+                if ((rc = l.h_pack.ensure((size_t)n_stream)) != CG_OK) break;
+                const int64_t lo = std::max(a0, offsets[0]), hi = offsets[r1];
+                for (auto &v : c->exc_scratch) v.clear();
+                const int64_t JOB = 1 << 16;
+                uint8_t *h_pack = l.h_pack.p;
+                const clk::time_point t_pack0 = clk::now();
+                c->pool->run((n_stream + JOB - 1) / JOB, [&](int64_t j, int w) {
+                    cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), h_pack,
+                                   c->exc_scratch[(size_t)w]);
+                });
+                pack_s = secs(t_pack0, clk::now());
+                c->prof[2] += pack_s;
+                size_t n_exc = 0;
+                for (auto &v : c->exc_scratch) n_exc += v.size();
+                if ((int64_t)n_exc * 16 <= 3 * n_stream) {   // mostly A/C/G/T/N: send the stream, else the raw bytes
+                    if ((rc = l.d_pack.ensure((size_t)n_stream)) != CG_OK) break;
+                    if ((rc = l.d_seq.ensure((size_t)std::max<int64_t>(n_stream * 3, span) + 64)) != CG_OK) break;
+                    if (n_exc) {
+                        if ((rc = l.h_exc.ensure(n_exc)) != CG_OK) break;
+                        if ((rc = l.d_exc.ensure(n_exc)) != CG_OK) break;
+                        size_t k = 0;
+                        for (auto &v : c->exc_scratch) {
+                            if (!v.empty()) memcpy(l.h_exc.p + k, v.data(), v.size() * sizeof(uint64_t));
+                            k += v.size();
+                        }
+                        CU(cudaMemcpyAsync(l.d_exc.p, l.h_exc.p, n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
                     }
-                    CU(cudaMemcpyAsync(l.d_exc.p, l.h_exc.p, n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice, l.stream));
+                    CU(cudaMemcpyAsync(l.d_pack.p, l.h_pack.p, (size_t)n_stream, cudaMemcpyHostToDevice, l.stream));
+                    CU(cg_launch_unpack3(l.d_pack.p, n_stream, l.d_seq.p, (const unsigned long long *)l.d_exc.p,
+                                         (long long)n_exc, l.stream));
+                    c->launches += n_exc ? 2 : 1;
+                    c->h2d_bytes += n_stream + (long long)(n_exc * sizeof(uint64_t));
+                    c->prof[6] += (double)std::min<int64_t>(3 * n_stream, span);
+                    packed_bytes = 3 * n_stream;
                 }
-                CU(cudaMemcpyAsync(l.d_pack.p, l.h_pack.p, (size_t)n_stream, cudaMemcpyHostToDevice, l.stream));
-                CU(cg_launch_unpack3(l.d_pack.p, n_stream, l.d_seq.p, (const unsigned long long *)l.d_exc.p,
-                                     (long long)n_exc, l.stream));
-                c->launches += n_exc ? 2 : 1;
-                c->h2d_bytes += n_stream + (long long)(n_exc * sizeof(uint64_t));
-                packed_ok = true;
             }
         }
-        if (!packed_ok) {
+        if (a0 + packed_bytes < offsets[r1]) {
             // raw bytes (bounced through pinned memory unless the caller's buffer already is)
-            if ((rc = l.d_seq.ensure((size_t)nbytes + 64)) != CG_OK) break;
-            const uint8_t *src_seq = seq + byte0;
+            if ((rc = l.d_seq.ensure((size_t)(offsets[r1] - a0) + 64)) != CG_OK) break;
+            const int64_t from = std::max(a0 + packed_bytes, byte0);     // absolute position of the first raw byte
+            const int64_t n_raw = offsets[r1] - from;
+            const uint8_t *src_seq = seq + from;
             if (!seq_pinned) {
-                if ((rc = l.h_seq.ensure((size_t)nbytes + 16)) != CG_OK) break;
-                memcpy(l.h_seq.p, src_seq, (size_t)nbytes);
+                if ((rc = l.h_seq.ensure((size_t)n_raw + 16)) != CG_OK) break;
+                parallel_copy(c, l.h_seq.p, src_seq, (size_t)n_raw);
                 src_seq = l.h_seq.p;
             }
-            if (nbytes) CU(cudaMemcpyAsync(l.d_seq.p + pad, src_seq, (size_t)nbytes, cudaMemcpyHostToDevice, l.stream));
-            c->h2d_bytes += nbytes;
+            CU(cudaMemcpyAsync(l.d_seq.p + (from - a0), src_seq, (size_t)n_raw, cudaMemcpyHostToDevice, l.stream));
+            c->h2d_bytes += n_raw;
         }
+        if (pack && pack_mode == 1 && n_chunk >= n_lanes) {
+            // Feedback: waiting for a lane means the device side (PCIe) is behind -> pack more; never waiting
+            // means the host is behind -> pack less.
+            const double step = 0.03;
+            if (lane_wait_s > 0.2 * std::max(pack_s, 1e-4)) c->pack_fraction = std::min(1.0, c->pack_fraction + step);
+            else c->pack_fraction = std::max(0.0, c->pack_fraction - step);
+        }
+        ++n_chunk;
         if (want_q) {
             const uint8_t *src_q = qual + byte0;
             if (!qual_pinned) {
@@ -920,10 +949,14 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     return check_err_flag(c);
 }
 
+extern "C" int cg_host_cpus_available(void) { return cg_host_cpus(); }
+extern "C" int cg_host_threads(void) { return cg_host_threads_default(); }
+
 extern "C" int cg_ctx_host_profile(cg_ctx *c, double *out, int reset)
 {
     if (!c || !out) return fail(CG_EINVAL, "cg_ctx_host_profile: NULL argument");
     for (int i = 0; i < 8; ++i) out[i] = c->prof[i];
+    out[7] = c->pack_fraction;
     if (reset) for (int i = 0; i < 8; ++i) c->prof[i] = 0.0;
     return CG_OK;
 }

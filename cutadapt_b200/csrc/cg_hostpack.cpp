@@ -1,8 +1,12 @@
 // cg_hostpack.cpp -- host worker pool and the base-6 read packer (see cg_hostpack.h)
 #include "cg_hostpack.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #if defined(__x86_64__) || defined(__i386__)
 #include <immintrin.h>
@@ -11,19 +15,41 @@
 #define CG_CPU_RELAX() ((void)0)
 #endif
 
+// CPUs this process may actually use: the affinity mask, cut down by a cgroup CPU quota if there is one
+// (a container on a shared host usually sees every hardware thread but may only run on a few).
+int cg_host_cpus()
+{
+    int n = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) n = c; }
+    double quota = -1.0;
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {                       // cgroup v2: "<quota|max> <period>"
+        char q[64]; long long period = 0;
+        if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) quota = atof(q) / (double)period;
+        fclose(f);
+    } else {
+        long long q = -1, period = 0;                                            // cgroup v1
+        if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(g, "%lld", &q) != 1) q = -1; fclose(g); }
+        if (FILE *g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(g, "%lld", &period) != 1) period = 0; fclose(g); }
+        if (q > 0 && period > 0) quota = (double)q / (double)period;
+    }
+    if (quota > 0.0 && quota < n) n = (int)(quota + 0.5);
+#endif
+    return n < 1 ? 1 : n;
+}
+
 int cg_host_threads_default()
 {
     if (const char *e = getenv("CUTADAPT_B200_HOST_THREADS")) {
         int v = atoi(e);
         if (v >= 1) return v > 256 ? 256 : v;
     }
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
-    // leave the machine usable: at most half of the hardware threads, 48 at most
-    unsigned n = hw / 2;
-    if (n < 1) n = 1;
-    if (n > 48) n = 48;
-    return (int)n;
+    // leave the machine usable: at most half of the usable CPUs (all of a small quota), 32 at most
+    const int cpus = cg_host_cpus();
+    int n = cpus <= 16 ? cpus : cpus / 2;
+    if (n > 32) n = 32;
+    return n < 1 ? 1 : n;
 }
 
 CgHostPool::CgHostPool(int n_threads)
@@ -172,10 +198,55 @@ __attribute__((target("avx2"))) static int64_t pack3_avx2(const uint8_t *s, int6
     *any_escape = !_mm256_testz_si256(esc, esc);
     return k;
 }
+struct alignas(64) Pack512Tables {
+    uint8_t idx[64], w[64], code[64], chr[64];
+    Pack512Tables()
+    {
+        static const uint8_t code16[16] = {5, 0, 5, 1, 3, 5, 5, 2, 5, 5, 5, 5, 5, 5, 4, 5};
+        static const uint8_t char16[16] = {255, 'A', 255, 'C', 'T', 255, 255, 'G', 255, 255, 255, 255, 255, 255, 'N', 255};
+        for (int t = 0; t < 16; ++t) {
+            for (int b = 0; b < 4; ++b) idx[4 * t + b] = (uint8_t)(b < 3 ? 3 * t + b : 0);
+            w[4 * t] = 36; w[4 * t + 1] = 6; w[4 * t + 2] = 1; w[4 * t + 3] = 0;
+        }
+        for (int i = 0; i < 64; ++i) { code[i] = code16[i & 15]; chr[i] = char16[i & 15]; }
+    }
+};
+// AVX-512 (BW + VBMI) body: 48 characters -> 16 stream bytes per step, same scheme; one byte permutation
+// spreads the triples to 4-byte groups (c0 c1 c2 0).  Loads 64 bytes per step.
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) static int64_t pack3_avx512(const uint8_t *s, int64_t n_out,
+                                                                                    uint8_t *dst, bool *any_escape)
+{
+    static const Pack512Tables T;
+    const uint8_t *idx_b = T.idx, *w_b = T.w, *code_b = T.code, *char_b = T.chr;
+    const __m512i idx = _mm512_load_si512(idx_b), weights = _mm512_load_si512(w_b);
+    const __m512i lut_code = _mm512_load_si512(code_b), lut_char = _mm512_load_si512(char_b);
+    const __m512i nib = _mm512_set1_epi8(0x0F), five = _mm512_set1_epi8(CG_PACK_ESCAPE);
+    const __m512i ones = _mm512_set1_epi16(1);
+    const __mmask64 valid = 0x7777777777777777ull;
+    __mmask64 esc = 0;
+    int64_t k = 0;
+    for (; k + 16 <= n_out; k += 16, s += 48) {
+        const __m512i x = _mm512_permutexvar_epi8(idx, _mm512_loadu_si512((const void *)s));
+        const __m512i lo = _mm512_and_si512(x, nib);
+        const __m512i cand = _mm512_shuffle_epi8(lut_code, lo);
+        const __m512i expect = _mm512_shuffle_epi8(lut_char, lo);
+        const __mmask64 ok = _mm512_cmpeq_epi8_mask(x, expect);
+        const __m512i code = _mm512_mask_blend_epi8(ok, five, cand);     // weight 0 hides the filler bytes
+        esc |= ~ok & valid;
+        const __m512i m1 = _mm512_maddubs_epi16(code, weights);
+        const __m512i m2 = _mm512_madd_epi16(m1, ones);
+        _mm_storeu_si128((__m128i *)(dst + k), _mm512_cvtepi32_epi8(m2));
+    }
+    *any_escape = esc != 0;
+    return k;
+}
 static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+static const bool g_have_avx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi") &&
+                                  !getenv("CUTADAPT_B200_NO_AVX512");
 #else
-static const bool g_have_avx2 = false;
+static const bool g_have_avx2 = false, g_have_avx512 = false;
 static int64_t pack3_avx2(const uint8_t *, int64_t, uint8_t *, bool *) { return 0; }
+static int64_t pack3_avx512(const uint8_t *, int64_t, uint8_t *, bool *) { return 0; }
 #endif
 
 void cg_pack3_range(const uint8_t *seq, int64_t a0, int64_t lo, int64_t hi, int64_t i0, int64_t i1,
@@ -207,19 +278,20 @@ void cg_pack3_range(const uint8_t *seq, int64_t a0, int64_t lo, int64_t hi, int6
     if (k_in1 < k_in0) k_in1 = k_in0;
     for (; i < k_in0; ++i) slow(i);
     // fast part in blocks: escapes are detected per block and resolved by a second look
-    const int64_t BLOCK = 256;
+    const int64_t BLOCK = 4096;
     while (i < k_in1) {
         const int64_t e = i + BLOCK < k_in1 ? i + BLOCK : k_in1;
         const uint8_t *s = seq + a0 + 3 * i;
         unsigned any = 0;
         int64_t k = i;
         if (g_have_avx2) {
-            // the vector body reads 28 bytes per step: keep it 4 bytes away from `hi`
-            const int64_t k_safe = (hi - a0 - 4) / 3;
+            // the vector bodies read 28 / 64 bytes per step of 24 / 48: keep them 4 / 16 bytes away from `hi`
+            const int64_t k_safe = (hi - a0 - (g_have_avx512 ? 16 : 4)) / 3;
             const int64_t e_v = e < k_safe ? e : k_safe;
-            if (e_v - i >= 8) {
+            if (e_v - i >= 16) {
                 bool escaped = false;
-                const int64_t done = pack3_avx2(s, e_v - i, packed + i, &escaped);
+                const int64_t done = g_have_avx512 ? pack3_avx512(s, e_v - i, packed + i, &escaped)
+                                                   : pack3_avx2(s, e_v - i, packed + i, &escaped);
                 if (escaped) any |= 0x100;
                 k += done;
                 s += 3 * done;

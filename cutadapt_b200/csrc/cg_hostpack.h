@@ -43,6 +43,7 @@ private:
     std::atomic<bool> stop_{false};
 };
 
+int cg_host_cpus();              // usable CPUs (affinity mask, cgroup quota)
 int cg_host_threads_default();
 
 // Packed stream geometry: stream byte i holds the characters at absolute positions

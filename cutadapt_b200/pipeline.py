@@ -237,6 +237,7 @@ class FastqTrimmer:
         fp.discard_casava = int(bool(discard_casava))
         self.params = fp
         self.statistics = {}
+        self._out_bufs, self._out_keep = {}, {}
 
     def _submit(self, chunk) -> Tuple[int, int, object]:
         buf = np.frombuffer(chunk, dtype=np.uint8) if not isinstance(chunk, np.ndarray) else chunk
@@ -245,30 +246,46 @@ class FastqTrimmer:
                                               C.byref(slot)))
         return slot.value, buf.size, buf    # buf is kept alive until collect
 
-    def _collect(self, ticket) -> bytes:
+    def _out_buffer(self, slot: int, n_bytes: int) -> np.ndarray:
+        """Per-slot output buffer, pinned when torch can provide it (the download then needs no bounce)."""
+        buf = self._out_bufs.get(slot)
+        if buf is None or buf.size < n_bytes:
+            size = max(n_bytes + n_bytes // 4, 1 << 20)
+            try:
+                import torch
+
+                self._out_keep[slot] = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+                buf = self._out_keep[slot].numpy()
+            except Exception:
+                buf = np.empty(size, dtype=np.uint8)
+            self._out_bufs[slot] = buf
+        return buf
+
+    def _collect(self, ticket, copy: bool = True):
         slot, n_bytes, _ = ticket
         # trimming only ever shortens a record ("\r\n" -> "\n" and "+name" -> "+" too)
-        out = np.empty(max(n_bytes, 1), dtype=np.uint8)
+        out = self._out_buffer(slot, max(n_bytes, 1))
         res = _lib.cg_fastq_result()
         _lib.check(_lib.lib().cg_fastq_collect(
             self.ctx.handle, slot, self._set.handle if self._set is not None else None, C.byref(self.params),
             out.ctypes.data, out.size, C.byref(res)))
         for k, v in res.as_dict().items():
             self.statistics[k] = self.statistics.get(k, 0) + v
-        return out[: res.out_bytes].tobytes()
+        return out[: res.out_bytes].tobytes() if copy else out[: res.out_bytes]
 
     def process_chunk(self, chunk) -> bytes:
         return self._collect(self._submit(chunk))
 
-    def process_chunks(self, chunks):
+    def process_chunks(self, chunks, copy: bool = True):
+        """copy=False yields uint8 array views into per-slot buffers: valid until the next-but-one result."""
         pending = None
         for chunk in chunks:
             ticket = self._submit(chunk)
             if pending is not None:
-                yield self._collect(pending)
+                yield self._collect(pending, copy)
             pending = ticket
         if pending is not None:
-            yield self._collect(pending)
+            yield self._collect(pending, copy)
 
 
 class DeviceResult:

@@ -175,10 +175,15 @@ int cg_ctx_kernel_time(cg_ctx *ctx, double *total_ms, int64_t *launches, int res
  * crossed PCIe: the compressed read stream + exceptions, qualities, irregular offsets; the records back). */
 int cg_ctx_transfer_bytes(cg_ctx *ctx, int64_t *h2d, int64_t *d2h, int reset);
 
+/* CPUs this process may use (affinity mask, cut down by a cgroup CPU quota) and the number of worker
+ * threads the library's host side will start (CUTADAPT_B200_HOST_THREADS overrides). */
+int cg_host_cpus_available(void);
+int cg_host_threads(void);
+
 /* Where the host side of cg_process_batch spent its time, in seconds, accumulated over calls:
  * out[0] total, [1] scanning the offsets, [2] packing reads for the compressed transfer, [3] waiting for a
- * free lane (= the device or PCIe is the bottleneck), [4] draining the lanes at the end, [5] chunks;
- * out must hold 8 doubles. */
+ * free lane (= the device or PCIe is the bottleneck), [4] draining the lanes at the end, [5] chunks,
+ * [6] characters sent compressed, [7] the current compressed share of a chunk; out must hold 8 doubles. */
 int cg_ctx_host_profile(cg_ctx *ctx, double *out, int reset);
 
 /* ---- adapter set (replaces Aligner.__cinit__/_set_reference _align.pyx:195-277 and
@@ -208,11 +213,13 @@ int cg_adapterset_effective_length(const cg_adapterset *set, int32_t adapter, in
  *   qtrim   : 2 * n_reads int32 (start, stop) of quality_trim_index; may be NULL
  *
  * cg_process_batch: HOST pointers (pageable or pinned); the library overlaps H2D / kernels / D2H in
- *   sub-batches on its streams.  Batches of >= 65536 reads travel compressed: worker threads of the
- *   library (CUTADAPT_B200_HOST_THREADS, default half of the hardware threads, at most 48) pack the reads
- *   three characters per byte (A C G T N; every other byte goes verbatim into an exception list) and a
- *   device kernel restores the caller's bytes exactly, so results do not depend on it
- *   (CUTADAPT_B200_H2D_PACK=0 sends the raw bytes).
+ *   sub-batches on its streams.  Batches of >= 65536 reads travel partly compressed: worker threads of the
+ *   library (CUTADAPT_B200_HOST_THREADS; default: the CPUs the process may use, cgroup quota included, at
+ *   most 32) pack reads three characters per byte (A C G T N; every other byte goes verbatim into an
+ *   exception list) and a device kernel restores the caller's bytes exactly, so results do not depend on
+ *   it.  The share of each chunk that is packed follows a feedback rule (pack more while PCIe is the
+ *   bottleneck, less while the host threads are); CUTADAPT_B200_H2D_PACK=0 sends raw bytes only, =all
+ *   compresses everything.
  * cg_process_batch_device: DEVICE pointers (16-byte aligned seq/qual, readable up to the next
  *   16-byte boundary past offsets[n_reads]); runs asynchronously on the context stream.
  *   max_read_len must be >= the longest read in the batch (pass 0 to let the library

@@ -503,12 +503,17 @@ def test_compressed_transfer_is_lossless(monkeypatch):
         data, offsets = L.pack_strings(reads)
         qd = L.pack_strings(quals)[0] if use_q else None
         aset.ctx.transfer_bytes(reset=True)
-        monkeypatch.setenv("CUTADAPT_B200_H2D_PACK", "1")
+        monkeypatch.setenv("CUTADAPT_B200_H2D_PACK", "all")
         packed, qt_p = aset.process(data, offsets, qd, L.make_params(**kw))
         h2d_packed, d2h = aset.ctx.transfer_bytes(reset=True)
         monkeypatch.setenv("CUTADAPT_B200_H2D_PACK", "0")
         raw, qt_r = aset.process(data, offsets, qd, L.make_params(**kw))
         h2d_raw, _ = aset.ctx.transfer_bytes(reset=True)
+        monkeypatch.setenv("CUTADAPT_B200_H2D_PACK", "1")      # adaptive split: part compressed, part raw
+        for _ in range(2):
+            mixed, _ = aset.process(data, offsets, qd, L.make_params(**kw))
+            assert (mixed == raw).all()
+        aset.ctx.transfer_bytes(reset=True)
         assert (packed == raw).all()
         if use_q:
             assert (qt_p == qt_r).all()
