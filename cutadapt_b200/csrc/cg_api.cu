@@ -698,38 +698,37 @@ static int lane_finish(cg_ctx *c, Lane &l)
 
 // Longest read / equal lengths / validity of offsets[r0 .. r1], on the worker pool for large chunks.
 struct OffsetScan { int64_t max_len = 0; bool uniform = true, valid = true; };
+static OffsetScan scan_offsets_part(const int64_t *offsets, int64_t len0, int64_t a, int64_t b)
+{
+    OffsetScan o;
+    for (int64_t r = a; r < b; ++r) {
+        const int64_t len = offsets[r + 1] - offsets[r];
+        if (len < 0 || len > 2000000000LL) o.valid = false;
+        if (len > o.max_len) o.max_len = len;
+        o.uniform = o.uniform && len == len0;
+    }
+    return o;
+}
+static void scan_merge(OffsetScan &t, const OffsetScan &o)
+{
+    t.max_len = std::max(t.max_len, o.max_len);
+    t.uniform = t.uniform && o.uniform;
+    t.valid = t.valid && o.valid;
+}
+static const int64_t SCAN_JOB = 1 << 15;
 static OffsetScan scan_offsets(cg_ctx *c, const int64_t *offsets, int64_t r0, int64_t r1)
 {
     const int64_t len0 = offsets[r0 + 1] - offsets[r0];
-    auto part = [&](int64_t a, int64_t b) {
-        OffsetScan o;
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t len = offsets[r + 1] - offsets[r];
-            if (len < 0 || len > 2000000000LL) o.valid = false;
-            if (len > o.max_len) o.max_len = len;
-            o.uniform = o.uniform && len == len0;
-        }
-        return o;
-    };
     const int64_t nr = r1 - r0;
-    if (!c->pool || nr < (1 << 16)) return part(r0, r1);
-    const int64_t JOB = 1 << 15;
-    const int64_t n_jobs = (nr + JOB - 1) / JOB;
+    if (!c->pool || nr < (1 << 16)) return scan_offsets_part(offsets, len0, r0, r1);
+    const int64_t n_jobs = (nr + SCAN_JOB - 1) / SCAN_JOB;
     std::vector<OffsetScan> parts((size_t)c->pool->size());
     c->pool->run(n_jobs, [&](int64_t j, int w) {
-        const int64_t a = r0 + j * JOB, b = std::min(r1, a + JOB);
-        const OffsetScan o = part(a, b);
-        OffsetScan &t = parts[(size_t)w];
-        t.max_len = std::max(t.max_len, o.max_len);
-        t.uniform = t.uniform && o.uniform;
-        t.valid = t.valid && o.valid;
+        const int64_t a = r0 + j * SCAN_JOB, b = std::min(r1, a + SCAN_JOB);
+        scan_merge(parts[(size_t)w], scan_offsets_part(offsets, len0, a, b));
     });
     OffsetScan t;
-    for (const OffsetScan &o : parts) {
-        t.max_len = std::max(t.max_len, o.max_len);
-        t.uniform = t.uniform && o.uniform;
-        t.valid = t.valid && o.valid;
-    }
+    for (const OffsetScan &o : parts) scan_merge(t, o);
     return t;
 }
 
@@ -777,11 +776,16 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     using clk = std::chrono::steady_clock;
     auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const clk::time_point t_begin = clk::now();
+    clk::time_point fb_t0 = t_begin;
+    double fb_wait = 0.0;
+    int64_t ahead_r0 = -1, ahead_r1 = -1;
+    OffsetScan ahead_sc;
     while (r0 < n_reads && rc == CG_OK) {
         // chunk [r0, r1): bounded by reads and bytes; also find the longest read
         int64_t r1 = std::min(n_reads, r0 + CHUNK_READS);
         const clk::time_point t_scan0 = clk::now();
-        OffsetScan sc = scan_offsets(c, offsets, r0, r1);
+        // (while a chunk is packed, the workers also scan the offsets of the next one)
+        OffsetScan sc = (ahead_r0 == r0 && ahead_r1 == r1) ? ahead_sc : scan_offsets(c, offsets, r0, r1);
         c->prof[1] += secs(t_scan0, clk::now());
         c->prof[5] += 1;
         if (!sc.valid) return fail(CG_EINVAL, "offsets must be non-decreasing");
@@ -831,10 +835,26 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
                 const int64_t JOB = 1 << 16;
                 uint8_t *h_pack = l.h_pack.p;
                 const clk::time_point t_pack0 = clk::now();
-                c->pool->run((n_stream + JOB - 1) / JOB, [&](int64_t j, int w) {
-                    cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), h_pack,
-                                   c->exc_scratch[(size_t)w]);
+                // ... and, in the same job set, the offsets of the next chunk
+                const int64_t nx0 = r1, nx1 = std::min(n_reads, r1 + CHUNK_READS);
+                const int64_t n_pack_jobs = (n_stream + JOB - 1) / JOB;
+                const int64_t n_scan_jobs = nx1 > nx0 ? (nx1 - nx0 + SCAN_JOB - 1) / SCAN_JOB : 0;
+                const int64_t nx_len0 = nx1 > nx0 ? offsets[nx0 + 1] - offsets[nx0] : 0;
+                std::vector<OffsetScan> parts((size_t)c->pool->size());
+                c->pool->run(n_pack_jobs + n_scan_jobs, [&](int64_t j, int w) {
+                    if (j < n_pack_jobs) {
+                        cg_pack3_range(seq, a0, lo, hi, j * JOB, std::min(n_stream, (j + 1) * JOB), h_pack,
+                                       c->exc_scratch[(size_t)w]);
+                    } else {
+                        const int64_t a = nx0 + (j - n_pack_jobs) * SCAN_JOB, b = std::min(nx1, a + SCAN_JOB);
+                        scan_merge(parts[(size_t)w], scan_offsets_part(offsets, nx_len0, a, b));
+                    }
                 });
+                if (n_scan_jobs) {
+                    ahead_sc = OffsetScan();
+                    for (const OffsetScan &o : parts) scan_merge(ahead_sc, o);
+                    ahead_r0 = nx0; ahead_r1 = nx1;
+                }
                 pack_s = secs(t_pack0, clk::now());
                 c->prof[2] += pack_s;
                 size_t n_exc = 0;
@@ -876,12 +896,19 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
             CU(cudaMemcpyAsync(l.d_seq.p + (from - a0), src_seq, (size_t)n_raw, cudaMemcpyHostToDevice, l.stream));
             c->h2d_bytes += n_raw;
         }
-        if (pack && pack_mode == 1 && n_chunk >= n_lanes) {
-            // Feedback: waiting for a lane means the device side (PCIe) is behind -> pack more; never waiting
-            // means the host is behind -> pack less.
-            const double step = 0.03;
-            if (lane_wait_s > 0.2 * std::max(pack_s, 1e-4)) c->pack_fraction = std::min(1.0, c->pack_fraction + step);
-            else c->pack_fraction = std::max(0.0, c->pack_fraction - step);
+        if (pack && pack_mode == 1) {
+            // Feedback over windows of 8 chunks: time spent waiting for a free lane means the device side (PCIe)
+            // is behind -> pack a larger share; (almost) never waiting means the host is behind -> pack less.
+            if (n_chunk >= n_lanes) fb_wait += lane_wait_s;
+            if (n_chunk >= n_lanes && (n_chunk - n_lanes) % 8 == 7) {
+                const double window = secs(fb_t0, clk::now());
+                if (fb_wait > 0.08 * window) c->pack_fraction = std::min(1.0, c->pack_fraction + 0.04);
+                else if (fb_wait < 0.02 * window) c->pack_fraction = std::max(0.0, c->pack_fraction - 0.04);
+                fb_wait = 0.0;
+                fb_t0 = clk::now();
+            } else if (n_chunk < n_lanes) {
+                fb_t0 = clk::now();
+            }
         }
         ++n_chunk;
         if (want_q) {

@@ -45,9 +45,11 @@ int cg_host_threads_default()
         int v = atoi(e);
         if (v >= 1) return v > 256 ? 256 : v;
     }
-    // leave the machine usable: at most half of the usable CPUs (all of a small quota), 32 at most
+    // leave the machine usable: at most half of the usable CPUs, 32 at most.  Under a small quota: all but
+    // two (the CUDA runtime's own threads and the caller need some; exceeding a cgroup quota stalls every
+    // thread of the process until the next period).
     const int cpus = cg_host_cpus();
-    int n = cpus <= 16 ? cpus : cpus / 2;
+    int n = cpus <= 16 ? cpus - 2 : cpus / 2;
     if (n > 32) n = 32;
     return n < 1 ? 1 : n;
 }
