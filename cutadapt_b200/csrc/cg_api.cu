@@ -101,7 +101,7 @@ struct Lane {
 };
 
 // One FASTQ chunk in flight (cg_fastq_submit ... cg_fastq_collect)
-#define CG_FQ_SLOTS 2
+#define CG_FQ_SLOTS 4
 struct FastqSlot {
     cudaStream_t stream = nullptr;
     bool busy = false;
@@ -109,7 +109,7 @@ struct FastqSlot {
     DevBuf<uint8_t> d_in, d_out, d_seq, d_qual;
     DevBuf<uint32_t> d_tiles, d_nl;
     DevBuf<CgFastqRecord> d_rec;
-    DevBuf<int32_t> d_len, d_interval, d_outlen, d_qtrim;
+    DevBuf<int32_t> d_len, d_interval, d_outlen, d_qtrim, d_mask;
     DevBuf<int64_t> d_offs, d_outoff;
     DevBuf<unsigned long long> d_scan;
     DevBuf<cg_match_rec> d_matches;
@@ -247,7 +247,7 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
     c->pass_tmp.release(); c->view_base.release(); c->view_back.release();
     for (FastqSlot &f : c->fq) {
         f.d_in.release(); f.d_out.release(); f.d_seq.release(); f.d_qual.release(); f.d_tiles.release(); f.d_nl.release();
-        f.d_rec.release(); f.d_len.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
+        f.d_rec.release(); f.d_len.release(); f.d_mask.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
         f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release();
         f.h_in.release(); f.h_out.release(); f.h_counters.release();
         if (f.d_counters) cudaFree(f.d_counters);
@@ -1253,22 +1253,29 @@ extern "C" int cg_fastq_submit(cg_ctx *c, const uint8_t *fastq, int64_t n_bytes,
     return CG_OK;
 }
 
-extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
-                                uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
+// One mate of a chunk between submit and the verdict
+struct FqStage {
+    long long n = 0, n_nl = 0;
+    int times = 1, slots = 1;
+    int32_t *d_qtrim = nullptr;
+    const cg_match_rec *d_matches = nullptr;
+};
+
+static int fastq_enabled_filters(const cg_fastq_params *fp)
 {
-    if (!c || !fp || !res || slot < 0 || slot >= CG_FQ_SLOTS) return fail(CG_EINVAL, "cg_fastq_collect: bad argument");
-    if (s && s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
-    FastqSlot &f = c->fq[slot];
-    if (!f.busy) return fail(CG_EINVAL, "cg_fastq_collect: nothing was submitted to this slot");
-    CU(cudaSetDevice(c->device));
-    f.busy = false;
-    memset(res, 0, sizeof *res);
-    cudaStream_t st = f.stream;
-    CU(cudaStreamSynchronize(st));
+    return (fp->minimum_length > 0 ? 1 : 0) | (fp->maximum_length >= 0 ? 2 : 0) | (fp->max_n >= 0.0 ? 4 : 0) |
+           (fp->max_expected_errors >= 0.0 ? 8 : 0) | (fp->discard_casava ? 16 : 0) | (fp->discard_trimmed ? 32 : 0) |
+           (fp->discard_untrimmed ? 64 : 0);
+}
+
+// index the chunk, build the record table, run the modifiers (trimming pass included), evaluate the filters
+static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s, const cg_fastq_params *fp, int poly_a_mode,
+                                cudaStream_t st, FqStage &g)
+{
+    CU(cudaStreamSynchronize(f.stream));        // upload + newline count of this slot
     const int64_t n_bytes = f.n_bytes;
-    const long long n_nl = (long long)f.h_counters.p[0];
-    // the last line may come without its newline
-    long long n_lines = n_nl;
+    g.n_nl = (long long)f.h_counters.p[0];
+    long long n_lines = g.n_nl;                 // the last line may come without its newline
     if (n_bytes > 0) {
         uint8_t last = 0;
         CU(cudaMemcpyAsync(&last, f.d_in.p + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
@@ -1278,35 +1285,34 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
     if (n_lines % 4 != 0)
         return fail(CG_EINVAL, "FASTQ chunk does not consist of complete 4-line records (" + std::to_string(n_lines) +
                                    " lines)");
-    const long long n = n_lines / 4;
-    res->n_records = n;
+    const long long n = g.n = n_lines / 4;
     if (n == 0) return CG_OK;
     const cg_params *p = &fp->trim;
     const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
-    const int times = p->times < 1 ? 1 : p->times;
-    const int slots = s ? s->host.slots : 1;
+    g.times = p->times < 1 ? 1 : p->times;
+    g.slots = s ? s->host.slots : 1;
+    if (fp->cut_front < 0 || fp->cut_back < 0) return fail(CG_EINVAL, "cg_fastq: cut_front / cut_back must be >= 0");
     int rc;
-    if ((rc = f.d_nl.ensure((size_t)n_nl + 1)) != CG_OK) return rc;
+    if ((rc = f.d_nl.ensure((size_t)g.n_nl + 1)) != CG_OK) return rc;
     if ((rc = f.d_rec.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_len.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_interval.ensure((size_t)n * 2)) != CG_OK) return rc;
+    if ((rc = f.d_mask.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_outlen.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_outoff.ensure((size_t)n + 1)) != CG_OK) return rc;
     if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(n) + 1)) != CG_OK) return rc;
     if (want_q && (rc = f.d_qtrim.ensure((size_t)n * 2)) != CG_OK) return rc;
     CU(cg_launch_fastq_index(f.d_in.p, n_bytes, f.d_tiles.p, nullptr, f.d_nl.p, 1, st));
-    if (fp->cut_front < 0 || fp->cut_back < 0) return fail(CG_EINVAL, "cg_fastq_collect: cut_front / cut_back must be >= 0");
-    CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, n_nl, n, fp->cut_front, fp->cut_back, f.d_rec.p, f.d_len.p,
+    CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, g.n_nl, n, fp->cut_front, fp->cut_back, f.d_rec.p, f.d_len.p,
                                f.d_err, st));
     c->launches += 2;
-    int32_t *d_qtrim = want_q ? f.d_qtrim.p : nullptr;
-    const cg_match_rec *d_matches = nullptr;
+    g.d_qtrim = want_q ? f.d_qtrim.p : nullptr;
     if (s) {
         // packed reads for the trimming kernels
         if ((rc = f.d_offs.ensure((size_t)n + 1)) != CG_OK) return rc;
         if ((rc = f.d_seq.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
         if (want_q && (rc = f.d_qual.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
-        if ((rc = f.d_matches.ensure((size_t)n * times * slots)) != CG_OK) return rc;
+        if ((rc = f.d_matches.ensure((size_t)n * g.times * g.slots)) != CG_OK) return rc;
         CU(cg_launch_scan_i32(f.d_len.p, n, f.d_scan.p, f.d_offs.p, st));
         CU(cg_launch_fastq_gather(f.d_in.p, f.d_rec.p, f.d_offs.p, n, f.d_seq.p, want_q ? f.d_qual.p : nullptr, st));
         c->launches += 4;
@@ -1320,65 +1326,130 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
         CU(cudaStreamSynchronize(st));
         if (fq_err[0]) return fastq_format_error(fq_err);
         rc = launch_trim(c, s, f.d_seq.p, want_q ? f.d_qual.p : nullptr, f.d_offs.p, n, max_len, p, f.d_matches.p,
-                         d_qtrim, st, true);
+                         g.d_qtrim, st, true);
         if (rc != CG_OK) return rc;
-        d_matches = f.d_matches.p;
+        g.d_matches = f.d_matches.p;
     } else if (want_q) {
         CU(cg_launch_fastq_pretrim(f.d_in.p, f.d_rec.p, f.d_len.p, n, (p->quality_trim ? 1 : 0) | (p->nextseq_trim ? 2 : 0),
                                    p->cutoff_front, p->cutoff_back,
-                                   (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8), d_qtrim, st));
+                                   (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8), g.d_qtrim, st));
         c->launches += 1;
     }
-    {
-        CgFastqFilter flt;
-        flt.minimum_length = fp->minimum_length;
-        flt.maximum_length = fp->maximum_length;
-        flt.discard_trimmed = fp->discard_trimmed;
-        flt.discard_untrimmed = fp->discard_untrimmed;
-        flt.max_n = fp->max_n;
-        flt.max_ee = fp->max_expected_errors;
-        flt.poly_a = fp->poly_a;
-        flt.shorten = !fp->shorten ? 0 : (fp->shorten_length >= 0 ? fp->shorten_length + 1 : fp->shorten_length);
-        flt.trim_n = fp->trim_n;
-        flt.discard_casava = fp->discard_casava;
-        CU(cg_launch_fastq_outlen(f.d_in.p, f.d_rec.p, f.d_len.p, n, d_matches, times, slots, d_qtrim, flt, c->d_phred,
-                                  f.d_interval.p, f.d_outlen.p, f.d_counters + 1, f.d_err, st));
-        CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
-        c->launches += 4;
-        long long total = 0;
-        int fq_err[2];
-        CU(cudaMemcpyAsync(&total, f.d_outoff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(f.h_counters.p, f.d_counters, (1 + CG_FQ_COUNTERS) * sizeof(unsigned long long),
-                           cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (fq_err[0]) return fastq_format_error(fq_err);
-        const unsigned long long *k = f.h_counters.p + 1;
-        res->n_written = (int64_t)k[0]; res->bp_in = (int64_t)k[1]; res->bp_out = (int64_t)k[2];
-        res->with_adapters = (int64_t)k[3]; res->too_short = (int64_t)k[4]; res->too_long = (int64_t)k[5];
-        res->quality_trimmed_bp = (int64_t)k[6]; res->discarded = (int64_t)k[7]; res->too_many_n = (int64_t)k[8];
-        res->too_many_expected_errors = (int64_t)k[9];
-        res->casava_filtered = (int64_t)k[10];
-        res->out_bytes = total;
-        if (total > out_capacity)
-            return fail(CG_EINVAL, "cg_fastq_collect: output buffer too small (" + std::to_string(total) + " bytes needed)");
-        if (total > 0) {
-            if (!out) return fail(CG_EINVAL, "cg_fastq_collect: out is NULL");
-            if ((rc = f.d_out.ensure((size_t)total + 64)) != CG_OK) return rc;
-            CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, n, f.d_out.p, st));
-            c->launches += 1;
-            if (is_pinned(out)) {
-                CU(cudaMemcpyAsync(out, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-            } else {
-                if ((rc = f.h_out.ensure((size_t)total)) != CG_OK) return rc;
-                CU(cudaMemcpyAsync(f.h_out.p, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                parallel_copy(c, out, f.h_out.p, (size_t)total);
-            }
-            c->d2h_bytes += total;
+    CgFastqFilter flt;
+    flt.minimum_length = fp->minimum_length;
+    flt.maximum_length = fp->maximum_length;
+    flt.discard_trimmed = fp->discard_trimmed;
+    flt.discard_untrimmed = fp->discard_untrimmed;
+    flt.max_n = fp->max_n;
+    flt.max_ee = fp->max_expected_errors;
+    flt.poly_a = fp->poly_a ? poly_a_mode : 0;
+    flt.shorten = !fp->shorten ? 0 : (fp->shorten_length >= 0 ? fp->shorten_length + 1 : fp->shorten_length);
+    flt.trim_n = fp->trim_n;
+    flt.discard_casava = fp->discard_casava;
+    CU(cg_launch_fastq_evaluate(f.d_in.p, f.d_rec.p, f.d_len.p, n, g.d_matches, g.times, g.slots, g.d_qtrim, flt,
+                                c->d_phred, f.d_interval.p, f.d_mask.p, f.d_counters + 1, f.d_err, st));
+    c->launches += 1;
+    return CG_OK;
+}
+
+// sizes -> offsets -> formatted records -> host; counters
+static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStream_t st, uint8_t *out,
+                              int64_t out_capacity, cg_fastq_result *res)
+{
+    const long long n = g.n;
+    int rc;
+    CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
+    c->launches += 3;
+    long long total = 0;
+    int fq_err[2];
+    CU(cudaMemcpyAsync(&total, f.d_outoff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(f.h_counters.p, f.d_counters, (1 + CG_FQ_COUNTERS) * sizeof(unsigned long long),
+                       cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (fq_err[0]) return fastq_format_error(fq_err);
+    const unsigned long long *k = f.h_counters.p + 1;
+    res->n_records = n;
+    res->n_written = (int64_t)k[0]; res->bp_in = (int64_t)k[1]; res->bp_out = (int64_t)k[2];
+    res->with_adapters = (int64_t)k[3]; res->too_short = (int64_t)k[4]; res->too_long = (int64_t)k[5];
+    res->quality_trimmed_bp = (int64_t)k[6]; res->discarded = (int64_t)k[7]; res->too_many_n = (int64_t)k[8];
+    res->too_many_expected_errors = (int64_t)k[9];
+    res->casava_filtered = (int64_t)k[10];
+    res->out_bytes = total;
+    if (total > out_capacity)
+        return fail(CG_EINVAL, "cg_fastq_collect: output buffer too small (" + std::to_string(total) + " bytes needed)");
+    if (total > 0) {
+        if (!out) return fail(CG_EINVAL, "cg_fastq_collect: out is NULL");
+        if ((rc = f.d_out.ensure((size_t)total + 64)) != CG_OK) return rc;
+        CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, n, f.d_out.p, st));
+        c->launches += 1;
+        if (is_pinned(out)) {
+            CU(cudaMemcpyAsync(out, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        } else {
+            if ((rc = f.h_out.ensure((size_t)total)) != CG_OK) return rc;
+            CU(cudaMemcpyAsync(f.h_out.p, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            parallel_copy(c, out, f.h_out.p, (size_t)total);
         }
+        c->d2h_bytes += total;
     }
+    return CG_OK;
+}
+
+extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                                uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
+{
+    if (!c || !fp || !res || slot < 0 || slot >= CG_FQ_SLOTS) return fail(CG_EINVAL, "cg_fastq_collect: bad argument");
+    if (s && s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
+    FastqSlot &f = c->fq[slot];
+    if (!f.busy) return fail(CG_EINVAL, "cg_fastq_collect: nothing was submitted to this slot");
+    CU(cudaSetDevice(c->device));
+    f.busy = false;
+    memset(res, 0, sizeof *res);
+    FqStage g;
+    int rc = fastq_stage_evaluate(c, f, s, fp, 1, f.stream, g);
+    if (rc != CG_OK || g.n == 0) return rc;
+    CU(cg_launch_fastq_finish(g.n, f.d_rec.p, f.d_interval.p, f.d_mask.p, fastq_enabled_filters(fp), f.d_outlen.p,
+                              f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, f.stream));
+    c->launches += 1;
+    if ((rc = fastq_stage_output(c, f, g, f.stream, out, out_capacity, res)) != CG_OK) return rc;
+    return check_err_flag(c);
+}
+
+extern "C" int cg_fastq_collect_paired(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *s1,
+                                       const cg_adapterset *s2, const cg_fastq_params *fp1, const cg_fastq_params *fp2,
+                                       int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
+                                       int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2)
+{
+    if (!c || !fp1 || !fp2 || !res1 || !res2 || slot1 < 0 || slot1 >= CG_FQ_SLOTS || slot2 < 0 || slot2 >= CG_FQ_SLOTS ||
+        slot1 == slot2 || pair_filter_mode < 0 || pair_filter_mode > 2)
+        return fail(CG_EINVAL, "cg_fastq_collect_paired: bad argument");
+    if ((s1 && s1->ctx != c) || (s2 && s2->ctx != c)) return fail(CG_EINVAL, "adapter set belongs to another context");
+    FastqSlot &f1 = c->fq[slot1], &f2 = c->fq[slot2];
+    if (!f1.busy || !f2.busy) return fail(CG_EINVAL, "cg_fastq_collect_paired: nothing was submitted to a slot");
+    CU(cudaSetDevice(c->device));
+    f1.busy = f2.busy = false;
+    memset(res1, 0, sizeof *res1);
+    memset(res2, 0, sizeof *res2);
+    // after its upload everything of the second mate runs on the first mate's stream
+    cudaStream_t st = f1.stream;
+    FqStage g1, g2;
+    int rc = fastq_stage_evaluate(c, f1, s1, fp1, 1, st, g1);
+    if (rc != CG_OK) { cudaStreamSynchronize(f2.stream); return rc; }
+    if ((rc = fastq_stage_evaluate(c, f2, s2, fp2, 2, st, g2)) != CG_OK) return rc;
+    if (g1.n != g2.n)
+        return fail(CG_EINVAL, "paired FASTQ chunks differ in their number of records (" + std::to_string(g1.n) + " vs " +
+                                   std::to_string(g2.n) + ")");
+    if (g1.n == 0) return CG_OK;
+    // --discard-untrimmed with adapters on one mate only tests "both" (cli.py:859-893)
+    const int mode_untrimmed = (!s1 || !s2) ? 1 : pair_filter_mode;
+    CU(cg_launch_fastq_finish(g1.n, f1.d_rec.p, f1.d_interval.p, f1.d_mask.p, fastq_enabled_filters(fp1), f1.d_outlen.p,
+                              f1.d_counters + 1, f2.d_rec.p, f2.d_interval.p, f2.d_mask.p, fastq_enabled_filters(fp2),
+                              f2.d_outlen.p, f2.d_counters + 1, pair_filter_mode, mode_untrimmed, st));
+    c->launches += 1;
+    if ((rc = fastq_stage_output(c, f1, g1, st, out1, out_capacity1, res1)) != CG_OK) return rc;
+    if ((rc = fastq_stage_output(c, f2, g2, st, out2, out_capacity2, res2)) != CG_OK) return rc;
     return check_err_flag(c);
 }
 

@@ -287,17 +287,19 @@ __global__ void fq_pretrim_kernel(const uint8_t *buf, const CgFastqRecord *rec, 
     qtrim[2 * r + 1] = e;
 }
 
-// What is left of every read (modifiers.py:858 then adapters.py:453-454, 486-487 per round), the filters
-// (TooShort / TooLong, predicates.py:29-66; DiscardTrimmed / DiscardUntrimmed, predicates.py:127-160; in the
-// order cli.py builds them: length filters first) and the size of the output record.
-__global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
-                                 const cg_match_rec *matches, int times, int slots, const int32_t *qtrim,
-                                 CgFastqFilter f, const double *phred, int32_t *interval, int32_t *out_len,
-                                 unsigned long long *counters, int *err)
+// What is left of every read (modifiers.py:858 then adapters.py:453-454, 486-487 per round; PolyATrimmer,
+// Shortener, NEndTrimmer after the adapters) and which filters it fails, one bit per filter in the order
+// cli.py:700-830 + 870-910 appends them:
+//   bit 0 TooShort, 1 TooLong (predicates.py:29-53), 2 TooManyN (96-122), 3 TooManyExpectedErrors (56-71),
+//   4 CasavaFiltered (125-139), 5 IsTrimmed (--discard-trimmed), 6 IsUntrimmed (--discard-untrimmed).
+// Every predicate is evaluated (a pair filter may need the verdict of a filter that the mate passes).
+__global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
+                                   const cg_match_rec *matches, int times, int slots, const int32_t *qtrim,
+                                   CgFastqFilter f, const double *phred, int32_t *interval, int32_t *fail_mask,
+                                   unsigned long long *counters, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c_written = 0, c_bp_out = 0, c_short = 0, c_long = 0, c_adapt = 0, c_bp_in = 0, c_qbp = 0,
-                       c_dis = 0, c_n = 0, c_ee = 0, c_cas = 0;
+    unsigned long long c_adapt = 0, c_bp_in = 0, c_qbp = 0;
     if (r < n_records) {
         const int n = seq_len[r];
         int start = 0, stop = n;
@@ -315,8 +317,10 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
                 }
         }
         const uint8_t *sq0 = buf + rec[r].seq_start;
-        if (f.poly_a)                                      // PolyATrimmer (modifiers.py:861-879): read[:index]
-            stop = start + poly_a_trim_core(sq0 + start, stop - start, 0);
+        if (f.poly_a)                                      // PolyATrimmer (modifiers.py:861-879)
+            stop = f.poly_a == 2 ? stop : start + poly_a_trim_core(sq0 + start, stop - start, 0);
+        if (f.poly_a == 2)                                 // ... its revcomp form for R2: read[index:]
+            start = start + poly_a_trim_core(sq0 + start, stop - start, 1);
         if (f.shorten > 0) {                               // Shortener (modifiers.py:882-899): read[:length]
             if (stop - start > f.shorten - 1) stop = start + (f.shorten - 1);
         } else if (f.shorten < 0) {                        //                                   read[length:]
@@ -329,66 +333,108 @@ __global__ void fq_outlen_kernel(const uint8_t *buf, const CgFastqRecord *rec, c
             start = a; stop = b < a ? a : b;
         }
         const int left = stop - start;
-        int keep = 1;
-        if (f.minimum_length > 0 && left < f.minimum_length) { keep = 0; c_short = 1; }
-        else if (f.maximum_length >= 0 && left > f.maximum_length) { keep = 0; c_long = 1; }
-        if (keep && f.max_n >= 0.0) {
-            // TooManyN (predicates.py:96-122): count of 'N'/'n', absolute or as a proportion of the length
-            const uint8_t *sq = buf + rec[r].seq_start + start;
+        int mask = 0;
+        if (f.minimum_length > 0 && left < f.minimum_length) mask |= 1;
+        if (f.maximum_length >= 0 && left > f.maximum_length) mask |= 2;
+        if (f.max_n >= 0.0) {
+            const uint8_t *sq = sq0 + start;
             int n_count = 0;
             for (int j = 0; j < left; ++j) n_count += (sq[j] | 0x20) == 'n';
             const bool too_many = f.max_n < 1.0 ? (left > 0 && (double)n_count / (double)left > f.max_n)
                                                 : (double)n_count > f.max_n;
-            if (too_many) { keep = 0; c_n = 1; }
+            if (too_many) mask |= 4;
         }
-        if (keep && f.max_ee >= 0.0) {
-            // TooManyExpectedErrors (predicates.py:56-71): expected_errors(qualities) with its default base 33
+        if (f.max_ee >= 0.0) {
+            // expected_errors(qualities) with its default base 33
             const double ee = expected_errors_core(buf + rec[r].qual_start + start, left, 33, phred);
             if (ee < 0.0) { atomicMin((unsigned int *)&err[1], (unsigned int)r); atomicMax(&err[0], 4); }
-            else if (ee > f.max_ee) { keep = 0; c_ee = 1; }
+            else if (ee > f.max_ee) mask |= 8;
         }
-        if (keep && f.discard_casava) {
-            // CasavaFiltered (predicates.py:125-139): name.partition(" ")[2][1:4] == ":Y:"
+        if (f.discard_casava) {
+            // name.partition(" ")[2][1:4] == ":Y:"
             const uint8_t *h = buf + rec[r].hdr_start;
             const int hl = rec[r].hdr_len;
             int sp = 0;
             while (sp < hl && h[sp] != ' ') ++sp;
-            if (sp + 4 < hl && h[sp + 2] == ':' && h[sp + 3] == 'Y' && h[sp + 4] == ':') { keep = 0; c_cas = 1; }
+            if (sp + 4 < hl && h[sp + 2] == ':' && h[sp + 3] == 'Y' && h[sp + 4] == ':') mask |= 16;
         }
-        // the final sink: DiscardTrimmed / DiscardUntrimmed (predicates.py:142-175)
-        if (keep && ((f.discard_trimmed && matched) || (f.discard_untrimmed && !matched))) { keep = 0; c_dis = 1; }
+        if (matched) mask |= 32; else mask |= 64;          // masked by the enabled filters in the finish step
         interval[2 * r] = start;
         interval[2 * r + 1] = stop;
-        // "@" header "\n" sequence "\n+\n" qualities "\n"
-        out_len[r] = keep ? rec[r].hdr_len + 2 * left + 6 : 0;
-        c_written = keep; c_bp_out = keep ? left : 0; c_adapt = matched; c_bp_in = n;
+        fail_mask[r] = mask;
+        c_adapt = matched; c_bp_in = n;
     }
-    // one atomic per warp and counter
-    c_written = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_written);
-    c_short = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_short);
-    c_long = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_long);
     c_adapt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_adapt);
-    c_dis = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_dis);
-    c_n = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_n);
-    c_ee = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_ee);
-    c_cas = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_cas);
     for (int d = 16; d; d >>= 1) {
-        c_bp_out += __shfl_down_sync(0xFFFFFFFFu, c_bp_out, d);
         c_bp_in += __shfl_down_sync(0xFFFFFFFFu, c_bp_in, d);
         c_qbp += __shfl_down_sync(0xFFFFFFFFu, c_qbp, d);
     }
     if ((threadIdx.x & 31) == 0) {
-        if (c_written) atomicAdd(&counters[0], c_written);
         if (c_bp_in) atomicAdd(&counters[1], c_bp_in);
-        if (c_bp_out) atomicAdd(&counters[2], c_bp_out);
         if (c_adapt) atomicAdd(&counters[3], c_adapt);
-        if (c_short) atomicAdd(&counters[4], c_short);
-        if (c_long) atomicAdd(&counters[5], c_long);
         if (c_qbp) atomicAdd(&counters[6], c_qbp);
-        if (c_dis) atomicAdd(&counters[7], c_dis);
-        if (c_n) atomicAdd(&counters[8], c_n);
-        if (c_ee) atomicAdd(&counters[9], c_ee);
-        if (c_cas) atomicAdd(&counters[10], c_cas);
+    }
+}
+
+// counter slot of filter bit k (the layout of cg_fastq_result): 4 too_short, 5 too_long, 8 too_many_n,
+// 9 too_many_expected_errors, 10 casava_filtered, 7 discarded (trimmed / untrimmed)
+__device__ __constant__ int kFilterCounter[7] = {4, 5, 8, 9, 10, 7, 7};
+
+// The verdict on a read (mask2 == nullptr) or a pair.  For every enabled filter, in chain order, the pair is
+// filtered according to PairedEndFilter (steps.py:105-180): a filter given for one mate only tests that mate;
+// otherwise mode 0 "any", 1 "both", 2 "first" (mode_untrimmed: cli.py:859-893 overrides the mode of
+// --discard-untrimmed to "both" when only one mate has adapters).  The first filter that fires gets the count.
+// out_len = size of the formatted record ("@" name "\n" sequence "\n+\n" qualities "\n") or 0.
+__global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1, const int32_t *interval1,
+                                 const int32_t *mask1, int enabled1, int32_t *out_len1, unsigned long long *counters1,
+                                 const CgFastqRecord *rec2, const int32_t *interval2, const int32_t *mask2, int enabled2,
+                                 int32_t *out_len2, unsigned long long *counters2, int mode, int mode_untrimmed)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int fired = -1;
+    unsigned long long bp1 = 0, bp2 = 0;
+    unsigned written = 0;
+    if (r < n_records) {
+        const int m1 = mask1[r], m2 = mask2 ? mask2[r] : 0;
+        for (int k = 0; k < 7 && fired < 0; ++k) {
+            const int bit = 1 << k;
+            const bool e1 = enabled1 & bit, e2 = mask2 && (enabled2 & bit);
+            if (!e1 && !e2) continue;
+            const bool f1 = m1 & bit, f2 = m2 & bit;
+            const int md = k == 6 ? mode_untrimmed : mode;
+            bool hit;
+            if (!e2) hit = f1;
+            else if (!e1) hit = f2;
+            else hit = md == 0 ? (f1 || f2) : md == 1 ? (f1 && f2) : f1;
+            if (hit) fired = k;
+        }
+        const int left1 = interval1[2 * r + 1] - interval1[2 * r];
+        out_len1[r] = fired < 0 ? rec1[r].hdr_len + 2 * left1 + 6 : 0;
+        if (mask2) {
+            const int left2 = interval2[2 * r + 1] - interval2[2 * r];
+            out_len2[r] = fired < 0 ? rec2[r].hdr_len + 2 * left2 + 6 : 0;
+            bp2 = fired < 0 ? left2 : 0;
+        }
+        written = fired < 0;
+        bp1 = fired < 0 ? left1 : 0;
+    }
+    const unsigned w = __reduce_add_sync(0xFFFFFFFFu, written);
+    for (int d = 16; d; d >>= 1) {
+        bp1 += __shfl_down_sync(0xFFFFFFFFu, bp1, d);
+        bp2 += __shfl_down_sync(0xFFFFFFFFu, bp2, d);
+    }
+    // filter counters: one atomic per warp and filter that fired
+    for (int k = 0; k < 7; ++k) {
+        const unsigned cnt = __popc(__ballot_sync(0xFFFFFFFFu, fired == k));
+        if (cnt && (threadIdx.x & 31) == 0) {
+            atomicAdd(&counters1[kFilterCounter[k]], (unsigned long long)cnt);
+            if (counters2) atomicAdd(&counters2[kFilterCounter[k]], (unsigned long long)cnt);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (w) { atomicAdd(&counters1[0], (unsigned long long)w); if (counters2) atomicAdd(&counters2[0], (unsigned long long)w); }
+        if (bp1) atomicAdd(&counters1[2], bp1);
+        if (bp2 && counters2) atomicAdd(&counters2[2], bp2);
     }
 }
 
@@ -480,15 +526,29 @@ cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d
     return cudaGetLastError();
 }
 
-cudaError_t cg_launch_fastq_outlen(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
-                                   long long n_records, const cg_match_rec *d_matches, int times, int slots,
-                                   const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
-                                   int32_t *d_out_len, unsigned long long *d_counters, int *d_err, cudaStream_t st)
+cudaError_t cg_launch_fastq_evaluate(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                     long long n_records, const cg_match_rec *d_matches, int times, int slots,
+                                     const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
+                                     int32_t *d_fail_mask, unsigned long long *d_counters, int *d_err, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
-    fq_outlen_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches,
-                                                                         times, slots, d_qtrim, f, d_phred, d_interval,
-                                                                         d_out_len, d_counters, d_err);
+    fq_evaluate_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches,
+                                                                           times, slots, d_qtrim, f, d_phred, d_interval,
+                                                                           d_fail_mask, d_counters, d_err);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_rec1, const int32_t *d_interval1,
+                                   const int32_t *d_mask1, int enabled1, int32_t *d_out_len1,
+                                   unsigned long long *d_counters1, const CgFastqRecord *d_rec2,
+                                   const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
+                                   unsigned long long *d_counters2, int mode, int mode_untrimmed, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_finish_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(n_records, d_rec1, d_interval1, d_mask1, enabled1,
+                                                                         d_out_len1, d_counters1, d_rec2, d_interval2,
+                                                                         d_mask2, enabled2, d_out_len2, d_counters2, mode,
+                                                                         mode_untrimmed);
     return cudaGetLastError();
 }
 

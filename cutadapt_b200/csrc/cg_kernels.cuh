@@ -110,7 +110,7 @@ struct CgFastqFilter {
     int discard_trimmed, discard_untrimmed;
     double max_n;            // < 0 = off; < 1: proportion of the length
     double max_ee;           // < 0 = off
-    int poly_a;              // PolyATrimmer after the adapter rounds
+    int poly_a;              // PolyATrimmer after the adapter rounds: 1 = poly-A tail (R1), 2 = poly-T head (R2)
     int shorten;             // Shortener: 0 = off, L + 1 for --length L >= 0, L for --length L < 0
     int trim_n;              // NEndTrimmer
     int discard_casava;      // CasavaFiltered
@@ -133,9 +133,17 @@ cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_
 cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
                                     long long n_records, int flags, int cutoff_front, int cutoff_back, int qbase,
                                     int32_t *d_qtrim, cudaStream_t st);
-cudaError_t cg_launch_fastq_outlen(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
-                                   long long n_records, const cg_match_rec *d_matches, int times, int slots,
-                                   const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
-                                   int32_t *d_out_len, unsigned long long *d_counters, int *d_err, cudaStream_t st);
+// kept interval + one bit per filter the read fails (bit order: too short, too long, too many N, too many expected
+// errors, casava, trimmed, untrimmed); per-read counters (bp_in, with_adapters, quality_trimmed_bp)
+cudaError_t cg_launch_fastq_evaluate(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                     long long n_records, const cg_match_rec *d_matches, int times, int slots,
+                                     const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
+                                     int32_t *d_fail_mask, unsigned long long *d_counters, int *d_err, cudaStream_t st);
+// verdict per read (second mate = nullptr) or pair -> sizes of the output records, filter counters
+cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_rec1, const int32_t *d_interval1,
+                                   const int32_t *d_mask1, int enabled1, int32_t *d_out_len1,
+                                   unsigned long long *d_counters1, const CgFastqRecord *d_rec2,
+                                   const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
+                                   unsigned long long *d_counters2, int mode, int mode_untrimmed, cudaStream_t st);
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
                                   const int64_t *d_out_off, long long n_records, uint8_t *d_out, cudaStream_t st);

@@ -175,6 +175,43 @@ class BatchTrimmer:
         return [stats[id(o)] for o in owners]
 
 
+def _fastq_params(times=1, quality_cutoff=None, quality_base=33, nextseq_cutoff=None, minimum_length=0,
+                  maximum_length=None, max_n=None, max_expected_errors=None, discard_trimmed=False,
+                  discard_untrimmed=False, cut=(), poly_a=False, length=None, trim_n=False,
+                  discard_casava=False) -> "_lib.cg_fastq_params":
+    fp = _lib.cg_fastq_params()
+    fp.trim = _lib.make_params(
+        quality_trim=quality_cutoff is not None,
+        cutoff_front=quality_cutoff[0] if quality_cutoff else 0,
+        cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
+        quality_base=quality_base, times=times, nextseq_cutoff=nextseq_cutoff)
+    fp.minimum_length = int(minimum_length or 0)
+    fp.maximum_length = -1 if maximum_length is None else int(maximum_length)
+    fp.max_n = -1.0 if max_n is None else float(max_n)
+    fp.max_expected_errors = -1.0 if max_expected_errors is None else float(max_expected_errors)
+    fp.discard_trimmed = int(bool(discard_trimmed))
+    fp.discard_untrimmed = int(bool(discard_untrimmed))
+    # -u N removes N bases from the 5' end, -u -N from the 3' end; several values add up per end
+    fp.cut_front = sum(int(c) for c in cut if c > 0)
+    fp.cut_back = sum(-int(c) for c in cut if c < 0)
+    fp.poly_a = int(bool(poly_a))
+    fp.shorten = int(length is not None)
+    fp.shorten_length = int(length or 0)
+    fp.trim_n = int(bool(trim_n))
+    fp.discard_casava = int(bool(discard_casava))
+    return fp
+
+
+def _device_set(adapters, ctx):
+    if adapters is not None and not isinstance(adapters, Matchable):
+        adapters = MultipleAdapters(list(adapters)) if len(adapters) else None
+    if adapters is None:
+        return None, None
+    singles, groups, _ = adapters._flatten()
+    spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups, adapters._flatten_indexes())
+    return adapters, _lib.AdapterSet(spec, ctx)
+
+
 class FastqTrimmer:
     """
     FASTQ chunks in, trimmed FASTQ chunks out -- the per-chunk worker of the reference
@@ -206,36 +243,11 @@ class FastqTrimmer:
                  discard_untrimmed: bool = False, cut: Sequence[int] = (), poly_a: bool = False,
                  length: Optional[int] = None, trim_n: bool = False, discard_casava: bool = False,
                  ctx: Optional[_lib.Context] = None):
-        if adapters is not None and not isinstance(adapters, Matchable):
-            adapters = MultipleAdapters(list(adapters)) if len(adapters) else None
-        self.adapters = adapters
         self.ctx = ctx or _lib.default_context()
-        self._set = None
-        if adapters is not None:
-            singles, groups, _ = adapters._flatten()
-            spec = _lib.AdapterSetSpec([s.descriptor() for s in singles], groups, adapters._flatten_indexes())
-            self._set = _lib.AdapterSet(spec, self.ctx)
-        fp = _lib.cg_fastq_params()
-        fp.trim = _lib.make_params(
-            quality_trim=quality_cutoff is not None,
-            cutoff_front=quality_cutoff[0] if quality_cutoff else 0,
-            cutoff_back=quality_cutoff[1] if quality_cutoff else 0,
-            quality_base=quality_base, times=times, nextseq_cutoff=nextseq_cutoff)
-        fp.minimum_length = int(minimum_length or 0)
-        fp.maximum_length = -1 if maximum_length is None else int(maximum_length)
-        fp.max_n = -1.0 if max_n is None else float(max_n)
-        fp.max_expected_errors = -1.0 if max_expected_errors is None else float(max_expected_errors)
-        fp.discard_trimmed = int(bool(discard_trimmed))
-        fp.discard_untrimmed = int(bool(discard_untrimmed))
-        # -u N removes N bases from the 5' end, -u -N from the 3' end; several values add up per end
-        fp.cut_front = sum(int(c) for c in cut if c > 0)
-        fp.cut_back = sum(-int(c) for c in cut if c < 0)
-        fp.poly_a = int(bool(poly_a))
-        fp.shorten = int(length is not None)
-        fp.shorten_length = int(length or 0)
-        fp.trim_n = int(bool(trim_n))
-        fp.discard_casava = int(bool(discard_casava))
-        self.params = fp
+        self.adapters, self._set = _device_set(adapters, self.ctx)
+        self.params = _fastq_params(times, quality_cutoff, quality_base, nextseq_cutoff, minimum_length, maximum_length,
+                                    max_n, max_expected_errors, discard_trimmed, discard_untrimmed, cut, poly_a, length,
+                                    trim_n, discard_casava)
         self.statistics = {}
         self._out_bufs, self._out_keep = {}, {}
 
@@ -286,6 +298,53 @@ class FastqTrimmer:
             pending = ticket
         if pending is not None:
             yield self._collect(pending, copy)
+
+
+class PairedFastqTrimmer:
+    """
+    Paired-end FASTQ chunks (``PairedEndPipeline.process_reads``, pipeline.py:125-153): record i of the two
+    chunks is one pair.  ``adapters1`` / ``adapters2`` are the -a / -A adapters (None or [] for none),
+    ``options1`` / ``options2`` dicts with FastqTrimmer's keyword arguments for each mate (-q / -Q, -u / -U,
+    -l / -L ...; filters such as ``minimum_length`` or ``discard_trimmed`` go into both unless the command
+    line gives them for one mate only).  ``pair_filter`` is "any" (default), "both" or "first"
+    (PairedEndFilter, steps.py:105-180).  ``process_chunk(chunk1, chunk2) -> (bytes, bytes)``;
+    ``statistics`` = (dict for R1, dict for R2).
+    """
+
+    MODES = {"any": 0, "both": 1, "first": 2}
+
+    def __init__(self, adapters1=None, adapters2=None, options1: Optional[dict] = None,
+                 options2: Optional[dict] = None, pair_filter: str = "any", ctx: Optional[_lib.Context] = None):
+        if pair_filter not in self.MODES:
+            raise ValueError("pair_filter must be 'any', 'both' or 'first'")
+        self.ctx = ctx or _lib.default_context()
+        self.adapters1, self._set1 = _device_set(adapters1, self.ctx)
+        self.adapters2, self._set2 = _device_set(adapters2, self.ctx)
+        self.params1 = _fastq_params(**(options1 or {}))
+        self.params2 = _fastq_params(**(options2 or {}))
+        self.mode = self.MODES[pair_filter]
+        self.statistics = ({}, {})
+
+    def _submit(self, chunk):
+        buf = np.frombuffer(chunk, dtype=np.uint8) if not isinstance(chunk, np.ndarray) else chunk
+        slot = C.c_int32(-1)
+        _lib.check(_lib.lib().cg_fastq_submit(self.ctx.handle, buf.ctypes.data if buf.size else None, buf.size,
+                                              C.byref(slot)))
+        return slot.value, buf
+
+    def process_chunk(self, chunk1, chunk2) -> Tuple[bytes, bytes]:
+        (s1, b1), (s2, b2) = self._submit(chunk1), self._submit(chunk2)
+        out1 = np.empty(max(b1.size, 1), dtype=np.uint8)
+        out2 = np.empty(max(b2.size, 1), dtype=np.uint8)
+        r1, r2 = _lib.cg_fastq_result(), _lib.cg_fastq_result()
+        _lib.check(_lib.lib().cg_fastq_collect_paired(
+            self.ctx.handle, s1, s2, self._set1.handle if self._set1 is not None else None,
+            self._set2.handle if self._set2 is not None else None, C.byref(self.params1), C.byref(self.params2),
+            self.mode, out1.ctypes.data, out1.size, out2.ctypes.data, out2.size, C.byref(r1), C.byref(r2)))
+        for st, res in zip(self.statistics, (r1, r2)):
+            for k, v in res.as_dict().items():
+                st[k] = st.get(k, 0) + v
+        return out1[: r1.out_bytes].tobytes(), out2[: r2.out_bytes].tobytes()
 
 
 class DeviceResult:

@@ -309,6 +309,18 @@ int cg_fastq_submit(cg_ctx *ctx, const uint8_t *fastq, int64_t n_bytes, int32_t 
 int cg_fastq_collect(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, const cg_fastq_params *params,
                      uint8_t *out, int64_t out_capacity, cg_fastq_result *res);
 
+/* Paired-end chunks (PairedEndPipeline.process_reads, pipeline.py:125-153): record i of the two chunks is one
+ * pair.  Each mate has its own adapter set (-a / -A; NULL = none) and parameters (-q / -Q, -u / -U, ...); --poly-a
+ * trims the poly-T head of the second mate (PolyATrimmer(revcomp=True), cli.py:968-971).  Filters work on the
+ * pair like PairedEndFilter (steps.py:105-180): pair_filter_mode 0 "any" (default), 1 "both", 2 "first"; a filter
+ * enabled in only one mate's parameters tests that mate alone; with adapters on one mate only,
+ * --discard-untrimmed tests "both" (cli.py:859-893).  Pair-level counters (n_written, too_short, ...) are
+ * reported in both results, per-mate ones (bp_in, bp_out, with_adapters, quality_trimmed_bp) in their own. */
+int cg_fastq_collect_paired(cg_ctx *ctx, int32_t slot1, int32_t slot2, const cg_adapterset *set1,
+                            const cg_adapterset *set2, const cg_fastq_params *params1, const cg_fastq_params *params2,
+                            int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
+                            int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2);
+
 /* ---- trim statistics (the payload of the end-of-run all-reduce, report.py:81-126) --------
  * Device-side reduction of a batch's match records into a fixed-layout int64 vector:
  *   [0] n_reads  [1] total_bp  [2] reads_with_adapters  [3] quality_trimmed_bp

@@ -344,13 +344,17 @@ def parse_fastq(data: bytes):
     return records
 
 
-def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=False, cutoff_front=0, cutoff_back=0,
-                      quality_base=33, times=1, nextseq_cutoff=None, minimum_length=0, maximum_length=-1,
-                      discard_trimmed=False, discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0,
-                      cut=(), poly_a=False, length=None, trim_n=False, discard_casava=False):
-    """(output bytes, counters dict).  Modifiers as oracle_process; then the filters in the order cli.py:700-830
-    appends them: TooShort, TooLong, TooManyN, TooManyExpectedErrors (predicates.py:29-122), and finally
-    DiscardTrimmed / DiscardUntrimmed (predicates.py:127-160)."""
+FILTER_CHAIN = ("too_short", "too_long", "too_many_n", "too_many_expected_errors", "casava_filtered",
+                "discard_trimmed", "discard_untrimmed")     # the order cli.py:700-830, 870-910 appends them
+_FILTER_COUNTER = {"discard_trimmed": "discarded", "discard_untrimmed": "discarded"}
+
+
+def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, cutoff_back=0, quality_base=33, times=1,
+                    nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
+                    discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
+                    trim_n=False, discard_casava=False, second_mate=False):
+    """Modifier chain on every record of a chunk + the verdict of every enabled filter.
+    Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters)."""
     records = parse_fastq(data)
     for c_len in cut:                                   # UnconditionalCutter, first in the chain (modifiers.py:66-95)
         records = [(nm, sq[c_len:], q[c_len:]) if c_len > 0 else (nm, sq[:c_len], q[:c_len]) for nm, sq, q in records]
@@ -370,9 +374,11 @@ def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=Fals
             if quality_trim:
                 s, e = quality_trim_index(q[:e], cutoff_front, cutoff_back, quality_base)
             qtrim[i] = (s, e)
+    enabled = [name for name, on in zip(FILTER_CHAIN, (minimum_length > 0, maximum_length >= 0, max_n >= 0,
+                                                       max_expected_errors >= 0, discard_casava, discard_trimmed,
+                                                       discard_untrimmed)) if on]
+    c = dict(n_records=n, bp_in=0, with_adapters=0, quality_trimmed_bp=0)
     out = []
-    c = dict(n_records=n, n_written=0, bp_in=0, bp_out=0, with_adapters=0, quality_trimmed_bp=0, too_short=0,
-             too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0, casava_filtered=0)
     for i, (name, seq, q) in enumerate(records):
         s, e = int(qtrim[i, 0]), int(qtrim[i, 1])
         c["bp_in"] += len(seq)
@@ -391,36 +397,97 @@ def oracle_fastq_trim(data: bytes, adapters=None, groups=None, quality_trim=Fals
                         s = s + int(m["rstop"])
         c["with_adapters"] += matched
         ts, tq = seq[s:e], q[s:e]
-        if poly_a:                                      # PolyATrimmer (modifiers.py:861-879)
-            idx = poly_a_trim_index(ts)
-            ts, tq = ts[:idx], tq[:idx]
+        if poly_a:                                      # PolyATrimmer (modifiers.py:861-879); revcomp form for R2
+            if second_mate:
+                idx = poly_a_trim_index(ts, revcomp=True)
+                ts, tq = ts[idx:], tq[idx:]
+            else:
+                idx = poly_a_trim_index(ts)
+                ts, tq = ts[:idx], tq[:idx]
         if length is not None:                          # Shortener (modifiers.py:882-899)
             ts, tq = (ts[:length], tq[:length]) if length >= 0 else (ts[length:], tq[length:])
         if trim_n:                                      # NEndTrimmer (modifiers.py:902-918): upper-case N only
             a = len(ts) - len(ts.lstrip("N"))
             b = len(ts.rstrip("N"))
             ts, tq = ts[a:b], tq[a:b]
-        if minimum_length > 0 and len(ts) < minimum_length:
-            c["too_short"] += 1
-            continue
-        if maximum_length >= 0 and len(ts) > maximum_length:
-            c["too_long"] += 1
-            continue
-        if max_n >= 0:
-            n_count = ts.lower().count("n")
-            if (max_n < 1.0 and len(ts) > 0 and n_count / len(ts) > max_n) or (max_n >= 1.0 and n_count > max_n):
-                c["too_many_n"] += 1
-                continue
-        if max_expected_errors >= 0 and expected_errors(tq) > max_expected_errors:
-            c["too_many_expected_errors"] += 1
-            continue
-        if discard_casava and name.partition(" ")[2][1:4] == ":Y:":     # predicates.py:125-139
-            c["casava_filtered"] += 1
-            continue
-        if (discard_trimmed and matched) or (discard_untrimmed and not matched):
-            c["discarded"] += 1
+        n_count = ts.lower().count("n")
+        fails = {
+            "too_short": len(ts) < minimum_length,                                        # predicates.py:29-40
+            "too_long": len(ts) > maximum_length,                                         # predicates.py:43-53
+            "too_many_n": (n_count / len(ts) > max_n if len(ts) else False) if max_n < 1.0 else n_count > max_n,
+            "too_many_expected_errors": max_expected_errors >= 0 and expected_errors(tq) > max_expected_errors,
+            "casava_filtered": name.partition(" ")[2][1:4] == ":Y:",                      # predicates.py:125-139
+            "discard_trimmed": matched, "discard_untrimmed": not matched,                 # predicates.py:142-175
+        }
+        out.append((name, ts, tq, fails))
+    return out, enabled, c
+
+
+def _fastq_record(name, ts, tq):
+    return f"@{name}\n{ts}\n+\n{tq}\n".encode("latin-1")
+
+
+def oracle_fastq_trim(data: bytes, adapters=None, groups=None, **options):
+    """(output bytes, counters dict) of one single-end chunk.  Options: see _fastq_evaluate.  Filters in the order
+    cli.py appends them; the first that matches counts the read (SingleEndFilter, steps.py:70-102)."""
+    evaluated, enabled, c = _fastq_evaluate(data, adapters, groups, **options)
+    c.update(n_written=0, bp_out=0, too_short=0, too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0,
+             casava_filtered=0)
+    out = []
+    for name, ts, tq, fails in evaluated:
+        fired = next((f for f in enabled if fails[f]), None)
+        if fired is not None:
+            c[_FILTER_COUNTER.get(fired, fired)] += 1
             continue
         c["n_written"] += 1
         c["bp_out"] += len(ts)
-        out.append(f"@{name}\n{ts}\n+\n{tq}\n".encode("latin-1"))
+        out.append(_fastq_record(name, ts, tq))
     return b"".join(out), c
+
+
+def oracle_fastq_trim_paired(data1: bytes, data2: bytes, adapters1=None, groups1=None, adapters2=None, groups2=None,
+                             options1=None, options2=None, pair_filter="any"):
+    """(out1, out2, counters1, counters2) of one paired-end chunk (PairedEndPipeline.process_reads, pipeline.py:125-153).
+    Each filter works on the pair like PairedEndFilter (steps.py:105-180); with adapters on one mate only,
+    --discard-untrimmed tests "both" (cli.py:859-893)."""
+    ev1, en1, c1 = _fastq_evaluate(data1, adapters1, groups1, **(options1 or {}))
+    ev2, en2, c2 = _fastq_evaluate(data2, adapters2, groups2, second_mate=True, **(options2 or {}))
+    if len(ev1) != len(ev2):
+        raise FastqFormatError("paired FASTQ chunks differ in their number of records")
+    for c in (c1, c2):
+        c.update(n_written=0, bp_out=0, too_short=0, too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0,
+                 casava_filtered=0)
+    out1, out2 = [], []
+    for (n1, s1, q1, f1), (n2, s2, q2, f2) in zip(ev1, ev2):
+        fired = None
+        for flt in FILTER_CHAIN:
+            e1, e2 = flt in en1, flt in en2
+            if not e1 and not e2:
+                continue
+            mode = pair_filter
+            if flt == "discard_untrimmed" and (not adapters1 or not adapters2):
+                mode = "both"
+            if not e2:
+                hit = f1[flt]
+            elif not e1:
+                hit = f2[flt]
+            elif mode == "any":
+                hit = f1[flt] or f2[flt]
+            elif mode == "both":
+                hit = f1[flt] and f2[flt]
+            else:
+                hit = f1[flt]
+            if hit:
+                fired = flt
+                break
+        if fired is not None:
+            for c in (c1, c2):
+                c[_FILTER_COUNTER.get(fired, fired)] += 1
+            continue
+        for c in (c1, c2):
+            c["n_written"] += 1
+        c1["bp_out"] += len(s1)
+        c2["bp_out"] += len(s2)
+        out1.append(_fastq_record(n1, s1, q1))
+        out2.append(_fastq_record(n2, s2, q2))
+    return b"".join(out1), b"".join(out2), c1, c2

@@ -63,6 +63,59 @@ CASES = [
 ]
 
 
+# paired-end: name, reference test (test_paired.py line), command line, in1, in2, expected1, expected2, options
+Q10 = dict(quality_cutoff=[0, 10])
+Q20 = dict(quality_cutoff=[0, 20])
+PAIRED = [
+    ("m14", 48, "-a TTAGACATAT -m 14 -q 10", "paired.1.fastq", "paired.2.fastq", "paired.m14.1.fastq", "paired.m14.2.fastq",
+     dict(adapters1=[["back", "TTAGACATAT"]], adapters2=[], options1=dict(minimum_length=14, **Q10),
+          options2=dict(minimum_length=14, **Q10))),
+    ("m27", 260, "-a XXX -m 27", "paired.1.fastq", "paired.2.fastq", "paired-m27.1.fastq", "paired-m27.2.fastq",
+     dict(adapters1=[["back", "XXX"]], adapters2=[], options1=dict(minimum_length=27), options2=dict(minimum_length=27))),
+    ("both_adapters", 272, "-a TTAGACATAT -A CAGTGGAGTA -m 14", "paired.1.fastq", "paired.2.fastq", "paired.1.fastq",
+     "paired.2.fastq", dict(adapters1=[["back", "TTAGACATAT"]], adapters2=[["back", "CAGTGGAGTA"]],
+                            options1=dict(minimum_length=14), options2=dict(minimum_length=14))),
+    ("qualtrim", 295, "-q 20 -a TTAGACATAT -A CAGTGGAGTA -m 14 -M 90", "paired.1.fastq", "paired.2.fastq",
+     "pairedq.1.fastq", "pairedq.2.fastq",
+     dict(adapters1=[["back", "TTAGACATAT"]], adapters2=[["back", "CAGTGGAGTA"]],
+          options1=dict(minimum_length=14, maximum_length=90, **Q20),
+          options2=dict(minimum_length=14, maximum_length=90, **Q20))),
+    ("qualtrim_swapped", 307, "-q 20 -a CAGTGGAGTA -A TTAGACATAT -m 14", "paired.2.fastq", "paired.1.fastq",
+     "pairedq.2.fastq", "pairedq.1.fastq",
+     dict(adapters1=[["back", "CAGTGGAGTA"]], adapters2=[["back", "TTAGACATAT"]],
+          options1=dict(minimum_length=14, **Q20), options2=dict(minimum_length=14, **Q20))),
+    ("q10_Q0", 325, "-q 10 -Q 0", "lowqual.fastq", "lowqual.fastq", "lowqual.fastq", "lowqual.unchanged.fastq",
+     dict(adapters1=[], adapters2=[], options1=dict(**Q10), options2=dict())),
+    ("Q10_only", 323, "-Q 10", "lowqual.fastq", "lowqual.fastq", "lowqual.unchanged.fastq", "lowqual.fastq",
+     dict(adapters1=[], adapters2=[], options1=dict(), options2=dict(**Q10))),
+    ("cut", 340, "-u 3 -u -1 -U 4 -U -2", "paired.1.fastq", "paired.2.fastq", "pairedu.1.fastq", "pairedu.2.fastq",
+     dict(adapters1=[], adapters2=[], options1=dict(cut=[3, -1]), options2=dict(cut=[4, -2]))),
+    ("length5", 351, "--length 5", "paired.1.fastq", "paired.2.fastq", "length5.1.fastq", "length5.2.fastq",
+     dict(adapters1=[], adapters2=[], options1=dict(length=5), options2=dict(length=5))),
+    ("length_neg5", 362, "--length -5", "paired.1.fastq", "paired.2.fastq", "length-5.1.fastq", "length-5.2.fastq",
+     dict(adapters1=[], adapters2=[], options1=dict(length=-5), options2=dict(length=-5))),
+    ("L5_only", 384, "-L 5", "paired.1.fastq", "paired.2.fastq", "paired-unchanged.1.fastq", "length5.2.fastq",
+     dict(adapters1=[], adapters2=[], options1=dict(), options2=dict(length=5))),
+    ("only_A", 396, "-A CAGTGGAGTA", "paired.1.fastq", "paired.2.fastq", "paired-onlyA.1.fastq", "paired-onlyA.2.fastq",
+     dict(adapters1=[], adapters2=[["back", "CAGTGGAGTA"]], options1=dict(), options2=dict())),
+    ("discard_untrimmed", 408, "-a CTCCAGCTTAGACATATC -A XXXXXXXX --discard-untrimmed", "paired.1.fastq",
+     "paired.2.fastq", "empty.fastq", "empty.fastq",
+     dict(adapters1=[["back", "CTCCAGCTTAGACATATC"]], adapters2=[["back", "XXXXXXXX"]],
+          options1=dict(discard_untrimmed=True), options2=dict(discard_untrimmed=True))),
+    ("discard_trimmed", 419, "-A C -O 1 --discard-trimmed", "paired.1.fastq", "paired.2.fastq", "empty.fastq",
+     "empty.fastq", dict(adapters1=[], adapters2=[["back", "C"]], min_overlap=1,
+                         options1=dict(discard_trimmed=True), options2=dict(discard_trimmed=True))),
+    ("filter_both", 493, "--pair-filter=both -a TTAGACATAT -A GGAGTA -m 14", "paired.1.fastq", "paired.2.fastq",
+     "paired-filterboth.1.fastq", "paired-filterboth.2.fastq",
+     dict(adapters1=[["back", "TTAGACATAT"]], adapters2=[["back", "GGAGTA"]], pair_filter="both",
+          options1=dict(minimum_length=14), options2=dict(minimum_length=14))),
+    ("filter_first", 504, "--pair-filter=first -a TTAGACATAT -A GGAGTA -m 14", "paired.1.fastq", "paired.2.fastq",
+     "paired-filterfirst.1.fastq", "paired-filterfirst.2.fastq",
+     dict(adapters1=[["back", "TTAGACATAT"]], adapters2=[["back", "GGAGTA"]], pair_filter="first",
+          options1=dict(minimum_length=14), options2=dict(minimum_length=14))),
+]
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
     index = []
@@ -80,6 +133,17 @@ def main():
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(index, f, indent=1)
     print(len(index), "cases")
+    pindex = []
+    for name, line, cmd, in1, in2, exp1, exp2, opts in PAIRED:
+        for k, (inp, exp) in enumerate(((in1, exp1), (in2, exp2)), 1):
+            shutil.copyfile(os.path.join(REF, "data", inp), os.path.join(HERE, f"paired_{name}.in{k}.fastq"))
+            shutil.copyfile(os.path.join(REF, "cut", exp), os.path.join(HERE, f"paired_{name}.out{k}.fastq"))
+        pindex.append(dict(name=name, reference_test=f"tests/test_paired.py:{line}", command=cmd,
+                           inputs=[f"tests/data/{in1}", f"tests/data/{in2}"],
+                           expected=[f"tests/cut/{exp1}", f"tests/cut/{exp2}"], options=opts))
+    with open(os.path.join(HERE, "paired_cases.json"), "w") as f:
+        json.dump(pindex, f, indent=1)
+    print(len(pindex), "paired cases")
 
 
 if __name__ == "__main__":

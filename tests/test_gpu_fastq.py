@@ -10,9 +10,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from cutadapt_b200.pipeline import FastqTrimmer  # noqa: E402
+from cutadapt_b200.pipeline import FastqTrimmer, PairedFastqTrimmer  # noqa: E402
 from oracle import oracle  # noqa: E402
-from util import fastq_cases, fastq_case_adapters, fastq_case_kwargs, spec_of  # noqa: E402
+from util import (fastq_cases, fastq_case_adapters, fastq_case_kwargs, spec_of, fastq_paired_cases,  # noqa: E402
+                  oracle_paired)
 
 
 def trimmer_for(options, **extra):
@@ -161,3 +162,58 @@ def test_large_chunk_properties():
     kept_names = {exp_lines[k] for k in range(0, len(exp_lines) - 1, 4)}
     for i in idx:
         assert ((b"@r%d" % i) in by_name) == ((b"@r%d" % i) in kept_names)
+
+
+# ---- paired-end ----------------------------------------------------------------------------------------
+
+def trimmer_kwargs(options):
+    kw = fastq_case_kwargs(options)
+    if kw.pop("quality_trim", False):
+        kw["quality_cutoff"] = (kw.pop("cutoff_front"), kw.pop("cutoff_back"))
+    return kw
+
+
+def paired_trimmer_for(options):
+    return PairedFastqTrimmer(fastq_case_adapters(options, "adapters1"), fastq_case_adapters(options, "adapters2"),
+                              trimmer_kwargs(options["options1"]), trimmer_kwargs(options["options2"]),
+                              options.get("pair_filter", "any"))
+
+
+def test_paired_reference_goldens():
+    """The paired-end FASTQ known-answer cases of the reference's tests/test_paired.py, byte for byte."""
+    for c in fastq_paired_cases():
+        t = paired_trimmer_for(c["options"])
+        got = t.process_chunk(*c["input_bytes"])
+        assert list(got) == c["expected_bytes"], c["name"]
+        _, _, c1, c2 = oracle_paired(oracle, c["options"], *c["input_bytes"])
+        for st, cc in zip(t.statistics, (c1, c2)):
+            for k, v in cc.items():
+                assert st[k] == v, (c["name"], k)
+
+
+@pytest.mark.parametrize("mode", ["any", "both", "first"])
+def test_paired_random_chunks_against_oracle(mode):
+    data1 = synthetic_fastq(5000, seed=71)
+    data2 = synthetic_fastq(5000, seed=72)
+    options = dict(
+        adapters1=[["back", "AGATCGGAAGAGC"]], adapters2=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]],
+        pair_filter=mode,
+        options1=dict(quality_cutoff=[0, 20], minimum_length=30, max_n=2, cut=[2], poly_a=True, discard_casava=True,
+                      max_expected_errors=3.0),
+        options2=dict(quality_cutoff=[3, 15], minimum_length=25, maximum_length=200, max_n=2, cut=[-3], poly_a=True,
+                      trim_n=True, discard_casava=True, max_expected_errors=3.0))
+    t = paired_trimmer_for(options)
+    got = t.process_chunk(data1, data2)
+    e1, e2, c1, c2 = oracle_paired(oracle, options, data1, data2)
+    assert got == (e1, e2)
+    for st, cc in zip(t.statistics, (c1, c2)):
+        for k, v in cc.items():
+            assert st[k] == v, k
+    # one-sided adapters with --discard-untrimmed: the pair mode of that filter becomes "both"
+    options = dict(adapters1=[["back", "AGATCGGAAGAGC"]], adapters2=[], pair_filter=mode,
+                   options1=dict(discard_untrimmed=True, minimum_length=20), options2=dict(discard_untrimmed=True))
+    t = paired_trimmer_for(options)
+    e1, e2, _, _ = oracle_paired(oracle, options, data1, data2)
+    assert t.process_chunk(data1, data2) == (e1, e2)
+    with pytest.raises(ValueError):
+        t.process_chunk(data1, synthetic_fastq(4999, seed=72))

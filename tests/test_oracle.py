@@ -151,3 +151,15 @@ def test_fastq_oracle_reproduces_the_reference_command_line_goldens():
         oracle.parse_fastq(b"@r\nACGT\n+\nII\n")
     with pytest.raises(oracle.FastqFormatError):
         oracle.parse_fastq(b"@r\nACGT\n+\n")
+
+
+def test_paired_fastq_oracle_reproduces_the_reference_goldens():
+    """oracle.oracle_fastq_trim_paired against the expected files of the reference's tests/test_paired.py."""
+    from util import fastq_paired_cases, oracle_paired
+
+    cases = fastq_paired_cases()
+    assert len(cases) >= 16
+    for c in cases:
+        o1, o2, c1, c2 = oracle_paired(oracle, c["options"], *c["input_bytes"])
+        assert [o1, o2] == c["expected_bytes"], c["name"]
+        assert c1["n_written"] == c2["n_written"] <= c1["n_records"] == c2["n_records"]

@@ -156,13 +156,41 @@ def fastq_cases():
     return cases
 
 
-def fastq_case_adapters(options):
-    """The adapters of a case as the command line would build them (-e, default -O 3): cutadapt_b200 objects."""
+def fastq_case_adapters(options, key="adapters"):
+    """The adapters of a case as the command line would build them (-e, -O, default 3): cutadapt_b200 objects."""
     import cutadapt_b200.adapters as PA
 
     kinds = {"back": PA.BackAdapter, "front": PA.FrontAdapter, "anywhere": PA.AnywhereAdapter}
     e = options.get("error_rate", 0.1)
-    return [kinds[k](seq, max_errors=e, min_overlap=3, name=f"a{i}") for i, (k, seq) in enumerate(options["adapters"])]
+    o = options.get("min_overlap", 3)
+    return [kinds[k](seq, max_errors=e, min_overlap=o, name=f"a{i}") for i, (k, seq) in enumerate(options[key])]
+
+
+def fastq_paired_cases():
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastq")
+    cases = json.load(open(os.path.join(here, "paired_cases.json")))
+    for c in cases:
+        c["input_bytes"] = [open(os.path.join(here, f"paired_{c['name']}.in{k}.fastq"), "rb").read() for k in (1, 2)]
+        c["expected_bytes"] = [open(os.path.join(here, f"paired_{c['name']}.out{k}.fastq"), "rb").read() for k in (1, 2)]
+    return cases
+
+
+def oracle_paired(oracle, options, data1, data2):
+    """oracle.oracle_fastq_trim_paired for a paired case's options."""
+    import cutadapt_b200.adapters as PA
+
+    sets = []
+    for key in ("adapters1", "adapters2"):
+        ads = fastq_case_adapters(options, key)
+        if ads:
+            spec = spec_of(PA.MultipleAdapters(ads))
+            sets.append((spec.adapters, spec.groups))
+        else:
+            sets.append((None, None))
+    return oracle.oracle_fastq_trim_paired(
+        data1, data2, sets[0][0], sets[0][1], sets[1][0], sets[1][1],
+        fastq_case_kwargs(options["options1"]), fastq_case_kwargs(options["options2"]), options.get("pair_filter", "any"))
 
 
 def fastq_case_kwargs(options):
