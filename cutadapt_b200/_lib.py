@@ -174,6 +174,8 @@ def _declare(lib) -> None:
     lib.cg_fastq_trim_chunk.argtypes = [vp, vp, vp, i64, C.POINTER(cg_fastq_params), vp, i64,
                                         C.POINTER(cg_fastq_result)]
     lib.cg_fastq_submit.argtypes = [vp, vp, i64, C.POINTER(i32)]
+    lib.cg_fastq_collect_demux.argtypes = [vp, i32, vp, C.POINTER(cg_fastq_params), vp, i32, vp, i64,
+                                           C.POINTER(cg_fastq_result), vp]
     lib.cg_fastq_collect_paired.argtypes = [vp, i32, i32, vp, vp, C.POINTER(cg_fastq_params), C.POINTER(cg_fastq_params),
                                             i32, vp, i64, vp, i64, C.POINTER(cg_fastq_result), C.POINTER(cg_fastq_result)]
     lib.cg_fastq_collect.argtypes = [vp, i32, vp, C.POINTER(cg_fastq_params), vp, i64, C.POINTER(cg_fastq_result)]

@@ -109,7 +109,8 @@ struct FastqSlot {
     DevBuf<uint8_t> d_in, d_out, d_seq, d_qual;
     DevBuf<uint32_t> d_tiles, d_nl;
     DevBuf<CgFastqRecord> d_rec;
-    DevBuf<int32_t> d_len, d_interval, d_outlen, d_qtrim, d_mask;
+    DevBuf<int32_t> d_len, d_interval, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes;
+    DevBuf<int64_t> d_dmbase;
     DevBuf<int64_t> d_offs, d_outoff;
     DevBuf<unsigned long long> d_scan;
     DevBuf<cg_match_rec> d_matches;
@@ -247,7 +248,8 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
     c->pass_tmp.release(); c->view_base.release(); c->view_back.release();
     for (FastqSlot &f : c->fq) {
         f.d_in.release(); f.d_out.release(); f.d_seq.release(); f.d_qual.release(); f.d_tiles.release(); f.d_nl.release();
-        f.d_rec.release(); f.d_len.release(); f.d_mask.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
+        f.d_rec.release(); f.d_len.release(); f.d_mask.release(); f.d_adest.release(); f.d_dmbytes.release();
+        f.d_dmbase.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
         f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release();
         f.h_in.release(); f.h_out.release(); f.h_counters.release();
         if (f.d_counters) cudaFree(f.d_counters);
@@ -1353,16 +1355,41 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
 }
 
 // sizes -> offsets -> formatted records -> host; counters
+struct FqDemux {                      // optional: route the records by the adapter of their last match
+    const int32_t *adapter_dest = nullptr;   // host, one destination per adapter, values in [0, n_named)
+    int n_adapters = 0, n_named = 0;
+    int64_t *segments = nullptr;             // host out, n_named + 2 offsets into the output
+};
+
 static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStream_t st, uint8_t *out,
-                              int64_t out_capacity, cg_fastq_result *res)
+                              int64_t out_capacity, cg_fastq_result *res, const FqDemux *dm = nullptr)
 {
     const long long n = g.n;
     int rc;
-    CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
-    c->launches += 3;
     long long total = 0;
     int fq_err[2];
-    CU(cudaMemcpyAsync(&total, f.d_outoff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    if (dm) {
+        const int n_dest = dm->n_named + 1;
+        const long long tiles = cg_demux_tiles(n), cells = tiles * n_dest;
+        if ((rc = f.d_adest.ensure((size_t)dm->n_adapters)) != CG_OK) return rc;
+        if ((rc = f.d_dmbytes.ensure((size_t)cells)) != CG_OK) return rc;
+        if ((rc = f.d_dmbase.ensure((size_t)cells + 1)) != CG_OK) return rc;
+        if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(cells) + 1)) != CG_OK) return rc;
+        CU(cudaMemcpyAsync(f.d_adest.p, dm->adapter_dest, (size_t)dm->n_adapters * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cg_launch_fastq_demux(0, f.d_outlen.p, f.d_mask.p, n, f.d_adest.p, n_dest, f.d_dmbytes.p, nullptr, nullptr, st));
+        CU(cg_launch_scan_i32(f.d_dmbytes.p, cells, f.d_scan.p, f.d_dmbase.p, st));
+        CU(cg_launch_fastq_demux(1, f.d_outlen.p, f.d_mask.p, n, f.d_adest.p, n_dest, nullptr, f.d_dmbase.p, f.d_outoff.p, st));
+        c->launches += 5;
+        // segment d starts at base[d][tile 0]; the last entry is the total
+        CU(cudaMemcpy2DAsync(dm->segments, sizeof(int64_t), f.d_dmbase.p, (size_t)tiles * sizeof(int64_t), sizeof(int64_t),
+                             (size_t)n_dest, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(dm->segments + n_dest, f.d_dmbase.p + cells, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&total, f.d_dmbase.p + cells, sizeof total, cudaMemcpyDeviceToHost, st));
+    } else {
+        CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
+        c->launches += 3;
+        CU(cudaMemcpyAsync(&total, f.d_outoff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(f.h_counters.p, f.d_counters, (1 + CG_FQ_COUNTERS) * sizeof(unsigned long long),
                        cudaMemcpyDeviceToHost, st));
@@ -1381,7 +1408,7 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
     if (total > 0) {
         if (!out) return fail(CG_EINVAL, "cg_fastq_collect: out is NULL");
         if ((rc = f.d_out.ensure((size_t)total + 64)) != CG_OK) return rc;
-        CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, n, f.d_out.p, st));
+        CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, f.d_outlen.p, n, f.d_out.p, st));
         c->launches += 1;
         if (is_pinned(out)) {
             CU(cudaMemcpyAsync(out, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
@@ -1397,8 +1424,8 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
     return CG_OK;
 }
 
-extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
-                                uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
+static int fastq_collect_impl(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                              uint8_t *out, int64_t out_capacity, cg_fastq_result *res, const FqDemux *dm)
 {
     if (!c || !fp || !res || slot < 0 || slot >= CG_FQ_SLOTS) return fail(CG_EINVAL, "cg_fastq_collect: bad argument");
     if (s && s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
@@ -1413,8 +1440,29 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
     CU(cg_launch_fastq_finish(g.n, f.d_rec.p, f.d_interval.p, f.d_mask.p, fastq_enabled_filters(fp), f.d_outlen.p,
                               f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, f.stream));
     c->launches += 1;
-    if ((rc = fastq_stage_output(c, f, g, f.stream, out, out_capacity, res)) != CG_OK) return rc;
+    if ((rc = fastq_stage_output(c, f, g, f.stream, out, out_capacity, res, dm)) != CG_OK) return rc;
     return check_err_flag(c);
+}
+
+extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                                uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
+{
+    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr);
+}
+
+extern "C" int cg_fastq_collect_demux(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                                      const int32_t *adapter_dest, int32_t n_named, uint8_t *out, int64_t out_capacity,
+                                      cg_fastq_result *res, int64_t *segments)
+{
+    if (!s || !adapter_dest || !segments || n_named < 1 || n_named > 4096)
+        return fail(CG_EINVAL, "cg_fastq_collect_demux: bad argument");
+    for (int a = 0; a < s->host.n_adapters; ++a)
+        if (adapter_dest[a] < 0 || adapter_dest[a] >= n_named)
+            return fail(CG_EINVAL, "cg_fastq_collect_demux: adapter_dest out of range");
+    for (int d = 0; d < n_named + 2; ++d) segments[d] = 0;
+    FqDemux dm;
+    dm.adapter_dest = adapter_dest; dm.n_adapters = s->host.n_adapters; dm.n_named = n_named; dm.segments = segments;
+    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, &dm);
 }
 
 extern "C" int cg_fastq_collect_paired(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *s1,

@@ -306,12 +306,14 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
         if (qtrim) { start = qtrim[2 * r]; stop = qtrim[2 * r + 1]; }
         c_qbp = (unsigned long long)(n - (stop - start));
         bool matched = false;
+        int last_adapter = -1;                 // info.matches[-1].adapter: where a demultiplexer sends the read
         if (matches) {
             for (int t = 0; t < times; ++t)
                 for (int s = 0; s < slots; ++s) {
                     const cg_match_rec m = matches[((size_t)r * times + t) * slots + s];
                     if (m.adapter < 0) continue;
                     matched = true;
+                    last_adapter = m.adapter;
                     if ((m.info >> 8) & 1) stop = start + m.rstart;    // RemoveAfterMatch
                     else start = start + m.rstop;                      // RemoveBeforeMatch
                 }
@@ -361,7 +363,7 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
         if (matched) mask |= 32; else mask |= 64;          // masked by the enabled filters in the finish step
         interval[2 * r] = start;
         interval[2 * r + 1] = stop;
-        fail_mask[r] = mask;
+        fail_mask[r] = mask | ((last_adapter + 1) << 8);
         c_adapt = matched; c_bp_in = n;
     }
     c_adapt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_adapt);
@@ -440,13 +442,14 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
 
 // the trimmed records, one warp per record
 __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *interval,
-                                                        const int64_t *out_off, long long n_records, uint8_t *out)
+                                                        const int64_t *out_off, const int32_t *out_len,
+                                                        long long n_records, uint8_t *out)
 {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_records; r += warps) {
+        if (out_len[r] == 0) continue;         // filtered
         const long long o = out_off[r];
-        if (out_off[r + 1] == o) continue;     // filtered
         const CgFastqRecord m = rec[r];
         const int start = interval[2 * r], left = interval[2 * r + 1] - start;
         uint8_t *p = out + o;
@@ -459,6 +462,50 @@ __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const
         if (lane < 3) p[lane] = lane == 1 ? '+' : '\n';
         for (int j = lane; j < left; j += 32) p[3 + j] = buf[m.qual_start + start + j];
         if (lane == 0) p[3 + left] = '\n';
+    }
+}
+
+// ---- demultiplexing (Demultiplexer.__call__, steps.py:397-409): records go to the output of the adapter of
+// their most recent match, reads without a match to "unknown"; inside every output the input order is kept.
+// A stable partition of the OUTPUT BYTES: per tile of 256 records the bytes per destination, an exclusive scan
+// over (destination-major, tile-minor), then every record's offset = base(destination, tile) + bytes of the
+// earlier records of its tile with the same destination.
+constexpr int DM_TILE = 256;
+
+__device__ __forceinline__ int demux_dest(int mask, const int32_t *adapter_dest, int n_dest)
+{
+    const int adapter = (mask >> 8) - 1;
+    return adapter < 0 ? n_dest - 1 : adapter_dest[adapter];
+}
+
+__global__ void __launch_bounds__(DM_TILE) fq_demux_hist_kernel(const int32_t *out_len, const int32_t *mask, long long n,
+                                                                 const int32_t *adapter_dest, int n_dest, long long n_tiles,
+                                                                 int32_t *bytes)
+{
+    extern __shared__ int hist[];
+    for (int d = threadIdx.x; d < n_dest; d += DM_TILE) hist[d] = 0;
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * DM_TILE + threadIdx.x;
+    if (r < n && out_len[r] > 0) atomicAdd(&hist[demux_dest(mask[r], adapter_dest, n_dest)], out_len[r]);
+    __syncthreads();
+    for (int d = threadIdx.x; d < n_dest; d += DM_TILE) bytes[(long long)d * n_tiles + blockIdx.x] = hist[d];
+}
+
+__global__ void __launch_bounds__(DM_TILE) fq_demux_offsets_kernel(const int32_t *out_len, const int32_t *mask, long long n,
+                                                                    const int32_t *adapter_dest, int n_dest,
+                                                                    long long n_tiles, const int64_t *base, int64_t *out_off)
+{
+    __shared__ int s_dest[DM_TILE], s_len[DM_TILE];
+    const long long r = (long long)blockIdx.x * DM_TILE + threadIdx.x;
+    const int len = r < n ? out_len[r] : 0;
+    const int dest = len > 0 ? demux_dest(mask[r], adapter_dest, n_dest) : -1;
+    s_dest[threadIdx.x] = dest;
+    s_len[threadIdx.x] = len;
+    __syncthreads();
+    if (len > 0) {
+        long long before = 0;
+        for (int j = 0; j < (int)threadIdx.x; ++j) before += s_dest[j] == dest ? s_len[j] : 0;
+        out_off[r] = base[(long long)dest * n_tiles + blockIdx.x] + before;
     }
 }
 
@@ -553,11 +600,30 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
 }
 
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
-                                  const int64_t *d_out_off, long long n_records, uint8_t *d_out, cudaStream_t st)
+                                  const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
+                                  uint8_t *d_out, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     long long grid = (n_records + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
-    fq_write_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_interval, d_out_off, n_records, d_out);
+    fq_write_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_interval, d_out_off, d_out_len, n_records, d_out);
+    return cudaGetLastError();
+}
+
+long long cg_demux_tiles(long long n_records) { return (n_records + DM_TILE - 1) / DM_TILE; }
+
+cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_mask, long long n_records,
+                                  const int32_t *d_adapter_dest, int n_dest, int32_t *d_bytes, const int64_t *d_base,
+                                  int64_t *d_out_off, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    const long long tiles = cg_demux_tiles(n_records);
+    if (phase == 0)
+        fq_demux_hist_kernel<<<(unsigned)tiles, DM_TILE, (size_t)n_dest * sizeof(int), st>>>(d_out_len, d_mask, n_records,
+                                                                                           d_adapter_dest, n_dest, tiles,
+                                                                                           d_bytes);
+    else
+        fq_demux_offsets_kernel<<<(unsigned)tiles, DM_TILE, 0, st>>>(d_out_len, d_mask, n_records, d_adapter_dest, n_dest,
+                                                                    tiles, d_base, d_out_off);
     return cudaGetLastError();
 }

@@ -146,4 +146,12 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
                                    const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
                                    unsigned long long *d_counters2, int mode, int mode_untrimmed, cudaStream_t st);
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
-                                  const int64_t *d_out_off, long long n_records, uint8_t *d_out, cudaStream_t st);
+                                  const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
+                                  uint8_t *d_out, cudaStream_t st);
+// demultiplexing: phase 0 fills d_bytes[n_dest][tiles] (output bytes per destination and tile of 256 records);
+// after an exclusive scan of that array (d_base), phase 1 writes every record's output offset.
+// d_adapter_dest: destination of every adapter; reads without a match go to destination n_dest - 1.
+long long cg_demux_tiles(long long n_records);
+cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_mask, long long n_records,
+                                  const int32_t *d_adapter_dest, int n_dest, int32_t *d_bytes, const int64_t *d_base,
+                                  int64_t *d_out_off, cudaStream_t st);

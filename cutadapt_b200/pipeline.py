@@ -288,6 +288,35 @@ class FastqTrimmer:
     def process_chunk(self, chunk) -> bytes:
         return self._collect(self._submit(chunk))
 
+    def _demux_names(self):
+        """(names of the outputs, destination number of every adapter): the name of the adapter of a read's most
+        recent match selects its output (Demultiplexer, steps.py:397-409); a LinkedAdapter's parts share its name."""
+        if self.adapters is None:
+            raise ValueError("demultiplexing needs adapters")
+        singles, groups, owners = self.adapters._flatten()
+        names = [s.name for s in singles]
+        for (typ, a0, a1, _, _), owner in zip(groups, owners):
+            if typ == _lib.CG_GROUP_LINKED:
+                names[a0] = names[a1] = owner.name
+        outputs = list(dict.fromkeys(names))
+        number = {name: i for i, name in enumerate(outputs)}
+        return outputs, np.array([number[n] for n in names], dtype=np.int32)
+
+    def process_chunk_demux(self, chunk, unknown: str = "unknown") -> dict:
+        """{adapter name: FASTQ bytes} + {unknown: reads without a match} -- what ``-o 'demux-{name}.fastq'`` writes
+        for this chunk (every output in input order); ``cg_fastq_collect_demux``."""
+        outputs, dest = self._demux_names()
+        slot, n_bytes, _ = self._submit(chunk)
+        out = self._out_buffer(slot, max(n_bytes, 1))
+        res = _lib.cg_fastq_result()
+        segments = np.zeros(len(outputs) + 2, dtype=np.int64)
+        _lib.check(_lib.lib().cg_fastq_collect_demux(
+            self.ctx.handle, slot, self._set.handle, C.byref(self.params), dest.ctypes.data, len(outputs),
+            out.ctypes.data, out.size, C.byref(res), segments.ctypes.data))
+        for k, v in res.as_dict().items():
+            self.statistics[k] = self.statistics.get(k, 0) + v
+        return {name: out[segments[i]:segments[i + 1]].tobytes() for i, name in enumerate(outputs + [unknown])}
+
     def process_chunks(self, chunks, copy: bool = True):
         """copy=False yields uint8 array views into per-slot buffers: valid until the next-but-one result."""
         pending = None

@@ -309,6 +309,15 @@ int cg_fastq_submit(cg_ctx *ctx, const uint8_t *fastq, int64_t n_bytes, int32_t 
 int cg_fastq_collect(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, const cg_fastq_params *params,
                      uint8_t *out, int64_t out_capacity, cg_fastq_result *res);
 
+/* Demultiplexing (Demultiplexer.__call__, steps.py:397-409): every surviving record
+ * goes to the output of the adapter of its most recent match, records without a match to the last output
+ * ("unknown"; combine with discard_untrimmed to drop them).  adapter_dest[a] in [0, n_named) names the output of
+ * adapter a (adapters that share a file share a number).  `out` receives the n_named + 1 outputs back to back, each
+ * in input order: output d is out[segments[d] .. segments[d + 1]); segments must hold n_named + 2 values. */
+int cg_fastq_collect_demux(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, const cg_fastq_params *params,
+                           const int32_t *adapter_dest, int32_t n_named, uint8_t *out, int64_t out_capacity,
+                           cg_fastq_result *res, int64_t *segments);
+
 /* Paired-end chunks (PairedEndPipeline.process_reads, pipeline.py:125-153): record i of the two chunks is one
  * pair.  Each mate has its own adapter set (-a / -A; NULL = none) and parameters (-q / -Q, -u / -U, ...); --poly-a
  * trims the poly-T head of the second mate (PolyATrimmer(revcomp=True), cli.py:968-971).  Filters work on the

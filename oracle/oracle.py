@@ -352,7 +352,7 @@ _FILTER_COUNTER = {"discard_trimmed": "discarded", "discard_untrimmed": "discard
 def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, cutoff_back=0, quality_base=33, times=1,
                     nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
                     discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
-                    trim_n=False, discard_casava=False, second_mate=False):
+                    trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False):
     """Modifier chain on every record of a chunk + the verdict of every enabled filter.
     Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters)."""
     records = parse_fastq(data)
@@ -384,6 +384,7 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
         c["bp_in"] += len(seq)
         c["quality_trimmed_bp"] += len(seq) - (e - s)
         matched = False
+        last_adapter = -1
         if matches is not None:
             for r in range(matches.shape[1]):
                 for slot in range(matches.shape[2]):
@@ -391,6 +392,7 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                     if m["adapter"] < 0:
                         continue
                     matched = True
+                    last_adapter = int(m["adapter"])
                     if (int(m["info"]) >> 8) & 1:      # RemoveAfterMatch: read[:rstart]      adapters.py:486-487
                         e = s + int(m["rstart"])
                     else:                               # RemoveBeforeMatch: read[rstop:]      adapters.py:453-454
@@ -419,12 +421,25 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
             "casava_filtered": name.partition(" ")[2][1:4] == ":Y:",                      # predicates.py:125-139
             "discard_trimmed": matched, "discard_untrimmed": not matched,                 # predicates.py:142-175
         }
-        out.append((name, ts, tq, fails))
+        out.append((name, ts, tq, fails, last_adapter) if want_last_adapter else (name, ts, tq, fails))
     return out, enabled, c
 
 
 def _fastq_record(name, ts, tq):
     return f"@{name}\n{ts}\n+\n{tq}\n".encode("latin-1")
+
+
+def oracle_fastq_demux(data: bytes, adapters, groups, adapter_names, unknown="unknown", **options):
+    """{name: bytes}: Demultiplexer.__call__ (steps.py:397-409) after the filters -- a surviving read goes to the
+    output named after the adapter of its most recent match (adapter_names[i] = output of adapter i), else to
+    `unknown`."""
+    evaluated, enabled, _ = _fastq_evaluate(data, adapters, groups, want_last_adapter=True, **options)
+    outputs = {name: [] for name in list(dict.fromkeys(adapter_names)) + [unknown]}
+    for name, ts, tq, fails, last in evaluated:
+        if any(fails[f] for f in enabled):
+            continue
+        outputs[adapter_names[last] if last >= 0 else unknown].append(_fastq_record(name, ts, tq))
+    return {k: b"".join(v) for k, v in outputs.items()}
 
 
 def oracle_fastq_trim(data: bytes, adapters=None, groups=None, **options):

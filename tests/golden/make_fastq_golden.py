@@ -141,6 +141,22 @@ def main():
         pindex.append(dict(name=name, reference_test=f"tests/test_paired.py:{line}", command=cmd,
                            inputs=[f"tests/data/{in1}", f"tests/data/{in2}"],
                            expected=[f"tests/cut/{exp1}", f"tests/cut/{exp2}"], options=opts))
+    # demultiplexing (test_commandline.py:581-601: -a first=AATTTCAGGAATT -a second=GTTCTCTAGTTCT -o {name}.fasta
+    # twoadapters.fasta): the reference's vectors are FASTA; they are stored as FASTQ with constant qualities 'I'
+    # (single-line records, so the conversion is 1:1 and the expected sequences are untouched)
+    def fasta_to_fastq(path):
+        lines = open(path).read().split("\n")
+        recs = []
+        for i in range(0, len(lines) - 1, 2):
+            assert lines[i].startswith(">")
+            recs.append("@%s\n%s\n+\n%s\n" % (lines[i][1:], lines[i + 1], "I" * len(lines[i + 1])))
+        return "".join(recs).encode()
+
+    with open(os.path.join(HERE, "demux_twoadapters.in.fastq"), "wb") as f:
+        f.write(fasta_to_fastq(os.path.join(REF, "data", "twoadapters.fasta")))
+    for name in ("first", "second", "unknown"):
+        with open(os.path.join(HERE, f"demux_twoadapters.{name}.out.fastq"), "wb") as f:
+            f.write(fasta_to_fastq(os.path.join(REF, "cut", f"twoadapters.{name}.fasta")))
     with open(os.path.join(HERE, "paired_cases.json"), "w") as f:
         json.dump(pindex, f, indent=1)
     print(len(pindex), "paired cases")

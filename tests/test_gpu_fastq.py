@@ -86,8 +86,11 @@ def synthetic_fastq(n, seed, crlf=False, final_newline=True):
 def test_random_chunks_against_oracle(variant):
     options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20])
     extra = {}
-    data = synthetic_fastq(6000, seed=hash(variant) % 1000, crlf=variant == "crlf",
-                           final_newline=variant != "no_final_newline")
+    seed = {"plain": 1, "crlf": 2, "no_final_newline": 3, "filters": 4, "quality_only": 5, "times2": 6,
+            "modifiers": 7, "modifiers2": 8}[variant]
+    data = synthetic_fastq(6000, seed=seed, crlf=variant == "crlf")
+    if variant == "no_final_newline":       # a last record whose quality line is not terminated
+        data += b"@last\nACGTACGTAGATCGGAAGAGCAAA\n+\nIIIIIIIIIIIIIIIIIIIIIIII"
     if variant == "filters":
         extra = dict(minimum_length=20, maximum_length=140, max_n=0.1, max_expected_errors=2.5, discard_untrimmed=True)
     elif variant == "quality_only":
@@ -217,3 +220,48 @@ def test_paired_random_chunks_against_oracle(mode):
     assert t.process_chunk(data1, data2) == (e1, e2)
     with pytest.raises(ValueError):
         t.process_chunk(data1, synthetic_fastq(4999, seed=72))
+
+
+# ---- demultiplexing ----------------------------------------------------------------------------------
+
+def test_demultiplex_reference_golden_and_barcodes():
+    import cutadapt_b200.adapters as PA
+    from util import fastq_demux_case
+
+    c = fastq_demux_case()
+    ads = [PA.BackAdapter(seq, max_errors=0.1, min_overlap=3, name=name) for name, seq in c["adapters"]]
+    t = FastqTrimmer(ads)
+    assert t.process_chunk_demux(c["input_bytes"]) == c["expected"]
+
+    # BASELINE config 5 in small: 24 anchored 5' barcodes (device index), several tiles of records, filters on
+    rng = random.Random(5)
+    barcodes = []
+    while len(barcodes) < 24:
+        b = "".join(rng.choice("ACGT") for _ in range(10))
+        if all(sum(x != y for x, y in zip(b, o)) >= 3 for o in barcodes):
+            barcodes.append(b)
+    recs = []
+    for i in range(20000):
+        r = rng.random()
+        bc = rng.choice(barcodes) if r < 0.95 else "".join(rng.choice("ACGT") for _ in range(10))
+        if rng.random() < 0.05:
+            p = rng.randrange(10)
+            bc = bc[:p] + rng.choice("ACGT") + bc[p + 1:]
+        ins = "".join(rng.choice("ACGT") for _ in range(rng.choice((0, 5, 40, 140))))
+        seq = bc + ins
+        recs.append(f"@r{i}\n{seq}\n+\n{'F' * len(seq)}\n")
+    data = "".join(recs).encode()
+    members = [PA.PrefixAdapter(b, max_errors=0.1, name=f"bc{j}") for j, b in enumerate(barcodes)]
+    multi = PA.MultipleAdapters(members)                                   # 24 adapters compared one by one
+    indexed = PA.MultipleAdapters([PA.IndexedPrefixAdapters([PA.PrefixAdapter(b, max_errors=0.1, name=f"bc{j}")
+                                                             for j, b in enumerate(barcodes)])])   # the device index
+    for extra in ({}, {"minimum_length": 6, "discard_untrimmed": True}):
+        t = FastqTrimmer(multi, **extra)
+        got = t.process_chunk_demux(data)
+        spec = spec_of(multi)
+        exp = oracle.oracle_fastq_demux(data, spec.adapters, spec.groups, [m.name for m in members], **extra)
+        assert set(got) == set(exp)
+        for k in exp:
+            assert got[k] == exp[k], k
+        assert sum(len(v) for v in got.values()) == t.statistics["out_bytes"]
+        assert FastqTrimmer(indexed, **extra).process_chunk_demux(data) == got

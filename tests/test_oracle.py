@@ -163,3 +163,14 @@ def test_paired_fastq_oracle_reproduces_the_reference_goldens():
         o1, o2, c1, c2 = oracle_paired(oracle, c["options"], *c["input_bytes"])
         assert [o1, o2] == c["expected_bytes"], c["name"]
         assert c1["n_written"] == c2["n_written"] <= c1["n_records"] == c2["n_records"]
+
+
+def test_demultiplex_oracle_reproduces_the_reference_golden():
+    from util import fastq_demux_case, spec_of
+    import cutadapt_b200.adapters as PA
+
+    c = fastq_demux_case()
+    ads = [PA.BackAdapter(seq, max_errors=0.1, min_overlap=3, name=name) for name, seq in c["adapters"]]
+    spec = spec_of(PA.MultipleAdapters(ads))
+    got = oracle.oracle_fastq_demux(c["input_bytes"], spec.adapters, spec.groups, [a.name for a in ads])
+    assert got == c["expected"]

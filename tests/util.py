@@ -204,3 +204,12 @@ def fastq_case_kwargs(options):
         if k in options:
             kw[k] = options[k]
     return kw
+
+
+def fastq_demux_case():
+    """tests/test_commandline.py:581-601 of the reference (FASTA vectors stored as FASTQ, see make_fastq_golden.py)."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastq")
+    rd = lambda name: open(os.path.join(here, name), "rb").read()
+    return dict(adapters=[("first", "AATTTCAGGAATT"), ("second", "GTTCTCTAGTTCT")],
+                input_bytes=rd("demux_twoadapters.in.fastq"),
+                expected={n: rd(f"demux_twoadapters.{n}.out.fastq") for n in ("first", "second", "unknown")})
