@@ -275,8 +275,9 @@ class FastqTrimmer:
 
     def _collect(self, ticket, copy: bool = True):
         slot, n_bytes, _ = ticket
-        # trimming only ever shortens a record ("\r\n" -> "\n" and "+name" -> "+" too)
-        out = self._out_buffer(slot, max(n_bytes, 1))
+        # trimming only ever shortens a record ("\r\n" -> "\n" and "+name" -> "+" too); the one byte a record
+        # can grow by is the newline that a chunk without a final newline gets
+        out = self._out_buffer(slot, n_bytes + 16)
         res = _lib.cg_fastq_result()
         _lib.check(_lib.lib().cg_fastq_collect(
             self.ctx.handle, slot, self._set.handle if self._set is not None else None, C.byref(self.params),
@@ -307,7 +308,7 @@ class FastqTrimmer:
         for this chunk (every output in input order); ``cg_fastq_collect_demux``."""
         outputs, dest = self._demux_names()
         slot, n_bytes, _ = self._submit(chunk)
-        out = self._out_buffer(slot, max(n_bytes, 1))
+        out = self._out_buffer(slot, n_bytes + 16)
         res = _lib.cg_fastq_result()
         segments = np.zeros(len(outputs) + 2, dtype=np.int64)
         _lib.check(_lib.lib().cg_fastq_collect_demux(
@@ -363,8 +364,8 @@ class PairedFastqTrimmer:
 
     def process_chunk(self, chunk1, chunk2) -> Tuple[bytes, bytes]:
         (s1, b1), (s2, b2) = self._submit(chunk1), self._submit(chunk2)
-        out1 = np.empty(max(b1.size, 1), dtype=np.uint8)
-        out2 = np.empty(max(b2.size, 1), dtype=np.uint8)
+        out1 = np.empty(b1.size + 16, dtype=np.uint8)
+        out2 = np.empty(b2.size + 16, dtype=np.uint8)
         r1, r2 = _lib.cg_fastq_result(), _lib.cg_fastq_result()
         _lib.check(_lib.lib().cg_fastq_collect_paired(
             self.ctx.handle, s1, s2, self._set1.handle if self._set1 is not None else None,

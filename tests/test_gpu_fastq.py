@@ -125,6 +125,9 @@ def test_many_chunks_in_flight_and_format_errors():
             t.process_chunk(bad)
     # the context stays usable after an error
     assert t.process_chunk(chunks[3]) == exp[3]
+    # nothing to trim and no final newline: the output is one byte longer than the input
+    plain = b"@r1\nACGTTGCA\n+\nIIIIIIII\n@r2\nTTGACCAT\n+\nIIIIIIII"
+    assert FastqTrimmer(None, minimum_length=1).process_chunk(plain) == plain + b"\n"
 
 
 def test_large_chunk_properties():
@@ -264,4 +267,25 @@ def test_demultiplex_reference_golden_and_barcodes():
         for k in exp:
             assert got[k] == exp[k], k
         assert sum(len(v) for v in got.values()) == t.statistics["out_bytes"]
-        assert FastqTrimmer(indexed, **extra).process_chunk_demux(data) == got
+        # the same through the device index (its matches may differ from one-by-one alignment, as in the
+        # reference): routing must agree with the index's own match records, order inside an output = input order
+        ti = FastqTrimmer(indexed, **extra)
+        gi = ti.process_chunk_demux(data)
+        flat = ti.process_chunk(data)
+
+        def records(b):
+            lines = b.split(b"\n")
+            return [tuple(lines[k:k + 4]) for k in range(0, len(lines) - 1, 4)]
+
+        assert sorted(r for v in gi.values() for r in records(v)) == sorted(records(flat))
+        seqs = [r.split("\n")[1] for r in recs]
+        from cutadapt_b200 import _lib as L
+        m, _ = indexed.adapter_set().process(*L.pack_strings(seqs))
+        where = {}
+        for name, v in gi.items():
+            ids = [int(r[0][2:]) for r in records(v)]
+            assert ids == sorted(ids), name
+            where.update({i: name for i in ids})
+        for i, name in where.items():
+            a = int(m["adapter"][i, 0, 0])
+            assert name == (f"bc{a}" if a >= 0 else "unknown"), i
