@@ -389,6 +389,7 @@ def main():
                "h2d_bytes_per_step": h2d_bytes // e2e_steps, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                "steps": e2e_steps, "launches": host_ctx.launch_count() - l0,
                "host_threads": host_threads, "host_cpus_available": int(_lib.lib().cg_host_cpus_available()),
+               "host_numa_node": int(_lib.lib().cg_ctx_numa_node(host_ctx.handle)),
                "host_profile": {k: (round(v, 4) if isinstance(v, float) else v)
                                 for k, v in host_ctx.host_profile().items()},
                "raw_transfer_value": n * world / raw_wall,

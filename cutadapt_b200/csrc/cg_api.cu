@@ -148,6 +148,7 @@ struct cg_ctx {
     long long h2d_bytes = 0, d2h_bytes = 0;
     double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cg_ctx_host_profile
     double pack_fraction = 0.6;                  // share of a chunk that travels compressed (adapted)
+    int numa_node = -1;                          // node the worker pool was bound to, or -1
     // ordering of the trimming passes of different lanes over the shared scratch
     cudaEvent_t scratch_ev = nullptr;
     cudaStream_t scratch_stream = nullptr;
@@ -769,6 +770,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         c->pool = new CgHostPool(cg_host_threads_default());
         c->exc_scratch.resize((size_t)c->pool->size());
     }
+    if (pack) c->numa_node = c->pool->follow_memory(seq);
     const int n_lanes = pack ? CG_N_LANES : 2;
     const int64_t CHUNK_READS = pack ? (1 << 20) : (1 << 18);
     const int64_t CHUNK_BYTES = pack ? (192LL << 20) : (48LL << 20);
@@ -980,6 +982,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
 
 extern "C" int cg_host_cpus_available(void) { return cg_host_cpus(); }
 extern "C" int cg_host_threads(void) { return cg_host_threads_default(); }
+extern "C" int cg_ctx_numa_node(cg_ctx *c) { return c ? c->numa_node : -1; }
 
 extern "C" int cg_ctx_host_profile(cg_ctx *c, double *out, int reset)
 {

@@ -5,7 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 #if defined(__linux__)
+#include <pthread.h>
 #include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #endif
 
 #if defined(__x86_64__) || defined(__i386__)
@@ -123,6 +126,48 @@ void CgHostPool::run(int64_t n_jobs, const std::function<void(int64_t, int)> &fn
         else std::this_thread::yield();
     }
     fn_ = nullptr;
+}
+
+int CgHostPool::follow_memory(const void *addr)
+{
+    if (followed_node_ != -2) return followed_node_;
+    followed_node_ = -1;
+#if defined(__linux__) && defined(__x86_64__)
+    if (const char *e = getenv("CUTADAPT_B200_NUMA")) if (e[0] == '0') return -1;
+    if (workers_.empty()) return -1;
+    // which node holds the page?  get_mempolicy(&node, NULL, 0, addr, MPOL_F_NODE | MPOL_F_ADDR)
+    int node = -1;
+    if (syscall(SYS_get_mempolicy, &node, nullptr, 0UL, addr, 3UL) != 0 || node < 0) return -1;
+    char path[96];
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    char list[1024] = {0};
+    const bool ok = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!ok) return -1;
+    // is there more than one node at all?
+    if (FILE *g = fopen("/sys/devices/system/node/node1/cpulist", "r")) fclose(g); else return -1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n_cpus = 0;
+    for (char *p = list; *p;) {                       // "0-31,64-95"
+        char *end;
+        const long a = strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, &set); ++n_cpus; }
+        p = *end == ',' ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    if (n_cpus < (int)workers_.size()) return -1;     // do not squeeze the pool onto fewer CPUs than workers
+    for (auto &t : workers_) pthread_setaffinity_np(t.native_handle(), sizeof set, &set);
+    followed_node_ = node;
+#else
+    (void)addr;
+#endif
+    return followed_node_;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -25,8 +25,13 @@ public:
     ~CgHostPool();
     int size() const { return (int)workers_.size() + 1; }
     void run(int64_t n_jobs, const std::function<void(int64_t job, int worker)> &fn);
+    // Run the workers on the CPUs of the NUMA node that holds `addr` (the caller's read buffer): the packer is
+    // bound by memory latency, and remote reads cost about half of a thread's bandwidth.  Best effort (Linux,
+    // more than one node, get_mempolicy permitted); done once per pool.  Returns the node or -1.
+    int follow_memory(const void *addr);
 
 private:
+    int followed_node_ = -2;   // -2: not tried yet
     // Workers spin on `generation_` for a while after a job set (the calls of one cg_process_batch come
     // back to back) and only then go to sleep on the condition variable: waking 60 sleeping threads
     // through a mutex costs more than packing a chunk.

@@ -179,6 +179,8 @@ int cg_ctx_transfer_bytes(cg_ctx *ctx, int64_t *h2d, int64_t *d2h, int reset);
  * threads the library's host side will start (CUTADAPT_B200_HOST_THREADS overrides). */
 int cg_host_cpus_available(void);
 int cg_host_threads(void);
+/* NUMA node the context's worker threads were bound to (the node holding the first packed read buffer), -1 = none */
+int cg_ctx_numa_node(cg_ctx *ctx);
 
 /* Where the host side of cg_process_batch spent its time, in seconds, accumulated over calls:
  * out[0] total, [1] scanning the offsets, [2] packing reads for the compressed transfer, [3] waiting for a
