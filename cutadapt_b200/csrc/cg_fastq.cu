@@ -314,8 +314,14 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
                     if (m.adapter < 0) continue;
                     matched = true;
                     last_adapter = m.adapter;
-                    if ((m.info >> 8) & 1) stop = start + m.rstart;    // RemoveAfterMatch
-                    else start = start + m.rstop;                      // RemoveBeforeMatch
+                    // read[:rstart] / read[rstop:] with Python's slice clamping: an index match on a read that is
+                    // shorter than the matched key reports rstop > len or rstart < 0 (adapters.py:1342-1365)
+                    const int cur = stop - start;
+                    if ((m.info >> 8) & 1)                             // RemoveAfterMatch
+                        stop = start + (m.rstart >= 0 ? (m.rstart < cur ? m.rstart : cur)
+                                                      : (cur + m.rstart > 0 ? cur + m.rstart : 0));
+                    else                                               // RemoveBeforeMatch
+                        start = start + (m.rstop < cur ? m.rstop : cur);
                 }
         }
         const uint8_t *sq0 = buf + rec[r].seq_start;

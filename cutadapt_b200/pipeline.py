@@ -79,8 +79,12 @@ def kept_intervals(matches: np.ndarray, qtrim: Optional[np.ndarray], lengths: np
             rec = matches[:, r, s]
             present = rec["adapter"] >= 0
             after = ((rec["info"] >> 8) & 1).astype(bool)
-            new_stop = start + rec["rstart"]
-            new_start = start + rec["rstop"]
+            # read[:rstart] / read[rstop:] with Python's slice clamping (an index match on a read shorter than
+            # the matched key reports rstop > len or rstart < 0, adapters.py:1342-1365)
+            cur = stop - start
+            rs = rec["rstart"].astype(np.int64)
+            new_stop = start + np.where(rs >= 0, np.minimum(rs, cur), np.maximum(cur + rs, 0))
+            new_start = start + np.minimum(rec["rstop"].astype(np.int64), cur)
             stop = np.where(present & after, new_stop, stop)
             start = np.where(present & ~after, new_start, start)
     return np.stack([start, stop], axis=1)

@@ -393,10 +393,12 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                         continue
                     matched = True
                     last_adapter = int(m["adapter"])
+                    cur = range(s, e)                   # Python slicing of the current read, clamping included
                     if (int(m["info"]) >> 8) & 1:      # RemoveAfterMatch: read[:rstart]      adapters.py:486-487
-                        e = s + int(m["rstart"])
+                        cur = cur[:int(m["rstart"])]
                     else:                               # RemoveBeforeMatch: read[rstop:]      adapters.py:453-454
-                        s = s + int(m["rstop"])
+                        cur = cur[int(m["rstop"]):]
+                    s, e = (cur.start, cur.stop) if len(cur) else (s, s)
         c["with_adapters"] += matched
         ts, tq = seq[s:e], q[s:e]
         if poly_a:                                      # PolyATrimmer (modifiers.py:861-879); revcomp form for R2
