@@ -295,8 +295,8 @@ __global__ void fq_pretrim_kernel(const uint8_t *buf, const CgFastqRecord *rec, 
 // Every predicate is evaluated (a pair filter may need the verdict of a filter that the mate passes).
 __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
                                    const cg_match_rec *matches, int times, int slots, const int32_t *qtrim,
-                                   CgFastqFilter f, const double *phred, int32_t *interval, int32_t *fail_mask,
-                                   unsigned long long *counters, int *err)
+                                   CgFastqFilter f, const double *phred, int32_t *interval, int32_t *keep_interval,
+                                   int32_t *fail_mask, unsigned long long *counters, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long c_adapt = 0, c_bp_in = 0, c_qbp = 0;
@@ -325,10 +325,71 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
                 }
         }
         const uint8_t *sq0 = buf + rec[r].seq_start;
-        if (f.poly_a)                                      // PolyATrimmer (modifiers.py:861-879)
-            stop = f.poly_a == 2 ? stop : start + poly_a_trim_core(sq0 + start, stop - start, 0);
-        if (f.poly_a == 2)                                 // ... its revcomp form for R2: read[index:]
-            start = start + poly_a_trim_core(sq0 + start, stop - start, 1);
+        // AdapterCutter's action (modifiers.py:236-249): what is written instead of the trimmed read.  [k0, k1) is
+        // the part that stays as it is ("remainder"), [start, stop) from here on the part that is output; all
+        // relative to the read the cutter saw (after -u and quality trimming), whose interval is [b0, b1).
+        const int b0 = qtrim ? qtrim[2 * r] : 0, b1 = qtrim ? qtrim[2 * r + 1] : n;
+        int k0 = start, k1 = stop;
+        if (f.action != CG_FQ_ACTION_TRIM) {
+            if (!matched) { start = b0; stop = b1; k0 = b0; k1 = b1; }
+            else if (f.action == CG_FQ_ACTION_RETAIN || f.action == CG_FQ_ACTION_CROP) {
+                // times == 1: slot 0 = the match (or the front match of a LinkedAdapter), slot 1 = a linked back match
+                const cg_match_rec m0 = matches[(size_t)r * times * slots];
+                cg_match_rec m1; m1.adapter = -1;
+                if (slots > 1) m1 = matches[(size_t)r * times * slots + 1];
+                const int len = b1 - b0;
+                int a, b;
+                if (f.action == CG_FQ_ACTION_CROP) {                   // read[m.rstart:m.rstop] (modifiers.py:195-198)
+                    const cg_match_rec m = m0.adapter >= 0 ? m0 : m1;
+                    a = m.rstart; b = m.rstop;
+                } else if (m0.adapter >= 0 && ((m0.info >> 8) & 1)) {  // RemoveAfterMatch: (0, rstop)  adapters.py:479-480
+                    a = 0; b = m0.rstop;
+                } else {                                               // RemoveBeforeMatch (adapters.py:446-447) /
+                    a = m0.adapter >= 0 ? m0.rstart : 0;               // LinkedMatch (adapters.py:1145-1155)
+                    const int offset = m0.adapter >= 0 ? m0.rstop : 0;
+                    b = m1.adapter >= 0 ? m1.rstop + offset : len;
+                }
+                a = a < 0 ? 0 : (a > len ? len : a);                   // Python slice clamping
+                b = b < 0 ? 0 : (b > len ? len : b);
+                if (b < a) b = a;
+                start = b0 + a; stop = b0 + b; k0 = start; k1 = stop;
+            } else {                                                   // none / mask / lowercase: the whole read
+                start = b0; stop = b1;
+                if (f.action == CG_FQ_ACTION_NONE) { k0 = b0; k1 = b1; }
+            }
+        }
+        // the character at position j as it will be written
+        const int action = f.action;
+        auto ch = [&](int j) -> uint8_t {
+            const uint8_t c = sq0[j];
+            if (action == CG_FQ_ACTION_MASK) return (j >= k0 && j < k1) ? c : (uint8_t)'N';
+            if (action == CG_FQ_ACTION_LOWERCASE) {
+                const bool alpha = (uint8_t)((c | 0x20) - 'a') < 26;
+                return !alpha ? c : ((j >= k0 && j < k1) ? (uint8_t)(c & ~0x20) : (uint8_t)(c | 0x20));
+            }
+            return c;
+        };
+        if (f.poly_a) {                                    // PolyATrimmer (modifiers.py:861-879), qualtrim.pyx:120-169
+            const int len = stop - start;
+            int best_score = 0, score = 0, errors = 0;
+            if (f.poly_a == 2) {                           // poly-T head of the second mate: read[index:]
+                int best_index = 0;
+                for (int i = 0; i < len; ++i) {
+                    if (ch(start + i) == 'T') score += 1; else { score -= 2; errors += 1; }
+                    if (score > best_score && errors * 5 <= i + 1) { best_score = score; best_index = i + 1; }
+                }
+                if (best_index < 3) best_index = 0;
+                start += best_index;
+            } else {                                       // poly-A tail: read[:index]
+                int best_index = len;
+                for (int i = len - 1; i >= 0; --i) {
+                    if (ch(start + i) == 'A') score += 1; else { score -= 2; errors += 1; }
+                    if (score > best_score && errors * 5 <= len - i) { best_score = score; best_index = i; }
+                }
+                if (best_index > len - 3) best_index = len;
+                stop = start + best_index;
+            }
+        }
         if (f.shorten > 0) {                               // Shortener (modifiers.py:882-899): read[:length]
             if (stop - start > f.shorten - 1) stop = start + (f.shorten - 1);
         } else if (f.shorten < 0) {                        //                                   read[length:]
@@ -336,8 +397,8 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
         }
         if (f.trim_n) {                                    // NEndTrimmer (modifiers.py:902-918): upper-case N only
             int a = start, b = stop;
-            while (a < stop && sq0[a] == 'N') ++a;
-            while (b > start && sq0[b - 1] == 'N') --b;
+            while (a < stop && ch(a) == 'N') ++a;
+            while (b > start && ch(b - 1) == 'N') --b;
             start = a; stop = b < a ? a : b;
         }
         const int left = stop - start;
@@ -345,9 +406,8 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
         if (f.minimum_length > 0 && left < f.minimum_length) mask |= 1;
         if (f.maximum_length >= 0 && left > f.maximum_length) mask |= 2;
         if (f.max_n >= 0.0) {
-            const uint8_t *sq = sq0 + start;
             int n_count = 0;
-            for (int j = 0; j < left; ++j) n_count += (sq[j] | 0x20) == 'n';
+            for (int j = 0; j < left; ++j) n_count += (ch(start + j) | 0x20) == 'n';
             const bool too_many = f.max_n < 1.0 ? (left > 0 && (double)n_count / (double)left > f.max_n)
                                                 : (double)n_count > f.max_n;
             if (too_many) mask |= 4;
@@ -369,6 +429,7 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
         if (matched) mask |= 32; else mask |= 64;          // masked by the enabled filters in the finish step
         interval[2 * r] = start;
         interval[2 * r + 1] = stop;
+        if (keep_interval) { keep_interval[2 * r] = k0; keep_interval[2 * r + 1] = k1; }
         fail_mask[r] = mask | ((last_adapter + 1) << 8);
         c_adapt = matched; c_bp_in = n;
     }
@@ -449,7 +510,8 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
 // the trimmed records, one warp per record
 __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *interval,
                                                         const int64_t *out_off, const int32_t *out_len,
-                                                        long long n_records, uint8_t *out)
+                                                        long long n_records, uint8_t *out, int action,
+                                                        const int32_t *keep_interval)
 {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -463,7 +525,19 @@ __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const
         for (int j = lane; j < m.hdr_len; j += 32) p[1 + j] = buf[m.hdr_start + j];
         p += 1 + m.hdr_len;
         if (lane == 0) p[0] = '\n';
-        for (int j = lane; j < left; j += 32) p[1 + j] = buf[m.seq_start + start + j];
+        if (action == CG_FQ_ACTION_MASK || action == CG_FQ_ACTION_LOWERCASE) {
+            // --action=mask / lowercase (modifiers.py:175-193): N / lower case outside the remainder
+            const int k0 = keep_interval[2 * r], k1 = keep_interval[2 * r + 1];
+            for (int j = lane; j < left; j += 32) {
+                uint8_t c = buf[m.seq_start + start + j];
+                const bool in = start + j >= k0 && start + j < k1;
+                if (action == CG_FQ_ACTION_MASK) c = in ? c : (uint8_t)'N';
+                else if ((uint8_t)((c | 0x20) - 'a') < 26) c = in ? (uint8_t)(c & ~0x20) : (uint8_t)(c | 0x20);
+                p[1 + j] = c;
+            }
+        } else {
+            for (int j = lane; j < left; j += 32) p[1 + j] = buf[m.seq_start + start + j];
+        }
         p += 1 + left;
         if (lane < 3) p[lane] = lane == 1 ? '+' : '\n';
         for (int j = lane; j < left; j += 32) p[3 + j] = buf[m.qual_start + start + j];
@@ -582,12 +656,13 @@ cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d
 cudaError_t cg_launch_fastq_evaluate(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
                                      long long n_records, const cg_match_rec *d_matches, int times, int slots,
                                      const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
-                                     int32_t *d_fail_mask, unsigned long long *d_counters, int *d_err, cudaStream_t st)
+                                     int32_t *d_keep_interval, int32_t *d_fail_mask, unsigned long long *d_counters,
+                                     int *d_err, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_evaluate_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches,
                                                                            times, slots, d_qtrim, f, d_phred, d_interval,
-                                                                           d_fail_mask, d_counters, d_err);
+                                                                           d_keep_interval, d_fail_mask, d_counters, d_err);
     return cudaGetLastError();
 }
 
@@ -607,12 +682,13 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
 
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
                                   const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
-                                  uint8_t *d_out, cudaStream_t st)
+                                  uint8_t *d_out, int action, const int32_t *d_keep_interval, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     long long grid = (n_records + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
-    fq_write_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_interval, d_out_off, d_out_len, n_records, d_out);
+    fq_write_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_interval, d_out_off, d_out_len, n_records, d_out, action,
+                                                    d_keep_interval);
     return cudaGetLastError();
 }
 

@@ -114,7 +114,14 @@ struct CgFastqFilter {
     int shorten;             // Shortener: 0 = off, L + 1 for --length L >= 0, L for --length L < 0
     int trim_n;              // NEndTrimmer
     int discard_casava;      // CasavaFiltered
+    int action;              // CG_FQ_ACTION_*: AdapterCutter's action
 };
+#define CG_FQ_ACTION_TRIM 0
+#define CG_FQ_ACTION_NONE 1
+#define CG_FQ_ACTION_MASK 2
+#define CG_FQ_ACTION_LOWERCASE 3
+#define CG_FQ_ACTION_RETAIN 4
+#define CG_FQ_ACTION_CROP 5
 #define CG_FQ_COUNTERS 16    // written, bp_in, bp_out, with_adapters, too_short, too_long, quality_trimmed_bp,
                              // discarded (trimmed/untrimmed), too_many_n, too_many_expected_errors, casava_filtered
 long long cg_fastq_tiles(long long n_bytes);
@@ -138,7 +145,8 @@ cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d
 cudaError_t cg_launch_fastq_evaluate(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
                                      long long n_records, const cg_match_rec *d_matches, int times, int slots,
                                      const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
-                                     int32_t *d_fail_mask, unsigned long long *d_counters, int *d_err, cudaStream_t st);
+                                     int32_t *d_keep_interval, int32_t *d_fail_mask, unsigned long long *d_counters,
+                                     int *d_err, cudaStream_t st);
 // verdict per read (second mate = nullptr) or pair -> sizes of the output records, filter counters
 cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_rec1, const int32_t *d_interval1,
                                    const int32_t *d_mask1, int enabled1, int32_t *d_out_len1,
@@ -147,7 +155,7 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
                                    unsigned long long *d_counters2, int mode, int mode_untrimmed, cudaStream_t st);
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
                                   const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
-                                  uint8_t *d_out, cudaStream_t st);
+                                  uint8_t *d_out, int action, const int32_t *d_keep_interval, cudaStream_t st);
 // demultiplexing: phase 0 fills d_bytes[n_dest][tiles] (output bytes per destination and tile of 256 records);
 // after an exclusive scan of that array (d_base), phase 1 writes every record's output offset.
 // d_adapter_dest: destination of every adapter; reads without a match go to destination n_dest - 1.
