@@ -120,7 +120,8 @@ class cg_fastq_params(C.Structure):
         ("shorten_length", C.c_int32),
         ("trim_n", C.c_int32),
         ("discard_casava", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("action", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 

@@ -109,7 +109,7 @@ struct FastqSlot {
     DevBuf<uint8_t> d_in, d_out, d_seq, d_qual;
     DevBuf<uint32_t> d_tiles, d_nl;
     DevBuf<CgFastqRecord> d_rec;
-    DevBuf<int32_t> d_len, d_interval, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes;
+    DevBuf<int32_t> d_len, d_interval, d_keep, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes;
     DevBuf<int64_t> d_dmbase;
     DevBuf<int64_t> d_offs, d_outoff;
     DevBuf<unsigned long long> d_scan;
@@ -250,7 +250,7 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
     for (FastqSlot &f : c->fq) {
         f.d_in.release(); f.d_out.release(); f.d_seq.release(); f.d_qual.release(); f.d_tiles.release(); f.d_nl.release();
         f.d_rec.release(); f.d_len.release(); f.d_mask.release(); f.d_adest.release(); f.d_dmbytes.release();
-        f.d_dmbase.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
+        f.d_dmbase.release(); f.d_keep.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
         f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release();
         f.h_in.release(); f.h_out.release(); f.h_counters.release();
         if (f.d_counters) cudaFree(f.d_counters);
@@ -1264,6 +1264,7 @@ struct FqStage {
     int times = 1, slots = 1;
     int32_t *d_qtrim = nullptr;
     const cg_match_rec *d_matches = nullptr;
+    int action = 0;
 };
 
 static int fastq_enabled_filters(const cg_fastq_params *fp)
@@ -1297,12 +1298,17 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
     g.times = p->times < 1 ? 1 : p->times;
     g.slots = s ? s->host.slots : 1;
     if (fp->cut_front < 0 || fp->cut_back < 0) return fail(CG_EINVAL, "cg_fastq: cut_front / cut_back must be >= 0");
+    if (fp->action < CG_FQ_ACTION_TRIM || fp->action > CG_FQ_ACTION_CROP) return fail(CG_EINVAL, "cg_fastq: unknown action");
+    if ((fp->action == CG_FQ_ACTION_RETAIN || fp->action == CG_FQ_ACTION_CROP) && g.times > 1)
+        return fail(CG_EINVAL, "'retain' and 'crop' cannot be combined with times > 1");   // modifiers.py:117-118
+    g.action = s ? fp->action : CG_FQ_ACTION_TRIM;
     int rc;
     if ((rc = f.d_nl.ensure((size_t)g.n_nl + 1)) != CG_OK) return rc;
     if ((rc = f.d_rec.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_len.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_interval.ensure((size_t)n * 2)) != CG_OK) return rc;
     if ((rc = f.d_mask.ensure((size_t)n)) != CG_OK) return rc;
+    if ((rc = f.d_keep.ensure((size_t)n * 2)) != CG_OK) return rc;
     if ((rc = f.d_outlen.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_outoff.ensure((size_t)n + 1)) != CG_OK) return rc;
     if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(n) + 1)) != CG_OK) return rc;
@@ -1351,8 +1357,9 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
     flt.shorten = !fp->shorten ? 0 : (fp->shorten_length >= 0 ? fp->shorten_length + 1 : fp->shorten_length);
     flt.trim_n = fp->trim_n;
     flt.discard_casava = fp->discard_casava;
+    flt.action = g.action;
     CU(cg_launch_fastq_evaluate(f.d_in.p, f.d_rec.p, f.d_len.p, n, g.d_matches, g.times, g.slots, g.d_qtrim, flt,
-                                c->d_phred, f.d_interval.p, f.d_mask.p, f.d_counters + 1, f.d_err, st));
+                                c->d_phred, f.d_interval.p, f.d_keep.p, f.d_mask.p, f.d_counters + 1, f.d_err, st));
     c->launches += 1;
     return CG_OK;
 }
@@ -1411,7 +1418,8 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
     if (total > 0) {
         if (!out) return fail(CG_EINVAL, "cg_fastq_collect: out is NULL");
         if ((rc = f.d_out.ensure((size_t)total + 64)) != CG_OK) return rc;
-        CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, f.d_outlen.p, n, f.d_out.p, st));
+        CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, f.d_outlen.p, n, f.d_out.p, g.action,
+                                 f.d_keep.p, st));
         c->launches += 1;
         if (is_pinned(out)) {
             CU(cudaMemcpyAsync(out, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));

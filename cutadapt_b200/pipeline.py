@@ -182,7 +182,7 @@ class BatchTrimmer:
 def _fastq_params(times=1, quality_cutoff=None, quality_base=33, nextseq_cutoff=None, minimum_length=0,
                   maximum_length=None, max_n=None, max_expected_errors=None, discard_trimmed=False,
                   discard_untrimmed=False, cut=(), poly_a=False, length=None, trim_n=False,
-                  discard_casava=False) -> "_lib.cg_fastq_params":
+                  discard_casava=False, action="trim") -> "_lib.cg_fastq_params":
     fp = _lib.cg_fastq_params()
     fp.trim = _lib.make_params(
         quality_trim=quality_cutoff is not None,
@@ -203,6 +203,12 @@ def _fastq_params(times=1, quality_cutoff=None, quality_base=33, nextseq_cutoff=
     fp.shorten_length = int(length or 0)
     fp.trim_n = int(bool(trim_n))
     fp.discard_casava = int(bool(discard_casava))
+    actions = {"trim": 0, None: 1, "none": 1, "mask": 2, "lowercase": 3, "retain": 4, "crop": 5}
+    if action not in actions:
+        raise ValueError(f"unknown action {action!r}")
+    if action in ("retain", "crop") and times > 1:
+        raise ValueError("'retain' and 'crop' cannot be combined with times > 1")     # modifiers.py:117-118
+    fp.action = actions[action]
     return fp
 
 
@@ -233,6 +239,8 @@ class FastqTrimmer:
     cut                 -u values (UnconditionalCutter, modifiers.py:66-95), applied first
     poly_a, length, trim_n           --poly-a / --length / --trim-n, after the adapters (modifiers.py:861-918)
     discard_casava      --discard-casava                                     (predicates.py:125-139)
+    action              --action: "trim" (default), "none"/None, "mask", "lowercase", "retain", "crop"
+                        (AdapterCutter, modifiers.py:175-249)
 
     ``process_chunk(bytes) -> bytes``; ``process_chunks(iterable)`` keeps one chunk in flight so that the
     upload of chunk i+1 overlaps the download of chunk i.  ``statistics`` accumulates the counters of
@@ -246,12 +254,12 @@ class FastqTrimmer:
                  max_expected_errors: Optional[float] = None, discard_trimmed: bool = False,
                  discard_untrimmed: bool = False, cut: Sequence[int] = (), poly_a: bool = False,
                  length: Optional[int] = None, trim_n: bool = False, discard_casava: bool = False,
-                 ctx: Optional[_lib.Context] = None):
+                 action: Optional[str] = "trim", ctx: Optional[_lib.Context] = None):
         self.ctx = ctx or _lib.default_context()
         self.adapters, self._set = _device_set(adapters, self.ctx)
         self.params = _fastq_params(times, quality_cutoff, quality_base, nextseq_cutoff, minimum_length, maximum_length,
                                     max_n, max_expected_errors, discard_trimmed, discard_untrimmed, cut, poly_a, length,
-                                    trim_n, discard_casava)
+                                    trim_n, discard_casava, action)
         self.statistics = {}
         self._out_bufs, self._out_keep = {}, {}
 

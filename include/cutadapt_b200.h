@@ -275,6 +275,13 @@ int cg_poly_a_trim_batch(cg_ctx *ctx, const uint8_t *seq, const int64_t *offsets
  * ("@name\nsequence\n+\nqualities\n", SingleEndSink steps.py:299-319).  Here the chunk is indexed, packed,
  * trimmed, filtered and formatted on the device; it crosses PCIe once in each direction.
  * "\r\n" line ends are accepted (and written back as "\n", like dnaio). */
+/* What AdapterCutter does with a read that has matches (modifiers.py:175-249) */
+#define CG_ACTION_TRIM 0       /* remove the adapters (default)                                            */
+#define CG_ACTION_NONE 1       /* leave the read as it is (matches still drive --discard-(un)trimmed)       */
+#define CG_ACTION_MASK 2       /* N outside the part that would remain                                      */
+#define CG_ACTION_LOWERCASE 3  /* whole read upper case, lower case outside the part that would remain      */
+#define CG_ACTION_RETAIN 4     /* trim but keep the adapter itself (times must be 1)                        */
+#define CG_ACTION_CROP 5       /* keep only the matched part read[rstart:rstop] (times must be 1)           */
 typedef struct cg_fastq_params {
     cg_params trim;
     int32_t minimum_length;      /* -m; 0 = off                                                       */
@@ -290,7 +297,8 @@ typedef struct cg_fastq_params {
     int32_t shorten_length;      /* ... its value: >= 0 keeps read[:L], < 0 keeps read[L:]            */
     int32_t trim_n;              /* --trim-n (NEndTrimmer, modifiers.py:902-918)                      */
     int32_t discard_casava;      /* --discard-casava (CasavaFiltered, predicates.py:125-139)          */
-    int32_t reserved[5];
+    int32_t action;              /* CG_ACTION_*: --action of the AdapterCutter (modifiers.py:236-249)   */
+    int32_t reserved[4];
 } cg_fastq_params;
 typedef struct cg_fastq_result {
     int64_t n_records, n_written;

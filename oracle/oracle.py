@@ -352,7 +352,7 @@ _FILTER_COUNTER = {"discard_trimmed": "discarded", "discard_untrimmed": "discard
 def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, cutoff_back=0, quality_base=33, times=1,
                     nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
                     discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
-                    trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False):
+                    trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False, action="trim"):
     """Modifier chain on every record of a chunk + the verdict of every enabled filter.
     Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters)."""
     records = parse_fastq(data)
@@ -401,6 +401,32 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                     s, e = (cur.start, cur.stop) if len(cur) else (s, s)
         c["with_adapters"] += matched
         ts, tq = seq[s:e], q[s:e]
+        if action != "trim":                           # AdapterCutter.match_and_trim, modifiers.py:214-251
+            b0, b1 = int(qtrim[i, 0]), int(qtrim[i, 1])
+            rseq, rq = seq[b0:b1], q[b0:b1]             # the read as the cutter saw it
+            k0, k1 = s - b0, e - b0                     # remainder(matches), adapters.py:1588-1602
+            if action == "lowercase":
+                rseq = rseq.upper()                     # modifiers.py:222-223, also for reads without a match
+            if not matched or action in (None, "none"):
+                ts, tq = rseq, rq
+            elif action == "mask":                      # masked_read, modifiers.py:175-182
+                ts, tq = "N" * k0 + rseq[k0:k1] + "N" * (len(rseq) - k1), rq
+            elif action == "lowercase":                 # lowercased_read, modifiers.py:184-193
+                ts, tq = rseq[:k0].lower() + rseq[k0:k1].upper() + rseq[k1:].lower(), rq
+            else:
+                m0 = matches[i, 0, 0]
+                m1 = matches[i, 0, 1] if matches.shape[2] > 1 else None
+                has0, has1 = m0["adapter"] >= 0, m1 is not None and m1["adapter"] >= 0
+                if action == "crop":                    # cropped_read, modifiers.py:195-198
+                    m = m0 if has0 else m1
+                    a, b = int(m["rstart"]), int(m["rstop"])
+                elif has0 and (int(m0["info"]) >> 8) & 1:          # RemoveAfterMatch.retained_adapter_interval
+                    a, b = 0, int(m0["rstop"])                      # adapters.py:479-480
+                else:                                   # RemoveBeforeMatch (446-447) / LinkedMatch (1145-1155)
+                    a = int(m0["rstart"]) if has0 else 0
+                    offset = int(m0["rstop"]) if has0 else 0
+                    b = int(m1["rstop"]) + offset if has1 else len(rseq)
+                ts, tq = rseq[a:b], rq[a:b]
         if poly_a:                                      # PolyATrimmer (modifiers.py:861-879); revcomp form for R2
             if second_mate:
                 idx = poly_a_trim_index(ts, revcomp=True)

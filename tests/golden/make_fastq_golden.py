@@ -58,6 +58,17 @@ CASES = [
     ("shortened_negative", 742, "--length -5", "small.fastq", "shortened-negative.fastq",
      dict(adapters=[], length=-5)),
     ("casava", 770, "--discard-casava", "casava.fastq", "casava.fastq", dict(adapters=[], discard_casava=True)),
+    ("action_none", 291, "--action=none --discard-untrimmed -a CCCTAGTTAAAC", "small.fastq", "no-trim.fastq",
+     dict(adapters=[["back", "CCCTAGTTAAAC"]], action="none", discard_untrimmed=True)),
+    ("action_mask", 305, "-b CAAG -n 3 --action=mask", "anywhere_repeat.fastq", "anywhere_repeat.fastq",
+     dict(adapters=[["anywhere", "CAAG"]], times=3, action="mask")),
+    # FASTA vectors of the reference, stored as FASTQ with constant qualities (single-line records: 1:1)
+    ("action_lowercase", 309, "-b CAAG -n 3 --action=lowercase", "action_lowercase.fasta", "action_lowercase.fasta",
+     dict(adapters=[["anywhere", "CAAG"]], times=3, action="lowercase")),
+    ("action_retain", 317, "-g GGTTAACC -a CAAG --action=retain", "action_retain.fasta", "action_retain.fasta",
+     dict(adapters=[["front", "GGTTAACC"], ["back", "CAAG"]], action="retain")),
+    ("action_crop", 330, "-g GGTTAA -a CAAG --action=crop --discard-untrimmed", "action_retain.fasta",
+     "action_crop.fasta", dict(adapters=[["front", "GGTTAA"], ["back", "CAAG"]], action="crop", discard_untrimmed=True)),
     ("maxee", 838, "--max-ee=0.9", "maxee.fastq", "maxee.fastq",
      dict(adapters=[], max_expected_errors=0.9)),
 ]
@@ -116,6 +127,15 @@ PAIRED = [
 ]
 
 
+def fasta_to_fastq(path):
+    lines = open(path).read().split("\n")
+    recs = []
+    for i in range(0, len(lines) - 1, 2):
+        assert lines[i].startswith(">") and not lines[i + 1].startswith(">")
+        recs.append("@%s\n%s\n+\n%s\n" % (lines[i][1:], lines[i + 1], "I" * len(lines[i + 1])))
+    return "".join(recs).encode()
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
     index = []
@@ -125,9 +145,16 @@ def main():
         if inp.endswith(".gz"):
             with gzip.open(src, "rb") as f, open(dst_in, "wb") as g:
                 g.write(f.read())
+        elif inp.endswith(".fasta"):
+            with open(dst_in, "wb") as g:
+                g.write(fasta_to_fastq(src))
         else:
             shutil.copyfile(src, dst_in)
-        shutil.copyfile(os.path.join(REF, "cut", exp), os.path.join(HERE, f"{name}.out.fastq"))
+        if exp.endswith(".fasta"):
+            with open(os.path.join(HERE, f"{name}.out.fastq"), "wb") as g:
+                g.write(fasta_to_fastq(os.path.join(REF, "cut", exp)))
+        else:
+            shutil.copyfile(os.path.join(REF, "cut", exp), os.path.join(HERE, f"{name}.out.fastq"))
         index.append(dict(name=name, reference_test=f"tests/test_commandline.py:{line}", command=cmd,
                           input=f"tests/data/{inp}", expected=f"tests/cut/{exp}", options=opts))
     with open(os.path.join(HERE, "cases.json"), "w") as f:
@@ -144,14 +171,6 @@ def main():
     # demultiplexing (test_commandline.py:581-601: -a first=AATTTCAGGAATT -a second=GTTCTCTAGTTCT -o {name}.fasta
     # twoadapters.fasta): the reference's vectors are FASTA; they are stored as FASTQ with constant qualities 'I'
     # (single-line records, so the conversion is 1:1 and the expected sequences are untouched)
-    def fasta_to_fastq(path):
-        lines = open(path).read().split("\n")
-        recs = []
-        for i in range(0, len(lines) - 1, 2):
-            assert lines[i].startswith(">")
-            recs.append("@%s\n%s\n+\n%s\n" % (lines[i][1:], lines[i + 1], "I" * len(lines[i + 1])))
-        return "".join(recs).encode()
-
     with open(os.path.join(HERE, "demux_twoadapters.in.fastq"), "wb") as f:
         f.write(fasta_to_fastq(os.path.join(REF, "data", "twoadapters.fasta")))
     for name in ("first", "second", "unknown"):

@@ -82,12 +82,12 @@ def synthetic_fastq(n, seed, crlf=False, final_newline=True):
 
 
 @pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "filters", "quality_only", "times2",
-                                     "modifiers", "modifiers2"])
+                                     "modifiers", "modifiers2", "mask", "lowercase", "none", "retain", "crop"])
 def test_random_chunks_against_oracle(variant):
     options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20])
     extra = {}
     seed = {"plain": 1, "crlf": 2, "no_final_newline": 3, "filters": 4, "quality_only": 5, "times2": 6,
-            "modifiers": 7, "modifiers2": 8}[variant]
+            "modifiers": 7, "modifiers2": 8, "mask": 9, "lowercase": 10, "none": 11, "retain": 12, "crop": 13}[variant]
     data = synthetic_fastq(6000, seed=seed, crlf=variant == "crlf")
     if variant == "no_final_newline":       # a last record whose quality line is not terminated
         data += b"@last\nACGTACGTAGATCGGAAGAGCAAA\n+\nIIIIIIIIIIIIIIIIIIIIIIII"
@@ -103,6 +103,19 @@ def test_random_chunks_against_oracle(variant):
     elif variant == "modifiers2":
         options = dict(adapters=[["anywhere", "AGATCGGAAGAGC"]])
         extra = dict(cut=[-4, -3, 2], poly_a=True, length=60, trim_n=True, max_n=0, discard_trimmed=True)
+    elif variant == "mask":
+        extra = dict(action="mask", times=2, trim_n=True, max_n=0.3, minimum_length=5)
+    elif variant == "lowercase":
+        extra = dict(action="lowercase", times=2, poly_a=True)
+    elif variant == "none":
+        extra = dict(action="none", discard_untrimmed=True, length=100)
+    elif variant == "retain":
+        options = dict(adapters=[["linked", "TTGACNNACG", "AGATCGGAAGAGC"], ["back", "CACGTCTGAACTC"],
+                                 ["front", "ACGTACGTAC"]], quality_cutoff=[0, 15])
+        extra = dict(action="retain", minimum_length=1)
+    elif variant == "crop":
+        options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"], ["anywhere", "CACGTCTGAA"]])
+        extra = dict(action="crop", discard_untrimmed=True, trim_n=True)
     t = trimmer_for(options, **extra)
     got = t.process_chunk(data)
     exp, counters = oracle_for(options, data, **extra)

@@ -163,7 +163,16 @@ def fastq_case_adapters(options, key="adapters"):
     kinds = {"back": PA.BackAdapter, "front": PA.FrontAdapter, "anywhere": PA.AnywhereAdapter}
     e = options.get("error_rate", 0.1)
     o = options.get("min_overlap", 3)
-    return [kinds[k](seq, max_errors=e, min_overlap=o, name=f"a{i}") for i, (k, seq) in enumerate(options[key])]
+    out = []
+    for i, spec in enumerate(options[key]):
+        if spec[0] == "linked":        # ["linked", front sequence, back sequence]: -a FRONT...BACK (front not anchored)
+            _, f, b = spec
+            out.append(PA.LinkedAdapter(PA.FrontAdapter(f, max_errors=e, min_overlap=o, name=f"a{i}f"),
+                                        PA.BackAdapter(b, max_errors=e, min_overlap=o, name=f"a{i}b"),
+                                        False, False, f"a{i}"))
+        else:
+            out.append(kinds[spec[0]](spec[1], max_errors=e, min_overlap=o, name=f"a{i}"))
+    return out
 
 
 def fastq_paired_cases():
@@ -200,7 +209,7 @@ def fastq_case_kwargs(options):
         kw.update(quality_trim=True, cutoff_front=options["quality_cutoff"][0], cutoff_back=options["quality_cutoff"][1])
     for k in ("quality_base", "nextseq_cutoff", "max_expected_errors", "discard_trimmed", "discard_untrimmed",
               "minimum_length", "maximum_length", "max_n", "times", "cut", "poly_a", "length", "trim_n",
-              "discard_casava"):
+              "discard_casava", "action"):
         if k in options:
             kw[k] = options[k]
     return kw
