@@ -269,7 +269,7 @@ int cg_poly_a_trim_batch(cg_ctx *ctx, const uint8_t *seq, const int64_t *offsets
  * The per-chunk worker of the reference as one call: WorkerProcess.run (runners.py:174-214) parses a chunk of
  * complete 4-line records (dnaio.read_chunks, runners.py:116-126), runs the modifiers per read
  * (pipeline.py:47-73, in the order cli.py:937-975 builds them: UnconditionalCutter, NextseqQualityTrimmer,
- * QualityTrimmer, AdapterCutter with action "trim", PolyATrimmer, Shortener, NEndTrimmer), the filters
+ * QualityTrimmer, AdapterCutter with its action, PolyATrimmer, Shortener, NEndTrimmer), the filters
  * (TooShort, TooLong, TooManyN, TooManyExpectedErrors, CasavaFiltered, then DiscardTrimmed /
  * DiscardUntrimmed: predicates.py:29-160 in the order of cli.py:700-830) and formats the surviving records
  * ("@name\nsequence\n+\nqualities\n", SingleEndSink steps.py:299-319).  Here the chunk is indexed, packed,
