@@ -90,6 +90,66 @@ def kept_intervals(matches: np.ndarray, qtrim: Optional[np.ndarray], lengths: np
     return np.stack([start, stop], axis=1)
 
 
+def action_intervals(matches: np.ndarray, qtrim: Optional[np.ndarray], lengths: np.ndarray,
+                     action: Optional[str] = "trim") -> Tuple[np.ndarray, np.ndarray]:
+    """
+    What ``AdapterCutter`` writes for each read under its ``action`` (modifiers.py:214-251), from the match
+    records: ``(out, keep)``, two (n, 2) arrays relative to the original read.  The output is
+    ``read[out[i, 0]:out[i, 1]]``; under "mask" the characters outside ``keep`` become ``N``, under "lowercase"
+    the read is upper-cased inside ``keep`` and lower-cased outside (``apply_action`` does that).
+    The same rules as ``fq_evaluate_kernel``.
+    """
+    n = matches.shape[0]
+    kept = kept_intervals(matches, qtrim, lengths)
+    if action == "trim":
+        return kept, kept.copy()
+    if qtrim is not None:
+        base = qtrim.astype(np.int64)
+    else:
+        base = np.stack([np.zeros(n, dtype=np.int64), lengths.astype(np.int64)], axis=1)
+    matched = (matches["adapter"] >= 0).any(axis=(1, 2))
+    out, keep = base.copy(), base.copy()
+    if action in ("mask", "lowercase"):
+        keep[matched] = kept[matched]
+    elif action in ("retain", "crop"):
+        if matches.shape[1] != 1:
+            raise ValueError("'retain' and 'crop' cannot be combined with times > 1")       # modifiers.py:117-118
+        m0 = matches[:, 0, 0]
+        has0 = m0["adapter"] >= 0
+        if matches.shape[2] > 1:
+            m1 = matches[:, 0, 1]
+            has1 = m1["adapter"] >= 0
+        else:
+            m1, has1 = m0, np.zeros(n, dtype=bool)
+        length = base[:, 1] - base[:, 0]
+        if action == "crop":                                  # read[m.rstart:m.rstop]
+            a = np.where(has0, m0["rstart"], m1["rstart"]).astype(np.int64)
+            b = np.where(has0, m0["rstop"], m1["rstop"]).astype(np.int64)
+        else:                                                 # retained_adapter_interval, adapters.py:446-447, 479-480, 1145-1155
+            after0 = has0 & (((m0["info"] >> 8) & 1) == 1)
+            a = np.where(after0, 0, np.where(has0, m0["rstart"], 0)).astype(np.int64)
+            offset = np.where(has0, m0["rstop"], 0).astype(np.int64)
+            b = np.where(after0, m0["rstop"], np.where(has1, m1["rstop"] + offset, length)).astype(np.int64)
+        a = np.clip(a, 0, length)
+        b = np.maximum(np.clip(b, 0, length), a)
+        cut = np.stack([base[:, 0] + a, base[:, 0] + b], axis=1)
+        out[matched] = cut[matched]
+        keep[matched] = cut[matched]
+    elif action not in (None, "none"):
+        raise ValueError(f"unknown action {action!r}")
+    return out, keep
+
+
+def apply_action(sequence: str, out, keep, action: Optional[str] = "trim") -> str:
+    """The sequence ``AdapterCutter`` returns for one read, given its rows of ``action_intervals``."""
+    o0, o1, k0, k1 = int(out[0]), int(out[1]), int(keep[0]), int(keep[1])
+    if action == "mask":
+        sequence = "N" * k0 + sequence[k0:k1] + "N" * (len(sequence) - k1)
+    elif action == "lowercase":
+        sequence = sequence[:k0].lower() + sequence[k0:k1].upper() + sequence[k1:].lower()
+    return sequence[o0:o1]
+
+
 class TrimResult:
     """Outcome of one chunk: raw records plus the derived kept interval of every read."""
 

@@ -251,3 +251,39 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "libhostsim" not in text, f
+
+
+def test_action_intervals_reproduce_the_reference_goldens():
+    """
+    pipeline.action_intervals / apply_action (host logic on match records) against the expected files of the
+    reference's command-line tests for every --action; the records come from the oracle, so this runs without a GPU.
+    """
+    from oracle import oracle
+    from util import fastq_cases, fastq_case_adapters, fastq_case_kwargs, spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.pipeline import action_intervals, apply_action
+
+    seen = set()
+    for c in fastq_cases():
+        opts = c["options"]
+        if not opts["adapters"] or any(k in opts for k in ("cut", "length", "discard_casava", "max_expected_errors")):
+            continue
+        spec = spec_of(PA.MultipleAdapters(fastq_case_adapters(opts)))
+        kw = fastq_case_kwargs(opts)
+        action = kw.pop("action", "trim")
+        filters = {k: kw.pop(k) for k in ("discard_trimmed", "discard_untrimmed") if k in kw}
+        records = oracle.parse_fastq(c["input_bytes"])
+        seqs, quals = [r[1] for r in records], [r[2] for r in records]
+        matches, qtrim = oracle.oracle_process(spec.adapters, spec.groups, seqs, quals, **kw)
+        lengths = np.array([len(x) for x in seqs])
+        out, keep = action_intervals(matches, qtrim if kw.get("quality_trim") else None, lengths, action)
+        got = []
+        for i, (name, seq, q) in enumerate(records):
+            matched = (matches["adapter"][i] >= 0).any()
+            if (filters.get("discard_trimmed") and matched) or (filters.get("discard_untrimmed") and not matched):
+                continue
+            ts = apply_action(seq.upper() if action == "lowercase" else seq, out[i], keep[i], action)
+            got.append(f"@{name}\n{ts}\n+\n{q[out[i, 0]:out[i, 1]]}\n".encode())
+        assert b"".join(got) == c["expected_bytes"], c["name"]
+        seen.add(action)
+    assert seen >= {"trim", "none", "mask", "lowercase", "retain", "crop"}
