@@ -150,6 +150,52 @@ def apply_action(sequence: str, out, keep, action: Optional[str] = "trim") -> st
     return sequence[o0:o1]
 
 
+def info_file_rows(names: Sequence[str], sequences: Sequence[str], qualities: Optional[Sequence[str]],
+                   matches: np.ndarray, adapters: Matchable, final_reads=None) -> List[str]:
+    """
+    The lines ``--info-file`` gets for a chunk (InfoFileWriter.__call__, steps.py:232-253;
+    SingleMatch.get_info_records, adapters.py:395-417; LinkedMatch.get_info_records, adapters.py:1157-1171),
+    built from the match records: per match ``name, errors, rstart, rstop, before, match, after, adapter name,
+    three quality parts, rc flag``; the parts of a linked match carry the linked adapter's name + ";1" / ";2";
+    reads without a match give ``name, -1, sequence, qualities`` of the read as written.  ``sequences`` /
+    ``qualities`` are the ORIGINAL reads (``info.original_read``): the reference applies the coordinates of every
+    round to them as they are.  ``final_reads``: optional (sequence, qualities) per read for the unmatched rows
+    (default: the originals).
+    """
+    singles, groups, owners = adapters._flatten()
+    rows = []
+    for i, name in enumerate(names):
+        cur_s = sequences[i]
+        cur_q = qualities[i] if qualities is not None else None
+        any_match = False
+        for r in range(matches.shape[1]):
+            if not (matches["adapter"][i, r] >= 0).any():
+                break
+            any_match = True
+            for slot in range(matches.shape[2]):
+                m = matches[i, r, slot]
+                if m["adapter"] < 0:
+                    continue
+                g = int(m["info"]) & 255
+                if groups[g][0] == _lib.CG_GROUP_LINKED:
+                    adapter_name = ("none" if owners[g].name is None else owners[g].name) + (";1", ";2")[slot]
+                else:
+                    adapter_name = singles[int(m["adapter"])].name
+                rs, re_ = int(m["rstart"]), int(m["rstop"])
+                q3 = [cur_q[0:rs], cur_q[rs:re_], cur_q[re_:]] if cur_q else ["", "", ""]
+                rows.append("\t".join([name, str(int(m["errors"])), str(rs), str(re_), cur_s[0:rs], cur_s[rs:re_],
+                                       cur_s[re_:], adapter_name] + q3 + [""]))
+                # current_read = match.trimmed(current_read)
+                if (int(m["info"]) >> 8) & 1:
+                    cur_s, cur_q = cur_s[:rs], (cur_q[:rs] if cur_q is not None else None)
+                else:
+                    cur_s, cur_q = cur_s[re_:], (cur_q[re_:] if cur_q is not None else None)
+        if not any_match:
+            fs, fq = final_reads[i] if final_reads is not None else (sequences[i], qualities[i] if qualities else "")
+            rows.append("\t".join([name, "-1", fs, fq or ""]))
+    return rows
+
+
 class TrimResult:
     """Outcome of one chunk: raw records plus the derived kept interval of every read."""
 

@@ -176,6 +176,10 @@ def main():
     for name in ("first", "second", "unknown"):
         with open(os.path.join(HERE, f"demux_twoadapters.{name}.out.fastq"), "wb") as f:
             f.write(fasta_to_fastq(os.path.join(REF, "cut", f"twoadapters.{name}.fasta")))
+    # --info-file known answers (tests/test_info_file.py:14-55, tests/test_commandline.py linked info): the text files
+    for src, dst in (("cut/illumina.info.txt", "info_illumina.txt"), ("cut/illumina5.info.txt", "info_illumina5.txt"),
+                     ("data/illumina5.fastq", "info_illumina5.in.fastq")):
+        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
     with open(os.path.join(HERE, "paired_cases.json"), "w") as f:
         json.dump(pindex, f, indent=1)
     print(len(pindex), "paired cases")

@@ -287,3 +287,27 @@ def test_action_intervals_reproduce_the_reference_goldens():
         assert b"".join(got) == c["expected_bytes"], c["name"]
         seen.add(action)
     assert seen >= {"trim", "none", "mask", "lowercase", "retain", "crop"}
+
+
+def test_info_file_rows_reproduce_the_reference_goldens():
+    """pipeline.info_file_rows against tests/cut/illumina.info.txt and illumina5.info.txt (--times 2) of the reference
+    (tests/test_info_file.py:14-55); records from the oracle, so no GPU is needed."""
+    from oracle import oracle
+    from util import spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.pipeline import info_file_rows
+
+    here = os.path.join(ROOT, "tests", "golden", "fastq")
+    cases = [("iupac.in.fastq", "info_illumina.txt", [("adapt", "GCCGAACTTCTTAGACTGCCTTAAGGACGT")], 1),
+             ("info_illumina5.in.fastq", "info_illumina5.txt", [("adapt", "GCCGAACTTCTTA"), ("adapt2", "GACTGCCTTAAGGACGT")], 2)]
+    for fastq, expected, ads, times in cases:
+        records = oracle.parse_fastq(open(os.path.join(here, fastq), "rb").read())
+        multi = PA.MultipleAdapters([PA.BackAdapter(s, max_errors=0.1, min_overlap=3, name=n) for n, s in ads])
+        spec = spec_of(multi)
+        names, seqs, quals = zip(*records)
+        matches, _ = oracle.oracle_process(spec.adapters, spec.groups, list(seqs), list(quals), times=times)
+        got = info_file_rows(names, seqs, quals, matches, multi)
+        want = open(os.path.join(here, expected)).read().split("\n")
+        if want[-1] == "":
+            want.pop()
+        assert [g.rstrip() for g in got] == [w.rstrip() for w in want]      # assert_files_equal(ignore_trailing_space)
