@@ -207,6 +207,33 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(index):
+    """
+    Run the calling thread (and the threads it starts later) on the CPUs of the NUMA node the GPU hangs off, so
+    that the pinned host buffers of the end-to-end leg are allocated there: neither the DMA engine nor the packing
+    threads then read them across the socket link.  Best effort; returns the node or None.
+    """
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        domain, bus, rest = out.split(":")
+        path = f"/sys/bus/pci/devices/{domain[-4:]}:{bus}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,6 +356,10 @@ def main():
     if not args.no_e2e:
         hw = min(n, HOST_WINDOW_READS)
         passes = (n + hw - 1) // hw
+        # the visible device of this rank, as nvidia-smi numbers it
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        smi_index = visible.split(",")[local_rank] if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        gpu_node = bind_to_gpu_numa_node(smi_index)
         h_seq = torch.empty(hw * READ_LEN, dtype=torch.uint8, pin_memory=True)
         h_seq.copy_(seq[: hw * READ_LEN])
         h_off = torch.empty(hw + 1, dtype=torch.int64, pin_memory=True)
@@ -389,7 +420,7 @@ def main():
                "h2d_bytes_per_step": h2d_bytes // e2e_steps, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                "steps": e2e_steps, "launches": host_ctx.launch_count() - l0,
                "host_threads": host_threads, "host_cpus_available": int(_lib.lib().cg_host_cpus_available()),
-               "host_numa_node": int(_lib.lib().cg_ctx_numa_node(host_ctx.handle)),
+               "host_numa_node": int(_lib.lib().cg_ctx_numa_node(host_ctx.handle)), "gpu_numa_node": gpu_node,
                "host_profile": {k: (round(v, 4) if isinstance(v, float) else v)
                                 for k, v in host_ctx.host_profile().items()},
                "raw_transfer_value": n * world / raw_wall,
