@@ -285,6 +285,82 @@ class BatchTrimmer:
         return [stats[id(o)] for o in owners]
 
 
+def _fastq_head(buf, end: int) -> int:
+    """Length of the longest prefix of buf[:end] that consists of complete 4-line records (the buffer starts at a
+    record; same counting rule as dnaio's chunk reader, which the reference uses at runners.py:116-126)."""
+    linebreaks = buf.count(b"\n", 0, end)
+    right = end
+    for _ in range(linebreaks % 4 + 1):
+        right = buf.rfind(b"\n", 0, right)
+        if right < 0:
+            return 0
+    return right + 1
+
+
+def _cut_records(buf, end: int, n_records: int) -> int:
+    """Offset just behind the first n_records records of buf[:end]."""
+    pos = 0
+    for _ in range(4 * n_records):
+        pos = buf.find(b"\n", pos, end) + 1
+    return pos
+
+
+def read_fastq_chunks(f, buffer_size: int = 4 * 1024 * 1024):
+    """
+    Chunks of complete FASTQ records from a binary file object -- what ``dnaio.read_chunks`` hands the reference's
+    workers (runners.py:116-126) and what ``FastqTrimmer.process_chunk(s)`` takes.  The last chunk may lack the
+    final newline.  A record larger than the buffer makes the buffer grow.
+    """
+    buf = bytearray(buffer_size)
+    start = 0
+    while True:
+        if start == len(buf):
+            buf.extend(bytes(len(buf)))
+        n = f.readinto(memoryview(buf)[start:])
+        if not n:
+            break
+        end = start + n
+        head = _fastq_head(buf, end)
+        if head:
+            yield bytes(buf[:head])
+            buf[0:end - head] = buf[head:end]
+            start = end - head
+        else:
+            start = end
+    if start:
+        yield bytes(buf[:start])
+
+
+def read_paired_fastq_chunks(f1, f2, buffer_size: int = 4 * 1024 * 1024):
+    """Pairs of chunks with the same number of complete records each (``dnaio.read_paired_chunks``)."""
+    bufs = [bytearray(buffer_size), bytearray(buffer_size)]
+    starts = [0, 0]
+    files = (f1, f2)
+    eof = [False, False]
+    while True:
+        ends = list(starts)
+        for k in (0, 1):
+            if starts[k] == len(bufs[k]):
+                bufs[k].extend(bytes(len(bufs[k])))
+            n = 0 if eof[k] else files[k].readinto(memoryview(bufs[k])[starts[k]:])
+            eof[k] = eof[k] or not n
+            ends[k] = starts[k] + (n or 0)
+        if eof[0] and eof[1]:
+            break
+        heads = [_fastq_head(bufs[k], ends[k]) for k in (0, 1)]
+        records = min(bufs[k].count(b"\n", 0, heads[k]) // 4 for k in (0, 1))
+        if records:
+            cuts = [_cut_records(bufs[k], ends[k], records) for k in (0, 1)]
+            yield bytes(bufs[0][:cuts[0]]), bytes(bufs[1][:cuts[1]])
+            for k in (0, 1):
+                bufs[k][0:ends[k] - cuts[k]] = bufs[k][cuts[k]:ends[k]]
+                starts[k] = ends[k] - cuts[k]
+        else:
+            starts = ends
+    if starts[0] or starts[1]:
+        yield bytes(bufs[0][:starts[0]]), bytes(bufs[1][:starts[1]])
+
+
 def _fastq_params(times=1, quality_cutoff=None, quality_base=33, nextseq_cutoff=None, minimum_length=0,
                   maximum_length=None, max_n=None, max_expected_errors=None, discard_trimmed=False,
                   discard_untrimmed=False, cut=(), poly_a=False, length=None, trim_n=False,

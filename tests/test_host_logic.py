@@ -311,3 +311,43 @@ def test_info_file_rows_reproduce_the_reference_goldens():
         if want[-1] == "":
             want.pop()
         assert [g.rstrip() for g in got] == [w.rstrip() for w in want]      # assert_files_equal(ignore_trailing_space)
+
+
+def test_fastq_chunk_readers():
+    """read_fastq_chunks / read_paired_fastq_chunks: chunks of complete records, in order, for any buffer size --
+    also when quality lines start with '@' or '+' and the file lacks a final newline."""
+    import io
+    import random
+    from cutadapt_b200.pipeline import read_fastq_chunks, read_paired_fastq_chunks
+    from oracle import oracle
+
+    rng = random.Random(3)
+
+    def fastq(n, seed):
+        r = random.Random(seed)
+        out = []
+        for i in range(n):
+            ln = r.choice((0, 1, 7, 50, 151))
+            seq = "".join(r.choice("ACGT") for _ in range(ln))
+            qual = "".join(r.choice("@+I#5") for _ in range(ln))
+            out.append(f"@r{i} x\n{seq}\n+\n{qual}\n")
+        return "".join(out).encode()
+
+    data = fastq(700, 1)
+    for tail in (data, data[:-1]):
+        for size in (64, 100, 1000, 4096, 1 << 20):
+            chunks = list(read_fastq_chunks(io.BytesIO(tail), size))
+            assert b"".join(chunks) == tail
+            for c in chunks:
+                recs = oracle.parse_fastq(c)          # raises on incomplete records
+                assert recs and all(name.startswith("r") for name, _, _ in recs)
+            if size < 200:
+                assert len(chunks) > 50
+    d1, d2 = fastq(500, 2), fastq(500, 3)
+    for size in (128, 999, 1 << 16):
+        pairs = list(read_paired_fastq_chunks(io.BytesIO(d1), io.BytesIO(d2), size))
+        assert b"".join(a for a, _ in pairs) == d1 and b"".join(b for _, b in pairs) == d2
+        for a, b in pairs:
+            ra, rb = oracle.parse_fastq(a), oracle.parse_fastq(b)
+            assert len(ra) == len(rb) > 0 and [x[0] for x in ra] == [x[0] for x in rb]
+    assert list(read_fastq_chunks(io.BytesIO(b""))) == []
