@@ -207,31 +207,60 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 
-def bind_to_gpu_numa_node(index):
-    """
-    Run the calling thread (and the threads it starts later) on the CPUs of the NUMA node the GPU hangs off, so
-    that the pinned host buffers of the end-to-end leg are allocated there: neither the DMA engine nor the packing
-    threads then read them across the socket link.  Best effort; returns the node or None.
-    """
+def numa_nodes():
+    """{node: set of CPUs this process may use} for the NUMA nodes of the host."""
+    nodes = {}
     try:
-        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
-                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
-        domain, bus, rest = out.split(":")
-        path = f"/sys/bus/pci/devices/{domain[-4:]}:{bus}:{rest}/numa_node"
-        node = int(open(path).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
+        allowed = os.sched_getaffinity(0)
+        for entry in sorted(os.listdir("/sys/devices/system/node")):
+            if not entry.startswith("node") or not entry[4:].isdigit():
+                continue
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/{entry}/cpulist").read().strip().split(","):
+                if part:
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+            if cpus & allowed:
+                nodes[int(entry[4:])] = cpus & allowed
     except Exception:
-        return None
+        return {}
+    return nodes
+
+
+def best_numa_node_for(dev, torch):
+    """
+    The NUMA node whose memory the GPU reads fastest, MEASURED: pinned buffers are allocated by a thread running on
+    each node in turn (first touch puts them there) and copied to the device.  A deployment would place its read
+    buffers like this; the topology files are not reliable inside containers.  Returns (node or None, {node: GB/s}).
+    """
+    nodes = numa_nodes()
+    if len(nodes) < 2:
+        return None, {}
+    saved = os.sched_getaffinity(0)
+    rates = {}
+    try:
+        dst = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for node, cpus in nodes.items():
+            os.sched_setaffinity(0, cpus)
+            src = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+            src.fill_(65)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            rates[node] = 4 * src.numel() / (e0.elapsed_time(e1) / 1000.0) / 1e9
+            del src
+    except Exception:
+        rates = {}
+    finally:
+        os.sched_setaffinity(0, saved)
+    if not rates:
+        return None, {}
+    return max(rates, key=rates.get), {k: round(v, 1) for k, v in rates.items()}
 
 
 def main():
@@ -356,15 +385,18 @@ def main():
     if not args.no_e2e:
         hw = min(n, HOST_WINDOW_READS)
         passes = (n + hw - 1) // hw
-        # the visible device of this rank, as nvidia-smi numbers it
-        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-        smi_index = visible.split(",")[local_rank] if visible and visible.split(",")[local_rank].isdigit() else local_rank
-        gpu_node = bind_to_gpu_numa_node(smi_index)
+        # host buffers on the NUMA node the GPU reads fastest (measured), like a deployment would place them
+        gpu_node, node_rates = best_numa_node_for(dev, torch)
+        saved_affinity = os.sched_getaffinity(0)
+        if gpu_node is not None:
+            os.sched_setaffinity(0, numa_nodes()[gpu_node])
         h_seq = torch.empty(hw * READ_LEN, dtype=torch.uint8, pin_memory=True)
         h_seq.copy_(seq[: hw * READ_LEN])
         h_off = torch.empty(hw + 1, dtype=torch.int64, pin_memory=True)
         h_off.copy_(offsets[: hw + 1])
         h_out = torch.empty((hw, 8), dtype=torch.int32, pin_memory=True)
+        h_out.zero_()
+        os.sched_setaffinity(0, saved_affinity)
         # worker threads of the library's host side (packing for the compressed transfer): this rank's
         # share of the host cores
         if world > 1:
@@ -420,7 +452,7 @@ def main():
                "h2d_bytes_per_step": h2d_bytes // e2e_steps, "d2h_bytes_per_step": d2h_bytes // e2e_steps,
                "steps": e2e_steps, "launches": host_ctx.launch_count() - l0,
                "host_threads": host_threads, "host_cpus_available": int(_lib.lib().cg_host_cpus_available()),
-               "host_numa_node": int(_lib.lib().cg_ctx_numa_node(host_ctx.handle)), "gpu_numa_node": gpu_node,
+               "host_numa_node": int(_lib.lib().cg_ctx_numa_node(host_ctx.handle)), "host_buffer_node": gpu_node, "h2d_GBps_by_node": node_rates,
                "host_profile": {k: (round(v, 4) if isinstance(v, float) else v)
                                 for k, v in host_ctx.host_profile().items()},
                "raw_transfer_value": n * world / raw_wall,
