@@ -196,6 +196,52 @@ def info_file_rows(names: Sequence[str], sequences: Sequence[str], qualities: Op
     return rows
 
 
+def _last_matches(sequences, matches):
+    """Per read: (record of info.matches[-1] or None, the sequence that round searched)."""
+    for i, seq in enumerate(sequences):
+        cur, last = seq, None
+        for r in range(matches.shape[1]):
+            present = [m for m in matches[i, r] if m["adapter"] >= 0]
+            if not present:
+                break
+            for m in present:
+                last = (m, cur)
+                cur = cur[:int(m["rstart"])] if (int(m["info"]) >> 8) & 1 else cur[int(m["rstop"]):]
+        yield last
+
+
+def rest_file_rows(names: Sequence[str], sequences: Sequence[str], matches: np.ndarray) -> List[str]:
+    """The lines of ``--rest-file`` (RestFileWriter, steps.py:193-206; SingleMatch.rest, adapters.py:430-437,
+    463-470): for the last match of a read, what lies before a 5' adapter / behind a 3' adapter, if not empty."""
+    rows = []
+    for name, last in zip(names, _last_matches(sequences, matches)):
+        if last is None:
+            continue
+        m, cur = last
+        rest = cur[int(m["rstop"]):] if (int(m["info"]) >> 8) & 1 else cur[:int(m["rstart"])]
+        if rest:
+            rows.append(f"{rest} {name}")
+    return rows
+
+
+def wildcard_file_rows(names: Sequence[str], sequences: Sequence[str], matches: np.ndarray,
+                       adapters: Matchable) -> List[str]:
+    """The lines of ``--wildcard-file`` (WildcardFileWriter, steps.py:209-220; SingleMatch.wildcards,
+    adapters.py:378-393): the read characters under the ``N`` positions of the adapter of the last match."""
+    singles, _, _ = adapters._flatten()
+    rows = []
+    for name, last in zip(names, _last_matches(sequences, matches)):
+        if last is None:
+            continue
+        m, cur = last
+        aseq = singles[int(m["adapter"])].sequence
+        astart, rstart = int(m["astart"]), int(m["rstart"])
+        chars = [cur[rstart + i] for i in range(int(m["astop"]) - astart)
+                 if aseq[astart + i] == "N" and rstart + i < len(cur)]
+        rows.append(f"{''.join(chars)} {name}")
+    return rows
+
+
 class TrimResult:
     """Outcome of one chunk: raw records plus the derived kept interval of every read."""
 

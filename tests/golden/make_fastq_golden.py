@@ -180,6 +180,10 @@ def main():
     for src, dst in (("cut/illumina.info.txt", "info_illumina.txt"), ("cut/illumina5.info.txt", "info_illumina5.txt"),
                      ("data/illumina5.fastq", "info_illumina5.in.fastq")):
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+    # --rest-file / --wildcard-file known answers (test_commandline.py:110-122, 345-367)
+    for src, dst in (("data/rest.fa", "rest.in.fasta"), ("data/rest.txt", "rest.txt"),
+                     ("data/restfront.txt", "restfront.txt"), ("data/wildcard_adapter.fa", "wildcard_adapter.in.fasta")):
+        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
     with open(os.path.join(HERE, "paired_cases.json"), "w") as f:
         json.dump(pindex, f, indent=1)
     print(len(pindex), "paired cases")

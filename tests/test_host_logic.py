@@ -351,3 +351,32 @@ def test_fastq_chunk_readers():
             ra, rb = oracle.parse_fastq(a), oracle.parse_fastq(b)
             assert len(ra) == len(rb) > 0 and [x[0] for x in ra] == [x[0] for x in rb]
     assert list(read_fastq_chunks(io.BytesIO(b""))) == []
+
+
+def test_rest_and_wildcard_file_rows_reproduce_the_reference_goldens():
+    """pipeline.rest_file_rows / wildcard_file_rows against tests/data/rest.txt, restfront.txt and the expected lines of
+    test_adapter_wildcard (reference tests/test_commandline.py:110-122, 345-367); records from the oracle."""
+    from oracle import oracle
+    from util import spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.pipeline import rest_file_rows, wildcard_file_rows
+
+    here = os.path.join(ROOT, "tests", "golden", "fastq")
+
+    def fasta(name):
+        lines = open(os.path.join(here, name)).read().split("\n")
+        return [l[1:] for l in lines[0::2] if l], [l for l in lines[1::2]][:len([l for l in lines[0::2] if l])]
+
+    names, seqs = fasta("rest.in.fasta")
+    for cls, expected in ((PA.AnywhereAdapter, "rest.txt"), (PA.FrontAdapter, "restfront.txt")):
+        multi = PA.MultipleAdapters([cls("ADAPTER", max_errors=0.1, min_overlap=3, adapter_wildcards=False, name="a")])
+        spec = spec_of(multi)
+        matches, _ = oracle.oracle_process(spec.adapters, spec.groups, seqs)
+        want = open(os.path.join(here, expected)).read().split("\n")
+        assert rest_file_rows(names, seqs, matches) == [w for w in want if w]
+    names, seqs = fasta("wildcard_adapter.in.fasta")
+    for cls in (PA.BackAdapter, PA.AnywhereAdapter):
+        multi = PA.MultipleAdapters([cls("ACGTNNNACGT", max_errors=0.1, min_overlap=3, name="a")])
+        spec = spec_of(multi)
+        matches, _ = oracle.oracle_process(spec.adapters, spec.groups, seqs)
+        assert wildcard_file_rows(names, seqs, matches, multi) == ["AAA 1", "GGG 2", "CCC 3b", "TTT 4b"]
