@@ -2,8 +2,8 @@
 """
 Copies the FASTQ known-answer cases of the reference's own command-line tests
 (/root/reference/tests/test_commandline.py: run(params, expected, input) compares cutadapt's output
-with tests/cut/<expected>) into tests/golden/fastq/ as (<case>.in.fastq, <case>.out.fastq) pairs plus
-cases.json, which restates each command line in terms of cutadapt_b200's FASTQ entry point.
+with tests/cut/<expected>) into tests/golden/fastq_kat.json.gz: the (<case>.in.fastq, <case>.out.fastq) pairs as
+text plus the case lists, which restate each command line in terms of cutadapt_b200's FASTQ entry point.
 These are test vectors (inputs and expected outputs), not source code.
 
     python tests/golden/make_fastq_golden.py      (needs /root/reference; run once, results committed)
@@ -14,7 +14,17 @@ import os
 import shutil
 
 REF = "/root/reference/tests"
-HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fastq")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fastq_kat.json.gz")
+FILES = {}     # fixture name -> content (latin-1 text)
+
+
+def put(name, data):
+    FILES[name] = (data if isinstance(data, bytes) else data.encode()).decode("latin-1")
+
+
+def copy(src, name):
+    with open(src, "rb") as f:
+        put(name, f.read())
 
 # name, reference test (test_commandline.py line), command line, input, expected, options for the product
 CASES = [
@@ -137,56 +147,49 @@ def fasta_to_fastq(path):
 
 
 def main():
-    os.makedirs(HERE, exist_ok=True)
     index = []
     for name, line, cmd, inp, exp, opts in CASES:
         src = os.path.join(REF, "data", inp)
-        dst_in = os.path.join(HERE, f"{name}.in.fastq")
         if inp.endswith(".gz"):
-            with gzip.open(src, "rb") as f, open(dst_in, "wb") as g:
-                g.write(f.read())
+            with gzip.open(src, "rb") as f:
+                put(f"{name}.in.fastq", f.read())
         elif inp.endswith(".fasta"):
-            with open(dst_in, "wb") as g:
-                g.write(fasta_to_fastq(src))
+            put(f"{name}.in.fastq", fasta_to_fastq(src))
         else:
-            shutil.copyfile(src, dst_in)
+            copy(src, f"{name}.in.fastq")
         if exp.endswith(".fasta"):
-            with open(os.path.join(HERE, f"{name}.out.fastq"), "wb") as g:
-                g.write(fasta_to_fastq(os.path.join(REF, "cut", exp)))
+            put(f"{name}.out.fastq", fasta_to_fastq(os.path.join(REF, "cut", exp)))
         else:
-            shutil.copyfile(os.path.join(REF, "cut", exp), os.path.join(HERE, f"{name}.out.fastq"))
+            copy(os.path.join(REF, "cut", exp), f"{name}.out.fastq")
         index.append(dict(name=name, reference_test=f"tests/test_commandline.py:{line}", command=cmd,
                           input=f"tests/data/{inp}", expected=f"tests/cut/{exp}", options=opts))
-    with open(os.path.join(HERE, "cases.json"), "w") as f:
-        json.dump(index, f, indent=1)
     print(len(index), "cases")
     pindex = []
     for name, line, cmd, in1, in2, exp1, exp2, opts in PAIRED:
         for k, (inp, exp) in enumerate(((in1, exp1), (in2, exp2)), 1):
-            shutil.copyfile(os.path.join(REF, "data", inp), os.path.join(HERE, f"paired_{name}.in{k}.fastq"))
-            shutil.copyfile(os.path.join(REF, "cut", exp), os.path.join(HERE, f"paired_{name}.out{k}.fastq"))
+            copy(os.path.join(REF, "data", inp), f"paired_{name}.in{k}.fastq")
+            copy(os.path.join(REF, "cut", exp), f"paired_{name}.out{k}.fastq")
         pindex.append(dict(name=name, reference_test=f"tests/test_paired.py:{line}", command=cmd,
                            inputs=[f"tests/data/{in1}", f"tests/data/{in2}"],
                            expected=[f"tests/cut/{exp1}", f"tests/cut/{exp2}"], options=opts))
+    print(len(pindex), "paired cases")
     # demultiplexing (test_commandline.py:581-601: -a first=AATTTCAGGAATT -a second=GTTCTCTAGTTCT -o {name}.fasta
     # twoadapters.fasta): the reference's vectors are FASTA; they are stored as FASTQ with constant qualities 'I'
     # (single-line records, so the conversion is 1:1 and the expected sequences are untouched)
-    with open(os.path.join(HERE, "demux_twoadapters.in.fastq"), "wb") as f:
-        f.write(fasta_to_fastq(os.path.join(REF, "data", "twoadapters.fasta")))
+    put("demux_twoadapters.in.fastq", fasta_to_fastq(os.path.join(REF, "data", "twoadapters.fasta")))
     for name in ("first", "second", "unknown"):
-        with open(os.path.join(HERE, f"demux_twoadapters.{name}.out.fastq"), "wb") as f:
-            f.write(fasta_to_fastq(os.path.join(REF, "cut", f"twoadapters.{name}.fasta")))
-    # --info-file known answers (tests/test_info_file.py:14-55, tests/test_commandline.py linked info): the text files
+        put(f"demux_twoadapters.{name}.out.fastq", fasta_to_fastq(os.path.join(REF, "cut", f"twoadapters.{name}.fasta")))
+    # --info-file known answers (tests/test_info_file.py:14-55): the text files
     for src, dst in (("cut/illumina.info.txt", "info_illumina.txt"), ("cut/illumina5.info.txt", "info_illumina5.txt"),
                      ("data/illumina5.fastq", "info_illumina5.in.fastq")):
-        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+        copy(os.path.join(REF, src), dst)
     # --rest-file / --wildcard-file known answers (test_commandline.py:110-122, 345-367)
     for src, dst in (("data/rest.fa", "rest.in.fasta"), ("data/rest.txt", "rest.txt"),
                      ("data/restfront.txt", "restfront.txt"), ("data/wildcard_adapter.fa", "wildcard_adapter.in.fasta")):
-        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
-    with open(os.path.join(HERE, "paired_cases.json"), "w") as f:
-        json.dump(pindex, f, indent=1)
-    print(len(pindex), "paired cases")
+        copy(os.path.join(REF, src), dst)
+    with gzip.open(OUT, "wt", compresslevel=9) as f:
+        json.dump(dict(cases=index, paired_cases=pindex, files=FILES), f)
+    print(len(FILES), "fixture files ->", OUT, os.path.getsize(OUT), "bytes")
 
 
 if __name__ == "__main__":

@@ -297,17 +297,17 @@ def test_info_file_rows_reproduce_the_reference_goldens():
     import cutadapt_b200.adapters as PA
     from cutadapt_b200.pipeline import info_file_rows
 
-    here = os.path.join(ROOT, "tests", "golden", "fastq")
+    from util import fastq_file
     cases = [("iupac.in.fastq", "info_illumina.txt", [("adapt", "GCCGAACTTCTTAGACTGCCTTAAGGACGT")], 1),
              ("info_illumina5.in.fastq", "info_illumina5.txt", [("adapt", "GCCGAACTTCTTA"), ("adapt2", "GACTGCCTTAAGGACGT")], 2)]
     for fastq, expected, ads, times in cases:
-        records = oracle.parse_fastq(open(os.path.join(here, fastq), "rb").read())
+        records = oracle.parse_fastq(fastq_file(fastq))
         multi = PA.MultipleAdapters([PA.BackAdapter(s, max_errors=0.1, min_overlap=3, name=n) for n, s in ads])
         spec = spec_of(multi)
         names, seqs, quals = zip(*records)
         matches, _ = oracle.oracle_process(spec.adapters, spec.groups, list(seqs), list(quals), times=times)
         got = info_file_rows(names, seqs, quals, matches, multi)
-        want = open(os.path.join(here, expected)).read().split("\n")
+        want = fastq_file(expected).decode().split("\n")
         if want[-1] == "":
             want.pop()
         assert [g.rstrip() for g in got] == [w.rstrip() for w in want]      # assert_files_equal(ignore_trailing_space)
@@ -361,10 +361,10 @@ def test_rest_and_wildcard_file_rows_reproduce_the_reference_goldens():
     import cutadapt_b200.adapters as PA
     from cutadapt_b200.pipeline import rest_file_rows, wildcard_file_rows
 
-    here = os.path.join(ROOT, "tests", "golden", "fastq")
+    from util import fastq_file
 
     def fasta(name):
-        lines = open(os.path.join(here, name)).read().split("\n")
+        lines = fastq_file(name).decode().split("\n")
         return [l[1:] for l in lines[0::2] if l], [l for l in lines[1::2]][:len([l for l in lines[0::2] if l])]
 
     names, seqs = fasta("rest.in.fasta")
@@ -372,7 +372,7 @@ def test_rest_and_wildcard_file_rows_reproduce_the_reference_goldens():
         multi = PA.MultipleAdapters([cls("ADAPTER", max_errors=0.1, min_overlap=3, adapter_wildcards=False, name="a")])
         spec = spec_of(multi)
         matches, _ = oracle.oracle_process(spec.adapters, spec.groups, seqs)
-        want = open(os.path.join(here, expected)).read().split("\n")
+        want = fastq_file(expected).decode().split("\n")
         assert rest_file_rows(names, seqs, matches) == [w for w in want if w]
     names, seqs = fasta("wildcard_adapter.in.fasta")
     for cls in (PA.BackAdapter, PA.AnywhereAdapter):

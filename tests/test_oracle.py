@@ -131,7 +131,7 @@ def test_trim_scans_golden():
 def test_fastq_oracle_reproduces_the_reference_command_line_goldens():
     """
     oracle.oracle_fastq_trim (parse -> modifiers -> filters -> format) against the expected output files of
-    the reference's own command-line tests (tests/golden/fastq/cases.json names test and command line).
+    the reference's own command-line tests (the case list in tests/golden/fastq_kat.json.gz names test and command line).
     """
     from util import fastq_cases, fastq_case_adapters, fastq_case_kwargs, spec_of
     import cutadapt_b200.adapters as PA

@@ -144,15 +144,25 @@ def random_reads(rng, adapters, n_reads, alpha="ACGT", max_len=80):
     return reads
 
 
-# ---- FASTQ known-answer cases of the reference's command-line tests (tests/golden/fastq) -----------------
+# ---- FASTQ known-answer cases of the reference's command-line tests (tests/golden/fastq_kat.json.gz) -----------------
+
+_FASTQ_KAT = None
+
+
+def fastq_file(name) -> bytes:
+    """One fixture of tests/golden/fastq_kat.json.gz (made by tests/golden/make_fastq_golden.py)."""
+    global _FASTQ_KAT
+    if _FASTQ_KAT is None:
+        _FASTQ_KAT = golden("fastq_kat.json.gz")
+    return _FASTQ_KAT["files"][name].encode("latin-1")
+
 
 def fastq_cases():
-    import json
-    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastq")
-    cases = json.load(open(os.path.join(here, "cases.json")))
+    fastq_file("small.in.fastq")
+    cases = [dict(c) for c in _FASTQ_KAT["cases"]]
     for c in cases:
-        c["input_bytes"] = open(os.path.join(here, c["name"] + ".in.fastq"), "rb").read()
-        c["expected_bytes"] = open(os.path.join(here, c["name"] + ".out.fastq"), "rb").read()
+        c["input_bytes"] = fastq_file(c["name"] + ".in.fastq")
+        c["expected_bytes"] = fastq_file(c["name"] + ".out.fastq")
     return cases
 
 
@@ -176,12 +186,11 @@ def fastq_case_adapters(options, key="adapters"):
 
 
 def fastq_paired_cases():
-    import json
-    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastq")
-    cases = json.load(open(os.path.join(here, "paired_cases.json")))
+    fastq_file("small.in.fastq")
+    cases = [dict(c) for c in _FASTQ_KAT["paired_cases"]]
     for c in cases:
-        c["input_bytes"] = [open(os.path.join(here, f"paired_{c['name']}.in{k}.fastq"), "rb").read() for k in (1, 2)]
-        c["expected_bytes"] = [open(os.path.join(here, f"paired_{c['name']}.out{k}.fastq"), "rb").read() for k in (1, 2)]
+        c["input_bytes"] = [fastq_file(f"paired_{c['name']}.in{k}.fastq") for k in (1, 2)]
+        c["expected_bytes"] = [fastq_file(f"paired_{c['name']}.out{k}.fastq") for k in (1, 2)]
     return cases
 
 
@@ -217,8 +226,6 @@ def fastq_case_kwargs(options):
 
 def fastq_demux_case():
     """tests/test_commandline.py:581-601 of the reference (FASTA vectors stored as FASTQ, see make_fastq_golden.py)."""
-    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fastq")
-    rd = lambda name: open(os.path.join(here, name), "rb").read()
     return dict(adapters=[("first", "AATTTCAGGAATT"), ("second", "GTTCTCTAGTTCT")],
-                input_bytes=rd("demux_twoadapters.in.fastq"),
-                expected={n: rd(f"demux_twoadapters.{n}.out.fastq") for n in ("first", "second", "unknown")})
+                input_bytes=fastq_file("demux_twoadapters.in.fastq"),
+                expected={n: fastq_file(f"demux_twoadapters.{n}.out.fastq") for n in ("first", "second", "unknown")})
