@@ -60,6 +60,23 @@ def allreduce_statistics(stats, group=None):
     return stats
 
 
+FASTQ_COUNTERS = ("n_records", "n_written", "bp_in", "bp_out", "out_bytes", "with_adapters", "quality_trimmed_bp",
+                  "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded", "casava_filtered")
+
+
+def allreduce_fastq_statistics(statistics: dict, group=None, device=None) -> dict:
+    """
+    Sum the counters of ``FastqTrimmer.statistics`` (``cg_fastq_result``) over all ranks: every rank trims its own
+    FASTQ chunks, the totals of the run are one small all-reduce at the end -- where the reference adds the
+    per-worker ``Statistics`` in the parent (runners.py:372-373, report.py:81-126).  Returns a new dict.
+    """
+    import torch
+
+    t = torch.tensor([int(statistics.get(k, 0)) for k in FASTQ_COUNTERS], dtype=torch.int64, device=device)
+    allreduce_statistics(t, group)
+    return dict(zip(FASTQ_COUNTERS, (int(x) for x in t.tolist())))
+
+
 def kept_intervals(matches: np.ndarray, qtrim: Optional[np.ndarray], lengths: np.ndarray) -> np.ndarray:
     """
     (n, 2) array of the part of every read that survives quality trimming and all rounds of

@@ -51,6 +51,16 @@ def run(rank, world, port, out_dir):
     local = host_statistics(matches, None, lengths, 1, 150, 3)
     t = torch.from_numpy(local.copy())
     allreduce_statistics(t)
+    # FASTQ-level counters: every rank "trims" its shard of a FASTQ file with the oracle; the totals are all-reduced
+    import json
+    from cutadapt_b200.pipeline import allreduce_fastq_statistics
+    from oracle import oracle
+
+    fq = "".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads[lo:hi])).encode()
+    _, counters = oracle.oracle_fastq_trim(fq, spec.adapters, spec.groups, minimum_length=100)
+    counters["out_bytes"] = 0
+    with open(os.path.join(out_dir, f"fq{rank}.json"), "w") as f:
+        json.dump({"local": counters, "total": allreduce_fastq_statistics(counters)}, f)
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), t.numpy())
     np.save(os.path.join(out_dir, f"local{rank}.npy"), local)
     dist.barrier()

@@ -47,6 +47,17 @@ def test_two_rank_statistics_allreduce(tmp_path):
     total = _dist_worker.host_statistics(matches, None, np.array([len(r) for r in reads]), 1, 150, 3)
     assert (total == r0).all()
     assert r0[0] == 3001 and 1300 < r0[2] < 1700
+    # the FASTQ counters of both ranks add up to the single-process totals
+    import json
+    from oracle import oracle
+
+    f0, f1 = (json.load(open(tmp_path / f"fq{r}.json")) for r in (0, 1))
+    assert f0["total"] == f1["total"]
+    fq = "".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)).encode()
+    _, whole = oracle.oracle_fastq_trim(fq, spec.adapters, spec.groups, minimum_length=100)
+    for k, v in whole.items():
+        assert f0["total"][k] == v == f0["local"][k] + f1["local"][k], k
+    assert whole["n_written"] + whole["too_short"] == 3001 and whole["too_short"] > 100
 
 
 def test_kept_intervals_compose_like_the_reference():
