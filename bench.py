@@ -103,6 +103,24 @@ def reference_kind():
     return "port"
 
 
+def cpus_available():
+    """CPUs this process may use: the affinity mask, cut down by a cgroup CPU quota (containers on a shared host)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, round(int(quota) / int(period))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                n = min(n, max(1, round(q / p)))
+        except Exception:
+            pass
+    return n
+
+
 class CpuArm:
     """All host cores running the reference hot path on pre-parsed reads (spawned workers)."""
 
@@ -301,6 +319,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "sample": f"{vals[0][1]} reads per step over {cores} host cores"},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
+                             "cpus_available": cpus_available(),
                              "sample": f"{vals[0][1]} pre-parsed reads per step, Adapter.match_to + Match.trimmed"},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -337,7 +356,7 @@ def main():
         arm = CpuArm(sample)
         v, nproc, wall = arm.run(12.0)
         arm.close()
-        cpu = {"value": v, "unit": "reads/s", "cores": arm.cores, "kind": arm.kind,
+        cpu = {"value": v, "unit": "reads/s", "cores": arm.cores, "kind": arm.kind, "cpus_available": cpus_available(),
                "sample": f"{nproc} pre-parsed reads in {wall:.1f}s: Adapter.match_to + Match.trimmed over {arm.cores} processes"}
 
     seq, _ = make_read_tensor(n, config=2, shard=rank, device=str(dev))
