@@ -6,7 +6,7 @@
  * batched per chunk of reads.  Every entry point below states which reference interface it
  * replaces (file:line relative to the reference checkout).  Plain C types only: no torch,
  * no C++ types, no Python objects cross this boundary.  The Python host layer
- * (cutadapt_b200/*.py) binds it with ctypes; INTEGRATION.md shows the stub a cutadapt
+ * (the modules of cutadapt_b200) binds it with ctypes; INTEGRATION.md shows the stub a cutadapt
  * maintainer would add.
  *
  * Conventions

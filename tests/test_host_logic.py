@@ -380,3 +380,28 @@ def test_rest_and_wildcard_file_rows_reproduce_the_reference_goldens():
         spec = spec_of(multi)
         matches, _ = oracle.oracle_process(spec.adapters, spec.groups, seqs)
         assert wildcard_file_rows(names, seqs, matches, multi) == ["AAA 1", "GGG 2", "CCC 3b", "TTT 4b"]
+
+
+def test_public_header_is_plain_c_and_matches_the_ctypes_structs():
+    """include/cutadapt_b200.h compiles as C99 on its own, and the ctypes mirrors have the sizes the C compiler
+    gives the structs (a layout drift between header and binding would corrupt every call)."""
+    import subprocess
+    import tempfile
+    from cutadapt_b200 import _lib
+
+    header = os.path.join(ROOT, "include", "cutadapt_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", header])
+    names = ["cg_kmer_entry", "cg_adapter_desc", "cg_group_desc", "cg_index_desc", "cg_params", "cg_match",
+             "cg_fastq_params", "cg_fastq_result"]
+    prog = '#include <stdio.h>\n#include "%s"\nint main(void){%s return 0;}' % (
+        header, "".join('printf("%%zu\\n", sizeof(%s));' % n for n in names))
+    with tempfile.TemporaryDirectory() as d:
+        src, exe = os.path.join(d, "s.c"), os.path.join(d, "s")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-o", exe, src])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    mirrors = [_lib.cg_kmer_entry, _lib.cg_adapter_desc, _lib.cg_group_desc, _lib.cg_index_desc, _lib.cg_params,
+               None, _lib.cg_fastq_params, _lib.cg_fastq_result]
+    for name, size, mirror in zip(names, sizes, mirrors):
+        got = _lib.MATCH_DTYPE.itemsize if mirror is None else ctypes.sizeof(mirror)
+        assert got == size, (name, got, size)
