@@ -405,3 +405,42 @@ def test_public_header_is_plain_c_and_matches_the_ctypes_structs():
     for name, size, mirror in zip(names, sizes, mirrors):
         got = _lib.MATCH_DTYPE.itemsize if mirror is None else ctypes.sizeof(mirror)
         assert got == size, (name, got, size)
+
+
+def test_action_intervals_random_against_the_fastq_oracle():
+    """
+    action_intervals / apply_action on records of the host build of the device functions (tests/hostsim) must give
+    the reads oracle_fastq_trim writes, for every action, linked adapters and several rounds.
+    """
+    import random
+    from oracle import oracle
+    from util import hostsim_process, spec_of, random_reads
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200 import _lib as L
+    from cutadapt_b200.pipeline import action_intervals, apply_action
+
+    rng = random.Random(8)
+    seqs_a = ["AGATCGGAAGAGC", "TTGACNNACG", "CACGTCTGAA"]
+    reads = [r for r in random_reads(rng, seqs_a, 1500, max_len=90)]
+    reads += [r.lower() for r in reads[:100]]
+    quals = ["".join(chr(33 + rng.randrange(2, 41)) for _ in r) for r in reads]
+    fastq = "".join(f"@r{i}\n{s}\n+\n{q}\n" for i, (s, q) in enumerate(zip(reads, quals))).encode()
+    sets = [
+        [PA.BackAdapter(seqs_a[0], max_errors=0.1, name="a"), PA.FrontAdapter(seqs_a[1], max_errors=0.2, name="b")],
+        [PA.LinkedAdapter(PA.FrontAdapter(seqs_a[1], max_errors=0.2, name="f"), PA.BackAdapter(seqs_a[0], name="k"),
+                          False, False, "lnk"), PA.AnywhereAdapter(seqs_a[2], name="c")],
+    ]
+    for ads in sets:
+        spec = spec_of(PA.MultipleAdapters(ads))
+        for action, times, qt in (("trim", 2, True), ("none", 1, False), ("mask", 2, True), ("lowercase", 3, False),
+                                  ("retain", 1, True), ("crop", 1, False)):
+            params = L.make_params(quality_trim=qt, cutoff_front=3, cutoff_back=15, times=times)
+            matches, qtrim = hostsim_process(spec, reads, quals if qt else None, params)
+            out, keep = action_intervals(matches, qtrim if qt else None, np.array([len(r) for r in reads]), action)
+            got = []
+            for i, (s, q) in enumerate(zip(reads, quals)):
+                ts = apply_action(s.upper() if action == "lowercase" else s, out[i], keep[i], action)
+                got.append(f"@r{i}\n{ts}\n+\n{q[out[i, 0]:out[i, 1]]}\n")
+            exp, _ = oracle.oracle_fastq_trim(fastq, spec.adapters, spec.groups, quality_trim=qt, cutoff_front=3,
+                                              cutoff_back=15, times=times, action=action)
+            assert "".join(got).encode() == exp, (action, [a.name for a in ads])
