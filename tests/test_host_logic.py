@@ -444,3 +444,51 @@ def test_action_intervals_random_against_the_fastq_oracle():
             exp, _ = oracle.oracle_fastq_trim(fastq, spec.adapters, spec.groups, quality_trim=qt, cutoff_front=3,
                                               cutoff_back=15, times=times, action=action)
             assert "".join(got).encode() == exp, (action, [a.name for a in ads])
+
+
+def test_bitsliced_scan_prototype_equals_kmers_present():
+    """tools/bitsliced_scan_prototype.py (the scan formulation planned for the next round):
+    its verdict equals KmerFinder.kmers_present (the oracle) for every adapter type's search sets, with and without
+    wildcards, and its chunk end positions equal a brute-force search."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bitsliced_scan_prototype as B
+    from oracle import oracle
+    from cutadapt_b200.kmer_heuristic import create_positions_and_kmers
+
+    rng = random.Random(12)
+    checked = 0
+    for _ in range(120):
+        m = rng.randrange(4, 34)
+        ref_wc = rng.random() < 0.4
+        alphabet = "ACGTNRYSWKMBDHV" if ref_wc else "ACGT"
+        adapter = "".join(rng.choice(alphabet if rng.random() < 0.3 else "ACGT") for _ in range(m))
+        if set(adapter) <= set("N"):
+            continue
+        query_wc = rng.random() < 0.2
+        rate = rng.choice((0.0, 0.1, 0.15, 0.2))
+        back, front = rng.choice(((True, False), (False, True), (True, True)))
+        internal = rng.random() < 0.8
+        try:
+            pk = create_positions_and_kmers(adapter, min(3, m), rate, back, front, internal)
+        except NotImplementedError:
+            continue
+        if any(k == "" for _, _, ks in pk for k in ks):
+            continue                      # the reference's empty-k-mer quirk (DESIGN.md section 2) is out of scope here
+        try:
+            kt = oracle.KmerTables(pk, ref_wc, query_wc)
+        except ValueError:
+            continue
+        for _ in range(60):
+            n = rng.choice((0, 1, 3, 8, 20, 50, 150))
+            read = "".join(rng.choice("ACGTNacgtRYX") if rng.random() < 0.1 else rng.choice("ACGT") for _ in range(n))
+            if n > m and rng.random() < 0.6:
+                p = rng.randrange(0, n)
+                piece = "".join(c if c in "ACGT" else rng.choice("ACGT") for c in adapter)
+                read = (read[:p] + piece + read)[:n]
+            assert B.kmers_present(pk, ref_wc, query_wc, read) == kt.present(read), (adapter, pk, read)
+            checked += 1
+    assert checked > 3000
+    ends = B.chunk_end_positions(["AGATCG", "GAAGAGC"], False, False, "TTAGATCGGAAGAGCAGATCGAAGATC")
+    assert ends["AGATCG"] == (1 << 7) | (1 << 20) and ends["GAAGAGC"] == 1 << 14
