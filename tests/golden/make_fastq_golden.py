@@ -84,6 +84,65 @@ CASES = [
 ]
 
 
+# More single-end known answers of test_commandline.py whose vectors are FASTA: stored as FASTQ with constant qualities
+# and checked against the oracle on the CPU (tests/test_oracle.py).  "specs" are the command line's -a/-g/-b values.
+FASTA_CASES = [
+    ("example", 75, "-N -b ADAPTER", "example.fa", "example.fa", dict(specs=[["anywhere", "ADAPTER"]], no_wildcards=True)),
+    ("minlen", 139, "-m 5 -a TTAGACATATCTCCGTCG", "lengths.fa", "minlen.fa",
+     dict(specs=[["back", "TTAGACATATCTCCGTCG"]], minimum_length=5)),
+    ("maxlen", 186, "-M 5 -a TTAGACATATCTCCGTCG", "lengths.fa", "maxlen.fa",
+     dict(specs=[["back", "TTAGACATATCTCCGTCG"]], maximum_length=5)),
+    ("overlapb", 239, "-O 10 -b TTAGACATATCTCCGTCG", "overlapb.fa", "overlapb.fa",
+     dict(specs=[["anywhere", "TTAGACATATCTCCGTCG"]], min_overlap=10)),
+    ("trim_n", 243, "--trim-n", "trim-n.fasta", "trim-n.fasta", dict(specs=[], trim_n=True)),
+    ("twoadapters", 263, "-a AATTTCAGGAATT -a GTTCTCTAGTTCT", "twoadapters.fasta", "twoadapters.fasta",
+     dict(specs=[["back", "AATTTCAGGAATT"], ["back", "GTTCTCTAGTTCT"]])),
+    ("polya_legacy", 277, "-O 10 -a A{35}", "polya.1.fasta", "polya.legacy.1.fasta",
+     dict(specs=[["back", "A{35}"]], min_overlap=10)),
+    ("polya", 281, "--poly-a", "polya.1.fasta", "polya.1.fasta", dict(specs=[], poly_a=True)),
+    ("read_wildcard", 339, "--match-read-wildcards -b ACGTACGT", "wildcard.fa", "wildcard.fa",
+     dict(specs=[["anywhere", "ACGTACGT"]], read_wildcards=True)),
+    ("wildcard_n", 372, "-e 0 -a GGGGGGG --match-read-wildcards", "wildcardN.fa", "wildcardN.fa",
+     dict(specs=[["back", "GGGGGGG"]], error_rate=0, read_wildcards=True)),
+    ("examplefront", 381, "--front ADAPTER -N", "example.fa", "examplefront.fa",
+     dict(specs=[["front", "ADAPTER"]], no_wildcards=True)),
+    ("literal_n3", 386, "-N -e 0.2 -a NNNNNNNNNNNNNN", "trimN3.fasta", "trimN3.fasta",
+     dict(specs=[["back", "NNNNNNNNNNNNNN"]], no_wildcards=True, error_rate=0.2)),
+    ("literal_n5", 390, "-N -O 1 -g NNNNNNNNNNNNNN", "trimN5.fasta", "trimN5.fasta",
+     dict(specs=[["front", "N{14}"]], no_wildcards=True, min_overlap=1)),
+    ("anchored_front", 403, "-g ^FRONTADAPT -N", "anchored.fasta", "anchored.fasta",
+     dict(specs=[["front", "^FRONTADAPT"]], no_wildcards=True)),
+    ("anchored_front_ellipsis", 407, "-a ^FRONTADAPT... -N", "anchored.fasta", "anchored.fasta",
+     dict(specs=[["back", "^FRONTADAPT..."]], no_wildcards=True)),
+    ("anchored_back", 411, "-a BACKADAPTER$ -N", "anchored-back.fasta", "anchored-back.fasta",
+     dict(specs=[["back", "BACKADAPTER$"]], no_wildcards=True)),
+    ("anchored_back_ellipsis", 415, "-a ...BACKADAPTER$ -N", "anchored-back.fasta", "anchored-back.fasta",
+     dict(specs=[["back", "...BACKADAPTER$"]], no_wildcards=True)),
+    ("anchored_back_no_indels", 419, "-a BACKADAPTER$ -N --no-indels", "anchored-back.fasta", "anchored-back.fasta",
+     dict(specs=[["back", "BACKADAPTER$"]], no_wildcards=True, no_indels=True)),
+    ("no_indels", 423, "-a TTAGACATAT -g GAGATTGCCA --no-indels", "no_indels.fasta", "no_indels.fasta",
+     dict(specs=[["back", "TTAGACATAT"], ["front", "GAGATTGCCA"]], no_indels=True)),
+    ("multiprefix", 615, "-g ^GTACGGATTGTTCAGTA -g ^TATTAAGCTCATTC", "multi.fasta", "multiprefix.fasta",
+     dict(specs=[["front", "^GTACGGATTGTTCAGTA"], ["front", "^TATTAAGCTCATTC"]])),
+    ("maxn0", 635, "--max-n 0", "maxn.fasta", "maxn0.fasta", dict(specs=[], max_n=0)),
+    ("maxn1", 636, "--max-n 1", "maxn.fasta", "maxn1.fasta", dict(specs=[], max_n=1)),
+    ("maxn2", 637, "--max-n 2", "maxn.fasta", "maxn2.fasta", dict(specs=[], max_n=2)),
+    ("maxn0_2", 638, "--max-n 0.2", "maxn.fasta", "maxn0.2.fasta", dict(specs=[], max_n=0.2)),
+    ("maxn0_4", 639, "--max-n 0.4", "maxn.fasta", "maxn0.4.fasta", dict(specs=[], max_n=0.4)),
+    ("linked", 671, "-a ^AAAAAAAAAA...TTTTTTTTTT", "linked.fasta", "linked.fasta",
+     dict(specs=[["back", "^AAAAAAAAAA...TTTTTTTTTT"]])),
+    ("linked_anchored", 683, "-a ^AAAAAAAAAA...TTTTT$", "linked.fasta", "linked-anchored.fasta",
+     dict(specs=[["back", "^AAAAAAAAAA...TTTTT$"]])),
+    ("linked_not_anchored", 687, "-g AAAAAAAAAA...TTTTTTTTTT", "linked.fasta", "linked-not-anchored.fasta",
+     dict(specs=[["front", "AAAAAAAAAA...TTTTTTTTTT"]])),
+    ("xadapter", 746, "-g XTCCGAATAGA", "xadapterx.fasta", "xadapter.fasta", dict(specs=[["front", "XTCCGAATAGA"]])),
+    ("adapterx", 750, "-a TCCGAATAGAX", "xadapterx.fasta", "adapterx.fasta", dict(specs=[["back", "TCCGAATAGAX"]])),
+    ("adapterorder_ga", 799, "-g ^AAACC -a CCGGG", "adapterorder.fasta", "adapterorder-ga.fasta",
+     dict(specs=[["front", "^AAACC"], ["back", "CCGGG"]])),
+    ("adapterorder_ag", 800, "-a CCGGG -g ^AAACC", "adapterorder.fasta", "adapterorder-ag.fasta",
+     dict(specs=[["back", "CCGGG"], ["front", "^AAACC"]])),
+]
+
 # paired-end: name, reference test (test_paired.py line), command line, in1, in2, expected1, expected2, options
 Q10 = dict(quality_cutoff=[0, 10])
 Q20 = dict(quality_cutoff=[0, 20])
@@ -138,12 +197,18 @@ PAIRED = [
 
 
 def fasta_to_fastq(path):
-    lines = open(path).read().split("\n")
-    recs = []
-    for i in range(0, len(lines) - 1, 2):
-        assert lines[i].startswith(">") and not lines[i + 1].startswith(">")
-        recs.append("@%s\n%s\n+\n%s\n" % (lines[i][1:], lines[i + 1], "I" * len(lines[i + 1])))
-    return "".join(recs).encode()
+    """FASTA records (sequences may span lines) as FASTQ with constant qualities 'I'."""
+    recs, name, seq = [], None, []
+    for line in open(path).read().split("\n"):
+        if line.startswith(">"):
+            if name is not None:
+                recs.append((name, "".join(seq)))
+            name, seq = line[1:], []
+        elif name is not None:
+            seq.append(line.strip())
+    if name is not None:
+        recs.append((name, "".join(seq)))
+    return "".join("@%s\n%s\n+\n%s\n" % (n, s, "I" * len(s)) for n, s in recs).encode()
 
 
 def main():
@@ -164,6 +229,13 @@ def main():
         index.append(dict(name=name, reference_test=f"tests/test_commandline.py:{line}", command=cmd,
                           input=f"tests/data/{inp}", expected=f"tests/cut/{exp}", options=opts))
     print(len(index), "cases")
+    findex = []
+    for name, line, cmd, inp, exp, opts in FASTA_CASES:
+        put(f"fa_{name}.in.fastq", fasta_to_fastq(os.path.join(REF, "data", inp)))
+        put(f"fa_{name}.out.fastq", fasta_to_fastq(os.path.join(REF, "cut", exp)))
+        findex.append(dict(name=name, reference_test=f"tests/test_commandline.py:{line}", command=cmd,
+                           input=f"tests/data/{inp}", expected=f"tests/cut/{exp}", options=opts))
+    print(len(findex), "FASTA cases")
     pindex = []
     for name, line, cmd, in1, in2, exp1, exp2, opts in PAIRED:
         for k, (inp, exp) in enumerate(((in1, exp1), (in2, exp2)), 1):
@@ -188,7 +260,7 @@ def main():
                      ("data/restfront.txt", "restfront.txt"), ("data/wildcard_adapter.fa", "wildcard_adapter.in.fasta")):
         copy(os.path.join(REF, src), dst)
     with gzip.open(OUT, "wt", compresslevel=9) as f:
-        json.dump(dict(cases=index, paired_cases=pindex, files=FILES), f)
+        json.dump(dict(cases=index, fasta_cases=findex, paired_cases=pindex, files=FILES), f)
     print(len(FILES), "fixture files ->", OUT, os.path.getsize(OUT), "bytes")
 
 

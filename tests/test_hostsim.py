@@ -253,3 +253,42 @@ def test_fused_nextseq_and_quality_trim_against_oracle():
                 raise
             assert (gqt == eqt).all(), mode
             assert (got == exp).all(), mode
+
+
+def test_reference_fasta_goldens_through_the_device_functions():
+    """
+    The command-line known answers of the reference with anchored / non-internal / linked adapters, --no-indels, -N
+    and --match-read-wildcards (tests/golden/fastq_kat.json.gz, "fasta_cases"): match records from the host build of
+    the device functions + pipeline.kept_intervals must give the expected reads.
+    """
+    import numpy as np
+    from oracle import oracle
+    from util import golden, fastq_file, adapter_from_spec, hostsim_process, spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.pipeline import kept_intervals
+
+    done = 0
+    for c in golden("fastq_kat.json.gz")["fasta_cases"]:
+        o = c["options"]
+        if not o["specs"] or any(k in o for k in ("trim_n", "poly_a", "max_n")):
+            continue
+        params = dict(max_errors=o.get("error_rate", 0.1), min_overlap=o.get("min_overlap", 3),
+                      adapter_wildcards=not o.get("no_wildcards", False), read_wildcards=o.get("read_wildcards", False),
+                      indels=not o.get("no_indels", False))
+        ads = [adapter_from_spec(spec, kind, name=f"a{i}", **params) for i, (kind, spec) in enumerate(o["specs"])]
+        spec = spec_of(PA.MultipleAdapters(ads))
+        records = oracle.parse_fastq(fastq_file(f"fa_{c['name']}.in.fastq"))
+        seqs = [r[1] for r in records]
+        matches, _ = hostsim_process(spec, seqs)
+        iv = kept_intervals(matches, None, np.array([len(x) for x in seqs]))
+        got = []
+        for (name, seq, q), (a, b) in zip(records, iv):
+            a, b = int(a), int(b)
+            if o.get("minimum_length") and b - a < o["minimum_length"]:
+                continue
+            if "maximum_length" in o and b - a > o["maximum_length"]:
+                continue
+            got.append(f"@{name}\n{seq[a:b]}\n+\n{q[a:b]}\n")
+        assert "".join(got).encode() == fastq_file(f"fa_{c['name']}.out.fastq"), (c["name"], c["command"])
+        done += 1
+    assert done >= 22

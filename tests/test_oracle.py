@@ -174,3 +174,26 @@ def test_demultiplex_oracle_reproduces_the_reference_golden():
     spec = spec_of(PA.MultipleAdapters(ads))
     got = oracle.oracle_fastq_demux(c["input_bytes"], spec.adapters, spec.groups, [a.name for a in ads])
     assert got == c["expected"]
+
+
+def test_fastq_oracle_reproduces_the_fasta_goldens_of_the_reference():
+    """32 more command-line known answers of the reference (anchored / non-internal / linked adapters, --no-indels,
+    -N, --match-read-wildcards, --trim-n, --poly-a, --max-n ...) whose vectors are FASTA: the oracle must reproduce
+    the expected sequences (tests/golden/make_fastq_golden.py stores them as FASTQ with constant qualities)."""
+    from util import golden, fastq_file, adapter_from_spec, fastq_case_kwargs, spec_of
+    import cutadapt_b200.adapters as PA
+
+    cases = golden("fastq_kat.json.gz")["fasta_cases"]
+    assert len(cases) >= 30
+    for c in cases:
+        o = c["options"]
+        params = dict(max_errors=o.get("error_rate", 0.1), min_overlap=o.get("min_overlap", 3),
+                      adapter_wildcards=not o.get("no_wildcards", False), read_wildcards=o.get("read_wildcards", False),
+                      indels=not o.get("no_indels", False))
+        ads = [adapter_from_spec(spec, kind, name=f"a{i}", **params) for i, (kind, spec) in enumerate(o["specs"])]
+        descs = groups = None
+        if ads:
+            spec = spec_of(PA.MultipleAdapters(ads))
+            descs, groups = spec.adapters, spec.groups
+        got, _ = oracle.oracle_fastq_trim(fastq_file(f"fa_{c['name']}.in.fastq"), descs, groups, **fastq_case_kwargs(o))
+        assert got == fastq_file(f"fa_{c['name']}.out.fastq"), (c["name"], c["command"])

@@ -229,3 +229,67 @@ def fastq_demux_case():
     return dict(adapters=[("first", "AATTTCAGGAATT"), ("second", "GTTCTCTAGTTCT")],
                 input_bytes=fastq_file("demux_twoadapters.in.fastq"),
                 expected={n: fastq_file(f"demux_twoadapters.{n}.out.fastq") for n in ("first", "second", "unknown")})
+
+
+# ---- adapter specification strings of the reference's command line (test helper) -------------------------------
+
+def adapter_from_spec(spec, adapter_type, name=None, **params):
+    """
+    One -a / -g / -b value as the reference's command line builds it (src/cutadapt/parser.py:129-149, 221-365,
+    440-550): placement restrictions ^ADAPTER / ADAPTER$ / XADAPTER / ADAPTERX, x{n} repeats, linked
+    ADAPTER1...ADAPTER2 (-g requires both parts, -a only the anchored ones), ...ADAPTER / ADAPTER...; name=SEQ.
+    Search parameters after ';' are not supported.  Returns a cutadapt_b200 adapter object.
+    """
+    import re
+    import cutadapt_b200.adapters as PA
+
+    def expand_braces(seq):
+        return re.sub(r"(.)\{(\d+)\}", lambda m: m.group(1) * int(m.group(2)), seq)
+
+    def parse(one, kind):
+        nm = None
+        if "=" in one:
+            nm, one = one.split("=", 1)
+        one = expand_braces(one.strip())
+        if len(one.strip("X")) == 0:
+            return nm, None, one, kind
+        front = back = None
+        if one.startswith("^"):
+            front, one = "anchored", one[1:]
+        if one.upper().startswith("X"):
+            assert front is None
+            front, one = "noninternal", one.lstrip("xX")
+        if one.endswith("$"):
+            back, one = "anchored", one[:-1]
+        if one.upper().endswith("X"):
+            assert back is None
+            back, one = "noninternal", one.rstrip("xX")
+        assert not (front and back)
+        assert not (kind == "front" and back) and not (kind == "back" and front) and not (kind == "anywhere" and (front or back))
+        return nm, front or back, one, kind
+
+    def cls_of(kind, restriction):
+        return {("front", None): PA.FrontAdapter, ("front", "anchored"): PA.PrefixAdapter,
+                ("front", "noninternal"): PA.NonInternalFrontAdapter, ("back", None): PA.BackAdapter,
+                ("back", "anchored"): PA.SuffixAdapter, ("back", "noninternal"): PA.NonInternalBackAdapter,
+                ("anywhere", None): PA.AnywhereAdapter}[(kind, restriction)]
+
+    spec1, middle, spec2 = spec.partition("...")
+    if middle and spec1 and spec2:
+        assert adapter_type != "anywhere"
+        n1, r1, s1, _ = parse(spec1, "front")
+        _, r2, s2, _ = parse(spec2, "back")
+        required = (True, True) if adapter_type == "front" else (r1 is not None, r2 is not None)
+        return PA.LinkedAdapter(cls_of("front", r1)(s1, name="linked_front", **params),
+                                cls_of("back", r2)(s2, name="linked_back", **params),
+                                required[0], required[1], name or n1 or "linked")
+    if middle:
+        assert adapter_type != "anywhere"
+        if not spec1:
+            assert adapter_type == "back"
+            spec = spec2
+        else:
+            spec = spec1
+            adapter_type = "front"
+    nm, restriction, seq, kind = parse(spec, adapter_type)
+    return cls_of(kind, restriction)(seq, name=name or nm or "adapter", **params)
