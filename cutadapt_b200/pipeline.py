@@ -259,6 +259,29 @@ def wildcard_file_rows(names: Sequence[str], sequences: Sequence[str], matches: 
     return rows
 
 
+_COMPLEMENT = bytes.maketrans(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn", b"TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn")
+
+
+def reverse_complement(sequence: str) -> str:
+    """``SequenceRecord.reverse_complement`` of dnaio for the sequence: IUPAC-aware, case preserved, every other
+    character unchanged (qualities are simply reversed)."""
+    return sequence.encode("latin-1").translate(_COMPLEMENT)[::-1].decode("latin-1")
+
+
+def revcomp_select(matches_forward: np.ndarray, matches_reverse: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """
+    ``ReverseComplementer.__call__`` (modifiers.py:278-308) on match records: a read is replaced by its reverse
+    complement iff the scores of its matches there add up to MORE than those of the forward read (a LinkedMatch
+    counts with the sum of its parts, adapters.py:1113-1118).  Returns (is_rc[n] bool, the chosen records).
+    """
+    def total(m):
+        return np.where(m["adapter"] >= 0, m["score"], 0).astype(np.int64).sum(axis=(1, 2))
+
+    is_rc = total(matches_reverse) > total(matches_forward)
+    chosen = np.where(is_rc[:, None, None], matches_reverse, matches_forward)
+    return is_rc, chosen
+
+
 class TrimResult:
     """Outcome of one chunk: raw records plus the derived kept interval of every read."""
 
@@ -318,6 +341,21 @@ class BatchTrimmer:
                 raise HasNoQualities("Cannot do quality trimming when no qualities are available")
             qual, _ = _lib.pack_strings(qualities, "Quality data")
         return self.process_packed(seq, offsets, qual)
+
+    def process_revcomp(self, sequences: Sequence[str], qualities: Optional[Sequence[str]] = None):
+        """
+        ``--revcomp``: every read and its reverse complement go through the same pass (two batches); the better
+        orientation wins (``revcomp_select``).  Returns (TrimResult of the chosen orientation, is_rc[n]); intervals
+        and records of reads with ``is_rc`` refer to ``reverse_complement(read)`` and its reversed qualities.
+        As in the reference, quality trimming has to happen before (ReverseComplementer wraps only the AdapterCutter).
+        """
+        if self.quality_cutoff is not None or self.nextseq_cutoff is not None:
+            raise ValueError("process_revcomp searches adapters only; quality-trim the reads first")
+        forward = self.process(sequences)
+        reverse = self.process([reverse_complement(s) for s in sequences])
+        is_rc, chosen = revcomp_select(forward.matches, reverse.matches)
+        lengths = np.array([len(s) for s in sequences], dtype=np.int64)
+        return TrimResult(chosen, None, kept_intervals(chosen, None, lengths)), is_rc
 
     def match_objects(self, result: TrimResult, sequences: Sequence[str]) -> List[List]:
         """Per read, the list of reference-style Match objects of its rounds (info.matches)."""

@@ -255,6 +255,9 @@ def main():
     for src, dst in (("cut/illumina.info.txt", "info_illumina.txt"), ("cut/illumina5.info.txt", "info_illumina5.txt"),
                      ("data/illumina5.fastq", "info_illumina5.in.fastq")):
         copy(os.path.join(REF, src), dst)
+    # --revcomp known answer (test_commandline.py:827-835)
+    copy(os.path.join(REF, "data", "revcomp.1.fastq"), "revcomp.in.fastq")
+    copy(os.path.join(REF, "cut", "revcomp-single-normalize.fastq"), "revcomp.out.fastq")
     # --rest-file / --wildcard-file known answers (test_commandline.py:110-122, 345-367)
     for src, dst in (("data/rest.fa", "rest.in.fasta"), ("data/rest.txt", "rest.txt"),
                      ("data/restfront.txt", "restfront.txt"), ("data/wildcard_adapter.fa", "wildcard_adapter.in.fasta")):

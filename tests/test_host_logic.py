@@ -492,3 +492,28 @@ def test_bitsliced_scan_prototype_equals_kmers_present():
     assert checked > 3000
     ends = B.chunk_end_positions(["AGATCG", "GAAGAGC"], False, False, "TTAGATCGGAAGAGCAGATCGAAGATC")
     assert ends["AGATCG"] == (1 << 7) | (1 << 20) and ends["GAAGAGC"] == 1 << 14
+
+
+def test_revcomp_select_reproduces_the_reference_golden():
+    """--revcomp --no-index -g ^TTATTTGTCT -g ^TCCGCACTGG on revcomp.1.fastq (reference test_commandline.py:827-835):
+    reverse_complement + revcomp_select + kept_intervals on oracle records give tests/cut/revcomp-single-normalize.fastq."""
+    from oracle import oracle
+    from util import fastq_file, spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.pipeline import reverse_complement, revcomp_select, kept_intervals
+
+    records = oracle.parse_fastq(fastq_file("revcomp.in.fastq"))
+    names, seqs, quals = zip(*records)
+    spec = spec_of(PA.MultipleAdapters([PA.PrefixAdapter("TTATTTGTCT", name="a"), PA.PrefixAdapter("TCCGCACTGG", name="b")]))
+    fwd, _ = oracle.oracle_process(spec.adapters, spec.groups, list(seqs))
+    rev, _ = oracle.oracle_process(spec.adapters, spec.groups, [reverse_complement(s) for s in seqs])
+    is_rc, chosen = revcomp_select(fwd, rev)
+    assert int(is_rc.sum()) == 2                      # stats.reverse_complemented == 2 in the reference's test
+    iv = kept_intervals(chosen, None, np.array([len(s) for s in seqs]))
+    out = []
+    for i, name in enumerate(names):
+        s, q = (reverse_complement(seqs[i]), quals[i][::-1]) if is_rc[i] else (seqs[i], quals[i])
+        a, b = int(iv[i, 0]), int(iv[i, 1])
+        out.append(f"@{name}{' rc' if is_rc[i] else ''}\n{s[a:b]}\n+\n{q[a:b]}\n")
+    assert "".join(out).encode() == fastq_file("revcomp.out.fastq")
+    assert reverse_complement("ACGTNnRyKm-x") == "x-kMrYnNACGT"
