@@ -282,6 +282,69 @@ def revcomp_select(matches_forward: np.ndarray, matches_reverse: np.ndarray) -> 
     return is_rc, chosen
 
 
+def pair_adapters_select(per_adapter1: Sequence[np.ndarray], per_adapter2: Sequence[np.ndarray]):
+    """
+    ``PairedAdapterCutter._find_best_match_pair`` (modifiers.py:480-503) on match records: ``per_adapter1[i]`` /
+    ``per_adapter2[i]`` are the records (n, 1, slots) of adapter pair i matched ALONE against R1 / R2.  A pair of
+    reads is trimmed only by an adapter pair that matches both mates; among those the highest score sum wins, then
+    the fewest errors, then the first listed.  Returns (pair index per read or -1, records for R1, records for R2).
+    """
+    k = len(per_adapter1)
+    if k == 0 or k != len(per_adapter2):
+        raise ValueError("The number of adapters to trim from R1 and R2 must be the same and not zero")
+    n = per_adapter1[0].shape[0]
+    best = np.full(n, -1, dtype=np.int64)
+    best_score = np.zeros(n, dtype=np.int64)
+    best_errors = np.zeros(n, dtype=np.int64)
+    for i in range(k):
+        m1, m2 = per_adapter1[i], per_adapter2[i]
+        p1, p2 = m1["adapter"] >= 0, m2["adapter"] >= 0
+        both = p1.any(axis=(1, 2)) & p2.any(axis=(1, 2))
+        score = (np.where(p1, m1["score"], 0).sum(axis=(1, 2)) + np.where(p2, m2["score"], 0).sum(axis=(1, 2))).astype(np.int64)
+        errors = (np.where(p1, m1["errors"], 0).sum(axis=(1, 2)) + np.where(p2, m2["errors"], 0).sum(axis=(1, 2))).astype(np.int64)
+        better = both & ((best < 0) | (score > best_score) | ((score == best_score) & (errors < best_errors)))
+        best = np.where(better, i, best)
+        best_score = np.where(better, score, best_score)
+        best_errors = np.where(better, errors, best_errors)
+    out1 = per_adapter1[0].copy()
+    out2 = per_adapter2[0].copy()
+    out1["adapter"] = -1
+    out2["adapter"] = -1
+    for i in range(k):
+        sel = best == i
+        out1[sel] = per_adapter1[i][sel]
+        out2[sel] = per_adapter2[i][sel]
+    return best, out1, out2
+
+
+class PairedAdapterBatch:
+    """
+    ``--pair-adapters`` for whole chunks (PairedAdapterCutter, modifiers.py:410-478): adapter i of the first list is
+    only accepted together with adapter i of the second.  Every adapter runs as its own pass over its mate
+    (2 k passes), ``pair_adapters_select`` combines the records.  ``process(seqs1, seqs2)`` returns
+    (pair index per read pair, TrimResult for R1, TrimResult for R2); the adapter numbers in the records are the
+    positions in the lists.
+    """
+
+    def __init__(self, adapters1: Sequence, adapters2: Sequence, ctx: Optional[_lib.Context] = None):
+        if len(adapters1) != len(adapters2) or not adapters1:
+            raise ValueError("The number of adapters to trim from R1 and R2 must be the same and not zero")
+        self._trimmers1 = [BatchTrimmer([a], ctx=ctx) for a in adapters1]
+        self._trimmers2 = [BatchTrimmer([a], ctx=ctx) for a in adapters2]
+
+    def process(self, sequences1: Sequence[str], sequences2: Sequence[str]):
+        s1, o1 = _lib.pack_strings(sequences1)
+        s2, o2 = _lib.pack_strings(sequences2)
+        m1 = [t.adapter_set.process(s1, o1, None, t.params)[0] for t in self._trimmers1]
+        m2 = [t.adapter_set.process(s2, o2, None, t.params)[0] for t in self._trimmers2]
+        for i, (a, b) in enumerate(zip(m1, m2)):        # adapter numbers = positions in the lists
+            a["adapter"] = np.where(a["adapter"] >= 0, i, -1)
+            b["adapter"] = np.where(b["adapter"] >= 0, i, -1)
+        best, r1, r2 = pair_adapters_select(m1, m2)
+        return (best, TrimResult(r1, None, kept_intervals(r1, None, np.diff(o1))),
+                TrimResult(r2, None, kept_intervals(r2, None, np.diff(o2))))
+
+
 class TrimResult:
     """Outcome of one chunk: raw records plus the derived kept interval of every read."""
 

@@ -255,6 +255,10 @@ def main():
     for src, dst in (("cut/illumina.info.txt", "info_illumina.txt"), ("cut/illumina5.info.txt", "info_illumina5.txt"),
                      ("data/illumina5.fastq", "info_illumina5.in.fastq")):
         copy(os.path.join(REF, src), dst)
+    # --pair-adapters known answer (test_paired.py:668-676)
+    for k in (1, 2):
+        copy(os.path.join(REF, "data", f"paired.{k}.fastq"), f"pair_adapters.in{k}.fastq")
+        copy(os.path.join(REF, "cut", f"pair-adapters.{k}.fastq"), f"pair_adapters.out{k}.fastq")
     # --revcomp known answer (test_commandline.py:827-835)
     copy(os.path.join(REF, "data", "revcomp.1.fastq"), "revcomp.in.fastq")
     copy(os.path.join(REF, "cut", "revcomp-single-normalize.fastq"), "revcomp.out.fastq")

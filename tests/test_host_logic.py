@@ -517,3 +517,54 @@ def test_revcomp_select_reproduces_the_reference_golden():
         out.append(f"@{name}{' rc' if is_rc[i] else ''}\n{s[a:b]}\n+\n{q[a:b]}\n")
     assert "".join(out).encode() == fastq_file("revcomp.out.fastq")
     assert reverse_complement("ACGTNnRyKm-x") == "x-kMrYnNACGT"
+
+
+def test_pair_adapters_select_reproduces_the_reference_golden():
+    """--pair-adapters -a GTCTCCAGCT -A GACAAATAAC on paired.{1,2}.fastq (reference tests/test_paired.py:668-676):
+    per-adapter records from the oracle + pair_adapters_select + kept_intervals give pair-adapters.{1,2}.fastq;
+    plus a randomized comparison with a plain restatement of _find_best_match_pair."""
+    import random
+    from oracle import oracle
+    from util import fastq_file, spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.pipeline import pair_adapters_select, kept_intervals
+
+    def records_for(adapter, seqs):
+        spec = spec_of(PA.MultipleAdapters([adapter]))
+        return oracle.oracle_process(spec.adapters, spec.groups, list(seqs))[0]
+
+    outs = []
+    recs = [oracle.parse_fastq(fastq_file(f"pair_adapters.in{k}.fastq")) for k in (1, 2)]
+    m1 = [records_for(PA.BackAdapter("GTCTCCAGCT", name="a"), [r[1] for r in recs[0]])]
+    m2 = [records_for(PA.BackAdapter("GACAAATAAC", name="b"), [r[1] for r in recs[1]])]
+    best, r1, r2 = pair_adapters_select(m1, m2)
+    for rec, m in ((recs[0], r1), (recs[1], r2)):
+        iv = kept_intervals(m, None, np.array([len(r[1]) for r in rec]))
+        outs.append("".join(f"@{n}\n{s[a:b]}\n+\n{q[a:b]}\n" for (n, s, q), (a, b) in zip(rec, iv.tolist())).encode())
+    assert outs == [fastq_file("pair_adapters.out1.fastq"), fastq_file("pair_adapters.out2.fastq")]
+    assert 0 < int((best >= 0).sum()) < len(best)
+
+    rng = random.Random(2)
+    ad1 = [PA.BackAdapter("AGATCGGAAG", name="x"), PA.FrontAdapter("TTGACCA", max_errors=0.2, name="y"), PA.BackAdapter("CCGTA", name="z")]
+    ad2 = [PA.BackAdapter("CTGTCTCTTA", name="x"), PA.BackAdapter("GGCATT", name="y"), PA.AnywhereAdapter("TTAGG", name="z")]
+    def rnd():
+        s = "".join(rng.choice("ACGT") for _ in range(rng.randrange(0, 60)))
+        for a in rng.sample(ad1 + ad2, 2):
+            if rng.random() < 0.5:
+                p = rng.randrange(0, len(s) + 1)
+                s = s[:p] + a.sequence + s[p:]
+        return s
+    s1, s2 = [rnd() for _ in range(800)], [rnd() for _ in range(800)]
+    m1 = [records_for(a, s1) for a in ad1]
+    m2 = [records_for(a, s2) for a in ad2]
+    best, _, _ = pair_adapters_select(m1, m2)
+    for j in range(800):
+        want, key = -1, None
+        for i in range(3):
+            a, b = m1[i][j, 0, 0], m2[i][j, 0, 0]
+            if a["adapter"] < 0 or b["adapter"] < 0:
+                continue
+            k = (int(a["score"]) + int(b["score"]), -(int(a["errors"]) + int(b["errors"])))
+            if key is None or k > key:
+                want, key = i, k
+        assert best[j] == want
