@@ -568,3 +568,43 @@ def test_pair_adapters_select_reproduces_the_reference_golden():
             if key is None or k > key:
                 want, key = i, k
         assert best[j] == want
+
+
+def test_composition_glue_with_an_oracle_backed_adapter_set(monkeypatch):
+    """BatchTrimmer.process_revcomp and PairedAdapterBatch.process (GPU-backed in the product) with the device call
+    replaced by the oracle: exercises the glue code (packing, renumbering, selection, intervals) without a GPU."""
+    from oracle import oracle
+    from util import fastq_file, spec_of
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200 import pipeline
+
+    class FakeSet:
+        def __init__(self, multi):
+            self.spec = spec_of(multi)
+            self.slots = 1
+
+        def process(self, seq, offsets, qual=None, params=None, want_qtrim=False):
+            raw = bytes(seq)
+            seqs = [raw[offsets[i]:offsets[i + 1]].decode() for i in range(len(offsets) - 1)]
+            return oracle.oracle_process(self.spec.adapters, self.spec.groups, seqs, times=params.times if params else 1)
+
+    monkeypatch.setattr(PA.Matchable, "adapter_set", lambda self: FakeSet(self))
+    # --revcomp golden through BatchTrimmer.process_revcomp
+    records = oracle.parse_fastq(fastq_file("revcomp.in.fastq"))
+    names, seqs, quals = zip(*records)
+    bt = pipeline.BatchTrimmer([PA.PrefixAdapter("TTATTTGTCT", name="a"), PA.PrefixAdapter("TCCGCACTGG", name="b")])
+    res, is_rc = bt.process_revcomp(list(seqs))
+    out = []
+    for i, name in enumerate(names):
+        s, q = (pipeline.reverse_complement(seqs[i]), quals[i][::-1]) if is_rc[i] else (seqs[i], quals[i])
+        a, b = (int(x) for x in res.intervals[i])
+        out.append(f"@{name}{' rc' if is_rc[i] else ''}\n{s[a:b]}\n+\n{q[a:b]}\n")
+    assert "".join(out).encode() == fastq_file("revcomp.out.fastq")
+    # --pair-adapters golden through PairedAdapterBatch
+    recs = [oracle.parse_fastq(fastq_file(f"pair_adapters.in{k}.fastq")) for k in (1, 2)]
+    pb = pipeline.PairedAdapterBatch([PA.BackAdapter("GTCTCCAGCT", name="a")], [PA.BackAdapter("GACAAATAAC", name="b")])
+    best, t1, t2 = pb.process([r[1] for r in recs[0]], [r[1] for r in recs[1]])
+    for rec, t, k in ((recs[0], t1, 1), (recs[1], t2, 2)):
+        text = "".join(f"@{n}\n{s[a:b]}\n+\n{q[a:b]}\n" for (n, s, q), (a, b) in zip(rec, t.intervals.tolist()))
+        assert text.encode() == fastq_file(f"pair_adapters.out{k}.fastq")
+    assert set(np.unique(t1.matches["adapter"])) <= {-1, 0}
