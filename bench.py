@@ -11,8 +11,11 @@ no data-path collective; the trim statistics are all-reduced once per step).
 
 One "step" = one pass of the hot path over the whole per-GPU batch.
   value  : whole-job reads/s with the batch resident in HBM (CUDA events, max over ranks).
-  e2e    : the same through the host-facing C ABI (cg_process_batch): pinned host buffers,
-           H2D copies, kernel, D2H copy of the match records all inside the timed region.
+  e2e    : the same through the host-facing C ABI (cg_process_batch): pinned host buffers, the
+           library's host-side packing (reads travel partly as a 3-bases-per-byte stream), H2D
+           copies, kernels, D2H copy of the match records all inside the timed region; the byte
+           counts come from the library (cg_ctx_transfer_bytes), raw_transfer_value is the same
+           call with CUTADAPT_B200_H2D_PACK=0.
   roofline.achieved : algorithmic bytes (190 B/read: 150 sequence + 8 offset + 32 result)
            x reads per pass / mean device time of ALL kernels of the trimming pass (scan,
            plan, DP rounds), measured with CUDA events on the launching stream inside the
