@@ -287,12 +287,7 @@ __global__ void fq_pretrim_kernel(const uint8_t *buf, const CgFastqRecord *rec, 
     qtrim[2 * r + 1] = e;
 }
 
-// What is left of every read (modifiers.py:858 then adapters.py:453-454, 486-487 per round; PolyATrimmer,
-// Shortener, NEndTrimmer after the adapters) and which filters it fails, one bit per filter in the order
-// cli.py:700-830 + 870-910 appends them:
-//   bit 0 TooShort, 1 TooLong (predicates.py:29-53), 2 TooManyN (96-122), 3 TooManyExpectedErrors (56-71),
-//   4 CasavaFiltered (125-139), 5 IsTrimmed (--discard-trimmed), 6 IsUntrimmed (--discard-untrimmed).
-// Every predicate is evaluated (a pair filter may need the verdict of a filter that the mate passes).
+// kept interval + failed filters of every record: fq_evaluate_core (cg_fastq_core.cuh); per-read counters
 __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
                                    const cg_match_rec *matches, int times, int slots, const int32_t *qtrim,
                                    CgFastqFilter f, const double *phred, int32_t *interval, int32_t *keep_interval,
@@ -302,136 +297,16 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
     unsigned long long c_adapt = 0, c_bp_in = 0, c_qbp = 0;
     if (r < n_records) {
         const int n = seq_len[r];
-        int start = 0, stop = n;
-        if (qtrim) { start = qtrim[2 * r]; stop = qtrim[2 * r + 1]; }
-        c_qbp = (unsigned long long)(n - (stop - start));
-        bool matched = false;
-        int last_adapter = -1;                 // info.matches[-1].adapter: where a demultiplexer sends the read
-        if (matches) {
-            for (int t = 0; t < times; ++t)
-                for (int s = 0; s < slots; ++s) {
-                    const cg_match_rec m = matches[((size_t)r * times + t) * slots + s];
-                    if (m.adapter < 0) continue;
-                    matched = true;
-                    last_adapter = m.adapter;
-                    // read[:rstart] / read[rstop:] with Python's slice clamping: an index match on a read that is
-                    // shorter than the matched key reports rstop > len or rstart < 0 (adapters.py:1342-1365)
-                    const int cur = stop - start;
-                    if ((m.info >> 8) & 1)                             // RemoveAfterMatch
-                        stop = start + (m.rstart >= 0 ? (m.rstart < cur ? m.rstart : cur)
-                                                      : (cur + m.rstart > 0 ? cur + m.rstart : 0));
-                    else                                               // RemoveBeforeMatch
-                        start = start + (m.rstop < cur ? m.rstop : cur);
-                }
-        }
-        const uint8_t *sq0 = buf + rec[r].seq_start;
-        // AdapterCutter's action (modifiers.py:236-249): what is written instead of the trimmed read.  [k0, k1) is
-        // the part that stays as it is ("remainder"), [start, stop) from here on the part that is output; all
-        // relative to the read the cutter saw (after -u and quality trimming), whose interval is [b0, b1).
-        const int b0 = qtrim ? qtrim[2 * r] : 0, b1 = qtrim ? qtrim[2 * r + 1] : n;
-        int k0 = start, k1 = stop;
-        if (f.action != CG_FQ_ACTION_TRIM) {
-            if (!matched) { start = b0; stop = b1; k0 = b0; k1 = b1; }
-            else if (f.action == CG_FQ_ACTION_RETAIN || f.action == CG_FQ_ACTION_CROP) {
-                // times == 1: slot 0 = the match (or the front match of a LinkedAdapter), slot 1 = a linked back match
-                const cg_match_rec m0 = matches[(size_t)r * times * slots];
-                cg_match_rec m1; m1.adapter = -1;
-                if (slots > 1) m1 = matches[(size_t)r * times * slots + 1];
-                const int len = b1 - b0;
-                int a, b;
-                if (f.action == CG_FQ_ACTION_CROP) {                   // read[m.rstart:m.rstop] (modifiers.py:195-198)
-                    const cg_match_rec m = m0.adapter >= 0 ? m0 : m1;
-                    a = m.rstart; b = m.rstop;
-                } else if (m0.adapter >= 0 && ((m0.info >> 8) & 1)) {  // RemoveAfterMatch: (0, rstop)  adapters.py:479-480
-                    a = 0; b = m0.rstop;
-                } else {                                               // RemoveBeforeMatch (adapters.py:446-447) /
-                    a = m0.adapter >= 0 ? m0.rstart : 0;               // LinkedMatch (adapters.py:1145-1155)
-                    const int offset = m0.adapter >= 0 ? m0.rstop : 0;
-                    b = m1.adapter >= 0 ? m1.rstop + offset : len;
-                }
-                a = a < 0 ? 0 : (a > len ? len : a);                   // Python slice clamping
-                b = b < 0 ? 0 : (b > len ? len : b);
-                if (b < a) b = a;
-                start = b0 + a; stop = b0 + b; k0 = start; k1 = stop;
-            } else {                                                   // none / mask / lowercase: the whole read
-                start = b0; stop = b1;
-                if (f.action == CG_FQ_ACTION_NONE) { k0 = b0; k1 = b1; }
-            }
-        }
-        // the character at position j as it will be written
-        const int action = f.action;
-        auto ch = [&](int j) -> uint8_t {
-            const uint8_t c = sq0[j];
-            if (action == CG_FQ_ACTION_MASK) return (j >= k0 && j < k1) ? c : (uint8_t)'N';
-            if (action == CG_FQ_ACTION_LOWERCASE) {
-                const bool alpha = (uint8_t)((c | 0x20) - 'a') < 26;
-                return !alpha ? c : ((j >= k0 && j < k1) ? (uint8_t)(c & ~0x20) : (uint8_t)(c | 0x20));
-            }
-            return c;
-        };
-        if (f.poly_a) {                                    // PolyATrimmer (modifiers.py:861-879), qualtrim.pyx:120-169
-            const int len = stop - start;
-            int best_score = 0, score = 0, errors = 0;
-            if (f.poly_a == 2) {                           // poly-T head of the second mate: read[index:]
-                int best_index = 0;
-                for (int i = 0; i < len; ++i) {
-                    if (ch(start + i) == 'T') score += 1; else { score -= 2; errors += 1; }
-                    if (score > best_score && errors * 5 <= i + 1) { best_score = score; best_index = i + 1; }
-                }
-                if (best_index < 3) best_index = 0;
-                start += best_index;
-            } else {                                       // poly-A tail: read[:index]
-                int best_index = len;
-                for (int i = len - 1; i >= 0; --i) {
-                    if (ch(start + i) == 'A') score += 1; else { score -= 2; errors += 1; }
-                    if (score > best_score && errors * 5 <= len - i) { best_score = score; best_index = i; }
-                }
-                if (best_index > len - 3) best_index = len;
-                stop = start + best_index;
-            }
-        }
-        if (f.shorten > 0) {                               // Shortener (modifiers.py:882-899): read[:length]
-            if (stop - start > f.shorten - 1) stop = start + (f.shorten - 1);
-        } else if (f.shorten < 0) {                        //                                   read[length:]
-            if (stop - start > -f.shorten) start = stop + f.shorten;
-        }
-        if (f.trim_n) {                                    // NEndTrimmer (modifiers.py:902-918): upper-case N only
-            int a = start, b = stop;
-            while (a < stop && ch(a) == 'N') ++a;
-            while (b > start && ch(b - 1) == 'N') --b;
-            start = a; stop = b < a ? a : b;
-        }
-        const int left = stop - start;
-        int mask = 0;
-        if (f.minimum_length > 0 && left < f.minimum_length) mask |= 1;
-        if (f.maximum_length >= 0 && left > f.maximum_length) mask |= 2;
-        if (f.max_n >= 0.0) {
-            int n_count = 0;
-            for (int j = 0; j < left; ++j) n_count += (ch(start + j) | 0x20) == 'n';
-            const bool too_many = f.max_n < 1.0 ? (left > 0 && (double)n_count / (double)left > f.max_n)
-                                                : (double)n_count > f.max_n;
-            if (too_many) mask |= 4;
-        }
-        if (f.max_ee >= 0.0) {
-            // expected_errors(qualities) with its default base 33
-            const double ee = expected_errors_core(buf + rec[r].qual_start + start, left, 33, phred);
-            if (ee < 0.0) { atomicMin((unsigned int *)&err[1], (unsigned int)r); atomicMax(&err[0], 4); }
-            else if (ee > f.max_ee) mask |= 8;
-        }
-        if (f.discard_casava) {
-            // name.partition(" ")[2][1:4] == ":Y:"
-            const uint8_t *h = buf + rec[r].hdr_start;
-            const int hl = rec[r].hdr_len;
-            int sp = 0;
-            while (sp < hl && h[sp] != ' ') ++sp;
-            if (sp + 4 < hl && h[sp + 2] == ':' && h[sp + 3] == 'Y' && h[sp + 4] == ':') mask |= 16;
-        }
-        if (matched) mask |= 32; else mask |= 64;          // masked by the enabled filters in the finish step
-        interval[2 * r] = start;
-        interval[2 * r + 1] = stop;
-        if (keep_interval) { keep_interval[2 * r] = k0; keep_interval[2 * r + 1] = k1; }
-        fail_mask[r] = mask | ((last_adapter + 1) << 8);
-        c_adapt = matched; c_bp_in = n;
+        const int qs = qtrim ? qtrim[2 * r] : 0, qe = qtrim ? qtrim[2 * r + 1] : n;
+        c_qbp = (unsigned long long)(n - (qe - qs));
+        const FqVerdict v = fq_evaluate_core(buf, rec[r], n, matches ? matches + (size_t)r * times * slots : nullptr, times,
+                                             slots, qtrim != nullptr, qs, qe, f, phred);
+        if (v.bad_quality) { atomicMin((unsigned int *)&err[1], (unsigned int)r); atomicMax(&err[0], 4); }
+        interval[2 * r] = v.start;
+        interval[2 * r + 1] = v.stop;
+        if (keep_interval) { keep_interval[2 * r] = v.k0; keep_interval[2 * r + 1] = v.k1; }
+        fail_mask[r] = v.mask | ((v.last_adapter + 1) << 8);
+        c_adapt = v.matched; c_bp_in = n;
     }
     c_adapt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_adapt);
     for (int d = 16; d; d >>= 1) {
@@ -464,19 +339,7 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
     unsigned long long bp1 = 0, bp2 = 0;
     unsigned written = 0;
     if (r < n_records) {
-        const int m1 = mask1[r], m2 = mask2 ? mask2[r] : 0;
-        for (int k = 0; k < 7 && fired < 0; ++k) {
-            const int bit = 1 << k;
-            const bool e1 = enabled1 & bit, e2 = mask2 && (enabled2 & bit);
-            if (!e1 && !e2) continue;
-            const bool f1 = m1 & bit, f2 = m2 & bit;
-            const int md = k == 6 ? mode_untrimmed : mode;
-            bool hit;
-            if (!e2) hit = f1;
-            else if (!e1) hit = f2;
-            else hit = md == 0 ? (f1 || f2) : md == 1 ? (f1 && f2) : f1;
-            if (hit) fired = k;
-        }
+        fired = fq_finish_core(mask1[r], mask2 ? mask2[r] : 0, mask2 != nullptr, enabled1, enabled2, mode, mode_untrimmed);
         const int left1 = interval1[2 * r + 1] - interval1[2 * r];
         out_len1[r] = fired < 0 ? rec1[r].hdr_len + 2 * left1 + 6 : 0;
         if (mask2) {

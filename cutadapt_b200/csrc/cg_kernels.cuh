@@ -98,30 +98,7 @@ cudaError_t cg_launch_unpack3(const uint8_t *d_packed, long long packed_bytes, u
                               const unsigned long long *d_exc, long long n_exc, cudaStream_t st);
 
 // ---- FASTQ chunk parse / trimmed-record formatting (cg_fastq.cu) ---------------------------------------
-struct CgFastqRecord {       // one 4-line record of the chunk
-    uint32_t hdr_start;      // first character of the name (after '@')
-    int32_t hdr_len;
-    uint32_t seq_start;
-    uint32_t qual_start;
-};
-struct CgFastqFilter {
-    int minimum_length;      // 0 = off
-    int maximum_length;      // < 0 = off
-    int discard_trimmed, discard_untrimmed;
-    double max_n;            // < 0 = off; < 1: proportion of the length
-    double max_ee;           // < 0 = off
-    int poly_a;              // PolyATrimmer after the adapter rounds: 1 = poly-A tail (R1), 2 = poly-T head (R2)
-    int shorten;             // Shortener: 0 = off, L + 1 for --length L >= 0, L for --length L < 0
-    int trim_n;              // NEndTrimmer
-    int discard_casava;      // CasavaFiltered
-    int action;              // CG_FQ_ACTION_*: AdapterCutter's action
-};
-#define CG_FQ_ACTION_TRIM 0
-#define CG_FQ_ACTION_NONE 1
-#define CG_FQ_ACTION_MASK 2
-#define CG_FQ_ACTION_LOWERCASE 3
-#define CG_FQ_ACTION_RETAIN 4
-#define CG_FQ_ACTION_CROP 5
+#include "cg_fastq_core.cuh"   // CgFastqRecord, CgFastqFilter, CG_FQ_ACTION_*, the per-record logic
 #define CG_FQ_COUNTERS 16    // written, bp_in, bp_out, with_adapters, too_short, too_long, quality_trimmed_bp,
                              // discarded (trimmed/untrimmed), too_many_n, too_many_expected_errors, casava_filtered
 long long cg_fastq_tiles(long long n_bytes);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../cutadapt_b200/csrc/cg_core.cuh"
+#include "../../cutadapt_b200/csrc/cg_fastq_core.cuh"
 #include "../../cutadapt_b200/csrc/cg_setbuild.h"
 
 static thread_local std::string g_err;
@@ -149,4 +150,44 @@ extern "C" double hs_expected_errors(const uint8_t *qual, int n, int base)
     double table[256];
     cg_build_phred_table(table);
     return expected_errors_core(qual, n, base, table);
+}
+
+
+// ---- FASTQ path: the per-record logic of cg_fastq.cu (cg_fastq_core.cuh) on the host ---------------------------
+// rec4: hdr_start, hdr_len, seq_start, qual_start per record; iparams: minimum_length, maximum_length,
+// discard_trimmed, discard_untrimmed, poly_a, shorten, trim_n, discard_casava, action; dparams: max_n, max_ee.
+extern "C" int hs_fastq_evaluate(const uint8_t *buf, int64_t n_records, const uint32_t *rec4, const int32_t *seq_len,
+                                 const cg_match *matches, int times, int slots, const int32_t *qtrim,
+                                 const int32_t *iparams, const double *dparams, int32_t *interval, int32_t *keep,
+                                 int32_t *mask, int32_t *last_adapter)
+{
+    CgFastqFilter f;
+    f.minimum_length = iparams[0]; f.maximum_length = iparams[1]; f.discard_trimmed = iparams[2];
+    f.discard_untrimmed = iparams[3]; f.poly_a = iparams[4]; f.shorten = iparams[5]; f.trim_n = iparams[6];
+    f.discard_casava = iparams[7]; f.action = iparams[8];
+    f.max_n = dparams[0]; f.max_ee = dparams[1];
+    double phred[256];
+    cg_build_phred_table(phred);
+    int bad = 0;
+    for (int64_t r = 0; r < n_records; ++r) {
+        CgFastqRecord rec;
+        rec.hdr_start = rec4[4 * r]; rec.hdr_len = (int32_t)rec4[4 * r + 1];
+        rec.seq_start = rec4[4 * r + 2]; rec.qual_start = rec4[4 * r + 3];
+        const int n = seq_len[r];
+        const int qs = qtrim ? qtrim[2 * r] : 0, qe = qtrim ? qtrim[2 * r + 1] : n;
+        const FqVerdict v = fq_evaluate_core(buf, rec, n, matches ? (const cg_match_rec *)matches + (size_t)r * times * slots : nullptr,
+                                             times, slots, qtrim != nullptr, qs, qe, f, phred);
+        interval[2 * r] = v.start; interval[2 * r + 1] = v.stop;
+        keep[2 * r] = v.k0; keep[2 * r + 1] = v.k1;
+        mask[r] = v.mask; last_adapter[r] = v.last_adapter;
+        bad |= v.bad_quality ? 1 : 0;
+    }
+    return bad;
+}
+
+extern "C" void hs_fastq_finish(int64_t n_records, const int32_t *mask1, const int32_t *mask2, int enabled1, int enabled2,
+                                int mode, int mode_untrimmed, int32_t *fired)
+{
+    for (int64_t r = 0; r < n_records; ++r)
+        fired[r] = fq_finish_core(mask1[r], mask2 ? mask2[r] : 0, mask2 != nullptr, enabled1, enabled2, mode, mode_untrimmed);
 }

@@ -292,3 +292,169 @@ def test_reference_fasta_goldens_through_the_device_functions():
         assert "".join(got).encode() == fastq_file(f"fa_{c['name']}.out.fastq"), (c["name"], c["command"])
         done += 1
     assert done >= 22
+
+
+# ---- FASTQ path: cg_fastq_core.cuh on the host --------------------------------------------------------------
+
+def _fastq_table(data, cut=()):
+    """Record table of a FASTQ chunk as fq_records_kernel builds it (positions in `data`, -u cuts applied)."""
+    cut_front = sum(c for c in cut if c > 0)
+    cut_back = sum(-c for c in cut if c < 0)
+    rec, lens, pos = [], [], 0
+    lines = data.split(b"\n")
+    if lines[-1] == b"":
+        lines.pop()
+    starts = []
+    for ln in lines:
+        starts.append(pos)
+        pos += len(ln) + 1
+    for r in range(len(lines) // 4):
+        h, s, q = lines[4 * r], lines[4 * r + 1], lines[4 * r + 3]
+        strip = lambda x: x[:-1] if x.endswith(b"\r") else x
+        h, s, q = strip(h), strip(s), strip(q)
+        n = len(s)
+        cf = min(cut_front, n)
+        n -= cf
+        n = n - cut_back if cut_back < n else 0
+        rec.append((starts[4 * r] + 1, len(h) - 1, starts[4 * r + 1] + cf, starts[4 * r + 3] + cf))
+        lens.append(n)
+    return np.array(rec, dtype=np.uint32).reshape(-1, 4), np.array(lens, dtype=np.int32)
+
+
+def _hostsim_fastq(data, ads, opts, second_mate=False):
+    """(per-record names, evaluate outputs) of one mate through hostsim: trimming pass + fq_evaluate_core."""
+    import ctypes as C
+    from cutadapt_b200 import _lib as L
+    from cutadapt_b200.pipeline import _fastq_params
+    from util import hostsim_lib, hostsim_process, spec_of
+    import cutadapt_b200.adapters as PA
+
+    fp = _fastq_params(**opts)
+    rec, lens = _fastq_table(data, opts.get("cut", ()))
+    buf = np.frombuffer(data, dtype=np.uint8)
+    seqs = [data[int(r[2]):int(r[2]) + int(n)].decode("latin-1") for r, n in zip(rec, lens)]
+    quals = [data[int(r[3]):int(r[3]) + int(n)].decode("latin-1") for r, n in zip(rec, lens)]
+    want_q = bool(fp.trim.quality_trim or fp.trim.nextseq_trim)
+    matches = qtrim = None
+    times, slots = max(1, fp.trim.times), 1
+    if ads:
+        spec = spec_of(PA.MultipleAdapters(ads))
+        matches, qtrim = hostsim_process(spec, seqs, quals if want_q else None, fp.trim)
+        slots = spec.slots
+        if not want_q:
+            qtrim = None
+    elif want_q:
+        from oracle import oracle
+        qtrim = np.zeros((len(seqs), 2), dtype=np.int32)
+        for i, (s_, q_) in enumerate(zip(seqs, quals)):
+            e = oracle.nextseq_trim_index(s_, q_, fp.trim.nextseq_cutoff, fp.trim.quality_base) if fp.trim.nextseq_trim else len(s_)
+            qtrim[i] = oracle.quality_trim_index(q_[:e], fp.trim.cutoff_front, fp.trim.cutoff_back, fp.trim.quality_base) \
+                if fp.trim.quality_trim else (0, e)
+    n = len(seqs)
+    shorten = 0 if not fp.shorten else (fp.shorten_length + 1 if fp.shorten_length >= 0 else fp.shorten_length)
+    ip = np.array([fp.minimum_length, fp.maximum_length, fp.discard_trimmed, fp.discard_untrimmed,
+                   (2 if second_mate else 1) if fp.poly_a else 0, shorten, fp.trim_n, fp.discard_casava,
+                   fp.action if ads else 0], dtype=np.int32)
+    dp = np.array([fp.max_n, fp.max_expected_errors], dtype=np.float64)
+    interval = np.zeros((n, 2), dtype=np.int32)
+    keep = np.zeros((n, 2), dtype=np.int32)
+    mask = np.zeros(n, dtype=np.int32)
+    last = np.zeros(n, dtype=np.int32)
+    lib = hostsim_lib()
+    lib.hs_fastq_evaluate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p] + [C.c_void_p] * 6
+    bad = lib.hs_fastq_evaluate(buf.ctypes.data, n, rec.ctypes.data, lens.ctypes.data,
+                                matches.ctypes.data if matches is not None else None, times, slots,
+                                qtrim.ctypes.data if qtrim is not None else None, ip.ctypes.data, dp.ctypes.data,
+                                interval.ctypes.data, keep.ctypes.data, mask.ctypes.data, last.ctypes.data)
+    assert bad == 0
+    enabled = (1 if fp.minimum_length > 0 else 0) | (2 if fp.maximum_length >= 0 else 0) | (4 if fp.max_n >= 0 else 0) | \
+        (8 if fp.max_expected_errors >= 0 else 0) | (16 if fp.discard_casava else 0) | (32 if fp.discard_trimmed else 0) | \
+        (64 if fp.discard_untrimmed else 0)
+    return dict(data=data, rec=rec, interval=interval, keep=keep, mask=mask, enabled=enabled, action=int(ip[8]), last=last)
+
+
+def _format_fastq(ev, fired):
+    """fq_write_kernel in Python: the surviving records with the action's character transform."""
+    out = []
+    data = ev["data"]
+    for r in range(len(ev["mask"])):
+        if fired[r] >= 0:
+            continue
+        hs, hl, ss, qs = (int(x) for x in ev["rec"][r])
+        a, b = (int(x) for x in ev["interval"][r])
+        k0, k1 = (int(x) for x in ev["keep"][r])
+        seq = bytearray(data[ss + a:ss + b])
+        for j in range(a, b):
+            inside = k0 <= j < k1
+            c = seq[j - a]
+            if ev["action"] == 2:
+                seq[j - a] = c if inside else ord("N")
+            elif ev["action"] == 3 and chr(c).isalpha():
+                seq[j - a] = ord(chr(c).upper()) if inside else ord(chr(c).lower())
+        out.append(b"@" + data[hs:hs + hl] + b"\n" + bytes(seq) + b"\n+\n" + data[qs + a:qs + b] + b"\n")
+    return b"".join(out)
+
+
+def _finish(ev1, ev2=None, mode=0, mode_untrimmed=0):
+    import ctypes as C
+    from util import hostsim_lib
+
+    n = len(ev1["mask"])
+    fired = np.zeros(n, dtype=np.int32)
+    lib = hostsim_lib()
+    lib.hs_fastq_finish.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.hs_fastq_finish(n, ev1["mask"].ctypes.data, ev2["mask"].ctypes.data if ev2 else None, ev1["enabled"],
+                        ev2["enabled"] if ev2 else 0, mode, mode_untrimmed, fired.ctypes.data)
+    return fired
+
+
+def test_fastq_logic_of_the_device_functions_against_the_oracle():
+    """fq_evaluate_core / fq_finish_core (the per-record logic of the FASTQ kernels, compiled for the host) + the
+    host build of the trimming pass must write what oracle_fastq_trim(_paired) writes: every variant of
+    tests/test_gpu_fastq.py's randomized test, the command-line goldens, and paired chunks in all three filter modes."""
+    from oracle import oracle
+    from test_gpu_fastq import synthetic_fastq, oracle_for, trimmer_kwargs
+    from util import fastq_cases, fastq_case_adapters, fastq_paired_cases, oracle_paired
+
+    variants = {
+        "plain": (dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20]), {}),
+        "filters": (dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20]),
+                    dict(minimum_length=20, maximum_length=140, max_n=0.1, max_expected_errors=2.5, discard_untrimmed=True)),
+        "quality_only": (dict(adapters=[], quality_cutoff=[0, 25], nextseq_cutoff=20), dict(minimum_length=1, max_n=3)),
+        "modifiers": (dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20]),
+                      dict(cut=[3, -2], poly_a=True, length=-90, trim_n=True, discard_casava=True, minimum_length=1)),
+        "modifiers2": (dict(adapters=[["anywhere", "AGATCGGAAGAGC"]]),
+                       dict(cut=[-4, -3, 2], poly_a=True, length=60, trim_n=True, max_n=0, discard_trimmed=True)),
+        "mask": (dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20]),
+                 dict(action="mask", times=2, trim_n=True, max_n=0.3, minimum_length=5)),
+        "lowercase": (dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]]), dict(action="lowercase", times=2, poly_a=True)),
+        "none": (dict(adapters=[["back", "AGATCGGAAGAGC"]]), dict(action="none", discard_untrimmed=True, length=100)),
+        "retain": (dict(adapters=[["linked", "TTGACNNACG", "AGATCGGAAGAGC"], ["back", "CACGTCTGAACTC"], ["front", "ACGTACGTAC"]],
+                        quality_cutoff=[0, 15]), dict(action="retain", minimum_length=1)),
+        "crop": (dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"], ["anywhere", "CACGTCTGAA"]]),
+                 dict(action="crop", discard_untrimmed=True, trim_n=True)),
+    }
+    for k, (name, (options, extra)) in enumerate(variants.items()):
+        data = synthetic_fastq(1500, seed=40 + k, crlf=name == "filters")
+        opts = dict(options)
+        opts.update(extra)
+        kw = trimmer_kwargs({x: y for x, y in opts.items() if x != "adapters"})
+        ev = _hostsim_fastq(data, fastq_case_adapters(options), kw)
+        got = _format_fastq(ev, _finish(ev))
+        exp, _ = oracle_for(options, data, **extra)
+        assert got == exp, name
+    for c in fastq_cases():
+        kw = trimmer_kwargs({x: y for x, y in c["options"].items() if x not in ("adapters", "error_rate", "min_overlap")})
+        ev = _hostsim_fastq(c["input_bytes"], fastq_case_adapters(c["options"]), kw)
+        assert _format_fastq(ev, _finish(ev)) == c["expected_bytes"], c["name"]
+    for c in fastq_paired_cases():
+        o = c["options"]
+        evs = []
+        for k, key in enumerate(("adapters1", "adapters2")):
+            kw = trimmer_kwargs(o[f"options{k + 1}"])
+            evs.append(_hostsim_fastq(c["input_bytes"][k], fastq_case_adapters(o, key), kw, second_mate=k == 1))
+        mode = {"any": 0, "both": 1, "first": 2}[o.get("pair_filter", "any")]
+        mode_untrimmed = 1 if (not o["adapters1"] or not o["adapters2"]) else mode
+        fired = _finish(evs[0], evs[1], mode, mode_untrimmed)
+        assert [_format_fastq(evs[0], fired), _format_fastq(evs[1], fired)] == c["expected_bytes"], c["name"]
