@@ -124,48 +124,21 @@ __global__ void __launch_bounds__(FQ_THREADS) fq_index_kernel(const uint8_t *buf
     }
 }
 
-// line k of the chunk: [start, end) without the line terminator ("\n" or "\r\n")
-__device__ __forceinline__ void line_span(const uint8_t *buf, const uint32_t *nl_pos, long long n_nl, long long n,
-                                          long long k, uint32_t *start, uint32_t *end)
-{
-    const uint32_t s = k == 0 ? 0u : nl_pos[k - 1] + 1u;
-    uint32_t e = k < n_nl ? nl_pos[k] : (uint32_t)n;     // the last line may lack its newline
-    if (e > s && buf[e - 1] == '\r') --e;
-    *start = s; *end = e;
-}
-
-// record r = lines 4r .. 4r+3.  Checks what dnaio's parser checks (first characters, equal lengths).
-// cut_front / cut_back: UnconditionalCutter (-u, modifiers.py:66-95), the first modifier of the chain: the
-// record table simply describes the read without those bases.
+// record r = lines 4r .. 4r+3: fq_record_core (cg_fastq_core.cuh) builds the table entry and checks the format
 __global__ void fq_records_kernel(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl,
                                   long long n_records, int cut_front, int cut_back, CgFastqRecord *rec,
                                   int32_t *seq_len, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_records) return;
-    uint32_t hs, he, ss, se, ps, pe, qs, qe;
-    line_span(buf, nl_pos, n_nl, n, 4 * r, &hs, &he);
-    line_span(buf, nl_pos, n_nl, n, 4 * r + 1, &ss, &se);
-    line_span(buf, nl_pos, n_nl, n, 4 * r + 2, &ps, &pe);
-    line_span(buf, nl_pos, n_nl, n, 4 * r + 3, &qs, &qe);
-    int bad = 0;
-    if (he == hs || buf[hs] != '@') bad = 1;
-    else if (pe == ps || buf[ps] != '+') bad = 2;
-    else if (se - ss != qe - qs) bad = 3;
+    CgFastqRecord o;
+    int len;
+    const int bad = fq_record_core(buf, n, nl_pos, n_nl, r, cut_front, cut_back, &o, &len);
     if (bad) {
         // report the first bad record: err[0] = code, err[1] = record number (smallest; initialised to INT_MAX)
         atomicMin((unsigned int *)&err[1], (unsigned int)r);
         atomicMax(&err[0], bad);
     }
-    int len = bad ? 0 : (int32_t)(se - ss);
-    const int cf = cut_front < len ? cut_front : len;      // read[cut_front:]
-    len -= cf;
-    len = cut_back < len ? len - cut_back : 0;             // read[:-cut_back]
-    CgFastqRecord o;
-    o.hdr_start = hs + 1;                       // without the '@'
-    o.hdr_len = (int32_t)(he - hs) - 1;
-    o.seq_start = ss + (uint32_t)cf;
-    o.qual_start = qs + (uint32_t)cf;
     rec[r] = o;
     seq_len[r] = len;
 }

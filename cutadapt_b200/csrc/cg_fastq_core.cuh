@@ -31,6 +31,45 @@ struct CgFastqFilter {
 #define CG_FQ_ACTION_RETAIN 4
 #define CG_FQ_ACTION_CROP 5
 
+// line k of the chunk: [start, end) without the line terminator ("\n" or "\r\n"); nl_pos = positions of all
+// newlines, n = size of the chunk (the last line may lack its newline)
+CG_HD void fq_line_span(const uint8_t *buf, const uint32_t *nl_pos, long long n_nl, long long n, long long k,
+                        uint32_t *start, uint32_t *end)
+{
+    const uint32_t s = k == 0 ? 0u : nl_pos[k - 1] + 1u;
+    uint32_t e = k < n_nl ? nl_pos[k] : (uint32_t)n;
+    if (e > s && buf[e - 1] == '\r') --e;
+    *start = s; *end = e;
+}
+
+// Record r = lines 4r .. 4r+3.  Checks what dnaio's parser checks: 1 = the record does not start with '@',
+// 2 = the third line does not start with '+', 3 = sequence and qualities differ in length; 0 = fine.
+// cut_front / cut_back: UnconditionalCutter (-u, modifiers.py:66-95), the first modifier of the chain: the record
+// table simply describes the read without those bases (read[cut_front:] then read[:-cut_back]).
+CG_HD int fq_record_core(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl, long long r,
+                         int cut_front, int cut_back, CgFastqRecord *rec, int *seq_len)
+{
+    uint32_t hs, he, ss, se, ps, pe, qs, qe;
+    fq_line_span(buf, nl_pos, n_nl, n, 4 * r, &hs, &he);
+    fq_line_span(buf, nl_pos, n_nl, n, 4 * r + 1, &ss, &se);
+    fq_line_span(buf, nl_pos, n_nl, n, 4 * r + 2, &ps, &pe);
+    fq_line_span(buf, nl_pos, n_nl, n, 4 * r + 3, &qs, &qe);
+    int bad = 0;
+    if (he == hs || buf[hs] != '@') bad = 1;
+    else if (pe == ps || buf[ps] != '+') bad = 2;
+    else if (se - ss != qe - qs) bad = 3;
+    int len = bad ? 0 : (int32_t)(se - ss);
+    const int cf = cut_front < len ? cut_front : len;
+    len -= cf;
+    len = cut_back < len ? len - cut_back : 0;
+    rec->hdr_start = hs + 1;                    // without the '@'
+    rec->hdr_len = (int32_t)(he - hs) - 1;
+    rec->seq_start = ss + (uint32_t)cf;
+    rec->qual_start = qs + (uint32_t)cf;
+    *seq_len = len;
+    return bad;
+}
+
 struct FqVerdict {
     int start, stop;         // what is written: read[start:stop] (relative to the record's sequence after -u)
     int k0, k1;              // the part the action leaves untouched ("remainder")

@@ -191,3 +191,25 @@ extern "C" void hs_fastq_finish(int64_t n_records, const int32_t *mask1, const i
     for (int64_t r = 0; r < n_records; ++r)
         fired[r] = fq_finish_core(mask1[r], mask2 ? mask2[r] : 0, mask2 != nullptr, enabled1, enabled2, mode, mode_untrimmed);
 }
+
+// record table of a chunk (fq_record_core); nl_pos is computed here the plain way.  Returns the first error code
+// (0 = none) and its record in *bad_record.
+extern "C" int hs_fastq_records(const uint8_t *buf, int64_t n, int cut_front, int cut_back, int64_t n_records,
+                                uint32_t *rec4, int32_t *seq_len, int64_t *bad_record)
+{
+    std::vector<uint32_t> nl;
+    for (int64_t i = 0; i < n; ++i)
+        if (buf[i] == '\n') nl.push_back((uint32_t)i);
+    int first = 0;
+    *bad_record = -1;
+    for (int64_t r = 0; r < n_records; ++r) {
+        CgFastqRecord rec;
+        int len;
+        const int bad = fq_record_core(buf, n, nl.data(), (long long)nl.size(), r, cut_front, cut_back, &rec, &len);
+        if (bad && *bad_record < 0) { first = bad; *bad_record = r; }
+        rec4[4 * r] = rec.hdr_start; rec4[4 * r + 1] = (uint32_t)rec.hdr_len;
+        rec4[4 * r + 2] = rec.seq_start; rec4[4 * r + 3] = rec.qual_start;
+        seq_len[r] = len;
+    }
+    return first;
+}

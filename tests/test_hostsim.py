@@ -458,3 +458,37 @@ def test_fastq_logic_of_the_device_functions_against_the_oracle():
         mode_untrimmed = 1 if (not o["adapters1"] or not o["adapters2"]) else mode
         fired = _finish(evs[0], evs[1], mode, mode_untrimmed)
         assert [_format_fastq(evs[0], fired), _format_fastq(evs[1], fired)] == c["expected_bytes"], c["name"]
+
+
+def test_fastq_record_table_of_the_device_functions():
+    """fq_record_core (record table + dnaio's format checks + -u cuts) on the host: against the Python table of this
+    file for LF / CRLF / missing final newline, and the error codes for malformed records."""
+    import ctypes as C
+    from test_gpu_fastq import synthetic_fastq
+    from util import hostsim_lib
+
+    lib = hostsim_lib()
+    lib.hs_fastq_records.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def table(data, cut=(), n_records=None):
+        buf = np.frombuffer(data, dtype=np.uint8)
+        lines = data.count(b"\n") + (0 if data.endswith(b"\n") or not data else 1)
+        n = lines // 4 if n_records is None else n_records
+        rec = np.zeros((n, 4), dtype=np.uint32)
+        lens = np.zeros(n, dtype=np.int32)
+        bad = C.c_int64(-1)
+        code = lib.hs_fastq_records(buf.ctypes.data, len(data), sum(c for c in cut if c > 0), sum(-c for c in cut if c < 0),
+                                    n, rec.ctypes.data, lens.ctypes.data, C.byref(bad))
+        return code, bad.value, rec, lens
+
+    for k, (crlf, cut) in enumerate(((False, ()), (True, ()), (False, (3, -2)), (True, (-1, 200)))):
+        data = synthetic_fastq(800, seed=60 + k, crlf=crlf)
+        for tail in (data, data + b"@last\nACGT\n+\nIIII"):
+            code, bad, rec, lens = table(tail, cut)
+            want_rec, want_lens = _fastq_table(tail, cut)
+            assert code == 0 and bad == -1
+            assert (rec == want_rec).all() and (lens == want_lens).all()
+    for text, want in ((b"r\nACGT\n+\nIIII\n", 1), (b"@r\nACGT\n-\nIIII\n", 2), (b"@r\nACGT\n+\nIII\n", 3),
+                       (b"@a\nAC\n+\nII\n@b\nACGT\n\nIIII\n", 2)):
+        code, bad, _, _ = table(text)
+        assert code == want and bad == text.count(b"@a")
