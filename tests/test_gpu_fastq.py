@@ -303,21 +303,3 @@ def test_demultiplex_reference_golden_and_barcodes():
             a = int(m["adapter"][i, 0, 0])
             assert name == (f"bc{a}" if a >= 0 else "unknown"), i
 
-
-def test_reference_fasta_goldens():
-    """32 further command-line known answers of the reference whose vectors are FASTA (anchored / non-internal / linked
-    adapters, --no-indels, -N, --match-read-wildcards, --trim-n, --poly-a, --max-n; stored as FASTQ with constant
-    qualities, tests/golden/make_fastq_golden.py): byte-identical output of the device path."""
-    from util import golden, fastq_file, adapter_from_spec
-
-    cases = golden("fastq_kat.json.gz")["fasta_cases"]
-    assert len(cases) >= 30
-    for c in cases:
-        o = c["options"]
-        params = dict(max_errors=o.get("error_rate", 0.1), min_overlap=o.get("min_overlap", 3),
-                      adapter_wildcards=not o.get("no_wildcards", False), read_wildcards=o.get("read_wildcards", False),
-                      indels=not o.get("no_indels", False))
-        ads = [adapter_from_spec(spec, kind, name=f"a{i}", **params) for i, (kind, spec) in enumerate(o["specs"])]
-        t = FastqTrimmer(ads, **trimmer_kwargs(o))
-        assert t.process_chunk(fastq_file(f"fa_{c['name']}.in.fastq")) == fastq_file(f"fa_{c['name']}.out.fastq"), \
-            (c["name"], c["command"])

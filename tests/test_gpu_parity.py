@@ -641,29 +641,3 @@ def test_multipass_schedule_agrees_with_one_phase_and_oracle():
                 del os.environ["CUTADAPT_B200_KERNEL"]
             assert (other == exp).all(), ("general", k, qt)
 
-
-def test_revcomp_and_pair_adapters_compositions():
-    """--revcomp and --pair-adapters as compositions of device passes (BatchTrimmer.process_revcomp,
-    PairedAdapterBatch) on the reference's known answers (test_commandline.py:827-835, test_paired.py:668-676)."""
-    import cutadapt_b200.adapters as PA
-    from cutadapt_b200 import pipeline
-    from util import fastq_file
-
-    records = oracle.parse_fastq(fastq_file("revcomp.in.fastq"))
-    names, seqs, quals = zip(*records)
-    bt = pipeline.BatchTrimmer([PA.PrefixAdapter("TTATTTGTCT", name="a"), PA.PrefixAdapter("TCCGCACTGG", name="b")])
-    res, is_rc = bt.process_revcomp(list(seqs))
-    assert int(is_rc.sum()) == 2
-    out = []
-    for i, name in enumerate(names):
-        s, q = (pipeline.reverse_complement(seqs[i]), quals[i][::-1]) if is_rc[i] else (seqs[i], quals[i])
-        a, b = (int(x) for x in res.intervals[i])
-        out.append(f"@{name}{' rc' if is_rc[i] else ''}\n{s[a:b]}\n+\n{q[a:b]}\n")
-    assert "".join(out).encode() == fastq_file("revcomp.out.fastq")
-
-    recs = [oracle.parse_fastq(fastq_file(f"pair_adapters.in{k}.fastq")) for k in (1, 2)]
-    pb = pipeline.PairedAdapterBatch([PA.BackAdapter("GTCTCCAGCT", name="a")], [PA.BackAdapter("GACAAATAAC", name="b")])
-    best, t1, t2 = pb.process([r[1] for r in recs[0]], [r[1] for r in recs[1]])
-    for rec, t, k in ((recs[0], t1, 1), (recs[1], t2, 2)):
-        text = "".join(f"@{n}\n{s[a:b]}\n+\n{q[a:b]}\n" for (n, s, q), (a, b) in zip(rec, t.intervals.tolist()))
-        assert text.encode() == fastq_file(f"pair_adapters.out{k}.fastq")
