@@ -24,3 +24,10 @@ def _built():
     from oracle import oracle
 
     oracle.build()
+
+
+def pytest_collection_modifyitems(session, config, items):
+    """GPU run order: the hot path's parity tests first, then the FASTQ path, then the late additions -- with -x a
+    failure in a later layer must not hide the state of the core."""
+    rank = {"test_gpu_parity.py": 0, "test_gpu_fastq.py": 1, "test_gpu_z_more_goldens.py": 2}
+    items.sort(key=lambda it: rank.get(os.path.basename(str(it.fspath)), -1))
