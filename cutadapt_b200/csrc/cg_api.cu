@@ -434,17 +434,26 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     const bool force_block = kernel_env && strcmp(kernel_env, "block") == 0;
     const bool force_warp = kernel_env && strcmp(kernel_env, "warp") == 0;
     bool split = false;
+    int plane_w = 0;
     size_t scan_smem = 0, list_smem = 0;
     int scan_occ = 0, plan_occ = 0, run_occ = 0;
     if (simple && s->host.max_m <= 64 && !force_block && !force_warp) {
         const long long mini = ((long long)32 * max_read_len + 32 + 15) / 16 * 16;
-        const long long cslot = ((long long)max_read_len + 4 + 15) / 16 * 16 + 16;   // + 4: word-granular reads past the last group
+        const long long cslot = ((long long)max_read_len + 4 + 15) / 16 * 16 + 32;   // + 4: word-granular reads past the last group
+        // bit-plane first stage (plane_scan_core) when the adapter has a plane program and the reads fit 8 plane
+        // words; CUTADAPT_B200_SCAN=shiftand keeps the shift-and scan kernel (parity tests run both)
+        const CgSetHeader *hdr = (const CgSetHeader *)s->host.blob.data();
+        const char *scan_env = getenv("CUTADAPT_B200_SCAN");
+        if (hdr->plane_count > 0 && max_read_len <= 256 && !(scan_env && strcmp(scan_env, "shiftand") == 0))
+            plane_w = max_read_len <= 160 ? 5 : 8;
         if (mini < (1 << 20)) {
             a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
-            scan_smem = cg_scan_smem_bytes(a.blob_bytes, a.mini_cap, want_q);
+            scan_smem = plane_w ? cg_pscan_smem_bytes(a.blob_bytes, a.mini_cap, want_q)
+                                : cg_scan_smem_bytes(a.blob_bytes, a.mini_cap, want_q);
             list_smem = cg_dp_smem_bytes(a.blob_bytes, a.carry_slot);
             if (scan_smem <= c->smem_optin && list_smem <= c->smem_optin) {
-                CU(cg_scan_occupancy(want_q, scan_smem, &scan_occ));
+                if (plane_w) CU(cg_pscan_occupancy(want_q, plane_w, scan_smem, &scan_occ));
+                else CU(cg_scan_occupancy(want_q, scan_smem, &scan_occ));
                 CU(cg_list_occupancy(true, s->host.max_m, list_smem, &plan_occ));
                 CU(cg_list_occupancy(false, s->host.max_m, list_smem, &run_occ));
                 split = scan_occ >= 1 && plan_occ >= 1 && run_occ >= 1;
@@ -502,7 +511,8 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             const long long need = (n_mt + 3) / 4;
             auto grid_for = [&](int occ) { return (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, need)); };
             b.tasks = c->tasks.p; b.task_count = cnt;
-            CU(cg_launch_scan(b, want_q, grid_for(scan_occ), scan_smem, st));
+            if (plane_w) CU(cg_launch_pscan(b, want_q, plane_w, grid_for(scan_occ), scan_smem, st));
+            else CU(cg_launch_scan(b, want_q, grid_for(scan_occ), scan_smem, st));
             b.tasks2 = c->tasks2.p; b.task2_count = cnt + 1;
             CU(cg_launch_list(b, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
             c->launches += 2;

@@ -665,6 +665,230 @@ CG_HD ScanOut scan_core(const CgScanWord *words, int n_words, const uint8_t *poo
     return scan_core_dir<false>(words, n_words, pool, rv.p, rv.n, gs, always_pass);
 }
 
+// ---------------------------------------------------------------------------------------
+// Bit-plane scan (split pipeline, first stage for plain A/C/G/T adapters).
+//
+// The searched window of a read (n <= 32 W characters) becomes four W-word bit planes -- bit i of plane X
+// is set iff character i is X or x -- and every k-mer of the scan program is matched against all
+// positions at once: ends(kmer) = AND_t (plane[kmer[t]] << (len - 1 - t)), 1.5 instructions per k-mer
+// character and 32 positions instead of ~7 per read character of the shift-and scan.  The window is
+// RIGHT-aligned in the planes (its last character is bit 32 W - 1), so that the suffix windows of the
+// KmerFinder entries of a 3' adapter (_kmer_finder.pyx:188-204 with start < 0) are the last word(s).
+//
+// Planes come from bits 1 and 2 of the ASCII code alone (A 00, C 01, T 10, G 11; case-insensitive),
+// four characters per dp4a: sum_i ((word >> (8 i + 1)) & 1) << i.  Any other byte aliases one of the four
+// letters, so the planes give a SUPERSET of the true k-mer occurrences:
+//   * no occurrence of any k-mer in the planes  =>  KmerFinder.kmers_present is False  =>  no match;
+//   * an exact occurrence of the whole adapter found in the planes is confirmed by comparing the read
+//     bytes with the adapter; if it is also the leftmost place any locator chunk points at, the
+//     reference returns (0, m, s0, s0 + m, m, 0) (proof below) -- no DP;
+//   * every other read goes to the exact path (cg_list_kernel<plan> re-scans it with scan_core).
+//
+// Exact-occurrence rule (adapters without START_IN_REFERENCE, k <= m/2, unit costs, plain A/C/G/T).
+// Let s0 be the start of an exact occurrence and assume no locator chunk occurs anywhere in the read at
+// a place that implies an adapter start < s0.  Column s0 + m of the DP has bottom cell (0, m, s0): a
+// cost-0 path is the diagonal, so it is unique.  A bottom-row candidate accepted at an earlier column has
+// cost >= 1 (cost 0 would be an exact occurrence with a smaller start, whose chunks contradict the
+// assumption), hence score < m, and by the pigeonhole principle it contains a chunk exactly; its start
+// is within k of the start that chunk implies, i.e. >= s0 - k >= s0 - m/2.  So at column s0 + m the
+// replacement test of _align.pyx:521-525 succeeds (origin s0 <= best.origin + m/2 and score m > best.score)
+// and the search stops there (_align.pyx:531-533); the last-column scan that follows cannot beat score m.
+// ---------------------------------------------------------------------------------------
+CG_HD uint32_t cg_dp4a(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+    return c;
+#endif
+}
+CG_HD uint32_t cg_funnel_l(uint32_t lo, uint32_t hi, uint32_t s)   // (hi:lo) << s, upper word; s in 0..31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+CG_HD uint32_t cg_funnel_rb(uint32_t lo, uint32_t hi, uint32_t s)  // (hi:lo) >> s, lower word; s in 0..31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+
+struct PlaneOut {
+    int cls;         // 0: no match, 1: exact occurrence at s0, 2: undecided (exact path)
+    int s0;
+    uint32_t bad;    // OR of the window's bytes (bit 7 of any byte set = non-ASCII input)
+};
+#define CG_PLANE_NONE 0
+#define CG_PLANE_EXACT 1
+#define CG_PLANE_SLOW 2
+
+// acc &= plane << s   (multi-word, s in 0..31), words b0 .. W-1 only
+template <int W>
+CG_HD void plane_and_shift(uint32_t (&acc)[W], const uint32_t (&P)[W], uint32_t s, int b0, bool first)
+{
+#pragma unroll
+    for (int b = W - 1; b >= 0; --b) {
+        if (b < b0) continue;
+        const uint32_t x = b == 0 ? (P[0] << s) : cg_funnel_l(P[b - 1], P[b], s);
+        acc[b] = first ? x : (acc[b] & x);
+    }
+}
+
+// x <<= s  (multi-word, s in 0..63)
+template <int W>
+CG_HD void plane_shl(uint32_t (&x)[W], uint32_t s)
+{
+    if (s >= 32) {
+#pragma unroll
+        for (int b = W - 1; b >= 1; --b) x[b] = x[b - 1];
+        x[0] = 0;
+        s -= 32;
+    }
+#pragma unroll
+    for (int b = W - 1; b >= 1; --b) x[b] = cg_funnel_l(x[b - 1], x[b], s);
+    x[0] <<= s;
+}
+
+// `end` points just past the last character of the searched window; n = its length (1 <= n <= 32 W;
+// the caller routes everything else to the exact path).  The bytes [end - 32 W - 3, end + 4) must be
+// readable (their values outside the window do not matter).
+template <int W>
+CG_HD PlaneOut plane_scan_core(const CgPlaneKmer *prog, int n_prog, int plane_flags, const CgAdapter &A,
+                               const uint8_t *ref, const uint8_t *end, int n, bool always_pass)
+{
+    PlaneOut out; out.cls = CG_PLANE_SLOW; out.s0 = 0; out.bad = 0;
+    const int off0 = 32 * W - n;                     // plane index of the window's first character
+    const uint8_t *base = end - 32 * W;              // plane index 0
+    uint32_t LO[W], HI[W];
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)base & 3u);
+        const uint32_t sh = 8u * mis;
+        const uint32_t *wp = (const uint32_t *)(base - mis);
+        uint32_t carry = wp[0];
+        uint32_t bad = 0;
+#pragma unroll
+        for (int b = 0; b < W; ++b) {
+            uint32_t x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t nxt = wp[8 * b + j + 1];
+                x[j] = cg_funnel_rb(carry, nxt, sh);
+                carry = nxt;
+            }
+            if (off0 > 32 * b) {                     // leading block(s): blank the bytes in front of the window
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int fv = off0 - (32 * b + 4 * j);          // first valid byte of this word
+                    const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 4 ? 0u : (0xFFFFFFFFu << (8 * fv)));
+                    x[j] &= keep;
+                }
+            }
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint32_t a = x[2 * p], c = x[2 * p + 1];
+                bad |= a | c;
+                uint32_t pl = cg_dp4a(a & 0x02020202u, 0x08040201u, 0u);
+                pl = cg_dp4a(c & 0x02020202u, 0x80402010u, pl);      // 2 x (8 plane bits)
+                uint32_t ph = cg_dp4a(a & 0x04040404u, 0x08040201u, 0u);
+                ph = cg_dp4a(c & 0x04040404u, 0x80402010u, ph);      // 4 x (8 plane bits)
+                lo += p == 0 ? (pl >> 1) : (pl << (8 * p - 1));
+                hi += p == 0 ? (ph >> 2) : (ph << (8 * p - 2));
+            }
+            LO[b] = lo; HI[b] = hi;
+        }
+        out.bad = bad;
+    }
+    // planes of the four letters, blanked in front of the window
+    uint32_t PA[W], PC[W], PG[W], PT[W];
+#pragma unroll
+    for (int b = 0; b < W; ++b) {
+        const int fv = off0 - 32 * b;
+        const uint32_t len = fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
+        PA[b] = ~LO[b] & ~HI[b] & len;
+        PC[b] = LO[b] & ~HI[b] & len;
+        PT[b] = ~LO[b] & HI[b] & len;
+        PG[b] = LO[b] & HI[b] & len;
+    }
+    bool pass = always_pass, anyhit = false;
+    uint32_t M[W], E[W];                             // locator hits / all chunks, by the end of the WHOLE adapter
+#pragma unroll
+    for (int b = 0; b < W; ++b) { M[b] = 0; E[b] = 0xFFFFFFFFu; }
+    for (int q = 0; q < n_prog; ++q) {
+        const CgPlaneKmer K = prog[q];
+        const int len = K.len;
+        // words that can hold the end of an occurrence inside the k-mer's window
+        int b0 = 0;
+        if (K.type == CG_SCAN_SUFFIX) b0 = cg_max(0, (32 * W - (int)K.window) >> 5);
+        uint32_t acc[W];
+#pragma unroll
+        for (int b = 0; b < W; ++b) acc[b] = 0;
+        for (int t = 0; t < len; ++t) {
+            const uint32_t code = (uint32_t)(K.codes >> (2 * t)) & 3u;
+            const uint32_t s = (uint32_t)(len - 1 - t);
+            const bool first = t == 0;
+            if (code == 0) plane_and_shift<W>(acc, PA, s, b0, first);
+            else if (code == 1) plane_and_shift<W>(acc, PC, s, b0, first);
+            else if (code == 2) plane_and_shift<W>(acc, PT, s, b0, first);
+            else plane_and_shift<W>(acc, PG, s, b0, first);
+        }
+        // acc: bit e set iff the k-mer ends at plane index e (occurrences reaching in front of the window
+        // are impossible: the planes are blank there)
+        uint32_t any = 0;
+        if (K.type == CG_SCAN_SUFFIX) {
+            // the occurrence must start inside the last `window` characters: e >= 32 W - window + len - 1
+            const int e_min = 32 * W - (int)K.window + len - 1;
+#pragma unroll
+            for (int b = 0; b < W; ++b) {
+                const int fv = e_min - 32 * b;
+                const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
+                if (b >= b0) any |= acc[b] & keep;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < W; ++b) any |= acc[b];
+        }
+        if ((K.flags & CG_PLANE_PASS) && any) pass = true;
+        if (K.flags & CG_PLANE_LOC) {
+            if (any) anyhit = true;
+            plane_shl<W>(acc, (uint32_t)(A.m - (int)K.bend));
+#pragma unroll
+            for (int b = 0; b < W; ++b) { M[b] |= acc[b]; E[b] &= acc[b]; }
+        }
+    }
+    if (!anyhit && !pass) { out.cls = CG_PLANE_NONE; return out; }
+    if (!(plane_flags & 1) || !anyhit) return out;
+    // the leftmost adapter end any chunk points at (a chunk whose implied end lies beyond the window is
+    // shifted out: it implies a larger start than anything that remains)
+    bool found = false, ex = false;
+    int low = 0;
+#pragma unroll
+    for (int b = 0; b < W; ++b) {
+        if (!found && M[b]) {
+            found = true;
+            const int bit = cg_ctz(M[b]);
+            low = 32 * b + bit;
+            ex = ((E[b] >> bit) & 1u) != 0;
+        }
+    }
+    if (!found || !ex) return out;
+    const int s0 = low - (A.m - 1) - off0;
+    if (s0 < 0 || s0 + A.m > n) return out;          // (cannot happen: the planes are blank outside the window)
+    const uint8_t *w = base + (low - (A.m - 1));
+    bool same = true;
+    for (int i = 0; i < A.m; ++i) same = same && ((w[i] & 0xDFu) == ref[i]);
+    if (!same) return out;
+    out.cls = CG_PLANE_EXACT; out.s0 = s0;
+    return out;
+}
+
 // Groups of characters the DP must visit, given the locator hits (see locate_core).
 CG_HD uint32_t window_cover(const CgAdapter &A, int n, int gs, uint32_t hits)
 {
@@ -2001,4 +2225,36 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
         }
     }
     store_hit(out, hit, 0, nn);
+}
+
+// Host-sim driver of the bit-plane first stage (tests/hostsim, mode 256): plane_scan_core decides what it
+// can, everything else takes the planned scheduling above -- exactly what cg_pscan_kernel + cg_list_kernel do.
+CG_HD const CgPlaneKmer *plane_program(const SetView &S)
+{
+    return (const CgPlaneKmer *)((const uint8_t *)S.h + S.h->plane_off);
+}
+
+CG_HD void process_read_planes(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
+                               int quality_trim, int cutoff_front, int cutoff_back, int qbase,
+                               cg_match_rec *out, int32_t *qtrim_out)
+{
+    int s = 0, e = n;
+    if (quality_trim) pre_trim_core(seq, qual, n, quality_trim, cutoff_front, cutoff_back, qbase, &s, &e);
+    if (qtrim_out) { qtrim_out[0] = s; qtrim_out[1] = e; }
+    const CgAdapter &A = S.ad[0];
+    const int nn = e - s;
+    if (S.h->plane_count > 0 && nn >= 1 && nn <= 256) {
+        const uint8_t *ref = S.pool + A.ref_off;
+        const PlaneOut po = nn <= 160
+            ? plane_scan_core<5>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + e, nn, A.pf_count == 0)
+            : plane_scan_core<8>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + e, nn, A.pf_count == 0);
+        if (po.cls != CG_PLANE_SLOW) {
+            CgHit hit; hit.adapter = -1; hit.remove = 0;
+            hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+            if (po.cls == CG_PLANE_EXACT) hit_exact(A, nn, po.s0, hit);
+            store_hit(out, hit, 0, nn);
+            return;
+        }
+    }
+    process_read_planned(S, seq + s, nullptr, nn, 0, 0, 0, qbase, out, nullptr);
 }

@@ -70,6 +70,9 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
 cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
+size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
+cudaError_t cg_pscan_occupancy(bool has_qual, int w, size_t smem, int *blocks_per_sm);
+cudaError_t cg_launch_pscan(const CgKernelArgs &a, bool has_qual, int w, int grid, size_t smem, cudaStream_t st);
 size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes);
 cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_list(const CgKernelArgs &a, bool plan, int mr, int grid, size_t smem, cudaStream_t st);

@@ -152,9 +152,84 @@ void pack_words(const std::vector<ScanKmer> &kmers, uint32_t type, bool gap, std
     }
 }
 
+// 2-bit code of a k-mer position that matches exactly one of A/C/G/T in both cases, else -1
+int plane_code(const std::array<uint64_t, 2> &set)
+{
+    for (const char *b = "ACGT"; *b; ++b) {
+        std::array<uint64_t, 2> want = {0, 0};
+        const int up = *b, lo = *b | 0x20;
+        want[up >> 6] |= 1ULL << (up & 63);
+        want[lo >> 6] |= 1ULL << (lo & 63);
+        if (set == want) return (up >> 1) & 3;
+    }
+    return -1;
+}
+
+// The bit-plane form of the scan program (plane_scan_core in cg_core.cuh).  Empty if the adapter does not
+// qualify: every k-mer position must be a plain A/C/G/T, no prefix windows, suffix windows of <= 64
+// characters, a forward adapter of <= 64 characters with locator chunks.
+void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowed, int exact_ok, int myers,
+                         const std::vector<ScanKmer> &whole, const std::vector<ScanKmer> &suffix,
+                         const std::vector<ScanKmer> &prefix, std::vector<CgPlaneKmer> &out, int &flags)
+{
+    out.clear();
+    flags = 0;
+    if (!windowed || myers || A.reverse || !prefix.empty() || A.m > 64 || !A.compare_ascii) return;
+    std::vector<CgPlaneKmer> prog;
+    bool any_loc = false, unambiguous = true;
+    auto add = [&](const ScanKmer &k, uint32_t type) -> bool {
+        if (k.len < 1 || k.len > 32) return false;
+        CgPlaneKmer pk;
+        memset(&pk, 0, sizeof pk);
+        for (int t = 0; t < k.len; ++t) {
+            const int code = plane_code(k.cols[t]);
+            if (code < 0) return false;
+            pk.codes |= (uint64_t)code << (2 * t);
+        }
+        pk.len = (uint8_t)k.len; pk.type = (uint8_t)type;
+        pk.flags = (uint8_t)((k.pass ? CG_PLANE_PASS : 0u) | (k.loc ? CG_PLANE_LOC : 0u));
+        if (k.loc) {
+            any_loc = true;
+            unambiguous = unambiguous && k.bmin == k.bmax;
+            pk.bend = (uint8_t)k.bmax;
+        }
+        if (type == CG_SCAN_SUFFIX) {
+            if (k.window < 1 || k.window > 64) return false;
+            pk.window = (uint16_t)k.window;
+        }
+        prog.push_back(pk);
+        return true;
+    };
+    for (auto &k : whole) if (!add(k, CG_SCAN_WHOLE)) return;
+    for (auto &k : suffix) if (!add(k, CG_SCAN_SUFFIX)) return;
+    if (!any_loc || prog.size() > 32) return;
+    // an exact occurrence may be reported straight from the planes if the locator is unambiguous
+    // (exact_ok), the adapter itself is plain A/C/G/T, and KmerFinder.kmers_present is certain to say
+    // yes for a read that contains the whole adapter: some whole-read k-mer of the prefilter is a
+    // substring of the adapter (or there is no prefilter at all)
+    bool plain = true;
+    std::vector<int> acode(A.m);
+    for (int i = 0; i < A.m; ++i) {
+        const uint8_t c = enc_ref[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') plain = false;
+        acode[i] = (c >> 1) & 3;
+    }
+    bool implies_pass = A.pf_count == 0;
+    for (auto &pk : prog) {
+        if (implies_pass || pk.type != CG_SCAN_WHOLE || !(pk.flags & CG_PLANE_PASS)) continue;
+        for (int s = 0; s + pk.len <= A.m && !implies_pass; ++s) {
+            bool eq = true;
+            for (int t = 0; t < pk.len && eq; ++t) eq = acode[s + t] == (int)((pk.codes >> (2 * t)) & 3);
+            implies_pass = eq;
+        }
+    }
+    if (exact_ok && unambiguous && plain && implies_pass) flags |= 1;
+    out.swap(prog);
+}
+
 bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc768,
                         const uint8_t *enc_ref, std::vector<uint8_t> &pool, std::vector<CgScanWord> &words,
-                        int &windowed, int &exact_ok, int &myers)
+                        int &windowed, int &exact_ok, int &myers, std::vector<CgPlaneKmer> &planes, int &plane_flags)
 {
     myers = 0;
     std::vector<ScanKmer> whole, suffix, prefix;
@@ -254,6 +329,7 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
     pack_words(whole, CG_SCAN_WHOLE, false, pool, words);
     pack_words(suffix, CG_SCAN_SUFFIX, true, pool, words);
     pack_words(prefix, CG_SCAN_PREFIX, true, pool, words);
+    build_plane_program(A, enc_ref, windowed, exact_ok, myers, whole, suffix, prefix, planes, plane_flags);
     return words.size() <= 64;
 }
 
@@ -515,17 +591,21 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
 
     // two-phase program for the common case: one SINGLE aligner adapter with packed cells
     std::vector<CgScanWord> scan_words;
+    std::vector<CgPlaneKmer> plane_kmers;
+    int plane_flags = 0;
     int simple_ok = 0, windowed = 0, exact_ok = 0, myers = 0;
     if (n_adapters == 1 && n_groups == 1 && G[0].type == CG_GROUP_SINGLE && A[0].kind == CG_KIND_ALIGNER &&
         A[0].cell_mode == CG_CELL_PACKED32) {
         std::vector<uint8_t> pool2 = pool;
         std::vector<CgScanWord> words;
-        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed, exact_ok, myers)) {
+        if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed, exact_ok, myers,
+                               plane_kmers, plane_flags)) {
             pool.swap(pool2);
             scan_words.swap(words);
             simple_ok = 1;
         } else {
             windowed = 0; exact_ok = 0; myers = 0;
+            plane_kmers.clear(); plane_flags = 0;
         }
     }
 
@@ -540,6 +620,8 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     H.entries_off = off; off += (uint32_t)(E.size() * sizeof(CgEntry)); off = align_up(off, 16);
     H.scan_off = off; off += (uint32_t)(scan_words.size() * sizeof(CgScanWord)); off = align_up(off, 16);
     H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed; H.exact_ok = exact_ok; H.myers = myers;
+    H.plane_off = off; off += (uint32_t)(plane_kmers.size() * sizeof(CgPlaneKmer)); off = align_up(off, 16);
+    H.plane_count = (int32_t)plane_kmers.size(); H.plane_flags = plane_flags;
     H.pool_off = off; off += (uint32_t)pool.size(); off = align_up(off, 16);
     H.total_bytes = off;
     out.blob.assign(off, 0);
@@ -549,6 +631,8 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     if (!E.empty()) memcpy(out.blob.data() + H.entries_off, E.data(), E.size() * sizeof(CgEntry));
     if (!scan_words.empty())
         memcpy(out.blob.data() + H.scan_off, scan_words.data(), scan_words.size() * sizeof(CgScanWord));
+    if (!plane_kmers.empty())
+        memcpy(out.blob.data() + H.plane_off, plane_kmers.data(), plane_kmers.size() * sizeof(CgPlaneKmer));
     if (!pool.empty()) memcpy(out.blob.data() + H.pool_off, pool.data(), pool.size());
     out.n_adapters = n_adapters; out.n_groups = n_groups; out.simple_ok = simple_ok;
     if (out.masks64.empty()) out.masks64.assign(128, 0);   // never hand the kernel a null table

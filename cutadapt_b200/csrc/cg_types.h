@@ -90,8 +90,27 @@ struct CgSetHeader {        // 80 bytes
     int32_t exact_ok;       // 1: an exact, leftmost occurrence found by the locator needs no DP at all
     int32_t myers;          // 1: the plan stage finds the DP runs with a bit-vector edit-distance pass over the
                             //    read instead of locator chunks (adapters whose chunks would hit everywhere)
-    int32_t pad[3];
+    // bit-plane scan program (plane_scan_core): the same k-mers as 2-bit codes, matched word-parallel
+    int32_t plane_count;    // number of CgPlaneKmer (0: the adapter does not qualify)
+    uint32_t plane_off;     // blob offset of CgPlaneKmer[plane_count]
+    int32_t plane_flags;    // bit 0: an exact occurrence found by the planes may be reported without DP
 };
+
+// One k-mer of the bit-plane scan.  Characters are 2-bit codes taken from bits 1 and 2 of the ASCII
+// code (A = 0, C = 1, T = 2, G = 3; the same for lower case); only k-mers whose every position matches
+// exactly one of A/C/G/T (either case) can be expressed, which the host checks.
+#define CG_PLANE_PASS 1u    // a k-mer of the KmerFinder (prefilter verdict)
+#define CG_PLANE_LOC 2u     // a locator chunk (one of the k+1 pieces of the adapter)
+struct CgPlaneKmer {        // 16 bytes
+    uint64_t codes;         // 2 bits per character, first character in the low bits
+    uint8_t len;            // 1..32
+    uint8_t type;           // CG_SCAN_WHOLE or CG_SCAN_SUFFIX
+    uint8_t flags;          // CG_PLANE_*
+    uint8_t bend;           // locator chunk: adapter offset (exclusive) at which it ends
+    uint16_t window;        // SUFFIX: the k-mer must lie within the last `window` characters (<= 64)
+    uint16_t pad;
+};
+static_assert(sizeof(CgPlaneKmer) == 16, "CgPlaneKmer layout");
 
 // Anchored-adapter index (AdapterIndex, adapters.py:1289-1551) as an open-addressing hash table.
 struct CgIndexEntry {       // 16 bytes; len == 0 marks an empty slot

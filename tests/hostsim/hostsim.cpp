@@ -29,7 +29,8 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     if (rc != CG_OK) return rc;
     if (force_wide & 4) {   // query only: bit 0 two-phase program available, 1 windowed, 2 exact shortcut, 3 myers
         const CgSetHeader *h = (const CgSetHeader *)set.blob.data();
-        return (set.simple_ok ? 1 : 0) | (h->windowed ? 2 : 0) | (h->exact_ok ? 4 : 0) | (h->myers ? 8 : 0);
+        return (set.simple_ok ? 1 : 0) | (h->windowed ? 2 : 0) | (h->exact_ok ? 4 : 0) | (h->myers ? 8 : 0) |
+               (h->plane_count > 0 ? 16 : 0) | ((h->plane_flags & 1) ? 32 : 0);
     }
     if (force_wide & 1) {
         CgSetHeader *h = (CgSetHeader *)set.blob.data();
@@ -102,16 +103,21 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     PackedCol pc; pc.base = colp.data(); pc.stride = 1;
     WideCol wc; wc.base = colw.data(); wc.stride = 1;
     // word-granular character loads may touch up to 7 bytes before/after a read: work on a padded copy
-    std::vector<uint8_t> padded((size_t)offsets[n_reads] + 64, 0);
-    if (offsets[n_reads]) memcpy(padded.data() + 32, seq, (size_t)offsets[n_reads]);
-    seq = padded.data() + 32;
+    // (the bit-plane scan reads up to 32 * 8 + 3 bytes in front of a read's end; fill with non-letters)
+    std::vector<uint8_t> padded((size_t)offsets[n_reads] + 640, 0x7f);
+    if (offsets[n_reads]) memcpy(padded.data() + 320, seq, (size_t)offsets[n_reads]);
+    seq = padded.data() + 320;
     const int times = params->times < 1 ? 1 : params->times;
     if (tflags && !qual) { g_err = "no qualities"; return CG_ENOQUAL; }
     for (int64_t r = 0; r < n_reads; ++r) {
         const int n = (int)(offsets[r + 1] - offsets[r]);
         const uint8_t *s = seq + offsets[r];
         for (int i = 0; i < n; ++i) if (s[i] & 0x80) { g_err = "non-ASCII"; return CG_ENONASCII; }
-        if ((force_wide & 64) && S.h->simple_ok && times == 1 && S.ad[0].m <= 64)
+        if ((force_wide & 256) && S.h->simple_ok && times == 1 && S.ad[0].m <= 64)
+            process_read_planes(S, s, qual ? qual + offsets[r] : nullptr, n, tflags,
+                                params->cutoff_front, params->cutoff_back, tbase,
+                                (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);
+        else if ((force_wide & 64) && S.h->simple_ok && times == 1 && S.ad[0].m <= 64)
             process_read_planned(S, s, qual ? qual + offsets[r] : nullptr, n, tflags,
                                  params->cutoff_front, params->cutoff_back, tbase,
                                  (cg_match_rec *)(matches + (size_t)r * set.slots), qtrim ? qtrim + 2 * r : nullptr);
@@ -125,6 +131,33 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
                            params->cutoff_front, params->cutoff_back, tbase, times, pc,
                            wc, (cg_match_rec *)(matches + (size_t)r * times * set.slots),
                            qtrim ? qtrim + 2 * r : nullptr);
+    }
+    return CG_OK;
+}
+
+// class of every read in the bit-plane first stage (0 none, 1 exact, 2 exact path; -1: no plane program)
+extern "C" int hs_plane_classify(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
+                                 const uint8_t *seq, const int64_t *offsets, int64_t n_reads, int32_t *cls)
+{
+    CgBuiltSet set;
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err, nullptr, 0);
+    if (rc != CG_OK) return rc;
+    uint8_t enc[768];
+    cg_build_enc_tables(enc);
+    SetView S = make_set_view(set.blob.data(), set.masks64.data(), enc, nullptr);
+    std::vector<uint8_t> padded((size_t)offsets[n_reads] + 640, 0x7f);
+    if (offsets[n_reads]) memcpy(padded.data() + 320, seq, (size_t)offsets[n_reads]);
+    seq = padded.data() + 320;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int n = (int)(offsets[r + 1] - offsets[r]);
+        cls[r] = -1;
+        if (S.h->plane_count <= 0 || n < 1 || n > 256) continue;
+        const CgAdapter &A = S.ad[0];
+        const uint8_t *ref = S.pool + A.ref_off;
+        const PlaneOut po = n <= 160
+            ? plane_scan_core<5>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + offsets[r + 1], n, A.pf_count == 0)
+            : plane_scan_core<8>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + offsets[r + 1], n, A.pf_count == 0);
+        cls[r] = po.cls;
     }
     return CG_OK;
 }

@@ -595,6 +595,42 @@ def test_both_kernel_schedules_agree():
             finally:
                 del os.environ["CUTADAPT_B200_KERNEL"]
             assert (other == exp).all(), (variant, repr(adapter))
+        os.environ["CUTADAPT_B200_SCAN"] = "shiftand"           # split pipeline with the shift-and first stage
+        try:
+            other, _ = run_set([d], None, reads)
+        finally:
+            del os.environ["CUTADAPT_B200_SCAN"]
+        assert (other == exp).all(), ("shiftand", repr(adapter))
+
+
+def test_bitplane_first_stage_kernel_against_oracle():
+    """
+    cg_pscan_kernel (bit-plane first stage of plain A/C/G/T 3' adapters) + the exact path behind it: ragged reads of
+    0..256 characters (both plane widths) and longer ones (the batch falls back to the shift-and scan), N / lower
+    case / other letters, several adapter copies, with and without fused quality trimming.
+    """
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(99)
+    for trial in range(24):
+        m = rng.choice([8, 13, 13, 20, 33, 33, 50])
+        seq = "AGATCGGAAGAGC" if trial == 0 else "".join(rng.choice("ACGT") for _ in range(m))
+        ad = PA.BackAdapter(seq, max_errors=rng.choice([0.05, 0.1, 0.1, 0.2]), min_overlap=rng.randint(1, 5), name="x")
+        d = ad.descriptor()
+        alpha = rng.choice(["ACGT", "ACGTN", "ACGTNacgtn", "ACGTRYKMEUXacgt"])
+        max_len = rng.choice([100, 150, 150, 160, 240, 256, 500])
+        reads = random_reads(rng, [seq], 3000, alpha, max_len - len(seq) - 2 if max_len <= 256 else max_len)
+        if max_len <= 256:
+            reads = [r[:max_len] for r in reads]
+        for _ in range(3000):
+            ins = rng.randint(0, max_len)
+            r = ("".join(rng.choice(alpha) for _ in range(ins)) + seq + "".join(rng.choice("ACGT") for _ in range(max_len)))[:max_len]
+            reads.append(r.lower() if rng.random() < 0.1 else r)
+        quals = ["".join(chr(33 + rng.choice([2, 2, 20, 30, 38])) for _ in r) for r in reads]
+        qt = trial % 3 == 0
+        got, gqt = run_set([d], None, reads, quals if qt else None, quality_trim=qt, cutoff_front=5, cutoff_back=20)
+        exp, eqt = oracle.oracle_process([d], None, reads, quals if qt else None, quality_trim=qt, cutoff_front=5, cutoff_back=20)
+        assert (gqt == eqt).all() and (got == exp).all(), (trial, repr(ad), max_len)
 
 
 def test_multipass_schedule_agrees_with_one_phase_and_oracle():

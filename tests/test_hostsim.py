@@ -20,7 +20,7 @@ def _single(ref, rate, flags, wr, wq, ic, mo, kind=0):
                                   wildcard_query=wq, indel_cost=ic, min_overlap=mo, kind=kind)])
 
 
-@pytest.mark.parametrize("force_wide", [0, 1, 2, 10, 18, 34, 64])   # packed, wide, two-phase: smem column / registers+refine / registers+inline runs / split main+end passes / planned runs + exact shortcut
+@pytest.mark.parametrize("force_wide", [0, 1, 2, 10, 18, 34, 64, 256])   # packed, wide, two-phase: smem column / registers+refine / registers+inline runs / split main+end passes / planned runs + exact shortcut
 def test_locate_golden(force_wide):
     cases = golden("locate_kat.json.gz")
     for ref, q, rate, flags, wr, wq, ic, mo, expected in cases:
@@ -130,11 +130,57 @@ def test_two_phase_path_equals_general_path():
         qt = rng.random() < 0.3
         params = L.make_params(quality_trim=qt, cutoff_front=5, cutoff_back=20)
         a, qa = hostsim_process(spec, reads, quals if qt else None, params, 0)
-        for mode in (2, 10, 18, 34, 64):
+        for mode in (2, 10, 18, 34, 64, 256):
             b, qb = hostsim_process(spec, reads, quals if qt else None, params, mode)
             assert (a == b).all() and (qa == qb).all(), (mode, repr(ad))
         n_windowed += 1
     assert n_windowed == 250
+
+
+def test_bitplane_first_stage_against_oracle():
+    """
+    plane_scan_core (the first stage of the split pipeline for plain A/C/G/T 3' adapters): reads it settles
+    itself ("no match", exact occurrence) and reads it hands to the exact path must all come out as the
+    oracle says -- adapters of 5..60 bases, error rates up to 0.3, reads of 0..400 characters with N, lower
+    case and other letters, several copies, with and without quality trimming.
+    """
+    import cutadapt_b200.adapters as PA
+    from util import hostsim_plane_classes
+
+    rng = random.Random(4242)
+    seen = np.zeros(4, dtype=np.int64)
+    n_planes = 0
+    for trial in range(160):
+        m = rng.choice([rng.randint(5, 12), 13, rng.randint(14, 33), 33, rng.randint(34, 60)])
+        seq = "".join(rng.choice("ACGT") for _ in range(m))
+        if trial == 0:
+            seq = "AGATCGGAAGAGC"
+        kw = dict(max_errors=rng.choice([0, 0.05, 0.1, 0.1, 0.15, 0.2, 0.3]), min_overlap=rng.randint(1, 6))
+        ad = PA.BackAdapter(seq, name="x", **kw)
+        spec = spec_of(ad)
+        alpha = rng.choice(["ACGT", "ACGT", "ACGTN", "ACGTNacgtn", "ACGTRYKMEUXacgt"])
+        max_len = rng.choice([40, 150, 150, 158, 200, 256, 400])
+        reads = random_reads(rng, [seq], 60, alpha, max_len)
+        # reads made the way the benchmark makes them: insert + adapter + tail, cut to a fixed length
+        for _ in range(40):
+            L0 = rng.choice([100, 150, 160, 161, 250])
+            ins = rng.randint(0, L0)
+            r = ("".join(rng.choice(alpha) for _ in range(ins)) + seq + "".join(rng.choice("ACGT") for _ in range(L0)))[:L0]
+            if rng.random() < 0.3:
+                r = r.lower() if rng.random() < 0.5 else r[: ins // 2] + r[ins // 2:].lower()
+            reads.append(r)
+        quals = ["".join(chr(33 + rng.choice([2, 2, 20, 30, 38])) for _ in r) for r in reads]
+        qt = rng.random() < 0.3
+        params = L.make_params(quality_trim=qt, cutoff_front=5, cutoff_back=20)
+        exp, eqt = oracle.oracle_process(spec.adapters, spec.groups, reads, quals if qt else None, qt, 5, 20, 33, 1)
+        got, gqt = hostsim_process(spec, reads, quals if qt else None, params, 256)
+        assert (gqt == eqt).all() and (got == exp).all(), repr(ad)
+        cls = hostsim_plane_classes(spec, reads)
+        if (cls >= 0).any():
+            n_planes += 1
+        seen += np.bincount(cls + 1, minlength=4)
+    # the stage must actually decide reads: most adapters qualify, and all three classes occur
+    assert n_planes > 80 and seen[1] > 1000 and seen[2] > 1000 and seen[3] > 500, (n_planes, seen)
 
 
 def test_two_phase_on_golden_single_adapters():
@@ -147,7 +193,7 @@ def test_two_phase_on_golden_single_adapters():
         multi = build_adapters(PA, case["adapters"])
         spec = spec_of(multi)
         reads = [r for r, _ in case["reads"]]
-        for mode in (2, 10, 18, 34, 64):
+        for mode in (2, 10, 18, 34, 64, 256):
             recs, _ = hostsim_process(spec, reads, force_wide=mode)
             for i, (read, expected) in enumerate(case["reads"]):
                 assert match_desc(multi.matches_from_records(recs[i, 0], read)) == expected, (mode, case["adapters"], read)
@@ -243,7 +289,7 @@ def test_fused_nextseq_and_quality_trim_against_oracle():
                                nextseq_cutoff=rng.choice([10, 20, 30]))
         exp, eqt = oracle.oracle_process(spec.adapters, spec.groups, reads, quals, qt, params.cutoff_front, 20, 33, 1,
                                          nextseq_cutoff=params.nextseq_cutoff)
-        modes = [0, 128] if len(ads) > 1 else [0, 2, 10, 34, 64]
+        modes = [0, 128] if len(ads) > 1 else [0, 2, 10, 34, 64, 256]
         for mode in modes:
             try:
                 got, gqt = hostsim_process(spec, reads, quals, params, force_wide=mode)

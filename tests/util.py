@@ -79,6 +79,21 @@ def hostsim_process(spec, seqs, quals=None, params=None, force_wide=0):
     return out, qt
 
 
+def hostsim_plane_classes(spec, seqs):
+    """Class of every read in the bit-plane first stage: 0 no match, 1 exact occurrence, 2 exact path, -1 n/a."""
+    from cutadapt_b200 import _lib as L
+
+    arr, n, garr, ng = spec.to_ctypes()
+    data, offs = L.pack_strings(seqs)
+    cls = np.zeros(len(seqs), dtype=np.int32)
+    lib = hostsim_lib()
+    rc = lib.hs_plane_classify(arr, n, garr, ng, C.c_void_p(data.ctypes.data), C.c_void_p(offs.ctypes.data),
+                               C.c_int64(len(seqs)), C.c_void_p(cls.ctypes.data))
+    if rc:
+        raise RuntimeError((rc, lib.hs_last_error()))
+    return cls
+
+
 # ---- building adapters from the golden "adapters_kat" specs ----------------------------------
 
 
