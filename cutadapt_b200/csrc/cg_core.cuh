@@ -729,16 +729,13 @@ struct PlaneOut {
 #define CG_PLANE_EXACT 1
 #define CG_PLANE_SLOW 2
 
-// acc &= plane << s   (multi-word, s in 0..31), words b0 .. W-1 only
+// one chain step: acc = (acc << 1 | newbit) & plane
 template <int W>
-CG_HD void plane_and_shift(uint32_t (&acc)[W], const uint32_t (&P)[W], uint32_t s, int b0, bool first)
+CG_HD void plane_step(uint32_t (&acc)[W], const uint32_t (&P)[W], uint32_t newbit)
 {
 #pragma unroll
-    for (int b = W - 1; b >= 0; --b) {
-        if (b < b0) continue;
-        const uint32_t x = b == 0 ? (P[0] << s) : cg_funnel_l(P[b - 1], P[b], s);
-        acc[b] = first ? x : (acc[b] & x);
-    }
+    for (int b = W - 1; b >= 1; --b) acc[b] = cg_funnel_l(acc[b - 1], acc[b], 1) & P[b];
+    acc[0] = ((acc[0] << 1) | newbit) & P[0];
 }
 
 // x <<= s  (multi-word, s in 0..63)
@@ -760,7 +757,7 @@ CG_HD void plane_shl(uint32_t (&x)[W], uint32_t s)
 // the caller routes everything else to the exact path).  The bytes [end - 32 W - 3, end + 4) must be
 // readable (their values outside the window do not matter).
 template <int W>
-CG_HD PlaneOut plane_scan_core(const CgPlaneKmer *prog, int n_prog, int plane_flags, const CgAdapter &A,
+CG_HD PlaneOut plane_scan_core(const uint32_t *ops, int n_ops, int plane_flags, const CgAdapter &A,
                                const uint8_t *ref, const uint8_t *end, int n, bool always_pass)
 {
     PlaneOut out; out.cls = CG_PLANE_SLOW; out.s0 = 0; out.bad = 0;
@@ -821,46 +818,58 @@ CG_HD PlaneOut plane_scan_core(const CgPlaneKmer *prog, int n_prog, int plane_fl
     uint32_t M[W], E[W];                             // locator hits / all chunks, by the end of the WHOLE adapter
 #pragma unroll
     for (int b = 0; b < W; ++b) { M[b] = 0; E[b] = 0xFFFFFFFFu; }
-    for (int q = 0; q < n_prog; ++q) {
-        const CgPlaneKmer K = prog[q];
-        const int len = K.len;
-        // words that can hold the end of an occurrence inside the k-mer's window
-        int b0 = 0;
-        if (K.type == CG_SCAN_SUFFIX) b0 = cg_max(0, (32 * W - (int)K.window) >> 5);
-        uint32_t acc[W];
+    const CgPlaneEmit *emits = (const CgPlaneEmit *)((const uint8_t *)ops + (((size_t)n_ops * 4 + 7) & ~(size_t)7));
+    uint32_t acc[W];
 #pragma unroll
-        for (int b = 0; b < W; ++b) acc[b] = 0;
-        for (int t = 0; t < len; ++t) {
-            const uint32_t code = (uint32_t)(K.codes >> (2 * t)) & 3u;
-            const uint32_t s = (uint32_t)(len - 1 - t);
-            const bool first = t == 0;
-            if (code == 0) plane_and_shift<W>(acc, PA, s, b0, first);
-            else if (code == 1) plane_and_shift<W>(acc, PC, s, b0, first);
-            else if (code == 2) plane_and_shift<W>(acc, PT, s, b0, first);
-            else plane_and_shift<W>(acc, PG, s, b0, first);
-        }
-        // acc: bit e set iff the k-mer ends at plane index e (occurrences reaching in front of the window
-        // are impossible: the planes are blank there)
-        uint32_t any = 0;
-        if (K.type == CG_SCAN_SUFFIX) {
-            // the occurrence must start inside the last `window` characters: e >= 32 W - window + len - 1
-            const int e_min = 32 * W - (int)K.window + len - 1;
+    for (int b = 0; b < W; ++b) acc[b] = 0;
+#if defined(__CUDA_ARCH__)
+    // keep the four planes in registers: left alone, ptxas re-derives them from LO / HI / len inside every
+    // chain step (two LOP3 per word instead of one)
 #pragma unroll
-            for (int b = 0; b < W; ++b) {
-                const int fv = e_min - 32 * b;
-                const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
-                if (b >= b0) any |= acc[b] & keep;
+    for (int b = 0; b < W; ++b)
+        asm volatile("" : "+r"(PA[b]), "+r"(PC[b]), "+r"(PT[b]), "+r"(PG[b]));
+#endif
+    for (int i = 0; i < n_ops; ++i) {
+        const uint32_t op = ops[i];
+        const uint32_t code = op & 3u;
+        if (op & CG_PLANE_OP_NEW) {                  // first character of a chain: acc = plane
+#pragma unroll
+            for (int b = 0; b < W; ++b) acc[b] = code == 0 ? PA[b] : (code == 1 ? PC[b] : (code == 2 ? PT[b] : PG[b]));
+        } else if (code == 0) plane_step<W>(acc, PA, 0u);
+        else if (code == 1) plane_step<W>(acc, PC, 0u);
+        else if (code == 2) plane_step<W>(acc, PT, 0u);
+        else plane_step<W>(acc, PG, 0u);
+        // acc: bit e set iff the chain's text so far ends at plane index e (occurrences reaching in front of
+        // the window are impossible: the planes are blank there)
+        uint32_t em = op >> 8;
+        while (em) {
+            const CgPlaneEmit K = emits[(em & 255u) - 1u];
+            em >>= 8;
+            uint32_t any = 0;
+            if (K.type == CG_SCAN_SUFFIX) {
+                // the occurrence must start inside the last `window` (<= 64) characters:
+                // e >= 32 W - window + len - 1, which lies in the last two words
+                const int e_min = 32 * W - (int)K.window + (int)K.len - 1;
+#pragma unroll
+                for (int b = (W >= 2 ? W - 2 : 0); b < W; ++b) {
+                    const int fv = e_min - 32 * b;
+                    const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
+                    any |= acc[b] & keep;
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < W; ++b) any |= acc[b];
             }
-        } else {
+            if ((K.flags & CG_PLANE_PASS) && any) pass = true;
+            if (K.flags & CG_PLANE_LOC) {
+                if (any) anyhit = true;
+                uint32_t f[W];
 #pragma unroll
-            for (int b = 0; b < W; ++b) any |= acc[b];
-        }
-        if ((K.flags & CG_PLANE_PASS) && any) pass = true;
-        if (K.flags & CG_PLANE_LOC) {
-            if (any) anyhit = true;
-            plane_shl<W>(acc, (uint32_t)(A.m - (int)K.bend));
+                for (int b = 0; b < W; ++b) f[b] = acc[b];
+                plane_shl<W>(f, (uint32_t)(A.m - (int)K.bend));
 #pragma unroll
-            for (int b = 0; b < W; ++b) { M[b] |= acc[b]; E[b] &= acc[b]; }
+                for (int b = 0; b < W; ++b) { M[b] |= f[b]; E[b] &= f[b]; }
+            }
         }
     }
     if (!anyhit && !pass) { out.cls = CG_PLANE_NONE; return out; }
@@ -2071,6 +2080,90 @@ CG_HD int end_overlap_myers_t(const CgAdapter &A, const uint32_t *peq, const int
     return inexact ? -1 : best;
 }
 
+// Does the restarted DP of the run [lo, hi] ever see a bottom-row cell with cost <= k?  The same bit-vector pass
+// as plan_runs_myers_t, restarted at column lo like the run (column lo: cost i; row 0 free): D'[m][j] for
+// j in (lo, hi].  The reference evaluates a bottom-row candidate only where that cost is <= k
+// (_align.pyx:490-514), so a run without such a column changes nothing and can be dropped -- a locator chunk
+// that occurs by chance, far from any real occurrence of the adapter.
+template <class T>
+CG_HD bool run_has_candidate_t(const CgAdapter &A, const uint32_t *peq, const uint8_t *p, int n, int lo, int hi)
+{
+    const int m = A.m, k = A.k;
+    const T mmask = m >= (int)(8 * sizeof(T)) ? (T) ~(T)0 : (T)(((T)1 << m) - 1);
+    const T top = (T)1 << (m - 1);
+    T Pv = mmask, Mv = 0;
+    int score = m;
+    CG_CHARPTR(cp, A.reverse ? p + (n - 1) : p);
+    CG_TABPTR(peq_t, peq);
+    const int cstride = A.reverse ? -1 : 1;
+    bool any = false;
+    for (int j = lo + 1; j <= hi; ++j) {
+        const int ch = (int)(CG_CHAR(cp + cstride * (j - 1)) & 127u);
+        T Eq = (T)CG_TAB32(peq_t, ch);
+        if (sizeof(T) > 4) Eq |= (T)((unsigned long long)CG_TAB32(peq_t, 128 + ch) << 32);
+        const T Xv = Eq | Mv;
+        const T Xh = (T)((((Eq & Pv) + Pv) ^ Pv) | Eq);
+        T Ph = (T)(Mv | ~(Xh | Pv));
+        T Mh = Pv & Xh;
+        score += (Ph & top) ? 1 : 0;
+        score -= (Mh & top) ? 1 : 0;
+        Ph = (T)(Ph << 1); Mh = (T)(Mh << 1);
+        Pv = (T)(Mh | ~(Xv | Ph));
+        Mv = Ph & Xv;
+        any = any || score <= k;
+    }
+    return any;
+}
+
+// Second half of the plan for windowed adapters: R = the runs around the locator hits (a superset is fine).
+//   * hit runs that are not also the final run are dropped when they hold no bottom-row candidate;
+//   * the end window of a 3' adapter (last-column scan, _align.pyx:536-572) is needed only if some cell
+//     (i, n) is acceptable; if nothing else is left and every acceptable cell is an exact overlap, the
+//     result is the longest one (end_overlap_myers_t).
+CG_HD void plan_finish(const SetView &S, const uint8_t *p, int n, const RunList &R0, RunPlan &P)
+{
+    const CgAdapter &A = S.ad[0];
+    const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
+    const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
+    const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
+    const bool eir = (A.flags & 4) != 0;
+    const int lo_end = cg_max(0, n - 1 - A.m - A.k);
+    const bool can_filter = A.m <= 64 && !(A.flags & 1) && (A.flags & 2) && (A.flags & 8) && A.indel_cost == 1;
+    RunList R;
+    R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    bool covered = false;                             // the last kept run is also the end window
+    for (int r = 0; r < R0.n; ++r) {
+        const int lo = r == 0 ? R0.lo0 : (r == 1 ? R0.lo1 : R0.lo2);
+        const int hi = r == 0 ? R0.hi0 : (r == 1 ? R0.hi1 : R0.hi2);
+        const bool is_final = eir && r == R0.n - 1 && lo <= lo_end && hi == n;
+        bool keep = true;
+        if (can_filter && !is_final)
+            keep = A.m <= 32 ? run_has_candidate_t<uint32_t>(A, peq, p, n, lo, hi)
+                             : run_has_candidate_t<unsigned long long>(A, peq, p, n, lo, hi);
+        if (!keep) continue;
+        if (R.n == 0) { R.lo0 = lo; R.hi0 = hi; }
+        else if (R.n == 1) { R.lo1 = lo; R.hi1 = hi; }
+        else { R.lo2 = lo; R.hi2 = hi; }
+        ++R.n;
+        covered = is_final;
+    }
+    P.n_runs = R.n; P.lo0 = R.lo0; P.hi0 = R.hi0; P.lo1 = R.lo1; P.hi1 = R.hi1; P.lo2 = R.lo2; P.hi2 = R.hi2;
+    if (!eir || covered) return;
+    if (can_filter) {                                 // what can the last-column scan accept?
+        const int r = A.m <= 32 ? end_overlap_myers_t<uint32_t>(A, peq, ncnt, maxcost, p, n, lo_end)
+                                : end_overlap_myers_t<unsigned long long>(A, peq, ncnt, maxcost, p, n, lo_end);
+        if (r == 0) return;                           // nothing: no end window
+        if (r > 0 && R.n == 0) { P.exact = 2; P.s0 = r; return; }
+    }
+    // every bottom-row cell with cost <= k lies inside a hit run, so the separate end window has none to evaluate
+    P.end_idx = R.n;
+    if (R.n == 0) { P.lo0 = lo_end; P.hi0 = n; }
+    else if (R.n == 1) { P.lo1 = lo_end; P.hi1 = n; }
+    else if (R.n == 2) { P.lo2 = lo_end; P.hi2 = n; }
+    else { P.lo3 = lo_end; P.hi3 = n; }
+    P.n_runs = R.n + 1;
+}
+
 CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, int gs, uint32_t rs0,
                      uint32_t rs1, RunPlan &P)
 {
@@ -2119,35 +2212,27 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
     if (A.reverse) plan_hit_runs_dir<true>(S.scan, S.h->scan_count, S.pool, A, p + (n - 1), n, hits, gs, rs0, rs1, want_exact, R, P.exact, P.s0);
     else plan_hit_runs_dir<false>(S.scan, S.h->scan_count, S.pool, A, p, n, hits, gs, rs0, rs1, want_exact, R, P.exact, P.s0);
     if (P.exact) return;
-    P.n_runs = R.n; P.lo0 = R.lo0; P.hi0 = R.hi0; P.lo1 = R.lo1; P.hi1 = R.hi1; P.lo2 = R.lo2; P.hi2 = R.hi2;
-    if (A.flags & 4) {                                           // STOP_IN_REFERENCE: last-column scan
-        const int lo_end = cg_max(0, n - 1 - A.m - A.k);
-        if (R.n == 0 && !(A.flags & 1) && A.m <= 64) {           // no hit anywhere: see end_overlap_myers_t
-            const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
-            const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
-            const uint32_t *peq = (const uint32_t *)(S.pool + A.peq_off);
-            const int r = A.m <= 32 ? end_overlap_myers_t<uint32_t>(A, peq, ncnt, maxcost, p, n, lo_end)
-                                    : end_overlap_myers_t<unsigned long long>(A, peq, ncnt, maxcost, p, n, lo_end);
-            if (r == 0) return;                                  // P.n_runs == 0: no match
-            if (r > 0) { P.exact = 2; P.s0 = r; return; }
-        }
-        bool covered = false;
-        if (R.n > 0) {
-            const int lo_last = R.n == 1 ? R.lo0 : (R.n == 2 ? R.lo1 : R.lo2);
-            const int hi_last = R.n == 1 ? R.hi0 : (R.n == 2 ? R.hi1 : R.hi2);
-            covered = lo_last <= lo_end && hi_last == n;
-        }
-        if (!covered) {
-            // every bottom-row cell with cost <= k lies inside a hit run, so the separate end window
-            // has none to evaluate
-            P.end_idx = R.n;
-            if (R.n == 0) { P.lo0 = lo_end; P.hi0 = n; }
-            else if (R.n == 1) { P.lo1 = lo_end; P.hi1 = n; }
-            else if (R.n == 2) { P.lo2 = lo_end; P.hi2 = n; }
-            else { P.lo3 = lo_end; P.hi3 = n; }
-            P.n_runs = R.n + 1;
-        }
+    plan_finish(S, p, n, R, P);
+}
+
+// The plan of a read whose locator hits come from the bit-plane stage: `hit_ends` holds up to 8 plane
+// indices (one byte each, ascending) of adapter ends the chunk hits point at, off0 the plane index of the
+// window's first character.  A hit that implies the adapter start s gives the run [s - k, s + m + k]
+// (the same window refine_runs / plan_hit_runs_dir derive from a chunk's end position).
+CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, uint32_t ends_lo, uint32_t ends_hi, int n_hits,
+                            int off0, RunPlan &P)
+{
+    const CgAdapter &A = S.ad[0];
+    P.n_runs = 0; P.lo0 = P.hi0 = P.lo1 = P.hi1 = P.lo2 = P.hi2 = P.lo3 = P.hi3 = 0;
+    P.end_idx = -1; P.exact = 0; P.s0 = 0;
+    RunList R;
+    R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
+    for (int h = 0; h < n_hits; ++h) {
+        const int e = (int)(((h < 4 ? ends_lo : ends_hi) >> (8 * (h & 3))) & 255u);
+        const int s = e - (A.m - 1) - off0;
+        runs_add(R, s - A.k, s + A.m + A.k, n);
     }
+    plan_finish(S, p, n, R, P);
 }
 
 // P.exact == 2: the exact overlap of the adapter's first `len` characters with the end of the read
@@ -2229,9 +2314,9 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
 
 // Host-sim driver of the bit-plane first stage (tests/hostsim, mode 256): plane_scan_core decides what it
 // can, everything else takes the planned scheduling above -- exactly what cg_pscan_kernel + cg_list_kernel do.
-CG_HD const CgPlaneKmer *plane_program(const SetView &S)
+CG_HD const uint32_t *plane_program(const SetView &S)
 {
-    return (const CgPlaneKmer *)((const uint8_t *)S.h + S.h->plane_off);
+    return (const uint32_t *)((const uint8_t *)S.h + S.h->plane_off);
 }
 
 CG_HD void process_read_planes(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,

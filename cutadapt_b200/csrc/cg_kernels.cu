@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(CG_NT) cg_pscan_kernel(const CgKernelArgs a)
     __syncthreads();
     const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
     const CgAdapter &A = S.ad[0];
-    const CgPlaneKmer *prog = plane_program(S);
+    const uint32_t *prog = plane_program(S);
     const int n_prog = S.h->plane_count, pflags = S.h->plane_flags;
     const uint8_t *ref = S.pool + A.ref_off;
     const bool always_pass = A.pf_count == 0;

@@ -170,9 +170,10 @@ int plane_code(const std::array<uint64_t, 2> &set)
 // characters, a forward adapter of <= 64 characters with locator chunks.
 void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowed, int exact_ok, int myers,
                          const std::vector<ScanKmer> &whole, const std::vector<ScanKmer> &suffix,
-                         const std::vector<ScanKmer> &prefix, std::vector<CgPlaneKmer> &out, int &flags)
+                         const std::vector<ScanKmer> &prefix, std::vector<uint8_t> &out, int &n_ops, int &flags)
 {
     out.clear();
+    n_ops = 0;
     flags = 0;
     if (!windowed || myers || A.reverse || !prefix.empty() || A.m > 64 || !A.compare_ascii) return;
     std::vector<CgPlaneKmer> prog;
@@ -224,12 +225,53 @@ void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowe
         }
     }
     if (exact_ok && unambiguous && plain && implies_pass) flags |= 1;
-    out.swap(prog);
+    // chains: sort the k-mers by their code strings; a k-mer that extends the chain in progress adds
+    // only its remaining characters
+    std::vector<int> order(prog.size());
+    for (size_t i = 0; i < prog.size(); ++i) order[i] = (int)i;
+    auto text = [&](int i) {
+        std::string t;
+        for (int c = 0; c < prog[i].len; ++c) t.push_back((char)('0' + ((prog[i].codes >> (2 * c)) & 3)));
+        return t;
+    };
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return text(a) < text(b); });
+    std::vector<uint32_t> ops;
+    std::vector<CgPlaneEmit> emits;
+    std::string chain;
+    for (int idx : order) {
+        const std::string t = text(idx);
+        CgPlaneEmit em;
+        memset(&em, 0, sizeof em);
+        em.len = prog[idx].len; em.type = prog[idx].type; em.flags = prog[idx].flags; em.bend = prog[idx].bend;
+        em.window = prog[idx].window;
+        emits.push_back(em);
+        const uint32_t eno = (uint32_t)emits.size();      // index + 1
+        const bool extends = !chain.empty() && t.size() >= chain.size() && t.compare(0, chain.size(), chain) == 0;
+        if (extends && t.size() == chain.size()) {         // same text: second emit slot of the last step
+            if (((ops.back() >> 16) & 255u) == 0) { ops.back() |= eno << 16; continue; }
+        }
+        size_t from = 0;
+        if (extends && t.size() > chain.size()) from = chain.size();
+        for (size_t c = from; c < t.size(); ++c) {
+            uint32_t op = (uint32_t)(t[c] - '0');
+            if (c == 0) op |= CG_PLANE_OP_NEW;
+            if (c + 1 == t.size()) op |= eno << 8;
+            ops.push_back(op);
+        }
+        chain = t;
+    }
+    if (emits.size() > 255 || ops.size() > 1024) return;
+    n_ops = (int)ops.size();
+    flags |= (int)(emits.size() << 8);
+    out.resize((ops.size() * 4 + 7) / 8 * 8 + emits.size() * sizeof(CgPlaneEmit));
+    memcpy(out.data(), ops.data(), ops.size() * 4);
+    memcpy(out.data() + (ops.size() * 4 + 7) / 8 * 8, emits.data(), emits.size() * sizeof(CgPlaneEmit));
 }
 
 bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc768,
                         const uint8_t *enc_ref, std::vector<uint8_t> &pool, std::vector<CgScanWord> &words,
-                        int &windowed, int &exact_ok, int &myers, std::vector<CgPlaneKmer> &planes, int &plane_flags)
+                        int &windowed, int &exact_ok, int &myers, std::vector<uint8_t> &planes, int &plane_ops,
+                        int &plane_flags)
 {
     myers = 0;
     std::vector<ScanKmer> whole, suffix, prefix;
@@ -329,7 +371,7 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
     pack_words(whole, CG_SCAN_WHOLE, false, pool, words);
     pack_words(suffix, CG_SCAN_SUFFIX, true, pool, words);
     pack_words(prefix, CG_SCAN_PREFIX, true, pool, words);
-    build_plane_program(A, enc_ref, windowed, exact_ok, myers, whole, suffix, prefix, planes, plane_flags);
+    build_plane_program(A, enc_ref, windowed, exact_ok, myers, whole, suffix, prefix, planes, plane_ops, plane_flags);
     return words.size() <= 64;
 }
 
@@ -591,21 +633,21 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
 
     // two-phase program for the common case: one SINGLE aligner adapter with packed cells
     std::vector<CgScanWord> scan_words;
-    std::vector<CgPlaneKmer> plane_kmers;
-    int plane_flags = 0;
+    std::vector<uint8_t> plane_kmers;      // ops + emits of the bit-plane program
+    int plane_flags = 0, plane_ops = 0;
     int simple_ok = 0, windowed = 0, exact_ok = 0, myers = 0;
     if (n_adapters == 1 && n_groups == 1 && G[0].type == CG_GROUP_SINGLE && A[0].kind == CG_KIND_ALIGNER &&
         A[0].cell_mode == CG_CELL_PACKED32) {
         std::vector<uint8_t> pool2 = pool;
         std::vector<CgScanWord> words;
         if (build_scan_program(ads[0], A[0], enc, pool.data() + A[0].ref_off, pool2, words, windowed, exact_ok, myers,
-                               plane_kmers, plane_flags)) {
+                               plane_kmers, plane_ops, plane_flags)) {
             pool.swap(pool2);
             scan_words.swap(words);
             simple_ok = 1;
         } else {
             windowed = 0; exact_ok = 0; myers = 0;
-            plane_kmers.clear(); plane_flags = 0;
+            plane_kmers.clear(); plane_flags = 0; plane_ops = 0;
         }
     }
 
@@ -620,8 +662,8 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     H.entries_off = off; off += (uint32_t)(E.size() * sizeof(CgEntry)); off = align_up(off, 16);
     H.scan_off = off; off += (uint32_t)(scan_words.size() * sizeof(CgScanWord)); off = align_up(off, 16);
     H.simple_ok = simple_ok; H.scan_count = (int32_t)scan_words.size(); H.windowed = windowed; H.exact_ok = exact_ok; H.myers = myers;
-    H.plane_off = off; off += (uint32_t)(plane_kmers.size() * sizeof(CgPlaneKmer)); off = align_up(off, 16);
-    H.plane_count = (int32_t)plane_kmers.size(); H.plane_flags = plane_flags;
+    H.plane_off = off; off += (uint32_t)plane_kmers.size(); off = align_up(off, 16);
+    H.plane_count = plane_ops; H.plane_flags = plane_flags;
     H.pool_off = off; off += (uint32_t)pool.size(); off = align_up(off, 16);
     H.total_bytes = off;
     out.blob.assign(off, 0);
@@ -632,7 +674,7 @@ int cg_build_set(const cg_adapter_desc *ads, int n_adapters, const cg_group_desc
     if (!scan_words.empty())
         memcpy(out.blob.data() + H.scan_off, scan_words.data(), scan_words.size() * sizeof(CgScanWord));
     if (!plane_kmers.empty())
-        memcpy(out.blob.data() + H.plane_off, plane_kmers.data(), plane_kmers.size() * sizeof(CgPlaneKmer));
+        memcpy(out.blob.data() + H.plane_off, plane_kmers.data(), plane_kmers.size());
     if (!pool.empty()) memcpy(out.blob.data() + H.pool_off, pool.data(), pool.size());
     out.n_adapters = n_adapters; out.n_groups = n_groups; out.simple_ok = simple_ok;
     if (out.masks64.empty()) out.masks64.assign(128, 0);   // never hand the kernel a null table

@@ -91,18 +91,22 @@ struct CgSetHeader {        // 80 bytes
     int32_t myers;          // 1: the plan stage finds the DP runs with a bit-vector edit-distance pass over the
                             //    read instead of locator chunks (adapters whose chunks would hit everywhere)
     // bit-plane scan program (plane_scan_core): the same k-mers as 2-bit codes, matched word-parallel
-    int32_t plane_count;    // number of CgPlaneKmer (0: the adapter does not qualify)
-    uint32_t plane_off;     // blob offset of CgPlaneKmer[plane_count]
-    int32_t plane_flags;    // bit 0: an exact occurrence found by the planes may be reported without DP
+    int32_t plane_count;    // number of op words (0: the adapter does not qualify)
+    uint32_t plane_off;     // blob offset of uint32 ops[plane_count], then (8-aligned) CgPlaneEmit[n_emits]
+    int32_t plane_flags;    // bit 0: an exact occurrence found by the planes may be reported without DP;
+                            // bits 8-15: n_emits
 };
 
-// One k-mer of the bit-plane scan.  Characters are 2-bit codes taken from bits 1 and 2 of the ASCII
-// code (A = 0, C = 1, T = 2, G = 3; the same for lower case); only k-mers whose every position matches
-// exactly one of A/C/G/T (either case) can be expressed, which the host checks.
+// Bit-plane scan program.  Characters are 2-bit codes taken from bits 1 and 2 of the ASCII code
+// (A = 0, C = 1, T = 2, G = 3; the same for lower case); only k-mers whose every position matches exactly
+// one of A/C/G/T (either case) can be expressed, which the host checks.  The k-mers are laid out as
+// CHAINS of one-character steps, acc = (acc << 1) & plane[code], so that k-mers sharing a prefix
+// (AGA, AGAT, AGATC, AGATCGG) share the steps; a step may EMIT up to two k-mers that end with it.
+//   op word: bits 0-1 code, bit 2 first step of a chain, bits 8-15 / 16-23: emit index + 1 (0 = none)
 #define CG_PLANE_PASS 1u    // a k-mer of the KmerFinder (prefilter verdict)
 #define CG_PLANE_LOC 2u     // a locator chunk (one of the k+1 pieces of the adapter)
-struct CgPlaneKmer {        // 16 bytes
-    uint64_t codes;         // 2 bits per character, first character in the low bits
+#define CG_PLANE_OP_NEW 4u
+struct CgPlaneEmit {        // 8 bytes
     uint8_t len;            // 1..32
     uint8_t type;           // CG_SCAN_WHOLE or CG_SCAN_SUFFIX
     uint8_t flags;          // CG_PLANE_*
@@ -110,7 +114,13 @@ struct CgPlaneKmer {        // 16 bytes
     uint16_t window;        // SUFFIX: the k-mer must lie within the last `window` characters (<= 64)
     uint16_t pad;
 };
-static_assert(sizeof(CgPlaneKmer) == 16, "CgPlaneKmer layout");
+static_assert(sizeof(CgPlaneEmit) == 8, "CgPlaneEmit layout");
+// host-side form of one k-mer (cg_setbuild.cpp)
+struct CgPlaneKmer {
+    uint64_t codes;         // 2 bits per character, first character in the low bits
+    uint8_t len, type, flags, bend;
+    uint16_t window, pad;
+};
 
 // Anchored-adapter index (AdapterIndex, adapters.py:1289-1551) as an open-addressing hash table.
 struct CgIndexEntry {       // 16 bytes; len == 0 marks an empty slot

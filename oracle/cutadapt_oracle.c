@@ -559,3 +559,157 @@ int oracle_locate_batch(const unsigned char *ref, int m, const unsigned char *se
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* The whole per-read pass in C (the composition oracle.py restates in Python), so that   */
+/* the parity tests can check >= 10^6 reads per configuration in seconds; oracle.py runs  */
+/* it from several threads over disjoint read ranges.                                     */
+/*   <Adapter>.match_to        adapters.py:707-724, 758-786, 815-832, 862-890, 915-935,   */
+/*                             963-975, 1000-1012                                         */
+/*   LinkedAdapter.match_to    adapters.py:1215-1227 (score/errors: 1113-1130)            */
+/*   MultipleAdapters.match_to adapters.py:1265-1286                                      */
+/*   NextseqQualityTrimmer, QualityTrimmer, AdapterCutter rounds                          */
+/*                             modifiers.py:825-858, 225-231 (order: cli.py:940-953)      */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    const unsigned char *seq;   /* adapter characters as the aligner gets them */
+    int32_t m;
+    int32_t flags, wildcard_ref, wildcard_query, indel_cost, min_overlap;
+    int32_t kind;               /* 0 aligner, 1 PrefixComparer, 2 SuffixComparer */
+    int32_t reverse_read;       /* Rightmost* adapters: search the reversed read (adapters.py:766, 870) */
+    int32_t remove;             /* 0 before, 1 after, 2 auto (AnywhereAdapter, adapters.py:930-935) */
+    int32_t n_entries;          /* 0: no KmerFinder (MockKmerFinder: always present) */
+    double max_error_rate;
+    const oracle_kmer_entry *entries;
+    const uint64_t *masks;
+} oracle_adapter;
+
+typedef struct { int32_t type, a0, a1, front_required, back_required; } oracle_group;   /* type 0 single, 1 linked */
+
+typedef struct { int adapter, astart, astop, rstart, rstop, score, errors, remove; } oracle_hit;
+
+/* returns 1 match, 0 none, < 0 error */
+static int batch_match_single(const oracle_adapter *A, int ai, const unsigned char *s, int n, unsigned char *tmp,
+                              oracle_hit *h)
+{
+    const unsigned char *q = s;
+    int out[6], rc, i;
+    if (A->reverse_read) {
+        for (i = 0; i < n; i++) tmp[i] = s[n - 1 - i];
+        q = tmp;
+    }
+    if (A->n_entries > 0) {
+        rc = oracle_kmers_present(A->entries, A->masks, A->n_entries, q, n);
+        if (rc <= 0) return rc;
+    }
+    if (A->kind == 0)
+        rc = oracle_locate(A->seq, A->m, q, n, A->max_error_rate, A->flags, A->wildcard_ref, A->wildcard_query,
+                           A->indel_cost, A->min_overlap, out);
+    else if (A->kind == 1)
+        rc = oracle_prefix_compare(A->seq, A->m, q, n, A->max_error_rate, A->wildcard_ref, A->wildcard_query,
+                                   A->min_overlap, out);
+    else
+        rc = oracle_suffix_compare(A->seq, A->m, q, n, A->max_error_rate, A->wildcard_ref, A->wildcard_query,
+                                   A->min_overlap, out);
+    if (rc <= 0) return rc;
+    h->adapter = ai;
+    h->astart = out[0]; h->astop = out[1]; h->rstart = out[2]; h->rstop = out[3];
+    h->score = out[4]; h->errors = out[5];
+    if (A->reverse_read) {                                        /* adapters.py:777-785, 881-889 */
+        h->astart = A->m - out[1]; h->astop = A->m - out[0];
+        h->rstart = n - out[3]; h->rstop = n - out[2];
+    }
+    h->remove = A->remove;
+    if (h->remove == 2) h->remove = h->rstart == 0 ? 0 : 1;       /* adapters.py:930-935 */
+    return 1;
+}
+
+static void batch_trim(const oracle_hit *h, int *s, int *e)       /* Match.trimmed: adapters.py:453-454, 486-487 */
+{
+    if (h->remove == 0) *s += h->rstop; else *e = *s + h->rstart;
+}
+
+static void batch_put(int32_t *rec, const oracle_hit *h, int group, int searched)
+{
+    rec[0] = h->adapter; rec[1] = h->astart; rec[2] = h->astop; rec[3] = h->rstart; rec[4] = h->rstop;
+    rec[5] = h->score; rec[6] = h->errors;
+    rec[7] = (int32_t)((uint32_t)(group & 255) | (h->remove == 1 ? 256u : 0u) | ((uint32_t)(searched & 0xFFFF) << 16));
+}
+
+/*
+ * records: (r_end - r_begin) x times x slots x 8 int32 in the cg_match layout (adapter = -1: none),
+ * qtrim: (r_end - r_begin) x 2.  Both are indexed relative to r_begin.  max_len bounds the reads.
+ */
+int oracle_process_batch(const oracle_adapter *ads, int n_ads, const oracle_group *groups, int n_groups,
+                         const unsigned char *seq, const unsigned char *qual, const int64_t *offsets,
+                         int64_t r_begin, int64_t r_end, int quality_trim, int cutoff_front, int cutoff_back,
+                         int qbase, int times, int use_nextseq, int nextseq_cutoff, int slots,
+                         int32_t *records, int32_t *qtrim)
+{
+    int64_t r;
+    int max_len = 0, rc = 0;
+    unsigned char *tmp;
+    (void)n_ads;
+    for (r = r_begin; r < r_end; r++)
+        if (offsets[r + 1] - offsets[r] > max_len) max_len = (int)(offsets[r + 1] - offsets[r]);
+    tmp = malloc((size_t)max_len + 1);
+    if (!tmp) return -4;
+    for (r = r_begin; r < r_end && rc >= 0; r++) {
+        const unsigned char *sq = seq + offsets[r];
+        const int n = (int)(offsets[r + 1] - offsets[r]);
+        int32_t *rec = records + (size_t)(r - r_begin) * times * slots * 8;
+        int s = 0, e = n, round, i;
+        for (i = 0; i < times * slots; i++) { memset(rec + 8 * i, 0, 32); rec[8 * i] = -1; }
+        if (use_nextseq) e = oracle_nextseq_trim_index(sq, qual + offsets[r], n, nextseq_cutoff, qbase);
+        if (quality_trim) oracle_quality_trim_index(qual + offsets[r], e, cutoff_front, cutoff_back, qbase, &s, &e);
+        qtrim[2 * (r - r_begin)] = s; qtrim[2 * (r - r_begin) + 1] = e;
+        for (round = 0; round < times; round++) {                 /* modifiers.py:225-231 */
+            int have = 0, best_group = -1, best_score = 0, best_errors = 0, g;
+            oracle_hit b0, b1;
+            b0.adapter = -1; b1.adapter = -1;
+            for (g = 0; g < n_groups; g++) {                      /* adapters.py:1271-1286 */
+                const oracle_group *G = &groups[g];
+                oracle_hit h0, h1;
+                int score, errors, f, bk;
+                h0.adapter = -1; h1.adapter = -1;
+                if (G->type == 0) {
+                    f = batch_match_single(&ads[G->a0], G->a0, sq + s, e - s, tmp, &h0);
+                    if (f < 0) { rc = f; break; }
+                    if (!f) continue;
+                    score = h0.score; errors = h0.errors;
+                } else {                                          /* adapters.py:1215-1227 */
+                    int s2 = 0, e2 = e - s;
+                    f = batch_match_single(&ads[G->a0], G->a0, sq + s, e - s, tmp, &h0);
+                    if (f < 0) { rc = f; break; }
+                    if (!f) h0.adapter = -1;
+                    if (G->front_required && !f) continue;
+                    if (f) batch_trim(&h0, &s2, &e2);
+                    bk = batch_match_single(&ads[G->a1], G->a1, sq + s + s2, e2 - s2, tmp, &h1);
+                    if (bk < 0) { rc = bk; break; }
+                    if (!bk) h1.adapter = -1;
+                    if (!bk && (G->back_required || !f)) continue;
+                    score = (f ? h0.score : 0) + (bk ? h1.score : 0);   /* adapters.py:1113-1130 */
+                    errors = (f ? h0.errors : 0) + (bk ? h1.errors : 0);
+                }
+                if (!have || score > best_score || (score == best_score && errors < best_errors)) {
+                    have = 1; best_score = score; best_errors = errors; best_group = g; b0 = h0; b1 = h1;
+                }
+            }
+            if (rc < 0 || !have) break;                           /* modifiers.py:227-229 */
+            {
+                const int searched = e - s;
+                int32_t *dst = rec + (size_t)round * slots * 8;
+                if (b0.adapter >= 0) batch_put(dst, &b0, best_group, searched);
+                if (b1.adapter >= 0 && slots > 1) {
+                    int s2 = 0, e2 = searched;
+                    if (b0.adapter >= 0) batch_trim(&b0, &s2, &e2);
+                    batch_put(dst + 8, &b1, best_group, e2 - s2);
+                }
+                if (b0.adapter >= 0) batch_trim(&b0, &s, &e);      /* modifiers.py:231 */
+                if (b1.adapter >= 0) batch_trim(&b1, &s, &e);
+            }
+        }
+    }
+    free(tmp);
+    return rc < 0 ? rc : 0;
+}

@@ -41,6 +41,18 @@ class KmerEntry(C.Structure):
                 ("init_mask", C.c_uint64), ("found_mask", C.c_uint64)]
 
 
+class OracleAdapter(C.Structure):
+    _fields_ = [("seq", C.c_char_p), ("m", C.c_int32), ("flags", C.c_int32), ("wildcard_ref", C.c_int32),
+                ("wildcard_query", C.c_int32), ("indel_cost", C.c_int32), ("min_overlap", C.c_int32),
+                ("kind", C.c_int32), ("reverse_read", C.c_int32), ("remove", C.c_int32), ("n_entries", C.c_int32),
+                ("max_error_rate", C.c_double), ("entries", C.POINTER(KmerEntry)), ("masks", C.c_void_p)]
+
+
+class OracleGroup(C.Structure):
+    _fields_ = [("type", C.c_int32), ("a0", C.c_int32), ("a1", C.c_int32), ("front_required", C.c_int32),
+                ("back_required", C.c_int32)]
+
+
 def build(force=False):
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
         subprocess.check_call(["gcc", "-O2", "-std=c99", "-shared", "-fPIC", "-o", SO, SRC, "-lm"])
@@ -72,6 +84,10 @@ def lib():
         handle.oracle_locate_batch.argtypes = [u8p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                                C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.POINTER(KmerEntry), C.c_void_p, C.c_int, C.c_void_p]
+        handle.oracle_process_batch.argtypes = [
+            C.POINTER(OracleAdapter), C.c_int, C.POINTER(OracleGroup), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+            C.c_void_p, C.c_void_p]
         _lib = handle
     return _lib
 
@@ -308,6 +324,71 @@ def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=Fal
                 s, e = _trim(h0, s, e)
             if h1 is not None:
                 s, e = _trim(h1, s, e)
+    return out, qtrim
+
+
+def oracle_process_packed(adapters, groups, data, offsets, qdata=None, quality_trim=False, cutoff_front=0,
+                          cutoff_back=0, quality_base=33, times=1, nextseq_cutoff=None, threads=None):
+    """
+    oracle_process on a packed batch (uint8 bytes + int64 offsets), run by the C loop oracle_process_batch from
+    `threads` Python threads over disjoint read ranges (ctypes releases the GIL): 10^6 reads in seconds.
+    Same results as oracle_process (tests/test_oracle.py checks that).
+    """
+    from concurrent.futures import ThreadPoolExecutor
+
+    if groups is None:
+        groups = [(GROUP_SINGLE, i, -1, 0, 0) for i in range(len(adapters))]
+    slots = 2 if any(g[0] == GROUP_LINKED for g in groups) else 1
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = offsets.size - 1
+    keep = []
+    ads = (OracleAdapter * max(len(adapters), 1))()
+    for i, a in enumerate(adapters):
+        seq = _b(a["sequence"])
+        keep.append(seq)
+        ads[i].seq = seq; ads[i].m = len(seq)
+        ads[i].flags = a.get("flags", 15)
+        ads[i].wildcard_ref = int(a.get("wildcard_ref", False)); ads[i].wildcard_query = int(a.get("wildcard_query", False))
+        ads[i].indel_cost = a.get("indel_cost", 1); ads[i].min_overlap = a.get("min_overlap", 1)
+        ads[i].kind = a.get("kind", KIND_ALIGNER); ads[i].reverse_read = int(bool(a.get("reverse_read")))
+        ads[i].remove = a.get("remove", REMOVE_AFTER)
+        ads[i].max_error_rate = a["max_error_rate"]
+        kt = _kmer_tables_of(a)
+        if kt is not None:
+            keep.append(kt)
+            ads[i].n_entries = kt.n
+            ads[i].entries = C.cast(kt.entries, C.POINTER(KmerEntry))
+            ads[i].masks = kt.masks.ctypes.data
+    grs = (OracleGroup * max(len(groups), 1))()
+    for i, g in enumerate(groups):
+        grs[i].type, grs[i].a0, grs[i].a1, grs[i].front_required, grs[i].back_required = [int(x) for x in g]
+    out = np.zeros((n, times, slots), dtype=MATCH_DTYPE)
+    qtrim = np.zeros((n, 2), dtype=np.int32)
+    if n == 0:
+        return out, qtrim
+    qd = np.ascontiguousarray(qdata, dtype=np.uint8) if qdata is not None else None
+    if (quality_trim or nextseq_cutoff is not None) and qd is None:
+        raise ValueError("qualities needed")
+    L = lib()
+    L.oracle_quality_trim_index(b"I", 1, 0, 0, 33, C.byref(C.c_int()), C.byref(C.c_int()))   # (init tables once)
+    L.oracle_locate(b"A", 1, b"A", 1, 0.0, 15, 1, 1, 1, 1, (C.c_int * 6)())
+    threads = threads or min(32, len(os.sched_getaffinity(0)))
+    step = max(1, (n + threads - 1) // threads)
+    rec_stride = times * slots * 32
+
+    def work(r0):
+        r1 = min(n, r0 + step)
+        return L.oracle_process_batch(
+            ads, len(adapters), grs, len(groups), data.ctypes.data, qd.ctypes.data if qd is not None else None,
+            offsets.ctypes.data, r0, r1, int(bool(quality_trim)), cutoff_front, cutoff_back, quality_base, times,
+            int(nextseq_cutoff is not None), nextseq_cutoff or 0, slots,
+            out.ctypes.data + r0 * rec_stride, qtrim.ctypes.data + r0 * 8)
+
+    with ThreadPoolExecutor(threads) as ex:
+        for rc in ex.map(work, range(0, n, step)):
+            if rc < 0:
+                _raise(rc)
     return out, qtrim
 
 

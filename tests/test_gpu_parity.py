@@ -630,7 +630,7 @@ def test_bitplane_first_stage_kernel_against_oracle():
         qt = trial % 3 == 0
         got, gqt = run_set([d], None, reads, quals if qt else None, quality_trim=qt, cutoff_front=5, cutoff_back=20)
         exp, eqt = oracle.oracle_process([d], None, reads, quals if qt else None, quality_trim=qt, cutoff_front=5, cutoff_back=20)
-        assert (gqt == eqt).all() and (got == exp).all(), (trial, repr(ad), max_len)
+        assert (not qt or (gqt == eqt).all()) and (got == exp).all(), (trial, repr(ad), max_len)
 
 
 def test_multipass_schedule_agrees_with_one_phase_and_oracle():
