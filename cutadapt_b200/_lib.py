@@ -188,6 +188,9 @@ def _declare(lib) -> None:
         C.POINTER(cg_index_desc), i32, C.POINTER(vp),
     ]
     lib.cg_adapterset_destroy.argtypes = [vp]
+    lib.cg_adapterset_jit_status.argtypes = [vp]
+    lib.cg_adapterset_jit_source.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
+    lib.cg_adapterset_jit_source.restype = C.c_int64
     lib.cg_adapterset_slots.argtypes = [vp]
     lib.cg_adapterset_effective_length.argtypes = [vp, i32, C.POINTER(i32)]
     lib.cg_process_batch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(cg_params), vp, vp]
@@ -235,6 +238,11 @@ _ERRORS = {
     CG_ECUDA: CutadaptB200Error,
     CG_EUNSUPPORTED: CutadaptB200Error,
 }
+
+
+def last_error() -> str:
+    message = lib().cg_last_error()
+    return message.decode("utf-8", "replace") if message else ""
 
 
 def check(rc: int) -> None:
@@ -477,6 +485,20 @@ class AdapterSet:
     @property
     def handle(self):
         return self._h
+
+    def jit_status(self) -> int:
+        """1: a first-stage kernel specialised for this set is in use, 0: not (yet), -1: its compilation failed
+        (the precompiled kernel runs; last_error() says why)."""
+        return int(lib().cg_adapterset_jit_status(self._h))
+
+    def jit_source(self, plane_words: int = 5, has_qual: bool = False) -> str:
+        """The translation unit the run-time specialisation compiles for this set ('' if it has no plane program)."""
+        n = int(lib().cg_adapterset_jit_source(self._h, plane_words, int(has_qual), None, 0))
+        if n == 0:
+            return ""
+        buf = C.create_string_buffer(n + 1)
+        lib().cg_adapterset_jit_source(self._h, plane_words, int(has_qual), buf, n + 1)
+        return buf.value.decode()
 
     def effective_length(self, adapter: int = 0) -> int:
         out = C.c_int32()

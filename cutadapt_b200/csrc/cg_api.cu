@@ -17,6 +17,7 @@
 #include "../../include/cutadapt_b200.h"
 #include "cg_hostpack.h"
 #include "cg_kernels.cuh"
+#include "cg_jit.h"
 #include "cg_setbuild.h"
 
 static_assert(sizeof(cg_match) == 32 && sizeof(cg_match_rec) == 32, "cg_match must be 32 bytes");
@@ -175,6 +176,11 @@ struct cg_adapterset {
     std::vector<int32_t> pass_map;
     int32_t *d_pass_map = nullptr;
     CgSelectTables select_tables;
+    // run-time specialisation of the bit-plane first stage (cg_jit.h): one kernel per (plane words, qualities)
+    mutable CgJitKernel *jit[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    mutable int jit_state[2][2] = {{0, 0}, {0, 0}};      // 0 not tried, 1 ready, -1 failed
+    mutable long long plane_reads = 0;                  // reads that went through the plane stage so far
+    mutable std::string jit_error;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -374,9 +380,41 @@ extern "C" int cg_adapterset_destroy(cg_adapterset *s)
     if (s->d_blob) cudaFree(s->d_blob);
     if (s->d_masks) cudaFree(s->d_masks);
     if (s->d_index) cudaFree(s->d_index);
+    for (int w = 0; w < 2; ++w)
+        for (int q = 0; q < 2; ++q) cg_jit_destroy(s->jit[w][q]);
     destroy_passes(s);
     delete s;
     return CG_OK;
+}
+
+// Run-time specialisation of the first stage (cg_jit.h): 1 = a specialised kernel is in use, 0 = not (yet),
+// -1 = compilation failed (the precompiled kernel runs; cg_last_error() holds the reason after this call).
+extern "C" int cg_adapterset_jit_status(const cg_adapterset *s)
+{
+    if (!s) return 0;
+    const cg_adapterset *t = (!s->passes.empty() && s->passes[0].sub) ? s->passes[0].sub : s;
+    int st = 0;
+    for (int w = 0; w < 2; ++w)
+        for (int q = 0; q < 2; ++q) {
+            if (t->jit_state[w][q] == 1) st = 1;
+            else if (t->jit_state[w][q] == -1 && st == 0) st = -1;
+        }
+    if (st == -1) g_err = "first-stage specialisation failed: " + t->jit_error;
+    return st;
+}
+
+// The translation unit cg_jit.cpp would compile for this set (plane_words 5 or 8); returns its length (0: the
+// set has no plane program) and copies at most cap - 1 characters.
+extern "C" int64_t cg_adapterset_jit_source(const cg_adapterset *s, int32_t plane_words, int32_t has_qual, char *buf, int64_t cap)
+{
+    if (!s) return 0;
+    const std::string src = cg_jit_pscan_source(s->host, plane_words, has_qual != 0);
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+        memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)src.size();
 }
 
 extern "C" int cg_adapterset_slots(const cg_adapterset *s) { return s ? s->host.slots : 0; }
@@ -476,6 +514,27 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             }
         }
     }
+    // Run-time specialisation of the first stage for this adapter set (cg_jit.h): compiled once the set has seen
+    // enough reads to pay for the ~1 s of NVRTC (CUTADAPT_B200_JIT=1: at once, =0: never); any failure keeps the
+    // precompiled interpreter kernel.
+    CgJitKernel *jit_kernel = nullptr;
+    int jit_occ = 0;
+    if (split && plane_w) {
+        const int wi = plane_w <= 5 ? 0 : 1, qi = want_q ? 1 : 0;
+        s->plane_reads += n_reads;
+        const char *je = getenv("CUTADAPT_B200_JIT");
+        const bool never = je && strcmp(je, "0") == 0, always = je && strcmp(je, "1") == 0;
+        if (!never && s->jit_state[wi][qi] == 0 && (always || s->plane_reads >= (4LL << 20))) {
+            std::string err;
+            s->jit[wi][qi] = cg_jit_build_pscan(s->host, plane_w, want_q, err);
+            s->jit_state[wi][qi] = s->jit[wi][qi] ? 1 : -1;
+            if (!s->jit[wi][qi]) s->jit_error = err;
+        }
+        if (!never && s->jit_state[wi][qi] == 1) {
+            jit_occ = cg_jit_occupancy(s->jit[wi][qi], CG_NT, scan_smem);
+            if (jit_occ >= 1) jit_kernel = s->jit[wi][qi];
+        }
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (timed && c->timing.size() < 8192) {
         for (cudaEvent_t *ev : {&ev0, &ev1}) {
@@ -492,7 +551,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         long long SUB = 32LL << 20;
         if (const char *e = getenv("CUTADAPT_B200_SUB_READS")) { const long long v = atoll(e); if (v >= 1024) SUB = v; }
         const long long cap = std::min<long long>(n_reads, SUB);
-        int rc = c->tasks.ensure((size_t)cap * 2);
+        int rc = c->tasks.ensure((size_t)cap * (plane_w ? 4 : 2));
         if (rc == CG_OK) rc = c->tasks2.ensure((size_t)cap * 4);
         if (rc == CG_OK) rc = c->tasks3.ensure((size_t)cap * 4);
         if (rc != CG_OK) return rc;
@@ -511,7 +570,12 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             const long long need = (n_mt + 3) / 4;
             auto grid_for = [&](int occ) { return (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, need)); };
             b.tasks = c->tasks.p; b.task_count = cnt;
-            if (plane_w) CU(cg_launch_pscan(b, want_q, plane_w, grid_for(scan_occ), scan_smem, st));
+            b.task_rec = plane_w ? 4 : 2;
+            if (plane_w && jit_kernel) {
+                const int rcj = cg_jit_launch(jit_kernel, grid_for(jit_occ), CG_NT, scan_smem, (void *)st, &b);
+                if (rcj != 0) return fail(CG_ECUDA, "launch of the specialised first stage failed (CUresult " + std::to_string(rcj) + ")");
+            }
+            else if (plane_w) CU(cg_launch_pscan(b, want_q, plane_w, grid_for(scan_occ), scan_smem, st));
             else CU(cg_launch_scan(b, want_q, grid_for(scan_occ), scan_smem, st));
             b.tasks2 = c->tasks2.p; b.task2_count = cnt + 1;
             CU(cg_launch_list(b, true, s->host.max_m, grid_for(plan_occ), list_smem, st));

@@ -724,177 +724,236 @@ struct PlaneOut {
     int cls;         // 0: no match, 1: exact occurrence at s0, 2: undecided (exact path)
     int s0;
     uint32_t bad;    // OR of the window's bytes (bit 7 of any byte set = non-ASCII input)
+    // cls 2: what the plan stage needs to go on without scanning the read again (plan_runs_planes)
+    uint32_t M[8];   // bit e of word b: a locator chunk occurs where the whole adapter would end at plane index 32 b + e
+    int end_hit;     // a chunk occurs so close to the end of the window that the adapter would reach beyond it
 };
 #define CG_PLANE_NONE 0
 #define CG_PLANE_EXACT 1
 #define CG_PLANE_SLOW 2
 
-// one chain step: acc = (acc << 1 | newbit) & plane
+// x <<= s  (multi-word, s in 0..63); returns the bits shifted out at the top (non-zero = some were)
 template <int W>
-CG_HD void plane_step(uint32_t (&acc)[W], const uint32_t (&P)[W], uint32_t newbit)
+CG_HD uint32_t plane_shl(uint32_t (&x)[W], uint32_t s)
 {
-#pragma unroll
-    for (int b = W - 1; b >= 1; --b) acc[b] = cg_funnel_l(acc[b - 1], acc[b], 1) & P[b];
-    acc[0] = ((acc[0] << 1) | newbit) & P[0];
-}
-
-// x <<= s  (multi-word, s in 0..63)
-template <int W>
-CG_HD void plane_shl(uint32_t (&x)[W], uint32_t s)
-{
+    uint32_t lost = 0;
     if (s >= 32) {
+        lost = x[W - 1];
 #pragma unroll
         for (int b = W - 1; b >= 1; --b) x[b] = x[b - 1];
         x[0] = 0;
         s -= 32;
     }
+    lost |= cg_funnel_l(x[W - 1], 0u, s);          // the top s bits of the last word
 #pragma unroll
     for (int b = W - 1; b >= 1; --b) x[b] = cg_funnel_l(x[b - 1], x[b], s);
     x[0] <<= s;
+    return lost;
 }
 
-// `end` points just past the last character of the searched window; n = its length (1 <= n <= 32 W;
-// the caller routes everything else to the exact path).  The bytes [end - 32 W - 3, end + 4) must be
-// readable (their values outside the window do not matter).
+// The stage is written as a state plus three operations -- load, chain step, emit -- and a decision, so
+// that the same code serves the interpreter of the op list in the adapter blob (RuntimePlaneProg: any
+// adapter, precompiled) and a program spelled out as a sequence of calls with literal arguments, which the
+// compiler folds into straight-line code (cg_jit.cpp compiles that per adapter set with NVRTC).
 template <int W>
-CG_HD PlaneOut plane_scan_core(const uint32_t *ops, int n_ops, int plane_flags, const CgAdapter &A,
-                               const uint8_t *ref, const uint8_t *end, int n, bool always_pass)
+struct PlaneState {
+    uint32_t PA[W], PC[W], PT[W], PG[W];   // bit i: character i of the (right-aligned) window is A / C / T / G
+    uint32_t acc[W];                       // ends of the chain's text so far
+    uint32_t M[W], E[W];                   // locator hits / all chunks, by the end of the WHOLE adapter
+    bool pass, anyhit, end_hit;
+};
+
+// `base` = address of plane index 0 (window end - 32 W); the bytes [base - 3, base + 32 W + 4) must be readable.
+// Returns the OR of the window's bytes.
+template <int W>
+CG_HD uint32_t plane_load(PlaneState<W> &st, const uint8_t *base, int off0)
 {
-    PlaneOut out; out.cls = CG_PLANE_SLOW; out.s0 = 0; out.bad = 0;
-    const int off0 = 32 * W - n;                     // plane index of the window's first character
-    const uint8_t *base = end - 32 * W;              // plane index 0
     uint32_t LO[W], HI[W];
-    {
-        const uint32_t mis = (uint32_t)((uintptr_t)base & 3u);
-        const uint32_t sh = 8u * mis;
-        const uint32_t *wp = (const uint32_t *)(base - mis);
-        uint32_t carry = wp[0];
-        uint32_t bad = 0;
+    const uint32_t mis = (uint32_t)((uintptr_t)base & 3u);
+    const uint32_t sh = 8u * mis;
+    const uint32_t *wp = (const uint32_t *)(base - mis);
+    uint32_t carry = wp[0];
+    uint32_t bad = 0;
 #pragma unroll
-        for (int b = 0; b < W; ++b) {
-            uint32_t x[8];
+    for (int b = 0; b < W; ++b) {
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t nxt = wp[8 * b + j + 1];
+            x[j] = cg_funnel_rb(carry, nxt, sh);
+            carry = nxt;
+        }
+        if (off0 > 32 * b) {                     // leading block(s): blank the bytes in front of the window
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t nxt = wp[8 * b + j + 1];
-                x[j] = cg_funnel_rb(carry, nxt, sh);
-                carry = nxt;
+                const int fv = off0 - (32 * b + 4 * j);          // first valid byte of this word
+                const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 4 ? 0u : (0xFFFFFFFFu << (8 * fv)));
+                x[j] &= keep;
             }
-            if (off0 > 32 * b) {                     // leading block(s): blank the bytes in front of the window
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int fv = off0 - (32 * b + 4 * j);          // first valid byte of this word
-                    const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 4 ? 0u : (0xFFFFFFFFu << (8 * fv)));
-                    x[j] &= keep;
-                }
-            }
-            uint32_t lo = 0, hi = 0;
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const uint32_t a = x[2 * p], c = x[2 * p + 1];
-                bad |= a | c;
-                uint32_t pl = cg_dp4a(a & 0x02020202u, 0x08040201u, 0u);
-                pl = cg_dp4a(c & 0x02020202u, 0x80402010u, pl);      // 2 x (8 plane bits)
-                uint32_t ph = cg_dp4a(a & 0x04040404u, 0x08040201u, 0u);
-                ph = cg_dp4a(c & 0x04040404u, 0x80402010u, ph);      // 4 x (8 plane bits)
-                lo += p == 0 ? (pl >> 1) : (pl << (8 * p - 1));
-                hi += p == 0 ? (ph >> 2) : (ph << (8 * p - 2));
-            }
-            LO[b] = lo; HI[b] = hi;
         }
-        out.bad = bad;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const uint32_t a = x[2 * p], c = x[2 * p + 1];
+            bad |= a | c;
+            uint32_t pl = cg_dp4a(a & 0x02020202u, 0x08040201u, 0u);
+            pl = cg_dp4a(c & 0x02020202u, 0x80402010u, pl);      // 2 x (8 plane bits)
+            uint32_t ph = cg_dp4a(a & 0x04040404u, 0x08040201u, 0u);
+            ph = cg_dp4a(c & 0x04040404u, 0x80402010u, ph);      // 4 x (8 plane bits)
+            lo += p == 0 ? (pl >> 1) : (pl << (8 * p - 1));
+            hi += p == 0 ? (ph >> 2) : (ph << (8 * p - 2));
+        }
+        LO[b] = lo; HI[b] = hi;
     }
     // planes of the four letters, blanked in front of the window
-    uint32_t PA[W], PC[W], PG[W], PT[W];
 #pragma unroll
     for (int b = 0; b < W; ++b) {
         const int fv = off0 - 32 * b;
         const uint32_t len = fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
-        PA[b] = ~LO[b] & ~HI[b] & len;
-        PC[b] = LO[b] & ~HI[b] & len;
-        PT[b] = ~LO[b] & HI[b] & len;
-        PG[b] = LO[b] & HI[b] & len;
+        st.PA[b] = ~LO[b] & ~HI[b] & len;
+        st.PC[b] = LO[b] & ~HI[b] & len;
+        st.PT[b] = ~LO[b] & HI[b] & len;
+        st.PG[b] = LO[b] & HI[b] & len;
     }
-    bool pass = always_pass, anyhit = false;
-    uint32_t M[W], E[W];                             // locator hits / all chunks, by the end of the WHOLE adapter
-#pragma unroll
-    for (int b = 0; b < W; ++b) { M[b] = 0; E[b] = 0xFFFFFFFFu; }
-    const CgPlaneEmit *emits = (const CgPlaneEmit *)((const uint8_t *)ops + (((size_t)n_ops * 4 + 7) & ~(size_t)7));
-    uint32_t acc[W];
-#pragma unroll
-    for (int b = 0; b < W; ++b) acc[b] = 0;
 #if defined(__CUDA_ARCH__)
     // keep the four planes in registers: left alone, ptxas re-derives them from LO / HI / len inside every
     // chain step (two LOP3 per word instead of one)
 #pragma unroll
     for (int b = 0; b < W; ++b)
-        asm volatile("" : "+r"(PA[b]), "+r"(PC[b]), "+r"(PT[b]), "+r"(PG[b]));
+        asm volatile("" : "+r"(st.PA[b]), "+r"(st.PC[b]), "+r"(st.PT[b]), "+r"(st.PG[b]));
 #endif
-    for (int i = 0; i < n_ops; ++i) {
-        const uint32_t op = ops[i];
-        const uint32_t code = op & 3u;
-        if (op & CG_PLANE_OP_NEW) {                  // first character of a chain: acc = plane
 #pragma unroll
-            for (int b = 0; b < W; ++b) acc[b] = code == 0 ? PA[b] : (code == 1 ? PC[b] : (code == 2 ? PT[b] : PG[b]));
-        } else if (code == 0) plane_step<W>(acc, PA, 0u);
-        else if (code == 1) plane_step<W>(acc, PC, 0u);
-        else if (code == 2) plane_step<W>(acc, PT, 0u);
-        else plane_step<W>(acc, PG, 0u);
-        // acc: bit e set iff the chain's text so far ends at plane index e (occurrences reaching in front of
-        // the window are impossible: the planes are blank there)
-        uint32_t em = op >> 8;
-        while (em) {
-            const CgPlaneEmit K = emits[(em & 255u) - 1u];
-            em >>= 8;
-            uint32_t any = 0;
-            if (K.type == CG_SCAN_SUFFIX) {
-                // the occurrence must start inside the last `window` (<= 64) characters:
-                // e >= 32 W - window + len - 1, which lies in the last two words
-                const int e_min = 32 * W - (int)K.window + (int)K.len - 1;
+    for (int b = 0; b < W; ++b) { st.acc[b] = 0; st.M[b] = 0; st.E[b] = 0xFFFFFFFFu; }
+    st.pass = false; st.anyhit = false; st.end_hit = false;
+    return bad;
+}
+
+// one chain step: acc = plane (first character of a chain) or (acc << 1) & plane
+template <int W>
+CG_HD void plane_chain_apply(uint32_t (&acc)[W], const uint32_t (&P)[W], bool first)
+{
+    if (first) {
 #pragma unroll
-                for (int b = (W >= 2 ? W - 2 : 0); b < W; ++b) {
-                    const int fv = e_min - 32 * b;
-                    const uint32_t keep = fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
-                    any |= acc[b] & keep;
-                }
-            } else {
+        for (int b = 0; b < W; ++b) acc[b] = P[b];
+    } else {
 #pragma unroll
-                for (int b = 0; b < W; ++b) any |= acc[b];
-            }
-            if ((K.flags & CG_PLANE_PASS) && any) pass = true;
-            if (K.flags & CG_PLANE_LOC) {
-                if (any) anyhit = true;
-                uint32_t f[W];
+        for (int b = W - 1; b >= 1; --b) acc[b] = cg_funnel_l(acc[b - 1], acc[b], 1) & P[b];
+        acc[0] = (acc[0] << 1) & P[0];
+    }
+}
+template <int W>
+CG_HD void plane_chain_step(PlaneState<W> &st, uint32_t code, bool first)
+{
+    // (branches, not a reference picked by `code`: the planes must stay in registers)
+    if (code == 0) plane_chain_apply<W>(st.acc, st.PA, first);
+    else if (code == 1) plane_chain_apply<W>(st.acc, st.PC, first);
+    else if (code == 2) plane_chain_apply<W>(st.acc, st.PT, first);
+    else plane_chain_apply<W>(st.acc, st.PG, first);
+}
+
+// A k-mer of `len` characters ends with the step just done: acc has bit e set iff it ends at plane index e
+// (occurrences reaching in front of the window are impossible: the planes are blank there).
+//   type/window : CG_SCAN_SUFFIX: the occurrence must start inside the last `window` (<= 64) characters, i.e.
+//                 e >= 32 W - window + len - 1, which lies in the last two words
+//   flags       : CG_PLANE_PASS / CG_PLANE_LOC;  shift = m - (adapter offset at which a locator chunk ends)
+template <int W>
+CG_HD void plane_emit(PlaneState<W> &st, int len, int type, int flags, int shift, int window)
+{
+    uint32_t x[W];
 #pragma unroll
-                for (int b = 0; b < W; ++b) f[b] = acc[b];
-                plane_shl<W>(f, (uint32_t)(A.m - (int)K.bend));
+    for (int b = 0; b < W; ++b) x[b] = st.acc[b];
+    uint32_t any = 0;
+    if (type == CG_SCAN_SUFFIX) {
+        const int e_min = 32 * W - window + len - 1;
 #pragma unroll
-                for (int b = 0; b < W; ++b) { M[b] |= f[b]; E[b] &= f[b]; }
+        for (int b = 0; b < W; ++b) {
+            const int fv = e_min - 32 * b;
+            x[b] &= fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
+        }
+#pragma unroll
+        for (int b = (W >= 2 ? W - 2 : 0); b < W; ++b) any |= x[b];
+    } else {
+#pragma unroll
+        for (int b = 0; b < W; ++b) any |= x[b];
+    }
+    if ((flags & (int)CG_PLANE_PASS) && any) st.pass = true;
+    if (flags & (int)CG_PLANE_LOC) {
+        if (any) st.anyhit = true;
+        if (plane_shl<W>(x, (uint32_t)shift)) st.end_hit = true;
+#pragma unroll
+        for (int b = 0; b < W; ++b) { st.M[b] |= x[b]; st.E[b] &= x[b]; }
+    }
+}
+
+// The interpreter of the op list in the adapter blob (cg_types.h: CG_PLANE_OP_*, CgPlaneEmit).
+struct RuntimePlaneProg {
+    template <int W>
+    CG_HD static void run(PlaneState<W> &st, const uint32_t *ops, int n_ops, int m)
+    {
+        const CgPlaneEmit *emits = (const CgPlaneEmit *)((const uint8_t *)ops + (((size_t)n_ops * 4 + 7) & ~(size_t)7));
+        for (int i = 0; i < n_ops; ++i) {
+            const uint32_t op = ops[i];
+            plane_chain_step<W>(st, op & 3u, (op & CG_PLANE_OP_NEW) != 0);
+            uint32_t em = op >> 8;
+            while (em) {
+                const CgPlaneEmit K = emits[(em & 255u) - 1u];
+                em >>= 8;
+                plane_emit<W>(st, (int)K.len, (int)K.type, (int)K.flags, m - (int)K.bend, (int)K.window);
             }
         }
     }
-    if (!anyhit && !pass) { out.cls = CG_PLANE_NONE; return out; }
-    if (!(plane_flags & 1) || !anyhit) return out;
-    // the leftmost adapter end any chunk points at (a chunk whose implied end lies beyond the window is
-    // shifted out: it implies a larger start than anything that remains)
-    bool found = false, ex = false;
-    int low = 0;
+};
+
+// What the planes settle, and what they hand on (see the head of this section for the rules).
+//   exact_ok : plane_flags bit 0;  m, ref: the adapter;  base / off0 / n as in plane_load
+template <int W>
+CG_HD void plane_decide(const PlaneState<W> &st, bool exact_ok, int m, const uint8_t *ref, const uint8_t *base,
+                        int off0, int n, bool always_pass, PlaneOut &out)
+{
+    out.cls = CG_PLANE_SLOW; out.s0 = 0; out.end_hit = st.end_hit ? 1 : 0;
+    if (!st.pass && !always_pass) { out.cls = CG_PLANE_NONE; return; }   // no k-mer even in the superset: kmers_present is False
+    if (exact_ok && st.anyhit) {
+        // the leftmost adapter end any chunk points at (a chunk whose implied end lies beyond the window is
+        // shifted out: it implies a larger start than anything that remains)
+        bool found = false, ex = false;
+        int low = 0;
 #pragma unroll
-    for (int b = 0; b < W; ++b) {
-        if (!found && M[b]) {
-            found = true;
-            const int bit = cg_ctz(M[b]);
-            low = 32 * b + bit;
-            ex = ((E[b] >> bit) & 1u) != 0;
+        for (int b = 0; b < W; ++b) {
+            if (!found && st.M[b]) {
+                found = true;
+                const int bit = cg_ctz(st.M[b]);
+                low = 32 * b + bit;
+                ex = ((st.E[b] >> bit) & 1u) != 0;
+            }
+        }
+        const int s0 = low - (m - 1) - off0;
+        if (found && ex && s0 >= 0 && s0 + m <= n) {
+            const uint8_t *w = base + (low - (m - 1));
+            bool same = true;
+            for (int i = 0; i < m; ++i) same = same && ((w[i] & 0xDFu) == ref[i]);
+            if (same) { out.cls = CG_PLANE_EXACT; out.s0 = s0; return; }
         }
     }
-    if (!found || !ex) return out;
-    const int s0 = low - (A.m - 1) - off0;
-    if (s0 < 0 || s0 + A.m > n) return out;          // (cannot happen: the planes are blank outside the window)
-    const uint8_t *w = base + (low - (A.m - 1));
-    bool same = true;
-    for (int i = 0; i < A.m; ++i) same = same && ((w[i] & 0xDFu) == ref[i]);
-    if (!same) return out;
-    out.cls = CG_PLANE_EXACT; out.s0 = s0;
+    // handed on: the plan stage gets the hits (plan_runs_planes) -- it still has to make sure the window holds
+    // plain A/C/G/T only, else the prefilter verdict of the planes is not certain (window_is_plain)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) out.M[b] = b < W ? st.M[b] : 0u;
+}
+
+// `end` points just past the last character of the searched window; n = its length (1 <= n <= 32 W;
+// the caller routes everything else to the exact path).  The bytes [end - 32 W - 3, end + 4) must be
+// readable (their values outside the window do not matter).
+template <int W, class Prog>
+CG_HD PlaneOut plane_scan_core(const uint32_t *ops, int n_ops, int plane_flags, int m, const uint8_t *ref,
+                               const uint8_t *end, int n, bool always_pass)
+{
+    PlaneOut out;
+    PlaneState<W> st;
+    const int off0 = 32 * W - n;                     // plane index of the window's first character
+    const uint8_t *base = end - 32 * W;              // plane index 0
+    out.bad = plane_load<W>(st, base, off0);
+    Prog::template run<W>(st, ops, n_ops, m);
+    plane_decide<W>(st, (plane_flags & 1) != 0, m, ref, base, off0, n, always_pass, out);
     return out;
 }
 
@@ -2215,11 +2274,24 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
     plan_finish(S, p, n, R, P);
 }
 
-// The plan of a read whose locator hits come from the bit-plane stage: `hit_ends` holds up to 8 plane
-// indices (one byte each, ascending) of adapter ends the chunk hits point at, off0 the plane index of the
-// window's first character.  A hit that implies the adapter start s gives the run [s - k, s + m + k]
-// (the same window refine_runs / plan_hit_runs_dir derive from a chunk's end position).
-CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, uint32_t ends_lo, uint32_t ends_hi, int n_hits,
+// Is every character of the window a plain A/C/G/T (either case)?  Then the bit-plane stage saw the read exactly
+// as KmerFinder.kmers_present and the locator do (any other byte aliases one of the four letters in the planes).
+CG_HD bool window_is_plain(const uint8_t *p, int n)
+{
+    CG_CHARPTR(q, p);
+    uint32_t bad = 0;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t idx = (CG_CHAR(q + i) & 0xDFu) - 'A';            // A 0, C 2, G 6, T 19
+        bad |= idx > 19u ? 1u : (~(0x80045u >> idx) & 1u);
+    }
+    return bad == 0;
+}
+
+// The plan of a read whose locator hits come from the bit-plane stage: M (W words, plane indices) marks the
+// adapter ends the chunk hits point at, off0 is the plane index of the window's first character.  A hit that
+// implies the adapter start s gives the run [s - k, s + m + k] (the same window refine_runs /
+// plan_hit_runs_dir derive from a chunk's end position).
+CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, const uint32_t *M, int W, int end_hit,
                             int off0, RunPlan &P)
 {
     const CgAdapter &A = S.ad[0];
@@ -2227,11 +2299,19 @@ CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, uint32_t 
     P.end_idx = -1; P.exact = 0; P.s0 = 0;
     RunList R;
     R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
-    for (int h = 0; h < n_hits; ++h) {
-        const int e = (int)(((h < 4 ? ends_lo : ends_hi) >> (8 * (h & 3))) & 255u);
-        const int s = e - (A.m - 1) - off0;
-        runs_add(R, s - A.k, s + A.m + A.k, n);
+    if (A.flags & 1) runs_add(R, 0, cg_min(n, A.m + A.k), n);              // START_IN_REFERENCE
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {                  // (unrolled: M stays in registers)
+        uint32_t x = b < W ? M[b] : 0u;
+        while (x) {
+            const int e = 32 * b + cg_ctz(x);
+            x &= x - 1;
+            const int s = e - (A.m - 1) - off0;
+            runs_add(R, s - A.k, s + A.m + A.k, n);
+        }
     }
+    // a chunk so close to the end that the whole adapter would not fit: its window lies inside the end window
+    if (end_hit) runs_add(R, cg_max(0, n - 1 - A.m - A.k), n, n);
     plan_finish(S, p, n, R, P);
 }
 
@@ -2275,6 +2355,28 @@ CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int h
     else locate_regs<MR, false, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
 }
 
+// The DP rounds of a planned read (what the cg_list_kernel<run> rounds do), host-sim only.
+CG_HD void finish_planned(const SetView &S, const uint8_t *w, int nn, const RunPlan &P, CgHit &hit)
+{
+    const CgAdapter &A = S.ad[0];
+    if (P.exact == 2) hit_end_overlap(A, nn, P.s0, hit);
+    else if (P.exact) hit_exact(A, nn, P.s0, hit);
+    else {
+        LocState st = loc_state_init(A.m, nn);
+        for (int r = 0; r < P.n_runs && !st.stopped; ++r) {
+            const int lo = r == 0 ? P.lo0 : (r == 1 ? P.lo1 : (r == 2 ? P.lo2 : P.lo3));
+            const int hi = r == 0 ? P.hi0 : (r == 1 ? P.hi1 : (r == 2 ? P.hi2 : P.hi3));
+            const uint8_t *bytes = A.reverse ? w + (nn - hi) : w + lo;
+            const bool last = r == P.n_runs - 1;
+            if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+            else if (A.m <= 32) run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+            else if (A.m <= 48) run_pass<48>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+            else run_pass<64>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+        }
+        hit_from_state(A, nn, st, hit);
+    }
+}
+
 // Host-sim driver of the planned scheduling for one read (tests/hostsim, mode 64).
 CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint8_t *qual, int n,
                                 int quality_trim, int cutoff_front, int cutoff_back, int qbase,
@@ -2292,22 +2394,7 @@ CG_HD void process_read_planned(const SetView &S, const uint8_t *seq, const uint
     if (sc.pass) {
         RunPlan P;
         plan_runs(S, seq + s, nn, sc.hits, gs, sc.rs0, sc.rs1, P);
-        if (P.exact == 2) hit_end_overlap(A, nn, P.s0, hit);
-        else if (P.exact) hit_exact(A, nn, P.s0, hit);
-        else {
-            LocState st = loc_state_init(A.m, nn);
-            for (int r = 0; r < P.n_runs && !st.stopped; ++r) {
-                const int lo = r == 0 ? P.lo0 : (r == 1 ? P.lo1 : (r == 2 ? P.lo2 : P.lo3));
-                const int hi = r == 0 ? P.hi0 : (r == 1 ? P.hi1 : (r == 2 ? P.hi2 : P.hi3));
-                const uint8_t *bytes = A.reverse ? seq + s + (nn - hi) : seq + s + lo;
-                const bool last = r == P.n_runs - 1;
-                if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-                else if (A.m <= 32) run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-                else if (A.m <= 48) run_pass<48>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-                else run_pass<64>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-            }
-            hit_from_state(A, nn, st, hit);
-        }
+        finish_planned(S, seq + s, nn, P, hit);
     }
     store_hit(out, hit, 0, nn);
 }
@@ -2331,12 +2418,22 @@ CG_HD void process_read_planes(const SetView &S, const uint8_t *seq, const uint8
     if (S.h->plane_count > 0 && nn >= 1 && nn <= 256) {
         const uint8_t *ref = S.pool + A.ref_off;
         const PlaneOut po = nn <= 160
-            ? plane_scan_core<5>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + e, nn, A.pf_count == 0)
-            : plane_scan_core<8>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + e, nn, A.pf_count == 0);
+            ? plane_scan_core<5, RuntimePlaneProg>(plane_program(S), S.h->plane_count, S.h->plane_flags, A.m, ref, seq + e, nn, A.pf_count == 0)
+            : plane_scan_core<8, RuntimePlaneProg>(plane_program(S), S.h->plane_count, S.h->plane_flags, A.m, ref, seq + e, nn, A.pf_count == 0);
         if (po.cls != CG_PLANE_SLOW) {
             CgHit hit; hit.adapter = -1; hit.remove = 0;
             hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
             if (po.cls == CG_PLANE_EXACT) hit_exact(A, nn, po.s0, hit);
+            store_hit(out, hit, 0, nn);
+            return;
+        }
+        if (window_is_plain(seq + s, nn)) {   // plan from the planes' hits, then the DP runs (cg_list_kernel)
+            const int W = nn <= 160 ? 5 : 8;
+            RunPlan P;
+            plan_runs_planes(S, seq + s, nn, po.M, W, po.end_hit, 32 * W - nn, P);
+            CgHit hit; hit.adapter = -1; hit.remove = 0;
+            hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+            finish_planned(S, seq + s, nn, P, hit);
             store_hit(out, hit, 0, nn);
             return;
         }

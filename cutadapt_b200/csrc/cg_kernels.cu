@@ -14,52 +14,8 @@
 // plus the stand-alone batched KmerFinder / quality_trim_index kernels and the statistics
 // reduction.
 #include "cg_kernels.cuh"
-
-// ------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA 1-D bulk copy
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-// Per-lane asynchronous copies (SASS LDGSTS): every lane moves its own bytes in 16-byte pieces into its
-// own shared-memory slot and waits for its own copy groups (no cross-lane synchronisation needed).
-__device__ __forceinline__ void cp_async16(void *dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__host__ __device__ inline size_t cg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+#include "cg_device.cuh"
+#include "cg_pscan.cuh"   // (ScanSmem, cg_pscan_body)
 
 // shared-memory carve-up of the fused kernel
 struct FastSmem {
@@ -575,7 +531,6 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 // registers cap the scan's occupancy.  The task list costs ~35 bytes of extra HBM traffic per read,
 // which is noise for a kernel that is instruction-issue bound.
 // ------------------------------------------------------------------------------------------
-struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_rel, qual_rel, total; };
 #ifndef CG_SCAN_STAGES
 #define CG_SCAN_STAGES 1     // per-warp staging depth of the scan kernel (1: more resident warps hide the TMA latency)
 #endif
@@ -748,151 +703,17 @@ cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------
-// cg_pscan_kernel -- the bit-plane first stage (plane_scan_core in cg_core.cuh) in the frame of
-// cg_scan_kernel: per-warp TMA-staged mini-tiles of 32 reads, one lane per read.  Reads it settles
-// ("no match": 47 % of the benchmark's reads; exact occurrence: 41 %) get their record here; the rest
-// (12 %) append a task flagged CG_TASK_RESCAN, which cg_list_kernel<plan> re-scans exactly.
-// A margin in front of every warp's tile keeps the right-aligned plane loads of the tile's first read
-// inside shared memory.
-// ------------------------------------------------------------------------------------------
-#define CG_PSCAN_MARGIN 272
-#define CG_TASK_RESCAN 0x100u
-__host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
-{
-    ScanSmem L;
-    size_t o = 0;
-    L.blob_off = o; o += cg_align_up(blob_bytes, 16);
-    L.enc_off = o; o += 768;
-    o = cg_align_up(o, 128);
-    L.warp_off = o;
-    size_t w = 0;
-    L.bar_rel = w; w += 16;
-    w = cg_align_up(w, 128);
-    w += CG_PSCAN_MARGIN;
-    L.seq_rel = w; w += (size_t)mini_cap;
-    L.qual_rel = w; if (has_qual) w += (size_t)mini_cap;
-    L.warp_stride = cg_align_up(w, 128);
-    L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
-    return L;
-}
+#include "cg_pscan.cuh"
+
 size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual)
 {
     return pscan_smem_layout(blob_bytes, mini_cap, has_qual).total;
 }
 
 template <bool HAS_QUAL, int W>
-__global__ void __launch_bounds__(CG_NT) cg_pscan_kernel(const CgKernelArgs a)
+__global__ void __launch_bounds__(CG_NT, W <= 5 ? CG_PSCAN_BLOCKS : 5) cg_pscan_kernel(const CgKernelArgs a)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const ScanSmem L = pscan_smem_layout(a.blob_bytes, a.mini_cap, HAS_QUAL);
-    uint8_t *s_blob = smem + L.blob_off;
-    uint8_t *s_enc = smem + L.enc_off;
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    uint8_t *wbase = smem + L.warp_off + (size_t)wib * L.warp_stride;
-    uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
-    uint8_t *s_seq = wbase + L.seq_rel;
-    uint8_t *s_qual = wbase + L.qual_rel;
-
-    for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
-    for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
-    if (lane == 0) {
-        mbar_init(&bars[0], 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
-    const CgAdapter &A = S.ad[0];
-    const uint32_t *prog = plane_program(S);
-    const int n_prog = S.h->plane_count, pflags = S.h->plane_flags;
-    const uint8_t *ref = S.pool + A.ref_off;
-    const bool always_pass = A.pf_count == 0;
-
-    const long long n_reads = a.n_reads;
-    const long long n_mt = (n_reads + 31) / 32;
-    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
-    const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
-    const uintptr_t seq_base = (uintptr_t)a.seq, qual_base = (uintptr_t)a.qual;
-
-    auto issue = [&](long long mt) {
-        const long long r0 = mt * 32;
-        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
-        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
-        if (b1 <= b0) return;
-        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
-        const uint32_t bytes = (uint32_t)(((seq_base + b1 + 15) & ~(uintptr_t)15) - sa0);
-        uint32_t qbytes = 0;
-        uintptr_t qa0 = 0;
-        if (HAS_QUAL) {
-            qa0 = (qual_base + b0) & ~(uintptr_t)15;
-            qbytes = (uint32_t)(((qual_base + b1 + 15) & ~(uintptr_t)15) - qa0);
-        }
-        mbar_expect_tx(&bars[0], bytes + qbytes);
-        tma_load_1d(s_seq, (const void *)sa0, bytes, &bars[0]);
-        if (HAS_QUAL) tma_load_1d(s_qual, (const void *)qa0, qbytes, &bars[0]);
-    };
-    if (lane == 0 && wg < n_mt) issue(wg);
-    uint32_t phase0 = 0;
-    for (long long mt = wg; mt < n_mt; mt += warps_total) {
-        const long long r0 = mt * 32;
-        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
-        const long long r = r0 + lane;
-        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
-        long long o0 = 0, o1 = 0;
-        if (r < n_reads) { o0 = a.offsets[r]; o1 = a.offsets[r + 1]; }
-        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
-        if (b1 > b0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
-        int cls = CG_PLANE_NONE, s0 = 0, ts = 0, te = 0;
-        bool mine = false;
-        if (r < n_reads) {
-            mine = true;
-            const int n = (int)(o1 - o0);
-            const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
-            ts = 0; te = n;
-            if (HAS_QUAL) {
-                const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
-                const uint8_t *q = s_qual + (size_t)((qual_base + o0) - qa0);
-                if (a.quality_trim) pre_trim_core(s_seq + off, q, n, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
-            }
-            if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
-            if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
-            const int nn = te - ts;
-            if (nn >= 1 && nn <= 32 * W) {
-                const PlaneOut po = plane_scan_core<W>(prog, n_prog, pflags, A, ref, s_seq + off + te, nn, always_pass);
-                cls = po.cls; s0 = po.s0;
-                if (po.bad & 0x80808080u) atomicOr(a.err_flag, 1);
-            } else {
-                cls = CG_PLANE_SLOW;                 // (empty or over-long window: the exact path checks its bytes)
-                uint32_t bad = 0;
-                for (int i = ts; i < te; ++i) bad |= s_seq[off + i];
-                if (bad & 0x80u) atomicOr(a.err_flag, 1);
-            }
-            if (cls != CG_PLANE_SLOW) {
-                CgHit hit; hit.adapter = -1; hit.remove = 0;
-                hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
-                if (cls == CG_PLANE_EXACT) hit_exact(A, nn, s0, hit);
-                store_hit(a.out + (size_t)r * a.slots, hit, 0, nn);
-            }
-        }
-        const bool slow = mine && cls == CG_PLANE_SLOW;
-        const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
-        if (ballot) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.task_count, (unsigned long long)__popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (slow) {
-                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-                a.tasks[2 * slot] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
-                                               (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
-                a.tasks[2 * slot + 1] = make_uint4(0u, 4u | CG_TASK_RESCAN, 0u, 0u);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const long long next = mt + warps_total;
-            if (next < n_mt) issue(next);
-        }
-    }
+    cg_pscan_body<HAS_QUAL, W, RuntimePlaneProg>(a);
 }
 
 typedef void (*pscan_kernel_t)(const CgKernelArgs);
@@ -978,7 +799,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
     unsigned long long n_tasks = *a.task_count;
     if (n_tasks > (unsigned long long)a.task_cap) n_tasks = (unsigned long long)a.task_cap;
     const uint4 *list = a.tasks;
-    const int rec = PLAN ? 2 : 4;
+    const int rec = PLAN ? a.task_rec : 4;     // the plan stage reads the scan kernel's (2) or cg_pscan_kernel's (4) tasks
     const long long n_groups = (long long)((n_tasks + 31) / 32);
     const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
     const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
@@ -992,7 +813,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
         ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0); tc = make_uint4(0, 0, 0, 0); td = make_uint4(0, 0, 0, 0);
         if (has) {
             ta = list[rec * t]; tb = list[rec * t + 1];
-            if (!PLAN) { tc = list[rec * t + 2]; td = list[rec * t + 3]; }
+            if (!PLAN || rec == 4) { tc = list[rec * t + 2]; td = list[rec * t + 3]; }
             const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
             uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + ta.z;
             uint32_t len = ta.w;
@@ -1053,11 +874,19 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                 uint32_t hits = tb.x, rs0 = tb.z, rs1 = tb.w;
                 int gs = (int)(tb.y & 0xffu);
                 bool pass = true;
-                if (tb.y & CG_TASK_RESCAN) {        // from cg_pscan_kernel: the exact scan of this read is still to do
+                bool planned = false;
+                if ((tb.y & CG_TASK_PLANES) && window_is_plain(p, n)) {
+                    const uint32_t M[8] = {tb.x, tb.z, tb.w, tc.x, tc.y, tc.z, tc.w, td.x};
+                    const int W = (int)((tb.y >> 12) & 15u);
+                    plan_runs_planes(S, p, n, M, W, (int)((tb.y >> 20) & 1u), 32 * W - n, P);
+                    planned = true;
+                } else if (tb.y & (CG_TASK_RESCAN | CG_TASK_PLANES)) {
+                    // the exact scan of this read is still to do (a window with other letters than A/C/G/T)
                     const ScanOut sc = simple_scan(S, p, n, &gs);
                     pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
                 }
-                if (pass) plan_runs(S, p, n, hits, gs, rs0, rs1, P);
+                if (planned) {}
+                else if (pass) plan_runs(S, p, n, hits, gs, rs0, rs1, P);
                 if (P.exact == 2) hit_end_overlap(A, n, P.s0, hit);
                 else if (P.exact) hit_exact(A, n, P.s0, hit);
                 else if (P.n_runs > 0) {

@@ -5,45 +5,7 @@
 
 #include "cg_core.cuh"
 
-#define CG_NT 128  // lanes (= reads) per CTA tile in the fused kernel
-
-struct CgKernelArgs {
-    // adapter tables (HBM)
-    const uint8_t *blob;
-    uint32_t blob_bytes;
-    const uint64_t *masks64;
-    const uint8_t *enc;  // 768 bytes
-    const uint8_t *index;  // CgIndexHeader[] | CgIndexEntry[] for INDEXED groups, or null
-    // batch (HBM)
-    const uint8_t *seq;
-    const uint8_t *qual;
-    const int64_t *offsets;
-    long long n_reads;
-    // parameters
-    int quality_trim, cutoff_front, cutoff_back, qbase, times, slots;
-    // outputs (HBM)
-    cg_match_rec *out;
-    int32_t *qtrim;
-    const int32_t *view;  // optional per-read (start, stop): search read[start:stop] instead of the
-                          // quality-trimmed read (per-adapter passes of the multi-pass schedule)
-    int *err_flag;
-    // fused-kernel geometry
-    int tile_cap;  // bytes per staged tile (multiple of 16)
-    int col_rows;  // max_m + 1
-    // warp-autonomous kernel geometry
-    int mini_cap;    // bytes per staged 32-read mini-tile (multiple of 16)
-    int carry_slot;  // bytes per carried task (multiple of 16)
-    // split pipeline (scan kernel -> task list in HBM -> DP kernel)
-    uint4 *tasks;                     // 2 x uint4 per task
-    unsigned long long *task_count;   // number of tasks appended by the scan kernel
-    long long task_cap;
-    uint4 *tasks2;                    // output list of the plan / run kernels: 4 x uint4 per record
-    unsigned long long *task2_count;
-    // generic-kernel scratch
-    uint32_t *scratch_p;
-    int *scratch_w;
-    long long scratch_stride;
-};
+#include "cg_args.h"
 
 // Multi-pass schedule (several adapters, one round): every component adapter runs as its own pass into a
 // scratch array of records; cg_select_kernel then applies MultipleAdapters.match_to / LinkedAdapter.match_to

@@ -1,0 +1,171 @@
+// cg_pscan.cuh -- body of the bit-plane first stage of the split pipeline.
+//
+// Included twice: by cg_kernels.cu, which instantiates it with RuntimePlaneProg (the interpreter of the op list
+// in the adapter blob: any adapter, compiled ahead of time), and by the translation unit cg_jit.cpp builds per
+// adapter set for NVRTC, where the program is a sequence of plane_chain_step / plane_emit calls with literal
+// arguments that the compiler folds into straight-line code.
+#pragma once
+#include "cg_core.cuh"
+#include "cg_args.h"
+#include "cg_device.cuh"
+
+struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_rel, qual_rel, total; };
+
+// ------------------------------------------------------------------------------------------
+// cg_pscan_kernel -- the bit-plane first stage (plane_scan_core in cg_core.cuh) in the frame of
+// cg_scan_kernel: per-warp TMA-staged mini-tiles of 32 reads, one lane per read.  Reads it settles
+// ("no match": 47 % of the benchmark's reads; exact occurrence: 41 %) get their record here; the rest
+// (12 %) append a task flagged CG_TASK_RESCAN, which cg_list_kernel<plan> re-scans exactly.
+// A margin in front of every warp's tile keeps the right-aligned plane loads of the tile's first read
+// inside shared memory.
+// ------------------------------------------------------------------------------------------
+#define CG_PSCAN_MARGIN 272
+#ifndef CG_PSCAN_BLOCKS
+#define CG_PSCAN_BLOCKS 8     // resident CTAs per SM the 5-word variant is compiled for (64 registers)
+#endif
+#define CG_TASK_RESCAN 0x100u     // the plan stage must scan the read itself (shift-and scan_core)
+#define CG_TASK_PLANES 0x200u     // a 4 x uint4 task of cg_pscan_kernel: {read lo, read hi, trim start, length},
+                                  // {M0, flags, M1, M2}, {M3 .. M6}, {M7, 0, 0, 0} with M = PlaneOut::M;
+                                  // flags bits 12-15: plane words W, bit 20: PlaneOut::end_hit
+__host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
+{
+    ScanSmem L;
+    size_t o = 0;
+    L.blob_off = o; o += cg_align_up(blob_bytes, 16);
+    L.enc_off = o; o += 768;
+    o = cg_align_up(o, 128);
+    L.warp_off = o;
+    size_t w = 0;
+    L.bar_rel = w; w += 16;
+    w = cg_align_up(w, 128);
+    w += CG_PSCAN_MARGIN;
+    L.seq_rel = w; w += (size_t)mini_cap;
+    L.qual_rel = w; if (has_qual) w += (size_t)mini_cap;
+    L.warp_stride = cg_align_up(w, 128);
+    L.total = L.warp_off + (CG_NT / 32) * L.warp_stride;
+    return L;
+}
+
+template <bool HAS_QUAL, int W, class Prog>
+__device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const ScanSmem L = pscan_smem_layout(a.blob_bytes, a.mini_cap, HAS_QUAL);
+    uint8_t *s_blob = smem + L.blob_off;
+    uint8_t *s_enc = smem + L.enc_off;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    uint8_t *wbase = smem + L.warp_off + (size_t)wib * L.warp_stride;
+    uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
+    uint8_t *s_seq = wbase + L.seq_rel;
+    uint8_t *s_qual = wbase + L.qual_rel;
+
+    for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
+    for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const SetView S = make_set_view(s_blob, a.masks64, s_enc, a.index);
+    const CgAdapter &A = S.ad[0];
+    const uint32_t *prog = plane_program(S);
+    const int n_prog = S.h->plane_count, pflags = S.h->plane_flags;
+    const uint8_t *ref = S.pool + A.ref_off;
+    const bool always_pass = A.pf_count == 0;
+
+    const long long n_reads = a.n_reads;
+    const long long n_mt = (n_reads + 31) / 32;
+    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
+    const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
+    const uintptr_t seq_base = (uintptr_t)a.seq, qual_base = (uintptr_t)a.qual;
+
+    auto issue = [&](long long mt) {
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        if (b1 <= b0) return;
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        const uint32_t bytes = (uint32_t)(((seq_base + b1 + 15) & ~(uintptr_t)15) - sa0);
+        uint32_t qbytes = 0;
+        uintptr_t qa0 = 0;
+        if (HAS_QUAL) {
+            qa0 = (qual_base + b0) & ~(uintptr_t)15;
+            qbytes = (uint32_t)(((qual_base + b1 + 15) & ~(uintptr_t)15) - qa0);
+        }
+        mbar_expect_tx(&bars[0], bytes + qbytes);
+        tma_load_1d(s_seq, (const void *)sa0, bytes, &bars[0]);
+        if (HAS_QUAL) tma_load_1d(s_qual, (const void *)qa0, qbytes, &bars[0]);
+    };
+    if (lane == 0 && wg < n_mt) issue(wg);
+    uint32_t phase0 = 0;
+    for (long long mt = wg; mt < n_mt; mt += warps_total) {
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long r = r0 + lane;
+        const long long b0 = a.offsets[r0], b1 = a.offsets[r1];
+        long long o0 = 0, o1 = 0;
+        if (r < n_reads) { o0 = a.offsets[r]; o1 = a.offsets[r + 1]; }
+        const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
+        if (b1 > b0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+        int cls = CG_PLANE_NONE, s0 = 0, ts = 0, te = 0;
+        uint32_t t_flags = 4u | CG_TASK_RESCAN;
+        uint32_t tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool mine = false;
+        if (r < n_reads) {
+            mine = true;
+            const int n = (int)(o1 - o0);
+            const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
+            ts = 0; te = n;
+            if (HAS_QUAL) {
+                const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+                const uint8_t *q = s_qual + (size_t)((qual_base + o0) - qa0);
+                if (a.quality_trim) pre_trim_core(s_seq + off, q, n, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
+            }
+            if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
+            if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
+            const int nn = te - ts;
+            if (nn >= 1 && nn <= 32 * W) {
+                const PlaneOut po = plane_scan_core<W, Prog>(prog, n_prog, pflags, A.m, ref, s_seq + off + te, nn, always_pass);
+                cls = po.cls; s0 = po.s0;
+                if (po.bad & 0x80808080u) atomicOr(a.err_flag, 1);
+                if (cls == CG_PLANE_SLOW) {
+                    t_flags = 4u | CG_TASK_PLANES | ((uint32_t)W << 12) | ((uint32_t)po.end_hit << 20);
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) tm[b] = po.M[b];
+                }
+            } else {
+                cls = CG_PLANE_SLOW;                 // (empty or over-long window: the exact path checks its bytes)
+                uint32_t bad = 0;
+                for (int i = ts; i < te; ++i) bad |= s_seq[off + i];
+                if (bad & 0x80u) atomicOr(a.err_flag, 1);
+            }
+            if (cls != CG_PLANE_SLOW) {
+                CgHit hit; hit.adapter = -1; hit.remove = 0;
+                hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
+                if (cls == CG_PLANE_EXACT) hit_exact(A, nn, s0, hit);
+                store_hit(a.out + (size_t)r * a.slots, hit, 0, nn);
+            }
+        }
+        const bool slow = mine && cls == CG_PLANE_SLOW;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
+        if (ballot) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.task_count, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (slow) {
+                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                a.tasks[4 * slot] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
+                                               (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
+                a.tasks[4 * slot + 1] = make_uint4(tm[0], t_flags, tm[1], tm[2]);
+                a.tasks[4 * slot + 2] = make_uint4(tm[3], tm[4], tm[5], tm[6]);
+                a.tasks[4 * slot + 3] = make_uint4(tm[7], 0u, 0u, 0u);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const long long next = mt + warps_total;
+            if (next < n_mt) issue(next);
+        }
+    }
+}
+

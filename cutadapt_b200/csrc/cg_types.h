@@ -10,7 +10,19 @@
 // bases).  The 128 x uint64 needle masks of the k-mer prefilter live in a second HBM array
 // (L1/L2 resident; 1 KiB per search word).
 #pragma once
+#if defined(__CUDACC_RTC__)      // NVRTC (cg_jit.cpp): no host headers
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+#else
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define CG_HD __host__ __device__ __forceinline__

@@ -197,6 +197,14 @@ int cg_adapterset_create_indexed(cg_ctx *ctx, const cg_adapter_desc *adapters, i
                                  const cg_group_desc *groups, int32_t n_groups,
                                  const cg_index_desc *indexes, int32_t n_indexes, cg_adapterset **out);
 int cg_adapterset_destroy(cg_adapterset *set);
+
+/* Run-time specialisation of the bit-plane first stage for this adapter set (compiled with NVRTC once the set has
+ * processed a few million reads; CUTADAPT_B200_JIT=1 at once, =0 never).  1 = in use, 0 = not (yet), -1 = the
+ * compilation failed and the precompiled kernel keeps running (cg_last_error() then says why).  There is no
+ * counterpart in the reference; results do not depend on it. */
+int cg_adapterset_jit_status(const cg_adapterset *set);
+/* The generated translation unit (for inspection).  Returns its length; copies at most cap - 1 characters. */
+int64_t cg_adapterset_jit_source(const cg_adapterset *set, int32_t plane_words, int32_t has_qual, char *buf, int64_t cap);
 int cg_adapterset_slots(const cg_adapterset *set); /* 1, or 2 if any group is LINKED */
 /* Aligner.effective_length / PrefixComparer.effective_length (_align.pyx:188,268-271,626-630) */
 int cg_adapterset_effective_length(const cg_adapterset *set, int32_t adapter, int32_t *out);

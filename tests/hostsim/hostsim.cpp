@@ -12,6 +12,7 @@
 #include "../../cutadapt_b200/csrc/cg_core.cuh"
 #include "../../cutadapt_b200/csrc/cg_fastq_core.cuh"
 #include "../../cutadapt_b200/csrc/cg_setbuild.h"
+#include "../../cutadapt_b200/csrc/cg_jit.h"
 
 static thread_local std::string g_err;
 
@@ -135,7 +136,8 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     return CG_OK;
 }
 
-// class of every read in the bit-plane first stage (0 none, 1 exact, 2 exact path; -1: no plane program)
+// class of every read in the bit-plane first stage (0 none, 1 exact, 2 exact path after a re-scan, 3 exact path
+// from the planes' hits; -1: no plane program)
 extern "C" int hs_plane_classify(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
                                  const uint8_t *seq, const int64_t *offsets, int64_t n_reads, int32_t *cls)
 {
@@ -155,11 +157,30 @@ extern "C" int hs_plane_classify(const cg_adapter_desc *adapters, int n_adapters
         const CgAdapter &A = S.ad[0];
         const uint8_t *ref = S.pool + A.ref_off;
         const PlaneOut po = n <= 160
-            ? plane_scan_core<5>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + offsets[r + 1], n, A.pf_count == 0)
-            : plane_scan_core<8>(plane_program(S), S.h->plane_count, S.h->plane_flags, A, ref, seq + offsets[r + 1], n, A.pf_count == 0);
-        cls[r] = po.cls;
+            ? plane_scan_core<5, RuntimePlaneProg>(plane_program(S), S.h->plane_count, S.h->plane_flags, A.m, ref, seq + offsets[r + 1], n, A.pf_count == 0)
+            : plane_scan_core<8, RuntimePlaneProg>(plane_program(S), S.h->plane_count, S.h->plane_flags, A.m, ref, seq + offsets[r + 1], n, A.pf_count == 0);
+        cls[r] = (po.cls == CG_PLANE_SLOW && window_is_plain(seq + offsets[r], n)) ? 3 : po.cls;   // 3: exact path without a re-scan
     }
     return CG_OK;
+}
+
+// The run-time specialisation of the first stage (cg_jit.cpp): generate the translation unit for this adapter set
+// and compile it with NVRTC for sm_100a (no device needed).  Returns the cubin size, 0 if the set has no plane
+// program, -1 if the compilation failed (log says why), -2 if libnvrtc is not there.
+extern "C" long hs_jit_compile(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
+                               int plane_words, int has_qual, char *src, long src_cap, char *log, long log_cap)
+{
+    CgBuiltSet set;
+    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err, nullptr, 0);
+    if (rc != CG_OK) return rc;
+    const std::string text = cg_jit_pscan_source(set, plane_words, has_qual != 0);
+    if (src && src_cap > 0) { strncpy(src, text.c_str(), (size_t)src_cap - 1); src[src_cap - 1] = 0; }
+    if (text.empty()) return 0;
+    std::string l;
+    const long n = cg_jit_compile_only(set, plane_words, has_qual != 0, l);
+    if (log && log_cap > 0) { strncpy(log, l.c_str(), (size_t)log_cap - 1); log[log_cap - 1] = 0; }
+    if (n < 0 && l.find("libnvrtc") != std::string::npos) return -2;
+    return n;
 }
 
 extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,

@@ -603,6 +603,36 @@ def test_both_kernel_schedules_agree():
         assert (other == exp).all(), ("shiftand", repr(adapter))
 
 
+def test_specialised_first_stage_matches_the_interpreter_and_the_oracle(monkeypatch):
+    """
+    The run-time specialisation of the first stage (cg_jit.cpp: the plane program written out as calls with literal
+    arguments, compiled with NVRTC) must give the records of the precompiled interpreter kernel and of the oracle.
+    """
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_reads
+
+    rng = random.Random(5)
+    for trial, seq in enumerate(["AGATCGGAAGAGC", "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA", "CTGTCTCTTATACACATCT", "TGGAATTCTCGGGTGCCAAGG"]):
+        ad = PA.BackAdapter(seq, max_errors=0.1, min_overlap=3, name="x")
+        d = ad.descriptor()
+        reads, quals = make_reads(30000, config=2, seed=100 + trial, with_qualities=True, adapter=seq)
+        reads += random_reads(rng, [seq], 3000, "ACGTNacgt", 200 if trial == 2 else 130)
+        quals += ["".join(chr(33 + rng.choice([2, 20, 30, 38])) for _ in r) for r in reads[30000:]]
+        qt = trial % 2 == 1
+        kw = dict(quality_trim=qt, cutoff_front=0, cutoff_back=20)
+        exp, eqt = oracle.oracle_process([d], None, reads, quals if qt else None, quality_trim=qt, cutoff_back=20)
+        monkeypatch.setenv("CUTADAPT_B200_JIT", "0")
+        plain, _ = run_set([d], None, reads, quals if qt else None, **kw)
+        monkeypatch.setenv("CUTADAPT_B200_JIT", "1")
+        aset = L.AdapterSet(L.AdapterSetSpec([d]))
+        data, offsets = L.pack_strings(reads)
+        qd = L.pack_strings(quals)[0] if qt else None
+        got, gqt = aset.process(data, offsets, qd, L.make_params(**kw))
+        assert aset.jit_status() == 1, L.last_error()
+        assert "plane_chain_step<W>" in aset.jit_source(5 if max(map(len, reads)) <= 160 else 8, qt)
+        assert (got == exp).all() and (plain == exp).all() and (not qt or (gqt == eqt).all()), seq
+
+
 def test_bitplane_first_stage_kernel_against_oracle():
     """
     cg_pscan_kernel (bit-plane first stage of plain A/C/G/T 3' adapters) + the exact path behind it: ragged reads of

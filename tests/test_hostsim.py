@@ -148,7 +148,7 @@ def test_bitplane_first_stage_against_oracle():
     from util import hostsim_plane_classes
 
     rng = random.Random(4242)
-    seen = np.zeros(4, dtype=np.int64)
+    seen = np.zeros(5, dtype=np.int64)
     n_planes = 0
     for trial in range(160):
         m = rng.choice([rng.randint(5, 12), 13, rng.randint(14, 33), 33, rng.randint(34, 60)])
@@ -178,9 +178,9 @@ def test_bitplane_first_stage_against_oracle():
         cls = hostsim_plane_classes(spec, reads)
         if (cls >= 0).any():
             n_planes += 1
-        seen += np.bincount(cls + 1, minlength=4)
+        seen += np.bincount(cls + 1, minlength=5)
     # the stage must actually decide reads: most adapters qualify, and all three classes occur
-    assert n_planes > 80 and seen[1] > 1000 and seen[2] > 1000 and seen[3] > 500, (n_planes, seen)
+    assert n_planes > 80 and seen[1] > 1000 and seen[2] > 1000 and seen[3] > 50 and seen[4] > 500, (n_planes, seen)
 
 
 def test_two_phase_on_golden_single_adapters():

@@ -80,7 +80,7 @@ def hostsim_process(spec, seqs, quals=None, params=None, force_wide=0):
 
 
 def hostsim_plane_classes(spec, seqs):
-    """Class of every read in the bit-plane first stage: 0 no match, 1 exact occurrence, 2 exact path, -1 n/a."""
+    """Class of every read in the bit-plane first stage: 0 no match, 1 exact occurrence, 2 re-scan, 3 plan from the planes' hits, -1 n/a."""
     from cutadapt_b200 import _lib as L
 
     arr, n, garr, ng = spec.to_ctypes()
