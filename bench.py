@@ -381,6 +381,8 @@ def main():
         step()
     barrier()
     batch.ctx.kernel_time(reset=True)
+    if os.environ.get("CUTADAPT_B200_STAGE_TIMES"):
+        batch.ctx.stage_times(reset=True)
     launches0 = batch.ctx.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -394,6 +396,7 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = batch.ctx.launch_count() - launches0
     kern_ms, kern_n = batch.ctx.kernel_time(reset=True)
+    stage_ms = batch.ctx.stage_times(reset=True) if os.environ.get("CUTADAPT_B200_STAGE_TIMES") else None
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -513,6 +516,7 @@ def main():
                          "kernel": "trim pipeline: cg_scan_kernel -> cg_list_kernel<plan> -> 4x cg_list_kernel<run> "
                                    "(all kernels of one pass; per-kernel shares in profiles/)",
                          "kernel_ms_per_launch": per_launch_ms,
+                         "stage_ms_per_launch": ({k: v / max(kern_n, 1) for k, v in stage_ms.items()} if stage_ms else None),
                          "algorithmic_bytes_per_read": ALGO_BYTES_PER_READ},
             "cpu_baseline": cpu,
             "e2e": e2e,

@@ -188,6 +188,7 @@ def _declare(lib) -> None:
         C.POINTER(cg_index_desc), i32, C.POINTER(vp),
     ]
     lib.cg_adapterset_destroy.argtypes = [vp]
+    lib.cg_ctx_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     lib.cg_adapterset_jit_status.argtypes = [vp]
     lib.cg_adapterset_jit_source.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]
     lib.cg_adapterset_jit_source.restype = C.c_int64
@@ -426,6 +427,12 @@ class Context:
         launches = C.c_int64()
         check(lib().cg_ctx_kernel_time(self._h, C.byref(total), C.byref(launches), int(reset)))
         return total.value, launches.value
+
+    def stage_times(self, reset: bool = False) -> dict:
+        """ms per stage of the split pipeline (only recorded while CUTADAPT_B200_STAGE_TIMES is set)."""
+        out = (C.c_double * 3)()
+        check(lib().cg_ctx_stage_times(self._h, out, int(reset)))
+        return {"first_stage_ms": out[0], "plan_ms": out[1], "dp_rounds_ms": out[2]}
 
     def host_profile(self, reset: bool = False) -> dict:
         """Seconds the host side of cg_process_batch spent per phase (cg_ctx_host_profile)."""

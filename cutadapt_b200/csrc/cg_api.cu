@@ -16,6 +16,8 @@
 
 #include "../../include/cutadapt_b200.h"
 #include "cg_hostpack.h"
+#include <array>
+
 #include "cg_kernels.cuh"
 #include "cg_jit.h"
 #include "cg_setbuild.h"
@@ -143,6 +145,9 @@ struct cg_ctx {
     std::vector<cudaEvent_t> event_pool;
     double timed_ms = 0.0;
     long long timed_n = 0;
+    // per-stage event timing of the split pipeline (CUTADAPT_B200_STAGE_TIMES=1; cg_ctx_stage_times)
+    std::vector<std::array<cudaEvent_t, 4>> stage_events;
+    double stage_ms[3] = {0, 0, 0};
     // host side of cg_process_batch
     CgHostPool *pool = nullptr;
     std::vector<std::vector<uint64_t>> exc_scratch;
@@ -283,6 +288,27 @@ extern "C" int cg_ctx_synchronize(cg_ctx *c)
 }
 
 extern "C" int64_t cg_ctx_launch_count(cg_ctx *c) { return c ? c->launches : 0; }
+
+// Device time of the three stages of the split pipeline (first stage, plan, DP rounds) since the last reset, in ms;
+// only recorded while CUTADAPT_B200_STAGE_TIMES is set in the environment (profiles/, tools).
+extern "C" int cg_ctx_stage_times(cg_ctx *c, double *out3, int reset)
+{
+    if (!c || !out3) return fail(CG_EINVAL, "cg_ctx_stage_times: NULL argument");
+    CU(cudaSetDevice(c->device));
+    for (auto &e : c->stage_events) {
+        CU(cudaEventSynchronize(e[3]));
+        for (int i = 0; i < 3; ++i) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+            c->stage_ms[i] += ms;
+        }
+        for (auto ev : e) cudaEventDestroy(ev);
+    }
+    c->stage_events.clear();
+    for (int i = 0; i < 3; ++i) out3[i] = c->stage_ms[i];
+    if (reset) c->stage_ms[0] = c->stage_ms[1] = c->stage_ms[2] = 0;
+    return CG_OK;
+}
 
 extern "C" int cg_ctx_kernel_time(cg_ctx *c, double *total_ms, int64_t *launches, int reset)
 {
@@ -535,6 +561,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             if (jit_occ >= 1) jit_kernel = s->jit[wi][qi];
         }
     }
+    const bool stage_times = getenv("CUTADAPT_B200_STAGE_TIMES") != nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (timed && c->timing.size() < 8192) {
         for (cudaEvent_t *ev : {&ev0, &ev1}) {
@@ -569,6 +596,11 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             const long long n_mt = (n_sub + 31) / 32;
             const long long need = (n_mt + 3) / 4;
             auto grid_for = [&](int occ) { return (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, need)); };
+            std::array<cudaEvent_t, 4> sev = {nullptr, nullptr, nullptr, nullptr};
+            if (stage_times && c->stage_events.size() < 4096) {
+                for (auto &e : sev) CU(cudaEventCreate(&e));
+                CU(cudaEventRecord(sev[0], st));
+            }
             b.tasks = c->tasks.p; b.task_count = cnt;
             b.task_rec = plane_w ? 4 : 2;
             if (plane_w && jit_kernel) {
@@ -577,9 +609,22 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             }
             else if (plane_w) CU(cg_launch_pscan(b, want_q, plane_w, grid_for(scan_occ), scan_smem, st));
             else CU(cg_launch_scan(b, want_q, grid_for(scan_occ), scan_smem, st));
+            if (sev[0]) CU(cudaEventRecord(sev[1], st));
             b.tasks2 = c->tasks2.p; b.task2_count = cnt + 1;
+            b.tasks3 = c->tasks3.p; b.task3_count = cnt + 2;
             CU(cg_launch_list(b, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
             c->launches += 2;
+            if (plane_w) {
+                // second plan launch: the reads the first one set aside (windows with other letters than A/C/G/T),
+                // scanned exactly on dense warps; its run records continue the same list
+                CgKernelArgs b2 = b;
+                b2.tasks = c->tasks3.p; b2.task_count = cnt + 2; b2.task_rec = 2;
+                b2.tasks3 = nullptr; b2.task3_count = cnt + 3;
+                CU(cg_launch_list(b2, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
+                CU(cudaMemsetAsync(cnt + 2, 0, sizeof(unsigned long long), st));
+                c->launches += 1;
+            }
+            if (sev[0]) CU(cudaEventRecord(sev[2], st));
             uint4 *lists[2] = {c->tasks2.p, c->tasks3.p};
             for (int round = 0; round < 4; ++round) {
                 const int in = round & 1, outl = in ^ 1;
@@ -589,6 +634,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
                 CU(cg_launch_list(b, false, s->host.max_m, grid_for(run_occ), list_smem, st));
                 c->launches += 1;
             }
+            if (sev[0]) { CU(cudaEventRecord(sev[3], st)); c->stage_events.push_back(sev); }
         }
         c->launches -= 1;    // the common tail below adds one
     } else if (warpk) {

@@ -39,6 +39,8 @@ struct CgKernelArgs {
     long long task_cap;
     uint4 *tasks2;                    // output list of the plan / run kernels: 4 x uint4 per record
     unsigned long long *task2_count;
+    uint4 *tasks3;                    // plan stage only: reads of cg_pscan_kernel whose window holds other letters than
+    unsigned long long *task3_count;  //   A/C/G/T go here (2 x uint4, CG_TASK_RESCAN) for a second, dense plan launch
     // generic-kernel scratch
     uint32_t *scratch_p;
     int *scratch_w;

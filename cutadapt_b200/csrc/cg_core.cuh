@@ -2278,11 +2278,35 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
 // as KmerFinder.kmers_present and the locator do (any other byte aliases one of the four letters in the planes).
 CG_HD bool window_is_plain(const uint8_t *p, int n)
 {
-    CG_CHARPTR(q, p);
+    // four characters at a time (aligned words; the bytes in front of / behind the window are masked off):
+    // with x = c & 0xDF, a byte is one of A C G T iff x ^ 0x41 is 0x00, 0x02, 0x06 or 0x15, i.e. iff
+    // y = x ^ 0x41 has no bit outside 0x17 and (y & 0x11) is 0x00 or 0x11 with (y & 0x06) in {0, 2, 6} for 0x00
+    // and exactly 0x04 for 0x11.  Spelled out per byte with carry-free SWAR logic below.
+    const uint32_t mis = (uint32_t)((uintptr_t)p & 3u);
+    const int total = n + (int)mis;                        // bytes from the aligned start
     uint32_t bad = 0;
-    for (int i = 0; i < n; ++i) {
-        const uint32_t idx = (CG_CHAR(q + i) & 0xDFu) - 'A';            // A 0, C 2, G 6, T 19
-        bad |= idx > 19u ? 1u : (~(0x80045u >> idx) & 1u);
+#if defined(__CUDA_ARCH__)
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(p - mis);
+#else
+    const uint8_t *base = p - mis;
+#endif
+    for (int o = 0; o < total; o += 4) {
+#if defined(__CUDA_ARCH__)
+        uint32_t w = cg_lds_u32(base + (uint32_t)o);
+#else
+        uint32_t w = (uint32_t)base[o] | ((uint32_t)base[o + 1] << 8) | ((uint32_t)base[o + 2] << 16) | ((uint32_t)base[o + 3] << 24);
+#endif
+        uint32_t keep = 0xFFFFFFFFu;
+        if (o == 0) keep &= 0xFFFFFFFFu << (8 * mis);
+        if (o + 4 > total) keep &= 0xFFFFFFFFu >> (8 * (uint32_t)(o + 4 - total));
+        const uint32_t y = (w & 0xDFDFDFDFu) ^ 0x41414141u;
+        // T: y == 0x15 (bits 4, 2, 0); A / C / G: y in {0x00, 0x02, 0x06}
+        const uint32_t t = (y >> 4) & 0x01010101u;         // 1 for a byte that claims to be T
+        const uint32_t tm = t * 0xFFu;                     // 0xFF in those bytes
+        const uint32_t want_t = y ^ 0x15151515u;           // 0 iff T
+        const uint32_t acg = (y & 0xF9F9F9F9u) | ((y & 0x04040404u) & ~((y << 1) & 0x04040404u));   // 0 iff 0x00 / 0x02 / 0x06
+        const uint32_t err = (want_t & tm) | (acg & ~tm);
+        bad |= err & keep;
     }
     return bad == 0;
 }

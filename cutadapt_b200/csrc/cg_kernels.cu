@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
         CgHit hit;
         hit.adapter = -1; hit.remove = 0;
         hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
-        bool cont = false;
+        bool cont = false, defer = false;
         uint4 ob = make_uint4(0, 0, 0, 0), oc = make_uint4(0, 0, 0, 0), od = make_uint4(0, 0, 0, 0);
         if (PLAN) {
             if (has_task) {
@@ -875,13 +875,20 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                 int gs = (int)(tb.y & 0xffu);
                 bool pass = true;
                 bool planned = false;
-                if ((tb.y & CG_TASK_PLANES) && window_is_plain(p, n)) {
-                    const uint32_t M[8] = {tb.x, tb.z, tb.w, tc.x, tc.y, tc.z, tc.w, td.x};
-                    const int W = (int)((tb.y >> 12) & 15u);
-                    plan_runs_planes(S, p, n, M, W, (int)((tb.y >> 20) & 1u), 32 * W - n, P);
-                    planned = true;
-                } else if (tb.y & (CG_TASK_RESCAN | CG_TASK_PLANES)) {
-                    // the exact scan of this read is still to do (a window with other letters than A/C/G/T)
+                if (tb.y & CG_TASK_PLANES) {
+                    if (window_is_plain(p, n)) {
+                        const uint32_t M[8] = {tb.x, tb.z, tb.w, tc.x, tc.y, tc.z, tc.w, td.x};
+                        const int W = (int)((tb.y >> 12) & 15u);
+                        plan_runs_planes(S, p, n, M, W, (int)((tb.y >> 20) & 1u), 32 * W - n, P);
+                        planned = true;
+                    } else {
+                        // other letters than A/C/G/T: the exact scan is still to do.  Such reads are rare (an N in
+                        // 1 of 7 reads), but one per warp would make every warp walk the scan: they are collected
+                        // and planned by a second launch on dense warps.
+                        defer = true;
+                        pass = false;
+                    }
+                } else if (tb.y & CG_TASK_RESCAN) {
                     const ScanOut sc = simple_scan(S, p, n, &gs);
                     pass = sc.pass; hits = sc.hits; rs0 = sc.rs0; rs1 = sc.rs1;
                 }
@@ -917,7 +924,20 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                 }
             }
         }
-        if (has_task && !cont) store_hit(a.out + (size_t)r * a.slots, hit, 0, n);
+        if (has_task && !cont && !defer) store_hit(a.out + (size_t)r * a.slots, hit, 0, n);
+        if (PLAN) {
+            const uint32_t dballot = __ballot_sync(0xffffffffu, defer);
+            if (dballot) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.task3_count, (unsigned long long)__popc(dballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (defer) {
+                    const unsigned long long slot = base + __popc(dballot & ((1u << lane) - 1u));
+                    a.tasks3[2 * slot] = ta;
+                    a.tasks3[2 * slot + 1] = make_uint4(0u, 4u | CG_TASK_RESCAN, 0u, 0u);
+                }
+            }
+        }
         const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
         if (ballot) {
             unsigned long long base = 0;

@@ -170,6 +170,9 @@ int64_t cg_ctx_launch_count(cg_ctx *ctx);
 /* Average device time in ms of the fused trimming kernel since the last reset, measured with
  * CUDA events on the launching stream; launches = number of samples. */
 int cg_ctx_kernel_time(cg_ctx *ctx, double *total_ms, int64_t *launches, int reset);
+/* Device time (ms) of the three stages of the split pipeline -- first stage, plan, DP rounds -- since the last reset;
+ * recorded only while CUTADAPT_B200_STAGE_TIMES is set in the environment (measurement aid, no reference counterpart). */
+int cg_ctx_stage_times(cg_ctx *ctx, double *out3, int reset);
 
 /* Bytes cg_process_batch has copied host->device / device->host on this context so far (what actually
  * crossed PCIe: the compressed read stream + exceptions, qualities, irregular offsets; the records back). */

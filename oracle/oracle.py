@@ -327,6 +327,149 @@ def oracle_process(adapters, groups, sequences, qualities=None, quality_trim=Fal
     return out, qtrim
 
 
+# ---- AdapterIndex (adapters.py:1289-1551): anchored adapters looked up in a dictionary of their neighbourhoods ----
+
+
+def hamming_sphere(s, k):
+    """All strings at Hamming distance exactly k from s over ACGT (_align.pyx:717-782)."""
+    import itertools
+
+    for positions in itertools.combinations(range(len(s)), k):
+        choices = [[c for c in "ACGT" if c != s[p]] for p in positions]
+        for repl in itertools.product(*choices):
+            t = list(s)
+            for p, c in zip(positions, repl):
+                t[p] = c
+            yield "".join(t)
+
+
+def edit_environment(t, k):
+    """
+    (s, errors, matches) for every string s over ACGT within edit distance k of t (_align.pyx:785-882): a depth-first
+    walk over the strings with one DP row per character; `matches` is carried along the same tie-broken optimal
+    path as there (diagonal if <= both, else left if <= up, else up).
+    """
+    n = len(t)
+    big = (k + 1) * 0x01010101
+    costs = [[big] * (n + 1) for _ in range(n + k + 1)]
+    matches = [[0] * (n + 1) for _ in range(n + k + 1)]
+    for i in range(n + k + 1):
+        costs[i][0] = i
+    for j in range(n + 1):
+        costs[0][j] = j
+    s = [0] * (n + k + 1)
+    tt = ["ACGT".index(c) for c in t.upper()]
+    i = 0
+    while True:
+        if i > 0:
+            ch = s[i - 1]
+            min_cost = 999999999
+            for j in range(max(1, i - k), min(n + 1, i + k + 1)):
+                match = 0 if tt[j - 1] == ch else 1
+                diag = costs[i - 1][j - 1] + match
+                left = costs[i][j - 1] + 1
+                up = costs[i - 1][j] + 1
+                if diag <= left and diag <= up:
+                    c, m = diag, matches[i - 1][j - 1] + (1 - match)
+                elif left <= up:
+                    c, m = left, matches[i][j - 1]
+                else:
+                    c, m = up, matches[i - 1][j]
+                costs[i][j] = c
+                matches[i][j] = m
+                min_cost = min(min_cost, c)
+        else:
+            min_cost = 0
+        if costs[i][n] <= k:
+            yield "".join("ACGT"[c] for c in s[:i]), costs[i][n], matches[i][n]
+        if min_cost <= k and i < n + k:
+            s[i] = 0
+            i += 1
+        else:
+            while True:
+                if i == 0:
+                    return
+                i -= 1
+                # (the rows above i keep stale cells of the previous branch outside their band, exactly like the
+                # reference's single matrix: they are re-initialised only where the band writes)
+                if s[i] < 3:
+                    break
+            s[i] += 1
+            i += 1
+
+
+def index_build(sequences, max_error_rate, indels):
+    """AdapterIndex._make_index (adapters.py:1398-1472): (lengths descending, {string: (adapter no, errors, matches)})."""
+    index, lengths, ambiguous = {}, set(), {}
+    for a, sequence in enumerate(sequences):
+        k = int(max_error_rate * len(sequence))
+        if indels:
+            env = edit_environment(sequence, k)
+        else:
+            env = ((s, e, len(sequence) - e) for e in range(k + 1) for s in hamming_sphere(sequence, e))
+        for s, errors, matches in env:
+            if s in index:
+                _, _, other_matches = index[s]
+                if matches < other_matches:
+                    continue
+                if other_matches == matches and s not in ambiguous:
+                    ambiguous[s] = True
+            index[s] = (a, errors, matches)
+            lengths.add(len(s))
+    for s in ambiguous:
+        del index[s]
+    return sorted(lengths, reverse=True), index
+
+
+def oracle_index_process(sequences, max_error_rate, indels, prefix, data, offsets, descriptors=None):
+    """
+    IndexedPrefixAdapters / IndexedSuffixAdapters.match_to over a packed batch (adapters.py:1474-1551): records with
+    the fields adapter, astart, astop, rstart, rstop, score (= matches), errors.  `descriptors` (one adapter
+    description per sequence, as for oracle_process) are needed only for reads with an N in the looked-up affix
+    (_lookup_with_n re-aligns with the adapter itself).
+    """
+    lengths, index = index_build(sequences, max_error_rate, indels)
+    bindex = {k.encode(): v for k, v in index.items()}
+    n = offsets.size - 1
+    out = np.zeros(n, dtype=MATCH_DTYPE)
+    out["adapter"] = -1
+    raw = np.ascontiguousarray(data, dtype=np.uint8).tobytes()
+    for i in range(n):
+        seq = raw[offsets[i]:offsets[i + 1]].upper()
+        best = None
+        best_m, best_e, best_len = -1, 1000, 0
+        for length in lengths:
+            if length < best_m:
+                break
+            affix = seq[:length] if prefix else seq[-length:]
+            if b"N" in affix:
+                hit = bindex.get(affix.replace(b"N", b"A"))
+                if hit is None:
+                    continue
+                m = match_single(descriptors[hit[0]], affix.decode())
+                if m is None:
+                    continue
+                a, e, mm = hit[0], m["errors"], m["score"]
+            else:
+                hit = bindex.get(affix)
+                if hit is None:
+                    continue
+                a, e, mm = hit
+            if mm > best_m or (mm == best_m and e < best_e):
+                best, best_e, best_m, best_len = a, e, mm, length
+        if best_m == -1:
+            continue
+        r = out[i]
+        r["adapter"] = best
+        r["astart"], r["astop"] = 0, len(sequences[best])
+        if prefix:
+            r["rstart"], r["rstop"] = 0, best_len
+        else:
+            r["rstart"], r["rstop"] = len(seq) - best_len, len(seq)
+        r["score"], r["errors"] = best_m, best_e
+    return out
+
+
 def oracle_process_packed(adapters, groups, data, offsets, qdata=None, quality_trim=False, cutoff_front=0,
                           cutoff_back=0, quality_base=33, times=1, nextseq_cutoff=None, threads=None):
     """

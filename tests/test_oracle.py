@@ -197,3 +197,69 @@ def test_fastq_oracle_reproduces_the_fasta_goldens_of_the_reference():
             descs, groups = spec.adapters, spec.groups
         got, _ = oracle.oracle_fastq_trim(fastq_file(f"fa_{c['name']}.in.fastq"), descs, groups, **fastq_case_kwargs(o))
         assert got == fastq_file(f"fa_{c['name']}.out.fastq"), (c["name"], c["command"])
+
+
+def test_packed_batch_loop_equals_the_per_read_composition():
+    """oracle_process_packed (the C loop the 10^6-read gate tests use) == oracle_process on every adapter type."""
+    import numpy as np
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200 import _lib as L
+    from util import random_reads
+
+    rng = random.Random(12)
+    for trial in range(25):
+        ads = ["".join(rng.choice("ACGT") for _ in range(rng.randint(5, 40))) for _ in range(rng.randint(1, 4))]
+        types = [PA.BackAdapter, PA.FrontAdapter, PA.AnywhereAdapter, PA.RightmostFrontAdapter, PA.RightmostBackAdapter,
+                 PA.PrefixAdapter, PA.SuffixAdapter, PA.NonInternalBackAdapter]
+        objs = [rng.choice(types)(a, max_errors=rng.choice([0.1, 0.2]), indels=rng.random() < 0.8, name="a") for a in ads]
+        if rng.random() < 0.4:
+            objs.append(PA.LinkedAdapter(PA.PrefixAdapter(ads[0][:10], max_errors=0.2), PA.BackAdapter(ads[-1], max_errors=0.1),
+                                         rng.random() < 0.5, rng.random() < 0.5, "l"))
+        multi = PA.MultipleAdapters(objs)
+        singles, groups, _ = multi._flatten()
+        descs = [s.descriptor() for s in singles]
+        reads = random_reads(rng, ads, 300, rng.choice(["ACGT", "ACGTN"]), 120)
+        quals = ["".join(chr(33 + rng.choice([2, 2, 15, 30, 38])) for _ in r) for r in reads]
+        qt, times = rng.random() < 0.5, rng.choice([1, 1, 2, 3])
+        nx = rng.choice([None, None, 20])
+        a, aq = oracle.oracle_process(descs, groups, reads, quals, qt, 5, 20, 33, times, nextseq_cutoff=nx)
+        data, offs = L.pack_strings(reads)
+        qd, _ = L.pack_strings(quals)
+        b, bq = oracle.oracle_process_packed(descs, groups, data, offs, qd, qt, 5, 20, 33, times, nextseq_cutoff=nx,
+                                             threads=rng.choice([1, 3]))
+        assert (a == b).all() and (aq == bq).all(), trial
+
+
+def test_neighbourhoods_and_index_golden():
+    """edit_environment / hamming_sphere / AdapterIndex of the oracle against the reference's own (goldens + _ref)."""
+    for t, k, ee, he in golden("environment_kat.json.gz"):
+        assert sorted(map(list, oracle.edit_environment(t, k))) == sorted(ee), (t, k)
+        ham = [[s, e, len(t) - e] for e in range(k + 1) for s in oracle.hamming_sphere(t, e)]
+        assert sorted(ham) == sorted(he), (t, k)
+    ref = reference_or_none()
+    if ref is None:
+        return
+    import numpy as np
+    import cutadapt.adapters as RA
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.configs import config5_barcodes, make_config_batch, to_strings
+
+    bcs = config5_barcodes()
+    for indels in (True, False):
+        lengths, index = oracle.index_build(bcs, 0.1, indels)
+        idx = RA.IndexedPrefixAdapters([RA.PrefixAdapter(b, max_errors=0.1, indels=indels, name=f"bc{i}") for i, b in enumerate(bcs)])
+        assert set(idx._index._index) == set(index) and list(idx._index._lengths) == lengths
+        seq = make_config_batch(5, 3000, seed=77)["seq"]
+        seq[::50, 3] = ord("N")
+        host = seq.numpy().reshape(-1)
+        offs = np.arange(3001, dtype=np.int64) * 150
+        descs = [PA.PrefixAdapter(b, max_errors=0.1, indels=indels, name=f"bc{i}").descriptor() for i, b in enumerate(bcs)]
+        out = oracle.oracle_index_process(bcs, 0.1, indels, True, host, offs, descs)
+        for i, r in enumerate(to_strings(seq)):
+            m = idx.match_to(r)
+            rec = out[i]
+            if m is None:
+                assert rec["adapter"] < 0
+            else:
+                assert (int(m.adapter.name[2:]), m.astart, m.astop, m.rstart, m.rstop, m.score, m.errors) == tuple(
+                    int(rec[f]) for f in ("adapter", "astart", "astop", "rstart", "rstop", "score", "errors")), r
