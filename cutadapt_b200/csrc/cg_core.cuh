@@ -887,6 +887,14 @@ CG_HD void plane_emit(PlaneState<W> &st, int len, int type, int flags, int shift
 
 // The interpreter of the op list in the adapter blob (cg_types.h: CG_PLANE_OP_*, CgPlaneEmit).
 struct RuntimePlaneProg {
+    // do the m characters at w spell the adapter (either case)?
+    CG_HD static bool same_adapter(const uint8_t *w, const uint8_t *ref, int m)
+    {
+        bool same = true;
+        for (int i = 0; i < m; ++i) same = same && ((w[i] & 0xDFu) == ref[i]);
+        return same;
+    }
+    CG_HD static int adapter_length(int m) { return m; }
     template <int W>
     CG_HD static void run(PlaneState<W> &st, const uint32_t *ops, int n_ops, int m)
     {
@@ -906,7 +914,7 @@ struct RuntimePlaneProg {
 
 // What the planes settle, and what they hand on (see the head of this section for the rules).
 //   exact_ok : plane_flags bit 0;  m, ref: the adapter;  base / off0 / n as in plane_load
-template <int W>
+template <int W, class Prog>
 CG_HD void plane_decide(const PlaneState<W> &st, bool exact_ok, int m, const uint8_t *ref, const uint8_t *base,
                         int off0, int n, bool always_pass, PlaneOut &out)
 {
@@ -928,10 +936,7 @@ CG_HD void plane_decide(const PlaneState<W> &st, bool exact_ok, int m, const uin
         }
         const int s0 = low - (m - 1) - off0;
         if (found && ex && s0 >= 0 && s0 + m <= n) {
-            const uint8_t *w = base + (low - (m - 1));
-            bool same = true;
-            for (int i = 0; i < m; ++i) same = same && ((w[i] & 0xDFu) == ref[i]);
-            if (same) { out.cls = CG_PLANE_EXACT; out.s0 = s0; return; }
+            if (Prog::same_adapter(base + (low - (m - 1)), ref, m)) { out.cls = CG_PLANE_EXACT; out.s0 = s0; return; }
         }
     }
     // handed on: the plan stage gets the hits (plan_runs_planes) -- it still has to make sure the window holds
@@ -952,8 +957,9 @@ CG_HD PlaneOut plane_scan_core(const uint32_t *ops, int n_ops, int plane_flags, 
     const int off0 = 32 * W - n;                     // plane index of the window's first character
     const uint8_t *base = end - 32 * W;              // plane index 0
     out.bad = plane_load<W>(st, base, off0);
+    m = Prog::adapter_length(m);                     // (a literal in a specialised program)
     Prog::template run<W>(st, ops, n_ops, m);
-    plane_decide<W>(st, (plane_flags & 1) != 0, m, ref, base, off0, n, always_pass, out);
+    plane_decide<W, Prog>(st, (plane_flags & 1) != 0, m, ref, base, off0, n, always_pass, out);
     return out;
 }
 
@@ -2278,37 +2284,40 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
 // as KmerFinder.kmers_present and the locator do (any other byte aliases one of the four letters in the planes).
 CG_HD bool window_is_plain(const uint8_t *p, int n)
 {
-    // four characters at a time (aligned words; the bytes in front of / behind the window are masked off):
-    // with x = c & 0xDF, a byte is one of A C G T iff x ^ 0x41 is 0x00, 0x02, 0x06 or 0x15, i.e. iff
-    // y = x ^ 0x41 has no bit outside 0x17 and (y & 0x11) is 0x00 or 0x11 with (y & 0x06) in {0, 2, 6} for 0x00
-    // and exactly 0x04 for 0x11.  Spelled out per byte with carry-free SWAR logic below.
+    // Four characters per aligned word.  A byte c is one of A C G T a c g t iff
+    //   bit 7 = 0, bit 3 = 0, bit 6 = 1            (bit 5 is the case bit),
+    //   bit 4 = bit 2 & ~bit 1                     (only T, 101_0100, has bit 4; it is the code with bit 2 and not bit 1),
+    //   bit 0 != bit 4                             (A C G end in 1, T in 0).
+    // The three conditions are accumulated over the words (two ORs of violations, one AND for bit 6); the bytes
+    // of the first and last word that lie outside the window are replaced by 'A'.
+    if (n <= 0) return true;
     const uint32_t mis = (uint32_t)((uintptr_t)p & 3u);
     const int total = n + (int)mis;                        // bytes from the aligned start
-    uint32_t bad = 0;
+    const int n_words = (total + 3) >> 2;
 #if defined(__CUDA_ARCH__)
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(p - mis);
+#define CG_PLAIN_WORD(i) cg_lds_u32(base + 4u * (uint32_t)(i))
 #else
     const uint8_t *base = p - mis;
+#define CG_PLAIN_WORD(i) ((uint32_t)base[4 * (i)] | ((uint32_t)base[4 * (i) + 1] << 8) | ((uint32_t)base[4 * (i) + 2] << 16) | \
+                          ((uint32_t)base[4 * (i) + 3] << 24))
 #endif
-    for (int o = 0; o < total; o += 4) {
-#if defined(__CUDA_ARCH__)
-        uint32_t w = cg_lds_u32(base + (uint32_t)o);
-#else
-        uint32_t w = (uint32_t)base[o] | ((uint32_t)base[o + 1] << 8) | ((uint32_t)base[o + 2] << 16) | ((uint32_t)base[o + 3] << 24);
-#endif
-        uint32_t keep = 0xFFFFFFFFu;
-        if (o == 0) keep &= 0xFFFFFFFFu << (8 * mis);
-        if (o + 4 > total) keep &= 0xFFFFFFFFu >> (8 * (uint32_t)(o + 4 - total));
-        const uint32_t y = (w & 0xDFDFDFDFu) ^ 0x41414141u;
-        // T: y == 0x15 (bits 4, 2, 0); A / C / G: y in {0x00, 0x02, 0x06}
-        const uint32_t t = (y >> 4) & 0x01010101u;         // 1 for a byte that claims to be T
-        const uint32_t tm = t * 0xFFu;                     // 0xFF in those bytes
-        const uint32_t want_t = y ^ 0x15151515u;           // 0 iff T
-        const uint32_t acg = (y & 0xF9F9F9F9u) | ((y & 0x04040404u) & ~((y << 1) & 0x04040404u));   // 0 iff 0x00 / 0x02 / 0x06
-        const uint32_t err = (want_t & tm) | (acg & ~tm);
-        bad |= err & keep;
+    uint32_t hi_or = 0, lo_or = 0, six_and = 0xFFFFFFFFu;
+    for (int i = 0; i < n_words; ++i) {
+        uint32_t w = CG_PLAIN_WORD(i);
+        if (i == 0 || i == n_words - 1) {
+            uint32_t keep = 0xFFFFFFFFu;
+            if (i == 0) keep &= 0xFFFFFFFFu << (8 * mis);
+            if (i == n_words - 1 && (total & 3)) keep &= 0xFFFFFFFFu >> (8 * (4 - (total & 3)));
+            w = (w & keep) | (0x41414141u & ~keep);
+        }
+        const uint32_t s1 = w >> 1, s2 = w >> 2, s4 = w >> 4;
+        hi_or |= w & 0x88888888u;                                      // bits 7 and 3 must be clear
+        six_and &= w;                                                  // bit 6 must be set
+        lo_or |= ((s2 & ~s1) ^ s4) | ~(w ^ s4);                        // bit 0 of every byte: a violation
     }
-    return bad == 0;
+#undef CG_PLAIN_WORD
+    return hi_or == 0 && (six_and & 0x40404040u) == 0x40404040u && (lo_or & 0x01010101u) == 0;
 }
 
 // The plan of a read whose locator hits come from the bit-plane stage: M (W words, plane indices) marks the

@@ -18,7 +18,8 @@ N_REF = 100_000
 
 
 def _flat(multi):
-    singles, groups, _ = multi._flatten()
+    singles, groups, owners = multi._flatten()
+    multi._device_set = (None, singles, owners)        # lets matches_from_records() map records back to objects
     return [s.descriptor() for s in singles], groups
 
 
