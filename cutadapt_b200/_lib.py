@@ -206,7 +206,7 @@ def _declare(lib) -> None:
     lib.cg_stats_size.argtypes = [i32, i32, i32]
     lib.cg_stats_size.restype = i64
     lib.cg_stats_accumulate_device.argtypes = [
-        vp, vp, vp, i64, C.POINTER(cg_params), vp, vp, i32, i32, vp,
+        vp, vp, vp, vp, i64, C.POINTER(cg_params), vp, vp, i32, i32, vp,
     ]
     lib.cg_edit_environment.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i64]
     lib.cg_edit_environment.restype = i64

@@ -65,15 +65,15 @@ class EndStatistics:
     ``errors[l][e]``, ``adjacent_bases``, ``lengths``, the adapter's parameters.
     """
 
+    # the adapter parameters the report prints next to the counts (and __iadd__ compares)
+    _COPIED = ("max_error_rate", "sequence", "effective_length", "indels", "allows_partial_matches")
+
     def __init__(self, adapter: "SingleAdapter"):
-        self.max_error_rate: float = adapter.max_error_rate
-        self.sequence: str = adapter.sequence
-        self.effective_length: int = adapter.effective_length
+        for field in self._COPIED:
+            setattr(self, field, getattr(adapter, field))
         self.has_wildcards: bool = adapter.adapter_wildcards
-        self.indels: bool = adapter.indels
         self.adapter_type: str = adapter.descriptive_identifier()
-        self.allows_partial_matches: bool = adapter.allows_partial_matches
-        self._remove_prefix = isinstance(adapter, FrontAdapter)
+        self._remove_prefix = isinstance(adapter, FrontAdapter)   # (which way random_match_probabilities reads)
         self._counts: Counter = Counter()                    # (length, errors) -> n
         self.adjacent_bases: Dict[str, int] = {k: 0 for k in ADJACENT_KEYS}
 

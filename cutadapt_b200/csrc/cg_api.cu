@@ -1294,10 +1294,10 @@ extern "C" int cg_poly_a_trim_batch(cg_ctx *c, const uint8_t *seq, const int64_t
 extern "C" int64_t cg_stats_size(int32_t n_adapters, int32_t max_len, int32_t kmax)
 {
     if (n_adapters < 0 || max_len < 0 || kmax < 0) return -1;
-    return 8 + (int64_t)n_adapters * (max_len + 1) * (kmax + 1);
+    return cg_stats_total(n_adapters, max_len, kmax);
 }
 
-extern "C" int cg_stats_accumulate_device(cg_ctx *c, const cg_adapterset *s, const int64_t *d_offsets,
+extern "C" int cg_stats_accumulate_device(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const int64_t *d_offsets,
                                           int64_t n_reads, const cg_params *p, const cg_match *d_matches,
                                           const int32_t *d_qtrim, int32_t max_len, int32_t kmax,
                                           int64_t *d_stats)
@@ -1307,7 +1307,7 @@ extern "C" int cg_stats_accumulate_device(cg_ctx *c, const cg_adapterset *s, con
     if (n_reads <= 0) return CG_OK;
     CU(cudaSetDevice(c->device));
     const int times = p->times < 1 ? 1 : p->times;
-    CU(cg_launch_stats(d_offsets, n_reads, (p->quality_trim || p->nextseq_trim) && d_qtrim, times, s->host.slots,
+    CU(cg_launch_stats(d_seq, d_offsets, n_reads, (p->quality_trim || p->nextseq_trim) && d_qtrim, times, s->host.slots,
                        (const cg_match_rec *)d_matches, d_qtrim, s->host.n_adapters, max_len, kmax,
                        (unsigned long long *)d_stats, c->stream));
     c->launches += 1;

@@ -1241,6 +1241,63 @@ CG_HD void process_read(const SetView &S, const uint8_t *seq, const uint8_t *qua
 }
 
 // ---------------------------------------------------------------------------------------
+// Statistics of one read (cg_stats_kernel; tests/hostsim runs the same function).  `add(index, n)` adds to an
+// entry of the vector relative to its histogram part (index 0 = first entry of the read-length histogram);
+// the five scalar sums are returned through `sc` (n is counted by the caller).
+//   seq   : the read's bytes or null (then no adjacent bases are counted)
+//   recs  : times x slots records of this read
+// Window bookkeeping as the reference does it: the rounds work on what the previous ones left
+// (modifiers.py:225-231), a linked adapter's 3' part on what its 5' part left (adapters.py:1220-1222).
+// ---------------------------------------------------------------------------------------
+struct StatsScalars { unsigned long long bp, with_adapters, qtrim_bp, adapter_bp; };
+
+template <class Add>
+CG_HD void stats_read_core(const uint8_t *seq, int len, bool have_qtrim, int qs, int qe, const cg_match_rec *recs,
+                           int times, int slots, int n_adapters, int max_len, int kmax, StatsScalars &sc, Add add)
+{
+    sc.bp += (unsigned long long)len;
+    int ws = 0, we = len;                                   // current window [ws, we) of the original read
+    if (have_qtrim) { ws = qs; we = qe; sc.qtrim_bp += (unsigned long long)(len - (qe - qs)); }
+    const long long end_size = cg_stats_end_size(max_len, kmax);
+    const long long adapters_rel = max_len + 1;             // relative to the read-length histogram
+    bool any = false;
+    for (int t = 0; t < times; ++t) {
+        for (int s = 0; s < slots; ++s) {
+            const cg_match_rec m = recs[(size_t)t * slots + s];
+            if (m.adapter < 0) continue;
+            any = true;
+            const bool after = (m.info & 256) != 0;
+            const int cur = we - ws;
+            const int removed = after ? cur - m.rstart : m.rstop;
+            sc.adapter_bp += (unsigned long long)(removed < 0 ? 0 : removed);
+            if (m.adapter < n_adapters) {
+                const int L = removed < 0 ? 0 : (removed > max_len ? max_len : removed);
+                const int E = m.errors < 0 ? 0 : (m.errors > kmax ? kmax : m.errors);
+                const long long blk = adapters_rel + (2LL * m.adapter + (after ? 1 : 0)) * end_size;
+                add(blk + CG_STATS_ADJ + (long long)L * (kmax + 1) + E, 1u);
+                if (after && seq) {
+                    // Match.adjacent_base(): the character in front of the match, "" at the start of the read;
+                    // anything but an upper-case A/C/G/T counts as "" (adapters.py:193-199, 488-489)
+                    int k = 4;
+                    const int pos = ws + m.rstart - 1;
+                    if (m.rstart > 0 && pos >= 0 && pos < len) {
+                        const uint8_t c = seq[pos];
+                        k = c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
+                    }
+                    add(blk + k, 1u);
+                }
+            }
+            // Match.trimmed(): python slice semantics (indexes beyond the window clamp)
+            if (after) { const int rs = m.rstart < 0 ? 0 : (m.rstart > cur ? cur : m.rstart); we = ws + rs; }
+            else { const int rp = m.rstop < 0 ? 0 : (m.rstop > cur ? cur : m.rstop); ws += rp; }
+        }
+    }
+    sc.with_adapters += any ? 1 : 0;
+    const int fin = we - ws;
+    add((long long)(fin < 0 ? 0 : (fin > max_len ? max_len : fin)), 1u);
+}
+
+// ---------------------------------------------------------------------------------------
 // Multi-pass schedule: every component adapter of a set is located on its own (one pass each, into
 // a scratch array of records), then these two functions apply the composition rules.
 // ---------------------------------------------------------------------------------------

@@ -1298,68 +1298,56 @@ cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *
 // (Statistics.__iadd__ report.py:81-126; EndStatistics.errors adapters.py:96-111,193-199)
 // ------------------------------------------------------------------------------------------
 template <bool SMEM_HIST>
-__global__ void cg_stats_kernel(const int64_t *offsets, long long n_reads, int quality_trim, int times,
+__global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long long n_reads, int quality_trim, int times,
                                 int slots, const cg_match_rec *matches, const int32_t *qtrim,
                                 int n_adapters, int max_len, int kmax, unsigned long long *stats)
 {
     // per-CTA histogram in shared memory (32-bit counts, flushed once); the global histogram would
     // otherwise take one contended atomic per match
     extern __shared__ unsigned int s_hist[];
-    const int nbins = n_adapters * (max_len + 1) * (kmax + 1);
+    const long long nbins = cg_stats_total(n_adapters, max_len, kmax) - CG_STATS_SCALARS;
     if (SMEM_HIST) {
-        for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0;
+        for (long long i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
     }
     const long long nthreads = (long long)gridDim.x * blockDim.x;
-    unsigned long long n = 0, bp = 0, with_ad = 0, qbp = 0, abp = 0;
-    unsigned long long *hist = stats + 8;
+    unsigned long long n = 0;
+    StatsScalars sc; sc.bp = sc.with_adapters = sc.qtrim_bp = sc.adapter_bp = 0;
+    unsigned long long *hist = stats + CG_STATS_SCALARS;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
-        const long long len = offsets[r + 1] - offsets[r];
-        n += 1; bp += (unsigned long long)len;
-        long long cur = len;
-        if (quality_trim && qtrim) { cur = qtrim[2 * r + 1] - qtrim[2 * r]; qbp += (unsigned long long)(len - cur); }
-        bool any = false;
-        for (int t = 0; t < times; ++t) {
-            for (int s = 0; s < slots; ++s) {
-                const cg_match_rec m = load_rec(matches + ((size_t)r * times + t) * slots + s);
-                if (m.adapter < 0) continue;
-                any = true;
-                const int searched = (m.info >> 16) & 0xFFFF;
-                const int removed = (m.info & 256) ? searched - m.rstart : m.rstop;
-                abp += (unsigned long long)removed;
-                if (m.adapter < n_adapters) {
-                    const int L = removed < 0 ? 0 : (removed > max_len ? max_len : removed);
-                    const int E = m.errors < 0 ? 0 : (m.errors > kmax ? kmax : m.errors);
-                    const size_t bin = ((size_t)m.adapter * (max_len + 1) + L) * (kmax + 1) + E;
-                    if (SMEM_HIST) atomicAdd(&s_hist[bin], 1u);
-                    else atomicAdd(&hist[bin], 1ULL);
-                }
-            }
-        }
-        with_ad += any ? 1 : 0;
+        const long long o0 = offsets[r];
+        const int len = (int)(offsets[r + 1] - o0);
+        n += 1;
+        const bool hq = quality_trim && qtrim;
+        stats_read_core(seq ? seq + o0 : nullptr, len, hq, hq ? qtrim[2 * r] : 0, hq ? qtrim[2 * r + 1] : len,
+                        matches + (size_t)r * times * slots, times, slots, n_adapters, max_len, kmax, sc,
+                        [&](long long idx, unsigned int v) {
+                            if (SMEM_HIST) atomicAdd(&s_hist[idx], v);
+                            else atomicAdd(&hist[idx], (unsigned long long)v);
+                        });
     }
     // warp-reduce the scalar counters, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
         n += __shfl_xor_sync(0xffffffffu, n, o);
-        bp += __shfl_xor_sync(0xffffffffu, bp, o);
-        with_ad += __shfl_xor_sync(0xffffffffu, with_ad, o);
-        qbp += __shfl_xor_sync(0xffffffffu, qbp, o);
-        abp += __shfl_xor_sync(0xffffffffu, abp, o);
+        sc.bp += __shfl_xor_sync(0xffffffffu, sc.bp, o);
+        sc.with_adapters += __shfl_xor_sync(0xffffffffu, sc.with_adapters, o);
+        sc.qtrim_bp += __shfl_xor_sync(0xffffffffu, sc.qtrim_bp, o);
+        sc.adapter_bp += __shfl_xor_sync(0xffffffffu, sc.adapter_bp, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&stats[0], n); atomicAdd(&stats[1], bp); atomicAdd(&stats[2], with_ad);
-        atomicAdd(&stats[3], qbp); atomicAdd(&stats[4], abp);
+        atomicAdd(&stats[0], n); atomicAdd(&stats[1], sc.bp); atomicAdd(&stats[2], sc.with_adapters);
+        atomicAdd(&stats[3], sc.qtrim_bp); atomicAdd(&stats[4], sc.adapter_bp);
     }
     if (SMEM_HIST) {
         __syncthreads();
-        for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+        for (long long i = threadIdx.x; i < nbins; i += blockDim.x) {
             const unsigned int v = s_hist[i];
             if (v) atomicAdd(&hist[i], (unsigned long long)v);
         }
     }
 }
 
-cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
+cudaError_t cg_launch_stats(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
                             int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
                             int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
                             cudaStream_t st)
@@ -1368,13 +1356,13 @@ cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int qua
     long long grid = (n_reads + block - 1) / block;
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    const size_t hist_bytes = (size_t)n_adapters * (max_len + 1) * (kmax + 1) * sizeof(unsigned int);
+    const size_t hist_bytes = (size_t)(cg_stats_total(n_adapters, max_len, kmax) - CG_STATS_SCALARS) * sizeof(unsigned int);
     // a CTA handles n_reads / grid reads, so 32-bit per-CTA counts cannot overflow below 2^32 reads per CTA
     if (hist_bytes <= 48 * 1024 && n_reads / grid < (1LL << 31))
-        cg_stats_kernel<true><<<(int)grid, block, hist_bytes, st>>>(d_offsets, n_reads, quality_trim, times, slots,
+        cg_stats_kernel<true><<<(int)grid, block, hist_bytes, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots,
                                                                      d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats);
     else
-        cg_stats_kernel<false><<<(int)grid, block, 0, st>>>(d_offsets, n_reads, quality_trim, times, slots, d_matches,
+        cg_stats_kernel<false><<<(int)grid, block, 0, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots, d_matches,
                                                              d_qtrim, n_adapters, max_len, kmax, d_stats);
     return cudaGetLastError();
 }

@@ -46,7 +46,7 @@ cudaError_t cg_launch_quality_trim(const uint8_t *d_qual, const int64_t *d_offse
                                    int cutoff_front, int cutoff_back, int base, int32_t *d_out,
                                    cudaStream_t st);
 cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *d_out, cudaStream_t st);
-cudaError_t cg_launch_stats(const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
+cudaError_t cg_launch_stats(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
                             int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
                             int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
                             cudaStream_t st);

@@ -159,6 +159,29 @@ struct CgSelectTables {
     int8_t front_required[CG_MAX_PASSES], back_required[CG_MAX_PASSES];
 };
 
+// Trim statistics vector (cg_stats_accumulate_device; the payload of the end-of-run all-reduce):
+//   [0] n_reads  [1] total_bp  [2] reads_with_adapters  [3] quality_trimmed_bp  [4] bp_removed_by_adapters
+//   [5] reverse_complemented  [6] n_written  [7] bp_written  [8..14] filtered[7]: too_short, too_long,
+//   too_many_n, too_many_expected_errors, casava_filtered, discard_trimmed, discard_untrimmed  [15] reserved
+//       ([5..14] belong to steps outside the match records -- ReverseComplementer, the filters, the writer -- and are
+//        filled by whoever runs those steps; they are part of the vector so that ONE all-reduce carries everything
+//        Statistics.__iadd__ adds up, report.py:81-126)
+//   [16 .. 16 + max_len]   read-length histogram: final length of every read after all trimming
+//                          (ReadLengthStatistics, statistics.py:5-48, before filters)
+//   then per adapter a, per end (0 = 5' side: matches that remove what precedes them, 1 = 3' side):
+//       adjacent[8]: counts of the base in front of a 3' match, order A C G T other (EndStatistics.adjacent_bases,
+//                    adapters.py:84, 193-199); [5..7] unused
+//       hist[removed_len (0..max_len)][errors (0..kmax)]          (EndStatistics.errors, adapters.py:82)
+#define CG_STATS_SCALARS 16
+#define CG_STATS_ADJ 8
+CG_HD long long cg_stats_end_size(int max_len, int kmax) { return CG_STATS_ADJ + (long long)(max_len + 1) * (kmax + 1); }
+CG_HD long long cg_stats_lengths_off() { return CG_STATS_SCALARS; }
+CG_HD long long cg_stats_adapters_off(int max_len) { return CG_STATS_SCALARS + (max_len + 1); }
+CG_HD long long cg_stats_total(int n_adapters, int max_len, int kmax)
+{
+    return cg_stats_adapters_off(max_len) + 2LL * n_adapters * cg_stats_end_size(max_len, kmax);
+}
+
 // One result of locating a single adapter in a (sub)sequence; coordinates as SingleMatch.
 struct CgHit {
     int32_t adapter;        // -1 = none

@@ -11,12 +11,29 @@ The order of k-mers *within* one search set is unspecified in the reference too 
 Python sets, kmer_heuristic.py:21-26); only the boolean outcome matters.  Here the order is
 made deterministic (first occurrence in the adapter).
 """
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Set, Tuple
 
 SearchSet = Tuple[int, Optional[int], List[str]]
 
 
-def kmer_chunks(sequence: str, chunks: int) -> List[str]:
+def kmer_chunks(sequence: str, chunks: int) -> Set[str]:
+    """The pieces as a set, the reference's return type (kmer_heuristic.py:6-22); the tables are built from the
+    ordered form, ``_ordered_chunks``."""
+    return set(_ordered_chunks(sequence, chunks))
+
+
+def create_back_overlap_searchsets(adapter: str, min_overlap: int, error_rate: float):
+    """The reference's name and return type for ``_back_overlap_search_sets`` (kmer_heuristic.py:87-117)."""
+    return [(start, stop, set(kmers)) for start, stop, kmers in _back_overlap_search_sets(adapter, min_overlap, error_rate)]
+
+
+def minimize_kmer_search_list(kmer_search_list):
+    """(kmer, start, stop) triples with every k-mer kept only in its widest window(s) (kmer_heuristic.py:29-84)."""
+    merged = _merge_windows([(start, stop, [kmer]) for kmer, start, stop in kmer_search_list])
+    return [(kmer, start, stop) for start, stop, kmers in merged for kmer in kmers]
+
+
+def _ordered_chunks(sequence: str, chunks: int) -> List[str]:
     """
     Split ``sequence`` into ``chunks`` nearly equal pieces, the longer ones first, and
     return the distinct pieces in order of appearance (kmer_heuristic.py:6-22).
@@ -54,7 +71,7 @@ def _back_overlap_search_sets(adapter: str, min_overlap: int, error_rate: float)
             for size in range(shortest, 5):
                 search_sets.append((-size, None, [adapter[:size]]))
             shortest = 5
-        search_sets.append((-longest, None, kmer_chunks(adapter[:shortest], errors + 1)))
+        search_sets.append((-longest, None, _ordered_chunks(adapter[:shortest], errors + 1)))
         shortest = longest + 1
     return search_sets
 
@@ -111,5 +128,5 @@ def create_positions_and_kmers(
             search_sets.append((0, -start, [kmer[::-1] for kmer in kmers]))
     if internal:
         max_errors = int(len(adapter) * error_rate)
-        search_sets.append((0, None, kmer_chunks(adapter, max_errors + 1)))
+        search_sets.append((0, None, _ordered_chunks(adapter, max_errors + 1)))
     return _merge_windows(search_sets)

@@ -31,14 +31,64 @@ from .adapters import Matchable, MultipleAdapters
 # ---- statistics vector layout (include/cutadapt_b200.h: cg_stats_accumulate_device) ----------
 
 STAT_N_READS, STAT_TOTAL_BP, STAT_WITH_ADAPTERS, STAT_QUALITY_TRIMMED_BP, STAT_ADAPTER_BP = 0, 1, 2, 3, 4
+STAT_REVERSE_COMPLEMENTED, STAT_N_WRITTEN, STAT_BP_WRITTEN, STAT_FILTERED = 5, 6, 7, 8
+FILTER_NAMES = ("too_short", "too_long", "too_many_n", "too_many_expected_errors", "casava_filtered", "discard_trimmed",
+                "discard_untrimmed")
+_SCALARS, _ADJ = 16, 8
 
 
 def stats_layout(n_adapters: int, max_len: int, kmax: int) -> dict:
+    """Where the parts of the statistics vector are (cg_types.h: cg_stats_*)."""
+    end = _ADJ + (max_len + 1) * (kmax + 1)
+    adapters = _SCALARS + max_len + 1
     return {
-        "size": 8 + n_adapters * (max_len + 1) * (kmax + 1),
-        "hist": 8,
-        "shape": (n_adapters, max_len + 1, kmax + 1),
+        "size": adapters + 2 * n_adapters * end,
+        "lengths": _SCALARS,                 # read-length histogram: max_len + 1 entries
+        "adapters": adapters,                # per adapter, per end (0: 5' side, 1: 3' side): adjacent[8] + hist
+        "end_size": end,
+        "hist_shape": (max_len + 1, kmax + 1),
     }
+
+
+def end_block(stats, layout: dict, adapter: int, end: int):
+    """(adjacent[5], hist[max_len + 1, kmax + 1]) of one end of one adapter: views into the vector."""
+    off = layout["adapters"] + (2 * adapter + end) * layout["end_size"]
+    return stats[off:off + 5], stats[off + _ADJ:off + layout["end_size"]].reshape(layout["hist_shape"])
+
+
+def adapter_statistics_from_vector(stats, adapters, max_len: int, kmax: int):
+    """
+    The reference-style AdapterStatistics objects of every adapter of ``adapters`` (a Matchable), rebuilt from the
+    (all-reduced) statistics vector: what the reference gets by adding up the workers' Statistics objects
+    (adapters.py:96-111, report.py:81-126).  Removed lengths above ``max_len`` and error counts above ``kmax``
+    were clamped when counting.
+    """
+    from .adapters import LinkedAdapter, SingleAdapter
+
+    stats = np.asarray(stats)
+    singles, _, owners = adapters._flatten()
+    number = {id(s): i for i, s in enumerate(singles)}
+    lay = stats_layout(len(singles), max_len, kmax)
+    out = []
+    seen = set()
+    for owner in owners:
+        if id(owner) in seen:
+            continue
+        seen.add(id(owner))
+        members = [owner] if isinstance(owner, (SingleAdapter, LinkedAdapter)) else list(owner._index._adapters)
+        for adapter in members:
+            st = adapter.create_statistics()
+            if isinstance(adapter, LinkedAdapter):
+                parts = ((st.front, adapter.front_adapter, 0), (st.back, adapter.back_adapter, 1))
+            else:
+                parts = ((st.front, adapter, 0), (st.back, adapter, 1))
+            for end_stats, single, end in parts:
+                if end_stats is None:
+                    continue
+                adjacent, hist = end_block(stats, lay, number[id(single)], end)
+                end_stats.add_counts(hist, adjacent if end == 1 else None)
+            out.append(st)
+    return out
 
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -736,11 +786,12 @@ class PairedFastqTrimmer:
 
 
 class DeviceResult:
-    def __init__(self, matches, qtrim, n_reads, offsets):
+    def __init__(self, matches, qtrim, n_reads, offsets, seq=None):
         self.matches = matches    # torch int32 [n * times * slots, 8]
         self.qtrim = qtrim        # torch int32 [n, 2] or None
         self.n_reads = n_reads
         self.offsets = offsets
+        self.seq = seq            # the reads (for the adjacent-base counts of the statistics)
 
 
 class DeviceBatch:
@@ -788,7 +839,7 @@ class DeviceBatch:
                 qtrim_out.data_ptr() if qtrim_out is not None else None,
             )
         )
-        return DeviceResult(out, qtrim_out, n, offsets)
+        return DeviceResult(out, qtrim_out, n, offsets, seq)
 
     def statistics(self, result: DeviceResult, max_len: int = 150, kmax: int = 3, into=None):
         """Device-side reduction of a batch into the fixed-layout int64 statistics vector."""
@@ -798,7 +849,8 @@ class DeviceBatch:
         stats = into if into is not None else torch.zeros(size, dtype=torch.int64, device=result.matches.device)
         _lib.check(
             _lib.lib().cg_stats_accumulate_device(
-                self.ctx.handle, self.adapter_set.handle, result.offsets.data_ptr(), result.n_reads,
+                self.ctx.handle, self.adapter_set.handle,
+                result.seq.data_ptr() if result.seq is not None else None, result.offsets.data_ptr(), result.n_reads,
                 C.byref(self.params), result.matches.data_ptr(),
                 result.qtrim.data_ptr() if result.qtrim is not None else None, max_len, kmax, stats.data_ptr(),
             )

@@ -352,13 +352,21 @@ int cg_fastq_collect_paired(cg_ctx *ctx, int32_t slot1, int32_t slot2, const cg_
                             int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2);
 
 /* ---- trim statistics (the payload of the end-of-run all-reduce, report.py:81-126) --------
- * Device-side reduction of a batch's match records into a fixed-layout int64 vector:
- *   [0] n_reads  [1] total_bp  [2] reads_with_adapters  [3] quality_trimmed_bp
- *   [4] bp_removed_by_adapters  [5..7] reserved
- *   then per adapter a: errors histogram  hist[a][removed_len (0..max_len)][errors (0..kmax)]
- * cg_stats_size() returns the vector length for given (n_adapters, max_len, kmax). */
+ * Device-side reduction of a batch's match records into a fixed-layout int64 vector that carries everything the
+ * reference's Statistics.__iadd__ adds up (report.py:81-126), so that one all-reduce merges the ranks:
+ *   [0] n_reads  [1] total_bp  [2] reads_with_adapters  [3] quality_trimmed_bp  [4] bp_removed_by_adapters
+ *   [5] reverse_complemented  [6] n_written  [7] bp_written
+ *   [8..14] filtered: too_short, too_long, too_many_n, too_many_expected_errors, casava_filtered, discard_trimmed,
+ *           discard_untrimmed   [15] reserved
+ *       ([5..14] are produced by steps outside the match records; this function leaves them alone)
+ *   [16 .. 16 + max_len]  read-length histogram after trimming (ReadLengthStatistics, statistics.py:5-48)
+ *   then per adapter a and end e (0: matches removing what precedes them, 1: what follows them), i.e. the two
+ *   EndStatistics of AdapterStatistics.end_statistics() (adapters.py:142-289):
+ *       adjacent[8]: A C G T other (EndStatistics.adjacent_bases; only filled when d_seq is given), 3 unused
+ *       hist[removed_len (0..max_len)][errors (0..kmax)]                        (EndStatistics.errors)
+ * cg_stats_size() returns the vector length for given (n_adapters, max_len, kmax).  d_seq may be NULL. */
 int64_t cg_stats_size(int32_t n_adapters, int32_t max_len, int32_t kmax);
-int cg_stats_accumulate_device(cg_ctx *ctx, const cg_adapterset *set, const int64_t *d_offsets,
+int cg_stats_accumulate_device(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *d_seq, const int64_t *d_offsets,
                                int64_t n_reads, const cg_params *params,
                                const cg_match *d_matches, const int32_t *d_qtrim,
                                int32_t max_len, int32_t kmax, int64_t *d_stats);

@@ -183,6 +183,24 @@ extern "C" long hs_jit_compile(const cg_adapter_desc *adapters, int n_adapters, 
     return n;
 }
 
+// The statistics vector of a batch (stats_read_core, the function cg_stats_kernel runs per read), on the host.
+extern "C" int hs_statistics(const uint8_t *seq, const int64_t *offsets, int64_t n_reads, const cg_match *matches,
+                             const int32_t *qtrim, int times, int slots, int n_adapters, int max_len, int kmax,
+                             int64_t *stats)
+{
+    StatsScalars sc; sc.bp = sc.with_adapters = sc.qtrim_bp = sc.adapter_bp = 0;
+    int64_t *hist = stats + CG_STATS_SCALARS;
+    for (int64_t r = 0; r < n_reads; ++r) {
+        const int len = (int)(offsets[r + 1] - offsets[r]);
+        stats_read_core(seq ? seq + offsets[r] : nullptr, len, qtrim != nullptr, qtrim ? qtrim[2 * r] : 0,
+                        qtrim ? qtrim[2 * r + 1] : len, (const cg_match_rec *)matches + (size_t)r * times * slots, times,
+                        slots, n_adapters, max_len, kmax, sc, [&](long long idx, unsigned int v) { hist[idx] += v; });
+    }
+    stats[0] += n_reads; stats[1] += (int64_t)sc.bp; stats[2] += (int64_t)sc.with_adapters;
+    stats[3] += (int64_t)sc.qtrim_bp; stats[4] += (int64_t)sc.adapter_bp;
+    return 0;
+}
+
 extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
                                 const cg_group_desc *groups, int n_groups, const uint8_t *seq,
                                 const uint8_t *qual, const int64_t *offsets, int64_t n_reads,

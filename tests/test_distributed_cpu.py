@@ -40,21 +40,65 @@ def test_two_rank_statistics_allreduce(tmp_path):
     r1 = np.load(tmp_path / "rank1.npy")
     assert (r0 == r1).all()
     assert (np.load(tmp_path / "local0.npy") + np.load(tmp_path / "local1.npy") == r0).all()
-    # single-process reference of the same totals
-    reads, _ = make_reads(3001, config=2, seed=99)
-    spec = spec_of(PA.MultipleAdapters([PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a")]))
+    # single-process totals of the same reads
+    reads, multi = _dist_worker.workload()
+    spec = spec_of(multi)
     matches, _ = hostsim_process(spec, reads)
-    total = _dist_worker.host_statistics(matches, None, np.array([len(r) for r in reads]), 1, 150, 3)
+    total = _dist_worker.host_statistics(reads, matches, None, len(spec.adapters), 200, 3)
     assert (total == r0).all()
-    assert r0[0] == 3001 and 1300 < r0[2] < 1700
+    assert r0[0] == len(reads) and 1500 < r0[2] < 3500
+    # ... and the reduced vector rebuilds the per-adapter statistics objects: errors[length][errors] and adjacent
+    # bases of every end, equal to feeding every Match to add_match() like the reference's AdapterCutter does
+    from cutadapt_b200.pipeline import adapter_statistics_from_vector, stats_layout
+
+    rebuilt = adapter_statistics_from_vector(r0, multi, 200, 3)
+    fed = [a.create_statistics() for a in multi]
+    by_adapter = {id(a): st for a, st in zip(multi, fed)}
+    lengths = np.zeros(201, dtype=np.int64)
+    for i, read in enumerate(reads):
+        m = multi.matches_from_records(matches[i, 0], read)
+        lengths[len(read) if m is None else len(m.trimmed(read))] += 1
+        if m is not None:
+            by_adapter[id(m.adapter)].add_match(m)
+    assert len(rebuilt) == len(fed) == 4
+    for a, b in zip(rebuilt, fed):
+        for ea, eb in zip(a.end_statistics(), b.end_statistics()):
+            assert (ea is None) == (eb is None)
+            if ea is not None:
+                assert ea.errors == eb.errors and ea.adjacent_bases == eb.adjacent_bases, a.name
+    lay = stats_layout(len(spec.adapters), 200, 3)
+    assert (r0[lay["lengths"]:lay["lengths"] + 201] == lengths).all()
+    # against the reference itself, where it travelled along: its AdapterStatistics fed with its own matches
+    from util import reference_or_none
+
+    if reference_or_none() is not None:
+        import cutadapt.adapters as RA
+
+        robjs = [RA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a"), RA.FrontAdapter("ACGTTGCATTGAC", max_errors=0.1, name="f"),
+                 RA.AnywhereAdapter("CTGTCTCTTATACACATCT", max_errors=0.1, name="w"),
+                 RA.LinkedAdapter(RA.PrefixAdapter("GTTCAGAGTTCTACAGTCCGACGATC", max_errors=0.1, name="lf"),
+                                  RA.BackAdapter("TGGAATTCTCGGGTGCCAAGG", max_errors=0.1, name="lb"), False, False, "linked")]
+        rmulti = RA.MultipleAdapters(robjs)
+        rstats = {id(a): a.create_statistics() for a in robjs}
+        for read in reads:
+            m = rmulti.match_to(read)
+            if m is not None:
+                rstats[id(m.adapter)].add_match(m)
+        for mine, robj in zip(rebuilt, robjs):
+            for ea, eb in zip(mine.end_statistics(), rstats[id(robj)].end_statistics()):
+                assert (ea is None) == (eb is None)
+                if ea is not None:
+                    assert ea.errors == {k: dict(v) for k, v in eb.errors.items() if v} and ea.adjacent_bases == eb.adjacent_bases
     # the FASTQ counters of both ranks add up to the single-process totals
     import json
     from oracle import oracle
 
     f0, f1 = (json.load(open(tmp_path / f"fq{r}.json")) for r in (0, 1))
     assert f0["total"] == f1["total"]
-    fq = "".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)).encode()
-    _, whole = oracle.oracle_fastq_trim(fq, spec.adapters, spec.groups, minimum_length=100)
+    reads2, _ = make_reads(3001, config=2, seed=99)
+    spec2 = spec_of(PA.MultipleAdapters([PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a")]))
+    fq = "".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads2)).encode()
+    _, whole = oracle.oracle_fastq_trim(fq, spec2.adapters, spec2.groups, minimum_length=100)
     for k, v in whole.items():
         assert f0["total"][k] == v == f0["local"][k] + f1["local"][k], k
     assert whole["n_written"] + whole["too_short"] == 3001 and whole["too_short"] > 100

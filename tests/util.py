@@ -79,6 +79,23 @@ def hostsim_process(spec, seqs, quals=None, params=None, force_wide=0):
     return out, qt
 
 
+def hostsim_statistics(seqs, matches, qtrim, n_adapters, max_len=150, kmax=3):
+    """The statistics vector of a batch computed by the host build of stats_read_core (what cg_stats_kernel runs)."""
+    from cutadapt_b200 import _lib as L
+    from cutadapt_b200.pipeline import stats_layout
+
+    data, offs = L.pack_strings(seqs)
+    out = np.zeros(stats_layout(n_adapters, max_len, kmax)["size"], dtype=np.int64)
+    m = np.ascontiguousarray(matches)
+    q = np.ascontiguousarray(qtrim, dtype=np.int32) if qtrim is not None else None
+    rc = hostsim_lib().hs_statistics(C.c_void_p(data.ctypes.data), C.c_void_p(offs.ctypes.data), C.c_int64(len(seqs)),
+                                     C.c_void_p(m.ctypes.data), C.c_void_p(q.ctypes.data) if q is not None else None,
+                                     C.c_int(m.shape[1]), C.c_int(m.shape[2]), C.c_int(n_adapters), C.c_int(max_len),
+                                     C.c_int(kmax), C.c_void_p(out.ctypes.data))
+    assert rc == 0
+    return out
+
+
 def hostsim_plane_classes(spec, seqs):
     """Class of every read in the bit-plane first stage: 0 no match, 1 exact occurrence, 2 re-scan, 3 plan from the planes' hits, -1 n/a."""
     from cutadapt_b200 import _lib as L
