@@ -805,59 +805,48 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
     const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
     const uintptr_t seq_base = (uintptr_t)a.seq;
 
-    auto fetch = [&](long long g, int st, uint4 &ta, uint4 &tb, uint4 &tc, uint4 &td, uint32_t &soff) {
+    // A task is fetched in two steps so that the dependent global loads of the NEXT group (list record ->
+    // offsets[read] -> address) are in flight while the current group is worked on: load_task() only issues loads
+    // into registers, stage() starts the per-lane cp.async copy of the read window into this lane's slot.
+    struct Task { uint4 ta, tb, tc, td; uintptr_t src; uint32_t bytes, soff; };
+    auto load_task = [&](long long g, Task &T) {
         const unsigned long long t = (unsigned long long)g * 32 + lane;
-        const bool has = t < n_tasks;
-        uint32_t bytes = 0;
-        uintptr_t src = 0;
-        ta = make_uint4(0, 0, 0, 0); tb = make_uint4(0, 4, 0, 0); tc = make_uint4(0, 0, 0, 0); td = make_uint4(0, 0, 0, 0);
-        if (has) {
-            ta = list[rec * t]; tb = list[rec * t + 1];
-            if (!PLAN || rec == 4) { tc = list[rec * t + 2]; td = list[rec * t + 3]; }
-            const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
-            uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + ta.z;
-            uint32_t len = ta.w;
-            if (!PLAN) {
-                const int n = (int)ta.w, ri = (int)tc.z;
-                const uint32_t pk = ri == 0 ? td.x : (ri == 1 ? td.y : (ri == 2 ? td.z : td.w));
-                const int lo = (int)(pk & 0xffffu), hi = (int)(pk >> 16);
-                // (flag sets without both query ends free can have an empty column range: lo > hi)
-                len = hi > lo ? (uint32_t)(hi - lo) : 0u;
-                if (len) addr += (uintptr_t)(A.reverse ? n - hi : lo);
-            }
-            src = addr & ~(uintptr_t)15;
-            bytes = len ? (uint32_t)(((addr + len + 15) & ~(uintptr_t)15) - src) : 0u;
-            soff = (uint32_t)(addr - src);
+        T.ta = make_uint4(0, 0, 0, 0); T.tb = make_uint4(0, 4, 0, 0); T.tc = make_uint4(0, 0, 0, 0); T.td = make_uint4(0, 0, 0, 0);
+        T.src = 0; T.bytes = 0; T.soff = 0;
+        if (t >= n_tasks) return;
+        T.ta = list[rec * t]; T.tb = list[rec * t + 1];
+        if (!PLAN || rec == 4) { T.tc = list[rec * t + 2]; T.td = list[rec * t + 3]; }
+        const long long r = (long long)(((unsigned long long)T.ta.y << 32) | T.ta.x);
+        uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + T.ta.z;
+        uint32_t len = T.ta.w;
+        if (!PLAN) {
+            const int n = (int)T.ta.w, ri = (int)T.tc.z;
+            const uint32_t pk = ri == 0 ? T.td.x : (ri == 1 ? T.td.y : (ri == 2 ? T.td.z : T.td.w));
+            const int lo = (int)(pk & 0xffffu), hi = (int)(pk >> 16);
+            // (flag sets without both query ends free can have an empty column range: lo > hi)
+            len = hi > lo ? (uint32_t)(hi - lo) : 0u;
+            if (len) addr += (uintptr_t)(A.reverse ? n - hi : lo);
         }
-        uint8_t *dst = s_slot + ((size_t)st * 32 + lane) * slot_bytes;
-        for (uint32_t o = 0; o < bytes; o += 16) cp_async16(dst + o, (const void *)(src + o));
+        T.src = addr & ~(uintptr_t)15;
+        T.bytes = len ? (uint32_t)(((addr + len + 15) & ~(uintptr_t)15) - T.src) : 0u;
+        T.soff = (uint32_t)(addr - T.src);
+    };
+    auto stage = [&](const Task &T) {
+        uint8_t *dst = s_slot + (size_t)lane * slot_bytes;
+        for (uint32_t o = 0; o < T.bytes; o += 16) cp_async16(dst + o, (const void *)(T.src + o));
         cp_async_commit();
-        return true;
     };
 
-    uint4 ta_n, tb_n, tc_n, td_n;
-    uint32_t soff_n = 0;
-    bool loaded_n = false;
-    if (CG_LIST_STAGES > 1 && wg < n_groups) loaded_n = fetch(wg, 0, ta_n, tb_n, tc_n, td_n, soff_n);
-    int it = 0;
-    for (long long g = wg; g < n_groups; g += warps_total, ++it) {
-        const int st = CG_LIST_STAGES > 1 ? (it & 1) : 0;
-        if (CG_LIST_STAGES == 1) {
-            fetch(g, 0, ta_n, tb_n, tc_n, td_n, soff_n);
-            cp_async_wait<0>();
-        }
-        const uint4 ta = ta_n, tb = tb_n, tc = tc_n, td = td_n;
-        const uint32_t soff = soff_n;
-        if (CG_LIST_STAGES > 1) {
-            const bool loaded = loaded_n;
-            const long long gn = g + warps_total;
-            loaded_n = false;
-            if (gn < n_groups) loaded_n = fetch(gn, st ^ 1, ta_n, tb_n, tc_n, td_n, soff_n);
-            if (loaded) {
-                if (loaded_n) cp_async_wait<1>();       // the copies of the next group may stay in flight
-                else cp_async_wait<0>();
-            }
-        }
+    Task next;
+    if (wg < n_groups) load_task(wg, next);
+    for (long long g = wg; g < n_groups; g += warps_total) {
+        const Task cur = next;
+        stage(cur);
+        if (g + warps_total < n_groups) load_task(g + warps_total, next);
+        cp_async_wait<0>();
+        const uint4 ta = cur.ta, tb = cur.tb, tc = cur.tc, td = cur.td;
+        const uint32_t soff = cur.soff;
+        const int st = 0;
         const bool has_task = (unsigned long long)g * 32 + lane < n_tasks;
         const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * slot_bytes + soff;
         const int n = (int)ta.w;

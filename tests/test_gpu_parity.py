@@ -563,10 +563,29 @@ def test_device_resident_api_and_statistics():
     assert stats[3] == (150 - (qt[:, 1] - qt[:, 0])).sum()
     removed = (qt[:, 1] - qt[:, 0]) - recs["rstart"][:, 0, 0]
     assert stats[4] == removed[hit].sum()
-    hist = stats[lay["hist"]:].reshape(1, 151, 4)
-    assert hist.sum() == hit.sum()
+    from cutadapt_b200.pipeline import end_block, adapter_statistics_from_vector
+    from util import hostsim_statistics
+
+    adjacent, hist = end_block(stats, lay, 0, 1)           # the 3' end of the one adapter
+    assert hist.sum() == hit.sum() and end_block(stats, lay, 0, 0)[1].sum() == 0
     L_, E_ = 20, 0
-    assert hist[0, L_, E_] == ((removed == L_) & (recs["errors"][:, 0, 0] == E_) & hit).sum()
+    assert hist[L_, E_] == ((removed == L_) & (recs["errors"][:, 0, 0] == E_) & hit).sum()
+    # adjacent bases: the character in front of the match in the quality-trimmed read
+    pos = qt[:, 0] + recs["rstart"][:, 0, 0] - 1
+    base = np.where(hit & (recs["rstart"][:, 0, 0] > 0), host.reshape(n, 150)[np.arange(n), np.clip(pos, 0, 149)], 0)
+    for k, c in enumerate(b"ACGT"):
+        assert adjacent[k] == (hit & (base == c)).sum()
+    assert adjacent.sum() == hit.sum()
+    # read lengths after trimming
+    final = np.where(hit, recs["rstart"][:, 0, 0], qt[:, 1] - qt[:, 0])
+    assert (stats[lay["lengths"]:lay["lengths"] + 151] == np.bincount(final, minlength=151)).all()
+    # the whole vector equals the host build of the same per-read function, and rebuilds the statistics objects
+    reads = [host[i * 150:(i + 1) * 150].tobytes().decode() for i in range(20000)]
+    sub = batch.statistics(batch.run(seq[:20000].reshape(-1), torch.arange(20001, device="cuda", dtype=torch.int64) * 150,
+                                     qual[:20000].reshape(-1), max_read_len=150)).cpu().numpy()
+    assert (sub == hostsim_statistics(reads, recs[:20000], qt[:20000], 1, 150, 3)).all()
+    st = adapter_statistics_from_vector(stats, multi, 150, 3)[0]
+    assert sum(st.end.lengths.values()) == hit.sum() and st.end.adjacent_bases["A"] == adjacent[0]
 
 
 def test_both_kernel_schedules_agree():
