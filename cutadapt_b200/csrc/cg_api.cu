@@ -135,6 +135,7 @@ struct cg_ctx {
     double *d_phred = nullptr;  // 256 doubles: 10^(-q/10)
     DevBuf<uint32_t> scratch_p;
     DevBuf<int> scratch_w;
+    DevBuf<unsigned long long> d_stats;  // cg_process_batch_stats: the statistics vector of the batch in flight
     DevBuf<uint4> tasks;                 // split pipeline: 2 x uint4 per read of a sub-batch
     DevBuf<uint4> tasks2, tasks3;        // run-record lists (ping-pong): 4 x uint4 per read of a sub-batch
     unsigned long long *d_task_count = nullptr;
@@ -154,6 +155,11 @@ struct cg_ctx {
     long long h2d_bytes = 0, d2h_bytes = 0;
     double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // cg_ctx_host_profile
     double pack_fraction = 0.6;                  // share of a chunk that travels compressed (adapted)
+    // hill climbing on the measured chunk rate (cg_process_batch): the share that gave the best rate so far, that
+    // rate, the direction of the next probe, and whether the reference rate has to be measured again
+    double pack_ref_fraction = 0.6, pack_ref_rate = 0.0;
+    int pack_dir = +1;
+    bool pack_have_ref = false;
     int numa_node = -1;                          // node the worker pool was bound to, or -1
     // ordering of the trimming passes of different lanes over the shared scratch
     cudaEvent_t scratch_ev = nullptr;
@@ -864,9 +870,31 @@ static int h2d_pack_mode()
     return 1;
 }
 
+static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
+                              const int64_t *offsets, int64_t n_reads, const cg_params *p,
+                              cg_match *matches, int32_t *qtrim, int stats_max_len, int stats_kmax, int64_t *stats);
+
 extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
                                 const int64_t *offsets, int64_t n_reads, const cg_params *p,
                                 cg_match *matches, int32_t *qtrim)
+{
+    return process_batch_impl(c, s, seq, qual, offsets, n_reads, p, matches, qtrim, 0, 0, nullptr);
+}
+
+// cg_process_batch plus the statistics vector of the batch (layout of cg_stats_accumulate_device), reduced on the
+// device chunk by chunk and ADDED to the caller's host vector at the end: the payload a worker hands to the
+// end-of-run merge (Statistics.__iadd__, report.py:81-126) without a second pass over the records.
+extern "C" int cg_process_batch_stats(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
+                                      const int64_t *offsets, int64_t n_reads, const cg_params *p,
+                                      cg_match *matches, int32_t *qtrim, int32_t max_len, int32_t kmax, int64_t *stats)
+{
+    if (!stats || max_len < 0 || kmax < 0) return fail(CG_EINVAL, "cg_process_batch_stats: bad statistics arguments");
+    return process_batch_impl(c, s, seq, qual, offsets, n_reads, p, matches, qtrim, max_len, kmax, stats);
+}
+
+static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *seq, const uint8_t *qual,
+                              const int64_t *offsets, int64_t n_reads, const cg_params *p,
+                              cg_match *matches, int32_t *qtrim, int stats_max_len, int stats_kmax, int64_t *stats)
 {
     if (!c || !s || !p || !offsets || !matches) return fail(CG_EINVAL, "cg_process_batch: NULL argument");
     if (s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
@@ -884,6 +912,12 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
 
     // Large batches travel compressed (three characters per byte, cg_hostpack.h): PCIe, not the
     // kernels, bounds this entry point.  Small ones are not worth waking the worker pool for.
+    const size_t n_stats = stats ? (size_t)cg_stats_total(s->host.n_adapters, stats_max_len, stats_kmax) : 0;
+    if (stats) {
+        int rcs = c->d_stats.ensure(n_stats);
+        if (rcs != CG_OK) return rcs;
+        CU(cudaMemset(c->d_stats.p, 0, n_stats * sizeof(unsigned long long)));
+    }
     const int pack_mode = h2d_pack_mode();
     const bool pack = pack_mode != 0 && n_reads >= (1 << 16);
     if (pack && !c->pool) {
@@ -901,7 +935,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
     auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const clk::time_point t_begin = clk::now();
     clk::time_point fb_t0 = t_begin;
-    double fb_wait = 0.0;
+    int64_t fb_reads = 0;
     int64_t ahead_r0 = -1, ahead_r1 = -1;
     OffsetScan ahead_sc;
     while (r0 < n_reads && rc == CG_OK) {
@@ -940,7 +974,7 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         if (want_q && (rc = l.d_qual.ensure((size_t)nbytes + 64)) != CG_OK) break;
         if ((rc = l.d_offs.ensure((size_t)nr + 1)) != CG_OK) break;
         if ((rc = l.d_out.ensure((size_t)nr * rec_per_read)) != CG_OK) break;
-        if (qtrim && (rc = l.d_qtrim.ensure((size_t)nr * 2)) != CG_OK) break;
+        if ((qtrim || (stats && want_q)) && (rc = l.d_qtrim.ensure((size_t)nr * 2)) != CG_OK) break;
         // ---- H2D of the sequences ----
         // The first `packed_bytes` of the chunk's buffer travel as the compressed stream, the rest raw: packing
         // costs host time, raw bytes cost PCIe time, and the split (c->pack_fraction) follows whichever of the
@@ -1021,17 +1055,30 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
             c->h2d_bytes += n_raw;
         }
         if (pack && pack_mode == 1) {
-            // Feedback over windows of 8 chunks: time spent waiting for a free lane means the device side (PCIe)
-            // is behind -> pack a larger share; (almost) never waiting means the host is behind -> pack less.
-            if (n_chunk >= n_lanes) fb_wait += lane_wait_s;
+            // The share of a chunk that travels compressed is tuned on what matters, the rate at which chunks get
+            // through: over windows of 8 chunks the reads per second are measured; a probe to a neighbouring share
+            // is kept if it was faster, else the best share so far is restored and the next probe goes the other
+            // way.  Raw transfer is share 0, so the compressed path can never settle below the raw rate (packing
+            // pays when host threads are plentiful, not when 8 ranks share them).
+            if (n_chunk >= n_lanes && (n_chunk - n_lanes) % 8 == 0) { fb_t0 = clk::now(); fb_reads = 0; }
+            if (n_chunk >= n_lanes) fb_reads += nr;
             if (n_chunk >= n_lanes && (n_chunk - n_lanes) % 8 == 7) {
-                const double window = secs(fb_t0, clk::now());
-                if (fb_wait > 0.08 * window) c->pack_fraction = std::min(1.0, c->pack_fraction + 0.04);
-                else if (fb_wait < 0.02 * window) c->pack_fraction = std::max(0.0, c->pack_fraction - 0.04);
-                fb_wait = 0.0;
-                fb_t0 = clk::now();
-            } else if (n_chunk < n_lanes) {
-                fb_t0 = clk::now();
+                const double rate = (double)fb_reads / std::max(1e-9, secs(fb_t0, clk::now()));
+                const double step = 0.08;
+                auto clamp01 = [](double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); };
+                if (!c->pack_have_ref) {
+                    c->pack_ref_rate = rate; c->pack_ref_fraction = c->pack_fraction; c->pack_have_ref = true;
+                    if (clamp01(c->pack_fraction + c->pack_dir * step) == c->pack_fraction) c->pack_dir = -c->pack_dir;
+                    c->pack_fraction = clamp01(c->pack_fraction + c->pack_dir * step);
+                } else if (rate > c->pack_ref_rate * 1.01) {
+                    c->pack_ref_rate = rate; c->pack_ref_fraction = c->pack_fraction;
+                    if (clamp01(c->pack_fraction + c->pack_dir * step) == c->pack_fraction) c->pack_dir = -c->pack_dir;
+                    c->pack_fraction = clamp01(c->pack_fraction + c->pack_dir * step);
+                } else {
+                    c->pack_fraction = c->pack_ref_fraction;      // the probe did not pay: back, and look the other way
+                    c->pack_dir = -c->pack_dir;
+                    c->pack_have_ref = false;                     // (the reference rate is re-measured: conditions drift)
+                }
             }
         }
         ++n_chunk;
@@ -1063,9 +1110,14 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         // in this chunk's buffer with the same 16-byte phase as in the caller's array
         const uint8_t *vseq = l.d_seq.p - a0;
         const uint8_t *vqual = want_q ? l.d_qual.p - a0 : nullptr;
-        rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, qtrim ? l.d_qtrim.p : nullptr,
-                         l.stream, true);
+        int32_t *d_qt = (qtrim || (stats && want_q)) ? l.d_qtrim.p : nullptr;
+        rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, d_qt, l.stream, true);
         if (rc != CG_OK) break;
+        if (stats) {
+            CU(cg_launch_stats(vseq, l.d_offs.p, nr, want_q && d_qt, times, s->host.slots, l.d_out.p, d_qt,
+                               s->host.n_adapters, stats_max_len, stats_kmax, c->d_stats.p, l.stream));
+            c->launches += 1;
+        }
         // D2H
         cg_match_rec *dst = (cg_match_rec *)matches + (size_t)r0 * rec_per_read;
         l.n_out = (size_t)nr * rec_per_read; l.dst_out = dst; l.out_bounced = !out_pinned;
@@ -1095,6 +1147,12 @@ extern "C" int cg_process_batch(cg_ctx *c, const cg_adapterset *s, const uint8_t
         if (rc == CG_OK) rc = rc2;
     }
     c->prof[4] += secs(t_drain0, clk::now());
+    if (rc == CG_OK && stats) {
+        std::vector<unsigned long long> h(n_stats);
+        CU(cudaMemcpy(h.data(), c->d_stats.p, n_stats * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n_stats; ++i) stats[i] += (int64_t)h[i];
+        c->d2h_bytes += (long long)(n_stats * sizeof(unsigned long long));
+    }
     c->prof[0] += secs(t_begin, clk::now());
     if (rc != CG_OK) return rc;
     return check_err_flag(c);

@@ -1291,14 +1291,14 @@ __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long
                                 int slots, const cg_match_rec *matches, const int32_t *qtrim,
                                 int n_adapters, int max_len, int kmax, unsigned long long *stats)
 {
-    // per-CTA histogram in shared memory (32-bit counts, flushed once); the global histogram would
-    // otherwise take one contended atomic per match
+    // per-CTA histograms in shared memory (32-bit counts, flushed once): the read-length histogram always (every
+    // read adds to it, mostly to the same few bins), the per-adapter part if it fits (SMEM_HIST); a global
+    // histogram would otherwise take one contended atomic per read
     extern __shared__ unsigned int s_hist[];
     const long long nbins = cg_stats_total(n_adapters, max_len, kmax) - CG_STATS_SCALARS;
-    if (SMEM_HIST) {
-        for (long long i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-    }
+    const long long n_local = SMEM_HIST ? nbins : (long long)(max_len + 1);
+    for (long long i = threadIdx.x; i < n_local; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     unsigned long long n = 0;
     StatsScalars sc; sc.bp = sc.with_adapters = sc.qtrim_bp = sc.adapter_bp = 0;
@@ -1311,7 +1311,7 @@ __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long
         stats_read_core(seq ? seq + o0 : nullptr, len, hq, hq ? qtrim[2 * r] : 0, hq ? qtrim[2 * r + 1] : len,
                         matches + (size_t)r * times * slots, times, slots, n_adapters, max_len, kmax, sc,
                         [&](long long idx, unsigned int v) {
-                            if (SMEM_HIST) atomicAdd(&s_hist[idx], v);
+                            if (idx < n_local) atomicAdd(&s_hist[idx], v);
                             else atomicAdd(&hist[idx], (unsigned long long)v);
                         });
     }
@@ -1327,12 +1327,10 @@ __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long
         atomicAdd(&stats[0], n); atomicAdd(&stats[1], sc.bp); atomicAdd(&stats[2], sc.with_adapters);
         atomicAdd(&stats[3], sc.qtrim_bp); atomicAdd(&stats[4], sc.adapter_bp);
     }
-    if (SMEM_HIST) {
-        __syncthreads();
-        for (long long i = threadIdx.x; i < nbins; i += blockDim.x) {
-            const unsigned int v = s_hist[i];
-            if (v) atomicAdd(&hist[i], (unsigned long long)v);
-        }
+    __syncthreads();
+    for (long long i = threadIdx.x; i < n_local; i += blockDim.x) {
+        const unsigned int v = s_hist[i];
+        if (v) atomicAdd(&hist[i], (unsigned long long)v);
     }
 }
 
@@ -1346,12 +1344,14 @@ cudaError_t cg_launch_stats(const uint8_t *d_seq, const int64_t *d_offsets, long
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
     const size_t hist_bytes = (size_t)(cg_stats_total(n_adapters, max_len, kmax) - CG_STATS_SCALARS) * sizeof(unsigned int);
+    const size_t len_bytes = (size_t)(max_len + 1) * sizeof(unsigned int);
+    if (len_bytes > 48 * 1024) return cudaErrorInvalidValue;
     // a CTA handles n_reads / grid reads, so 32-bit per-CTA counts cannot overflow below 2^32 reads per CTA
     if (hist_bytes <= 48 * 1024 && n_reads / grid < (1LL << 31))
         cg_stats_kernel<true><<<(int)grid, block, hist_bytes, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots,
                                                                      d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats);
     else
-        cg_stats_kernel<false><<<(int)grid, block, 0, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots, d_matches,
-                                                             d_qtrim, n_adapters, max_len, kmax, d_stats);
+        cg_stats_kernel<false><<<(int)grid, block, len_bytes, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots,
+                                                                     d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats);
     return cudaGetLastError();
 }

@@ -370,6 +370,13 @@ int cg_stats_accumulate_device(cg_ctx *ctx, const cg_adapterset *set, const uint
                                int64_t n_reads, const cg_params *params,
                                const cg_match *d_matches, const int32_t *d_qtrim,
                                int32_t max_len, int32_t kmax, int64_t *d_stats);
+/* cg_process_batch plus the statistics vector of the batch (same layout), reduced on the device chunk by chunk and
+ * ADDED to the caller's host vector `stats` (cg_stats_size(n_adapters, max_len, kmax) entries) at the end: what a
+ * worker of the reference accumulates in its Statistics object while it processes a chunk (pipeline.py:60-69,
+ * modifiers.py:202-205), ready for the end-of-run merge. */
+int cg_process_batch_stats(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *seq, const uint8_t *qual,
+                           const int64_t *offsets, int64_t n_reads, const cg_params *params,
+                           cg_match *matches, int32_t *qtrim, int32_t max_len, int32_t kmax, int64_t *stats);
 
 /* ---- host-side index helpers (adapters.py:1416-1442 use these to build AdapterIndex) ----
  * edit_environment (_align.pyx:785-882) / hamming_sphere-based environment
