@@ -727,10 +727,12 @@ struct PlaneOut {
     // cls 2: what the plan stage needs to go on without scanning the read again (plan_runs_planes)
     uint32_t M[8];   // bit e of word b: a locator chunk occurs where the whole adapter would end at plane index 32 b + e
     int end_hit;     // a chunk occurs so close to the end of the window that the adapter would reach beyond it
+    int no_end;      // the last-column scan cannot accept anything: the plan needs no end window
 };
 #define CG_PLANE_NONE 0
 #define CG_PLANE_EXACT 1
 #define CG_PLANE_SLOW 2
+#define CG_PLANE_OVERLAP 3   // the read ends with the adapter's first s0 characters and nothing else can match
 
 // x <<= s  (multi-word, s in 0..63); returns the bits shifted out at the top (non-zero = some were)
 template <int W>
@@ -761,6 +763,8 @@ struct PlaneState {
     uint32_t acc[W];                       // ends of the chain's text so far
     uint32_t M[W], E[W];                   // locator hits / all chunks, by the end of the WHOLE adapter
     bool pass, anyhit, end_hit;
+    bool guard;                            // a guard piece occurs at the end (see CG_PLANE_GUARD)
+    int ovl;                               // longest exact overlap (adapter prefix = read suffix) the planes see
 };
 
 // `base` = address of plane index 0 (window end - 32 W); the bytes [base - 3, base + 32 W + 4) must be readable.
@@ -825,6 +829,7 @@ CG_HD uint32_t plane_load(PlaneState<W> &st, const uint8_t *base, int off0)
 #pragma unroll
     for (int b = 0; b < W; ++b) { st.acc[b] = 0; st.M[b] = 0; st.E[b] = 0xFFFFFFFFu; }
     st.pass = false; st.anyhit = false; st.end_hit = false;
+    st.guard = false; st.ovl = 0;
     return bad;
 }
 
@@ -859,6 +864,10 @@ CG_HD void plane_chain_step(PlaneState<W> &st, uint32_t code, bool first)
 template <int W>
 CG_HD void plane_emit(PlaneState<W> &st, int len, int type, int flags, int shift, int window)
 {
+    if (type == CG_SCAN_OVERLAP) {                   // does the window END with these `len` characters?
+        if ((st.acc[W - 1] >> 31) && len > st.ovl) st.ovl = len;
+        return;
+    }
     uint32_t x[W];
 #pragma unroll
     for (int b = 0; b < W; ++b) x[b] = st.acc[b];
@@ -871,11 +880,12 @@ CG_HD void plane_emit(PlaneState<W> &st, int len, int type, int flags, int shift
             x[b] &= fv <= 0 ? 0xFFFFFFFFu : (fv >= 32 ? 0u : (0xFFFFFFFFu << fv));
         }
 #pragma unroll
-        for (int b = (W >= 2 ? W - 2 : 0); b < W; ++b) any |= x[b];
+        for (int b = (W >= 3 ? W - 3 : 0); b < W; ++b) any |= x[b];      // windows of <= 64 characters + a k-mer
     } else {
 #pragma unroll
         for (int b = 0; b < W; ++b) any |= x[b];
     }
+    if ((flags & (int)CG_PLANE_GUARD) && any) st.guard = true;
     if ((flags & (int)CG_PLANE_PASS) && any) st.pass = true;
     if (flags & (int)CG_PLANE_LOC) {
         if (any) st.anyhit = true;
@@ -895,6 +905,7 @@ struct RuntimePlaneProg {
         return same;
     }
     CG_HD static int adapter_length(int m) { return m; }
+    CG_HD static unsigned long long overlap_ok(unsigned long long from_blob) { return from_blob; }
     template <int W>
     CG_HD static void run(PlaneState<W> &st, const uint32_t *ops, int n_ops, int m)
     {
@@ -915,10 +926,11 @@ struct RuntimePlaneProg {
 // What the planes settle, and what they hand on (see the head of this section for the rules).
 //   exact_ok : plane_flags bit 0;  m, ref: the adapter;  base / off0 / n as in plane_load
 template <int W, class Prog>
-CG_HD void plane_decide(const PlaneState<W> &st, bool exact_ok, int m, const uint8_t *ref, const uint8_t *base,
-                        int off0, int n, bool always_pass, PlaneOut &out)
+CG_HD void plane_decide(const PlaneState<W> &st, int plane_flags, unsigned long long overlap_ok, int m, const uint8_t *ref,
+                        const uint8_t *base, int off0, int n, bool always_pass, PlaneOut &out)
 {
-    out.cls = CG_PLANE_SLOW; out.s0 = 0; out.end_hit = st.end_hit ? 1 : 0;
+    const bool exact_ok = (plane_flags & 1) != 0, end_ok = (plane_flags & 2) != 0;
+    out.cls = CG_PLANE_SLOW; out.s0 = 0; out.end_hit = st.end_hit ? 1 : 0; out.no_end = 0;
     if (!st.pass && !always_pass) { out.cls = CG_PLANE_NONE; return; }   // no k-mer even in the superset: kmers_present is False
     if (exact_ok && st.anyhit) {
         // the leftmost adapter end any chunk points at (a chunk whose implied end lies beyond the window is
@@ -937,6 +949,21 @@ CG_HD void plane_decide(const PlaneState<W> &st, bool exact_ok, int m, const uin
         const int s0 = low - (m - 1) - off0;
         if (found && ex && s0 >= 0 && s0 + m <= n) {
             if (Prog::same_adapter(base + (low - (m - 1)), ref, m)) { out.cls = CG_PLANE_EXACT; out.s0 = s0; return; }
+        }
+    }
+    // End analysis (3' adapters, program with guard pieces and overlap emits; cg_setbuild.cpp build_plane_program).
+    // No guard piece at the end => every acceptable cell of the last column is an exact overlap of one of the
+    // emitted lengths, and the scan takes the longest (a shorter one scores less, _align.pyx:561-570).
+    if (end_ok && !st.guard && !st.end_hit) {
+        if (!st.anyhit) {
+            // no locator chunk anywhere: no bottom-row candidate either, only the last column can match
+            if (st.ovl == 0) { out.cls = CG_PLANE_NONE; return; }
+            if (st.ovl <= n && ((overlap_ok >> st.ovl) & 1ULL) && Prog::same_adapter(base + 32 * W - st.ovl, ref, st.ovl)) {
+                // (kmers_present is True for such a read: the overlap itself holds a k-mer in its window)
+                out.cls = CG_PLANE_OVERLAP; out.s0 = st.ovl; return;
+            }
+        } else if (st.ovl == 0) {
+            out.no_end = 1;                       // hits to examine, but the end of the read cannot match
         }
     }
     // handed on: the plan stage gets the hits (plan_runs_planes) -- it still has to make sure the window holds
@@ -959,7 +986,13 @@ CG_HD PlaneOut plane_scan_core(const uint32_t *ops, int n_ops, int plane_flags, 
     out.bad = plane_load<W>(st, base, off0);
     m = Prog::adapter_length(m);                     // (a literal in a specialised program)
     Prog::template run<W>(st, ops, n_ops, m);
-    plane_decide<W, Prog>(st, (plane_flags & 1) != 0, m, ref, base, off0, n, always_pass, out);
+    unsigned long long overlap_ok = 0;
+    if (plane_flags & 2) {
+        const int n_emits = (plane_flags >> 8) & 255;
+        const uint8_t *after = (const uint8_t *)ops + (((size_t)n_ops * 4 + 7) & ~(size_t)7) + (size_t)n_emits * sizeof(CgPlaneEmit);
+        overlap_ok = Prog::overlap_ok(*(const unsigned long long *)after);
+    }
+    plane_decide<W, Prog>(st, plane_flags, overlap_ok, m, ref, base, off0, n, always_pass, out);
     return out;
 }
 
@@ -2242,7 +2275,7 @@ CG_HD bool run_has_candidate_t(const CgAdapter &A, const uint32_t *peq, const ui
 //   * the end window of a 3' adapter (last-column scan, _align.pyx:536-572) is needed only if some cell
 //     (i, n) is acceptable; if nothing else is left and every acceptable cell is an exact overlap, the
 //     result is the longest one (end_overlap_myers_t).
-CG_HD void plan_finish(const SetView &S, const uint8_t *p, int n, const RunList &R0, RunPlan &P)
+CG_HD void plan_finish(const SetView &S, const uint8_t *p, int n, const RunList &R0, RunPlan &P, bool skip_end = false)
 {
     const CgAdapter &A = S.ad[0];
     const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
@@ -2270,7 +2303,7 @@ CG_HD void plan_finish(const SetView &S, const uint8_t *p, int n, const RunList 
         covered = is_final;
     }
     P.n_runs = R.n; P.lo0 = R.lo0; P.hi0 = R.hi0; P.lo1 = R.lo1; P.hi1 = R.hi1; P.lo2 = R.lo2; P.hi2 = R.hi2;
-    if (!eir || covered) return;
+    if (!eir || covered || skip_end) return;
     if (can_filter) {                                 // what can the last-column scan accept?
         const int r = A.m <= 32 ? end_overlap_myers_t<uint32_t>(A, peq, ncnt, maxcost, p, n, lo_end)
                                 : end_overlap_myers_t<unsigned long long>(A, peq, ncnt, maxcost, p, n, lo_end);
@@ -2382,7 +2415,7 @@ CG_HD bool window_is_plain(const uint8_t *p, int n)
 // implies the adapter start s gives the run [s - k, s + m + k] (the same window refine_runs /
 // plan_hit_runs_dir derive from a chunk's end position).
 CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, const uint32_t *M, int W, int end_hit,
-                            int off0, RunPlan &P)
+                            int no_end, int off0, RunPlan &P)
 {
     const CgAdapter &A = S.ad[0];
     P.n_runs = 0; P.lo0 = P.hi0 = P.lo1 = P.hi1 = P.lo2 = P.hi2 = P.lo3 = P.hi3 = 0;
@@ -2402,7 +2435,8 @@ CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, const uin
     }
     // a chunk so close to the end that the whole adapter would not fit: its window lies inside the end window
     if (end_hit) runs_add(R, cg_max(0, n - 1 - A.m - A.k), n, n);
-    plan_finish(S, p, n, R, P);
+    // no_end: the bit-plane stage has shown that the last-column scan cannot accept anything
+    plan_finish(S, p, n, R, P, no_end != 0 && !end_hit);
 }
 
 // P.exact == 2: the exact overlap of the adapter's first `len` characters with the end of the read
@@ -2514,13 +2548,14 @@ CG_HD void process_read_planes(const SetView &S, const uint8_t *seq, const uint8
             CgHit hit; hit.adapter = -1; hit.remove = 0;
             hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
             if (po.cls == CG_PLANE_EXACT) hit_exact(A, nn, po.s0, hit);
+            else if (po.cls == CG_PLANE_OVERLAP) hit_end_overlap(A, nn, po.s0, hit);
             store_hit(out, hit, 0, nn);
             return;
         }
         if (window_is_plain(seq + s, nn)) {   // plan from the planes' hits, then the DP runs (cg_list_kernel)
             const int W = nn <= 160 ? 5 : 8;
             RunPlan P;
-            plan_runs_planes(S, seq + s, nn, po.M, W, po.end_hit, 32 * W - nn, P);
+            plan_runs_planes(S, seq + s, nn, po.M, W, po.end_hit, po.no_end, 32 * W - nn, P);
             CgHit hit; hit.adapter = -1; hit.remove = 0;
             hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
             finish_planned(S, seq + s, nn, P, hit);

@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                     if (window_is_plain(p, n)) {
                         const uint32_t M[8] = {tb.x, tb.z, tb.w, tc.x, tc.y, tc.z, tc.w, td.x};
                         const int W = (int)((tb.y >> 12) & 15u);
-                        plan_runs_planes(S, p, n, M, W, (int)((tb.y >> 20) & 1u), 32 * W - n, P);
+                        plan_runs_planes(S, p, n, M, W, (int)((tb.y >> 20) & 1u), (int)((tb.y >> 21) & 1u), 32 * W - n, P);
                         planned = true;
                     } else {
                         // other letters than A/C/G/T: the exact scan is still to do.  Such reads are rare (an N in

@@ -26,7 +26,7 @@ struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_
 #define CG_TASK_RESCAN 0x100u     // the plan stage must scan the read itself (shift-and scan_core)
 #define CG_TASK_PLANES 0x200u     // a 4 x uint4 task of cg_pscan_kernel: {read lo, read hi, trim start, length},
                                   // {M0, flags, M1, M2}, {M3 .. M6}, {M7, 0, 0, 0} with M = PlaneOut::M;
-                                  // flags bits 12-15: plane words W, bit 20: PlaneOut::end_hit
+                                  // flags bits 12-15: plane words W, bit 20: PlaneOut::end_hit, bit 21: PlaneOut::no_end
 __host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
 {
     ScanSmem L;
@@ -129,7 +129,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 cls = po.cls; s0 = po.s0;
                 if (po.bad & 0x80808080u) atomicOr(a.err_flag, 1);
                 if (cls == CG_PLANE_SLOW) {
-                    t_flags = 4u | CG_TASK_PLANES | ((uint32_t)W << 12) | ((uint32_t)po.end_hit << 20);
+                    t_flags = 4u | CG_TASK_PLANES | ((uint32_t)W << 12) | ((uint32_t)po.end_hit << 20) | ((uint32_t)po.no_end << 21);
 #pragma unroll
                     for (int b = 0; b < 8; ++b) tm[b] = po.M[b];
                 }
@@ -143,6 +143,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 CgHit hit; hit.adapter = -1; hit.remove = 0;
                 hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
                 if (cls == CG_PLANE_EXACT) hit_exact(A, nn, s0, hit);
+                else if (cls == CG_PLANE_OVERLAP) hit_end_overlap(A, nn, s0, hit);
                 store_hit(a.out + (size_t)r * a.slots, hit, 0, nn);
             }
         }

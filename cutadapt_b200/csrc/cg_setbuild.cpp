@@ -48,6 +48,7 @@ struct ScanKmer {
     int window = 0;                       // SUFFIX: characters from the end; PREFIX: from the start
     bool pass = false, loc = false;
     int bmin = 255, bmax = 0;             // locator: adapter offsets (exclusive end) of this chunk
+    std::vector<int> bends;               // ... every one of them (equal chunks of a repetitive adapter share a pattern)
     std::vector<std::array<uint64_t, 2>> cols;   // per character: set of matching ASCII codes
     bool same_pattern(const ScanKmer &o) const { return len == o.len && cols == o.cols; }
 };
@@ -168,7 +169,29 @@ int plane_code(const std::array<uint64_t, 2> &set)
 // The bit-plane form of the scan program (plane_scan_core in cg_core.cuh).  Empty if the adapter does not
 // qualify: every k-mer position must be a plain A/C/G/T, no prefix windows, suffix windows of <= 64
 // characters, a forward adapter of <= 64 characters with locator chunks.
-void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowed, int exact_ok, int myers,
+// KmerFinder.kmers_present (_kmer_finder.pyx:170-213) of the reference-form entries on a short string, host side
+bool entries_present(const cg_adapter_desc &d, const uint8_t *s, int n)
+{
+    for (int e = 0; e < d.n_kmer_entries; ++e) {
+        const cg_kmer_entry &k = d.kmer_entries[e];
+        const uint64_t *mk = d.kmer_masks + 128 * (size_t)e;
+        long long start = k.search_start, stop = k.search_stop;
+        if (start < 0) { start += n; if (start < 0) start = 0; }
+        else if (start > n) continue;
+        if (stop < 0) { stop += n; if (stop <= 0) continue; }
+        else if (stop == 0) stop = n;
+        if (stop > n) stop = n;
+        uint64_t R = 0;
+        for (long long i = start; i < stop; ++i) {
+            R = ((R << 1) | k.init_mask) & mk[s[i] & 127];
+            if (R & k.found_mask) return true;
+        }
+    }
+    return false;
+}
+
+void build_plane_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc_ref, const int32_t *maxcost,
+                         int windowed, int exact_ok, int myers,
                          const std::vector<ScanKmer> &whole, const std::vector<ScanKmer> &suffix,
                          const std::vector<ScanKmer> &prefix, std::vector<uint8_t> &out, int &n_ops, int &flags)
 {
@@ -189,14 +212,21 @@ void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowe
         }
         pk.len = (uint8_t)k.len; pk.type = (uint8_t)type;
         pk.flags = (uint8_t)((k.pass ? CG_PLANE_PASS : 0u) | (k.loc ? CG_PLANE_LOC : 0u));
-        if (k.loc) {
-            any_loc = true;
-            unambiguous = unambiguous && k.bmin == k.bmax;
-            pk.bend = (uint8_t)k.bmax;
-        }
         if (type == CG_SCAN_SUFFIX) {
             if (k.window < 1 || k.window > 64) return false;
             pk.window = (uint16_t)k.window;
+        }
+        if (k.loc) {
+            any_loc = true;
+            unambiguous = unambiguous && k.bmin == k.bmax;
+            // a pattern that occurs at several adapter offsets (repetitive adapter) points at several adapter ends:
+            // one locator entry per offset
+            for (size_t i = 0; i < k.bends.size(); ++i) {
+                pk.bend = (uint8_t)k.bends[i];
+                if (i > 0) pk.flags = (uint8_t)CG_PLANE_LOC;      // (the prefilter verdict is taken once)
+                prog.push_back(pk);
+            }
+            return true;
         }
         prog.push_back(pk);
         return true;
@@ -204,6 +234,8 @@ void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowe
     for (auto &k : whole) if (!add(k, CG_SCAN_WHOLE)) return;
     for (auto &k : suffix) if (!add(k, CG_SCAN_SUFFIX)) return;
     if (!any_loc || prog.size() > 32) return;
+    const size_t n_base = prog.size();
+    (void)n_base;
     // an exact occurrence may be reported straight from the planes if the locator is unambiguous
     // (exact_ok), the adapter itself is plain A/C/G/T, and KmerFinder.kmers_present is certain to say
     // yes for a read that contains the whole adapter: some whole-read k-mer of the prefilter is a
@@ -225,6 +257,53 @@ void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowe
         }
     }
     if (exact_ok && unambiguous && plain && implies_pass) flags |= 1;
+    // End analysis for 3' adapters (flags BACK: free read ends, partial adapter allowed at the end): what can the
+    // last-column scan (_align.pyx:536-572) accept?  Cell (i, n) with c errors, 1 <= c <= maxcost[i] = e: the first
+    // lo_e = min{i: maxcost[i] >= e} adapter characters are aligned with <= e errors inside the last i + e characters
+    // of the read, so one of e + 1 disjoint pieces of adapter[:lo_e] occurs there exactly (pigeonhole).  GUARD
+    // k-mers = those pieces, searched in the last hi_e + e characters (hi_e = longest prefix with maxcost == e): if
+    // none occurs, every acceptable cell is an exact overlap, and of a length < lo_1 (a longer one contains the
+    // pieces of level 1).  OVERLAP emits report those exact overlaps (lengths min_overlap .. lo_1 - 1).
+    uint64_t overlap_ok = 0;
+    if ((A.flags & 15) == 14 && A.indel_cost == 1 && plain && (flags & 1) && A.m <= 63 && maxcost) {
+        int top = 0;
+        for (int i = 0; i <= A.m; ++i) top = std::max(top, (int)maxcost[i]);
+        bool fits = true;
+        int lo1 = A.m + 1;
+        auto add_text = [&](int from, int len, uint8_t type, uint8_t fl, int window) {
+            CgPlaneKmer pk;
+            memset(&pk, 0, sizeof pk);
+            if (len < 1 || len > 32) { fits = false; return; }
+            for (int t = 0; t < len; ++t) pk.codes |= (uint64_t)acode[from + t] << (2 * t);
+            pk.len = (uint8_t)len; pk.type = type; pk.flags = fl; pk.window = (uint16_t)window;
+            prog.push_back(pk);
+        };
+        for (int e = 1; e <= top && fits; ++e) {
+            int lo = -1, hi = -1;
+            for (int i = A.min_overlap; i <= A.m; ++i) {
+                if (maxcost[i] >= e && lo < 0) lo = i;
+                if (maxcost[i] == e) hi = i;
+            }
+            if (lo < 0 || hi < 0) continue;               // no overlap length with exactly this budget
+            if (e == 1) lo1 = lo;
+            if (lo < e + 1 || hi + e > 64) { fits = false; break; }
+            const int base = lo / (e + 1), extra = lo % (e + 1);
+            int pos = 0;
+            for (int c = 0; c <= e; ++c) {
+                const int len = base + (c < extra ? 1 : 0);
+                add_text(pos, len, CG_SCAN_SUFFIX, (uint8_t)CG_PLANE_GUARD, hi + e);
+                pos += len;
+            }
+        }
+        // budgets that exist but start below min_overlap would need lo = min_overlap: covered (lo is searched from it)
+        for (int i = A.min_overlap; i < lo1 && i <= A.m && fits; ++i) {
+            if (i > 32) { fits = false; break; }
+            add_text(0, i, CG_SCAN_OVERLAP, 0, 0);
+            if (A.pf_count == 0 || entries_present(d, enc_ref, i)) overlap_ok |= 1ULL << i;
+        }
+        if (fits && prog.size() <= 48) flags |= 2;
+        else { while (!prog.empty() && (prog.back().type == CG_SCAN_OVERLAP || (prog.back().flags & CG_PLANE_GUARD))) prog.pop_back(); }
+    }
     // chains: sort the k-mers by their code strings; a k-mer that extends the chain in progress adds
     // only its remaining characters
     std::vector<int> order(prog.size());
@@ -263,9 +342,10 @@ void build_plane_program(const CgAdapter &A, const uint8_t *enc_ref, int windowe
     if (emits.size() > 255 || ops.size() > 1024) return;
     n_ops = (int)ops.size();
     flags |= (int)(emits.size() << 8);
-    out.resize((ops.size() * 4 + 7) / 8 * 8 + emits.size() * sizeof(CgPlaneEmit));
+    out.resize((ops.size() * 4 + 7) / 8 * 8 + emits.size() * sizeof(CgPlaneEmit) + 8);
     memcpy(out.data(), ops.data(), ops.size() * 4);
     memcpy(out.data() + (ops.size() * 4 + 7) / 8 * 8, emits.data(), emits.size() * sizeof(CgPlaneEmit));
+    memcpy(out.data() + out.size() - 8, &overlap_ok, 8);
 }
 
 bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint8_t *enc768,
@@ -319,9 +399,10 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
             }
             pos += len;
             k.bmin = k.bmax = pos;
+            k.bends.push_back(pos);
             bool dup = false;
             for (auto &o : chunks)
-                if (o.same_pattern(k)) { dup = true; o.bmin = std::min(o.bmin, pos); o.bmax = std::max(o.bmax, pos); }
+                if (o.same_pattern(k)) { dup = true; o.bmin = std::min(o.bmin, pos); o.bmax = std::max(o.bmax, pos); o.bends.push_back(pos); }
             if (!dup) chunks.push_back(k);
         }
         // How often do the chunks hit by chance?  p_hit = expected hits per read position for uniform
@@ -348,7 +429,7 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
             for (auto &c : chunks) {
                 bool merged = false;
                 for (auto &w : whole)
-                    if (w.same_pattern(c)) { w.loc = true; w.bmin = c.bmin; w.bmax = c.bmax; merged = true; break; }
+                    if (w.same_pattern(c)) { w.loc = true; w.bmin = c.bmin; w.bmax = c.bmax; w.bends = c.bends; merged = true; break; }
                 if (!merged) whole.push_back(c);
             }
             windowed = 1;
@@ -371,7 +452,8 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
     pack_words(whole, CG_SCAN_WHOLE, false, pool, words);
     pack_words(suffix, CG_SCAN_SUFFIX, true, pool, words);
     pack_words(prefix, CG_SCAN_PREFIX, true, pool, words);
-    build_plane_program(A, enc_ref, windowed, exact_ok, myers, whole, suffix, prefix, planes, plane_ops, plane_flags);
+    build_plane_program(d, A, enc_ref, (const int32_t *)(pool.data() + A.maxcost_off), windowed, exact_ok, myers, whole, suffix,
+                        prefix, planes, plane_ops, plane_flags);
     return words.size() <= 64;
 }
 

@@ -106,7 +106,9 @@ struct CgSetHeader {        // 80 bytes
     int32_t plane_count;    // number of op words (0: the adapter does not qualify)
     uint32_t plane_off;     // blob offset of uint32 ops[plane_count], then (8-aligned) CgPlaneEmit[n_emits]
     int32_t plane_flags;    // bit 0: an exact occurrence found by the planes may be reported without DP;
-                            // bits 8-15: n_emits
+                            // bit 1: the program holds the end analysis (guard pieces + overlap emits; the
+                            //        uint64 after the emits marks the overlap lengths whose string alone
+                            //        makes KmerFinder.kmers_present true); bits 8-15: n_emits
 };
 
 // Bit-plane scan program.  Characters are 2-bit codes taken from bits 1 and 2 of the ASCII code
@@ -117,7 +119,10 @@ struct CgSetHeader {        // 80 bytes
 //   op word: bits 0-1 code, bit 2 first step of a chain, bits 8-15 / 16-23: emit index + 1 (0 = none)
 #define CG_PLANE_PASS 1u    // a k-mer of the KmerFinder (prefilter verdict)
 #define CG_PLANE_LOC 2u     // a locator chunk (one of the k+1 pieces of the adapter)
+#define CG_PLANE_GUARD 4u   // a piece of an adapter prefix, searched at the end of the read: if none occurs, no
+                            // cell of the last column with errors can be acceptable (see plane_decide)
 #define CG_PLANE_OP_NEW 4u
+#define CG_SCAN_OVERLAP 3   // emit type: the adapter's first `len` characters; does the read END with them?
 struct CgPlaneEmit {        // 8 bytes
     uint8_t len;            // 1..32
     uint8_t type;           // CG_SCAN_WHOLE or CG_SCAN_SUFFIX

@@ -31,7 +31,7 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
     if (force_wide & 4) {   // query only: bit 0 two-phase program available, 1 windowed, 2 exact shortcut, 3 myers
         const CgSetHeader *h = (const CgSetHeader *)set.blob.data();
         return (set.simple_ok ? 1 : 0) | (h->windowed ? 2 : 0) | (h->exact_ok ? 4 : 0) | (h->myers ? 8 : 0) |
-               (h->plane_count > 0 ? 16 : 0) | ((h->plane_flags & 1) ? 32 : 0);
+               (h->plane_count > 0 ? 16 : 0) | ((h->plane_flags & 1) ? 32 : 0) | ((h->plane_flags & 2) ? 64 : 0);
     }
     if (force_wide & 1) {
         CgSetHeader *h = (CgSetHeader *)set.blob.data();
@@ -137,7 +137,7 @@ extern "C" int hs_process_batch_indexed(const cg_adapter_desc *adapters, int n_a
 }
 
 // class of every read in the bit-plane first stage (0 none, 1 exact, 2 exact path after a re-scan, 3 exact path
-// from the planes' hits; -1: no plane program)
+// from the planes' hits, 4 exact overlap at the end, 5 like 3 without an end window; -1: no plane program)
 extern "C" int hs_plane_classify(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
                                  const uint8_t *seq, const int64_t *offsets, int64_t n_reads, int32_t *cls)
 {
@@ -159,7 +159,7 @@ extern "C" int hs_plane_classify(const cg_adapter_desc *adapters, int n_adapters
         const PlaneOut po = n <= 160
             ? plane_scan_core<5, RuntimePlaneProg>(plane_program(S), S.h->plane_count, S.h->plane_flags, A.m, ref, seq + offsets[r + 1], n, A.pf_count == 0)
             : plane_scan_core<8, RuntimePlaneProg>(plane_program(S), S.h->plane_count, S.h->plane_flags, A.m, ref, seq + offsets[r + 1], n, A.pf_count == 0);
-        cls[r] = (po.cls == CG_PLANE_SLOW && window_is_plain(seq + offsets[r], n)) ? 3 : po.cls;   // 3: exact path without a re-scan
+        cls[r] = po.cls == CG_PLANE_OVERLAP ? 4 : ((po.cls == CG_PLANE_SLOW && window_is_plain(seq + offsets[r], n)) ? (po.no_end ? 5 : 3) : po.cls);
     }
     return CG_OK;
 }

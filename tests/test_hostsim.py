@@ -148,7 +148,7 @@ def test_bitplane_first_stage_against_oracle():
     from util import hostsim_plane_classes
 
     rng = random.Random(4242)
-    seen = np.zeros(5, dtype=np.int64)
+    seen = np.zeros(7, dtype=np.int64)
     n_planes = 0
     for trial in range(160):
         m = rng.choice([rng.randint(5, 12), 13, rng.randint(14, 33), 33, rng.randint(34, 60)])
@@ -178,9 +178,54 @@ def test_bitplane_first_stage_against_oracle():
         cls = hostsim_plane_classes(spec, reads)
         if (cls >= 0).any():
             n_planes += 1
-        seen += np.bincount(cls + 1, minlength=5)
+        seen += np.bincount(cls + 1, minlength=7)
     # the stage must actually decide reads: most adapters qualify, and all three classes occur
-    assert n_planes > 80 and seen[1] > 1000 and seen[2] > 1000 and seen[3] > 50 and seen[4] > 500, (n_planes, seen)
+    # (classes: none, exact occurrence, re-scan, plan from the planes' hits, exact overlap at the end, plan without end window)
+    assert n_planes > 80 and seen[1] > 1000 and seen[2] > 1000 and seen[3] > 50 and seen[4] > 300 and seen[5] > 50 and seen[6] > 100, (n_planes, seen)
+
+
+def test_bitplane_end_analysis_and_repetitive_adapters():
+    """
+    The end analysis of the bit-plane stage (guard pieces, exact overlaps at the end of the read, "no end window")
+    and locator chunks that repeat inside the adapter: reads ending with adapter prefixes of every length with 0..2
+    edits, adapter pieces elsewhere, repetitive adapters -- first-stage decisions + hand-off == the plain path.
+    """
+    import cutadapt_b200.adapters as PA
+    from util import hostsim_plane_classes
+
+    rng = random.Random(2718)
+    seen = np.zeros(7, dtype=np.int64)
+    for trial in range(150):
+        m = rng.choice([6, 8, 10, 13, 13, 16, 20, 25, 33, 40])
+        seq = "".join(rng.choice("ACGT") for _ in range(m))
+        if rng.random() < 0.25:
+            seq = (seq[:rng.choice([1, 2, 3])] * 40)[:m]
+        ad = PA.BackAdapter(seq, max_errors=rng.choice([0.05, 0.1, 0.1, 0.15, 0.2, 0.25]), min_overlap=rng.randint(1, 7), name="x")
+        spec = spec_of(ad)
+        reads = []
+        for _ in range(120):
+            n = rng.choice([60, 100, 150, 160])
+            piece = list(seq[:rng.randint(0, m)])
+            for _ in range(rng.choice([0, 0, 0, 1, 1, 2])):
+                if piece:
+                    p, r = rng.randrange(len(piece)), rng.random()
+                    if r < 0.4:
+                        piece[p] = rng.choice("ACGTN")
+                    elif r < 0.7:
+                        del piece[p]
+                    else:
+                        piece.insert(p, rng.choice("ACGT"))
+            body = "".join(rng.choice("ACGT") for _ in range(n))
+            if rng.random() < 0.3:
+                q, j = rng.randrange(n), rng.randint(0, m - 1)
+                body = body[:q] + seq[j:j + rng.randint(3, m)] + body[q:]
+            read = (body + "".join(piece))[-n:]
+            reads.append(read.lower() if rng.random() < 0.1 else read)
+        a, _ = hostsim_process(spec, reads, force_wide=0)
+        b, _ = hostsim_process(spec, reads, force_wide=256)
+        assert (a == b).all(), repr(ad)
+        seen += np.bincount(hostsim_plane_classes(spec, reads) + 1, minlength=7)
+    assert seen[5] > 1000 and seen[6] > 200, seen
 
 
 def test_two_phase_on_golden_single_adapters():
