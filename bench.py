@@ -394,6 +394,8 @@ def main():
                     help="BASELINE.json configuration (SURVEY.md section 8(d) numbering); 2 = the headline metric")
     ap.add_argument("--reads", type=int, default=int(os.environ.get("BENCH_READS", 0)),
                     help="reads (config 4: pairs) per GPU; default: the size BASELINE.json names for the configuration")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --reads per GPU (default); strong: --reads in total, split evenly over the GPUs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -402,6 +404,8 @@ def main():
         args.reads = DEFAULT_READS[cfg]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "strong":
+        args.reads = max(1, args.reads // world)       # the job stays the same size, every GPU gets its share
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     reads_per_unit = 2 if cfg == 4 else 1
     unit = "pairs" if cfg == 4 else "reads"
@@ -671,7 +675,7 @@ def main():
         line = {
             "metric": metric, "value": value, "unit": "reads/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload, "baseline_config": cfg, f"{unit}_per_gpu": n, "reads_per_step_per_gpu": reads_per_step,
                        "l2": f"inputs ({reads_per_step * algo / 1e9:.1f} GB/GPU touched per step) larger than L2",

@@ -598,7 +598,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             b.qtrim = a.qtrim ? a.qtrim + 2 * r0 : nullptr;
             b.view = a.view ? a.view + 2 * r0 : nullptr;
             b.task_cap = n_sub;
-            CU(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), st));
             const long long n_mt = (n_sub + 31) / 32;
             const long long need = (n_mt + 3) / 4;
             auto grid_for = [&](int occ) { return (int)std::max<long long>(1, std::min<long long>((long long)occ * c->sm_count, need)); };
@@ -609,6 +609,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             }
             b.tasks = c->tasks.p; b.task_count = cnt;
             b.task_rec = plane_w ? 4 : 2;
+            b.task_count_b = plane_w ? cnt + 4 : nullptr;
             if (plane_w && jit_kernel) {
                 const int rcj = cg_jit_launch(jit_kernel, grid_for(jit_occ), CG_NT, scan_smem, (void *)st, &b);
                 if (rcj != 0) return fail(CG_ECUDA, "launch of the specialised first stage failed (CUresult " + std::to_string(rcj) + ")");
@@ -625,7 +626,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
                 // scanned exactly on dense warps; its run records continue the same list
                 CgKernelArgs b2 = b;
                 b2.tasks = c->tasks3.p; b2.task_count = cnt + 2; b2.task_rec = 2;
-                b2.tasks3 = nullptr; b2.task3_count = cnt + 3;
+                b2.tasks3 = nullptr; b2.task3_count = cnt + 3; b2.task_count_b = nullptr;
                 CU(cg_launch_list(b2, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
                 CU(cudaMemsetAsync(cnt + 2, 0, sizeof(unsigned long long), st));
                 c->launches += 1;

@@ -36,6 +36,9 @@ struct CgKernelArgs {
     int task_rec;                     // uint4 words per task of the plan stage's input list (2: scan, 4: pscan)
     uint4 *tasks;                     // task_rec x uint4 per task
     unsigned long long *task_count;   // number of tasks appended by the scan kernel
+    unsigned long long *task_count_b; // cg_pscan_kernel: tasks WITHOUT locator hits are filed from the end of `tasks`
+                                      // backwards and counted here, so that the warps of the plan stage work on reads
+                                      // of one kind (null: one list)
     long long task_cap;
     uint4 *tasks2;                    // output list of the plan / run kernels: 4 x uint4 per record
     unsigned long long *task2_count;

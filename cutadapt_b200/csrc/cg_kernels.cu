@@ -773,7 +773,8 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 //               finished (early exit or last run) get their record, the others move to the output
 //               list with the updated selection state.
 #ifndef CG_PLAN_BLOCKS
-#define CG_PLAN_BLOCKS 7      // resident CTAs per SM the plan kernel is compiled for (72 registers, no spills)
+#define CG_PLAN_BLOCKS 6      // resident CTAs per SM the plan kernel is compiled for (80 registers; measured: 7 CTAs at
+                              // 72 registers spill in the bit-vector loops and run 25 % slower)
 #endif
 #ifndef CG_RUN16_BLOCKS
 #define CG_RUN16_BLOCKS 4     // same for the run kernel with a 16-row column (measured: 4 beats 5)
@@ -798,9 +799,14 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
 
     unsigned long long n_tasks = *a.task_count;
     if (n_tasks > (unsigned long long)a.task_cap) n_tasks = (unsigned long long)a.task_cap;
+    // second list of the plan stage's input (tasks without locator hits, filed from the end of the buffer): its
+    // groups follow those of the first list, so that no warp mixes the two kinds
+    unsigned long long n_tasks_b = (PLAN && a.task_count_b) ? *a.task_count_b : 0ull;
+    if (n_tasks + n_tasks_b > (unsigned long long)a.task_cap) n_tasks_b = (unsigned long long)a.task_cap - n_tasks;
+    const long long n_groups_a = (long long)((n_tasks + 31) / 32);
     const uint4 *list = a.tasks;
     const int rec = PLAN ? a.task_rec : 4;     // the plan stage reads the scan kernel's (2) or cg_pscan_kernel's (4) tasks
-    const long long n_groups = (long long)((n_tasks + 31) / 32);
+    const long long n_groups = n_groups_a + (long long)((n_tasks_b + 31) / 32);
     const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
     const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
     const uintptr_t seq_base = (uintptr_t)a.seq;
@@ -809,11 +815,20 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
     // offsets[read] -> address) are in flight while the current group is worked on: load_task() only issues loads
     // into registers, stage() starts the per-lane cp.async copy of the read window into this lane's slot.
     struct Task { uint4 ta, tb, tc, td; uintptr_t src; uint32_t bytes, soff; };
+    // physical record of lane `lane` of group g, or -1
+    auto task_index = [&](long long g) -> long long {
+        if (g < n_groups_a) {
+            const unsigned long long t = (unsigned long long)g * 32 + lane;
+            return t < n_tasks ? (long long)t : -1;
+        }
+        const unsigned long long t = (unsigned long long)(g - n_groups_a) * 32 + lane;
+        return t < n_tasks_b ? (long long)a.task_cap - 1 - (long long)t : -1;
+    };
     auto load_task = [&](long long g, Task &T) {
-        const unsigned long long t = (unsigned long long)g * 32 + lane;
+        const long long t = task_index(g);
         T.ta = make_uint4(0, 0, 0, 0); T.tb = make_uint4(0, 4, 0, 0); T.tc = make_uint4(0, 0, 0, 0); T.td = make_uint4(0, 0, 0, 0);
         T.src = 0; T.bytes = 0; T.soff = 0;
-        if (t >= n_tasks) return;
+        if (t < 0) return;
         T.ta = list[rec * t]; T.tb = list[rec * t + 1];
         if (!PLAN || rec == 4) { T.tc = list[rec * t + 2]; T.td = list[rec * t + 3]; }
         const long long r = (long long)(((unsigned long long)T.ta.y << 32) | T.ta.x);
@@ -847,7 +862,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
         const uint4 ta = cur.ta, tb = cur.tb, tc = cur.tc, td = cur.td;
         const uint32_t soff = cur.soff;
         const int st = 0;
-        const bool has_task = (unsigned long long)g * 32 + lane < n_tasks;
+        const bool has_task = task_index(g) >= 0;
         const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * slot_bytes + soff;
         const int n = (int)ta.w;
         const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);

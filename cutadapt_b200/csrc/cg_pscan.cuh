@@ -148,13 +148,26 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
             }
         }
         const bool slow = mine && cls == CG_PLANE_SLOW;
-        const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
-        if (ballot) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.task_count, (unsigned long long)__popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, 0);
+        // two lists: reads with locator hits (and everything the planes could not look at) from the front, reads
+        // without from the back -- the plan stage does different work for the two kinds, and a warp is as slow as
+        // its slowest lane
+        const bool kind_b = slow && a.task_count_b != nullptr && (t_flags & CG_TASK_PLANES) && !(t_flags & (1u << 20)) &&
+                            (tm[0] | tm[1] | tm[2] | tm[3] | tm[4] | tm[5] | tm[6] | tm[7]) == 0u;
+        const uint32_t ballot_a = __ballot_sync(0xffffffffu, slow && !kind_b);
+        const uint32_t ballot_b = __ballot_sync(0xffffffffu, kind_b);
+        if (ballot_a | ballot_b) {
+            unsigned long long base_a = 0, base_b = 0;
+            if (lane == 0) {
+                if (ballot_a) base_a = atomicAdd(a.task_count, (unsigned long long)__popc(ballot_a));
+                if (ballot_b) base_b = atomicAdd(a.task_count_b, (unsigned long long)__popc(ballot_b));
+            }
+            base_a = __shfl_sync(0xffffffffu, base_a, 0);
+            base_b = __shfl_sync(0xffffffffu, base_b, 0);
             if (slow) {
-                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                const uint32_t below = (1u << lane) - 1u;
+                const unsigned long long slot = kind_b
+                    ? (unsigned long long)a.task_cap - 1ull - (base_b + __popc(ballot_b & below))
+                    : base_a + __popc(ballot_a & below);
                 a.tasks[4 * slot] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
                                                (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
                 a.tasks[4 * slot + 1] = make_uint4(tm[0], t_flags, tm[1], tm[2]);

@@ -7,6 +7,7 @@
 #include "cg_setbuild.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -265,7 +266,13 @@ void build_plane_program(const cg_adapter_desc &d, const CgAdapter &A, const uin
     // none occurs, every acceptable cell is an exact overlap, and of a length < lo_1 (a longer one contains the
     // pieces of level 1).  OVERLAP emits report those exact overlaps (lengths min_overlap .. lo_1 - 1).
     uint64_t overlap_ok = 0;
-    if ((A.flags & 15) == 14 && A.indel_cost == 1 && plain && (flags & 1) && A.m <= 63 && maxcost) {
+    // (Measured on the benchmark shape: the two guard emits, seven overlap emits and two extra chain steps cost the
+    //  first stage more (+0.43 ms per 100 M reads) than the plan stage saves, because a warp of the plan stage only
+    //  gets faster when all of its 32 reads skip the end window.  Kept for adapters / data where the end of the read
+    //  is where the work is; CUTADAPT_B200_END_ANALYSIS=1 turns it on.)
+    const char *end_env = getenv("CUTADAPT_B200_END_ANALYSIS");
+    const bool end_analysis = end_env && end_env[0] == '1';
+    if (end_analysis && (A.flags & 15) == 14 && A.indel_cost == 1 && plain && (flags & 1) && A.m <= 63 && maxcost) {
         int top = 0;
         for (int i = 0; i <= A.m; ++i) top = std::max(top, (int)maxcost[i]);
         bool fits = true;
