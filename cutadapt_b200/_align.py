@@ -128,15 +128,49 @@ class Aligner(_Located):
             f"min_overlap={self._min_overlap})"
         )
 
-    # The reference can dump its DP matrices for one read (enable_debug, _align.pyx:291-296).
-    # The device kernel keeps a single packed column per read and never materialises them.
+    # -- debugging aid: the DP matrices of one read (enable_debug / dpmatrix / scorematrix, _align.pyx:279-296) -------
     dpmatrix = None
     scorematrix = None
 
     def enable_debug(self):
-        raise NotImplementedError(
-            "DP matrix dumps are not available from the GPU aligner; use the oracle for triage"
-        )
+        """Keep the dynamic-programming matrices of every following locate() call in .dpmatrix / .scorematrix."""
+        self._debug = True
+
+    def locate(self, query: str) -> Optional[Alignment]:
+        if not getattr(self, "_debug", False):
+            return super().locate(query)
+        if not isinstance(query, str):
+            raise TypeError("query must be str")
+        import ctypes as C
+
+        spec = _lib.AdapterSetSpec([self._descriptor()])
+        arr, _, _, _ = spec.to_ctypes()
+        q = query.encode("ascii", "replace") if query.isascii() else query.encode("latin-1", "replace")
+        m, n = len(self.reference), len(q)
+        cost = np.empty((m + 1, n + 1), dtype=np.int32)
+        score = np.empty((m + 1, n + 1), dtype=np.int32)
+        res = np.zeros(8, dtype=np.int32)
+        _lib.check(_lib.lib().cg_locate_debug(_lib.default_context().handle, arr, q, n, cost.ctypes.data,
+                                              score.ctypes.data, res.ctypes.data))
+        self.dpmatrix = DPMatrix(self.reference, query, cost)
+        self.scorematrix = DPMatrix(self.reference, query, score)
+        return tuple(int(x) for x in res[1:7]) if res[0] else None
+
+
+class DPMatrix:
+    """The cells the search computed, None where it never went; prints like the reference's (_align.pyx:58-90)."""
+
+    NONE = -(1 << 31)
+
+    def __init__(self, reference: str, query: str, values):
+        self.reference, self.query = reference, query
+        self._rows = [[None if v == self.NONE else int(v) for v in row] for row in values]
+
+    def __str__(self):
+        lines = ["     " + " ".join(c.rjust(2) for c in self.query)]
+        for label, row in zip(" " + self.reference, self._rows):
+            lines.append(label + " " + " ".join("  " if v is None else f"{v:2d}" for v in row))
+        return "\n".join(lines)
 
 
 class PrefixComparer(_Located):

@@ -208,6 +208,7 @@ def _declare(lib) -> None:
     lib.cg_stats_accumulate_device.argtypes = [
         vp, vp, vp, vp, i64, C.POINTER(cg_params), vp, vp, i32, i32, vp,
     ]
+    lib.cg_locate_debug.argtypes = [vp, C.POINTER(cg_adapter_desc), vp, i32, vp, vp, vp]
     lib.cg_process_batch_stats.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(cg_params), vp, vp, i32, i32, vp]
     lib.cg_edit_environment.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i64]
     lib.cg_edit_environment.restype = i64

@@ -581,10 +581,11 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         // reads per sub-batch: bounds the lists to 1 + 2 x 2 GiB at the default 32 Mi (measured: fewer,
         // larger sub-batches amortise the kernel tails and the small late DP rounds; 32 Mi vs 4 Mi = +15 % on the 100 M-read bench).
         // CUTADAPT_B200_SUB_READS overrides it for experiments.
-        long long SUB = 32LL << 20;
+        long long SUB = plane_w ? (16LL << 20) : (32LL << 20);     // (plane tasks carry the window: 240 bytes each)
         if (const char *e = getenv("CUTADAPT_B200_SUB_READS")) { const long long v = atoll(e); if (v >= 1024) SUB = v; }
         const long long cap = std::min<long long>(n_reads, SUB);
-        int rc = c->tasks.ensure((size_t)cap * (plane_w ? 4 : 2));
+        const int plane_rec = plane_w ? 4 + 2 * plane_w + 1 : 2;      // header + the window bytes (cg_pscan.cuh)
+        int rc = c->tasks.ensure((size_t)cap * plane_rec);
         if (rc == CG_OK) rc = c->tasks2.ensure((size_t)cap * 4);
         if (rc == CG_OK) rc = c->tasks3.ensure((size_t)cap * 4);
         if (rc != CG_OK) return rc;
@@ -608,8 +609,11 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
                 CU(cudaEventRecord(sev[0], st));
             }
             b.tasks = c->tasks.p; b.task_count = cnt;
-            b.task_rec = plane_w ? 4 : 2;
-            b.task_count_b = plane_w ? cnt + 4 : nullptr;
+            b.task_rec = plane_rec;
+            // (two input lists for the plan stage -- reads with / without locator hits -- were measured: the first
+            //  stage got 2.3x slower and the plan stage no faster, it is bound by its memory traffic; kept as an
+            //  experiment: CUTADAPT_B200_TWO_LISTS=1)
+            b.task_count_b = (plane_w && getenv("CUTADAPT_B200_TWO_LISTS")) ? cnt + 4 : nullptr;
             if (plane_w && jit_kernel) {
                 const int rcj = cg_jit_launch(jit_kernel, grid_for(jit_occ), CG_NT, scan_smem, (void *)st, &b);
                 if (rcj != 0) return fail(CG_ECUDA, "launch of the specialised first stage failed (CUresult " + std::to_string(rcj) + ")");
@@ -751,6 +755,53 @@ static int launch_trim_inner(cg_ctx *c, const cg_adapterset *s, const uint8_t *d
         CU(cudaEventRecord(ev1, st));
         c->timing.emplace_back(ev0, ev1);
     }
+    return CG_OK;
+}
+
+// Aligner.enable_debug() (_align.pyx:291-296): the DP matrices of ONE read against ONE aligner adapter, every cell
+// the search computes (cost and score; CG_DEBUG_NONE where the band never went).  A triage aid: one thread, exact
+// int32 cells, no prefilter.  cost / score: (m + 1) x (n + 1) int32, row-major; result8: found, then the six numbers
+// of Aligner.locate().
+extern "C" int cg_locate_debug(cg_ctx *c, const cg_adapter_desc *adapter, const uint8_t *query, int32_t n,
+                               int32_t *cost, int32_t *score, int32_t *result8)
+{
+    if (!c || !adapter || !cost || !score || !result8 || n < 0 || (n && !query))
+        return fail(CG_EINVAL, "cg_locate_debug: bad argument");
+    if (adapter->kind != CG_KIND_ALIGNER) return fail(CG_EINVAL, "cg_locate_debug: only aligner adapters have a DP matrix");
+    for (int32_t i = 0; i < n; ++i) if (query[i] & 0x80) return fail(CG_ENONASCII, "String must contain only ASCII characters");
+    CU(cudaSetDevice(c->device));
+    cg_adapter_desc d = *adapter;
+    d.n_kmer_entries = 0; d.kmer_entries = nullptr; d.kmer_masks = nullptr; d.reverse_read = 0;
+    cg_group_desc g;
+    memset(&g, 0, sizeof g);
+    g.type = CG_GROUP_SINGLE; g.a0 = 0; g.a1 = -1;
+    CgBuiltSet set;
+    std::string err;
+    int rc = cg_build_set(&d, 1, &g, 1, set, err);
+    if (rc != CG_OK) return fail(rc, err);
+    const int m = set.max_m;
+    const size_t cells = (size_t)(m + 1) * ((size_t)n + 1);
+    DevBuf<uint8_t> d_blob, d_query;
+    DevBuf<int> d_scratch;
+    DevBuf<int32_t> d_mat, d_res;
+    struct Free {
+        DevBuf<uint8_t> &a, &b; DevBuf<int> &s; DevBuf<int32_t> &m, &r;
+        ~Free() { a.release(); b.release(); s.release(); m.release(); r.release(); }
+    } free_all{d_blob, d_query, d_scratch, d_mat, d_res};
+    if ((rc = d_blob.ensure(set.blob.size())) != CG_OK || (rc = d_query.ensure((size_t)n + 16)) != CG_OK ||
+        (rc = d_scratch.ensure(3 * ((size_t)m + 2))) != CG_OK || (rc = d_mat.ensure(2 * cells)) != CG_OK ||
+        (rc = d_res.ensure(8)) != CG_OK)
+        return rc;
+    std::vector<int32_t> none(2 * cells, CG_DEBUG_NONE);
+    CU(cudaMemcpy(d_blob.p, set.blob.data(), set.blob.size(), cudaMemcpyHostToDevice));
+    if (n) CU(cudaMemcpy(d_query.p, query, (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_mat.p, none.data(), 2 * cells * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(cg_launch_locate_debug(d_blob.p, c->d_enc, d_query.p, n, d_scratch.p, d_mat.p, d_mat.p + cells, d_res.p, c->stream));
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(cost, d_mat.p, cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(score, d_mat.p + cells, cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(result8, d_res.p, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return CG_OK;
 }
 

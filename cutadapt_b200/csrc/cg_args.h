@@ -33,7 +33,8 @@ struct CgKernelArgs {
     int mini_cap;    // bytes per staged 32-read mini-tile (multiple of 16)
     int carry_slot;  // bytes per carried task (multiple of 16)
     // split pipeline (scan kernel -> task list in HBM -> DP kernel)
-    int task_rec;                     // uint4 words per task of the plan stage's input list (2: scan, 4: pscan)
+    int task_rec;                     // uint4 words per task of the plan stage's input list (2: scan kernel; cg_pscan_kernel:
+                                      // 4 + 2 W + 1, header + the window bytes)
     uint4 *tasks;                     // task_rec x uint4 per task
     unsigned long long *task_count;   // number of tasks appended by the scan kernel
     unsigned long long *task_count_b; // cg_pscan_kernel: tasks WITHOUT locator hits are filed from the end of `tasks`

@@ -233,10 +233,14 @@ CG_HD bool kmers_present_core(const CgEntry *ents, int count, const uint64_t *ma
 // k-mers (pigeonhole: an alignment with <= k errors contains one of the k+1 adapter chunks
 // exactly) that every bottom-row cell with cost <= k, and the cells the last-column scan can
 // accept, lie at least m + k columns to the right of their run's start.
+// dbg_cost / dbg_score (optional, (m + 1) x (n + 1) row-major int32, pre-filled by the caller with the "not
+// computed" marker): every cell the search computes is recorded -- the DPMatrix of Aligner.enable_debug()
+// (_align.pyx:291-296, 385-390, 484-489).
 template <class Cell, class Col>
 CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *ncnt,
                        const int32_t *maxcost, const uint8_t *enc, const ReadView &rv, Col &col,
-                       int *out6, uint32_t cover = 0xFFFFFFFFu, int gs = 0)
+                       int *out6, uint32_t cover = 0xFFFFFFFFu, int gs = 0, int32_t *dbg_cost = nullptr,
+                       int32_t *dbg_score = nullptr)
 {
     typedef typename Cell::T T;
     const int m = A.m, n = rv.n, k = A.k, ic = A.indel_cost;
@@ -281,6 +285,10 @@ CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *nc
             else if (!sir && siq) { s = -2 * i; c = (long long)i * ic; o = cg_max(0, min_n - i); }
             else { s = 0; c = (long long)cg_min(i, min_n) * ic; o = min_n - i; }
             col.set(i, Cell::make(c, s, o));
+            if (dbg_cost) {
+                dbg_cost[(size_t)i * (n + 1) + min_n] = Cell::cost(col.get(i));
+                dbg_score[(size_t)i * (n + 1) + min_n] = s;
+            }
         }
         last = sir ? m : cg_min(m, k + 1);                      // _align.pyx:399-401
       } else {
@@ -308,6 +316,13 @@ CG_HD bool locate_core(const CgAdapter &A, const uint8_t *ref, const int32_t *nc
         }
         if (last >= 1) stale = up;
         last_filled = last;                                     // _align.pyx:484
+        if (dbg_cost) {
+            for (int i = 0; i <= last; ++i) {
+                const T w = col.get(i);
+                dbg_cost[(size_t)i * (n + 1) + j] = Cell::cost(w);
+                dbg_score[(size_t)i * (n + 1) + j] = Cell::score(w);
+            }
+        }
         // `while last >= 0 and column[last].cost > k: last -= 1` == lastok   (_align.pyx:490-491)
         if (lastok < m) {
             last = lastok + 1;                                  // _align.pyx:494-495

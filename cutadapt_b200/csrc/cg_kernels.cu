@@ -805,7 +805,8 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
     if (n_tasks + n_tasks_b > (unsigned long long)a.task_cap) n_tasks_b = (unsigned long long)a.task_cap - n_tasks;
     const long long n_groups_a = (long long)((n_tasks + 31) / 32);
     const uint4 *list = a.tasks;
-    const int rec = PLAN ? a.task_rec : 4;     // the plan stage reads the scan kernel's (2) or cg_pscan_kernel's (4) tasks
+    const int rec = PLAN ? a.task_rec : 4;     // the plan stage reads the scan kernel's (2 words) or cg_pscan_kernel's
+                                               // (4 + the window bytes) tasks
     const long long n_groups = n_groups_a + (long long)((n_tasks_b + 31) / 32);
     const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
     const long long wg = (long long)blockIdx.x * (CG_NT / 32) + wib;
@@ -830,7 +831,13 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
         T.src = 0; T.bytes = 0; T.soff = 0;
         if (t < 0) return;
         T.ta = list[rec * t]; T.tb = list[rec * t + 1];
-        if (!PLAN || rec == 4) { T.tc = list[rec * t + 2]; T.td = list[rec * t + 3]; }
+        if (!PLAN || rec >= 4) { T.tc = list[rec * t + 2]; T.td = list[rec * t + 3]; }
+        if (PLAN && (T.tb.y & CG_TASK_BYTES)) {          // the window travels with the task (cg_pscan_kernel)
+            T.src = (uintptr_t)(list + rec * t + 4);
+            T.bytes = 16u * (uint32_t)(rec - 4);
+            T.soff = T.td.y;
+            return;
+        }
         const long long r = (long long)(((unsigned long long)T.ta.y << 32) | T.ta.x);
         uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + T.ta.z;
         uint32_t len = T.ta.w;
@@ -1056,6 +1063,31 @@ __global__ void cg_trim_generic_kernel(const CgKernelArgs a)
                            a.out + (size_t)r * a.times * a.slots, a.qtrim ? a.qtrim + 2 * r : nullptr,
                                     a.view ? a.view + 2 * r : nullptr);
     }
+}
+
+// One read, one aligner adapter, exact int32 cells, every computed cell recorded: Aligner.enable_debug()'s matrices.
+__global__ void cg_locate_debug_kernel(const uint8_t *blob, const uint8_t *enc768, const uint8_t *query, int n,
+                                       int *scratch /* 3 (m + 1) */, int32_t *cost, int32_t *score, int32_t *result8)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const SetView S = make_set_view(blob, nullptr, enc768, nullptr);
+    const CgAdapter &A = S.ad[0];
+    ReadView rv; rv.p = query; rv.n = n; rv.rev = 0;
+    WideCol col; col.base = scratch; col.stride = 1;
+    int o[6] = {0, 0, 0, 0, 0, 0};
+    const bool found = locate_core<WideCell, WideCol>(A, S.pool + A.ref_off, (const int32_t *)(S.pool + A.ncount_off),
+                                                      (const int32_t *)(S.pool + A.maxcost_off), enc768 + 256 * A.query_enc,
+                                                      rv, col, o, 0xFFFFFFFFu, 0, cost, score);
+    result8[0] = found ? 1 : 0;
+    for (int i = 0; i < 6; ++i) result8[1 + i] = o[i];
+    result8[7] = 0;
+}
+
+cudaError_t cg_launch_locate_debug(const uint8_t *d_blob, const uint8_t *d_enc, const uint8_t *d_query, int n,
+                                   int *d_scratch, int32_t *d_cost, int32_t *d_score, int32_t *d_result, cudaStream_t st)
+{
+    cg_locate_debug_kernel<<<1, 32, 0, st>>>(d_blob, d_enc, d_query, n, d_scratch, d_cost, d_score, d_result);
+    return cudaGetLastError();
 }
 
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st)

@@ -39,6 +39,8 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes);
 cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_list(const CgKernelArgs &a, bool plan, int mr, int grid, size_t smem, cudaStream_t st);
 cudaError_t cg_launch_generic(const CgKernelArgs &a, int grid, int block, cudaStream_t st);
+cudaError_t cg_launch_locate_debug(const uint8_t *d_blob, const uint8_t *d_enc, const uint8_t *d_query, int n,
+                                   int *d_scratch, int32_t *d_cost, int32_t *d_score, int32_t *d_result, cudaStream_t st);
 cudaError_t cg_launch_kmers_present(const CgEntry *d_entries, int n_entries, const uint64_t *d_masks,
                                     const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads,
                                     uint8_t *d_out, int *d_err, cudaStream_t st);

@@ -24,8 +24,12 @@ struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_
 #define CG_PSCAN_BLOCKS 8     // resident CTAs per SM the 5-word variant is compiled for (64 registers)
 #endif
 #define CG_TASK_RESCAN 0x100u     // the plan stage must scan the read itself (shift-and scan_core)
+#define CG_TASK_BYTES 0x400u      // the task carries the read window itself: 2 W + 1 16-byte pieces after the four header
+                                  // words (the aligned stretch of shared memory that covers the 32 W characters in front
+                                  // of the window's end); td.y = offset of the window's first character in them.  The
+                                  // plan stage then streams its input instead of gathering windows from all over HBM.
 #define CG_TASK_PLANES 0x200u     // a 4 x uint4 task of cg_pscan_kernel: {read lo, read hi, trim start, length},
-                                  // {M0, flags, M1, M2}, {M3 .. M6}, {M7, 0, 0, 0} with M = PlaneOut::M;
+                                  // {M0, flags, M1, M2}, {M3 .. M6}, {M7, window offset, 0, 0} with M = PlaneOut::M (+ CG_TASK_BYTES);
                                   // flags bits 12-15: plane words W, bit 20: PlaneOut::end_hit, bit 21: PlaneOut::no_end
 __host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
 {
@@ -110,6 +114,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
         int cls = CG_PLANE_NONE, s0 = 0, ts = 0, te = 0;
         uint32_t t_flags = 4u | CG_TASK_RESCAN;
         uint32_t tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t win_region = 0, win_off = 0;         // shared-memory address of the carried bytes, window offset in them
         bool mine = false;
         if (r < n_reads) {
             mine = true;
@@ -129,7 +134,10 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 cls = po.cls; s0 = po.s0;
                 if (po.bad & 0x80808080u) atomicOr(a.err_flag, 1);
                 if (cls == CG_PLANE_SLOW) {
-                    t_flags = 4u | CG_TASK_PLANES | ((uint32_t)W << 12) | ((uint32_t)po.end_hit << 20) | ((uint32_t)po.no_end << 21);
+                    t_flags = 4u | CG_TASK_PLANES | CG_TASK_BYTES | ((uint32_t)W << 12) | ((uint32_t)po.end_hit << 20) | ((uint32_t)po.no_end << 21);
+                    const uint32_t wend = smem_u32(s_seq + off + te);
+                    win_region = (wend - 32u * W) & ~15u;
+                    win_off = (wend - (uint32_t)nn) - win_region;
 #pragma unroll
                     for (int b = 0; b < 8; ++b) tm[b] = po.M[b];
                 }
@@ -168,11 +176,21 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 const unsigned long long slot = kind_b
                     ? (unsigned long long)a.task_cap - 1ull - (base_b + __popc(ballot_b & below))
                     : base_a + __popc(ballot_a & below);
-                a.tasks[4 * slot] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
-                                               (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
-                a.tasks[4 * slot + 1] = make_uint4(tm[0], t_flags, tm[1], tm[2]);
-                a.tasks[4 * slot + 2] = make_uint4(tm[3], tm[4], tm[5], tm[6]);
-                a.tasks[4 * slot + 3] = make_uint4(tm[7], 0u, 0u, 0u);
+                uint4 *rec = a.tasks + (size_t)a.task_rec * slot;
+                rec[0] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
+                                    (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
+                rec[1] = make_uint4(tm[0], t_flags, tm[1], tm[2]);
+                rec[2] = make_uint4(tm[3], tm[4], tm[5], tm[6]);
+                rec[3] = make_uint4(tm[7], win_off, 0u, 0u);
+                if (t_flags & CG_TASK_BYTES) {
+#pragma unroll
+                    for (int c = 0; c < 2 * W + 1; ++c) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(win_region + 16u * (uint32_t)c));
+                        rec[4 + c] = v;
+                    }
+                }
             }
         }
         __syncwarp();

@@ -199,6 +199,14 @@ int cg_adapterset_create(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n
 int cg_adapterset_create_indexed(cg_ctx *ctx, const cg_adapter_desc *adapters, int32_t n_adapters,
                                  const cg_group_desc *groups, int32_t n_groups,
                                  const cg_index_desc *indexes, int32_t n_indexes, cg_adapterset **out);
+/* Aligner.enable_debug() / .dpmatrix / .scorematrix (_align.pyx:279-296): the dynamic-programming matrices of ONE
+ * read against ONE aligner adapter as the search fills them -- (m + 1) x (n + 1) int32 each, row-major, CG_DEBUG_NONE
+ * where a cell was never computed (outside the Ukkonen band or after the early exit).  result8 = found (0/1) and the
+ * six numbers of Aligner.locate().  A triage aid (one device thread, exact cells, no prefilter). */
+#define CG_DEBUG_NONE (-2147483647 - 1)
+int cg_locate_debug(cg_ctx *ctx, const cg_adapter_desc *adapter, const uint8_t *query, int32_t n,
+                    int32_t *cost, int32_t *score, int32_t *result8);
+
 int cg_adapterset_destroy(cg_adapterset *set);
 
 /* Run-time specialisation of the bit-plane first stage for this adapter set (compiled with NVRTC once the set has

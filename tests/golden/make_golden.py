@@ -433,6 +433,28 @@ def env_kat():
     dump("environment_kat.json.gz", out)
 
 
+def dp_debug_kat():
+    """Aligner.enable_debug(): the printed cost and score matrices of the reference for a few searches."""
+    rng = random.Random(77)
+    out = []
+    for trial in range(40):
+        ref = rnd(rng, rng.choice(["ACGT", "ACGTN"]), rng.randint(3, 14))
+        q = mutate(rng, ref, "ACGT", rng.choice([0, 1, 2]))
+        q = rnd(rng, "ACGT", rng.randint(0, 8)) + q + rnd(rng, "ACGT", rng.randint(0, 8))
+        rate = rng.choice([0.1, 0.2, 0.3])
+        flags = rng.choice([14, 11, 15, 8, 2, 0])
+        wr = "N" in ref and rng.random() < 0.7
+        mo = rng.randint(1, 3)
+        try:
+            al = Aligner(ref, rate, flags, wr, False, 1, mo)
+        except ValueError:
+            continue
+        al.enable_debug()
+        res = al.locate(q)
+        out.append([ref, q, rate, flags, wr, mo, list(res) if res else None, str(al.dpmatrix), str(al.scorematrix)])
+    dump("dp_debug_kat.json.gz", out)
+
+
 def tables():
     import base64
 
@@ -454,4 +476,5 @@ if __name__ == "__main__":
     index_kat()
     info_file_kat()
     env_kat()
+    dp_debug_kat()
     tables()

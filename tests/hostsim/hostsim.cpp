@@ -201,6 +201,36 @@ extern "C" int hs_statistics(const uint8_t *seq, const int64_t *offsets, int64_t
     return 0;
 }
 
+// The DP matrices of one read (locate_core with its debug outputs: what cg_locate_debug_kernel runs), on the host.
+extern "C" int hs_locate_debug(const cg_adapter_desc *adapter, const uint8_t *query, int n, int32_t *cost, int32_t *score,
+                               int32_t *result8)
+{
+    cg_adapter_desc d = *adapter;
+    d.n_kmer_entries = 0; d.kmer_entries = nullptr; d.kmer_masks = nullptr; d.reverse_read = 0;
+    cg_group_desc g;
+    memset(&g, 0, sizeof g);
+    g.type = CG_GROUP_SINGLE; g.a0 = 0; g.a1 = -1;
+    CgBuiltSet set;
+    int rc = cg_build_set(&d, 1, &g, 1, set, g_err);
+    if (rc != CG_OK) return rc;
+    uint8_t enc[768];
+    cg_build_enc_tables(enc);
+    SetView S = make_set_view(set.blob.data(), set.masks64.data(), enc, nullptr);
+    const CgAdapter &A = S.ad[0];
+    const int m = A.m;
+    for (size_t i = 0; i < (size_t)(m + 1) * (n + 1); ++i) cost[i] = score[i] = CG_DEBUG_NONE;
+    std::vector<int> colw(3 * ((size_t)m + 2));
+    WideCol wc; wc.base = colw.data(); wc.stride = 1;
+    ReadView rv; rv.p = query; rv.n = n; rv.rev = 0;
+    int o[6] = {0, 0, 0, 0, 0, 0};
+    const bool found = locate_core<WideCell, WideCol>(A, S.pool + A.ref_off, (const int32_t *)(S.pool + A.ncount_off),
+                                                      (const int32_t *)(S.pool + A.maxcost_off), enc + 256 * A.query_enc, rv,
+                                                      wc, o, 0xFFFFFFFFu, 0, cost, score);
+    result8[0] = found ? 1 : 0;
+    for (int i = 0; i < 6; ++i) result8[1 + i] = o[i];
+    return 0;
+}
+
 extern "C" int hs_process_batch(const cg_adapter_desc *adapters, int n_adapters,
                                 const cg_group_desc *groups, int n_groups, const uint8_t *seq,
                                 const uint8_t *qual, const int64_t *offsets, int64_t n_reads,

@@ -47,6 +47,20 @@ def test_aligner_locate_golden():
             assert (list(g) if g is not None else None) == expected, (ref, q, rate, flags, wr, wq, ic, mo)
 
 
+def test_aligner_debug_matrices_golden():
+    """Aligner.enable_debug() / .dpmatrix / .scorematrix through cg_locate_debug, against the reference's printouts."""
+    from cutadapt_b200._align import Aligner
+
+    for ref, q, rate, flags, wr, mo, expected, dp_text, score_text in golden("dp_debug_kat.json.gz"):
+        al = Aligner(ref, rate, flags, wr, False, 1, mo)
+        plain = al.locate(q)
+        assert al.dpmatrix is None
+        al.enable_debug()
+        res = al.locate(q)
+        assert (list(res) if res else None) == expected == (list(plain) if plain else None)
+        assert str(al.dpmatrix) == dp_text and str(al.scorematrix) == score_text, (ref, q, flags)
+
+
 def test_reference_known_answer_tests():
     """tests/test_align.py:69-146 of the reference, verbatim expectations."""
     from cutadapt_b200._align import Aligner

@@ -30,6 +30,28 @@ def test_locate_golden(force_wide):
         assert got == expected, (ref, q, rate, flags, wr, wq, ic, mo)
 
 
+def test_dp_matrix_dump_golden():
+    """Aligner.enable_debug(): the cells locate_core records print like the reference's DPMatrix (cost and score)."""
+    import ctypes as C
+    from cutadapt_b200._align import DPMatrix
+    from util import hostsim_lib
+
+    lib = hostsim_lib()
+    for ref, q, rate, flags, wr, mo, expected, dp_text, score_text in golden("dp_debug_kat.json.gz"):
+        spec = _single(ref, rate, flags, wr, False, 1, mo)
+        arr, _, _, _ = spec.to_ctypes()
+        m, n = len(ref), len(q)
+        cost = np.empty((m + 1, n + 1), dtype=np.int32)
+        score = np.empty((m + 1, n + 1), dtype=np.int32)
+        res = np.zeros(8, dtype=np.int32)
+        rc = lib.hs_locate_debug(arr, q.encode(), C.c_int(n), C.c_void_p(cost.ctypes.data), C.c_void_p(score.ctypes.data),
+                                 C.c_void_p(res.ctypes.data))
+        assert rc == 0
+        assert (list(map(int, res[1:7])) if res[0] else None) == expected
+        assert str(DPMatrix(ref, q, cost)) == dp_text, (ref, q, flags)
+        assert str(DPMatrix(ref, q, score)) == score_text, (ref, q, flags)
+
+
 def test_comparers_golden():
     for ref, q, rate, wr, wq, mo, p, s in golden("comparer_kat.json.gz"):
         for kind, expected in ((1, p), (2, s)):
