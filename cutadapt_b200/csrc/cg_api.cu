@@ -516,8 +516,10 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         const char *scan_env = getenv("CUTADAPT_B200_SCAN");
         if (hdr->plane_count > 0 && max_read_len <= 256 && !(scan_env && strcmp(scan_env, "shiftand") == 0))
             plane_w = max_read_len <= 160 ? 5 : 8;
+        long long cslot_need = cslot;
+        if (plane_w) cslot_need = std::max<long long>(cslot, 16LL * (2 * plane_w + 1) + 16);   // the window bytes a plane task carries
         if (mini < (1 << 20)) {
-            a.mini_cap = (int)mini; a.carry_slot = (int)cslot;
+            a.mini_cap = (int)mini; a.carry_slot = (int)cslot_need;
             scan_smem = plane_w ? cg_pscan_smem_bytes(a.blob_bytes, a.mini_cap, want_q)
                                 : cg_scan_smem_bytes(a.blob_bytes, a.mini_cap, want_q);
             list_smem = cg_dp_smem_bytes(a.blob_bytes, a.carry_slot);
