@@ -583,10 +583,14 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         // reads per sub-batch: bounds the lists to 1 + 2 x 2 GiB at the default 32 Mi (measured: fewer,
         // larger sub-batches amortise the kernel tails and the small late DP rounds; 32 Mi vs 4 Mi = +15 % on the 100 M-read bench).
         // CUTADAPT_B200_SUB_READS overrides it for experiments.
-        long long SUB = plane_w ? (16LL << 20) : (32LL << 20);     // (plane tasks carry the window: 240 bytes each)
+        long long SUB = (plane_w && getenv("CUTADAPT_B200_TASK_BYTES")) ? (16LL << 20) : (32LL << 20);   // (tasks with bytes: 240 B each)
         if (const char *e = getenv("CUTADAPT_B200_SUB_READS")) { const long long v = atoll(e); if (v >= 1024) SUB = v; }
         const long long cap = std::min<long long>(n_reads, SUB);
-        const int plane_rec = plane_w ? 4 + 2 * plane_w + 1 : 2;      // header + the window bytes (cg_pscan.cuh)
+        // header (4 words) and, with CUTADAPT_B200_TASK_BYTES=1, the window bytes (cg_pscan.cuh).  Carrying the bytes
+        // turns the plan stage's gather into a stream but was measured neutral (plan 2.55 -> 2.65 ms, first stage
+        // 4.44 -> 4.64 ms per 100 M reads): the plan stage is bound by its dependent shared-memory chains, not by HBM.
+        const bool task_bytes = plane_w && getenv("CUTADAPT_B200_TASK_BYTES") != nullptr;
+        const int plane_rec = plane_w ? (task_bytes ? 4 + 2 * plane_w + 1 : 4) : 2;
         int rc = c->tasks.ensure((size_t)cap * plane_rec);
         if (rc == CG_OK) rc = c->tasks2.ensure((size_t)cap * 4);
         if (rc == CG_OK) rc = c->tasks3.ensure((size_t)cap * 4);

@@ -134,7 +134,8 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 cls = po.cls; s0 = po.s0;
                 if (po.bad & 0x80808080u) atomicOr(a.err_flag, 1);
                 if (cls == CG_PLANE_SLOW) {
-                    t_flags = 4u | CG_TASK_PLANES | CG_TASK_BYTES | ((uint32_t)W << 12) | ((uint32_t)po.end_hit << 20) | ((uint32_t)po.no_end << 21);
+                    t_flags = 4u | CG_TASK_PLANES | (a.task_rec > 4 ? CG_TASK_BYTES : 0u) | ((uint32_t)W << 12) |
+                              ((uint32_t)po.end_hit << 20) | ((uint32_t)po.no_end << 21);
                     const uint32_t wend = smem_u32(s_seq + off + te);
                     win_region = (wend - 32u * W) & ~15u;
                     win_off = (wend - (uint32_t)nn) - win_region;
