@@ -121,15 +121,16 @@ class cg_fastq_params(C.Structure):
         ("trim_n", C.c_int32),
         ("discard_casava", C.c_int32),
         ("action", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("revcomp", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
 class cg_fastq_result(C.Structure):
     _fields_ = [(name, C.c_int64) for name in (
         "n_records", "n_written", "bp_in", "bp_out", "out_bytes", "with_adapters", "quality_trimmed_bp",
-        "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded", "casava_filtered")] + [
-        ("reserved", C.c_int64 * 3)]
+        "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded", "casava_filtered",
+        "reverse_complemented")] + [("reserved", C.c_int64 * 2)]
 
     def as_dict(self) -> dict:
         return {name: int(getattr(self, name)) for name, _ in self._fields_ if name != "reserved"}

@@ -116,7 +116,8 @@ struct FastqSlot {
     DevBuf<int64_t> d_dmbase;
     DevBuf<int64_t> d_offs, d_outoff;
     DevBuf<unsigned long long> d_scan;
-    DevBuf<cg_match_rec> d_matches;
+    DevBuf<cg_match_rec> d_matches, d_matches_rc;
+    DevBuf<uint8_t> d_isrc;
     unsigned long long *d_counters = nullptr;   // [0] newline total, [1..] CG_FQ_COUNTERS
     int *d_err = nullptr;                       // [0] code, [1] record
     PinBuf<uint8_t> h_in, h_out;
@@ -1501,6 +1502,10 @@ struct FqStage {
     int32_t *d_qtrim = nullptr;
     const cg_match_rec *d_matches = nullptr;
     int action = 0;
+    bool want_q = false;                 // quality trimming still to be done by the trimming kernels
+    int max_len = 0;                     // longest packed read
+    const uint8_t *d_is_rc = nullptr;    // --revcomp: the record was replaced by its reverse complement
+    int rc_suffix = 0;                   // ... and gets " rc" appended to its name
 };
 
 static int fastq_enabled_filters(const cg_fastq_params *fp)
@@ -1511,8 +1516,8 @@ static int fastq_enabled_filters(const cg_fastq_params *fp)
 }
 
 // index the chunk, build the record table, run the modifiers (trimming pass included), evaluate the filters
-static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s, const cg_fastq_params *fp, int poly_a_mode,
-                                cudaStream_t st, FqStage &g)
+// Line table -> record table of one mate (format checks, -u, bases read); sizes every per-record buffer.
+static int fastq_stage_records(cg_ctx *c, FastqSlot &f, const cg_fastq_params *fp, bool has_set, cudaStream_t st, FqStage &g)
 {
     CU(cudaStreamSynchronize(f.stream));        // upload + newline count of this slot
     const int64_t n_bytes = f.n_bytes;
@@ -1530,14 +1535,14 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
     const long long n = g.n = n_lines / 4;
     if (n == 0) return CG_OK;
     const cg_params *p = &fp->trim;
-    const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
+    g.want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
     g.times = p->times < 1 ? 1 : p->times;
-    g.slots = s ? s->host.slots : 1;
     if (fp->cut_front < 0 || fp->cut_back < 0) return fail(CG_EINVAL, "cg_fastq: cut_front / cut_back must be >= 0");
     if (fp->action < CG_FQ_ACTION_TRIM || fp->action > CG_FQ_ACTION_CROP) return fail(CG_EINVAL, "cg_fastq: unknown action");
     if ((fp->action == CG_FQ_ACTION_RETAIN || fp->action == CG_FQ_ACTION_CROP) && g.times > 1)
         return fail(CG_EINVAL, "'retain' and 'crop' cannot be combined with times > 1");   // modifiers.py:117-118
-    g.action = s ? fp->action : CG_FQ_ACTION_TRIM;
+    if (fp->revcomp < 0 || fp->revcomp > 2) return fail(CG_EINVAL, "cg_fastq: revcomp must be 0, 1 or 2");
+    g.action = has_set ? fp->action : CG_FQ_ACTION_TRIM;
     int rc;
     if ((rc = f.d_nl.ensure((size_t)g.n_nl + 1)) != CG_OK) return rc;
     if ((rc = f.d_rec.ensure((size_t)n)) != CG_OK) return rc;
@@ -1548,40 +1553,69 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
     if ((rc = f.d_outlen.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_outoff.ensure((size_t)n + 1)) != CG_OK) return rc;
     if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(n) + 1)) != CG_OK) return rc;
-    if (want_q && (rc = f.d_qtrim.ensure((size_t)n * 2)) != CG_OK) return rc;
+    if (g.want_q && (rc = f.d_qtrim.ensure((size_t)n * 2)) != CG_OK) return rc;
     CU(cg_launch_fastq_index(f.d_in.p, n_bytes, f.d_tiles.p, nullptr, f.d_nl.p, 1, st));
     CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, g.n_nl, n, fp->cut_front, fp->cut_back, f.d_rec.p, f.d_len.p,
-                               f.d_err, st));
+                               f.d_counters + 1, f.d_err, st));
     c->launches += 2;
-    g.d_qtrim = want_q ? f.d_qtrim.p : nullptr;
-    if (s) {
-        // packed reads for the trimming kernels
-        if ((rc = f.d_offs.ensure((size_t)n + 1)) != CG_OK) return rc;
-        if ((rc = f.d_seq.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
-        if (want_q && (rc = f.d_qual.ensure((size_t)n_bytes + 64)) != CG_OK) return rc;
-        if ((rc = f.d_matches.ensure((size_t)n * g.times * g.slots)) != CG_OK) return rc;
+    g.d_qtrim = g.want_q ? f.d_qtrim.p : nullptr;
+    return CG_OK;
+}
+
+// NextseqQualityTrimmer + QualityTrimmer as a pass of their own on the chunk
+static int fastq_stage_pretrim(cg_ctx *c, FastqSlot &f, const cg_params *p, cudaStream_t st, FqStage &g)
+{
+    CU(cg_launch_fastq_pretrim(f.d_in.p, f.d_rec.p, f.d_len.p, g.n, (p->quality_trim ? 1 : 0) | (p->nextseq_trim ? 2 : 0),
+                               p->cutoff_front, p->cutoff_back,
+                               (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8), g.d_qtrim, st));
+    c->launches += 1;
+    return CG_OK;
+}
+
+// ... after which the quality-trimmed read IS the record: what --revcomp and --pair-adapters work on
+static int fastq_stage_fold_qtrim(cg_ctx *c, FastqSlot &f, const cg_params *p, cudaStream_t st, FqStage &g)
+{
+    if (!g.want_q) return CG_OK;
+    int rc = fastq_stage_pretrim(c, f, p, st, g);
+    if (rc != CG_OK) return rc;
+    CU(cg_launch_fastq_fold_qtrim(f.d_rec.p, f.d_len.p, g.d_qtrim, g.n, f.d_counters + 1, st));
+    c->launches += 1;
+    g.d_qtrim = nullptr;
+    g.want_q = false;
+    return CG_OK;
+}
+
+// Packed reads for the trimming kernels (d_offs, d_seq, d_qual) + the longest read; reports format errors.
+static int fastq_stage_pack(cg_ctx *c, FastqSlot &f, cudaStream_t st, FqStage &g, bool reverse_complement)
+{
+    const long long n = g.n;
+    int rc;
+    if ((rc = f.d_offs.ensure((size_t)n + 1)) != CG_OK) return rc;
+    if ((rc = f.d_seq.ensure((size_t)f.n_bytes + 64)) != CG_OK) return rc;
+    if (g.want_q && (rc = f.d_qual.ensure((size_t)f.n_bytes + 64)) != CG_OK) return rc;
+    if (!reverse_complement) {
         CU(cg_launch_scan_i32(f.d_len.p, n, f.d_scan.p, f.d_offs.p, st));
-        CU(cg_launch_fastq_gather(f.d_in.p, f.d_rec.p, f.d_offs.p, n, f.d_seq.p, want_q ? f.d_qual.p : nullptr, st));
-        c->launches += 4;
-        CU(cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), st));
-        CU(cg_launch_max_len(f.d_offs.p, n, c->d_err + 1, st));
-        c->launches += 1;
-        int max_len = 0;
-        int fq_err[2];
-        CU(cudaMemcpyAsync(&max_len, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (fq_err[0]) return fastq_format_error(fq_err);
-        rc = launch_trim(c, s, f.d_seq.p, want_q ? f.d_qual.p : nullptr, f.d_offs.p, n, max_len, p, f.d_matches.p,
-                         g.d_qtrim, st, true);
-        if (rc != CG_OK) return rc;
-        g.d_matches = f.d_matches.p;
-    } else if (want_q) {
-        CU(cg_launch_fastq_pretrim(f.d_in.p, f.d_rec.p, f.d_len.p, n, (p->quality_trim ? 1 : 0) | (p->nextseq_trim ? 2 : 0),
-                                   p->cutoff_front, p->cutoff_back,
-                                   (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8), g.d_qtrim, st));
-        c->launches += 1;
+        c->launches += 3;
     }
+    CU(cg_launch_fastq_gather(f.d_in.p, f.d_rec.p, f.d_offs.p, n, f.d_seq.p, g.want_q ? f.d_qual.p : nullptr,
+                              reverse_complement ? 1 : 0, st));
+    c->launches += 1;
+    if (reverse_complement) return CG_OK;       // offsets, longest read and format are those of the forward pass
+    CU(cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), st));
+    CU(cg_launch_max_len(f.d_offs.p, n, c->d_err + 1, st));
+    c->launches += 1;
+    int fq_err[2];
+    CU(cudaMemcpyAsync(&g.max_len, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(fq_err, f.d_err, sizeof fq_err, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (fq_err[0]) return fastq_format_error(fq_err);
+    return CG_OK;
+}
+
+// What is left of every record and which filters it fails (fq_evaluate_core)
+static int fastq_stage_verdict(cg_ctx *c, FastqSlot &f, const cg_fastq_params *fp, int poly_a_mode, cudaStream_t st,
+                               const FqStage &g)
+{
     CgFastqFilter flt;
     flt.minimum_length = fp->minimum_length;
     flt.maximum_length = fp->maximum_length;
@@ -1594,10 +1628,55 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
     flt.trim_n = fp->trim_n;
     flt.discard_casava = fp->discard_casava;
     flt.action = g.action;
-    CU(cg_launch_fastq_evaluate(f.d_in.p, f.d_rec.p, f.d_len.p, n, g.d_matches, g.times, g.slots, g.d_qtrim, flt,
-                                c->d_phred, f.d_interval.p, f.d_keep.p, f.d_mask.p, f.d_counters + 1, f.d_err, st));
+    CU(cg_launch_fastq_evaluate(f.d_in.p, f.d_rec.p, f.d_len.p, g.n, g.d_matches, g.times, g.slots, g.d_qtrim, flt,
+                                c->d_phred, g.d_is_rc, f.d_interval.p, f.d_keep.p, f.d_mask.p, f.d_counters + 1, f.d_err,
+                                st));
     c->launches += 1;
     return CG_OK;
+}
+
+static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s, const cg_fastq_params *fp, int poly_a_mode,
+                                cudaStream_t st, FqStage &g)
+{
+    int rc = fastq_stage_records(c, f, fp, s != nullptr, st, g);
+    if (rc != CG_OK || g.n == 0) return rc;
+    const long long n = g.n;
+    const cg_params *p = &fp->trim;
+    g.slots = s ? s->host.slots : 1;
+    if (s && fp->revcomp) {
+        // ReverseComplementer (modifiers.py:264-308): the adapter rounds on the read and on its reverse complement, both
+        // AFTER the quality trimmers; fq_revcomp_commit_kernel keeps the better orientation in the chunk itself.
+        if ((rc = fastq_stage_fold_qtrim(c, f, p, st, g)) != CG_OK) return rc;
+        cg_params pt = *p;
+        pt.quality_trim = 0;
+        pt.nextseq_trim = 0;
+        const size_t per_read = (size_t)g.times * g.slots;
+        if ((rc = f.d_matches.ensure((size_t)n * per_read)) != CG_OK) return rc;
+        if ((rc = f.d_matches_rc.ensure((size_t)n * per_read)) != CG_OK) return rc;
+        if ((rc = f.d_isrc.ensure((size_t)n)) != CG_OK) return rc;
+        if ((rc = fastq_stage_pack(c, f, st, g, false)) != CG_OK) return rc;
+        rc = launch_trim(c, s, f.d_seq.p, nullptr, f.d_offs.p, n, g.max_len, &pt, f.d_matches.p, nullptr, st, true);
+        if (rc != CG_OK) return rc;
+        if ((rc = fastq_stage_pack(c, f, st, g, true)) != CG_OK) return rc;
+        rc = launch_trim(c, s, f.d_seq.p, nullptr, f.d_offs.p, n, g.max_len, &pt, f.d_matches_rc.p, nullptr, st, true);
+        if (rc != CG_OK) return rc;
+        CU(cg_launch_fastq_revcomp_commit(f.d_in.p, f.d_rec.p, f.d_len.p, n, f.d_matches.p, f.d_matches_rc.p, (int)per_read,
+                                          f.d_isrc.p, f.d_counters + 1, st));
+        c->launches += 1;
+        g.d_matches = f.d_matches.p;
+        g.d_is_rc = f.d_isrc.p;
+        g.rc_suffix = fp->revcomp == 1;
+    } else if (s) {
+        if ((rc = f.d_matches.ensure((size_t)n * g.times * g.slots)) != CG_OK) return rc;
+        if ((rc = fastq_stage_pack(c, f, st, g, false)) != CG_OK) return rc;
+        rc = launch_trim(c, s, f.d_seq.p, g.want_q ? f.d_qual.p : nullptr, f.d_offs.p, n, g.max_len, p, f.d_matches.p,
+                         g.d_qtrim, st, true);
+        if (rc != CG_OK) return rc;
+        g.d_matches = f.d_matches.p;
+    } else if (g.want_q) {
+        if ((rc = fastq_stage_pretrim(c, f, p, st, g)) != CG_OK) return rc;
+    }
+    return fastq_stage_verdict(c, f, fp, poly_a_mode, st, g);
 }
 
 // sizes -> offsets -> formatted records -> host; counters
@@ -1648,6 +1727,7 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
     res->quality_trimmed_bp = (int64_t)k[6]; res->discarded = (int64_t)k[7]; res->too_many_n = (int64_t)k[8];
     res->too_many_expected_errors = (int64_t)k[9];
     res->casava_filtered = (int64_t)k[10];
+    res->reverse_complemented = (int64_t)k[11];
     res->out_bytes = total;
     if (total > out_capacity)
         return fail(CG_EINVAL, "cg_fastq_collect: output buffer too small (" + std::to_string(total) + " bytes needed)");
@@ -1655,7 +1735,7 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
         if (!out) return fail(CG_EINVAL, "cg_fastq_collect: out is NULL");
         if ((rc = f.d_out.ensure((size_t)total + 64)) != CG_OK) return rc;
         CU(cg_launch_fastq_write(f.d_in.p, f.d_rec.p, f.d_interval.p, f.d_outoff.p, f.d_outlen.p, n, f.d_out.p, g.action,
-                                 f.d_keep.p, st));
+                                 f.d_keep.p, f.d_mask.p, g.rc_suffix, st));
         c->launches += 1;
         if (is_pinned(out)) {
             CU(cudaMemcpyAsync(out, f.d_out.p, (size_t)total, cudaMemcpyDeviceToHost, st));
@@ -1685,7 +1765,7 @@ static int fastq_collect_impl(cg_ctx *c, int32_t slot, const cg_adapterset *s, c
     int rc = fastq_stage_evaluate(c, f, s, fp, 1, f.stream, g);
     if (rc != CG_OK || g.n == 0) return rc;
     CU(cg_launch_fastq_finish(g.n, f.d_rec.p, f.d_interval.p, f.d_mask.p, fastq_enabled_filters(fp), f.d_outlen.p,
-                              f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, f.stream));
+                              f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, g.rc_suffix, f.stream));
     c->launches += 1;
     if ((rc = fastq_stage_output(c, f, g, f.stream, out, out_capacity, res, dm)) != CG_OK) return rc;
     return check_err_flag(c);
@@ -1741,7 +1821,7 @@ extern "C" int cg_fastq_collect_paired(cg_ctx *c, int32_t slot1, int32_t slot2, 
     const int mode_untrimmed = (!s1 || !s2) ? 1 : pair_filter_mode;
     CU(cg_launch_fastq_finish(g1.n, f1.d_rec.p, f1.d_interval.p, f1.d_mask.p, fastq_enabled_filters(fp1), f1.d_outlen.p,
                               f1.d_counters + 1, f2.d_rec.p, f2.d_interval.p, f2.d_mask.p, fastq_enabled_filters(fp2),
-                              f2.d_outlen.p, f2.d_counters + 1, pair_filter_mode, mode_untrimmed, st));
+                              f2.d_outlen.p, f2.d_counters + 1, pair_filter_mode, mode_untrimmed, 0, st));
     c->launches += 1;
     if ((rc = fastq_stage_output(c, f1, g1, st, out1, out_capacity1, res1)) != CG_OK) return rc;
     if ((rc = fastq_stage_output(c, f2, g2, st, out2, out_capacity2, res2)) != CG_OK) return rc;

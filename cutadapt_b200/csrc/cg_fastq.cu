@@ -127,20 +127,27 @@ __global__ void __launch_bounds__(FQ_THREADS) fq_index_kernel(const uint8_t *buf
 // record r = lines 4r .. 4r+3: fq_record_core (cg_fastq_core.cuh) builds the table entry and checks the format
 __global__ void fq_records_kernel(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl,
                                   long long n_records, int cut_front, int cut_back, CgFastqRecord *rec,
-                                  int32_t *seq_len, int *err)
+                                  int32_t *seq_len, unsigned long long *counters, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_records) return;
-    CgFastqRecord o;
-    int len;
-    const int bad = fq_record_core(buf, n, nl_pos, n_nl, r, cut_front, cut_back, &o, &len);
-    if (bad) {
-        // report the first bad record: err[0] = code, err[1] = record number (smallest; initialised to INT_MAX)
-        atomicMin((unsigned int *)&err[1], (unsigned int)r);
-        atomicMax(&err[0], bad);
+    unsigned bp = 0;
+    if (r < n_records) {
+        CgFastqRecord o;
+        int len, full;
+        const int bad = fq_record_core(buf, n, nl_pos, n_nl, r, cut_front, cut_back, &o, &len, &full);
+        if (bad) {
+            // report the first bad record: err[0] = code, err[1] = record number (smallest; initialised to INT_MAX)
+            atomicMin((unsigned int *)&err[1], (unsigned int)r);
+            atomicMax(&err[0], bad);
+        }
+        rec[r] = o;
+        seq_len[r] = len;
+        bp = (unsigned)full;
     }
-    rec[r] = o;
-    seq_len[r] = len;
+    // bases read: the length before any modifier (pipeline.py:58-64)
+    unsigned long long sum = bp;
+    for (int d = 16; d; d >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, d);
+    if ((threadIdx.x & 31) == 0 && sum && counters) atomicAdd(&counters[1], sum);
 }
 
 // ---- exclusive scan int32 -> int64 (n+1 outputs), any n: tile sums, one-CTA scan of the sums, apply ----
@@ -231,9 +238,9 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int32_t *in, long
     }
 }
 
-// packed reads for the trimming kernels: read r at offsets[r] in seq_out / qual_out
+// packed reads for the trimming kernels: read r at offsets[r] in seq_out / qual_out; rc: its reverse complement
 __global__ void __launch_bounds__(256) fq_gather_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int64_t *offsets,
-                                                         long long n_records, uint8_t *seq_out, uint8_t *qual_out)
+                                                         long long n_records, uint8_t *seq_out, uint8_t *qual_out, int rc)
 {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -241,10 +248,80 @@ __global__ void __launch_bounds__(256) fq_gather_kernel(const uint8_t *buf, cons
         const CgFastqRecord m = rec[r];
         const long long o = offsets[r];
         const int len = (int)(offsets[r + 1] - o);
+        if (rc) {
+            for (int j = lane; j < len; j += 32) seq_out[o + j] = fq_complement(buf[m.seq_start + len - 1 - j]);
+            if (qual_out)
+                for (int j = lane; j < len; j += 32) qual_out[o + j] = buf[m.qual_start + len - 1 - j];
+            continue;
+        }
         for (int j = lane; j < len; j += 32) seq_out[o + j] = buf[m.seq_start + j];
         if (qual_out)
             for (int j = lane; j < len; j += 32) qual_out[o + j] = buf[m.qual_start + j];
     }
+}
+
+// The quality-trimmed interval becomes the record (like -u in fq_record_core): the modifiers after the quality
+// trimmers then see the read they see in the reference (used where a later step needs the trimmed read as an
+// object of its own: --revcomp, --pair-adapters).  counters[6] += bases removed.
+__global__ void fq_fold_qtrim_kernel(CgFastqRecord *rec, int32_t *seq_len, const int32_t *qtrim, long long n_records,
+                                     unsigned long long *counters)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long removed = 0;
+    if (r < n_records) {
+        const int n = seq_len[r], qs = qtrim[2 * r], qe = qtrim[2 * r + 1];
+        rec[r].seq_start += (uint32_t)qs;
+        rec[r].qual_start += (uint32_t)qs;
+        seq_len[r] = qe - qs;
+        removed = (unsigned long long)(n - (qe - qs));
+    }
+    for (int d = 16; d; d >>= 1) removed += __shfl_down_sync(0xFFFFFFFFu, removed, d);
+    if ((threadIdx.x & 31) == 0 && removed) atomicAdd(&counters[6], removed);
+}
+
+// ReverseComplementer.__call__ (modifiers.py:278-308), one warp per record: the reverse complement replaces the
+// read iff the scores of its matches add up to MORE than those of the forward read (a linked match counts with
+// both parts).  The replacement happens IN the chunk (sequence reverse-complemented, qualities reversed, in
+// place), the reverse matches become the record's matches, is_rc[r] = 1: every later kernel works on the
+// chosen orientation without knowing about it (the writer appends the name suffix).  counters[11] += replaced.
+__global__ void __launch_bounds__(256) fq_revcomp_commit_kernel(uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len,
+                                                                 long long n_records, cg_match_rec *matches,
+                                                                 const cg_match_rec *matches_rc, int per_read,
+                                                                 uint8_t *is_rc, unsigned long long *counters)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned replaced = 0;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_records; r += warps) {
+        long long fwd = 0, rev = 0;
+        for (int k = lane; k < per_read; k += 32) {
+            const cg_match_rec a = matches[(size_t)r * per_read + k], b = matches_rc[(size_t)r * per_read + k];
+            if (a.adapter >= 0) fwd += a.score;
+            if (b.adapter >= 0) rev += b.score;
+        }
+        for (int d = 16; d; d >>= 1) {
+            fwd += __shfl_xor_sync(0xFFFFFFFFu, fwd, d);
+            rev += __shfl_xor_sync(0xFFFFFFFFu, rev, d);
+        }
+        const bool use = rev > fwd;
+        if (lane == 0) is_rc[r] = use;
+        if (!use) continue;
+        replaced += lane == 0;
+        const CgFastqRecord m = rec[r];
+        const int len = seq_len[r];
+        uint8_t *sq = buf + m.seq_start, *ql = buf + m.qual_start;
+        for (int j = lane; 2 * j < len; j += 32) {       // pair (j, len-1-j); the middle of an odd length meets itself
+            const int k = len - 1 - j;
+            const uint8_t a = sq[j], b = sq[k], qa = ql[j], qb = ql[k];
+            sq[j] = fq_complement(b); sq[k] = fq_complement(a);
+            ql[j] = qb; ql[k] = qa;
+        }
+        const int words = per_read * (int)(sizeof(cg_match_rec) / sizeof(int32_t));
+        int32_t *dst = (int32_t *)(matches + (size_t)r * per_read);
+        const int32_t *src = (const int32_t *)(matches_rc + (size_t)r * per_read);
+        for (int k = lane; k < words; k += 32) dst[k] = src[k];
+    }
+    if (lane == 0 && replaced) atomicAdd(&counters[11], (unsigned long long)replaced);
 }
 
 // quality-driven trimming only (no adapter set): NextseqQualityTrimmer + QualityTrimmer straight on the chunk
@@ -263,11 +340,11 @@ __global__ void fq_pretrim_kernel(const uint8_t *buf, const CgFastqRecord *rec, 
 // kept interval + failed filters of every record: fq_evaluate_core (cg_fastq_core.cuh); per-read counters
 __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len, long long n_records,
                                    const cg_match_rec *matches, int times, int slots, const int32_t *qtrim,
-                                   CgFastqFilter f, const double *phred, int32_t *interval, int32_t *keep_interval,
-                                   int32_t *fail_mask, unsigned long long *counters, int *err)
+                                   CgFastqFilter f, const double *phred, const uint8_t *is_rc, int32_t *interval,
+                                   int32_t *keep_interval, int32_t *fail_mask, unsigned long long *counters, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c_adapt = 0, c_bp_in = 0, c_qbp = 0;
+    unsigned long long c_adapt = 0, c_qbp = 0;
     if (r < n_records) {
         const int n = seq_len[r];
         const int qs = qtrim ? qtrim[2 * r] : 0, qe = qtrim ? qtrim[2 * r + 1] : n;
@@ -278,16 +355,12 @@ __global__ void fq_evaluate_kernel(const uint8_t *buf, const CgFastqRecord *rec,
         interval[2 * r] = v.start;
         interval[2 * r + 1] = v.stop;
         if (keep_interval) { keep_interval[2 * r] = v.k0; keep_interval[2 * r + 1] = v.k1; }
-        fail_mask[r] = v.mask | ((v.last_adapter + 1) << 8);
-        c_adapt = v.matched; c_bp_in = n;
+        fail_mask[r] = v.mask | ((v.last_adapter + 1) << 8) | ((is_rc && is_rc[r]) ? CG_FQ_MASK_RC : 0);
+        c_adapt = v.matched;
     }
     c_adapt = __reduce_add_sync(0xFFFFFFFFu, (unsigned)c_adapt);
-    for (int d = 16; d; d >>= 1) {
-        c_bp_in += __shfl_down_sync(0xFFFFFFFFu, c_bp_in, d);
-        c_qbp += __shfl_down_sync(0xFFFFFFFFu, c_qbp, d);
-    }
+    for (int d = 16; d; d >>= 1) c_qbp += __shfl_down_sync(0xFFFFFFFFu, c_qbp, d);
     if ((threadIdx.x & 31) == 0) {
-        if (c_bp_in) atomicAdd(&counters[1], c_bp_in);
         if (c_adapt) atomicAdd(&counters[3], c_adapt);
         if (c_qbp) atomicAdd(&counters[6], c_qbp);
     }
@@ -305,7 +378,8 @@ __device__ __constant__ int kFilterCounter[7] = {4, 5, 8, 9, 10, 7, 7};
 __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1, const int32_t *interval1,
                                  const int32_t *mask1, int enabled1, int32_t *out_len1, unsigned long long *counters1,
                                  const CgFastqRecord *rec2, const int32_t *interval2, const int32_t *mask2, int enabled2,
-                                 int32_t *out_len2, unsigned long long *counters2, int mode, int mode_untrimmed)
+                                 int32_t *out_len2, unsigned long long *counters2, int mode, int mode_untrimmed,
+                                 int rc_suffix)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int fired = -1;
@@ -314,10 +388,13 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
     if (r < n_records) {
         fired = fq_finish_core(mask1[r], mask2 ? mask2[r] : 0, mask2 != nullptr, enabled1, enabled2, mode, mode_untrimmed);
         const int left1 = interval1[2 * r + 1] - interval1[2 * r];
-        out_len1[r] = fired < 0 ? rec1[r].hdr_len + 2 * left1 + 6 : 0;
+        // a reverse-complemented read gets " rc" appended to its name (modifiers.py:295-296)
+        const int extra1 = (rc_suffix && (mask1[r] & CG_FQ_MASK_RC)) ? 3 : 0;
+        out_len1[r] = fired < 0 ? rec1[r].hdr_len + extra1 + 2 * left1 + 6 : 0;
         if (mask2) {
             const int left2 = interval2[2 * r + 1] - interval2[2 * r];
-            out_len2[r] = fired < 0 ? rec2[r].hdr_len + 2 * left2 + 6 : 0;
+            const int extra2 = (rc_suffix && (mask2[r] & CG_FQ_MASK_RC)) ? 3 : 0;
+            out_len2[r] = fired < 0 ? rec2[r].hdr_len + extra2 + 2 * left2 + 6 : 0;
             bp2 = fired < 0 ? left2 : 0;
         }
         written = fired < 0;
@@ -347,7 +424,7 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
 __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const CgFastqRecord *rec, const int32_t *interval,
                                                         const int64_t *out_off, const int32_t *out_len,
                                                         long long n_records, uint8_t *out, int action,
-                                                        const int32_t *keep_interval)
+                                                        const int32_t *keep_interval, const int32_t *mask, int rc_suffix)
 {
     const int lane = threadIdx.x & 31;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -360,6 +437,10 @@ __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const
         if (lane == 0) p[0] = '@';
         for (int j = lane; j < m.hdr_len; j += 32) p[1 + j] = buf[m.hdr_start + j];
         p += 1 + m.hdr_len;
+        if (rc_suffix && (mask[r] & CG_FQ_MASK_RC)) {
+            if (lane < 3) p[lane] = lane == 0 ? ' ' : (lane == 1 ? 'r' : 'c');
+            p += 3;
+        }
         if (lane == 0) p[0] = '\n';
         if (action == CG_FQ_ACTION_MASK || action == CG_FQ_ACTION_LOWERCASE) {
             // --action=mask / lowercase (modifiers.py:175-193): N / lower case outside the remainder
@@ -390,7 +471,7 @@ constexpr int DM_TILE = 256;
 
 __device__ __forceinline__ int demux_dest(int mask, const int32_t *adapter_dest, int n_dest)
 {
-    const int adapter = (mask >> 8) - 1;
+    const int adapter = CG_FQ_MASK_ADAPTER(mask);
     return adapter < 0 ? n_dest - 1 : adapter_dest[adapter];
 }
 
@@ -448,11 +529,12 @@ cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint3
 
 cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
                                     long long n_records, int cut_front, int cut_back, CgFastqRecord *d_rec,
-                                    int32_t *d_seq_len, int *d_err, cudaStream_t st)
+                                    int32_t *d_seq_len, unsigned long long *d_counters, int *d_err, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_records_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, n_bytes, d_nl_pos, n_newlines, n_records,
-                                                                          cut_front, cut_back, d_rec, d_seq_len, d_err);
+                                                                          cut_front, cut_back, d_rec, d_seq_len, d_counters,
+                                                                          d_err);
     return cudaGetLastError();
 }
 
@@ -470,12 +552,32 @@ cudaError_t cg_launch_scan_i32(const int32_t *d_in, long long n, unsigned long l
 }
 
 cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int64_t *d_offsets,
-                                   long long n_records, uint8_t *d_seq, uint8_t *d_qual, cudaStream_t st)
+                                   long long n_records, uint8_t *d_seq, uint8_t *d_qual, int rc, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     long long grid = (n_records + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
-    fq_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_offsets, n_records, d_seq, d_qual);
+    fq_gather_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_offsets, n_records, d_seq, d_qual, rc);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_fold_qtrim(CgFastqRecord *d_rec, int32_t *d_seq_len, const int32_t *d_qtrim, long long n_records,
+                                       unsigned long long *d_counters, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_fold_qtrim_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_rec, d_seq_len, d_qtrim, n_records, d_counters);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_revcomp_commit(uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                           long long n_records, cg_match_rec *d_matches, const cg_match_rec *d_matches_rc,
+                                           int per_read, uint8_t *d_is_rc, unsigned long long *d_counters, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    long long grid = (n_records + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    fq_revcomp_commit_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches, d_matches_rc,
+                                                             per_read, d_is_rc, d_counters);
     return cudaGetLastError();
 }
 
@@ -491,14 +593,15 @@ cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d
 
 cudaError_t cg_launch_fastq_evaluate(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
                                      long long n_records, const cg_match_rec *d_matches, int times, int slots,
-                                     const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
-                                     int32_t *d_keep_interval, int32_t *d_fail_mask, unsigned long long *d_counters,
-                                     int *d_err, cudaStream_t st)
+                                     const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, const uint8_t *d_is_rc,
+                                     int32_t *d_interval, int32_t *d_keep_interval, int32_t *d_fail_mask,
+                                     unsigned long long *d_counters, int *d_err, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_evaluate_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches,
-                                                                           times, slots, d_qtrim, f, d_phred, d_interval,
-                                                                           d_keep_interval, d_fail_mask, d_counters, d_err);
+                                                                           times, slots, d_qtrim, f, d_phred, d_is_rc,
+                                                                           d_interval, d_keep_interval, d_fail_mask,
+                                                                           d_counters, d_err);
     return cudaGetLastError();
 }
 
@@ -506,25 +609,27 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
                                    const int32_t *d_mask1, int enabled1, int32_t *d_out_len1,
                                    unsigned long long *d_counters1, const CgFastqRecord *d_rec2,
                                    const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
-                                   unsigned long long *d_counters2, int mode, int mode_untrimmed, cudaStream_t st)
+                                   unsigned long long *d_counters2, int mode, int mode_untrimmed, int rc_suffix,
+                                   cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_finish_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(n_records, d_rec1, d_interval1, d_mask1, enabled1,
                                                                          d_out_len1, d_counters1, d_rec2, d_interval2,
                                                                          d_mask2, enabled2, d_out_len2, d_counters2, mode,
-                                                                         mode_untrimmed);
+                                                                         mode_untrimmed, rc_suffix);
     return cudaGetLastError();
 }
 
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
                                   const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
-                                  uint8_t *d_out, int action, const int32_t *d_keep_interval, cudaStream_t st)
+                                  uint8_t *d_out, int action, const int32_t *d_keep_interval, const int32_t *d_mask,
+                                  int rc_suffix, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     long long grid = (n_records + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
     fq_write_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_interval, d_out_off, d_out_len, n_records, d_out, action,
-                                                    d_keep_interval);
+                                                    d_keep_interval, d_mask, rc_suffix);
     return cudaGetLastError();
 }
 

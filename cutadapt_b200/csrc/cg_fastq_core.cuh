@@ -30,6 +30,25 @@ struct CgFastqFilter {
 #define CG_FQ_ACTION_LOWERCASE 3
 #define CG_FQ_ACTION_RETAIN 4
 #define CG_FQ_ACTION_CROP 5
+// fail_mask word of a record: bits 0-6 failed filters, bits 8-29 adapter of the most recent match + 1,
+// bit 30: the record was replaced by its reverse complement (--revcomp)
+#define CG_FQ_MASK_RC (1 << 30)
+#define CG_FQ_MASK_ADAPTER(mask) ((((mask) >> 8) & 0x3FFFFF) - 1)
+
+// SequenceRecord.reverse_complement of dnaio: IUPAC-aware, case preserved, every other character unchanged
+CG_HD uint8_t fq_complement(uint8_t c)
+{
+    const uint8_t u = (uint8_t)(c & ~0x20), low = (uint8_t)(c & 0x20);
+    uint8_t o;
+    switch (u) {
+    case 'A': o = 'T'; break; case 'C': o = 'G'; break; case 'G': o = 'C'; break; case 'T': o = 'A'; break;
+    case 'U': o = 'A'; break; case 'M': o = 'K'; break; case 'R': o = 'Y'; break; case 'Y': o = 'R'; break;
+    case 'K': o = 'M'; break; case 'V': o = 'B'; break; case 'H': o = 'D'; break; case 'D': o = 'H'; break;
+    case 'B': o = 'V'; break;
+    default: return c;          // W, S, N and everything that is not a nucleotide code
+    }
+    return (uint8_t)(o | low);
+}
 
 // line k of the chunk: [start, end) without the line terminator ("\n" or "\r\n"); nl_pos = positions of all
 // newlines, n = size of the chunk (the last line may lack its newline)
@@ -46,8 +65,9 @@ CG_HD void fq_line_span(const uint8_t *buf, const uint32_t *nl_pos, long long n_
 // 2 = the third line does not start with '+', 3 = sequence and qualities differ in length; 0 = fine.
 // cut_front / cut_back: UnconditionalCutter (-u, modifiers.py:66-95), the first modifier of the chain: the record
 // table simply describes the read without those bases (read[cut_front:] then read[:-cut_back]).
+// *full_len: the length before -u (what the pipeline counts as "bp processed", pipeline.py:58-64, 142-143).
 CG_HD int fq_record_core(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl, long long r,
-                         int cut_front, int cut_back, CgFastqRecord *rec, int *seq_len)
+                         int cut_front, int cut_back, CgFastqRecord *rec, int *seq_len, int *full_len = nullptr)
 {
     uint32_t hs, he, ss, se, ps, pe, qs, qe;
     fq_line_span(buf, nl_pos, n_nl, n, 4 * r, &hs, &he);
@@ -59,6 +79,7 @@ CG_HD int fq_record_core(const uint8_t *buf, long long n, const uint32_t *nl_pos
     else if (pe == ps || buf[ps] != '+') bad = 2;
     else if (se - ss != qe - qs) bad = 3;
     int len = bad ? 0 : (int32_t)(se - ss);
+    if (full_len) *full_len = len;
     const int cf = cut_front < len ? cut_front : len;
     len -= cf;
     len = cut_back < len ? len - cut_back : 0;

@@ -75,31 +75,40 @@ cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint3
                                   unsigned long long *d_total, uint32_t *d_nl_pos, int phase, cudaStream_t st);
 cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
                                     long long n_records, int cut_front, int cut_back, CgFastqRecord *d_rec,
-                                    int32_t *d_seq_len, int *d_err, cudaStream_t st);
+                                    int32_t *d_seq_len, unsigned long long *d_counters, int *d_err, cudaStream_t st);
 // exclusive scan int32 -> int64, n + 1 outputs; d_tile_scratch: cg_scan_tiles(n) words
 cudaError_t cg_launch_scan_i32(const int32_t *d_in, long long n, unsigned long long *d_tile_scratch, int64_t *d_out,
                                cudaStream_t st);
 cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int64_t *d_offsets,
-                                   long long n_records, uint8_t *d_seq, uint8_t *d_qual, cudaStream_t st);
+                                   long long n_records, uint8_t *d_seq, uint8_t *d_qual, int rc, cudaStream_t st);
+// the quality-trimmed interval becomes the record (counters[6] += removed bases)
+cudaError_t cg_launch_fastq_fold_qtrim(CgFastqRecord *d_rec, int32_t *d_seq_len, const int32_t *d_qtrim, long long n_records,
+                                       unsigned long long *d_counters, cudaStream_t st);
+// --revcomp: choose the orientation per record, rewrite the chosen reads in place (counters[11] += replaced)
+cudaError_t cg_launch_fastq_revcomp_commit(uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+                                           long long n_records, cg_match_rec *d_matches, const cg_match_rec *d_matches_rc,
+                                           int per_read, uint8_t *d_is_rc, unsigned long long *d_counters, cudaStream_t st);
 cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
                                     long long n_records, int flags, int cutoff_front, int cutoff_back, int qbase,
                                     int32_t *d_qtrim, cudaStream_t st);
 // kept interval + one bit per filter the read fails (bit order: too short, too long, too many N, too many expected
-// errors, casava, trimmed, untrimmed); per-read counters (bp_in, with_adapters, quality_trimmed_bp)
+// errors, casava, trimmed, untrimmed; CG_FQ_MASK_RC from d_is_rc); per-read counters (with_adapters, quality_trimmed_bp)
 cudaError_t cg_launch_fastq_evaluate(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
                                      long long n_records, const cg_match_rec *d_matches, int times, int slots,
-                                     const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, int32_t *d_interval,
-                                     int32_t *d_keep_interval, int32_t *d_fail_mask, unsigned long long *d_counters,
-                                     int *d_err, cudaStream_t st);
+                                     const int32_t *d_qtrim, CgFastqFilter f, const double *d_phred, const uint8_t *d_is_rc,
+                                     int32_t *d_interval, int32_t *d_keep_interval, int32_t *d_fail_mask,
+                                     unsigned long long *d_counters, int *d_err, cudaStream_t st);
 // verdict per read (second mate = nullptr) or pair -> sizes of the output records, filter counters
 cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_rec1, const int32_t *d_interval1,
                                    const int32_t *d_mask1, int enabled1, int32_t *d_out_len1,
                                    unsigned long long *d_counters1, const CgFastqRecord *d_rec2,
                                    const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
-                                   unsigned long long *d_counters2, int mode, int mode_untrimmed, cudaStream_t st);
+                                   unsigned long long *d_counters2, int mode, int mode_untrimmed, int rc_suffix,
+                                   cudaStream_t st);
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
                                   const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
-                                  uint8_t *d_out, int action, const int32_t *d_keep_interval, cudaStream_t st);
+                                  uint8_t *d_out, int action, const int32_t *d_keep_interval, const int32_t *d_mask,
+                                  int rc_suffix, cudaStream_t st);
 // demultiplexing: phase 0 fills d_bytes[n_dest][tiles] (output bytes per destination and tile of 256 records);
 // after an exclusive scan of that array (d_base), phase 1 writes every record's output offset.
 // d_adapter_dest: destination of every adapter; reads without a match go to destination n_dest - 1.

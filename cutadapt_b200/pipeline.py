@@ -111,7 +111,8 @@ def allreduce_statistics(stats, group=None):
 
 
 FASTQ_COUNTERS = ("n_records", "n_written", "bp_in", "bp_out", "out_bytes", "with_adapters", "quality_trimmed_bp",
-                  "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded", "casava_filtered")
+                  "too_short", "too_long", "too_many_n", "too_many_expected_errors", "discarded", "casava_filtered",
+                  "reverse_complemented")
 
 
 def allreduce_fastq_statistics(statistics: dict, group=None, device=None) -> dict:
@@ -578,7 +579,7 @@ def read_paired_fastq_chunks(f1, f2, buffer_size: int = 4 * 1024 * 1024):
 def _fastq_params(times=1, quality_cutoff=None, quality_base=33, nextseq_cutoff=None, minimum_length=0,
                   maximum_length=None, max_n=None, max_expected_errors=None, discard_trimmed=False,
                   discard_untrimmed=False, cut=(), poly_a=False, length=None, trim_n=False,
-                  discard_casava=False, action="trim") -> "_lib.cg_fastq_params":
+                  discard_casava=False, action="trim", revcomp=False, rc_suffix=True) -> "_lib.cg_fastq_params":
     fp = _lib.cg_fastq_params()
     fp.trim = _lib.make_params(
         quality_trim=quality_cutoff is not None,
@@ -605,6 +606,7 @@ def _fastq_params(times=1, quality_cutoff=None, quality_base=33, nextseq_cutoff=
     if action in ("retain", "crop") and times > 1:
         raise ValueError("'retain' and 'crop' cannot be combined with times > 1")     # modifiers.py:117-118
     fp.action = actions[action]
+    fp.revcomp = 0 if not revcomp else (1 if rc_suffix else 2)
     return fp
 
 
@@ -637,6 +639,9 @@ class FastqTrimmer:
     discard_casava      --discard-casava                                     (predicates.py:125-139)
     action              --action: "trim" (default), "none"/None, "mask", "lowercase", "retain", "crop"
                         (AdapterCutter, modifiers.py:175-249)
+    revcomp, rc_suffix  --revcomp: adapters are searched on the read and on its reverse complement and the better
+                        orientation is written (" rc" appended to the name unless rc_suffix is False;
+                        ReverseComplementer, modifiers.py:264-308), all on the device
 
     ``process_chunk(bytes) -> bytes``; ``process_chunks(iterable)`` keeps one chunk in flight so that the
     upload of chunk i+1 overlaps the download of chunk i.  ``statistics`` accumulates the counters of
@@ -650,12 +655,13 @@ class FastqTrimmer:
                  max_expected_errors: Optional[float] = None, discard_trimmed: bool = False,
                  discard_untrimmed: bool = False, cut: Sequence[int] = (), poly_a: bool = False,
                  length: Optional[int] = None, trim_n: bool = False, discard_casava: bool = False,
-                 action: Optional[str] = "trim", ctx: Optional[_lib.Context] = None):
+                 action: Optional[str] = "trim", revcomp: bool = False, rc_suffix: bool = True,
+                 ctx: Optional[_lib.Context] = None):
         self.ctx = ctx or _lib.default_context()
         self.adapters, self._set = _device_set(adapters, self.ctx)
         self.params = _fastq_params(times, quality_cutoff, quality_base, nextseq_cutoff, minimum_length, maximum_length,
                                     max_n, max_expected_errors, discard_trimmed, discard_untrimmed, cut, poly_a, length,
-                                    trim_n, discard_casava, action)
+                                    trim_n, discard_casava, action, revcomp, rc_suffix)
         self.statistics = {}
         self._out_bufs, self._out_keep = {}, {}
 

@@ -317,7 +317,11 @@ typedef struct cg_fastq_params {
     int32_t trim_n;              /* --trim-n (NEndTrimmer, modifiers.py:902-918)                      */
     int32_t discard_casava;      /* --discard-casava (CasavaFiltered, predicates.py:125-139)          */
     int32_t action;              /* CG_ACTION_*: --action of the AdapterCutter (modifiers.py:236-249)   */
-    int32_t reserved[4];
+    int32_t revcomp;             /* --revcomp (ReverseComplementer, modifiers.py:264-308; single-end collects): the
+                                    adapters are searched on the read and on its reverse complement, the better
+                                    orientation is kept.  1 = append " rc" to the name of a replaced read, 2 = do not
+                                    (--rename given, cli.py:1082-1116)                                  */
+    int32_t reserved[3];
 } cg_fastq_params;
 typedef struct cg_fastq_result {
     int64_t n_records, n_written;
@@ -325,7 +329,8 @@ typedef struct cg_fastq_result {
     int64_t out_bytes;           /* size of the formatted output                                      */
     int64_t with_adapters, quality_trimmed_bp;
     int64_t too_short, too_long, too_many_n, too_many_expected_errors, discarded, casava_filtered;
-    int64_t reserved[3];
+    int64_t reverse_complemented; /* --revcomp: reads replaced by their reverse complement             */
+    int64_t reserved[2];
 } cg_fastq_result;
 /* set may be NULL: quality trimming and filters only.  fastq / out: HOST pointers (pinned or pageable).
  * Errors: CG_EINVAL for malformed FASTQ (message names the record), a too small output buffer (out_bytes in

@@ -576,16 +576,48 @@ _FILTER_COUNTER = {"discard_trimmed": "discarded", "discard_untrimmed": "discard
 def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, cutoff_back=0, quality_base=33, times=1,
                     nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
                     discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
-                    trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False, action="trim"):
+                    trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False, action="trim",
+                    revcomp=False, rc_suffix=True):
     """Modifier chain on every record of a chunk + the verdict of every enabled filter.
     Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters)."""
     records = parse_fastq(data)
+    bp_in = sum(len(r[1]) for r in records)             # before any modifier (pipeline.py:58-64)
     for c_len in cut:                                   # UnconditionalCutter, first in the chain (modifiers.py:66-95)
         records = [(nm, sq[c_len:], q[c_len:]) if c_len > 0 else (nm, sq[:c_len], q[:c_len]) for nm, sq, q in records]
     seqs = [r[1] for r in records]
     quals = [r[2] for r in records]
     n = len(records)
-    if adapters:
+    pre_trimmed_bp = 0
+    reverse_complemented = 0
+    if adapters and revcomp:
+        # ReverseComplementer (modifiers.py:264-308) wraps the AdapterCutter only: the quality trimmers come first
+        trimmed = []
+        for name, seq, q in records:
+            s, e = 0, len(seq)
+            if nextseq_cutoff is not None:
+                e = nextseq_trim_index(seq, q, nextseq_cutoff, quality_base)
+            if quality_trim:
+                s, e = quality_trim_index(q[:e], cutoff_front, cutoff_back, quality_base)
+            pre_trimmed_bp += len(seq) - (e - s)
+            trimmed.append((name, seq[s:e], q[s:e]))
+        records = trimmed
+        seqs = [r[1] for r in records]
+        comp = bytes.maketrans(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn", b"TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn")
+        rc_seqs = [sq.encode("latin-1").translate(comp)[::-1].decode("latin-1") for sq in seqs]
+        fwd, _ = oracle_process(adapters, groups, seqs, None, False, 0, 0, quality_base, times, None)
+        rev, _ = oracle_process(adapters, groups, rc_seqs, None, False, 0, 0, quality_base, times, None)
+        matches = fwd.copy()
+        for i in range(n):
+            score_f = int(fwd[i]["score"][fwd[i]["adapter"] >= 0].sum())
+            score_r = int(rev[i]["score"][rev[i]["adapter"] >= 0].sum())
+            if score_r > score_f:
+                reverse_complemented += 1
+                matches[i] = rev[i]
+                name, _, q = records[i]
+                records[i] = (name + (" rc" if rc_suffix else ""), rc_seqs[i], q[::-1])
+        quals = [r[2] for r in records]
+        qtrim = np.array([(0, len(r[1])) for r in records], dtype=np.int32).reshape(n, 2)
+    elif adapters:
         matches, qtrim = oracle_process(adapters, groups, seqs, quals, quality_trim, cutoff_front, cutoff_back,
                                         quality_base, times, nextseq_cutoff)
     else:
@@ -601,11 +633,11 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
     enabled = [name for name, on in zip(FILTER_CHAIN, (minimum_length > 0, maximum_length >= 0, max_n >= 0,
                                                        max_expected_errors >= 0, discard_casava, discard_trimmed,
                                                        discard_untrimmed)) if on]
-    c = dict(n_records=n, bp_in=0, with_adapters=0, quality_trimmed_bp=0)
+    c = dict(n_records=n, bp_in=bp_in, with_adapters=0, quality_trimmed_bp=pre_trimmed_bp,
+             reverse_complemented=reverse_complemented)
     out = []
     for i, (name, seq, q) in enumerate(records):
         s, e = int(qtrim[i, 0]), int(qtrim[i, 1])
-        c["bp_in"] += len(seq)
         c["quality_trimmed_bp"] += len(seq) - (e - s)
         matched = False
         last_adapter = -1

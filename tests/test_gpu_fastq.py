@@ -82,13 +82,17 @@ def synthetic_fastq(n, seed, crlf=False, final_newline=True):
 
 
 @pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "filters", "quality_only", "times2",
-                                     "modifiers", "modifiers2", "mask", "lowercase", "none", "retain", "crop"])
+                                     "modifiers", "modifiers2", "mask", "lowercase", "none", "retain", "crop",
+                                     "revcomp", "revcomp_quality", "revcomp_linked"])
 def test_random_chunks_against_oracle(variant):
     options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20])
     extra = {}
     seed = {"plain": 1, "crlf": 2, "no_final_newline": 3, "filters": 4, "quality_only": 5, "times2": 6,
-            "modifiers": 7, "modifiers2": 8, "mask": 9, "lowercase": 10, "none": 11, "retain": 12, "crop": 13}[variant]
+            "modifiers": 7, "modifiers2": 8, "mask": 9, "lowercase": 10, "none": 11, "retain": 12, "crop": 13,
+            "revcomp": 14, "revcomp_quality": 15, "revcomp_linked": 16}[variant]
     data = synthetic_fastq(6000, seed=seed, crlf=variant == "crlf")
+    if variant.startswith("revcomp"):       # every other record arrives as its reverse complement
+        data = flip_records(data, seed)
     if variant == "no_final_newline":       # a last record whose quality line is not terminated
         data += b"@last\nACGTACGTAGATCGGAAGAGCAAA\n+\nIIIIIIIIIIIIIIIIIIIIIIII"
     if variant == "filters":
@@ -116,12 +120,45 @@ def test_random_chunks_against_oracle(variant):
     elif variant == "crop":
         options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"], ["anywhere", "CACGTCTGAA"]])
         extra = dict(action="crop", discard_untrimmed=True, trim_n=True)
+    elif variant == "revcomp":
+        options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]])
+        extra = dict(revcomp=True, minimum_length=10, trim_n=True)
+    elif variant == "revcomp_quality":      # the quality trimmers run before the reverse complementer
+        extra = dict(revcomp=True, rc_suffix=False, nextseq_cutoff=15, cut=[2, -3], times=2, discard_untrimmed=True)
+    elif variant == "revcomp_linked":
+        options = dict(adapters=[["linked", "TTGACNNACG", "AGATCGGAAGAGC"], ["back", "CACGTCTGAACTC"]], quality_cutoff=[0, 15])
+        extra = dict(revcomp=True, action="mask", poly_a=True)
     t = trimmer_for(options, **extra)
     got = t.process_chunk(data)
     exp, counters = oracle_for(options, data, **extra)
     assert got == exp
     for k, v in counters.items():
         assert t.statistics[k] == v, k
+    if variant.startswith("revcomp"):
+        assert 0 < t.statistics["reverse_complemented"] < 6000
+
+
+def flip_records(data: bytes, seed: int) -> bytes:
+    from cutadapt_b200.pipeline import reverse_complement
+
+    rng = random.Random(seed)
+    out = []
+    for name, seq, qual in oracle.parse_fastq(data):
+        if rng.random() < 0.5:
+            seq, qual = reverse_complement(seq), qual[::-1]
+        out.append(f"@{name}\n{seq}\n+\n{qual}\n")
+    return "".join(out).encode("latin-1")
+
+
+def test_revcomp_reference_golden_on_the_device():
+    """--revcomp --no-index -g ^TTATTTGTCT -g ^TCCGCACTGG on revcomp.1.fastq (reference test_commandline.py:827-835):
+    both orientations, the choice, the in-place replacement and the " rc" suffix inside the FASTQ kernels."""
+    import cutadapt_b200.adapters as PA
+    from util import fastq_file
+
+    t = FastqTrimmer([PA.PrefixAdapter("TTATTTGTCT", name="a"), PA.PrefixAdapter("TCCGCACTGG", name="b")], revcomp=True)
+    assert t.process_chunk(fastq_file("revcomp.in.fastq")) == fastq_file("revcomp.out.fastq")
+    assert t.statistics["reverse_complemented"] == 2
 
 
 def test_many_chunks_in_flight_and_format_errors():
