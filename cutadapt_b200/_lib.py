@@ -180,6 +180,12 @@ def _declare(lib) -> None:
                                            C.POINTER(cg_fastq_result), vp]
     lib.cg_fastq_collect_paired.argtypes = [vp, i32, i32, vp, vp, C.POINTER(cg_fastq_params), C.POINTER(cg_fastq_params),
                                             i32, vp, i64, vp, i64, C.POINTER(cg_fastq_result), C.POINTER(cg_fastq_result)]
+    lib.cg_fastq_collect_pair_adapters.argtypes = [vp, i32, i32, vp, vp, i32, C.POINTER(cg_fastq_params),
+                                                   C.POINTER(cg_fastq_params), i32, vp, i64, vp, i64,
+                                                   C.POINTER(cg_fastq_result), C.POINTER(cg_fastq_result)]
+    lib.cg_fastq_collect_paired_demux.argtypes = [vp, i32, i32, vp, vp, C.POINTER(cg_fastq_params),
+                                                  C.POINTER(cg_fastq_params), i32, vp, i32, vp, i32, vp, vp, i64, vp, i64,
+                                                  C.POINTER(cg_fastq_result), C.POINTER(cg_fastq_result), vp, vp]
     lib.cg_fastq_collect.argtypes = [vp, i32, vp, C.POINTER(cg_fastq_params), vp, i64, C.POINTER(cg_fastq_result)]
     lib.cg_adapterset_create.argtypes = [
         vp, C.POINTER(cg_adapter_desc), i32, C.POINTER(cg_group_desc), i32, C.POINTER(vp),

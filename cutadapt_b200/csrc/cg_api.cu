@@ -112,7 +112,8 @@ struct FastqSlot {
     DevBuf<uint8_t> d_in, d_out, d_seq, d_qual;
     DevBuf<uint32_t> d_tiles, d_nl;
     DevBuf<CgFastqRecord> d_rec;
-    DevBuf<int32_t> d_len, d_interval, d_keep, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes;
+    DevBuf<int32_t> d_len, d_interval, d_keep, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes, d_dest, d_pairkey;
+    DevBuf<uint8_t> d_destkeep;
     DevBuf<int64_t> d_dmbase;
     DevBuf<int64_t> d_offs, d_outoff;
     DevBuf<unsigned long long> d_scan;
@@ -269,7 +270,8 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
         f.d_in.release(); f.d_out.release(); f.d_seq.release(); f.d_qual.release(); f.d_tiles.release(); f.d_nl.release();
         f.d_rec.release(); f.d_len.release(); f.d_mask.release(); f.d_adest.release(); f.d_dmbytes.release();
         f.d_dmbase.release(); f.d_keep.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
-        f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release();
+        f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release(); f.d_matches_rc.release();
+        f.d_isrc.release(); f.d_dest.release(); f.d_pairkey.release(); f.d_destkeep.release();
         f.h_in.release(); f.h_out.release(); f.h_counters.release();
         if (f.d_counters) cudaFree(f.d_counters);
         if (f.d_err) cudaFree(f.d_err);
@@ -1679,36 +1681,64 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
     return fastq_stage_verdict(c, f, fp, poly_a_mode, st, g);
 }
 
-// sizes -> offsets -> formatted records -> host; counters
-struct FqDemux {                      // optional: route the records by the adapter of their last match
-    const int32_t *adapter_dest = nullptr;   // host, one destination per adapter, values in [0, n_named)
-    int n_adapters = 0, n_named = 0;
-    int64_t *segments = nullptr;             // host out, n_named + 2 offsets into the output
+// Optional routing of the records (demultiplexing): destinations are decided once per chunk (fastq_stage_route, on
+// the first mate's slot), then every mate's output is partitioned by them.
+struct FqDemux {
+    const int32_t *adapter_dest1 = nullptr;  // host, one destination per adapter of R1, values in [0, n_named1)
+    int n_adapters1 = 0, n_named1 = 0;
+    const int32_t *adapter_dest2 = nullptr;  // combinatorial: the same for R2 (nullptr: route by R1 alone)
+    int n_adapters2 = 0, n_named2 = 0;
+    const uint8_t *dest_keep = nullptr;      // host, optional: destinations without a writer drop their records
+    int n_dest() const { return (n_named1 + 1) * (adapter_dest2 ? n_named2 + 1 : 1); }
+    const int32_t *d_dest = nullptr;         // device, filled by fastq_stage_route
+    const uint8_t *d_dest_keep = nullptr;
 };
 
+static int fastq_stage_route(cg_ctx *c, FastqSlot &f1, FastqSlot *f2, long long n, FqDemux &dm, cudaStream_t st)
+{
+    int rc;
+    if ((rc = f1.d_adest.ensure((size_t)dm.n_adapters1 + dm.n_adapters2 + 1)) != CG_OK) return rc;
+    if ((rc = f1.d_dest.ensure((size_t)n)) != CG_OK) return rc;
+    CU(cudaMemcpyAsync(f1.d_adest.p, dm.adapter_dest1, (size_t)dm.n_adapters1 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (dm.adapter_dest2)
+        CU(cudaMemcpyAsync(f1.d_adest.p + dm.n_adapters1, dm.adapter_dest2, (size_t)dm.n_adapters2 * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, st));
+    CU(cg_launch_fastq_dest(f1.d_mask.p, dm.adapter_dest2 ? f2->d_mask.p : nullptr, n, f1.d_adest.p, dm.n_named1,
+                            f1.d_adest.p + dm.n_adapters1, dm.n_named2, f1.d_dest.p, st));
+    c->launches += 1;
+    dm.d_dest = f1.d_dest.p;
+    if (dm.dest_keep) {
+        if ((rc = f1.d_destkeep.ensure((size_t)dm.n_dest())) != CG_OK) return rc;
+        CU(cudaMemcpyAsync(f1.d_destkeep.p, dm.dest_keep, (size_t)dm.n_dest(), cudaMemcpyHostToDevice, st));
+        dm.d_dest_keep = f1.d_destkeep.p;
+    }
+    return CG_OK;
+}
+
+// sizes -> offsets -> formatted records -> host; counters.  segments (host, n_dest + 1 values): where each destination
+// starts in `out`.
 static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStream_t st, uint8_t *out,
-                              int64_t out_capacity, cg_fastq_result *res, const FqDemux *dm = nullptr)
+                              int64_t out_capacity, cg_fastq_result *res, const FqDemux *dm = nullptr,
+                              int64_t *segments = nullptr)
 {
     const long long n = g.n;
     int rc;
     long long total = 0;
     int fq_err[2];
     if (dm) {
-        const int n_dest = dm->n_named + 1;
+        const int n_dest = dm->n_dest();
         const long long tiles = cg_demux_tiles(n), cells = tiles * n_dest;
-        if ((rc = f.d_adest.ensure((size_t)dm->n_adapters)) != CG_OK) return rc;
         if ((rc = f.d_dmbytes.ensure((size_t)cells)) != CG_OK) return rc;
         if ((rc = f.d_dmbase.ensure((size_t)cells + 1)) != CG_OK) return rc;
         if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(cells) + 1)) != CG_OK) return rc;
-        CU(cudaMemcpyAsync(f.d_adest.p, dm->adapter_dest, (size_t)dm->n_adapters * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        CU(cg_launch_fastq_demux(0, f.d_outlen.p, f.d_mask.p, n, f.d_adest.p, n_dest, f.d_dmbytes.p, nullptr, nullptr, st));
+        CU(cg_launch_fastq_demux(0, f.d_outlen.p, dm->d_dest, n, n_dest, f.d_dmbytes.p, nullptr, nullptr, st));
         CU(cg_launch_scan_i32(f.d_dmbytes.p, cells, f.d_scan.p, f.d_dmbase.p, st));
-        CU(cg_launch_fastq_demux(1, f.d_outlen.p, f.d_mask.p, n, f.d_adest.p, n_dest, nullptr, f.d_dmbase.p, f.d_outoff.p, st));
+        CU(cg_launch_fastq_demux(1, f.d_outlen.p, dm->d_dest, n, n_dest, nullptr, f.d_dmbase.p, f.d_outoff.p, st));
         c->launches += 5;
         // segment d starts at base[d][tile 0]; the last entry is the total
-        CU(cudaMemcpy2DAsync(dm->segments, sizeof(int64_t), f.d_dmbase.p, (size_t)tiles * sizeof(int64_t), sizeof(int64_t),
+        CU(cudaMemcpy2DAsync(segments, sizeof(int64_t), f.d_dmbase.p, (size_t)tiles * sizeof(int64_t), sizeof(int64_t),
                              (size_t)n_dest, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(dm->segments + n_dest, f.d_dmbase.p + cells, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(segments + n_dest, f.d_dmbase.p + cells, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(&total, f.d_dmbase.p + cells, sizeof total, cudaMemcpyDeviceToHost, st));
     } else {
         CU(cg_launch_scan_i32(f.d_outlen.p, n, f.d_scan.p, f.d_outoff.p, st));
@@ -1752,7 +1782,7 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
 }
 
 static int fastq_collect_impl(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
-                              uint8_t *out, int64_t out_capacity, cg_fastq_result *res, const FqDemux *dm)
+                              uint8_t *out, int64_t out_capacity, cg_fastq_result *res, FqDemux *dm, int64_t *segments)
 {
     if (!c || !fp || !res || slot < 0 || slot >= CG_FQ_SLOTS) return fail(CG_EINVAL, "cg_fastq_collect: bad argument");
     if (s && s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
@@ -1764,43 +1794,111 @@ static int fastq_collect_impl(cg_ctx *c, int32_t slot, const cg_adapterset *s, c
     FqStage g;
     int rc = fastq_stage_evaluate(c, f, s, fp, 1, f.stream, g);
     if (rc != CG_OK || g.n == 0) return rc;
+    if (dm && (rc = fastq_stage_route(c, f, nullptr, g.n, *dm, f.stream)) != CG_OK) return rc;
     CU(cg_launch_fastq_finish(g.n, f.d_rec.p, f.d_interval.p, f.d_mask.p, fastq_enabled_filters(fp), f.d_outlen.p,
-                              f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, g.rc_suffix, f.stream));
+                              f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, g.rc_suffix,
+                              dm ? dm->d_dest : nullptr, dm ? dm->d_dest_keep : nullptr, f.stream));
     c->launches += 1;
-    if ((rc = fastq_stage_output(c, f, g, f.stream, out, out_capacity, res, dm)) != CG_OK) return rc;
+    if ((rc = fastq_stage_output(c, f, g, f.stream, out, out_capacity, res, dm, segments)) != CG_OK) return rc;
     return check_err_flag(c);
 }
 
 extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
                                 uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
 {
-    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr);
+    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr, nullptr);
+}
+
+static int demux_check(const cg_adapterset *s, const int32_t *adapter_dest, int32_t n_named, const char *who)
+{
+    if (!s || !adapter_dest || n_named < 1 || n_named > 4096) return fail(CG_EINVAL, std::string(who) + ": bad argument");
+    for (int a = 0; a < s->host.n_adapters; ++a)
+        if (adapter_dest[a] < 0 || adapter_dest[a] >= n_named)
+            return fail(CG_EINVAL, std::string(who) + ": adapter_dest out of range");
+    return CG_OK;
 }
 
 extern "C" int cg_fastq_collect_demux(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
                                       const int32_t *adapter_dest, int32_t n_named, uint8_t *out, int64_t out_capacity,
                                       cg_fastq_result *res, int64_t *segments)
 {
-    if (!s || !adapter_dest || !segments || n_named < 1 || n_named > 4096)
-        return fail(CG_EINVAL, "cg_fastq_collect_demux: bad argument");
-    for (int a = 0; a < s->host.n_adapters; ++a)
-        if (adapter_dest[a] < 0 || adapter_dest[a] >= n_named)
-            return fail(CG_EINVAL, "cg_fastq_collect_demux: adapter_dest out of range");
+    if (!segments) return fail(CG_EINVAL, "cg_fastq_collect_demux: bad argument");
+    int rc = demux_check(s, adapter_dest, n_named, "cg_fastq_collect_demux");
+    if (rc != CG_OK) return rc;
     for (int d = 0; d < n_named + 2; ++d) segments[d] = 0;
     FqDemux dm;
-    dm.adapter_dest = adapter_dest; dm.n_adapters = s->host.n_adapters; dm.n_named = n_named; dm.segments = segments;
-    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, &dm);
+    dm.adapter_dest1 = adapter_dest; dm.n_adapters1 = s->host.n_adapters; dm.n_named1 = n_named;
+    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, &dm, segments);
 }
 
-extern "C" int cg_fastq_collect_paired(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *s1,
-                                       const cg_adapterset *s2, const cg_fastq_params *fp1, const cg_fastq_params *fp2,
-                                       int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
-                                       int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2)
+// --pair-adapters: sets1[i] / sets2[i] hold adapter i of the -a / -A lists alone
+struct FqPairAdapters {
+    const cg_adapterset *const *sets1 = nullptr;
+    const cg_adapterset *const *sets2 = nullptr;
+    int n_pairs = 0;
+};
+
+// PairedAdapterCutter (modifiers.py:412-503) for a chunk of pairs: every adapter pair is matched alone against both
+// mates (two trimming passes), fq_pair_select_kernel keeps the best pair that matches BOTH mates.  The records the
+// verdict kernels then see name the pair in `adapter`.
+static int fastq_stage_pair_adapters(cg_ctx *c, FastqSlot &f1, FastqSlot &f2, const FqPairAdapters &pa,
+                                     const cg_fastq_params *fp1, const cg_fastq_params *fp2, cudaStream_t st, FqStage &g1,
+                                     FqStage &g2)
+{
+    int rc;
+    if ((rc = fastq_stage_records(c, f1, fp1, true, st, g1)) != CG_OK) return rc;
+    if ((rc = fastq_stage_records(c, f2, fp2, true, st, g2)) != CG_OK) return rc;
+    if (g1.n != g2.n || g1.n == 0) return CG_OK;       // the caller reports the mismatch
+    for (const cg_fastq_params *fp : {fp1, fp2})
+        if (fp->action == CG_FQ_ACTION_LOWERCASE || fp->action == CG_FQ_ACTION_CROP)
+            return fail(CG_EINVAL, "--pair-adapters supports the actions trim, none, mask and retain");
+    const long long n = g1.n;
+    int slots = 1;
+    for (int i = 0; i < pa.n_pairs; ++i) slots = std::max(slots, std::max(pa.sets1[i]->host.slots, pa.sets2[i]->host.slots));
+    g1.times = g2.times = 1;
+    g1.slots = g2.slots = slots;
+    // the quality trimmers come before the cutter in the chain (cli.py:940-1000): fold them into the records
+    if ((rc = fastq_stage_fold_qtrim(c, f1, &fp1->trim, st, g1)) != CG_OK) return rc;
+    if ((rc = fastq_stage_fold_qtrim(c, f2, &fp2->trim, st, g2)) != CG_OK) return rc;
+    if ((rc = fastq_stage_pack(c, f1, st, g1, false)) != CG_OK) return rc;
+    if ((rc = fastq_stage_pack(c, f2, st, g2, false)) != CG_OK) return rc;
+    for (FastqSlot *f : {&f1, &f2}) {
+        if ((rc = f->d_matches.ensure((size_t)n * slots)) != CG_OK) return rc;
+        if ((rc = f->d_matches_rc.ensure((size_t)n * slots)) != CG_OK) return rc;     // records of the pair being tried
+    }
+    if ((rc = f1.d_pairkey.ensure((size_t)n * 2)) != CG_OK) return rc;
+    cg_params p1 = fp1->trim, p2 = fp2->trim;
+    p1.quality_trim = p1.nextseq_trim = p2.quality_trim = p2.nextseq_trim = 0;
+    p1.times = p2.times = 1;
+    for (int i = 0; i < pa.n_pairs; ++i) {
+        rc = launch_trim(c, pa.sets1[i], f1.d_seq.p, nullptr, f1.d_offs.p, n, g1.max_len, &p1, f1.d_matches_rc.p, nullptr, st,
+                         true);
+        if (rc != CG_OK) return rc;
+        rc = launch_trim(c, pa.sets2[i], f2.d_seq.p, nullptr, f2.d_offs.p, n, g2.max_len, &p2, f2.d_matches_rc.p, nullptr, st,
+                         true);
+        if (rc != CG_OK) return rc;
+        CU(cg_launch_fastq_pair_select(n, i, f1.d_matches_rc.p, pa.sets1[i]->host.slots, f2.d_matches_rc.p,
+                                       pa.sets2[i]->host.slots, f1.d_matches.p, f2.d_matches.p, slots, f1.d_pairkey.p, st));
+        c->launches += 1;
+    }
+    g1.d_matches = f1.d_matches.p;
+    g2.d_matches = f2.d_matches.p;
+    if ((rc = fastq_stage_verdict(c, f1, fp1, 1, st, g1)) != CG_OK) return rc;
+    return fastq_stage_verdict(c, f2, fp2, 2, st, g2);
+}
+
+static int fastq_collect_paired_impl(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *s1,
+                                     const cg_adapterset *s2, const FqPairAdapters *pa, const cg_fastq_params *fp1,
+                                     const cg_fastq_params *fp2, int32_t pair_filter_mode, uint8_t *out1,
+                                     int64_t out_capacity1, uint8_t *out2, int64_t out_capacity2, cg_fastq_result *res1,
+                                     cg_fastq_result *res2, FqDemux *dm, int64_t *segments1, int64_t *segments2)
 {
     if (!c || !fp1 || !fp2 || !res1 || !res2 || slot1 < 0 || slot1 >= CG_FQ_SLOTS || slot2 < 0 || slot2 >= CG_FQ_SLOTS ||
         slot1 == slot2 || pair_filter_mode < 0 || pair_filter_mode > 2)
         return fail(CG_EINVAL, "cg_fastq_collect_paired: bad argument");
     if ((s1 && s1->ctx != c) || (s2 && s2->ctx != c)) return fail(CG_EINVAL, "adapter set belongs to another context");
+    if (fp1->revcomp || fp2->revcomp)
+        return fail(CG_EINVAL, "--revcomp on pairs (PairedReverseComplementer) is not available on the device path");
     FastqSlot &f1 = c->fq[slot1], &f2 = c->fq[slot2];
     if (!f1.busy || !f2.busy) return fail(CG_EINVAL, "cg_fastq_collect_paired: nothing was submitted to a slot");
     CU(cudaSetDevice(c->device));
@@ -1810,22 +1908,81 @@ extern "C" int cg_fastq_collect_paired(cg_ctx *c, int32_t slot1, int32_t slot2, 
     // after its upload everything of the second mate runs on the first mate's stream
     cudaStream_t st = f1.stream;
     FqStage g1, g2;
-    int rc = fastq_stage_evaluate(c, f1, s1, fp1, 1, st, g1);
-    if (rc != CG_OK) { cudaStreamSynchronize(f2.stream); return rc; }
-    if ((rc = fastq_stage_evaluate(c, f2, s2, fp2, 2, st, g2)) != CG_OK) return rc;
+    int rc;
+    if (pa) {
+        CU(cudaStreamSynchronize(f2.stream));
+        if ((rc = fastq_stage_pair_adapters(c, f1, f2, *pa, fp1, fp2, st, g1, g2)) != CG_OK) return rc;
+    } else {
+        rc = fastq_stage_evaluate(c, f1, s1, fp1, 1, st, g1);
+        if (rc != CG_OK) { cudaStreamSynchronize(f2.stream); return rc; }
+        if ((rc = fastq_stage_evaluate(c, f2, s2, fp2, 2, st, g2)) != CG_OK) return rc;
+    }
     if (g1.n != g2.n)
         return fail(CG_EINVAL, "paired FASTQ chunks differ in their number of records (" + std::to_string(g1.n) + " vs " +
                                    std::to_string(g2.n) + ")");
     if (g1.n == 0) return CG_OK;
+    if (dm && (rc = fastq_stage_route(c, f1, &f2, g1.n, *dm, st)) != CG_OK) return rc;
     // --discard-untrimmed with adapters on one mate only tests "both" (cli.py:859-893)
-    const int mode_untrimmed = (!s1 || !s2) ? 1 : pair_filter_mode;
+    const int mode_untrimmed = (!pa && (!s1 || !s2)) ? 1 : pair_filter_mode;
     CU(cg_launch_fastq_finish(g1.n, f1.d_rec.p, f1.d_interval.p, f1.d_mask.p, fastq_enabled_filters(fp1), f1.d_outlen.p,
                               f1.d_counters + 1, f2.d_rec.p, f2.d_interval.p, f2.d_mask.p, fastq_enabled_filters(fp2),
-                              f2.d_outlen.p, f2.d_counters + 1, pair_filter_mode, mode_untrimmed, 0, st));
+                              f2.d_outlen.p, f2.d_counters + 1, pair_filter_mode, mode_untrimmed, 0,
+                              dm ? dm->d_dest : nullptr, dm ? dm->d_dest_keep : nullptr, st));
     c->launches += 1;
-    if ((rc = fastq_stage_output(c, f1, g1, st, out1, out_capacity1, res1)) != CG_OK) return rc;
-    if ((rc = fastq_stage_output(c, f2, g2, st, out2, out_capacity2, res2)) != CG_OK) return rc;
+    if ((rc = fastq_stage_output(c, f1, g1, st, out1, out_capacity1, res1, dm, segments1)) != CG_OK) return rc;
+    if ((rc = fastq_stage_output(c, f2, g2, st, out2, out_capacity2, res2, dm, segments2)) != CG_OK) return rc;
     return check_err_flag(c);
+}
+
+extern "C" int cg_fastq_collect_paired(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *s1,
+                                       const cg_adapterset *s2, const cg_fastq_params *fp1, const cg_fastq_params *fp2,
+                                       int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
+                                       int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2)
+{
+    return fastq_collect_paired_impl(c, slot1, slot2, s1, s2, nullptr, fp1, fp2, pair_filter_mode, out1, out_capacity1, out2,
+                                     out_capacity2, res1, res2, nullptr, nullptr, nullptr);
+}
+
+extern "C" int cg_fastq_collect_pair_adapters(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *const *sets1,
+                                              const cg_adapterset *const *sets2, int32_t n_pairs,
+                                              const cg_fastq_params *fp1, const cg_fastq_params *fp2,
+                                              int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
+                                              int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2)
+{
+    if (!c || !sets1 || !sets2 || n_pairs < 1)
+        return fail(CG_EINVAL, "cg_fastq_collect_pair_adapters: the adapter lists must have the same, non-zero length");
+    for (int i = 0; i < n_pairs; ++i) {
+        if (!sets1[i] || !sets2[i] || sets1[i]->ctx != c || sets2[i]->ctx != c)
+            return fail(CG_EINVAL, "cg_fastq_collect_pair_adapters: bad adapter set");
+        if (sets1[i]->host.n_groups != 1 || sets2[i]->host.n_groups != 1)
+            return fail(CG_EINVAL, "cg_fastq_collect_pair_adapters: every set must hold exactly one adapter");
+    }
+    FqPairAdapters pa;
+    pa.sets1 = sets1; pa.sets2 = sets2; pa.n_pairs = n_pairs;
+    return fastq_collect_paired_impl(c, slot1, slot2, sets1[0], sets2[0], &pa, fp1, fp2, pair_filter_mode, out1, out_capacity1,
+                                     out2, out_capacity2, res1, res2, nullptr, nullptr, nullptr);
+}
+
+extern "C" int cg_fastq_collect_paired_demux(cg_ctx *c, int32_t slot1, int32_t slot2, const cg_adapterset *s1,
+                                             const cg_adapterset *s2, const cg_fastq_params *fp1, const cg_fastq_params *fp2,
+                                             int32_t pair_filter_mode, const int32_t *adapter_dest1, int32_t n_named1,
+                                             const int32_t *adapter_dest2, int32_t n_named2, const uint8_t *dest_keep,
+                                             uint8_t *out1, int64_t out_capacity1, uint8_t *out2, int64_t out_capacity2,
+                                             cg_fastq_result *res1, cg_fastq_result *res2, int64_t *segments1,
+                                             int64_t *segments2)
+{
+    if (!segments1 || !segments2) return fail(CG_EINVAL, "cg_fastq_collect_paired_demux: bad argument");
+    int rc = demux_check(s1, adapter_dest1, n_named1, "cg_fastq_collect_paired_demux");
+    if (rc != CG_OK) return rc;
+    if (adapter_dest2 && (rc = demux_check(s2, adapter_dest2, n_named2, "cg_fastq_collect_paired_demux")) != CG_OK) return rc;
+    FqDemux dm;
+    dm.adapter_dest1 = adapter_dest1; dm.n_adapters1 = s1->host.n_adapters; dm.n_named1 = n_named1;
+    if (adapter_dest2) { dm.adapter_dest2 = adapter_dest2; dm.n_adapters2 = s2->host.n_adapters; dm.n_named2 = n_named2; }
+    dm.dest_keep = dest_keep;
+    if ((long long)dm.n_dest() > 8192) return fail(CG_EINVAL, "cg_fastq_collect_paired_demux: more than 8192 destinations");
+    for (int d = 0; d < dm.n_dest() + 1; ++d) segments1[d] = segments2[d] = 0;
+    return fastq_collect_paired_impl(c, slot1, slot2, s1, s2, nullptr, fp1, fp2, pair_filter_mode, out1, out_capacity1, out2,
+                                     out_capacity2, res1, res2, &dm, segments1, segments2);
 }
 
 extern "C" int cg_fastq_trim_chunk(cg_ctx *c, const cg_adapterset *s, const uint8_t *fastq, int64_t n_bytes,

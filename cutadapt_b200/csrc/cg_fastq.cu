@@ -379,7 +379,7 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
                                  const int32_t *mask1, int enabled1, int32_t *out_len1, unsigned long long *counters1,
                                  const CgFastqRecord *rec2, const int32_t *interval2, const int32_t *mask2, int enabled2,
                                  int32_t *out_len2, unsigned long long *counters2, int mode, int mode_untrimmed,
-                                 int rc_suffix)
+                                 int rc_suffix, const int32_t *dest, const uint8_t *dest_keep)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int fired = -1;
@@ -387,6 +387,8 @@ __global__ void fq_finish_kernel(long long n_records, const CgFastqRecord *rec1,
     unsigned written = 0;
     if (r < n_records) {
         fired = fq_finish_core(mask1[r], mask2 ? mask2[r] : 0, mask2 != nullptr, enabled1, enabled2, mode, mode_untrimmed);
+        // a demultiplexer without a writer for this destination drops the pair without counting it (steps.py:574-577)
+        if (fired < 0 && dest_keep && !dest_keep[dest[r]]) fired = 7;
         const int left1 = interval1[2 * r + 1] - interval1[2 * r];
         // a reverse-complemented read gets " rc" appended to its name (modifiers.py:295-296)
         const int extra1 = (rc_suffix && (mask1[r] & CG_FQ_MASK_RC)) ? 3 : 0;
@@ -469,33 +471,42 @@ __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const
 // earlier records of its tile with the same destination.
 constexpr int DM_TILE = 256;
 
-__device__ __forceinline__ int demux_dest(int mask, const int32_t *adapter_dest, int n_dest)
+// destination of every record: by the adapter of the most recent match of the read (Demultiplexer / PairedDemultiplexer:
+// of R1), or of both mates (CombinatorialDemultiplexer, steps.py:565-577): d1 * (n_named2 + 1) + d2; "no match" is the
+// last value of its dimension.
+__global__ void fq_dest_kernel(const int32_t *mask1, const int32_t *mask2, long long n, const int32_t *adapter_dest1,
+                               int n_named1, const int32_t *adapter_dest2, int n_named2, int32_t *dest)
 {
-    const int adapter = CG_FQ_MASK_ADAPTER(mask);
-    return adapter < 0 ? n_dest - 1 : adapter_dest[adapter];
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int a1 = CG_FQ_MASK_ADAPTER(mask1[r]);
+    int d = a1 < 0 ? n_named1 : adapter_dest1[a1];
+    if (mask2) {
+        const int a2 = CG_FQ_MASK_ADAPTER(mask2[r]);
+        d = d * (n_named2 + 1) + (a2 < 0 ? n_named2 : adapter_dest2[a2]);
+    }
+    dest[r] = d;
 }
 
-__global__ void __launch_bounds__(DM_TILE) fq_demux_hist_kernel(const int32_t *out_len, const int32_t *mask, long long n,
-                                                                 const int32_t *adapter_dest, int n_dest, long long n_tiles,
-                                                                 int32_t *bytes)
+__global__ void __launch_bounds__(DM_TILE) fq_demux_hist_kernel(const int32_t *out_len, const int32_t *dest, long long n,
+                                                                 int n_dest, long long n_tiles, int32_t *bytes)
 {
     extern __shared__ int hist[];
     for (int d = threadIdx.x; d < n_dest; d += DM_TILE) hist[d] = 0;
     __syncthreads();
     const long long r = (long long)blockIdx.x * DM_TILE + threadIdx.x;
-    if (r < n && out_len[r] > 0) atomicAdd(&hist[demux_dest(mask[r], adapter_dest, n_dest)], out_len[r]);
+    if (r < n && out_len[r] > 0) atomicAdd(&hist[dest[r]], out_len[r]);
     __syncthreads();
     for (int d = threadIdx.x; d < n_dest; d += DM_TILE) bytes[(long long)d * n_tiles + blockIdx.x] = hist[d];
 }
 
-__global__ void __launch_bounds__(DM_TILE) fq_demux_offsets_kernel(const int32_t *out_len, const int32_t *mask, long long n,
-                                                                    const int32_t *adapter_dest, int n_dest,
+__global__ void __launch_bounds__(DM_TILE) fq_demux_offsets_kernel(const int32_t *out_len, const int32_t *dest_of, long long n,
                                                                     long long n_tiles, const int64_t *base, int64_t *out_off)
 {
     __shared__ int s_dest[DM_TILE], s_len[DM_TILE];
     const long long r = (long long)blockIdx.x * DM_TILE + threadIdx.x;
     const int len = r < n ? out_len[r] : 0;
-    const int dest = len > 0 ? demux_dest(mask[r], adapter_dest, n_dest) : -1;
+    const int dest = len > 0 ? dest_of[r] : -1;
     s_dest[threadIdx.x] = dest;
     s_len[threadIdx.x] = len;
     __syncthreads();
@@ -503,6 +514,43 @@ __global__ void __launch_bounds__(DM_TILE) fq_demux_offsets_kernel(const int32_t
         long long before = 0;
         for (int j = 0; j < (int)threadIdx.x; ++j) before += s_dest[j] == dest ? s_len[j] : 0;
         out_off[r] = base[(long long)dest * n_tiles + blockIdx.x] + before;
+    }
+}
+
+// ---- --pair-adapters (PairedAdapterCutter._find_best_match_pair, modifiers.py:480-503) ----
+// After adapter pair `pair` was matched alone against both mates (cur1 / cur2, slots1 / slots2 records per read):
+// a pair that matches BOTH mates replaces the best pair so far if its score sum is higher, or equal with fewer
+// errors.  best1 / best2 hold `slots` records per read (adapter = the pair's number), best_key = (score, errors).
+__global__ void fq_pair_select_kernel(long long n, int pair, const cg_match_rec *cur1, int slots1, const cg_match_rec *cur2,
+                                      int slots2, cg_match_rec *best1, cg_match_rec *best2, int slots, int32_t *best_key)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (pair == 0) {
+        for (int k = 0; k < slots; ++k) { best1[r * slots + k].adapter = -1; best2[r * slots + k].adapter = -1; }
+        best_key[2 * r] = 0; best_key[2 * r + 1] = 0;
+    }
+    int score = 0, errors = 0;
+    bool has1 = false, has2 = false;
+    for (int k = 0; k < slots1; ++k) {
+        const cg_match_rec m = cur1[r * slots1 + k];
+        if (m.adapter >= 0) { has1 = true; score += m.score; errors += m.errors; }
+    }
+    for (int k = 0; k < slots2; ++k) {
+        const cg_match_rec m = cur2[r * slots2 + k];
+        if (m.adapter >= 0) { has2 = true; score += m.score; errors += m.errors; }
+    }
+    if (!has1 || !has2) return;
+    const bool have = best1[r * slots].adapter >= 0 || (slots > 1 && best1[r * slots + 1].adapter >= 0);
+    if (have && !(score > best_key[2 * r] || (score == best_key[2 * r] && errors < best_key[2 * r + 1]))) return;
+    best_key[2 * r] = score; best_key[2 * r + 1] = errors;
+    for (int k = 0; k < slots; ++k) {
+        cg_match_rec m; m.adapter = -1; m.astart = m.astop = m.rstart = m.rstop = m.score = m.errors = m.info = 0;
+        cg_match_rec a = m, b = m;
+        if (k < slots1) { a = cur1[r * slots1 + k]; if (a.adapter >= 0) a.adapter = pair; }
+        if (k < slots2) { b = cur2[r * slots2 + k]; if (b.adapter >= 0) b.adapter = pair; }
+        best1[r * slots + k] = a;
+        best2[r * slots + k] = b;
     }
 }
 
@@ -610,13 +658,13 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
                                    unsigned long long *d_counters1, const CgFastqRecord *d_rec2,
                                    const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
                                    unsigned long long *d_counters2, int mode, int mode_untrimmed, int rc_suffix,
-                                   cudaStream_t st)
+                                   const int32_t *d_dest, const uint8_t *d_dest_keep, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_finish_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(n_records, d_rec1, d_interval1, d_mask1, enabled1,
                                                                          d_out_len1, d_counters1, d_rec2, d_interval2,
                                                                          d_mask2, enabled2, d_out_len2, d_counters2, mode,
-                                                                         mode_untrimmed, rc_suffix);
+                                                                         mode_untrimmed, rc_suffix, d_dest, d_dest_keep);
     return cudaGetLastError();
 }
 
@@ -635,18 +683,35 @@ cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_r
 
 long long cg_demux_tiles(long long n_records) { return (n_records + DM_TILE - 1) / DM_TILE; }
 
-cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_mask, long long n_records,
-                                  const int32_t *d_adapter_dest, int n_dest, int32_t *d_bytes, const int64_t *d_base,
-                                  int64_t *d_out_off, cudaStream_t st)
+cudaError_t cg_launch_fastq_dest(const int32_t *d_mask1, const int32_t *d_mask2, long long n_records,
+                                 const int32_t *d_adapter_dest1, int n_named1, const int32_t *d_adapter_dest2, int n_named2,
+                                 int32_t *d_dest, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_dest_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_mask1, d_mask2, n_records, d_adapter_dest1, n_named1,
+                                                                       d_adapter_dest2, n_named2, d_dest);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_dest, long long n_records,
+                                  int n_dest, int32_t *d_bytes, const int64_t *d_base, int64_t *d_out_off, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     const long long tiles = cg_demux_tiles(n_records);
     if (phase == 0)
-        fq_demux_hist_kernel<<<(unsigned)tiles, DM_TILE, (size_t)n_dest * sizeof(int), st>>>(d_out_len, d_mask, n_records,
-                                                                                           d_adapter_dest, n_dest, tiles,
-                                                                                           d_bytes);
+        fq_demux_hist_kernel<<<(unsigned)tiles, DM_TILE, (size_t)n_dest * sizeof(int), st>>>(d_out_len, d_dest, n_records,
+                                                                                           n_dest, tiles, d_bytes);
     else
-        fq_demux_offsets_kernel<<<(unsigned)tiles, DM_TILE, 0, st>>>(d_out_len, d_mask, n_records, d_adapter_dest, n_dest,
-                                                                    tiles, d_base, d_out_off);
+        fq_demux_offsets_kernel<<<(unsigned)tiles, DM_TILE, 0, st>>>(d_out_len, d_dest, n_records, tiles, d_base, d_out_off);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_pair_select(long long n_records, int pair, const cg_match_rec *d_cur1, int slots1,
+                                        const cg_match_rec *d_cur2, int slots2, cg_match_rec *d_best1, cg_match_rec *d_best2,
+                                        int slots, int32_t *d_best_key, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    fq_pair_select_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(n_records, pair, d_cur1, slots1, d_cur2, slots2,
+                                                                              d_best1, d_best2, slots, d_best_key);
     return cudaGetLastError();
 }

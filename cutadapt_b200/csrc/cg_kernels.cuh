@@ -104,15 +104,22 @@ cudaError_t cg_launch_fastq_finish(long long n_records, const CgFastqRecord *d_r
                                    unsigned long long *d_counters1, const CgFastqRecord *d_rec2,
                                    const int32_t *d_interval2, const int32_t *d_mask2, int enabled2, int32_t *d_out_len2,
                                    unsigned long long *d_counters2, int mode, int mode_untrimmed, int rc_suffix,
-                                   cudaStream_t st);
+                                   const int32_t *d_dest, const uint8_t *d_dest_keep, cudaStream_t st);
 cudaError_t cg_launch_fastq_write(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_interval,
                                   const int64_t *d_out_off, const int32_t *d_out_len, long long n_records,
                                   uint8_t *d_out, int action, const int32_t *d_keep_interval, const int32_t *d_mask,
                                   int rc_suffix, cudaStream_t st);
-// demultiplexing: phase 0 fills d_bytes[n_dest][tiles] (output bytes per destination and tile of 256 records);
-// after an exclusive scan of that array (d_base), phase 1 writes every record's output offset.
-// d_adapter_dest: destination of every adapter; reads without a match go to destination n_dest - 1.
+// demultiplexing: cg_launch_fastq_dest gives every record its destination (adapter of the most recent match of R1, or
+// of both mates: d1 * (n_named2 + 1) + d2; reads without a match: the last value of the dimension); phase 0 fills
+// d_bytes[n_dest][tiles] (output bytes per destination and tile of 256 records); after an exclusive scan of that
+// array (d_base), phase 1 writes every record's output offset.
 long long cg_demux_tiles(long long n_records);
-cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_mask, long long n_records,
-                                  const int32_t *d_adapter_dest, int n_dest, int32_t *d_bytes, const int64_t *d_base,
-                                  int64_t *d_out_off, cudaStream_t st);
+cudaError_t cg_launch_fastq_dest(const int32_t *d_mask1, const int32_t *d_mask2, long long n_records,
+                                 const int32_t *d_adapter_dest1, int n_named1, const int32_t *d_adapter_dest2, int n_named2,
+                                 int32_t *d_dest, cudaStream_t st);
+cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_dest, long long n_records,
+                                  int n_dest, int32_t *d_bytes, const int64_t *d_base, int64_t *d_out_off, cudaStream_t st);
+// --pair-adapters: fold the records of adapter pair `pair` into the best pair per read (modifiers.py:480-503)
+cudaError_t cg_launch_fastq_pair_select(long long n_records, int pair, const cg_match_rec *d_cur1, int slots1,
+                                        const cg_match_rec *d_cur2, int slots2, cg_match_rec *d_best1, cg_match_rec *d_best2,
+                                        int slots, int32_t *d_best_key, cudaStream_t st);

@@ -620,6 +620,21 @@ def _device_set(adapters, ctx):
     return adapters, _lib.AdapterSet(spec, ctx)
 
 
+def _demux_names(adapters):
+    """(names of the outputs, destination number of every adapter): the name of the adapter of a read's most
+    recent match selects its output (Demultiplexer, steps.py:397-409); a LinkedAdapter's parts share its name."""
+    if adapters is None:
+        raise ValueError("demultiplexing needs adapters")
+    singles, groups, owners = adapters._flatten()
+    names = [s.name for s in singles]
+    for (typ, a0, a1, _, _), owner in zip(groups, owners):
+        if typ == _lib.CG_GROUP_LINKED:
+            names[a0] = names[a1] = owner.name
+    outputs = list(dict.fromkeys(names))
+    number = {name: i for i, name in enumerate(outputs)}
+    return outputs, np.array([number[n] for n in names], dtype=np.int32)
+
+
 class FastqTrimmer:
     """
     FASTQ chunks in, trimmed FASTQ chunks out -- the per-chunk worker of the reference
@@ -704,18 +719,7 @@ class FastqTrimmer:
         return self._collect(self._submit(chunk))
 
     def _demux_names(self):
-        """(names of the outputs, destination number of every adapter): the name of the adapter of a read's most
-        recent match selects its output (Demultiplexer, steps.py:397-409); a LinkedAdapter's parts share its name."""
-        if self.adapters is None:
-            raise ValueError("demultiplexing needs adapters")
-        singles, groups, owners = self.adapters._flatten()
-        names = [s.name for s in singles]
-        for (typ, a0, a1, _, _), owner in zip(groups, owners):
-            if typ == _lib.CG_GROUP_LINKED:
-                names[a0] = names[a1] = owner.name
-        outputs = list(dict.fromkeys(names))
-        number = {name: i for i, name in enumerate(outputs)}
-        return outputs, np.array([number[n] for n in names], dtype=np.int32)
+        return _demux_names(self.adapters)
 
     def process_chunk_demux(self, chunk, unknown: str = "unknown") -> dict:
         """{adapter name: FASTQ bytes} + {unknown: reads without a match} -- what ``-o 'demux-{name}.fastq'`` writes
@@ -758,16 +762,36 @@ class PairedFastqTrimmer:
     MODES = {"any": 0, "both": 1, "first": 2}
 
     def __init__(self, adapters1=None, adapters2=None, options1: Optional[dict] = None,
-                 options2: Optional[dict] = None, pair_filter: str = "any", ctx: Optional[_lib.Context] = None):
+                 options2: Optional[dict] = None, pair_filter: str = "any", pair_adapters: bool = False,
+                 ctx: Optional[_lib.Context] = None):
         if pair_filter not in self.MODES:
             raise ValueError("pair_filter must be 'any', 'both' or 'first'")
         self.ctx = ctx or _lib.default_context()
-        self.adapters1, self._set1 = _device_set(adapters1, self.ctx)
-        self.adapters2, self._set2 = _device_set(adapters2, self.ctx)
         self.params1 = _fastq_params(**(options1 or {}))
         self.params2 = _fastq_params(**(options2 or {}))
         self.mode = self.MODES[pair_filter]
         self.statistics = ({}, {})
+        self._pairs = None
+        if pair_adapters:
+            # --pair-adapters (PairedAdapterCutter.__init__, modifiers.py:417-442): one device set per adapter
+            adapters1, adapters2 = list(adapters1 or []), list(adapters2 or [])
+            if len(adapters1) != len(adapters2):
+                raise ValueError("The number of adapters to trim from R1 and R2 must be the same. "
+                                 f"Given: {len(adapters1)} for R1, {len(adapters2)} for R2")
+            if not adapters1:
+                raise ValueError("No adapters given")
+            if self.params1.revcomp or self.params2.revcomp:
+                raise ValueError("Cannot use --revcomp with --pair-adapters")        # cli.py:1087
+            self.adapters1, self.adapters2 = adapters1, adapters2
+            self._pairs = [(_device_set([a1], self.ctx)[1], _device_set([a2], self.ctx)[1])
+                           for a1, a2 in zip(adapters1, adapters2)]
+            self._set1 = self._set2 = None
+            k = len(self._pairs)
+            self._pair_handles = ((C.c_void_p * k)(*[p[0].handle for p in self._pairs]),
+                                  (C.c_void_p * k)(*[p[1].handle for p in self._pairs]))
+        else:
+            self.adapters1, self._set1 = _device_set(adapters1, self.ctx)
+            self.adapters2, self._set2 = _device_set(adapters2, self.ctx)
 
     def _submit(self, chunk):
         buf = np.frombuffer(chunk, dtype=np.uint8) if not isinstance(chunk, np.ndarray) else chunk
@@ -776,19 +800,67 @@ class PairedFastqTrimmer:
                                               C.byref(slot)))
         return slot.value, buf
 
+    def _account(self, r1, r2):
+        for st, res in zip(self.statistics, (r1, r2)):
+            for k, v in res.as_dict().items():
+                st[k] = st.get(k, 0) + v
+
     def process_chunk(self, chunk1, chunk2) -> Tuple[bytes, bytes]:
         (s1, b1), (s2, b2) = self._submit(chunk1), self._submit(chunk2)
         out1 = np.empty(b1.size + 16, dtype=np.uint8)
         out2 = np.empty(b2.size + 16, dtype=np.uint8)
         r1, r2 = _lib.cg_fastq_result(), _lib.cg_fastq_result()
-        _lib.check(_lib.lib().cg_fastq_collect_paired(
-            self.ctx.handle, s1, s2, self._set1.handle if self._set1 is not None else None,
-            self._set2.handle if self._set2 is not None else None, C.byref(self.params1), C.byref(self.params2),
-            self.mode, out1.ctypes.data, out1.size, out2.ctypes.data, out2.size, C.byref(r1), C.byref(r2)))
-        for st, res in zip(self.statistics, (r1, r2)):
-            for k, v in res.as_dict().items():
-                st[k] = st.get(k, 0) + v
+        if self._pairs is not None:
+            _lib.check(_lib.lib().cg_fastq_collect_pair_adapters(
+                self.ctx.handle, s1, s2, self._pair_handles[0], self._pair_handles[1], len(self._pairs),
+                C.byref(self.params1), C.byref(self.params2), self.mode, out1.ctypes.data, out1.size, out2.ctypes.data,
+                out2.size, C.byref(r1), C.byref(r2)))
+        else:
+            _lib.check(_lib.lib().cg_fastq_collect_paired(
+                self.ctx.handle, s1, s2, self._set1.handle if self._set1 is not None else None,
+                self._set2.handle if self._set2 is not None else None, C.byref(self.params1), C.byref(self.params2),
+                self.mode, out1.ctypes.data, out1.size, out2.ctypes.data, out2.size, C.byref(r1), C.byref(r2)))
+        self._account(r1, r2)
         return out1[: r1.out_bytes].tobytes(), out2[: r2.out_bytes].tobytes()
+
+    def process_chunk_demux(self, chunk1, chunk2, combinatorial: bool = False, discard_untrimmed: bool = False,
+                            unknown: str = "unknown") -> dict:
+        """
+        Demultiplexed pairs of one chunk on the device (``cg_fastq_collect_paired_demux``).
+
+        combinatorial=False: ``PairedDemultiplexer`` (steps.py:422-503) -- {adapter name of R1's most recent match or
+        ``unknown``: (R1 bytes, R2 bytes)}; with ``discard_untrimmed`` the ``unknown`` output is not produced.
+        combinatorial=True: ``CombinatorialDemultiplexer`` (steps.py:506-581) -- keys are (name1, name2) with None for a
+        mate without a match; with ``discard_untrimmed`` only pairs with matches on both mates are kept.  Pairs
+        without an output are dropped without being counted, as in the reference.
+        """
+        if self._pairs is not None:
+            raise ValueError("demultiplexing with --pair-adapters is not supported")
+        names1, dest1 = _demux_names(self.adapters1)
+        n1 = len(names1)
+        if combinatorial:
+            names2, dest2 = _demux_names(self.adapters2)
+            n2 = len(names2)
+            keys = [(a, b) for a in names1 + [None] for b in names2 + [None]]
+            keep = np.array([not discard_untrimmed or (a is not None and b is not None) for a, b in keys], dtype=np.uint8)
+        else:
+            dest2, n2 = None, 0
+            keys = names1 + [unknown]
+            keep = np.array([1] * n1 + [0 if discard_untrimmed else 1], dtype=np.uint8)
+        (s1, b1), (s2, b2) = self._submit(chunk1), self._submit(chunk2)
+        out1 = np.empty(b1.size + 16, dtype=np.uint8)
+        out2 = np.empty(b2.size + 16, dtype=np.uint8)
+        r1, r2 = _lib.cg_fastq_result(), _lib.cg_fastq_result()
+        seg1 = np.zeros(len(keys) + 1, dtype=np.int64)
+        seg2 = np.zeros(len(keys) + 1, dtype=np.int64)
+        _lib.check(_lib.lib().cg_fastq_collect_paired_demux(
+            self.ctx.handle, s1, s2, self._set1.handle, self._set2.handle if self._set2 is not None else None,
+            C.byref(self.params1), C.byref(self.params2), self.mode, dest1.ctypes.data, n1,
+            dest2.ctypes.data if dest2 is not None else None, n2, keep.ctypes.data, out1.ctypes.data, out1.size,
+            out2.ctypes.data, out2.size, C.byref(r1), C.byref(r2), seg1.ctypes.data, seg2.ctypes.data))
+        self._account(r1, r2)
+        return {key: (out1[seg1[i]:seg1[i + 1]].tobytes(), out2[seg2[i]:seg2[i + 1]].tobytes())
+                for i, key in enumerate(keys) if keep[i]}
 
 
 class DeviceResult:

@@ -364,6 +364,30 @@ int cg_fastq_collect_paired(cg_ctx *ctx, int32_t slot1, int32_t slot2, const cg_
                             int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
                             int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2);
 
+/* --pair-adapters (PairedAdapterCutter, modifiers.py:412-503): adapter i of the -a list is removed from R1 only
+ * together with adapter i of the -A list from R2.  sets1[i] / sets2[i] hold adapter i alone (one group each); every
+ * pair is matched against both mates on the device and the best pair that matches BOTH mates wins (highest score
+ * sum, then fewest errors, then the first listed).  `adapter` of the resulting matches is the pair's number.  The
+ * quality trimmers of params1 / params2 run first, times is 1; actions: trim, none, mask, retain. */
+int cg_fastq_collect_pair_adapters(cg_ctx *ctx, int32_t slot1, int32_t slot2, const cg_adapterset *const *sets1,
+                                   const cg_adapterset *const *sets2, int32_t n_pairs, const cg_fastq_params *params1,
+                                   const cg_fastq_params *params2, int32_t pair_filter_mode, uint8_t *out1,
+                                   int64_t out_capacity1, uint8_t *out2, int64_t out_capacity2, cg_fastq_result *res1,
+                                   cg_fastq_result *res2);
+
+/* Paired-end demultiplexing.  adapter_dest2 == NULL: PairedDemultiplexer (steps.py:422-503), both mates go to the
+ * output of the adapter of R1's most recent match, destinations 0 .. n_named1 (the last = no match).  Otherwise
+ * CombinatorialDemultiplexer (steps.py:506-581): destination d1 * (n_named2 + 1) + d2 from the matches on both mates.
+ * dest_keep (optional, one byte per destination): pairs routed to a destination with 0 are dropped without being
+ * counted (a combination without a writer, steps.py:574-577).  out1 / out2 receive the destinations back to back;
+ * segments1 / segments2 (n_dest + 1 values each) say where each starts. */
+int cg_fastq_collect_paired_demux(cg_ctx *ctx, int32_t slot1, int32_t slot2, const cg_adapterset *set1,
+                                  const cg_adapterset *set2, const cg_fastq_params *params1, const cg_fastq_params *params2,
+                                  int32_t pair_filter_mode, const int32_t *adapter_dest1, int32_t n_named1,
+                                  const int32_t *adapter_dest2, int32_t n_named2, const uint8_t *dest_keep, uint8_t *out1,
+                                  int64_t out_capacity1, uint8_t *out2, int64_t out_capacity2, cg_fastq_result *res1,
+                                  cg_fastq_result *res2, int64_t *segments1, int64_t *segments2);
+
 /* ---- trim statistics (the payload of the end-of-run all-reduce, report.py:81-126) --------
  * Device-side reduction of a batch's match records into a fixed-layout int64 vector that carries everything the
  * reference's Statistics.__iadd__ adds up (report.py:81-126), so that one all-reduce merges the ranks:

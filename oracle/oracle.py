@@ -568,6 +568,27 @@ def parse_fastq(data: bytes):
     return records
 
 
+def _apply_cuts(records, cut):
+    """UnconditionalCutter, first in the chain (modifiers.py:66-95)"""
+    for c_len in cut:
+        records = [(nm, sq[c_len:], q[c_len:]) if c_len > 0 else (nm, sq[:c_len], q[:c_len]) for nm, sq, q in records]
+    return records
+
+
+def _quality_trimmed(records, quality_trim, cutoff_front, cutoff_back, quality_base, nextseq_cutoff):
+    """NextseqQualityTrimmer + QualityTrimmer as modifiers of their own: (records, bases removed)"""
+    trimmed, removed = [], 0
+    for name, seq, q in records:
+        s, e = 0, len(seq)
+        if nextseq_cutoff is not None:
+            e = nextseq_trim_index(seq, q, nextseq_cutoff, quality_base)
+        if quality_trim:
+            s, e = quality_trim_index(q[:e], cutoff_front, cutoff_back, quality_base)
+        removed += len(seq) - (e - s)
+        trimmed.append((name, seq[s:e], q[s:e]))
+    return trimmed, removed
+
+
 FILTER_CHAIN = ("too_short", "too_long", "too_many_n", "too_many_expected_errors", "casava_filtered",
                 "discard_trimmed", "discard_untrimmed")     # the order cli.py:700-830, 870-910 appends them
 _FILTER_COUNTER = {"discard_trimmed": "discarded", "discard_untrimmed": "discarded"}
@@ -577,44 +598,40 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                     nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
                     discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
                     trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False, action="trim",
-                    revcomp=False, rc_suffix=True):
+                    revcomp=False, rc_suffix=True, match_override=None):
     """Modifier chain on every record of a chunk + the verdict of every enabled filter.
-    Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters)."""
+    Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters).
+    match_override: match records (n, 1, slots) found by the caller on the quality-trimmed reads (--pair-adapters)."""
     records = parse_fastq(data)
     bp_in = sum(len(r[1]) for r in records)             # before any modifier (pipeline.py:58-64)
-    for c_len in cut:                                   # UnconditionalCutter, first in the chain (modifiers.py:66-95)
-        records = [(nm, sq[c_len:], q[c_len:]) if c_len > 0 else (nm, sq[:c_len], q[:c_len]) for nm, sq, q in records]
+    records = _apply_cuts(records, cut)
     seqs = [r[1] for r in records]
     quals = [r[2] for r in records]
     n = len(records)
     pre_trimmed_bp = 0
     reverse_complemented = 0
-    if adapters and revcomp:
-        # ReverseComplementer (modifiers.py:264-308) wraps the AdapterCutter only: the quality trimmers come first
-        trimmed = []
-        for name, seq, q in records:
-            s, e = 0, len(seq)
-            if nextseq_cutoff is not None:
-                e = nextseq_trim_index(seq, q, nextseq_cutoff, quality_base)
-            if quality_trim:
-                s, e = quality_trim_index(q[:e], cutoff_front, cutoff_back, quality_base)
-            pre_trimmed_bp += len(seq) - (e - s)
-            trimmed.append((name, seq[s:e], q[s:e]))
-        records = trimmed
+    if (adapters and revcomp) or match_override is not None:
+        # ReverseComplementer (modifiers.py:264-308) wraps the AdapterCutter only, PairedAdapterCutter replaces it:
+        # the quality trimmers come first, the cutter sees the trimmed read
+        records, pre_trimmed_bp = _quality_trimmed(records, quality_trim, cutoff_front, cutoff_back, quality_base,
+                                                   nextseq_cutoff)
         seqs = [r[1] for r in records]
-        comp = bytes.maketrans(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn", b"TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn")
-        rc_seqs = [sq.encode("latin-1").translate(comp)[::-1].decode("latin-1") for sq in seqs]
-        fwd, _ = oracle_process(adapters, groups, seqs, None, False, 0, 0, quality_base, times, None)
-        rev, _ = oracle_process(adapters, groups, rc_seqs, None, False, 0, 0, quality_base, times, None)
-        matches = fwd.copy()
-        for i in range(n):
-            score_f = int(fwd[i]["score"][fwd[i]["adapter"] >= 0].sum())
-            score_r = int(rev[i]["score"][rev[i]["adapter"] >= 0].sum())
-            if score_r > score_f:
-                reverse_complemented += 1
-                matches[i] = rev[i]
-                name, _, q = records[i]
-                records[i] = (name + (" rc" if rc_suffix else ""), rc_seqs[i], q[::-1])
+        if match_override is not None:
+            matches = match_override
+        else:
+            comp = bytes.maketrans(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn", b"TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn")
+            rc_seqs = [sq.encode("latin-1").translate(comp)[::-1].decode("latin-1") for sq in seqs]
+            fwd, _ = oracle_process(adapters, groups, seqs, None, False, 0, 0, quality_base, times, None)
+            rev, _ = oracle_process(adapters, groups, rc_seqs, None, False, 0, 0, quality_base, times, None)
+            matches = fwd.copy()
+            for i in range(n):
+                score_f = int(fwd[i]["score"][fwd[i]["adapter"] >= 0].sum())
+                score_r = int(rev[i]["score"][rev[i]["adapter"] >= 0].sum())
+                if score_r > score_f:
+                    reverse_complemented += 1
+                    matches[i] = rev[i]
+                    name, _, q = records[i]
+                    records[i] = (name + (" rc" if rc_suffix else ""), rc_seqs[i], q[::-1])
         quals = [r[2] for r in records]
         qtrim = np.array([(0, len(r[1])) for r in records], dtype=np.int32).reshape(n, 2)
     elif adapters:
@@ -745,19 +762,28 @@ def oracle_fastq_trim(data: bytes, adapters=None, groups=None, **options):
 
 
 def oracle_fastq_trim_paired(data1: bytes, data2: bytes, adapters1=None, groups1=None, adapters2=None, groups2=None,
-                             options1=None, options2=None, pair_filter="any"):
+                             options1=None, options2=None, pair_filter="any", pair_specs=None, route=None):
     """(out1, out2, counters1, counters2) of one paired-end chunk (PairedEndPipeline.process_reads, pipeline.py:125-153).
     Each filter works on the pair like PairedEndFilter (steps.py:105-180); with adapters on one mate only,
-    --discard-untrimmed tests "both" (cli.py:859-893)."""
-    ev1, en1, c1 = _fastq_evaluate(data1, adapters1, groups1, **(options1 or {}))
-    ev2, en2, c2 = _fastq_evaluate(data2, adapters2, groups2, second_mate=True, **(options2 or {}))
+    --discard-untrimmed tests "both" (cli.py:859-893).
+    pair_specs: --pair-adapters, [((adapters, groups) of adapter i alone for R1, the same for R2)].
+    route: demultiplexing, a function (last adapter of R1 or -1, of R2 or -1) -> key or None (no writer: dropped, not
+    counted); out1 / out2 are then dicts key -> bytes."""
+    options1, options2 = dict(options1 or {}), dict(options2 or {})
+    if pair_specs:
+        adapters1, groups1 = pair_specs[0][0]
+        adapters2, groups2 = pair_specs[0][1]
+        options1["match_override"], options2["match_override"] = _best_adapter_pairs(data1, data2, pair_specs, options1,
+                                                                                     options2)
+    ev1, en1, c1 = _fastq_evaluate(data1, adapters1, groups1, want_last_adapter=True, **options1)
+    ev2, en2, c2 = _fastq_evaluate(data2, adapters2, groups2, want_last_adapter=True, second_mate=True, **options2)
     if len(ev1) != len(ev2):
         raise FastqFormatError("paired FASTQ chunks differ in their number of records")
     for c in (c1, c2):
         c.update(n_written=0, bp_out=0, too_short=0, too_long=0, too_many_n=0, too_many_expected_errors=0, discarded=0,
                  casava_filtered=0)
-    out1, out2 = [], []
-    for (n1, s1, q1, f1), (n2, s2, q2, f2) in zip(ev1, ev2):
+    out1, out2 = ({}, {}) if route else ([], [])
+    for (n1, s1, q1, f1, last1), (n2, s2, q2, f2, last2) in zip(ev1, ev2):
         fired = None
         for flt in FILTER_CHAIN:
             e1, e2 = flt in en1, flt in en2
@@ -783,10 +809,61 @@ def oracle_fastq_trim_paired(data1: bytes, data2: bytes, adapters1=None, groups1
             for c in (c1, c2):
                 c[_FILTER_COUNTER.get(fired, fired)] += 1
             continue
+        key = None
+        if route:
+            key = route(last1, last2)
+            if key is None:
+                continue
         for c in (c1, c2):
             c["n_written"] += 1
         c1["bp_out"] += len(s1)
         c2["bp_out"] += len(s2)
-        out1.append(_fastq_record(n1, s1, q1))
-        out2.append(_fastq_record(n2, s2, q2))
+        if route:
+            out1[key] = out1.get(key, b"") + _fastq_record(n1, s1, q1)
+            out2[key] = out2.get(key, b"") + _fastq_record(n2, s2, q2)
+        else:
+            out1.append(_fastq_record(n1, s1, q1))
+            out2.append(_fastq_record(n2, s2, q2))
+    if route:
+        return out1, out2, c1, c2
     return b"".join(out1), b"".join(out2), c1, c2
+
+
+def _best_adapter_pairs(data1, data2, pair_specs, options1, options2):
+    """PairedAdapterCutter._find_best_match_pair (modifiers.py:480-503) for every pair of reads: match records
+    (n, 1, slots) for R1 and R2, `adapter` = number of the chosen adapter pair, -1 where no pair matches both mates."""
+    seqs = []
+    for data, o in ((data1, options1), (data2, options2)):
+        records = _apply_cuts(parse_fastq(data), o.get("cut", ()))
+        records, _ = _quality_trimmed(records, o.get("quality_trim", False), o.get("cutoff_front", 0), o.get("cutoff_back", 0),
+                                      o.get("quality_base", 33), o.get("nextseq_cutoff"))
+        seqs.append([r[1] for r in records])
+    if len(seqs[0]) != len(seqs[1]):
+        raise FastqFormatError("paired FASTQ chunks differ in their number of records")
+    n = len(seqs[0])
+    per_pair = []
+    for (a1, g1), (a2, g2) in pair_specs:
+        m1, _ = oracle_process(a1, g1, seqs[0], None, False, 0, 0, 33, 1, None)
+        m2, _ = oracle_process(a2, g2, seqs[1], None, False, 0, 0, 33, 1, None)
+        per_pair.append((m1, m2))
+    slots = max(max(m1.shape[2], m2.shape[2]) for m1, m2 in per_pair)
+    best1 = np.zeros((n, 1, slots), dtype=per_pair[0][0].dtype)
+    best2 = np.zeros((n, 1, slots), dtype=per_pair[0][0].dtype)
+    best1["adapter"] = -1
+    best2["adapter"] = -1
+    for i in range(n):
+        best = None
+        for k, (m1, m2) in enumerate(per_pair):
+            h1 = m1[i, 0][m1[i, 0]["adapter"] >= 0]
+            h2 = m2[i, 0][m2[i, 0]["adapter"] >= 0]
+            if not len(h1) or not len(h2):
+                continue
+            key = (int(h1["score"].sum() + h2["score"].sum()), int(h1["errors"].sum() + h2["errors"].sum()))
+            if best is None or key[0] > best[0] or (key[0] == best[0] and key[1] < best[1]):
+                best = (key[0], key[1], k)
+        if best is not None:
+            for src, dst in ((per_pair[best[2]][0], best1), (per_pair[best[2]][1], best2)):
+                row = src[i, 0].copy()
+                row["adapter"] = np.where(row["adapter"] >= 0, best[2], -1)
+                dst[i, 0, :len(row)] = row
+    return best1, best2

@@ -340,3 +340,138 @@ def test_demultiplex_reference_golden_and_barcodes():
             a = int(m["adapter"][i, 0, 0])
             assert name == (f"bc{a}" if a >= 0 else "unknown"), i
 
+
+
+# ---- --pair-adapters and paired demultiplexing on the device --------------------------------------------
+
+def _single_spec(adapter):
+    import cutadapt_b200.adapters as PA
+
+    spec = spec_of(PA.MultipleAdapters([adapter]))
+    return spec.adapters, spec.groups
+
+
+def test_pair_adapters_reference_golden_on_the_device():
+    """--pair-adapters -a GTCTCCAGCT -A GACAAATAAC (reference test_paired.py:668-676) through
+    cg_fastq_collect_pair_adapters."""
+    import cutadapt_b200.adapters as PA
+    from util import fastq_file
+
+    t = PairedFastqTrimmer([PA.BackAdapter("GTCTCCAGCT", name="a")], [PA.BackAdapter("GACAAATAAC", name="b")],
+                           pair_adapters=True)
+    got = t.process_chunk(fastq_file("pair_adapters.in1.fastq"), fastq_file("pair_adapters.in2.fastq"))
+    assert got == (fastq_file("pair_adapters.out1.fastq"), fastq_file("pair_adapters.out2.fastq"))
+    with pytest.raises(ValueError):
+        PairedFastqTrimmer([PA.BackAdapter("GTCTCCAGCT")], [], pair_adapters=True)
+
+
+@pytest.mark.parametrize("variant", ["trim", "mask_quality", "retain_linked"])
+def test_pair_adapters_random_chunks_against_oracle(variant):
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(91)
+    firsts = ["AGATCGGAAGAGC", "CTGTCTCTTATACAC", "TGGAATTCTCGGGTGCC"]
+    seconds = ["AGATCGGAAGAGC", "GACAAATAACGGT", "CACGTCTGAACTC"]
+    n = 4000
+    recs1, recs2 = [], []
+    for i in range(n):
+        def read(adapter):
+            ln = rng.choice((40, 90, 150))
+            seq = "".join(rng.choice("ACGT") for _ in range(ln))
+            if adapter is not None:
+                cut = rng.randrange(5, ln - 3)
+                ad = "".join(c if rng.random() > 0.04 else rng.choice("ACGT") for c in adapter)
+                seq = (seq[:cut] + ad + seq)[:ln]
+            qual = "".join(chr(33 + min(41, max(2, int(rng.gauss(34 - 25 * (j / ln) ** 2, 6))))) for j in range(ln))
+            return seq, qual
+        k = rng.randrange(len(firsts))
+        r = rng.random()
+        # both mates carry pair k / different pairs / only one mate / none
+        a1 = firsts[k] if r < 0.8 else None
+        a2 = seconds[k] if r < 0.5 else (seconds[(k + 1) % 3] if r < 0.65 else (None if r < 0.9 else seconds[k]))
+        (s1, q1), (s2, q2) = read(a1), read(a2)
+        recs1.append(f"@p{i}/1\n{s1}\n+\n{q1}\n")
+        recs2.append(f"@p{i}/2\n{s2}\n+\n{q2}\n")
+    data1, data2 = "".join(recs1).encode(), "".join(recs2).encode()
+    if variant == "retain_linked":
+        ads1 = [PA.LinkedAdapter(PA.PrefixAdapter("ACGTAC", name="f"), PA.BackAdapter(firsts[0], name="b"), False, True, "l0"),
+                PA.BackAdapter(firsts[1], name="a1"), PA.BackAdapter(firsts[2], name="a2")]
+        o1 = dict(action="retain", minimum_length=5)
+        o2 = dict(action="retain", minimum_length=5)
+    else:
+        ads1 = [PA.BackAdapter(s, name=f"a{i}") for i, s in enumerate(firsts)]
+        o1 = dict(minimum_length=20, discard_untrimmed=True) if variant == "trim" else \
+            dict(action="mask", quality_cutoff=(0, 20), cut=[1])
+        o2 = dict(minimum_length=20, discard_untrimmed=True) if variant == "trim" else \
+            dict(action="mask", quality_cutoff=(5, 15), nextseq_cutoff=None)
+    ads2 = [PA.BackAdapter(s, name=f"b{i}") for i, s in enumerate(seconds)]
+    t = PairedFastqTrimmer(ads1, ads2, o1, o2, "any", pair_adapters=True)
+    got = t.process_chunk(data1, data2)
+
+    def okw(o):
+        o = dict(o)
+        if "quality_cutoff" in o:
+            c = o.pop("quality_cutoff")
+            o.update(quality_trim=True, cutoff_front=c[0], cutoff_back=c[1])
+        return o
+    e1, e2, c1, c2 = oracle.oracle_fastq_trim_paired(
+        data1, data2, options1=okw(o1), options2=okw(o2), pair_filter="any",
+        pair_specs=[(_single_spec(a), _single_spec(b)) for a, b in zip(ads1, ads2)])
+    assert got == (e1, e2)
+    for st, cc in zip(t.statistics, (c1, c2)):
+        for k, v in cc.items():
+            assert st[k] == v, k
+    assert 0 < t.statistics[0]["with_adapters"] < n
+
+
+@pytest.mark.parametrize("combinatorial", [False, True])
+@pytest.mark.parametrize("discard_untrimmed", [False, True])
+def test_paired_demultiplexing_against_oracle(combinatorial, discard_untrimmed):
+    """PairedDemultiplexer / CombinatorialDemultiplexer (steps.py:422-581): both mates partitioned by the adapter of the
+    most recent match of R1 (or of both mates) on the device, every output in input order."""
+    import cutadapt_b200.adapters as PA
+
+    rng = random.Random(17 + combinatorial)
+    bc1 = ["ACGTACGTAC", "TTGCAAGGTC", "GGATCCTTAA", "CATGCATGGA"]
+    bc2 = ["TCAGTCAGTC", "AACCGGTTAC", "GTGTGACACA"]
+    n = 7000
+    recs1, recs2 = [], []
+    for i in range(n):
+        def read(barcodes):
+            seq = "".join(rng.choice("ACGT") for _ in range(rng.choice((30, 60, 100))))
+            if rng.random() < 0.85:
+                b = rng.choice(barcodes)
+                if rng.random() < 0.2:
+                    j = rng.randrange(len(b))
+                    b = b[:j] + rng.choice("ACGT") + b[j + 1:]
+                seq = b + seq
+            return seq
+        s1, s2 = read(bc1), read(bc2)
+        recs1.append(f"@p{i}/1\n{s1}\n+\n{'I' * len(s1)}\n")
+        recs2.append(f"@p{i}/2\n{s2}\n+\n{'F' * len(s2)}\n")
+    data1, data2 = "".join(recs1).encode(), "".join(recs2).encode()
+    ads1 = [PA.PrefixAdapter(b, max_errors=1, name=f"x{i}", indels=False) for i, b in enumerate(bc1)]
+    ads2 = [PA.PrefixAdapter(b, max_errors=1, name=f"y{i}", indels=False) for i, b in enumerate(bc2)]
+    o = dict(minimum_length=35)
+    t = PairedFastqTrimmer(ads1, ads2, o, o, "any")
+    got = t.process_chunk_demux(data1, data2, combinatorial=combinatorial, discard_untrimmed=discard_untrimmed)
+    names1, names2 = [a.name for a in ads1], [a.name for a in ads2]
+
+    def route(last1, last2):
+        k1 = names1[last1] if last1 >= 0 else None
+        k2 = names2[last2] if last2 >= 0 else None
+        if combinatorial:
+            return None if discard_untrimmed and (k1 is None or k2 is None) else (k1, k2)
+        if k1 is None:
+            return None if discard_untrimmed else "unknown"
+        return k1
+    s1 = spec_of(PA.MultipleAdapters(ads1))
+    s2 = spec_of(PA.MultipleAdapters(ads2))
+    e1, e2, c1, c2 = oracle.oracle_fastq_trim_paired(data1, data2, s1.adapters, s1.groups, s2.adapters, s2.groups, o, o, "any",
+                                                     route=route)
+    assert set(e1) <= set(got)
+    for key, (g1, g2) in got.items():
+        assert g1 == e1.get(key, b"") and g2 == e2.get(key, b""), key
+    for st, cc in zip(t.statistics, (c1, c2)):
+        for k, v in cc.items():
+            assert st[k] == v, k
