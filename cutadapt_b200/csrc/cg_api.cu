@@ -112,8 +112,10 @@ struct FastqSlot {
     DevBuf<uint8_t> d_in, d_out, d_seq, d_qual;
     DevBuf<uint32_t> d_tiles, d_nl;
     DevBuf<CgFastqRecord> d_rec;
-    DevBuf<int32_t> d_len, d_interval, d_keep, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes, d_dest, d_pairkey;
-    DevBuf<uint8_t> d_destkeep;
+    DevBuf<int32_t> d_len, d_interval, d_keep, d_outlen, d_qtrim, d_mask, d_adest, d_dmbytes, d_dest, d_pairkey, d_origin;
+    DevBuf<uint8_t> d_destkeep, d_names, d_infoout;
+    DevBuf<int32_t> d_nameoff, d_inforow;
+    DevBuf<int64_t> d_infooff;
     DevBuf<int64_t> d_dmbase;
     DevBuf<int64_t> d_offs, d_outoff;
     DevBuf<unsigned long long> d_scan;
@@ -271,7 +273,8 @@ extern "C" int cg_ctx_destroy(cg_ctx *c)
         f.d_rec.release(); f.d_len.release(); f.d_mask.release(); f.d_adest.release(); f.d_dmbytes.release();
         f.d_dmbase.release(); f.d_keep.release(); f.d_interval.release(); f.d_outlen.release(); f.d_qtrim.release();
         f.d_offs.release(); f.d_outoff.release(); f.d_scan.release(); f.d_matches.release(); f.d_matches_rc.release();
-        f.d_isrc.release(); f.d_dest.release(); f.d_pairkey.release(); f.d_destkeep.release();
+        f.d_isrc.release(); f.d_dest.release(); f.d_pairkey.release(); f.d_destkeep.release(); f.d_origin.release();
+        f.d_names.release(); f.d_infoout.release(); f.d_nameoff.release(); f.d_inforow.release(); f.d_infooff.release();
         f.h_in.release(); f.h_out.release(); f.h_counters.release();
         if (f.d_counters) cudaFree(f.d_counters);
         if (f.d_err) cudaFree(f.d_err);
@@ -1549,6 +1552,7 @@ static int fastq_stage_records(cg_ctx *c, FastqSlot &f, const cg_fastq_params *f
     if ((rc = f.d_nl.ensure((size_t)g.n_nl + 1)) != CG_OK) return rc;
     if ((rc = f.d_rec.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_len.ensure((size_t)n)) != CG_OK) return rc;
+    if ((rc = f.d_origin.ensure((size_t)n * 2)) != CG_OK) return rc;
     if ((rc = f.d_interval.ensure((size_t)n * 2)) != CG_OK) return rc;
     if ((rc = f.d_mask.ensure((size_t)n)) != CG_OK) return rc;
     if ((rc = f.d_keep.ensure((size_t)n * 2)) != CG_OK) return rc;
@@ -1558,7 +1562,7 @@ static int fastq_stage_records(cg_ctx *c, FastqSlot &f, const cg_fastq_params *f
     if (g.want_q && (rc = f.d_qtrim.ensure((size_t)n * 2)) != CG_OK) return rc;
     CU(cg_launch_fastq_index(f.d_in.p, n_bytes, f.d_tiles.p, nullptr, f.d_nl.p, 1, st));
     CU(cg_launch_fastq_records(f.d_in.p, n_bytes, f.d_nl.p, g.n_nl, n, fp->cut_front, fp->cut_back, f.d_rec.p, f.d_len.p,
-                               f.d_counters + 1, f.d_err, st));
+                               f.d_origin.p, f.d_counters + 1, f.d_err, st));
     c->launches += 2;
     g.d_qtrim = g.want_q ? f.d_qtrim.p : nullptr;
     return CG_OK;
@@ -1580,7 +1584,7 @@ static int fastq_stage_fold_qtrim(cg_ctx *c, FastqSlot &f, const cg_params *p, c
     if (!g.want_q) return CG_OK;
     int rc = fastq_stage_pretrim(c, f, p, st, g);
     if (rc != CG_OK) return rc;
-    CU(cg_launch_fastq_fold_qtrim(f.d_rec.p, f.d_len.p, g.d_qtrim, g.n, f.d_counters + 1, st));
+    CU(cg_launch_fastq_fold_qtrim(f.d_rec.p, f.d_len.p, g.d_qtrim, g.n, f.d_origin.p, f.d_counters + 1, st));
     c->launches += 1;
     g.d_qtrim = nullptr;
     g.want_q = false;
@@ -1662,7 +1666,7 @@ static int fastq_stage_evaluate(cg_ctx *c, FastqSlot &f, const cg_adapterset *s,
         if ((rc = fastq_stage_pack(c, f, st, g, true)) != CG_OK) return rc;
         rc = launch_trim(c, s, f.d_seq.p, nullptr, f.d_offs.p, n, g.max_len, &pt, f.d_matches_rc.p, nullptr, st, true);
         if (rc != CG_OK) return rc;
-        CU(cg_launch_fastq_revcomp_commit(f.d_in.p, f.d_rec.p, f.d_len.p, n, f.d_matches.p, f.d_matches_rc.p, (int)per_read,
+        CU(cg_launch_fastq_revcomp_commit(f.d_in.p, f.d_rec.p, f.d_len.p, f.d_origin.p, n, f.d_matches.p, f.d_matches_rc.p, (int)per_read,
                                           f.d_isrc.p, f.d_counters + 1, st));
         c->launches += 1;
         g.d_matches = f.d_matches.p;
@@ -1781,8 +1785,56 @@ static int fastq_stage_output(cg_ctx *c, FastqSlot &f, const FqStage &g, cudaStr
     return CG_OK;
 }
 
+// --info-file rows of a chunk, an extra output of a collect
+struct FqInfo {
+    const char *names = nullptr;          // host: adapter names back to back ...
+    const int32_t *name_off = nullptr;    // ... and n_adapters + 1 offsets
+    int n_adapters = 0;
+    uint8_t *out = nullptr;               // host
+    int64_t capacity = 0;
+    int64_t *bytes = nullptr;             // host out
+};
+
+static int fastq_stage_info(cg_ctx *c, FastqSlot &f, const FqStage &g, const cg_fastq_params *fp, const FqInfo &info,
+                            cudaStream_t st)
+{
+    const long long n = g.n;
+    int rc;
+    const size_t name_bytes = (size_t)info.name_off[info.n_adapters];
+    if ((rc = f.d_names.ensure(name_bytes + 1)) != CG_OK) return rc;
+    if ((rc = f.d_nameoff.ensure((size_t)info.n_adapters + 1)) != CG_OK) return rc;
+    if ((rc = f.d_inforow.ensure((size_t)n)) != CG_OK) return rc;
+    if ((rc = f.d_infooff.ensure((size_t)n + 1)) != CG_OK) return rc;
+    if ((rc = f.d_scan.ensure((size_t)cg_scan_tiles(n) + 1)) != CG_OK) return rc;
+    if (name_bytes) CU(cudaMemcpyAsync(f.d_names.p, info.names, name_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(f.d_nameoff.p, info.name_off, ((size_t)info.n_adapters + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const int upper = g.action == CG_FQ_ACTION_LOWERCASE;
+    CU(cg_launch_fastq_info(0, f.d_in.p, f.d_rec.p, f.d_origin.p, f.d_interval.p, f.d_mask.p, g.d_matches, g.times, g.slots,
+                            f.d_names.p, f.d_nameoff.p, fp->revcomp != 0, g.rc_suffix, upper, n, f.d_inforow.p, nullptr, nullptr,
+                            st));
+    CU(cg_launch_scan_i32(f.d_inforow.p, n, f.d_scan.p, f.d_infooff.p, st));
+    long long total = 0;
+    CU(cudaMemcpyAsync(&total, f.d_infooff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->launches += 4;
+    *info.bytes = total;
+    if (total > info.capacity)
+        return fail(CG_EINVAL, "cg_fastq_collect_info: info buffer too small (" + std::to_string(total) + " bytes needed)");
+    if (total == 0) return CG_OK;
+    if ((rc = f.d_infoout.ensure((size_t)total + 64)) != CG_OK) return rc;
+    CU(cg_launch_fastq_info(1, f.d_in.p, f.d_rec.p, f.d_origin.p, f.d_interval.p, f.d_mask.p, g.d_matches, g.times, g.slots,
+                            f.d_names.p, f.d_nameoff.p, fp->revcomp != 0, g.rc_suffix, upper, n, nullptr, f.d_infooff.p,
+                            f.d_infoout.p, st));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(info.out, f.d_infoout.p, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->d2h_bytes += total;
+    return CG_OK;
+}
+
 static int fastq_collect_impl(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
-                              uint8_t *out, int64_t out_capacity, cg_fastq_result *res, FqDemux *dm, int64_t *segments)
+                              uint8_t *out, int64_t out_capacity, cg_fastq_result *res, FqDemux *dm, int64_t *segments,
+                              const FqInfo *info = nullptr)
 {
     if (!c || !fp || !res || slot < 0 || slot >= CG_FQ_SLOTS) return fail(CG_EINVAL, "cg_fastq_collect: bad argument");
     if (s && s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
@@ -1794,6 +1846,7 @@ static int fastq_collect_impl(cg_ctx *c, int32_t slot, const cg_adapterset *s, c
     FqStage g;
     int rc = fastq_stage_evaluate(c, f, s, fp, 1, f.stream, g);
     if (rc != CG_OK || g.n == 0) return rc;
+    if (info && (rc = fastq_stage_info(c, f, g, fp, *info, f.stream)) != CG_OK) return rc;
     if (dm && (rc = fastq_stage_route(c, f, nullptr, g.n, *dm, f.stream)) != CG_OK) return rc;
     CU(cg_launch_fastq_finish(g.n, f.d_rec.p, f.d_interval.p, f.d_mask.p, fastq_enabled_filters(fp), f.d_outlen.p,
                               f.d_counters + 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 0, g.rc_suffix,
@@ -1807,6 +1860,23 @@ extern "C" int cg_fastq_collect(cg_ctx *c, int32_t slot, const cg_adapterset *s,
                                 uint8_t *out, int64_t out_capacity, cg_fastq_result *res)
 {
     return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr, nullptr);
+}
+
+extern "C" int cg_fastq_collect_info(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                                     const char *adapter_names, const int32_t *name_offsets, uint8_t *out,
+                                     int64_t out_capacity, uint8_t *info_out, int64_t info_capacity, cg_fastq_result *res,
+                                     int64_t *info_bytes)
+{
+    if (!s || !adapter_names || !name_offsets || !info_bytes || info_capacity < 0 || (info_capacity && !info_out))
+        return fail(CG_EINVAL, "cg_fastq_collect_info: bad argument");
+    *info_bytes = 0;
+    FqInfo info;
+    info.names = adapter_names; info.name_off = name_offsets; info.n_adapters = s->host.n_adapters;
+    info.out = info_out; info.capacity = info_capacity; info.bytes = info_bytes;
+    for (int a = 0; a < info.n_adapters; ++a)
+        if (name_offsets[a] < 0 || name_offsets[a + 1] < name_offsets[a])
+            return fail(CG_EINVAL, "cg_fastq_collect_info: name_offsets must not decrease");
+    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr, nullptr, &info);
 }
 
 static int demux_check(const cg_adapterset *s, const int32_t *adapter_dest, int32_t n_named, const char *who)

@@ -127,14 +127,16 @@ __global__ void __launch_bounds__(FQ_THREADS) fq_index_kernel(const uint8_t *buf
 // record r = lines 4r .. 4r+3: fq_record_core (cg_fastq_core.cuh) builds the table entry and checks the format
 __global__ void fq_records_kernel(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl,
                                   long long n_records, int cut_front, int cut_back, CgFastqRecord *rec,
-                                  int32_t *seq_len, unsigned long long *counters, int *err)
+                                  int32_t *seq_len, int32_t *origin, unsigned long long *counters, int *err)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bp = 0;
     if (r < n_records) {
         CgFastqRecord o;
-        int len, full;
-        const int bad = fq_record_core(buf, n, nl_pos, n_nl, r, cut_front, cut_back, &o, &len, &full);
+        int len, full, cf;
+        const int bad = fq_record_core(buf, n, nl_pos, n_nl, r, cut_front, cut_back, &o, &len, &full, &cf);
+        // where the record lies in the read as it came: (bases in front of it, length of the whole read)
+        if (origin) { origin[2 * r] = cf; origin[2 * r + 1] = full; }
         if (bad) {
             // report the first bad record: err[0] = code, err[1] = record number (smallest; initialised to INT_MAX)
             atomicMin((unsigned int *)&err[1], (unsigned int)r);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(256) fq_gather_kernel(const uint8_t *buf, cons
 // trimmers then see the read they see in the reference (used where a later step needs the trimmed read as an
 // object of its own: --revcomp, --pair-adapters).  counters[6] += bases removed.
 __global__ void fq_fold_qtrim_kernel(CgFastqRecord *rec, int32_t *seq_len, const int32_t *qtrim, long long n_records,
-                                     unsigned long long *counters)
+                                     int32_t *origin, unsigned long long *counters)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long removed = 0;
@@ -273,6 +275,7 @@ __global__ void fq_fold_qtrim_kernel(CgFastqRecord *rec, int32_t *seq_len, const
         rec[r].seq_start += (uint32_t)qs;
         rec[r].qual_start += (uint32_t)qs;
         seq_len[r] = qe - qs;
+        if (origin) origin[2 * r] += qs;
         removed = (unsigned long long)(n - (qe - qs));
     }
     for (int d = 16; d; d >>= 1) removed += __shfl_down_sync(0xFFFFFFFFu, removed, d);
@@ -281,11 +284,14 @@ __global__ void fq_fold_qtrim_kernel(CgFastqRecord *rec, int32_t *seq_len, const
 
 // ReverseComplementer.__call__ (modifiers.py:278-308), one warp per record: the reverse complement replaces the
 // read iff the scores of its matches add up to MORE than those of the forward read (a linked match counts with
-// both parts).  The replacement happens IN the chunk (sequence reverse-complemented, qualities reversed, in
-// place), the reverse matches become the record's matches, is_rc[r] = 1: every later kernel works on the
-// chosen orientation without knowing about it (the writer appends the name suffix).  counters[11] += replaced.
-__global__ void __launch_bounds__(256) fq_revcomp_commit_kernel(uint8_t *buf, const CgFastqRecord *rec, const int32_t *seq_len,
-                                                                 long long n_records, cg_match_rec *matches,
+// both parts).  The replacement happens IN the chunk: the WHOLE read as it came is reverse-complemented in place
+// (qualities reversed), so that the part the modifiers in front of the cutter left -- the record -- is the reverse
+// complement of what it was and the rest still surrounds it (info.original_read.reverse_complement() of the info
+// file, steps.py:233-235); the record table follows, the reverse matches become the record's matches,
+// is_rc[r] = 1.  Every later kernel works on the chosen orientation without knowing about it (the writer appends
+// the name suffix).  counters[11] += replaced.
+__global__ void __launch_bounds__(256) fq_revcomp_commit_kernel(uint8_t *buf, CgFastqRecord *rec, const int32_t *seq_len,
+                                                                 int32_t *origin, long long n_records, cg_match_rec *matches,
                                                                  const cg_match_rec *matches_rc, int per_read,
                                                                  uint8_t *is_rc, unsigned long long *counters)
 {
@@ -308,13 +314,22 @@ __global__ void __launch_bounds__(256) fq_revcomp_commit_kernel(uint8_t *buf, co
         if (!use) continue;
         replaced += lane == 0;
         const CgFastqRecord m = rec[r];
-        const int len = seq_len[r];
-        uint8_t *sq = buf + m.seq_start, *ql = buf + m.qual_start;
-        for (int j = lane; 2 * j < len; j += 32) {       // pair (j, len-1-j); the middle of an odd length meets itself
-            const int k = len - 1 - j;
+        const int front = origin[2 * r], full = origin[2 * r + 1];
+        uint8_t *sq = buf + m.seq_start - front, *ql = buf + m.qual_start - front;
+        for (int j = lane; 2 * j < full; j += 32) {      // pair (j, full-1-j); the middle of an odd length meets itself
+            const int k = full - 1 - j;
             const uint8_t a = sq[j], b = sq[k], qa = ql[j], qb = ql[k];
             sq[j] = fq_complement(b); sq[k] = fq_complement(a);
             ql[j] = qb; ql[k] = qa;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int new_front = full - front - seq_len[r];
+            CgFastqRecord o = m;
+            o.seq_start = m.seq_start - (uint32_t)front + (uint32_t)new_front;
+            o.qual_start = m.qual_start - (uint32_t)front + (uint32_t)new_front;
+            rec[r] = o;
+            origin[2 * r] = new_front;
         }
         const int words = per_read * (int)(sizeof(cg_match_rec) / sizeof(int32_t));
         int32_t *dst = (int32_t *)(matches + (size_t)r * per_read);
@@ -464,6 +479,155 @@ __global__ void __launch_bounds__(256) fq_write_kernel(const uint8_t *buf, const
     }
 }
 
+// ---- --info-file rows (InfoFileWriter.__call__, steps.py:222-253; SingleMatch.get_info_records, adapters.py:395-417;
+// LinkedMatch.get_info_records, adapters.py:1157-1171) --------------------------------------------------------------
+// Per match: name, errors, rstart, rstop, before, match, after, adapter name, three quality parts, rc flag; the
+// coordinates of every round are applied to info.original_read -- the read AS IT CAME (before -u and the quality
+// trimmers; reverse-complemented if the reverse complement was chosen) -- from its first base, and the read is then
+// cut the way the match cuts it.  Reads without a match: name, -1, sequence and qualities of the read as written.
+// The same walk runs twice: with a counting sink (row bytes per record) and, after a scan, with a writing sink.
+struct InfoCountSink {
+    long long n = 0;
+    __device__ void bytes(const uint8_t *, int len, bool = false) { n += len; }
+    __device__ void ch(uint8_t) { n += 1; }
+    __device__ void number(int v)
+    {
+        unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+        int d = 1;
+        while (u >= 10u) { u /= 10u; ++d; }
+        n += d + (v < 0 ? 1 : 0);
+    }
+};
+struct InfoWriteSink {                  // all 32 lanes of a warp walk together
+    uint8_t *p;
+    int lane;
+    __device__ void bytes(const uint8_t *src, int len, bool upper = false)
+    {
+        for (int j = lane; j < len; j += 32) {
+            uint8_t c = src[j];
+            if (upper && (uint8_t)(c - 'a') < 26) c = (uint8_t)(c & ~0x20);
+            p[j] = c;
+        }
+        p += len;
+    }
+    __device__ void ch(uint8_t c) { if (lane == 0) *p = c; ++p; }
+    __device__ void number(int v)
+    {
+        unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+        int d = 1;
+        for (unsigned t = u; t >= 10u; t /= 10u) ++d;
+        const int total = d + (v < 0 ? 1 : 0);
+        if (lane == 0) {
+            if (v < 0) p[0] = '-';
+            for (int k = total - 1; k >= (v < 0 ? 1 : 0); --k) { p[k] = (uint8_t)('0' + u % 10u); u /= 10u; }
+        }
+        p += total;
+    }
+};
+
+// Python's seq[a:b] for a sequence of length len: (start, count)
+__device__ __forceinline__ void py_slice(int a, int b, int len, int *start, int *count)
+{
+    if (a < 0) { a += len; if (a < 0) a = 0; } else if (a > len) a = len;
+    if (b < 0) { b += len; if (b < 0) b = 0; } else if (b > len) b = len;
+    *start = a;
+    *count = b > a ? b - a : 0;
+}
+
+struct InfoArgs {
+    const uint8_t *buf;
+    const CgFastqRecord *rec;
+    const int32_t *origin;       // (bases of the read in front of the record, length of the whole read)
+    const int32_t *interval;     // the read as written, relative to the record
+    const int32_t *mask;
+    const cg_match_rec *matches;
+    int times, slots;
+    const uint8_t *names;        // adapter names, back to back
+    const int32_t *name_off;     // n_adapters + 1 offsets into names
+    int revcomp;                 // 0: no rc column content; else "1" / "0"
+    int rc_suffix;
+    int upper_unmatched;         // --action=lowercase writes reads without a match in upper case (modifiers.py:222-223)
+};
+
+template <class Sink>
+__device__ void info_rows(const InfoArgs &a, long long r, Sink &out)
+{
+    const CgFastqRecord m = a.rec[r];
+    const int front = a.origin[2 * r], full = a.origin[2 * r + 1];
+    const uint8_t *sq = a.buf + m.seq_start - front, *ql = a.buf + m.qual_start - front;
+    const bool is_rc = (a.mask[r] & CG_FQ_MASK_RC) != 0;
+    auto name = [&]() {
+        out.bytes(a.buf + m.hdr_start, m.hdr_len);
+        if (is_rc && a.rc_suffix) { out.ch(' '); out.ch('r'); out.ch('c'); }
+    };
+    int ws = 0, we = full;                              // current_read = original_read[ws:we]
+    bool any = false;
+    if (a.matches) {
+        const cg_match_rec *mr = a.matches + (size_t)r * a.times * a.slots;
+        for (int t = 0; t < a.times; ++t) {
+            bool round_hit = false;
+            for (int k = 0; k < a.slots; ++k) round_hit |= mr[t * a.slots + k].adapter >= 0;
+            if (!round_hit) break;
+            any = true;
+            for (int k = 0; k < a.slots; ++k) {
+                const cg_match_rec h = mr[t * a.slots + k];
+                if (h.adapter < 0) continue;
+                const int cur = we - ws;
+                int s0, c0, s1, c1, s2, c2;
+                py_slice(0, h.rstart, cur, &s0, &c0);
+                py_slice(h.rstart, h.rstop, cur, &s1, &c1);
+                py_slice(h.rstop, cur, cur, &s2, &c2);
+                name();
+                out.ch('\t'); out.number(h.errors);
+                out.ch('\t'); out.number(h.rstart);
+                out.ch('\t'); out.number(h.rstop);
+                out.ch('\t'); out.bytes(sq + ws + s0, c0);
+                out.ch('\t'); out.bytes(sq + ws + s1, c1);
+                out.ch('\t'); out.bytes(sq + ws + s2, c2);
+                out.ch('\t'); out.bytes(a.names + a.name_off[h.adapter], a.name_off[h.adapter + 1] - a.name_off[h.adapter]);
+                out.ch('\t'); out.bytes(ql + ws + s0, c0);
+                out.ch('\t'); out.bytes(ql + ws + s1, c1);
+                out.ch('\t'); out.bytes(ql + ws + s2, c2);
+                out.ch('\t');
+                if (a.revcomp) out.ch(is_rc ? '1' : '0');
+                out.ch('\n');
+                // current_read = match.trimmed(current_read)
+                if (h.info & 256) { int s, c; py_slice(0, h.rstart, cur, &s, &c); we = ws + c; }
+                else { int s, c; py_slice(h.rstop, cur, cur, &s, &c); ws += s; }
+            }
+        }
+    }
+    if (!any) {
+        const int start = a.interval[2 * r], left = a.interval[2 * r + 1] - start;
+        name();
+        out.ch('\t'); out.ch('-'); out.ch('1');
+        out.ch('\t'); out.bytes(a.buf + m.seq_start + start, left, a.upper_unmatched != 0);
+        out.ch('\t'); out.bytes(a.buf + m.qual_start + start, left);
+        out.ch('\n');
+    }
+}
+
+__global__ void fq_info_count_kernel(InfoArgs a, long long n_records, int32_t *row_bytes)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_records) return;
+    InfoCountSink sink;
+    info_rows(a, r, sink);
+    row_bytes[r] = (int32_t)sink.n;
+}
+
+__global__ void __launch_bounds__(256) fq_info_write_kernel(InfoArgs a, long long n_records, const int64_t *row_off, uint8_t *out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_records; r += warps) {
+        InfoWriteSink sink;
+        sink.p = out + row_off[r];
+        sink.lane = lane;
+        info_rows(a, r, sink);
+    }
+}
+
 // ---- demultiplexing (Demultiplexer.__call__, steps.py:397-409): records go to the output of the adapter of
 // their most recent match, reads without a match to "unknown"; inside every output the input order is kept.
 // A stable partition of the OUTPUT BYTES: per tile of 256 records the bytes per destination, an exclusive scan
@@ -577,12 +741,13 @@ cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint3
 
 cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
                                     long long n_records, int cut_front, int cut_back, CgFastqRecord *d_rec,
-                                    int32_t *d_seq_len, unsigned long long *d_counters, int *d_err, cudaStream_t st)
+                                    int32_t *d_seq_len, int32_t *d_origin, unsigned long long *d_counters, int *d_err,
+                                    cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     fq_records_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_buf, n_bytes, d_nl_pos, n_newlines, n_records,
-                                                                          cut_front, cut_back, d_rec, d_seq_len, d_counters,
-                                                                          d_err);
+                                                                          cut_front, cut_back, d_rec, d_seq_len, d_origin,
+                                                                          d_counters, d_err);
     return cudaGetLastError();
 }
 
@@ -610,22 +775,23 @@ cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_
 }
 
 cudaError_t cg_launch_fastq_fold_qtrim(CgFastqRecord *d_rec, int32_t *d_seq_len, const int32_t *d_qtrim, long long n_records,
-                                       unsigned long long *d_counters, cudaStream_t st)
+                                       int32_t *d_origin, unsigned long long *d_counters, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
-    fq_fold_qtrim_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_rec, d_seq_len, d_qtrim, n_records, d_counters);
+    fq_fold_qtrim_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(d_rec, d_seq_len, d_qtrim, n_records, d_origin,
+                                                                             d_counters);
     return cudaGetLastError();
 }
 
-cudaError_t cg_launch_fastq_revcomp_commit(uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+cudaError_t cg_launch_fastq_revcomp_commit(uint8_t *d_buf, CgFastqRecord *d_rec, const int32_t *d_seq_len, int32_t *d_origin,
                                            long long n_records, cg_match_rec *d_matches, const cg_match_rec *d_matches_rc,
                                            int per_read, uint8_t *d_is_rc, unsigned long long *d_counters, cudaStream_t st)
 {
     if (n_records <= 0) return cudaSuccess;
     long long grid = (n_records + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
-    fq_revcomp_commit_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_seq_len, n_records, d_matches, d_matches_rc,
-                                                             per_read, d_is_rc, d_counters);
+    fq_revcomp_commit_kernel<<<(unsigned)grid, 256, 0, st>>>(d_buf, d_rec, d_seq_len, d_origin, n_records, d_matches,
+                                                             d_matches_rc, per_read, d_is_rc, d_counters);
     return cudaGetLastError();
 }
 
@@ -713,5 +879,26 @@ cudaError_t cg_launch_fastq_pair_select(long long n_records, int pair, const cg_
     if (n_records <= 0) return cudaSuccess;
     fq_pair_select_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, st>>>(n_records, pair, d_cur1, slots1, d_cur2, slots2,
                                                                               d_best1, d_best2, slots, d_best_key);
+    return cudaGetLastError();
+}
+
+cudaError_t cg_launch_fastq_info(int phase, const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_origin,
+                                 const int32_t *d_interval, const int32_t *d_mask, const cg_match_rec *d_matches, int times,
+                                 int slots, const uint8_t *d_names, const int32_t *d_name_off, int revcomp, int rc_suffix,
+                                 int upper_unmatched, long long n_records, int32_t *d_row_bytes, const int64_t *d_row_off,
+                                 uint8_t *d_out, cudaStream_t st)
+{
+    if (n_records <= 0) return cudaSuccess;
+    InfoArgs a;
+    a.buf = d_buf; a.rec = d_rec; a.origin = d_origin; a.interval = d_interval; a.mask = d_mask; a.matches = d_matches;
+    a.times = times; a.slots = slots; a.names = d_names; a.name_off = d_name_off; a.revcomp = revcomp;
+    a.rc_suffix = rc_suffix; a.upper_unmatched = upper_unmatched;
+    if (phase == 0) {
+        fq_info_count_kernel<<<(unsigned)((n_records + 127) / 128), 128, 0, st>>>(a, n_records, d_row_bytes);
+    } else {
+        long long grid = (n_records + 7) / 8;
+        if (grid > 148 * 16) grid = 148 * 16;
+        fq_info_write_kernel<<<(unsigned)grid, 256, 0, st>>>(a, n_records, d_row_off, d_out);
+    }
     return cudaGetLastError();
 }

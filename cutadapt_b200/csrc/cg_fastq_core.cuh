@@ -67,7 +67,8 @@ CG_HD void fq_line_span(const uint8_t *buf, const uint32_t *nl_pos, long long n_
 // table simply describes the read without those bases (read[cut_front:] then read[:-cut_back]).
 // *full_len: the length before -u (what the pipeline counts as "bp processed", pipeline.py:58-64, 142-143).
 CG_HD int fq_record_core(const uint8_t *buf, long long n, const uint32_t *nl_pos, long long n_nl, long long r,
-                         int cut_front, int cut_back, CgFastqRecord *rec, int *seq_len, int *full_len = nullptr)
+                         int cut_front, int cut_back, CgFastqRecord *rec, int *seq_len, int *full_len = nullptr,
+                         int *cut_applied = nullptr)
 {
     uint32_t hs, he, ss, se, ps, pe, qs, qe;
     fq_line_span(buf, nl_pos, n_nl, n, 4 * r, &hs, &he);
@@ -83,6 +84,7 @@ CG_HD int fq_record_core(const uint8_t *buf, long long n, const uint32_t *nl_pos
     const int cf = cut_front < len ? cut_front : len;
     len -= cf;
     len = cut_back < len ? len - cut_back : 0;
+    if (cut_applied) *cut_applied = cf;
     rec->hdr_start = hs + 1;                    // without the '@'
     rec->hdr_len = (int32_t)(he - hs) - 1;
     rec->seq_start = ss + (uint32_t)cf;

@@ -75,7 +75,8 @@ cudaError_t cg_launch_fastq_index(const uint8_t *d_buf, long long n_bytes, uint3
                                   unsigned long long *d_total, uint32_t *d_nl_pos, int phase, cudaStream_t st);
 cudaError_t cg_launch_fastq_records(const uint8_t *d_buf, long long n_bytes, const uint32_t *d_nl_pos, long long n_newlines,
                                     long long n_records, int cut_front, int cut_back, CgFastqRecord *d_rec,
-                                    int32_t *d_seq_len, unsigned long long *d_counters, int *d_err, cudaStream_t st);
+                                    int32_t *d_seq_len, int32_t *d_origin, unsigned long long *d_counters, int *d_err,
+                                    cudaStream_t st);
 // exclusive scan int32 -> int64, n + 1 outputs; d_tile_scratch: cg_scan_tiles(n) words
 cudaError_t cg_launch_scan_i32(const int32_t *d_in, long long n, unsigned long long *d_tile_scratch, int64_t *d_out,
                                cudaStream_t st);
@@ -83,9 +84,9 @@ cudaError_t cg_launch_fastq_gather(const uint8_t *d_buf, const CgFastqRecord *d_
                                    long long n_records, uint8_t *d_seq, uint8_t *d_qual, int rc, cudaStream_t st);
 // the quality-trimmed interval becomes the record (counters[6] += removed bases)
 cudaError_t cg_launch_fastq_fold_qtrim(CgFastqRecord *d_rec, int32_t *d_seq_len, const int32_t *d_qtrim, long long n_records,
-                                       unsigned long long *d_counters, cudaStream_t st);
+                                       int32_t *d_origin, unsigned long long *d_counters, cudaStream_t st);
 // --revcomp: choose the orientation per record, rewrite the chosen reads in place (counters[11] += replaced)
-cudaError_t cg_launch_fastq_revcomp_commit(uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
+cudaError_t cg_launch_fastq_revcomp_commit(uint8_t *d_buf, CgFastqRecord *d_rec, const int32_t *d_seq_len, int32_t *d_origin,
                                            long long n_records, cg_match_rec *d_matches, const cg_match_rec *d_matches_rc,
                                            int per_read, uint8_t *d_is_rc, unsigned long long *d_counters, cudaStream_t st);
 cudaError_t cg_launch_fastq_pretrim(const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_seq_len,
@@ -119,6 +120,12 @@ cudaError_t cg_launch_fastq_dest(const int32_t *d_mask1, const int32_t *d_mask2,
                                  int32_t *d_dest, cudaStream_t st);
 cudaError_t cg_launch_fastq_demux(int phase, const int32_t *d_out_len, const int32_t *d_dest, long long n_records,
                                   int n_dest, int32_t *d_bytes, const int64_t *d_base, int64_t *d_out_off, cudaStream_t st);
+// --info-file rows: phase 0 = bytes of every record's rows, phase 1 (after a scan) = the rows
+cudaError_t cg_launch_fastq_info(int phase, const uint8_t *d_buf, const CgFastqRecord *d_rec, const int32_t *d_origin,
+                                 const int32_t *d_interval, const int32_t *d_mask, const cg_match_rec *d_matches, int times,
+                                 int slots, const uint8_t *d_names, const int32_t *d_name_off, int revcomp, int rc_suffix,
+                                 int upper_unmatched, long long n_records, int32_t *d_row_bytes, const int64_t *d_row_off,
+                                 uint8_t *d_out, cudaStream_t st);
 // --pair-adapters: fold the records of adapter pair `pair` into the best pair per read (modifiers.py:480-503)
 cudaError_t cg_launch_fastq_pair_select(long long n_records, int pair, const cg_match_rec *d_cur1, int slots1,
                                         const cg_match_rec *d_cur2, int slots2, cg_match_rec *d_best1, cg_match_rec *d_best2,

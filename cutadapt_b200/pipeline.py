@@ -736,6 +736,47 @@ class FastqTrimmer:
             self.statistics[k] = self.statistics.get(k, 0) + v
         return {name: out[segments[i]:segments[i + 1]].tobytes() for i, name in enumerate(outputs + [unknown])}
 
+    def _info_names(self):
+        """Adapter names as the info file shows them: the parts of a linked adapter are "name;1" / "name;2"
+        (LinkedMatch.get_info_records, adapters.py:1157-1171)."""
+        singles, groups, owners = self.adapters._flatten()
+        names = [s.name for s in singles]
+        for (typ, a0, a1, _, _), owner in zip(groups, owners):
+            if typ == _lib.CG_GROUP_LINKED:
+                base = "none" if owner.name is None else owner.name
+                names[a0], names[a1] = base + ";1", base + ";2"
+        blobs = [n.encode("latin-1") for n in names]
+        offsets = np.zeros(len(blobs) + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(b) for b in blobs])
+        return b"".join(blobs), offsets
+
+    def process_chunk_info(self, chunk) -> Tuple[bytes, bytes]:
+        """(trimmed FASTQ, the rows ``--info-file`` gets for the chunk), both formatted on the device
+        (``cg_fastq_collect_info``; InfoFileWriter, steps.py:222-253)."""
+        if self.adapters is None:
+            raise ValueError("the info file needs adapters")
+        blob, offsets = self._info_names()
+        per_read = max(1, self.params.trim.times) * 2
+        n_bytes = len(chunk)
+        capacity = per_read * 2 * n_bytes + (1 << 20)
+        while True:
+            slot, _, _ = self._submit(chunk)
+            out = self._out_buffer(slot, n_bytes + 16)
+            info = np.empty(capacity, dtype=np.uint8)
+            res = _lib.cg_fastq_result()
+            info_bytes = C.c_int64(0)
+            rc = _lib.lib().cg_fastq_collect_info(
+                self.ctx.handle, slot, self._set.handle, C.byref(self.params), blob, offsets.ctypes.data, out.ctypes.data,
+                out.size, info.ctypes.data, info.size, C.byref(res), C.byref(info_bytes))
+            if rc != 0 and info_bytes.value > capacity:      # many short reads: rows larger than estimated
+                capacity = info_bytes.value
+                continue
+            _lib.check(rc)
+            break
+        for k, v in res.as_dict().items():
+            self.statistics[k] = self.statistics.get(k, 0) + v
+        return out[: res.out_bytes].tobytes(), info[: info_bytes.value].tobytes()
+
     def process_chunks(self, chunks, copy: bool = True):
         """copy=False yields uint8 array views into per-slot buffers: valid until the next-but-one result."""
         pending = None

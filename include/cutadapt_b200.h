@@ -364,6 +364,17 @@ int cg_fastq_collect_paired(cg_ctx *ctx, int32_t slot1, int32_t slot2, const cg_
                             int32_t pair_filter_mode, uint8_t *out1, int64_t out_capacity1, uint8_t *out2,
                             int64_t out_capacity2, cg_fastq_result *res1, cg_fastq_result *res2);
 
+/* cg_fastq_collect plus the rows --info-file gets for the chunk (InfoFileWriter.__call__, steps.py:222-253;
+ * SingleMatch / LinkedMatch.get_info_records, adapters.py:395-417, 1157-1171), formatted on the device: one row per
+ * match (name, errors, rstart, rstop, the three parts of the read and of its qualities, adapter name, "1" / "0" if
+ * --revcomp is on), coordinates applied to the read as it came; reads without a match: name, -1, the read as written.
+ * Rows of ALL records, filtered or not (the writer sits in front of the filters).  adapter_names: the names of the
+ * set's adapters back to back (the parts of a linked adapter as "name;1" / "name;2"), name_offsets: n_adapters + 1
+ * offsets into it.  *info_bytes: size of the rows; CG_EINVAL if info_capacity is too small. */
+int cg_fastq_collect_info(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, const cg_fastq_params *params,
+                          const char *adapter_names, const int32_t *name_offsets, uint8_t *out, int64_t out_capacity,
+                          uint8_t *info_out, int64_t info_capacity, cg_fastq_result *res, int64_t *info_bytes);
+
 /* --pair-adapters (PairedAdapterCutter, modifiers.py:412-503): adapter i of the -a list is removed from R1 only
  * together with adapter i of the -A list from R2.  sets1[i] / sets2[i] hold adapter i alone (one group each); every
  * pair is matched against both mates on the device and the best pair that matches BOTH mates wins (highest score

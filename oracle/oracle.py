@@ -598,11 +598,15 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                     nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
                     discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
                     trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False, action="trim",
-                    revcomp=False, rc_suffix=True, match_override=None):
+                    revcomp=False, rc_suffix=True, match_override=None, info_names=None, info_rows=None):
     """Modifier chain on every record of a chunk + the verdict of every enabled filter.
     Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters).
-    match_override: match records (n, 1, slots) found by the caller on the quality-trimmed reads (--pair-adapters)."""
+    match_override: match records (n, 1, slots) found by the caller on the quality-trimmed reads (--pair-adapters).
+    info_names / info_rows: name per adapter + a list that receives the --info-file rows (InfoFileWriter.__call__,
+    steps.py:222-253: coordinates applied to info.original_read, the read as it came)."""
     records = parse_fastq(data)
+    originals = list(records)
+    is_rc = [False] * len(records)
     bp_in = sum(len(r[1]) for r in records)             # before any modifier (pipeline.py:58-64)
     records = _apply_cuts(records, cut)
     seqs = [r[1] for r in records]
@@ -629,6 +633,7 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                 score_r = int(rev[i]["score"][rev[i]["adapter"] >= 0].sum())
                 if score_r > score_f:
                     reverse_complemented += 1
+                    is_rc[i] = True
                     matches[i] = rev[i]
                     name, _, q = records[i]
                     records[i] = (name + (" rc" if rc_suffix else ""), rc_seqs[i], q[::-1])
@@ -713,6 +718,30 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
             a = len(ts) - len(ts.lstrip("N"))
             b = len(ts.rstrip("N"))
             ts, tq = ts[a:b], tq[a:b]
+        if info_rows is not None:
+            _, cur_s, cur_q = originals[i]
+            if is_rc[i]:
+                comp = bytes.maketrans(b"ACGTUMRWSYKVHDBNacgtumrwsykvhdbn", b"TGCAAKYWSRMBDHVNtgcaakywsrmbdhvn")
+                cur_s, cur_q = cur_s.encode("latin-1").translate(comp)[::-1].decode("latin-1"), cur_q[::-1]
+            flag = ("1" if is_rc[i] else "0") if revcomp else ""
+            if matched:
+                for r in range(matches.shape[1]):
+                    if not (matches[i, r]["adapter"] >= 0).any():
+                        break
+                    for slot in range(matches.shape[2]):
+                        m = matches[i, r, slot]
+                        if m["adapter"] < 0:
+                            continue
+                        rs, re_ = int(m["rstart"]), int(m["rstop"])
+                        info_rows.append("\t".join([name, str(int(m["errors"])), str(rs), str(re_), cur_s[0:rs], cur_s[rs:re_],
+                                                    cur_s[re_:], info_names[int(m["adapter"])], cur_q[0:rs], cur_q[rs:re_],
+                                                    cur_q[re_:], flag]))
+                        if (int(m["info"]) >> 8) & 1:
+                            cur_s, cur_q = cur_s[:rs], cur_q[:rs]
+                        else:
+                            cur_s, cur_q = cur_s[re_:], cur_q[re_:]
+            else:
+                info_rows.append("\t".join([name, "-1", ts, tq]))
         n_count = ts.lower().count("n")
         fails = {
             "too_short": len(ts) < minimum_length,                                        # predicates.py:29-40

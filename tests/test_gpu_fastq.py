@@ -475,3 +475,53 @@ def test_paired_demultiplexing_against_oracle(combinatorial, discard_untrimmed):
     for st, cc in zip(t.statistics, (c1, c2)):
         for k, v in cc.items():
             assert st[k] == v, k
+
+
+# ---- --info-file rows on the device ------------------------------------------------------------------------
+
+def test_info_file_reference_goldens_on_the_device():
+    """tests/cut/illumina.info.txt and illumina5.info.txt (--times 2) of the reference (tests/test_info_file.py:14-55):
+    the rows come formatted from the device (cg_fastq_collect_info)."""
+    import cutadapt_b200.adapters as PA
+    from util import fastq_file
+
+    cases = [("iupac.in.fastq", "info_illumina.txt", [("adapt", "GCCGAACTTCTTAGACTGCCTTAAGGACGT")], 1),
+             ("info_illumina5.in.fastq", "info_illumina5.txt", [("adapt", "GCCGAACTTCTTA"), ("adapt2", "GACTGCCTTAAGGACGT")], 2)]
+    for fastq, expected, ads, times in cases:
+        t = FastqTrimmer([PA.BackAdapter(s, max_errors=0.1, min_overlap=3, name=n) for n, s in ads], times=times)
+        _, info = t.process_chunk_info(fastq_file(fastq))
+        want = [w.rstrip() for w in fastq_file(expected).decode().split("\n")]
+        got = [g.rstrip() for g in info.decode("latin-1").split("\n")]
+        assert got[-1] == "" and got == want                        # assert_files_equal(ignore_trailing_space)
+
+
+@pytest.mark.parametrize("variant", ["plain", "times_linked", "revcomp_cuts", "lowercase_filters"])
+def test_info_rows_random_chunks_against_oracle(variant):
+    import cutadapt_b200.adapters as PA
+
+    seed = {"plain": 31, "times_linked": 32, "revcomp_cuts": 33, "lowercase_filters": 34}[variant]
+    data = synthetic_fastq(5000, seed=seed)
+    options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"]], quality_cutoff=[5, 20])
+    extra = {}
+    if variant == "times_linked":
+        options = dict(adapters=[["linked", "TTGACNNACG", "AGATCGGAAGAGC"], ["back", "CACGTCTGAACTC"],
+                                 ["anywhere", "ACGTACGTAC"]], quality_cutoff=[0, 15])
+        extra = dict(times=3, poly_a=True)
+    elif variant == "revcomp_cuts":
+        data = flip_records(data, seed)
+        extra = dict(revcomp=True, cut=[3, -2], nextseq_cutoff=12, times=2, trim_n=True)
+    elif variant == "lowercase_filters":
+        extra = dict(action="lowercase", minimum_length=40, discard_trimmed=True, length=70)
+    t = trimmer_for(options, **extra)
+    out, info = t.process_chunk_info(data)
+    ads = fastq_case_adapters(options)
+    singles, groups, owners = PA.MultipleAdapters(ads)._flatten()
+    names = [s.name for s in singles]
+    for (typ, a0, a1, _, _), owner in zip(groups, owners):
+        if typ == 1:
+            names[a0], names[a1] = owner.name + ";1", owner.name + ";2"
+    rows = []
+    exp, counters = oracle_for(options, data, info_names=names, info_rows=rows, **extra)
+    assert out == exp
+    assert info.decode("latin-1") == "".join(r + "\n" for r in rows)
+    assert len(rows) >= 5000
