@@ -1454,7 +1454,8 @@ static void parallel_copy(cg_ctx *c, void *dst, const void *src, size_t n)
 static int fastq_format_error(const int err[2])
 {
     static const char *what[] = {"", "a record does not start with '@'", "the third line of a record does not start with '+'",
-                                 "sequence and qualities differ in length", "invalid quality value"};
+                                 "sequence and qualities differ in length", "invalid quality value",
+                                 "sequence descriptions don't match (the second one must be empty or equal to the first)"};
     return fail(CG_EINVAL, std::string("FASTQ format error in record ") + std::to_string(err[1]) + ": " + what[err[0] & 7]);
 }
 

@@ -62,7 +62,8 @@ CG_HD void fq_line_span(const uint8_t *buf, const uint32_t *nl_pos, long long n_
 }
 
 // Record r = lines 4r .. 4r+3.  Checks what dnaio's parser checks: 1 = the record does not start with '@',
-// 2 = the third line does not start with '+', 3 = sequence and qualities differ in length; 0 = fine.
+// 2 = the third line does not start with '+', 3 = sequence and qualities differ in length, 5 = the description
+// repeated after the '+' differs from the first one; 0 = fine.
 // cut_front / cut_back: UnconditionalCutter (-u, modifiers.py:66-95), the first modifier of the chain: the record
 // table simply describes the read without those bases (read[cut_front:] then read[:-cut_back]).
 // *full_len: the length before -u (what the pipeline counts as "bp processed", pipeline.py:58-64, 142-143).
@@ -78,7 +79,13 @@ CG_HD int fq_record_core(const uint8_t *buf, long long n, const uint32_t *nl_pos
     int bad = 0;
     if (he == hs || buf[hs] != '@') bad = 1;
     else if (pe == ps || buf[ps] != '+') bad = 2;
-    else if (se - ss != qe - qs) bad = 3;
+    else if (pe - ps > 1) {
+        // a repeated description after the '+' must equal the first one (dnaio: "Sequence descriptions don't match")
+        bool same = pe - ps == he - hs;
+        for (uint32_t j = 1; same && j < pe - ps; ++j) same = buf[ps + j] == buf[hs + j];
+        if (!same) bad = 5;
+    }
+    if (!bad && se - ss != qe - qs) bad = 3;
     int len = bad ? 0 : (int32_t)(se - ss);
     if (full_len) *full_len = len;
     const int cf = cut_front < len ? cut_front : len;

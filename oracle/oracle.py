@@ -562,6 +562,8 @@ def parse_fastq(data: bytes):
             raise FastqFormatError(f"record {r}: a record does not start with '@'")
         if not p.startswith(b"+"):
             raise FastqFormatError(f"record {r}: the third line of a record does not start with '+'")
+        if len(p) > 1 and p[1:] != h[1:]:
+            raise FastqFormatError(f"record {r}: sequence descriptions don't match")
         if len(s) != len(q):
             raise FastqFormatError(f"record {r}: sequence and qualities differ in length")
         records.append((h[1:].decode("latin-1"), s.decode("latin-1"), q.decode("latin-1")))

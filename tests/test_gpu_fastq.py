@@ -170,9 +170,12 @@ def test_many_chunks_in_flight_and_format_errors():
     exp = [oracle_for(options, c, minimum_length=10)[0] for c in chunks]
     assert got == exp
     assert t.statistics["n_records"] == sum((1, 3000, 0, 17, 40000, 5, 2500))
-    for bad in (b"@r\nACGT\n+\nIII\n", b"@r\nACGT\n+\n", b"r\nACGT\n+\nIIII\n", b"@r\nACGT\n-\nIIII\n"):
+    for bad in (b"@r\nACGT\n+\nIII\n", b"@r\nACGT\n+\n", b"r\nACGT\n+\nIIII\n", b"@r\nACGT\n-\nIIII\n",
+                b"@r 1\nACGT\n+r 2\nIIII\n"):
         with pytest.raises(ValueError):
             t.process_chunk(bad)
+        with pytest.raises(oracle.FastqFormatError):
+            oracle.parse_fastq(bad)
     # the context stays usable after an error
     assert t.process_chunk(chunks[3]) == exp[3]
     # nothing to trim and no final newline: the output is one byte longer than the input

@@ -604,6 +604,7 @@ def test_fastq_record_table_of_the_device_functions():
             assert code == 0 and bad == -1
             assert (rec == want_rec).all() and (lens == want_lens).all()
     for text, want in ((b"r\nACGT\n+\nIIII\n", 1), (b"@r\nACGT\n-\nIIII\n", 2), (b"@r\nACGT\n+\nIII\n", 3),
-                       (b"@a\nAC\n+\nII\n@b\nACGT\n\nIIII\n", 2)):
+                       (b"@a\nAC\n+\nII\n@b\nACGT\n\nIIII\n", 2), (b"@r 1\nACGT\n+r 2\nIIII\n", 5),
+                       (b"@r 1\nACGT\n+r\nIIII\n", 5), (b"@a\nAC\n+a\nII\n@b x\nACGT\n+b y\nIIII\n", 5)):
         code, bad, _, _ = table(text)
         assert code == want and bad == text.count(b"@a")
