@@ -849,6 +849,9 @@ CG_HD uint32_t plane_load(PlaneState<W> &st, const uint8_t *base, int off0)
 }
 
 // one chain step: acc = plane (first character of a chain) or (acc << 1) & plane
+#ifndef CG_CHAIN_IMAD
+#define CG_CHAIN_IMAD 0xFF          // words of the accumulator whose shift runs on the multiply pipe (bit b = word b)
+#endif
 template <int W>
 CG_HD void plane_chain_apply(uint32_t (&acc)[W], const uint32_t (&P)[W], bool first)
 {
@@ -856,9 +859,32 @@ CG_HD void plane_chain_apply(uint32_t (&acc)[W], const uint32_t (&P)[W], bool fi
 #pragma unroll
         for (int b = 0; b < W; ++b) acc[b] = P[b];
     } else {
+#if defined(__CUDA_ARCH__) && CG_CHAIN_IMAD
+        // The first stage is bound by the ALU pipe (LOP3 / SHF / compares issue every other cycle per scheduler, the
+        // multiply pipe idles): for the words in CG_CHAIN_IMAD the shift is a widening multiply by two -- one
+        // IMAD.WIDE.U32 on the other pipe yields x << 1 AND x >> 31 -- and the carry joins in the LOP3 that was needed
+        // for the AND anyway: (lo | carry_in) & plane.
+        uint32_t lo[W], hi[W];
+#pragma unroll
+        for (int b = 0; b < W; ++b) {
+            if ((CG_CHAIN_IMAD >> b) & 1 || (b + 1 < W && ((CG_CHAIN_IMAD >> (b + 1)) & 1))) {
+                unsigned long long t;
+                asm("mul.wide.u32 %0, %1, 2;" : "=l"(t) : "r"(acc[b]));
+                lo[b] = (uint32_t)t;
+                hi[b] = (uint32_t)(t >> 32);
+            }
+        }
+#pragma unroll
+        for (int b = W - 1; b >= 1; --b) {
+            if ((CG_CHAIN_IMAD >> b) & 1) acc[b] = (lo[b] | hi[b - 1]) & P[b];
+            else acc[b] = cg_funnel_l(acc[b - 1], acc[b], 1) & P[b];
+        }
+        acc[0] = ((CG_CHAIN_IMAD & 1) ? lo[0] : (acc[0] << 1)) & P[0];
+#else
 #pragma unroll
         for (int b = W - 1; b >= 1; --b) acc[b] = cg_funnel_l(acc[b - 1], acc[b], 1) & P[b];
         acc[0] = (acc[0] << 1) & P[0];
+#endif
     }
 }
 template <int W>

@@ -608,3 +608,23 @@ def test_fastq_record_table_of_the_device_functions():
                        (b"@r 1\nACGT\n+r\nIIII\n", 5), (b"@a\nAC\n+a\nII\n@b x\nACGT\n+b y\nIIII\n", 5)):
         code, bad, _, _ = table(text)
         assert code == want and bad == text.count(b"@a")
+
+
+def test_first_stage_specialisation_compiles_without_a_device():
+    """cg_jit.cpp: the translation unit generated for an adapter set (straight-line plane_chain_step / plane_emit calls)
+    goes through NVRTC for sm_100a here, for 5- and 8-word planes, with and without qualities; a set without a plane
+    program (wildcards) yields no source."""
+    import cutadapt_b200.adapters as PA
+    from util import hostsim_jit_compile, spec_of
+
+    for seq, words, qual in (("AGATCGGAAGAGC", 5, False), ("AGATCGGAAGAGCACACGTCTGAACTCCAGTCA", 8, True),
+                             ("CTGTCTCTTATACACATCT", 5, True)):
+        spec = spec_of(PA.MultipleAdapters([PA.BackAdapter(seq, max_errors=0.1, name="a")]))
+        n, src, log = hostsim_jit_compile(spec, words, qual)
+        if n == -2:
+            pytest.skip("libnvrtc is not installed")
+        assert n > 10000, log
+        assert src.count("plane_chain_step") >= len(seq) and f"cg_pscan_body<{str(qual).lower()}, {words}, StaticPlaneProg>" in src
+    spec = spec_of(PA.MultipleAdapters([PA.BackAdapter("AGATCNNNNGAGC", max_errors=0.1, name="a")]))
+    n, src, _ = hostsim_jit_compile(spec)
+    assert n == 0 and src == ""

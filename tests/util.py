@@ -325,3 +325,18 @@ def adapter_from_spec(spec, adapter_type, name=None, **params):
             adapter_type = "front"
     nm, restriction, seq, kind = parse(spec, adapter_type)
     return cls_of(kind, restriction)(seq, name=name or nm or "adapter", **params)
+
+
+def hostsim_jit_compile(spec, plane_words=5, has_qual=False):
+    """(cubin size or error code, generated source, NVRTC log) of the run-time specialisation of the first stage
+    (cg_jit.cpp) for this adapter set -- NVRTC compiles for sm_100a without a device."""
+    lib = hostsim_lib()
+    lib.hs_jit_compile.restype = C.c_long
+    lib.hs_jit_compile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_long,
+                                   C.c_char_p, C.c_long]
+    ads, na, groups, ng = spec.to_ctypes()
+    src = C.create_string_buffer(1 << 20)
+    log = C.create_string_buffer(1 << 16)
+    n = lib.hs_jit_compile(C.cast(ads, C.c_void_p), na, C.cast(groups, C.c_void_p), ng, plane_words, int(has_qual), src,
+                           len(src), log, len(log))
+    return n, src.value.decode(), log.value.decode()
