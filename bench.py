@@ -492,9 +492,9 @@ def main():
         results = []
         pos = 0
         for m in mates:
-            res = m["batch"].run(m["seq"], offsets, m["qual"], max_read_len=READ_LEN, out=m["out"], qtrim_out=m["qt"])
             m["stats"].zero_()
-            m["batch"].statistics(res, READ_LEN, 3, into=m["stats"])
+            res, _ = m["batch"].run_with_statistics(m["seq"], offsets, m["qual"], max_read_len=READ_LEN, out=m["out"],
+                                                    qtrim_out=m["qt"], max_len=READ_LEN, kmax=3, into=m["stats"])
             all_stats[pos:pos + m["stats"].numel()] = m["stats"]
             pos += m["stats"].numel()
             results.append(res)

@@ -207,6 +207,9 @@ def _declare(lib) -> None:
     lib.cg_process_batch_device.argtypes = [
         vp, vp, vp, vp, vp, i64, i32, C.POINTER(cg_params), vp, vp,
     ]
+    lib.cg_process_batch_device_stats.argtypes = [
+        vp, vp, vp, vp, vp, i64, i32, C.POINTER(cg_params), vp, vp, i32, i32, vp,
+    ]
     lib.cg_kmers_present_batch.argtypes = [vp, C.POINTER(cg_kmer_entry), vp, i32, vp, vp, i64, vp]
     lib.cg_quality_trim_batch.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.cg_nextseq_trim_batch.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]

@@ -140,6 +140,9 @@ struct cg_ctx {
     DevBuf<uint32_t> scratch_p;
     DevBuf<int> scratch_w;
     DevBuf<unsigned long long> d_stats;  // cg_process_batch_stats: the statistics vector of the batch in flight
+    // statistics wanted together with the next trimming pass (launch_trim_with_stats): the split pipeline counts the
+    // reads its first stage settles while it has them in shared memory and the others from its task list
+    struct { unsigned long long *d_stats = nullptr; int max_len = 0, kmax = 0; bool armed = false, done = false; } fuse;
     DevBuf<uint4> tasks;                 // split pipeline: 2 x uint4 per read of a sub-batch
     DevBuf<uint4> tasks2, tasks3;        // run-record lists (ping-pong): 4 x uint4 per read of a sub-batch
     unsigned long long *d_task_count = nullptr;
@@ -584,6 +587,18 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         }
         CU(cudaEventRecord(ev0, st));
     }
+    // fused statistics: one plain adapter, one round, the whole set in this call (not a pass of the multi-pass schedule)
+    const bool fuse_stats = split && plane_w && c->fuse.armed && !d_view && s->host.n_adapters == 1 && times == 1 &&
+                            s->host.slots == 1 && (!want_q || d_qtrim) && !getenv("CUTADAPT_B200_TWO_LISTS") &&
+                            c->fuse.max_len <= 4096 && !getenv("CUTADAPT_B200_NO_FUSED_STATS");
+    if (fuse_stats) {
+        a.stats = c->fuse.d_stats; a.stats_max_len = c->fuse.max_len; a.stats_kmax = c->fuse.kmax;
+        scan_smem = cg_pscan_smem_bytes(a.blob_bytes, a.mini_cap, want_q, a.stats_max_len);
+        if (scan_smem > c->smem_optin) return fail(CG_EINVAL, "statistics histogram does not fit the first stage's shared memory");
+        if (jit_kernel) jit_occ = cg_jit_occupancy(jit_kernel, CG_NT, scan_smem);
+        else CU(cg_pscan_occupancy(want_q, plane_w, scan_smem, &scan_occ));
+        if ((jit_kernel ? jit_occ : scan_occ) < 1) return fail(CG_ECUDA, "first stage does not fit with the statistics histogram");
+    }
     if (split) {
         // scan -> plan -> up to four DP rounds (one run of every unfinished read per round)
         // reads per sub-batch: bounds the lists to 1 + 2 x 2 GiB at the default 32 Mi (measured: fewer,
@@ -658,7 +673,15 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
                 c->launches += 1;
             }
             if (sev[0]) { CU(cudaEventRecord(sev[3], st)); c->stage_events.push_back(sev); }
+            if (fuse_stats) {
+                // the reads the first stage handed on: their records are final now
+                if (ev0 && r0 + SUB >= n_reads) { CU(cudaEventRecord(ev1, st)); c->timing.emplace_back(ev0, ev1); ev0 = nullptr; }
+                CU(cg_launch_stats(b.seq, b.offsets, n_sub, want_q && b.qtrim, 1, 1, b.out, b.qtrim, 1, a.stats_max_len,
+                                   a.stats_kmax, a.stats, st, c->tasks.p, plane_rec, cnt));
+                c->launches += 1;
+            }
         }
+        if (fuse_stats) c->fuse.done = true;
         c->launches -= 1;    // the common tail below adds one
     } else if (warpk) {
         const long long n_mt = (n_reads + 31) / 32;
@@ -708,6 +731,10 @@ static int launch_trim_inner(cg_ctx *c, const cg_adapterset *s, const uint8_t *d
                                   st, timed);
     const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
     if (want_q && !d_qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
+    // the passes below see single-adapter sub-sets: their statistics are not the set's (no fusing; the caller runs the
+    // statistics kernel on the selected records)
+    struct Disarm { cg_ctx *c; bool was; ~Disarm() { c->fuse.armed = was; } } disarm{c, c->fuse.armed};
+    c->fuse.armed = false;
     const int np = (int)s->passes.size();
     long long SUB = 32LL << 20;
     if (const char *e = getenv("CUTADAPT_B200_SUB_READS")) { const long long v = atoll(e); if (v >= 1024) SUB = v; }
@@ -833,6 +860,28 @@ static int launch_trim(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, 
     return rc;
 }
 
+// A trimming pass plus the statistics of its reads (cg_stats_*) added to d_stats: fused into the split pipeline where
+// that is possible, otherwise cg_stats_kernel over the records afterwards.
+static int launch_trim_with_stats(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq, const uint8_t *d_qual,
+                                  const int64_t *d_offsets, int64_t n_reads, int max_read_len, const cg_params *p,
+                                  cg_match_rec *d_out, int32_t *d_qtrim, cudaStream_t st, bool timed,
+                                  unsigned long long *d_stats, int stats_max_len, int stats_kmax)
+{
+    if (n_reads <= 0) return CG_OK;
+    c->fuse.d_stats = d_stats; c->fuse.max_len = stats_max_len; c->fuse.kmax = stats_kmax;
+    c->fuse.armed = true; c->fuse.done = false;
+    const int rc = launch_trim(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, d_out, d_qtrim, st, timed);
+    c->fuse.armed = false;
+    if (rc != CG_OK) return rc;
+    if (!c->fuse.done) {
+        const int times = p->times < 1 ? 1 : p->times;
+        CU(cg_launch_stats(d_seq, d_offsets, n_reads, (p->quality_trim || p->nextseq_trim) && d_qtrim, times, s->host.slots,
+                           d_out, d_qtrim, s->host.n_adapters, stats_max_len, stats_kmax, d_stats, st));
+        c->launches += 1;
+    }
+    return CG_OK;
+}
+
 static int check_err_flag(cg_ctx *c)
 {
     int flags[2] = {0, 0};
@@ -864,6 +913,31 @@ extern "C" int cg_process_batch_device(cg_ctx *c, const cg_adapterset *s, const 
     }
     return launch_trim(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, (cg_match_rec *)d_matches,
                        d_qtrim, c->stream, true);
+}
+
+extern "C" int cg_process_batch_device_stats(cg_ctx *c, const cg_adapterset *s, const uint8_t *d_seq,
+                                             const uint8_t *d_qual, const int64_t *d_offsets, int64_t n_reads,
+                                             int32_t max_read_len, const cg_params *p, cg_match *d_matches,
+                                             int32_t *d_qtrim, int32_t stats_max_len, int32_t stats_kmax, int64_t *d_stats)
+{
+    if (!c || !s || !p || !d_seq || !d_offsets || !d_matches || !d_stats || stats_max_len < 0 || stats_kmax < 0)
+        return fail(CG_EINVAL, "cg_process_batch_device_stats: bad argument");
+    if (s->ctx != c) return fail(CG_EINVAL, "adapter set belongs to another context");
+    if (((uintptr_t)d_seq & 15) || (d_qual && ((uintptr_t)d_qual & 15)))
+        return fail(CG_EINVAL, "device sequence/quality buffers must be 16-byte aligned");
+    if (n_reads < 0) return fail(CG_EINVAL, "n_reads < 0");
+    if ((p->quality_trim || p->nextseq_trim) && !d_qtrim)
+        return fail(CG_EINVAL, "cg_process_batch_device_stats: quality trimming needs d_qtrim (the statistics read it)");
+    CU(cudaSetDevice(c->device));
+    if (max_read_len <= 0) {
+        CU(cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream));
+        CU(cg_launch_max_len(d_offsets, n_reads, c->d_err + 1, c->stream));
+        c->launches += 1;
+        CU(cudaMemcpyAsync(&max_read_len, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return launch_trim_with_stats(c, s, d_seq, d_qual, d_offsets, n_reads, max_read_len, p, (cg_match_rec *)d_matches,
+                                  d_qtrim, c->stream, true, (unsigned long long *)d_stats, stats_max_len, stats_kmax);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1175,13 +1249,12 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         const uint8_t *vseq = l.d_seq.p - a0;
         const uint8_t *vqual = want_q ? l.d_qual.p - a0 : nullptr;
         int32_t *d_qt = (qtrim || (stats && want_q)) ? l.d_qtrim.p : nullptr;
-        rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, d_qt, l.stream, true);
+        if (stats)
+            rc = launch_trim_with_stats(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, d_qt, l.stream, true,
+                                        c->d_stats.p, stats_max_len, stats_kmax);
+        else
+            rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, d_qt, l.stream, true);
         if (rc != CG_OK) break;
-        if (stats) {
-            CU(cg_launch_stats(vseq, l.d_offs.p, nr, want_q && d_qt, times, s->host.slots, l.d_out.p, d_qt,
-                               s->host.n_adapters, stats_max_len, stats_kmax, c->d_stats.p, l.stream));
-            c->launches += 1;
-        }
         // D2H
         cg_match_rec *dst = (cg_match_rec *)matches + (size_t)r0 * rec_per_read;
         l.n_out = (size_t)nr * rec_per_read; l.dst_out = dst; l.out_bounced = !out_pinned;

@@ -45,6 +45,10 @@ struct CgKernelArgs {
     unsigned long long *task2_count;
     uint4 *tasks3;                    // plan stage only: reads of cg_pscan_kernel whose window holds other letters than
     unsigned long long *task3_count;  //   A/C/G/T go here (2 x uint4, CG_TASK_RESCAN) for a second, dense plan launch
+    // statistics fused into the first stage (cg_pscan.cuh): the reads it settles are counted here, the rest by
+    // cg_stats_tasks_kernel over the task list once their records are final.  null = not fused.
+    unsigned long long *stats;
+    int stats_max_len, stats_kmax;
     // generic-kernel scratch
     uint32_t *scratch_p;
     int *scratch_w;

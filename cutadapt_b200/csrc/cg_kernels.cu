@@ -705,9 +705,9 @@ cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_
 
 #include "cg_pscan.cuh"
 
-size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual)
+size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual, int stats_max_len)
 {
-    return pscan_smem_layout(blob_bytes, mini_cap, has_qual).total;
+    return pscan_smem_layout(blob_bytes, mini_cap, has_qual, stats_max_len).total;
 }
 
 template <bool HAS_QUAL, int W>
@@ -1336,7 +1336,8 @@ cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *
 template <bool SMEM_HIST>
 __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long long n_reads, int quality_trim, int times,
                                 int slots, const cg_match_rec *matches, const int32_t *qtrim,
-                                int n_adapters, int max_len, int kmax, unsigned long long *stats)
+                                int n_adapters, int max_len, int kmax, unsigned long long *stats,
+                                const uint4 *task_list, int task_rec, const unsigned long long *task_count)
 {
     // per-CTA histograms in shared memory (32-bit counts, flushed once): the read-length histogram always (every
     // read adds to it, mostly to the same few bins), the per-adapter part if it fits (SMEM_HIST); a global
@@ -1350,7 +1351,18 @@ __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long
     unsigned long long n = 0;
     StatsScalars sc; sc.bp = sc.with_adapters = sc.qtrim_bp = sc.adapter_bp = 0;
     unsigned long long *hist = stats + CG_STATS_SCALARS;
-    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += nthreads) {
+    // task_list: only the reads of a task list of the split pipeline (those its first stage did not count itself)
+    long long n_items = n_reads;
+    if (task_list) {
+        const unsigned long long t = *task_count;
+        n_items = t < (unsigned long long)n_reads ? (long long)t : n_reads;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += nthreads) {
+        long long r = i;
+        if (task_list) {
+            const uint4 t = task_list[(size_t)task_rec * i];
+            r = (long long)(((unsigned long long)t.y << 32) | t.x);
+        }
         const long long o0 = offsets[r];
         const int len = (int)(offsets[r + 1] - o0);
         n += 1;
@@ -1384,7 +1396,7 @@ __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long
 cudaError_t cg_launch_stats(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
                             int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
                             int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
-                            cudaStream_t st)
+                            cudaStream_t st, const uint4 *d_task_list, int task_rec, const unsigned long long *d_task_count)
 {
     const int block = 256;
     long long grid = (n_reads + block - 1) / block;
@@ -1396,9 +1408,11 @@ cudaError_t cg_launch_stats(const uint8_t *d_seq, const int64_t *d_offsets, long
     // a CTA handles n_reads / grid reads, so 32-bit per-CTA counts cannot overflow below 2^32 reads per CTA
     if (hist_bytes <= 48 * 1024 && n_reads / grid < (1LL << 31))
         cg_stats_kernel<true><<<(int)grid, block, hist_bytes, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots,
-                                                                     d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats);
+                                                                     d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats,
+                                                                     d_task_list, task_rec, d_task_count);
     else
         cg_stats_kernel<false><<<(int)grid, block, len_bytes, st>>>(d_seq, d_offsets, n_reads, quality_trim, times, slots,
-                                                                     d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats);
+                                                                     d_matches, d_qtrim, n_adapters, max_len, kmax, d_stats,
+                                                                     d_task_list, task_rec, d_task_count);
     return cudaGetLastError();
 }

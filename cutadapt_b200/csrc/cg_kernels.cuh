@@ -32,7 +32,7 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
 cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
-size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
+size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual, int stats_max_len = -1);   // >= 0: + fused statistics
 cudaError_t cg_pscan_occupancy(bool has_qual, int w, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_pscan(const CgKernelArgs &a, bool has_qual, int w, int grid, size_t smem, cudaStream_t st);
 size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes);
@@ -51,7 +51,8 @@ cudaError_t cg_launch_max_len(const int64_t *d_offsets, long long n_reads, int *
 cudaError_t cg_launch_stats(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int quality_trim, int times,
                             int slots, const cg_match_rec *d_matches, const int32_t *d_qtrim,
                             int n_adapters, int max_len, int kmax, unsigned long long *d_stats,
-                            cudaStream_t st);
+                            cudaStream_t st, const uint4 *d_task_list = nullptr, int task_rec = 0,
+                            const unsigned long long *d_task_count = nullptr);   // task list: only its reads
 cudaError_t cg_launch_nextseq_trim(const uint8_t *d_seq, const uint8_t *d_qual, const int64_t *d_offsets,
                                    long long n_reads, int cutoff, int base, int32_t *d_out, cudaStream_t st);
 cudaError_t cg_launch_poly_a_trim(const uint8_t *d_seq, const int64_t *d_offsets, long long n_reads, int revcomp,

@@ -9,7 +9,7 @@
 #include "cg_args.h"
 #include "cg_device.cuh"
 
-struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_rel, qual_rel, total; };
+struct ScanSmem { size_t blob_off, enc_off, stats_off, warp_off, warp_stride, bar_rel, seq_rel, qual_rel, total; };
 
 // ------------------------------------------------------------------------------------------
 // cg_pscan_kernel -- the bit-plane first stage (plane_scan_core in cg_core.cuh) in the frame of
@@ -31,12 +31,16 @@ struct ScanSmem { size_t blob_off, enc_off, warp_off, warp_stride, bar_rel, seq_
 #define CG_TASK_PLANES 0x200u     // a 4 x uint4 task of cg_pscan_kernel: {read lo, read hi, trim start, length},
                                   // {M0, flags, M1, M2}, {M3 .. M6}, {M7, window offset, 0, 0} with M = PlaneOut::M (+ CG_TASK_BYTES);
                                   // flags bits 12-15: plane words W, bit 20: PlaneOut::end_hit, bit 21: PlaneOut::no_end
-__host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual)
+// stats_max_len >= 0: room for the per-CTA histograms of the fused statistics (read lengths, removed lengths at 0
+// errors for 5' and for 3' matches, adjacent bases): 3 (max_len + 1) + 8 counters, then 8 64-bit scalars
+__host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int mini_cap, bool has_qual, int stats_max_len = -1)
 {
     ScanSmem L;
     size_t o = 0;
     L.blob_off = o; o += cg_align_up(blob_bytes, 16);
     L.enc_off = o; o += 768;
+    L.stats_off = o;
+    if (stats_max_len >= 0) o += cg_align_up((size_t)(3 * (stats_max_len + 1) + 8) * sizeof(uint32_t), 8) + 8 * sizeof(unsigned long long);
     o = cg_align_up(o, 128);
     L.warp_off = o;
     size_t w = 0;
@@ -54,7 +58,7 @@ template <bool HAS_QUAL, int W, class Prog>
 __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    const ScanSmem L = pscan_smem_layout(a.blob_bytes, a.mini_cap, HAS_QUAL);
+    const ScanSmem L = pscan_smem_layout(a.blob_bytes, a.mini_cap, HAS_QUAL, a.stats ? a.stats_max_len : -1);
     uint8_t *s_blob = smem + L.blob_off;
     uint8_t *s_enc = smem + L.enc_off;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -62,7 +66,20 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
     uint64_t *bars = (uint64_t *)(wbase + L.bar_rel);
     uint8_t *s_seq = wbase + L.seq_rel;
     uint8_t *s_qual = wbase + L.qual_rel;
-
+    // fused statistics: per-CTA histograms, flushed at the end (layout: cg_types.h, stats_read_core).  Everything is
+    // re-derived from the kernel arguments where it is used: nothing of it may occupy a register across the plane code.
+#define CG_PSCAN_STATS_VIEW                                                                                              \
+    const int st_len = a.stats_max_len;                                                                                  \
+    uint32_t *s_hlen = (uint32_t *)(smem + pscan_smem_layout(a.blob_bytes, a.mini_cap, HAS_QUAL, st_len).stats_off);     \
+    uint32_t *s_hrem = s_hlen + (st_len + 1);   /* removed lengths at 0 errors: 5' matches, then 3' matches */           \
+    uint32_t *s_hadj = s_hrem + 2 * (st_len + 1);                                                                        \
+    unsigned long long *s_scal = (unsigned long long *)((uint8_t *)s_hlen + cg_align_up((size_t)(3 * (st_len + 1) + 8) * sizeof(uint32_t), 8));
+    if (a.stats) {
+        CG_PSCAN_STATS_VIEW
+        (void)s_hrem; (void)s_hadj;
+        for (int i = threadIdx.x; i < 3 * (st_len + 1) + 8; i += CG_NT) s_hlen[i] = 0;
+        if (threadIdx.x < 8) s_scal[threadIdx.x] = 0;     // reads, bases, with adapters, quality-trimmed, adapter bases
+    }
     for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
     for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
     if (lane == 0) {
@@ -112,6 +129,9 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
         const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
         if (b1 > b0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
         int cls = CG_PLANE_NONE, s0 = 0, ts = 0, te = 0;
+        int st_fin = -1;                              // fused statistics: this lane's final-length bin, -1 = none
+        uint32_t st_bp = 0, st_qbp = 0, st_abp = 0;   // ... and its contributions to the scalars
+        bool st_hit = false;
         uint32_t t_flags = 4u | CG_TASK_RESCAN;
         uint32_t tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t win_region = 0, win_off = 0;         // shared-memory address of the carried bytes, window offset in them
@@ -154,6 +174,52 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 if (cls == CG_PLANE_EXACT) hit_exact(A, nn, s0, hit);
                 else if (cls == CG_PLANE_OVERLAP) hit_end_overlap(A, nn, s0, hit);
                 store_hit(a.out + (size_t)r * a.slots, hit, 0, nn);
+                if (a.stats) {
+                    // what stats_read_core adds for this read (one round, one slot)
+                    CG_PSCAN_STATS_VIEW
+                    (void)s_hlen; (void)s_scal;
+                    st_bp = (uint32_t)n;
+                    if (a.quality_trim && a.qtrim) st_qbp = (uint32_t)(n - nn);
+                    int fin = nn;
+                    if (hit.adapter >= 0) {
+                        const bool after = hit.remove == CGK_REMOVE_AFTER;
+                        const int removed = after ? nn - hit.rstart : hit.rstop;
+                        st_hit = true;
+                        st_abp = (uint32_t)(removed < 0 ? 0 : removed);
+                        atomicAdd(&s_hrem[(after ? st_len + 1 : 0) + (removed < 0 ? 0 : (removed > st_len ? st_len : removed))], 1u);
+                        if (after) {
+                            int k = 4;
+                            if (hit.rstart > 0) {
+                                const uint8_t c = s_seq[off + ts + hit.rstart - 1];
+                                k = c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
+                            }
+                            atomicAdd(&s_hadj[k], 1u);
+                            fin = hit.rstart;
+                        } else {
+                            fin = nn - hit.rstop;
+                        }
+                    }
+                    st_fin = fin < 0 ? 0 : (fin > st_len ? st_len : fin);
+                }
+            }
+        }
+        if (a.stats) {
+            CG_PSCAN_STATS_VIEW
+            (void)s_hrem; (void)s_hadj;
+            // most reads of a tile end in the same length bin: one shared-memory atomic per distinct bin of the warp
+            const unsigned peers = __match_any_sync(0xffffffffu, st_fin);
+            if (st_fin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hlen[st_fin], (uint32_t)__popc(peers));
+            const uint32_t c_reads = __popc(__ballot_sync(0xffffffffu, st_fin >= 0));
+            const uint32_t c_with = __popc(__ballot_sync(0xffffffffu, st_hit));
+            const uint32_t c_bp = __reduce_add_sync(0xffffffffu, st_bp);
+            const uint32_t c_qbp = __reduce_add_sync(0xffffffffu, st_qbp);
+            const uint32_t c_abp = __reduce_add_sync(0xffffffffu, st_abp);
+            if (lane == 0 && c_reads) {
+                atomicAdd(&s_scal[0], (unsigned long long)c_reads);
+                atomicAdd(&s_scal[1], (unsigned long long)c_bp);
+                if (c_with) atomicAdd(&s_scal[2], (unsigned long long)c_with);
+                if (c_qbp) atomicAdd(&s_scal[3], (unsigned long long)c_qbp);
+                if (c_abp) atomicAdd(&s_scal[4], (unsigned long long)c_abp);
             }
         }
         const bool slow = mine && cls == CG_PLANE_SLOW;
@@ -199,6 +265,25 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
             const long long next = mt + warps_total;
             if (next < n_mt) issue(next);
         }
+    }
+    if (a.stats) {
+        CG_PSCAN_STATS_VIEW
+        __syncthreads();
+        if (threadIdx.x < 5 && s_scal[threadIdx.x]) atomicAdd(&a.stats[threadIdx.x], s_scal[threadIdx.x]);
+        // one adapter: lengths, then its 5' block and its 3' block (adjacent bases, removed length x errors)
+        unsigned long long *hist = a.stats + CG_STATS_SCALARS;
+        const long long end_size = cg_stats_end_size(st_len, a.stats_kmax);
+        for (int i = threadIdx.x; i <= st_len; i += CG_NT) {
+            const uint32_t v = s_hlen[i];
+            if (v) atomicAdd(&hist[i], (unsigned long long)v);
+            for (int kind = 0; kind < 2; ++kind) {
+                const uint32_t w = s_hrem[kind * (st_len + 1) + i];
+                if (w) atomicAdd(&hist[(st_len + 1) + kind * end_size + CG_STATS_ADJ + (long long)i * (a.stats_kmax + 1)],
+                                 (unsigned long long)w);
+            }
+        }
+        if (threadIdx.x < 8 && s_hadj[threadIdx.x])
+            atomicAdd(&hist[(st_len + 1) + end_size + threadIdx.x], (unsigned long long)s_hadj[threadIdx.x]);
     }
 }
 

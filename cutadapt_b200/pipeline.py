@@ -960,6 +960,32 @@ class DeviceBatch:
         )
         return DeviceResult(out, qtrim_out, n, offsets, seq)
 
+    def run_with_statistics(self, seq, offsets, qual=None, max_read_len: int = 0, out=None, qtrim_out=None,
+                            max_len: int = 150, kmax: int = 3, into=None):
+        """``run`` + ``statistics`` as ONE library call (``cg_process_batch_device_stats``): for a set of one plain
+        adapter the statistics are gathered inside the trimming pass instead of from the records afterwards; the
+        resulting vector is the same.  Returns (DeviceResult, statistics vector)."""
+        import torch
+
+        n = int(offsets.numel() - 1)
+        slots = self.adapter_set.slots
+        if out is None:
+            out = torch.empty((n * self.times * slots, 8), dtype=torch.int32, device=seq.device)
+        want_q = bool(self.params.quality_trim or self.params.nextseq_trim)
+        if want_q and qtrim_out is None:
+            qtrim_out = torch.empty((n, 2), dtype=torch.int32, device=seq.device)
+        size = int(_lib.lib().cg_stats_size(self.n_adapters, max_len, kmax))
+        stats = into if into is not None else torch.zeros(size, dtype=torch.int64, device=seq.device)
+        _lib.check(
+            _lib.lib().cg_process_batch_device_stats(
+                self.ctx.handle, self.adapter_set.handle, seq.data_ptr(),
+                qual.data_ptr() if (qual is not None and want_q) else None, offsets.data_ptr(), n,
+                int(max_read_len), C.byref(self.params), out.data_ptr(),
+                qtrim_out.data_ptr() if qtrim_out is not None else None, max_len, kmax, stats.data_ptr(),
+            )
+        )
+        return DeviceResult(out, qtrim_out, n, offsets, seq), stats
+
     def statistics(self, result: DeviceResult, max_len: int = 150, kmax: int = 3, into=None):
         """Device-side reduction of a batch into the fixed-layout int64 statistics vector."""
         import torch

@@ -253,6 +253,15 @@ int cg_process_batch_device(cg_ctx *ctx, const cg_adapterset *set, const uint8_t
                             const uint8_t *d_qual, const int64_t *d_offsets, int64_t n_reads,
                             int32_t max_read_len, const cg_params *params, cg_match *d_matches,
                             int32_t *d_qtrim);
+/* The same plus the statistics of these reads ADDED to d_stats (int64[cg_stats_size(n_adapters, stats_max_len,
+ * stats_kmax)], device memory; what cg_stats_accumulate_device computes from the records).  For a set of one plain
+ * adapter the split pipeline counts the reads its first stage settles while they are in shared memory and the rest
+ * from its task list, so the records are not read back; any other set runs the statistics kernel after the pass.
+ * With quality trimming d_qtrim is required. */
+int cg_process_batch_device_stats(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *d_seq, const uint8_t *d_qual,
+                                  const int64_t *d_offsets, int64_t n_reads, int32_t max_read_len, const cg_params *params,
+                                  cg_match *d_matches, int32_t *d_qtrim, int32_t stats_max_len, int32_t stats_kmax,
+                                  int64_t *d_stats);
 
 /* The host half of that compressed transfer, callable without a device (tests): packs the characters
  * at absolute positions a0 .. a0 + 3 * n_stream of `seq` (positions outside [lo, hi) are not read and

@@ -602,6 +602,50 @@ def test_device_resident_api_and_statistics():
     assert sum(st.end.lengths.values()) == hit.sum() and st.end.adjacent_bases["A"] == adjacent[0]
 
 
+@pytest.mark.parametrize("jit", ["0", "1"])
+def test_statistics_fused_into_the_pass_equal_the_statistics_kernel(jit, monkeypatch):
+    """cg_process_batch_device_stats: the first stage counts the reads it settles, the task list supplies the rest --
+    the vector must equal cg_stats_accumulate_device on the records, for 3' / 5' / anywhere adapters, with and without
+    quality trimming, ragged reads, several sub-batches, interpreted and specialised first stage; sets the fused
+    path does not cover (two adapters) take the kernel and give the same."""
+    import torch
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200.synth import make_read_tensor
+    from cutadapt_b200.pipeline import DeviceBatch
+
+    monkeypatch.setenv("CUTADAPT_B200_JIT", jit)
+    monkeypatch.setenv("CUTADAPT_B200_SUB_READS", "70000")
+    n = 200_000
+    seq, qual = make_read_tensor(n, config=4, device="cuda", with_qualities=True)
+    rng = np.random.default_rng(5)
+    lens = torch.from_numpy(rng.integers(0, 151, n)).cuda()
+    lens[::7] = 150
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    offsets[1:] = torch.cumsum(lens, 0)
+    # ragged copy: read i = the first lens[i] characters of row i
+    keep = (torch.arange(150, device="cuda")[None, :] < lens[:, None])
+    rseq = torch.cat([seq[keep], torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    rqual = torch.cat([qual[keep], torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    cases = [([PA.BackAdapter("AGATCGGAAGAGC", max_errors=0.1, name="a")], None),
+             ([PA.BackAdapter("AGATCGGAAGAGCACACGTCTGAACTCCAGTCA", max_errors=0.1, name="a")], (0, 20)),
+             ([PA.FrontAdapter("GATCGGAAGAGCA", max_errors=0.1, name="f")], (5, 15)),
+             ([PA.AnywhereAdapter("AGATCGGAAGAGC", max_errors=0.2, name="w")], None),
+             ([PA.BackAdapter("AGATCGGAAGAGC", name="a"), PA.BackAdapter("CACGTCTGAACTC", name="b")], (0, 20))]
+    for ads, qc in cases:
+        batch = DeviceBatch(PA.MultipleAdapters(ads), quality_cutoff=qc)
+        for sq, ql, offs in ((seq.reshape(-1), qual.reshape(-1), torch.arange(n + 1, device="cuda", dtype=torch.int64) * 150),
+                             (rseq, rqual, offsets)):
+            res = batch.run(sq, offs, ql if qc else None, max_read_len=150)
+            want = batch.statistics(res, 150, 3)
+            res2, got = batch.run_with_statistics(sq, offs, ql if qc else None, max_read_len=150, max_len=150, kmax=3)
+            assert torch.equal(res.matches, res2.matches)
+            assert torch.equal(got, want), (ads, qc, torch.nonzero(got != want)[:5].tolist())
+            # a histogram narrower than the reads: everything beyond lands in the last bin, in both paths
+            want40 = batch.statistics(res, 40, 1)
+            _, got40 = batch.run_with_statistics(sq, offs, ql if qc else None, max_read_len=150, max_len=40, kmax=1)
+            assert torch.equal(got40, want40)
+
+
 def test_both_kernel_schedules_agree():
     """The two-phase kernel (default for one adapter) and the one-phase kernel give identical records."""
     import os
