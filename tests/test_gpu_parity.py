@@ -82,7 +82,7 @@ def test_reference_known_answer_tests():
 def test_comparers_golden():
     from cutadapt_b200._align import PrefixComparer, SuffixComparer
 
-    for ref, q, rate, wr, wq, mo, p, s in golden("comparer_kat.json.gz")[:400]:
+    for ref, q, rate, wr, wq, mo, p, s in golden("comparer_kat.json.gz"):
         got = PrefixComparer(ref, rate, wr, wq, mo).locate(q)
         assert (list(got) if got else None) == p, ("prefix", ref, q)
         got = SuffixComparer(ref, rate, wr, wq, mo).locate(q)
@@ -216,6 +216,18 @@ def test_config5_demultiplex_96_anchored_barcodes():
         assert g.errors >= r.errors if has_n else g.errors == r.errors
         assert sum(x != y for x, y in zip(g.adapter.sequence, read[:10])) == g.errors
     assert n_hit > 15000
+    # ... and the index path equals the oracle's own index (built from the oracle's Hamming spheres), record by record
+    data = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    offsets = np.arange(len(reads) + 1, dtype=np.int64) * 150
+    exp = oracle.oracle_index_process(barcodes, 0.1, False, True, data, offsets, [a.descriptor() for a in pre])
+    for i, g in enumerate(got):
+        if g is None:
+            assert exp["adapter"][i] < 0, i
+        else:
+            e = exp[i]
+            assert (barcodes.index(g.adapter.sequence), g.astart, g.astop, g.rstart, g.rstop, g.score, g.errors) == \
+                (int(e["adapter"]), int(e["astart"]), int(e["astop"]), int(e["rstart"]), int(e["rstop"]), int(e["score"]),
+                 int(e["errors"])), i
 
 
 def test_match_objects_behave_like_the_reference():
