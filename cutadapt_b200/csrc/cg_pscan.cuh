@@ -80,6 +80,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
         for (int i = threadIdx.x; i < 3 * (st_len + 1) + 8; i += CG_NT) s_hlen[i] = 0;
         if (threadIdx.x < 8) s_scal[threadIdx.x] = 0;     // reads, bases, with adapters, quality-trimmed, adapter bases
     }
+    unsigned long long st_acc = 0;     // fused statistics: lane L of a warp accumulates scalar L (see the tile loop)
     for (uint32_t i = tid; i < a.blob_bytes / 16; i += CG_NT) ((uint4 *)s_blob)[i] = ((const uint4 *)a.blob)[i];
     for (uint32_t i = tid; i < 768 / 16; i += CG_NT) ((uint4 *)s_enc)[i] = ((const uint4 *)a.enc)[i];
     if (lane == 0) {
@@ -130,8 +131,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
         if (b1 > b0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
         int cls = CG_PLANE_NONE, s0 = 0, ts = 0, te = 0;
         int st_fin = -1;                              // fused statistics: this lane's final-length bin, -1 = none
-        uint32_t st_bp = 0, st_qbp = 0, st_abp = 0;   // ... and its contributions to the scalars
-        bool st_hit = false;
+        uint32_t st_p1 = 0, st_p2 = 0, st_p3 = 0;     // ... and its contributions to the scalars, packed (below)
         uint32_t t_flags = 4u | CG_TASK_RESCAN;
         uint32_t tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t win_region = 0, win_off = 0;         // shared-memory address of the carried bytes, window offset in them
@@ -175,25 +175,27 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 else if (cls == CG_PLANE_OVERLAP) hit_end_overlap(A, nn, s0, hit);
                 store_hit(a.out + (size_t)r * a.slots, hit, 0, nn);
                 if (a.stats) {
-                    // what stats_read_core adds for this read (one round, one slot)
+                    // what stats_read_core adds for this read (one round, one slot), packed for three warp sums:
+                    // p1 = bases | quality-trimmed bases << 16, p2 = adapter bases | read << 16 | match << 22,
+                    // p3 = one 6-bit count per adjacent-base class
                     CG_PSCAN_STATS_VIEW
-                    (void)s_hlen; (void)s_scal;
-                    st_bp = (uint32_t)n;
-                    if (a.quality_trim && a.qtrim) st_qbp = (uint32_t)(n - nn);
+                    (void)s_hlen; (void)s_scal; (void)s_hadj;
+                    st_p1 = (uint32_t)n | ((a.quality_trim && a.qtrim) ? (uint32_t)(n - nn) << 16 : 0u);
+                    st_p2 = 1u << 16;
                     int fin = nn;
                     if (hit.adapter >= 0) {
                         const bool after = hit.remove == CGK_REMOVE_AFTER;
-                        const int removed = after ? nn - hit.rstart : hit.rstop;
-                        st_hit = true;
-                        st_abp = (uint32_t)(removed < 0 ? 0 : removed);
-                        atomicAdd(&s_hrem[(after ? st_len + 1 : 0) + (removed < 0 ? 0 : (removed > st_len ? st_len : removed))], 1u);
+                        int removed = after ? nn - hit.rstart : hit.rstop;
+                        removed = removed < 0 ? 0 : removed;
+                        st_p2 |= (uint32_t)removed | (1u << 22);
+                        atomicAdd(&s_hrem[(after ? st_len + 1 : 0) + (removed > st_len ? st_len : removed)], 1u);
                         if (after) {
                             int k = 4;
                             if (hit.rstart > 0) {
                                 const uint8_t c = s_seq[off + ts + hit.rstart - 1];
                                 k = c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
                             }
-                            atomicAdd(&s_hadj[k], 1u);
+                            st_p3 = 1u << (6 * k);
                             fin = hit.rstart;
                         } else {
                             fin = nn - hit.rstop;
@@ -205,21 +207,30 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
         }
         if (a.stats) {
             CG_PSCAN_STATS_VIEW
-            (void)s_hrem; (void)s_hadj;
-            // most reads of a tile end in the same length bin: one shared-memory atomic per distinct bin of the warp
-            const unsigned peers = __match_any_sync(0xffffffffu, st_fin);
-            if (st_fin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_hlen[st_fin], (uint32_t)__popc(peers));
-            const uint32_t c_reads = __popc(__ballot_sync(0xffffffffu, st_fin >= 0));
-            const uint32_t c_with = __popc(__ballot_sync(0xffffffffu, st_hit));
-            const uint32_t c_bp = __reduce_add_sync(0xffffffffu, st_bp);
-            const uint32_t c_qbp = __reduce_add_sync(0xffffffffu, st_qbp);
-            const uint32_t c_abp = __reduce_add_sync(0xffffffffu, st_abp);
-            if (lane == 0 && c_reads) {
-                atomicAdd(&s_scal[0], (unsigned long long)c_reads);
-                atomicAdd(&s_scal[1], (unsigned long long)c_bp);
-                if (c_with) atomicAdd(&s_scal[2], (unsigned long long)c_with);
-                if (c_qbp) atomicAdd(&s_scal[3], (unsigned long long)c_qbp);
-                if (c_abp) atomicAdd(&s_scal[4], (unsigned long long)c_abp);
+            (void)s_hrem; (void)s_hadj; (void)s_scal;
+            // most reads of a tile end in the same length bin: one shared-memory atomic for the bin of the first
+            // counted lane and its peers, one each for the others
+            const uint32_t counted = __ballot_sync(0xffffffffu, st_fin >= 0);
+            if (counted) {
+                const int leader = __ffs(counted) - 1;
+                const int common = __shfl_sync(0xffffffffu, st_fin, leader);
+                const uint32_t same = __ballot_sync(0xffffffffu, st_fin == common);
+                if (lane == leader) atomicAdd(&s_hlen[common], (uint32_t)__popc(same));
+                else if (st_fin >= 0 && st_fin != common) atomicAdd(&s_hlen[st_fin], 1u);
+                const uint32_t s1 = __reduce_add_sync(0xffffffffu, st_p1);
+                const uint32_t s2 = __reduce_add_sync(0xffffffffu, st_p2);
+                const uint32_t s3 = __reduce_add_sync(0xffffffffu, st_p3);
+                // lane L keeps scalar L of the warp: reads, matches, bases, quality-trimmed, adapter bases, adjacent x 5
+                uint32_t mine_add = 0;
+                switch (lane) {
+                case 0: mine_add = (s2 >> 16) & 63u; break;
+                case 1: mine_add = s2 >> 22; break;
+                case 2: mine_add = s1 & 0xffffu; break;
+                case 3: mine_add = s1 >> 16; break;
+                case 4: mine_add = s2 & 0xffffu; break;
+                default: if (lane < 10) mine_add = (s3 >> (6 * (lane - 5))) & 63u; break;
+                }
+                st_acc += mine_add;
             }
         }
         const bool slow = mine && cls == CG_PLANE_SLOW;
@@ -268,8 +279,12 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
     }
     if (a.stats) {
         CG_PSCAN_STATS_VIEW
+        if (st_acc) {
+            // lanes 0..4: reads, matches, bases, quality-trimmed, adapter bases -> stats[0, 2, 1, 3, 4]; 5..9: adjacent bases
+            if (lane < 5) atomicAdd(&a.stats[lane == 1 ? 2 : (lane == 2 ? 1 : lane)], st_acc);
+            else if (lane < 10) atomicAdd(&s_hadj[lane - 5], (uint32_t)st_acc);
+        }
         __syncthreads();
-        if (threadIdx.x < 5 && s_scal[threadIdx.x]) atomicAdd(&a.stats[threadIdx.x], s_scal[threadIdx.x]);
         // one adapter: lengths, then its 5' block and its 3' block (adjacent bases, removed length x errors)
         unsigned long long *hist = a.stats + CG_STATS_SCALARS;
         const long long end_size = cg_stats_end_size(st_len, a.stats_kmax);
