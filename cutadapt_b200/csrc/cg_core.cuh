@@ -850,7 +850,9 @@ CG_HD uint32_t plane_load(PlaneState<W> &st, const uint8_t *base, int off0)
 
 // one chain step: acc = plane (first character of a chain) or (acc << 1) & plane
 #ifndef CG_CHAIN_IMAD
-#define CG_CHAIN_IMAD 0xFF          // words of the accumulator whose shift runs on the multiply pipe (bit b = word b)
+#define CG_CHAIN_IMAD 0             // words of the accumulator whose shift runs on the multiply pipe (bit b = word b);
+                                    // measured on B200: 0xFF is 2 % SLOWER than funnel shifts (IMAD.WIDE issues at half
+                                    // rate), so the default keeps the shifts on the ALU pipe
 #endif
 template <int W>
 CG_HD void plane_chain_apply(uint32_t (&acc)[W], const uint32_t (&P)[W], bool first)

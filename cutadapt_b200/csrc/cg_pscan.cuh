@@ -23,6 +23,10 @@ struct ScanSmem { size_t blob_off, enc_off, stats_off, warp_off, warp_stride, ba
 #ifndef CG_PSCAN_BLOCKS
 #define CG_PSCAN_BLOCKS 8     // resident CTAs per SM the 5-word variant is compiled for (64 registers)
 #endif
+#ifndef CG_PSCAN_STATS
+#define CG_PSCAN_STATS 1      // 0: the statistics fused into this stage are compiled out (the specialised kernels unless
+                              // CUTADAPT_B200_FUSED_STATS is set: the code costs 3 % even when it is not used)
+#endif
 #define CG_TASK_RESCAN 0x100u     // the plan stage must scan the read itself (shift-and scan_core)
 #define CG_TASK_BYTES 0x400u      // the task carries the read window itself: 2 W + 1 16-byte pieces after the four header
                                   // words (the aligned stretch of shared memory that covers the 32 W characters in front
@@ -74,7 +78,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
     uint32_t *s_hrem = s_hlen + (st_len + 1);   /* removed lengths at 0 errors: 5' matches, then 3' matches */           \
     uint32_t *s_hadj = s_hrem + 2 * (st_len + 1);                                                                        \
     unsigned long long *s_scal = (unsigned long long *)((uint8_t *)s_hlen + cg_align_up((size_t)(3 * (st_len + 1) + 8) * sizeof(uint32_t), 8));
-    if (a.stats) {
+    if (CG_PSCAN_STATS && a.stats) {
         CG_PSCAN_STATS_VIEW
         (void)s_hrem; (void)s_hadj;
         for (int i = threadIdx.x; i < 3 * (st_len + 1) + 8; i += CG_NT) s_hlen[i] = 0;
@@ -174,7 +178,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 if (cls == CG_PLANE_EXACT) hit_exact(A, nn, s0, hit);
                 else if (cls == CG_PLANE_OVERLAP) hit_end_overlap(A, nn, s0, hit);
                 store_hit(a.out + (size_t)r * a.slots, hit, 0, nn);
-                if (a.stats) {
+                if (CG_PSCAN_STATS && a.stats) {
                     // what stats_read_core adds for this read (one round, one slot), packed for three warp sums:
                     // p1 = bases | quality-trimmed bases << 16, p2 = adapter bases | read << 16 | match << 22,
                     // p3 = one 6-bit count per adjacent-base class
@@ -205,7 +209,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                 }
             }
         }
-        if (a.stats) {
+        if (CG_PSCAN_STATS && a.stats) {
             CG_PSCAN_STATS_VIEW
             (void)s_hrem; (void)s_hadj; (void)s_scal;
             // most reads of a tile end in the same length bin: one shared-memory atomic for the bin of the first
@@ -277,7 +281,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
             if (next < n_mt) issue(next);
         }
     }
-    if (a.stats) {
+    if (CG_PSCAN_STATS && a.stats) {
         CG_PSCAN_STATS_VIEW
         if (st_acc) {
             // lanes 0..4: reads, matches, bases, quality-trimmed, adapter bases -> stats[0, 2, 1, 3, 4]; 5..9: adjacent bases

@@ -254,9 +254,10 @@ int cg_process_batch_device(cg_ctx *ctx, const cg_adapterset *set, const uint8_t
                             int32_t max_read_len, const cg_params *params, cg_match *d_matches,
                             int32_t *d_qtrim);
 /* The same plus the statistics of these reads ADDED to d_stats (int64[cg_stats_size(n_adapters, stats_max_len,
- * stats_kmax)], device memory; what cg_stats_accumulate_device computes from the records).  For a set of one plain
- * adapter the split pipeline counts the reads its first stage settles while they are in shared memory and the rest
- * from its task list, so the records are not read back; any other set runs the statistics kernel after the pass.
+ * stats_kmax)], device memory; what cg_stats_accumulate_device computes from the records).  With
+ * CUTADAPT_B200_FUSED_STATS=1 and a set of one plain adapter the split pipeline counts the reads its first stage
+ * settles while they are in shared memory and the rest from its task list, so the records are not read back;
+ * otherwise the statistics kernel runs after the pass.
  * With quality trimming d_qtrim is required. */
 int cg_process_batch_device_stats(cg_ctx *ctx, const cg_adapterset *set, const uint8_t *d_seq, const uint8_t *d_qual,
                                   const int64_t *d_offsets, int64_t n_reads, int32_t max_read_len, const cg_params *params,

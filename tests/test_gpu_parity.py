@@ -626,6 +626,7 @@ def test_statistics_fused_into_the_pass_equal_the_statistics_kernel(jit, monkeyp
     from cutadapt_b200.pipeline import DeviceBatch
 
     monkeypatch.setenv("CUTADAPT_B200_JIT", jit)
+    monkeypatch.setenv("CUTADAPT_B200_FUSED_STATS", "1")
     monkeypatch.setenv("CUTADAPT_B200_SUB_READS", "70000")
     n = 200_000
     seq, qual = make_read_tensor(n, config=4, device="cuda", with_qualities=True)
