@@ -609,6 +609,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         // CUTADAPT_B200_SUB_READS overrides it for experiments.
         long long SUB = (plane_w && getenv("CUTADAPT_B200_TASK_BYTES")) ? (16LL << 20) : (32LL << 20);   // (tasks with bytes: 240 B each)
         if (const char *e = getenv("CUTADAPT_B200_SUB_READS")) { const long long v = atoll(e); if (v >= 1024) SUB = v; }
+        SUB = std::min<long long>(SUB, 1LL << 31);     // tasks name their read with 32 bits
         const long long cap = std::min<long long>(n_reads, SUB);
         // header (4 words) and, with CUTADAPT_B200_TASK_BYTES=1, the window bytes (cg_pscan.cuh).  Carrying the bytes
         // turns the plan stage's gather into a stream but was measured neutral (plan 2.55 -> 2.65 ms, first stage

@@ -2436,19 +2436,20 @@ CG_HD bool window_is_plain(const uint8_t *p, int n)
                           ((uint32_t)base[4 * (i) + 3] << 24))
 #endif
     uint32_t hi_or = 0, lo_or = 0, six_and = 0xFFFFFFFFu;
-    for (int i = 0; i < n_words; ++i) {
-        uint32_t w = CG_PLAIN_WORD(i);
-        if (i == 0 || i == n_words - 1) {
-            uint32_t keep = 0xFFFFFFFFu;
-            if (i == 0) keep &= 0xFFFFFFFFu << (8 * mis);
-            if (i == n_words - 1 && (total & 3)) keep &= 0xFFFFFFFFu >> (8 * (4 - (total & 3)));
-            w = (w & keep) | (0x41414141u & ~keep);
-        }
+    auto take = [&](uint32_t w) {
         const uint32_t s1 = w >> 1, s2 = w >> 2, s4 = w >> 4;
         hi_or |= w & 0x88888888u;                                      // bits 7 and 3 must be clear
         six_and &= w;                                                  // bit 6 must be set
         lo_or |= ((s2 & ~s1) ^ s4) | ~(w ^ s4);                        // bit 0 of every byte: a violation
-    }
+    };
+    // first and last word: the bytes outside the window count as 'A'; the words between them need no masks
+    uint32_t keep0 = 0xFFFFFFFFu << (8 * mis);
+    const uint32_t keep_last = (total & 3) ? 0xFFFFFFFFu >> (8 * (4 - (total & 3))) : 0xFFFFFFFFu;
+    if (n_words == 1) keep0 &= keep_last;
+    take((CG_PLAIN_WORD(0) & keep0) | (0x41414141u & ~keep0));
+#pragma unroll 4
+    for (int i = 1; i < n_words - 1; ++i) take(CG_PLAIN_WORD(i));
+    if (n_words > 1) take((CG_PLAIN_WORD(n_words - 1) & keep_last) | (0x41414141u & ~keep_last));
 #undef CG_PLAIN_WORD
     return hi_or == 0 && (six_and & 0x40404040u) == 0x40404040u && (lo_or & 0x01010101u) == 0;
 }

@@ -676,8 +676,10 @@ __global__ void __launch_bounds__(CG_NT) cg_scan_kernel(const CgKernelArgs a)
             base = __shfl_sync(0xffffffffu, base, 0);
             if (pass) {
                 const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-                a.tasks[2 * slot] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
-                                               (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
+                // {read (relative to the sub-batch), byte offset of the window in the batch (hi, lo), window length}:
+                // the list kernels fetch the window without a dependent load of offsets[read]
+                const unsigned long long woff = (unsigned long long)(o0 + ts);
+                a.tasks[2 * slot] = make_uint4((uint32_t)r, (uint32_t)(woff >> 32), (uint32_t)woff, (uint32_t)(te - ts));
                 a.tasks[2 * slot + 1] = make_uint4(hits, (uint32_t)gs, rs0, rs1);
             }
         }
@@ -838,8 +840,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
             T.soff = T.td.y;
             return;
         }
-        const long long r = (long long)(((unsigned long long)T.ta.y << 32) | T.ta.x);
-        uintptr_t addr = seq_base + (uintptr_t)a.offsets[r] + T.ta.z;
+        uintptr_t addr = seq_base + (uintptr_t)(((unsigned long long)T.ta.y << 32) | T.ta.z);
         uint32_t len = T.ta.w;
         if (!PLAN) {
             const int n = (int)T.ta.w, ri = (int)T.tc.z;
@@ -872,7 +873,7 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
         const bool has_task = task_index(g) >= 0;
         const uint8_t *p = s_slot + ((size_t)st * 32 + lane) * slot_bytes + soff;
         const int n = (int)ta.w;
-        const long long r = (long long)(((unsigned long long)ta.y << 32) | ta.x);
+        const long long r = (long long)ta.x;
         CgHit hit;
         hit.adapter = -1; hit.remove = 0;
         hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
@@ -1361,7 +1362,7 @@ __global__ void cg_stats_kernel(const uint8_t *seq, const int64_t *offsets, long
         long long r = i;
         if (task_list) {
             const uint4 t = task_list[(size_t)task_rec * i];
-            r = (long long)(((unsigned long long)t.y << 32) | t.x);
+            r = (long long)t.x;
         }
         const long long o0 = offsets[r];
         const int len = (int)(offsets[r + 1] - o0);

@@ -32,7 +32,7 @@ struct ScanSmem { size_t blob_off, enc_off, stats_off, warp_off, warp_stride, ba
                                   // words (the aligned stretch of shared memory that covers the 32 W characters in front
                                   // of the window's end); td.y = offset of the window's first character in them.  The
                                   // plan stage then streams its input instead of gathering windows from all over HBM.
-#define CG_TASK_PLANES 0x200u     // a 4 x uint4 task of cg_pscan_kernel: {read lo, read hi, trim start, length},
+#define CG_TASK_PLANES 0x200u     // a 4 x uint4 task of cg_pscan_kernel: {read, window offset hi, lo, length},
                                   // {M0, flags, M1, M2}, {M3 .. M6}, {M7, window offset, 0, 0} with M = PlaneOut::M (+ CG_TASK_BYTES);
                                   // flags bits 12-15: plane words W, bit 20: PlaneOut::end_hit, bit 21: PlaneOut::no_end
 // stats_max_len >= 0: room for the per-CTA histograms of the fused statistics (read lengths, removed lengths at 0
@@ -259,8 +259,8 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
                     ? (unsigned long long)a.task_cap - 1ull - (base_b + __popc(ballot_b & below))
                     : base_a + __popc(ballot_a & below);
                 uint4 *rec = a.tasks + (size_t)a.task_rec * slot;
-                rec[0] = make_uint4((uint32_t)((unsigned long long)r & 0xffffffffu),
-                                    (uint32_t)((unsigned long long)r >> 32), (uint32_t)ts, (uint32_t)(te - ts));
+                const unsigned long long woff = (unsigned long long)(o0 + ts);     // where the window lies in the batch
+                rec[0] = make_uint4((uint32_t)r, (uint32_t)(woff >> 32), (uint32_t)woff, (uint32_t)(te - ts));
                 rec[1] = make_uint4(tm[0], t_flags, tm[1], tm[2]);
                 rec[2] = make_uint4(tm[3], tm[4], tm[5], tm[6]);
                 rec[3] = make_uint4(tm[7], win_off, 0u, 0u);
