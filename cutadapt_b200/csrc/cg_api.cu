@@ -654,6 +654,8 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             if (sev[0]) CU(cudaEventRecord(sev[1], st));
             b.tasks2 = c->tasks2.p; b.task2_count = cnt + 1;
             b.tasks3 = c->tasks3.p; b.task3_count = cnt + 2;
+            // run records of the plane path go to two lists (banded first runs / the others): cnt[5] counts the second
+            b.task2_count_b = (plane_w && !getenv("CUTADAPT_B200_NO_BAND_LISTS")) ? cnt + 5 : nullptr;
             CU(cg_launch_list(b, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
             c->launches += 2;
             if (plane_w) {
@@ -672,7 +674,10 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
                 const int in = round & 1, outl = in ^ 1;
                 if (round > 0) CU(cudaMemsetAsync(cnt + 1 + outl, 0, sizeof(unsigned long long), st));
                 b.tasks = lists[in]; b.task_count = cnt + 1 + in;
+                b.task_count_b = round == 0 ? b.task2_count_b : nullptr;     // the plan stage's second list
                 b.tasks2 = lists[outl]; b.task2_count = cnt + 1 + outl;
+                if (round == 0) b.task2_count_b = nullptr;                   // later rounds: one list
+                else b.task_count_b = nullptr;
                 CU(cg_launch_list(b, false, s->host.max_m, grid_for(run_occ), list_smem, st));
                 c->launches += 1;
             }

@@ -43,6 +43,8 @@ struct CgKernelArgs {
     long long task_cap;
     uint4 *tasks2;                    // output list of the plan / run kernels: 4 x uint4 per record
     unsigned long long *task2_count;
+    unsigned long long *task2_count_b; // plan stage: run records whose first run has no band (run_band_d) are filed from
+                                      // the end of tasks2 backwards and counted here (null: one list)
     uint4 *tasks3;                    // plan stage only: reads of cg_pscan_kernel whose window holds other letters than
     unsigned long long *task3_count;  //   A/C/G/T go here (2 x uint4, CG_TASK_RESCAN) for a second, dense plan launch
     // statistics fused into the first stage (cg_pscan.cuh): the reads it settles are counted here, the rest by

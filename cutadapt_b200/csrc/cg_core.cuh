@@ -1684,10 +1684,13 @@ CG_HD bool loc_state_result(const LocState &st, int *out6)
 // Processes runs [0, n_use) of R starting from the selection state `st` and leaves the updated state
 // in `st`; the last-column scan (_align.pyx:536-572) is done only when final_scan is set (i.e. when
 // this call covers the read's last run).
-template <int MR, bool NC = false, bool SMEM = false>
+#ifndef CG_BAND_SLACK
+#define CG_BAND_SLACK 0     // test hook: > 0 cuts rows the band needs (tools/fuzz_band.py must then report mismatches)
+#endif
+template <int MR, bool NC = false, bool SMEM = false, bool BAND = false>
 CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *maxcost,
                        const uint32_t *peq, const ReadView &rv, const RunList &R, int n_use, bool has_task,
-                       bool final_scan, LocState &st, bool eval_bottom = true)
+                       bool final_scan, LocState &st, bool eval_bottom = true, int band_d = -1)
 {
     typedef Packed32 C;
     uint32_t c[MR + 1];
@@ -1741,6 +1744,9 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
         }
         const int my_len = mine ? hi - lo : 0;
         const int len = CG_WARP_MAX(my_len);
+        // band (run_band_d): warp-uniform, so every lane of the warp must have one; the widest d decides
+        const bool band_on = BAND && !CG_WARP_ANY(mine && band_d < 0);
+        const int band_off = band_on ? CG_WARP_MAX(mine ? band_d : 0) + 2 * k : 0;
         for (int t = 0; t < len; ++t) {
             const bool act = mine && !stopped && t < my_len;
             // (all lanes stopped early: rare, so the vote is only taken every 8th column)
@@ -1764,9 +1770,18 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
             uint32_t up = w0;
             int lastok = (act && w0 < kthr) ? 0 : -1;
             const int wmax = CG_WARP_MAX(my_last);
+            // rows below `skip` were already outside the band in the previous column (their values are not needed
+            // as diagonal neighbours either)
+            const int skip = band_on ? t - band_off + CG_BAND_SLACK : 0;
 #pragma unroll
             for (int i0 = 1; i0 <= MR; i0 += 4) {
-                if (i0 <= wmax) {                               // warp-uniform
+                if (BAND && i0 + 3 < skip) {                    // warp-uniform
+#pragma unroll
+                    for (int i = i0; i < i0 + 4; ++i)
+                        if (i <= MR) c[i] = C::INF;
+                    diag = C::INF;
+                    up = C::INF;
+                } else if (i0 <= wmax) {                        // warp-uniform
 #pragma unroll
                     for (int i = i0; i < i0 + 4; ++i) {
                         if (i <= MR) {
@@ -2072,7 +2087,27 @@ struct RunPlan {
     int exact;                     // 1: finished by the exact-occurrence shortcut at start s0;
                                    // 2: by the end-overlap shortcut, s0 = overlap length
     int s0;
+    int banded;                    // the hit runs come from the bit-plane stage's mask of ALL locator hits: run_band_d
 };
+
+// Rows of a hit run that no alignment through the run's hits can touch.  The mask M of the bit-plane stage holds every
+// exact occurrence of a locator chunk, so every alignment with <= k errors in the read starts within k of a start s
+// that some hit implies, and a run [lo, hi) = [s_min - k, s_max + m + k) (merged hits) holds all alignments of its
+// hits.  A cell (i, j) on a path that started at read position c <= s_max + k with <= k errors has
+// i >= (j - c) - k >= j - s_max - 2k: in the column computed at step t of the run (j = lo + t + 1) the rows
+// i < t + 1 - d - 2k with d = s_max - lo = hi - m - k - lo cannot lie on such a path.  Their cells can neither be
+// reported (a bottom-row cell with cost <= k is a full alignment, hence on such a path) nor win or tie the minimum
+// of a cell that is (that would make an alignment from a later start succeed, which has a hit of its own inside
+// the merged run), and the stale cells beyond the Ukkonen bound always enter with cost + 1 > k + 1: so the DP may
+// treat them as infinite.  Not for runs that reach the end of the read (the last-column scan accepts partial
+// adapters from any start) and not for adapters with a free adapter start.  Returns d, or -1: no band.
+CG_HD int run_band_d(const CgAdapter &A, int n, int lo, int hi, bool hit_derived, bool is_end_run)
+{
+    const bool can = A.m <= 64 && !(A.flags & 1) && (A.flags & 2) && (A.flags & 8) && A.indel_cost == 1;
+    if (!can || !hit_derived || is_end_run || hi >= n) return -1;
+    const int d = hi - A.m - A.k - lo;
+    return d >= 0 ? d : -1;
+}
 
 template <bool REV>
 CG_HD void plan_hit_runs_dir(const CgScanWord *words, int n_words, const uint8_t *pool, const CgAdapter &A,
@@ -2367,7 +2402,7 @@ CG_HD void plan_runs(const SetView &S, const uint8_t *p, int n, uint32_t hits, i
 {
     const CgAdapter &A = S.ad[0];
     P.n_runs = 0; P.lo0 = P.hi0 = P.lo1 = P.hi1 = P.lo2 = P.hi2 = P.lo3 = P.hi3 = 0;
-    P.end_idx = -1; P.exact = 0; P.s0 = 0;
+    P.end_idx = -1; P.exact = 0; P.s0 = 0; P.banded = 0;
     if (S.h->myers && (A.flags & 2) && (A.flags & 8) && n > 0) {
         const int32_t *ncnt = (const int32_t *)(S.pool + A.ncount_off);
         const int32_t *maxcost = (const int32_t *)(S.pool + A.maxcost_off);
@@ -2463,7 +2498,7 @@ CG_HD void plan_runs_planes(const SetView &S, const uint8_t *p, int n, const uin
 {
     const CgAdapter &A = S.ad[0];
     P.n_runs = 0; P.lo0 = P.hi0 = P.lo1 = P.hi1 = P.lo2 = P.hi2 = P.lo3 = P.hi3 = 0;
-    P.end_idx = -1; P.exact = 0; P.s0 = 0;
+    P.end_idx = -1; P.exact = 0; P.s0 = 0; P.banded = 1;
     RunList R;
     R.n = 0; R.lo0 = R.hi0 = R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     if (A.flags & 1) runs_add(R, 0, cg_min(n, A.m + A.k), n);              // START_IN_REFERENCE
@@ -2506,7 +2541,7 @@ CG_HD void hit_exact(const CgAdapter &A, int n, int s0, CgHit &hit)
 // [lo, hi) for forward reads, [n - hi, n - lo) for reversed reads.  ALL lanes of a warp must call it.
 template <int MR>
 CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int hi, bool eval_bottom,
-                    bool final_scan, bool has_task, LocState &st)
+                    bool final_scan, bool has_task, LocState &st, int band_d = -1)
 {
     const CgAdapter &A = S.ad[0];
     ReadView rv;
@@ -2519,8 +2554,8 @@ CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int h
     R.n = 1; R.lo0 = lo; R.hi0 = hi; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     // free start in the read bounds every cost by the row number, so short adapters never saturate
     // (run_pass is only called with the run's bytes staged in shared memory on the device)
-    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
-    else locate_regs<MR, false, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom);
+    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true, true, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom, band_d);
+    else locate_regs<MR, false, true, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom, band_d);
 }
 
 // The DP rounds of a planned read (what the cg_list_kernel<run> rounds do), host-sim only.
@@ -2536,10 +2571,11 @@ CG_HD void finish_planned(const SetView &S, const uint8_t *w, int nn, const RunP
             const int hi = r == 0 ? P.hi0 : (r == 1 ? P.hi1 : (r == 2 ? P.hi2 : P.hi3));
             const uint8_t *bytes = A.reverse ? w + (nn - hi) : w + lo;
             const bool last = r == P.n_runs - 1;
-            if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-            else if (A.m <= 32) run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-            else if (A.m <= 48) run_pass<48>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
-            else run_pass<64>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st);
+            const int band = run_band_d(A, nn, lo, hi, P.banded != 0, r == P.end_idx);
+            if (A.m <= 16) run_pass<16>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st, band);
+            else if (A.m <= 32) run_pass<32>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st, band);
+            else if (A.m <= 48) run_pass<48>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st, band);
+            else run_pass<64>(S, bytes, nn, lo, hi, r != P.end_idx, last, true, st, band);
         }
         hit_from_state(A, nn, st, hit);
     }

@@ -801,9 +801,10 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
 
     unsigned long long n_tasks = *a.task_count;
     if (n_tasks > (unsigned long long)a.task_cap) n_tasks = (unsigned long long)a.task_cap;
-    // second list of the plan stage's input (tasks without locator hits, filed from the end of the buffer): its
-    // groups follow those of the first list, so that no warp mixes the two kinds
-    unsigned long long n_tasks_b = (PLAN && a.task_count_b) ? *a.task_count_b : 0ull;
+    // second input list, filed from the end of the buffer backwards: its groups follow those of the first list, so that
+    // no warp mixes the two kinds (plan stage: tasks without locator hits, an experiment; first DP round: runs
+    // without a band, see below)
+    unsigned long long n_tasks_b = a.task_count_b ? *a.task_count_b : 0ull;
     if (n_tasks + n_tasks_b > (unsigned long long)a.task_cap) n_tasks_b = (unsigned long long)a.task_cap - n_tasks;
     const long long n_groups_a = (long long)((n_tasks + 31) / 32);
     const uint4 *list = a.tasks;
@@ -877,12 +878,12 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
         CgHit hit;
         hit.adapter = -1; hit.remove = 0;
         hit.astart = hit.astop = hit.rstart = hit.rstop = hit.score = hit.errors = 0;
-        bool cont = false, defer = false;
+        bool cont = false, cont_b = false, defer = false;
         uint4 ob = make_uint4(0, 0, 0, 0), oc = make_uint4(0, 0, 0, 0), od = make_uint4(0, 0, 0, 0);
         if (PLAN) {
             if (has_task) {
                 RunPlan P;
-                P.n_runs = 0; P.exact = 0; P.s0 = 0; P.end_idx = -1;
+                P.n_runs = 0; P.exact = 0; P.s0 = 0; P.end_idx = -1; P.banded = 0;
                 uint32_t hits = tb.x, rs0 = tb.z, rs1 = tb.w;
                 int gs = (int)(tb.y & 0xffu);
                 bool pass = true;
@@ -910,7 +911,13 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                 else if (P.exact) hit_exact(A, n, P.s0, hit);
                 else if (P.n_runs > 0) {
                     cont = true;
-                    oc = make_uint4((uint32_t)A.m, (uint32_t)n, 0u, (uint32_t)P.n_runs | ((uint32_t)(P.end_idx & 15) << 8));
+                    // bit 16: the runs come from the bit-plane stage's hit mask (run_band_d applies)
+                    oc = make_uint4((uint32_t)A.m, (uint32_t)n, 0u, (uint32_t)P.n_runs | ((uint32_t)(P.end_idx & 15) << 8) |
+                                                                   (P.banded ? 1u << 16 : 0u));
+                    // the first DP round works on two lists: runs with a band first, the others (end windows,
+                    // runs that reach the end of the read) after them -- the band is warp-uniform
+                    cont_b = a.task2_count_b != nullptr &&
+                             run_band_d(A, n, P.lo0, P.hi0, P.banded != 0, P.end_idx == 0) < 0;
                     od = make_uint4((uint32_t)P.lo0 | ((uint32_t)P.hi0 << 16), (uint32_t)P.lo1 | ((uint32_t)P.hi1 << 16),
                                     (uint32_t)P.lo2 | ((uint32_t)P.hi2 << 16), (uint32_t)P.lo3 | ((uint32_t)P.hi3 << 16));
                 }
@@ -925,7 +932,8 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
             ls.have = (int)tb.x; ls.b_origin = (int)tb.y; ls.b_cost = (int)tb.z; ls.b_score = (int)tb.w;
             ls.b_ref_stop = (int)tc.x; ls.b_q_stop = (int)tc.y; ls.stopped = 0;
             const bool last = ri == n_runs - 1;
-            run_pass<MR>(S, p, n, lo, hi, ri != end_idx, last, has_task, ls);
+            const int band = has_task ? run_band_d(A, n, lo, hi, (tc.w >> 16) & 1u, ri == end_idx) : -1;
+            run_pass<MR>(S, p, n, lo, hi, ri != end_idx, last, has_task, ls, band);
             if (has_task) {
                 if (ls.stopped || last) hit_from_state(A, n, ls, hit);
                 else {
@@ -950,13 +958,20 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                 }
             }
         }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
-        if (ballot) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(a.task2_count, (unsigned long long)__popc(ballot));
+        const uint32_t ballot = __ballot_sync(0xffffffffu, cont && !cont_b);
+        const uint32_t ballot_b = __ballot_sync(0xffffffffu, cont && cont_b);
+        if (ballot | ballot_b) {
+            unsigned long long base = 0, base_b = 0;
+            if (lane == 0) {
+                if (ballot) base = atomicAdd(a.task2_count, (unsigned long long)__popc(ballot));
+                if (ballot_b) base_b = atomicAdd(a.task2_count_b, (unsigned long long)__popc(ballot_b));
+            }
             base = __shfl_sync(0xffffffffu, base, 0);
+            base_b = __shfl_sync(0xffffffffu, base_b, 0);
             if (cont) {
-                const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                const uint32_t below = (1u << lane) - 1u;
+                const unsigned long long slot = cont_b ? (unsigned long long)a.task_cap - 1ull - (base_b + __popc(ballot_b & below))
+                                                       : base + __popc(ballot & below);
                 a.tasks2[4 * slot] = ta;
                 a.tasks2[4 * slot + 1] = ob;
                 a.tasks2[4 * slot + 2] = oc;

@@ -44,7 +44,7 @@ def hostsim_lib():
     if _hs is None:
         from cutadapt_b200 import _lib as L
 
-        lib = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+        lib = C.CDLL(os.environ.get("CUTADAPT_B200_HOSTSIM_LIB") or os.path.join(HERE, "hostsim", "libhostsim.so"))
         lib.hs_last_error.restype = C.c_char_p
         lib.hs_process_batch.argtypes = [
             C.POINTER(L.cg_adapter_desc), C.c_int, C.POINTER(L.cg_group_desc), C.c_int, C.c_void_p,
