@@ -628,3 +628,35 @@ def test_first_stage_specialisation_compiles_without_a_device():
     spec = spec_of(PA.MultipleAdapters([PA.BackAdapter("AGATCNNNNGAGC", max_errors=0.1, name="a")]))
     n, src, _ = hostsim_jit_compile(spec)
     assert n == 0 and src == ""
+
+
+def test_banded_dp_runs_on_crowded_reads():
+    """run_band_d (cg_core.cuh): the DP runs of the bit-plane path skip the rows no alignment through the run's hits
+    can touch.  Reads crowded with mutated adapter copies a few bases apart, overlapping copies, partial copies and
+    repetitive adapters (tools/fuzz_band.py makes them) must still come out as the oracle says; a band cut two rows
+    too deep is caught by this generator within a few hundred reads (checked when the band was introduced)."""
+    import importlib.util
+    import os
+    import cutadapt_b200.adapters as PA
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec_ = importlib.util.spec_from_file_location("fuzz_band", os.path.join(root, "tools", "fuzz_band.py"))
+    fb = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(fb)
+    total = 0
+    for trial in range(40):
+        rng = random.Random(777 + trial)
+        m = rng.choice([rng.randint(6, 12), 13, 13, rng.randint(14, 33), 33, rng.randint(34, 60)])
+        seq = "".join(rng.choice("ACGT") for _ in range(m))
+        if trial % 4 == 0:
+            unit = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 4)))
+            seq = (unit * m)[:m]
+        cls = rng.choice([PA.BackAdapter, PA.BackAdapter, PA.FrontAdapter, PA.AnywhereAdapter])
+        ad = cls(seq, name="x", max_errors=rng.choice([0.1, 0.1, 0.15, 0.2, 0.3]), min_overlap=rng.randint(1, 6))
+        spec = spec_of(ad)
+        reads = [fb.make_read(rng, seq, rng.choice([60, 150, 150, 200, 256])) for _ in range(250)]
+        exp, _ = oracle.oracle_process(spec.adapters, spec.groups, reads, None, False, 0, 0, 33, 1)
+        got, _ = hostsim_process(spec, reads, None, L.make_params(quality_trim=False), 256)
+        assert (got == exp).all(), repr(ad)
+        total += int((exp["adapter"] >= 0).sum())
+    assert total > 5000
