@@ -490,6 +490,7 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     a.qbase = (p->quality_base & 255) | (int)((unsigned)p->nextseq_cutoff << 8); a.times = times; a.slots = s->host.slots;
     a.out = d_out; a.qtrim = d_qtrim; a.view = d_view; a.err_flag = c->d_err;
     a.col_rows = s->host.max_m + 1;
+    a.no_band = getenv("CUTADAPT_B200_NO_BAND") != nullptr;
 
     const long long tile_cap_ll = ((long long)CG_NT * max_read_len + 32 + 15) / 16 * 16;
     bool fast = !s->host.any_wide && max_read_len <= CG_PACKED_MAX_N && tile_cap_ll < (1 << 24);

@@ -47,6 +47,7 @@ struct CgKernelArgs {
                                       // the end of tasks2 backwards and counted here (null: one list)
     uint4 *tasks3;                    // plan stage only: reads of cg_pscan_kernel whose window holds other letters than
     unsigned long long *task3_count;  //   A/C/G/T go here (2 x uint4, CG_TASK_RESCAN) for a second, dense plan launch
+    int no_band;                      // 1: the DP runs keep all rows (CUTADAPT_B200_NO_BAND=1, for A/B runs)
     // statistics fused into the first stage (cg_pscan.cuh): the reads it settles are counted here, the rest by
     // cg_stats_tasks_kernel over the task list once their records are final.  null = not fused.
     unsigned long long *stats;

@@ -913,11 +913,11 @@ __global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_
                     cont = true;
                     // bit 16: the runs come from the bit-plane stage's hit mask (run_band_d applies)
                     oc = make_uint4((uint32_t)A.m, (uint32_t)n, 0u, (uint32_t)P.n_runs | ((uint32_t)(P.end_idx & 15) << 8) |
-                                                                   (P.banded ? 1u << 16 : 0u));
+                                                                   ((P.banded && !a.no_band) ? 1u << 16 : 0u));
                     // the first DP round works on two lists: runs with a band first, the others (end windows,
                     // runs that reach the end of the read) after them -- the band is warp-uniform
                     cont_b = a.task2_count_b != nullptr &&
-                             run_band_d(A, n, P.lo0, P.hi0, P.banded != 0, P.end_idx == 0) < 0;
+                             run_band_d(A, n, P.lo0, P.hi0, P.banded != 0 && !a.no_band, P.end_idx == 0) < 0;
                     od = make_uint4((uint32_t)P.lo0 | ((uint32_t)P.hi0 << 16), (uint32_t)P.lo1 | ((uint32_t)P.hi1 << 16),
                                     (uint32_t)P.lo2 | ((uint32_t)P.hi2 << 16), (uint32_t)P.lo3 | ((uint32_t)P.hi3 << 16));
                 }
