@@ -1684,6 +1684,9 @@ CG_HD bool loc_state_result(const LocState &st, int *out6)
 // Processes runs [0, n_use) of R starting from the selection state `st` and leaves the updated state
 // in `st`; the last-column scan (_align.pyx:536-572) is done only when final_scan is set (i.e. when
 // this call covers the read's last run).
+#ifndef CG_RUN_BAND
+#define CG_RUN_BAND 1       // 0: the DP runs are compiled without the band (run_band_d)
+#endif
 #ifndef CG_BAND_SLACK
 #define CG_BAND_SLACK 0     // test hook: > 0 cuts rows the band needs (tools/fuzz_band.py must then report mismatches)
 #endif
@@ -1746,7 +1749,7 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
         const int len = CG_WARP_MAX(my_len);
         // band (run_band_d): warp-uniform, so every lane of the warp must have one; the widest d decides
         const bool band_on = BAND && !CG_WARP_ANY(mine && band_d < 0);
-        const int band_off = band_on ? CG_WARP_MAX(mine ? band_d : 0) + 2 * k : 0;
+        const int band_off = band_on ? CG_WARP_MAX(mine ? band_d : 0) + 2 * k : (1 << 28);
         for (int t = 0; t < len; ++t) {
             const bool act = mine && !stopped && t < my_len;
             // (all lanes stopped early: rare, so the vote is only taken every 8th column)
@@ -1772,15 +1775,12 @@ CG_HD void locate_regs(const CgAdapter &A, const int32_t *ncnt, const int32_t *m
             const int wmax = CG_WARP_MAX(my_last);
             // rows below `skip` were already outside the band in the previous column (their values are not needed
             // as diagonal neighbours either)
-            const int skip = band_on ? t - band_off + CG_BAND_SLACK : 0;
+            const int skip = t - band_off + CG_BAND_SLACK;
 #pragma unroll
             for (int i0 = 1; i0 <= MR; i0 += 4) {
-                if (BAND && i0 + 3 < skip) {                    // warp-uniform
-#pragma unroll
-                    for (int i = i0; i < i0 + 4; ++i)
-                        if (i <= MR) c[i] = C::INF;
-                    diag = C::INF;
-                    up = C::INF;
+                if (BAND && i0 + 3 < skip) {                    // warp-uniform: these four rows are dead for the rest
+                    diag = C::INF;                              // of the run -- their cells are never read again,
+                    up = C::INF;                                // only their place as neighbours of row i0 + 4
                 } else if (i0 <= wmax) {                        // warp-uniform
 #pragma unroll
                     for (int i = i0; i < i0 + 4; ++i) {
@@ -2554,8 +2554,8 @@ CG_HD void run_pass(const SetView &S, const uint8_t *bytes, int n, int lo, int h
     R.n = 1; R.lo0 = lo; R.hi0 = hi; R.lo1 = R.hi1 = R.lo2 = R.hi2 = 0;
     // free start in the read bounds every cost by the row number, so short adapters never saturate
     // (run_pass is only called with the run's bytes staged in shared memory on the device)
-    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true, true, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom, band_d);
-    else locate_regs<MR, false, true, true>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom, band_d);
+    if (MR <= 16 && (A.flags & 2)) locate_regs<MR, true, true, CG_RUN_BAND != 0>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom, band_d);
+    else locate_regs<MR, false, true, CG_RUN_BAND != 0>(A, ncnt, maxcost, peq, rv, R, 1, has_task, final_scan, st, eval_bottom, band_d);
 }
 
 // The DP rounds of a planned read (what the cg_list_kernel<run> rounds do), host-sim only.

@@ -781,8 +781,11 @@ size_t cg_dp_smem_bytes(uint32_t blob_bytes, int slot_bytes) { return dp_smem_la
 #ifndef CG_RUN16_BLOCKS
 #define CG_RUN16_BLOCKS 4     // same for the run kernel with a 16-row column (measured: 4 beats 5)
 #endif
+#ifndef CG_RUN48_BLOCKS
+#define CG_RUN48_BLOCKS 3      // resident CTAs per SM of the 48-row run kernel (168 registers, some spills; 2 = 255 registers)
+#endif
 template <bool PLAN, int MR>
-__global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_RUN16_BLOCKS : (MR <= 48 ? 3 : 2))) cg_list_kernel(const CgKernelArgs a)
+__global__ void __launch_bounds__(CG_NT, PLAN ? CG_PLAN_BLOCKS : (MR <= 16 ? CG_RUN16_BLOCKS : (MR <= 32 ? 3 : (MR <= 48 ? CG_RUN48_BLOCKS : 2)))) cg_list_kernel(const CgKernelArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int slot_bytes = a.carry_slot;
