@@ -656,7 +656,8 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             b.tasks2 = c->tasks2.p; b.task2_count = cnt + 1;
             b.tasks3 = c->tasks3.p; b.task3_count = cnt + 2;
             // run records of the plane path go to two lists (banded first runs / the others): cnt[5] counts the second
-            b.task2_count_b = (plane_w && !getenv("CUTADAPT_B200_NO_BAND_LISTS")) ? cnt + 5 : nullptr;
+            // (only with the band compiled in, CG_RUN_BAND)
+            b.task2_count_b = (CG_RUN_BAND && plane_w && !getenv("CUTADAPT_B200_NO_BAND_LISTS")) ? cnt + 5 : nullptr;
             CU(cg_launch_list(b, true, s->host.max_m, grid_for(plan_occ), list_smem, st));
             c->launches += 2;
             if (plane_w) {

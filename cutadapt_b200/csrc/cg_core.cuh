@@ -1685,7 +1685,11 @@ CG_HD bool loc_state_result(const LocState &st, int *out6)
 // in `st`; the last-column scan (_align.pyx:536-572) is done only when final_scan is set (i.e. when
 // this call covers the read's last run).
 #ifndef CG_RUN_BAND
-#define CG_RUN_BAND 1       // 0: the DP runs are compiled without the band (run_band_d)
+#define CG_RUN_BAND 0       // 1: the DP runs skip the rows outside the band (run_band_d).  Exact (tests/hostsim is built
+                            // with it: test_banded_dp_runs_on_crowded_reads) but measured SLOWER on B200: DP rounds of
+                            // config 2 1.52 -> 1.56 ms, of config 4 (33-row adapters) 16.6 -> 18.7 ms -- the four-row
+                            // chunks above the band are few once the Ukkonen bound has cut the column, and the extra
+                            // live values push the 48-row kernel into spills
 #endif
 #ifndef CG_BAND_SLACK
 #define CG_BAND_SLACK 0     // test hook: > 0 cuts rows the band needs (tools/fuzz_band.py must then report mismatches)
