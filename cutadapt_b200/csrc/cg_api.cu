@@ -603,7 +603,14 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         else CU(cg_pscan_occupancy(want_q, plane_w, scan_smem, &scan_occ));
         if ((jit_kernel ? jit_occ : scan_occ) < 1) return fail(CG_ECUDA, "first stage does not fit with the statistics histogram");
     }
-    if (split) {
+    // sets of index lookups only (demultiplexing), no quality trimming: the light kernel -- nothing to stage
+    const bool light = s->host.all_indexed && !want_q && !s->host.any_wide && s->host.max_m + 1 <= CG_LIGHT_ROWS &&
+                       !(kernel_env && strcmp(kernel_env, "general") == 0) && !getenv("CUTADAPT_B200_NO_LIGHT");
+    if (light) {
+        const long long need = (n_reads + CG_NT - 1) / CG_NT;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 16, need));
+        CU(cg_launch_light(a, grid, st));
+    } else if (split) {
         // scan -> plan -> up to four DP rounds (one run of every unfinished read per round)
         // reads per sub-batch: bounds the lists to 1 + 2 x 2 GiB at the default 32 Mi (measured: fewer,
         // larger sub-batches amortise the kernel tails and the small late DP rounds; 32 Mi vs 4 Mi = +15 % on the 100 M-read bench).

@@ -1084,6 +1084,58 @@ __global__ void cg_trim_generic_kernel(const CgKernelArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// cg_trim_light_kernel -- sets made of index lookups only (demultiplexing: IndexedPrefixAdapters /
+// IndexedSuffixAdapters, adapters.py:1289-1571).  A read costs a handful of characters at one of its ends, packed to
+// 2 bits each, and one probe sequence in the hash table (match_indexed): nothing to stage, no tiles, no DP column
+// -- one lane per read straight from HBM, the adapter tables read through L2, the column of the rare re-alignment
+// (an N in the looked-up affix, _lookup_with_n) in local memory.  The other characters of the read are only touched
+// by the check for non-ASCII bytes, which the warp does cooperatively with 16-byte loads over its 32 reads.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CG_NT) cg_trim_light_kernel(const CgKernelArgs a)
+{
+    const SetView S = make_set_view(a.blob, a.masks64, a.enc, a.index);
+    uint32_t lcol[CG_LIGHT_ROWS];
+    PackedCol colp; colp.base = lcol; colp.stride = 1;
+    WideCol colw; colw.base = nullptr; colw.stride = 0;
+    const int lane = threadIdx.x & 31;
+    const long long n_reads = a.n_reads;
+    const long long n_mt = (n_reads + 31) / 32;
+    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
+    const uintptr_t seq_base = (uintptr_t)a.seq;
+    for (long long mt = (long long)blockIdx.x * (CG_NT / 32) + (threadIdx.x >> 5); mt < n_mt; mt += warps_total) {
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long r = r0 + lane;
+        // the reference raises on non-ASCII characters: all bytes of the warp's reads, coalesced
+        const uintptr_t s = seq_base + (uintptr_t)a.offsets[r0], e = seq_base + (uintptr_t)a.offsets[r1];
+        const uintptr_t as = (s + 15) & ~(uintptr_t)15, ae = e & ~(uintptr_t)15;
+        uint32_t bad = 0;
+        if (as >= ae) {
+            for (uintptr_t q = s + lane; q < e; q += 32) bad |= *(const uint8_t *)q;
+        } else {
+            for (uintptr_t q = s + lane; q < as; q += 32) bad |= *(const uint8_t *)q;
+            for (uintptr_t q = ae + lane; q < e; q += 32) bad |= *(const uint8_t *)q;
+            for (uintptr_t q = as + 16u * lane; q < ae; q += 512) {
+                const uint4 v = *(const uint4 *)q;
+                bad |= v.x | v.y | v.z | v.w;
+            }
+        }
+        if (bad & 0x80808080u) atomicOr(a.err_flag, 1);
+        if (r < n_reads) {
+            const long long o0 = a.offsets[r], o1 = a.offsets[r + 1];
+            process_read<false>(S, a.seq + o0, nullptr, (int)(o1 - o0), 0, 0, 0, a.qbase, a.times, colp, colw,
+                                a.out + (size_t)r * a.times * a.slots, nullptr, a.view ? a.view + 2 * r : nullptr);
+        }
+    }
+}
+
+cudaError_t cg_launch_light(const CgKernelArgs &a, int grid, cudaStream_t st)
+{
+    cg_trim_light_kernel<<<grid, CG_NT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 // One read, one aligner adapter, exact int32 cells, every computed cell recorded: Aligner.enable_debug()'s matrices.
 __global__ void cg_locate_debug_kernel(const uint8_t *blob, const uint8_t *enc768, const uint8_t *query, int n,
                                        int *scratch /* 3 (m + 1) */, int32_t *cost, int32_t *score, int32_t *result8)

@@ -32,6 +32,9 @@ cudaError_t cg_launch_warp(const CgKernelArgs &a, bool has_qual, int grid, size_
 size_t cg_scan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual);
 cudaError_t cg_scan_occupancy(bool has_qual, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_t smem, cudaStream_t st);
+// sets of index lookups only (cg_trim_light_kernel): rows of the local-memory column for the rare re-alignment
+#define CG_LIGHT_ROWS 68
+cudaError_t cg_launch_light(const CgKernelArgs &a, int grid, cudaStream_t st);
 size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual, int stats_max_len = -1);   // >= 0: + fused statistics
 cudaError_t cg_pscan_occupancy(bool has_qual, int w, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_pscan(const CgKernelArgs &a, bool has_qual, int w, int grid, size_t smem, cudaStream_t st);

@@ -15,6 +15,7 @@ struct CgBuiltSet {
     std::vector<uint8_t> index_blob; // CgIndexHeader[n_indexes] | CgIndexEntry tables (HBM), may be empty
     int slots = 1;
     int n_adapters = 0, n_groups = 0, max_m = 0, any_wide = 0, simple_ok = 0;
+    int all_indexed = 0;             // every group is an index lookup (IndexedPrefixAdapters / IndexedSuffixAdapters)
 };
 
 // 3 x 256 bytes: upper, acgt, iupac  (src/cutadapt/_match_tables.py:4-66)
