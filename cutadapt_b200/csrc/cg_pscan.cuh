@@ -15,7 +15,8 @@ struct ScanSmem { size_t blob_off, enc_off, stats_off, warp_off, warp_stride, ba
 // cg_pscan_kernel -- the bit-plane first stage (plane_scan_core in cg_core.cuh) in the frame of
 // cg_scan_kernel: per-warp TMA-staged mini-tiles of 32 reads, one lane per read.  Reads it settles
 // ("no match": 47 % of the benchmark's reads; exact occurrence: 41 %) get their record here; the rest
-// (12 %) append a task flagged CG_TASK_RESCAN, which cg_list_kernel<plan> re-scans exactly.
+// (12 %) append a CG_TASK_PLANES task with the hit mask M, from which cg_list_kernel<plan> derives the DP runs
+// (reads the planes cannot represent -- empty or longer than 32 W -- go as CG_TASK_RESCAN).
 // A margin in front of every warp's tile keeps the right-aligned plane loads of the tile's first read
 // inside shared memory.
 // ------------------------------------------------------------------------------------------
