@@ -1017,10 +1017,15 @@ static OffsetScan scan_offsets(cg_ctx *c, const int64_t *offsets, int64_t r0, in
     return t;
 }
 
-// CUTADAPT_B200_H2D_PACK: "0" = raw bytes only, "all" = everything compressed, otherwise adaptive
-static int h2d_pack_mode()
+// CUTADAPT_B200_H2D_PACK: "0" = raw bytes only, "all" = everything compressed, "0.xx" = that share compressed (fixed,
+// for sweeps), otherwise adaptive
+static int h2d_pack_mode(double *fixed_share = nullptr)
 {
     const char *e = getenv("CUTADAPT_B200_H2D_PACK");
+    if (e && e[0] == '0' && e[1] == '.') {
+        const double v = atof(e);
+        if (v > 0.0 && v < 1.0) { if (fixed_share) *fixed_share = v; return 3; }
+    }
     if (e && e[0] == '0') return 0;
     if (e && strcmp(e, "all") == 0) return 2;
     return 1;
@@ -1074,8 +1079,10 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         if (rcs != CG_OK) return rcs;
         CU(cudaMemset(c->d_stats.p, 0, n_stats * sizeof(unsigned long long)));
     }
-    const int pack_mode = h2d_pack_mode();
+    double fixed_share = 0.0;
+    const int pack_mode = h2d_pack_mode(&fixed_share);
     const bool pack = pack_mode != 0 && n_reads >= (1 << 16);
+    if (pack_mode == 3) c->pack_fraction = fixed_share;
     if (pack && !c->pool) {
         c->pool = new CgHostPool(cg_host_threads_default());
         c->exc_scratch.resize((size_t)c->pool->size());
