@@ -1062,6 +1062,7 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     if (n_reads < 0) return fail(CG_EINVAL, "n_reads < 0");
     if (n_reads == 0) return CG_OK;
     if (!seq) return fail(CG_EINVAL, "cg_process_batch: seq is NULL");
+    const std::chrono::steady_clock::time_point t_enter = std::chrono::steady_clock::now();
     const bool want_q = p->quality_trim != 0 || p->nextseq_trim != 0;
     if (want_q && !qual) return fail(CG_ENOQUAL, "Cannot do quality trimming when no qualities are available");
     CU(cudaSetDevice(c->device));
@@ -1098,6 +1099,9 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const clk::time_point t_begin = clk::now();
     clk::time_point fb_t0 = t_begin;
+    // CUTADAPT_B200_HOST_TRACE=1: where the host side of this call spent its time (stderr, one line per call)
+    const bool trace = getenv("CUTADAPT_B200_HOST_TRACE") != nullptr;
+    double tr_setup = secs(t_enter, t_begin), tr_alloc = 0, tr_h2d = 0, tr_launch = 0, tr_d2h = 0, tr_tail = 0;
     int64_t fb_reads = 0;
     int64_t ahead_r0 = -1, ahead_r1 = -1;
     OffsetScan ahead_sc;
@@ -1134,10 +1138,13 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
             c->prof[3] += lane_wait_s;
             if (rc != CG_OK) break;
         }
+        const clk::time_point t_alloc0 = clk::now();
         if (want_q && (rc = l.d_qual.ensure((size_t)nbytes + 64)) != CG_OK) break;
         if ((rc = l.d_offs.ensure((size_t)nr + 1)) != CG_OK) break;
         if ((rc = l.d_out.ensure((size_t)nr * rec_per_read)) != CG_OK) break;
         if ((qtrim || (stats && want_q)) && (rc = l.d_qtrim.ensure((size_t)nr * 2)) != CG_OK) break;
+        const clk::time_point t_h2d0 = clk::now();
+        tr_alloc += secs(t_alloc0, t_h2d0);
         // ---- H2D of the sequences ----
         // The first `packed_bytes` of the chunk's buffer travel as the compressed stream, the rest raw: packing
         // costs host time, raw bytes cost PCIe time, and the split (c->pack_fraction) follows whichever of the
@@ -1274,12 +1281,16 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         const uint8_t *vseq = l.d_seq.p - a0;
         const uint8_t *vqual = want_q ? l.d_qual.p - a0 : nullptr;
         int32_t *d_qt = (qtrim || (stats && want_q)) ? l.d_qtrim.p : nullptr;
+        const clk::time_point t_launch0 = clk::now();
+        tr_h2d += secs(t_h2d0, t_launch0);
         if (stats)
             rc = launch_trim_with_stats(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, d_qt, l.stream, true,
                                         c->d_stats.p, stats_max_len, stats_kmax);
         else
             rc = launch_trim(c, s, vseq, vqual, l.d_offs.p, nr, max_len, p, l.d_out.p, d_qt, l.stream, true);
         if (rc != CG_OK) break;
+        const clk::time_point t_d2h0 = clk::now();
+        tr_launch += secs(t_launch0, t_d2h0);
         // D2H
         cg_match_rec *dst = (cg_match_rec *)matches + (size_t)r0 * rec_per_read;
         l.n_out = (size_t)nr * rec_per_read; l.dst_out = dst; l.out_bounced = !out_pinned;
@@ -1302,6 +1313,7 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
         }
         l.busy = true;
         r0 = r1;
+        tr_d2h += secs(t_d2h0, clk::now());
     }
     const clk::time_point t_drain0 = clk::now();
     for (int i = 0; i < CG_N_LANES; ++i) {
@@ -1317,7 +1329,16 @@ static int process_batch_impl(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     }
     c->prof[0] += secs(t_begin, clk::now());
     if (rc != CG_OK) return rc;
-    return check_err_flag(c);
+    const clk::time_point t_tail0 = clk::now();
+    const int rce = check_err_flag(c);
+    tr_tail = secs(t_tail0, clk::now());
+    if (trace)
+        fprintf(stderr, "[cutadapt_b200] process_batch %lld reads, %d chunks: total %.4f s = setup %.4f + alloc %.4f + h2d (incl. packing, "
+                        "h2d also counts the pack feedback) %.4f + launch %.4f + d2h issue %.4f + drain/stats/tail %.4f; share %.2f\n",
+                (long long)n_reads, n_chunk, secs(t_enter, clk::now()), tr_setup, tr_alloc, tr_h2d, tr_launch, tr_d2h,
+                secs(t_drain0, clk::now()), c->pack_fraction);
+    (void)tr_tail;
+    return rce;
 }
 
 extern "C" int cg_host_cpus_available(void) { return cg_host_cpus(); }
