@@ -44,7 +44,7 @@ READ_LEN = 150
 ALGO_BYTES = {2: READ_LEN + 8 + 32, 3: READ_LEN + 8 + 32, 4: 2 * READ_LEN + 8 + 32, 5: READ_LEN + 8 + 32}
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of all kernels of one pass divided by the reads
 # (profiles/README.md); measured once per round, not in the timed run.  None: not captured for that configuration.
-NCU_DRAM_BYTES_PER_READ = {2: 243, 3: None, 4: None, 5: None}
+NCU_DRAM_BYTES_PER_READ = {2: 259, 3: None, 4: None, 5: 189}     # profiles/r2_launches_config{2_16M,5_25M}.csv
 DEFAULT_READS = {2: 100_000_000, 3: 100_000_000, 4: 50_000_000, 5: 25_000_000}   # config 4: pairs
 CONFIG_TEXT = {
     2: "one 3' adapter AGATCGGAAGAGC, e=0.1",
@@ -615,7 +615,9 @@ def main():
         host_ctx.host_profile(reset=True)
         l0 = host_ctx.launch_count()
         t0 = time.perf_counter()
-        e2e_steps = max(1, args.steps)
+        # all --steps, and at least 3e8 reads in the timed region: a step of a small configuration (25 M reads) lasts
+        # 50 ms, which one scheduling hiccup of a host thread would double
+        e2e_steps = max(1, args.steps, -(-300_000_000 // max(1, reads_per_step)))
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
