@@ -606,7 +606,23 @@ static int launch_trim_single(cg_ctx *c, const cg_adapterset *s, const uint8_t *
     // sets of index lookups only (demultiplexing), no quality trimming: the light kernel -- nothing to stage
     const bool light = s->host.all_indexed && !want_q && !s->host.any_wide && s->host.max_m + 1 <= CG_LIGHT_ROWS &&
                        !(kernel_env && strcmp(kernel_env, "general") == 0) && !getenv("CUTADAPT_B200_NO_LIGHT");
-    if (light) {
+    if (light && times == 1 && !d_view && a.slots == 1 && !getenv("CUTADAPT_B200_NO_INDEX_KERNEL")) {
+        // the lookups alone (cg_index_kernel), in sub-batches so that 32-bit read numbers and one list suffice
+        const long long SUBI = 64LL << 20;
+        int rc = c->tasks.ensure((size_t)((std::min<long long>(n_reads, SUBI) + 3) / 4));
+        if (rc != CG_OK) return rc;
+        for (long long r0 = 0; r0 < n_reads; r0 += SUBI) {
+            const long long n_sub = std::min<long long>(SUBI, n_reads - r0);
+            CgKernelArgs b = a;
+            b.offsets = a.offsets + r0; b.n_reads = n_sub; b.out = a.out + (size_t)r0 * a.slots;
+            b.tasks = c->tasks.p; b.task_count = c->d_task_count;
+            CU(cudaMemsetAsync(c->d_task_count, 0, sizeof(unsigned long long), st));
+            const long long need = (n_sub + CG_NT - 1) / CG_NT;
+            const int grid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 16, need));
+            CU(cg_launch_index(b, grid, st));
+            c->launches += 1;
+        }
+    } else if (light) {
         const long long need = (n_reads + CG_NT - 1) / CG_NT;
         const int grid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 16, need));
         CU(cg_launch_light(a, grid, st));

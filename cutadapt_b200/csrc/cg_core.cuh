@@ -1154,7 +1154,7 @@ CG_HD bool match_single(const SetView &S, int ai, const uint8_t *p, int n, Packe
 
 template <bool ALLOW_WIDE>
 CG_HD bool match_indexed(const SetView &S, int index_no, const uint8_t *p, int n, PackedCol &colp,
-                         WideCol &colw, CgHit &hit)
+                         WideCol &colw, CgHit &hit, bool *needs_realign = nullptr)
 {
     const CgIndexHeader &H = S.index_hdr[index_no];
     const CgIndexEntry *tab = S.index_tab + H.table_off;
@@ -1189,6 +1189,7 @@ CG_HD bool match_indexed(const SetView &S, int index_no, const uint8_t *p, int n
         if (!found) continue;
         const int a = (int)(val >> 16);
         int e = (int)((val >> 8) & 255u), m = (int)(val & 255u);
+        if (has_n && needs_realign) { *needs_realign = true; return false; }   // (the caller has no DP column: cg_index_kernel)
         if (has_n) {                                             // adapters.py:1535-1551: re-align
             CgHit h;
             if (!match_single<ALLOW_WIDE>(S, a, q, cnt, colp, colw, h)) continue;

@@ -1136,6 +1136,100 @@ cudaError_t cg_launch_light(const CgKernelArgs &a, int grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// cg_index_kernel -- the lookups themselves, for sets of index groups, one round, no quality trimming: what
+// MultipleAdapters.match_to does over IndexedPrefixAdapters / IndexedSuffixAdapters groups (best score, then fewest
+// errors, then first listed; adapters.py:1271-1286) with match_indexed per group.  No DP column and no per-read
+// generality (45 registers instead of the 127 of process_read): the latency of the dependent probes is covered by
+// three times as many resident warps.  The one thing it cannot do is re-align a key that was looked up with an N in
+// it (_lookup_with_n): such reads (about 1 %) are listed in a.tasks (one 32-bit read number each) and go through
+// cg_trim_light_kernel afterwards.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CG_NT) cg_index_kernel(const CgKernelArgs a)
+{
+    const SetView S = make_set_view(a.blob, a.masks64, a.enc, a.index);
+    PackedCol colp; colp.base = nullptr; colp.stride = 0;
+    WideCol colw; colw.base = nullptr; colw.stride = 0;
+    const int lane = threadIdx.x & 31;
+    const long long n_reads = a.n_reads;
+    const long long n_mt = (n_reads + 31) / 32;
+    const long long warps_total = (long long)gridDim.x * (CG_NT / 32);
+    const uintptr_t seq_base = (uintptr_t)a.seq;
+    uint32_t *slow_list = (uint32_t *)a.tasks;
+    for (long long mt = (long long)blockIdx.x * (CG_NT / 32) + (threadIdx.x >> 5); mt < n_mt; mt += warps_total) {
+        const long long r0 = mt * 32;
+        const long long r1 = (r0 + 32 < n_reads) ? r0 + 32 : n_reads;
+        const long long r = r0 + lane;
+        // non-ASCII check over the warp's reads, coalesced (as in cg_trim_light_kernel)
+        const uintptr_t s = seq_base + (uintptr_t)a.offsets[r0], e = seq_base + (uintptr_t)a.offsets[r1];
+        const uintptr_t as = (s + 15) & ~(uintptr_t)15, ae = e & ~(uintptr_t)15;
+        uint32_t bad = 0;
+        if (as >= ae) {
+            for (uintptr_t q = s + lane; q < e; q += 32) bad |= *(const uint8_t *)q;
+        } else {
+            for (uintptr_t q = s + lane; q < as; q += 32) bad |= *(const uint8_t *)q;
+            for (uintptr_t q = ae + lane; q < e; q += 32) bad |= *(const uint8_t *)q;
+            for (uintptr_t q = as + 16u * lane; q < ae; q += 512) {
+                const uint4 v = *(const uint4 *)q;
+                bad |= v.x | v.y | v.z | v.w;
+            }
+        }
+        if (bad & 0x80808080u) atomicOr(a.err_flag, 1);
+        bool slow = false;
+        if (r < n_reads) {
+            const long long o0 = a.offsets[r], o1 = a.offsets[r + 1];
+            const int n = (int)(o1 - o0);
+            CgHit best; best.adapter = -1; best.remove = 0;
+            best.astart = best.astop = best.rstart = best.rstop = best.score = best.errors = 0;
+            int best_group = 0;
+            bool have = false;
+            for (int g = 0; g < S.h->n_groups && !slow; ++g) {
+                CgHit h;
+                if (!match_indexed<false>(S, S.gr[g].a0, a.seq + o0, n, colp, colw, h, &slow)) continue;
+                if (!have || h.score > best.score || (h.score == best.score && h.errors < best.errors)) {
+                    have = true; best = h; best_group = g;
+                }
+            }
+            if (!slow) store_hit(a.out + (size_t)r * a.slots, best, have ? best_group : 0, have ? n : 0);
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, slow);
+        if (ballot) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.task_count, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (slow) slow_list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)r;
+        }
+    }
+}
+
+// the reads cg_index_kernel listed: the general per-read pass, one lane per listed read
+__global__ void __launch_bounds__(CG_NT) cg_trim_listed_kernel(const CgKernelArgs a)
+{
+    const SetView S = make_set_view(a.blob, a.masks64, a.enc, a.index);
+    uint32_t lcol[CG_LIGHT_ROWS];
+    PackedCol colp; colp.base = lcol; colp.stride = 1;
+    WideCol colw; colw.base = nullptr; colw.stride = 0;
+    const uint32_t *list = (const uint32_t *)a.tasks;
+    const unsigned long long n_listed = *a.task_count;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_listed; i += nthreads) {
+        const long long r = (long long)list[i];
+        const long long o0 = a.offsets[r], o1 = a.offsets[r + 1];
+        process_read<false>(S, a.seq + o0, nullptr, (int)(o1 - o0), 0, 0, 0, a.qbase, 1, colp, colw,
+                            a.out + (size_t)r * a.slots, nullptr, nullptr);
+    }
+}
+
+cudaError_t cg_launch_index(const CgKernelArgs &a, int grid, cudaStream_t st)
+{
+    cg_index_kernel<<<grid, CG_NT, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // (few reads are listed: a fixed small grid, grid-stride)
+    cg_trim_listed_kernel<<<148, CG_NT, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 // One read, one aligner adapter, exact int32 cells, every computed cell recorded: Aligner.enable_debug()'s matrices.
 __global__ void cg_locate_debug_kernel(const uint8_t *blob, const uint8_t *enc768, const uint8_t *query, int n,
                                        int *scratch /* 3 (m + 1) */, int32_t *cost, int32_t *score, int32_t *result8)

@@ -35,6 +35,9 @@ cudaError_t cg_launch_scan(const CgKernelArgs &a, bool has_qual, int grid, size_
 // sets of index lookups only (cg_trim_light_kernel): rows of the local-memory column for the rare re-alignment
 #define CG_LIGHT_ROWS 68
 cudaError_t cg_launch_light(const CgKernelArgs &a, int grid, cudaStream_t st);
+// one round over index groups without views: cg_index_kernel + cg_trim_listed_kernel for the reads it lists in
+// a.tasks (32-bit read numbers, counted in a.task_count, which must be zero)
+cudaError_t cg_launch_index(const CgKernelArgs &a, int grid, cudaStream_t st);
 size_t cg_pscan_smem_bytes(uint32_t blob_bytes, int mini_cap, bool has_qual, int stats_max_len = -1);   // >= 0: + fused statistics
 cudaError_t cg_pscan_occupancy(bool has_qual, int w, size_t smem, int *blocks_per_sm);
 cudaError_t cg_launch_pscan(const CgKernelArgs &a, bool has_qual, int w, int grid, size_t smem, cudaStream_t st);
