@@ -991,6 +991,7 @@ static list_kernel_t pick_list(bool plan, int mr)
     if (plan) return cg_list_kernel<true, 16>;
     if (mr <= 16) return cg_list_kernel<false, 16>;
     if (mr <= 32) return cg_list_kernel<false, 32>;
+    if (mr <= 40) return cg_list_kernel<false, 40>;      // (the 33/34-base Illumina adapters: 8 rows fewer in registers)
     return mr <= 48 ? cg_list_kernel<false, 48> : cg_list_kernel<false, 64>;
 }
 cudaError_t cg_list_occupancy(bool plan, int mr, size_t smem, int *blocks_per_sm)
