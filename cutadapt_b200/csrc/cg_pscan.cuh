@@ -59,6 +59,81 @@ __host__ __device__ inline ScanSmem pscan_smem_layout(uint32_t blob_bytes, int m
     return L;
 }
 
+// ------------------------------------------------------------------------------------------
+// Quality trimming of a warp's 32 reads (quality_trim_index, qualtrim.pyx:22-73; the per-lane form is
+// quality_trim_core).  The scan from an end stops at the first negative partial sum: for a good read after ONE
+// character, for a read with a bad tail after the whole tail -- and a warp runs as long as its slowest lane.  So
+// every lane looks at its first character itself, and the reads that go on (typically 3 of 32) are then scanned by
+// the whole warp, 32 characters per step: inclusive prefix sums by shuffles, the first negative sum by ballot, the
+// (first) maximum by a warp reduction -- exactly the loop's `if (s < 0) break; if (s > best) { best = s; pos = i }`.
+// DIR = +1: the 5' scan (returns the new start), -1: the 3' scan (returns the new stop).  q_smem: shared-memory
+// address of this lane's qualities.  All 32 lanes must call it.
+// ------------------------------------------------------------------------------------------
+template <int DIR>
+__device__ __forceinline__ int trim_scan_warp(uint32_t q_smem, int n, int cutoff, int base, int lane)
+{
+#if defined(__CUDA_ARCH__)
+    int res = DIR > 0 ? 0 : n;
+    bool more = false;
+    if (n > 0) {
+        const int d0 = cutoff - ((int)(signed char)cg_lds_u8(q_smem + (uint32_t)(DIR > 0 ? 0 : n - 1)) - base);
+        more = d0 >= 0;
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, more);
+    while (todo) {
+        const int T = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t qT = __shfl_sync(0xffffffffu, q_smem, T);
+        const int nT = __shfl_sync(0xffffffffu, n, T);
+        int carry = 0, best = 0, resT = DIR > 0 ? 0 : nT;
+        for (int j0 = 0; j0 < nT; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = j < nT;
+            int P = 0;
+            if (valid) P = cutoff - ((int)(signed char)cg_lds_u8(qT + (uint32_t)(DIR > 0 ? j : nT - 1 - j)) - base);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, P, o);
+                if (lane >= o) P += t;
+            }
+            P += carry;
+            const uint32_t neg = __ballot_sync(0xffffffffu, valid && P < 0);
+            const int first_neg = neg ? __ffs(neg) - 1 : 32;
+            const bool ok = valid && lane < first_neg;
+            const int M = __reduce_max_sync(0xffffffffu, ok ? P : (int)0x80000000);
+            if (M > best) {
+                best = M;
+                const int w = __ffs(__ballot_sync(0xffffffffu, ok && P == M)) - 1;
+                resT = DIR > 0 ? j0 + w + 1 : nT - 1 - (j0 + w);
+            }
+            if (first_neg < 32) break;
+            carry = __shfl_sync(0xffffffffu, P, 31);
+        }
+        if (lane == T) res = resT;
+    }
+    return res;
+#else
+    return 0;       // (host pass of nvcc: never called)
+#endif
+}
+
+// pre_trim_core for a whole warp (NextSeq trimming stays per lane; it only runs with --nextseq-trim)
+__device__ __forceinline__ void pre_trim_warp(const uint8_t *seq, const uint8_t *qual, int n, int flags, int cutoff_front,
+                                              int cutoff_back, int qbase, int lane, int *s_out, int *e_out)
+{
+    const int base = qbase & 255;
+    int start = 0, stop = n;
+    if (flags & 2) stop = nextseq_trim_core(seq, qual, n, qbase >> 8, base);
+    if (flags & 1) {
+        const uint32_t q_smem = (uint32_t)__cvta_generic_to_shared(qual);
+        const int nq = stop;
+        start = trim_scan_warp<+1>(q_smem, nq, cutoff_front, base, lane);
+        stop = trim_scan_warp<-1>(q_smem, nq, cutoff_back, base, lane);
+        if (start >= stop) { start = 0; stop = 0; }                 // qualtrim.pyx:71-72
+    }
+    *s_out = start; *e_out = stop;
+}
+
 template <bool HAS_QUAL, int W, class Prog>
 __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
 {
@@ -134,6 +209,14 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
         if (r < n_reads) { o0 = a.offsets[r]; o1 = a.offsets[r + 1]; }
         const uintptr_t sa0 = (seq_base + b0) & ~(uintptr_t)15;
         if (b1 > b0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+        // quality trimming: the whole warp together (lanes without a read take part with an empty one)
+        int q_ts = 0, q_te = 0;
+        if (HAS_QUAL && a.quality_trim) {
+            const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
+            const bool has = r < n_reads;
+            pre_trim_warp(s_seq + (size_t)(has ? (seq_base + o0) - sa0 : 0), s_qual + (size_t)(has ? (qual_base + o0) - qa0 : 0),
+                          has ? (int)(o1 - o0) : 0, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, lane, &q_ts, &q_te);
+        }
         int cls = CG_PLANE_NONE, s0 = 0, ts = 0, te = 0;
         int st_fin = -1;                              // fused statistics: this lane's final-length bin, -1 = none
         uint32_t st_p1 = 0, st_p2 = 0, st_p3 = 0;     // ... and its contributions to the scalars, packed (below)
@@ -146,11 +229,7 @@ __device__ __forceinline__ void cg_pscan_body(const CgKernelArgs &a)
             const int n = (int)(o1 - o0);
             const uint32_t off = (uint32_t)((seq_base + o0) - sa0);
             ts = 0; te = n;
-            if (HAS_QUAL) {
-                const uintptr_t qa0 = (qual_base + b0) & ~(uintptr_t)15;
-                const uint8_t *q = s_qual + (size_t)((qual_base + o0) - qa0);
-                if (a.quality_trim) pre_trim_core(s_seq + off, q, n, a.quality_trim, a.cutoff_front, a.cutoff_back, a.qbase, &ts, &te);
-            }
+            if (HAS_QUAL && a.quality_trim) { ts = q_ts; te = q_te; }
             if (a.qtrim) { a.qtrim[2 * r] = ts; a.qtrim[2 * r + 1] = te; }
             if (a.view) { ts = a.view[2 * r]; te = a.view[2 * r + 1]; }
             const int nn = te - ts;
