@@ -385,12 +385,54 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
     if (full_range && A.k >= 0 && pieces > m && m <= 64) myers = 1;
     if (full_range && A.k >= 0 && pieces <= m) {
         const int base = m / pieces, extra = m % pieces;
+        // Piece lengths.  Plain adapters: nearly equal pieces (the partition KmerFinder uses too, so the chunks
+        // coincide with its whole-read k-mers).  Adapters with wildcard positions (N runs of UMIs, IUPAC codes): any
+        // partition into k + 1 contiguous pieces serves the pigeonhole argument, so the cuts are placed where they
+        // balance the INFORMATION of the pieces, log2(4 / letters matched) per position -- a piece made of Ns hits
+        // everywhere and would push the adapter onto the bit-vector plan although its other pieces are selective.
+        std::vector<int> piece_len(pieces);
+        for (int c = 0; c < pieces; ++c) piece_len[c] = base + (c < extra ? 1 : 0);
+        {
+            const uint8_t *qenc0 = enc768 + 256 * A.query_enc;
+            std::vector<double> info(m);
+            double total = 0.0;
+            bool any_wild = false;
+            for (int t = 0; t < m; ++t) {
+                int cnt = 0;
+                for (const char *b = "ACGT"; *b; ++b) {
+                    const uint8_t rc = enc_ref[t];
+                    cnt += A.compare_ascii ? (rc == qenc0[(int)*b]) : ((rc & qenc0[(int)*b]) != 0);
+                }
+                any_wild = any_wild || cnt != 1;
+                info[t] = cnt >= 1 && cnt <= 4 ? std::log2(4.0 / cnt) : 2.0;
+                total += info[t];
+            }
+            if (any_wild && total > 0.0) {
+                // cut after the position where the running information passes c / pieces of the total; every piece
+                // keeps at least one position
+                std::vector<int> cuts;
+                double run = 0.0;
+                int next = 1;
+                for (int t = 0; t < m && next < pieces; ++t) {
+                    run += info[t];
+                    const int left_pos = m - (t + 1), left_pieces = pieces - next;
+                    if (run >= total * next / pieces - 1e-9 || left_pos == left_pieces) {
+                        if (left_pos >= left_pieces) { cuts.push_back(t + 1); ++next; }
+                    }
+                }
+                if ((int)cuts.size() == pieces - 1) {
+                    int prev = 0;
+                    for (int c = 0; c < pieces - 1; ++c) { piece_len[c] = cuts[c] - prev; prev = cuts[c]; }
+                    piece_len[pieces - 1] = m - prev;
+                }
+            }
+        }
         std::vector<ScanKmer> chunks;
         bool ok = true;
         int pos = 0;
         for (int c = 0; c < pieces && ok; ++c) {
-            const int len = base + (c < extra ? 1 : 0);
-            if (len > 32) { ok = false; break; }
+            const int len = piece_len[c];
+            if (len > 32 || len < 1) { ok = false; break; }
             ScanKmer k;
             k.len = len; k.loc = true;
             k.cols.resize(len);
