@@ -471,12 +471,8 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
                 p_hit += p;
             }
         }
-        // (Round 2: where the plan stage can test a hit run for a bottom-row candidate first -- run_has_candidate_t, a
-        // bit-vector pass over the run's m + 2k + 1 columns only -- a false hit costs that pass, not the DP window.)
         const double myers_cost = m <= 32 ? 17.0 : 34.0;
-        const bool can_filter = m <= 64 && !(A.flags & 1) && (A.flags & 2) && (A.flags & 8) && d.indel_cost == 1;
-        const double false_hit_cost = can_filter ? myers_cost * (m + 2.0 * A.k + 1.0) + 60.0 : 12.0 * m * (m + 2.0 * A.k);
-        if (m <= 64 && (!ok || p_hit * false_hit_cost > myers_cost)) {
+        if (m <= 64 && (!ok || p_hit * 12.0 * m * (m + 2.0 * A.k) > myers_cost)) {
             myers = 1;
         } else if (ok && m <= 250) {
             for (auto &c : chunks) {

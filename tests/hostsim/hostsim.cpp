@@ -315,17 +315,3 @@ extern "C" int hs_fastq_records(const uint8_t *buf, int64_t n, int cut_front, in
     }
     return first;
 }
-
-// Header flags of the set the host compiler builds (which first stage / plan an adapter gets): out[0..6] = simple_ok,
-// windowed, exact_ok, myers, scan_count, plane_count, plane_flags.
-extern "C" int hs_set_info(const cg_adapter_desc *adapters, int n_adapters, const cg_group_desc *groups, int n_groups,
-                           int32_t *out)
-{
-    CgBuiltSet set;
-    int rc = cg_build_set(adapters, n_adapters, groups, n_groups, set, g_err, nullptr, 0);
-    if (rc != CG_OK) return rc;
-    const CgSetHeader *H = (const CgSetHeader *)set.blob.data();
-    out[0] = H->simple_ok; out[1] = H->windowed; out[2] = H->exact_ok; out[3] = H->myers; out[4] = H->scan_count;
-    out[5] = H->plane_count; out[6] = H->plane_flags;
-    return CG_OK;
-}
