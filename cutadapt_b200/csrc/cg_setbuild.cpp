@@ -471,6 +471,10 @@ bool build_scan_program(const cg_adapter_desc &d, const CgAdapter &A, const uint
                 p_hit += p;
             }
         }
+        // (Round 2 re-measured the balance with the plan stage's candidate filter in place -- a false hit then costs a
+        //  bit-vector pass over the run, not a DP window -- on BASELINE config 3: moving its 21-base linked 3' adapter
+        //  and the N-run adapter from the bit-vector plan to locator chunks made the pass 14 % SLOWER (plan 86 -> 99 ms,
+        //  DP rounds 42 -> 57 ms per 100 M reads): at e = 0.15 the 5-base chunks hit every second read.  The model stays.)
         const double myers_cost = m <= 32 ? 17.0 : 34.0;
         if (m <= 64 && (!ok || p_hit * 12.0 * m * (m + 2.0 * A.k) > myers_cost)) {
             myers = 1;
