@@ -396,6 +396,55 @@ class PairedAdapterBatch:
                 TrimResult(r2, None, kept_intervals(r2, None, np.diff(o2))))
 
 
+def paired_revcomp_select(m11: Optional[np.ndarray], m22: Optional[np.ndarray], m12: Optional[np.ndarray],
+                          m21: Optional[np.ndarray]):
+    """
+    ``PairedReverseComplementer.__call__`` (modifiers.py:334-400) on match records.  ``m11`` / ``m22``: the -a adapters
+    on R1, the -A adapters on R2 (the pair as it came); ``m12`` / ``m21``: the -a adapters on R2, the -A adapters on R1
+    (the pair with its mates swapped, "equivalent to reverse complementing").  None = that mate has no adapters.  A
+    pair is swapped iff the scores of the swapped search add up to MORE.  Returns (swapped[n] bool, records of the new
+    R1, records of the new R2); for a swapped pair the new R1 is the OLD R2 and vice versa.
+    """
+    def total(m):
+        return 0 if m is None else np.where(m["adapter"] >= 0, m["score"], 0).astype(np.int64).sum(axis=(1, 2))
+
+    swapped = np.asarray(total(m12) + total(m21) > total(m11) + total(m22))
+    pick = lambda a, b: None if a is None else np.where(swapped[:, None, None], b, a)     # noqa: E731
+    return swapped, pick(m11, m12), pick(m22, m21)
+
+
+class PairedRevcompBatch:
+    """
+    ``--revcomp`` on pairs (PairedReverseComplementer, modifiers.py:311-400): four batched passes -- every mate against
+    both adapter lists -- and ``paired_revcomp_select``.  ``process(seqs1, seqs2)`` returns (swapped[n], TrimResult of
+    the new R1, TrimResult of the new R2); the caller writes old R2 as new R1 for a swapped pair and appends the
+    name suffix.  (The FASTQ kernels do the single-end form, ``FastqTrimmer(revcomp=True)``; this is the record-level
+    composition for pairs.)
+    """
+
+    def __init__(self, adapters1: Optional[Sequence], adapters2: Optional[Sequence], ctx: Optional[_lib.Context] = None):
+        self._t1 = BatchTrimmer(adapters1, ctx=ctx) if adapters1 else None
+        self._t2 = BatchTrimmer(adapters2, ctx=ctx) if adapters2 else None
+        if self._t1 is None and self._t2 is None:
+            raise ValueError("no adapters given")
+
+    def process(self, sequences1: Sequence[str], sequences2: Sequence[str]):
+        s1, o1 = _lib.pack_strings(sequences1)
+        s2, o2 = _lib.pack_strings(sequences2)
+        run = lambda t, s, o: None if t is None else t.adapter_set.process(s, o, None, t.params)[0]   # noqa: E731
+        m11, m22 = run(self._t1, s1, o1), run(self._t2, s2, o2)
+        m12, m21 = run(self._t1, s2, o2), run(self._t2, s1, o1)
+        swapped, r1, r2 = paired_revcomp_select(m11, m22, m12, m21)
+        len1 = np.where(swapped, np.diff(o2), np.diff(o1))
+        len2 = np.where(swapped, np.diff(o1), np.diff(o2))
+
+        def result(records, lengths):
+            if records is None:
+                return None
+            return TrimResult(records, None, kept_intervals(records, None, lengths))
+        return swapped, result(r1, len1), result(r2, len2)
+
+
 class TrimResult:
     """Outcome of one chunk: raw records plus the derived kept interval of every read."""
 

@@ -262,6 +262,11 @@ def main():
     # --revcomp known answer (test_commandline.py:827-835)
     copy(os.path.join(REF, "data", "revcomp.1.fastq"), "revcomp.in.fastq")
     copy(os.path.join(REF, "cut", "revcomp-single-normalize.fastq"), "revcomp.out.fastq")
+    # --revcomp on pairs (test_paired.py:786-833): adapters on one mate only (either one), adapters on both
+    copy(os.path.join(REF, "data", "revcomp.2.fastq"), "revcomp.in2.fastq")
+    for k in (1, 2):
+        copy(os.path.join(REF, "cut", f"revcomp.{k}.fastq"), f"revcomp_one_mate.out{k}.fastq")
+        copy(os.path.join(REF, "cut", f"revcomp-r1r2.{k}.fastq"), f"revcomp_r1r2.out{k}.fastq")
     # --rest-file / --wildcard-file known answers (test_commandline.py:110-122, 345-367)
     for src, dst in (("data/rest.fa", "rest.in.fasta"), ("data/rest.txt", "rest.txt"),
                      ("data/restfront.txt", "restfront.txt"), ("data/wildcard_adapter.fa", "wildcard_adapter.in.fasta")):

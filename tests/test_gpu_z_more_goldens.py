@@ -56,3 +56,34 @@ def test_revcomp_and_pair_adapters_compositions():
     for rec, t, k in ((recs[0], t1, 1), (recs[1], t2, 2)):
         text = "".join(f"@{n}\n{s[a:b]}\n+\n{q[a:b]}\n" for (n, s, q), (a, b) in zip(rec, t.intervals.tolist()))
         assert text.encode() == fastq_file(f"pair_adapters.out{k}.fastq")
+
+
+def test_paired_revcomp_composition():
+    """--revcomp on pairs (PairedReverseComplementer, modifiers.py:311-400) as four device passes + paired_revcomp_select:
+    the reference's known answers with adapters on R1 only, on R2 only and on both (test_paired.py:786-833)."""
+    import cutadapt_b200.adapters as PA
+    from cutadapt_b200 import pipeline
+    from util import fastq_file
+
+    rec1, rec2 = (oracle.parse_fastq(fastq_file(f)) for f in ("revcomp.in.fastq", "revcomp.in2.fastq"))
+
+    def written(swapped, t1, t2, first, second):
+        out = []
+        for (a, b), res in (((first, second), t1), ((second, first), t2)):
+            lines = []
+            for i in range(len(first)):
+                name, s, q = (b if swapped[i] else a)[i]
+                lo, hi = (int(x) for x in res.intervals[i]) if res is not None else (0, len(s))
+                lines.append(f"@{name}{' rc' if swapped[i] else ''}\n{s[lo:hi]}\n+\n{q[lo:hi]}\n")
+            out.append("".join(lines).encode())
+        return out
+
+    both = [PA.PrefixAdapter("TTATTTGTCT", name="a"), PA.PrefixAdapter("TCCGCACTGGC", name="b")]
+    one = [fastq_file("revcomp_one_mate.out1.fastq"), fastq_file("revcomp_one_mate.out2.fastq")]
+    swapped, t1, t2 = pipeline.PairedRevcompBatch(both, None).process([r[1] for r in rec1], [r[1] for r in rec2])
+    assert written(swapped, t1, t2, rec1, rec2) == one
+    swapped, t1, t2 = pipeline.PairedRevcompBatch(None, both).process([r[1] for r in rec2], [r[1] for r in rec1])
+    assert written(swapped, t1, t2, rec2, rec1) == one[::-1]
+    swapped, t1, t2 = pipeline.PairedRevcompBatch(both[:1], both[1:]).process([r[1] for r in rec1], [r[1] for r in rec2])
+    assert int(swapped.sum()) == 2
+    assert written(swapped, t1, t2, rec1, rec2) == [fastq_file("revcomp_r1r2.out1.fastq"), fastq_file("revcomp_r1r2.out2.fastq")]

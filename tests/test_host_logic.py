@@ -608,6 +608,30 @@ def test_composition_glue_with_an_oracle_backed_adapter_set(monkeypatch):
         text = "".join(f"@{n}\n{s[a:b]}\n+\n{q[a:b]}\n" for (n, s, q), (a, b) in zip(rec, t.intervals.tolist()))
         assert text.encode() == fastq_file(f"pair_adapters.out{k}.fastq")
     assert set(np.unique(t1.matches["adapter"])) <= {-1, 0}
+    # --revcomp on pairs through PairedRevcompBatch: the reference's three known answers (test_paired.py:786-833)
+    rec1, rec2 = (oracle.parse_fastq(fastq_file(f)) for f in ("revcomp.in.fastq", "revcomp.in2.fastq"))
+
+    def written(swapped, t1, t2, first, second):
+        out = []
+        for new, (a, b), res in ((first, (first, second), t1), (second, (second, first), t2)):
+            lines = []
+            for i in range(len(first)):
+                name, s, q = (b if swapped[i] else a)[i]
+                lo, hi = (int(x) for x in res.intervals[i]) if res is not None else (0, len(s))
+                lines.append(f"@{name}{' rc' if swapped[i] else ''}\n{s[lo:hi]}\n+\n{q[lo:hi]}\n")
+            out.append("".join(lines).encode())
+        return out
+
+    g1, g2 = [PA.PrefixAdapter("TTATTTGTCT", name="a"), PA.PrefixAdapter("TCCGCACTGGC", name="b")], None
+    swapped, t1, t2 = pipeline.PairedRevcompBatch(g1, g2).process([r[1] for r in rec1], [r[1] for r in rec2])
+    assert written(swapped, t1, t2, rec1, rec2) == [fastq_file("revcomp_one_mate.out1.fastq"), fastq_file("revcomp_one_mate.out2.fastq")]
+    swapped, t1, t2 = pipeline.PairedRevcompBatch(None, g1).process([r[1] for r in rec2], [r[1] for r in rec1])
+    assert written(swapped, t1, t2, rec2, rec1) == [fastq_file("revcomp_one_mate.out2.fastq"), fastq_file("revcomp_one_mate.out1.fastq")]
+    swapped, t1, t2 = pipeline.PairedRevcompBatch([PA.PrefixAdapter("TTATTTGTCT", name="a")],
+                                                  [PA.PrefixAdapter("TCCGCACTGGC", name="b")]).process(
+        [r[1] for r in rec1], [r[1] for r in rec2])
+    assert int(swapped.sum()) == 2                    # stats.reverse_complemented == 2 in the reference's test
+    assert written(swapped, t1, t2, rec1, rec2) == [fastq_file("revcomp_r1r2.out1.fastq"), fastq_file("revcomp_r1r2.out2.fastq")]
 
 
 def test_every_python_file_compiles():
