@@ -182,6 +182,8 @@ def _declare(lib) -> None:
                                             i32, vp, i64, vp, i64, C.POINTER(cg_fastq_result), C.POINTER(cg_fastq_result)]
     lib.cg_fastq_collect_info.argtypes = [vp, i32, vp, C.POINTER(cg_fastq_params), C.c_char_p, vp, vp, i64, vp, i64,
                                           C.POINTER(cg_fastq_result), C.POINTER(i64)]
+    lib.cg_fastq_collect_rows.argtypes = [vp, i32, vp, C.POINTER(cg_fastq_params), i32, C.c_char_p, vp, vp, i64, vp, i64,
+                                          C.POINTER(cg_fastq_result), C.POINTER(i64)]
     lib.cg_fastq_collect_pair_adapters.argtypes = [vp, i32, i32, vp, vp, i32, C.POINTER(cg_fastq_params),
                                                    C.POINTER(cg_fastq_params), i32, vp, i64, vp, i64,
                                                    C.POINTER(cg_fastq_result), C.POINTER(cg_fastq_result)]

@@ -1929,6 +1929,7 @@ struct FqInfo {
     uint8_t *out = nullptr;               // host
     int64_t capacity = 0;
     int64_t *bytes = nullptr;             // host out
+    int kind = 0;                         // 0 info rows, 1 rest rows, 2 wildcard rows (names = adapter sequences)
 };
 
 static int fastq_stage_info(cg_ctx *c, FastqSlot &f, const FqStage &g, const cg_fastq_params *fp, const FqInfo &info,
@@ -1947,7 +1948,7 @@ static int fastq_stage_info(cg_ctx *c, FastqSlot &f, const FqStage &g, const cg_
     const int upper = g.action == CG_FQ_ACTION_LOWERCASE;
     CU(cg_launch_fastq_info(0, f.d_in.p, f.d_rec.p, f.d_origin.p, f.d_interval.p, f.d_mask.p, g.d_matches, g.times, g.slots,
                             f.d_names.p, f.d_nameoff.p, fp->revcomp != 0, g.rc_suffix, upper, n, f.d_inforow.p, nullptr, nullptr,
-                            st));
+                            st, info.kind, g.d_qtrim, f.d_len.p));
     CU(cg_launch_scan_i32(f.d_inforow.p, n, f.d_scan.p, f.d_infooff.p, st));
     long long total = 0;
     CU(cudaMemcpyAsync(&total, f.d_infooff.p + n, sizeof total, cudaMemcpyDeviceToHost, st));
@@ -1960,7 +1961,7 @@ static int fastq_stage_info(cg_ctx *c, FastqSlot &f, const FqStage &g, const cg_
     if ((rc = f.d_infoout.ensure((size_t)total + 64)) != CG_OK) return rc;
     CU(cg_launch_fastq_info(1, f.d_in.p, f.d_rec.p, f.d_origin.p, f.d_interval.p, f.d_mask.p, g.d_matches, g.times, g.slots,
                             f.d_names.p, f.d_nameoff.p, fp->revcomp != 0, g.rc_suffix, upper, n, nullptr, f.d_infooff.p,
-                            f.d_infoout.p, st));
+                            f.d_infoout.p, st, info.kind, g.d_qtrim, f.d_len.p));
     c->launches += 1;
     CU(cudaMemcpyAsync(info.out, f.d_infoout.p, (size_t)total, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -2012,6 +2013,27 @@ extern "C" int cg_fastq_collect_info(cg_ctx *c, int32_t slot, const cg_adapterse
     for (int a = 0; a < info.n_adapters; ++a)
         if (name_offsets[a] < 0 || name_offsets[a + 1] < name_offsets[a])
             return fail(CG_EINVAL, "cg_fastq_collect_info: name_offsets must not decrease");
+    return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr, nullptr, &info);
+}
+
+extern "C" int cg_fastq_collect_rows(cg_ctx *c, int32_t slot, const cg_adapterset *s, const cg_fastq_params *fp,
+                                     int32_t kind, const char *adapter_text, const int32_t *text_offsets, uint8_t *out,
+                                     int64_t out_capacity, uint8_t *rows_out, int64_t rows_capacity, cg_fastq_result *res,
+                                     int64_t *rows_bytes)
+{
+    if (kind < 0 || kind > 2) return fail(CG_EINVAL, "cg_fastq_collect_rows: kind must be 0 (info), 1 (rest) or 2 (wildcard)");
+    if (kind == 0)
+        return cg_fastq_collect_info(c, slot, s, fp, adapter_text, text_offsets, out, out_capacity, rows_out, rows_capacity,
+                                     res, rows_bytes);
+    if (!s || !adapter_text || !text_offsets || !rows_bytes || rows_capacity < 0 || (rows_capacity && !rows_out))
+        return fail(CG_EINVAL, "cg_fastq_collect_rows: bad argument");
+    *rows_bytes = 0;
+    FqInfo info;
+    info.names = adapter_text; info.name_off = text_offsets; info.n_adapters = s->host.n_adapters;
+    info.out = rows_out; info.capacity = rows_capacity; info.bytes = rows_bytes; info.kind = kind;
+    for (int a = 0; a < info.n_adapters; ++a)
+        if (text_offsets[a] < 0 || text_offsets[a + 1] < text_offsets[a])
+            return fail(CG_EINVAL, "cg_fastq_collect_rows: text_offsets must not decrease");
     return fastq_collect_impl(c, slot, s, fp, out, out_capacity, res, nullptr, nullptr, &info);
 }
 

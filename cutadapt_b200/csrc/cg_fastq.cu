@@ -547,6 +547,9 @@ struct InfoArgs {
     int revcomp;                 // 0: no rc column content; else "1" / "0"
     int rc_suffix;
     int upper_unmatched;         // --action=lowercase writes reads without a match in upper case (modifiers.py:222-223)
+    int kind;                    // 0: --info-file rows; 1: --rest-file rows; 2: --wildcard-file rows (names = the adapters' sequences)
+    const int32_t *qtrim;        // quality-trimmed interval of the record (the read the cutter saw), or null
+    const int32_t *seq_len;
 };
 
 template <class Sink>
@@ -607,12 +610,66 @@ __device__ void info_rows(const InfoArgs &a, long long r, Sink &out)
     }
 }
 
+// --rest-file (RestFileWriter, steps.py:193-206; SingleMatch.rest, adapters.py:430-437, 463-470) and --wildcard-file
+// rows (WildcardFileWriter, steps.py:209-220; SingleMatch.wildcards, adapters.py:378-393): both look at the LAST match
+// of a read and at the sequence that match's round searched (the read after the earlier rounds).
+//   rest:     what lies behind a 3' adapter / in front of a 5' adapter, if not empty, then " name"
+//   wildcard: the read characters under the adapter's N positions (alignment-free, like the reference), then " name"
+template <class Sink>
+__device__ void aux_rows(const InfoArgs &a, long long r, Sink &out)
+{
+    if (!a.matches) return;
+    const CgFastqRecord m = a.rec[r];
+    int ws = a.qtrim ? a.qtrim[2 * r] : 0, we = a.qtrim ? a.qtrim[2 * r + 1] : a.seq_len[r];
+    cg_match_rec last; last.adapter = -1;
+    int last_ws = 0, last_we = 0;
+    const cg_match_rec *mr = a.matches + (size_t)r * a.times * a.slots;
+    for (int t = 0; t < a.times; ++t) {
+        bool round_hit = false;
+        for (int k = 0; k < a.slots; ++k) {
+            const cg_match_rec h = mr[t * a.slots + k];
+            if (h.adapter < 0) continue;
+            round_hit = true;
+            last = h; last_ws = ws; last_we = we;
+            const int cur = we - ws;
+            int s, c;
+            if (h.info & 256) { py_slice(0, h.rstart, cur, &s, &c); we = ws + c; }
+            else { py_slice(h.rstop, cur, cur, &s, &c); ws += s; }
+        }
+        if (!round_hit) break;
+    }
+    if (last.adapter < 0) return;
+    const uint8_t *cur_p = a.buf + m.seq_start + last_ws;
+    const int cur = last_we - last_ws;
+    const bool is_rc = (a.mask[r] & CG_FQ_MASK_RC) != 0;
+    if (a.kind == 1) {
+        int s, c;
+        if (last.info & 256) py_slice(last.rstop, cur, cur, &s, &c);
+        else py_slice(0, last.rstart, cur, &s, &c);
+        if (c == 0) return;
+        out.bytes(cur_p + s, c);
+    } else {
+        const uint8_t *aseq = a.names + a.name_off[last.adapter];
+        const int alen = a.name_off[last.adapter + 1] - a.name_off[last.adapter];
+        for (int i = 0; i < last.astop - last.astart; ++i) {
+            const int ai = last.astart + i, ri = last.rstart + i;
+            if (ai < 0 || ai >= alen || aseq[ai] != 'N' || ri >= cur) continue;
+            const int idx = ri < 0 ? ri + cur : ri;          // Python indexing
+            if (idx >= 0) out.ch(cur_p[idx]);
+        }
+    }
+    out.ch(' ');
+    out.bytes(a.buf + m.hdr_start, m.hdr_len);
+    if (is_rc && a.rc_suffix) { out.ch(' '); out.ch('r'); out.ch('c'); }
+    out.ch('\n');
+}
+
 __global__ void fq_info_count_kernel(InfoArgs a, long long n_records, int32_t *row_bytes)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_records) return;
     InfoCountSink sink;
-    info_rows(a, r, sink);
+    if (a.kind == 0) info_rows(a, r, sink); else aux_rows(a, r, sink);
     row_bytes[r] = (int32_t)sink.n;
 }
 
@@ -624,7 +681,7 @@ __global__ void __launch_bounds__(256) fq_info_write_kernel(InfoArgs a, long lon
         InfoWriteSink sink;
         sink.p = out + row_off[r];
         sink.lane = lane;
-        info_rows(a, r, sink);
+        if (a.kind == 0) info_rows(a, r, sink); else aux_rows(a, r, sink);
     }
 }
 
@@ -886,10 +943,11 @@ cudaError_t cg_launch_fastq_info(int phase, const uint8_t *d_buf, const CgFastqR
                                  const int32_t *d_interval, const int32_t *d_mask, const cg_match_rec *d_matches, int times,
                                  int slots, const uint8_t *d_names, const int32_t *d_name_off, int revcomp, int rc_suffix,
                                  int upper_unmatched, long long n_records, int32_t *d_row_bytes, const int64_t *d_row_off,
-                                 uint8_t *d_out, cudaStream_t st)
+                                 uint8_t *d_out, cudaStream_t st, int kind, const int32_t *d_qtrim, const int32_t *d_seq_len)
 {
     if (n_records <= 0) return cudaSuccess;
     InfoArgs a;
+    a.kind = kind; a.qtrim = d_qtrim; a.seq_len = d_seq_len;
     a.buf = d_buf; a.rec = d_rec; a.origin = d_origin; a.interval = d_interval; a.mask = d_mask; a.matches = d_matches;
     a.times = times; a.slots = slots; a.names = d_names; a.name_off = d_name_off; a.revcomp = revcomp;
     a.rc_suffix = rc_suffix; a.upper_unmatched = upper_unmatched;

@@ -799,32 +799,48 @@ class FastqTrimmer:
         offsets[1:] = np.cumsum([len(b) for b in blobs])
         return b"".join(blobs), offsets
 
-    def process_chunk_info(self, chunk) -> Tuple[bytes, bytes]:
-        """(trimmed FASTQ, the rows ``--info-file`` gets for the chunk), both formatted on the device
-        (``cg_fastq_collect_info``; InfoFileWriter, steps.py:222-253)."""
+    def _process_chunk_rows(self, chunk, kind: int, blob: bytes, offsets: np.ndarray) -> Tuple[bytes, bytes]:
         if self.adapters is None:
-            raise ValueError("the info file needs adapters")
-        blob, offsets = self._info_names()
+            raise ValueError("these outputs need adapters")
         per_read = max(1, self.params.trim.times) * 2
         n_bytes = len(chunk)
         capacity = per_read * 2 * n_bytes + (1 << 20)
         while True:
             slot, _, _ = self._submit(chunk)
             out = self._out_buffer(slot, n_bytes + 16)
-            info = np.empty(capacity, dtype=np.uint8)
+            rows = np.empty(capacity, dtype=np.uint8)
             res = _lib.cg_fastq_result()
-            info_bytes = C.c_int64(0)
-            rc = _lib.lib().cg_fastq_collect_info(
-                self.ctx.handle, slot, self._set.handle, C.byref(self.params), blob, offsets.ctypes.data, out.ctypes.data,
-                out.size, info.ctypes.data, info.size, C.byref(res), C.byref(info_bytes))
-            if rc != 0 and info_bytes.value > capacity:      # many short reads: rows larger than estimated
-                capacity = info_bytes.value
+            n_rows = C.c_int64(0)
+            rc = _lib.lib().cg_fastq_collect_rows(
+                self.ctx.handle, slot, self._set.handle, C.byref(self.params), kind, blob, offsets.ctypes.data,
+                out.ctypes.data, out.size, rows.ctypes.data, rows.size, C.byref(res), C.byref(n_rows))
+            if rc != 0 and n_rows.value > capacity:      # many short reads: rows larger than estimated
+                capacity = n_rows.value
                 continue
             _lib.check(rc)
             break
         for k, v in res.as_dict().items():
             self.statistics[k] = self.statistics.get(k, 0) + v
-        return out[: res.out_bytes].tobytes(), info[: info_bytes.value].tobytes()
+        return out[: res.out_bytes].tobytes(), rows[: n_rows.value].tobytes()
+
+    def process_chunk_info(self, chunk) -> Tuple[bytes, bytes]:
+        """(trimmed FASTQ, the rows ``--info-file`` gets for the chunk), both formatted on the device
+        (``cg_fastq_collect_rows`` kind 0; InfoFileWriter, steps.py:222-253)."""
+        if self.adapters is None:
+            raise ValueError("the info file needs adapters")
+        blob, offsets = self._info_names()
+        return self._process_chunk_rows(chunk, 0, blob, offsets)
+
+    def process_chunk_rest(self, chunk) -> Tuple[bytes, bytes]:
+        """(trimmed FASTQ, the rows of ``--rest-file``): RestFileWriter, steps.py:193-206."""
+        return self._process_chunk_rows(chunk, 1, b"", np.zeros(len(self.adapters._flatten()[0]) + 1, dtype=np.int32))
+
+    def process_chunk_wildcards(self, chunk) -> Tuple[bytes, bytes]:
+        """(trimmed FASTQ, the rows of ``--wildcard-file``): WildcardFileWriter, steps.py:209-220."""
+        blobs = [s.sequence.encode("latin-1") for s in self.adapters._flatten()[0]]
+        offsets = np.zeros(len(blobs) + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(b) for b in blobs])
+        return self._process_chunk_rows(chunk, 2, b"".join(blobs), offsets)
 
     def process_chunks(self, chunks, copy: bool = True):
         """copy=False yields uint8 array views into per-slot buffers: valid until the next-but-one result."""

@@ -385,6 +385,16 @@ int cg_fastq_collect_info(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, c
                           const char *adapter_names, const int32_t *name_offsets, uint8_t *out, int64_t out_capacity,
                           uint8_t *info_out, int64_t info_capacity, cg_fastq_result *res, int64_t *info_bytes);
 
+/* The same for the other per-read text outputs.  kind 0: --info-file (as above); 1: --rest-file (RestFileWriter,
+ * steps.py:193-206; SingleMatch.rest, adapters.py:430-437, 463-470): for the last match of a read, what lies behind a
+ * 3' adapter / in front of a 5' adapter, if not empty, then " name"; 2: --wildcard-file (WildcardFileWriter,
+ * steps.py:209-220; SingleMatch.wildcards, adapters.py:378-393): the read characters under the N positions of the adapter
+ * of the last match, then " name" -- adapter_text holds the adapters' SEQUENCES for kind 2 (their names for kind 0,
+ * anything for kind 1).  Linked adapters: undefined, as in the reference (its writers fail on a LinkedMatch). */
+int cg_fastq_collect_rows(cg_ctx *ctx, int32_t slot, const cg_adapterset *set, const cg_fastq_params *params, int32_t kind,
+                          const char *adapter_text, const int32_t *text_offsets, uint8_t *out, int64_t out_capacity,
+                          uint8_t *rows_out, int64_t rows_capacity, cg_fastq_result *res, int64_t *rows_bytes);
+
 /* --pair-adapters (PairedAdapterCutter, modifiers.py:412-503): adapter i of the -a list is removed from R1 only
  * together with adapter i of the -A list from R2.  sets1[i] / sets2[i] hold adapter i alone (one group each); every
  * pair is matched against both mates on the device and the best pair that matches BOTH mates wins (highest score

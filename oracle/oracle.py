@@ -600,7 +600,8 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                     nextseq_cutoff=None, minimum_length=0, maximum_length=-1, discard_trimmed=False,
                     discard_untrimmed=False, max_n=-1.0, max_expected_errors=-1.0, cut=(), poly_a=False, length=None,
                     trim_n=False, discard_casava=False, second_mate=False, want_last_adapter=False, action="trim",
-                    revcomp=False, rc_suffix=True, match_override=None, info_names=None, info_rows=None):
+                    revcomp=False, rc_suffix=True, match_override=None, info_names=None, info_rows=None,
+                    rest_rows=None, wildcard_rows=None, adapter_sequences=None):
     """Modifier chain on every record of a chunk + the verdict of every enabled filter.
     Returns ([(name, sequence, qualities, {filter: bool})], enabled filters, per-read counters).
     match_override: match records (n, 1, slots) found by the caller on the quality-trimmed reads (--pair-adapters).
@@ -744,6 +745,28 @@ def _fastq_evaluate(data, adapters, groups, quality_trim=False, cutoff_front=0, 
                             cur_s, cur_q = cur_s[re_:], cur_q[re_:]
             else:
                 info_rows.append("\t".join([name, "-1", ts, tq]))
+        if (rest_rows is not None or wildcard_rows is not None) and matched:
+            # RestFileWriter / WildcardFileWriter (steps.py:193-220): the LAST match and the sequence its round searched
+            cur = seq[int(qtrim[i, 0]):int(qtrim[i, 1])]
+            last = None
+            for r in range(matches.shape[1]):
+                present = [m for m in matches[i, r] if m["adapter"] >= 0]
+                if not present:
+                    break
+                for m in present:
+                    last = (m, cur)
+                    cur = cur[:int(m["rstart"])] if (int(m["info"]) >> 8) & 1 else cur[int(m["rstop"]):]
+            m, cur = last
+            if rest_rows is not None:
+                rest = cur[int(m["rstop"]):] if (int(m["info"]) >> 8) & 1 else cur[:int(m["rstart"])]
+                if rest:
+                    rest_rows.append(f"{rest} {name}")
+            if wildcard_rows is not None:
+                aseq = adapter_sequences[int(m["adapter"])]
+                astart, rstart = int(m["astart"]), int(m["rstart"])
+                chars = [cur[rstart + k] for k in range(int(m["astop"]) - astart)
+                         if aseq[astart + k] == "N" and rstart + k < len(cur)]
+                wildcard_rows.append(f"{''.join(chars)} {name}")
         n_count = ts.lower().count("n")
         fails = {
             "too_short": len(ts) < minimum_length,                                        # predicates.py:29-40

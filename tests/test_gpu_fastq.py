@@ -528,3 +528,43 @@ def test_info_rows_random_chunks_against_oracle(variant):
     assert out == exp
     assert info.decode("latin-1") == "".join(r + "\n" for r in rows)
     assert len(rows) >= 5000
+
+
+def test_rest_and_wildcard_rows_on_the_device():
+    """--rest-file / --wildcard-file rows formatted on the device (cg_fastq_collect_rows): the reference's known answers
+    (tests/data/rest.txt, restfront.txt, test_adapter_wildcard; test_commandline.py:110-122, 345-367) and randomized
+    chunks against the oracle (several rounds, quality trimming in front, --revcomp)."""
+    import cutadapt_b200.adapters as PA
+    from util import fastq_file
+
+    def fasta_as_fastq(name):
+        lines = [l for l in fastq_file(name).decode().split("\n") if l]
+        return "".join(f"@{h[1:]}\n{s}\n+\n{'I' * len(s)}\n" for h, s in zip(lines[0::2], lines[1::2])).encode()
+
+    data = fasta_as_fastq("rest.in.fasta")
+    for cls, expected in ((PA.AnywhereAdapter, "rest.txt"), (PA.FrontAdapter, "restfront.txt")):
+        t = FastqTrimmer([cls("ADAPTER", max_errors=0.1, min_overlap=3, adapter_wildcards=False, name="a")])
+        _, rows = t.process_chunk_rest(data)
+        assert rows == fastq_file(expected), expected
+    data = fasta_as_fastq("wildcard_adapter.in.fasta")
+    for cls in (PA.BackAdapter, PA.AnywhereAdapter):
+        t = FastqTrimmer([cls("ACGTNNNACGT", max_errors=0.1, min_overlap=3, name="a")])
+        _, rows = t.process_chunk_wildcards(data)
+        assert rows == b"AAA 1\nGGG 2\nCCC 3b\nTTT 4b\n"
+    # randomized
+    for seed, extra in ((41, dict(times=2)), (42, dict(revcomp=True, cut=[2]))):
+        chunk = synthetic_fastq(4000, seed=seed)
+        if extra.get("revcomp"):
+            chunk = flip_records(chunk, seed)
+        options = dict(adapters=[["back", "AGATCGGAAGAGC"], ["front", "TTGACNNACG"], ["anywhere", "CACGTNTGAAC"]],
+                       quality_cutoff=[5, 20])
+        ads = fastq_case_adapters(options)
+        seqs = [s.sequence for s in PA.MultipleAdapters(ads)._flatten()[0]]
+        rest, wild = [], []
+        exp, _ = oracle_for(options, chunk, rest_rows=rest, wildcard_rows=wild, adapter_sequences=seqs, **extra)
+        t = trimmer_for(options, **extra)
+        out, rows = t.process_chunk_rest(chunk)
+        assert out == exp and rows.decode("latin-1") == "".join(r + "\n" for r in rest)
+        out, rows = trimmer_for(options, **extra).process_chunk_wildcards(chunk)
+        assert out == exp and rows.decode("latin-1") == "".join(r + "\n" for r in wild)
+        assert len(rest) > 500 and len(wild) > 1000
