@@ -1159,24 +1159,33 @@ CG_HD bool match_indexed(const SetView &S, int index_no, const uint8_t *p, int n
     const CgIndexHeader &H = S.index_hdr[index_no];
     const CgIndexEntry *tab = S.index_tab + H.table_off;
     int best_a = -1, best_len = 0, best_m = -1, best_e = 1000;
+    // The affix is packed ONCE, for the longest key (the lengths are descending): 2 bits per character at bit 2 i,
+    // A C G T = 0 1 2 3 (bits 1-2 of the ASCII code give A C T G = 0 1 2 3; x ^ (x >> 1) swaps the last two), either
+    // case (sequence.upper()), N as A (_lookup_with_n); one bit per position for "N" and for "not a nucleotide".
+    // The key of a shorter length is a mask (prefix) or a shift (suffix) away.
+    const int cnt_max = cg_min((int)H.lengths[0], cg_min(n, 32));
+    const uint8_t *q_max = H.prefix ? p : p + (n - cnt_max);
+    uint64_t packed = 0;
+    uint32_t n_mask = 0, bad_mask = 0;
+    for (int i = 0; i < cnt_max; ++i) {
+        const uint32_t c = q_max[i], u = c & 0xDFu, x = (c >> 1) & 3u;
+        const bool is_n = u == 'N';
+        const bool acgt = u == 'A' || u == 'C' || u == 'G' || u == 'T';
+        const uint64_t code = is_n ? 0u : (x ^ (x >> 1));
+        packed |= code << (2 * i);
+        n_mask |= (is_n ? 1u : 0u) << i;
+        bad_mask |= ((acgt || is_n) ? 0u : 1u) << i;
+    }
     for (int li = 0; li < H.n_lengths; ++li) {
         const int L = H.lengths[li];
         if (L < best_m) break;                                   // adapters.py:1506-1508
         const int cnt = cg_min(L, n);                            // sequence[:L] / sequence[-L:]
         if (cnt > 32 || cnt <= 0) continue;
         const uint8_t *q = H.prefix ? p : p + (n - cnt);
-        uint64_t bases = 0;
-        bool has_n = false, valid = true;
-        for (int i = 0; i < cnt; ++i) {
-            uint8_t c = q[i];
-            if (c >= 'a' && c <= 'z') c -= 32;                   // sequence.upper()
-            uint64_t code = 0;
-            if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2;
-            else if (c == 'T') code = 3;
-            else if (c == 'N') { has_n = true; code = 0; }       // _lookup_with_n: N -> A
-            else valid = false;
-            bases |= code << (2 * i);
-        }
+        const int skip = H.prefix ? 0 : cnt_max - cnt;           // position of the key's first character in the packed affix
+        const uint32_t span = (cnt >= 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u)) << skip;
+        const uint64_t bases = (packed >> (2 * skip)) & (cnt >= 32 ? ~0ULL : ((1ULL << (2 * cnt)) - 1ULL));
+        const bool has_n = (n_mask & span) != 0, valid = (bad_mask & span) == 0;
         if (!valid) continue;
         uint32_t val = 0;
         bool found = false;
