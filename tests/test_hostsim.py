@@ -5,6 +5,7 @@ lane -- packed-cell DP, wide-cell DP, prefilter, comparers, quality trimming, li
 composition, rounds -- without a GPU.  The host build lives under tests/ and is never loaded by
 the product.
 """
+import os
 import random
 
 import numpy as np
@@ -660,3 +661,18 @@ def test_banded_dp_runs_on_crowded_reads():
         assert (got == exp).all(), repr(ad)
         total += int((exp["adapter"] >= 0).sum())
     assert total > 5000
+
+
+def test_index_lookups_on_random_barcode_sets():
+    """match_indexed (the affix is packed once, keys of shorter lengths are a mask / shift away): random barcode sets of
+    equal and mixed lengths, 5' and 3', with and without indels, mutated barcodes with N, lower case and other letters,
+    reads shorter than the keys -- the host build against the oracle's own index (tools/fuzz_index.py runs the same
+    with more trials)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_index.py"), "5", "25"], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "ok, hits" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert int(out.stdout.strip().split()[-1]) > 2000
